@@ -1,0 +1,698 @@
+// AV1 OBU packing + tile entropy coding on the host.  See bitstream.h.
+// Section numbers refer to the AV1 Bitstream & Decoding Process Specification.
+#include "bitstream.h"
+#include <string.h>
+#include <algorithm>
+#include <thread>
+#include <atomic>
+#include "av1_tables.h"
+
+namespace av1b {
+
+// ------------------------------------------------------------------------------------------------
+// Range encoder (the inverse of spec 8.2.6 "symbol decoding process")
+// ------------------------------------------------------------------------------------------------
+void RangeEncoder::encode(int s, const uint16_t* icdf, int n) {
+  // The decoder partitions [0, rng) from the top: symbol k owns [cur_k, cur_{k-1}) with
+  // cur_k = ((rng >> 8) * (icdf[k] >> 6) >> 1) + 4 * (n - 1 - k), cur_{-1} = rng.
+  uint32_t r = rng_, l = low_;
+  const int N = n - 1;
+  uint32_t v = ((r >> 8) * (uint32_t)(icdf[s] >> 6) >> 1) + 4 * (N - s);
+  if (s > 0) {
+    uint32_t u = ((r >> 8) * (uint32_t)(icdf[s - 1] >> 6) >> 1) + 4 * (N - (s - 1));
+    l += r - u;
+    r = u - v;
+  } else {
+    r -= v;
+  }
+  // renormalise
+  int d = 15 - (31 - __builtin_clz(r));   // r < 2^16, make bit 15 the top bit
+  int c = cnt_;
+  int sft = c + d;
+  if (sft >= 0) {
+    c += 16;
+    uint32_t m = (1u << c) - 1;
+    if (sft >= 8) {
+      pre_.push_back((uint16_t)(l >> c));
+      l &= m;
+      c -= 8;
+      m >>= 8;
+    }
+    pre_.push_back((uint16_t)(l >> c));
+    sft = c + d - 24;
+    l &= m;
+  }
+  low_ = l << d;
+  rng_ = r << d;
+  cnt_ = sft;
+}
+
+void RangeEncoder::symbol(int s, uint16_t* icdf, int n) {
+  encode(s, icdf, n);
+  if (adapt_) {
+    // spec 8.2.6 CDF adaptation, expressed on the inverted CDF
+    const int cnt = icdf[n];
+    const int rate = 3 + (cnt > 15) + (cnt > 31) + std::min(31 - __builtin_clz((unsigned)n), 2);
+    for (int i = 0; i < n - 1; i++) {
+      if (i < s) icdf[i] += (uint16_t)((32768 - icdf[i]) >> rate);
+      else icdf[i] -= (uint16_t)(icdf[i] >> rate);
+    }
+    icdf[n] = (uint16_t)(cnt + (cnt < 32));
+  }
+}
+
+void RangeEncoder::finish(std::vector<uint8_t>& out) {
+  // emit enough bits that any continuation decodes the same symbols, plus the terminating 1 bit
+  uint32_t l = low_;
+  int c = cnt_;
+  int s = 10;
+  const uint32_t m = 0x3FFF;
+  uint32_t e = ((l + m) & ~m) | (m + 1);
+  s += c;
+  if (s > 0) {
+    uint32_t n = (1u << (c + 16)) - 1;
+    do {
+      pre_.push_back((uint16_t)(e >> (c + 16)));
+      e &= n;
+      s -= 8;
+      c -= 8;
+      n >>= 8;
+    } while (s > 0);
+  }
+  // carry propagation, last to first
+  size_t base = out.size();
+  out.resize(base + pre_.size());
+  uint32_t carry = 0;
+  for (size_t i = pre_.size(); i-- > 0;) {
+    carry += pre_[i];
+    out[base + i] = (uint8_t)carry;
+    carry >>= 8;
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// OBU plumbing
+// ------------------------------------------------------------------------------------------------
+static void put_leb128(std::vector<uint8_t>& out, uint64_t v) {
+  do {
+    uint8_t b = v & 0x7F;
+    v >>= 7;
+    if (v) b |= 0x80;
+    out.push_back(b);
+  } while (v);
+}
+
+void append_obu(std::vector<uint8_t>& out, int obu_type, const std::vector<uint8_t>& payload) {
+  out.push_back((uint8_t)((obu_type << 3) | 2));   // has_size_field = 1
+  put_leb128(out, payload.size());
+  out.insert(out.end(), payload.begin(), payload.end());
+}
+
+void write_temporal_delimiter(std::vector<uint8_t>& out) {
+  std::vector<uint8_t> empty;
+  append_obu(out, 2, empty);
+}
+
+static int bits_for(uint32_t v) { int n = 0; while (v) { n++; v >>= 1; } return n ? n : 1; }
+
+void write_sequence_header(const Av1bSeqParams& seq, std::vector<uint8_t>& out) {
+  BitWriter w;
+  w.put(0, 3);   // seq_profile 0 (4:2:0, 8/10 bit)
+  w.bit(0);      // still_picture
+  w.bit(0);      // reduced_still_picture_header
+  w.bit(0);      // timing_info_present_flag
+  w.bit(0);      // initial_display_delay_present_flag
+  w.put(0, 5);   // operating_points_cnt_minus_1
+  w.put(0, 12);  // operating_point_idc[0]
+  w.put(31, 5);  // seq_level_idx[0] = 31: "maximum parameters" (many-tile layouts exceed level limits)
+  w.bit(0);      // seq_tier[0]
+  int wb = bits_for(seq.width - 1), hb = bits_for(seq.height - 1);
+  w.put(wb - 1, 4);
+  w.put(hb - 1, 4);
+  w.put(seq.width - 1, wb);
+  w.put(seq.height - 1, hb);
+  w.bit(0);   // frame_id_numbers_present_flag
+  w.bit(0);   // use_128x128_superblock
+  w.bit(0);   // enable_filter_intra
+  w.bit(0);   // enable_intra_edge_filter
+  w.bit(0);   // enable_interintra_compound
+  w.bit(0);   // enable_masked_compound
+  w.bit(0);   // enable_warped_motion
+  w.bit(0);   // enable_dual_filter
+  w.bit(0);   // enable_order_hint
+  w.bit(0);   // seq_choose_screen_content_tools
+  w.bit(0);   // seq_force_screen_content_tools = 0  (=> seq_force_integer_mv = SELECT, not coded)
+  w.bit(0);   // enable_superres
+  w.bit(seq.enable_cdef ? 1 : 0);
+  w.bit(seq.enable_restoration ? 1 : 0);
+  // color_config()
+  w.bit(seq.bit_depth > 8);   // high_bitdepth
+  w.bit(0);                   // mono_chrome
+  if (seq.color_hdr) {
+    w.bit(1);                 // color_description_present_flag
+    w.put(9, 8);              // color_primaries  BT.2020
+    w.put(16, 8);             // transfer_characteristics  SMPTE 2084 (PQ)
+    w.put(9, 8);              // matrix_coefficients BT.2020 NCL
+  } else {
+    w.bit(0);
+  }
+  w.bit(0);                   // color_range (studio)
+  w.put(0, 2);                // chroma_sample_position
+  w.bit(0);                   // separate_uv_delta_q
+  w.bit(0);                   // film_grain_params_present
+  w.trailing_bits();
+  append_obu(out, 1, w.bytes());
+}
+
+// ------------------------------------------------------------------------------------------------
+// Frame header (spec 5.9)
+// ------------------------------------------------------------------------------------------------
+static void write_frame_header(const Av1bSeqParams& seq, const Av1bFrameParams& fp, const Av1bGeom& g,
+                               BitWriter& w) {
+  const bool key = fp.frame_type == AV1B_KEY_FRAME;
+  w.bit(0);                    // show_existing_frame
+  w.put(fp.frame_type, 2);
+  w.bit(1);                    // show_frame
+  if (!key) w.bit(0);          // error_resilient_mode (implied 1 for shown key frames)
+  w.bit(fp.disable_cdf_update ? 1 : 0);
+  w.bit(0);                    // frame_size_override_flag
+  // order_hint: 0 bits; primary_ref_frame: NONE for intra frames (not coded)
+  if (!key) w.put(0x01, 8);    // refresh_frame_flags for intra_only frames (must not be 0xFF)
+  // frame_size(): from the sequence header; superres off; render_size():
+  w.bit(0);                    // render_and_frame_size_different
+  if (!fp.disable_cdf_update) w.bit(1);   // disable_frame_end_update_cdf
+  // tile_info()
+  {
+    const int max_w_sb = 64, max_area_sb = 2304;
+    int min_cols = av1b_tile_log2(max_w_sb, g.sb_cols);
+    int max_cols = av1b_tile_log2(1, std::min(g.sb_cols, 64));
+    int max_rows = av1b_tile_log2(1, std::min(g.sb_rows, 64));
+    int min_tiles = std::max(min_cols, av1b_tile_log2(max_area_sb, g.sb_rows * g.sb_cols));
+    w.bit(1);                  // uniform_tile_spacing_flag
+    for (int k = min_cols; k < max_cols; k++) {
+      if (k < g.tile_cols_log2) w.bit(1); else { w.bit(0); break; }
+    }
+    int min_rows = std::max(min_tiles - g.tile_cols_log2, 0);
+    for (int k = min_rows; k < max_rows; k++) {
+      if (k < g.tile_rows_log2) w.bit(1); else { w.bit(0); break; }
+    }
+    if (g.tile_cols_log2 > 0 || g.tile_rows_log2 > 0) {
+      w.put(0, g.tile_cols_log2 + g.tile_rows_log2);   // context_update_tile_id
+      w.put(3, 2);                                     // tile_size_bytes_minus_1
+    }
+  }
+  // quantization_params()
+  w.put(fp.base_q_idx, 8);
+  w.bit(0);   // DeltaQYDc: delta_coded
+  w.bit(0);   // DeltaQUDc
+  w.bit(0);   // DeltaQUAc
+  w.bit(0);   // using_qmatrix
+  w.bit(0);   // segmentation_enabled
+  if (fp.base_q_idx > 0) w.bit(0);   // delta_q_present
+  // loop_filter_params()   (base_q_idx > 0 => not CodedLossless)
+  w.put(fp.lf_level[0], 6);
+  w.put(fp.lf_level[1], 6);
+  if (fp.lf_level[0] || fp.lf_level[1]) {
+    w.put(fp.lf_level[2], 6);
+    w.put(fp.lf_level[3], 6);
+  }
+  w.put(fp.lf_sharpness, 3);
+  w.bit(0);   // loop_filter_delta_enabled
+  // cdef_params()
+  if (seq.enable_cdef) {
+    w.put(fp.cdef_damping - 3, 2);
+    w.put(fp.cdef_bits, 2);
+    for (int i = 0; i < (1 << fp.cdef_bits); i++) {
+      w.put(fp.cdef_y_strength[i] >> 2, 4);
+      w.put(fp.cdef_y_strength[i] & 3, 2);
+      w.put(fp.cdef_uv_strength[i] >> 2, 4);
+      w.put(fp.cdef_uv_strength[i] & 3, 2);
+    }
+  }
+  // lr_params()
+  if (seq.enable_restoration) {
+    static const int remap[4] = {0, 2, 3, 1};   // our RESTORE_* -> coded lr_type
+    bool uses = false, uses_chroma = false;
+    for (int p = 0; p < 3; p++) {
+      w.put(remap[fp.lr_type[p]], 2);
+      if (fp.lr_type[p] != AV1B_RESTORE_NONE) { uses = true; if (p) uses_chroma = true; }
+    }
+    if (uses) {
+      w.bit(fp.lr_unit_shift > 0);
+      if (fp.lr_unit_shift > 0) w.bit(fp.lr_unit_shift > 1);
+      if (uses_chroma) w.bit(fp.lr_uv_shift);
+    }
+  }
+  w.bit(0);   // tx_mode_select = 0 -> TX_MODE_LARGEST
+  // frame_reference_mode / skip_mode_params / allow_warped_motion: nothing for intra frames
+  w.bit(0);   // reduced_tx_set
+  // global_motion_params(): nothing for intra frames; film grain: not present
+}
+
+// ------------------------------------------------------------------------------------------------
+// Tile entropy coding (spec 5.11, coefficients 5.11.39)
+// ------------------------------------------------------------------------------------------------
+namespace {
+
+struct TileCdfs {
+  uint16_t partition[20][11];
+  uint16_t skip[3][3];
+  uint16_t kf_y_mode[5][5][14];
+  uint16_t uv_mode[2][13][15];
+  uint16_t angle_delta[8][8];
+  uint16_t intra_ext_tx[3][4][13][17];
+  uint16_t txb_skip[5][13][3];
+  uint16_t eob_extra[5][2][9][3];
+  uint16_t dc_sign[2][3][3];
+  uint16_t eob_pt_16[2][2][6];
+  uint16_t eob_pt_32[2][2][7];
+  uint16_t eob_pt_64[2][2][8];
+  uint16_t eob_pt_128[2][2][9];
+  uint16_t eob_pt_256[2][2][10];
+  uint16_t eob_pt_512[2][2][11];
+  uint16_t eob_pt_1024[2][2][12];
+  uint16_t coeff_base_eob[5][2][4][4];
+  uint16_t coeff_base[5][2][42][5];
+  uint16_t coeff_br[5][2][21][5];
+  uint16_t cfl_sign[9];
+  uint16_t cfl_alpha[6][17];
+  uint16_t switchable_restore[4];
+  uint16_t wiener_restore[3];
+  uint16_t sgrproj_restore[3];
+};
+
+void init_cdfs(TileCdfs& c, int base_q_idx) {
+  const int q = base_q_idx <= 20 ? 0 : base_q_idx <= 60 ? 1 : base_q_idx <= 120 ? 2 : 3;
+#define CP(dst, src) memcpy(dst, src, sizeof(dst))
+  CP(c.partition, av1t_cdf_partition);
+  CP(c.skip, av1t_cdf_skip);
+  CP(c.kf_y_mode, av1t_cdf_kf_y_mode);
+  CP(c.uv_mode, av1t_cdf_uv_mode);
+  CP(c.angle_delta, av1t_cdf_angle_delta);
+  CP(c.intra_ext_tx, av1t_cdf_intra_ext_tx);
+  CP(c.txb_skip, av1t_cdf_txb_skip[q]);
+  CP(c.eob_extra, av1t_cdf_eob_extra[q]);
+  CP(c.dc_sign, av1t_cdf_dc_sign[q]);
+  CP(c.eob_pt_16, av1t_cdf_eob_pt_16[q]);
+  CP(c.eob_pt_32, av1t_cdf_eob_pt_32[q]);
+  CP(c.eob_pt_64, av1t_cdf_eob_pt_64[q]);
+  CP(c.eob_pt_128, av1t_cdf_eob_pt_128[q]);
+  CP(c.eob_pt_256, av1t_cdf_eob_pt_256[q]);
+  CP(c.eob_pt_512, av1t_cdf_eob_pt_512[q]);
+  CP(c.eob_pt_1024, av1t_cdf_eob_pt_1024[q]);
+  CP(c.coeff_base_eob, av1t_cdf_coeff_base_eob[q]);
+  CP(c.coeff_base, av1t_cdf_coeff_base[q]);
+  CP(c.coeff_br, av1t_cdf_coeff_br[q]);
+  CP(c.cfl_sign, av1t_cdf_cfl_sign);
+  CP(c.cfl_alpha, av1t_cdf_cfl_alpha);
+  CP(c.switchable_restore, av1t_cdf_switchable_restore);
+  CP(c.wiener_restore, av1t_cdf_wiener_restore);
+  CP(c.sgrproj_restore, av1t_cdf_sgrproj_restore);
+#undef CP
+}
+
+const uint8_t kIntraModeCtx[13] = {0, 1, 2, 3, 4, 4, 4, 4, 3, 0, 1, 2, 0};
+// Mode_To_Txfm (spec): default transform type of an intra mode, used for chroma
+const uint8_t kModeToTxfm[14] = {
+    AV1B_DCT_DCT, AV1B_ADST_DCT, AV1B_DCT_ADST, AV1B_DCT_DCT, AV1B_ADST_ADST, AV1B_ADST_DCT,
+    AV1B_DCT_ADST, AV1B_DCT_ADST, AV1B_ADST_DCT, AV1B_ADST_ADST, AV1B_ADST_DCT, AV1B_DCT_ADST,
+    AV1B_ADST_ADST, AV1B_DCT_DCT};
+
+enum { SET_DCTONLY = 0, SET_DCT_IDTX, SET_DTT4_IDTX, SET_DTT4_IDTX_1DDCT, SET_DTT9_IDTX_1DDCT, SET_ALL16 };
+
+// intra transform set type for a square transform of log2 size n (2..6) (spec get_tx_set, intra)
+inline int intra_tx_set_type(int tx_log2) {
+  if (tx_log2 >= 5) return SET_DCTONLY;
+  if (tx_log2 == 4) return SET_DTT4_IDTX;         // TX_SET_INTRA_2 (5 types)
+  return SET_DTT4_IDTX_1DDCT;                     // TX_SET_INTRA_1 (7 types)
+}
+inline int tx_class(int tx_type) {   // 0: 2D, 1: horizontal 1-D, 2: vertical 1-D
+  switch (tx_type) {
+    case AV1B_V_DCT: case AV1B_V_ADST: case AV1B_V_FLIPADST: return 2;
+    case AV1B_H_DCT: case AV1B_H_ADST: case AV1B_H_FLIPADST: return 1;
+    default: return 0;
+  }
+}
+
+const int16_t* scan_for(int ns_log2, int tx_type) {
+  const int cls = tx_class(tx_type);
+  switch (ns_log2) {
+    case 2: return cls == 2 ? av1t_scan_mrow_4x4 : cls == 1 ? av1t_scan_mcol_4x4 : av1t_scan_default_4x4;
+    case 3: return cls == 2 ? av1t_scan_mrow_8x8 : cls == 1 ? av1t_scan_mcol_8x8 : av1t_scan_default_8x8;
+    case 4: return cls == 2 ? av1t_scan_mrow_16x16 : cls == 1 ? av1t_scan_mcol_16x16 : av1t_scan_default_16x16;
+    default: return av1t_scan_default_32x32;
+  }
+}
+const int8_t* nz_offset_for(int ns_log2) {
+  switch (ns_log2) {
+    case 2: return av1t_nz_map_ctx_offset_4x4;
+    case 3: return av1t_nz_map_ctx_offset_8x8;
+    case 4: return av1t_nz_map_ctx_offset_16x16;
+    default: return av1t_nz_map_ctx_offset_32x32;
+  }
+}
+
+struct TileWriter {
+  const Av1bSeqParams& seq;
+  const Av1bFrameParams& fp;
+  const Av1bGeom& g;
+  const Av1bFrameSyms& sy;
+  RangeEncoder ec;
+  TileCdfs cdf;
+  int mi_row_start, mi_row_end, mi_col_start, mi_col_end;
+  // entropy contexts (4x4 units of each plane), above: indexed from tile start; left: within SB row
+  std::vector<uint8_t> above_lvl[3], above_dc[3];
+  uint8_t left_lvl[3][16], left_dc[3][16];
+  uint8_t lvl_buf[(32 + 4) * (32 + 4) + 8];
+
+  TileWriter(const Av1bSeqParams& s, const Av1bFrameParams& f, const Av1bGeom& gg, const Av1bFrameSyms& ss)
+      : seq(s), fp(f), g(gg), sy(ss), ec(!f.disable_cdf_update) {}
+
+  const Av1bBlockInfo& blk(int mi_row, int mi_col) const { return sy.blocks[(mi_row >> 1) * g.w8 + (mi_col >> 1)]; }
+  bool avail_u(int r) const { return r > mi_row_start; }
+  bool avail_l(int c) const { return c > mi_col_start; }
+
+  void run(int tile_row, int tile_col, std::vector<uint8_t>& out) {
+    mi_row_start = g.tile_row_start_sb[tile_row] * 16;
+    mi_row_end = std::min(g.tile_row_start_sb[tile_row + 1] * 16, g.mi_rows);
+    mi_col_start = g.tile_col_start_sb[tile_col] * 16;
+    mi_col_end = std::min(g.tile_col_start_sb[tile_col + 1] * 16, g.mi_cols);
+    init_cdfs(cdf, fp.base_q_idx);
+    const int tw4 = mi_col_end - mi_col_start;
+    for (int p = 0; p < 3; p++) {
+      above_lvl[p].assign(tw4 + 32, 0);
+      above_dc[p].assign(tw4 + 32, 0);
+    }
+    for (int r = mi_row_start; r < mi_row_end; r += 16) {
+      memset(left_lvl, 0, sizeof(left_lvl));
+      memset(left_dc, 0, sizeof(left_dc));
+      for (int c = mi_col_start; c < mi_col_end; c += 16) {
+        cdef_pending = true;   // clear_cdef(): cdef_idx is coded at the first non-skip block
+        // read_lr(): loop-restoration unit syntax is added with the LR stage
+        partition(r, c, 6);
+      }
+    }
+    ec.finish(out);
+  }
+
+  // square-only partition tree; bl = log2 of block size in samples (6..3)
+  void partition(int r, int c, int bl) {
+    if (r >= g.mi_rows || c >= g.mi_cols) return;
+    const int n4 = 1 << (bl - 2), half = n4 >> 1;
+    const bool has_rows = (r + half) < g.mi_rows, has_cols = (c + half) < g.mi_cols;
+    const Av1bBlockInfo& b = blk(r, c);
+    const bool split = b.blk_log2 < bl;
+    if (bl >= 3) {
+      const int bsl = bl - 2;   // Mi_Width_Log2 of this size
+      int above = avail_u(r) && (blk(r - 1, c).blk_log2 - 2) < bsl;
+      int left = avail_l(c) && (blk(r, c - 1).blk_log2 - 2) < bsl;
+      uint16_t* pc = cdf.partition[(bsl - 1) * 4 + left * 2 + above];
+      const int nsym = bl == 3 ? 4 : 10;
+      if (has_rows && has_cols) {
+        ec.symbol(split ? 3 : 0, pc, nsym);
+      } else if (has_cols || has_rows) {
+        // split_or_horz / split_or_vert: binary symbol with probability gathered from the CDF
+        // (spec 8.3.2, "psum").  We always choose split at frame edges.
+        auto prob = [&](int k) -> int {   // P(partition == k) * 32768 from the inverted CDF
+          int hi = k > 0 ? pc[k - 1] : 32768;
+          return hi - pc[k];
+        };
+        int psum;
+        if (has_cols) {   // !has_rows: split_or_horz, gather the "vertical alike" partitions
+          psum = prob(2) + prob(3);
+          if (bl != 3) psum += prob(4) + prob(6) + prob(7) + prob(9);   // HORZ_A VERT_A VERT_B VERT_4
+        } else {          // split_or_vert, gather "horizontal alike"
+          psum = prob(1) + prob(3);
+          if (bl != 3) psum += prob(4) + prob(5) + prob(6) + prob(8);   // HORZ_A HORZ_B VERT_A HORZ_4
+        }
+        uint16_t tmp[3] = {(uint16_t)psum, 0, 0};   // icdf[0] = 32768 - P(not split) = psum
+        ec.symbol(1, tmp, 2);                        // derived CDF: its adaptation is discarded
+      }
+    }
+    if (!split) {
+      block(r, c, bl);
+      return;
+    }
+    const int h = half;
+    partition(r, c, bl - 1);
+    partition(r, c + h, bl - 1);
+    partition(r + h, c, bl - 1);
+    partition(r + h, c + h, bl - 1);
+  }
+
+  void block(int r, int c, int bl) {
+    const Av1bBlockInfo& b = blk(r, c);
+    const int n4 = 1 << (bl - 2);
+    // intra_frame_mode_info()
+    {
+      int ctx = (avail_u(r) ? blk(r - 1, c).skip : 0) + (avail_l(c) ? blk(r, c - 1).skip : 0);
+      ec.symbol(b.skip ? 1 : 0, cdf.skip[ctx], 2);
+    }
+    // read_cdef(): cdef_idx literal at the first non-skip block of each 64x64
+    if (!b.skip && seq.enable_cdef && fp.cdef_bits > 0) {
+      if (cdef_pending) { ec.literal(sy.cdef_idx[(r >> 4) * g.sb_cols + (c >> 4)], fp.cdef_bits); cdef_pending = false; }
+    }
+    {
+      int am = avail_u(r) ? blk(r - 1, c).y_mode : AV1B_DC_PRED;
+      int lm = avail_l(c) ? blk(r, c - 1).y_mode : AV1B_DC_PRED;
+      ec.symbol(b.y_mode, cdf.kf_y_mode[kIntraModeCtx[am]][kIntraModeCtx[lm]], 13);
+    }
+    if (b.y_mode >= AV1B_V_PRED && b.y_mode <= AV1B_D67_PRED)
+      ec.symbol(b.angle_y + 3, cdf.angle_delta[b.y_mode - AV1B_V_PRED], 7);
+    {
+      const int cfl_allowed = bl <= 5;
+      ec.symbol(b.uv_mode, cdf.uv_mode[cfl_allowed][b.y_mode], cfl_allowed ? 14 : 13);
+      if (b.uv_mode == AV1B_UV_CFL_PRED) {
+        // cfl_alphas(): joint sign then magnitudes
+        const int su = b.cfl_alpha_u >> 5 & 3, sv = b.cfl_alpha_v >> 5 & 3;   // 0 zero, 1 neg, 2 pos
+        const int joint = su * 3 + sv - 1;
+        ec.symbol(joint, cdf.cfl_sign, 8);
+        if (su) ec.symbol(b.cfl_alpha_u & 15, cdf.cfl_alpha[(su - 1) * 3 + sv], 16);
+        if (sv) ec.symbol(b.cfl_alpha_v & 15, cdf.cfl_alpha[(sv - 1) * 3 + su], 16);
+      } else if (b.uv_mode >= AV1B_V_PRED && b.uv_mode <= AV1B_D67_PRED) {
+        ec.symbol(b.angle_uv + 3, cdf.angle_delta[b.uv_mode - AV1B_V_PRED], 7);
+      }
+    }
+    // TX_MODE_LARGEST: no tx_size syntax.  residual()
+    if (b.skip) {
+      for (int p = 0; p < 3; p++) {
+        const int ss = p > 0, x4 = (c - mi_col_start) >> ss, y4 = (r & 15) >> ss, n = std::max(1, n4 >> ss);
+        memset(&above_lvl[p][x4], 0, n); memset(&above_dc[p][x4], 0, n);
+        memset(&left_lvl[p][y4], 0, n); memset(&left_dc[p][y4], 0, n);
+      }
+      return;
+    }
+    for (int p = 0; p < 3; p++) {
+      const int ss = p > 0;
+      int tl = bl - ss;            // transform log2 size for this plane
+      if (tl > 6) tl = 6;
+      if (p > 0 && tl > 5) tl = 5;
+      int tx_type = AV1B_DCT_DCT;
+      if (p == 0) tx_type = b.tx_type_y;
+      else {
+        tx_type = kModeToTxfm[b.uv_mode];
+        if (!av1t_ext_tx_used[intra_tx_set_type(tl)][tx_type]) tx_type = AV1B_DCT_DCT;
+      }
+      coeffs(p, r, c, tl, b, tx_type);
+    }
+  }
+
+  bool cdef_pending = false;
+
+  // coefficient syntax for one transform block (one per plane per block in TX_MODE_LARGEST)
+  void coeffs(int plane, int mi_r, int mi_c, int tl, const Av1bBlockInfo& b, int tx_type) {
+    const int ss = plane > 0;
+    const int x0 = (mi_c * 4) >> ss, y0 = (mi_r * 4) >> ss;      // sample position in the plane
+    const int n = 1 << tl, w4 = n >> 2;
+    const int x4 = ((mi_c - mi_col_start) >> ss), y4 = (mi_r & 15) >> ss;
+    const int max_x4 = ((g.mi_cols - mi_col_start) + ss) >> ss;   // relative to tile start
+    const int max_y4 = (g.mi_rows + ss) >> ss;
+    const int abs_y4 = mi_r >> ss;
+    const int tx_ctx = tl - 2;                                    // square: txSzCtx = log2 - 2
+    const int ptype = plane > 0;
+    const int eob = b.eob[plane];
+    // all_zero context (spec: get_txb_skip ctx)
+    int ctx;
+    if (plane == 0) {
+      ctx = 0;   // transform covers the whole block
+    } else {
+      int above = 0, left = 0;
+      for (int k = 0; k < w4; k++) {
+        if (x4 + k < max_x4) above |= above_lvl[plane][x4 + k] | above_dc[plane][x4 + k];
+        if (abs_y4 + k < max_y4) left |= left_lvl[plane][y4 + k] | left_dc[plane][y4 + k];
+      }
+      ctx = 7 + (above != 0) + (left != 0);
+      // bw*bh > w*h only when the chroma block is larger than its transform (never here)
+    }
+    ec.symbol(eob == 0, cdf.txb_skip[tx_ctx][ctx], 2);
+    int cul = 0, dc_cat = 0;
+    if (eob > 0) {
+      if (plane == 0) {
+        const int set = intra_tx_set_type(tl);
+        if (set != SET_DCTONLY && fp.base_q_idx > 0) {
+          const int eset = set == SET_DTT4_IDTX_1DDCT ? 1 : 2;
+          const int nsym = set == SET_DTT4_IDTX_1DDCT ? 7 : 5;
+          ec.symbol(av1t_ext_tx_ind[set][tx_type], cdf.intra_ext_tx[eset][tl - 2][b.y_mode], nsym);
+        }
+      }
+      const int ns_log2 = std::min(tl, 5), ns = 1 << ns_log2;   // coded area is at most 32x32
+      const int16_t* scan = scan_for(ns_log2, tx_type);
+      const int cls = tx_class(tx_type);
+      const int16_t* cf = sy.coef[plane] + (size_t)y0 * sy.coef_stride[plane] + x0;
+      const int cs = sy.coef_stride[plane];
+      // eob position
+      {
+        int t = 0;
+        static const int16_t start[13] = {0, 1, 2, 3, 5, 9, 17, 33, 65, 129, 257, 513, 1025};
+        while (eob >= start[t + 1]) t++;     // eob in [start[t], start[t+1])
+        // t is eobPt (1-based); symbol = t - 1
+        const int eob_multi = 2 * ns_log2 - 4;
+        const int ectx = cls == 0 ? 0 : 1;
+        switch (eob_multi) {
+          case 0: ec.symbol(t - 1, cdf.eob_pt_16[ptype][ectx], 5); break;
+          case 1: ec.symbol(t - 1, cdf.eob_pt_32[ptype][ectx], 6); break;
+          case 2: ec.symbol(t - 1, cdf.eob_pt_64[ptype][ectx], 7); break;
+          case 3: ec.symbol(t - 1, cdf.eob_pt_128[ptype][ectx], 8); break;
+          case 4: ec.symbol(t - 1, cdf.eob_pt_256[ptype][ectx], 9); break;
+          case 5: ec.symbol(t - 1, cdf.eob_pt_512[ptype][ectx], 10); break;
+          default: ec.symbol(t - 1, cdf.eob_pt_1024[ptype][ectx], 11); break;
+        }
+        const int nbits = t >= 3 ? t - 2 : 0;
+        if (nbits > 0) {
+          const int extra = eob - start[t];
+          ec.symbol((extra >> (nbits - 1)) & 1, cdf.eob_extra[tx_ctx][ptype][t - 3], 2);
+          for (int i = nbits - 2; i >= 0; i--) ec.boolean((extra >> i) & 1);
+        }
+      }
+      // padded magnitude map for the neighbour contexts
+      const int stride = ns + 4;
+      memset(lvl_buf, 0, (size_t)stride * (ns + 4));
+      for (int i = 0; i < eob; i++) {
+        const int pos = scan[i], rr = pos >> ns_log2, cc = pos & (ns - 1);
+        int v = cf[rr * cs + cc];
+        v = v < 0 ? -v : v;
+        lvl_buf[rr * stride + cc] = (uint8_t)std::min(v, 127);
+      }
+      const int8_t* nz_off = nz_offset_for(ns_log2);
+      const int br_tx = std::min(tx_ctx, 3);
+      for (int i = eob - 1; i >= 0; i--) {
+        const int pos = scan[i], rr = pos >> ns_log2, cc = pos & (ns - 1);
+        const uint8_t* L = lvl_buf + rr * stride + cc;
+        const int level = L[0];
+        if (i == eob - 1) {
+          int c2 = i == 0 ? 0 : (i <= (ns * ns) / 8 ? 1 : (i <= (ns * ns) / 4 ? 2 : 3));
+          ec.symbol(std::min(level, 3) - 1, cdf.coeff_base_eob[tx_ctx][ptype][c2], 3);
+        } else {
+          int mag;
+          auto m3 = [](int v) { return v > 3 ? 3 : v; };
+          if (cls == 0) mag = m3(L[1]) + m3(L[stride]) + m3(L[stride + 1]) + m3(L[2]) + m3(L[2 * stride]);
+          else if (cls == 2) mag = m3(L[1]) + m3(L[stride]) + m3(L[2 * stride]) + m3(L[3 * stride]) + m3(L[4 * stride]);
+          else mag = m3(L[1]) + m3(L[stride]) + m3(L[2]) + m3(L[3]) + m3(L[4]);
+          int c2 = std::min((mag + 1) >> 1, 4);
+          if (cls == 0) {
+            c2 = (rr == 0 && cc == 0) ? 0 : c2 + nz_off[pos];
+          } else {
+            const int idx = cls == 2 ? rr : cc;
+            c2 += 26 + 5 * std::min(idx, 2);
+          }
+          ec.symbol(std::min(level, 3), cdf.coeff_base[tx_ctx][ptype][c2], 4);
+        }
+        if (level > 2) {
+          auto m15 = [](int v) { return v > 15 ? 15 : v; };
+          int mag;
+          if (cls == 0) mag = m15(L[1]) + m15(L[stride]) + m15(L[stride + 1]);
+          else if (cls == 1) mag = m15(L[1]) + m15(L[2]) + m15(L[stride]);
+          else mag = m15(L[stride]) + m15(L[2 * stride]) + m15(L[1]);
+          mag = std::min((mag + 1) >> 1, 6);
+          int c2;
+          if (pos == 0) c2 = mag;
+          else if (cls == 0) c2 = (rr < 2 && cc < 2) ? mag + 7 : mag + 14;
+          else if (cls == 1) c2 = cc == 0 ? mag + 7 : mag + 14;
+          else c2 = rr == 0 ? mag + 7 : mag + 14;
+          int rem = level - 3;   // coded in up to 4 symbols of 0..3
+          for (int k = 0; k < 4; k++) {
+            const int s = std::min(rem, 3);
+            ec.symbol(s, cdf.coeff_br[br_tx][ptype][c2], 4);
+            rem -= s;
+            if (s < 3) break;
+          }
+        }
+      }
+      // signs and Golomb remainders, forward scan order
+      for (int i = 0; i < eob; i++) {
+        const int pos = scan[i], rr = pos >> ns_log2, cc = pos & (ns - 1);
+        int v = cf[rr * cs + cc];
+        if (v == 0) continue;
+        const int sign = v < 0;
+        const int a = sign ? -v : v;
+        if (i == 0) {
+          int dcs = 0;
+          for (int k = 0; k < w4; k++) {
+            if (x4 + k < max_x4) { int s = above_dc[plane][x4 + k]; dcs += s == 1 ? -1 : s == 2 ? 1 : 0; }
+            if (abs_y4 + k < max_y4) { int s = left_dc[plane][y4 + k]; dcs += s == 1 ? -1 : s == 2 ? 1 : 0; }
+          }
+          ec.symbol(sign, cdf.dc_sign[ptype][dcs < 0 ? 1 : dcs > 0 ? 2 : 0], 2);
+          dc_cat = sign ? 1 : 2;
+        } else {
+          ec.boolean(sign);
+        }
+        if (a > 14) {
+          const uint32_t x = (uint32_t)(a - 14);   // >= 1
+          const int len = 32 - __builtin_clz(x);
+          for (int k = 0; k < len - 1; k++) ec.boolean(0);
+          for (int k = len - 1; k >= 0; k--) ec.boolean((x >> k) & 1);
+        }
+        cul += a;
+      }
+      cul = std::min(cul, 63);
+    }
+    for (int k = 0; k < w4; k++) {
+      above_lvl[plane][x4 + k] = (uint8_t)cul; above_dc[plane][x4 + k] = (uint8_t)dc_cat;
+      left_lvl[plane][y4 + k] = (uint8_t)cul;  left_dc[plane][y4 + k] = (uint8_t)dc_cat;
+    }
+  }
+};
+
+}  // namespace
+
+int write_frame(const Av1bSeqParams& seq, const Av1bFrameParams& fp, const Av1bGeom& g,
+                const Av1bFrameSyms& syms, std::vector<uint8_t>& out, int n_threads) {
+  BitWriter hw;
+  write_frame_header(seq, fp, g, hw);
+  hw.byte_align();
+  const int n_tiles = g.tile_cols * g.tile_rows;
+  BitWriter tg;
+  if (n_tiles > 1) tg.bit(0);   // tile_start_and_end_present_flag
+  tg.byte_align();
+  std::vector<std::vector<uint8_t>> tile_bytes(n_tiles);
+  std::atomic<int> next(0);
+  auto work = [&]() {
+    for (;;) {
+      int t = next.fetch_add(1);
+      if (t >= n_tiles) break;
+      TileWriter tw(seq, fp, g, syms);
+      tw.run(t / g.tile_cols, t % g.tile_cols, tile_bytes[t]);
+    }
+  };
+  if (n_threads <= 1 || n_tiles == 1) {
+    work();
+  } else {
+    std::vector<std::thread> th;
+    const int nt = std::min(n_threads, n_tiles);
+    for (int i = 0; i < nt; i++) th.emplace_back(work);
+    for (auto& t : th) t.join();
+  }
+  std::vector<uint8_t> payload = hw.bytes();
+  payload.insert(payload.end(), tg.bytes().begin(), tg.bytes().end());
+  for (int t = 0; t < n_tiles; t++) {
+    if (t != n_tiles - 1) {
+      uint32_t sz = (uint32_t)tile_bytes[t].size() - 1;   // tile_size_minus_1, 4 bytes LE
+      for (int k = 0; k < 4; k++) payload.push_back((uint8_t)(sz >> (8 * k)));
+    }
+    payload.insert(payload.end(), tile_bytes[t].begin(), tile_bytes[t].end());
+  }
+  append_obu(out, 6, payload);
+  return 0;
+}
+
+}  // namespace av1b

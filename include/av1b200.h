@@ -1,0 +1,89 @@
+/* av1b200 -- C ABI of the B200-native AV1 encode backend.
+ *
+ * This is the boundary a reference-side FFI binds (BASELINE.json north_star: "a new Rust crate
+ * (av1-cuda-sys plus a safe wrapper) calls hand-written CUDA kernels through a thin C-ABI").
+ * It replaces what the reference reaches by exec'ing `av1an`:
+ *   /root/reference/crates/daemon/src/encode/av1an.rs:79-107  build_av1an_command  -> av1b_config
+ *   /root/reference/crates/daemon/src/encode/av1an.rs:126-139 run_av1an            -> av1b_encode_chunk
+ *   /root/reference/crates/daemon/src/encode/av1an.rs:18-30   EncodeError          -> negative return codes
+ *   /root/reference/crates/daemon/src/startup.rs:98-116       `av1an --version`    -> av1b_version
+ * Conventions: 0 = OK, negative = error (av1b_last_error() gives the thread-local message); no
+ * exceptions or aborts cross the boundary; plain pointers and sizes only.  The caller owns input
+ * buffers for the duration of a call; packet memory handed to a callback is valid until it returns.
+ * One encoder handle = one GPU + one stream set; handles are independent and may be driven from
+ * different threads (one chunk stream per GPU).
+ */
+#ifndef AV1B200_H_
+#define AV1B200_H_
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define AV1B_OK 0
+#define AV1B_ERR_INVALID (-1)      /* bad argument / unsupported configuration           */
+#define AV1B_ERR_NO_DEVICE (-2)    /* no CUDA device: there is NO CPU fallback           */
+#define AV1B_ERR_CUDA (-3)         /* CUDA runtime error                                  */
+#define AV1B_ERR_NOMEM (-4)
+#define AV1B_ERR_CALLBACK (-5)     /* packet callback returned non-zero                   */
+#define AV1B_ERR_INTERNAL (-6)
+
+/* Mirrors the knobs the daemon passes through `--video-params` (av1an.rs:14 SVT_PARAMS) plus geometry. */
+typedef struct av1b_config {
+  int32_t width, height;          /* luma samples; multiples of 8                                  */
+  int32_t bit_depth;              /* 8 or 10 (input samples are uint16 either way)                 */
+  int32_t fps_num, fps_den;
+  int32_t crf;                    /* 0..63, SVT-AV1 --crf                                          */
+  int32_t preset;                 /* SVT-AV1 --preset (speed/quality trade-off)                    */
+  int32_t keyint;                 /* --keyint                                                      */
+  int32_t lookahead;              /* --lookahead (accepted; unused by the all-intra path)          */
+  int32_t film_grain;             /* --film-grain (accepted; synthesis not implemented: row f-4)   */
+  int32_t enable_qm, qm_min, qm_max; /* accepted; flat quantisation matrices only                  */
+  int32_t tile_cols_log2, tile_rows_log2; /* -1 = auto (fill the GPU)                              */
+  int32_t device_id;
+  int32_t hdr;                    /* 1: signal BT.2020/PQ in the sequence header                   */
+  int32_t host_threads;           /* entropy-coding threads, 0 = auto                              */
+  int32_t frames_in_flight;       /* frames batched per device pass, 0 = auto                      */
+  int32_t reserved[8];
+} av1b_config;
+
+typedef struct av1b_encoder av1b_encoder;
+
+/* One frame of 4:2:0 source, samples as uint16 (8-bit content in the low byte). Strides in samples. */
+typedef struct av1b_frame_src {
+  const uint16_t* planes[3];
+  int32_t stride[3];
+} av1b_frame_src;
+
+/* Called once per temporal unit (low-overhead OBU format), in display order. Non-zero aborts. */
+typedef int (*av1b_packet_cb)(void* user, const uint8_t* data, size_t size, int64_t frame_index, int is_key);
+/* Progress: frames done so far of the chunk (feeds JobMetrics.frames_encoded / fps, metrics.rs:16-24). */
+typedef void (*av1b_progress_cb)(void* user, int64_t frames_done, int64_t frames_total, double fps);
+
+int av1b_version(char* buf, size_t cap);
+int av1b_device_count(void);
+const char* av1b_last_error(void);
+
+void av1b_config_default(av1b_config* cfg);
+int av1b_encoder_create(const av1b_config* cfg, av1b_encoder** out);
+void av1b_encoder_destroy(av1b_encoder* enc);
+/* Encodes n_frames as one closed chunk: first TU carries the sequence header + key frame. */
+int av1b_encode_chunk(av1b_encoder* enc, const av1b_frame_src* frames, uint32_t n_frames,
+                      av1b_packet_cb out_cb, av1b_progress_cb prog_cb, void* user);
+/* Reconstruction of the most recently encoded frame `frame_in_chunk` of the last chunk (post loop
+ * filter), for the recon-vs-decode check. dst planes: uint16, strides in samples. */
+int av1b_get_recon(av1b_encoder* enc, uint32_t frame_in_chunk, uint16_t* const dst[3], const int32_t stride[3]);
+
+/* ---- host entropy coder over symbol streams (the part that "runs on the host") -------------- */
+struct Av1bSeqParams; struct Av1bFrameParams; struct Av1bFrameSyms;
+int av1b_pack_sequence_header(const struct Av1bSeqParams* seq, uint8_t* out, size_t cap, size_t* len);
+int av1b_pack_frame(const struct Av1bSeqParams* seq, const struct Av1bFrameParams* fp,
+                    const struct Av1bFrameSyms* syms, int n_threads, int with_temporal_delimiter,
+                    uint8_t* out, size_t cap, size_t* len);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* AV1B200_H_ */

@@ -1,0 +1,56 @@
+"""Test infrastructure (NOT product code): ctypes wrapper of liboracle.so (oracle/av1_oracle.cpp)."""
+import ctypes as C
+import os, subprocess
+import numpy as np
+from av1_base_b200 import abi
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+_lib = None
+
+def build():
+    subprocess.check_call(["make", "-s", "-C", _HERE])
+
+def lib():
+    global _lib
+    if _lib is None:
+        p = os.path.join(_HERE, "liboracle.so")
+        if not os.path.exists(p):
+            build()
+        _lib = C.CDLL(p)
+    return _lib
+
+def geom(width, height, tile_cols_log2=0, tile_rows_log2=0):
+    g = abi.Geom()
+    rc = lib().orc_geom_init(C.byref(g), width, height, tile_cols_log2, tile_rows_log2)
+    if rc:
+        raise ValueError("unsupported size %dx%d" % (width, height))
+    return g
+
+def ptr(a):
+    return a.ctypes.data_as(C.c_void_p)
+
+def partition_fixed(g, blk_log2):
+    m = np.zeros(g.h8 * g.w8, np.uint8)
+    lib().orc_partition_fixed(C.byref(g), blk_log2, ptr(m))
+    return m
+
+class IntraResult:
+    pass
+
+def encode_intra_frame(g, frame, bit_depth, base_q_idx, part_map, quant_rnd=48):
+    """frame: [Y,U,V] uint16. Returns IntraResult with rec[3] (padded), blocks, coef[3] (padded)."""
+    Y, U, V = [np.ascontiguousarray(p, dtype=np.uint16) for p in frame]
+    r = IntraResult()
+    r.rec = [np.zeros((g.rows[p], g.stride[p]), np.uint16) for p in range(3)]
+    r.coef = [np.zeros((g.rows[p], g.stride[p]), np.int16) for p in range(3)]
+    r.blocks = np.zeros(g.h8 * g.w8, abi.BLOCK_INFO_DTYPE)
+    rc = lib().orc_encode_intra_frame(C.byref(g), bit_depth, base_q_idx, quant_rnd, ptr(Y), ptr(U), ptr(V),
+                                      Y.shape[1], U.shape[1], ptr(part_map),
+                                      ptr(r.rec[0]), ptr(r.rec[1]), ptr(r.rec[2]), ptr(r.blocks),
+                                      ptr(r.coef[0]), ptr(r.coef[1]), ptr(r.coef[2]))
+    assert rc == 0
+    return r
+
+def crop(g, planes):
+    return [planes[0][:g.height, :g.width], planes[1][:g.height // 2, :g.width // 2],
+            planes[2][:g.height // 2, :g.width // 2]]
