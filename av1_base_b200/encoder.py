@@ -1,0 +1,117 @@
+"""Host-side mirror of the reference's encode-job interface over the C ABI.
+
+Reference interface mirrored (same names / meaning / error behaviour where they exist):
+  /root/reference/crates/daemon/src/encode/av1an.rs:36-62   Av1anEncodeParams  -> EncodeParams
+  /root/reference/crates/daemon/src/encode/av1an.rs:18-30   EncodeError        -> EncodeError
+  /root/reference/crates/daemon/src/encode/av1an.rs:126-139 run_av1an          -> Encoder.encode_chunk
+numpy is plumbing only; every pixel operation happens in libav1b200.so on the GPU.
+"""
+import ctypes as C
+import numpy as np
+from . import abi
+
+
+class EncodeError(RuntimeError):
+    """Mirror of EncodeError::{Av1anFailed(code), Io}: carries the negative C-ABI return code."""
+
+    def __init__(self, code, msg):
+        super().__init__("av1b200 failed with code %d: %s" % (code, msg))
+        self.code = code
+
+
+def _check(rc):
+    if rc != 0:
+        raise EncodeError(rc, abi.last_error())
+
+
+class Encoder:
+    def __init__(self, width, height, bit_depth=10, crf=30, preset=6, keyint=240, fps=(30, 1), device_id=0,
+                 tile_cols_log2=-1, tile_rows_log2=-1, hdr=False, host_threads=0, frames_in_flight=0,
+                 keep_debug=False, blk_log2=0):
+        L = abi.lib()
+        cfg = abi.Config()
+        L.av1b_config_default(C.byref(cfg))
+        cfg.width, cfg.height, cfg.bit_depth = width, height, bit_depth
+        cfg.crf, cfg.preset, cfg.keyint = crf, preset, keyint
+        cfg.fps_num, cfg.fps_den = fps
+        cfg.device_id = device_id
+        cfg.tile_cols_log2, cfg.tile_rows_log2 = tile_cols_log2, tile_rows_log2
+        cfg.hdr = int(hdr)
+        cfg.host_threads = host_threads
+        cfg.frames_in_flight = frames_in_flight
+        cfg.reserved[0] = int(keep_debug)
+        cfg.reserved[1] = blk_log2
+        self.cfg = cfg
+        self._h = C.c_void_p()
+        _check(L.av1b_encoder_create(C.byref(cfg), C.byref(self._h)))
+        self.geom = abi.Geom()
+        _check(L.av1b_get_geom(self._h, C.byref(self.geom)))
+
+    def close(self):
+        if self._h:
+            abi.lib().av1b_encoder_destroy(self._h)
+            self._h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def encode_chunk(self, frames, progress=None):
+        """frames: list of [Y,U,V] uint16 arrays. Returns the list of temporal units (bytes)."""
+        n = len(frames)
+        srcs = (abi.FrameSrc * n)()
+        keep = []
+        for i, fr in enumerate(frames):
+            for p in range(3):
+                a = np.ascontiguousarray(fr[p], dtype=np.uint16)
+                keep.append(a)
+                srcs[i].planes[p] = a.ctypes.data
+                srcs[i].stride[p] = a.shape[1]
+        out = []
+
+        def on_packet(user, data, size, idx, is_key):
+            out.append(C.string_at(data, size))
+            return 0
+
+        def on_progress(user, done, total, fps):
+            if progress:
+                progress(done, total, fps)
+
+        cb = abi.PACKET_CB(on_packet)
+        pcb = abi.PROGRESS_CB(on_progress)
+        _check(abi.lib().av1b_encode_chunk(self._h, srcs, n, cb, pcb, None))
+        return out
+
+    def recon(self, frame):
+        g = self.geom
+        planes = [np.zeros((g.height, g.width), np.uint16), np.zeros((g.height // 2, g.width // 2), np.uint16),
+                  np.zeros((g.height // 2, g.width // 2), np.uint16)]
+        dst = (C.c_void_p * 3)(*[p.ctypes.data for p in planes])
+        st = (C.c_int32 * 3)(*[p.shape[1] for p in planes])
+        _check(abi.lib().av1b_get_recon(self._h, frame, dst, st))
+        return planes
+
+    def frame_syms(self, frame):
+        g = self.geom
+        blocks = np.zeros(g.w8 * g.h8, abi.BLOCK_INFO_DTYPE)
+        coef = [np.zeros((g.rows[p], g.stride[p]), np.int16) for p in range(3)]
+        cp = (C.c_void_p * 3)(*[c.ctypes.data for c in coef])
+        _check(abi.lib().av1b_get_frame_syms(self._h, frame, blocks.ctypes.data_as(C.c_void_p), cp))
+        return blocks, coef
+
+    def stats(self):
+        s = (C.c_double * 6)()
+        _check(abi.lib().av1b_get_stats(self._h, s, 6))
+        return dict(h2d_ms=s[0], kernel_ms=s[1], d2h_ms=s[2], pack_ms=s[3], kernel_launches=int(s[4]), base_q_idx=int(s[5]))
+
+
+def device_count():
+    return abi.lib().av1b_device_count()
+
+
+def version():
+    b = C.create_string_buffer(128)
+    abi.lib().av1b_version(b, 128)
+    return b.value.decode()

@@ -46,7 +46,7 @@ typedef struct av1b_config {
   int32_t hdr;                    /* 1: signal BT.2020/PQ in the sequence header                   */
   int32_t host_threads;           /* entropy-coding threads, 0 = auto                              */
   int32_t frames_in_flight;       /* frames batched per device pass, 0 = auto                      */
-  int32_t reserved[8];
+  int32_t reserved[8];            /* [0]: keep recon+symbols per frame (tests); [1]: fixed block log2 (3..6), 0 = default */
 } av1b_config;
 
 typedef struct av1b_encoder av1b_encoder;
@@ -75,6 +75,13 @@ int av1b_encode_chunk(av1b_encoder* enc, const av1b_frame_src* frames, uint32_t 
 /* Reconstruction of the most recently encoded frame `frame_in_chunk` of the last chunk (post loop
  * filter), for the recon-vs-decode check. dst planes: uint16, strides in samples. */
 int av1b_get_recon(av1b_encoder* enc, uint32_t frame_in_chunk, uint16_t* const dst[3], const int32_t stride[3]);
+
+/* ---- diagnostics (need config.reserved[0] = 1: keep per-frame reconstruction and symbols) ---- */
+struct Av1bBlockInfo; struct Av1bGeom;
+int av1b_get_frame_syms(av1b_encoder* enc, uint32_t frame_in_chunk, struct Av1bBlockInfo* blocks, int16_t* const coef[3]);
+int av1b_get_geom(av1b_encoder* enc, struct Av1bGeom* geom);
+/* stats[0..5] = h2d_ms, kernel_ms, d2h_ms, pack_ms, kernel_launches, base_q_idx of the last chunk */
+int av1b_get_stats(av1b_encoder* enc, double* stats, int n);
 
 /* ---- host entropy coder over symbol streams (the part that "runs on the host") -------------- */
 struct Av1bSeqParams; struct Av1bFrameParams; struct Av1bFrameSyms;

@@ -82,6 +82,10 @@ def load(pattern=LIBAOM_GLOB):
             break
     assert base is not None
     _loaded[pattern] = (lib, base, es)
+    # libaom's *_c functions call a few helpers through run-time CPU dispatch pointers; fill them
+    for init in ("av1_rtcd", "aom_dsp_rtcd", "aom_scale_rtcd"):
+        if init in es.syms:
+            ctypes.CFUNCTYPE(None)(base + es.syms[init][0][0])()
     return _loaded[pattern]
 
 def func(name, restype, argtypes, pattern=LIBAOM_GLOB, which=0):
