@@ -655,8 +655,7 @@ struct TileWriter {
 
 }  // namespace
 
-int write_frame(const Av1bSeqParams& seq, const Av1bFrameParams& fp, const Av1bGeom& g,
-                const Av1bFrameSyms& syms, std::vector<uint8_t>& out, int n_threads) {
+void pack_frame_header(const Av1bSeqParams& seq, const Av1bFrameParams& fp, const Av1bGeom& g, FramePack& fpk) {
   BitWriter hw;
   write_frame_header(seq, fp, g, hw);
   hw.byte_align();
@@ -664,14 +663,45 @@ int write_frame(const Av1bSeqParams& seq, const Av1bFrameParams& fp, const Av1bG
   BitWriter tg;
   if (n_tiles > 1) tg.bit(0);   // tile_start_and_end_present_flag
   tg.byte_align();
-  std::vector<std::vector<uint8_t>> tile_bytes(n_tiles);
+  fpk.header = hw.bytes();
+  fpk.header.insert(fpk.header.end(), tg.bytes().begin(), tg.bytes().end());
+  fpk.tiles.assign(n_tiles, std::vector<uint8_t>());
+}
+
+void pack_tile(const Av1bSeqParams& seq, const Av1bFrameParams& fp, const Av1bGeom& g, const Av1bFrameSyms& syms,
+               int tile, std::vector<uint8_t>& out) {
+  TileWriter tw(seq, fp, g, syms);
+  tw.run(tile / g.tile_cols, tile % g.tile_cols, out);
+}
+
+void assemble_frame(const FramePack& fpk, std::vector<uint8_t>& out) {
+  size_t total = fpk.header.size();
+  const int n_tiles = (int)fpk.tiles.size();
+  for (auto& t : fpk.tiles) total += t.size() + 4;
+  std::vector<uint8_t> payload;
+  payload.reserve(total);
+  payload = fpk.header;
+  for (int t = 0; t < n_tiles; t++) {
+    if (t != n_tiles - 1) {
+      uint32_t sz = (uint32_t)fpk.tiles[t].size() - 1;   // tile_size_minus_1, 4 bytes LE
+      for (int k = 0; k < 4; k++) payload.push_back((uint8_t)(sz >> (8 * k)));
+    }
+    payload.insert(payload.end(), fpk.tiles[t].begin(), fpk.tiles[t].end());
+  }
+  append_obu(out, 6, payload);
+}
+
+int write_frame(const Av1bSeqParams& seq, const Av1bFrameParams& fp, const Av1bGeom& g,
+                const Av1bFrameSyms& syms, std::vector<uint8_t>& out, int n_threads) {
+  FramePack fpk;
+  pack_frame_header(seq, fp, g, fpk);
+  const int n_tiles = (int)fpk.tiles.size();
   std::atomic<int> next(0);
   auto work = [&]() {
     for (;;) {
       int t = next.fetch_add(1);
       if (t >= n_tiles) break;
-      TileWriter tw(seq, fp, g, syms);
-      tw.run(t / g.tile_cols, t % g.tile_cols, tile_bytes[t]);
+      pack_tile(seq, fp, g, syms, t, fpk.tiles[t]);
     }
   };
   if (n_threads <= 1 || n_tiles == 1) {
@@ -682,16 +712,7 @@ int write_frame(const Av1bSeqParams& seq, const Av1bFrameParams& fp, const Av1bG
     for (int i = 0; i < nt; i++) th.emplace_back(work);
     for (auto& t : th) t.join();
   }
-  std::vector<uint8_t> payload = hw.bytes();
-  payload.insert(payload.end(), tg.bytes().begin(), tg.bytes().end());
-  for (int t = 0; t < n_tiles; t++) {
-    if (t != n_tiles - 1) {
-      uint32_t sz = (uint32_t)tile_bytes[t].size() - 1;   // tile_size_minus_1, 4 bytes LE
-      for (int k = 0; k < 4; k++) payload.push_back((uint8_t)(sz >> (8 * k)));
-    }
-    payload.insert(payload.end(), tile_bytes[t].begin(), tile_bytes[t].end());
-  }
-  append_obu(out, 6, payload);
+  assemble_frame(fpk, out);
   return 0;
 }
 

@@ -49,6 +49,17 @@ class RangeEncoder {
 void append_obu(std::vector<uint8_t>& out, int obu_type, const std::vector<uint8_t>& payload);
 void write_temporal_delimiter(std::vector<uint8_t>& out);
 void write_sequence_header(const Av1bSeqParams& seq, std::vector<uint8_t>& out);
+// Frame packing split into independent per-tile tasks (tiles share no entropy state), so that the
+// encoder can spread (frame, tile) tasks of a whole batch over its host thread pool.
+struct FramePack {
+  std::vector<uint8_t> header;                  // frame header + tile group header, byte aligned
+  std::vector<std::vector<uint8_t>> tiles;      // entropy-coded tile payloads
+};
+void pack_frame_header(const Av1bSeqParams& seq, const Av1bFrameParams& fp, const Av1bGeom& g, FramePack& fpk);
+void pack_tile(const Av1bSeqParams& seq, const Av1bFrameParams& fp, const Av1bGeom& g, const Av1bFrameSyms& syms,
+               int tile, std::vector<uint8_t>& out);
+void assemble_frame(const FramePack& fpk, std::vector<uint8_t>& out);   // appends one OBU_FRAME
+
 // One OBU_FRAME (frame header + all tiles). n_threads > 1 entropy-codes tiles in parallel.
 // Returns 0 on success.
 int write_frame(const Av1bSeqParams& seq, const Av1bFrameParams& fp, const Av1bGeom& g,

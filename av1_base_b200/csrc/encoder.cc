@@ -1,11 +1,18 @@
-// C-ABI encoder object: owns the device buffers and streams of ONE GPU and drives, per batch of
+// C-ABI encoder object: owns the device buffers and stream of ONE GPU and drives, per batch of
 // frames, source upload -> device encode kernels -> symbol-stream download -> host entropy coding.
+// Two buffer slots are ping-ponged so that the host entropy-codes batch k-1 while the GPU encodes
+// batch k ("double-buffered D2H").
 // Boundary replaced: /root/reference/crates/daemon/src/encode/av1an.rs:126-139 (run_av1an).
 // There is no CPU fallback: without a CUDA device av1b_encoder_create fails with AV1B_ERR_NO_DEVICE.
 #include <cuda_runtime.h>
 #include <stdio.h>
 #include <string.h>
+#include <atomic>
 #include <chrono>
+#include <condition_variable>
+#include <functional>
+#include <mutex>
+#include <thread>
 #include <vector>
 #include "../../include/av1b200.h"
 #include "av1_tables.h"
@@ -24,39 +31,233 @@ using namespace av1b;
     }                                                                                 \
   } while (0)
 
+namespace {
+
+// Minimal persistent pool: parallel_for blocks the caller (who also works) until all tasks ran.
+class ThreadPool {
+ public:
+  explicit ThreadPool(int n) {
+    for (int i = 0; i < n - 1; i++) th_.emplace_back([this] { loop(); });
+  }
+  ~ThreadPool() {
+    { std::lock_guard<std::mutex> l(m_); stop_ = true; }
+    cv_.notify_all();
+    for (auto& t : th_) t.join();
+  }
+  void parallel_for(int n, const std::function<void(int)>& fn) {
+    if (n <= 0) return;
+    {
+      std::lock_guard<std::mutex> l(m_);
+      fn_ = &fn; n_ = n; next_ = 0; left_ = n; gen_++;
+    }
+    cv_.notify_all();
+    work();
+    std::unique_lock<std::mutex> l(m_);
+    done_.wait(l, [this] { return left_ == 0; });
+    fn_ = nullptr;
+  }
+ private:
+  void work() {
+    for (;;) {
+      int i;
+      const std::function<void(int)>* f;
+      {
+        std::lock_guard<std::mutex> l(m_);
+        if (!fn_ || next_ >= n_) return;
+        i = next_++; f = fn_;
+      }
+      (*f)(i);
+      {
+        std::lock_guard<std::mutex> l(m_);
+        if (--left_ == 0) done_.notify_all();
+      }
+    }
+  }
+  void loop() {
+    uint64_t seen = 0;
+    for (;;) {
+      {
+        std::unique_lock<std::mutex> l(m_);
+        cv_.wait(l, [&] { return stop_ || (gen_ != seen && fn_); });
+        if (stop_) return;
+        seen = gen_;
+      }
+      work();
+    }
+  }
+  std::vector<std::thread> th_;
+  std::mutex m_;
+  std::condition_variable cv_, done_;
+  const std::function<void(int)>* fn_ = nullptr;
+  int n_ = 0, next_ = 0, left_ = 0;
+  uint64_t gen_ = 0;
+  bool stop_ = false;
+};
+
 struct KeptFrame {
   std::vector<uint16_t> rec[3];
   std::vector<int16_t> coef[3];
   std::vector<Av1bBlockInfo> blocks;
 };
 
+struct Slot {
+  uint16_t* d_src[3] = {nullptr, nullptr, nullptr};
+  uint16_t* d_rec[3] = {nullptr, nullptr, nullptr};
+  int16_t* d_coef[3] = {nullptr, nullptr, nullptr};
+  Av1bBlockInfo* d_blocks = nullptr;
+  uint8_t* d_map = nullptr;
+  uint16_t* h_src[3] = {nullptr, nullptr, nullptr};   // pinned staging
+  uint16_t* h_rec[3] = {nullptr, nullptr, nullptr};
+  int16_t* h_coef[3] = {nullptr, nullptr, nullptr};
+  Av1bBlockInfo* h_blocks = nullptr;
+  cudaEvent_t ev[5] = {nullptr, nullptr, nullptr, nullptr, nullptr};   // h2d start, kernels start, intra start, kernels end, d2h end
+  int n_frames = 0;
+  int64_t first_index = 0;
+};
+
+}  // namespace
+
 struct av1b_encoder {
   av1b_config cfg;
   Av1bSeqParams seq;
   Av1bGeom g;
   int batch = 0;
-  int host_threads = 1;
   int base_q_idx = 0;
   int blk_log2 = 4;
   bool keep = false;
   cudaStream_t stream = nullptr;
   size_t plane_elems[3] = {0, 0, 0};
   size_t map_elems = 0;
-  uint16_t* d_src[3] = {nullptr, nullptr, nullptr};
-  uint16_t* d_rec[3] = {nullptr, nullptr, nullptr};
-  int16_t* d_coef[3] = {nullptr, nullptr, nullptr};
-  Av1bBlockInfo* d_blocks = nullptr;
-  uint8_t* d_map = nullptr;
-  uint16_t* h_src[3] = {nullptr, nullptr, nullptr};   // pinned
-  uint16_t* h_rec[3] = {nullptr, nullptr, nullptr};
-  int16_t* h_coef[3] = {nullptr, nullptr, nullptr};
-  Av1bBlockInfo* h_blocks = nullptr;
+  Slot slot[2];
+  ThreadPool* pool = nullptr;
+  int host_threads = 1;
   std::vector<KeptFrame> kept;
-  // statistics of the last chunk (bench.py reads them through av1b_get_stats)
-  double t_h2d_ms = 0, t_kernel_ms = 0, t_d2h_ms = 0, t_pack_ms = 0;
-  int64_t kernel_launches = 0;
-  cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
+  // statistics of the last chunk / resident run
+  double t_h2d_ms = 0, t_kernel_ms = 0, t_intra_ms = 0, t_d2h_ms = 0, t_pack_ms = 0;
+  int64_t kernel_launches = 0, intra_launches = 0, frames_done = 0, bytes_out = 0;
 };
+
+static void free_all(av1b_encoder* e) {
+  for (auto& s : e->slot) {
+    for (int p = 0; p < 3; p++) {
+      cudaFree(s.d_src[p]); cudaFree(s.d_rec[p]); cudaFree(s.d_coef[p]);
+      cudaFreeHost(s.h_src[p]); cudaFreeHost(s.h_rec[p]); cudaFreeHost(s.h_coef[p]);
+    }
+    cudaFree(s.d_blocks); cudaFree(s.d_map); cudaFreeHost(s.h_blocks);
+    for (auto& ev : s.ev) if (ev) cudaEventDestroy(ev);
+  }
+  if (e->stream) cudaStreamDestroy(e->stream);
+  delete e->pool;
+}
+
+// upload n frames (host pointers) into a slot; asynchronous on the encoder stream
+static int stage(av1b_encoder* e, Slot& s, const av1b_frame_src* frames, int n) {
+  const Av1bGeom& g = e->g;
+  CK(cudaEventRecord(s.ev[0], e->stream));
+  for (int b = 0; b < n; b++) {
+    for (int p = 0; p < 3; p++) {
+      const int w = p ? g.width >> 1 : g.width, h = p ? g.height >> 1 : g.height;
+      uint16_t* hs = s.h_src[p] + (size_t)b * e->plane_elems[p];
+      const uint16_t* sp = frames[b].planes[p];
+      const int sst = frames[b].stride[p];
+      for (int y = 0; y < h; y++) memcpy(hs + (size_t)y * g.stride[p], sp + (size_t)y * sst, (size_t)w * 2);
+      CK(cudaMemcpyAsync(s.d_src[p] + (size_t)b * e->plane_elems[p], hs, (size_t)g.stride[p] * h * 2,
+                         cudaMemcpyHostToDevice, e->stream));
+    }
+  }
+  return AV1B_OK;
+}
+
+// kernels + symbol download for the n frames resident in the slot; asynchronous
+static int launch(av1b_encoder* e, Slot& s, int n, int64_t first_index) {
+  const Av1bGeom& g = e->g;
+  const int bd = e->cfg.bit_depth;
+  s.n_frames = n; s.first_index = first_index;
+  CK(cudaEventRecord(s.ev[1], e->stream));
+  IntraLaunch L;
+  L.g = g; L.bit_depth = bd; L.base_q_idx = e->base_q_idx; L.quant_rnd = 48;
+  L.dc_q = bd == 8 ? av1t_dc_q_8[e->base_q_idx] : av1t_dc_q_10[e->base_q_idx];
+  L.ac_q = bd == 8 ? av1t_ac_q_8[e->base_q_idx] : av1t_ac_q_10[e->base_q_idx];
+  for (int p = 0; p < 3; p++) { L.src[p] = s.d_src[p]; L.rec[p] = s.d_rec[p]; L.coef[p] = s.d_coef[p]; L.plane_elems[p] = e->plane_elems[p]; }
+  L.blocks = s.d_blocks; L.part_map = s.d_map; L.map_elems = e->map_elems;
+  CK(launch_partition_fixed(g, e->blk_log2, s.d_map, n, e->stream));
+  CK(cudaEventRecord(s.ev[2], e->stream));
+  CK(launch_intra_encode(L, n, e->stream));
+  CK(cudaEventRecord(s.ev[3], e->stream));
+  e->kernel_launches += 2; e->intra_launches += 1;
+  for (int p = 0; p < 3; p++) {
+    CK(cudaMemcpyAsync(s.h_coef[p], s.d_coef[p], e->plane_elems[p] * n * 2, cudaMemcpyDeviceToHost, e->stream));
+    if (e->keep) CK(cudaMemcpyAsync(s.h_rec[p], s.d_rec[p], e->plane_elems[p] * n * 2, cudaMemcpyDeviceToHost, e->stream));
+  }
+  CK(cudaMemcpyAsync(s.h_blocks, s.d_blocks, e->map_elems * n * sizeof(Av1bBlockInfo), cudaMemcpyDeviceToHost, e->stream));
+  CK(cudaEventRecord(s.ev[4], e->stream));
+  return AV1B_OK;
+}
+
+// wait for the slot's download, entropy-code its frames on the host pool, hand out packets in order
+static int finish(av1b_encoder* e, Slot& s, bool staged, av1b_packet_cb out_cb, av1b_progress_cb prog_cb, void* user,
+                  int64_t total_frames, std::chrono::steady_clock::time_point t_start) {
+  const Av1bGeom& g = e->g;
+  CK(cudaEventSynchronize(s.ev[4]));
+  float ms;
+  if (staged) { cudaEventElapsedTime(&ms, s.ev[0], s.ev[1]); e->t_h2d_ms += ms; }
+  cudaEventElapsedTime(&ms, s.ev[1], s.ev[3]); e->t_kernel_ms += ms;
+  cudaEventElapsedTime(&ms, s.ev[2], s.ev[3]); e->t_intra_ms += ms;
+  cudaEventElapsedTime(&ms, s.ev[3], s.ev[4]); e->t_d2h_ms += ms;
+  const auto tp0 = std::chrono::steady_clock::now();
+  const int n = s.n_frames, n_tiles = g.tile_cols * g.tile_rows;
+  Av1bFrameParams fp;
+  memset(&fp, 0, sizeof(fp));
+  fp.frame_type = AV1B_KEY_FRAME;
+  fp.base_q_idx = e->base_q_idx;
+  fp.disable_cdf_update = 0;
+  fp.tile_cols_log2 = g.tile_cols_log2; fp.tile_rows_log2 = g.tile_rows_log2;
+  fp.cdef_damping = 3;
+  std::vector<Av1bFrameSyms> sy(n);
+  std::vector<FramePack> packs(n);
+  for (int b = 0; b < n; b++) {
+    memset(&sy[b], 0, sizeof(Av1bFrameSyms));
+    sy[b].blocks = s.h_blocks + (size_t)b * e->map_elems;
+    for (int p = 0; p < 3; p++) { sy[b].coef[p] = s.h_coef[p] + (size_t)b * e->plane_elems[p]; sy[b].coef_stride[p] = g.stride[p]; }
+    pack_frame_header(e->seq, fp, g, packs[b]);
+  }
+  e->pool->parallel_for(n * n_tiles, [&](int t) {
+    const int b = t / n_tiles, tile = t % n_tiles;
+    pack_tile(e->seq, fp, g, sy[b], tile, packs[b].tiles[tile]);
+  });
+  std::vector<uint8_t> tu;
+  for (int b = 0; b < n; b++) {
+    tu.clear();
+    write_temporal_delimiter(tu);
+    if (s.first_index + b == 0) write_sequence_header(e->seq, tu);
+    assemble_frame(packs[b], tu);
+    if (e->keep) {
+      e->kept.emplace_back();
+      KeptFrame& k = e->kept.back();
+      for (int p = 0; p < 3; p++) {
+        k.rec[p].assign(s.h_rec[p] + (size_t)b * e->plane_elems[p], s.h_rec[p] + (size_t)(b + 1) * e->plane_elems[p]);
+        k.coef[p].assign(s.h_coef[p] + (size_t)b * e->plane_elems[p], s.h_coef[p] + (size_t)(b + 1) * e->plane_elems[p]);
+      }
+      k.blocks.assign(sy[b].blocks, sy[b].blocks + e->map_elems);
+    }
+    e->bytes_out += (int64_t)tu.size();
+    if (out_cb && out_cb(user, tu.data(), tu.size(), s.first_index + b, 1)) { set_error("packet callback aborted"); return AV1B_ERR_CALLBACK; }
+  }
+  e->frames_done += n;
+  const auto tp1 = std::chrono::steady_clock::now();
+  e->t_pack_ms += std::chrono::duration<double, std::milli>(tp1 - tp0).count();
+  if (prog_cb) {
+    const double el = std::chrono::duration<double>(tp1 - t_start).count();
+    prog_cb(user, e->frames_done, total_frames, el > 0 ? e->frames_done / el : 0.0);
+  }
+  return AV1B_OK;
+}
+
+static void reset_stats(av1b_encoder* e) {
+  e->kept.clear();
+  e->t_h2d_ms = e->t_kernel_ms = e->t_intra_ms = e->t_d2h_ms = e->t_pack_ms = 0;
+  e->kernel_launches = e->intra_launches = e->frames_done = e->bytes_out = 0;
+}
 
 extern "C" {
 
@@ -73,32 +274,22 @@ void av1b_config_default(av1b_config* c) {
   c->tile_cols_log2 = -1; c->tile_rows_log2 = -1;
 }
 
-static void free_all(av1b_encoder* e) {
-  for (int p = 0; p < 3; p++) {
-    cudaFree(e->d_src[p]); cudaFree(e->d_rec[p]); cudaFree(e->d_coef[p]);
-    cudaFreeHost(e->h_src[p]); cudaFreeHost(e->h_rec[p]); cudaFreeHost(e->h_coef[p]);
-  }
-  cudaFree(e->d_blocks); cudaFree(e->d_map); cudaFreeHost(e->h_blocks);
-  for (auto& ev : e->ev) if (ev) cudaEventDestroy(ev);
-  if (e->stream) cudaStreamDestroy(e->stream);
-}
-
 int av1b_encoder_create(const av1b_config* cfg, av1b_encoder** out) {
   if (!cfg || !out) { set_error("null argument"); return AV1B_ERR_INVALID; }
   *out = nullptr;
   if (cfg->bit_depth != 8 && cfg->bit_depth != 10) { set_error("bit_depth must be 8 or 10"); return AV1B_ERR_INVALID; }
   if (cfg->crf < 0 || cfg->crf > 63) { set_error("crf out of range 0..63"); return AV1B_ERR_INVALID; }
+  Av1bGeom probe;
+  if (av1b_geom_init(&probe, cfg->width, cfg->height, 0, 0)) {
+    set_error("unsupported frame size %dx%d (multiples of 8, 16..8192 x 16..4352)", cfg->width, cfg->height);
+    return AV1B_ERR_INVALID;
+  }
   int ndev = av1b_device_count();
   if (ndev <= 0) { set_error("no CUDA device visible (av1b200 has no CPU fallback)"); return AV1B_ERR_NO_DEVICE; }
   if (cfg->device_id < 0 || cfg->device_id >= ndev) { set_error("device_id %d out of range", cfg->device_id); return AV1B_ERR_INVALID; }
   av1b_encoder* e = new av1b_encoder();
   e->cfg = *cfg;
   // tiles: auto = about 4x4 superblocks per tile (tiles x frames-in-flight CTAs fill the 148 SMs)
-  Av1bGeom probe;
-  if (av1b_geom_init(&probe, cfg->width, cfg->height, 0, 0)) {
-    set_error("unsupported frame size %dx%d (multiples of 8, 16..8192 x 16..4352)", cfg->width, cfg->height);
-    delete e; return AV1B_ERR_INVALID;
-  }
   int tcl = cfg->tile_cols_log2, trl = cfg->tile_rows_log2;
   if (tcl < 0) tcl = av1b_tile_log2(4, probe.sb_cols);
   if (trl < 0) trl = av1b_tile_log2(4, probe.sb_rows);
@@ -109,29 +300,34 @@ int av1b_encoder_create(const av1b_config* cfg, av1b_encoder** out) {
   e->base_q_idx = av1t_quantizer_to_qindex[cfg->crf];
   if (e->base_q_idx < 1) e->base_q_idx = 1;   // lossless (qindex 0) is not supported
   e->blk_log2 = cfg->reserved[1] ? cfg->reserved[1] : 4;
+  if (e->blk_log2 < 3 || e->blk_log2 > 6) { set_error("block log2 must be 3..6"); delete e; return AV1B_ERR_INVALID; }
   e->keep = cfg->reserved[0] != 0;
   e->batch = cfg->frames_in_flight > 0 ? cfg->frames_in_flight : 8;
-  e->host_threads = cfg->host_threads > 0 ? cfg->host_threads : 8;
+  e->host_threads = cfg->host_threads > 0 ? cfg->host_threads : (int)std::max(1u, std::thread::hardware_concurrency());
   if (cudaSetDevice(cfg->device_id) != cudaSuccess) { set_error("cudaSetDevice failed"); delete e; return AV1B_ERR_CUDA; }
   cudaError_t err = cudaSuccess;
   auto A = [&](cudaError_t r) { if (err == cudaSuccess && r != cudaSuccess) err = r; };
   A(cudaStreamCreateWithFlags(&e->stream, cudaStreamNonBlocking));
-  for (auto& ev : e->ev) A(cudaEventCreate(&ev));
   e->map_elems = (size_t)e->g.w8 * e->g.h8;
-  for (int p = 0; p < 3; p++) {
-    e->plane_elems[p] = (size_t)e->g.stride[p] * e->g.rows[p];
-    const size_t n = e->plane_elems[p] * e->batch;
-    A(cudaMalloc(&e->d_src[p], n * 2)); A(cudaMalloc(&e->d_rec[p], n * 2)); A(cudaMalloc(&e->d_coef[p], n * 2));
-    A(cudaMallocHost(&e->h_src[p], n * 2)); A(cudaMallocHost(&e->h_rec[p], n * 2)); A(cudaMallocHost(&e->h_coef[p], n * 2));
-    if (err == cudaSuccess) { A(cudaMemset(e->d_src[p], 0, n * 2)); A(cudaMemset(e->d_coef[p], 0, n * 2)); A(cudaMemset(e->d_rec[p], 0, n * 2)); }
+  for (int p = 0; p < 3; p++) e->plane_elems[p] = (size_t)e->g.stride[p] * e->g.rows[p];
+  for (auto& s : e->slot) {
+    for (auto& ev : s.ev) A(cudaEventCreate(&ev));
+    for (int p = 0; p < 3; p++) {
+      const size_t n = e->plane_elems[p] * e->batch;
+      A(cudaMalloc(&s.d_src[p], n * 2)); A(cudaMalloc(&s.d_rec[p], n * 2)); A(cudaMalloc(&s.d_coef[p], n * 2));
+      A(cudaMallocHost(&s.h_src[p], n * 2)); A(cudaMallocHost(&s.h_coef[p], n * 2));
+      if (e->keep) A(cudaMallocHost(&s.h_rec[p], n * 2));
+      if (err == cudaSuccess) { A(cudaMemset(s.d_src[p], 0, n * 2)); A(cudaMemset(s.d_coef[p], 0, n * 2)); A(cudaMemset(s.d_rec[p], 0, n * 2)); }
+    }
+    A(cudaMalloc(&s.d_blocks, e->map_elems * e->batch * sizeof(Av1bBlockInfo)));
+    A(cudaMalloc(&s.d_map, e->map_elems * e->batch));
+    A(cudaMallocHost(&s.h_blocks, e->map_elems * e->batch * sizeof(Av1bBlockInfo)));
   }
-  A(cudaMalloc(&e->d_blocks, e->map_elems * e->batch * sizeof(Av1bBlockInfo)));
-  A(cudaMalloc(&e->d_map, e->map_elems * e->batch));
-  A(cudaMallocHost(&e->h_blocks, e->map_elems * e->batch * sizeof(Av1bBlockInfo)));
   if (err != cudaSuccess) {
     set_error("device/pinned allocation failed: %s", cudaGetErrorString(err));
     free_all(e); delete e; return AV1B_ERR_NOMEM;
   }
+  e->pool = new ThreadPool(e->host_threads);
   *out = e;
   return AV1B_OK;
 }
@@ -139,6 +335,7 @@ int av1b_encoder_create(const av1b_config* cfg, av1b_encoder** out) {
 void av1b_encoder_destroy(av1b_encoder* e) {
   if (!e) return;
   cudaSetDevice(e->cfg.device_id);
+  cudaStreamSynchronize(e->stream);
   free_all(e);
   delete e;
 }
@@ -147,85 +344,48 @@ int av1b_encode_chunk(av1b_encoder* e, const av1b_frame_src* frames, uint32_t n_
                       av1b_progress_cb prog_cb, void* user) {
   if (!e || !frames || !out_cb) { set_error("null argument"); return AV1B_ERR_INVALID; }
   CK(cudaSetDevice(e->cfg.device_id));
-  const Av1bGeom& g = e->g;
-  e->kept.clear();
-  e->t_h2d_ms = e->t_kernel_ms = e->t_d2h_ms = e->t_pack_ms = 0;
-  e->kernel_launches = 0;
-  const auto t_start = std::chrono::steady_clock::now();
-  const int bd = e->cfg.bit_depth;
-  std::vector<uint8_t> tu;
-  for (uint32_t f0 = 0; f0 < n_frames; f0 += e->batch) {
+  reset_stats(e);
+  const auto t0 = std::chrono::steady_clock::now();
+  int rc, i = 0;
+  for (uint32_t f0 = 0; f0 < n_frames; f0 += e->batch, i++) {
     const int nb = (int)std::min<uint32_t>(e->batch, n_frames - f0);
-    // stage + upload the source frames into the padded device planes
-    CK(cudaEventRecord(e->ev[0], e->stream));
-    for (int b = 0; b < nb; b++) {
-      const av1b_frame_src& fs = frames[f0 + b];
-      for (int p = 0; p < 3; p++) {
-        const int w = p ? g.width >> 1 : g.width, h = p ? g.height >> 1 : g.height;
-        uint16_t* hs = e->h_src[p] + (size_t)b * e->plane_elems[p];
-        for (int y = 0; y < h; y++) memcpy(hs + (size_t)y * g.stride[p], fs.planes[p] + (size_t)y * fs.stride[p], (size_t)w * 2);
-        CK(cudaMemcpyAsync(e->d_src[p] + (size_t)b * e->plane_elems[p], hs, (size_t)g.stride[p] * h * 2,
-                           cudaMemcpyHostToDevice, e->stream));
-      }
-    }
-    CK(cudaEventRecord(e->ev[1], e->stream));
-    IntraLaunch L;
-    L.g = g; L.bit_depth = bd; L.base_q_idx = e->base_q_idx; L.quant_rnd = 48;
-    L.dc_q = bd == 8 ? av1t_dc_q_8[e->base_q_idx] : av1t_dc_q_10[e->base_q_idx];
-    L.ac_q = bd == 8 ? av1t_ac_q_8[e->base_q_idx] : av1t_ac_q_10[e->base_q_idx];
-    for (int p = 0; p < 3; p++) { L.src[p] = e->d_src[p]; L.rec[p] = e->d_rec[p]; L.coef[p] = e->d_coef[p]; L.plane_elems[p] = e->plane_elems[p]; }
-    L.blocks = e->d_blocks; L.part_map = e->d_map; L.map_elems = e->map_elems;
-    CK(launch_partition_fixed(g, e->blk_log2, e->d_map, nb, e->stream));
-    CK(launch_intra_encode(L, nb, e->stream));
-    e->kernel_launches += 2;
-    CK(cudaEventRecord(e->ev[2], e->stream));
-    for (int p = 0; p < 3; p++) {
-      CK(cudaMemcpyAsync(e->h_coef[p], e->d_coef[p], e->plane_elems[p] * nb * 2, cudaMemcpyDeviceToHost, e->stream));
-      if (e->keep) CK(cudaMemcpyAsync(e->h_rec[p], e->d_rec[p], e->plane_elems[p] * nb * 2, cudaMemcpyDeviceToHost, e->stream));
-    }
-    CK(cudaMemcpyAsync(e->h_blocks, e->d_blocks, e->map_elems * nb * sizeof(Av1bBlockInfo), cudaMemcpyDeviceToHost, e->stream));
-    CK(cudaEventRecord(e->ev[3], e->stream));
-    CK(cudaStreamSynchronize(e->stream));
-    float ms;
-    cudaEventElapsedTime(&ms, e->ev[0], e->ev[1]); e->t_h2d_ms += ms;
-    cudaEventElapsedTime(&ms, e->ev[1], e->ev[2]); e->t_kernel_ms += ms;
-    cudaEventElapsedTime(&ms, e->ev[2], e->ev[3]); e->t_d2h_ms += ms;
-    // host entropy coding + packetisation, in display order
-    const auto tp0 = std::chrono::steady_clock::now();
-    for (int b = 0; b < nb; b++) {
-      Av1bFrameParams fp;
-      memset(&fp, 0, sizeof(fp));
-      fp.frame_type = AV1B_KEY_FRAME;
-      fp.base_q_idx = e->base_q_idx;
-      fp.disable_cdf_update = 0;
-      fp.tile_cols_log2 = g.tile_cols_log2; fp.tile_rows_log2 = g.tile_rows_log2;
-      fp.cdef_damping = 3;
-      Av1bFrameSyms sy;
-      memset(&sy, 0, sizeof(sy));
-      sy.blocks = e->h_blocks + (size_t)b * e->map_elems;
-      for (int p = 0; p < 3; p++) { sy.coef[p] = e->h_coef[p] + (size_t)b * e->plane_elems[p]; sy.coef_stride[p] = g.stride[p]; }
-      tu.clear();
-      write_temporal_delimiter(tu);
-      if (f0 + b == 0) write_sequence_header(e->seq, tu);
-      if (write_frame(e->seq, fp, g, sy, tu, e->host_threads)) { set_error("write_frame failed"); return AV1B_ERR_INTERNAL; }
-      if (e->keep) {
-        e->kept.emplace_back();
-        KeptFrame& k = e->kept.back();
-        for (int p = 0; p < 3; p++) {
-          k.rec[p].assign(e->h_rec[p] + (size_t)b * e->plane_elems[p], e->h_rec[p] + (size_t)(b + 1) * e->plane_elems[p]);
-          k.coef[p].assign(e->h_coef[p] + (size_t)b * e->plane_elems[p], e->h_coef[p] + (size_t)(b + 1) * e->plane_elems[p]);
-        }
-        k.blocks.assign(sy.blocks, sy.blocks + e->map_elems);
-      }
-      if (out_cb(user, tu.data(), tu.size(), (int64_t)(f0 + b), 1)) { set_error("packet callback aborted"); return AV1B_ERR_CALLBACK; }
-    }
-    const auto tp1 = std::chrono::steady_clock::now();
-    e->t_pack_ms += std::chrono::duration<double, std::milli>(tp1 - tp0).count();
-    if (prog_cb) {
-      const double el = std::chrono::duration<double>(tp1 - t_start).count();
-      prog_cb(user, (int64_t)(f0 + nb), (int64_t)n_frames, el > 0 ? (f0 + nb) / el : 0.0);
-    }
+    Slot& s = e->slot[i & 1];
+    if ((rc = stage(e, s, frames + f0, nb)) != AV1B_OK) return rc;
+    if ((rc = launch(e, s, nb, f0)) != AV1B_OK) return rc;
+    if (i > 0 && (rc = finish(e, e->slot[(i - 1) & 1], true, out_cb, prog_cb, user, n_frames, t0)) != AV1B_OK) return rc;
   }
+  if (i > 0 && (rc = finish(e, e->slot[(i - 1) & 1], true, out_cb, prog_cb, user, n_frames, t0)) != AV1B_OK) return rc;
+  return AV1B_OK;
+}
+
+// ---- device-resident flow (bench: "inputs already resident in HBM") -----------------------------
+int av1b_stage_frames(av1b_encoder* e, int slot, const av1b_frame_src* frames, uint32_t n_frames) {
+  if (!e || !frames || slot < 0 || slot > 1 || n_frames == 0 || (int)n_frames > e->batch) { set_error("bad argument"); return AV1B_ERR_INVALID; }
+  CK(cudaSetDevice(e->cfg.device_id));
+  int rc = stage(e, e->slot[slot], frames, (int)n_frames);
+  if (rc) return rc;
+  e->slot[slot].n_frames = (int)n_frames;
+  CK(cudaStreamSynchronize(e->stream));
+  return AV1B_OK;
+}
+
+int av1b_encode_resident(av1b_encoder* e, uint32_t n_steps, av1b_packet_cb out_cb, void* user) {
+  if (!e || n_steps == 0) { set_error("bad argument"); return AV1B_ERR_INVALID; }
+  if (e->slot[0].n_frames <= 0 || e->slot[1].n_frames <= 0) { set_error("stage both slots first"); return AV1B_ERR_INVALID; }
+  CK(cudaSetDevice(e->cfg.device_id));
+  reset_stats(e);
+  const auto t0 = std::chrono::steady_clock::now();
+  int rc;
+  int64_t idx = 0;
+  const int n0 = e->slot[0].n_frames, n1 = e->slot[1].n_frames;
+  for (uint32_t i = 0; i < n_steps; i++) {
+    Slot& s = e->slot[i & 1];
+    const int nb = (i & 1) ? n1 : n0;
+    if ((rc = launch(e, s, nb, idx)) != AV1B_OK) return rc;
+    idx += nb;
+    if (i > 0 && (rc = finish(e, e->slot[(i - 1) & 1], false, out_cb, nullptr, user, 0, t0)) != AV1B_OK) return rc;
+  }
+  if ((rc = finish(e, e->slot[(n_steps - 1) & 1], false, out_cb, nullptr, user, 0, t0)) != AV1B_OK) return rc;
   return AV1B_OK;
 }
 
@@ -240,7 +400,6 @@ int av1b_get_recon(av1b_encoder* e, uint32_t frame, uint16_t* const dst[3], cons
   return AV1B_OK;
 }
 
-// Test/diagnostic access to the device-produced symbol streams of a kept frame (padded layouts).
 int av1b_get_frame_syms(av1b_encoder* e, uint32_t frame, Av1bBlockInfo* blocks, int16_t* const coef[3]) {
   if (!e || !e->keep || frame >= e->kept.size()) { set_error("symbols not kept or bad index"); return AV1B_ERR_INVALID; }
   if (blocks) memcpy(blocks, e->kept[frame].blocks.data(), e->map_elems * sizeof(Av1bBlockInfo));
@@ -254,11 +413,12 @@ int av1b_get_geom(av1b_encoder* e, Av1bGeom* g) {
   return AV1B_OK;
 }
 
-// stats[0..5] = h2d_ms, kernel_ms, d2h_ms, pack_ms, kernel_launches, base_q_idx  (last chunk)
 int av1b_get_stats(av1b_encoder* e, double* stats, int n) {
   if (!e || !stats) return AV1B_ERR_INVALID;
-  const double v[6] = {e->t_h2d_ms, e->t_kernel_ms, e->t_d2h_ms, e->t_pack_ms, (double)e->kernel_launches, (double)e->base_q_idx};
-  for (int i = 0; i < n && i < 6; i++) stats[i] = v[i];
+  const double v[10] = {e->t_h2d_ms, e->t_kernel_ms, e->t_d2h_ms, e->t_pack_ms, (double)e->kernel_launches,
+                        (double)e->base_q_idx, e->t_intra_ms, (double)e->intra_launches, (double)e->frames_done,
+                        (double)e->bytes_out};
+  for (int i = 0; i < n && i < 10; i++) stats[i] = v[i];
   return AV1B_OK;
 }
 

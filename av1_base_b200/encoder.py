@@ -102,9 +102,40 @@ class Encoder:
         return blocks, coef
 
     def stats(self):
-        s = (C.c_double * 6)()
-        _check(abi.lib().av1b_get_stats(self._h, s, 6))
-        return dict(h2d_ms=s[0], kernel_ms=s[1], d2h_ms=s[2], pack_ms=s[3], kernel_launches=int(s[4]), base_q_idx=int(s[5]))
+        s = (C.c_double * 10)()
+        _check(abi.lib().av1b_get_stats(self._h, s, 10))
+        return dict(h2d_ms=s[0], kernel_ms=s[1], d2h_ms=s[2], pack_ms=s[3], kernel_launches=int(s[4]),
+                    base_q_idx=int(s[5]), intra_ms=s[6], intra_launches=int(s[7]), frames_done=int(s[8]),
+                    bytes_out=int(s[9]))
+
+    def _srcs(self, frames):
+        n = len(frames)
+        srcs = (abi.FrameSrc * n)()
+        keep = []
+        for i, fr in enumerate(frames):
+            for p in range(3):
+                a = np.ascontiguousarray(fr[p], dtype=np.uint16)
+                keep.append(a)
+                srcs[i].planes[p] = a.ctypes.data
+                srcs[i].stride[p] = a.shape[1]
+        return srcs, keep
+
+    def stage_frames(self, slot, frames):
+        """Upload frames into device slot 0/1 (inputs resident in HBM for encode_resident)."""
+        srcs, keep = self._srcs(frames)
+        _check(abi.lib().av1b_stage_frames(self._h, slot, srcs, len(frames)))
+
+    def encode_resident(self, n_steps, collect=False):
+        out = []
+
+        def on_packet(user, data, size, idx, is_key):
+            if collect:
+                out.append(C.string_at(data, size))
+            return 0
+
+        cb = abi.PACKET_CB(on_packet)
+        _check(abi.lib().av1b_encode_resident(self._h, n_steps, cb, None))
+        return out
 
 
 def device_count():

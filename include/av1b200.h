@@ -76,11 +76,18 @@ int av1b_encode_chunk(av1b_encoder* enc, const av1b_frame_src* frames, uint32_t 
  * filter), for the recon-vs-decode check. dst planes: uint16, strides in samples. */
 int av1b_get_recon(av1b_encoder* enc, uint32_t frame_in_chunk, uint16_t* const dst[3], const int32_t stride[3]);
 
+/* ---- device-resident flow: upload up to frames_in_flight frames into slot 0 and slot 1 once, then
+ * encode them n_steps times (slot = step & 1) with the same pipelining as av1b_encode_chunk. Used to
+ * measure throughput with the inputs already resident in HBM. out_cb may be NULL. ---- */
+int av1b_stage_frames(av1b_encoder* enc, int slot, const av1b_frame_src* frames, uint32_t n_frames);
+int av1b_encode_resident(av1b_encoder* enc, uint32_t n_steps, av1b_packet_cb out_cb, void* user);
+
 /* ---- diagnostics (need config.reserved[0] = 1: keep per-frame reconstruction and symbols) ---- */
 struct Av1bBlockInfo; struct Av1bGeom;
 int av1b_get_frame_syms(av1b_encoder* enc, uint32_t frame_in_chunk, struct Av1bBlockInfo* blocks, int16_t* const coef[3]);
 int av1b_get_geom(av1b_encoder* enc, struct Av1bGeom* geom);
-/* stats[0..5] = h2d_ms, kernel_ms, d2h_ms, pack_ms, kernel_launches, base_q_idx of the last chunk */
+/* stats[0..9] = h2d_ms, kernel_ms, d2h_ms, pack_ms, kernel_launches, base_q_idx, intra_kernel_ms,
+ * intra_kernel_launches, frames_done, bytes_out of the last chunk / resident run (CUDA-event times) */
 int av1b_get_stats(av1b_encoder* enc, double* stats, int n);
 
 /* ---- host entropy coder over symbol streams (the part that "runs on the host") -------------- */
