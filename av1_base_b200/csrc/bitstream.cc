@@ -378,6 +378,7 @@ struct TileWriter {
     mi_col_start = g.tile_col_start_sb[tile_col] * 16;
     mi_col_end = std::min(g.tile_col_start_sb[tile_col + 1] * 16, g.mi_cols);
     init_cdfs(cdf, fp.base_q_idx);
+    reset_lr_refs();
     const int tw4 = mi_col_end - mi_col_start;
     for (int p = 0; p < 3; p++) {
       above_lvl[p].assign(tw4 + 32, 0);
@@ -388,11 +389,87 @@ struct TileWriter {
       memset(left_dc, 0, sizeof(left_dc));
       for (int c = mi_col_start; c < mi_col_end; c += 16) {
         cdef_pending = true;   // clear_cdef(): cdef_idx is coded at the first non-skip block
-        // read_lr(): loop-restoration unit syntax is added with the LR stage
+        if (seq.enable_restoration) write_lr(r, c);
         partition(r, c, 6);
       }
     }
     ec.finish(out);
+  }
+
+  // ---- loop restoration unit syntax (spec 5.11.57 read_lr / 5.11.58 read_lr_unit) ----
+  int ref_wiener[3][2][3], ref_sgr[3][2];
+  void reset_lr_refs() {
+    for (int p = 0; p < 3; p++) {
+      for (int k = 0; k < 2; k++) { ref_wiener[p][k][0] = 3; ref_wiener[p][k][1] = -7; ref_wiener[p][k][2] = 15; }
+      ref_sgr[p][0] = -32; ref_sgr[p][1] = 31;
+    }
+  }
+  void put_uniform(int v, int n) {
+    const int w = 32 - __builtin_clz((unsigned)n), m = (1 << w) - n;
+    if (v < m) { ec.literal(v, w - 1); }
+    else { ec.literal(m + ((v - m) >> 1), w - 1); ec.literal((v - m) & 1, 1); }
+  }
+  void put_subexp(int x, int num_syms, int k) {
+    int i = 0, mk = 0;
+    for (;;) {
+      const int b2 = i ? k + i - 1 : k, a = 1 << b2;
+      if (num_syms <= mk + 3 * a) { put_uniform(x - mk, num_syms - mk); return; }
+      const int more = x >= mk + a;
+      ec.literal(more, 1);
+      if (more) { i++; mk += a; }
+      else { ec.literal(x - mk, b2); return; }
+    }
+  }
+  static int recenter(int r, int v) { return v > 2 * r ? v : (v >= r ? (v - r) << 1 : ((r - v) << 1) - 1); }
+  void put_signed_subexp_with_ref(int v, int low, int high, int k, int r) {
+    const int mx = high - low, vv = v - low, rr = r - low;
+    const int x = (rr << 1) <= mx ? recenter(rr, vv) : recenter(mx - 1 - rr, mx - 1 - vv);
+    put_subexp(x, mx, k);
+  }
+  void write_lr(int r, int c) {
+    static const int tap_min[3] = {-5, -23, -17}, tap_max[3] = {10, 8, 46}, tap_k[3] = {1, 2, 3};
+    for (int p = 0; p < 3; p++) {
+      if (fp.lr_type[p] == AV1B_RESTORE_NONE) continue;
+      const int ss = p > 0;
+      int us = 64 << fp.lr_unit_shift;
+      if (ss) us >>= fp.lr_uv_shift;
+      const int unit_rows = std::max((((g.height + ss) >> ss) + (us >> 1)) / us, 1);
+      const int unit_cols = std::max((((g.width + ss) >> ss) + (us >> 1)) / us, 1);
+      const int m = 4 >> ss;
+      const int row0 = (r * m + us - 1) / us, row1 = std::min(((r + 16) * m + us - 1) / us, unit_rows);
+      const int col0 = (c * m + us - 1) / us, col1 = std::min(((c + 16) * m + us - 1) / us, unit_cols);
+      for (int ur = row0; ur < row1; ur++)
+        for (int uc = col0; uc < col1; uc++) {
+          const Av1bLrUnit& u = sy.lr_units[p][ur * sy.lr_unit_cols[p] + uc];
+          if (fp.lr_type[p] == AV1B_RESTORE_WIENER) ec.symbol(u.type == AV1B_RESTORE_WIENER, cdf.wiener_restore, 2);
+          else if (fp.lr_type[p] == AV1B_RESTORE_SGRPROJ) ec.symbol(u.type == AV1B_RESTORE_SGRPROJ, cdf.sgrproj_restore, 2);
+          else ec.symbol(u.type, cdf.switchable_restore, 3);   // NONE 0, WIENER 1, SGRPROJ 2
+          if (u.type == AV1B_RESTORE_WIENER) {
+            for (int pass = 0; pass < 2; pass++) {
+              const int8_t* co = pass ? u.wiener_h : u.wiener_v;
+              for (int j = p ? 1 : 0; j < 3; j++) {
+                put_signed_subexp_with_ref(co[j], tap_min[j], tap_max[j] + 1, tap_k[j], ref_wiener[p][pass][j]);
+                ref_wiener[p][pass][j] = co[j];
+              }
+            }
+          } else if (u.type == AV1B_RESTORE_SGRPROJ) {
+            static const int xqd_min[2] = {-96, -32}, xqd_max[2] = {31, 95};
+            ec.literal(u.sgr_set, 4);
+            for (int i = 0; i < 2; i++) {
+              const int radius = av1t_sgr_params[u.sgr_set][i];
+              if (radius) {
+                put_signed_subexp_with_ref(u.sgr_xqd[i], xqd_min[i], xqd_max[i] + 1, 4, ref_sgr[p][i]);
+                ref_sgr[p][i] = u.sgr_xqd[i];
+              } else {
+                // not coded: decoder infers 0 (i == 0) or clip(128 - ref[0]) (i == 1)
+                int v = 0;
+                if (i == 1) v = std::min(std::max(128 - ref_sgr[p][0], xqd_min[1]), xqd_max[1]);
+                ref_sgr[p][i] = v;
+              }
+            }
+          }
+        }
+    }
   }
 
   // square-only partition tree; bl = log2 of block size in samples (6..3)

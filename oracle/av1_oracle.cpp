@@ -514,3 +514,390 @@ extern "C" int orc_encode_intra_frame(const Av1bGeom* g, int bit_depth, int base
 }
 
 extern "C" int orc_geom_init(Av1bGeom* g, int w, int h, int tcl, int trl) { return av1b_geom_init(g, w, h, tcl, trl); }
+
+// ------------------------------------------------------------------------------------------------
+// Deblocking loop filter (spec 7.14), restated per sample line.  All blocks are intra, so every
+// transform edge is filtered; levels are uniform per plane/direction (no segment or ref deltas).
+// ------------------------------------------------------------------------------------------------
+// px[-8..7] around the edge: px[-1] = p0, px[0] = q0.  filter_size 4, 6 (chroma), 8 or 16.
+static void lf_filter_line(uint16_t* s, int step, int filter_size, int lvl, int sharp, int bd) {
+  int shift = sharp > 4 ? 2 : (sharp > 0 ? 1 : 0);
+  int limit = sharp > 0 ? clampi(lvl >> shift, 1, 9 - sharp) : std::max(1, lvl >> shift);
+  int blimit = 2 * (lvl + 2) + limit;
+  int thresh = lvl >> 4;
+  const int sb = bd - 8;
+  limit <<= sb; blimit <<= sb; thresh <<= sb;
+  const int one = 1 << sb;
+  auto P = [&](int i) -> int { return s[-(i + 1) * step]; };   // p_i
+  auto Q = [&](int i) -> int { return s[i * step]; };          // q_i
+  const int p0 = P(0), p1 = P(1), q0 = Q(0), q1 = Q(1);
+  bool hev = abs(p1 - p0) > thresh || abs(q1 - q0) > thresh;
+  bool mask = abs(p1 - p0) <= limit && abs(q1 - q0) <= limit && abs(p0 - q0) * 2 + abs(p1 - q1) / 2 <= blimit;
+  bool flat = false, flat2 = false;
+  if (filter_size >= 6) {
+    const int p2 = P(2), q2 = Q(2);
+    mask = mask && abs(p2 - p1) <= limit && abs(q2 - q1) <= limit;
+    flat = abs(p1 - p0) <= one && abs(q1 - q0) <= one && abs(p2 - p0) <= one && abs(q2 - q0) <= one;
+  }
+  if (filter_size >= 8) {
+    const int p3 = P(3), q3 = Q(3);
+    mask = mask && abs(p3 - P(2)) <= limit && abs(q3 - Q(2)) <= limit;
+    flat = flat && abs(p3 - p0) <= one && abs(q3 - q0) <= one;
+  }
+  if (filter_size == 16) {
+    flat2 = abs(P(4) - p0) <= one && abs(P(5) - p0) <= one && abs(P(6) - p0) <= one &&
+            abs(Q(4) - q0) <= one && abs(Q(5) - q0) <= one && abs(Q(6) - q0) <= one;
+  }
+  if (!mask) return;
+  if (filter_size == 4 || !flat) {
+    const int lo = -(1 << (bd - 1)), hi = (1 << (bd - 1)) - 1, off = 0x80 << sb;
+    const int ps1 = p1 - off, ps0 = p0 - off, qs0 = q0 - off, qs1 = q1 - off;
+    int f = hev ? clampi(ps1 - qs1, lo, hi) : 0;
+    f = clampi(f + 3 * (qs0 - ps0), lo, hi);
+    const int f1 = clampi(f + 4, lo, hi) >> 3, f2 = clampi(f + 3, lo, hi) >> 3;
+    s[0] = (uint16_t)(clampi(qs0 - f1, lo, hi) + off);
+    s[-step] = (uint16_t)(clampi(ps0 + f2, lo, hi) + off);
+    if (!hev) {
+      const int f3 = (f1 + 1) >> 1;
+      s[step] = (uint16_t)(clampi(qs1 - f3, lo, hi) + off);
+      s[-2 * step] = (uint16_t)(clampi(ps1 + f3, lo, hi) + off);
+    }
+    return;
+  }
+  // wide filters (spec 7.14.6.4): window of 2n+1 taps, the centre (2*n2+1) taps doubled
+  int n, log2sz, n2;
+  if (filter_size == 16 && flat2) { n = 6; log2sz = 4; n2 = 1; }
+  else if (filter_size == 6) { n = 2; log2sz = 3; n2 = 1; }
+  else { n = 3; log2sz = 3; n2 = 0; }
+  int in[16], out[16];
+  for (int i = -(n + 1); i <= n; i++) in[i + 8] = s[i * step];
+  for (int i = -n; i < n; i++) {
+    int t = 0;
+    for (int j = -n; j <= n; j++) {
+      const int p = clampi(i + j, -(n + 1), n);
+      t += in[p + 8] * (abs(j) <= n2 ? 2 : 1);
+    }
+    out[i + 8] = (t + (1 << (log2sz - 1))) >> log2sz;
+  }
+  for (int i = -n; i < n; i++) s[i * step] = (uint16_t)out[i + 8];
+}
+
+extern "C" void orc_lf_filter_line(uint16_t* s, int step, int filter_size, int lvl, int sharp, int bd) {
+  lf_filter_line(s, step, filter_size, lvl, sharp, bd);
+}
+
+// rec: padded planes (geometry strides); blocks: per-8x8 side info.  lf_level: Y-vertical-edges,
+// Y-horizontal-edges, U, V (frame header loop_filter_level[0..3]).
+extern "C" void orc_deblock_frame(const Av1bGeom* g, int bd, const Av1bBlockInfo* blocks, uint16_t* rec_y,
+                                  uint16_t* rec_u, uint16_t* rec_v, const int32_t* lf_level, int sharp) {
+  uint16_t* rec[3] = {rec_y, rec_u, rec_v};
+  for (int p = 0; p < 3; p++) {
+    if (p == 0 && !lf_level[0] && !lf_level[1]) break;
+    if (p > 0 && !lf_level[p + 1]) continue;
+    const int ss = p > 0;
+    const int rows4 = g->mi_rows >> ss, cols4 = g->mi_cols >> ss;   // plane 4x4 units
+    const int stride = g->stride[p];
+    for (int pass = 0; pass < 2; pass++) {
+      const int lvl = p == 0 ? lf_level[pass] : lf_level[p + 1];
+      if (!lvl) continue;
+      for (int r4 = 0; r4 < rows4; r4++)
+        for (int c4 = 0; c4 < cols4; c4++) {
+          // block-info unit of this 4x4 and of the previous one across the edge
+          const int ur = ss ? r4 : r4 >> 1, uc = ss ? c4 : c4 >> 1;
+          const int pr4 = pass ? r4 - 1 : r4, pc4 = pass ? c4 : c4 - 1;
+          if (pr4 < 0 || pc4 < 0) continue;   // picture edge
+          const int pur = ss ? pr4 : pr4 >> 1, puc = ss ? pc4 : pc4 >> 1;
+          const int n_cur = std::min(1 << (blocks[ur * g->w8 + uc].blk_log2 - ss), ss ? 32 : 64);
+          const int n_prev = std::min(1 << (blocks[pur * g->w8 + puc].blk_log2 - ss), ss ? 32 : 64);
+          const int pos = (pass ? r4 : c4) * 4;
+          if (pos % n_cur) continue;          // not a transform edge
+          const int fs = std::min(std::min(n_cur, n_prev), ss ? 8 : 16);
+          const int filter_size = ss ? (fs == 8 ? 6 : 4) : fs;
+          for (int i = 0; i < 4; i++) {
+            uint16_t* s = pass ? rec[p] + (size_t)(r4 * 4) * stride + c4 * 4 + i
+                               : rec[p] + (size_t)(r4 * 4 + i) * stride + c4 * 4;
+            lf_filter_line(s, pass ? stride : 1, filter_size, lvl, sharp, bd);
+          }
+        }
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// CDEF (spec 7.15).  Input: deblocked frame; output: separate frame (all taps read the input).
+// ------------------------------------------------------------------------------------------------
+static const int8_t kCdefDirections[8][2][2] = {{{-1, 1}, {-2, 2}}, {{0, 1}, {-1, 2}}, {{0, 1}, {0, 2}}, {{0, 1}, {1, 2}},
+                                                {{1, 1}, {2, 2}},   {{1, 0}, {2, 1}},  {{1, 0}, {2, 0}}, {{1, 0}, {2, -1}}};
+static const int kCdefDivTable[9] = {0, 840, 420, 280, 210, 168, 140, 120, 105};
+
+// 8x8 luma block direction search (spec 7.15.2). Returns direction, *var.
+extern "C" int orc_cdef_find_dir(const uint16_t* img, int stride, int32_t* var, int bd) {
+  int32_t cost[8] = {0}, partial[8][15];
+  memset(partial, 0, sizeof(partial));
+  for (int i = 0; i < 8; i++)
+    for (int j = 0; j < 8; j++) {
+      const int x = (img[i * stride + j] >> (bd - 8)) - 128;
+      partial[0][i + j] += x;
+      partial[1][i + j / 2] += x;
+      partial[2][i] += x;
+      partial[3][3 + i - j / 2] += x;
+      partial[4][7 + i - j] += x;
+      partial[5][3 - i / 2 + j] += x;
+      partial[6][j] += x;
+      partial[7][i / 2 + j] += x;
+    }
+  for (int i = 0; i < 8; i++) {
+    cost[2] += partial[2][i] * partial[2][i];
+    cost[6] += partial[6][i] * partial[6][i];
+  }
+  cost[2] *= kCdefDivTable[8];
+  cost[6] *= kCdefDivTable[8];
+  for (int i = 0; i < 7; i++) {
+    cost[0] += (partial[0][i] * partial[0][i] + partial[0][14 - i] * partial[0][14 - i]) * kCdefDivTable[i + 1];
+    cost[4] += (partial[4][i] * partial[4][i] + partial[4][14 - i] * partial[4][14 - i]) * kCdefDivTable[i + 1];
+  }
+  cost[0] += partial[0][7] * partial[0][7] * kCdefDivTable[8];
+  cost[4] += partial[4][7] * partial[4][7] * kCdefDivTable[8];
+  for (int i = 1; i < 8; i += 2) {
+    for (int j = 0; j < 5; j++) cost[i] += partial[i][3 + j] * partial[i][3 + j];
+    cost[i] *= kCdefDivTable[8];
+    for (int j = 0; j < 3; j++)
+      cost[i] += (partial[i][j] * partial[i][j] + partial[i][10 - j] * partial[i][10 - j]) * kCdefDivTable[2 * j + 2];
+  }
+  int best = 0, dir = 0;
+  for (int d = 0; d < 8; d++) if (cost[d] > best) { best = cost[d]; dir = d; }
+  *var = (best - cost[(dir + 4) & 7]) >> 10;
+  return dir;
+}
+
+static inline int floor_log2(unsigned v) { int k = -1; while (v) { k++; v >>= 1; } return k; }
+static inline int cdef_constrain(int diff, int threshold, int damping) {
+  if (!threshold) return 0;
+  const int adj = std::max(0, damping - floor_log2((unsigned)threshold));
+  const int mag = abs(diff);
+  const int v = clampi(threshold - (mag >> adj), 0, mag);
+  return diff < 0 ? -v : v;
+}
+
+// one block (w x h samples at (x0,y0) of a plane). in: deblocked plane; out: CDEF plane.
+static void cdef_filter_block(const uint16_t* in, uint16_t* out, int stride, int x0, int y0, int w, int h, int plane_w,
+                              int plane_h, int pri, int sec, int damping, int dir, int coeff_shift) {
+  for (int i = 0; i < h; i++)
+    for (int j = 0; j < w; j++) {
+      const int x = in[(size_t)(y0 + i) * stride + x0 + j];
+      int sum = 0, mx = x, mn = x;
+      for (int k = 0; k < 2; k++)
+        for (int sign = -1; sign <= 1; sign += 2) {
+          {
+            const int yy = y0 + i + sign * kCdefDirections[dir][k][0], xx = x0 + j + sign * kCdefDirections[dir][k][1];
+            if (yy >= 0 && yy < plane_h && xx >= 0 && xx < plane_w) {
+              const int p = in[(size_t)yy * stride + xx];
+              sum += av1t_cdef_pri_taps[(pri >> coeff_shift) & 1][k] * cdef_constrain(p - x, pri, damping);
+              mx = std::max(mx, p); mn = std::min(mn, p);
+            }
+          }
+          for (int doff = -2; doff <= 2; doff += 4) {
+            const int d2 = (dir + doff) & 7;
+            const int yy = y0 + i + sign * kCdefDirections[d2][k][0], xx = x0 + j + sign * kCdefDirections[d2][k][1];
+            if (yy >= 0 && yy < plane_h && xx >= 0 && xx < plane_w) {
+              const int s = in[(size_t)yy * stride + xx];
+              sum += av1t_cdef_sec_taps[k] * cdef_constrain(s - x, sec, damping);
+              mx = std::max(mx, s); mn = std::min(mn, s);
+            }
+          }
+        }
+      out[(size_t)(y0 + i) * stride + x0 + j] = (uint16_t)clampi(x + ((8 + sum - (sum < 0)) >> 4), mn, mx);
+    }
+}
+
+// Whole frame. in[3]: deblocked padded planes, out[3]: result (must be a different buffer).
+// cdef_idx: per 64x64 strength index; the per-SB "-1" (no non-skip block) state is derived from the
+// block info exactly as the decoder derives it (read_cdef is only reached by non-skip blocks).
+extern "C" void orc_cdef_frame(const Av1bGeom* g, int bd, const Av1bBlockInfo* blocks, const Av1bFrameParams* fp,
+                               const uint8_t* cdef_idx, const uint16_t* in_y, const uint16_t* in_u,
+                               const uint16_t* in_v, uint16_t* out_y, uint16_t* out_u, uint16_t* out_v) {
+  const uint16_t* in[3] = {in_y, in_u, in_v};
+  uint16_t* out[3] = {out_y, out_u, out_v};
+  const int cs = bd - 8;
+  for (int p = 0; p < 3; p++) memcpy(out[p], in[p], (size_t)g->stride[p] * g->rows[p] * 2);
+  for (int r8 = 0; r8 < g->h8; r8++)
+    for (int c8 = 0; c8 < g->w8; c8++) {
+      const Av1bBlockInfo& b = blocks[r8 * g->w8 + c8];
+      if (b.skip) continue;
+      const int idx = cdef_idx[(r8 >> 3) * g->sb_cols + (c8 >> 3)];
+      int32_t var;
+      const int ydir = orc_cdef_find_dir(in[0] + (size_t)(r8 * 8) * g->stride[0] + c8 * 8, g->stride[0], &var, bd);
+      int pri = (fp->cdef_y_strength[idx] >> 2) << cs;
+      int sec = fp->cdef_y_strength[idx] & 3; if (sec == 3) sec = 4; sec <<= cs;
+      int dir = pri == 0 ? 0 : ydir;
+      const int var_str = (var >> 6) ? std::min(floor_log2((unsigned)(var >> 6)), 12) : 0;
+      pri = var ? (pri * (4 + var_str) + 8) >> 4 : 0;
+      cdef_filter_block(in[0], out[0], g->stride[0], c8 * 8, r8 * 8, 8, 8, g->mi_cols * 4, g->mi_rows * 4, pri, sec,
+                        fp->cdef_damping + cs, dir, cs);
+      pri = (fp->cdef_uv_strength[idx] >> 2) << cs;
+      sec = fp->cdef_uv_strength[idx] & 3; if (sec == 3) sec = 4; sec <<= cs;
+      dir = pri == 0 ? 0 : ydir;
+      for (int p = 1; p < 3; p++)
+        cdef_filter_block(in[p], out[p], g->stride[p], c8 * 4, r8 * 4, 4, 4, g->mi_cols * 2, g->mi_rows * 2, pri, sec,
+                          fp->cdef_damping + cs - 1, dir, cs);
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// Loop restoration (spec 7.17): Wiener and self-guided filters, 64-row stripes offset by 8 luma
+// rows; outside the stripe the DEBLOCKED (pre-CDEF) rows are used, at most 2 rows deep.
+// ------------------------------------------------------------------------------------------------
+struct LrPlane {
+  const uint16_t* cdef;      // CDEF output
+  const uint16_t* deblocked; // pre-CDEF
+  int stride, plane_w, plane_h;
+  int stripe_start, stripe_end;
+  inline int sample(int x, int y) const {
+    x = clampi(x, 0, plane_w - 1);
+    y = clampi(y, 0, plane_h - 1);
+    if (y < stripe_start) { y = std::max(stripe_start - 2, y); return deblocked[(size_t)y * stride + x]; }
+    if (y > stripe_end) { y = std::min(stripe_end + 2, y); return deblocked[(size_t)y * stride + x]; }
+    return cdef[(size_t)y * stride + x];
+  }
+};
+
+static inline int count_units(int unit, int size) { return std::max((size + (unit >> 1)) / unit, 1); }
+
+extern "C" void orc_lr_unit_grid(const Av1bGeom* g, const Av1bFrameParams* fp, int plane, int32_t* unit_size,
+                                 int32_t* unit_rows, int32_t* unit_cols) {
+  const int ss = plane > 0;
+  int us = 64 << fp->lr_unit_shift;
+  if (ss) us >>= fp->lr_uv_shift;
+  *unit_size = us;
+  *unit_rows = count_units(us, (g->height + ss) >> ss);
+  *unit_cols = count_units(us, (g->width + ss) >> ss);
+}
+
+static void wiener_taps(const int8_t* c, int* f) {   // c: 3 coded taps -> 7-tap symmetric filter
+  f[3] = 128;
+  for (int i = 0; i < 3; i++) { f[i] = c[i]; f[6 - i] = c[i]; f[3] -= 2 * c[i]; }
+}
+
+// self-guided filter for one sample region is evaluated sample by sample through A/B planes that
+// are computed per 4x4 block with a 1-sample apron (spec 7.17.3 box filter process).
+static void sgr_box(const LrPlane& P, int x0, int y0, int w, int h, int r, int s, int bd, int32_t* A, int32_t* B,
+                    int astride) {
+  // A,B cover rows -1..h, cols -1..w  (index (i+1)*astride + (j+1))
+  const int n = (2 * r + 1) * (2 * r + 1);
+  const int one_by_n = av1t_one_by_x[n - 1];
+  for (int i = -1; i <= h; i++)
+    for (int j = -1; j <= w; j++) {
+      uint32_t a = 0, b = 0;
+      for (int dy = -r; dy <= r; dy++)
+        for (int dx = -r; dx <= r; dx++) {
+          const uint32_t c = (uint32_t)P.sample(x0 + j + dx, y0 + i + dy);
+          a += c * c; b += c;
+        }
+      const uint32_t a_r = (bd > 8) ? (a + (1u << (2 * (bd - 8) - 1))) >> (2 * (bd - 8)) : a;
+      const uint32_t d = (bd > 8) ? (b + (1u << (bd - 8 - 1))) >> (bd - 8) : b;
+      const uint32_t p = (a_r * n < d * d) ? 0 : a_r * n - d * d;
+      const uint32_t z = (uint32_t)(((uint64_t)p * (uint32_t)s + (1u << 19)) >> 20);
+      const uint32_t a2 = av1t_x_by_xplus1[std::min<uint32_t>(z, 255)];
+      const uint32_t b2 = (256 - a2) * b * (uint32_t)one_by_n;
+      A[(i + 1) * astride + j + 1] = (int32_t)a2;
+      B[(i + 1) * astride + j + 1] = (int32_t)((b2 + (1u << 11)) >> 12);
+    }
+}
+
+// Whole frame.  cdef[3]: CDEF output; deb[3]: deblocked (pre-CDEF); out[3]: result.
+// units[p]: [unit_rows][unit_cols] parameters (NULL when lr_type[p] == NONE).
+extern "C" void orc_lr_frame(const Av1bGeom* g, int bd, const Av1bFrameParams* fp, const uint16_t* cdef_y,
+                             const uint16_t* cdef_u, const uint16_t* cdef_v, const uint16_t* deb_y,
+                             const uint16_t* deb_u, const uint16_t* deb_v, uint16_t* out_y, uint16_t* out_u,
+                             uint16_t* out_v, const Av1bLrUnit* units_y, const Av1bLrUnit* units_u,
+                             const Av1bLrUnit* units_v) {
+  const uint16_t* cdef[3] = {cdef_y, cdef_u, cdef_v};
+  const uint16_t* deb[3] = {deb_y, deb_u, deb_v};
+  uint16_t* out[3] = {out_y, out_u, out_v};
+  const Av1bLrUnit* units[3] = {units_y, units_u, units_v};
+  const int round0 = 3, round1 = 11;   // 8/10-bit (spec 7.17.2 rounding variables)
+  for (int p = 0; p < 3; p++) {
+    memcpy(out[p], cdef[p], (size_t)g->stride[p] * g->rows[p] * 2);
+    if (fp->lr_type[p] == AV1B_RESTORE_NONE || !units[p]) continue;
+    const int ss = p > 0;
+    int us, urows, ucols;
+    orc_lr_unit_grid(g, fp, p, &us, &urows, &ucols);
+    LrPlane P;
+    P.cdef = cdef[p]; P.deblocked = deb[p]; P.stride = g->stride[p];
+    P.plane_w = (g->width + ss) >> ss; P.plane_h = (g->height + ss) >> ss;
+    const int bw = 4 >> 0, bh = 4 >> 0;   // process 4x4 sample blocks of the plane (MI_SIZE >> ss would be 2 for chroma;
+                                           // any tiling that does not straddle a stripe or a unit gives the same result)
+    for (int y = 0; y < P.plane_h; y += bh)
+      for (int x = 0; x < P.plane_w; x += bw) {
+        const int luma_y = y << ss;
+        const int stripe = (luma_y + 8) / 64;
+        P.stripe_start = (-8 + stripe * 64) >> ss;
+        P.stripe_end = P.stripe_start + (64 >> ss) - 1;
+        const int urow = std::min(urows - 1, ((luma_y + 8) >> ss) / us);
+        const int ucol = std::min(ucols - 1, x / us);
+        const Av1bLrUnit& u = units[p][urow * ucols + ucol];
+        const int w = std::min(bw, P.plane_w - x), h = std::min(bh, P.plane_h - y);
+        if (u.type == AV1B_RESTORE_WIENER) {
+          int vf[7], hf[7];
+          wiener_taps(u.wiener_v, vf);
+          wiener_taps(u.wiener_h, hf);
+          const int offset = 1 << (bd + 7 - round0 - 1), limit = (1 << (bd + 1 + 7 - round0)) - 1;
+          int inter[10][4];
+          for (int r = 0; r < h + 6; r++)
+            for (int c = 0; c < w; c++) {
+              int s = 0;
+              for (int t = 0; t < 7; t++) s += hf[t] * P.sample(x + c + t - 3, y + r - 3);
+              const int v = (s + (1 << (round0 - 1))) >> round0;
+              inter[r][c] = clampi(v, -offset, limit - offset);
+            }
+          for (int r = 0; r < h; r++)
+            for (int c = 0; c < w; c++) {
+              int s = 0;
+              for (int t = 0; t < 7; t++) s += vf[t] * inter[r + t][c];
+              const int v = (s + (1 << (round1 - 1))) >> round1;
+              out[p][(size_t)(y + r) * P.stride + x + c] = (uint16_t)clampi(v, 0, (1 << bd) - 1);
+            }
+        } else if (u.type == AV1B_RESTORE_SGRPROJ) {
+          const int set = u.sgr_set;
+          const int r0 = av1t_sgr_params[set][0], r1 = av1t_sgr_params[set][1];
+          const int s0 = av1t_sgr_params[set][2], s1 = av1t_sgr_params[set][3];
+          int32_t A0[6 * 6], B0[6 * 6], A1[6 * 6], B1[6 * 6];
+          if (r0) sgr_box(P, x, y, w, h, r0, s0, bd, A0, B0, 6);
+          if (r1) sgr_box(P, x, y, w, h, r1, s1, bd, A1, B1, 6);
+          const int w0 = u.sgr_xqd[0], w1 = u.sgr_xqd[1], w2 = 128 - w0 - w1;
+          for (int i = 0; i < h; i++)
+            for (int j = 0; j < w; j++) {
+              const int src = cdef[p][(size_t)(y + i) * P.stride + x + j];
+              const int uu = src << 4;
+              int flt0 = uu, flt1 = uu;
+              if (r0) {   // radius-2 pass: A/B only from odd rows (relative to an even origin)
+                int a = 0, b = 0, shift;
+                const int32_t* Ap = A0 + (i + 1) * 6 + j + 1;
+                const int32_t* Bp = B0 + (i + 1) * 6 + j + 1;
+                if ((y + i) & 1) {
+                  shift = 4;
+                  a = 6 * Ap[0] + 5 * (Ap[-1] + Ap[1]);
+                  b = 6 * Bp[0] + 5 * (Bp[-1] + Bp[1]);
+                } else {
+                  shift = 5;
+                  a = 6 * (Ap[-6] + Ap[6]) + 5 * (Ap[-7] + Ap[-5] + Ap[5] + Ap[7]);
+                  b = 6 * (Bp[-6] + Bp[6]) + 5 * (Bp[-7] + Bp[-5] + Bp[5] + Bp[7]);
+                }
+                const int v = a * src + b;
+                flt0 = (v + (1 << (8 + shift - 4 - 1))) >> (8 + shift - 4);
+              }
+              if (r1) {
+                const int32_t* Ap = A1 + (i + 1) * 6 + j + 1;
+                const int32_t* Bp = B1 + (i + 1) * 6 + j + 1;
+                const int a = 4 * (Ap[0] + Ap[-1] + Ap[1] + Ap[-6] + Ap[6]) + 3 * (Ap[-7] + Ap[-5] + Ap[5] + Ap[7]);
+                const int b = 4 * (Bp[0] + Bp[-1] + Bp[1] + Bp[-6] + Bp[6]) + 3 * (Bp[-7] + Bp[-5] + Bp[5] + Bp[7]);
+                const int v = a * src + b;
+                flt1 = (v + (1 << (8 + 5 - 4 - 1))) >> (8 + 5 - 4);
+              }
+              const int v = w1 * uu + w0 * flt0 + w2 * flt1;
+              out[p][(size_t)(y + i) * P.stride + x + j] = (uint16_t)clampi((v + (1 << 10)) >> 11, 0, (1 << bd) - 1);
+            }
+        }
+      }
+  }
+}

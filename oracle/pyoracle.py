@@ -54,3 +54,29 @@ def encode_intra_frame(g, frame, bit_depth, base_q_idx, part_map, quant_rnd=48):
 def crop(g, planes):
     return [planes[0][:g.height, :g.width], planes[1][:g.height // 2, :g.width // 2],
             planes[2][:g.height // 2, :g.width // 2]]
+
+def deblock_frame(g, bit_depth, blocks, rec, lf_level, sharpness=0):
+    """In-place deblocking of padded planes rec[3]."""
+    lv = (C.c_int32 * 4)(*lf_level)
+    lib().orc_deblock_frame(C.byref(g), bit_depth, ptr(blocks), ptr(rec[0]), ptr(rec[1]), ptr(rec[2]), lv, sharpness)
+
+def cdef_frame(g, bit_depth, blocks, fp, cdef_idx, rec):
+    """Returns new padded planes = CDEF(rec)."""
+    out = [np.zeros_like(p) for p in rec]
+    lib().orc_cdef_frame(C.byref(g), bit_depth, ptr(blocks), C.byref(fp), ptr(cdef_idx), ptr(rec[0]), ptr(rec[1]),
+                         ptr(rec[2]), ptr(out[0]), ptr(out[1]), ptr(out[2]))
+    return out
+
+def lr_unit_grid(g, fp, plane):
+    us, ur, uc = C.c_int32(), C.c_int32(), C.c_int32()
+    lib().orc_lr_unit_grid(C.byref(g), C.byref(fp), plane, C.byref(us), C.byref(ur), C.byref(uc))
+    return us.value, ur.value, uc.value
+
+def lr_frame(g, bit_depth, fp, cdef, deblocked, units):
+    """units: 3 structured arrays (abi.LR_UNIT_DTYPE, shape [rows, cols]) or None. Returns new planes."""
+    out = [np.zeros_like(p) for p in cdef]
+    up = [ptr(u) if u is not None else None for u in units]
+    lib().orc_lr_frame(C.byref(g), bit_depth, C.byref(fp), ptr(cdef[0]), ptr(cdef[1]), ptr(cdef[2]),
+                       ptr(deblocked[0]), ptr(deblocked[1]), ptr(deblocked[2]), ptr(out[0]), ptr(out[1]), ptr(out[2]),
+                       up[0], up[1], up[2])
+    return out
