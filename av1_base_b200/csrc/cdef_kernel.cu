@@ -1,0 +1,298 @@
+// AV1 constrained directional enhancement filter (spec 7.15) for sm_100a, with the per-superblock
+// strength decision: one CTA per 64x64 superblock per frame.  The CTA stages the deblocked
+// superblock (+2-sample halo) and the source superblock in shared memory, finds the direction and
+// variance of every 8x8 luma block, evaluates each of the frame's 2^cdef_bits strength presets on
+// Y+U+V against the source (sum of squared errors over the non-skip blocks, warp-shuffle + one
+// shared 64-bit atomic per warp), keeps the preset with the smallest error and writes the filtered
+// superblock and its cdef_idx.  The frame is read twice (deblocked + source) and written once:
+// algorithmic bytes 3*S with the decision, 2*S for the normative filter alone.
+//
+// Replaces arithmetic the reference delegates to av1an + SVT-AV1
+// (/root/reference/crates/daemon/src/encode/av1an.rs:126-139).
+// Bit-exact against oracle/av1_oracle.cpp orc_cdef_frame / orc_cdef_find_dir / orc_cdef_search.
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include "kernels.cuh"
+
+namespace av1b {
+namespace {
+
+constexpr int kThreads = 256;
+constexpr int kHalo = 2;
+constexpr int kLW = 64 + 16;          // staged luma columns: x0-8 .. x0+71 (16-byte aligned vectors)
+constexpr int kLStride = kLW + 2;     // 82
+constexpr int kLRows = 64 + 2 * kHalo;
+constexpr int kCW = 32 + 16;
+constexpr int kCStride = kCW + 2;     // 50
+constexpr int kCRows = 32 + 2 * kHalo;
+constexpr uint16_t kUnavail = 0xFFFF; // sample outside the picture (CdefAvailable == 0)
+
+__constant__ int8_t c_dirs[8][2][2] = {{{-1, 1}, {-2, 2}}, {{0, 1}, {-1, 2}}, {{0, 1}, {0, 2}}, {{0, 1}, {1, 2}},
+                                       {{1, 1}, {2, 2}},   {{1, 0}, {2, 1}},  {{1, 0}, {2, 0}}, {{1, 0}, {2, -1}}};
+
+struct Smem {
+  uint16_t y[kLRows * kLStride];
+  uint16_t c[2][kCRows * kCStride];
+  uint16_t sy[64 * 64];
+  uint16_t sc[2][32 * 32];
+  unsigned long long sse[8];
+  int16_t off_y[8][2], off_c[8][2];   // tap offsets (in samples of the staged window) per direction
+  uint8_t skip[8][8];
+  uint8_t dir[8][8];
+  int var[8][8];
+  int best;
+};
+
+__device__ __forceinline__ int clampi(int v, int lo, int hi) { return v < lo ? lo : (v > hi ? hi : v); }
+__device__ __forceinline__ int flog2(unsigned v) { return 31 - __clz(v); }
+
+__device__ __forceinline__ int constrain(int diff, int thr, int adj) {
+  const int mag = diff < 0 ? -diff : diff;
+  const int v = clampi(thr - (mag >> adj), 0, mag);
+  return diff < 0 ? -v : v;
+}
+
+// one filtered sample. c: centre in the staged window; off: this plane's offset table
+__device__ __forceinline__ int cdef_px(const uint16_t* c, const int16_t (*off)[2], int pri, int sec, int dir,
+                                       int damping, int cs) {
+  const int x = c[0];
+  if (!pri && !sec) return x;
+  int sum = 0, mx = x, mn = x;
+  if (pri) {
+    const int adj = max(0, damping - flog2((unsigned)pri));
+    const int t0 = ((pri >> cs) & 1) ? 3 : 4, t1 = ((pri >> cs) & 1) ? 3 : 2;
+#pragma unroll
+    for (int k = 0; k < 2; k++) {
+      const int o = off[dir][k], tap = k ? t1 : t0;
+      const int a = c[o], b = c[-o];
+      if (a != kUnavail) { sum += tap * constrain(a - x, pri, adj); mx = max(mx, a); mn = min(mn, a); }
+      if (b != kUnavail) { sum += tap * constrain(b - x, pri, adj); mx = max(mx, b); mn = min(mn, b); }
+    }
+  }
+  if (sec) {
+    const int adj = max(0, damping - flog2((unsigned)sec));
+#pragma unroll
+    for (int k = 0; k < 2; k++) {
+      const int tap = k ? 1 : 2;
+#pragma unroll
+      for (int dd = 2; dd <= 6; dd += 4) {
+        const int o = off[(dir + dd) & 7][k];
+        const int a = c[o], b = c[-o];
+        if (a != kUnavail) { sum += tap * constrain(a - x, sec, adj); mx = max(mx, a); mn = min(mn, a); }
+        if (b != kUnavail) { sum += tap * constrain(b - x, sec, adj); mx = max(mx, b); mn = min(mn, b); }
+      }
+    }
+  }
+  return clampi(x + ((8 + sum - (sum < 0)) >> 4), mn, mx);
+}
+
+// direction and variance of one 8x8 luma block (spec 7.15.2).  The 64 samples are held in
+// registers and the eight directions are accumulated one after the other (15 partial sums live at a
+// time) to keep the register count low; all indices are compile-time constants after unrolling.
+__device__ __forceinline__ constexpr int dir_line(int d, int i, int j) {
+  return d == 0 ? i + j : d == 1 ? i + j / 2 : d == 2 ? i : d == 3 ? 3 + i - j / 2 : d == 4 ? 7 + i - j
+         : d == 5 ? 3 - i / 2 + j : d == 6 ? j : i / 2 + j;
+}
+template <int D>
+__device__ __forceinline__ int dir_cost(const int* px) {
+  int part[15];
+#pragma unroll
+  for (int k = 0; k < 15; k++) part[k] = 0;
+#pragma unroll
+  for (int i = 0; i < 8; i++)
+#pragma unroll
+    for (int j = 0; j < 8; j++) part[dir_line(D, i, j)] += px[i * 8 + j];
+  constexpr int div[9] = {0, 840, 420, 280, 210, 168, 140, 120, 105};
+  int cost = 0;
+  if (D == 2 || D == 6) {
+#pragma unroll
+    for (int i = 0; i < 8; i++) cost += part[i] * part[i];
+    cost *= div[8];
+  } else if (D == 0 || D == 4) {
+#pragma unroll
+    for (int i = 0; i < 7; i++) cost += (part[i] * part[i] + part[14 - i] * part[14 - i]) * div[i + 1];
+    cost += part[7] * part[7] * div[8];
+  } else {
+#pragma unroll
+    for (int j = 0; j < 5; j++) cost += part[3 + j] * part[3 + j];
+    cost *= div[8];
+#pragma unroll
+    for (int j = 0; j < 3; j++) cost += (part[j] * part[j] + part[10 - j] * part[10 - j]) * div[2 * j + 2];
+  }
+  return cost;
+}
+__device__ void find_dir(const uint16_t* img, int stride, int bd, int* dir_out, int* var_out) {
+  int px[64];
+#pragma unroll
+  for (int i = 0; i < 8; i++) {
+    const uint32_t* row = reinterpret_cast<const uint32_t*>(img + i * stride);
+#pragma unroll
+    for (int j = 0; j < 4; j++) {
+      const uint32_t w = row[j];
+      px[i * 8 + 2 * j] = (int)((w & 0xFFFFu) >> (bd - 8)) - 128;
+      px[i * 8 + 2 * j + 1] = (int)((w >> 16) >> (bd - 8)) - 128;
+    }
+  }
+  int cost[8];
+  cost[0] = dir_cost<0>(px); cost[1] = dir_cost<1>(px); cost[2] = dir_cost<2>(px); cost[3] = dir_cost<3>(px);
+  cost[4] = dir_cost<4>(px); cost[5] = dir_cost<5>(px); cost[6] = dir_cost<6>(px); cost[7] = dir_cost<7>(px);
+  int best = 0, dir = 0;
+#pragma unroll
+  for (int d = 0; d < 8; d++) if (cost[d] > best) { best = cost[d]; dir = d; }
+  int ortho = 0;
+#pragma unroll
+  for (int d = 0; d < 8; d++) if (d == ((dir + 4) & 7)) ortho = cost[d];
+  *dir_out = dir;
+  *var_out = (best - ortho) >> 10;
+}
+
+__global__ void __launch_bounds__(kThreads) cdef_kernel(const CdefLaunch P) {
+  __shared__ Smem sm;
+  const Av1bGeom& g = P.g;
+  const int tid = threadIdx.x, lane = tid & 31;
+  const int sbx = blockIdx.x, sby = blockIdx.y, frame = blockIdx.z;
+  const int bd = P.bit_depth, cs = bd - 8;
+  const Av1bBlockInfo* blocks = P.blocks + (size_t)frame * P.map_elems;
+  // ---- stage: deblocked windows (unavailable samples marked), source tiles, skip flags ----
+  for (int p = 0; p < 3; p++) {
+    const int ss = p > 0, T = 64 >> ss;
+    const int stride = g.stride[p];
+    const int pw = (g.mi_cols * 4) >> ss, ph = (g.mi_rows * 4) >> ss;
+    const int x0 = sbx * T, y0 = sby * T;
+    const uint16_t* in = P.in[p] + (size_t)frame * P.plane_elems[p];
+    const uint16_t* src = P.src[p] + (size_t)frame * P.plane_elems[p];
+    uint16_t* win = p == 0 ? sm.y : sm.c[p - 1];
+    const int wstride = p == 0 ? kLStride : kCStride;
+    const int vecs = (T + 16) / 8, wrows = T + 2 * kHalo;
+    for (int o = tid; o < wrows * vecs; o += kThreads) {
+      const int r = o / vecs, v = o % vecs;
+      const int y = y0 - kHalo + r, x = x0 - 8 + v * 8;
+      uint4 d = make_uint4(0xFFFFFFFFu, 0xFFFFFFFFu, 0xFFFFFFFFu, 0xFFFFFFFFu);
+      // picture width/height are multiples of 8 (4 for chroma): a vector is inside or outside as a whole,
+      // except chroma where pw may be 4 mod 8
+      if (y >= 0 && y < ph && x >= 0 && x < pw) {
+        d = *reinterpret_cast<const uint4*>(in + (size_t)y * stride + x);
+        if (x + 8 > pw) { d.z = 0xFFFFFFFFu; d.w = 0xFFFFFFFFu; }
+      }
+      uint32_t* w = reinterpret_cast<uint32_t*>(win + r * wstride + v * 8);
+      w[0] = d.x; w[1] = d.y; w[2] = d.z; w[3] = d.w;
+    }
+    uint16_t* st = p == 0 ? sm.sy : sm.sc[p - 1];
+    for (int o = tid; o < T * (T / 8); o += kThreads) {
+      const int r = o / (T / 8), v = o % (T / 8);
+      *reinterpret_cast<uint4*>(st + r * T + v * 8) =
+          *reinterpret_cast<const uint4*>(src + (size_t)(y0 + r) * stride + x0 + v * 8);
+    }
+  }
+  if (tid < 64) {
+    const int by = tid >> 3, bx = tid & 7;
+    const int uy = sby * 8 + by, ux = sbx * 8 + bx;
+    sm.skip[by][bx] = (uy < g.h8 && ux < g.w8) ? (blocks[uy * g.w8 + ux].skip != 0) : 1;
+  }
+  if (tid < 16) {
+    const int d = tid >> 1, k = tid & 1;
+    sm.off_y[d][k] = (int16_t)(c_dirs[d][k][0] * kLStride + c_dirs[d][k][1]);
+    sm.off_c[d][k] = (int16_t)(c_dirs[d][k][0] * kCStride + c_dirs[d][k][1]);
+  }
+  if (tid < 8) sm.sse[tid] = 0;
+  __syncthreads();
+  // ---- direction / variance of every non-skip 8x8 luma block ----
+  if (tid < 64) {
+    const int by = tid >> 3, bx = tid & 7;
+    int dir = 0, var = 0;
+    if (!sm.skip[by][bx]) find_dir(sm.y + (kHalo + by * 8) * kLStride + 8 + bx * 8, kLStride, bd, &dir, &var);
+    sm.dir[by][bx] = (uint8_t)dir;
+    sm.var[by][bx] = var;
+  }
+  __syncthreads();
+  const int n_cand = 1 << P.cdef_bits;
+  const int damping = P.cdef_damping + cs;
+
+  auto luma_px = [&](int q, int ystr, bool& live, int& srcv) -> int {
+    const int r = q >> 6, c = q & 63, by = r >> 3, bx = c >> 3;
+    live = !sm.skip[by][bx];
+    const uint16_t* ctr = sm.y + (kHalo + r) * kLStride + 8 + c;
+    srcv = sm.sy[q];
+    if (!live) return ctr[0];
+    int pri = (ystr >> 2) << cs, sec = ystr & 3;
+    if (sec == 3) sec = 4;
+    sec <<= cs;
+    const int dir = pri ? sm.dir[by][bx] : 0;
+    const int var = sm.var[by][bx];
+    const int vs = (var >> 6) ? min(flog2((unsigned)(var >> 6)), 12) : 0;
+    pri = var ? (pri * (4 + vs) + 8) >> 4 : 0;
+    return cdef_px(ctr, sm.off_y, pri, sec, dir, damping, cs);
+  };
+  auto chroma_px = [&](int q, int uvstr, bool& live, int& srcv) -> int {
+    const int pl = q >> 10, r = (q >> 5) & 31, c = q & 31, by = r >> 2, bx = c >> 2;
+    live = !sm.skip[by][bx];
+    const uint16_t* ctr = sm.c[pl] + (kHalo + r) * kCStride + 8 + c;
+    srcv = sm.sc[pl][q & 1023];
+    if (!live) return ctr[0];
+    const int pri = (uvstr >> 2) << cs;
+    int sec = uvstr & 3;
+    if (sec == 3) sec = 4;
+    sec <<= cs;
+    const int dir = pri ? sm.dir[by][bx] : 0;
+    return cdef_px(ctr, sm.off_c, pri, sec, dir, damping - 1, cs);
+  };
+
+  int best = 0;
+  const size_t sb_index = (size_t)frame * g.sb_rows * g.sb_cols + sby * g.sb_cols + sbx;
+  if (P.forced_idx) {
+    best = P.forced_idx[sb_index];
+  } else if (n_cand > 1) {
+    for (int cand = 0; cand < n_cand; cand++) {
+      const int ystr = P.y_strength[cand], uvstr = P.uv_strength[cand];
+      unsigned acc = 0;
+      for (int q = tid; q < 4096; q += kThreads) {
+        bool live; int s;
+        const int v = luma_px(q, ystr, live, s);
+        if (live) { const int d = v - s; acc += (unsigned)(d * d); }
+      }
+      for (int q = tid; q < 2048; q += kThreads) {
+        bool live; int s;
+        const int v = chroma_px(q, uvstr, live, s);
+        if (live) { const int d = v - s; acc += (unsigned)(d * d); }
+      }
+      for (int o = 16; o; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+      if (lane == 0 && acc) atomicAdd(&sm.sse[cand], (unsigned long long)acc);
+    }
+    __syncthreads();
+    if (tid == 0) {
+      int b = 0;
+      unsigned long long bv = sm.sse[0];
+      for (int cand = 1; cand < n_cand; cand++) if (sm.sse[cand] < bv) { bv = sm.sse[cand]; b = cand; }
+      sm.best = b;
+    }
+    __syncthreads();
+    best = sm.best;
+  }
+  if (tid == 0 && P.cdef_idx) P.cdef_idx[sb_index] = (uint8_t)best;
+  // ---- final filter with the chosen preset ----
+  {
+    const int ystr = P.y_strength[best], uvstr = P.uv_strength[best];
+    uint16_t* out = P.out[0] + (size_t)frame * P.plane_elems[0];
+    for (int q = tid; q < 4096; q += kThreads) {
+      bool live; int s;
+      const int v = luma_px(q, ystr, live, s);
+      out[(size_t)(sby * 64 + (q >> 6)) * g.stride[0] + sbx * 64 + (q & 63)] = (uint16_t)v;
+    }
+    for (int q = tid; q < 2048; q += kThreads) {
+      bool live; int s;
+      const int v = chroma_px(q, uvstr, live, s);
+      uint16_t* oc = P.out[1 + (q >> 10)] + (size_t)frame * P.plane_elems[1];
+      oc[(size_t)(sby * 32 + ((q >> 5) & 31)) * g.stride[1] + sbx * 32 + (q & 31)] = (uint16_t)v;
+    }
+  }
+}
+
+}  // namespace
+
+cudaError_t launch_cdef(const CdefLaunch& p, int n_frames, cudaStream_t s) {
+  dim3 grid(p.g.sb_cols, p.g.sb_rows, n_frames);
+  cdef_kernel<<<grid, kThreads, 0, s>>>(p);
+  return cudaGetLastError();
+}
+
+}  // namespace av1b

@@ -23,7 +23,58 @@ struct IntraLaunch {
   size_t map_elems;
 };
 
+// Deblocking filter (deblock_kernel.cu): in -> out, one CTA per superblock.
+struct DeblockLaunch {
+  Av1bGeom g;
+  int32_t bit_depth;
+  int32_t lf_level[4];        // Y vertical edges, Y horizontal edges, U, V
+  int32_t sharpness;
+  const uint16_t* in[3];
+  uint16_t* out[3];
+  size_t plane_elems[3];
+  const Av1bBlockInfo* blocks;
+  size_t map_elems;
+};
+
+// CDEF with per-superblock preset decision (cdef_kernel.cu): in = deblocked frame.
+struct CdefLaunch {
+  Av1bGeom g;
+  int32_t bit_depth;
+  int32_t cdef_damping, cdef_bits;
+  int32_t y_strength[8], uv_strength[8];
+  const uint16_t* in[3];
+  const uint16_t* src[3];     // source frame (decision only; may alias `in` when cdef_bits == 0)
+  uint16_t* out[3];
+  size_t plane_elems[3];
+  const Av1bBlockInfo* blocks;
+  size_t map_elems;
+  uint8_t* cdef_idx;          // [n_frames][sb_rows*sb_cols] (chosen preset) or nullptr
+  const uint8_t* forced_idx;  // non-null: use these presets instead of deciding (kernel suite)
+};
+
+// Loop restoration (lr_kernel.cu): cdef = CDEF output, deb = deblocked (pre-CDEF) frame.
+struct LrLaunch {
+  Av1bGeom g;
+  int32_t bit_depth;
+  int32_t lr_type[3];
+  int32_t unit_size[3], unit_rows[3], unit_cols[3];
+  const uint16_t* cdef[3];
+  const uint16_t* deb[3];
+  uint16_t* out[3];
+  size_t plane_elems[3];
+  const Av1bLrUnit* units[3]; // [n_frames][unit_rows*unit_cols] per plane, or nullptr
+};
+
+// Batched normative inverse transform + reconstruction, all 19 AV1 sizes (txfm_kernel.cu).
+// Block b: dequantised coefficients at coef + b*32*32 (row-major, min(w,32) columns per row),
+// prediction/reconstruction at dst + b*w*h (row-major).
+cudaError_t launch_inv_txfm_add(const int32_t* coef, uint16_t* dst, int n_blocks, int w, int h, int tx_type,
+                                int bit_depth, cudaStream_t s);
+
 void upload_tables_once();
+cudaError_t launch_deblock(const DeblockLaunch& p, int n_frames, cudaStream_t s);
+cudaError_t launch_cdef(const CdefLaunch& p, int n_frames, cudaStream_t s);
+cudaError_t launch_lr(const LrLaunch& p, int n_frames, cudaStream_t s);
 cudaError_t launch_partition_fixed(const Av1bGeom& g, int blk_log2, uint8_t* map, int n_frames, cudaStream_t s);
 cudaError_t launch_intra_encode(const IntraLaunch& p, int n_frames, cudaStream_t s);
 

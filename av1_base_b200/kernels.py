@@ -1,0 +1,86 @@
+"""ctypes mirror of the kernel-suite entry points of the C ABI (include/av1b200.h, av1b_k_*).
+numpy is plumbing; each call runs exactly one CUDA kernel on the device and returns its result
+(and the mean CUDA-event time per launch when reps > 0)."""
+import ctypes as C
+import numpy as np
+from . import abi
+
+
+class KernelError(RuntimeError):
+    def __init__(self, code):
+        super().__init__("av1b200 kernel suite failed with code %d: %s" % (code, abi.last_error()))
+        self.code = code
+
+
+def _ck(rc):
+    if rc:
+        raise KernelError(rc)
+
+
+def _p3(planes):
+    return (C.c_void_p * 3)(*[p.ctypes.data for p in planes])
+
+
+def inv_txfm_add(coef, pred, w, h, tx_type, bit_depth, device=0, reps=1):
+    """coef: [n, ch, cw] int32 (ch = min(h,32), cw = min(w,32)); pred: [n, h, w] uint16. Returns (recon, ms)."""
+    n = coef.shape[0]
+    cbuf = np.zeros((n, 1024), np.int32)
+    cbuf[:, :coef.shape[1] * coef.shape[2]] = coef.reshape(n, -1)
+    dst = np.ascontiguousarray(pred, np.uint16).copy()
+    ms = C.c_double(0)
+    _ck(abi.lib().av1b_k_inv_txfm_add(device, cbuf.ctypes.data_as(C.c_void_p), dst.ctypes.data_as(C.c_void_p), n, w, h,
+                                      tx_type, bit_depth, reps, C.byref(ms)))
+    return dst, ms.value
+
+
+def _stack(planes_list):
+    """list over frames of 3 padded planes -> 3 arrays [n, rows, stride]"""
+    return [np.ascontiguousarray(np.stack([f[p] for f in planes_list])) for p in range(3)]
+
+
+def deblock(width, height, bit_depth, blocks, rec, lf_level, sharpness=0, device=0, reps=1):
+    """blocks: [n, h8*w8] structured; rec: list (frames) of 3 padded planes. Returns (list of planes, ms)."""
+    n = len(rec)
+    inp = _stack(rec)
+    out = [np.zeros_like(a) for a in inp]
+    blocks = np.ascontiguousarray(blocks)
+    lv = (C.c_int32 * 4)(*lf_level)
+    ms = C.c_double(0)
+    _ck(abi.lib().av1b_k_deblock(device, width, height, bit_depth, n, blocks.ctypes.data_as(C.c_void_p), _p3(inp), _p3(out),
+                                 lv, sharpness, reps, C.byref(ms)))
+    return [[out[p][i] for p in range(3)] for i in range(n)], ms.value
+
+
+def cdef(width, height, bit_depth, blocks, fp, rec, src=None, forced_idx=None, device=0, reps=1):
+    """Returns (list of planes, cdef_idx [n, n_sb], ms)."""
+    n = len(rec)
+    inp = _stack(rec)
+    out = [np.zeros_like(a) for a in inp]
+    blocks = np.ascontiguousarray(blocks)
+    srcp = None
+    if src is not None:
+        s = _stack(src)
+        srcp = _p3(s)
+    fo = None
+    if forced_idx is not None:
+        forced_idx = np.ascontiguousarray(forced_idx, np.uint8)
+        fo = forced_idx.ctypes.data_as(C.c_void_p)
+    nsb = ((height + 63) // 64) * ((width + 63) // 64)
+    idx = np.zeros((n, nsb), np.uint8)
+    ms = C.c_double(0)
+    _ck(abi.lib().av1b_k_cdef(device, width, height, bit_depth, n, blocks.ctypes.data_as(C.c_void_p), C.byref(fp), _p3(inp),
+                              srcp, fo, _p3(out), idx.ctypes.data_as(C.c_void_p), reps, C.byref(ms)))
+    return [[out[p][i] for p in range(3)] for i in range(n)], idx, ms.value
+
+
+def loop_restoration(width, height, bit_depth, fp, cdef_planes, deb_planes, units, device=0, reps=1):
+    """units: 3 arrays [n, rows, cols] of abi.LR_UNIT_DTYPE or None. Returns (list of planes, ms)."""
+    n = len(cdef_planes)
+    c = _stack(cdef_planes)
+    d = _stack(deb_planes)
+    out = [np.zeros_like(a) for a in c]
+    us = [np.ascontiguousarray(u) if u is not None else None for u in units]
+    up = (C.c_void_p * 3)(*[u.ctypes.data if u is not None else None for u in us])
+    ms = C.c_double(0)
+    _ck(abi.lib().av1b_k_lr(device, width, height, bit_depth, n, C.byref(fp), _p3(c), _p3(d), up, _p3(out), reps, C.byref(ms)))
+    return [[out[p][i] for p in range(3)] for i in range(n)], ms.value

@@ -90,6 +90,31 @@ int av1b_get_geom(av1b_encoder* enc, struct Av1bGeom* geom);
  * intra_kernel_launches, frames_done, bytes_out of the last chunk / resident run (CUDA-event times) */
 int av1b_get_stats(av1b_encoder* enc, double* stats, int n);
 
+/* ---- kernel suite (BASELINE.json config 2 "kernel bit-exact suite") -----------------------------
+ * Each call uploads the host buffers to `device`, runs ONE CUDA kernel `reps` times between CUDA
+ * events (mean milliseconds per launch -> *ms_per_launch, may be NULL) and downloads the result.
+ * Frame planes use the padded layout of Av1bGeom (rows[p] x stride[p] uint16 samples per plane,
+ * n_frames planes back to back); `blocks` is [n_frames][h8*w8].
+ * These are the units libaom's C reference (av1_inv_txfm2d_add_*_c, aom_highbd_lpf_*_c, cdef_*_c,
+ * restoration) is compared with; they replace arithmetic behind av1an.rs:126-139. */
+struct Av1bLrUnit;
+/* coef: n_blocks x 1024 int32 (row-major, min(w,32) values per row); dst: n_blocks x (w*h) prediction in,
+ * reconstruction out */
+int av1b_k_inv_txfm_add(int device, const int32_t* coef, uint16_t* dst, int n_blocks, int w, int h, int tx_type,
+                        int bit_depth, int reps, double* ms_per_launch);
+int av1b_k_deblock(int device, int width, int height, int bit_depth, int n_frames, const struct Av1bBlockInfo* blocks,
+                   const uint16_t* const in[3], uint16_t* const out[3], const int32_t lf_level[4], int sharpness,
+                   int reps, double* ms_per_launch);
+/* src != NULL: decide the preset per superblock against the source (written to cdef_idx_out);
+ * forced_idx != NULL: apply the given presets (normative filter only). */
+int av1b_k_cdef(int device, int width, int height, int bit_depth, int n_frames, const struct Av1bBlockInfo* blocks,
+                const struct Av1bFrameParams* fp, const uint16_t* const in[3], const uint16_t* const src[3],
+                const uint8_t* forced_idx, uint16_t* const out[3], uint8_t* cdef_idx_out, int reps,
+                double* ms_per_launch);
+int av1b_k_lr(int device, int width, int height, int bit_depth, int n_frames, const struct Av1bFrameParams* fp,
+              const uint16_t* const cdef[3], const uint16_t* const deb[3], const struct Av1bLrUnit* const units[3],
+              uint16_t* const out[3], int reps, double* ms_per_launch);
+
 /* ---- host entropy coder over symbol streams (the part that "runs on the host") -------------- */
 struct Av1bSeqParams; struct Av1bFrameParams; struct Av1bFrameSyms;
 int av1b_pack_sequence_header(const struct Av1bSeqParams* seq, uint8_t* out, size_t cap, size_t* len);

@@ -743,6 +743,44 @@ extern "C" void orc_cdef_frame(const Av1bGeom* g, int bd, const Av1bBlockInfo* b
     }
 }
 
+// Encoder-side CDEF decision (ours): per 64x64 superblock the preset (index into the frame's
+// 2^cdef_bits strength pairs) with the smallest sum of squared errors against the source over the
+// Y, U and V samples of the non-skip 8x8 blocks; ties go to the lowest index.  src: padded planes.
+extern "C" void orc_cdef_search(const Av1bGeom* g, int bd, const Av1bBlockInfo* blocks, const Av1bFrameParams* fp,
+                                const uint16_t* in_y, const uint16_t* in_u, const uint16_t* in_v,
+                                const uint16_t* src_y, const uint16_t* src_u, const uint16_t* src_v,
+                                uint8_t* cdef_idx) {
+  const uint16_t* src[3] = {src_y, src_u, src_v};
+  const int nsb = g->sb_rows * g->sb_cols, ncand = 1 << fp->cdef_bits;
+  std::vector<uint64_t> best(nsb, ~(uint64_t)0);
+  std::vector<uint8_t> idx(nsb);
+  std::vector<uint16_t> out[3];
+  for (int p = 0; p < 3; p++) out[p].resize((size_t)g->stride[p] * g->rows[p]);
+  for (int i = 0; i < nsb; i++) cdef_idx[i] = 0;
+  for (int cand = 0; cand < ncand; cand++) {
+    std::fill(idx.begin(), idx.end(), (uint8_t)cand);
+    orc_cdef_frame(g, bd, blocks, fp, idx.data(), in_y, in_u, in_v, out[0].data(), out[1].data(), out[2].data());
+    std::vector<uint64_t> sse(nsb, 0);
+    for (int r8 = 0; r8 < g->h8; r8++)
+      for (int c8 = 0; c8 < g->w8; c8++) {
+        if (blocks[r8 * g->w8 + c8].skip) continue;
+        uint64_t e = 0;
+        for (int p = 0; p < 3; p++) {
+          const int n = p ? 4 : 8;
+          for (int i = 0; i < n; i++)
+            for (int j = 0; j < n; j++) {
+              const size_t o = (size_t)(r8 * n + i) * g->stride[p] + c8 * n + j;
+              const int d = (int)out[p][o] - (int)src[p][o];
+              e += (uint64_t)(d * d);
+            }
+        }
+        sse[(r8 >> 3) * g->sb_cols + (c8 >> 3)] += e;
+      }
+    for (int i = 0; i < nsb; i++)
+      if (sse[i] < best[i]) { best[i] = sse[i]; cdef_idx[i] = (uint8_t)cand; }
+  }
+}
+
 // ------------------------------------------------------------------------------------------------
 // Loop restoration (spec 7.17): Wiener and self-guided filters, 64-row stripes offset by 8 luma
 // rows; outside the stripe the DEBLOCKED (pre-CDEF) rows are used, at most 2 rows deep.

@@ -80,3 +80,20 @@ def lr_frame(g, bit_depth, fp, cdef, deblocked, units):
                        ptr(deblocked[0]), ptr(deblocked[1]), ptr(deblocked[2]), ptr(out[0]), ptr(out[1]), ptr(out[2]),
                        up[0], up[1], up[2])
     return out
+
+
+def cdef_search(g, bit_depth, blocks, fp, rec, src):
+    """Encoder-side CDEF preset decision per superblock (rec = deblocked padded planes, src = padded source)."""
+    idx = np.zeros(g.sb_rows * g.sb_cols, np.uint8)
+    lib().orc_cdef_search(C.byref(g), bit_depth, ptr(blocks), C.byref(fp), ptr(rec[0]), ptr(rec[1]), ptr(rec[2]),
+                          ptr(src[0]), ptr(src[1]), ptr(src[2]), ptr(idx))
+    return idx
+
+
+def pad_planes(g, frame):
+    """[Y,U,V] picture-sized arrays -> padded planes with the geometry's strides (zeros outside)."""
+    out = [np.zeros((g.rows[p], g.stride[p]), np.uint16) for p in range(3)]
+    for p in range(3):
+        h, w = frame[p].shape
+        out[p][:h, :w] = frame[p]
+    return out

@@ -1,0 +1,187 @@
+"""Kernel bit-exact suite (BASELINE.json config 2): each CUDA kernel, called through the C ABI, against
+libaom 3.13.1's own C functions (inverse transforms) and against the CPU oracle, which is itself
+pinned against libaom's C line filters and both decoders (deblock / CDEF / loop restoration)."""
+import ctypes as C
+import numpy as np
+import pytest
+from av1_base_b200 import abi, kernels, synth
+from oracle import aomsym, pyoracle as O
+
+pytestmark = pytest.mark.gpu
+
+SIZES = [(4, 4), (8, 8), (16, 16), (32, 32), (64, 64), (4, 8), (8, 4), (8, 16), (16, 8), (16, 32), (32, 16),
+         (32, 64), (64, 32), (4, 16), (16, 4), (8, 32), (32, 8), (16, 64), (64, 16)]   # (w, h)
+I32P = C.POINTER(C.c_int32)
+
+
+def legal_types(w, h):
+    m = max(w, h)
+    return [0] if m == 64 else ([0, 9] if m == 32 else list(range(16)))
+
+
+@pytest.mark.parametrize("w,h", SIZES)
+@pytest.mark.parametrize("bd", [8, 10])
+def test_inv_txfm_add_vs_libaom_and_oracle(w, h, bd):
+    f = aomsym.func("av1_inv_txfm2d_add_%dx%d_c" % (w, h), None, [I32P, C.c_void_p, C.c_int, C.c_int, C.c_int])
+    rng = np.random.default_rng(w * 131 + h * 7 + bd)
+    cw, ch = min(w, 32), min(h, 32)
+    lim = 1 << (bd + 7)
+    n = 96
+    for tx in legal_types(w, h):
+        co = rng.integers(-lim, lim, (n, ch, cw))
+        co[n // 3:2 * n // 3] = rng.integers(-300, 300, (n // 3, ch, cw)) * (rng.random((n // 3, ch, cw)) < 0.15)
+        co[2 * n // 3:] = rng.choice([-lim, lim - 1], (n - 2 * n // 3, ch, cw))
+        co[0] = 0
+        co = np.ascontiguousarray(co, np.int32)
+        pred = rng.integers(0, 1 << bd, (n, h, w)).astype(np.uint16)
+        got, _ = kernels.inv_txfm_add(co, pred, w, h, tx, bd)
+        for b in range(0, n, 5):
+            mine = pred[b].copy()
+            O.lib().orc_inv_txfm2d_add(O.ptr(co[b]), cw, O.ptr(mine), w, w, h, tx, bd)
+            assert np.array_equal(got[b], mine), ("oracle", w, h, tx, b)
+            theirs = pred[b].copy()
+            buf = np.zeros(64 * 64, np.int32)
+            ci = np.ascontiguousarray(co[b].T, np.int32)
+            buf[:ci.size] = ci.ravel()
+            f(buf.ctypes.data_as(I32P), O.ptr(theirs), w, tx, bd)
+            assert np.array_equal(got[b], theirs), ("libaom", w, h, tx, b)
+
+
+def random_partition(g, rng):
+    pm = O.partition_fixed(g, 6).reshape(g.h8, g.w8).copy()
+    for y in range(0, g.h8, 8):
+        for x in range(0, g.w8, 8):
+            sub = pm[y:y + 8, x:x + 8]
+            sub[...] = np.minimum(sub, int(rng.integers(3, 7)))
+            for yy in range(0, 8, 4):
+                for xx in range(0, 8, 4):
+                    s2 = sub[yy:yy + 4, xx:xx + 4]
+                    s2[...] = np.minimum(s2, int(rng.integers(3, 7)))
+    return pm.ravel()
+
+
+def encoded_frames(w, h, bd, q, n, seed):
+    """n frames encoded by the oracle with random partitions: realistic blocking + side info."""
+    rng = np.random.default_rng(seed)
+    g = O.geom(w, h, 0, 0)
+    frames = synth.synth_clip(w, h, bd, n, seed=seed, scene_len=1)
+    res = [O.encode_intra_frame(g, fr, bd, q, random_partition(g, rng)) for fr in frames]
+    return g, frames, res, rng
+
+
+FRAME_CASES = [(64, 64, 8, 150), (200, 136, 10, 180), (328, 248, 8, 220), (640, 360, 10, 120)]
+
+
+@pytest.mark.parametrize("w,h,bd,q", FRAME_CASES)
+def test_deblock_vs_oracle(w, h, bd, q):
+    g, frames, res, rng = encoded_frames(w, h, bd, q, 2, w + q)
+    for trial in range(3):
+        lf = [int(rng.integers(0, 64)) for _ in range(4)] if trial else [0, 0, 9, 9]
+        if trial == 2:
+            lf[1] = 0
+        sharp = int(rng.integers(0, 8))
+        blocks = np.stack([r.blocks for r in res])
+        got, _ = kernels.deblock(w, h, bd, blocks, [r.rec for r in res], lf, sharp)
+        for i, r in enumerate(res):
+            ref = [p.copy() for p in r.rec]
+            O.deblock_frame(g, bd, r.blocks, ref, lf, sharp)
+            for p in range(3):
+                assert np.array_equal(O.crop(g, got[i])[p], O.crop(g, ref)[p]), (trial, i, p, lf, sharp)
+
+
+def cdef_params(rng, bits):
+    fp = abi.FrameParams()
+    fp.cdef_damping = int(rng.integers(3, 7))
+    fp.cdef_bits = bits
+    for i in range(1 << bits):
+        fp.cdef_y_strength[i] = int(rng.integers(0, 64))
+        fp.cdef_uv_strength[i] = int(rng.integers(0, 64))
+    return fp
+
+
+@pytest.mark.parametrize("w,h,bd,q", FRAME_CASES)
+def test_cdef_filter_and_decision_vs_oracle(w, h, bd, q):
+    g, frames, res, rng = encoded_frames(w, h, bd, q, 2, w * 3 + q)
+    for r in res:
+        O.deblock_frame(g, bd, r.blocks, r.rec, [12, 12, 8, 8], 0)
+    blocks = np.stack([r.blocks for r in res])
+    for bits in (0, 2, 3):
+        fp = cdef_params(rng, bits)
+        if bits == 2:
+            fp.cdef_y_strength[0] = 0; fp.cdef_uv_strength[0] = 0
+        # normative filter with forced presets
+        forced = rng.integers(0, 1 << bits, (len(res), g.sb_rows * g.sb_cols)).astype(np.uint8)
+        got, _, _ = kernels.cdef(w, h, bd, blocks, fp, [r.rec for r in res], forced_idx=forced)
+        for i, r in enumerate(res):
+            ref = O.cdef_frame(g, bd, r.blocks, fp, forced[i], r.rec)
+            for p in range(3):
+                assert np.array_equal(O.crop(g, got[i])[p], O.crop(g, ref)[p]), ("forced", bits, i, p)
+        # decision against the source
+        srcs = [O.pad_planes(g, fr) for fr in frames]
+        got, idx, _ = kernels.cdef(w, h, bd, blocks, fp, [r.rec for r in res], src=srcs)
+        for i, r in enumerate(res):
+            want = O.cdef_search(g, bd, r.blocks, fp, r.rec, srcs[i])
+            sb_live = np.zeros(g.sb_rows * g.sb_cols, bool)
+            sk = r.blocks["skip"].reshape(g.h8, g.w8)
+            for sr in range(g.sb_rows):
+                for sc in range(g.sb_cols):
+                    sb_live[sr * g.sb_cols + sc] = not sk[sr * 8:sr * 8 + 8, sc * 8:sc * 8 + 8].all()
+            assert np.array_equal(idx[i][sb_live], want[sb_live]), ("decision", bits, i)
+            ref = O.cdef_frame(g, bd, r.blocks, fp, idx[i], r.rec)
+            for p in range(3):
+                assert np.array_equal(O.crop(g, got[i])[p], O.crop(g, ref)[p]), ("decided", bits, i, p)
+
+
+SGR_R = [(2, 1)] * 10 + [(0, 1)] * 4 + [(2, 0)] * 2
+
+
+def random_lr_units(g, fp, rng, n):
+    tmin, tmax = [-5, -23, -17], [10, 8, 46]
+    units = []
+    for p in range(3):
+        lt = fp.lr_type[p]
+        if lt == 0:
+            units.append(None)
+            continue
+        us, ur, uc = O.lr_unit_grid(g, fp, p)
+        u = np.zeros((n, ur, uc), abi.LR_UNIT_DTYPE)
+        for f in range(n):
+            for a in range(ur):
+                for b in range(uc):
+                    t = int(rng.integers(0, 3)) if lt == 3 else int(rng.integers(0, 2)) * (1 if lt == 1 else 2)
+                    u[f, a, b]["type"] = t
+                    if t == 1:
+                        for nm in ("wiener_v", "wiener_h"):
+                            for j in range(3):
+                                u[f, a, b][nm][j] = 0 if (p > 0 and j == 0) else int(rng.integers(tmin[j], tmax[j] + 1))
+                    elif t == 2:
+                        st = int(rng.integers(0, 16))
+                        r0, r1 = SGR_R[st]
+                        x0 = int(rng.integers(-96, 32)) if r0 else 0
+                        x1 = int(rng.integers(-32, 96)) if r1 else min(max(128 - x0, -32), 95)
+                        u[f, a, b]["sgr_set"] = st
+                        u[f, a, b]["sgr_xqd"][0] = x0
+                        u[f, a, b]["sgr_xqd"][1] = x1
+        units.append(u)
+    return units
+
+
+@pytest.mark.parametrize("w,h,bd,q", FRAME_CASES)
+@pytest.mark.parametrize("lrt,ushift,uvshift", [((1, 1, 1), 0, 0), ((2, 2, 2), 0, 1), ((3, 3, 3), 1, 1), ((3, 0, 2), 2, 0)])
+def test_loop_restoration_vs_oracle(w, h, bd, q, lrt, ushift, uvshift):
+    g, frames, res, rng = encoded_frames(w, h, bd, q, 2, w * 5 + q + ushift)
+    fp = cdef_params(rng, 1)
+    for p in range(3):
+        fp.lr_type[p] = lrt[p]
+    fp.lr_unit_shift, fp.lr_uv_shift = ushift, uvshift
+    deb, cdf = [], []
+    for r in res:
+        O.deblock_frame(g, bd, r.blocks, r.rec, [20, 20, 10, 10], 0)
+        deb.append(r.rec)
+        cdf.append(O.cdef_frame(g, bd, r.blocks, fp, rng.integers(0, 2, g.sb_rows * g.sb_cols).astype(np.uint8), r.rec))
+    units = random_lr_units(g, fp, rng, len(res))
+    got, _ = kernels.loop_restoration(w, h, bd, fp, cdf, deb, units)
+    for i in range(len(res)):
+        ref = O.lr_frame(g, bd, fp, cdf[i], deb[i], [u[i] if u is not None else None for u in units])
+        for p in range(3):
+            assert np.array_equal(O.crop(g, got[i])[p], O.crop(g, ref)[p]), (i, p)
