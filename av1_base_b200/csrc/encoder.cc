@@ -98,11 +98,16 @@ struct KeptFrame {
   std::vector<uint16_t> rec[3];
   std::vector<int16_t> coef[3];
   std::vector<Av1bBlockInfo> blocks;
+  std::vector<uint8_t> cdef_idx;
 };
 
 struct Slot {
   uint16_t* d_src[3] = {nullptr, nullptr, nullptr};
-  uint16_t* d_rec[3] = {nullptr, nullptr, nullptr};
+  uint16_t* d_rec[3] = {nullptr, nullptr, nullptr};   // reconstruction before the loop filters
+  uint16_t* d_deb[3] = {nullptr, nullptr, nullptr};   // deblocked
+  uint16_t* d_fin[3] = {nullptr, nullptr, nullptr};   // after CDEF (+ loop restoration): the decoder's output
+  uint8_t* d_cdef_idx = nullptr;
+  uint8_t* h_cdef_idx = nullptr;
   int16_t* d_coef[3] = {nullptr, nullptr, nullptr};
   Av1bBlockInfo* d_blocks = nullptr;
   uint8_t* d_map = nullptr;
@@ -110,7 +115,8 @@ struct Slot {
   uint16_t* h_rec[3] = {nullptr, nullptr, nullptr};
   int16_t* h_coef[3] = {nullptr, nullptr, nullptr};
   Av1bBlockInfo* h_blocks = nullptr;
-  cudaEvent_t ev[5] = {nullptr, nullptr, nullptr, nullptr, nullptr};   // h2d start, kernels start, intra start, kernels end, d2h end
+  // h2d start, kernels start, intra start, kernels end, d2h end, intra end, deblock end
+  cudaEvent_t ev[7] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
   int n_frames = 0;
   int64_t first_index = 0;
 };
@@ -125,6 +131,8 @@ struct av1b_encoder {
   int base_q_idx = 0;
   int blk_log2 = 4;
   bool keep = false;
+  bool loop_filters = true;
+  Av1bFrameParams fp_key;       // frame-level parameters of key frames (levels / strengths from the quantiser)
   cudaStream_t stream = nullptr;
   size_t plane_elems[3] = {0, 0, 0};
   size_t map_elems = 0;
@@ -133,17 +141,18 @@ struct av1b_encoder {
   int host_threads = 1;
   std::vector<KeptFrame> kept;
   // statistics of the last chunk / resident run
-  double t_h2d_ms = 0, t_kernel_ms = 0, t_intra_ms = 0, t_d2h_ms = 0, t_pack_ms = 0;
+  double t_h2d_ms = 0, t_kernel_ms = 0, t_intra_ms = 0, t_d2h_ms = 0, t_pack_ms = 0, t_deblock_ms = 0, t_cdef_ms = 0;
   int64_t kernel_launches = 0, intra_launches = 0, frames_done = 0, bytes_out = 0;
 };
 
 static void free_all(av1b_encoder* e) {
   for (auto& s : e->slot) {
     for (int p = 0; p < 3; p++) {
-      cudaFree(s.d_src[p]); cudaFree(s.d_rec[p]); cudaFree(s.d_coef[p]);
+      cudaFree(s.d_src[p]); cudaFree(s.d_rec[p]); cudaFree(s.d_coef[p]); cudaFree(s.d_deb[p]); cudaFree(s.d_fin[p]);
       cudaFreeHost(s.h_src[p]); cudaFreeHost(s.h_rec[p]); cudaFreeHost(s.h_coef[p]);
     }
     cudaFree(s.d_blocks); cudaFree(s.d_map); cudaFreeHost(s.h_blocks);
+    cudaFree(s.d_cdef_idx); cudaFreeHost(s.h_cdef_idx);
     for (auto& ev : s.ev) if (ev) cudaEventDestroy(ev);
   }
   if (e->stream) cudaStreamDestroy(e->stream);
@@ -183,12 +192,31 @@ static int launch(av1b_encoder* e, Slot& s, int n, int64_t first_index) {
   CK(launch_partition_fixed(g, e->blk_log2, s.d_map, n, e->stream));
   CK(cudaEventRecord(s.ev[2], e->stream));
   CK(launch_intra_encode(L, n, e->stream));
-  CK(cudaEventRecord(s.ev[3], e->stream));
+  CK(cudaEventRecord(s.ev[5], e->stream));
   e->kernel_launches += 2; e->intra_launches += 1;
+  if (e->loop_filters) {
+    const Av1bFrameParams& fp = e->fp_key;
+    DeblockLaunch D;
+    D.g = g; D.bit_depth = bd; D.sharpness = fp.lf_sharpness;
+    for (int i = 0; i < 4; i++) D.lf_level[i] = fp.lf_level[i];
+    for (int p = 0; p < 3; p++) { D.in[p] = s.d_rec[p]; D.out[p] = s.d_deb[p]; D.plane_elems[p] = e->plane_elems[p]; }
+    D.blocks = s.d_blocks; D.map_elems = e->map_elems;
+    CK(launch_deblock(D, n, e->stream));
+    CK(cudaEventRecord(s.ev[6], e->stream));
+    CdefLaunch Cd;
+    Cd.g = g; Cd.bit_depth = bd; Cd.cdef_damping = fp.cdef_damping; Cd.cdef_bits = fp.cdef_bits;
+    for (int i = 0; i < 8; i++) { Cd.y_strength[i] = fp.cdef_y_strength[i]; Cd.uv_strength[i] = fp.cdef_uv_strength[i]; }
+    for (int p = 0; p < 3; p++) { Cd.in[p] = s.d_deb[p]; Cd.src[p] = s.d_src[p]; Cd.out[p] = s.d_fin[p]; Cd.plane_elems[p] = e->plane_elems[p]; }
+    Cd.blocks = s.d_blocks; Cd.map_elems = e->map_elems; Cd.cdef_idx = s.d_cdef_idx; Cd.forced_idx = nullptr;
+    CK(launch_cdef(Cd, n, e->stream));
+    e->kernel_launches += 2;
+  }
+  CK(cudaEventRecord(s.ev[3], e->stream));
   for (int p = 0; p < 3; p++) {
     CK(cudaMemcpyAsync(s.h_coef[p], s.d_coef[p], e->plane_elems[p] * n * 2, cudaMemcpyDeviceToHost, e->stream));
-    if (e->keep) CK(cudaMemcpyAsync(s.h_rec[p], s.d_rec[p], e->plane_elems[p] * n * 2, cudaMemcpyDeviceToHost, e->stream));
+    if (e->keep) CK(cudaMemcpyAsync(s.h_rec[p], e->loop_filters ? s.d_fin[p] : s.d_rec[p], e->plane_elems[p] * n * 2, cudaMemcpyDeviceToHost, e->stream));
   }
+  CK(cudaMemcpyAsync(s.h_cdef_idx, s.d_cdef_idx, (size_t)g.sb_rows * g.sb_cols * n, cudaMemcpyDeviceToHost, e->stream));
   CK(cudaMemcpyAsync(s.h_blocks, s.d_blocks, e->map_elems * n * sizeof(Av1bBlockInfo), cudaMemcpyDeviceToHost, e->stream));
   CK(cudaEventRecord(s.ev[4], e->stream));
   return AV1B_OK;
@@ -202,23 +230,22 @@ static int finish(av1b_encoder* e, Slot& s, bool staged, av1b_packet_cb out_cb, 
   float ms;
   if (staged) { cudaEventElapsedTime(&ms, s.ev[0], s.ev[1]); e->t_h2d_ms += ms; }
   cudaEventElapsedTime(&ms, s.ev[1], s.ev[3]); e->t_kernel_ms += ms;
-  cudaEventElapsedTime(&ms, s.ev[2], s.ev[3]); e->t_intra_ms += ms;
+  cudaEventElapsedTime(&ms, s.ev[2], s.ev[5]); e->t_intra_ms += ms;
+  if (e->loop_filters) {
+    cudaEventElapsedTime(&ms, s.ev[5], s.ev[6]); e->t_deblock_ms += ms;
+    cudaEventElapsedTime(&ms, s.ev[6], s.ev[3]); e->t_cdef_ms += ms;
+  }
   cudaEventElapsedTime(&ms, s.ev[3], s.ev[4]); e->t_d2h_ms += ms;
   const auto tp0 = std::chrono::steady_clock::now();
   const int n = s.n_frames, n_tiles = g.tile_cols * g.tile_rows;
-  Av1bFrameParams fp;
-  memset(&fp, 0, sizeof(fp));
-  fp.frame_type = AV1B_KEY_FRAME;
-  fp.base_q_idx = e->base_q_idx;
-  fp.disable_cdf_update = 0;
-  fp.tile_cols_log2 = g.tile_cols_log2; fp.tile_rows_log2 = g.tile_rows_log2;
-  fp.cdef_damping = 3;
+  const Av1bFrameParams fp = e->fp_key;
   std::vector<Av1bFrameSyms> sy(n);
   std::vector<FramePack> packs(n);
   for (int b = 0; b < n; b++) {
     memset(&sy[b], 0, sizeof(Av1bFrameSyms));
     sy[b].blocks = s.h_blocks + (size_t)b * e->map_elems;
     for (int p = 0; p < 3; p++) { sy[b].coef[p] = s.h_coef[p] + (size_t)b * e->plane_elems[p]; sy[b].coef_stride[p] = g.stride[p]; }
+    sy[b].cdef_idx = s.h_cdef_idx + (size_t)b * g.sb_rows * g.sb_cols;
     pack_frame_header(e->seq, fp, g, packs[b]);
   }
   e->pool->parallel_for(n * n_tiles, [&](int t) {
@@ -239,6 +266,7 @@ static int finish(av1b_encoder* e, Slot& s, bool staged, av1b_packet_cb out_cb, 
         k.coef[p].assign(s.h_coef[p] + (size_t)b * e->plane_elems[p], s.h_coef[p] + (size_t)(b + 1) * e->plane_elems[p]);
       }
       k.blocks.assign(sy[b].blocks, sy[b].blocks + e->map_elems);
+      k.cdef_idx.assign(sy[b].cdef_idx, sy[b].cdef_idx + (size_t)g.sb_rows * g.sb_cols);
     }
     e->bytes_out += (int64_t)tu.size();
     if (out_cb && out_cb(user, tu.data(), tu.size(), s.first_index + b, 1)) { set_error("packet callback aborted"); return AV1B_ERR_CALLBACK; }
@@ -255,7 +283,7 @@ static int finish(av1b_encoder* e, Slot& s, bool staged, av1b_packet_cb out_cb, 
 
 static void reset_stats(av1b_encoder* e) {
   e->kept.clear();
-  e->t_h2d_ms = e->t_kernel_ms = e->t_intra_ms = e->t_d2h_ms = e->t_pack_ms = 0;
+  e->t_h2d_ms = e->t_kernel_ms = e->t_intra_ms = e->t_d2h_ms = e->t_pack_ms = e->t_deblock_ms = e->t_cdef_ms = 0;
   e->kernel_launches = e->intra_launches = e->frames_done = e->bytes_out = 0;
 }
 
@@ -295,13 +323,16 @@ int av1b_encoder_create(const av1b_config* cfg, av1b_encoder** out) {
   if (trl < 0) trl = av1b_tile_log2(4, probe.sb_rows);
   av1b_geom_init(&e->g, cfg->width, cfg->height, tcl, trl);
   e->seq.width = cfg->width; e->seq.height = cfg->height; e->seq.bit_depth = cfg->bit_depth;
-  e->seq.enable_cdef = 0; e->seq.enable_restoration = 0;
+  e->loop_filters = cfg->reserved[2] == 0;     // reserved[2] = 1 switches the in-loop filters off (tests)
+  e->seq.enable_cdef = e->loop_filters ? 1 : 0; e->seq.enable_restoration = 0;
   e->seq.fps_num = cfg->fps_num; e->seq.fps_den = cfg->fps_den; e->seq.color_hdr = cfg->hdr;
   e->base_q_idx = av1t_quantizer_to_qindex[cfg->crf];
   if (e->base_q_idx < 1) e->base_q_idx = 1;   // lossless (qindex 0) is not supported
   e->blk_log2 = cfg->reserved[1] ? cfg->reserved[1] : 4;
   if (e->blk_log2 < 3 || e->blk_log2 > 6) { set_error("block log2 must be 3..6"); delete e; return AV1B_ERR_INVALID; }
   e->keep = cfg->reserved[0] != 0;
+  av1b_select_frame_params(cfg->bit_depth, e->base_q_idx, AV1B_KEY_FRAME, e->loop_filters ? 1 : 0, &e->fp_key);
+  e->fp_key.tile_cols_log2 = e->g.tile_cols_log2; e->fp_key.tile_rows_log2 = e->g.tile_rows_log2;
   e->batch = cfg->frames_in_flight > 0 ? cfg->frames_in_flight : 8;
   e->host_threads = cfg->host_threads > 0 ? cfg->host_threads : (int)std::max(1u, std::thread::hardware_concurrency());
   if (cudaSetDevice(cfg->device_id) != cudaSuccess) { set_error("cudaSetDevice failed"); delete e; return AV1B_ERR_CUDA; }
@@ -315,6 +346,7 @@ int av1b_encoder_create(const av1b_config* cfg, av1b_encoder** out) {
     for (int p = 0; p < 3; p++) {
       const size_t n = e->plane_elems[p] * e->batch;
       A(cudaMalloc(&s.d_src[p], n * 2)); A(cudaMalloc(&s.d_rec[p], n * 2)); A(cudaMalloc(&s.d_coef[p], n * 2));
+      if (e->loop_filters) { A(cudaMalloc(&s.d_deb[p], n * 2)); A(cudaMalloc(&s.d_fin[p], n * 2)); }
       A(cudaMallocHost(&s.h_src[p], n * 2)); A(cudaMallocHost(&s.h_coef[p], n * 2));
       if (e->keep) A(cudaMallocHost(&s.h_rec[p], n * 2));
       if (err == cudaSuccess) { A(cudaMemset(s.d_src[p], 0, n * 2)); A(cudaMemset(s.d_coef[p], 0, n * 2)); A(cudaMemset(s.d_rec[p], 0, n * 2)); }
@@ -322,6 +354,8 @@ int av1b_encoder_create(const av1b_config* cfg, av1b_encoder** out) {
     A(cudaMalloc(&s.d_blocks, e->map_elems * e->batch * sizeof(Av1bBlockInfo)));
     A(cudaMalloc(&s.d_map, e->map_elems * e->batch));
     A(cudaMallocHost(&s.h_blocks, e->map_elems * e->batch * sizeof(Av1bBlockInfo)));
+    A(cudaMalloc(&s.d_cdef_idx, (size_t)e->g.sb_rows * e->g.sb_cols * e->batch));
+    A(cudaMallocHost(&s.h_cdef_idx, (size_t)e->g.sb_rows * e->g.sb_cols * e->batch));
   }
   if (err != cudaSuccess) {
     set_error("device/pinned allocation failed: %s", cudaGetErrorString(err));
@@ -407,6 +441,18 @@ int av1b_get_frame_syms(av1b_encoder* e, uint32_t frame, Av1bBlockInfo* blocks, 
   return AV1B_OK;
 }
 
+int av1b_get_frame_params(av1b_encoder* e, Av1bFrameParams* fp) {
+  if (!e || !fp) return AV1B_ERR_INVALID;
+  *fp = e->fp_key;
+  return AV1B_OK;
+}
+
+int av1b_get_cdef_idx(av1b_encoder* e, uint32_t frame, uint8_t* idx) {
+  if (!e || !idx || !e->keep || frame >= e->kept.size()) { set_error("cdef_idx not kept or bad index"); return AV1B_ERR_INVALID; }
+  memcpy(idx, e->kept[frame].cdef_idx.data(), e->kept[frame].cdef_idx.size());
+  return AV1B_OK;
+}
+
 int av1b_get_geom(av1b_encoder* e, Av1bGeom* g) {
   if (!e || !g) return AV1B_ERR_INVALID;
   *g = e->g;
@@ -415,10 +461,10 @@ int av1b_get_geom(av1b_encoder* e, Av1bGeom* g) {
 
 int av1b_get_stats(av1b_encoder* e, double* stats, int n) {
   if (!e || !stats) return AV1B_ERR_INVALID;
-  const double v[10] = {e->t_h2d_ms, e->t_kernel_ms, e->t_d2h_ms, e->t_pack_ms, (double)e->kernel_launches,
+  const double v[12] = {e->t_h2d_ms, e->t_kernel_ms, e->t_d2h_ms, e->t_pack_ms, (double)e->kernel_launches,
                         (double)e->base_q_idx, e->t_intra_ms, (double)e->intra_launches, (double)e->frames_done,
-                        (double)e->bytes_out};
-  for (int i = 0; i < n && i < 10; i++) stats[i] = v[i];
+                        (double)e->bytes_out, e->t_deblock_ms, e->t_cdef_ms};
+  for (int i = 0; i < n && i < 12; i++) stats[i] = v[i];
   return AV1B_OK;
 }
 

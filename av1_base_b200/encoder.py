@@ -27,7 +27,7 @@ def _check(rc):
 class Encoder:
     def __init__(self, width, height, bit_depth=10, crf=30, preset=6, keyint=240, fps=(30, 1), device_id=0,
                  tile_cols_log2=-1, tile_rows_log2=-1, hdr=False, host_threads=0, frames_in_flight=0,
-                 keep_debug=False, blk_log2=0):
+                 keep_debug=False, blk_log2=0, loop_filters=True):
         L = abi.lib()
         cfg = abi.Config()
         L.av1b_config_default(C.byref(cfg))
@@ -41,6 +41,7 @@ class Encoder:
         cfg.frames_in_flight = frames_in_flight
         cfg.reserved[0] = int(keep_debug)
         cfg.reserved[1] = blk_log2
+        cfg.reserved[2] = 0 if loop_filters else 1
         self.cfg = cfg
         self._h = C.c_void_p()
         _check(L.av1b_encoder_create(C.byref(cfg), C.byref(self._h)))
@@ -102,11 +103,22 @@ class Encoder:
         return blocks, coef
 
     def stats(self):
-        s = (C.c_double * 10)()
-        _check(abi.lib().av1b_get_stats(self._h, s, 10))
+        s = (C.c_double * 12)()
+        _check(abi.lib().av1b_get_stats(self._h, s, 12))
         return dict(h2d_ms=s[0], kernel_ms=s[1], d2h_ms=s[2], pack_ms=s[3], kernel_launches=int(s[4]),
                     base_q_idx=int(s[5]), intra_ms=s[6], intra_launches=int(s[7]), frames_done=int(s[8]),
-                    bytes_out=int(s[9]))
+                    bytes_out=int(s[9]), deblock_ms=s[10], cdef_ms=s[11])
+
+    def frame_params(self):
+        fp = abi.FrameParams()
+        _check(abi.lib().av1b_get_frame_params(self._h, C.byref(fp)))
+        return fp
+
+    def cdef_idx(self, frame):
+        g = self.geom
+        idx = np.zeros(g.sb_rows * g.sb_cols, np.uint8)
+        _check(abi.lib().av1b_get_cdef_idx(self._h, frame, idx.ctypes.data_as(C.c_void_p)))
+        return idx
 
     def _srcs(self, frames):
         n = len(frames)

@@ -18,6 +18,9 @@ def run():
     assert len(dec) == len(frames)
     for i, fr in enumerate(frames):
         ref = O.encode_intra_frame(g, fr, bd, q, pm)
+        fp = enc.frame_params()
+        O.deblock_frame(g, bd, ref.blocks, ref.rec, list(fp.lf_level), fp.lf_sharpness)
+        ref.rec = O.cdef_frame(g, bd, ref.blocks, fp, O.cdef_search(g, bd, ref.blocks, fp, ref.rec, O.pad_planes(g, fr)), ref.rec)
         rec = enc.recon(i)
         orc = O.crop(g, ref.rec)
         for p in range(3):
