@@ -37,8 +37,9 @@ class Geom(C.Structure):
 
 BLOCK_INFO_DTYPE = np.dtype([("blk_log2", "u1"), ("y_mode", "u1"), ("uv_mode", "u1"), ("skip", "u1"),
                              ("angle_y", "i1"), ("angle_uv", "i1"), ("tx_type_y", "u1"), ("cfl_alpha_u", "u1"),
-                             ("eob", "<u2", (3,)), ("cfl_alpha_v", "u1"), ("reserved", "u1")])
-assert BLOCK_INFO_DTYPE.itemsize == 16
+                             ("eob", "<u2", (3,)), ("cfl_alpha_v", "u1"), ("is_inter", "u1"),
+                             ("mv", "<i2", (2,))])
+assert BLOCK_INFO_DTYPE.itemsize == 20
 
 LR_UNIT_DTYPE = np.dtype([("type", "i1"), ("sgr_set", "i1"), ("wiener_v", "i1", (3,)), ("wiener_h", "i1", (3,)),
                           ("sgr_xqd", "i1", (2,)), ("pad", "i1", (6,))])

@@ -34,7 +34,7 @@ typedef struct Av1bSeqParams {
 } Av1bSeqParams;
 
 typedef struct Av1bFrameParams {
-  int32_t frame_type;
+  int32_t frame_type;           // AV1B_KEY_FRAME or AV1B_INTER_FRAME (single reference: the previous frame)
   int32_t base_q_idx;
   int32_t disable_cdf_update;   // 1: static default CDFs inside every tile
   int32_t tile_cols_log2, tile_rows_log2;
@@ -75,8 +75,9 @@ typedef struct Av1bBlockInfo {
   uint8_t cfl_alpha_u;  // reserved (CfL): signs/magnitudes packed
   uint16_t eob[3];    // per plane, valid at the block's top-left unit
   uint8_t cfl_alpha_v;
-  uint8_t reserved;
-} Av1bBlockInfo;        // 16 bytes
+  uint8_t is_inter;   // 1: inter block predicted from LAST_FRAME with mv (inter frames only)
+  int16_t mv[2];      // row, col in 1/8 luma samples (AV1 "Mv"), multiples of 2 (allow_high_precision_mv = 0)
+} Av1bBlockInfo;        // 20 bytes
 
 // Loop-restoration unit parameters
 typedef struct Av1bLrUnit {

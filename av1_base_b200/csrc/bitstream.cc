@@ -170,16 +170,30 @@ void write_sequence_header(const Av1bSeqParams& seq, std::vector<uint8_t>& out) 
 static void write_frame_header(const Av1bSeqParams& seq, const Av1bFrameParams& fp, const Av1bGeom& g,
                                BitWriter& w) {
   const bool key = fp.frame_type == AV1B_KEY_FRAME;
+  const bool inter = fp.frame_type == AV1B_INTER_FRAME;
   w.bit(0);                    // show_existing_frame
   w.put(fp.frame_type, 2);
   w.bit(1);                    // show_frame
   if (!key) w.bit(0);          // error_resilient_mode (implied 1 for shown key frames)
   w.bit(fp.disable_cdf_update ? 1 : 0);
+  // allow_screen_content_tools = seq_force_screen_content_tools = 0 (not coded); force_integer_mv = 0
   w.bit(0);                    // frame_size_override_flag
-  // order_hint: 0 bits; primary_ref_frame: NONE for intra frames (not coded)
-  if (!key) w.put(0x01, 8);    // refresh_frame_flags for intra_only frames (must not be 0xFF)
-  // frame_size(): from the sequence header; superres off; render_size():
-  w.bit(0);                    // render_and_frame_size_different
+  // order_hint: 0 bits (enable_order_hint = 0)
+  if (inter) w.put(7, 3);      // primary_ref_frame = PRIMARY_REF_NONE: every frame starts from the default CDFs
+  if (!key) w.put(inter ? 0xFF : 0x01, 8);   // refresh_frame_flags (intra_only frames must not use 0xFF)
+  if (inter) {
+    // single reference design: all seven reference names point at slot 0 = the previous frame
+    for (int i = 0; i < 7; i++) w.put(0, 3);   // ref_frame_idx[i]
+    // frame_size(): from the sequence header; superres off
+    w.bit(0);                  // render_and_frame_size_different
+    w.bit(0);                  // allow_high_precision_mv
+    w.bit(0);                  // is_filter_switchable
+    w.put(0, 2);               // interpolation_filter = EIGHTTAP (regular)
+    w.bit(0);                  // is_motion_mode_switchable
+    // use_ref_frame_mvs = 0 (enable_ref_frame_mvs = 0, not coded)
+  } else {
+    w.bit(0);                  // render_and_frame_size_different
+  }
   if (!fp.disable_cdf_update) w.bit(1);   // disable_frame_end_update_cdf
   // tile_info()
   {
@@ -244,9 +258,11 @@ static void write_frame_header(const Av1bSeqParams& seq, const Av1bFrameParams& 
     }
   }
   w.bit(0);   // tx_mode_select = 0 -> TX_MODE_LARGEST
-  // frame_reference_mode / skip_mode_params / allow_warped_motion: nothing for intra frames
+  if (inter) w.bit(0);   // reference_select = 0 (single reference)
+  // skip_mode_params: skip mode needs order hints (not coded); allow_warped_motion: enable_warped_motion = 0
   w.bit(0);   // reduced_tx_set
-  // global_motion_params(): nothing for intra frames; film grain: not present
+  if (inter) for (int i = 0; i < 7; i++) w.bit(0);   // global_motion_params(): is_global = 0 for LAST..ALTREF
+  // film grain: not present
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -279,6 +295,16 @@ struct TileCdfs {
   uint16_t switchable_restore[4];
   uint16_t wiener_restore[3];
   uint16_t sgrproj_restore[3];
+  // inter frames
+  uint16_t intra_inter[4][3];
+  uint16_t single_ref[3][6][3];
+  uint16_t newmv[6][3], zeromv[2][3], refmv[6][3], drl[3][3];
+  uint16_t inter_ext_tx[4][4][17];
+  uint16_t y_mode[4][14];
+  uint16_t mv_joints[5];
+  struct MvComp {
+    uint16_t classes[12], class0_fp[2][5], fp[5], sign[3], class0_hp[3], hp[3], class0[3], bits[10][3];
+  } mvc[2];
 };
 
 void init_cdfs(TileCdfs& c, int base_q_idx) {
@@ -308,6 +334,20 @@ void init_cdfs(TileCdfs& c, int base_q_idx) {
   CP(c.switchable_restore, av1t_cdf_switchable_restore);
   CP(c.wiener_restore, av1t_cdf_wiener_restore);
   CP(c.sgrproj_restore, av1t_cdf_sgrproj_restore);
+  CP(c.intra_inter, av1t_cdf_intra_inter);
+  CP(c.single_ref, av1t_cdf_single_ref);
+  CP(c.newmv, av1t_cdf_newmv); CP(c.zeromv, av1t_cdf_zeromv); CP(c.refmv, av1t_cdf_refmv); CP(c.drl, av1t_cdf_drl);
+  CP(c.inter_ext_tx, av1t_cdf_inter_ext_tx);
+  CP(c.y_mode, av1t_cdf_y_mode);
+  CP(c.mv_joints, av1t_cdf_nmv_joints);
+  CP(c.mvc[0].classes, av1t_cdf_nmv_c0_classes); CP(c.mvc[0].class0_fp, av1t_cdf_nmv_c0_class0_fp);
+  CP(c.mvc[0].fp, av1t_cdf_nmv_c0_fp); CP(c.mvc[0].sign, av1t_cdf_nmv_c0_sign);
+  CP(c.mvc[0].class0_hp, av1t_cdf_nmv_c0_class0_hp); CP(c.mvc[0].hp, av1t_cdf_nmv_c0_hp);
+  CP(c.mvc[0].class0, av1t_cdf_nmv_c0_class0); CP(c.mvc[0].bits, av1t_cdf_nmv_c0_bits);
+  CP(c.mvc[1].classes, av1t_cdf_nmv_c1_classes); CP(c.mvc[1].class0_fp, av1t_cdf_nmv_c1_class0_fp);
+  CP(c.mvc[1].fp, av1t_cdf_nmv_c1_fp); CP(c.mvc[1].sign, av1t_cdf_nmv_c1_sign);
+  CP(c.mvc[1].class0_hp, av1t_cdf_nmv_c1_class0_hp); CP(c.mvc[1].hp, av1t_cdf_nmv_c1_hp);
+  CP(c.mvc[1].class0, av1t_cdf_nmv_c1_class0); CP(c.mvc[1].bits, av1t_cdf_nmv_c1_bits);
 #undef CP
 }
 
@@ -325,6 +365,13 @@ inline int intra_tx_set_type(int tx_log2) {
   if (tx_log2 >= 5) return SET_DCTONLY;
   if (tx_log2 == 4) return SET_DTT4_IDTX;         // TX_SET_INTRA_2 (5 types)
   return SET_DTT4_IDTX_1DDCT;                     // TX_SET_INTRA_1 (7 types)
+}
+// inter transform set type (spec get_tx_set, is_inter = 1, reduced_tx_set = 0)
+inline int inter_tx_set_type(int tx_log2) {
+  if (tx_log2 >= 6) return SET_DCTONLY;
+  if (tx_log2 == 5) return SET_DCT_IDTX;           // TX_SET_INTER_3
+  if (tx_log2 == 4) return SET_DTT9_IDTX_1DDCT;    // TX_SET_INTER_2 (12 types)
+  return SET_ALL16;                                 // TX_SET_INTER_1
 }
 inline int tx_class(int tx_type) {   // 0: 2D, 1: horizontal 1-D, 2: vertical 1-D
   switch (tx_type) {
@@ -379,6 +426,10 @@ struct TileWriter {
     mi_col_end = std::min(g.tile_col_start_sb[tile_col + 1] * 16, g.mi_cols);
     init_cdfs(cdf, fp.base_q_idx);
     reset_lr_refs();
+    if (fp.frame_type == AV1B_INTER_FRAME) {
+      t8c0 = mi_col_start >> 1; t8r0 = mi_row_start >> 1; t8w = (mi_col_end - mi_col_start + 1) >> 1;
+      coded8.assign((size_t)t8w * ((mi_row_end - mi_row_start + 1) >> 1), 0);
+    }
     const int tw4 = mi_col_end - mi_col_start;
     for (int p = 0; p < 3; p++) {
       above_lvl[p].assign(tw4 + 32, 0);
@@ -517,9 +568,269 @@ struct TileWriter {
     partition(r + h, c + h, bl - 1);
   }
 
-  void block(int r, int c, int bl) {
+  // ---- inter frames (spec 5.11.18 inter_frame_mode_info, 7.10.2 motion vector prediction) ----
+  // Per 8x8 unit of the tile: 0 = not coded yet, 1 = intra, 2 = inter without NEWMV, 3 = inter NEWMV
+  std::vector<uint8_t> coded8;
+  int t8c0 = 0, t8r0 = 0, t8w = 0;
+  uint8_t& coded(int mi_r, int mi_c) { return coded8[(size_t)((mi_r >> 1) - t8r0) * t8w + ((mi_c >> 1) - t8c0)]; }
+  bool is_inside(int mi_r, int mi_c) const {
+    return mi_c >= mi_col_start && mi_c < mi_col_end && mi_r >= mi_row_start && mi_r < mi_row_end;
+  }
+
+  struct MvStack {
+    int n = 0, num_new = 0, found = 0;
+    int mv[8][2];
+    int weight[8];
+    int new_ctx = 0, ref_ctx = 0;
+  };
+
+  void add_ref_mv_candidate(MvStack& S, int mr, int mc, int weight) {
+    const Av1bBlockInfo& cb = blk(mr, mc);
+    if (!cb.is_inter) return;
+    int cand[2] = {cb.mv[0], cb.mv[1]};
+    for (int k = 0; k < 2; k++) if (cand[k] & 1) cand[k] += cand[k] > 0 ? -1 : 1;   // lower_mv_precision
+    if (coded(mr, mc) == 3) S.num_new++;
+    S.found = 1;
+    int idx = 0;
+    for (; idx < S.n; idx++) if (S.mv[idx][0] == cand[0] && S.mv[idx][1] == cand[1]) break;
+    if (idx < S.n) S.weight[idx] += weight;
+    else if (S.n < 8) { S.mv[S.n][0] = cand[0]; S.mv[S.n][1] = cand[1]; S.weight[S.n] = weight; S.n++; }
+  }
+  void scan_row(MvStack& S, int r, int c, int bw4, int delta_row) {
+    int delta_col = 0;
+    const int end4 = std::min(std::min(bw4, g.mi_cols - c), 16);
+    if (std::abs(delta_row) > 1) { delta_row += r & 1; delta_col = 1 - (c & 1); }
+    const bool step16 = bw4 >= 16;
+    for (int i = 0; i < end4;) {
+      const int mr = r + delta_row, mc = c + delta_col + i;
+      if (!is_inside(mr, mc)) break;
+      int len = std::min(bw4, 1 << (blk(mr, mc).blk_log2 - 2));
+      if (std::abs(delta_row) > 1) len = std::max(2, len);
+      if (step16) len = std::max(4, len);
+      add_ref_mv_candidate(S, mr, mc, len * 2);
+      i += len;
+    }
+  }
+  void scan_col(MvStack& S, int r, int c, int bh4, int delta_col) {
+    int delta_row = 0;
+    const int end4 = std::min(std::min(bh4, g.mi_rows - r), 16);
+    if (std::abs(delta_col) > 1) { delta_row = 1 - (r & 1); delta_col += c & 1; }
+    const bool step16 = bh4 >= 16;
+    for (int i = 0; i < end4;) {
+      const int mr = r + delta_row + i, mc = c + delta_col;
+      if (!is_inside(mr, mc)) break;
+      int len = std::min(bh4, 1 << (blk(mr, mc).blk_log2 - 2));
+      if (std::abs(delta_col) > 1) len = std::max(2, len);
+      if (step16) len = std::max(4, len);
+      add_ref_mv_candidate(S, mr, mc, len * 2);
+      i += len;
+    }
+  }
+  void scan_point(MvStack& S, int r, int c, int delta_row, int delta_col) {
+    const int mr = r + delta_row, mc = c + delta_col;
+    if (is_inside(mr, mc) && coded(mr, mc) != 0) add_ref_mv_candidate(S, mr, mc, 4);
+  }
+  static void sort_stack(MvStack& S, int start, int end) {
+    while (end > start) {
+      int new_end = start;
+      for (int idx = start + 1; idx < end; idx++) {
+        if (S.weight[idx - 1] < S.weight[idx]) {
+          std::swap(S.weight[idx - 1], S.weight[idx]);
+          std::swap(S.mv[idx - 1][0], S.mv[idx][0]);
+          std::swap(S.mv[idx - 1][1], S.mv[idx][1]);
+          new_end = idx;
+        }
+      }
+      end = new_end;
+    }
+  }
+  // single reference (LAST_FRAME), no temporal candidates (use_ref_frame_mvs = 0), identity global motion
+  void find_mv_stack(int r, int c, int bl, MvStack& S) {
+    const int bw4 = 1 << (bl - 2), bh4 = bw4;
+    S.found = 0;
+    scan_row(S, r, c, bw4, -1);
+    int found_above = S.found; S.found = 0;
+    scan_col(S, r, c, bh4, -1);
+    int found_left = S.found; S.found = 0;
+    if (std::max(bw4, bh4) <= 16) scan_point(S, r, c, -1, bw4);
+    if (S.found) found_above = 1;
+    const int close_matches = found_above + found_left;
+    const int num_nearest = S.n, num_new = S.num_new;
+    for (int i = 0; i < num_nearest; i++) S.weight[i] += 640;   // REF_CAT_LEVEL
+    S.found = 0;
+    scan_point(S, r, c, -1, -1);
+    if (S.found) found_above = 1;
+    S.found = 0;
+    scan_row(S, r, c, bw4, -3);
+    if (S.found) found_above = 1;
+    S.found = 0;
+    scan_col(S, r, c, bh4, -3);
+    if (S.found) found_left = 1;
+    S.found = 0;
+    scan_row(S, r, c, bw4, -5);
+    if (S.found) found_above = 1;
+    S.found = 0;
+    scan_col(S, r, c, bh4, -5);
+    if (S.found) found_left = 1;
+    const int total_matches = found_above + found_left;
+    sort_stack(S, 0, num_nearest);
+    sort_stack(S, num_nearest, S.n);
+    // extra search: every inter block uses the same reference, so row -1 / column -1 were already
+    // collected above; the remaining entries up to two are the (zero) global motion vector
+    for (int i = S.n; i < 2; i++) { S.mv[i][0] = 0; S.mv[i][1] = 0; S.weight[i] = 0; }
+    if (close_matches == 0) { S.new_ctx = std::min(total_matches, 1); S.ref_ctx = total_matches; }
+    else if (close_matches == 1) { S.new_ctx = 3 - std::min(num_new, 1); S.ref_ctx = 2 + total_matches; }
+    else { S.new_ctx = 5 - std::min(num_new, 1); S.ref_ctx = 5; }
+    // clamp (spec 7.10.2.14): MV_BORDER = 128 plus the block size, in 1/8 samples
+    const int border_r = 128 + bh4 * 4 * 8, border_c = 128 + bw4 * 4 * 8;
+    const int top = -(r * 4 * 8) - border_r, bottom = (g.mi_rows - bh4 - r) * 4 * 8 + border_r;
+    const int left = -(c * 4 * 8) - border_c, right = (g.mi_cols - bw4 - c) * 4 * 8 + border_c;
+    for (int i = 0; i < S.n; i++) {
+      S.mv[i][0] = std::min(std::max(S.mv[i][0], top), bottom);
+      S.mv[i][1] = std::min(std::max(S.mv[i][1], left), right);
+    }
+  }
+
+  void write_mv_component(int comp, int diff) {
+    TileCdfs::MvComp& m = cdf.mvc[comp];
+    const int sign = diff < 0, mag = sign ? -diff : diff, offset = mag - 1;
+    int cls = 0;
+    if (offset >= 16) cls = 31 - __builtin_clz((unsigned)(offset >> 3));   // class c covers [2^(c+3), 2^(c+4))
+    const int base = cls ? (2 << (cls + 2)) : 0;
+    const int rem = offset - base, d = rem >> 3, fr = (rem >> 1) & 3;   // hp bit (rem & 1) is implied 1
+    ec.symbol(sign, m.sign, 2);
+    ec.symbol(cls, m.classes, 11);
+    if (cls == 0) {
+      ec.symbol(d, m.class0, 2);
+      ec.symbol(fr, m.class0_fp[d], 4);
+    } else {
+      for (int i = 0; i < cls; i++) ec.symbol((d >> i) & 1, m.bits[i], 2);
+      ec.symbol(fr, m.fp, 4);
+    }
+  }
+  void write_mv(const int diff[2]) {
+    const int joint = (diff[0] != 0 ? 2 : 0) | (diff[1] != 0 ? 1 : 0);   // ZERO, HNZVZ, HZVNZ, HNZVNZ
+    ec.symbol(joint, cdf.mv_joints, 4);
+    if (diff[0]) write_mv_component(0, diff[0]);
+    if (diff[1]) write_mv_component(1, diff[1]);
+  }
+
+  void inter_block(int r, int c, int bl) {
     const Av1bBlockInfo& b = blk(r, c);
     const int n4 = 1 << (bl - 2);
+    const bool au = avail_u(r), al = avail_l(c);
+    {
+      int ctx = (au ? blk(r - 1, c).skip : 0) + (al ? blk(r, c - 1).skip : 0);
+      ec.symbol(b.skip ? 1 : 0, cdf.skip[ctx], 2);
+    }
+    if (!b.skip && seq.enable_cdef && fp.cdef_bits > 0) {
+      if (cdef_pending) { ec.literal(sy.cdef_idx[(r >> 4) * g.sb_cols + (c >> 4)], fp.cdef_bits); cdef_pending = false; }
+    }
+    {
+      const bool ai = au && !blk(r - 1, c).is_inter, li = al && !blk(r, c - 1).is_inter;
+      int ctx;
+      if (au && al) ctx = (li && ai) ? 3 : ((li || ai) ? 1 : 0);
+      else if (au || al) ctx = 2 * (au ? (int)ai : (int)li);
+      else ctx = 0;
+      ec.symbol(b.is_inter ? 1 : 0, cdf.intra_inter[ctx], 2);
+    }
+    int mode_class = 1;
+    if (b.is_inter) {
+      // read_ref_frames(): LAST_FRAME = single_ref_p1 0, single_ref_p3 0, single_ref_p4 0
+      const int cnt = (au && blk(r - 1, c).is_inter) + (al && blk(r, c - 1).is_inter);
+      const int rctx = cnt == 0 ? 1 : 2;
+      ec.symbol(0, cdf.single_ref[rctx][0], 2);
+      ec.symbol(0, cdf.single_ref[rctx][2], 2);
+      ec.symbol(0, cdf.single_ref[rctx][3], 2);
+      MvStack S;
+      find_mv_stack(r, c, bl, S);
+      const int mv[2] = {b.mv[0], b.mv[1]};
+      auto same = [&](int i) { return S.mv[i][0] == mv[0] && S.mv[i][1] == mv[1]; };
+      int near_idx = -1;
+      for (int i = 1; i < std::min(S.n, 4); i++) if (same(i)) { near_idx = i; break; }
+      if (S.n > 0 && same(0)) {            // NEARESTMV
+        ec.symbol(1, cdf.newmv[S.new_ctx], 2);
+        ec.symbol(1, cdf.zeromv[0], 2);
+        ec.symbol(0, cdf.refmv[S.ref_ctx], 2);
+        mode_class = 2;
+      } else if (near_idx > 0) {           // NEARMV, RefMvIdx = near_idx
+        ec.symbol(1, cdf.newmv[S.new_ctx], 2);
+        ec.symbol(1, cdf.zeromv[0], 2);
+        ec.symbol(1, cdf.refmv[S.ref_ctx], 2);
+        for (int idx = 1; idx < 3; idx++) {
+          if (S.n > idx + 1) {
+            const int dctx = S.weight[idx] >= 640 ? (S.weight[idx + 1] >= 640 ? 0 : 1) : 2;
+            const int more = near_idx > idx;
+            ec.symbol(more, cdf.drl[dctx], 2);
+            if (!more) break;
+          }
+        }
+        mode_class = 2;
+      } else if (mv[0] == 0 && mv[1] == 0) {   // GLOBALMV (identity global motion)
+        ec.symbol(1, cdf.newmv[S.new_ctx], 2);
+        ec.symbol(0, cdf.zeromv[0], 2);
+        mode_class = 2;
+      } else {                             // NEWMV: predictor = the stack entry closest to mv
+        ec.symbol(0, cdf.newmv[S.new_ctx], 2);
+        int ref_idx = 0;
+        long best = -1;
+        const int n_pred = std::max(1, std::min(S.n, 3));
+        for (int i = 0; i < n_pred; i++) {
+          const long d = std::labs((long)mv[0] - S.mv[i][0]) + std::labs((long)mv[1] - S.mv[i][1]) + 4 * i;
+          if (best < 0 || d < best) { best = d; ref_idx = i; }
+        }
+        for (int idx = 0; idx < 2; idx++) {
+          if (S.n > idx + 1) {
+            const int dctx = S.weight[idx] >= 640 ? (S.weight[idx + 1] >= 640 ? 0 : 1) : 2;
+            const int more = ref_idx > idx;
+            ec.symbol(more, cdf.drl[dctx], 2);
+            if (!more) break;
+          }
+        }
+        const int diff[2] = {mv[0] - S.mv[ref_idx][0], mv[1] - S.mv[ref_idx][1]};
+        write_mv(diff);
+        mode_class = 3;
+      }
+      // interpolation filter fixed, motion mode SIMPLE, no compound: nothing else is coded
+    } else {
+      // intra block inside an inter frame is not produced by this encoder
+    }
+    for (int y = 0; y < n4; y += 2) for (int x = 0; x < n4; x += 2) coded(r + y, c + x) = (uint8_t)mode_class;
+    residual(r, c, bl, b, true);
+  }
+
+  void residual(int r, int c, int bl, const Av1bBlockInfo& b, bool is_inter) {
+    const int n4 = 1 << (bl - 2);
+    if (b.skip) {
+      for (int p = 0; p < 3; p++) {
+        const int ss = p > 0, x4 = (c - mi_col_start) >> ss, y4 = (r & 15) >> ss, n = std::max(1, n4 >> ss);
+        memset(&above_lvl[p][x4], 0, n); memset(&above_dc[p][x4], 0, n);
+        memset(&left_lvl[p][y4], 0, n); memset(&left_dc[p][y4], 0, n);
+      }
+      return;
+    }
+    for (int p = 0; p < 3; p++) {
+      const int ss = p > 0;
+      int tl = bl - ss;
+      if (tl > 6) tl = 6;
+      if (p > 0 && tl > 5) tl = 5;
+      int tx_type = AV1B_DCT_DCT;
+      if (p == 0) tx_type = b.tx_type_y;
+      else if (is_inter) {
+        // chroma of an inter block takes the luma transform type when the chroma set allows it
+        tx_type = b.tx_type_y;
+        if (!av1t_ext_tx_used[inter_tx_set_type(tl)][tx_type]) tx_type = AV1B_DCT_DCT;
+      } else {
+        tx_type = kModeToTxfm[b.uv_mode];
+        if (!av1t_ext_tx_used[intra_tx_set_type(tl)][tx_type]) tx_type = AV1B_DCT_DCT;
+      }
+      coeffs(p, r, c, tl, b, tx_type, is_inter);
+    }
+  }
+
+  void block(int r, int c, int bl) {
+    if (fp.frame_type == AV1B_INTER_FRAME) { inter_block(r, c, bl); return; }
+    const Av1bBlockInfo& b = blk(r, c);
     // intra_frame_mode_info()
     {
       int ctx = (avail_u(r) ? blk(r - 1, c).skip : 0) + (avail_l(c) ? blk(r, c - 1).skip : 0);
@@ -550,34 +861,14 @@ struct TileWriter {
         ec.symbol(b.angle_uv + 3, cdf.angle_delta[b.uv_mode - AV1B_V_PRED], 7);
       }
     }
-    // TX_MODE_LARGEST: no tx_size syntax.  residual()
-    if (b.skip) {
-      for (int p = 0; p < 3; p++) {
-        const int ss = p > 0, x4 = (c - mi_col_start) >> ss, y4 = (r & 15) >> ss, n = std::max(1, n4 >> ss);
-        memset(&above_lvl[p][x4], 0, n); memset(&above_dc[p][x4], 0, n);
-        memset(&left_lvl[p][y4], 0, n); memset(&left_dc[p][y4], 0, n);
-      }
-      return;
-    }
-    for (int p = 0; p < 3; p++) {
-      const int ss = p > 0;
-      int tl = bl - ss;            // transform log2 size for this plane
-      if (tl > 6) tl = 6;
-      if (p > 0 && tl > 5) tl = 5;
-      int tx_type = AV1B_DCT_DCT;
-      if (p == 0) tx_type = b.tx_type_y;
-      else {
-        tx_type = kModeToTxfm[b.uv_mode];
-        if (!av1t_ext_tx_used[intra_tx_set_type(tl)][tx_type]) tx_type = AV1B_DCT_DCT;
-      }
-      coeffs(p, r, c, tl, b, tx_type);
-    }
+    // TX_MODE_LARGEST: no tx_size syntax.
+    residual(r, c, bl, b, false);
   }
 
   bool cdef_pending = false;
 
   // coefficient syntax for one transform block (one per plane per block in TX_MODE_LARGEST)
-  void coeffs(int plane, int mi_r, int mi_c, int tl, const Av1bBlockInfo& b, int tx_type) {
+  void coeffs(int plane, int mi_r, int mi_c, int tl, const Av1bBlockInfo& b, int tx_type, bool is_inter) {
     const int ss = plane > 0;
     const int x0 = (mi_c * 4) >> ss, y0 = (mi_r * 4) >> ss;      // sample position in the plane
     const int n = 1 << tl, w4 = n >> 2;
@@ -604,7 +895,14 @@ struct TileWriter {
     ec.symbol(eob == 0, cdf.txb_skip[tx_ctx][ctx], 2);
     int cul = 0, dc_cat = 0;
     if (eob > 0) {
-      if (plane == 0) {
+      if (plane == 0 && is_inter) {
+        const int set = inter_tx_set_type(tl);
+        if (set != SET_DCTONLY && fp.base_q_idx > 0) {
+          const int eset = set == SET_ALL16 ? 1 : (set == SET_DTT9_IDTX_1DDCT ? 2 : 3);
+          const int nsym = set == SET_ALL16 ? 16 : (set == SET_DTT9_IDTX_1DDCT ? 12 : 2);
+          ec.symbol(av1t_ext_tx_ind[set][tx_type], cdf.inter_ext_tx[eset][tl - 2], nsym);
+        }
+      } else if (plane == 0) {
         const int set = intra_tx_set_type(tl);
         if (set != SET_DCTONLY && fp.base_q_idx > 0) {
           const int eset = set == SET_DTT4_IDTX_1DDCT ? 1 : 2;

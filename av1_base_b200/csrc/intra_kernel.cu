@@ -440,7 +440,7 @@ __global__ void __launch_bounds__(kThreads) intra_encode_kernel(const IntraLaunc
           info.skip = (sm.eob[0] | sm.eob[1] | sm.eob[2]) == 0;
           info.angle_y = 0; info.angle_uv = 0; info.tx_type_y = AV1B_DCT_DCT; info.cfl_alpha_u = 0;
           info.eob[0] = (uint16_t)sm.eob[0]; info.eob[1] = (uint16_t)sm.eob[1]; info.eob[2] = (uint16_t)sm.eob[2];
-          info.cfl_alpha_v = 0; info.reserved = 0;
+          info.cfl_alpha_v = 0; info.is_inter = 0; info.mv[0] = 0; info.mv[1] = 0;
           for (int o = tid; o < n8 * n8; o += kThreads) {
             const int yy = o / n8, xx = o % n8;
             blocks[((mi_r >> 1) + yy) * g.w8 + (mi_c >> 1) + xx] = info;

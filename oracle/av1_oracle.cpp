@@ -513,6 +513,176 @@ extern "C" int orc_encode_intra_frame(const Av1bGeom* g, int bit_depth, int base
   return 0;
 }
 
+// ------------------------------------------------------------------------------------------------
+// Inter prediction (spec 7.11.3.3 / 7.11.3.4), single reference, no scaling, EIGHTTAP (regular)
+// interpolation; blocks of width (height) <= 4 use the 4-tap kernels (spec: interpFilter index 4).
+// ref: plane of the reference frame (stride rstride, picture size ref_w x ref_h in samples of this
+// plane); (x, y): position of the block in the plane; mv in 1/8 LUMA samples (row, col); ss = 1 for
+// the 4:2:0 chroma planes.
+// ------------------------------------------------------------------------------------------------
+extern "C" void orc_inter_predict(const uint16_t* ref, int rstride, int ref_w, int ref_h, int x, int y, int w, int h,
+                                  int mv_row, int mv_col, int ss, int bd, uint16_t* dst, int dstride) {
+  const int x16 = (x << 4) + ((2 * mv_col) >> ss), y16 = (y << 4) + ((2 * mv_row) >> ss);   // 1/16 sample units
+  const int ix = x16 >> 4, iy = y16 >> 4, fx = x16 & 15, fy = y16 & 15;
+  const int16_t* kx = w <= 4 ? av1t_sub_pel_filters_4[fx] : av1t_sub_pel_filters_8[fx];
+  const int16_t* ky = h <= 4 ? av1t_sub_pel_filters_4[fy] : av1t_sub_pel_filters_8[fy];
+  std::vector<int32_t> inter((size_t)(h + 7) * w);
+  for (int r = 0; r < h + 7; r++) {
+    const int yy = clampi(iy + r - 3, 0, ref_h - 1);
+    for (int c = 0; c < w; c++) {
+      int s = 0;
+      for (int t = 0; t < 8; t++) s += kx[t] * (int)ref[(size_t)yy * rstride + clampi(ix + c + t - 3, 0, ref_w - 1)];
+      inter[(size_t)r * w + c] = (s + 4) >> 3;          // Round2(sum, InterRound0 = 3)
+    }
+  }
+  const int maxv = (1 << bd) - 1;
+  for (int r = 0; r < h; r++)
+    for (int c = 0; c < w; c++) {
+      int s = 0;
+      for (int t = 0; t < 8; t++) s += ky[t] * inter[(size_t)(r + t) * w + c];
+      dst[(size_t)r * dstride + c] = (uint16_t)clampi((s + 1024) >> 11, 0, maxv);   // Round2(sum, InterRound1 = 11)
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// Hierarchical motion estimation (encoder side, ours): open loop on SOURCE pictures.
+//   pyramid: L1 = 2x2 box average (a+b+c+d+2)>>2 of L0 luma, L2 likewise from L1;
+//   L2: every 8x8 block (32x32 luma) full search +-kR2, cost = SAD + |dx| + |dy|;
+//   L1: every 8x8 block (16x16 luma) +-2 around twice the parent vector, cost = SAD;
+//   L0: every 16x16 block +-2 around twice the L1 vector, cost = SAD.
+// Candidates are visited centre first, then in raster order; a candidate replaces the best only if
+// strictly cheaper.  Samples outside a picture are edge-replicated (for both pictures).
+// ------------------------------------------------------------------------------------------------
+extern "C" void orc_downscale2(const uint16_t* src, int sstride, int w, int h, uint16_t* dst, int dstride) {
+  for (int y = 0; y < h / 2; y++)
+    for (int x = 0; x < w / 2; x++) {
+      const uint16_t* p = src + (size_t)(2 * y) * sstride + 2 * x;
+      dst[(size_t)y * dstride + x] = (uint16_t)((p[0] + p[1] + p[sstride] + p[sstride + 1] + 2) >> 2);
+    }
+}
+
+static inline int px_clamped(const uint16_t* img, int stride, int w, int h, int x, int y) {
+  return img[(size_t)clampi(y, 0, h - 1) * stride + clampi(x, 0, w - 1)];
+}
+static int sad_block(const uint16_t* cur, const uint16_t* ref, int stride, int w, int h, int bx, int by, int n, int dx,
+                     int dy) {
+  int s = 0;
+  for (int i = 0; i < n; i++)
+    for (int j = 0; j < n; j++)
+      s += abs(px_clamped(cur, stride, w, h, bx + j, by + i) - px_clamped(ref, stride, w, h, bx + j + dx, by + i + dy));
+  return s;
+}
+enum { kR2 = 12 };
+// cur/ref: three luma levels each (L0 stride = g->stride[0]; L1, L2 have strides stride[0]/2, stride[0]/4).
+// mv_out: [h8*w8][2] (row, col) in 1/8 luma samples, the vector of a 16x16 block replicated on its 8x8 units.
+extern "C" void orc_hme(const Av1bGeom* g, const uint16_t* cur0, const uint16_t* cur1, const uint16_t* cur2,
+                        const uint16_t* ref0, const uint16_t* ref1, const uint16_t* ref2, int16_t* mv_out) {
+  const int W = g->width, H = g->height, s0 = g->stride[0], s1 = s0 / 2, s2 = s0 / 4;
+  const int w1 = W / 2, h1 = H / 2, w2 = W / 4, h2 = H / 4;
+  const int n2x = (W + 31) / 32, n2y = (H + 31) / 32, n1x = (W + 15) / 16, n1y = (H + 15) / 16;
+  std::vector<int> mv2((size_t)n2x * n2y * 2), mv1((size_t)n1x * n1y * 2);
+  for (int by = 0; by < n2y; by++)
+    for (int bx = 0; bx < n2x; bx++) {
+      int best = sad_block(cur2, ref2, s2, w2, h2, bx * 8, by * 8, 8, 0, 0), bdx = 0, bdy = 0;
+      for (int dy = -kR2; dy <= kR2; dy++)
+        for (int dx = -kR2; dx <= kR2; dx++) {
+          if (!dx && !dy) continue;
+          const int c = sad_block(cur2, ref2, s2, w2, h2, bx * 8, by * 8, 8, dx, dy) + abs(dx) + abs(dy);
+          if (c < best) { best = c; bdx = dx; bdy = dy; }
+        }
+      mv2[(by * n2x + bx) * 2] = bdy; mv2[(by * n2x + bx) * 2 + 1] = bdx;
+    }
+  for (int by = 0; by < n1y; by++)
+    for (int bx = 0; bx < n1x; bx++) {
+      const int py = 2 * mv2[((by >> 1) * n2x + (bx >> 1)) * 2], pxv = 2 * mv2[((by >> 1) * n2x + (bx >> 1)) * 2 + 1];
+      int best = sad_block(cur1, ref1, s1, w1, h1, bx * 8, by * 8, 8, pxv, py), bdx = 0, bdy = 0;
+      for (int dy = -2; dy <= 2; dy++)
+        for (int dx = -2; dx <= 2; dx++) {
+          if (!dx && !dy) continue;
+          const int c = sad_block(cur1, ref1, s1, w1, h1, bx * 8, by * 8, 8, pxv + dx, py + dy);
+          if (c < best) { best = c; bdx = dx; bdy = dy; }
+        }
+      mv1[(by * n1x + bx) * 2] = py + bdy; mv1[(by * n1x + bx) * 2 + 1] = pxv + bdx;
+    }
+  for (int by = 0; by < n1y; by++)
+    for (int bx = 0; bx < n1x; bx++) {
+      const int py = 2 * mv1[(by * n1x + bx) * 2], pxv = 2 * mv1[(by * n1x + bx) * 2 + 1];
+      int best = sad_block(cur0, ref0, s0, W, H, bx * 16, by * 16, 16, pxv, py), bdx = 0, bdy = 0;
+      for (int dy = -2; dy <= 2; dy++)
+        for (int dx = -2; dx <= 2; dx++) {
+          if (!dx && !dy) continue;
+          const int c = sad_block(cur0, ref0, s0, W, H, bx * 16, by * 16, 16, pxv + dx, py + dy);
+          if (c < best) { best = c; bdx = dx; bdy = dy; }
+        }
+      const int mvy = (py + bdy) * 8, mvx = (pxv + bdx) * 8;
+      for (int uy = by * 2; uy < std::min(by * 2 + 2, g->h8); uy++)
+        for (int ux = bx * 2; ux < std::min(bx * 2 + 2, g->w8); ux++) {
+          mv_out[(uy * g->w8 + ux) * 2] = (int16_t)mvy;
+          mv_out[(uy * g->w8 + ux) * 2 + 1] = (int16_t)mvx;
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// Inter frame encode: every block is predicted from the previous reconstructed frame with the given
+// vector (one per 8x8 unit; all units of a block carry the same vector), DCT_DCT residual coding with
+// the same quantiser as the intra path.  Blocks are independent of each other.
+// ------------------------------------------------------------------------------------------------
+extern "C" int orc_encode_inter_frame(const Av1bGeom* g, int bit_depth, int base_q_idx, int quant_rnd,
+                                      const uint16_t* src_y, const uint16_t* src_u, const uint16_t* src_v,
+                                      int sy_stride, int suv_stride, const uint8_t* part_map, const int16_t* mvs,
+                                      const uint16_t* ref_y, const uint16_t* ref_u, const uint16_t* ref_v,
+                                      uint16_t* rec_y, uint16_t* rec_u, uint16_t* rec_v, Av1bBlockInfo* blocks,
+                                      int16_t* coef_y, int16_t* coef_u, int16_t* coef_v) {
+  const uint16_t* src[3] = {src_y, src_u, src_v};
+  const int sstride[3] = {sy_stride, suv_stride, suv_stride};
+  const uint16_t* ref[3] = {ref_y, ref_u, ref_v};
+  uint16_t* rec[3] = {rec_y, rec_u, rec_v};
+  int16_t* coef[3] = {coef_y, coef_u, coef_v};
+  std::vector<uint16_t> pred(64 * 64);
+  std::vector<int16_t> resid(64 * 64);
+  std::vector<int32_t> cf(32 * 32), dq(32 * 32);
+  std::vector<int16_t> lv(32 * 32);
+  for (int uy = 0; uy < g->h8; uy++)
+    for (int ux = 0; ux < g->w8; ux++) {
+      const int bl = part_map[uy * g->w8 + ux], n8 = 1 << (bl - 3);
+      if ((ux | uy) & (n8 - 1)) continue;   // not the top-left unit of its block
+      Av1bBlockInfo info;
+      memset(&info, 0, sizeof(info));
+      info.blk_log2 = (uint8_t)bl;
+      info.is_inter = 1;
+      info.mv[0] = mvs[(uy * g->w8 + ux) * 2];
+      info.mv[1] = mvs[(uy * g->w8 + ux) * 2 + 1];
+      info.tx_type_y = AV1B_DCT_DCT;
+      for (int p = 0; p < 3; p++) {
+        const int ss = p > 0;
+        const int n = std::min(1 << (bl - ss), ss ? 32 : 64), bn = 1 << (bl - ss);   // transform / prediction size
+        const int x = (ux * 8) >> ss, y = (uy * 8) >> ss;
+        const int pw = g->width >> ss, ph = g->height >> ss;
+        (void)bn;
+        orc_inter_predict(ref[p], g->stride[p], pw, ph, x, y, n, n, info.mv[0], info.mv[1], ss, bit_depth, pred.data(), n);
+        for (int i = 0; i < n; i++) for (int j = 0; j < n; j++)
+          resid[i * n + j] = (int16_t)((int)src[p][(size_t)(y + i) * sstride[p] + x + j] - (int)pred[i * n + j]);
+        const int cn = std::min(n, 32);
+        orc_fwd_txfm2d(resid.data(), n, cf.data(), cn, n, n, AV1B_DCT_DCT);
+        orc_quant_dequant(cf.data(), cn, lv.data(), cn, dq.data(), cn, n, n, base_q_idx, bit_depth, quant_rnd);
+        const int16_t* scan = cn == 4 ? av1t_scan_default_4x4 : cn == 8 ? av1t_scan_default_8x8
+                              : cn == 16 ? av1t_scan_default_16x16 : av1t_scan_default_32x32;
+        int eob = 0;
+        for (int k = cn * cn - 1; k >= 0; k--) if (lv[scan[k]]) { eob = k + 1; break; }
+        info.eob[p] = (uint16_t)eob;
+        int16_t* cdst = coef[p] + (size_t)y * g->stride[p] + x;
+        for (int i = 0; i < cn; i++) for (int j = 0; j < cn; j++) cdst[(size_t)i * g->stride[p] + j] = lv[i * cn + j];
+        uint16_t* rdst = rec[p] + (size_t)y * g->stride[p] + x;
+        for (int i = 0; i < n; i++) for (int j = 0; j < n; j++) rdst[(size_t)i * g->stride[p] + j] = pred[i * n + j];
+        if (eob > 0) orc_inv_txfm2d_add(dq.data(), cn, rdst, g->stride[p], n, n, AV1B_DCT_DCT, bit_depth);
+      }
+      info.skip = (info.eob[0] == 0 && info.eob[1] == 0 && info.eob[2] == 0);
+      for (int yy = 0; yy < n8; yy++) for (int xx = 0; xx < n8; xx++) blocks[(uy + yy) * g->w8 + ux + xx] = info;
+    }
+  return 0;
+}
+
 extern "C" int orc_geom_init(Av1bGeom* g, int w, int h, int tcl, int trl) { return av1b_geom_init(g, w, h, tcl, trl); }
 
 // ------------------------------------------------------------------------------------------------

@@ -97,3 +97,47 @@ def pad_planes(g, frame):
         h, w = frame[p].shape
         out[p][:h, :w] = frame[p]
     return out
+
+
+def inter_predict(ref, x, y, w, h, mv, ss, bit_depth, ref_w=None, ref_h=None):
+    """Normative single-reference prediction of one block from plane `ref` (2-D uint16 array)."""
+    ref = np.ascontiguousarray(ref, np.uint16)
+    out = np.zeros((h, w), np.uint16)
+    lib().orc_inter_predict(ptr(ref), ref.shape[1], ref_w or ref.shape[1], ref_h or ref.shape[0], x, y, w, h,
+                            int(mv[0]), int(mv[1]), ss, bit_depth, ptr(out), w)
+    return out
+
+
+def pyramid(g, luma_padded):
+    """[L0, L1, L2] with strides stride0, stride0/2, stride0/4 (padded layout, picture area filled)."""
+    l0 = np.ascontiguousarray(luma_padded, np.uint16)
+    l1 = np.zeros((g.rows[0] // 2, g.stride[0] // 2), np.uint16)
+    l2 = np.zeros((g.rows[0] // 4, g.stride[0] // 4), np.uint16)
+    lib().orc_downscale2(ptr(l0), g.stride[0], g.width, g.height, ptr(l1), g.stride[0] // 2)
+    lib().orc_downscale2(ptr(l1), g.stride[0] // 2, g.width // 2, g.height // 2, ptr(l2), g.stride[0] // 4)
+    return [l0, l1, l2]
+
+
+def hme(g, cur_pyr, ref_pyr):
+    """Motion vectors [h8*w8, 2] (row, col) in 1/8 luma samples."""
+    mv = np.zeros((g.h8 * g.w8, 2), np.int16)
+    lib().orc_hme(C.byref(g), ptr(cur_pyr[0]), ptr(cur_pyr[1]), ptr(cur_pyr[2]), ptr(ref_pyr[0]), ptr(ref_pyr[1]),
+                  ptr(ref_pyr[2]), ptr(mv))
+    return mv
+
+
+def encode_inter_frame(g, frame, bit_depth, base_q_idx, part_map, mvs, ref_planes, quant_rnd=48):
+    """frame: [Y,U,V]; ref_planes: 3 padded planes (previous reconstructed frame); mvs: [h8*w8, 2] int16."""
+    Y, U, V = [np.ascontiguousarray(p, dtype=np.uint16) for p in frame]
+    mvs = np.ascontiguousarray(mvs, np.int16)
+    r = IntraResult()
+    r.rec = [np.zeros((g.rows[p], g.stride[p]), np.uint16) for p in range(3)]
+    r.coef = [np.zeros((g.rows[p], g.stride[p]), np.int16) for p in range(3)]
+    r.blocks = np.zeros(g.h8 * g.w8, abi.BLOCK_INFO_DTYPE)
+    rc = lib().orc_encode_inter_frame(C.byref(g), bit_depth, base_q_idx, quant_rnd, ptr(Y), ptr(U), ptr(V),
+                                      Y.shape[1], U.shape[1], ptr(part_map), ptr(mvs),
+                                      ptr(ref_planes[0]), ptr(ref_planes[1]), ptr(ref_planes[2]),
+                                      ptr(r.rec[0]), ptr(r.rec[1]), ptr(r.rec[2]), ptr(r.blocks),
+                                      ptr(r.coef[0]), ptr(r.coef[1]), ptr(r.coef[2]))
+    assert rc == 0
+    return r
