@@ -1,0 +1,309 @@
+// Inter frame encode on the device: motion-compensated prediction (normative 8-tap / 4-tap
+// interpolation, spec 7.11.3.4), residual, forward DCT, quantisation, normative dequantisation +
+// inverse DCT + reconstruction.  Blocks of an inter frame do not depend on each other, so the whole
+// frame runs in parallel: one CTA per 64x64 superblock, and inside it every transform block is owned
+// by a group of N threads (N = transform size: 16 luma / 8 chroma for 16x16 blocks, 8 / 4 for the
+// 8x8 blocks at the picture edge).  A group never leaves its warp, so the only synchronisation is
+// __syncwarp on the group's lanes.  Thread t of a group owns row t (residual, forward row pass,
+// quantiser, inverse row pass) and column t (forward column pass, inverse column pass + store), which
+// makes every transform-matrix operand warp-uniform (constant bank) and every shared-memory access
+// conflict-free.
+//
+// Replaces arithmetic the reference delegates to av1an + SVT-AV1
+// (/root/reference/crates/daemon/src/encode/av1an.rs:126-139; SURVEY.md 8a rows E4, E5 for inter frames).
+// Must match oracle/av1_oracle.cpp orc_encode_inter_frame bit for bit.
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include "av1_inv_txfm1d.h"
+#include "av1_tables_dev.cuh"
+#include "kernels.cuh"
+
+namespace av1b {
+using namespace av1tx;
+namespace {
+
+constexpr int kThreads = 256;
+constexpr int kPoolBytes = 16 * ((16 + 7) * 17 * 4 + 16 * 16 * 2);   // 16 groups of N = 16
+
+__device__ __forceinline__ int clampi(int v, int lo, int hi) { return v < lo ? lo : (v > hi ? hi : v); }
+
+template <int N> struct TxTab;
+template <> struct TxTab<4> {
+  static __device__ __forceinline__ int f(int k, int i) { return tbl::fwd_dct4[k][i]; }
+  static __device__ __forceinline__ int iscan(int p) { return tbl::iscan_default_4[p]; }
+  static constexpr int kLog2 = 2, kRowShift = 0;
+};
+template <> struct TxTab<8> {
+  static __device__ __forceinline__ int f(int k, int i) { return tbl::fwd_dct8[k][i]; }
+  static __device__ __forceinline__ int iscan(int p) { return tbl::iscan_default_8[p]; }
+  static constexpr int kLog2 = 3, kRowShift = 1;
+};
+template <> struct TxTab<16> {
+  static __device__ __forceinline__ int f(int k, int i) { return tbl::fwd_dct16[k][i]; }
+  static __device__ __forceinline__ int iscan(int p) { return tbl::iscan_default_16[p]; }
+  static constexpr int kLog2 = 4, kRowShift = 2;
+};
+
+struct TbOut { int eob; };
+
+// One transform block == one prediction block of plane `p` at (x, y), size N x N, owned by the N lanes
+// `gmask` of one warp; t = lane index inside the group.  buf: (N+7)*(N+1) int32, pred: N*N uint16.
+template <int N>
+__device__ __forceinline__ int code_tb(const InterLaunch& P, int p, int x, int y, int mv_row, int mv_col, int t,
+                                       unsigned gmask, int32_t* buf, uint16_t* pred, bool active) {
+  constexpr int S = N + 1;
+  const int ss = p > 0, bd = P.bit_depth;
+  const int stride = P.g.stride[p];
+  const int pw = P.g.width >> ss, ph = P.g.height >> ss;
+  const uint16_t* ref = P.ref[p];
+  // ---------------- prediction ----------------
+  const int x16 = (x << 4) + ((2 * mv_col) >> ss), y16 = (y << 4) + ((2 * mv_row) >> ss);
+  const int ix = x16 >> 4, iy = y16 >> 4, fx = x16 & 15, fy = y16 & 15;
+  if (fx == 0 && fy == 0) {
+    const uint16_t* rr = ref + (size_t)clampi(iy + t, 0, ph - 1) * stride;
+#pragma unroll
+    for (int c = 0; c < N; c++) pred[t * N + c] = rr[clampi(ix + c, 0, pw - 1)];
+  } else {
+    int kx[8], ky[8];
+#pragma unroll
+    for (int k = 0; k < 8; k++) {
+      kx[k] = N <= 4 ? tbl::sub_pel_filters_4[fx][k] : tbl::sub_pel_filters_8[fx][k];
+      ky[k] = N <= 4 ? tbl::sub_pel_filters_4[fy][k] : tbl::sub_pel_filters_8[fy][k];
+    }
+    for (int r = t; r < N + 7; r += N) {
+      const uint16_t* rr = ref + (size_t)clampi(iy + r - 3, 0, ph - 1) * stride;
+      int win[N + 7];
+#pragma unroll
+      for (int c = 0; c < N + 7; c++) win[c] = rr[clampi(ix + c - 3, 0, pw - 1)];
+#pragma unroll
+      for (int c = 0; c < N; c++) {
+        int s = 0;
+#pragma unroll
+        for (int k = 0; k < 8; k++) s += kx[k] * win[c + k];
+        buf[r * S + c] = (s + 4) >> 3;
+      }
+    }
+    __syncwarp(gmask);
+    const int maxv = (1 << bd) - 1;
+#pragma unroll
+    for (int c = 0; c < N; c++) {
+      int s = 0;
+#pragma unroll
+      for (int k = 0; k < 8; k++) s += ky[k] * buf[(t + k) * S + c];
+      pred[t * N + c] = (uint16_t)clampi((s + 1024) >> 11, 0, maxv);
+    }
+    __syncwarp(gmask);
+  }
+  // ---------------- residual (row t) -> shared, as the column pass reads columns ----------------
+  {
+    const uint16_t* sp = P.src[p] + (size_t)(y + t) * stride + x;
+#pragma unroll
+    for (int c = 0; c < N; c++) buf[t * S + c] = ((int)sp[c] - (int)pred[t * N + c]) * 4;
+  }
+  __syncwarp(gmask);
+  // ---------------- forward DCT: column pass (thread t = column t), then row pass (thread t = row t) -----
+  int32_t col[N];
+#pragma unroll
+  for (int k = 0; k < N; k++) {
+    int32_t acc = 0;
+#pragma unroll
+    for (int i = 0; i < N; i++) acc += TxTab<N>::f(k, i) * buf[i * S + t];
+    col[k] = (acc + 2048) >> 12;
+  }
+  __syncwarp(gmask);
+#pragma unroll
+  for (int k = 0; k < N; k++) buf[k * S + t] = col[k];
+  __syncwarp(gmask);
+  int32_t dq[N];
+  int eob = 0;
+  {
+    int32_t row[N];
+#pragma unroll
+    for (int j = 0; j < N; j++) row[j] = buf[t * S + j];
+    constexpr int sh = 24 + 2 * TxTab<N>::kLog2 - TxTab<N>::kRowShift - 4;
+    const int lim = (1 << (7 + bd)) - 1;
+    int16_t* cdst = P.coef[p] + (size_t)(y + t) * stride + x;
+#pragma unroll
+    for (int l = 0; l < N; l++) {
+      int64_t acc = 0;
+#pragma unroll
+      for (int j = 0; j < N; j++) acc += (int64_t)TxTab<N>::f(l, j) * row[j];
+      const int32_t c = (int32_t)((acc * 4096 + ((int64_t)1 << (sh - 1))) >> sh);
+      const int dqv = (t | l) ? P.ac_q : P.dc_q;
+      const uint32_t a = (uint32_t)(c < 0 ? -c : c);
+      uint32_t lv = (a + (uint32_t)((dqv * P.quant_rnd) >> 7)) / (uint32_t)dqv;
+      if (lv > 32767u) lv = 32767u;
+      int32_t d = (int32_t)((lv * (uint32_t)dqv) & 0xFFFFFFu);
+      if (d > lim) d = lim;
+      dq[l] = c < 0 ? -d : d;
+      if (active) cdst[l] = (int16_t)(c < 0 ? -(int32_t)lv : (int32_t)lv);
+      if (lv) eob = max(eob, TxTab<N>::iscan(t * N + l) + 1);
+    }
+  }
+#pragma unroll
+  for (int o = N / 2; o; o >>= 1) eob = max(eob, __shfl_xor_sync(gmask, eob, o));
+  // ---------------- reconstruction ----------------
+  uint16_t* rec = P.rec[p] + (size_t)y * stride + x;
+  const int maxv = (1 << bd) - 1;
+  if (eob == 0) {
+    if (active) {
+#pragma unroll
+      for (int i = 0; i < N; i++) rec[(size_t)i * stride + t] = pred[i * N + t];
+    }
+    return 0;
+  }
+  const int row_range = bd + 8, col_range = max(bd + 6, 16);
+  __syncwarp(gmask);
+  {
+#pragma unroll
+    for (int j = 0; j < N; j++) dq[j] = sat(dq[j], row_range);
+    idct<N>(dq, row_range);
+#pragma unroll
+    for (int j = 0; j < N; j++) {
+      int32_t v = dq[j];
+      if (TxTab<N>::kRowShift > 0) v = (v + (1 << (TxTab<N>::kRowShift > 0 ? TxTab<N>::kRowShift - 1 : 0))) >> TxTab<N>::kRowShift;
+      buf[t * S + j] = v;
+    }
+  }
+  __syncwarp(gmask);
+  {
+    int32_t xc[N];
+#pragma unroll
+    for (int i = 0; i < N; i++) xc[i] = sat(buf[i * S + t], col_range);
+    idct<N>(xc, col_range);
+    if (active) {
+#pragma unroll
+      for (int i = 0; i < N; i++) {
+        const int v = (xc[i] + 8) >> 4;
+        rec[(size_t)i * stride + t] = (uint16_t)clampi((int)pred[i * N + t] + v, 0, maxv);
+      }
+    }
+  }
+  __syncwarp(gmask);
+  return eob;
+}
+
+struct Smem {
+  alignas(16) unsigned char pool[kPoolBytes];
+  uint16_t eob[3][64];       // per plane, per 8x8 unit of the superblock (valid at a block's top-left unit)
+  uint8_t bl[64];            // blk_log2 per unit, 0 = outside the picture
+};
+
+template <int N>
+__device__ __forceinline__ void group_buffers(Smem& sm, int group, int32_t** buf, uint16_t** pred) {
+  constexpr int kBuf = (N + 7) * (N + 1) * 4, kPred = N * N * 2;
+  unsigned char* base = sm.pool + (size_t)group * (kBuf + kPred);
+  *buf = reinterpret_cast<int32_t*>(base);
+  *pred = reinterpret_cast<uint16_t*>(base + kBuf);
+}
+
+__global__ void __launch_bounds__(kThreads) inter_encode_kernel(const InterLaunch P) {
+  __shared__ Smem sm;
+  const Av1bGeom& g = P.g;
+  const int tid = threadIdx.x, lane = tid & 31;
+  const int sbx = blockIdx.x, sby = blockIdx.y;
+  if (tid < 64) {
+    const int uy = sby * 8 + (tid >> 3), ux = sbx * 8 + (tid & 7);
+    sm.bl[tid] = (uy < g.h8 && ux < g.w8) ? P.part_map[uy * g.w8 + ux] : 0;
+    sm.eob[0][tid] = 0; sm.eob[1][tid] = 0; sm.eob[2][tid] = 0;
+  }
+  __syncthreads();
+  // ---- luma of 16x16 blocks: 16 groups of 16 threads ----
+  {
+    const int group = tid >> 4, t = tid & 15;
+    const unsigned gmask = 0xFFFFu << (lane & 16);
+    const int u = (group >> 2) * 16 + (group & 3) * 2;      // top-left unit of the block
+    const bool active = sm.bl[u] == 4;
+    const int ux = sbx * 8 + (u & 7), uy = sby * 8 + (u >> 3);
+    int mvr = 0, mvc = 0;
+    if (active) { mvr = P.mvs[(uy * g.w8 + ux) * 2]; mvc = P.mvs[(uy * g.w8 + ux) * 2 + 1]; }
+    int32_t* buf; uint16_t* pred;
+    group_buffers<16>(sm, group, &buf, &pred);
+    // inactive groups run on the (always allocated) superblock origin and store nothing
+    const int x = active ? ux * 8 : sbx * 64, y = active ? uy * 8 : sby * 64;
+    const int eob = code_tb<16>(P, 0, x, y, mvr, mvc, t, gmask, buf, pred, active);
+    if (active && t == 0) sm.eob[0][u] = (uint16_t)eob;
+  }
+  __syncthreads();
+  // ---- chroma of 16x16 blocks: 32 groups of 8 threads (16 blocks x U, V) ----
+  {
+    const int group = tid >> 3, t = tid & 7;
+    const unsigned gmask = 0xFFu << (lane & 24);
+    const int b = group & 15, p = 1 + (group >> 4);
+    const int u = (b >> 2) * 16 + (b & 3) * 2;
+    const bool active = sm.bl[u] == 4;
+    const int ux = sbx * 8 + (u & 7), uy = sby * 8 + (u >> 3);
+    int mvr = 0, mvc = 0;
+    if (active) { mvr = P.mvs[(uy * g.w8 + ux) * 2]; mvc = P.mvs[(uy * g.w8 + ux) * 2 + 1]; }
+    int32_t* buf; uint16_t* pred;
+    group_buffers<8>(sm, group, &buf, &pred);
+    const int x = active ? ux * 4 : sbx * 32, y = active ? uy * 4 : sby * 32;
+    const int eob = code_tb<8>(P, p, x, y, mvr, mvc, t, gmask, buf, pred, active);
+    if (active && t == 0) sm.eob[p][u] = (uint16_t)eob;
+  }
+  __syncthreads();
+  // ---- 8x8 blocks (picture edge): luma 8x8 in groups of 8 threads, two rounds of 32 units ----
+  bool any8 = false;
+  for (int i = lane; i < 64; i += 32) any8 |= sm.bl[i] == 3;
+  any8 = __any_sync(0xffffffffu, any8);
+  if (any8) {
+    for (int round = 0; round < 2; round++) {
+      const int group = tid >> 3, t = tid & 7;
+      const unsigned gmask = 0xFFu << (lane & 24);
+      const int u = round * 32 + group;
+      const bool active = sm.bl[u] == 3;
+      const int ux = sbx * 8 + (u & 7), uy = sby * 8 + (u >> 3);
+      int mvr = 0, mvc = 0;
+      if (active) { mvr = P.mvs[(uy * g.w8 + ux) * 2]; mvc = P.mvs[(uy * g.w8 + ux) * 2 + 1]; }
+      int32_t* buf; uint16_t* pred;
+      group_buffers<8>(sm, group, &buf, &pred);
+      const int x = active ? ux * 8 : sbx * 64, y = active ? uy * 8 : sby * 64;
+      const int eob = code_tb<8>(P, 0, x, y, mvr, mvc, t, gmask, buf, pred, active);
+      if (active && t == 0) sm.eob[0][u] = (uint16_t)eob;
+      __syncthreads();
+    }
+    // chroma 4x4 of the 8x8 blocks: 64 groups of 4 threads, one round per plane
+    for (int p = 1; p < 3; p++) {
+      const int group = tid >> 2, t = tid & 3;
+      const unsigned gmask = 0xFu << (lane & 28);
+      const int u = group;
+      const bool active = sm.bl[u] == 3;
+      const int ux = sbx * 8 + (u & 7), uy = sby * 8 + (u >> 3);
+      int mvr = 0, mvc = 0;
+      if (active) { mvr = P.mvs[(uy * g.w8 + ux) * 2]; mvc = P.mvs[(uy * g.w8 + ux) * 2 + 1]; }
+      int32_t* buf; uint16_t* pred;
+      group_buffers<4>(sm, group, &buf, &pred);
+      const int x = active ? ux * 4 : sbx * 32, y = active ? uy * 4 : sby * 32;
+      const int eob = code_tb<4>(P, p, x, y, mvr, mvc, t, gmask, buf, pred, active);
+      if (active && t == 0) sm.eob[p][u] = (uint16_t)eob;
+      __syncthreads();
+    }
+  }
+  // ---- block side information ----
+  if (tid < 64) {
+    const int u = tid, bl = sm.bl[u];
+    if (bl) {
+      const int n8 = 1 << (bl - 3);
+      const int ox = (u & 7) & ~(n8 - 1), oy = (u >> 3) & ~(n8 - 1), o = oy * 8 + ox;   // block's top-left unit
+      const int ux = sbx * 8 + ox, uy = sby * 8 + oy;
+      Av1bBlockInfo info;
+      info.blk_log2 = (uint8_t)bl; info.y_mode = 0; info.uv_mode = 0;
+      info.eob[0] = sm.eob[0][o]; info.eob[1] = sm.eob[1][o]; info.eob[2] = sm.eob[2][o];
+      info.skip = (info.eob[0] | info.eob[1] | info.eob[2]) == 0;
+      info.angle_y = 0; info.angle_uv = 0; info.tx_type_y = AV1B_DCT_DCT; info.cfl_alpha_u = 0; info.cfl_alpha_v = 0;
+      info.is_inter = 1;
+      info.mv[0] = P.mvs[(uy * g.w8 + ux) * 2]; info.mv[1] = P.mvs[(uy * g.w8 + ux) * 2 + 1];
+      P.blocks[(sby * 8 + (u >> 3)) * g.w8 + sbx * 8 + (u & 7)] = info;
+    }
+  }
+}
+
+}  // namespace
+
+cudaError_t launch_inter_encode(const InterLaunch& p, cudaStream_t s) {
+  dim3 grid(p.g.sb_cols, p.g.sb_rows);
+  inter_encode_kernel<<<grid, kThreads, 0, s>>>(p);
+  return cudaGetLastError();
+}
+
+}  // namespace av1b

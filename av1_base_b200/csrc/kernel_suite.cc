@@ -9,6 +9,7 @@
 #include "../../include/av1b200.h"
 #include "capi_internal.h"
 #include "kernels.cuh"
+#include "av1_tables.h"
 
 using namespace av1b;
 
@@ -221,6 +222,92 @@ int av1b_k_lr(int device, int width, int height, int bit_depth, int n_frames, co
   }
   if ((rc = timed(t, reps, ms_per_launch, [&]() { return launch_lr(L, n_frames, t.s); }))) return rc;
   return download_planes(n_frames, out, bo, t.s);
+}
+
+int av1b_k_pyramid(int device, int width, int height, int n_frames, const uint16_t* l0, uint16_t* l1, uint16_t* l2,
+                   int reps, double* ms_per_launch) {
+  if (!l0 || !l1 || !l2 || n_frames <= 0) { set_error("bad argument"); return AV1B_ERR_INVALID; }
+  Av1bGeom g;
+  if (av1b_geom_init(&g, width, height, 0, 0)) { set_error("unsupported size"); return AV1B_ERR_INVALID; }
+  int rc = select_device(device);
+  if (rc) return rc;
+  Timer t; CKS(t.init());
+  const size_t e0 = (size_t)g.stride[0] * g.rows[0];
+  DevBuf d0, d1, d2;
+  CKS(d0.alloc(e0 * n_frames * 2)); CKS(d1.alloc(e0 / 4 * n_frames * 2)); CKS(d2.alloc(e0 / 16 * n_frames * 2));
+  CKS(cudaMemcpyAsync(d0.p, l0, e0 * n_frames * 2, cudaMemcpyHostToDevice, t.s));
+  if ((rc = timed(t, reps, ms_per_launch, [&]() {
+         return launch_pyramid(d0.as<uint16_t>(), d1.as<uint16_t>(), d2.as<uint16_t>(), g.stride[0], g.rows[0], e0, n_frames, t.s);
+       }))) return rc;
+  CKS(cudaMemcpyAsync(l1, d1.p, e0 / 4 * n_frames * 2, cudaMemcpyDeviceToHost, t.s));
+  CKS(cudaMemcpyAsync(l2, d2.p, e0 / 16 * n_frames * 2, cudaMemcpyDeviceToHost, t.s));
+  CKS(cudaStreamSynchronize(t.s));
+  return AV1B_OK;
+}
+
+int av1b_k_hme(int device, int width, int height, int n_frames, const uint16_t* cur_l0, const uint16_t* ref_l0,
+               int16_t* mv_out, int reps, double* ms_per_launch) {
+  if (!cur_l0 || !ref_l0 || !mv_out || n_frames <= 0) { set_error("bad argument"); return AV1B_ERR_INVALID; }
+  Av1bGeom g;
+  if (av1b_geom_init(&g, width, height, 0, 0)) { set_error("unsupported size"); return AV1B_ERR_INVALID; }
+  int rc = select_device(device);
+  if (rc) return rc;
+  Timer t; CKS(t.init());
+  const size_t e0 = (size_t)g.stride[0] * g.rows[0];
+  DevBuf c[3], r[3], m2, mo;
+  for (int l = 0; l < 3; l++) { CKS(c[l].alloc((e0 >> (2 * l)) * n_frames * 2)); CKS(r[l].alloc((e0 >> (2 * l)) * n_frames * 2)); }
+  const int n2 = ((width + 31) / 32) * ((height + 31) / 32);
+  CKS(m2.alloc((size_t)n2 * n_frames * 4));
+  CKS(mo.alloc((size_t)g.w8 * g.h8 * n_frames * 4));
+  CKS(cudaMemcpyAsync(c[0].p, cur_l0, e0 * n_frames * 2, cudaMemcpyHostToDevice, t.s));
+  CKS(cudaMemcpyAsync(r[0].p, ref_l0, e0 * n_frames * 2, cudaMemcpyHostToDevice, t.s));
+  CKS(launch_pyramid(c[0].as<uint16_t>(), c[1].as<uint16_t>(), c[2].as<uint16_t>(), g.stride[0], g.rows[0], e0, n_frames, t.s));
+  CKS(launch_pyramid(r[0].as<uint16_t>(), r[1].as<uint16_t>(), r[2].as<uint16_t>(), g.stride[0], g.rows[0], e0, n_frames, t.s));
+  HmeLaunch L;
+  L.width = width; L.height = height; L.stride0 = g.stride[0]; L.elems0 = e0;
+  for (int l = 0; l < 3; l++) { L.cur[l] = c[l].as<uint16_t>(); L.ref[l] = r[l].as<uint16_t>(); }
+  L.mv2 = m2.as<int16_t>(); L.mv_out = mo.as<int16_t>();
+  if ((rc = timed(t, reps, ms_per_launch, [&]() { return launch_hme(L, n_frames, t.s); }))) return rc;
+  CKS(cudaMemcpyAsync(mv_out, mo.p, (size_t)g.w8 * g.h8 * n_frames * 4, cudaMemcpyDeviceToHost, t.s));
+  CKS(cudaStreamSynchronize(t.s));
+  return AV1B_OK;
+}
+
+int av1b_k_inter_encode(int device, int width, int height, int bit_depth, int base_q_idx, const uint8_t* part_map,
+                        const int16_t* mvs, const uint16_t* const src[3], const uint16_t* const ref[3],
+                        uint16_t* const rec[3], int16_t* const coef[3], Av1bBlockInfo* blocks, int reps,
+                        double* ms_per_launch) {
+  if (!part_map || !mvs || !src || !ref || !rec || !coef || !blocks || base_q_idx < 1 || base_q_idx > 255) {
+    set_error("bad argument"); return AV1B_ERR_INVALID;
+  }
+  InterLaunch L;
+  if (av1b_geom_init(&L.g, width, height, 0, 0)) { set_error("unsupported size"); return AV1B_ERR_INVALID; }
+  int rc = select_device(device);
+  if (rc) return rc;
+  Timer t; CKS(t.init());
+  FrameBufs bs, br, bo;
+  if ((rc = upload_planes(L.g, 1, src, bs, t.s))) return rc;
+  if ((rc = upload_planes(L.g, 1, ref, br, t.s))) return rc;
+  if ((rc = upload_planes(L.g, 1, nullptr, bo, t.s))) return rc;
+  const size_t map = (size_t)L.g.w8 * L.g.h8;
+  DevBuf dc[3], dpm, dmv, dbl;
+  for (int p = 0; p < 3; p++) { CKS(dc[p].alloc(bs.elems[p] * 2)); CKS(cudaMemsetAsync(dc[p].p, 0, bs.elems[p] * 2, t.s)); }
+  CKS(dpm.alloc(map)); CKS(dmv.alloc(map * 4)); CKS(dbl.alloc(map * sizeof(Av1bBlockInfo)));
+  CKS(cudaMemcpyAsync(dpm.p, part_map, map, cudaMemcpyHostToDevice, t.s));
+  CKS(cudaMemcpyAsync(dmv.p, mvs, map * 4, cudaMemcpyHostToDevice, t.s));
+  CKS(cudaMemsetAsync(dbl.p, 0, map * sizeof(Av1bBlockInfo), t.s));
+  L.bit_depth = bit_depth; L.base_q_idx = base_q_idx; L.quant_rnd = 48;
+  L.dc_q = bit_depth == 8 ? av1t_dc_q_8[base_q_idx] : av1t_dc_q_10[base_q_idx];
+  L.ac_q = bit_depth == 8 ? av1t_ac_q_8[base_q_idx] : av1t_ac_q_10[base_q_idx];
+  for (int p = 0; p < 3; p++) {
+    L.src[p] = bs.d[p].as<uint16_t>(); L.ref[p] = br.d[p].as<uint16_t>(); L.rec[p] = bo.d[p].as<uint16_t>();
+    L.coef[p] = dc[p].as<int16_t>();
+  }
+  L.blocks = dbl.as<Av1bBlockInfo>(); L.part_map = dpm.as<uint8_t>(); L.mvs = dmv.as<int16_t>();
+  if ((rc = timed(t, reps, ms_per_launch, [&]() { return launch_inter_encode(L, t.s); }))) return rc;
+  for (int p = 0; p < 3; p++) CKS(cudaMemcpyAsync(coef[p], dc[p].p, bs.elems[p] * 2, cudaMemcpyDeviceToHost, t.s));
+  CKS(cudaMemcpyAsync(blocks, dbl.p, map * sizeof(Av1bBlockInfo), cudaMemcpyDeviceToHost, t.s));
+  return download_planes(1, rec, bo, t.s);
 }
 
 }  // extern "C"

@@ -71,6 +71,36 @@ struct LrLaunch {
 cudaError_t launch_inv_txfm_add(const int32_t* coef, uint16_t* dst, int n_blocks, int w, int h, int tx_type,
                                 int bit_depth, cudaStream_t s);
 
+// Source pyramid + hierarchical motion estimation (me_kernels.cu).  Level l of frame f starts at
+// cur[l] + f * (elems0 >> 2l); strides are stride0 >> l.  ref[] is laid out the same way (the previous
+// SOURCE picture of every frame).  mv2: scratch [n_frames][n2y*n2x][2]; mv_out: [n_frames][h8*w8][2].
+struct HmeLaunch {
+  int32_t width, height, stride0;
+  size_t elems0;
+  const uint16_t* cur[3];
+  const uint16_t* ref[3];
+  int16_t* mv2;
+  int16_t* mv_out;
+};
+cudaError_t launch_pyramid(const uint16_t* l0, uint16_t* l1, uint16_t* l2, int stride0, int rows0, size_t elems0,
+                           int n_frames, cudaStream_t s);
+cudaError_t launch_hme(const HmeLaunch& p, int n_frames, cudaStream_t s);
+
+// Inter frame encode (inter_kernel.cu): ONE frame per launch (frame k needs the filtered
+// reconstruction of frame k-1 as its reference).
+struct InterLaunch {
+  Av1bGeom g;
+  int32_t bit_depth, base_q_idx, quant_rnd, dc_q, ac_q;
+  const uint16_t* src[3];
+  const uint16_t* ref[3];     // previous frame after the in-loop filters (what the decoder holds)
+  uint16_t* rec[3];
+  int16_t* coef[3];
+  Av1bBlockInfo* blocks;
+  const uint8_t* part_map;    // 16x16 blocks, 8x8 at the picture edge (values 3 / 4)
+  const int16_t* mvs;         // [h8*w8][2] (row, col), 1/8 luma samples
+};
+cudaError_t launch_inter_encode(const InterLaunch& p, cudaStream_t s);
+
 void upload_tables_once();
 cudaError_t launch_deblock(const DeblockLaunch& p, int n_frames, cudaStream_t s);
 cudaError_t launch_cdef(const CdefLaunch& p, int n_frames, cudaStream_t s);

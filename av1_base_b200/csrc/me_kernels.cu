@@ -1,0 +1,225 @@
+// Source pyramid and hierarchical motion estimation (open loop, on SOURCE pictures) for sm_100a.
+//
+//   pyramid_kernel : L0 luma -> L1 (1/2) and L2 (1/4) in one pass; one thread per L2 sample reads a
+//                    4x4 patch (four 8-byte loads), writes 2x2 L1 samples and one L2 sample.
+//                    Streaming, HBM-bound: algorithmic bytes 1.3125 * Y.
+//   hme_l2_kernel  : full search +-12 on the 1/4 picture for every 8x8 block (= 32x32 luma).  One CTA
+//                    stages a 32x32 patch of the current picture and its (32+24)^2 search window of
+//                    the reference in shared memory; one warp per block, lanes = candidates,
+//                    warp-shuffle arg-min on (cost, visiting order).
+//   hme_refine_kernel : per 16x16 luma block, +-2 on L1 around twice the L2 vector, then +-2 on L0
+//                    around twice the L1 vector; one warp per block, windows staged in shared memory.
+//
+// Replaces arithmetic the reference delegates to av1an + SVT-AV1
+// (/root/reference/crates/daemon/src/encode/av1an.rs:126-139).
+// Decisions are defined by oracle/av1_oracle.cpp (orc_downscale2, orc_hme) and match it bit for bit.
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include "kernels.cuh"
+
+namespace av1b {
+namespace {
+
+__device__ __forceinline__ int clampi(int v, int lo, int hi) { return v < lo ? lo : (v > hi ? hi : v); }
+
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) pyramid_kernel(const uint16_t* __restrict__ l0, uint16_t* __restrict__ l1,
+                                                      uint16_t* __restrict__ l2, int stride0, int rows0,
+                                                      size_t elems0, int n_frames) {
+  const int s2 = stride0 >> 2, r2 = rows0 >> 2;
+  const size_t per = (size_t)s2 * r2;
+  const size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= per * n_frames) return;
+  const int f = (int)(idx / per);
+  const int rem = (int)(idx - (size_t)f * per), y2 = rem / s2, x2 = rem - y2 * s2;
+  const uint16_t* src = l0 + (size_t)f * elems0 + (size_t)(4 * y2) * stride0 + 4 * x2;
+  uint32_t a[4][2];
+#pragma unroll
+  for (int r = 0; r < 4; r++) {
+    const uint2 v = *reinterpret_cast<const uint2*>(src + (size_t)r * stride0);
+    a[r][0] = v.x; a[r][1] = v.y;
+  }
+  uint32_t q[2][2];
+#pragma unroll
+  for (int i = 0; i < 2; i++)
+#pragma unroll
+    for (int j = 0; j < 2; j++) {
+      const uint32_t t = a[2 * i][j], b = a[2 * i + 1][j];
+      q[i][j] = ((t & 0xFFFF) + (t >> 16) + (b & 0xFFFF) + (b >> 16) + 2) >> 2;
+    }
+  uint16_t* d1 = l1 + (size_t)f * (elems0 >> 2) + (size_t)(2 * y2) * (stride0 >> 1) + 2 * x2;
+  *reinterpret_cast<uint32_t*>(d1) = q[0][0] | (q[0][1] << 16);
+  *reinterpret_cast<uint32_t*>(d1 + (stride0 >> 1)) = q[1][0] | (q[1][1] << 16);
+  l2[(size_t)f * (elems0 >> 4) + (size_t)y2 * s2 + x2] = (uint16_t)((q[0][0] + q[0][1] + q[1][0] + q[1][1] + 2) >> 2);
+}
+
+// ---------------------------------------------------------------------------------------------
+constexpr int kR2 = 12;
+constexpr int kT2 = 32;                     // L2 samples per CTA side (4x4 blocks of 8x8)
+constexpr int kW2 = kT2 + 2 * kR2;          // 56
+constexpr int kW2S = kW2 + 1;
+
+struct L2Smem {
+  uint16_t cur[kT2 * kT2];
+  uint16_t ref[kW2 * kW2S];
+};
+
+__global__ void __launch_bounds__(256) hme_l2_kernel(const HmeLaunch P) {
+  __shared__ L2Smem sm;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int frame = blockIdx.z;
+  const int w2 = P.width >> 2, h2 = P.height >> 2, s2 = P.stride0 >> 2;
+  const size_t e2 = P.elems0 >> 4;
+  const uint16_t* cur = P.cur[2] + (size_t)frame * e2;
+  const uint16_t* ref = P.ref[2] + (size_t)frame * e2;
+  const int x0 = blockIdx.x * kT2, y0 = blockIdx.y * kT2;
+  for (int o = tid; o < kT2 * kT2; o += 256) {
+    const int r = o / kT2, c = o % kT2;
+    sm.cur[o] = cur[(size_t)clampi(y0 + r, 0, h2 - 1) * s2 + clampi(x0 + c, 0, w2 - 1)];
+  }
+  for (int o = tid; o < kW2 * kW2; o += 256) {
+    const int r = o / kW2, c = o % kW2;
+    sm.ref[r * kW2S + c] = ref[(size_t)clampi(y0 - kR2 + r, 0, h2 - 1) * s2 + clampi(x0 - kR2 + c, 0, w2 - 1)];
+  }
+  __syncthreads();
+  const int n2x = (P.width + 31) / 32, n2y = (P.height + 31) / 32;
+  constexpr int kSide = 2 * kR2 + 1, kCand = kSide * kSide, kCentre = kR2 * kSide + kR2;
+  for (int b = warp; b < 16; b += 8) {
+    const int bx = b & 3, by = b >> 2;
+    const int gbx = blockIdx.x * 4 + bx, gby = blockIdx.y * 4 + by;
+    if (gbx >= n2x || gby >= n2y) continue;
+    // current block in registers: 64 samples, two per 32-bit word
+    uint32_t c[32];
+#pragma unroll
+    for (int i = 0; i < 8; i++)
+#pragma unroll
+      for (int j = 0; j < 4; j++)
+        c[i * 4 + j] = *reinterpret_cast<const uint32_t*>(&sm.cur[(by * 8 + i) * kT2 + bx * 8 + 2 * j]);
+    unsigned best = 0xFFFFFFFFu;   // (cost << 10) | visiting order
+    for (int k = lane; k < kCand; k += 32) {
+      const int dy = k / kSide - kR2, dx = k % kSide - kR2;
+      const uint16_t* rp = sm.ref + (by * 8 + kR2 + dy) * kW2S + bx * 8 + kR2 + dx;
+      int sad = 0;
+#pragma unroll
+      for (int i = 0; i < 8; i++)
+#pragma unroll
+        for (int j = 0; j < 4; j++) {
+          const uint32_t cw = c[i * 4 + j];
+          sad += abs((int)(cw & 0xFFFF) - (int)rp[i * kW2S + 2 * j]) + abs((int)(cw >> 16) - (int)rp[i * kW2S + 2 * j + 1]);
+        }
+      // visiting order: centre first, then raster
+      const int order = k == kCentre ? 0 : (k < kCentre ? k + 1 : k);
+      const int cost = k == kCentre ? sad : sad + abs(dx) + abs(dy);
+      const unsigned key = ((unsigned)cost << 10) | (unsigned)order;
+      best = min(best, key);
+    }
+    for (int o = 16; o; o >>= 1) best = min(best, __shfl_xor_sync(0xffffffffu, best, o));
+    if (lane == 0) {
+      const int order = best & 1023;
+      const int k = order == 0 ? kCentre : (order <= kCentre ? order - 1 : order);
+      int16_t* out = P.mv2 + ((size_t)frame * n2x * n2y + (size_t)gby * n2x + gbx) * 2;
+      out[0] = (int16_t)(k / kSide - kR2);
+      out[1] = (int16_t)(k % kSide - kR2);
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+struct RefineSmem {
+  uint16_t cur1[8][8 * 8];
+  uint16_t ref1[8][12 * 13];
+  uint16_t cur0[8][16 * 16];
+  uint16_t ref0[8][20 * 21];
+};
+
+// 25 candidates (+-2), lanes = candidates; returns the chosen (dy, dx) in all lanes
+template <int N, int RS>
+__device__ __forceinline__ void refine25(const uint16_t* cur, const uint16_t* ref, int lane, int* bdy, int* bdx) {
+  unsigned key = 0xFFFFFFFFu;
+  if (lane < 25) {
+    const int dy = lane / 5 - 2, dx = lane % 5 - 2;
+    const uint16_t* rp = ref + (2 + dy) * RS + 2 + dx;
+    int sad = 0;
+    for (int i = 0; i < N; i++)
+#pragma unroll
+      for (int j = 0; j < N; j++) sad += abs((int)cur[i * N + j] - (int)rp[i * RS + j]);
+    const int order = lane == 12 ? 0 : (lane < 12 ? lane + 1 : lane);
+    key = ((unsigned)sad << 5) | (unsigned)order;
+  }
+  for (int o = 16; o; o >>= 1) key = min(key, __shfl_xor_sync(0xffffffffu, key, o));
+  const int order = key & 31;
+  const int k = order == 0 ? 12 : (order <= 12 ? order - 1 : order);
+  *bdy = k / 5 - 2;
+  *bdx = k % 5 - 2;
+}
+
+__global__ void __launch_bounds__(256) hme_refine_kernel(const HmeLaunch P) {
+  __shared__ RefineSmem sm;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int frame = blockIdx.z;
+  const int n1x = (P.width + 15) / 16, n1y = (P.height + 15) / 16;
+  const int n2x = (P.width + 31) / 32, n2y = (P.height + 31) / 32;
+  const int blk = blockIdx.x * 8 + warp;
+  if (blk >= n1x * n1y) return;
+  const int bx = blk % n1x, by = blk / n1x;
+  const int w1 = P.width >> 1, h1 = P.height >> 1, s1 = P.stride0 >> 1;
+  const uint16_t* cur1 = P.cur[1] + (size_t)frame * (P.elems0 >> 2);
+  const uint16_t* ref1 = P.ref[1] + (size_t)frame * (P.elems0 >> 2);
+  const uint16_t* cur0 = P.cur[0] + (size_t)frame * P.elems0;
+  const uint16_t* ref0 = P.ref[0] + (size_t)frame * P.elems0;
+  const int16_t* m2 = P.mv2 + ((size_t)frame * n2x * n2y + (size_t)(by >> 1) * n2x + (bx >> 1)) * 2;
+  const int py = 2 * m2[0], px = 2 * m2[1];
+  // ---- L1: 8x8 block at (8bx, 8by), +-2 around (px, py) ----
+  for (int o = lane; o < 64; o += 32)
+    sm.cur1[warp][o] = cur1[(size_t)clampi(by * 8 + (o >> 3), 0, h1 - 1) * s1 + clampi(bx * 8 + (o & 7), 0, w1 - 1)];
+  for (int o = lane; o < 144; o += 32) {
+    const int r = o / 12, c = o % 12;
+    sm.ref1[warp][r * 13 + c] = ref1[(size_t)clampi(by * 8 + py - 2 + r, 0, h1 - 1) * s1 + clampi(bx * 8 + px - 2 + c, 0, w1 - 1)];
+  }
+  __syncwarp();
+  int dy, dx;
+  refine25<8, 13>(sm.cur1[warp], sm.ref1[warp], lane, &dy, &dx);
+  const int qy = 2 * (py + dy), qx = 2 * (px + dx);
+  // ---- L0: 16x16 block at (16bx, 16by), +-2 around (qx, qy) ----
+  for (int o = lane; o < 256; o += 32)
+    sm.cur0[warp][o] = cur0[(size_t)clampi(by * 16 + (o >> 4), 0, P.height - 1) * P.stride0 + clampi(bx * 16 + (o & 15), 0, P.width - 1)];
+  for (int o = lane; o < 400; o += 32) {
+    const int r = o / 20, c = o % 20;
+    sm.ref0[warp][r * 21 + c] =
+        ref0[(size_t)clampi(by * 16 + qy - 2 + r, 0, P.height - 1) * P.stride0 + clampi(bx * 16 + qx - 2 + c, 0, P.width - 1)];
+  }
+  __syncwarp();
+  refine25<16, 21>(sm.cur0[warp], sm.ref0[warp], lane, &dy, &dx);
+  if (lane < 4) {
+    const int uy = by * 2 + (lane >> 1), ux = bx * 2 + (lane & 1);
+    const int w8 = P.width >> 3, h8 = P.height >> 3;
+    if (uy < h8 && ux < w8) {
+      int16_t* out = P.mv_out + ((size_t)frame * w8 * h8 + (size_t)uy * w8 + ux) * 2;
+      out[0] = (int16_t)((qy + dy) * 8);
+      out[1] = (int16_t)((qx + dx) * 8);
+    }
+  }
+}
+
+}  // namespace
+
+cudaError_t launch_pyramid(const uint16_t* l0, uint16_t* l1, uint16_t* l2, int stride0, int rows0, size_t elems0,
+                           int n_frames, cudaStream_t s) {
+  const size_t total = (size_t)(stride0 >> 2) * (rows0 >> 2) * n_frames;
+  pyramid_kernel<<<(unsigned)((total + 255) / 256), 256, 0, s>>>(l0, l1, l2, stride0, rows0, elems0, n_frames);
+  return cudaGetLastError();
+}
+
+cudaError_t launch_hme(const HmeLaunch& p, int n_frames, cudaStream_t s) {
+  const int n2x = (p.width + 31) / 32, n2y = (p.height + 31) / 32;
+  dim3 g2((n2x + 3) / 4, (n2y + 3) / 4, n_frames);
+  hme_l2_kernel<<<g2, 256, 0, s>>>(p);
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) return e;
+  const int n1 = ((p.width + 15) / 16) * ((p.height + 15) / 16);
+  dim3 g1((n1 + 7) / 8, 1, n_frames);
+  hme_refine_kernel<<<g1, 256, 0, s>>>(p);
+  return cudaGetLastError();
+}
+
+}  // namespace av1b

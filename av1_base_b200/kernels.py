@@ -84,3 +84,43 @@ def loop_restoration(width, height, bit_depth, fp, cdef_planes, deb_planes, unit
     ms = C.c_double(0)
     _ck(abi.lib().av1b_k_lr(device, width, height, bit_depth, n, C.byref(fp), _p3(c), _p3(d), up, _p3(out), reps, C.byref(ms)))
     return [[out[p][i] for p in range(3)] for i in range(n)], ms.value
+
+
+def pyramid(width, height, l0_frames, device=0, reps=1):
+    """l0_frames: [n, rows, stride] uint16 padded luma. Returns (l1, l2, ms)."""
+    l0 = np.ascontiguousarray(l0_frames, np.uint16)
+    n, rows, stride = l0.shape
+    l1 = np.zeros((n, rows // 2, stride // 2), np.uint16)
+    l2 = np.zeros((n, rows // 4, stride // 4), np.uint16)
+    ms = C.c_double(0)
+    _ck(abi.lib().av1b_k_pyramid(device, width, height, n, l0.ctypes.data_as(C.c_void_p), l1.ctypes.data_as(C.c_void_p),
+                                 l2.ctypes.data_as(C.c_void_p), reps, C.byref(ms)))
+    return l1, l2, ms.value
+
+
+def hme(width, height, cur_l0, ref_l0, device=0, reps=1):
+    """cur_l0 / ref_l0: [n, rows, stride] padded luma. Returns (mv [n, h8*w8, 2], ms)."""
+    cur = np.ascontiguousarray(cur_l0, np.uint16)
+    ref = np.ascontiguousarray(ref_l0, np.uint16)
+    n = cur.shape[0]
+    mv = np.zeros((n, (height // 8) * (width // 8), 2), np.int16)
+    ms = C.c_double(0)
+    _ck(abi.lib().av1b_k_hme(device, width, height, n, cur.ctypes.data_as(C.c_void_p), ref.ctypes.data_as(C.c_void_p),
+                             mv.ctypes.data_as(C.c_void_p), reps, C.byref(ms)))
+    return mv, ms.value
+
+
+def inter_encode(width, height, bit_depth, base_q_idx, part_map, mvs, src_padded, ref_padded, device=0, reps=1):
+    """Returns (rec[3], coef[3], blocks, ms); planes in the padded layout."""
+    src = [np.ascontiguousarray(p, np.uint16) for p in src_padded]
+    ref = [np.ascontiguousarray(p, np.uint16) for p in ref_padded]
+    rec = [np.zeros_like(p) for p in src]
+    coef = [np.zeros(p.shape, np.int16) for p in src]
+    pm = np.ascontiguousarray(part_map, np.uint8)
+    mv = np.ascontiguousarray(mvs, np.int16)
+    blocks = np.zeros(pm.size, abi.BLOCK_INFO_DTYPE)
+    ms = C.c_double(0)
+    _ck(abi.lib().av1b_k_inter_encode(device, width, height, bit_depth, base_q_idx, pm.ctypes.data_as(C.c_void_p),
+                                      mv.ctypes.data_as(C.c_void_p), _p3(src), _p3(ref), _p3(rec), _p3(coef),
+                                      blocks.ctypes.data_as(C.c_void_p), reps, C.byref(ms)))
+    return rec, coef, blocks, ms.value

@@ -124,6 +124,20 @@ int av1b_k_lr(int device, int width, int height, int bit_depth, int n_frames, co
               const uint16_t* const cdef[3], const uint16_t* const deb[3], const struct Av1bLrUnit* const units[3],
               uint16_t* const out[3], int reps, double* ms_per_launch);
 
+/* Source pyramid: l0 = n_frames padded luma planes; l1 / l2 = the 1/2 and 1/4 planes
+ * (strides stride0/2, stride0/4). */
+int av1b_k_pyramid(int device, int width, int height, int n_frames, const uint16_t* l0, uint16_t* l1, uint16_t* l2,
+                   int reps, double* ms_per_launch);
+/* Hierarchical motion estimation (E2): cur / ref = n_frames padded luma planes each; mv_out =
+ * [n_frames][h8*w8][2] (row, col) in 1/8 luma samples. The timed launch is the search (two kernels). */
+int av1b_k_hme(int device, int width, int height, int n_frames, const uint16_t* cur_l0, const uint16_t* ref_l0,
+               int16_t* mv_out, int reps, double* ms_per_launch);
+/* Inter frame encode (E4 + E5 for inter frames): one frame; part_map [h8*w8] with values 3 / 4. */
+int av1b_k_inter_encode(int device, int width, int height, int bit_depth, int base_q_idx, const uint8_t* part_map,
+                        const int16_t* mvs, const uint16_t* const src[3], const uint16_t* const ref[3],
+                        uint16_t* const rec[3], int16_t* const coef[3], struct Av1bBlockInfo* blocks, int reps,
+                        double* ms_per_launch);
+
 /* ---- host entropy coder over symbol streams (the part that "runs on the host") -------------- */
 struct Av1bSeqParams; struct Av1bFrameParams; struct Av1bFrameSyms;
 int av1b_pack_sequence_header(const struct Av1bSeqParams* seq, uint8_t* out, size_t cap, size_t* len);

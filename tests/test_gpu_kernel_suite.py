@@ -185,3 +185,59 @@ def test_loop_restoration_vs_oracle(w, h, bd, q, lrt, ushift, uvshift):
         ref = O.lr_frame(g, bd, fp, cdf[i], deb[i], [u[i] if u is not None else None for u in units])
         for p in range(3):
             assert np.array_equal(O.crop(g, got[i])[p], O.crop(g, ref)[p]), (i, p)
+
+
+ME_CASES = [(64, 64, 8), (200, 136, 10), (328, 248, 8), (640, 360, 10)]
+
+
+@pytest.mark.parametrize("w,h,bd", ME_CASES)
+def test_pyramid_and_hme_vs_oracle(w, h, bd):
+    g = O.geom(w, h, 0, 0)
+    frames = synth.synth_clip(w, h, bd, 4, seed=w + bd, scene_len=100)
+    l0 = np.stack([O.pad_planes(g, fr)[0] for fr in frames])
+    l1, l2, _ = kernels.pyramid(w, h, l0)
+    pyr = [O.pyramid(g, l0[i]) for i in range(len(frames))]
+    for i in range(len(frames)):
+        assert np.array_equal(l1[i][:h // 2, :w // 2], pyr[i][1][:h // 2, :w // 2])
+        assert np.array_equal(l2[i][:h // 4, :w // 4], pyr[i][2][:h // 4, :w // 4])
+    mv, _ = kernels.hme(w, h, l0[1:], l0[:-1])
+    for i in range(1, len(frames)):
+        want = O.hme(g, pyr[i], pyr[i - 1])
+        assert np.array_equal(mv[i - 1], want), i
+
+
+def random_mvs(g, pm, rng, integer):
+    step = 8 if integer else 2
+    m = (rng.integers(-6, 7, (g.h8, g.w8, 2)) * step).astype(np.int16)
+    pal = (rng.integers(-40, 41, (5, 2)) * step).astype(np.int16)
+    sel = rng.integers(0, 7, (g.h8, g.w8))
+    for k in range(5):
+        m[sel == k] = pal[k]
+    mv = np.zeros((g.h8, g.w8, 2), np.int16)
+    pmm = pm.reshape(g.h8, g.w8)
+    for uy in range(g.h8):
+        for ux in range(g.w8):
+            n8 = 1 << (int(pmm[uy, ux]) - 3)
+            mv[uy, ux] = m[uy & ~(n8 - 1), ux & ~(n8 - 1)]
+    return mv.reshape(-1, 2)
+
+
+@pytest.mark.parametrize("w,h,bd", ME_CASES)
+@pytest.mark.parametrize("q", [40, 140, 230])
+def test_inter_encode_vs_oracle(w, h, bd, q):
+    rng = np.random.default_rng(w + q)
+    g = O.geom(w, h, 0, 0)
+    frames = synth.synth_clip(w, h, bd, 2, seed=w + q, scene_len=100)
+    pm = O.partition_fixed(g, 4)
+    ref = O.encode_intra_frame(g, frames[0], bd, q, pm).rec
+    src = O.pad_planes(g, frames[1])
+    for integer in (True, False):
+        mvs = random_mvs(g, pm, rng, integer)
+        want = O.encode_inter_frame(g, frames[1], bd, q, pm, mvs, ref)
+        rec, coef, blocks, _ = kernels.inter_encode(w, h, bd, q, pm, mvs, src, ref)
+        for f in ("blk_log2", "skip", "eob", "is_inter", "mv", "tx_type_y"):
+            assert np.array_equal(blocks[f], want.blocks[f]), (f, integer)
+        for p in range(3):
+            hh, ww = (h, w) if p == 0 else (h // 2, w // 2)
+            assert np.array_equal(coef[p][:hh, :ww], want.coef[p][:hh, :ww]), ("coef", p, integer)
+            assert np.array_equal(rec[p][:hh, :ww], want.rec[p][:hh, :ww]), ("rec", p, integer)
