@@ -99,24 +99,21 @@ struct KeptFrame {
   std::vector<int16_t> coef[3];
   std::vector<Av1bBlockInfo> blocks;
   std::vector<uint8_t> cdef_idx;
+  int is_key = 1;
 };
 
+// Host-visible side of one batch: pinned staging of the sources and pinned mirrors of the symbol
+// streams.  Two slots are ping-ponged: the host entropy-codes slot k-1 while the GPU works on slot k.
 struct Slot {
   uint16_t* d_src[3] = {nullptr, nullptr, nullptr};
-  uint16_t* d_rec[3] = {nullptr, nullptr, nullptr};   // reconstruction before the loop filters
-  uint16_t* d_deb[3] = {nullptr, nullptr, nullptr};   // deblocked
-  uint16_t* d_fin[3] = {nullptr, nullptr, nullptr};   // after CDEF (+ loop restoration): the decoder's output
-  uint8_t* d_cdef_idx = nullptr;
-  uint8_t* h_cdef_idx = nullptr;
-  int16_t* d_coef[3] = {nullptr, nullptr, nullptr};
-  Av1bBlockInfo* d_blocks = nullptr;
-  uint8_t* d_map = nullptr;
-  uint16_t* h_src[3] = {nullptr, nullptr, nullptr};   // pinned staging
+  uint16_t* h_src[3] = {nullptr, nullptr, nullptr};
   uint16_t* h_rec[3] = {nullptr, nullptr, nullptr};
   int16_t* h_coef[3] = {nullptr, nullptr, nullptr};
   Av1bBlockInfo* h_blocks = nullptr;
-  // h2d start, kernels start, intra start, kernels end, d2h end, intra end, deblock end
-  cudaEvent_t ev[7] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
+  uint8_t* h_cdef_idx = nullptr;
+  cudaEvent_t ev_h2d = nullptr, ev_k0 = nullptr, ev_me = nullptr, ev_k1 = nullptr, ev_d2h = nullptr;
+  std::vector<cudaEvent_t> ev_frame;     // 4 per frame: before encode, after encode, after deblock, after CDEF
+  std::vector<uint8_t> is_key;
   int n_frames = 0;
   int64_t first_index = 0;
 };
@@ -130,31 +127,52 @@ struct av1b_encoder {
   int batch = 0;
   int base_q_idx = 0;
   int blk_log2 = 4;
+  int keyint = 240;
   bool keep = false;
   bool loop_filters = true;
-  Av1bFrameParams fp_key;       // frame-level parameters of key frames (levels / strengths from the quantiser)
+  bool intra_only = false;
+  Av1bFrameParams fp_key, fp_inter;   // frame-level parameters (levels / strengths from the quantiser)
   cudaStream_t stream = nullptr;
   size_t plane_elems[3] = {0, 0, 0};
   size_t map_elems = 0;
+  // device working set of one batch (single copy: all device work is ordered on one stream)
+  uint16_t* d_rec[3] = {nullptr, nullptr, nullptr};   // reconstruction before the loop filters   [batch]
+  uint16_t* d_deb[3] = {nullptr, nullptr, nullptr};   // deblocked                                 [batch]
+  uint16_t* d_fin[3] = {nullptr, nullptr, nullptr};   // decoder output; [0] = last frame of the previous batch [batch+1]
+  int16_t* d_coef[3] = {nullptr, nullptr, nullptr};
+  Av1bBlockInfo* d_blocks = nullptr;
+  uint8_t* d_map_key = nullptr;
+  uint8_t* d_map_inter = nullptr;
+  uint8_t* d_cdef_idx = nullptr;
+  uint16_t* d_pyr[3] = {nullptr, nullptr, nullptr};   // luma pyramid levels 0..2; [0] = last frame of the previous batch
+  int16_t* d_mv2 = nullptr;
+  int16_t* d_mvs = nullptr;
   Slot slot[2];
   ThreadPool* pool = nullptr;
   int host_threads = 1;
+  int64_t chunk_pos = 0;              // frames since the last key frame
   std::vector<KeptFrame> kept;
   // statistics of the last chunk / resident run
-  double t_h2d_ms = 0, t_kernel_ms = 0, t_intra_ms = 0, t_d2h_ms = 0, t_pack_ms = 0, t_deblock_ms = 0, t_cdef_ms = 0;
-  int64_t kernel_launches = 0, intra_launches = 0, frames_done = 0, bytes_out = 0;
+  double t_h2d_ms = 0, t_kernel_ms = 0, t_intra_ms = 0, t_inter_ms = 0, t_me_ms = 0, t_d2h_ms = 0, t_pack_ms = 0,
+         t_deblock_ms = 0, t_cdef_ms = 0;
+  int64_t kernel_launches = 0, intra_launches = 0, inter_launches = 0, frames_done = 0, bytes_out = 0, key_frames = 0;
 };
 
 static void free_all(av1b_encoder* e) {
   for (auto& s : e->slot) {
     for (int p = 0; p < 3; p++) {
-      cudaFree(s.d_src[p]); cudaFree(s.d_rec[p]); cudaFree(s.d_coef[p]); cudaFree(s.d_deb[p]); cudaFree(s.d_fin[p]);
+      cudaFree(s.d_src[p]);
       cudaFreeHost(s.h_src[p]); cudaFreeHost(s.h_rec[p]); cudaFreeHost(s.h_coef[p]);
     }
-    cudaFree(s.d_blocks); cudaFree(s.d_map); cudaFreeHost(s.h_blocks);
-    cudaFree(s.d_cdef_idx); cudaFreeHost(s.h_cdef_idx);
-    for (auto& ev : s.ev) if (ev) cudaEventDestroy(ev);
+    cudaFreeHost(s.h_blocks); cudaFreeHost(s.h_cdef_idx);
+    for (cudaEvent_t ev : {s.ev_h2d, s.ev_k0, s.ev_me, s.ev_k1, s.ev_d2h}) if (ev) cudaEventDestroy(ev);
+    for (cudaEvent_t ev : s.ev_frame) if (ev) cudaEventDestroy(ev);
   }
+  for (int p = 0; p < 3; p++) {
+    cudaFree(e->d_rec[p]); cudaFree(e->d_deb[p]); cudaFree(e->d_fin[p]); cudaFree(e->d_coef[p]); cudaFree(e->d_pyr[p]);
+  }
+  cudaFree(e->d_blocks); cudaFree(e->d_map_key); cudaFree(e->d_map_inter); cudaFree(e->d_cdef_idx);
+  cudaFree(e->d_mv2); cudaFree(e->d_mvs);
   if (e->stream) cudaStreamDestroy(e->stream);
   delete e->pool;
 }
@@ -162,7 +180,7 @@ static void free_all(av1b_encoder* e) {
 // upload n frames (host pointers) into a slot; asynchronous on the encoder stream
 static int stage(av1b_encoder* e, Slot& s, const av1b_frame_src* frames, int n) {
   const Av1bGeom& g = e->g;
-  CK(cudaEventRecord(s.ev[0], e->stream));
+  CK(cudaEventRecord(s.ev_h2d, e->stream));
   for (int b = 0; b < n; b++) {
     for (int p = 0; p < 3; p++) {
       const int w = p ? g.width >> 1 : g.width, h = p ? g.height >> 1 : g.height;
@@ -177,48 +195,104 @@ static int stage(av1b_encoder* e, Slot& s, const av1b_frame_src* frames, int n) 
   return AV1B_OK;
 }
 
-// kernels + symbol download for the n frames resident in the slot; asynchronous
+// device work + symbol download for the n frames resident in the slot; asynchronous
 static int launch(av1b_encoder* e, Slot& s, int n, int64_t first_index) {
   const Av1bGeom& g = e->g;
   const int bd = e->cfg.bit_depth;
+  const size_t nsb = (size_t)g.sb_rows * g.sb_cols;
   s.n_frames = n; s.first_index = first_index;
-  CK(cudaEventRecord(s.ev[1], e->stream));
-  IntraLaunch L;
-  L.g = g; L.bit_depth = bd; L.base_q_idx = e->base_q_idx; L.quant_rnd = 48;
-  L.dc_q = bd == 8 ? av1t_dc_q_8[e->base_q_idx] : av1t_dc_q_10[e->base_q_idx];
-  L.ac_q = bd == 8 ? av1t_ac_q_8[e->base_q_idx] : av1t_ac_q_10[e->base_q_idx];
-  for (int p = 0; p < 3; p++) { L.src[p] = s.d_src[p]; L.rec[p] = s.d_rec[p]; L.coef[p] = s.d_coef[p]; L.plane_elems[p] = e->plane_elems[p]; }
-  L.blocks = s.d_blocks; L.part_map = s.d_map; L.map_elems = e->map_elems;
-  CK(launch_partition_fixed(g, e->blk_log2, s.d_map, n, e->stream));
-  CK(cudaEventRecord(s.ev[2], e->stream));
-  CK(launch_intra_encode(L, n, e->stream));
-  CK(cudaEventRecord(s.ev[5], e->stream));
-  e->kernel_launches += 2; e->intra_launches += 1;
-  if (e->loop_filters) {
-    const Av1bFrameParams& fp = e->fp_key;
-    DeblockLaunch D;
-    D.g = g; D.bit_depth = bd; D.sharpness = fp.lf_sharpness;
-    for (int i = 0; i < 4; i++) D.lf_level[i] = fp.lf_level[i];
-    for (int p = 0; p < 3; p++) { D.in[p] = s.d_rec[p]; D.out[p] = s.d_deb[p]; D.plane_elems[p] = e->plane_elems[p]; }
-    D.blocks = s.d_blocks; D.map_elems = e->map_elems;
-    CK(launch_deblock(D, n, e->stream));
-    CK(cudaEventRecord(s.ev[6], e->stream));
-    CdefLaunch Cd;
-    Cd.g = g; Cd.bit_depth = bd; Cd.cdef_damping = fp.cdef_damping; Cd.cdef_bits = fp.cdef_bits;
-    for (int i = 0; i < 8; i++) { Cd.y_strength[i] = fp.cdef_y_strength[i]; Cd.uv_strength[i] = fp.cdef_uv_strength[i]; }
-    for (int p = 0; p < 3; p++) { Cd.in[p] = s.d_deb[p]; Cd.src[p] = s.d_src[p]; Cd.out[p] = s.d_fin[p]; Cd.plane_elems[p] = e->plane_elems[p]; }
-    Cd.blocks = s.d_blocks; Cd.map_elems = e->map_elems; Cd.cdef_idx = s.d_cdef_idx; Cd.forced_idx = nullptr;
-    CK(launch_cdef(Cd, n, e->stream));
-    e->kernel_launches += 2;
+  s.is_key.assign(n, 1);
+  bool any_inter = false;
+  for (int b = 0; b < n; b++) {
+    const bool key = e->intra_only || ((e->chunk_pos + b) % e->keyint == 0);
+    s.is_key[b] = key;
+    any_inter |= !key;
   }
-  CK(cudaEventRecord(s.ev[3], e->stream));
+  CK(cudaEventRecord(s.ev_k0, e->stream));
+  // ---- open-loop motion estimation for the whole batch (source pictures only) ----
+  if (!e->intra_only) {
+    const size_t e0 = e->plane_elems[0];
+    CK(cudaMemcpyAsync(e->d_pyr[0] + e0, s.d_src[0], e0 * n * 2, cudaMemcpyDeviceToDevice, e->stream));
+    CK(launch_pyramid(e->d_pyr[0] + e0, e->d_pyr[1] + e0 / 4, e->d_pyr[2] + e0 / 16, g.stride[0], g.rows[0], e0, n, e->stream));
+    e->kernel_launches += 1;
+    if (any_inter) {
+      HmeLaunch H;
+      H.width = g.width; H.height = g.height; H.stride0 = g.stride[0]; H.elems0 = e0;
+      for (int l = 0; l < 3; l++) { H.ref[l] = e->d_pyr[l]; H.cur[l] = e->d_pyr[l] + (e0 >> (2 * l)); }
+      H.mv2 = e->d_mv2; H.mv_out = e->d_mvs;
+      CK(launch_hme(H, n, e->stream));
+      e->kernel_launches += 2;
+    }
+    // the last picture of this batch is the reference of the next batch's first picture
+    for (int l = 0; l < 3; l++) {
+      const size_t el = e0 >> (2 * l);
+      CK(cudaMemcpyAsync(e->d_pyr[l], e->d_pyr[l] + el * n, el * 2, cudaMemcpyDeviceToDevice, e->stream));
+    }
+  }
+  CK(cudaEventRecord(s.ev_me, e->stream));
+  const int dcq = bd == 8 ? av1t_dc_q_8[e->base_q_idx] : av1t_dc_q_10[e->base_q_idx];
+  const int acq = bd == 8 ? av1t_ac_q_8[e->base_q_idx] : av1t_ac_q_10[e->base_q_idx];
+  for (int b = 0; b < n; b++) {
+    const bool key = s.is_key[b];
+    cudaEvent_t* ev = &s.ev_frame[(size_t)b * 4];
+    CK(cudaEventRecord(ev[0], e->stream));
+    uint16_t* rec[3]; uint16_t* deb[3]; uint16_t* fin[3]; const uint16_t* prev[3]; const uint16_t* src[3]; int16_t* coef[3];
+    for (int p = 0; p < 3; p++) {
+      const size_t off = (size_t)b * e->plane_elems[p];
+      rec[p] = e->d_rec[p] + off; deb[p] = e->d_deb[p] ? e->d_deb[p] + off : nullptr;
+      prev[p] = e->d_fin[p] + off; fin[p] = e->d_fin[p] + off + e->plane_elems[p];
+      src[p] = s.d_src[p] + off; coef[p] = e->d_coef[p] + off;
+    }
+    Av1bBlockInfo* blocks = e->d_blocks + (size_t)b * e->map_elems;
+    if (key) {
+      IntraLaunch L;
+      L.g = g; L.bit_depth = bd; L.base_q_idx = e->base_q_idx; L.quant_rnd = 48; L.dc_q = dcq; L.ac_q = acq;
+      for (int p = 0; p < 3; p++) { L.src[p] = src[p]; L.rec[p] = e->loop_filters ? rec[p] : fin[p]; L.coef[p] = coef[p]; L.plane_elems[p] = e->plane_elems[p]; }
+      L.blocks = blocks; L.part_map = e->d_map_key; L.map_elems = e->map_elems;
+      CK(launch_intra_encode(L, 1, e->stream));
+      e->kernel_launches += 1; e->intra_launches += 1; e->key_frames += 1;
+    } else {
+      InterLaunch L;
+      L.g = g; L.bit_depth = bd; L.base_q_idx = e->base_q_idx; L.quant_rnd = 48; L.dc_q = dcq; L.ac_q = acq;
+      for (int p = 0; p < 3; p++) { L.src[p] = src[p]; L.ref[p] = prev[p]; L.rec[p] = e->loop_filters ? rec[p] : fin[p]; L.coef[p] = coef[p]; }
+      L.blocks = blocks; L.part_map = e->d_map_inter; L.mvs = e->d_mvs + (size_t)b * e->map_elems * 2;
+      CK(launch_inter_encode(L, e->stream));
+      e->kernel_launches += 1; e->inter_launches += 1;
+    }
+    CK(cudaEventRecord(ev[1], e->stream));
+    if (e->loop_filters) {
+      const Av1bFrameParams& fp = key ? e->fp_key : e->fp_inter;
+      DeblockLaunch D;
+      D.g = g; D.bit_depth = bd; D.sharpness = fp.lf_sharpness;
+      for (int i = 0; i < 4; i++) D.lf_level[i] = fp.lf_level[i];
+      for (int p = 0; p < 3; p++) { D.in[p] = rec[p]; D.out[p] = deb[p]; D.plane_elems[p] = e->plane_elems[p]; }
+      D.blocks = blocks; D.map_elems = e->map_elems;
+      CK(launch_deblock(D, 1, e->stream));
+      CK(cudaEventRecord(ev[2], e->stream));
+      CdefLaunch Cd;
+      Cd.g = g; Cd.bit_depth = bd; Cd.cdef_damping = fp.cdef_damping; Cd.cdef_bits = fp.cdef_bits;
+      for (int i = 0; i < 8; i++) { Cd.y_strength[i] = fp.cdef_y_strength[i]; Cd.uv_strength[i] = fp.cdef_uv_strength[i]; }
+      for (int p = 0; p < 3; p++) { Cd.in[p] = deb[p]; Cd.src[p] = src[p]; Cd.out[p] = fin[p]; Cd.plane_elems[p] = e->plane_elems[p]; }
+      Cd.blocks = blocks; Cd.map_elems = e->map_elems; Cd.cdef_idx = e->d_cdef_idx + (size_t)b * nsb; Cd.forced_idx = nullptr;
+      CK(launch_cdef(Cd, 1, e->stream));
+      e->kernel_launches += 2;
+    } else {
+      CK(cudaEventRecord(ev[2], e->stream));
+    }
+    CK(cudaEventRecord(ev[3], e->stream));
+  }
+  e->chunk_pos += n;
+  CK(cudaEventRecord(s.ev_k1, e->stream));
   for (int p = 0; p < 3; p++) {
-    CK(cudaMemcpyAsync(s.h_coef[p], s.d_coef[p], e->plane_elems[p] * n * 2, cudaMemcpyDeviceToHost, e->stream));
-    if (e->keep) CK(cudaMemcpyAsync(s.h_rec[p], e->loop_filters ? s.d_fin[p] : s.d_rec[p], e->plane_elems[p] * n * 2, cudaMemcpyDeviceToHost, e->stream));
+    CK(cudaMemcpyAsync(s.h_coef[p], e->d_coef[p], e->plane_elems[p] * n * 2, cudaMemcpyDeviceToHost, e->stream));
+    if (e->keep) CK(cudaMemcpyAsync(s.h_rec[p], e->d_fin[p] + e->plane_elems[p], e->plane_elems[p] * n * 2, cudaMemcpyDeviceToHost, e->stream));
   }
-  CK(cudaMemcpyAsync(s.h_cdef_idx, s.d_cdef_idx, (size_t)g.sb_rows * g.sb_cols * n, cudaMemcpyDeviceToHost, e->stream));
-  CK(cudaMemcpyAsync(s.h_blocks, s.d_blocks, e->map_elems * n * sizeof(Av1bBlockInfo), cudaMemcpyDeviceToHost, e->stream));
-  CK(cudaEventRecord(s.ev[4], e->stream));
+  CK(cudaMemcpyAsync(s.h_cdef_idx, e->d_cdef_idx, nsb * n, cudaMemcpyDeviceToHost, e->stream));
+  CK(cudaMemcpyAsync(s.h_blocks, e->d_blocks, e->map_elems * n * sizeof(Av1bBlockInfo), cudaMemcpyDeviceToHost, e->stream));
+  // the last reconstructed picture becomes reference slot 0 of the next batch
+  for (int p = 0; p < 3; p++)
+    CK(cudaMemcpyAsync(e->d_fin[p], e->d_fin[p] + e->plane_elems[p] * n, e->plane_elems[p] * 2, cudaMemcpyDeviceToDevice, e->stream));
+  CK(cudaEventRecord(s.ev_d2h, e->stream));
   return AV1B_OK;
 }
 
@@ -226,19 +300,23 @@ static int launch(av1b_encoder* e, Slot& s, int n, int64_t first_index) {
 static int finish(av1b_encoder* e, Slot& s, bool staged, av1b_packet_cb out_cb, av1b_progress_cb prog_cb, void* user,
                   int64_t total_frames, std::chrono::steady_clock::time_point t_start) {
   const Av1bGeom& g = e->g;
-  CK(cudaEventSynchronize(s.ev[4]));
+  CK(cudaEventSynchronize(s.ev_d2h));
   float ms;
-  if (staged) { cudaEventElapsedTime(&ms, s.ev[0], s.ev[1]); e->t_h2d_ms += ms; }
-  cudaEventElapsedTime(&ms, s.ev[1], s.ev[3]); e->t_kernel_ms += ms;
-  cudaEventElapsedTime(&ms, s.ev[2], s.ev[5]); e->t_intra_ms += ms;
-  if (e->loop_filters) {
-    cudaEventElapsedTime(&ms, s.ev[5], s.ev[6]); e->t_deblock_ms += ms;
-    cudaEventElapsedTime(&ms, s.ev[6], s.ev[3]); e->t_cdef_ms += ms;
-  }
-  cudaEventElapsedTime(&ms, s.ev[3], s.ev[4]); e->t_d2h_ms += ms;
-  const auto tp0 = std::chrono::steady_clock::now();
+  if (staged) { cudaEventElapsedTime(&ms, s.ev_h2d, s.ev_k0); e->t_h2d_ms += ms; }
+  cudaEventElapsedTime(&ms, s.ev_k0, s.ev_k1); e->t_kernel_ms += ms;
+  cudaEventElapsedTime(&ms, s.ev_k0, s.ev_me); e->t_me_ms += ms;
+  cudaEventElapsedTime(&ms, s.ev_k1, s.ev_d2h); e->t_d2h_ms += ms;
   const int n = s.n_frames, n_tiles = g.tile_cols * g.tile_rows;
-  const Av1bFrameParams fp = e->fp_key;
+  for (int b = 0; b < n; b++) {
+    cudaEvent_t* ev = &s.ev_frame[(size_t)b * 4];
+    cudaEventElapsedTime(&ms, ev[0], ev[1]);
+    if (s.is_key[b]) e->t_intra_ms += ms; else e->t_inter_ms += ms;
+    if (e->loop_filters) {
+      cudaEventElapsedTime(&ms, ev[1], ev[2]); e->t_deblock_ms += ms;
+      cudaEventElapsedTime(&ms, ev[2], ev[3]); e->t_cdef_ms += ms;
+    }
+  }
+  const auto tp0 = std::chrono::steady_clock::now();
   std::vector<Av1bFrameSyms> sy(n);
   std::vector<FramePack> packs(n);
   for (int b = 0; b < n; b++) {
@@ -246,17 +324,17 @@ static int finish(av1b_encoder* e, Slot& s, bool staged, av1b_packet_cb out_cb, 
     sy[b].blocks = s.h_blocks + (size_t)b * e->map_elems;
     for (int p = 0; p < 3; p++) { sy[b].coef[p] = s.h_coef[p] + (size_t)b * e->plane_elems[p]; sy[b].coef_stride[p] = g.stride[p]; }
     sy[b].cdef_idx = s.h_cdef_idx + (size_t)b * g.sb_rows * g.sb_cols;
-    pack_frame_header(e->seq, fp, g, packs[b]);
+    pack_frame_header(e->seq, s.is_key[b] ? e->fp_key : e->fp_inter, g, packs[b]);
   }
   e->pool->parallel_for(n * n_tiles, [&](int t) {
     const int b = t / n_tiles, tile = t % n_tiles;
-    pack_tile(e->seq, fp, g, sy[b], tile, packs[b].tiles[tile]);
+    pack_tile(e->seq, s.is_key[b] ? e->fp_key : e->fp_inter, g, sy[b], tile, packs[b].tiles[tile]);
   });
   std::vector<uint8_t> tu;
   for (int b = 0; b < n; b++) {
     tu.clear();
     write_temporal_delimiter(tu);
-    if (s.first_index + b == 0) write_sequence_header(e->seq, tu);
+    if (s.is_key[b]) write_sequence_header(e->seq, tu);
     assemble_frame(packs[b], tu);
     if (e->keep) {
       e->kept.emplace_back();
@@ -267,9 +345,10 @@ static int finish(av1b_encoder* e, Slot& s, bool staged, av1b_packet_cb out_cb, 
       }
       k.blocks.assign(sy[b].blocks, sy[b].blocks + e->map_elems);
       k.cdef_idx.assign(sy[b].cdef_idx, sy[b].cdef_idx + (size_t)g.sb_rows * g.sb_cols);
+      k.is_key = s.is_key[b];
     }
     e->bytes_out += (int64_t)tu.size();
-    if (out_cb && out_cb(user, tu.data(), tu.size(), s.first_index + b, 1)) { set_error("packet callback aborted"); return AV1B_ERR_CALLBACK; }
+    if (out_cb && out_cb(user, tu.data(), tu.size(), s.first_index + b, s.is_key[b])) { set_error("packet callback aborted"); return AV1B_ERR_CALLBACK; }
   }
   e->frames_done += n;
   const auto tp1 = std::chrono::steady_clock::now();
@@ -283,8 +362,9 @@ static int finish(av1b_encoder* e, Slot& s, bool staged, av1b_packet_cb out_cb, 
 
 static void reset_stats(av1b_encoder* e) {
   e->kept.clear();
-  e->t_h2d_ms = e->t_kernel_ms = e->t_intra_ms = e->t_d2h_ms = e->t_pack_ms = e->t_deblock_ms = e->t_cdef_ms = 0;
-  e->kernel_launches = e->intra_launches = e->frames_done = e->bytes_out = 0;
+  e->t_h2d_ms = e->t_kernel_ms = e->t_intra_ms = e->t_inter_ms = e->t_me_ms = e->t_d2h_ms = e->t_pack_ms = 0;
+  e->t_deblock_ms = e->t_cdef_ms = 0;
+  e->kernel_launches = e->intra_launches = e->inter_launches = e->frames_done = e->bytes_out = e->key_frames = 0;
 }
 
 extern "C" {
@@ -331,8 +411,12 @@ int av1b_encoder_create(const av1b_config* cfg, av1b_encoder** out) {
   e->blk_log2 = cfg->reserved[1] ? cfg->reserved[1] : 4;
   if (e->blk_log2 < 3 || e->blk_log2 > 6) { set_error("block log2 must be 3..6"); delete e; return AV1B_ERR_INVALID; }
   e->keep = cfg->reserved[0] != 0;
+  e->intra_only = cfg->reserved[3] != 0;      // reserved[3] = 1: every frame is a key frame
+  e->keyint = cfg->keyint > 0 ? cfg->keyint : 240;
   av1b_select_frame_params(cfg->bit_depth, e->base_q_idx, AV1B_KEY_FRAME, e->loop_filters ? 1 : 0, &e->fp_key);
-  e->fp_key.tile_cols_log2 = e->g.tile_cols_log2; e->fp_key.tile_rows_log2 = e->g.tile_rows_log2;
+  av1b_select_frame_params(cfg->bit_depth, e->base_q_idx, AV1B_INTER_FRAME, e->loop_filters ? 1 : 0, &e->fp_inter);
+  e->fp_key.tile_cols_log2 = e->fp_inter.tile_cols_log2 = e->g.tile_cols_log2;
+  e->fp_key.tile_rows_log2 = e->fp_inter.tile_rows_log2 = e->g.tile_rows_log2;
   e->batch = cfg->frames_in_flight > 0 ? cfg->frames_in_flight : 8;
   e->host_threads = cfg->host_threads > 0 ? cfg->host_threads : (int)std::max(1u, std::thread::hardware_concurrency());
   if (cudaSetDevice(cfg->device_id) != cudaSuccess) { set_error("cudaSetDevice failed"); delete e; return AV1B_ERR_CUDA; }
@@ -340,22 +424,53 @@ int av1b_encoder_create(const av1b_config* cfg, av1b_encoder** out) {
   auto A = [&](cudaError_t r) { if (err == cudaSuccess && r != cudaSuccess) err = r; };
   A(cudaStreamCreateWithFlags(&e->stream, cudaStreamNonBlocking));
   e->map_elems = (size_t)e->g.w8 * e->g.h8;
+  const size_t nsb = (size_t)e->g.sb_rows * e->g.sb_cols;
   for (int p = 0; p < 3; p++) e->plane_elems[p] = (size_t)e->g.stride[p] * e->g.rows[p];
+  const int F = e->batch;
   for (auto& s : e->slot) {
-    for (auto& ev : s.ev) A(cudaEventCreate(&ev));
+    for (cudaEvent_t* ev : {&s.ev_h2d, &s.ev_k0, &s.ev_me, &s.ev_k1, &s.ev_d2h}) A(cudaEventCreate(ev));
+    s.ev_frame.assign((size_t)F * 4, nullptr);
+    for (auto& ev : s.ev_frame) A(cudaEventCreate(&ev));
     for (int p = 0; p < 3; p++) {
-      const size_t n = e->plane_elems[p] * e->batch;
-      A(cudaMalloc(&s.d_src[p], n * 2)); A(cudaMalloc(&s.d_rec[p], n * 2)); A(cudaMalloc(&s.d_coef[p], n * 2));
-      if (e->loop_filters) { A(cudaMalloc(&s.d_deb[p], n * 2)); A(cudaMalloc(&s.d_fin[p], n * 2)); }
+      const size_t n = e->plane_elems[p] * F;
+      A(cudaMalloc(&s.d_src[p], n * 2));
       A(cudaMallocHost(&s.h_src[p], n * 2)); A(cudaMallocHost(&s.h_coef[p], n * 2));
       if (e->keep) A(cudaMallocHost(&s.h_rec[p], n * 2));
-      if (err == cudaSuccess) { A(cudaMemset(s.d_src[p], 0, n * 2)); A(cudaMemset(s.d_coef[p], 0, n * 2)); A(cudaMemset(s.d_rec[p], 0, n * 2)); }
+      if (err == cudaSuccess) A(cudaMemset(s.d_src[p], 0, n * 2));
     }
-    A(cudaMalloc(&s.d_blocks, e->map_elems * e->batch * sizeof(Av1bBlockInfo)));
-    A(cudaMalloc(&s.d_map, e->map_elems * e->batch));
-    A(cudaMallocHost(&s.h_blocks, e->map_elems * e->batch * sizeof(Av1bBlockInfo)));
-    A(cudaMalloc(&s.d_cdef_idx, (size_t)e->g.sb_rows * e->g.sb_cols * e->batch));
-    A(cudaMallocHost(&s.h_cdef_idx, (size_t)e->g.sb_rows * e->g.sb_cols * e->batch));
+    A(cudaMallocHost(&s.h_blocks, e->map_elems * F * sizeof(Av1bBlockInfo)));
+    A(cudaMallocHost(&s.h_cdef_idx, nsb * F));
+  }
+  for (int p = 0; p < 3; p++) {
+    const size_t n = e->plane_elems[p] * F;
+    A(cudaMalloc(&e->d_rec[p], n * 2)); A(cudaMalloc(&e->d_coef[p], n * 2));
+    if (e->loop_filters) A(cudaMalloc(&e->d_deb[p], n * 2));
+    A(cudaMalloc(&e->d_fin[p], (n + e->plane_elems[p]) * 2));
+    if (err == cudaSuccess) {
+      A(cudaMemset(e->d_rec[p], 0, n * 2)); A(cudaMemset(e->d_coef[p], 0, n * 2));
+      A(cudaMemset(e->d_fin[p], 0, (n + e->plane_elems[p]) * 2));
+    }
+  }
+  A(cudaMalloc(&e->d_blocks, e->map_elems * F * sizeof(Av1bBlockInfo)));
+  A(cudaMalloc(&e->d_map_key, e->map_elems)); A(cudaMalloc(&e->d_map_inter, e->map_elems));
+  A(cudaMalloc(&e->d_cdef_idx, nsb * F));
+  if (err == cudaSuccess) { A(cudaMemset(e->d_blocks, 0, e->map_elems * F * sizeof(Av1bBlockInfo))); A(cudaMemset(e->d_cdef_idx, 0, nsb * F)); }
+  if (!e->intra_only) {
+    for (int l = 0; l < 3; l++) {
+      const size_t el = e->plane_elems[0] >> (2 * l);
+      A(cudaMalloc(&e->d_pyr[l], el * (F + 1) * 2));
+      if (err == cudaSuccess) A(cudaMemset(e->d_pyr[l], 0, el * (F + 1) * 2));
+    }
+    const size_t n2 = (size_t)((cfg->width + 31) / 32) * ((cfg->height + 31) / 32);
+    A(cudaMalloc(&e->d_mv2, n2 * F * 4));
+    A(cudaMalloc(&e->d_mvs, e->map_elems * F * 4));
+    if (err == cudaSuccess) A(cudaMemset(e->d_mvs, 0, e->map_elems * F * 4));
+  }
+  if (err == cudaSuccess) {
+    // partition maps are constant: fixed square blocks with forced splits at the picture edge
+    A(launch_partition_fixed(e->g, e->blk_log2, e->d_map_key, 1, e->stream));
+    A(launch_partition_fixed(e->g, 4, e->d_map_inter, 1, e->stream));
+    A(cudaStreamSynchronize(e->stream));
   }
   if (err != cudaSuccess) {
     set_error("device/pinned allocation failed: %s", cudaGetErrorString(err));
@@ -379,6 +494,7 @@ int av1b_encode_chunk(av1b_encoder* e, const av1b_frame_src* frames, uint32_t n_
   if (!e || !frames || !out_cb) { set_error("null argument"); return AV1B_ERR_INVALID; }
   CK(cudaSetDevice(e->cfg.device_id));
   reset_stats(e);
+  e->chunk_pos = 0;               // a chunk is a closed GOP: it starts with a key frame
   const auto t0 = std::chrono::steady_clock::now();
   int rc, i = 0;
   for (uint32_t f0 = 0; f0 < n_frames; f0 += e->batch, i++) {
@@ -408,6 +524,7 @@ int av1b_encode_resident(av1b_encoder* e, uint32_t n_steps, av1b_packet_cb out_c
   if (e->slot[0].n_frames <= 0 || e->slot[1].n_frames <= 0) { set_error("stage both slots first"); return AV1B_ERR_INVALID; }
   CK(cudaSetDevice(e->cfg.device_id));
   reset_stats(e);
+  e->chunk_pos = 0;
   const auto t0 = std::chrono::steady_clock::now();
   int rc;
   int64_t idx = 0;
@@ -447,6 +564,17 @@ int av1b_get_frame_params(av1b_encoder* e, Av1bFrameParams* fp) {
   return AV1B_OK;
 }
 
+int av1b_get_inter_frame_params(av1b_encoder* e, Av1bFrameParams* fp) {
+  if (!e || !fp) return AV1B_ERR_INVALID;
+  *fp = e->fp_inter;
+  return AV1B_OK;
+}
+
+int av1b_get_frame_is_key(av1b_encoder* e, uint32_t frame) {
+  if (!e || !e->keep || frame >= e->kept.size()) return AV1B_ERR_INVALID;
+  return e->kept[frame].is_key;
+}
+
 int av1b_get_cdef_idx(av1b_encoder* e, uint32_t frame, uint8_t* idx) {
   if (!e || !idx || !e->keep || frame >= e->kept.size()) { set_error("cdef_idx not kept or bad index"); return AV1B_ERR_INVALID; }
   memcpy(idx, e->kept[frame].cdef_idx.data(), e->kept[frame].cdef_idx.size());
@@ -461,10 +589,11 @@ int av1b_get_geom(av1b_encoder* e, Av1bGeom* g) {
 
 int av1b_get_stats(av1b_encoder* e, double* stats, int n) {
   if (!e || !stats) return AV1B_ERR_INVALID;
-  const double v[12] = {e->t_h2d_ms, e->t_kernel_ms, e->t_d2h_ms, e->t_pack_ms, (double)e->kernel_launches,
+  const double v[16] = {e->t_h2d_ms, e->t_kernel_ms, e->t_d2h_ms, e->t_pack_ms, (double)e->kernel_launches,
                         (double)e->base_q_idx, e->t_intra_ms, (double)e->intra_launches, (double)e->frames_done,
-                        (double)e->bytes_out, e->t_deblock_ms, e->t_cdef_ms};
-  for (int i = 0; i < n && i < 12; i++) stats[i] = v[i];
+                        (double)e->bytes_out, e->t_deblock_ms, e->t_cdef_ms, e->t_inter_ms, e->t_me_ms,
+                        (double)e->inter_launches, (double)e->key_frames};
+  for (int i = 0; i < n && i < 16; i++) stats[i] = v[i];
   return AV1B_OK;
 }
 

@@ -27,7 +27,7 @@ def _check(rc):
 class Encoder:
     def __init__(self, width, height, bit_depth=10, crf=30, preset=6, keyint=240, fps=(30, 1), device_id=0,
                  tile_cols_log2=-1, tile_rows_log2=-1, hdr=False, host_threads=0, frames_in_flight=0,
-                 keep_debug=False, blk_log2=0, loop_filters=True):
+                 keep_debug=False, blk_log2=0, loop_filters=True, intra_only=False):
         L = abi.lib()
         cfg = abi.Config()
         L.av1b_config_default(C.byref(cfg))
@@ -42,6 +42,7 @@ class Encoder:
         cfg.reserved[0] = int(keep_debug)
         cfg.reserved[1] = blk_log2
         cfg.reserved[2] = 0 if loop_filters else 1
+        cfg.reserved[3] = 1 if intra_only else 0
         self.cfg = cfg
         self._h = C.c_void_p()
         _check(L.av1b_encoder_create(C.byref(cfg), C.byref(self._h)))
@@ -103,16 +104,28 @@ class Encoder:
         return blocks, coef
 
     def stats(self):
-        s = (C.c_double * 12)()
-        _check(abi.lib().av1b_get_stats(self._h, s, 12))
+        s = (C.c_double * 16)()
+        _check(abi.lib().av1b_get_stats(self._h, s, 16))
         return dict(h2d_ms=s[0], kernel_ms=s[1], d2h_ms=s[2], pack_ms=s[3], kernel_launches=int(s[4]),
                     base_q_idx=int(s[5]), intra_ms=s[6], intra_launches=int(s[7]), frames_done=int(s[8]),
-                    bytes_out=int(s[9]), deblock_ms=s[10], cdef_ms=s[11])
+                    bytes_out=int(s[9]), deblock_ms=s[10], cdef_ms=s[11], inter_ms=s[12], me_ms=s[13],
+                    inter_launches=int(s[14]), key_frames=int(s[15]))
 
     def frame_params(self):
         fp = abi.FrameParams()
         _check(abi.lib().av1b_get_frame_params(self._h, C.byref(fp)))
         return fp
+
+    def inter_frame_params(self):
+        fp = abi.FrameParams()
+        _check(abi.lib().av1b_get_inter_frame_params(self._h, C.byref(fp)))
+        return fp
+
+    def frame_is_key(self, frame):
+        rc = abi.lib().av1b_get_frame_is_key(self._h, frame)
+        if rc < 0:
+            raise EncodeError(rc, "frame not kept")
+        return bool(rc)
 
     def cdef_idx(self, frame):
         g = self.geom

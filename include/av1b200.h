@@ -47,7 +47,7 @@ typedef struct av1b_config {
   int32_t host_threads;           /* entropy-coding threads, 0 = auto                              */
   int32_t frames_in_flight;       /* frames batched per device pass, 0 = auto                      */
   int32_t reserved[8];            /* [0]: keep recon+symbols per frame (tests); [1]: fixed block log2 (3..6), 0 = default;
-                                     [2]: 1 = in-loop filters off */
+                                     [2]: 1 = in-loop filters off; [3]: 1 = every frame is a key frame */
 } av1b_config;
 
 typedef struct av1b_encoder av1b_encoder;
@@ -90,13 +90,16 @@ int av1b_get_geom(av1b_encoder* enc, struct Av1bGeom* geom);
 struct Av1bFrameParams;
 /* frame-level parameters the encoder signals for key frames (deblock levels, CDEF presets, ...) */
 int av1b_get_frame_params(av1b_encoder* enc, struct Av1bFrameParams* fp);
+int av1b_get_inter_frame_params(av1b_encoder* enc, struct Av1bFrameParams* fp);
+/* 1 / 0: whether kept frame `frame_in_chunk` was coded as a key frame (needs config.reserved[0] = 1) */
+int av1b_get_frame_is_key(av1b_encoder* enc, uint32_t frame_in_chunk);
 /* chosen CDEF preset per 64x64 superblock of a kept frame: idx[sb_rows*sb_cols] */
 int av1b_get_cdef_idx(av1b_encoder* enc, uint32_t frame_in_chunk, uint8_t* idx);
 /* pure function (no device): deblock levels and CDEF presets from bit depth / quantiser / frame type */
 int av1b_select_frame_params(int bit_depth, int base_q_idx, int frame_type, int loop_filters, struct Av1bFrameParams* fp);
-/* stats[0..11] = h2d_ms, kernel_ms, d2h_ms, pack_ms, kernel_launches, base_q_idx, intra_kernel_ms,
- * intra_kernel_launches, frames_done, bytes_out, deblock_ms, cdef_ms of the last chunk / resident run
- * (CUDA-event times) */
+/* stats[0..15] = h2d_ms, kernel_ms, d2h_ms, pack_ms, kernel_launches, base_q_idx, intra_kernel_ms,
+ * intra_kernel_launches, frames_done, bytes_out, deblock_ms, cdef_ms, inter_kernel_ms, me_ms (pyramid + search),
+ * inter_kernel_launches, key_frames of the last chunk / resident run (CUDA-event times) */
 int av1b_get_stats(av1b_encoder* enc, double* stats, int n);
 
 /* ---- kernel suite (BASELINE.json config 2 "kernel bit-exact suite") -----------------------------

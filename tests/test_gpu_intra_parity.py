@@ -26,7 +26,7 @@ CASES = [
 def test_intra_frame_parity(w, h, bd, crf, blk, tcl, trl, lf):
     frames = synth.synth_clip(w, h, bd, 3, seed=w + h + bd, scene_len=2)
     enc = encoder.Encoder(w, h, bd, crf=crf, keep_debug=True, blk_log2=blk, tile_cols_log2=tcl, tile_rows_log2=trl,
-                          frames_in_flight=2, loop_filters=lf)
+                          frames_in_flight=2, loop_filters=lf, intra_only=True)
     fp = enc.frame_params()
     tus = enc.encode_chunk(frames)
     assert len(tus) == len(frames)
