@@ -92,16 +92,42 @@ def make_frames(w, h, bd, n, hdr):
     return synth.synth_clip(w, h, bd, n, seed=4, scene_len=max(1, n // 2), hdr=hdr)
 
 
-def oracle_fps(frames, w, h, bd, qidx, threads, blk_log2=4):
-    """CPU port of the same path (oracle/av1_oracle.cpp), one frame per thread (ctypes drops the GIL)."""
-    from concurrent.futures import ThreadPoolExecutor
+def oracle_chunk(frames, w, h, bd, qidx):
+    """CPU port of the same path (oracle/av1_oracle.cpp) for one chunk: key frame, then inter frames
+    (hierarchical ME on the source pyramid, motion-compensated residual coding), deblock + CDEF
+    decision + CDEF after every frame.  Scalar code, one thread per chunk."""
+    from av1_base_b200 import abi
     from oracle import pyoracle as O
+    import ctypes as C
     g = O.geom(w, h, 0, 0)
-    pm = O.partition_fixed(g, blk_log2)
+    pm = O.partition_fixed(g, 4)
+    fps = []
+    for ft in (0, 1):
+        fp = abi.FrameParams()
+        abi.lib().av1b_select_frame_params(bd, qidx, ft, 1, C.byref(fp))
+        fps.append(fp)
+    prev_fin = prev_pyr = None
+    for i, fr in enumerate(frames):
+        pyr = O.pyramid(g, O.pad_planes(g, fr)[0])
+        if i == 0:
+            r, fp = O.encode_intra_frame(g, fr, bd, qidx, pm), fps[0]
+        else:
+            r, fp = O.encode_inter_frame(g, fr, bd, qidx, pm, O.hme(g, pyr, prev_pyr), prev_fin), fps[1]
+        O.deblock_frame(g, bd, r.blocks, r.rec, list(fp.lf_level), fp.lf_sharpness)
+        src = O.pad_planes(g, fr)
+        prev_fin = O.cdef_frame(g, bd, r.blocks, fp, O.cdef_search(g, bd, r.blocks, fp, r.rec, src), r.rec)
+        prev_pyr = pyr
+    return len(frames)
+
+
+def oracle_fps(frames, w, h, bd, qidx, threads, chunk_len):
+    """threads independent chunks of chunk_len frames each (av1an-style chunk parallelism; ctypes drops the GIL)."""
+    from concurrent.futures import ThreadPoolExecutor
+    chunks = [[frames[(c + i) % len(frames)] for i in range(chunk_len)] for c in range(threads)]
     t0 = time.perf_counter()
     with ThreadPoolExecutor(threads) as ex:
-        list(ex.map(lambda fr: O.encode_intra_frame(g, fr, bd, qidx, pm), frames))
-    return len(frames) / (time.perf_counter() - t0)
+        n = sum(ex.map(lambda ch: oracle_chunk(ch, w, h, bd, qidx), chunks))
+    return n / (time.perf_counter() - t0)
 
 
 def run_reference(args, rank, world):
@@ -112,24 +138,26 @@ def run_reference(args, rank, world):
     cores = os.cpu_count() or 1
     from av1_base_b200 import abi  # noqa: F401  (tables only; no device use)
     qidx = 120   # CRF 30 -> quantizer_to_qindex[30]
-    per_step = max(1, min(cores, 16))
-    frames = make_frames(w, h, bd, min(per_step, 4), args.workload == "4k10")
-    frames = [frames[i % len(frames)] for i in range(per_step)]
-    for _ in range(args.warmup):
-        oracle_fps(frames[:max(1, per_step // 2)], w, h, bd, qidx, cores)
+    workers = max(1, min(cores, 32))
+    chunk_len = 2 if w > 2000 else 3   # bounded sample: key + inter frame(s) per worker and step
+    per_step = workers * chunk_len
+    frames = make_frames(w, h, bd, 4, args.workload == "4k10")
+    for _ in range(min(args.warmup, 1)):
+        oracle_fps(frames, w, h, bd, qidx, workers, 1)
     t0 = time.perf_counter()
     for _ in range(args.steps):
-        oracle_fps(frames, w, h, bd, qidx, cores)
+        oracle_fps(frames, w, h, bd, qidx, workers, chunk_len)
     dt = time.perf_counter() - t0
     fps = args.steps * per_step / dt
     line = {
         "impl": "reference", "metric": "AV1 encode fps", "value": fps, "unit": "frames/s", "n_gpus": args.gpus,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1000 * dt / args.steps,
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u16/i32", "data": "synthetic",
-        "config": {"workload": desc, "frames_per_step": per_step, "crf": 30, "all_intra": True},
-        "cpu_baseline": {"value": fps, "unit": "frames/s", "cores": cores, "kind": "port",
-                         "sample": "%d steps x %d frames of the workload, one frame per host thread, oracle/av1_oracle.cpp "
-                                   "(av1an+SVT-AV1 itself cannot run in this image: BASELINE.md section 2)" % (args.steps, per_step)},
+        "config": {"workload": desc, "frames_per_step": per_step, "crf": 30, "chunk_len": chunk_len},
+        "cpu_baseline": {"value": fps, "unit": "frames/s", "cores": workers, "kind": "port",
+                         "sample": "%d steps x %d chunks of %d frames (key + inter) of the workload, one chunk per host thread, "
+                                   "scalar oracle/av1_oracle.cpp (av1an+SVT-AV1 itself cannot run in this image: BASELINE.md "
+                                   "section 2)" % (args.steps, workers, chunk_len)},
         "e2e": {"value": fps, "unit": "frames/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "svt_av1_fps": None,
     }
@@ -145,6 +173,7 @@ def main():
     ap.add_argument("--workload", default="4k10", choices=sorted(WORKLOADS))
     ap.add_argument("--frames-per-step", type=int, default=8)
     ap.add_argument("--crf", type=int, default=30)
+    ap.add_argument("--keyint", type=int, default=240)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
 
@@ -174,17 +203,19 @@ def main():
     w, h, bd, desc = WORKLOADS[args.workload]
     F = args.frames_per_step
     hdr = args.workload == "4k10"
-    frames = make_frames(w, h, bd, 2 * F, hdr)          # two device slots of distinct frames (seeded per rank below)
+    frames = make_frames(w, h, bd, F, hdr)               # F consecutive frames of one scene
     if rank:
         frames = frames[rank % len(frames):] + frames[:rank % len(frames)]
-    enc = encoder.Encoder(w, h, bd, crf=args.crf, device_id=local_rank, hdr=hdr, frames_in_flight=F)
+    enc = encoder.Encoder(w, h, bd, crf=args.crf, device_id=local_rank, hdr=hdr, frames_in_flight=F, keyint=args.keyint)
     g = enc.geom
     frame_bytes = sum(g.stride[p] * (h if p == 0 else h // 2) * 2 for p in range(3))
-    alg_bytes_per_frame = 3 * int(1.5 * w * h * 2)     # src read + recon write + int16 levels write
+    S = int(1.5 * w * h * 2)                             # bytes of one 4:2:0 frame at 2 B/sample
 
     # ---------------- value: inputs resident in HBM ----------------
-    enc.stage_frames(0, frames[:F])
-    enc.stage_frames(1, frames[F:2 * F])
+    # slot 0 = frames 0..F-1, slot 1 = the same frames in reverse order: the resident sequence is a
+    # palindrome (0..F-1, F-1..0, 0..F-1, ...), i.e. continuous motion without artificial scene cuts
+    enc.stage_frames(0, frames)
+    enc.stage_frames(1, frames[::-1])
     enc.encode_resident(max(args.warmup, 3))
     sampler = ClockSampler(local_rank)
     barrier()
@@ -204,7 +235,8 @@ def main():
     value = world * args.steps * F / tmax
 
     # ---------------- e2e: host buffers through av1b_encode_chunk ----------------
-    chunk = [frames[i % len(frames)] for i in range(args.steps * F)]
+    pal = frames + frames[::-1]
+    chunk = [pal[i % len(pal)] for i in range(args.steps * F)]
     enc.encode_chunk(chunk[:2 * F])                      # warm-up
     barrier()
     t0 = time.perf_counter()
@@ -216,18 +248,32 @@ def main():
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         dte = float(t.item())
     e2e = world * len(chunk) / dte
-    d2h_per_step = F * (frame_bytes + g.w8 * g.h8 * 16)
+    d2h_per_step = F * (frame_bytes + g.w8 * g.h8 * 20 + g.sb_rows * g.sb_cols)
 
     if rank != 0:
         return
     pk, pk_src = peaks()
-    intra_ms = st["intra_ms"] / max(1, st["intra_launches"])
-    achieved = (alg_bytes_per_frame * F) / (intra_ms * 1e-3) / 1e9
+    n_inter, n_key = max(1, st["inter_launches"]), max(1, st["key_frames"])
+    nf = st["frames_done"]
+    # per-kernel CUDA-event time per launch (one launch = one frame, except ME = one batch) and
+    # algorithmic bytes per launch
+    kern = {
+        "inter_encode_kernel": (st["inter_ms"] / n_inter, 4 * S),
+        "intra_encode_kernel": (st["intra_ms"] / n_key, 3 * S),
+        "deblock_kernel": (st["deblock_ms"] / max(1, nf), 2 * S),
+        "cdef_kernel": (st["cdef_ms"] / max(1, nf), 3 * S),
+        "pyramid+hme (per batch)": (st["me_ms"] / max(1, args.steps), int((1.3125 + 0.625 + 2.0) * (w * h * 2)) * F),
+    }
+    share = {"inter_encode_kernel": st["inter_ms"], "intra_encode_kernel": st["intra_ms"], "deblock_kernel": st["deblock_ms"],
+             "cdef_kernel": st["cdef_ms"], "pyramid+hme (per batch)": st["me_ms"]}
+    dom = max(share, key=lambda k: share[k])
+    dom_ms, dom_bytes = kern[dom]
+    achieved = dom_bytes / (dom_ms * 1e-3) / 1e9 if dom_ms > 0 else 0.0
     traffic = None
-    tp = os.path.join(ROOT, "profiles", "intra_traffic.json")
+    tp = os.path.join(ROOT, "profiles", "traffic.json")
     if os.path.exists(tp):
         try:
-            traffic = json.load(open(tp)).get(args.workload)
+            traffic = json.load(open(tp)).get(args.workload, {}).get(dom)
         except Exception:
             traffic = None
     line = {
@@ -235,27 +281,34 @@ def main():
         "warmup": max(args.warmup, 3), "ms_per_step": 1000 * tmax / args.steps, "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": "u16/i32", "data": "synthetic",
         "config": {"workload": desc, "frames_per_step": F, "crf": args.crf, "base_q_idx": st["base_q_idx"],
-                   "all_intra": True, "tiles": "%dx%d" % (g.tile_cols, g.tile_rows),
-                   "l2": "inputs larger than L2 (%.0f MB per step)" % (3 * F * frame_bytes / 1e6),
+                   "keyint": args.keyint, "key_frames": st["key_frames"], "inter_frames": st["inter_launches"],
+                   "tiles": "%dx%d" % (g.tile_cols, g.tile_rows),
+                   "l2": "inputs larger than L2 (%.0f MB working set per step)" % (5 * F * frame_bytes / 1e6),
                    "timing": "wall clock between synchronize+barrier pairs (host entropy coding is part of the step); "
                              "kernel times from CUDA events on the encoder stream"},
         "e2e": {"value": e2e, "unit": "frames/s", "h2d_bytes_per_step": F * frame_bytes, "d2h_bytes_per_step": d2h_per_step,
                 "bitrate_bytes_per_frame": sum(map(len, tus)) / len(tus),
                 "breakdown_ms_per_step": {k: st_e[k] / args.steps for k in ("h2d_ms", "kernel_ms", "d2h_ms", "pack_ms")}},
         "gpu_launches": st["kernel_launches"],
-        "breakdown_ms_per_step": {k: st[k] / args.steps for k in ("kernel_ms", "d2h_ms", "pack_ms")},
-        "roofline": {"kernel": "intra_encode_kernel", "bound": "hbm", "achieved": achieved, "peak": pk["hbm_gbs"],
+        "breakdown_ms_per_step": {k: st[k] / args.steps for k in ("kernel_ms", "me_ms", "intra_ms", "inter_ms", "deblock_ms",
+                                                                   "cdef_ms", "d2h_ms", "pack_ms")},
+        "roofline": {"kernel": dom, "bound": "hbm", "achieved": achieved, "peak": pk["hbm_gbs"],
                      "unit": "GB/s", "frac": achieved / pk["hbm_gbs"], "traffic": traffic, "peak_source": pk_src,
-                     "ms_per_launch": intra_ms, "algorithmic_bytes_per_launch": alg_bytes_per_frame * F},
+                     "ms_per_launch": dom_ms, "algorithmic_bytes_per_launch": dom_bytes,
+                     "kernels": {k: {"ms_per_launch": v[0], "algorithmic_bytes": v[1],
+                                     "frac": (v[1] / (v[0] * 1e-3) / 1e9 / pk["hbm_gbs"]) if v[0] > 0 else None}
+                                 for k, v in kern.items()}},
         "clocks": clocks,
         "svt_av1_fps": None,
     }
     if not args.no_cpu_baseline and world == 1:
         cores = os.cpu_count() or 1
-        nsample = max(1, min(cores, F))
-        fps = oracle_fps(frames[:nsample], w, h, bd, st["base_q_idx"], cores)
-        line["cpu_baseline"] = {"value": fps, "unit": "frames/s", "cores": cores, "kind": "port",
-                                "sample": "%d frames of the workload, one per host thread (oracle/av1_oracle.cpp)" % nsample}
+        workers = max(1, min(cores, 32))
+        chunk_len = 2 if w > 2000 else 3
+        fps = oracle_fps(frames, w, h, bd, st["base_q_idx"], workers, chunk_len)
+        line["cpu_baseline"] = {"value": fps, "unit": "frames/s", "cores": workers, "kind": "port",
+                                "sample": "%d chunks of %d frames (key + inter) of the workload, one chunk per host thread, scalar "
+                                          "oracle/av1_oracle.cpp" % (workers, chunk_len)}
     print(json.dumps(line), flush=True)
     if dist is not None:
         dist.destroy_process_group()
