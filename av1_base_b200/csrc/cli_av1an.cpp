@@ -1,1 +1,537 @@
-int main() { return 0; }
+// `av1an`-compatible command line front end of the B200 AV1 encode backend: the PATH executable the
+// reference daemon execs (/root/reference/crates/daemon/src/encode/av1an.rs:79-107 build_av1an_command,
+// :126-139 run_av1an; `av1an --version` in startup.rs:98-116).  Same argv, same exit-code contract
+// (0 = success, non-zero = EncodeError::Av1anFailed(code)), complete file at -o or no file at all,
+// everything temporary under --temp.
+//
+//   av1an -i IN -o OUT --encoder svt-av1 --pix-format yuv420p10le --video-params "--crf 30 --preset 6 ..."
+//         --audio-params "-c:a copy" --workers N --temp DIR
+//
+// --workers N is the number of GPUs this job uses: the clip is cut into closed-GOP chunks of --keyint
+// frames (av1an-style chunking), chunk c is encoded by worker c mod N on its own GPU, and the chunk
+// streams are concatenated on the host in order (no exchange between GPUs).
+// Input: YUV4MPEG2 (4:2:0, 8 or 10 bit) read directly and seekably; anything else is decoded through
+// an `ffmpeg` pipe when ffmpeg is on PATH.  Output by extension: .mkv (Matroska, V_AV1), .ivf, .obu.
+#include <errno.h>
+#include <fcntl.h>
+#include <stdarg.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+#include <sys/file.h>
+#include <sys/stat.h>
+#include <unistd.h>
+#include <algorithm>
+#include <atomic>
+#include <chrono>
+#include <condition_variable>
+#include <deque>
+#include <mutex>
+#include <string>
+#include <thread>
+#include <vector>
+#include "../../include/av1b200.h"
+
+namespace {
+
+[[noreturn]] void die(int code, const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  fprintf(stderr, "av1an (av1b200): ");
+  vfprintf(stderr, fmt, ap);
+  fprintf(stderr, "\n");
+  va_end(ap);
+  exit(code);
+}
+
+struct Options {
+  std::string input, output, temp, encoder = "svt-av1", pix_format = "yuv420p10le", video_params, audio_params;
+  int workers = 1;
+  int crf = 30, preset = 6, keyint = 240, lookahead = 0, film_grain = 0, enable_qm = 0, qm_min = 0, qm_max = 15;
+  bool quiet = false;
+};
+
+// --video-params carries SVT-AV1 style flags (av1an.rs:14 SVT_PARAMS)
+void parse_video_params(const std::string& vp, Options& o) {
+  std::vector<std::string> tok;
+  size_t i = 0;
+  while (i < vp.size()) {
+    while (i < vp.size() && isspace((unsigned char)vp[i])) i++;
+    size_t j = i;
+    while (j < vp.size() && !isspace((unsigned char)vp[j])) j++;
+    if (j > i) tok.push_back(vp.substr(i, j - i));
+    i = j;
+  }
+  for (size_t k = 0; k + 1 < tok.size(); k++) {
+    const std::string& f = tok[k];
+    const int v = atoi(tok[k + 1].c_str());
+    if (f == "--crf") o.crf = v;
+    else if (f == "--preset") o.preset = v;
+    else if (f == "--keyint") o.keyint = v;
+    else if (f == "--lookahead") o.lookahead = v;
+    else if (f == "--film-grain") o.film_grain = v;
+    else if (f == "--enable-qm") o.enable_qm = v;
+    else if (f == "--qm-min") o.qm_min = v;
+    else if (f == "--qm-max") o.qm_max = v;
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// Input: YUV4MPEG2
+// ---------------------------------------------------------------------------------------------
+struct Y4m {
+  FILE* f = nullptr;
+  bool pipe = false;
+  int w = 0, h = 0, fps_num = 30, fps_den = 1, bits = 8;
+  long header_len = 0;
+  int64_t n_frames = -1;     // -1: unknown (pipe)
+  size_t frame_bytes = 0;
+};
+
+bool y4m_parse_header(Y4m& y) {
+  char line[512];
+  int n = 0, c;
+  while ((c = fgetc(y.f)) != EOF && c != '\n' && n < 511) line[n++] = (char)c;
+  line[n] = 0;
+  if (strncmp(line, "YUV4MPEG2", 9) != 0) return false;
+  y.header_len = n + 1;
+  std::string cs = "420";
+  for (char* t = strtok(line + 9, " "); t; t = strtok(nullptr, " ")) {
+    if (t[0] == 'W') y.w = atoi(t + 1);
+    else if (t[0] == 'H') y.h = atoi(t + 1);
+    else if (t[0] == 'F') sscanf(t + 1, "%d:%d", &y.fps_num, &y.fps_den);
+    else if (t[0] == 'C') cs = t + 1;
+  }
+  if (cs.compare(0, 3, "420") != 0) die(3, "unsupported Y4M colourspace C%s (only 4:2:0)", cs.c_str());
+  if (cs.find("p10") != std::string::npos) y.bits = 10;
+  else if (cs.find("p12") != std::string::npos || cs.find("p16") != std::string::npos) die(3, "unsupported Y4M bit depth (C%s)", cs.c_str());
+  const size_t bps = y.bits > 8 ? 2 : 1;
+  y.frame_bytes = ((size_t)y.w * y.h + 2 * (size_t)((y.w + 1) / 2) * ((y.h + 1) / 2)) * bps;
+  return y.w > 0 && y.h > 0;
+}
+
+// one frame as uint16 planes (contiguous Y, U, V); returns false at end of stream
+bool y4m_read_frame(Y4m& y, std::vector<uint8_t>& raw, uint16_t* dst, int shift) {
+  char hdr[256];
+  int n = 0, c;
+  while ((c = fgetc(y.f)) != EOF && c != '\n' && n < 255) hdr[n++] = (char)c;
+  if (c == EOF) return false;
+  hdr[n] = 0;
+  if (strncmp(hdr, "FRAME", 5) != 0) die(3, "corrupt Y4M stream (expected FRAME)");
+  raw.resize(y.frame_bytes);
+  if (fread(raw.data(), 1, y.frame_bytes, y.f) != y.frame_bytes) die(3, "truncated Y4M frame");
+  const size_t ns = y.bits > 8 ? y.frame_bytes / 2 : y.frame_bytes;
+  if (y.bits > 8) {
+    const uint16_t* s = reinterpret_cast<const uint16_t*>(raw.data());
+    for (size_t i = 0; i < ns; i++) dst[i] = s[i];
+  } else {
+    for (size_t i = 0; i < ns; i++) dst[i] = (uint16_t)(raw[i] << shift);
+  }
+  return true;
+}
+
+// ---------------------------------------------------------------------------------------------
+// Output containers
+// ---------------------------------------------------------------------------------------------
+struct Packet { std::vector<uint8_t> data; bool key; };
+
+void put_le(std::vector<uint8_t>& o, uint64_t v, int n) { for (int i = 0; i < n; i++) o.push_back((uint8_t)(v >> (8 * i))); }
+
+// strips the temporal delimiter OBU (type 2) at the head of a temporal unit
+const uint8_t* skip_td(const uint8_t* p, size_t& n) {
+  if (n >= 2 && ((p[0] >> 3) & 15) == 2 && p[1] == 0) { n -= 2; return p + 2; }
+  return p;
+}
+// first OBU of the given type inside a temporal unit (low-overhead format, obu_has_size_field = 1)
+bool find_obu(const uint8_t* p, size_t n, int type, const uint8_t** start, size_t* len) {
+  size_t i = 0;
+  while (i < n) {
+    const int t = (p[i] >> 3) & 15, ext = (p[i] >> 2) & 1;
+    size_t j = i + 1 + ext, sz = 0;
+    int sh = 0;
+    while (j < n) { const uint8_t b = p[j++]; sz |= (size_t)(b & 0x7F) << sh; sh += 7; if (!(b & 0x80)) break; }
+    if (t == type) { *start = p + i; *len = (j - i) + sz; return true; }
+    i = j + sz;
+  }
+  return false;
+}
+
+void ebml_id(std::vector<uint8_t>& o, uint32_t id) {
+  if (id > 0xFFFFFF) o.push_back((uint8_t)(id >> 24));
+  if (id > 0xFFFF) o.push_back((uint8_t)(id >> 16));
+  if (id > 0xFF) o.push_back((uint8_t)(id >> 8));
+  o.push_back((uint8_t)id);
+}
+void ebml_size(std::vector<uint8_t>& o, uint64_t n) {   // always 8 bytes: simple and patchable
+  o.push_back(0x01);
+  for (int i = 6; i >= 0; i--) o.push_back((uint8_t)(n >> (8 * i)));
+}
+void ebml_uint(std::vector<uint8_t>& o, uint32_t id, uint64_t v) {
+  ebml_id(o, id);
+  int n = 1;
+  while (n < 8 && (v >> (8 * n))) n++;
+  o.push_back((uint8_t)(0x80 | n));
+  for (int i = n - 1; i >= 0; i--) o.push_back((uint8_t)(v >> (8 * i)));
+}
+void ebml_bytes(std::vector<uint8_t>& o, uint32_t id, const void* p, size_t n) {
+  ebml_id(o, id);
+  ebml_size(o, n);
+  o.insert(o.end(), (const uint8_t*)p, (const uint8_t*)p + n);
+}
+void ebml_str(std::vector<uint8_t>& o, uint32_t id, const char* s) { ebml_bytes(o, id, s, strlen(s)); }
+void ebml_master(std::vector<uint8_t>& o, uint32_t id, const std::vector<uint8_t>& body) { ebml_bytes(o, id, body.data(), body.size()); }
+void ebml_float(std::vector<uint8_t>& o, uint32_t id, double v) {
+  ebml_id(o, id);
+  o.push_back(0x88);
+  uint64_t u;
+  memcpy(&u, &v, 8);
+  for (int i = 7; i >= 0; i--) o.push_back((uint8_t)(u >> (8 * i)));
+}
+
+// Minimal Matroska (video only): EBML header, Segment { Info, Tracks { V_AV1 }, Cluster* { SimpleBlock* } }
+bool write_mkv(const std::string& path, const std::vector<Packet>& pk, int w, int h, int fps_num, int fps_den, bool hbd) {
+  std::vector<uint8_t> out, hdr;
+  ebml_uint(hdr, 0x4286, 1); ebml_uint(hdr, 0x42F7, 1); ebml_uint(hdr, 0x42F2, 4); ebml_uint(hdr, 0x42F3, 8);
+  ebml_str(hdr, 0x4282, "matroska"); ebml_uint(hdr, 0x4287, 4); ebml_uint(hdr, 0x4285, 2);
+  ebml_master(out, 0x1A45DFA3, hdr);
+  std::vector<uint8_t> seg, info, tracks, te, video;
+  const double frame_ms = 1000.0 * fps_den / fps_num;
+  ebml_uint(info, 0x2AD7B1, 1000000);                           // TimestampScale: 1 ms
+  ebml_float(info, 0x4489, frame_ms * pk.size());               // Duration
+  ebml_str(info, 0x4D80, "av1b200"); ebml_str(info, 0x5741, "av1b200");
+  ebml_master(seg, 0x1549A966, info);
+  // CodecPrivate = AV1CodecConfigurationRecord: marker/version, profile/level, flags, then the sequence header OBU
+  std::vector<uint8_t> av1c;
+  const uint8_t* sh = nullptr; size_t shn = 0;
+  if (!pk.empty()) find_obu(pk[0].data.data(), pk[0].data.size(), 1, &sh, &shn);
+  av1c.push_back(0x81);
+  av1c.push_back((uint8_t)((0 << 5) | 31));                       // seq_profile 0, seq_level_idx_0 31
+  av1c.push_back((uint8_t)((0 << 7) | ((hbd ? 1 : 0) << 6) | (0 << 5) | (0 << 4) | (1 << 3) | (1 << 2) | 0));
+  av1c.push_back(0);
+  if (sh) av1c.insert(av1c.end(), sh, sh + shn);
+  ebml_uint(video, 0xB0, (uint64_t)w); ebml_uint(video, 0xBA, (uint64_t)h);
+  ebml_uint(te, 0xD7, 1); ebml_uint(te, 0x73C5, 1); ebml_uint(te, 0x83, 1); ebml_uint(te, 0x9C, 0);
+  ebml_str(te, 0x86, "V_AV1");
+  ebml_bytes(te, 0x63A2, av1c.data(), av1c.size());
+  ebml_uint(te, 0x23E383, (uint64_t)(frame_ms * 1e6));          // DefaultDuration (ns)
+  ebml_master(te, 0xE0, video);
+  ebml_master(tracks, 0xAE, te);
+  ebml_master(seg, 0x1654AE6B, tracks);
+  // clusters: a new one at every key frame and at least every 30000 ms of timestamps (int16 block offsets)
+  std::vector<uint8_t> cl;
+  double cl_t0 = 0;
+  auto flush = [&]() { if (!cl.empty()) { ebml_master(seg, 0x1F43B675, cl); cl.clear(); } };
+  for (size_t k = 0; k < pk.size(); k++) {
+    const double ts = frame_ms * k;
+    if (cl.empty() || pk[k].key || ts - cl_t0 > 30000) { flush(); cl_t0 = ts; ebml_uint(cl, 0xE7, (uint64_t)(ts + 0.5)); }
+    size_t n = pk[k].data.size();
+    const uint8_t* p = skip_td(pk[k].data.data(), n);
+    std::vector<uint8_t> blk;
+    blk.push_back(0x81);
+    const int rel = (int)(ts - cl_t0 + 0.5);
+    blk.push_back((uint8_t)(rel >> 8)); blk.push_back((uint8_t)rel);
+    blk.push_back(pk[k].key ? 0x80 : 0x00);
+    blk.insert(blk.end(), p, p + n);
+    ebml_bytes(cl, 0xA3, blk.data(), blk.size());
+  }
+  flush();
+  ebml_master(out, 0x18538067, seg);
+  FILE* f = fopen(path.c_str(), "wb");
+  if (!f) return false;
+  const bool ok = fwrite(out.data(), 1, out.size(), f) == out.size();
+  return fclose(f) == 0 && ok;
+}
+
+bool write_ivf(const std::string& path, const std::vector<Packet>& pk, int w, int h, int fps_num, int fps_den) {
+  std::vector<uint8_t> o;
+  o.insert(o.end(), {'D', 'K', 'I', 'F'});
+  put_le(o, 0, 2); put_le(o, 32, 2);
+  o.insert(o.end(), {'A', 'V', '0', '1'});
+  put_le(o, (uint64_t)w, 2); put_le(o, (uint64_t)h, 2); put_le(o, (uint64_t)fps_num, 4); put_le(o, (uint64_t)fps_den, 4);
+  put_le(o, pk.size(), 4); put_le(o, 0, 4);
+  for (size_t k = 0; k < pk.size(); k++) {
+    put_le(o, pk[k].data.size(), 4); put_le(o, k, 8);
+    o.insert(o.end(), pk[k].data.begin(), pk[k].data.end());
+  }
+  FILE* f = fopen(path.c_str(), "wb");
+  if (!f) return false;
+  const bool ok = fwrite(o.data(), 1, o.size(), f) == o.size();
+  return fclose(f) == 0 && ok;
+}
+
+bool write_obu(const std::string& path, const std::vector<Packet>& pk) {
+  FILE* f = fopen(path.c_str(), "wb");
+  if (!f) return false;
+  bool ok = true;
+  for (auto& p : pk) ok = ok && fwrite(p.data.data(), 1, p.data.size(), f) == p.data.size();
+  return fclose(f) == 0 && ok;
+}
+
+// ---------------------------------------------------------------------------------------------
+// GPU leases: concurrent jobs of the daemon (max_concurrent_jobs > 1) must not share a device
+// ---------------------------------------------------------------------------------------------
+int lease_device(int dev, bool block) {
+  char path[128];
+  snprintf(path, sizeof(path), "/tmp/av1b200-gpu%d.lock", dev);
+  const int fd = open(path, O_CREAT | O_RDWR, 0666);
+  if (fd < 0) return -1;
+  if (flock(fd, LOCK_EX | (block ? 0 : LOCK_NB)) != 0) { close(fd); return -1; }
+  return fd;
+}
+
+struct Part {
+  int64_t chunk = 0, first_frame = 0;
+  bool first_part = false;
+  int n = 0;
+  std::vector<uint16_t> samples;   // n frames, each Y U V contiguous
+};
+
+struct Shared {
+  std::mutex m;
+  std::vector<std::vector<Packet>> chunk_out;   // [chunk] packets in order
+  std::atomic<int64_t> frames_done{0};
+  std::atomic<int> failed{0};
+  std::string error;
+  int64_t total_frames = -1;
+  std::chrono::steady_clock::time_point t0;
+  std::string progress_path;
+  bool quiet = false;
+};
+
+struct PacketCtx { Shared* sh; int64_t chunk; };
+
+int on_packet(void* user, const uint8_t* data, size_t size, int64_t, int is_key) {
+  PacketCtx* c = static_cast<PacketCtx*>(user);
+  Packet p;
+  p.data.assign(data, data + size);
+  p.key = is_key != 0;
+  std::lock_guard<std::mutex> l(c->sh->m);
+  c->sh->chunk_out[(size_t)c->chunk].push_back(std::move(p));
+  return 0;
+}
+
+void report_progress(Shared& sh, bool final_line) {
+  const int64_t done = sh.frames_done.load();
+  const double el = std::chrono::duration<double>(std::chrono::steady_clock::now() - sh.t0).count();
+  const double fps = el > 0 ? done / el : 0;
+  char line[256];
+  snprintf(line, sizeof(line), "{\"frames_encoded\": %lld, \"total_frames\": %lld, \"fps\": %.2f, \"done\": %s}",
+           (long long)done, (long long)sh.total_frames, fps, final_line ? "true" : "false");
+  if (!sh.quiet) { printf("%s\n", line); fflush(stdout); }
+  if (!sh.progress_path.empty()) {
+    const std::string tmp = sh.progress_path + ".tmp";
+    if (FILE* f = fopen(tmp.c_str(), "w")) { fprintf(f, "%s\n", line); fclose(f); rename(tmp.c_str(), sh.progress_path.c_str()); }
+  }
+}
+
+}  // namespace
+
+int main(int argc, char** argv) {
+  Options o;
+  for (int i = 1; i < argc; i++) {
+    const std::string a = argv[i];
+    auto val = [&](const char* name) -> std::string {
+      if (i + 1 >= argc) die(2, "missing value for %s", name);
+      return argv[++i];
+    };
+    if (a == "--version" || a == "-V") {
+      char buf[128];
+      av1b_version(buf, sizeof(buf));
+      printf("av1an-compatible front end: %s\n", buf);
+      return 0;
+    } else if (a == "--help" || a == "-h") {
+      printf("usage: av1an -i IN -o OUT [--encoder svt-av1] [--pix-format yuv420p10le] [--video-params \"--crf N --preset N --keyint N ...\"]\n"
+             "             [--audio-params S] [--workers N(GPUs)] [--temp DIR] [--quiet]\n");
+      return 0;
+    } else if (a == "-i") o.input = val("-i");
+    else if (a == "-o") o.output = val("-o");
+    else if (a == "--encoder" || a == "-e") o.encoder = val("--encoder");
+    else if (a == "--pix-format") o.pix_format = val("--pix-format");
+    else if (a == "--video-params" || a == "-v") o.video_params = val("--video-params");
+    else if (a == "--audio-params" || a == "-a") o.audio_params = val("--audio-params");
+    else if (a == "--workers" || a == "-w") o.workers = atoi(val("--workers").c_str());
+    else if (a == "--temp") o.temp = val("--temp");
+    else if (a == "--quiet" || a == "-q") o.quiet = true;
+    else die(2, "unknown argument %s", a.c_str());
+  }
+  if (o.input.empty() || o.output.empty()) die(2, "-i and -o are required");
+  if (o.encoder != "svt-av1") die(2, "unsupported --encoder %s (the daemon passes svt-av1)", o.encoder.c_str());
+  if (o.workers < 1) die(2, "--workers must be >= 1");
+  parse_video_params(o.video_params, o);
+  if (o.crf < 0 || o.crf > 63) die(2, "--crf out of range 0..63");
+  if (o.keyint < 1) o.keyint = 240;
+  int out_bits = 10;
+  if (o.pix_format == "yuv420p") out_bits = 8;
+  else if (o.pix_format != "yuv420p10le") die(2, "unsupported --pix-format %s (yuv420p, yuv420p10le)", o.pix_format.c_str());
+
+  const int ndev = av1b_device_count();
+  if (ndev <= 0) die(4, "no CUDA device visible: this backend has no CPU fallback");
+  // AV1B_SHARE_GPU=1 (tests): let several workers share one device so that chunk scheduling and
+  // concatenation can be exercised on a single-GPU box
+  const bool share = getenv("AV1B_SHARE_GPU") && atoi(getenv("AV1B_SHARE_GPU")) != 0;
+  const int n_workers = share ? o.workers : std::min(o.workers, ndev);
+
+  // ---- input ----
+  Y4m in;
+  in.f = fopen(o.input.c_str(), "rb");
+  if (!in.f) die(3, "cannot open %s: %s", o.input.c_str(), strerror(errno));
+  if (!y4m_parse_header(in)) {
+    fclose(in.f);
+    if (system("ffmpeg -version > /dev/null 2>&1") != 0)
+      die(3, "%s is not YUV4MPEG2 and no ffmpeg is on PATH to decode it", o.input.c_str());
+    std::string q;
+    for (char c : o.input) { if (c == '\'') q += "'\\''"; else q += c; }
+    const std::string cmd = "ffmpeg -v error -i '" + q + "' -map 0:v:0 -pix_fmt " + o.pix_format + " -strict -1 -f yuv4mpegpipe -";
+    in.f = popen(cmd.c_str(), "r");
+    in.pipe = true;
+    if (!in.f || !y4m_parse_header(in)) die(3, "ffmpeg could not decode %s", o.input.c_str());
+  } else {
+    struct stat st;
+    if (fstat(fileno(in.f), &st) == 0 && S_ISREG(st.st_mode))
+      in.n_frames = (st.st_size - in.header_len) / (int64_t)(6 + in.frame_bytes);
+  }
+  if ((in.w & 7) || (in.h & 7)) die(3, "frame size %dx%d is not a multiple of 8", in.w, in.h);
+  if (in.bits > out_bits) die(3, "input is %d-bit but --pix-format asks for %d-bit", in.bits, out_bits);
+  const int shift = out_bits - in.bits;
+  const size_t frame_samples = (size_t)in.w * in.h * 3 / 2;
+
+  Shared sh;
+  sh.total_frames = in.n_frames;
+  sh.t0 = std::chrono::steady_clock::now();
+  sh.quiet = o.quiet;
+  if (!o.temp.empty()) { mkdir(o.temp.c_str(), 0777); sh.progress_path = o.temp + "/progress.json"; }
+
+  // ---- devices ----
+  std::vector<int> dev, lease;
+  for (int pass = 0; pass < 2 && (int)dev.size() < n_workers; pass++)
+    for (int d = 0; d < ndev && (int)dev.size() < n_workers; d++) {
+      if (std::find(dev.begin(), dev.end(), d) != dev.end()) continue;
+      const int fd = lease_device(d, pass == 1);
+      if (fd >= 0) { dev.push_back(d); lease.push_back(fd); }
+    }
+  if (dev.empty()) die(4, "no GPU lease available");
+  if (share) while ((int)dev.size() < n_workers) dev.push_back(dev[dev.size() % lease.size()]);
+
+  // ---- workers: one encoder handle (= one GPU) each, fed with chunk parts through a bounded queue ----
+  const int kPart = 32;
+  struct Queue { std::mutex m; std::condition_variable cv; std::deque<Part> q; bool closed = false; };
+  const int W = (int)dev.size();
+  std::vector<Queue> queues(W);
+  std::vector<std::thread> threads;
+  for (int wk = 0; wk < W; wk++) {
+    threads.emplace_back([&, wk]() {
+      av1b_config cfg;
+      av1b_config_default(&cfg);
+      cfg.width = in.w; cfg.height = in.h; cfg.bit_depth = out_bits;
+      cfg.fps_num = in.fps_num; cfg.fps_den = in.fps_den;
+      cfg.crf = o.crf; cfg.preset = o.preset; cfg.keyint = o.keyint; cfg.lookahead = o.lookahead;
+      cfg.film_grain = o.film_grain; cfg.enable_qm = o.enable_qm; cfg.qm_min = o.qm_min; cfg.qm_max = o.qm_max;
+      cfg.device_id = dev[wk];
+      cfg.host_threads = std::max(1u, std::thread::hardware_concurrency() / (unsigned)W);
+      av1b_encoder* enc = nullptr;
+      int rc = av1b_encoder_create(&cfg, &enc);
+      if (rc != AV1B_OK) {
+        std::lock_guard<std::mutex> l(sh.m);
+        if (!sh.failed) { sh.failed = -rc; sh.error = av1b_last_error(); }
+      }
+      for (;;) {
+        Part part;
+        {
+          std::unique_lock<std::mutex> l(queues[wk].m);
+          queues[wk].cv.wait(l, [&] { return !queues[wk].q.empty() || queues[wk].closed; });
+          if (queues[wk].q.empty()) break;
+          part = std::move(queues[wk].q.front());
+          queues[wk].q.pop_front();
+        }
+        queues[wk].cv.notify_all();
+        if (sh.failed || !enc) continue;   // drain
+        std::vector<av1b_frame_src> fs((size_t)part.n);
+        for (int k = 0; k < part.n; k++) {
+          uint16_t* b = part.samples.data() + (size_t)k * frame_samples;
+          fs[k].planes[0] = b; fs[k].planes[1] = b + (size_t)in.w * in.h; fs[k].planes[2] = b + (size_t)in.w * in.h * 5 / 4;
+          fs[k].stride[0] = in.w; fs[k].stride[1] = fs[k].stride[2] = in.w / 2;
+        }
+        PacketCtx ctx{&sh, part.chunk};
+        rc = av1b_encode_part(enc, fs.data(), (uint32_t)part.n, part.first_part ? 1 : 0, part.first_frame, on_packet, nullptr, &ctx);
+        if (rc != AV1B_OK) {
+          std::lock_guard<std::mutex> l(sh.m);
+          if (!sh.failed) { sh.failed = -rc; sh.error = av1b_last_error(); }
+          continue;
+        }
+        sh.frames_done += part.n;
+      }
+      if (enc) av1b_encoder_destroy(enc);
+    });
+  }
+
+  // ---- reader: sequential, chunk c -> worker c mod W ----
+  std::vector<uint8_t> raw;
+  int64_t frame = 0;
+  bool eof = false;
+  auto last_report = std::chrono::steady_clock::now();
+  while (!eof && !sh.failed) {
+    const int64_t chunk = frame / o.keyint;
+    const int in_chunk = (int)(frame % o.keyint);
+    const int want = std::min(kPart, o.keyint - in_chunk);
+    Part part;
+    part.chunk = chunk; part.first_frame = frame; part.first_part = in_chunk == 0;
+    part.samples.resize((size_t)want * frame_samples);
+    int got = 0;
+    while (got < want) {
+      if (!y4m_read_frame(in, raw, part.samples.data() + (size_t)got * frame_samples, shift)) { eof = true; break; }
+      got++;
+    }
+    if (got == 0) break;
+    part.n = got;
+    frame += got;
+    {
+      std::lock_guard<std::mutex> l(sh.m);
+      if ((int64_t)sh.chunk_out.size() <= chunk) sh.chunk_out.resize((size_t)chunk + 1);
+    }
+    Queue& q = queues[(size_t)(chunk % W)];
+    {
+      std::unique_lock<std::mutex> l(q.m);
+      q.cv.wait(l, [&] { return q.q.size() < 2; });
+      q.q.push_back(std::move(part));
+    }
+    q.cv.notify_all();
+    const auto now = std::chrono::steady_clock::now();
+    if (std::chrono::duration<double>(now - last_report).count() > 1.0) { report_progress(sh, false); last_report = now; }
+  }
+  for (auto& q : queues) { { std::lock_guard<std::mutex> l(q.m); q.closed = true; } q.cv.notify_all(); }
+  for (auto& t : threads) t.join();
+  if (in.pipe) pclose(in.f); else fclose(in.f);
+  for (int fd : lease) close(fd);
+  if (sh.total_frames < 0) sh.total_frames = frame;
+
+  if (sh.failed) {
+    unlink(o.output.c_str());
+    die(sh.failed, "encode failed: %s", sh.error.c_str());
+  }
+  if (frame == 0) die(3, "input has no frames");
+
+  // ---- concatenate the chunk streams in order and write the container ----
+  std::vector<Packet> all;
+  for (auto& c : sh.chunk_out) for (auto& p : c) all.push_back(std::move(p));
+  if ((int64_t)all.size() != frame) { unlink(o.output.c_str()); die(5, "internal error: %zu packets for %lld frames", all.size(), (long long)frame); }
+  const std::string tmp_out = o.output + ".part";
+  bool ok;
+  const size_t dot = o.output.rfind('.');
+  const std::string ext = dot == std::string::npos ? "" : o.output.substr(dot);
+  if (ext == ".ivf") ok = write_ivf(tmp_out, all, in.w, in.h, in.fps_num, in.fps_den);
+  else if (ext == ".obu") ok = write_obu(tmp_out, all);
+  else ok = write_mkv(tmp_out, all, in.w, in.h, in.fps_num, in.fps_den, out_bits > 8);
+  if (ok && in.pipe && ext != ".ivf" && ext != ".obu" && o.audio_params.find("copy") != std::string::npos) {
+    // the source went through ffmpeg, so ffmpeg is available: copy its audio streams next to our video
+    std::string qi, qo;
+    for (char c : o.input) { if (c == '\'') qi += "'\\''"; else qi += c; }
+    for (char c : tmp_out) { if (c == '\'') qo += "'\\''"; else qo += c; }
+    const std::string mux = "ffmpeg -v error -y -i '" + qo + "' -i '" + qi + "' -map 0:v:0 -map 1:a? -c copy -f matroska '" + qo + ".mux'";
+    if (system(mux.c_str()) == 0) rename((tmp_out + ".mux").c_str(), tmp_out.c_str());
+    else unlink((tmp_out + ".mux").c_str());   // keep the video-only file
+  }
+  if (!ok || rename(tmp_out.c_str(), o.output.c_str()) != 0) { unlink(tmp_out.c_str()); die(6, "cannot write %s", o.output.c_str()); }
+  report_progress(sh, true);
+  return 0;
+}

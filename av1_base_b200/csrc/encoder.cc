@@ -508,6 +508,27 @@ int av1b_encode_chunk(av1b_encoder* e, const av1b_frame_src* frames, uint32_t n_
   return AV1B_OK;
 }
 
+// Streaming variant: a chunk handed over in parts (bounded host memory for long chunks).  The part
+// with first_part != 0 starts a new closed GOP (key frame); every call returns after its frames have
+// been delivered to out_cb.
+int av1b_encode_part(av1b_encoder* e, const av1b_frame_src* frames, uint32_t n_frames, int first_part,
+                     int64_t first_frame_index, av1b_packet_cb out_cb, av1b_progress_cb prog_cb, void* user) {
+  if (!e || !frames || !out_cb || n_frames == 0) { set_error("null argument"); return AV1B_ERR_INVALID; }
+  CK(cudaSetDevice(e->cfg.device_id));
+  if (first_part) { reset_stats(e); e->chunk_pos = 0; }
+  const auto t0 = std::chrono::steady_clock::now();
+  int rc, i = 0;
+  for (uint32_t f0 = 0; f0 < n_frames; f0 += e->batch, i++) {
+    const int nb = (int)std::min<uint32_t>(e->batch, n_frames - f0);
+    Slot& s = e->slot[i & 1];
+    if ((rc = stage(e, s, frames + f0, nb)) != AV1B_OK) return rc;
+    if ((rc = launch(e, s, nb, first_frame_index + f0)) != AV1B_OK) return rc;
+    if (i > 0 && (rc = finish(e, e->slot[(i - 1) & 1], true, out_cb, prog_cb, user, 0, t0)) != AV1B_OK) return rc;
+  }
+  if (i > 0 && (rc = finish(e, e->slot[(i - 1) & 1], true, out_cb, prog_cb, user, 0, t0)) != AV1B_OK) return rc;
+  return AV1B_OK;
+}
+
 // ---- device-resident flow (bench: "inputs already resident in HBM") -----------------------------
 int av1b_stage_frames(av1b_encoder* e, int slot, const av1b_frame_src* frames, uint32_t n_frames) {
   if (!e || !frames || slot < 0 || slot > 1 || n_frames == 0 || (int)n_frames > e->batch) { set_error("bad argument"); return AV1B_ERR_INVALID; }

@@ -73,6 +73,10 @@ void av1b_encoder_destroy(av1b_encoder* enc);
 /* Encodes n_frames as one closed chunk: first TU carries the sequence header + key frame. */
 int av1b_encode_chunk(av1b_encoder* enc, const av1b_frame_src* frames, uint32_t n_frames,
                       av1b_packet_cb out_cb, av1b_progress_cb prog_cb, void* user);
+/* Streaming form of av1b_encode_chunk for long chunks: the chunk is handed over in parts; the part
+ * with first_part != 0 starts a new closed GOP.  frame_index passed to out_cb = first_frame_index + k. */
+int av1b_encode_part(av1b_encoder* enc, const av1b_frame_src* frames, uint32_t n_frames, int first_part,
+                     int64_t first_frame_index, av1b_packet_cb out_cb, av1b_progress_cb prog_cb, void* user);
 /* Reconstruction of the most recently encoded frame `frame_in_chunk` of the last chunk (post loop
  * filter), for the recon-vs-decode check. dst planes: uint16, strides in samples. */
 int av1b_get_recon(av1b_encoder* enc, uint32_t frame_in_chunk, uint16_t* const dst[3], const int32_t stride[3]);

@@ -1,0 +1,124 @@
+"""The av1an-compatible executable (the boundary the daemon execs: av1an.rs:79-139, startup.rs:98-116)."""
+import os, subprocess
+import numpy as np
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+CLI = os.path.join(ROOT, "av1_base_b200", "av1an")
+
+
+def write_y4m(path, frames, bd, fps=(30, 1)):
+    h, w = frames[0][0].shape
+    with open(path, "wb") as f:
+        f.write(("YUV4MPEG2 W%d H%d F%d:%d Ip A1:1 C%s\n" % (w, h, fps[0], fps[1], "420p10" if bd > 8 else "420jpeg")).encode())
+        for fr in frames:
+            f.write(b"FRAME\n")
+            for p in fr:
+                f.write(p.astype("<u2").tobytes() if bd > 8 else p.astype(np.uint8).tobytes())
+
+
+def test_version_exits_zero():
+    r = subprocess.run([CLI, "--version"], capture_output=True, text=True)
+    assert r.returncode == 0 and "av1b200" in r.stdout
+
+
+def test_bad_arguments_exit_nonzero(tmp_path):
+    assert subprocess.run([CLI], capture_output=True).returncode == 2
+    assert subprocess.run([CLI, "-i", "a", "-o", "b", "--encoder", "x264"], capture_output=True).returncode == 2
+    assert subprocess.run([CLI, "-i", "a", "-o", "b", "--frobnicate"], capture_output=True).returncode == 2
+
+
+def read_ebml_size(b, i):
+    first = b[i]
+    n = 1
+    while n <= 8 and not (first & (0x80 >> (n - 1))):
+        n += 1
+    v = first & (0xFF >> n)
+    for k in range(1, n):
+        v = (v << 8) | b[i + k]
+    return v, i + n
+
+
+def mkv_blocks(data):
+    """Walks our Matroska file: returns (codec_id, codec_private, [block payloads])."""
+    out, info = [], {}
+
+    def walk(b, lo, hi):
+        i = lo
+        while i < hi:
+            first = b[i]
+            n = 1
+            while not (first & (0x80 >> (n - 1))):
+                n += 1
+            eid = int.from_bytes(b[i:i + n], "big")
+            size, j = read_ebml_size(b, i + n)
+            if eid in (0x18538067, 0x1654AE6B, 0xAE, 0x1F43B675):
+                walk(b, j, j + size)
+            elif eid == 0x86:
+                info["codec"] = bytes(b[j:j + size]).decode()
+            elif eid == 0x63A2:
+                info["private"] = bytes(b[j:j + size])
+            elif eid == 0xA3:
+                out.append(bytes(b[j + 4:j + size]))
+            i = j + size
+    walk(data, 0, len(data))
+    return info.get("codec"), info.get("private"), out
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("bd", [8, 10])
+def test_cli_encodes_chunks_and_containers(tmp_path, bd):
+    from av1_base_b200 import encoder, synth
+    from oracle import decoders as D
+    w, h, n = 200, 136, 7
+    frames = synth.synth_clip(w, h, bd, n, seed=11, scene_len=100)
+    y4m = str(tmp_path / "in.y4m")
+    write_y4m(y4m, frames, bd)
+    outs = {}
+    for ext, workers in ((".obu", 1), (".ivf", 2), (".mkv", 3)):
+        out = str(tmp_path / ("out" + ext))
+        tmp = str(tmp_path / ("tmp" + ext))
+        env = dict(os.environ, AV1B_SHARE_GPU="1")
+        r = subprocess.run([CLI, "-i", y4m, "-o", out, "--encoder", "svt-av1", "--pix-format", "yuv420p10le" if bd > 8 else "yuv420p",
+                            "--video-params", "--crf 32 --preset 6 --keyint 3 --lookahead 40 --film-grain 0",
+                            "--audio-params", "-c:a copy", "--workers", str(workers), "--temp", tmp],
+                           capture_output=True, text=True, env=env)
+        assert r.returncode == 0, r.stderr
+        assert os.path.getsize(out) > 0 and os.path.exists(os.path.join(tmp, "progress.json"))
+        assert not os.path.exists(out + ".part")
+        outs[ext] = open(out, "rb").read()
+    # the same encode through the library API: chunks of keyint frames, concatenated
+    enc = encoder.Encoder(w, h, bd, crf=32, keyint=3, fps=(30, 1))
+    want = []
+    for c in range(0, n, 3):
+        want += enc.encode_chunk(frames[c:c + 3])
+    enc.close()
+    assert outs[".obu"] == b"".join(want)
+    # IVF: 32-byte header, then (size, pts) + TU
+    ivf, tus, i = outs[".ivf"], [], 32
+    assert ivf[:4] == b"DKIF" and ivf[8:12] == b"AV01"
+    while i < len(ivf):
+        sz = int.from_bytes(ivf[i:i + 4], "little")
+        tus.append(ivf[i + 12:i + 12 + sz])
+        i += 12 + sz
+    assert tus == want
+    codec, priv, blocks = mkv_blocks(outs[".mkv"])
+    assert codec == "V_AV1" and priv[0] == 0x81 and len(blocks) == n
+    assert [b"\x12\x00" + b for b in blocks] == want          # blocks = temporal units without the delimiter
+    dec = D.dav1d_decode(want)
+    assert len(dec) == n
+    for i in range(n):
+        mse = np.mean((dec[i][0].astype(np.float64) - frames[i][0]) ** 2)
+        psnr = 10 * np.log10(((1 << bd) - 1) ** 2 / mse)
+        assert psnr > 30, (i, psnr)
+
+
+@pytest.mark.gpu
+def test_cli_failure_leaves_no_output(tmp_path):
+    out = str(tmp_path / "o.mkv")
+    r = subprocess.run([CLI, "-i", str(tmp_path / "missing.y4m"), "-o", out], capture_output=True)
+    assert r.returncode == 3 and not os.path.exists(out)
+    bad = str(tmp_path / "bad.y4m")
+    open(bad, "wb").write(b"YUV4MPEG2 W64 H64 F30:1 C420jpeg\nFRAME\n" + b"\0" * 100)
+    r = subprocess.run([CLI, "-i", bad, "-o", out], capture_output=True)
+    assert r.returncode != 0 and not os.path.exists(out)
