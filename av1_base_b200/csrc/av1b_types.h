@@ -3,6 +3,7 @@
 // Plain C structs: also read by the test oracle so that both sides can be compared buffer by buffer.
 #pragma once
 #include <stdint.h>
+#include <stddef.h>
 
 #ifdef __cplusplus
 extern "C" {
@@ -91,14 +92,32 @@ typedef struct Av1bLrUnit {
 // Host view of one coded frame's symbol streams.
 typedef struct Av1bFrameSyms {
   const Av1bBlockInfo* blocks;   // [h8][w8]
-  const int16_t* coef[3];        // quantised levels, plane layout: the TB whose top-left sample is
-                                 // (x0,y0) stores level(row r, col c) at [(y0+r)*stride + x0+c],
-                                 // r,c < min(N,32)
-  int32_t coef_stride[3];
+  const int16_t* coef[3];        // quantised levels, transform-block contiguous (av1b_coef_offset):
+                                 // level(row r, col c) of a block at offset + r * min(N,32) + c
+  int32_t coef_stride[3];        // unused (kept for layout compatibility)
   const uint8_t* cdef_idx;       // [sb_rows][sb_cols]
   const Av1bLrUnit* lr_units[3]; // [unit_rows][unit_cols] per plane (may be NULL when lr_type==NONE)
   int32_t lr_unit_cols[3], lr_unit_rows[3];
 } Av1bFrameSyms;
+
+#ifdef __CUDACC__
+#define AV1B_HD __host__ __device__
+#else
+#define AV1B_HD
+#endif
+
+// Quantised levels are stored transform-block contiguous: superblock-major, and inside a superblock
+// in Morton order of its 8x8 luma units (4x4 chroma units), so that every aligned square block owns
+// one contiguous range.  Returns the offset (in int16 elements) of the block whose top-left sample
+// is (x, y) in `plane`; level (r, c) of that block is at offset + r * min(N, 32) + c.
+// The per-plane element count equals that of the padded sample plane (stride * rows).
+static inline AV1B_HD size_t av1b_coef_offset(int sb_cols, int plane, int x, int y) {
+  const int ss = plane > 0, lsb = 6 - ss, lu = 3 - ss;
+  const int ux = (x >> lu) & 7, uy = (y >> lu) & 7;
+  const int m = (ux & 1) | ((uy & 1) << 1) | ((ux & 2) << 1) | ((uy & 2) << 2) | ((ux & 4) << 2) | ((uy & 4) << 3);
+  const size_t sb = (size_t)(y >> lsb) * sb_cols + (x >> lsb);
+  return (sb << (2 * lsb)) + ((size_t)m << (2 * lu));
+}
 
 static inline int av1b_tile_log2(int blk, int target) {
   int k = 0;

@@ -12,55 +12,6 @@ namespace av1b {
 // ------------------------------------------------------------------------------------------------
 // Range encoder (the inverse of spec 8.2.6 "symbol decoding process")
 // ------------------------------------------------------------------------------------------------
-void RangeEncoder::encode(int s, const uint16_t* icdf, int n) {
-  // The decoder partitions [0, rng) from the top: symbol k owns [cur_k, cur_{k-1}) with
-  // cur_k = ((rng >> 8) * (icdf[k] >> 6) >> 1) + 4 * (n - 1 - k), cur_{-1} = rng.
-  uint32_t r = rng_, l = low_;
-  const int N = n - 1;
-  uint32_t v = ((r >> 8) * (uint32_t)(icdf[s] >> 6) >> 1) + 4 * (N - s);
-  if (s > 0) {
-    uint32_t u = ((r >> 8) * (uint32_t)(icdf[s - 1] >> 6) >> 1) + 4 * (N - (s - 1));
-    l += r - u;
-    r = u - v;
-  } else {
-    r -= v;
-  }
-  // renormalise
-  int d = 15 - (31 - __builtin_clz(r));   // r < 2^16, make bit 15 the top bit
-  int c = cnt_;
-  int sft = c + d;
-  if (sft >= 0) {
-    c += 16;
-    uint32_t m = (1u << c) - 1;
-    if (sft >= 8) {
-      pre_.push_back((uint16_t)(l >> c));
-      l &= m;
-      c -= 8;
-      m >>= 8;
-    }
-    pre_.push_back((uint16_t)(l >> c));
-    sft = c + d - 24;
-    l &= m;
-  }
-  low_ = l << d;
-  rng_ = r << d;
-  cnt_ = sft;
-}
-
-void RangeEncoder::symbol(int s, uint16_t* icdf, int n) {
-  encode(s, icdf, n);
-  if (adapt_) {
-    // spec 8.2.6 CDF adaptation, expressed on the inverted CDF
-    const int cnt = icdf[n];
-    const int rate = 3 + (cnt > 15) + (cnt > 31) + std::min(31 - __builtin_clz((unsigned)n), 2);
-    for (int i = 0; i < n - 1; i++) {
-      if (i < s) icdf[i] += (uint16_t)((32768 - icdf[i]) >> rate);
-      else icdf[i] -= (uint16_t)(icdf[i] >> rate);
-    }
-    icdf[n] = (uint16_t)(cnt + (cnt < 32));
-  }
-}
-
 void RangeEncoder::finish(std::vector<uint8_t>& out) {
   // emit enough bits that any continuation decodes the same symbols, plus the terminating 1 bit
   uint32_t l = low_;
@@ -72,7 +23,7 @@ void RangeEncoder::finish(std::vector<uint8_t>& out) {
   if (s > 0) {
     uint32_t n = (1u << (c + 16)) - 1;
     do {
-      pre_.push_back((uint16_t)(e >> (c + 16)));
+      put((uint16_t)(e >> (c + 16)));
       e &= n;
       s -= 8;
       c -= 8;
@@ -81,9 +32,9 @@ void RangeEncoder::finish(std::vector<uint8_t>& out) {
   }
   // carry propagation, last to first
   size_t base = out.size();
-  out.resize(base + pre_.size());
+  out.resize(base + n_);
   uint32_t carry = 0;
-  for (size_t i = pre_.size(); i-- > 0;) {
+  for (size_t i = n_; i-- > 0;) {
     carry += pre_[i];
     out[base + i] = (uint8_t)carry;
     carry >>= 8;
@@ -913,8 +864,8 @@ struct TileWriter {
       const int ns_log2 = std::min(tl, 5), ns = 1 << ns_log2;   // coded area is at most 32x32
       const int16_t* scan = scan_for(ns_log2, tx_type);
       const int cls = tx_class(tx_type);
-      const int16_t* cf = sy.coef[plane] + (size_t)y0 * sy.coef_stride[plane] + x0;
-      const int cs = sy.coef_stride[plane];
+      const int16_t* cf = sy.coef[plane] + av1b_coef_offset(g.sb_cols, plane, x0, y0);
+      const int cs = ns;
       // eob position
       {
         int t = 0;

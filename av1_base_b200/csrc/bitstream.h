@@ -5,6 +5,7 @@
 #pragma once
 #include <stdint.h>
 #include <stddef.h>
+#include <stdlib.h>
 #include <vector>
 #include "av1b_types.h"
 
@@ -28,19 +29,85 @@ class BitWriter {
 };
 
 // Multi-symbol range encoder producing the stream the AV1 symbol decoder (spec 8.2) reads.
+// Everything on the per-symbol path is inline: the tile writers call it a few hundred thousand
+// times per frame.
 class RangeEncoder {
  public:
-  explicit RangeEncoder(bool adapt) : adapt_(adapt) { pre_.reserve(1 << 16); }
+  explicit RangeEncoder(bool adapt) : adapt_(adapt) { grow(1 << 14); }
+  ~RangeEncoder() { free(pre_); }
+  RangeEncoder(const RangeEncoder&) = delete;
+  RangeEncoder& operator=(const RangeEncoder&) = delete;
   // icdf: inverted CDF (32768 - cdf), n symbols, icdf[n-1] == 0, icdf[n] = adaptation counter
-  void symbol(int s, uint16_t* icdf, int n);
-  void boolean(int b) { uint16_t c[3] = {16384, 0, 0}; encode(b, c, 2); }
-  void literal(uint32_t v, int n) { for (int i = n - 1; i >= 0; i--) boolean((v >> i) & 1); }
+  inline void symbol(int s, uint16_t* icdf, int n) {
+    encode(s, icdf, n);
+    if (adapt_) {
+      // spec 8.2.6 CDF adaptation, expressed on the inverted CDF
+      const int cnt = icdf[n];
+      const int rate = 3 + (cnt > 15) + (cnt > 31) + (n > 3 ? 2 : 1);   // + min(floor(log2(n)), 2)
+      for (int i = 0; i < n - 1; i++) {
+        if (i < s) icdf[i] += (uint16_t)((32768 - icdf[i]) >> rate);
+        else icdf[i] -= (uint16_t)(icdf[i] >> rate);
+      }
+      icdf[n] = (uint16_t)(cnt + (cnt < 32));
+    }
+  }
+  // binary symbol with an adaptive CDF: icdf[0] = 32768 - P(0), icdf[1] = 0, icdf[2] = counter
+  inline void bit(int b, uint16_t* icdf) {
+    encode(b, icdf, 2);
+    if (adapt_) {
+      const int cnt = icdf[2];
+      const int rate = 4 + (cnt > 15) + (cnt > 31);
+      if (b) icdf[0] += (uint16_t)((32768 - icdf[0]) >> rate);
+      else icdf[0] -= (uint16_t)(icdf[0] >> rate);
+      icdf[2] = (uint16_t)(cnt + (cnt < 32));
+    }
+  }
+  inline void boolean(int b) { const uint16_t c[3] = {16384, 0, 0}; encode(b, c, 2); }
+  inline void literal(uint32_t v, int n) { for (int i = n - 1; i >= 0; i--) boolean((v >> i) & 1); }
   // terminates the stream and appends the bytes to out
   void finish(std::vector<uint8_t>& out);
  private:
-  void encode(int s, const uint16_t* icdf, int n);
+  inline void put(uint16_t v) { if (n_ == cap_) grow(cap_ * 2); pre_[n_++] = v; }
+  void grow(size_t cap) {
+    pre_ = static_cast<uint16_t*>(realloc(pre_, cap * sizeof(uint16_t)));
+    cap_ = cap;
+  }
+  inline void encode(int s, const uint16_t* icdf, int n) {
+    // The decoder partitions [0, rng) from the top: symbol k owns [cur_k, cur_{k-1}) with
+    // cur_k = ((rng >> 8) * (icdf[k] >> 6) >> 1) + 4 * (n - 1 - k), cur_{-1} = rng.
+    uint32_t r = rng_, l = low_;
+    const int N = n - 1;
+    const uint32_t v = ((r >> 8) * (uint32_t)(icdf[s] >> 6) >> 1) + 4 * (N - s);
+    if (s > 0) {
+      const uint32_t u = ((r >> 8) * (uint32_t)(icdf[s - 1] >> 6) >> 1) + 4 * (N - (s - 1));
+      l += r - u;
+      r = u - v;
+    } else {
+      r -= v;
+    }
+    const int d = __builtin_clz(r) - 16;   // r < 2^16: make bit 15 the top bit
+    int c = cnt_;
+    int sft = c + d;
+    if (sft >= 0) {
+      c += 16;
+      uint32_t m = (1u << c) - 1;
+      if (sft >= 8) {
+        put((uint16_t)(l >> c));
+        l &= m;
+        c -= 8;
+        m >>= 8;
+      }
+      put((uint16_t)(l >> c));
+      sft = c + d - 24;
+      l &= m;
+    }
+    low_ = l << d;
+    rng_ = r << d;
+    cnt_ = sft;
+  }
   bool adapt_;
-  std::vector<uint16_t> pre_;
+  uint16_t* pre_ = nullptr;
+  size_t n_ = 0, cap_ = 0;
   uint32_t low_ = 0;
   uint32_t rng_ = 0x8000;
   int cnt_ = -9;

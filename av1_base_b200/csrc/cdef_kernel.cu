@@ -41,6 +41,12 @@ struct Smem {
   uint8_t dir[8][8];
   int var[8][8];
   int best;
+  // decision plan: the distinct primary / secondary strengths of the presets (luma [0], chroma [1])
+  int n_pri[2], n_sec[2];
+  int pri_val[2][8], sec_val[2][8];       // coded strengths (before the bit-depth shift)
+  int8_t p_pri[2][8], p_sec[2][8];        // per preset: index into pri_val / sec_val
+  int need_dir0[2];                       // some preset has pri == 0 and sec != 0 (filters along direction 0)
+  int16_t sums[14][kThreads];             // per thread: [0..7] primary, [8..10] secondary (strengths 1, 2, 4 at most), [11..13] secondary along direction 0
 };
 
 __device__ __forceinline__ int clampi(int v, int lo, int hi) { return v < lo ? lo : (v > hi ? hi : v); }
@@ -86,6 +92,87 @@ __device__ __forceinline__ int cdef_px(const uint16_t* c, const int16_t (*off)[2
   return clampi(x + ((8 + sum - (sum < 0)) >> 4), mn, mx);
 }
 
+// Squared error of EVERY preset for one sample: the 12 taps are read once, the constrained sums are
+// evaluated once per distinct primary / secondary strength, and the presets combine them.
+// vs < 0: chroma (no variance adjustment of the primary strength).
+__device__ __forceinline__ void cdef_px_all(const Smem& sm, int pl, const uint16_t* c, const int16_t (*off)[2], int bdir,
+                                            int var, int damping, int cs, int src, int n_cand, unsigned* acc) {
+  const int x = c[0];
+  int dp[4], ds[8], mn = x, mx = x;
+  auto tap = [&](int o, int& d) {
+    const int a = c[o];
+    if (a != kUnavail) { d = a - x; mx = max(mx, a); mn = min(mn, a); } else d = 0;
+  };
+#pragma unroll
+  for (int k = 0; k < 2; k++) {
+    const int o = off[bdir][k];
+    tap(o, dp[2 * k]); tap(-o, dp[2 * k + 1]);
+    const int o2 = off[(bdir + 2) & 7][k], o6 = off[(bdir + 6) & 7][k];
+    tap(o2, ds[4 * k]); tap(-o2, ds[4 * k + 1]); tap(o6, ds[4 * k + 2]); tap(-o6, ds[4 * k + 3]);
+  }
+  const int vs = (pl == 0 && (var >> 6)) ? min(flog2((unsigned)(var >> 6)), 12) : 0;
+  int16_t (*sums)[kThreads] = const_cast<int16_t (*)[kThreads]>(sm.sums);
+  const int me = threadIdx.x;
+  for (int u = 0; u < sm.n_pri[pl]; u++) {
+    int pri = sm.pri_val[pl][u] << cs, sp = 0;
+    if (pl == 0) pri = var ? (pri * (4 + vs) + 8) >> 4 : 0;
+    if (pri) {
+      const int adj = max(0, damping - flog2((unsigned)pri));
+      const int t0 = ((pri >> cs) & 1) ? 3 : 4, t1 = ((pri >> cs) & 1) ? 3 : 2;
+      sp = t0 * (constrain(dp[0], pri, adj) + constrain(dp[1], pri, adj)) +
+           t1 * (constrain(dp[2], pri, adj) + constrain(dp[3], pri, adj));
+    }
+    sums[u][me] = (int16_t)sp;
+  }
+  for (int u = 0; u < sm.n_sec[pl]; u++) {
+    const int sec = sm.sec_val[pl][u] << cs;
+    const int adj = max(0, damping - flog2((unsigned)sec));
+    sums[8 + u][me] = (int16_t)(2 * (constrain(ds[0], sec, adj) + constrain(ds[1], sec, adj) + constrain(ds[2], sec, adj) + constrain(ds[3], sec, adj)) +
+                      (constrain(ds[4], sec, adj) + constrain(ds[5], sec, adj) + constrain(ds[6], sec, adj) + constrain(ds[7], sec, adj)));
+  }
+  // presets without a primary strength filter along direction 0
+  int mn0 = x, mx0 = x;
+  if (sm.need_dir0[pl]) {
+    int d0[8], dummy;
+    auto tap0 = [&](int o, int& d) {
+      const int a = c[o];
+      if (a != kUnavail) { d = a - x; mx0 = max(mx0, a); mn0 = min(mn0, a); } else d = 0;
+    };
+#pragma unroll
+    for (int k = 0; k < 2; k++) {
+      const int o = off[0][k];
+      tap0(o, dummy); tap0(-o, dummy);
+      const int o2 = off[2][k], o6 = off[6][k];
+      tap0(o2, d0[4 * k]); tap0(-o2, d0[4 * k + 1]); tap0(o6, d0[4 * k + 2]); tap0(-o6, d0[4 * k + 3]);
+    }
+    for (int u = 0; u < sm.n_sec[pl]; u++) {
+      const int sec = sm.sec_val[pl][u] << cs;
+      const int adj = max(0, damping - flog2((unsigned)sec));
+      sums[11 + u][me] = (int16_t)(2 * (constrain(d0[0], sec, adj) + constrain(d0[1], sec, adj) + constrain(d0[2], sec, adj) + constrain(d0[3], sec, adj)) +
+                         (constrain(d0[4], sec, adj) + constrain(d0[5], sec, adj) + constrain(d0[6], sec, adj) + constrain(d0[7], sec, adj)));
+    }
+  }
+#pragma unroll
+  for (int i = 0; i < 8; i++) {
+    if (i < n_cand) {
+      const int ip = sm.p_pri[pl][i], is = sm.p_sec[pl][i];
+      int y;
+      if (ip < 0) {
+        if (is < 0) y = x;
+        else {
+          const int ss = sums[11 + is][me];
+          y = clampi(x + ((8 + ss - (ss < 0)) >> 4), mn0, mx0);
+        }
+      } else {
+        const int t = sums[ip][me] + (is < 0 ? 0 : sums[8 + is][me]);
+        y = clampi(x + ((8 + t - (t < 0)) >> 4), mn, mx);
+      }
+      const int d = y - src;
+      acc[i] += (unsigned)(d * d);
+    }
+  }
+}
+
 // direction and variance of one 8x8 luma block (spec 7.15.2).  The 64 samples are held in
 // registers and the eight directions are accumulated one after the other (15 partial sums live at a
 // time) to keep the register count low; all indices are compile-time constants after unrolling.
@@ -121,7 +208,9 @@ __device__ __forceinline__ int dir_cost(const int* px) {
   }
   return cost;
 }
-__device__ void find_dir(const uint16_t* img, int stride, int bd, int* dir_out, int* var_out) {
+// Four consecutive lanes share one 8x8 block: lane part computes the costs of directions 2*part and
+// 2*part + 1, the quad exchanges them with shuffles and every lane ends up with (dir, var).
+__device__ __forceinline__ void find_dir_quad(const uint16_t* img, int stride, int bd, int part, int* dir_out, int* var_out) {
   int px[64];
 #pragma unroll
   for (int i = 0; i < 8; i++) {
@@ -133,9 +222,18 @@ __device__ void find_dir(const uint16_t* img, int stride, int bd, int* dir_out, 
       px[i * 8 + 2 * j + 1] = (int)((w >> 16) >> (bd - 8)) - 128;
     }
   }
+  int c0, c1;
+  if (part == 0) { c0 = dir_cost<0>(px); c1 = dir_cost<1>(px); }
+  else if (part == 1) { c0 = dir_cost<2>(px); c1 = dir_cost<3>(px); }
+  else if (part == 2) { c0 = dir_cost<4>(px); c1 = dir_cost<5>(px); }
+  else { c0 = dir_cost<6>(px); c1 = dir_cost<7>(px); }
   int cost[8];
-  cost[0] = dir_cost<0>(px); cost[1] = dir_cost<1>(px); cost[2] = dir_cost<2>(px); cost[3] = dir_cost<3>(px);
-  cost[4] = dir_cost<4>(px); cost[5] = dir_cost<5>(px); cost[6] = dir_cost<6>(px); cost[7] = dir_cost<7>(px);
+  const int base = (threadIdx.x & 31) & ~3;
+#pragma unroll
+  for (int q = 0; q < 4; q++) {
+    cost[2 * q] = __shfl_sync(0xffffffffu, c0, base + q);
+    cost[2 * q + 1] = __shfl_sync(0xffffffffu, c1, base + q);
+  }
   int best = 0, dir = 0;
 #pragma unroll
   for (int d = 0; d < 8; d++) if (cost[d] > best) { best = cost[d]; dir = d; }
@@ -146,7 +244,7 @@ __device__ void find_dir(const uint16_t* img, int stride, int bd, int* dir_out, 
   *var_out = (best - ortho) >> 10;
 }
 
-__global__ void __launch_bounds__(kThreads) cdef_kernel(const CdefLaunch P) {
+__global__ void __launch_bounds__(kThreads, 3) cdef_kernel(const CdefLaunch P) {
   __shared__ Smem sm;
   const Av1bGeom& g = P.g;
   const int tid = threadIdx.x, lane = tid & 31;
@@ -195,14 +293,38 @@ __global__ void __launch_bounds__(kThreads) cdef_kernel(const CdefLaunch P) {
     sm.off_c[d][k] = (int16_t)(c_dirs[d][k][0] * kCStride + c_dirs[d][k][1]);
   }
   if (tid < 8) sm.sse[tid] = 0;
+  if (tid < 2) {
+    // distinct strengths of the presets of this plane type
+    const int pl = tid, nc = 1 << P.cdef_bits;
+    int np = 0, ns = 0, need0 = 0;
+    for (int i = 0; i < nc; i++) {
+      const int str = pl ? P.uv_strength[i] : P.y_strength[i];
+      const int pri = str >> 2;
+      int sec = str & 3;
+      if (sec == 3) sec = 4;
+      int ip = -1, is = -1;
+      if (pri) {
+        for (int u = 0; u < np; u++) if (sm.pri_val[pl][u] == pri) ip = u;
+        if (ip < 0) { ip = np; sm.pri_val[pl][np++] = pri; }
+      }
+      if (sec) {
+        for (int u = 0; u < ns; u++) if (sm.sec_val[pl][u] == sec) is = u;
+        if (is < 0) { is = ns; sm.sec_val[pl][ns++] = sec; }
+      }
+      if (!pri && sec) need0 = 1;
+      sm.p_pri[pl][i] = (int8_t)ip; sm.p_sec[pl][i] = (int8_t)is;
+    }
+    sm.n_pri[pl] = np; sm.n_sec[pl] = ns; sm.need_dir0[pl] = need0;
+  }
   __syncthreads();
   // ---- direction / variance of every non-skip 8x8 luma block ----
-  if (tid < 64) {
-    const int by = tid >> 3, bx = tid & 7;
+  {
+    const int b = tid >> 2, by = b >> 3, bx = b & 7;
     int dir = 0, var = 0;
-    if (!sm.skip[by][bx]) find_dir(sm.y + (kHalo + by * 8) * kLStride + 8 + bx * 8, kLStride, bd, &dir, &var);
-    sm.dir[by][bx] = (uint8_t)dir;
-    sm.var[by][bx] = var;
+    // all four lanes of a quad take the same branch (the skip flag is per block)
+    find_dir_quad(sm.y + (kHalo + by * 8) * kLStride + 8 + bx * 8, kLStride, bd, tid & 3, &dir, &var);
+    if (sm.skip[by][bx]) { dir = 0; var = 0; }
+    if ((tid & 3) == 0) { sm.dir[by][bx] = (uint8_t)dir; sm.var[by][bx] = var; }
   }
   __syncthreads();
   const int n_cand = 1 << P.cdef_bits;
@@ -242,21 +364,26 @@ __global__ void __launch_bounds__(kThreads) cdef_kernel(const CdefLaunch P) {
   if (P.forced_idx) {
     best = P.forced_idx[sb_index];
   } else if (n_cand > 1) {
-    for (int cand = 0; cand < n_cand; cand++) {
-      const int ystr = P.y_strength[cand], uvstr = P.uv_strength[cand];
-      unsigned acc = 0;
-      for (int q = tid; q < 4096; q += kThreads) {
-        bool live; int s;
-        const int v = luma_px(q, ystr, live, s);
-        if (live) { const int d = v - s; acc += (unsigned)(d * d); }
+    unsigned acc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+    for (int q = tid; q < 4096; q += kThreads) {
+      const int r = q >> 6, c = q & 63, by = r >> 3, bx = c >> 3;
+      if (sm.skip[by][bx]) continue;
+      cdef_px_all(sm, 0, sm.y + (kHalo + r) * kLStride + 8 + c, sm.off_y, sm.dir[by][bx], sm.var[by][bx], damping, cs,
+                  sm.sy[q], n_cand, acc);
+    }
+    for (int q = tid; q < 2048; q += kThreads) {
+      const int pl = q >> 10, r = (q >> 5) & 31, c = q & 31, by = r >> 2, bx = c >> 2;
+      if (sm.skip[by][bx]) continue;
+      cdef_px_all(sm, 1, sm.c[pl] + (kHalo + r) * kCStride + 8 + c, sm.off_c, sm.dir[by][bx], 0, damping - 1, cs,
+                  sm.sc[pl][q & 1023], n_cand, acc);
+    }
+#pragma unroll
+    for (int i = 0; i < 8; i++) {
+      if (i < n_cand) {
+        unsigned a = acc[i];
+        for (int o = 16; o; o >>= 1) a += __shfl_xor_sync(0xffffffffu, a, o);
+        if (lane == 0 && a) atomicAdd(&sm.sse[i], (unsigned long long)a);
       }
-      for (int q = tid; q < 2048; q += kThreads) {
-        bool live; int s;
-        const int v = chroma_px(q, uvstr, live, s);
-        if (live) { const int d = v - s; acc += (unsigned)(d * d); }
-      }
-      for (int o = 16; o; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
-      if (lane == 0 && acc) atomicAdd(&sm.sse[cand], (unsigned long long)acc);
     }
     __syncthreads();
     if (tid == 0) {

@@ -106,6 +106,10 @@ struct KeptFrame {
 // streams.  Two slots are ping-ponged: the host entropy-codes slot k-1 while the GPU works on slot k.
 struct Slot {
   uint16_t* d_src[3] = {nullptr, nullptr, nullptr};
+  int16_t* d_coef[3] = {nullptr, nullptr, nullptr};   // device side of the symbol streams (downloaded on the copy stream
+  Av1bBlockInfo* d_blocks = nullptr;                  //  while the next batch is being encoded)
+  uint8_t* d_cdef_idx = nullptr;
+  cudaEvent_t ev_src = nullptr;                       // sources of this slot are resident
   uint16_t* h_src[3] = {nullptr, nullptr, nullptr};
   uint16_t* h_rec[3] = {nullptr, nullptr, nullptr};
   int16_t* h_coef[3] = {nullptr, nullptr, nullptr};
@@ -132,18 +136,17 @@ struct av1b_encoder {
   bool loop_filters = true;
   bool intra_only = false;
   Av1bFrameParams fp_key, fp_inter;   // frame-level parameters (levels / strengths from the quantiser)
-  cudaStream_t stream = nullptr;
+  cudaStream_t stream = nullptr;      // compute
+  cudaStream_t s_in = nullptr;        // host -> device copies (overlap the previous batch's kernels)
+  cudaStream_t s_out = nullptr;       // device -> host copies (overlap the next batch's kernels)
   size_t plane_elems[3] = {0, 0, 0};
   size_t map_elems = 0;
   // device working set of one batch (single copy: all device work is ordered on one stream)
   uint16_t* d_rec[3] = {nullptr, nullptr, nullptr};   // reconstruction before the loop filters   [batch]
   uint16_t* d_deb[3] = {nullptr, nullptr, nullptr};   // deblocked                                 [batch]
   uint16_t* d_fin[3] = {nullptr, nullptr, nullptr};   // decoder output; [0] = last frame of the previous batch [batch+1]
-  int16_t* d_coef[3] = {nullptr, nullptr, nullptr};
-  Av1bBlockInfo* d_blocks = nullptr;
   uint8_t* d_map_key = nullptr;
   uint8_t* d_map_inter = nullptr;
-  uint8_t* d_cdef_idx = nullptr;
   uint16_t* d_pyr[3] = {nullptr, nullptr, nullptr};   // luma pyramid levels 0..2; [0] = last frame of the previous batch
   int16_t* d_mv2 = nullptr;
   int16_t* d_mvs = nullptr;
@@ -161,37 +164,47 @@ struct av1b_encoder {
 static void free_all(av1b_encoder* e) {
   for (auto& s : e->slot) {
     for (int p = 0; p < 3; p++) {
-      cudaFree(s.d_src[p]);
+      cudaFree(s.d_src[p]); cudaFree(s.d_coef[p]);
       cudaFreeHost(s.h_src[p]); cudaFreeHost(s.h_rec[p]); cudaFreeHost(s.h_coef[p]);
     }
     cudaFreeHost(s.h_blocks); cudaFreeHost(s.h_cdef_idx);
-    for (cudaEvent_t ev : {s.ev_h2d, s.ev_k0, s.ev_me, s.ev_k1, s.ev_d2h}) if (ev) cudaEventDestroy(ev);
+    cudaFree(s.d_blocks); cudaFree(s.d_cdef_idx);
+    for (cudaEvent_t ev : {s.ev_h2d, s.ev_k0, s.ev_me, s.ev_k1, s.ev_d2h, s.ev_src}) if (ev) cudaEventDestroy(ev);
     for (cudaEvent_t ev : s.ev_frame) if (ev) cudaEventDestroy(ev);
   }
   for (int p = 0; p < 3; p++) {
-    cudaFree(e->d_rec[p]); cudaFree(e->d_deb[p]); cudaFree(e->d_fin[p]); cudaFree(e->d_coef[p]); cudaFree(e->d_pyr[p]);
+    cudaFree(e->d_rec[p]); cudaFree(e->d_deb[p]); cudaFree(e->d_fin[p]); cudaFree(e->d_pyr[p]);
   }
-  cudaFree(e->d_blocks); cudaFree(e->d_map_key); cudaFree(e->d_map_inter); cudaFree(e->d_cdef_idx);
+  cudaFree(e->d_map_key); cudaFree(e->d_map_inter);
   cudaFree(e->d_mv2); cudaFree(e->d_mvs);
   if (e->stream) cudaStreamDestroy(e->stream);
+  if (e->s_in) cudaStreamDestroy(e->s_in);
+  if (e->s_out) cudaStreamDestroy(e->s_out);
   delete e->pool;
 }
 
-// upload n frames (host pointers) into a slot; asynchronous on the encoder stream
+// upload n frames (host pointers) into a slot: rows are gathered into the pinned staging buffer by the
+// host pool, then copied on the input copy stream (overlaps the kernels of the previous batch)
 static int stage(av1b_encoder* e, Slot& s, const av1b_frame_src* frames, int n) {
   const Av1bGeom& g = e->g;
-  CK(cudaEventRecord(s.ev_h2d, e->stream));
-  for (int b = 0; b < n; b++) {
-    for (int p = 0; p < 3; p++) {
-      const int w = p ? g.width >> 1 : g.width, h = p ? g.height >> 1 : g.height;
-      uint16_t* hs = s.h_src[p] + (size_t)b * e->plane_elems[p];
-      const uint16_t* sp = frames[b].planes[p];
-      const int sst = frames[b].stride[p];
-      for (int y = 0; y < h; y++) memcpy(hs + (size_t)y * g.stride[p], sp + (size_t)y * sst, (size_t)w * 2);
-      CK(cudaMemcpyAsync(s.d_src[p] + (size_t)b * e->plane_elems[p], hs, (size_t)g.stride[p] * h * 2,
-                         cudaMemcpyHostToDevice, e->stream));
-    }
+  const int kSplit = 4;   // row bands per plane
+  e->pool->parallel_for(n * 3 * kSplit, [&](int task) {
+    const int b = task / (3 * kSplit), p = (task / kSplit) % 3, band = task % kSplit;
+    const int w = p ? g.width >> 1 : g.width, h = p ? g.height >> 1 : g.height;
+    const int y0 = h * band / kSplit, y1 = h * (band + 1) / kSplit;
+    uint16_t* hs = s.h_src[p] + (size_t)b * e->plane_elems[p];
+    const uint16_t* sp = frames[b].planes[p];
+    const int sst = frames[b].stride[p];
+    for (int y = y0; y < y1; y++) memcpy(hs + (size_t)y * g.stride[p], sp + (size_t)y * sst, (size_t)w * 2);
+  });
+  CK(cudaEventRecord(s.ev_h2d, e->s_in));
+  for (int p = 0; p < 3; p++) {
+    const int h = p ? g.height >> 1 : g.height;
+    // one strided copy per plane (n frames): the padded rows below the picture stay zero on both sides
+    CK(cudaMemcpy2DAsync(s.d_src[p], e->plane_elems[p] * 2, s.h_src[p], e->plane_elems[p] * 2,
+                         (size_t)g.stride[p] * h * 2, n, cudaMemcpyHostToDevice, e->s_in));
   }
+  CK(cudaEventRecord(s.ev_src, e->s_in));
   return AV1B_OK;
 }
 
@@ -208,6 +221,7 @@ static int launch(av1b_encoder* e, Slot& s, int n, int64_t first_index) {
     s.is_key[b] = key;
     any_inter |= !key;
   }
+  CK(cudaStreamWaitEvent(e->stream, s.ev_src, 0));
   CK(cudaEventRecord(s.ev_k0, e->stream));
   // ---- open-loop motion estimation for the whole batch (source pictures only) ----
   if (!e->intra_only) {
@@ -241,9 +255,9 @@ static int launch(av1b_encoder* e, Slot& s, int n, int64_t first_index) {
       const size_t off = (size_t)b * e->plane_elems[p];
       rec[p] = e->d_rec[p] + off; deb[p] = e->d_deb[p] ? e->d_deb[p] + off : nullptr;
       prev[p] = e->d_fin[p] + off; fin[p] = e->d_fin[p] + off + e->plane_elems[p];
-      src[p] = s.d_src[p] + off; coef[p] = e->d_coef[p] + off;
+      src[p] = s.d_src[p] + off; coef[p] = s.d_coef[p] + off;
     }
-    Av1bBlockInfo* blocks = e->d_blocks + (size_t)b * e->map_elems;
+    Av1bBlockInfo* blocks = s.d_blocks + (size_t)b * e->map_elems;
     if (key) {
       IntraLaunch L;
       L.g = g; L.bit_depth = bd; L.base_q_idx = e->base_q_idx; L.quant_rnd = 48; L.dc_q = dcq; L.ac_q = acq;
@@ -273,7 +287,7 @@ static int launch(av1b_encoder* e, Slot& s, int n, int64_t first_index) {
       Cd.g = g; Cd.bit_depth = bd; Cd.cdef_damping = fp.cdef_damping; Cd.cdef_bits = fp.cdef_bits;
       for (int i = 0; i < 8; i++) { Cd.y_strength[i] = fp.cdef_y_strength[i]; Cd.uv_strength[i] = fp.cdef_uv_strength[i]; }
       for (int p = 0; p < 3; p++) { Cd.in[p] = deb[p]; Cd.src[p] = src[p]; Cd.out[p] = fin[p]; Cd.plane_elems[p] = e->plane_elems[p]; }
-      Cd.blocks = blocks; Cd.map_elems = e->map_elems; Cd.cdef_idx = e->d_cdef_idx + (size_t)b * nsb; Cd.forced_idx = nullptr;
+      Cd.blocks = blocks; Cd.map_elems = e->map_elems; Cd.cdef_idx = s.d_cdef_idx + (size_t)b * nsb; Cd.forced_idx = nullptr;
       CK(launch_cdef(Cd, 1, e->stream));
       e->kernel_launches += 2;
     } else {
@@ -282,17 +296,22 @@ static int launch(av1b_encoder* e, Slot& s, int n, int64_t first_index) {
     CK(cudaEventRecord(ev[3], e->stream));
   }
   e->chunk_pos += n;
-  CK(cudaEventRecord(s.ev_k1, e->stream));
-  for (int p = 0; p < 3; p++) {
-    CK(cudaMemcpyAsync(s.h_coef[p], e->d_coef[p], e->plane_elems[p] * n * 2, cudaMemcpyDeviceToHost, e->stream));
-    if (e->keep) CK(cudaMemcpyAsync(s.h_rec[p], e->d_fin[p] + e->plane_elems[p], e->plane_elems[p] * n * 2, cudaMemcpyDeviceToHost, e->stream));
-  }
-  CK(cudaMemcpyAsync(s.h_cdef_idx, e->d_cdef_idx, nsb * n, cudaMemcpyDeviceToHost, e->stream));
-  CK(cudaMemcpyAsync(s.h_blocks, e->d_blocks, e->map_elems * n * sizeof(Av1bBlockInfo), cudaMemcpyDeviceToHost, e->stream));
   // the last reconstructed picture becomes reference slot 0 of the next batch
+  if (e->keep) {
+    // debug mode keeps every reconstruction: download it before the ring is shifted
+    for (int p = 0; p < 3; p++)
+      CK(cudaMemcpyAsync(s.h_rec[p], e->d_fin[p] + e->plane_elems[p], e->plane_elems[p] * n * 2, cudaMemcpyDeviceToHost, e->stream));
+  }
   for (int p = 0; p < 3; p++)
     CK(cudaMemcpyAsync(e->d_fin[p], e->d_fin[p] + e->plane_elems[p] * n, e->plane_elems[p] * 2, cudaMemcpyDeviceToDevice, e->stream));
-  CK(cudaEventRecord(s.ev_d2h, e->stream));
+  CK(cudaEventRecord(s.ev_k1, e->stream));
+  // symbol streams go home on the output copy stream while the compute stream starts the next batch
+  CK(cudaStreamWaitEvent(e->s_out, s.ev_k1, 0));
+  for (int p = 0; p < 3; p++)
+    CK(cudaMemcpyAsync(s.h_coef[p], s.d_coef[p], e->plane_elems[p] * n * 2, cudaMemcpyDeviceToHost, e->s_out));
+  CK(cudaMemcpyAsync(s.h_cdef_idx, s.d_cdef_idx, nsb * n, cudaMemcpyDeviceToHost, e->s_out));
+  CK(cudaMemcpyAsync(s.h_blocks, s.d_blocks, e->map_elems * n * sizeof(Av1bBlockInfo), cudaMemcpyDeviceToHost, e->s_out));
+  CK(cudaEventRecord(s.ev_d2h, e->s_out));
   return AV1B_OK;
 }
 
@@ -302,7 +321,7 @@ static int finish(av1b_encoder* e, Slot& s, bool staged, av1b_packet_cb out_cb, 
   const Av1bGeom& g = e->g;
   CK(cudaEventSynchronize(s.ev_d2h));
   float ms;
-  if (staged) { cudaEventElapsedTime(&ms, s.ev_h2d, s.ev_k0); e->t_h2d_ms += ms; }
+  if (staged) { cudaEventElapsedTime(&ms, s.ev_h2d, s.ev_src); e->t_h2d_ms += ms; }
   cudaEventElapsedTime(&ms, s.ev_k0, s.ev_k1); e->t_kernel_ms += ms;
   cudaEventElapsedTime(&ms, s.ev_k0, s.ev_me); e->t_me_ms += ms;
   cudaEventElapsedTime(&ms, s.ev_k1, s.ev_d2h); e->t_d2h_ms += ms;
@@ -423,38 +442,40 @@ int av1b_encoder_create(const av1b_config* cfg, av1b_encoder** out) {
   cudaError_t err = cudaSuccess;
   auto A = [&](cudaError_t r) { if (err == cudaSuccess && r != cudaSuccess) err = r; };
   A(cudaStreamCreateWithFlags(&e->stream, cudaStreamNonBlocking));
+  A(cudaStreamCreateWithFlags(&e->s_in, cudaStreamNonBlocking));
+  A(cudaStreamCreateWithFlags(&e->s_out, cudaStreamNonBlocking));
   e->map_elems = (size_t)e->g.w8 * e->g.h8;
   const size_t nsb = (size_t)e->g.sb_rows * e->g.sb_cols;
   for (int p = 0; p < 3; p++) e->plane_elems[p] = (size_t)e->g.stride[p] * e->g.rows[p];
   const int F = e->batch;
   for (auto& s : e->slot) {
-    for (cudaEvent_t* ev : {&s.ev_h2d, &s.ev_k0, &s.ev_me, &s.ev_k1, &s.ev_d2h}) A(cudaEventCreate(ev));
+    for (cudaEvent_t* ev : {&s.ev_h2d, &s.ev_k0, &s.ev_me, &s.ev_k1, &s.ev_d2h, &s.ev_src}) A(cudaEventCreate(ev));
     s.ev_frame.assign((size_t)F * 4, nullptr);
     for (auto& ev : s.ev_frame) A(cudaEventCreate(&ev));
     for (int p = 0; p < 3; p++) {
       const size_t n = e->plane_elems[p] * F;
-      A(cudaMalloc(&s.d_src[p], n * 2));
+      A(cudaMalloc(&s.d_src[p], n * 2)); A(cudaMalloc(&s.d_coef[p], n * 2));
       A(cudaMallocHost(&s.h_src[p], n * 2)); A(cudaMallocHost(&s.h_coef[p], n * 2));
       if (e->keep) A(cudaMallocHost(&s.h_rec[p], n * 2));
-      if (err == cudaSuccess) A(cudaMemset(s.d_src[p], 0, n * 2));
+      if (err == cudaSuccess) { A(cudaMemset(s.d_src[p], 0, n * 2)); A(cudaMemset(s.d_coef[p], 0, n * 2)); memset(s.h_src[p], 0, n * 2); }
     }
     A(cudaMallocHost(&s.h_blocks, e->map_elems * F * sizeof(Av1bBlockInfo)));
     A(cudaMallocHost(&s.h_cdef_idx, nsb * F));
+    A(cudaMalloc(&s.d_blocks, e->map_elems * F * sizeof(Av1bBlockInfo)));
+    A(cudaMalloc(&s.d_cdef_idx, nsb * F));
+    if (err == cudaSuccess) { A(cudaMemset(s.d_blocks, 0, e->map_elems * F * sizeof(Av1bBlockInfo))); A(cudaMemset(s.d_cdef_idx, 0, nsb * F)); }
   }
   for (int p = 0; p < 3; p++) {
     const size_t n = e->plane_elems[p] * F;
-    A(cudaMalloc(&e->d_rec[p], n * 2)); A(cudaMalloc(&e->d_coef[p], n * 2));
+    A(cudaMalloc(&e->d_rec[p], n * 2));
     if (e->loop_filters) A(cudaMalloc(&e->d_deb[p], n * 2));
     A(cudaMalloc(&e->d_fin[p], (n + e->plane_elems[p]) * 2));
     if (err == cudaSuccess) {
-      A(cudaMemset(e->d_rec[p], 0, n * 2)); A(cudaMemset(e->d_coef[p], 0, n * 2));
+      A(cudaMemset(e->d_rec[p], 0, n * 2));
       A(cudaMemset(e->d_fin[p], 0, (n + e->plane_elems[p]) * 2));
     }
   }
-  A(cudaMalloc(&e->d_blocks, e->map_elems * F * sizeof(Av1bBlockInfo)));
   A(cudaMalloc(&e->d_map_key, e->map_elems)); A(cudaMalloc(&e->d_map_inter, e->map_elems));
-  A(cudaMalloc(&e->d_cdef_idx, nsb * F));
-  if (err == cudaSuccess) { A(cudaMemset(e->d_blocks, 0, e->map_elems * F * sizeof(Av1bBlockInfo))); A(cudaMemset(e->d_cdef_idx, 0, nsb * F)); }
   if (!e->intra_only) {
     for (int l = 0; l < 3; l++) {
       const size_t el = e->plane_elems[0] >> (2 * l);
@@ -484,7 +505,7 @@ int av1b_encoder_create(const av1b_config* cfg, av1b_encoder** out) {
 void av1b_encoder_destroy(av1b_encoder* e) {
   if (!e) return;
   cudaSetDevice(e->cfg.device_id);
-  cudaStreamSynchronize(e->stream);
+  cudaDeviceSynchronize();
   free_all(e);
   delete e;
 }
@@ -536,7 +557,7 @@ int av1b_stage_frames(av1b_encoder* e, int slot, const av1b_frame_src* frames, u
   int rc = stage(e, e->slot[slot], frames, (int)n_frames);
   if (rc) return rc;
   e->slot[slot].n_frames = (int)n_frames;
-  CK(cudaStreamSynchronize(e->stream));
+  CK(cudaStreamSynchronize(e->s_in));
   return AV1B_OK;
 }
 

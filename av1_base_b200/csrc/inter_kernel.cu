@@ -122,7 +122,7 @@ __device__ __forceinline__ int code_tb(const InterLaunch& P, int p, int x, int y
     for (int j = 0; j < N; j++) row[j] = buf[t * S + j];
     constexpr int sh = 24 + 2 * TxTab<N>::kLog2 - TxTab<N>::kRowShift - 4;
     const int lim = (1 << (7 + bd)) - 1;
-    int16_t* cdst = P.coef[p] + (size_t)(y + t) * stride + x;
+    int16_t* cdst = P.coef[p] + av1b_coef_offset(P.g.sb_cols, p, x, y) + t * N;
 #pragma unroll
     for (int l = 0; l < N; l++) {
       int64_t acc = 0;

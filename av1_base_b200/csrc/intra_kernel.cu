@@ -275,7 +275,7 @@ __device__ void code_plane(Smem& sm, const IntraLaunch& P, int plane, int slot, 
       if (d > lim) d = lim;
       if (c < 0) d = -d;
       sm.bufC[k * cn + l] = d;
-      coef[(size_t)k * stride + l] = (int16_t)(c < 0 ? -(int32_t)lv : (int32_t)lv);
+      coef[k * cn + l] = (int16_t)(c < 0 ? -(int32_t)lv : (int32_t)lv);
       if (lv) atomicMax(&sm.eob[plane], (int)iscan[k * cn + l] + 1);
     }
   }
@@ -430,7 +430,7 @@ __global__ void __launch_bounds__(kThreads) intra_encode_kernel(const IntraLaunc
             int tx_type = AV1B_DCT_DCT;
             if (p > 0 && n < 32) tx_type = c_mode_to_txfm[mode];
             code_plane(sm, P, p, k, n, ln, mode, tx_type, x, y, recp[p] + (size_t)y * g.stride[p] + x,
-                       coefp[p] + (size_t)y * g.stride[p] + x, g.stride[p], sm.dcval[k]);
+                       coefp[p] + av1b_coef_offset(g.sb_cols, p, x, y), g.stride[p], sm.dcval[k]);
           }
         }
         // publish the block's side information and mark it decoded

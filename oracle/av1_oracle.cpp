@@ -453,8 +453,8 @@ struct IntraEnc {
         int eob = 0;
         for (int k = cn * cn - 1; k >= 0; k--) if (lv[scan[k]]) { eob = k + 1; break; }
         info.eob[p] = (uint16_t)eob;
-        int16_t* cdst = coef[p] + (size_t)y * g->stride[p] + x;
-        for (int i = 0; i < cn; i++) for (int j = 0; j < cn; j++) cdst[(size_t)i * g->stride[p] + j] = lv[i * cn + j];
+        int16_t* cdst = coef[p] + av1b_coef_offset(g->sb_cols, p, x, y);
+        for (int i = 0; i < cn * cn; i++) cdst[i] = lv[i];
         uint16_t* rdst = rec[p] + (size_t)y * g->stride[p] + x;
         for (int i = 0; i < n; i++) for (int j = 0; j < n; j++) rdst[(size_t)i * g->stride[p] + j] = pred[i * n + j];
         if (eob > 0) orc_inv_txfm2d_add(dq, cn, rdst, g->stride[p], n, n, tx_type, bd);
@@ -671,8 +671,8 @@ extern "C" int orc_encode_inter_frame(const Av1bGeom* g, int bit_depth, int base
         int eob = 0;
         for (int k = cn * cn - 1; k >= 0; k--) if (lv[scan[k]]) { eob = k + 1; break; }
         info.eob[p] = (uint16_t)eob;
-        int16_t* cdst = coef[p] + (size_t)y * g->stride[p] + x;
-        for (int i = 0; i < cn; i++) for (int j = 0; j < cn; j++) cdst[(size_t)i * g->stride[p] + j] = lv[i * cn + j];
+        int16_t* cdst = coef[p] + av1b_coef_offset(g->sb_cols, p, x, y);
+        for (int i = 0; i < cn * cn; i++) cdst[i] = lv[i];
         uint16_t* rdst = rec[p] + (size_t)y * g->stride[p] + x;
         for (int i = 0; i < n; i++) for (int j = 0; j < n; j++) rdst[(size_t)i * g->stride[p] + j] = pred[i * n + j];
         if (eob > 0) orc_inv_txfm2d_add(dq.data(), cn, rdst, g->stride[p], n, n, AV1B_DCT_DCT, bit_depth);

@@ -56,7 +56,7 @@ def test_intra_frame_parity(w, h, bd, crf, blk, tcl, trl, lf):
         orc = O.crop(g, ref.rec)
         for p in range(3):
             hh, ww = (g.height, g.width) if p == 0 else (g.height // 2, g.width // 2)
-            assert np.array_equal(coef[p][:hh, :ww], ref.coef[p][:hh, :ww]), ("coef", i, p)
+            assert np.array_equal(coef[p], ref.coef[p]), ("coef", i, p)
             assert np.array_equal(rec[p], orc[p]), ("recon vs oracle", i, p)
             assert np.array_equal(dec_d[i][p], rec[p]), ("dav1d", i, p)
             assert np.array_equal(dec_a[i][p], rec[p]), ("libaom", i, p)

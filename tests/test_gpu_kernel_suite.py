@@ -239,5 +239,5 @@ def test_inter_encode_vs_oracle(w, h, bd, q):
             assert np.array_equal(blocks[f], want.blocks[f]), (f, integer)
         for p in range(3):
             hh, ww = (h, w) if p == 0 else (h // 2, w // 2)
-            assert np.array_equal(coef[p][:hh, :ww], want.coef[p][:hh, :ww]), ("coef", p, integer)
+            assert np.array_equal(coef[p], want.coef[p]), ("coef", p, integer)
             assert np.array_equal(rec[p][:hh, :ww], want.rec[p][:hh, :ww]), ("rec", p, integer)
