@@ -378,8 +378,20 @@ struct TileWriter {
     init_cdfs(cdf, fp.base_q_idx);
     reset_lr_refs();
     if (fp.frame_type == AV1B_INTER_FRAME) {
+      // compact tile-local copy of what motion vector prediction reads (8 bytes per 8x8 unit)
       t8c0 = mi_col_start >> 1; t8r0 = mi_row_start >> 1; t8w = (mi_col_end - mi_col_start + 1) >> 1;
-      coded8.assign((size_t)t8w * ((mi_row_end - mi_row_start + 1) >> 1), 0);
+      const int t8h = (mi_row_end - mi_row_start + 1) >> 1;
+      units.resize((size_t)t8w * t8h);
+      for (int y = 0; y < t8h; y++) {
+        const Av1bBlockInfo* src = sy.blocks + (size_t)(t8r0 + y) * g.w8 + t8c0;
+        Unit* dst = units.data() + (size_t)y * t8w;
+        for (int x = 0; x < t8w; x++) {
+          dst[x].mv[0] = src[x].mv[0]; dst[x].mv[1] = src[x].mv[1];
+          if (dst[x].mv[0] & 1) dst[x].mv[0] += dst[x].mv[0] > 0 ? -1 : 1;   // lower_mv_precision (allow_high_precision_mv = 0)
+          if (dst[x].mv[1] & 1) dst[x].mv[1] += dst[x].mv[1] > 0 ? -1 : 1;
+          dst[x].w4 = (uint8_t)(1 << (src[x].blk_log2 - 2)); dst[x].is_inter = src[x].is_inter; dst[x].skip = src[x].skip; dst[x].coded = 0;
+        }
+      }
     }
     const int tw4 = mi_col_end - mi_col_start;
     for (int p = 0; p < 3; p++) {
@@ -521,9 +533,11 @@ struct TileWriter {
 
   // ---- inter frames (spec 5.11.18 inter_frame_mode_info, 7.10.2 motion vector prediction) ----
   // Per 8x8 unit of the tile: 0 = not coded yet, 1 = intra, 2 = inter without NEWMV, 3 = inter NEWMV
-  std::vector<uint8_t> coded8;
+  struct Unit { int16_t mv[2]; uint8_t w4, is_inter, skip, coded; };
+  std::vector<Unit> units;
   int t8c0 = 0, t8r0 = 0, t8w = 0;
-  uint8_t& coded(int mi_r, int mi_c) { return coded8[(size_t)((mi_r >> 1) - t8r0) * t8w + ((mi_c >> 1) - t8c0)]; }
+  Unit& unit(int mi_r, int mi_c) { return units[(size_t)((mi_r >> 1) - t8r0) * t8w + ((mi_c >> 1) - t8c0)]; }
+  uint8_t& coded(int mi_r, int mi_c) { return unit(mi_r, mi_c).coded; }
   bool is_inside(int mi_r, int mi_c) const {
     return mi_c >= mi_col_start && mi_c < mi_col_end && mi_r >= mi_row_start && mi_r < mi_row_end;
   }
@@ -535,12 +549,10 @@ struct TileWriter {
     int new_ctx = 0, ref_ctx = 0;
   };
 
-  void add_ref_mv_candidate(MvStack& S, int mr, int mc, int weight) {
-    const Av1bBlockInfo& cb = blk(mr, mc);
+  void add_ref_mv_candidate(MvStack& S, const Unit& cb, int weight) {
     if (!cb.is_inter) return;
-    int cand[2] = {cb.mv[0], cb.mv[1]};
-    for (int k = 0; k < 2; k++) if (cand[k] & 1) cand[k] += cand[k] > 0 ? -1 : 1;   // lower_mv_precision
-    if (coded(mr, mc) == 3) S.num_new++;
+    const int cand[2] = {cb.mv[0], cb.mv[1]};
+    if (cb.coded == 3) S.num_new++;
     S.found = 1;
     int idx = 0;
     for (; idx < S.n; idx++) if (S.mv[idx][0] == cand[0] && S.mv[idx][1] == cand[1]) break;
@@ -555,10 +567,11 @@ struct TileWriter {
     for (int i = 0; i < end4;) {
       const int mr = r + delta_row, mc = c + delta_col + i;
       if (!is_inside(mr, mc)) break;
-      int len = std::min(bw4, 1 << (blk(mr, mc).blk_log2 - 2));
+      const Unit& cu = unit(mr, mc);
+      int len = std::min(bw4, (int)cu.w4);
       if (std::abs(delta_row) > 1) len = std::max(2, len);
       if (step16) len = std::max(4, len);
-      add_ref_mv_candidate(S, mr, mc, len * 2);
+      add_ref_mv_candidate(S, cu, len * 2);
       i += len;
     }
   }
@@ -570,16 +583,19 @@ struct TileWriter {
     for (int i = 0; i < end4;) {
       const int mr = r + delta_row + i, mc = c + delta_col;
       if (!is_inside(mr, mc)) break;
-      int len = std::min(bh4, 1 << (blk(mr, mc).blk_log2 - 2));
+      const Unit& cu = unit(mr, mc);
+      int len = std::min(bh4, (int)cu.w4);
       if (std::abs(delta_col) > 1) len = std::max(2, len);
       if (step16) len = std::max(4, len);
-      add_ref_mv_candidate(S, mr, mc, len * 2);
+      add_ref_mv_candidate(S, cu, len * 2);
       i += len;
     }
   }
   void scan_point(MvStack& S, int r, int c, int delta_row, int delta_col) {
     const int mr = r + delta_row, mc = c + delta_col;
-    if (is_inside(mr, mc) && coded(mr, mc) != 0) add_ref_mv_candidate(S, mr, mc, 4);
+    if (!is_inside(mr, mc)) return;
+    const Unit& cu = unit(mr, mc);
+    if (cu.coded != 0) add_ref_mv_candidate(S, cu, 4);
   }
   static void sort_stack(MvStack& S, int start, int end) {
     while (end > start) {

@@ -127,7 +127,8 @@ struct Slot {
 struct av1b_encoder {
   av1b_config cfg;
   Av1bSeqParams seq;
-  Av1bGeom g;
+  Av1bGeom g;                         // key frames: many small tiles (one CTA per tile in the intra kernel)
+  Av1bGeom g_inter;                   // inter frames: few large tiles (longer CDF adaptation, less host overhead)
   int batch = 0;
   int base_q_idx = 0;
   int blk_log2 = 4;
@@ -325,7 +326,7 @@ static int finish(av1b_encoder* e, Slot& s, bool staged, av1b_packet_cb out_cb, 
   cudaEventElapsedTime(&ms, s.ev_k0, s.ev_k1); e->t_kernel_ms += ms;
   cudaEventElapsedTime(&ms, s.ev_k0, s.ev_me); e->t_me_ms += ms;
   cudaEventElapsedTime(&ms, s.ev_k1, s.ev_d2h); e->t_d2h_ms += ms;
-  const int n = s.n_frames, n_tiles = g.tile_cols * g.tile_rows;
+  const int n = s.n_frames;
   for (int b = 0; b < n; b++) {
     cudaEvent_t* ev = &s.ev_frame[(size_t)b * 4];
     cudaEventElapsedTime(&ms, ev[0], ev[1]);
@@ -338,16 +339,19 @@ static int finish(av1b_encoder* e, Slot& s, bool staged, av1b_packet_cb out_cb, 
   const auto tp0 = std::chrono::steady_clock::now();
   std::vector<Av1bFrameSyms> sy(n);
   std::vector<FramePack> packs(n);
+  std::vector<std::pair<int, int>> tasks;   // (frame, tile)
   for (int b = 0; b < n; b++) {
+    const Av1bGeom& gb = s.is_key[b] ? e->g : e->g_inter;
     memset(&sy[b], 0, sizeof(Av1bFrameSyms));
     sy[b].blocks = s.h_blocks + (size_t)b * e->map_elems;
     for (int p = 0; p < 3; p++) { sy[b].coef[p] = s.h_coef[p] + (size_t)b * e->plane_elems[p]; sy[b].coef_stride[p] = g.stride[p]; }
     sy[b].cdef_idx = s.h_cdef_idx + (size_t)b * g.sb_rows * g.sb_cols;
-    pack_frame_header(e->seq, s.is_key[b] ? e->fp_key : e->fp_inter, g, packs[b]);
+    pack_frame_header(e->seq, s.is_key[b] ? e->fp_key : e->fp_inter, gb, packs[b]);
+    for (int t = 0; t < gb.tile_cols * gb.tile_rows; t++) tasks.emplace_back(b, t);
   }
-  e->pool->parallel_for(n * n_tiles, [&](int t) {
-    const int b = t / n_tiles, tile = t % n_tiles;
-    pack_tile(e->seq, s.is_key[b] ? e->fp_key : e->fp_inter, g, sy[b], tile, packs[b].tiles[tile]);
+  e->pool->parallel_for((int)tasks.size(), [&](int t) {
+    const int b = tasks[t].first, tile = tasks[t].second;
+    pack_tile(e->seq, s.is_key[b] ? e->fp_key : e->fp_inter, s.is_key[b] ? e->g : e->g_inter, sy[b], tile, packs[b].tiles[tile]);
   });
   std::vector<uint8_t> tu;
   for (int b = 0; b < n; b++) {
@@ -421,6 +425,12 @@ int av1b_encoder_create(const av1b_config* cfg, av1b_encoder** out) {
   if (tcl < 0) tcl = av1b_tile_log2(4, probe.sb_cols);
   if (trl < 0) trl = av1b_tile_log2(4, probe.sb_rows);
   av1b_geom_init(&e->g, cfg->width, cfg->height, tcl, trl);
+  {
+    // tiles of inter frames only serve host-side parallelism: about 12x12 superblocks each unless given explicitly
+    const int itc = cfg->tile_cols_log2 >= 0 ? cfg->tile_cols_log2 : av1b_tile_log2(12, probe.sb_cols);
+    const int itr = cfg->tile_rows_log2 >= 0 ? cfg->tile_rows_log2 : av1b_tile_log2(12, probe.sb_rows);
+    av1b_geom_init(&e->g_inter, cfg->width, cfg->height, itc, itr);
+  }
   e->seq.width = cfg->width; e->seq.height = cfg->height; e->seq.bit_depth = cfg->bit_depth;
   e->loop_filters = cfg->reserved[2] == 0;     // reserved[2] = 1 switches the in-loop filters off (tests)
   e->seq.enable_cdef = e->loop_filters ? 1 : 0; e->seq.enable_restoration = 0;
@@ -434,8 +444,8 @@ int av1b_encoder_create(const av1b_config* cfg, av1b_encoder** out) {
   e->keyint = cfg->keyint > 0 ? cfg->keyint : 240;
   av1b_select_frame_params(cfg->bit_depth, e->base_q_idx, AV1B_KEY_FRAME, e->loop_filters ? 1 : 0, &e->fp_key);
   av1b_select_frame_params(cfg->bit_depth, e->base_q_idx, AV1B_INTER_FRAME, e->loop_filters ? 1 : 0, &e->fp_inter);
-  e->fp_key.tile_cols_log2 = e->fp_inter.tile_cols_log2 = e->g.tile_cols_log2;
-  e->fp_key.tile_rows_log2 = e->fp_inter.tile_rows_log2 = e->g.tile_rows_log2;
+  e->fp_key.tile_cols_log2 = e->g.tile_cols_log2; e->fp_key.tile_rows_log2 = e->g.tile_rows_log2;
+  e->fp_inter.tile_cols_log2 = e->g_inter.tile_cols_log2; e->fp_inter.tile_rows_log2 = e->g_inter.tile_rows_log2;
   e->batch = cfg->frames_in_flight > 0 ? cfg->frames_in_flight : 8;
   e->host_threads = cfg->host_threads > 0 ? cfg->host_threads : (int)std::max(1u, std::thread::hardware_concurrency());
   if (cudaSetDevice(cfg->device_id) != cudaSuccess) { set_error("cudaSetDevice failed"); delete e; return AV1B_ERR_CUDA; }

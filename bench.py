@@ -206,7 +206,10 @@ def main():
     frames = make_frames(w, h, bd, F, hdr)               # F consecutive frames of one scene
     if rank:
         frames = frames[rank % len(frames):] + frames[:rank % len(frames)]
-    enc = encoder.Encoder(w, h, bd, crf=args.crf, device_id=local_rank, hdr=hdr, frames_in_flight=F, keyint=args.keyint)
+    from av1_base_b200 import sharding
+    # ranks share the node's host cores: each rank entropy-codes with its share of them
+    enc = encoder.Encoder(w, h, bd, crf=args.crf, device_id=local_rank, hdr=hdr, frames_in_flight=F, keyint=args.keyint,
+                          host_threads=sharding.host_threads_per_rank(world))
     g = enc.geom
     frame_bytes = sum(g.stride[p] * (h if p == 0 else h // 2) * 2 for p in range(3))
     S = int(1.5 * w * h * 2)                             # bytes of one 4:2:0 frame at 2 B/sample
@@ -227,11 +230,7 @@ def main():
     st = enc.stats()
     barrier()
     clocks = sampler.stop()
-    tmax = dt
-    if dist is not None:
-        t = torch.tensor([dt], device="cuda", dtype=torch.float64)
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        tmax = float(t.item())
+    tmax = sharding.max_over_ranks(dt, dist, "cuda")
     value = world * args.steps * F / tmax
 
     # ---------------- e2e: host buffers through av1b_encode_chunk ----------------
@@ -243,10 +242,7 @@ def main():
     tus = enc.encode_chunk(chunk)
     dte = time.perf_counter() - t0
     st_e = enc.stats()
-    if dist is not None:
-        t = torch.tensor([dte], device="cuda", dtype=torch.float64)
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        dte = float(t.item())
+    dte = sharding.max_over_ranks(dte, dist, "cuda")
     e2e = world * len(chunk) / dte
     d2h_per_step = F * (frame_bytes + g.w8 * g.h8 * 20 + g.sb_rows * g.sb_cols)
 
@@ -282,7 +278,7 @@ def main():
         "scaling": "weak", "vs_baseline": None, "dtype": "u16/i32", "data": "synthetic",
         "config": {"workload": desc, "frames_per_step": F, "crf": args.crf, "base_q_idx": st["base_q_idx"],
                    "keyint": args.keyint, "key_frames": st["key_frames"], "inter_frames": st["inter_launches"],
-                   "tiles": "%dx%d" % (g.tile_cols, g.tile_rows),
+                   "tiles_key_frames": "%dx%d" % (g.tile_cols, g.tile_rows), "host_threads": sharding.host_threads_per_rank(world),
                    "l2": "inputs larger than L2 (%.0f MB working set per step)" % (5 * F * frame_bytes / 1e6),
                    "timing": "wall clock between synchronize+barrier pairs (host entropy coding is part of the step); "
                              "kernel times from CUDA events on the encoder stream"},
