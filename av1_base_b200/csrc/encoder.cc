@@ -224,6 +224,7 @@ static int launch(av1b_encoder* e, Slot& s, int n, int64_t first_index) {
   }
   CK(cudaStreamWaitEvent(e->stream, s.ev_src, 0));
   CK(cudaEventRecord(s.ev_k0, e->stream));
+  const int acq0 = bd == 8 ? av1t_ac_q_8[e->base_q_idx] : av1t_ac_q_10[e->base_q_idx];
   // ---- open-loop motion estimation for the whole batch (source pictures only) ----
   if (!e->intra_only) {
     const size_t e0 = e->plane_elems[0];
@@ -235,6 +236,7 @@ static int launch(av1b_encoder* e, Slot& s, int n, int64_t first_index) {
       H.width = g.width; H.height = g.height; H.stride0 = g.stride[0]; H.elems0 = e0;
       for (int l = 0; l < 3; l++) { H.ref[l] = e->d_pyr[l]; H.cur[l] = e->d_pyr[l] + (e0 >> (2 * l)); }
       H.mv2 = e->d_mv2; H.mv_out = e->d_mvs;
+      H.lambda = acq0 >> 1;   // vector-deviation cost in SAD units (tuned on the oracle: about half the AC quantiser step)
       CK(launch_hme(H, n, e->stream));
       e->kernel_launches += 2;
     }
@@ -271,8 +273,10 @@ static int launch(av1b_encoder* e, Slot& s, int n, int64_t first_index) {
       L.g = g; L.bit_depth = bd; L.base_q_idx = e->base_q_idx; L.quant_rnd = 48; L.dc_q = dcq; L.ac_q = acq;
       for (int p = 0; p < 3; p++) { L.src[p] = src[p]; L.ref[p] = prev[p]; L.rec[p] = e->loop_filters ? rec[p] : fin[p]; L.coef[p] = coef[p]; }
       L.blocks = blocks; L.part_map = e->d_map_inter; L.mvs = e->d_mvs + (size_t)b * e->map_elems * 2;
+      L.tb_zero_thr = 0;
       CK(launch_inter_encode(L, e->stream));
-      e->kernel_launches += 1; e->inter_launches += 1;
+      CK(launch_merge_skip(g, blocks, e->stream));
+      e->kernel_launches += 2; e->inter_launches += 1;
     }
     CK(cudaEventRecord(ev[1], e->stream));
     if (e->loop_filters) {
@@ -620,6 +624,11 @@ int av1b_get_inter_frame_params(av1b_encoder* e, Av1bFrameParams* fp) {
   if (!e || !fp) return AV1B_ERR_INVALID;
   *fp = e->fp_inter;
   return AV1B_OK;
+}
+
+int av1b_get_me_lambda(av1b_encoder* e) {
+  if (!e) return AV1B_ERR_INVALID;
+  return (e->cfg.bit_depth == 8 ? av1t_ac_q_8[e->base_q_idx] : av1t_ac_q_10[e->base_q_idx]) >> 1;
 }
 
 int av1b_get_frame_is_key(av1b_encoder* e, uint32_t frame) {

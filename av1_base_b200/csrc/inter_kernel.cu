@@ -115,7 +115,7 @@ __device__ __forceinline__ int code_tb(const InterLaunch& P, int p, int x, int y
   for (int k = 0; k < N; k++) buf[k * S + t] = col[k];
   __syncwarp(gmask);
   int32_t dq[N];
-  int eob = 0;
+  int eob = 0, sum_abs = 0;
   {
     int32_t row[N];
 #pragma unroll
@@ -138,10 +138,23 @@ __device__ __forceinline__ int code_tb(const InterLaunch& P, int p, int x, int y
       dq[l] = c < 0 ? -d : d;
       if (active) cdst[l] = (int16_t)(c < 0 ? -(int32_t)lv : (int32_t)lv);
       if (lv) eob = max(eob, TxTab<N>::iscan(t * N + l) + 1);
+      sum_abs += (int)lv;
+    }
+#pragma unroll
+    for (int o = N / 2; o; o >>= 1) {
+      eob = max(eob, __shfl_xor_sync(gmask, eob, o));
+      sum_abs += __shfl_xor_sync(gmask, sum_abs, o);
+    }
+    const int thr = N >= 16 ? P.tb_zero_thr : (N == 8 ? P.tb_zero_thr >> 1 : 0);
+    if (eob > 0 && sum_abs <= thr) {
+      // not worth coding: drop the whole transform block
+      eob = 0;
+      if (active) {
+#pragma unroll
+        for (int l = 0; l < N; l++) cdst[l] = 0;
+      }
     }
   }
-#pragma unroll
-  for (int o = N / 2; o; o >>= 1) eob = max(eob, __shfl_xor_sync(gmask, eob, o));
   // ---------------- reconstruction ----------------
   uint16_t* rec = P.rec[p] + (size_t)y * stride + x;
   const int maxv = (1 << bd) - 1;
@@ -299,6 +312,48 @@ __global__ void __launch_bounds__(kThreads) inter_encode_kernel(const InterLaunc
 }
 
 }  // namespace
+
+// One CTA of 64 threads per superblock: thread u owns 8x8 unit u (row-major inside the superblock).
+__global__ void __launch_bounds__(64) merge_skip_kernel(Av1bGeom g, Av1bBlockInfo* blocks) {
+  __shared__ uint8_t bl[64], ok16[64];
+  __shared__ int16_t mv[64][2];
+  const int u = threadIdx.x, ux = blockIdx.x * 8 + (u & 7), uy = blockIdx.y * 8 + (u >> 3);
+  const bool inside = ux < g.w8 && uy < g.h8;
+  Av1bBlockInfo* b = inside ? blocks + (size_t)uy * g.w8 + ux : nullptr;
+  bl[u] = inside ? b->blk_log2 : 0;
+  ok16[u] = inside && b->is_inter && b->skip;
+  mv[u][0] = inside ? b->mv[0] : 0; mv[u][1] = inside ? b->mv[1] : 0;
+  __syncthreads();
+  if (u < 4) {
+    // 32x32 quadrant u: children are the 16x16 blocks whose top-left units are o, o+2, o+16, o+18
+    const int o = (u >> 1) * 32 + (u & 1) * 4;
+    bool ok = true;
+    for (int q = 0; q < 4; q++) {
+      const int c = o + (q >> 1) * 16 + (q & 1) * 2;
+      ok = ok && bl[c] == 4 && ok16[c] && mv[c][0] == mv[o][0] && mv[c][1] == mv[o][1];
+    }
+    // the whole 32x32 must lie inside the picture: its bottom-right unit exists
+    ok = ok && bl[o + 27] != 0;
+    if (ok) for (int yy = 0; yy < 4; yy++) for (int xx = 0; xx < 4; xx++) bl[o + yy * 8 + xx] = 5;
+  }
+  __syncthreads();
+  if (u == 0) {
+    bool ok = bl[63] != 0;
+    for (int q = 0; q < 4; q++) {
+      const int c = (q >> 1) * 32 + (q & 1) * 4;
+      ok = ok && bl[c] == 5 && mv[c][0] == mv[0][0] && mv[c][1] == mv[0][1];
+    }
+    if (ok) for (int i = 0; i < 64; i++) bl[i] = 6;
+  }
+  __syncthreads();
+  if (inside && b->blk_log2 != bl[u]) b->blk_log2 = bl[u];
+}
+
+cudaError_t launch_merge_skip(const Av1bGeom& g, Av1bBlockInfo* blocks, cudaStream_t s) {
+  dim3 grid(g.sb_cols, g.sb_rows);
+  merge_skip_kernel<<<grid, 64, 0, s>>>(g, blocks);
+  return cudaGetLastError();
+}
 
 cudaError_t launch_inter_encode(const InterLaunch& p, cudaStream_t s) {
   dim3 grid(p.g.sb_cols, p.g.sb_rows);

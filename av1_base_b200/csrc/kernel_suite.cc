@@ -246,7 +246,7 @@ int av1b_k_pyramid(int device, int width, int height, int n_frames, const uint16
 }
 
 int av1b_k_hme(int device, int width, int height, int n_frames, const uint16_t* cur_l0, const uint16_t* ref_l0,
-               int16_t* mv_out, int reps, double* ms_per_launch) {
+               int lambda, int16_t* mv_out, int reps, double* ms_per_launch) {
   if (!cur_l0 || !ref_l0 || !mv_out || n_frames <= 0) { set_error("bad argument"); return AV1B_ERR_INVALID; }
   Av1bGeom g;
   if (av1b_geom_init(&g, width, height, 0, 0)) { set_error("unsupported size"); return AV1B_ERR_INVALID; }
@@ -264,7 +264,7 @@ int av1b_k_hme(int device, int width, int height, int n_frames, const uint16_t* 
   CKS(launch_pyramid(c[0].as<uint16_t>(), c[1].as<uint16_t>(), c[2].as<uint16_t>(), g.stride[0], g.rows[0], e0, n_frames, t.s));
   CKS(launch_pyramid(r[0].as<uint16_t>(), r[1].as<uint16_t>(), r[2].as<uint16_t>(), g.stride[0], g.rows[0], e0, n_frames, t.s));
   HmeLaunch L;
-  L.width = width; L.height = height; L.stride0 = g.stride[0]; L.elems0 = e0;
+  L.width = width; L.height = height; L.stride0 = g.stride[0]; L.elems0 = e0; L.lambda = lambda;
   for (int l = 0; l < 3; l++) { L.cur[l] = c[l].as<uint16_t>(); L.ref[l] = r[l].as<uint16_t>(); }
   L.mv2 = m2.as<int16_t>(); L.mv_out = mo.as<int16_t>();
   if ((rc = timed(t, reps, ms_per_launch, [&]() { return launch_hme(L, n_frames, t.s); }))) return rc;
@@ -275,8 +275,8 @@ int av1b_k_hme(int device, int width, int height, int n_frames, const uint16_t* 
 
 int av1b_k_inter_encode(int device, int width, int height, int bit_depth, int base_q_idx, const uint8_t* part_map,
                         const int16_t* mvs, const uint16_t* const src[3], const uint16_t* const ref[3],
-                        uint16_t* const rec[3], int16_t* const coef[3], Av1bBlockInfo* blocks, int reps,
-                        double* ms_per_launch) {
+                        uint16_t* const rec[3], int16_t* const coef[3], Av1bBlockInfo* blocks, int tb_zero_thr,
+                        int merge_skip, int reps, double* ms_per_launch) {
   if (!part_map || !mvs || !src || !ref || !rec || !coef || !blocks || base_q_idx < 1 || base_q_idx > 255) {
     set_error("bad argument"); return AV1B_ERR_INVALID;
   }
@@ -303,8 +303,9 @@ int av1b_k_inter_encode(int device, int width, int height, int bit_depth, int ba
     L.src[p] = bs.d[p].as<uint16_t>(); L.ref[p] = br.d[p].as<uint16_t>(); L.rec[p] = bo.d[p].as<uint16_t>();
     L.coef[p] = dc[p].as<int16_t>();
   }
-  L.blocks = dbl.as<Av1bBlockInfo>(); L.part_map = dpm.as<uint8_t>(); L.mvs = dmv.as<int16_t>();
+  L.blocks = dbl.as<Av1bBlockInfo>(); L.part_map = dpm.as<uint8_t>(); L.mvs = dmv.as<int16_t>(); L.tb_zero_thr = tb_zero_thr;
   if ((rc = timed(t, reps, ms_per_launch, [&]() { return launch_inter_encode(L, t.s); }))) return rc;
+  if (merge_skip) CKS(launch_merge_skip(L.g, L.blocks, t.s));
   for (int p = 0; p < 3; p++) CKS(cudaMemcpyAsync(coef[p], dc[p].p, bs.elems[p] * 2, cudaMemcpyDeviceToHost, t.s));
   CKS(cudaMemcpyAsync(blocks, dbl.p, map * sizeof(Av1bBlockInfo), cudaMemcpyDeviceToHost, t.s));
   return download_planes(1, rec, bo, t.s);

@@ -76,6 +76,7 @@ cudaError_t launch_inv_txfm_add(const int32_t* coef, uint16_t* dst, int n_blocks
 // SOURCE picture of every frame).  mv2: scratch [n_frames][n2y*n2x][2]; mv_out: [n_frames][h8*w8][2].
 struct HmeLaunch {
   int32_t width, height, stride0;
+  int32_t lambda;             // cost of one integer sample of deviation from the parent vector (SAD units, L0)
   size_t elems0;
   const uint16_t* cur[3];
   const uint16_t* ref[3];
@@ -98,8 +99,11 @@ struct InterLaunch {
   Av1bBlockInfo* blocks;
   const uint8_t* part_map;    // 16x16 blocks, 8x8 at the picture edge (values 3 / 4)
   const int16_t* mvs;         // [h8*w8][2] (row, col), 1/8 luma samples
+  int32_t tb_zero_thr;        // drop transform blocks whose levels sum to <= thr (16x16) / thr/2 (8x8)
 };
 cudaError_t launch_inter_encode(const InterLaunch& p, cudaStream_t s);
+// Bottom-up merge of skipped inter siblings with equal vectors into 32x32 / 64x64 blocks (side info only).
+cudaError_t launch_merge_skip(const Av1bGeom& g, Av1bBlockInfo* blocks, cudaStream_t s);
 
 void upload_tables_once();
 cudaError_t launch_deblock(const DeblockLaunch& p, int n_frames, cudaStream_t s);

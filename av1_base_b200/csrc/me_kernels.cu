@@ -84,6 +84,7 @@ __global__ void __launch_bounds__(256) hme_l2_kernel(const HmeLaunch P) {
   __syncthreads();
   const int n2x = (P.width + 31) / 32, n2y = (P.height + 31) / 32;
   constexpr int kSide = 2 * kR2 + 1, kCand = kSide * kSide, kCentre = kR2 * kSide + kR2;
+  const int lam2 = max(1, P.lambda >> 4);
   for (int b = warp; b < 16; b += 8) {
     const int bx = b & 3, by = b >> 2;
     const int gbx = blockIdx.x * 4 + bx, gby = blockIdx.y * 4 + by;
@@ -109,7 +110,7 @@ __global__ void __launch_bounds__(256) hme_l2_kernel(const HmeLaunch P) {
         }
       // visiting order: centre first, then raster
       const int order = k == kCentre ? 0 : (k < kCentre ? k + 1 : k);
-      const int cost = k == kCentre ? sad : sad + abs(dx) + abs(dy);
+      const int cost = sad + lam2 * (abs(dx) + abs(dy));
       const unsigned key = ((unsigned)cost << 10) | (unsigned)order;
       best = min(best, key);
     }
@@ -133,9 +134,20 @@ struct RefineSmem {
 };
 
 // 25 candidates (+-2), lanes = candidates; returns the chosen (dy, dx) in all lanes
-template <int N, int RS>
-__device__ __forceinline__ void refine25(const uint16_t* cur, const uint16_t* ref, int lane, int* bdy, int* bdx) {
+__device__ __forceinline__ int subpel_parabola(int sm, int s0, int sp, int lambda) {
+  const int num = sm - sp, den = 2 * (sm - 2 * s0 + sp);
+  if (den <= 0) return 0;
+  if ((long long)num * num <= (long long)4 * den * lambda) return 0;
+  const int a = 8 * num + den, b = 2 * den;
+  const int q = a >= 0 ? a / b : -((-a + b - 1) / b);
+  return clampi(q, -2, 2);
+}
+
+template <int N, int RS, bool kSubpel>
+__device__ __forceinline__ void refine25(const uint16_t* cur, const uint16_t* ref, int lane, int lam, int lam_sub,
+                                         int* bdy, int* bdx, int* qy, int* qx) {
   unsigned key = 0xFFFFFFFFu;
+  int my_sad = 0;
   if (lane < 25) {
     const int dy = lane / 5 - 2, dx = lane % 5 - 2;
     const uint16_t* rp = ref + (2 + dy) * RS + 2 + dx;
@@ -144,13 +156,22 @@ __device__ __forceinline__ void refine25(const uint16_t* cur, const uint16_t* re
 #pragma unroll
       for (int j = 0; j < N; j++) sad += abs((int)cur[i * N + j] - (int)rp[i * RS + j]);
     const int order = lane == 12 ? 0 : (lane < 12 ? lane + 1 : lane);
-    key = ((unsigned)sad << 5) | (unsigned)order;
+    key = ((unsigned)(sad + lam * (abs(dy) + abs(dx))) << 5) | (unsigned)order;
+    my_sad = sad;
   }
   for (int o = 16; o; o >>= 1) key = min(key, __shfl_xor_sync(0xffffffffu, key, o));
   const int order = key & 31;
   const int k = order == 0 ? 12 : (order <= 12 ? order - 1 : order);
   *bdy = k / 5 - 2;
   *bdx = k % 5 - 2;
+  if (kSubpel) {
+    // quarter-sample offset per axis from the parabola through the SADs next to the winner
+    const int s0 = __shfl_sync(0xffffffffu, my_sad, k);
+    const int sl = __shfl_sync(0xffffffffu, my_sad, (k + 31) & 31), sr = __shfl_sync(0xffffffffu, my_sad, (k + 1) & 31);
+    const int su = __shfl_sync(0xffffffffu, my_sad, (k + 27) & 31), sd = __shfl_sync(0xffffffffu, my_sad, (k + 5) & 31);
+    *qx = (k % 5 >= 1 && k % 5 <= 3) ? subpel_parabola(sl, s0, sr, lam_sub) : 0;
+    *qy = (k / 5 >= 1 && k / 5 <= 3) ? subpel_parabola(su, s0, sd, lam_sub) : 0;
+  }
 }
 
 __global__ void __launch_bounds__(256) hme_refine_kernel(const HmeLaunch P) {
@@ -177,26 +198,26 @@ __global__ void __launch_bounds__(256) hme_refine_kernel(const HmeLaunch P) {
     sm.ref1[warp][r * 13 + c] = ref1[(size_t)clampi(by * 8 + py - 2 + r, 0, h1 - 1) * s1 + clampi(bx * 8 + px - 2 + c, 0, w1 - 1)];
   }
   __syncwarp();
-  int dy, dx;
-  refine25<8, 13>(sm.cur1[warp], sm.ref1[warp], lane, &dy, &dx);
-  const int qy = 2 * (py + dy), qx = 2 * (px + dx);
+  int dy, dx, qy = 0, qx = 0;
+  refine25<8, 13, false>(sm.cur1[warp], sm.ref1[warp], lane, P.lambda >> 2, 0, &dy, &dx, &qy, &qx);
+  const int qy0 = 2 * (py + dy), qx0 = 2 * (px + dx);
   // ---- L0: 16x16 block at (16bx, 16by), +-2 around (qx, qy) ----
   for (int o = lane; o < 256; o += 32)
     sm.cur0[warp][o] = cur0[(size_t)clampi(by * 16 + (o >> 4), 0, P.height - 1) * P.stride0 + clampi(bx * 16 + (o & 15), 0, P.width - 1)];
   for (int o = lane; o < 400; o += 32) {
     const int r = o / 20, c = o % 20;
     sm.ref0[warp][r * 21 + c] =
-        ref0[(size_t)clampi(by * 16 + qy - 2 + r, 0, P.height - 1) * P.stride0 + clampi(bx * 16 + qx - 2 + c, 0, P.width - 1)];
+        ref0[(size_t)clampi(by * 16 + qy0 - 2 + r, 0, P.height - 1) * P.stride0 + clampi(bx * 16 + qx0 - 2 + c, 0, P.width - 1)];
   }
   __syncwarp();
-  refine25<16, 21>(sm.cur0[warp], sm.ref0[warp], lane, &dy, &dx);
+  refine25<16, 21, true>(sm.cur0[warp], sm.ref0[warp], lane, P.lambda, P.lambda, &dy, &dx, &qy, &qx);
   if (lane < 4) {
     const int uy = by * 2 + (lane >> 1), ux = bx * 2 + (lane & 1);
     const int w8 = P.width >> 3, h8 = P.height >> 3;
     if (uy < h8 && ux < w8) {
       int16_t* out = P.mv_out + ((size_t)frame * w8 * h8 + (size_t)uy * w8 + ux) * 2;
-      out[0] = (int16_t)((qy + dy) * 8);
-      out[1] = (int16_t)((qx + dx) * 8);
+      out[0] = (int16_t)((qy0 + dy) * 8 + 2 * qy);
+      out[1] = (int16_t)((qx0 + dx) * 8 + 2 * qx);
     }
   }
 }

@@ -121,6 +121,10 @@ class Encoder:
         _check(abi.lib().av1b_get_inter_frame_params(self._h, C.byref(fp)))
         return fp
 
+    def me_lambda(self):
+        """Vector-deviation cost the encoder hands to the motion search (SAD units)."""
+        return int(abi.lib().av1b_get_me_lambda(self._h))
+
     def frame_is_key(self, frame):
         rc = abi.lib().av1b_get_frame_is_key(self._h, frame)
         if rc < 0:

@@ -98,7 +98,7 @@ def pyramid(width, height, l0_frames, device=0, reps=1):
     return l1, l2, ms.value
 
 
-def hme(width, height, cur_l0, ref_l0, device=0, reps=1):
+def hme(width, height, cur_l0, ref_l0, lam=0, device=0, reps=1):
     """cur_l0 / ref_l0: [n, rows, stride] padded luma. Returns (mv [n, h8*w8, 2], ms)."""
     cur = np.ascontiguousarray(cur_l0, np.uint16)
     ref = np.ascontiguousarray(ref_l0, np.uint16)
@@ -106,11 +106,12 @@ def hme(width, height, cur_l0, ref_l0, device=0, reps=1):
     mv = np.zeros((n, (height // 8) * (width // 8), 2), np.int16)
     ms = C.c_double(0)
     _ck(abi.lib().av1b_k_hme(device, width, height, n, cur.ctypes.data_as(C.c_void_p), ref.ctypes.data_as(C.c_void_p),
-                             mv.ctypes.data_as(C.c_void_p), reps, C.byref(ms)))
+                             int(lam), mv.ctypes.data_as(C.c_void_p), reps, C.byref(ms)))
     return mv, ms.value
 
 
-def inter_encode(width, height, bit_depth, base_q_idx, part_map, mvs, src_padded, ref_padded, device=0, reps=1):
+def inter_encode(width, height, bit_depth, base_q_idx, part_map, mvs, src_padded, ref_padded, tb_zero_thr=0,
+                 merge_skip=False, device=0, reps=1):
     """Returns (rec[3], coef[3], blocks, ms); planes in the padded layout."""
     src = [np.ascontiguousarray(p, np.uint16) for p in src_padded]
     ref = [np.ascontiguousarray(p, np.uint16) for p in ref_padded]
@@ -122,5 +123,5 @@ def inter_encode(width, height, bit_depth, base_q_idx, part_map, mvs, src_padded
     ms = C.c_double(0)
     _ck(abi.lib().av1b_k_inter_encode(device, width, height, bit_depth, base_q_idx, pm.ctypes.data_as(C.c_void_p),
                                       mv.ctypes.data_as(C.c_void_p), _p3(src), _p3(ref), _p3(rec), _p3(coef),
-                                      blocks.ctypes.data_as(C.c_void_p), reps, C.byref(ms)))
+                                      blocks.ctypes.data_as(C.c_void_p), int(tb_zero_thr), int(merge_skip), reps, C.byref(ms)))
     return rec, coef, blocks, ms.value

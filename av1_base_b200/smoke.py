@@ -23,7 +23,8 @@ def run():
         if i == 0:
             ref, fp = O.encode_intra_frame(g, fr, bd, q, pm), enc.frame_params()
         else:
-            ref, fp = O.encode_inter_frame(g, fr, bd, q, pm, O.hme(g, pyr, prev_pyr), prev_fin), enc.inter_frame_params()
+            ref, fp = O.encode_inter_frame(g, fr, bd, q, pm, O.hme(g, pyr, prev_pyr, enc.me_lambda()), prev_fin), enc.inter_frame_params()
+            O.merge_skip_blocks(g, ref.blocks)
         O.deblock_frame(g, bd, ref.blocks, ref.rec, list(fp.lf_level), fp.lf_sharpness)
         fin = O.cdef_frame(g, bd, ref.blocks, fp, O.cdef_search(g, bd, ref.blocks, fp, ref.rec, O.pad_planes(g, fr)), ref.rec)
         rec = enc.recon(i)

@@ -10,7 +10,7 @@ def _smooth_noise(rng, h, w, sigma):
     return n * sigma
 
 
-def synth_clip(width, height, bit_depth, n_frames, seed=1, scene_len=80, hdr=False):
+def synth_clip(width, height, bit_depth, n_frames, seed=1, scene_len=80, hdr=False, noise=1.0):
     """Returns a list of [Y, U, V] uint16 arrays."""
     scale = 1 << (bit_depth - 8)
     lo, hi = 16 * scale, 235 * scale
@@ -40,7 +40,7 @@ def synth_clip(width, height, bit_depth, n_frames, seed=1, scene_len=80, hdr=Fal
             tex = r["lum"] + r["amp"] * np.sin((xx - x0) * r["fx"]) * np.sin((yy - y0) * r["fy"])
             img = np.where(m, tex, img)
         nrng = np.random.default_rng(seed * 100000 + f)
-        img = img + _smooth_noise(nrng, height, width, 1.5) + nrng.standard_normal((height, width)) * 1.0
+        img = img + (_smooth_noise(nrng, height, width, 1.5) + nrng.standard_normal((height, width)) * 1.0) * noise
         if hdr:   # PQ-like: compress most codes into the lower half, sparse highlights
             img = 16 + (np.clip(img, 16, 235) - 16) ** 1.35 / (219 ** 0.35)
         Y = np.clip(np.rint(img * scale), lo, hi).astype(np.uint16)

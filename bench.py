@@ -92,6 +92,14 @@ def make_frames(w, h, bd, n, hdr):
     return synth.synth_clip(w, h, bd, n, seed=4, scene_len=max(1, n // 2), hdr=hdr)
 
 
+def abi_tables_acq(bd, qidx):
+    """AC quantiser step of a qindex (read from the generated table header: no device needed)."""
+    import re
+    txt = open(os.path.join(ROOT, "av1_base_b200", "csrc", "av1_tables.h")).read()
+    m = re.search(r"av1t_ac_q_%d\[\d+\] = \{(.*?)\};" % bd, txt, re.S)
+    return [int(v) for v in re.findall(r"-?\d+", m.group(1))][qidx]
+
+
 def oracle_chunk(frames, w, h, bd, qidx):
     """CPU port of the same path (oracle/av1_oracle.cpp) for one chunk: key frame, then inter frames
     (hierarchical ME on the source pyramid, motion-compensated residual coding), deblock + CDEF
@@ -101,6 +109,7 @@ def oracle_chunk(frames, w, h, bd, qidx):
     import ctypes as C
     g = O.geom(w, h, 0, 0)
     pm = O.partition_fixed(g, 4)
+    lam = (abi_tables_acq(bd, qidx)) >> 1
     fps = []
     for ft in (0, 1):
         fp = abi.FrameParams()
@@ -112,7 +121,8 @@ def oracle_chunk(frames, w, h, bd, qidx):
         if i == 0:
             r, fp = O.encode_intra_frame(g, fr, bd, qidx, pm), fps[0]
         else:
-            r, fp = O.encode_inter_frame(g, fr, bd, qidx, pm, O.hme(g, pyr, prev_pyr), prev_fin), fps[1]
+            r, fp = O.encode_inter_frame(g, fr, bd, qidx, pm, O.hme(g, pyr, prev_pyr, lam), prev_fin), fps[1]
+            O.merge_skip_blocks(g, r.blocks)
         O.deblock_frame(g, bd, r.blocks, r.rec, list(fp.lf_level), fp.lf_sharpness)
         src = O.pad_planes(g, fr)
         prev_fin = O.cdef_frame(g, bd, r.blocks, fp, O.cdef_search(g, bd, r.blocks, fp, r.rec, src), r.rec)

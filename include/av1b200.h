@@ -95,6 +95,8 @@ struct Av1bFrameParams;
 /* frame-level parameters the encoder signals for key frames (deblock levels, CDEF presets, ...) */
 int av1b_get_frame_params(av1b_encoder* enc, struct Av1bFrameParams* fp);
 int av1b_get_inter_frame_params(av1b_encoder* enc, struct Av1bFrameParams* fp);
+/* vector-deviation cost (SAD units) the encoder uses in its motion search: half the AC quantiser step */
+int av1b_get_me_lambda(av1b_encoder* enc);
 /* 1 / 0: whether kept frame `frame_in_chunk` was coded as a key frame (needs config.reserved[0] = 1) */
 int av1b_get_frame_is_key(av1b_encoder* enc, uint32_t frame_in_chunk);
 /* chosen CDEF preset per 64x64 superblock of a kept frame: idx[sb_rows*sb_cols] */
@@ -136,14 +138,17 @@ int av1b_k_lr(int device, int width, int height, int bit_depth, int n_frames, co
 int av1b_k_pyramid(int device, int width, int height, int n_frames, const uint16_t* l0, uint16_t* l1, uint16_t* l2,
                    int reps, double* ms_per_launch);
 /* Hierarchical motion estimation (E2): cur / ref = n_frames padded luma planes each; mv_out =
- * [n_frames][h8*w8][2] (row, col) in 1/8 luma samples. The timed launch is the search (two kernels). */
+ * [n_frames][h8*w8][2] (row, col) in 1/8 luma samples. lambda = cost of one sample of deviation from the
+ * parent vector (SAD units). The timed launch is the search (two kernels). */
 int av1b_k_hme(int device, int width, int height, int n_frames, const uint16_t* cur_l0, const uint16_t* ref_l0,
-               int16_t* mv_out, int reps, double* ms_per_launch);
-/* Inter frame encode (E4 + E5 for inter frames): one frame; part_map [h8*w8] with values 3 / 4. */
+               int lambda, int16_t* mv_out, int reps, double* ms_per_launch);
+/* Inter frame encode (E4 + E5 for inter frames): one frame; part_map [h8*w8] with values 3 / 4.
+ * tb_zero_thr: drop transform blocks whose levels sum to <= thr; merge_skip: afterwards merge skipped
+ * siblings with equal vectors into 32x32 / 64x64 blocks. */
 int av1b_k_inter_encode(int device, int width, int height, int bit_depth, int base_q_idx, const uint8_t* part_map,
                         const int16_t* mvs, const uint16_t* const src[3], const uint16_t* const ref[3],
-                        uint16_t* const rec[3], int16_t* const coef[3], struct Av1bBlockInfo* blocks, int reps,
-                        double* ms_per_launch);
+                        uint16_t* const rec[3], int16_t* const coef[3], struct Av1bBlockInfo* blocks, int tb_zero_thr,
+                        int merge_skip, int reps, double* ms_per_launch);
 
 /* ---- host entropy coder over symbol streams (the part that "runs on the host") -------------- */
 struct Av1bSeqParams; struct Av1bFrameParams; struct Av1bFrameSyms;

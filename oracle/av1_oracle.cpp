@@ -547,9 +547,10 @@ extern "C" void orc_inter_predict(const uint16_t* ref, int rstride, int ref_w, i
 // ------------------------------------------------------------------------------------------------
 // Hierarchical motion estimation (encoder side, ours): open loop on SOURCE pictures.
 //   pyramid: L1 = 2x2 box average (a+b+c+d+2)>>2 of L0 luma, L2 likewise from L1;
-//   L2: every 8x8 block (32x32 luma) full search +-kR2, cost = SAD + |dx| + |dy|;
-//   L1: every 8x8 block (16x16 luma) +-2 around twice the parent vector, cost = SAD;
-//   L0: every 16x16 block +-2 around twice the L1 vector, cost = SAD.
+//   L2: every 8x8 block (32x32 luma) full search +-kR2, cost = SAD + lam2 (|dx| + |dy|);
+//   L1: every 8x8 block (16x16 luma) +-2 around twice the parent vector, cost = SAD + lam1 (|dx| + |dy|);
+//   L0: every 16x16 block +-2 around twice the L1 vector, cost = SAD + lambda (|dx| + |dy|), then a quarter-sample offset per axis
+//       from the parabola through the SADs next to the winner.
 // Candidates are visited centre first, then in raster order; a candidate replaces the best only if
 // strictly cheaper.  Samples outside a picture are edge-replicated (for both pictures).
 // ------------------------------------------------------------------------------------------------
@@ -573,10 +574,23 @@ static int sad_block(const uint16_t* cur, const uint16_t* ref, int stride, int w
   return s;
 }
 enum { kR2 = 12 };
+// offset of the minimum in quarter samples (-2..2) from the costs at -1, 0, +1 (0 when the three points are not convex)
+static inline int subpel_parabola(int sm, int s0, int sp, int lambda) {
+  const int num = sm - sp, den = 2 * (sm - 2 * s0 + sp);
+  if (den <= 0) return 0;
+  if ((int64_t)num * num <= (int64_t)4 * den * lambda) return 0;   // predicted gain num^2 / (4 den) must exceed lambda
+  const int a = 8 * num + den, b = 2 * den;              // round(4 * num / den) = floor((8 num + den) / (2 den))
+  const int q = a >= 0 ? a / b : -((-a + b - 1) / b);
+  return clampi(q, -2, 2);
+}
 // cur/ref: three luma levels each (L0 stride = g->stride[0]; L1, L2 have strides stride[0]/2, stride[0]/4).
 // mv_out: [h8*w8][2] (row, col) in 1/8 luma samples, the vector of a 16x16 block replicated on its 8x8 units.
+// lambda: cost of one integer sample of deviation from the projected parent vector at L0, in SAD units
+// (L1 uses lambda/4, L2 max(1, lambda/16) per quarter-resolution sample from the zero vector); a
+// quarter-sample offset is kept on an axis only if the parabola predicts a SAD gain above lambda.
 extern "C" void orc_hme(const Av1bGeom* g, const uint16_t* cur0, const uint16_t* cur1, const uint16_t* cur2,
-                        const uint16_t* ref0, const uint16_t* ref1, const uint16_t* ref2, int16_t* mv_out) {
+                        const uint16_t* ref0, const uint16_t* ref1, const uint16_t* ref2, int lambda, int16_t* mv_out) {
+  const int lam1 = lambda >> 2, lam2 = std::max(1, lambda >> 4);
   const int W = g->width, H = g->height, s0 = g->stride[0], s1 = s0 / 2, s2 = s0 / 4;
   const int w1 = W / 2, h1 = H / 2, w2 = W / 4, h2 = H / 4;
   const int n2x = (W + 31) / 32, n2y = (H + 31) / 32, n1x = (W + 15) / 16, n1y = (H + 15) / 16;
@@ -587,7 +601,7 @@ extern "C" void orc_hme(const Av1bGeom* g, const uint16_t* cur0, const uint16_t*
       for (int dy = -kR2; dy <= kR2; dy++)
         for (int dx = -kR2; dx <= kR2; dx++) {
           if (!dx && !dy) continue;
-          const int c = sad_block(cur2, ref2, s2, w2, h2, bx * 8, by * 8, 8, dx, dy) + abs(dx) + abs(dy);
+          const int c = sad_block(cur2, ref2, s2, w2, h2, bx * 8, by * 8, 8, dx, dy) + lam2 * (abs(dx) + abs(dy));
           if (c < best) { best = c; bdx = dx; bdy = dy; }
         }
       mv2[(by * n2x + bx) * 2] = bdy; mv2[(by * n2x + bx) * 2 + 1] = bdx;
@@ -599,7 +613,7 @@ extern "C" void orc_hme(const Av1bGeom* g, const uint16_t* cur0, const uint16_t*
       for (int dy = -2; dy <= 2; dy++)
         for (int dx = -2; dx <= 2; dx++) {
           if (!dx && !dy) continue;
-          const int c = sad_block(cur1, ref1, s1, w1, h1, bx * 8, by * 8, 8, pxv + dx, py + dy);
+          const int c = sad_block(cur1, ref1, s1, w1, h1, bx * 8, by * 8, 8, pxv + dx, py + dy) + lam1 * (abs(dx) + abs(dy));
           if (c < best) { best = c; bdx = dx; bdy = dy; }
         }
       mv1[(by * n1x + bx) * 2] = py + bdy; mv1[(by * n1x + bx) * 2 + 1] = pxv + bdx;
@@ -607,14 +621,21 @@ extern "C" void orc_hme(const Av1bGeom* g, const uint16_t* cur0, const uint16_t*
   for (int by = 0; by < n1y; by++)
     for (int bx = 0; bx < n1x; bx++) {
       const int py = 2 * mv1[(by * n1x + bx) * 2], pxv = 2 * mv1[(by * n1x + bx) * 2 + 1];
-      int best = sad_block(cur0, ref0, s0, W, H, bx * 16, by * 16, 16, pxv, py), bdx = 0, bdy = 0;
+      int sads[25];
       for (int dy = -2; dy <= 2; dy++)
-        for (int dx = -2; dx <= 2; dx++) {
-          if (!dx && !dy) continue;
-          const int c = sad_block(cur0, ref0, s0, W, H, bx * 16, by * 16, 16, pxv + dx, py + dy);
-          if (c < best) { best = c; bdx = dx; bdy = dy; }
-        }
-      const int mvy = (py + bdy) * 8, mvx = (pxv + bdx) * 8;
+        for (int dx = -2; dx <= 2; dx++)
+          sads[(dy + 2) * 5 + dx + 2] = sad_block(cur0, ref0, s0, W, H, bx * 16, by * 16, 16, pxv + dx, py + dy);
+      int k = 12, best = sads[12];
+      for (int c = 0; c < 25; c++) {
+        const int cost = sads[c] + lambda * (abs(c / 5 - 2) + abs(c % 5 - 2));
+        if (c != 12 && cost < best) { best = cost; k = c; }
+      }
+      const int bdy = k / 5 - 2, bdx = k % 5 - 2;
+      // quarter-sample refinement: vertex of the parabola through the three SADs around the winner, per axis
+      int qx = 0, qy = 0;
+      if (k % 5 >= 1 && k % 5 <= 3) qx = subpel_parabola(sads[k - 1], sads[k], sads[k + 1], lambda);
+      if (k / 5 >= 1 && k / 5 <= 3) qy = subpel_parabola(sads[k - 5], sads[k], sads[k + 5], lambda);
+      const int mvy = (py + bdy) * 8 + 2 * qy, mvx = (pxv + bdx) * 8 + 2 * qx;
       for (int uy = by * 2; uy < std::min(by * 2 + 2, g->h8); uy++)
         for (int ux = bx * 2; ux < std::min(bx * 2 + 2, g->w8); ux++) {
           mv_out[(uy * g->w8 + ux) * 2] = (int16_t)mvy;
@@ -628,7 +649,9 @@ extern "C" void orc_hme(const Av1bGeom* g, const uint16_t* cur0, const uint16_t*
 // vector (one per 8x8 unit; all units of a block carry the same vector), DCT_DCT residual coding with
 // the same quantiser as the intra path.  Blocks are independent of each other.
 // ------------------------------------------------------------------------------------------------
-extern "C" int orc_encode_inter_frame(const Av1bGeom* g, int bit_depth, int base_q_idx, int quant_rnd,
+// tb_zero_thr: a transform block whose quantised levels sum (in magnitude) to at most the threshold is
+// dropped (all levels zero): thr for 16x16 blocks, thr/2 for 8x8, never for 4x4.
+extern "C" int orc_encode_inter_frame(const Av1bGeom* g, int bit_depth, int base_q_idx, int quant_rnd, int tb_zero_thr,
                                       const uint16_t* src_y, const uint16_t* src_u, const uint16_t* src_v,
                                       int sy_stride, int suv_stride, const uint8_t* part_map, const int16_t* mvs,
                                       const uint16_t* ref_y, const uint16_t* ref_u, const uint16_t* ref_v,
@@ -666,6 +689,12 @@ extern "C" int orc_encode_inter_frame(const Av1bGeom* g, int bit_depth, int base
         const int cn = std::min(n, 32);
         orc_fwd_txfm2d(resid.data(), n, cf.data(), cn, n, n, AV1B_DCT_DCT);
         orc_quant_dequant(cf.data(), cn, lv.data(), cn, dq.data(), cn, n, n, base_q_idx, bit_depth, quant_rnd);
+        {
+          const int thr = n >= 16 ? tb_zero_thr : (n == 8 ? tb_zero_thr >> 1 : 0);
+          int sum = 0;
+          for (int i = 0; i < cn * cn; i++) sum += abs(lv[i]);
+          if (sum <= thr) for (int i = 0; i < cn * cn; i++) { lv[i] = 0; dq[i] = 0; }
+        }
         const int16_t* scan = cn == 4 ? av1t_scan_default_4x4 : cn == 8 ? av1t_scan_default_8x8
                               : cn == 16 ? av1t_scan_default_16x16 : av1t_scan_default_32x32;
         int eob = 0;
@@ -681,6 +710,27 @@ extern "C" int orc_encode_inter_frame(const Av1bGeom* g, int bit_depth, int base
       for (int yy = 0; yy < n8; yy++) for (int xx = 0; xx < n8; xx++) blocks[(uy + yy) * g->w8 + ux + xx] = info;
     }
   return 0;
+}
+
+// Bottom-up merge of skipped inter blocks: four sibling blocks of one size that are all inter, all skip
+// and carry the same vector become one block of the next size (16 -> 32 -> 64).  The prediction of the
+// merged block is sample for sample that of its children, so only the side information changes
+// (and with it the deblocking edges: the merge runs before the loop filters).
+extern "C" void orc_merge_skip_blocks(const Av1bGeom* g, Av1bBlockInfo* blocks) {
+  for (int bl = 5; bl <= 6; bl++) {
+    const int n8 = 1 << (bl - 3), h8 = n8 >> 1;
+    for (int y0 = 0; y0 + n8 <= g->h8; y0 += n8)
+      for (int x0 = 0; x0 + n8 <= g->w8; x0 += n8) {
+        const Av1bBlockInfo& c0 = blocks[y0 * g->w8 + x0];
+        bool ok = true;
+        for (int q = 0; q < 4 && ok; q++) {
+          const Av1bBlockInfo& c = blocks[(y0 + (q >> 1) * h8) * g->w8 + x0 + (q & 1) * h8];
+          ok = c.blk_log2 == bl - 1 && c.is_inter && c.skip && c.mv[0] == c0.mv[0] && c.mv[1] == c0.mv[1];
+        }
+        if (!ok) continue;
+        for (int yy = 0; yy < n8; yy++) for (int xx = 0; xx < n8; xx++) blocks[(y0 + yy) * g->w8 + x0 + xx].blk_log2 = (uint8_t)bl;
+      }
+  }
 }
 
 extern "C" int orc_geom_init(Av1bGeom* g, int w, int h, int tcl, int trl) { return av1b_geom_init(g, w, h, tcl, trl); }

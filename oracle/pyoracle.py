@@ -118,15 +118,21 @@ def pyramid(g, luma_padded):
     return [l0, l1, l2]
 
 
-def hme(g, cur_pyr, ref_pyr):
-    """Motion vectors [h8*w8, 2] (row, col) in 1/8 luma samples."""
+def hme(g, cur_pyr, ref_pyr, lam=0):
+    """Motion vectors [h8*w8, 2] (row, col) in 1/8 luma samples. lam: vector-deviation cost (SAD units)."""
     mv = np.zeros((g.h8 * g.w8, 2), np.int16)
     lib().orc_hme(C.byref(g), ptr(cur_pyr[0]), ptr(cur_pyr[1]), ptr(cur_pyr[2]), ptr(ref_pyr[0]), ptr(ref_pyr[1]),
-                  ptr(ref_pyr[2]), ptr(mv))
+                  ptr(ref_pyr[2]), int(lam), ptr(mv))
     return mv
 
 
-def encode_inter_frame(g, frame, bit_depth, base_q_idx, part_map, mvs, ref_planes, quant_rnd=48):
+def merge_skip_blocks(g, blocks):
+    """In place: merges skipped inter siblings with equal vectors into 32x32 / 64x64 blocks."""
+    lib().orc_merge_skip_blocks(C.byref(g), ptr(blocks))
+    return blocks
+
+
+def encode_inter_frame(g, frame, bit_depth, base_q_idx, part_map, mvs, ref_planes, quant_rnd=48, tb_zero_thr=0):
     """frame: [Y,U,V]; ref_planes: 3 padded planes (previous reconstructed frame); mvs: [h8*w8, 2] int16."""
     Y, U, V = [np.ascontiguousarray(p, dtype=np.uint16) for p in frame]
     mvs = np.ascontiguousarray(mvs, np.int16)
@@ -134,7 +140,7 @@ def encode_inter_frame(g, frame, bit_depth, base_q_idx, part_map, mvs, ref_plane
     r.rec = [np.zeros((g.rows[p], g.stride[p]), np.uint16) for p in range(3)]
     r.coef = [np.zeros((g.rows[p], g.stride[p]), np.int16) for p in range(3)]
     r.blocks = np.zeros(g.h8 * g.w8, abi.BLOCK_INFO_DTYPE)
-    rc = lib().orc_encode_inter_frame(C.byref(g), bit_depth, base_q_idx, quant_rnd, ptr(Y), ptr(U), ptr(V),
+    rc = lib().orc_encode_inter_frame(C.byref(g), bit_depth, base_q_idx, quant_rnd, tb_zero_thr, ptr(Y), ptr(U), ptr(V),
                                       Y.shape[1], U.shape[1], ptr(part_map), ptr(mvs),
                                       ptr(ref_planes[0]), ptr(ref_planes[1]), ptr(ref_planes[2]),
                                       ptr(r.rec[0]), ptr(r.rec[1]), ptr(r.rec[2]), ptr(r.blocks),

@@ -46,8 +46,9 @@ def test_chunk_parity(w, h, bd, crf, tcl, trl, lf, nfr, fif, keyint):
         if key:
             ref = O.encode_intra_frame(g, fr, bd, q, pm)
         else:
-            mvs = O.hme(g, pyr, prev_pyr)
+            mvs = O.hme(g, pyr, prev_pyr, enc.me_lambda())
             ref = O.encode_inter_frame(g, fr, bd, q, pm, mvs, prev_fin)
+            O.merge_skip_blocks(g, ref.blocks)
         blocks, coef = enc.frame_syms(i)
         for f in ("blk_log2", "y_mode", "uv_mode", "skip", "eob", "is_inter", "mv"):
             assert np.array_equal(blocks[f], ref.blocks[f]), (f, i)

@@ -200,10 +200,11 @@ def test_pyramid_and_hme_vs_oracle(w, h, bd):
     for i in range(len(frames)):
         assert np.array_equal(l1[i][:h // 2, :w // 2], pyr[i][1][:h // 2, :w // 2])
         assert np.array_equal(l2[i][:h // 4, :w // 4], pyr[i][2][:h // 4, :w // 4])
-    mv, _ = kernels.hme(w, h, l0[1:], l0[:-1])
-    for i in range(1, len(frames)):
-        want = O.hme(g, pyr[i], pyr[i - 1])
-        assert np.array_equal(mv[i - 1], want), i
+    for lam in (0, 40 << (bd - 8), 300 << (bd - 8)):
+        mv, _ = kernels.hme(w, h, l0[1:], l0[:-1], lam=lam)
+        for i in range(1, len(frames)):
+            want = O.hme(g, pyr[i], pyr[i - 1], lam)
+            assert np.array_equal(mv[i - 1], want), (i, lam)
 
 
 def random_mvs(g, pm, rng, integer):
@@ -231,10 +232,16 @@ def test_inter_encode_vs_oracle(w, h, bd, q):
     pm = O.partition_fixed(g, 4)
     ref = O.encode_intra_frame(g, frames[0], bd, q, pm).rec
     src = O.pad_planes(g, frames[1])
-    for integer in (True, False):
+    for integer, thr, merge in ((True, 0, False), (False, 0, True), (True, 3, True)):
         mvs = random_mvs(g, pm, rng, integer)
-        want = O.encode_inter_frame(g, frames[1], bd, q, pm, mvs, ref)
-        rec, coef, blocks, _ = kernels.inter_encode(w, h, bd, q, pm, mvs, src, ref)
+        if merge:   # large uniform regions so that 32x32 / 64x64 merges happen
+            mvs = mvs.reshape(g.h8, g.w8, 2).copy()
+            mvs[:g.h8 // 2] = mvs[0, 0]
+            mvs = mvs.reshape(-1, 2)
+        want = O.encode_inter_frame(g, frames[1], bd, q, pm, mvs, ref, tb_zero_thr=thr)
+        if merge:
+            O.merge_skip_blocks(g, want.blocks)
+        rec, coef, blocks, _ = kernels.inter_encode(w, h, bd, q, pm, mvs, src, ref, tb_zero_thr=thr, merge_skip=merge)
         for f in ("blk_log2", "skip", "eob", "is_inter", "mv", "tx_type_y"):
             assert np.array_equal(blocks[f], want.blocks[f]), (f, integer)
         for p in range(3):
