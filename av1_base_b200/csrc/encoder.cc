@@ -130,7 +130,8 @@ struct av1b_encoder {
   Av1bGeom g;                         // key frames: many small tiles (one CTA per tile in the intra kernel)
   Av1bGeom g_inter;                   // inter frames: few large tiles (longer CDF adaptation, less host overhead)
   int batch = 0;
-  int base_q_idx = 0;
+  int base_q_idx = 0;                 // inter frames
+  int base_q_idx_key = 0;             // key frames: 3/4 of it (a better reference pays for itself over the GOP)
   int blk_log2 = 4;
   int keyint = 240;
   bool keep = false;
@@ -263,7 +264,9 @@ static int launch(av1b_encoder* e, Slot& s, int n, int64_t first_index) {
     Av1bBlockInfo* blocks = s.d_blocks + (size_t)b * e->map_elems;
     if (key) {
       IntraLaunch L;
-      L.g = g; L.bit_depth = bd; L.base_q_idx = e->base_q_idx; L.quant_rnd = 48; L.dc_q = dcq; L.ac_q = acq;
+      L.g = g; L.bit_depth = bd; L.base_q_idx = e->base_q_idx_key; L.quant_rnd = 48;
+      L.dc_q = bd == 8 ? av1t_dc_q_8[e->base_q_idx_key] : av1t_dc_q_10[e->base_q_idx_key];
+      L.ac_q = bd == 8 ? av1t_ac_q_8[e->base_q_idx_key] : av1t_ac_q_10[e->base_q_idx_key];
       for (int p = 0; p < 3; p++) { L.src[p] = src[p]; L.rec[p] = e->loop_filters ? rec[p] : fin[p]; L.coef[p] = coef[p]; L.plane_elems[p] = e->plane_elems[p]; }
       L.blocks = blocks; L.part_map = e->d_map_key; L.map_elems = e->map_elems;
       CK(launch_intra_encode(L, 1, e->stream));
@@ -441,12 +444,13 @@ int av1b_encoder_create(const av1b_config* cfg, av1b_encoder** out) {
   e->seq.fps_num = cfg->fps_num; e->seq.fps_den = cfg->fps_den; e->seq.color_hdr = cfg->hdr;
   e->base_q_idx = av1t_quantizer_to_qindex[cfg->crf];
   if (e->base_q_idx < 1) e->base_q_idx = 1;   // lossless (qindex 0) is not supported
+  e->base_q_idx_key = cfg->reserved[3] ? e->base_q_idx : std::max(1, e->base_q_idx * 3 / 4);
   e->blk_log2 = cfg->reserved[1] ? cfg->reserved[1] : 4;
   if (e->blk_log2 < 3 || e->blk_log2 > 6) { set_error("block log2 must be 3..6"); delete e; return AV1B_ERR_INVALID; }
   e->keep = cfg->reserved[0] != 0;
   e->intra_only = cfg->reserved[3] != 0;      // reserved[3] = 1: every frame is a key frame
   e->keyint = cfg->keyint > 0 ? cfg->keyint : 240;
-  av1b_select_frame_params(cfg->bit_depth, e->base_q_idx, AV1B_KEY_FRAME, e->loop_filters ? 1 : 0, &e->fp_key);
+  av1b_select_frame_params(cfg->bit_depth, e->base_q_idx_key, AV1B_KEY_FRAME, e->loop_filters ? 1 : 0, &e->fp_key);
   av1b_select_frame_params(cfg->bit_depth, e->base_q_idx, AV1B_INTER_FRAME, e->loop_filters ? 1 : 0, &e->fp_inter);
   e->fp_key.tile_cols_log2 = e->g.tile_cols_log2; e->fp_key.tile_rows_log2 = e->g.tile_rows_log2;
   e->fp_inter.tile_cols_log2 = e->g_inter.tile_cols_log2; e->fp_inter.tile_rows_log2 = e->g_inter.tile_rows_log2;

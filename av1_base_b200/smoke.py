@@ -21,7 +21,7 @@ def run():
     for i, fr in enumerate(frames):
         pyr = O.pyramid(g, O.pad_planes(g, fr)[0])
         if i == 0:
-            ref, fp = O.encode_intra_frame(g, fr, bd, q, pm), enc.frame_params()
+            ref, fp = O.encode_intra_frame(g, fr, bd, enc.frame_params().base_q_idx, pm), enc.frame_params()
         else:
             ref, fp = O.encode_inter_frame(g, fr, bd, q, pm, O.hme(g, pyr, prev_pyr, enc.me_lambda()), prev_fin), enc.inter_frame_params()
             O.merge_skip_blocks(g, ref.blocks)

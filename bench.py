@@ -113,13 +113,13 @@ def oracle_chunk(frames, w, h, bd, qidx):
     fps = []
     for ft in (0, 1):
         fp = abi.FrameParams()
-        abi.lib().av1b_select_frame_params(bd, qidx, ft, 1, C.byref(fp))
+        abi.lib().av1b_select_frame_params(bd, qidx if ft else max(1, qidx * 3 // 4), ft, 1, C.byref(fp))
         fps.append(fp)
     prev_fin = prev_pyr = None
     for i, fr in enumerate(frames):
         pyr = O.pyramid(g, O.pad_planes(g, fr)[0])
         if i == 0:
-            r, fp = O.encode_intra_frame(g, fr, bd, qidx, pm), fps[0]
+            r, fp = O.encode_intra_frame(g, fr, bd, max(1, qidx * 3 // 4), pm), fps[0]
         else:
             r, fp = O.encode_inter_frame(g, fr, bd, qidx, pm, O.hme(g, pyr, prev_pyr, lam), prev_fin), fps[1]
             O.merge_skip_blocks(g, r.blocks)

@@ -965,7 +965,7 @@ extern "C" void orc_cdef_frame(const Av1bGeom* g, int bd, const Av1bBlockInfo* b
 
 // Encoder-side CDEF decision (ours): per 64x64 superblock the preset (index into the frame's
 // 2^cdef_bits strength pairs) with the smallest sum of squared errors against the source over the
-// Y, U and V samples of the non-skip 8x8 blocks; ties go to the lowest index.  src: padded planes.
+// Y, U and V samples on the even rows of the non-skip 8x8 blocks; ties go to the lowest index.  src: padded planes.
 extern "C" void orc_cdef_search(const Av1bGeom* g, int bd, const Av1bBlockInfo* blocks, const Av1bFrameParams* fp,
                                 const uint16_t* in_y, const uint16_t* in_u, const uint16_t* in_v,
                                 const uint16_t* src_y, const uint16_t* src_u, const uint16_t* src_v,
@@ -987,7 +987,7 @@ extern "C" void orc_cdef_search(const Av1bGeom* g, int bd, const Av1bBlockInfo* 
         uint64_t e = 0;
         for (int p = 0; p < 3; p++) {
           const int n = p ? 4 : 8;
-          for (int i = 0; i < n; i++)
+          for (int i = 0; i < n; i += 2)      // even rows only (the decision subsamples rows)
             for (int j = 0; j < n; j++) {
               const size_t o = (size_t)(r8 * n + i) * g->stride[p] + c8 * n + j;
               const int d = (int)out[p][o] - (int)src[p][o];

@@ -44,7 +44,7 @@ def test_chunk_parity(w, h, bd, crf, tcl, trl, lf, nfr, fif, keyint):
         assert enc.frame_is_key(i) == key
         pyr = O.pyramid(g, O.pad_planes(g, fr)[0])
         if key:
-            ref = O.encode_intra_frame(g, fr, bd, q, pm)
+            ref = O.encode_intra_frame(g, fr, bd, fp_key.base_q_idx, pm)
         else:
             mvs = O.hme(g, pyr, prev_pyr, enc.me_lambda())
             ref = O.encode_inter_frame(g, fr, bd, q, pm, mvs, prev_fin)
