@@ -114,28 +114,34 @@ __device__ __forceinline__ int code_tb(const InterLaunch& P, int p, int x, int y
 #pragma unroll
   for (int k = 0; k < N; k++) buf[k * S + t] = col[k];
   __syncwarp(gmask);
-  int32_t dq[N];
   int eob = 0, sum_abs = 0;
+  int16_t* cdst = P.coef[p] + av1b_coef_offset(P.g.sb_cols, p, x, y) + t * N;
   {
     int32_t row[N];
 #pragma unroll
     for (int j = 0; j < N; j++) row[j] = buf[t * S + j];
     constexpr int sh = 24 + 2 * TxTab<N>::kLog2 - TxTab<N>::kRowShift - 4;
     const int lim = (1 << (7 + bd)) - 1;
-    int16_t* cdst = P.coef[p] + av1b_coef_offset(P.g.sb_cols, p, x, y) + t * N;
-#pragma unroll
+    const uint32_t rnd_dc = (uint32_t)((P.dc_q * P.quant_rnd) >> 7), rnd_ac = (uint32_t)((P.ac_q * P.quant_rnd) >> 7);
+    // the dequantised row goes back to this thread's own row of buf (it has been consumed into row[])
+#pragma unroll 2
     for (int l = 0; l < N; l++) {
       int64_t acc = 0;
 #pragma unroll
       for (int j = 0; j < N; j++) acc += (int64_t)TxTab<N>::f(l, j) * row[j];
       const int32_t c = (int32_t)((acc * 4096 + ((int64_t)1 << (sh - 1))) >> sh);
-      const int dqv = (t | l) ? P.ac_q : P.dc_q;
-      const uint32_t a = (uint32_t)(c < 0 ? -c : c);
-      uint32_t lv = (a + (uint32_t)((dqv * P.quant_rnd) >> 7)) / (uint32_t)dqv;
+      const bool dc = (t | l) == 0;
+      const uint32_t dqv = dc ? (uint32_t)P.dc_q : (uint32_t)P.ac_q;
+      const uint32_t a = (uint32_t)(c < 0 ? -c : c) + (dc ? rnd_dc : rnd_ac);
+      // exact floor(a / dqv) by multiplication with floor(2^32 / dqv) and at most two corrections
+      uint32_t lv = __umulhi(a, dc ? P.dc_magic : P.ac_magic);
+      uint32_t rem = a - lv * dqv;
+      if (rem >= dqv) { lv++; rem -= dqv; }
+      if (rem >= dqv) lv++;
       if (lv > 32767u) lv = 32767u;
-      int32_t d = (int32_t)((lv * (uint32_t)dqv) & 0xFFFFFFu);
+      int32_t d = (int32_t)((lv * dqv) & 0xFFFFFFu);
       if (d > lim) d = lim;
-      dq[l] = c < 0 ? -d : d;
+      buf[t * S + l] = c < 0 ? -d : d;
       if (active) cdst[l] = (int16_t)(c < 0 ? -(int32_t)lv : (int32_t)lv);
       if (lv) eob = max(eob, TxTab<N>::iscan(t * N + l) + 1);
       sum_abs += (int)lv;
@@ -166,10 +172,10 @@ __device__ __forceinline__ int code_tb(const InterLaunch& P, int p, int x, int y
     return 0;
   }
   const int row_range = bd + 8, col_range = max(bd + 6, 16);
-  __syncwarp(gmask);
   {
+    int32_t dq[N];
 #pragma unroll
-    for (int j = 0; j < N; j++) dq[j] = sat(dq[j], row_range);
+    for (int j = 0; j < N; j++) dq[j] = sat(buf[t * S + j], row_range);
     idct<N>(dq, row_range);
 #pragma unroll
     for (int j = 0; j < N; j++) {
@@ -355,7 +361,10 @@ cudaError_t launch_merge_skip(const Av1bGeom& g, Av1bBlockInfo* blocks, cudaStre
   return cudaGetLastError();
 }
 
-cudaError_t launch_inter_encode(const InterLaunch& p, cudaStream_t s) {
+cudaError_t launch_inter_encode(const InterLaunch& p0, cudaStream_t s) {
+  InterLaunch p = p0;
+  p.dc_magic = (uint32_t)(((uint64_t)1 << 32) / (uint32_t)p.dc_q);
+  p.ac_magic = (uint32_t)(((uint64_t)1 << 32) / (uint32_t)p.ac_q);
   dim3 grid(p.g.sb_cols, p.g.sb_rows);
   inter_encode_kernel<<<grid, kThreads, 0, s>>>(p);
   return cudaGetLastError();
