@@ -1,0 +1,50 @@
+"""BASELINE.json's full sizes (configs C1/C3/C4): the oracle is too slow there, so the check is the
+size-independent property the domain offers -- every produced stream must decode in dav1d AND libaom to
+exactly the encoder's own reconstruction (frame for frame, all planes), key and inter frames."""
+import numpy as np
+import pytest
+from av1_base_b200 import encoder, synth
+from oracle import decoders as D
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.mark.parametrize("w,h,bd,n,hdr", [(1920, 1080, 8, 5, False), (1920, 1080, 10, 5, False), (3840, 2160, 10, 4, True)])
+def test_decode_matches_reconstruction_at_full_size(w, h, bd, n, hdr):
+    frames = synth.synth_clip(w, h, bd, n, seed=3, scene_len=100, hdr=hdr)
+    enc = encoder.Encoder(w, h, bd, crf=30, keep_debug=True, frames_in_flight=3, hdr=hdr)
+    tus = enc.encode_chunk(frames)
+    assert len(tus) == n
+    assert enc.frame_is_key(0) and not enc.frame_is_key(1)
+    dec_d = D.dav1d_decode(tus)
+    dec_a = D.aom_decode(tus) if w <= 1920 else None      # libaom's decoder is slow at 4K; dav1d covers it
+    assert len(dec_d) == n
+    for i in range(n):
+        rec = enc.recon(i)
+        for p in range(3):
+            assert np.array_equal(dec_d[i][p], rec[p]), ("dav1d", i, p)
+            if dec_a is not None:
+                assert np.array_equal(dec_a[i][p], rec[p]), ("libaom", i, p)
+        psnr = D.psnr(rec[0], frames[i][0], bd)
+        assert psnr > 34, (i, psnr)
+    st = enc.stats()
+    assert st["key_frames"] == 1 and st["inter_launches"] == n - 1
+    enc.close()
+
+
+def test_empty_and_tiny_chunks():
+    """Edge cases: one-frame chunk (key only), smallest legal picture, chunk shorter than a batch."""
+    for w, h, n in [(16, 16, 1), (16, 16, 3), (64, 24, 2), (24, 64, 2)]:
+        frames = synth.synth_clip(w, h, 10, n, seed=1, scene_len=100)
+        enc = encoder.Encoder(w, h, 10, crf=40, keep_debug=True, frames_in_flight=2)
+        tus = enc.encode_chunk(frames)
+        dec = D.dav1d_decode(tus)
+        assert len(dec) == n
+        for i in range(n):
+            for p in range(3):
+                assert np.array_equal(dec[i][p], enc.recon(i)[p]), (w, h, i, p)
+        enc.close()
+    with pytest.raises(encoder.EncodeError):
+        encoder.Encoder(20, 16, 10)          # not a multiple of 8
+    with pytest.raises(encoder.EncodeError):
+        encoder.Encoder(64, 64, 12)          # unsupported bit depth
