@@ -269,8 +269,9 @@ static int launch(av1b_encoder* e, Slot& s, int n, int64_t first_index) {
       L.ac_q = bd == 8 ? av1t_ac_q_8[e->base_q_idx_key] : av1t_ac_q_10[e->base_q_idx_key];
       for (int p = 0; p < 3; p++) { L.src[p] = src[p]; L.rec[p] = e->loop_filters ? rec[p] : fin[p]; L.coef[p] = coef[p]; L.plane_elems[p] = e->plane_elems[p]; }
       L.blocks = blocks; L.part_map = e->d_map_key; L.map_elems = e->map_elems;
-      CK(launch_intra_encode(L, 1, e->stream));
-      e->kernel_launches += 1; e->intra_launches += 1; e->key_frames += 1;
+      if (e->blk_log2 == 4) { CK(launch_intra_fast(L, 1, e->stream)); e->kernel_launches += 3; }
+      else { CK(launch_intra_encode(L, 1, e->stream)); e->kernel_launches += 1; }
+      e->intra_launches += 1; e->key_frames += 1;
     } else {
       InterLaunch L;
       L.g = g; L.bit_depth = bd; L.base_q_idx = e->base_q_idx; L.quant_rnd = 48; L.dc_q = dcq; L.ac_q = acq;
@@ -427,10 +428,11 @@ int av1b_encoder_create(const av1b_config* cfg, av1b_encoder** out) {
   if (cfg->device_id < 0 || cfg->device_id >= ndev) { set_error("device_id %d out of range", cfg->device_id); return AV1B_ERR_INVALID; }
   av1b_encoder* e = new av1b_encoder();
   e->cfg = *cfg;
-  // tiles: auto = about 4x4 superblocks per tile (tiles x frames-in-flight CTAs fill the 148 SMs)
+  // key-frame tiles: auto = 2x2 superblocks per tile (every tile is one serial chain of the closed-loop intra
+  // kernel, so many small tiles = many parallel chains; key frames are rare, the extra tile overhead is cheap)
   int tcl = cfg->tile_cols_log2, trl = cfg->tile_rows_log2;
-  if (tcl < 0) tcl = av1b_tile_log2(4, probe.sb_cols);
-  if (trl < 0) trl = av1b_tile_log2(4, probe.sb_rows);
+  if (tcl < 0) tcl = av1b_tile_log2(2, probe.sb_cols);
+  if (trl < 0) trl = av1b_tile_log2(2, probe.sb_rows);
   av1b_geom_init(&e->g, cfg->width, cfg->height, tcl, trl);
   {
     // tiles of inter frames only serve host-side parallelism: about 12x12 superblocks each unless given explicitly

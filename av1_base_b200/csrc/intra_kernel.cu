@@ -361,10 +361,11 @@ __global__ void __launch_bounds__(kThreads) intra_encode_kernel(const IntraLaunc
           const int ha = mi_r > mi_row_start, hl = mi_c > mi_col_start;
           const int x4 = (mi_c - sb_c) >> ss, y4 = (mi_r - sb_r) >> ss, n4 = n >> 2;
           const int max_x = ((g.mi_cols * 4) >> ss) - 1, max_y = ((g.mi_rows * 4) >> ss) - 1;
+          // open-loop decision: the candidate predictors are built from the SOURCE picture's neighbours
           for (int k = 0; k < nplanes; k++) {
             const int p = pass + k;
             const int har = sm.decoded[p][y4][x4 + n4 + 1], hbl = sm.decoded[p][y4 + n4 + 1][x4];
-            build_edges(recp[p], g.stride[p], x, y, n, ha, hl, har, hbl, max_x, max_y, bd, sm.above[k], sm.left[k]);
+            build_edges(srcp[p], g.stride[p], x, y, n, ha, hl, har, hbl, max_x, max_y, bd, sm.above[k], sm.left[k]);
             const uint16_t* s = srcp[p] + (size_t)y * g.stride[p] + x;
             for (int q = tid; q < n * n; q += kThreads) sm.src[k * 1024 + q] = s[(size_t)(q >> ln) * g.stride[p] + (q & (n - 1))];
           }
@@ -425,6 +426,27 @@ __global__ void __launch_bounds__(kThreads) intra_encode_kernel(const IntraLaunc
           __syncthreads();
           const int mode = sm.best;
           if (pass == 0) y_mode = mode; else uv_mode = mode;
+          // closed loop: the coded prediction uses the reconstructed neighbours
+          for (int k = 0; k < nplanes; k++) {
+            const int p = pass + k;
+            const int har = sm.decoded[p][y4][x4 + n4 + 1], hbl = sm.decoded[p][y4 + n4 + 1][x4];
+            build_edges(recp[p], g.stride[p], x, y, n, ha, hl, har, hbl, max_x, max_y, bd, sm.above[k], sm.left[k]);
+          }
+          __syncthreads();
+          if ((tid >> 5) < nplanes) {
+            const int k = tid >> 5;
+            const uint16_t* A = sm.above[k] + 1;
+            const uint16_t* L = sm.left[k] + 1;
+            int s = 0;
+            for (int i = lane; i < n; i += 32) s += (ha ? A[i] : 0) + (hl ? L[i] : 0);
+            for (int o = 16; o; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+            int v;
+            if (ha && hl) v = (s + n) >> (ln + 1);
+            else if (ha || hl) v = (s + (n >> 1)) >> ln;
+            else v = 1 << (bd - 1);
+            if (lane == 0) sm.dcval[k] = v;
+          }
+          __syncthreads();
           for (int k = 0; k < nplanes; k++) {
             const int p = pass + k;
             int tx_type = AV1B_DCT_DCT;

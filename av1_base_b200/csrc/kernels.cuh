@@ -112,5 +112,8 @@ cudaError_t launch_cdef(const CdefLaunch& p, int n_frames, cudaStream_t s);
 cudaError_t launch_lr(const LrLaunch& p, int n_frames, cudaStream_t s);
 cudaError_t launch_partition_fixed(const Av1bGeom& g, int blk_log2, uint8_t* map, int n_frames, cudaStream_t s);
 cudaError_t launch_intra_encode(const IntraLaunch& p, int n_frames, cudaStream_t s);
+// Fast key-frame path for 16x16 blocks (8x8 at the picture edge): open-loop mode kernel + closed-loop
+// reconstruction kernel + skip flags (intra_fast.cu).  Same results as launch_intra_encode.
+cudaError_t launch_intra_fast(const IntraLaunch& p, int n_frames, cudaStream_t s);
 
 }  // namespace av1b

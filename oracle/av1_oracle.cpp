@@ -388,8 +388,10 @@ struct IntraEnc {
     (void)p; (void)mi_r; (void)mi_c; (void)bl; (void)sb_r; (void)sb_c;
   }
 
+  // from_source = true: edges taken from the SOURCE picture (open-loop mode decision);
+  // false: from the reconstruction (what the decoder predicts from).
   void edges_for(int p, int mi_r, int mi_c, int n, int sb_r, int sb_c, uint16_t* above, uint16_t* left,
-                 int* have_above, int* have_left) {
+                 int* have_above, int* have_left, bool from_source) {
     const int ss = p > 0;
     const int x = (mi_c * 4) >> ss, y = (mi_r * 4) >> ss;
     const int ha = mi_r > mi_row_start, hl = mi_c > mi_col_start;
@@ -397,7 +399,8 @@ struct IntraEnc {
     const int har = decoded[p][y4 - 1 + 1][x4 + n4 + 1];
     const int hbl = decoded[p][y4 + n4 + 1][x4 - 1 + 1];
     const int max_x = ((g->mi_cols * 4) >> ss) - 1, max_y = ((g->mi_rows * 4) >> ss) - 1;
-    build_edges(rec[p], g->stride[p], x, y, n, n, ha, hl, har, hbl, max_x, max_y, bd, above, left);
+    if (from_source) build_edges(src[p], sstride[p], x, y, n, n, ha, hl, har, hbl, max_x, max_y, bd, above, left);
+    else build_edges(rec[p], g->stride[p], x, y, n, n, ha, hl, har, hbl, max_x, max_y, bd, above, left);
     *have_above = ha; *have_left = hl;
   }
 
@@ -418,8 +421,10 @@ struct IntraEnc {
       const int ss = pass;
       const int n = std::min(1 << (bl - ss), pass ? 32 : 64);
       int ha = 0, hl = 0;
-      for (int p = p0; p <= p1; p++) edges_for(p, mi_r, mi_c, n, sb_r, sb_c, edge_a[p] + 1, edge_l[p] + 1, &ha, &hl);
-      // mode decision: minimum SATD over the candidate list, ties -> first in list
+      // mode decision (open loop): edges from the SOURCE picture, minimum SATD over the candidate list, ties ->
+      // first in list.  Decisions therefore do not depend on the reconstruction and can be taken for all
+      // blocks of a frame in parallel.
+      for (int p = p0; p <= p1; p++) edges_for(p, mi_r, mi_c, n, sb_r, sb_c, edge_a[p] + 1, edge_l[p] + 1, &ha, &hl, true);
       int best = -1; int64_t best_cost = 0;
       for (int k = 0; k < 13; k++) {
         int64_t cost = 0;
@@ -431,6 +436,8 @@ struct IntraEnc {
         if (best < 0 || cost < best_cost) { best = cand[k]; best_cost = cost; }
       }
       if (pass == 0) info.y_mode = (uint8_t)best; else info.uv_mode = (uint8_t)best;
+      // closed loop from here: the prediction that is coded uses the reconstructed neighbours
+      for (int p = p0; p <= p1; p++) edges_for(p, mi_r, mi_c, n, sb_r, sb_c, edge_a[p] + 1, edge_l[p] + 1, &ha, &hl, false);
       for (int p = p0; p <= p1; p++) {
         const int x = (mi_c * 4) >> ss, y = (mi_r * 4) >> ss;
         int tx_type = AV1B_DCT_DCT;
