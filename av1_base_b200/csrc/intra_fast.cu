@@ -110,7 +110,9 @@ __device__ __forceinline__ void build_edges_group(const uint16_t* img, int strid
 }
 
 // one predicted sample; A = above + 1, L = left + 1 (A[-1] = L[-1] = top-left)
-__device__ __forceinline__ int pred_px(int mode, int i, int j, int n, const uint16_t* A, const uint16_t* L, int dcv) {
+// w: smooth weights of block size n in SHARED memory (lanes index them differently: constant memory would serialise)
+__device__ __forceinline__ int pred_px(int mode, int i, int j, int n, const uint16_t* A, const uint16_t* L, int dcv,
+                                       const uint8_t* w) {
   switch (mode) {
     case AV1B_DC_PRED: return dcv;
     case AV1B_V_PRED: return A[j];
@@ -121,16 +123,13 @@ __device__ __forceinline__ int pred_px(int mode, int i, int j, int n, const uint
       return (pl <= pt && pl <= ptl) ? L[i] : (pt <= ptl ? A[j] : tl);
     }
     case AV1B_SMOOTH_PRED: {
-      const uint8_t* w = tbl::smooth_weights + n - 4;
       const int s = w[i] * A[j] + (256 - w[i]) * L[n - 1] + w[j] * L[i] + (256 - w[j]) * A[n - 1];
       return (s + 256) >> 9;
     }
     case AV1B_SMOOTH_V_PRED: {
-      const uint8_t* w = tbl::smooth_weights + n - 4;
       return (w[i] * A[j] + (256 - w[i]) * L[n - 1] + 128) >> 8;
     }
     case AV1B_SMOOTH_H_PRED: {
-      const uint8_t* w = tbl::smooth_weights + n - 4;
       return (w[j] * L[i] + (256 - w[j]) * A[n - 1] + 128) >> 8;
     }
     default: break;
@@ -186,12 +185,14 @@ __device__ __forceinline__ TileCtx tile_of_sb(const Av1bGeom& g, int sbx, int sb
 struct ModeSmem {
   uint16_t above[8][2][72];    // [warp][plane slot][1 + 2n], n <= 16 luma / 8 chroma
   uint16_t left[8][2][72];
+  uint8_t sw[32];              // smooth weights of sizes 4, 8, 16 at offsets 0, 4, 12 (as in the spec table)
 };
 
 // SATD cost of every candidate for nplanes planes of size n; returns the best mode (all lanes)
 template <int N>
 __device__ __forceinline__ int decide(const uint16_t* const src[2], int sstride, const uint16_t (*above)[72],
-                                      const uint16_t (*left)[72], const int dcv[2], int nplanes, int lane) {
+                                      const uint16_t (*left)[72], const int dcv[2], int nplanes, int lane,
+                                      const uint8_t* sw) {
   constexpr int LN = N == 16 ? 4 : (N == 8 ? 3 : 2);
   constexpr int NPX = N * N, ITER = (NPX + 31) / 32;
   // source samples of this lane in 4x4-tile-major order (a 16-lane half warp holds one 4x4 tile)
@@ -222,7 +223,7 @@ __device__ __forceinline__ int decide(const uint16_t* const src[2], int sstride,
         int v = 0;
         if (q < NPX) {
           const int tl = q >> 4, w = q & 15, ty = tl >> (LN - 2), tx = tl & ((1 << (LN - 2)) - 1);
-          v = sv[k][it] - pred_px(mode, ty * 4 + (w >> 2), tx * 4 + (w & 3), N, A, L, dcv[k]);
+          v = sv[k][it] - pred_px(mode, ty * 4 + (w >> 2), tx * 4 + (w & 3), N, A, L, dcv[k], sw + N - 4);
         }
 #pragma unroll
         for (int msk = 1; msk <= 8; msk <<= 1) {
@@ -247,6 +248,8 @@ __global__ void __launch_bounds__(256) intra_mode_kernel(const IntraLaunch P) {
   const int sb_r = sby * 16, sb_c = sbx * 16, bd = P.bit_depth;
   const uint8_t* pmap = P.part_map + (size_t)frame * P.map_elems;
   Av1bBlockInfo* blocks = P.blocks + (size_t)frame * P.map_elems;
+  if (tid < 28) sm.sw[tid] = tbl::smooth_weights[tid];
+  __syncthreads();
   for (int u = warp; u < 64; u += 8) {
     const int x8 = u & 7, y8 = u >> 3;
     const int mi_r = sb_r + 2 * y8, mi_c = sb_c + 2 * x8;
@@ -276,9 +279,9 @@ __global__ void __launch_bounds__(256) intra_mode_kernel(const IntraLaunch P) {
         dcv[k] = dc_value(sm.above[warp][k] + 1, sm.left[warp][k] + 1, n, ln, ha, hl, bd, lane, 32, 0xffffffffu);
       const int st = g.stride[pass];
       int mode;
-      if (n == 16) mode = decide<16>(srcp, st, sm.above[warp], sm.left[warp], dcv, nplanes, lane);
-      else if (n == 8) mode = decide<8>(srcp, st, sm.above[warp], sm.left[warp], dcv, nplanes, lane);
-      else mode = decide<4>(srcp, st, sm.above[warp], sm.left[warp], dcv, nplanes, lane);
+      if (n == 16) mode = decide<16>(srcp, st, sm.above[warp], sm.left[warp], dcv, nplanes, lane, sm.sw);
+      else if (n == 8) mode = decide<8>(srcp, st, sm.above[warp], sm.left[warp], dcv, nplanes, lane, sm.sw);
+      else mode = decide<4>(srcp, st, sm.above[warp], sm.left[warp], dcv, nplanes, lane, sm.sw);
       modes[pass] = mode;
     }
     // side-info skeleton on every unit of the block; the closed-loop kernel adds the end-of-block positions
@@ -323,6 +326,7 @@ __device__ __forceinline__ void inv_1d(int t, int32_t* x, int range) {
 }
 
 struct ReconGroup {
+  uint8_t sw[32];              // smooth weights (sizes 4, 8, 16 at offsets 0, 4, 12)
   uint16_t above[40];          // 1 + 2N, N <= 16
   uint16_t left[40];
   uint16_t pred[16 * 16];
@@ -349,7 +353,7 @@ __device__ __forceinline__ int intra_tb(const IntraLaunch& P, int frame, int p, 
     const uint16_t* sp = P.src[p] + (size_t)frame * P.plane_elems[p] + (size_t)(y + t) * stride + x;
 #pragma unroll
     for (int c = 0; c < N; c++) {
-      const int pv = pred_px(mode, t, c, N, A, L, dcv);
+      const int pv = pred_px(mode, t, c, N, A, L, dcv, G.sw + N - 4);
       G.pred[t * N + c] = (uint16_t)pv;
       G.buf[t * S + c] = ((int)sp[c] - pv) * 4;
     }
@@ -444,6 +448,8 @@ __global__ void __launch_bounds__(32) intra_recon_kernel(const IntraLaunch P) {
   T.mi_col_start = g.tile_col_start_sb[tc] * 16; T.mi_col_end = min(g.tile_col_start_sb[tc + 1] * 16, g.mi_cols);
   const uint8_t* pmap = P.part_map + (size_t)frame * P.map_elems;
   Av1bBlockInfo* blocks = P.blocks + (size_t)frame * P.map_elems;
+  if (lane < 28) { G[0].sw[lane] = tbl::smooth_weights[lane]; G[1].sw[lane] = tbl::smooth_weights[lane]; }
+  __syncwarp();
   for (int sb_r = T.mi_row_start; sb_r < T.mi_row_end; sb_r += 16) {
     for (int sb_c = T.mi_col_start; sb_c < T.mi_col_end; sb_c += 16) {
       for (int u = 0; u < 64; u++) {
