@@ -7,9 +7,10 @@
 //   av1an -i IN -o OUT --encoder svt-av1 --pix-format yuv420p10le --video-params "--crf 30 --preset 6 ..."
 //         --audio-params "-c:a copy" --workers N --temp DIR
 //
-// --workers N is the number of GPUs this job uses: the clip is cut into closed-GOP chunks of --keyint
-// frames (av1an-style chunking), chunk c is encoded by worker c mod N on its own GPU, and the chunk
-// streams are concatenated on the host in order (no exchange between GPUs).
+// --workers N is the number of GPUs this job uses: the clip is cut into closed-GOP chunks at detected
+// scene cuts and at the latest every --keyint frames (av1an-style chunking), chunk c
+// is encoded by worker c mod N on its own GPU, and the chunk streams are concatenated on the host in
+// order (no exchange between GPUs).
 // Input: YUV4MPEG2 (4:2:0, 8 or 10 bit) read directly and seekably; anything else is decoded through
 // an `ffmpeg` pipe when ffmpeg is on PATH.  Output by extension: .mkv (Matroska, V_AV1), .ivf, .obu.
 #include <errno.h>
@@ -50,6 +51,8 @@ struct Options {
   int workers = 1;
   int crf = 30, preset = 6, keyint = 240, lookahead = 0, film_grain = 0, enable_qm = 0, qm_min = 0, qm_max = 15;
   bool quiet = false;
+  bool no_scene_detection = false;   // --sc-method none / --no-scene-detection: split at --keyint only
+  int min_scene_len = 12;            // --min-scene-len
 };
 
 // --video-params carries SVT-AV1 style flags (av1an.rs:14 SVT_PARAMS)
@@ -297,6 +300,8 @@ struct Shared {
   std::chrono::steady_clock::time_point t0;
   std::string progress_path;
   bool quiet = false;
+  bool no_scene_detection = false;   // --sc-method none / --no-scene-detection: split at --keyint only
+  int min_scene_len = 12;            // --min-scene-len
 };
 
 struct PacketCtx { Shared* sh; int64_t chunk; };
@@ -353,6 +358,9 @@ int main(int argc, char** argv) {
     else if (a == "--workers" || a == "-w") o.workers = atoi(val("--workers").c_str());
     else if (a == "--temp") o.temp = val("--temp");
     else if (a == "--quiet" || a == "-q") o.quiet = true;
+    else if (a == "--no-scene-detection") o.no_scene_detection = true;
+    else if (a == "--min-scene-len") o.min_scene_len = atoi(val("--min-scene-len").c_str());
+    else if (a == "--sc-method" || a == "--split-method") { if (val(a.c_str()) == "none") o.no_scene_detection = true; }
     else die(2, "unknown argument %s", a.c_str());
   }
   if (o.input.empty() || o.output.empty()) die(2, "-i and -o are required");
@@ -465,40 +473,59 @@ int main(int argc, char** argv) {
     });
   }
 
-  // ---- reader: sequential, chunk c -> worker c mod W ----
+  // ---- reader: sequential; av1an-style chunking = a new closed GOP at every detected scene cut and at the
+  //      latest after --keyint frames; chunk c -> worker c mod W ----
   std::vector<uint8_t> raw;
-  int64_t frame = 0;
+  std::vector<uint16_t> cur(frame_samples), thumb_prev, thumb_cur;
+  int64_t frame = 0, chunk = 0;
+  int in_chunk = 0;
+  double score_avg = -1;
   bool eof = false;
   auto last_report = std::chrono::steady_clock::now();
-  while (!eof && !sh.failed) {
-    const int64_t chunk = frame / o.keyint;
-    const int in_chunk = (int)(frame % o.keyint);
-    const int want = std::min(kPart, o.keyint - in_chunk);
-    Part part;
-    part.chunk = chunk; part.first_frame = frame; part.first_part = in_chunk == 0;
-    part.samples.resize((size_t)want * frame_samples);
-    int got = 0;
-    while (got < want) {
-      if (!y4m_read_frame(in, raw, part.samples.data() + (size_t)got * frame_samples, shift)) { eof = true; break; }
-      got++;
-    }
-    if (got == 0) break;
-    part.n = got;
-    frame += got;
+  Part part;
+  auto flush_part = [&]() {
+    if (part.n == 0) return;
     {
       std::lock_guard<std::mutex> l(sh.m);
-      if ((int64_t)sh.chunk_out.size() <= chunk) sh.chunk_out.resize((size_t)chunk + 1);
+      if ((int64_t)sh.chunk_out.size() <= part.chunk) sh.chunk_out.resize((size_t)part.chunk + 1);
     }
-    Queue& q = queues[(size_t)(chunk % W)];
+    Queue& q = queues[(size_t)(part.chunk % W)];
     {
       std::unique_lock<std::mutex> l(q.m);
       q.cv.wait(l, [&] { return q.q.size() < 2; });
       q.q.push_back(std::move(part));
     }
     q.cv.notify_all();
+    part = Part();
+  };
+  while (!eof && !sh.failed) {
+    if (!y4m_read_frame(in, raw, cur.data(), shift)) { eof = true; break; }
+    // scene-cut score: mean absolute luma difference on a 1/8 x 1/8 subsampled picture, 8-bit units
+    thumb_cur.clear();
+    for (int y = 4; y < in.h; y += 8) for (int x = 4; x < in.w; x += 8) thumb_cur.push_back(cur[(size_t)y * in.w + x]);
+    bool cut = false;
+    if (!thumb_prev.empty() && !o.no_scene_detection) {
+      uint64_t sad = 0;
+      for (size_t i = 0; i < thumb_cur.size(); i++) sad += (uint64_t)std::abs((int)thumb_cur[i] - (int)thumb_prev[i]);
+      const double score = (double)sad / thumb_cur.size() / (1 << (out_bits - 8));
+      // a cut = a jump well above both an absolute floor and the recent level of change
+      if (in_chunk >= o.min_scene_len && score > 10.0 && (score_avg < 0 || score > 3.0 * score_avg + 2.0)) cut = true;
+      score_avg = score_avg < 0 ? score : 0.8 * score_avg + 0.2 * score;
+      if (cut) score_avg = -1;
+    }
+    thumb_prev.swap(thumb_cur);
+    if (frame > 0 && (cut || in_chunk >= o.keyint)) { flush_part(); chunk++; in_chunk = 0; }
+    if (part.n == 0) {
+      part.chunk = chunk; part.first_frame = frame; part.first_part = in_chunk == 0;
+      part.samples.resize((size_t)kPart * frame_samples);
+    }
+    memcpy(part.samples.data() + (size_t)part.n * frame_samples, cur.data(), frame_samples * sizeof(uint16_t));
+    part.n++; frame++; in_chunk++;
+    if (part.n == kPart) flush_part();
     const auto now = std::chrono::steady_clock::now();
     if (std::chrono::duration<double>(now - last_report).count() > 1.0) { report_progress(sh, false); last_report = now; }
   }
+  flush_part();
   for (auto& q : queues) { { std::lock_guard<std::mutex> l(q.m); q.closed = true; } q.cv.notify_all(); }
   for (auto& t : threads) t.join();
   if (in.pipe) pclose(in.f); else fclose(in.f);

@@ -122,3 +122,27 @@ def test_cli_failure_leaves_no_output(tmp_path):
     open(bad, "wb").write(b"YUV4MPEG2 W64 H64 F30:1 C420jpeg\nFRAME\n" + b"\0" * 100)
     r = subprocess.run([CLI, "-i", bad, "-o", out], capture_output=True)
     assert r.returncode != 0 and not os.path.exists(out)
+
+
+@pytest.mark.gpu
+def test_cli_splits_chunks_at_scene_cuts(tmp_path):
+    """E0: a hard scene cut starts a new closed GOP (chunk) even though --keyint is far away."""
+    from av1_base_b200 import encoder, synth
+    w, h, bd, n = 200, 136, 10, 9
+    frames = synth.synth_clip(w, h, bd, n, seed=21, scene_len=4)        # cuts before frames 4 and 8
+    y4m = str(tmp_path / "in.y4m")
+    write_y4m(y4m, frames, bd)
+    out = str(tmp_path / "out.obu")
+    r = subprocess.run([CLI, "-i", y4m, "-o", out, "--video-params", "--crf 32 --keyint 240", "--workers", "2",
+                        "--min-scene-len", "2", "--quiet"], capture_output=True, text=True, env=dict(os.environ, AV1B_SHARE_GPU="1"))
+    assert r.returncode == 0, r.stderr
+    enc = encoder.Encoder(w, h, bd, crf=32, keyint=240)
+    want = enc.encode_chunk(frames[0:4]) + enc.encode_chunk(frames[4:8]) + enc.encode_chunk(frames[8:9])
+    assert open(out, "rb").read() == b"".join(want)
+    # without detection the whole clip is one chunk
+    out2 = str(tmp_path / "out2.obu")
+    r = subprocess.run([CLI, "-i", y4m, "-o", out2, "--video-params", "--crf 32 --keyint 240", "--no-scene-detection", "--quiet"],
+                       capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+    assert open(out2, "rb").read() == b"".join(enc.encode_chunk(frames))
+    enc.close()
