@@ -89,28 +89,28 @@ __global__ void __launch_bounds__(256) hme_l2_kernel(const HmeLaunch P) {
     const int bx = b & 3, by = b >> 2;
     const int gbx = blockIdx.x * 4 + bx, gby = blockIdx.y * 4 + by;
     if (gbx >= n2x || gby >= n2y) continue;
-    // current block in registers: 64 samples, two per 32-bit word
-    uint32_t c[32];
+    // current block in registers: 64 samples
+    uint32_t c[64];
 #pragma unroll
     for (int i = 0; i < 8; i++)
 #pragma unroll
-      for (int j = 0; j < 4; j++)
-        c[i * 4 + j] = *reinterpret_cast<const uint32_t*>(&sm.cur[(by * 8 + i) * kT2 + bx * 8 + 2 * j]);
+      for (int j = 0; j < 4; j++) {
+        const uint32_t w = *reinterpret_cast<const uint32_t*>(&sm.cur[(by * 8 + i) * kT2 + bx * 8 + 2 * j]);
+        c[i * 8 + 2 * j] = w & 0xFFFF; c[i * 8 + 2 * j + 1] = w >> 16;
+      }
     unsigned best = 0xFFFFFFFFu;   // (cost << 10) | visiting order
     for (int k = lane; k < kCand; k += 32) {
       const int dy = k / kSide - kR2, dx = k % kSide - kR2;
       const uint16_t* rp = sm.ref + (by * 8 + kR2 + dy) * kW2S + bx * 8 + kR2 + dx;
-      int sad = 0;
+      // |a - b| + acc is one instruction (VABSDIFF.U32 with accumulate)
+      unsigned sad = 0;
 #pragma unroll
       for (int i = 0; i < 8; i++)
 #pragma unroll
-        for (int j = 0; j < 4; j++) {
-          const uint32_t cw = c[i * 4 + j];
-          sad += abs((int)(cw & 0xFFFF) - (int)rp[i * kW2S + 2 * j]) + abs((int)(cw >> 16) - (int)rp[i * kW2S + 2 * j + 1]);
-        }
+        for (int j = 0; j < 8; j++) sad = __usad(c[i * 8 + j], (unsigned)rp[i * kW2S + j], sad);
       // visiting order: centre first, then raster
       const int order = k == kCentre ? 0 : (k < kCentre ? k + 1 : k);
-      const int cost = sad + lam2 * (abs(dx) + abs(dy));
+      const int cost = (int)sad + lam2 * (abs(dx) + abs(dy));
       const unsigned key = ((unsigned)cost << 10) | (unsigned)order;
       best = min(best, key);
     }
@@ -151,10 +151,11 @@ __device__ __forceinline__ void refine25(const uint16_t* cur, const uint16_t* re
   if (lane < 25) {
     const int dy = lane / 5 - 2, dx = lane % 5 - 2;
     const uint16_t* rp = ref + (2 + dy) * RS + 2 + dx;
-    int sad = 0;
+    unsigned usad = 0;
     for (int i = 0; i < N; i++)
 #pragma unroll
-      for (int j = 0; j < N; j++) sad += abs((int)cur[i * N + j] - (int)rp[i * RS + j]);
+      for (int j = 0; j < N; j++) usad = __usad((unsigned)cur[i * N + j], (unsigned)rp[i * RS + j], usad);
+    const int sad = (int)usad;
     const int order = lane == 12 ? 0 : (lane < 12 ? lane + 1 : lane);
     key = ((unsigned)(sad + lam * (abs(dy) + abs(dx))) << 5) | (unsigned)order;
     my_sad = sad;

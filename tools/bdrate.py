@@ -56,13 +56,16 @@ def main():
     ap.add_argument("--cqs", default="24,32,40,48,56")
     ap.add_argument("--out", default="")
     ap.add_argument("--noise", type=float, default=1.0, help="scale of the synthetic sensor noise")
+    ap.add_argument("--tb-zero-thr", type=int, default=0)
+    ap.add_argument("--skip-libaom", action="store_true")
+    ap.add_argument("--lag", type=int, default=19, help="libaom lag_in_frames (0 = low delay, no alt-ref filtering)")
     a = ap.parse_args()
     w, h = map(int, a.size.split("x"))
     frames = synth.synth_clip(w, h, a.bd, a.frames, seed=a.seed, scene_len=1000, noise=a.noise)
     fps = 30.0
     res = {"clip": {"w": w, "h": h, "bit_depth": a.bd, "frames": a.frames, "seed": a.seed, "noise": a.noise}, "ours": [], "libaom_cpu6": []}
     for crf in map(int, a.crfs.split(",")):
-        enc = encoder.Encoder(w, h, a.bd, crf=crf, keyint=240, keep_debug=True)
+        enc = encoder.Encoder(w, h, a.bd, crf=crf, keyint=240, keep_debug=True, tb_zero_thr=a.tb_zero_thr)
         t0 = time.perf_counter()
         tus = enc.encode_chunk(frames)
         dt = time.perf_counter() - t0
@@ -77,16 +80,17 @@ def main():
         res["ours"].append(q)
         print(json.dumps({"ours": q}), flush=True)
     cores = os.cpu_count() or 1
-    for cq in map(int, a.cqs.split(",")):
+    for cq in ([] if a.skip_libaom else list(map(int, a.cqs.split(",")))):
         t0 = time.perf_counter()
-        tus = D.aom_encode(frames, a.bd, cq_level=cq, cpu_used=6, threads=cores, lag=19)
+        tus = D.aom_encode(frames, a.bd, cq_level=cq, cpu_used=6, threads=cores, lag=a.lag)
         dt = time.perf_counter() - t0
         dec = D.dav1d_decode(tus)
         q = quality(frames, dec, a.bd)
         q.update(cq=cq, kbps=sum(map(len, tus)) * 8 * fps / a.frames / 1000, enc_fps=a.frames / dt, cores=cores)
         res["libaom_cpu6"].append(q)
         print(json.dumps({"libaom_cpu6": q}), flush=True)
-    for m in ("psnr_y", "psnr_avg", "ssim_y"):
+    res["libaom_lag_in_frames"] = a.lag
+    for m in (() if a.skip_libaom else ("psnr_y", "psnr_avg", "ssim_y")):
         r1 = [x["kbps"] for x in res["libaom_cpu6"]]; q1 = [x[m] for x in res["libaom_cpu6"]]
         r2 = [x["kbps"] for x in res["ours"]]; q2 = [x[m] for x in res["ours"]]
         res["bd_rate_vs_libaom_cpu6_%s_pct" % m] = bd_rate(r1, q1, r2, q2)
