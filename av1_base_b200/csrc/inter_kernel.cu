@@ -44,8 +44,6 @@ template <> struct TxTab<16> {
   static constexpr int kLog2 = 4, kRowShift = 2;
 };
 
-struct TbOut { int eob; };
-
 // One transform block == one prediction block of plane `p` at (x, y), size N x N, owned by the N lanes
 // `gmask` of one warp; t = lane index inside the group.  buf: (N+7)*(N+1) int32, pred: N*N uint16.
 template <int N>

@@ -36,10 +36,6 @@ __constant__ uint8_t f_cand[kNumCand] = {AV1B_DC_PRED, AV1B_V_PRED, AV1B_H_PRED,
 // Mode_To_Txfm restricted to what the candidates produce: (vertical type, horizontal type)
 __constant__ uint8_t f_mode_vt[14] = {T_DCT, T_ADST, T_DCT, T_DCT, T_ADST, T_ADST, T_DCT, T_DCT, T_ADST, T_ADST, T_ADST, T_DCT, T_ADST, T_DCT};
 __constant__ uint8_t f_mode_ht[14] = {T_DCT, T_DCT, T_ADST, T_DCT, T_ADST, T_DCT, T_ADST, T_ADST, T_DCT, T_ADST, T_DCT, T_ADST, T_ADST, T_DCT};
-__constant__ uint8_t f_mode_tx[14] = {AV1B_DCT_DCT, AV1B_ADST_DCT, AV1B_DCT_ADST, AV1B_DCT_DCT, AV1B_ADST_ADST, AV1B_ADST_DCT,
-                                      AV1B_DCT_ADST, AV1B_DCT_ADST, AV1B_ADST_DCT, AV1B_ADST_ADST, AV1B_ADST_DCT, AV1B_DCT_ADST,
-                                      AV1B_ADST_ADST, AV1B_DCT_DCT};
-
 __device__ __forceinline__ int clampi(int v, int lo, int hi) { return v < lo ? lo : (v > hi ? hi : v); }
 
 __device__ __forceinline__ int morton(int x, int y) {

@@ -511,6 +511,4 @@ cudaError_t launch_intra_encode(const IntraLaunch& p, int n_frames, cudaStream_t
   return cudaGetLastError();
 }
 
-void upload_tables_once() {}
-
 }  // namespace av1b

@@ -106,7 +106,6 @@ cudaError_t launch_inter_encode(const InterLaunch& p, cudaStream_t s);
 // Bottom-up merge of skipped inter siblings with equal vectors into 32x32 / 64x64 blocks (side info only).
 cudaError_t launch_merge_skip(const Av1bGeom& g, Av1bBlockInfo* blocks, cudaStream_t s);
 
-void upload_tables_once();
 cudaError_t launch_deblock(const DeblockLaunch& p, int n_frames, cudaStream_t s);
 cudaError_t launch_cdef(const CdefLaunch& p, int n_frames, cudaStream_t s);
 cudaError_t launch_lr(const LrLaunch& p, int n_frames, cudaStream_t s);

@@ -381,13 +381,6 @@ struct IntraEnc {
     }
   }
 
-  // one transform block == one prediction block (TX_MODE_LARGEST, square partitions)
-  void code_plane(int p, int mi_r, int mi_c, int bl, int sb_r, int sb_c, Av1bBlockInfo* bi, int mode,
-                  int tx_type, bool decide, const uint8_t* cand, int ncand, int* best_mode) {
-    (void)decide; (void)cand; (void)ncand; (void)best_mode; (void)bi; (void)mode; (void)tx_type;
-    (void)p; (void)mi_r; (void)mi_c; (void)bl; (void)sb_r; (void)sb_c;
-  }
-
   // from_source = true: edges taken from the SOURCE picture (open-loop mode decision);
   // false: from the reconstruction (what the decoder predicts from).
   void edges_for(int p, int mi_r, int mi_c, int n, int sb_r, int sb_c, uint16_t* above, uint16_t* left,
