@@ -28,6 +28,7 @@
 #include <chrono>
 #include <condition_variable>
 #include <deque>
+#include <memory>
 #include <mutex>
 #include <string>
 #include <thread>
@@ -122,14 +123,13 @@ bool y4m_read_frame(Y4m& y, std::vector<uint8_t>& raw, uint16_t* dst, int shift)
   if (c == EOF) return false;
   hdr[n] = 0;
   if (strncmp(hdr, "FRAME", 5) != 0) die(3, "corrupt Y4M stream (expected FRAME)");
-  raw.resize(y.frame_bytes);
-  if (fread(raw.data(), 1, y.frame_bytes, y.f) != y.frame_bytes) die(3, "truncated Y4M frame");
-  const size_t ns = y.bits > 8 ? y.frame_bytes / 2 : y.frame_bytes;
   if (y.bits > 8) {
-    const uint16_t* s = reinterpret_cast<const uint16_t*>(raw.data());
-    for (size_t i = 0; i < ns; i++) dst[i] = s[i];
+    // little-endian 16-bit samples are already in our layout: read them in place
+    if (fread(dst, 1, y.frame_bytes, y.f) != y.frame_bytes) die(3, "truncated Y4M frame");
   } else {
-    for (size_t i = 0; i < ns; i++) dst[i] = (uint16_t)(raw[i] << shift);
+    raw.resize(y.frame_bytes);
+    if (fread(raw.data(), 1, y.frame_bytes, y.f) != y.frame_bytes) die(3, "truncated Y4M frame");
+    for (size_t i = 0; i < y.frame_bytes; i++) dst[i] = (uint16_t)(raw[i] << shift);
   }
   return true;
 }
@@ -283,11 +283,15 @@ int lease_device(int dev, bool block) {
   return fd;
 }
 
+// A group buffer holds kGroup consecutive frames (each Y U V contiguous); the parts cut out of it share it
+// and it goes back to the pool when the last of them has been encoded.
+struct GroupBuf { std::vector<uint16_t> v; };
 struct Part {
   int64_t chunk = 0, first_frame = 0;
   bool first_part = false;
   int n = 0;
-  std::vector<uint16_t> samples;   // n frames, each Y U V contiguous
+  std::shared_ptr<GroupBuf> buf;
+  size_t first_slot = 0;           // index of the part's first frame inside buf
 };
 
 struct Shared {
@@ -300,8 +304,7 @@ struct Shared {
   std::chrono::steady_clock::time_point t0;
   std::string progress_path;
   bool quiet = false;
-  bool no_scene_detection = false;   // --sc-method none / --no-scene-detection: split at --keyint only
-  int min_scene_len = 12;            // --min-scene-len
+  std::vector<GroupBuf*> free_bufs;   // recycled group buffers (allocation + first touch of ~0.4 GB is slow)
 };
 
 struct PacketCtx { Shared* sh; int64_t chunk; };
@@ -422,7 +425,7 @@ int main(int argc, char** argv) {
   if (share) while ((int)dev.size() < n_workers) dev.push_back(dev[dev.size() % lease.size()]);
 
   // ---- workers: one encoder handle (= one GPU) each, fed with chunk parts through a bounded queue ----
-  const int kPart = 32;
+  const int kPart = 16;   // frames per hand-over: two device batches; buffers are recycled through sh.free_bufs
   struct Queue { std::mutex m; std::condition_variable cv; std::deque<Part> q; bool closed = false; };
   const int W = (int)dev.size();
   std::vector<Queue> queues(W);
@@ -456,12 +459,13 @@ int main(int argc, char** argv) {
         if (sh.failed || !enc) continue;   // drain
         std::vector<av1b_frame_src> fs((size_t)part.n);
         for (int k = 0; k < part.n; k++) {
-          uint16_t* b = part.samples.data() + (size_t)k * frame_samples;
+          uint16_t* b = part.buf->v.data() + (part.first_slot + (size_t)k) * frame_samples;
           fs[k].planes[0] = b; fs[k].planes[1] = b + (size_t)in.w * in.h; fs[k].planes[2] = b + (size_t)in.w * in.h * 5 / 4;
           fs[k].stride[0] = in.w; fs[k].stride[1] = fs[k].stride[2] = in.w / 2;
         }
         PacketCtx ctx{&sh, part.chunk};
         rc = av1b_encode_part(enc, fs.data(), (uint32_t)part.n, part.first_part ? 1 : 0, part.first_frame, on_packet, nullptr, &ctx);
+        part.buf.reset();   // the last part of a group returns the buffer to the pool (custom deleter)
         if (rc != AV1B_OK) {
           std::lock_guard<std::mutex> l(sh.m);
           if (!sh.failed) { sh.failed = -rc; sh.error = av1b_last_error(); }
@@ -473,18 +477,20 @@ int main(int argc, char** argv) {
     });
   }
 
-  // ---- reader: sequential; av1an-style chunking = a new closed GOP at every detected scene cut and at the
-  //      latest after --keyint frames; chunk c -> worker c mod W ----
-  std::vector<uint8_t> raw;
-  std::vector<uint16_t> cur(frame_samples), thumb_prev, thumb_cur;
-  int64_t frame = 0, chunk = 0;
-  int in_chunk = 0;
-  double score_avg = -1;
-  bool eof = false;
-  auto last_report = std::chrono::steady_clock::now();
-  Part part;
-  auto flush_part = [&]() {
-    if (part.n == 0) return;
+  // ---- reader: av1an-style chunking = a new closed GOP at every detected scene cut and at the latest after
+  //      --keyint frames; chunk c -> worker c mod W.  Frames are read in groups of kPart; a regular Y4M file
+  //      is read with parallel pread(2) (one frame per task), a pipe sequentially. ----
+  auto take_buffer = [&]() -> std::shared_ptr<GroupBuf> {
+    GroupBuf* g = nullptr;
+    {
+      std::lock_guard<std::mutex> l(sh.m);
+      if (!sh.free_bufs.empty()) { g = sh.free_bufs.back(); sh.free_bufs.pop_back(); }
+    }
+    if (!g) { g = new GroupBuf(); g->v.resize((size_t)kPart * frame_samples); }
+    Shared* shp = &sh;
+    return std::shared_ptr<GroupBuf>(g, [shp](GroupBuf* p) { std::lock_guard<std::mutex> l(shp->m); shp->free_bufs.push_back(p); });
+  };
+  auto submit = [&](Part&& part) {
     {
       std::lock_guard<std::mutex> l(sh.m);
       if ((int64_t)sh.chunk_out.size() <= part.chunk) sh.chunk_out.resize((size_t)part.chunk + 1);
@@ -492,44 +498,104 @@ int main(int argc, char** argv) {
     Queue& q = queues[(size_t)(part.chunk % W)];
     {
       std::unique_lock<std::mutex> l(q.m);
-      q.cv.wait(l, [&] { return q.q.size() < 2; });
+      q.cv.wait(l, [&] { return q.q.size() < 3; });
       q.q.push_back(std::move(part));
     }
     q.cv.notify_all();
-    part = Part();
   };
+  const int tw = (in.w - 4 + 7) / 8, th = (in.h - 4 + 7) / 8;      // thumbnail: every 8th sample from (4, 4)
+  auto make_thumb = [&](const uint16_t* luma, uint16_t* t) {
+    for (int y = 4, k = 0; y < in.h; y += 8) for (int x = 4; x < in.w; x += 8) t[k++] = luma[(size_t)y * in.w + x];
+  };
+  const int fd = in.pipe ? -1 : fileno(in.f);
+  const int io_threads = in.pipe ? 1 : (int)std::max(1u, std::min(8u, std::thread::hardware_concurrency() / 2));
+  std::vector<uint16_t> thumbs((size_t)kPart * tw * th), thumb_prev;
+  std::vector<uint8_t> raw;
+  int64_t frame = 0, chunk = 0;
+  int in_chunk = 0;
+  double score_avg = -1;
+  bool eof = false;
+  auto last_report = std::chrono::steady_clock::now();
   while (!eof && !sh.failed) {
-    if (!y4m_read_frame(in, raw, cur.data(), shift)) { eof = true; break; }
-    // scene-cut score: mean absolute luma difference on a 1/8 x 1/8 subsampled picture, 8-bit units
-    thumb_cur.clear();
-    for (int y = 4; y < in.h; y += 8) for (int x = 4; x < in.w; x += 8) thumb_cur.push_back(cur[(size_t)y * in.w + x]);
-    bool cut = false;
-    if (!thumb_prev.empty() && !o.no_scene_detection) {
-      uint64_t sad = 0;
-      for (size_t i = 0; i < thumb_cur.size(); i++) sad += (uint64_t)std::abs((int)thumb_cur[i] - (int)thumb_prev[i]);
-      const double score = (double)sad / thumb_cur.size() / (1 << (out_bits - 8));
-      // a cut = a jump well above both an absolute floor and the recent level of change
-      if (in_chunk >= o.min_scene_len && score > 10.0 && (score_avg < 0 || score > 3.0 * score_avg + 2.0)) cut = true;
-      score_avg = score_avg < 0 ? score : 0.8 * score_avg + 0.2 * score;
-      if (cut) score_avg = -1;
+    std::shared_ptr<GroupBuf> buf = take_buffer();
+    int got = 0;
+    if (in.pipe || in.n_frames < 0) {
+      while (got < kPart) {
+        uint16_t* slot = buf->v.data() + (size_t)got * frame_samples;
+        if (!y4m_read_frame(in, raw, slot, shift)) { eof = true; break; }
+        make_thumb(slot, thumbs.data() + (size_t)got * tw * th);
+        got++;
+      }
+    } else {
+      got = (int)std::min<int64_t>(kPart, in.n_frames - frame);
+      if (got <= 0) { eof = true; break; }
+      std::atomic<int> next{0};
+      std::atomic<int> bad{0};
+      auto work = [&]() {
+        std::vector<uint8_t> tmp;
+        for (;;) {
+          const int k = next.fetch_add(1);
+          if (k >= got) break;
+          uint16_t* slot = buf->v.data() + (size_t)k * frame_samples;
+          const off_t off = (off_t)in.header_len + (off_t)(frame + k) * (off_t)(6 + in.frame_bytes) + 6;
+          uint8_t* dst = in.bits > 8 ? reinterpret_cast<uint8_t*>(slot) : (tmp.resize(in.frame_bytes), tmp.data());
+          size_t done = 0;
+          while (done < in.frame_bytes) {
+            const ssize_t r = pread(fd, dst + done, in.frame_bytes - done, off + (off_t)done);
+            if (r <= 0) { bad = 1; break; }
+            done += (size_t)r;
+          }
+          if (in.bits <= 8) for (size_t i = 0; i < in.frame_bytes; i++) slot[i] = (uint16_t)(tmp[i] << shift);
+          make_thumb(slot, thumbs.data() + (size_t)k * tw * th);
+        }
+      };
+      std::vector<std::thread> io;
+      for (int t = 1; t < io_threads; t++) io.emplace_back(work);
+      work();
+      for (auto& t : io) t.join();
+      if (bad) die(3, "truncated Y4M file");
+      if (frame + got >= in.n_frames) eof = true;
     }
-    thumb_prev.swap(thumb_cur);
-    if (frame > 0 && (cut || in_chunk >= o.keyint)) { flush_part(); chunk++; in_chunk = 0; }
-    if (part.n == 0) {
-      part.chunk = chunk; part.first_frame = frame; part.first_part = in_chunk == 0;
-      part.samples.resize((size_t)kPart * frame_samples);
+    // cut decisions in display order; a part never crosses a chunk boundary
+    int run_start = 0;
+    auto emit = [&](int from, int to) {
+      if (to <= from) return;
+      Part part;
+      part.chunk = chunk; part.first_frame = frame - (to - from); part.first_part = (in_chunk - (to - from)) == 0;
+      part.n = to - from; part.buf = buf; part.first_slot = (size_t)from;
+      submit(std::move(part));
+    };
+    for (int k = 0; k < got; k++) {
+      const uint16_t* tc = thumbs.data() + (size_t)k * tw * th;
+      bool cut = false;
+      if (!thumb_prev.empty() && !o.no_scene_detection) {
+        uint64_t sad = 0;
+        for (int i = 0; i < tw * th; i++) sad += (uint64_t)std::abs((int)tc[i] - (int)thumb_prev[i]);
+        // scene-cut score: mean absolute luma difference on the 1/8 x 1/8 thumbnails, in 8-bit units;
+        // a cut = a jump well above both an absolute floor and the recent level of change
+        const double score = (double)sad / (tw * th) / (1 << (out_bits - 8));
+        if (in_chunk >= o.min_scene_len && score > 10.0 && (score_avg < 0 || score > 3.0 * score_avg + 2.0)) cut = true;
+        score_avg = score_avg < 0 ? score : 0.8 * score_avg + 0.2 * score;
+        if (cut) score_avg = -1;
+      }
+      thumb_prev.assign(tc, tc + (size_t)tw * th);
+      if (frame > 0 && (cut || in_chunk >= o.keyint)) {
+        emit(run_start, k);
+        run_start = k;
+        chunk++; in_chunk = 0;
+      }
+      frame++; in_chunk++;
     }
-    memcpy(part.samples.data() + (size_t)part.n * frame_samples, cur.data(), frame_samples * sizeof(uint16_t));
-    part.n++; frame++; in_chunk++;
-    if (part.n == kPart) flush_part();
+    emit(run_start, got);
     const auto now = std::chrono::steady_clock::now();
     if (std::chrono::duration<double>(now - last_report).count() > 1.0) { report_progress(sh, false); last_report = now; }
   }
-  flush_part();
   for (auto& q : queues) { { std::lock_guard<std::mutex> l(q.m); q.closed = true; } q.cv.notify_all(); }
   for (auto& t : threads) t.join();
   if (in.pipe) pclose(in.f); else fclose(in.f);
-  for (int fd : lease) close(fd);
+  for (int lfd : lease) close(lfd);
+  for (GroupBuf* gb : sh.free_bufs) delete gb;
+  sh.free_bufs.clear();
   if (sh.total_frames < 0) sh.total_frames = frame;
 
   if (sh.failed) {
