@@ -834,6 +834,55 @@ struct TileWriter {
 
   bool cdef_pending = false;
 
+  // Coefficient syntax from the device-digested form: w[i] (scan order, i < eob) =
+  // sign << 15 | min(|level|, 15) << 11 | br context << 6 | base context; all levels are < 15, so there
+  // are no Golomb escapes.  Same symbols, in the same order, as the raster path below.
+  void coeffs_packed(const uint16_t* w, int eob, int ns, int tx_ctx, int ptype, int plane, int x4, int y4, int abs_y4,
+                     int w4, int max_x4, int max_y4, int* cul_out, int* dc_cat_out) {
+    const int br_tx = std::min(tx_ctx, 3);
+    for (int i = eob - 1; i >= 0; i--) {
+      const unsigned v = w[i];
+      const int level = (v >> 11) & 15;
+      if (i == eob - 1) {
+        const int c2 = i == 0 ? 0 : (i <= (ns * ns) / 8 ? 1 : (i <= (ns * ns) / 4 ? 2 : 3));
+        ec.symbol(std::min(level, 3) - 1, cdf.coeff_base_eob[tx_ctx][ptype][c2], 3);
+      } else {
+        ec.symbol(std::min(level, 3), cdf.coeff_base[tx_ctx][ptype][v & 63], 4);
+      }
+      if (level > 2) {
+        uint16_t* c = cdf.coeff_br[br_tx][ptype][(v >> 6) & 31];
+        int rem = level - 3;
+        for (int k = 0; k < 4; k++) {
+          const int s = std::min(rem, 3);
+          ec.symbol(s, c, 4);
+          rem -= s;
+          if (s < 3) break;
+        }
+      }
+    }
+    int cul = 0, dc_cat = 0;
+    for (int i = 0; i < eob; i++) {
+      const unsigned v = w[i];
+      const int a = (v >> 11) & 15;
+      if (!a) continue;
+      const int sign = v >> 15;
+      if (i == 0) {
+        int dcs = 0;
+        for (int k = 0; k < w4; k++) {
+          if (x4 + k < max_x4) { int s = above_dc[plane][x4 + k]; dcs += s == 1 ? -1 : s == 2 ? 1 : 0; }
+          if (abs_y4 + k < max_y4) { int s = left_dc[plane][y4 + k]; dcs += s == 1 ? -1 : s == 2 ? 1 : 0; }
+        }
+        ec.symbol(sign, cdf.dc_sign[ptype][dcs < 0 ? 1 : dcs > 0 ? 2 : 0], 2);
+        dc_cat = sign ? 1 : 2;
+      } else {
+        ec.boolean(sign);
+      }
+      cul += a;
+    }
+    *cul_out = cul;
+    *dc_cat_out = dc_cat;
+  }
+
   // coefficient syntax for one transform block (one per plane per block in TX_MODE_LARGEST)
   void coeffs(int plane, int mi_r, int mi_c, int tl, const Av1bBlockInfo& b, int tx_type, bool is_inter) {
     const int ss = plane > 0;
@@ -845,7 +894,8 @@ struct TileWriter {
     const int abs_y4 = mi_r >> ss;
     const int tx_ctx = tl - 2;                                    // square: txSzCtx = log2 - 2
     const int ptype = plane > 0;
-    const int eob = b.eob[plane];
+    const int eob = b.eob[plane] & 0x7FFF;
+    const bool packed = (b.eob[plane] & 0x8000) != 0;   // device-digested symbols (see coeffs_packed)
     // all_zero context (spec: get_txb_skip ctx)
     int ctx;
     if (plane == 0) {
@@ -906,6 +956,9 @@ struct TileWriter {
           for (int i = nbits - 2; i >= 0; i--) ec.boolean((extra >> i) & 1);
         }
       }
+      if (packed) {
+        coeffs_packed(reinterpret_cast<const uint16_t*>(cf), eob, ns, tx_ctx, ptype, plane, x4, y4, abs_y4, w4, max_x4, max_y4, &cul, &dc_cat);
+      } else {
       // padded magnitude map for the neighbour contexts
       const int stride = ns + 4;
       memset(lvl_buf, 0, (size_t)stride * (ns + 4));
@@ -985,6 +1038,7 @@ struct TileWriter {
           for (int k = len - 1; k >= 0; k--) ec.boolean((x >> k) & 1);
         }
         cul += a;
+      }
       }
       cul = std::min(cul, 63);
     }

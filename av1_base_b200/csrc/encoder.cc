@@ -277,6 +277,7 @@ static int launch(av1b_encoder* e, Slot& s, int n, int64_t first_index) {
       L.g = g; L.bit_depth = bd; L.base_q_idx = e->base_q_idx; L.quant_rnd = 48; L.dc_q = dcq; L.ac_q = acq;
       for (int p = 0; p < 3; p++) { L.src[p] = src[p]; L.ref[p] = prev[p]; L.rec[p] = e->loop_filters ? rec[p] : fin[p]; L.coef[p] = coef[p]; }
       L.blocks = blocks; L.part_map = e->d_map_inter; L.mvs = e->d_mvs + (size_t)b * e->map_elems * 2;
+      L.pack_levels = (e->keep || e->cfg.reserved[5]) ? 0 : 1;   // debug keeps raster levels for the oracle comparison
       L.tb_zero_thr = e->cfg.reserved[4];   // experiment knob: drop transform blocks with sum|level| <= thr
       CK(launch_inter_encode(L, e->stream));
       CK(launch_merge_skip(g, blocks, e->stream));

@@ -23,7 +23,7 @@ using namespace av1tx;
 namespace {
 
 constexpr int kThreads = 256;
-constexpr int kPoolBytes = 16 * ((16 + 7) * 17 * 4 + 16 * 16 * 2);   // 16 groups of N = 16
+constexpr int kPoolBytes = 16 * ((16 + 7) * 17 * 4 + 16 * 16 * 2 + 18 * 18 + 4);   // 16 groups of N = 16 (largest carving)
 
 __device__ __forceinline__ int clampi(int v, int lo, int hi) { return v < lo ? lo : (v > hi ? hi : v); }
 
@@ -31,16 +31,19 @@ template <int N> struct TxTab;
 template <> struct TxTab<4> {
   static __device__ __forceinline__ int f(int k, int i) { return tbl::fwd_dct4[k][i]; }
   static __device__ __forceinline__ int iscan(int p) { return tbl::iscan_default_4[p]; }
+  static __device__ __forceinline__ int nz_off(int p) { return tbl::nz_map_ctx_offset_4[p]; }
   static constexpr int kLog2 = 2, kRowShift = 0;
 };
 template <> struct TxTab<8> {
   static __device__ __forceinline__ int f(int k, int i) { return tbl::fwd_dct8[k][i]; }
   static __device__ __forceinline__ int iscan(int p) { return tbl::iscan_default_8[p]; }
+  static __device__ __forceinline__ int nz_off(int p) { return tbl::nz_map_ctx_offset_8[p]; }
   static constexpr int kLog2 = 3, kRowShift = 1;
 };
 template <> struct TxTab<16> {
   static __device__ __forceinline__ int f(int k, int i) { return tbl::fwd_dct16[k][i]; }
   static __device__ __forceinline__ int iscan(int p) { return tbl::iscan_default_16[p]; }
+  static __device__ __forceinline__ int nz_off(int p) { return tbl::nz_map_ctx_offset_16[p]; }
   static constexpr int kLog2 = 4, kRowShift = 2;
 };
 
@@ -48,7 +51,7 @@ template <> struct TxTab<16> {
 // `gmask` of one warp; t = lane index inside the group.  buf: (N+7)*(N+1) int32, pred: N*N uint16.
 template <int N>
 __device__ __forceinline__ int code_tb(const InterLaunch& P, int p, int x, int y, int mv_row, int mv_col, int t,
-                                       unsigned gmask, int32_t* buf, uint16_t* pred, bool active) {
+                                       unsigned gmask, int32_t* buf, uint16_t* pred, uint8_t* lv8, bool active) {
   constexpr int S = N + 1;
   const int ss = p > 0, bd = P.bit_depth;
   const int stride = P.g.stride[p];
@@ -113,7 +116,10 @@ __device__ __forceinline__ int code_tb(const InterLaunch& P, int p, int x, int y
   for (int k = 0; k < N; k++) buf[k * S + t] = col[k];
   __syncwarp(gmask);
   int eob = 0, sum_abs = 0;
-  int16_t* cdst = P.coef[p] + av1b_coef_offset(P.g.sb_cols, p, x, y) + t * N;
+  int16_t* cbase = P.coef[p] + av1b_coef_offset(P.g.sb_cols, p, x, y);
+  int16_t* cdst = cbase + t * N;
+  constexpr int S8 = N + 2;           // pitch of the capped-magnitude map (two zero guard rows / columns)
+  unsigned sign_bits = 0, max_lv = 0;
   {
     int32_t row[N];
 #pragma unroll
@@ -143,11 +149,20 @@ __device__ __forceinline__ int code_tb(const InterLaunch& P, int p, int x, int y
       if (active) cdst[l] = (int16_t)(c < 0 ? -(int32_t)lv : (int32_t)lv);
       if (lv) eob = max(eob, TxTab<N>::iscan(t * N + l) + 1);
       sum_abs += (int)lv;
+      lv8[t * S8 + l] = (uint8_t)min(lv, 15u);
+      sign_bits |= (c < 0 ? 1u : 0u) << l;
+      max_lv = max(max_lv, lv);
+    }
+    lv8[t * S8 + N] = 0; lv8[t * S8 + N + 1] = 0;
+    if (t < 2) {
+#pragma unroll
+      for (int cidx = 0; cidx < S8; cidx++) lv8[(N + t) * S8 + cidx] = 0;
     }
 #pragma unroll
     for (int o = N / 2; o; o >>= 1) {
       eob = max(eob, __shfl_xor_sync(gmask, eob, o));
       sum_abs += __shfl_xor_sync(gmask, sum_abs, o);
+      max_lv = max(max_lv, __shfl_xor_sync(gmask, max_lv, o));
     }
     const int thr = N >= 16 ? P.tb_zero_thr : (N == 8 ? P.tb_zero_thr >> 1 : 0);
     if (eob > 0 && sum_abs <= thr) {
@@ -156,6 +171,28 @@ __device__ __forceinline__ int code_tb(const InterLaunch& P, int p, int x, int y
       if (active) {
 #pragma unroll
         for (int l = 0; l < N; l++) cdst[l] = 0;
+      }
+    }
+  }
+  // ---------------- pre-digested symbol stream for the host entropy coder ----------------
+  // (levels up to 14 only: larger ones need Golomb escapes and stay in the raster form)
+  bool packed = false;
+  if (P.pack_levels && eob > 0 && max_lv < 15u) {
+    packed = true;
+    __syncwarp(gmask);
+    if (active) {
+      uint16_t* wdst = reinterpret_cast<uint16_t*>(cbase);
+#pragma unroll
+      for (int l = 0; l < N; l++) {
+        const int pos = t * N + l, si = TxTab<N>::iscan(pos);
+        if (si < eob) {
+          const uint8_t* L = lv8 + t * S8 + l;
+          const int m3 = min((int)L[1], 3) + min((int)L[S8], 3) + min((int)L[S8 + 1], 3) + min((int)L[2], 3) + min((int)L[2 * S8], 3);
+          const int bctx = pos == 0 ? 0 : min((m3 + 1) >> 1, 4) + TxTab<N>::nz_off(pos);
+          const int m15 = (int)L[1] + (int)L[S8] + (int)L[S8 + 1];
+          const int brctx = min((m15 + 1) >> 1, 6) + (pos == 0 ? 0 : ((t < 2 && l < 2) ? 7 : 14));
+          wdst[si] = (uint16_t)((((sign_bits >> l) & 1u) << 15) | ((unsigned)L[0] << 11) | ((unsigned)brctx << 6) | (unsigned)bctx);
+        }
       }
     }
   }
@@ -169,6 +206,7 @@ __device__ __forceinline__ int code_tb(const InterLaunch& P, int p, int x, int y
     }
     return 0;
   }
+  const int eob_out = packed ? (eob | 0x8000) : eob;
   const int row_range = bd + 8, col_range = max(bd + 6, 16);
   {
     int32_t dq[N];
@@ -197,7 +235,7 @@ __device__ __forceinline__ int code_tb(const InterLaunch& P, int p, int x, int y
     }
   }
   __syncwarp(gmask);
-  return eob;
+  return eob_out;
 }
 
 struct Smem {
@@ -207,11 +245,12 @@ struct Smem {
 };
 
 template <int N>
-__device__ __forceinline__ void group_buffers(Smem& sm, int group, int32_t** buf, uint16_t** pred) {
-  constexpr int kBuf = (N + 7) * (N + 1) * 4, kPred = N * N * 2;
-  unsigned char* base = sm.pool + (size_t)group * (kBuf + kPred);
+__device__ __forceinline__ void group_buffers(Smem& sm, int group, int32_t** buf, uint16_t** pred, uint8_t** lv8) {
+  constexpr int kBuf = (N + 7) * (N + 1) * 4, kPred = N * N * 2, kLv = ((N + 2) * (N + 2) + 3) & ~3;
+  unsigned char* base = sm.pool + (size_t)group * (kBuf + kPred + kLv);
   *buf = reinterpret_cast<int32_t*>(base);
   *pred = reinterpret_cast<uint16_t*>(base + kBuf);
+  *lv8 = base + kBuf + kPred;
 }
 
 __global__ void __launch_bounds__(kThreads) inter_encode_kernel(const InterLaunch P) {
@@ -235,10 +274,11 @@ __global__ void __launch_bounds__(kThreads) inter_encode_kernel(const InterLaunc
     int mvr = 0, mvc = 0;
     if (active) { mvr = P.mvs[(uy * g.w8 + ux) * 2]; mvc = P.mvs[(uy * g.w8 + ux) * 2 + 1]; }
     int32_t* buf; uint16_t* pred;
-    group_buffers<16>(sm, group, &buf, &pred);
+    uint8_t* lv8;
+    group_buffers<16>(sm, group, &buf, &pred, &lv8);
     // inactive groups run on the (always allocated) superblock origin and store nothing
     const int x = active ? ux * 8 : sbx * 64, y = active ? uy * 8 : sby * 64;
-    const int eob = code_tb<16>(P, 0, x, y, mvr, mvc, t, gmask, buf, pred, active);
+    const int eob = code_tb<16>(P, 0, x, y, mvr, mvc, t, gmask, buf, pred, lv8, active);
     if (active && t == 0) sm.eob[0][u] = (uint16_t)eob;
   }
   __syncthreads();
@@ -253,9 +293,10 @@ __global__ void __launch_bounds__(kThreads) inter_encode_kernel(const InterLaunc
     int mvr = 0, mvc = 0;
     if (active) { mvr = P.mvs[(uy * g.w8 + ux) * 2]; mvc = P.mvs[(uy * g.w8 + ux) * 2 + 1]; }
     int32_t* buf; uint16_t* pred;
-    group_buffers<8>(sm, group, &buf, &pred);
+    uint8_t* lv8;
+      group_buffers<8>(sm, group, &buf, &pred, &lv8);
     const int x = active ? ux * 4 : sbx * 32, y = active ? uy * 4 : sby * 32;
-    const int eob = code_tb<8>(P, p, x, y, mvr, mvc, t, gmask, buf, pred, active);
+    const int eob = code_tb<8>(P, p, x, y, mvr, mvc, t, gmask, buf, pred, lv8, active);
     if (active && t == 0) sm.eob[p][u] = (uint16_t)eob;
   }
   __syncthreads();
@@ -273,9 +314,10 @@ __global__ void __launch_bounds__(kThreads) inter_encode_kernel(const InterLaunc
       int mvr = 0, mvc = 0;
       if (active) { mvr = P.mvs[(uy * g.w8 + ux) * 2]; mvc = P.mvs[(uy * g.w8 + ux) * 2 + 1]; }
       int32_t* buf; uint16_t* pred;
-      group_buffers<8>(sm, group, &buf, &pred);
+      uint8_t* lv8;
+      group_buffers<8>(sm, group, &buf, &pred, &lv8);
       const int x = active ? ux * 8 : sbx * 64, y = active ? uy * 8 : sby * 64;
-      const int eob = code_tb<8>(P, 0, x, y, mvr, mvc, t, gmask, buf, pred, active);
+      const int eob = code_tb<8>(P, 0, x, y, mvr, mvc, t, gmask, buf, pred, lv8, active);
       if (active && t == 0) sm.eob[0][u] = (uint16_t)eob;
       __syncthreads();
     }
@@ -289,9 +331,10 @@ __global__ void __launch_bounds__(kThreads) inter_encode_kernel(const InterLaunc
       int mvr = 0, mvc = 0;
       if (active) { mvr = P.mvs[(uy * g.w8 + ux) * 2]; mvc = P.mvs[(uy * g.w8 + ux) * 2 + 1]; }
       int32_t* buf; uint16_t* pred;
-      group_buffers<4>(sm, group, &buf, &pred);
+      uint8_t* lv8;
+      group_buffers<4>(sm, group, &buf, &pred, &lv8);
       const int x = active ? ux * 4 : sbx * 32, y = active ? uy * 4 : sby * 32;
-      const int eob = code_tb<4>(P, p, x, y, mvr, mvc, t, gmask, buf, pred, active);
+      const int eob = code_tb<4>(P, p, x, y, mvr, mvc, t, gmask, buf, pred, lv8, active);
       if (active && t == 0) sm.eob[p][u] = (uint16_t)eob;
       __syncthreads();
     }

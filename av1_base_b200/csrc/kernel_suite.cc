@@ -303,7 +303,7 @@ int av1b_k_inter_encode(int device, int width, int height, int bit_depth, int ba
     L.src[p] = bs.d[p].as<uint16_t>(); L.ref[p] = br.d[p].as<uint16_t>(); L.rec[p] = bo.d[p].as<uint16_t>();
     L.coef[p] = dc[p].as<int16_t>();
   }
-  L.blocks = dbl.as<Av1bBlockInfo>(); L.part_map = dpm.as<uint8_t>(); L.mvs = dmv.as<int16_t>(); L.tb_zero_thr = tb_zero_thr;
+  L.blocks = dbl.as<Av1bBlockInfo>(); L.part_map = dpm.as<uint8_t>(); L.mvs = dmv.as<int16_t>(); L.tb_zero_thr = tb_zero_thr; L.pack_levels = 0;
   if ((rc = timed(t, reps, ms_per_launch, [&]() { return launch_inter_encode(L, t.s); }))) return rc;
   if (merge_skip) CKS(launch_merge_skip(L.g, L.blocks, t.s));
   for (int p = 0; p < 3; p++) CKS(cudaMemcpyAsync(coef[p], dc[p].p, bs.elems[p] * 2, cudaMemcpyDeviceToHost, t.s));

@@ -101,6 +101,8 @@ struct InterLaunch {
   const int16_t* mvs;         // [h8*w8][2] (row, col), 1/8 luma samples
   int32_t tb_zero_thr;        // drop transform blocks whose levels sum to <= thr (16x16) / thr/2 (8x8)
   uint32_t dc_magic, ac_magic; // floor(2^32 / dc_q), floor(2^32 / ac_q): set by launch_inter_encode
+  int32_t pack_levels;        // 1: transform blocks whose levels are all < 15 are stored as scan-ordered packed
+                              //    symbols (sign | level | br ctx | base ctx) and flagged with bit 15 of eob
 };
 cudaError_t launch_inter_encode(const InterLaunch& p, cudaStream_t s);
 // Bottom-up merge of skipped inter siblings with equal vectors into 32x32 / 64x64 blocks (side info only).

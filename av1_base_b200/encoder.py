@@ -27,7 +27,7 @@ def _check(rc):
 class Encoder:
     def __init__(self, width, height, bit_depth=10, crf=30, preset=6, keyint=240, fps=(30, 1), device_id=0,
                  tile_cols_log2=-1, tile_rows_log2=-1, hdr=False, host_threads=0, frames_in_flight=0,
-                 keep_debug=False, blk_log2=0, loop_filters=True, intra_only=False, tb_zero_thr=0):
+                 keep_debug=False, blk_log2=0, loop_filters=True, intra_only=False, tb_zero_thr=0, raster_levels=False):
         L = abi.lib()
         cfg = abi.Config()
         L.av1b_config_default(C.byref(cfg))
@@ -44,6 +44,7 @@ class Encoder:
         cfg.reserved[2] = 0 if loop_filters else 1
         cfg.reserved[3] = 1 if intra_only else 0
         cfg.reserved[4] = tb_zero_thr
+        cfg.reserved[5] = 1 if raster_levels else 0
         self.cfg = cfg
         self._h = C.c_void_p()
         _check(L.av1b_encoder_create(C.byref(cfg), C.byref(self._h)))

@@ -48,7 +48,8 @@ typedef struct av1b_config {
   int32_t frames_in_flight;       /* frames batched per device pass, 0 = auto                      */
   int32_t reserved[8];            /* [0]: keep recon+symbols per frame (tests); [1]: fixed block log2 (3..6), 0 = default;
                                      [2]: 1 = in-loop filters off; [3]: 1 = every frame is a key frame;
-                                     [4]: inter transform-block drop threshold (0 = off) */
+                                     [4]: inter transform-block drop threshold (0 = off);
+                                     [5]: 1 = keep raster levels (no device-digested coefficient symbols) */
 } av1b_config;
 
 typedef struct av1b_encoder av1b_encoder;

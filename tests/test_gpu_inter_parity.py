@@ -65,3 +65,23 @@ def test_chunk_parity(w, h, bd, crf, tcl, trl, lf, nfr, fif, keyint):
             assert np.array_equal(dec_a[i][p], rec[p]), ("libaom", i, p)
         prev_fin, prev_pyr = fin, pyr
     enc.close()
+
+
+@pytest.mark.parametrize("w,h,bd,crf", [(200, 136, 10, 20), (328, 248, 8, 40), (640, 360, 10, 30)])
+def test_device_digested_symbols_give_identical_streams(w, h, bd, crf):
+    """Production mode hands the host scan-ordered packed coefficient symbols instead of raster levels; the
+    bitstream must not change by a single byte, and it must still decode to the reconstruction."""
+    frames = synth.synth_clip(w, h, bd, 5, seed=3, scene_len=100)
+    a = encoder.Encoder(w, h, bd, crf=crf, frames_in_flight=2, raster_levels=True)
+    b = encoder.Encoder(w, h, bd, crf=crf, frames_in_flight=2)
+    ta, tb = a.encode_chunk(frames), b.encode_chunk(frames)
+    assert ta == tb
+    c = encoder.Encoder(w, h, bd, crf=crf, frames_in_flight=2, keep_debug=True)
+    tc = c.encode_chunk(frames)
+    assert tc == tb
+    dec = D.dav1d_decode(tb)
+    for i in range(len(frames)):
+        for p in range(3):
+            assert np.array_equal(dec[i][p], c.recon(i)[p])
+    for e in (a, b, c):
+        e.close()

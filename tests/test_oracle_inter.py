@@ -107,3 +107,79 @@ def test_hme_finds_global_translation():
                O.pyramid(g, O.pad_planes(g, [ref, ref[::2, ::2], ref[::2, ::2]])[0])).reshape(g.h8, g.w8, 2)
     inner = mv[4:-4, 4:-4]
     assert np.all(inner[..., 0] == 5 * 8) and np.all(inner[..., 1] == -9 * 8)
+
+
+def _tables():
+    import re, os
+    txt = open(os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "av1_base_b200", "csrc", "av1_tables.h")).read()
+
+    def tab(name):
+        m = re.search(r"%s\[\d+\] = \{(.*?)\};" % name, txt, re.S)
+        return np.array([int(v) for v in re.findall(r"-?\d+", m.group(1))])
+    return {n: (tab("av1t_scan_default_%dx%d" % (n, n)), tab("av1t_nz_map_ctx_offset_%dx%d" % (n, n))) for n in (4, 8, 16)}
+
+
+def digest_like_device(g, blocks, coef):
+    """Python restatement of what inter_kernel.cu writes with pack_levels = 1: transform blocks whose levels are
+    all < 15 become scan-ordered packed symbols (sign | level | br ctx | base ctx), flagged in bit 15 of eob."""
+    T = _tables()
+    blocks = blocks.copy()
+    coef = [c.copy() for c in coef]
+    bl = blocks["blk_log2"].reshape(g.h8, g.w8)
+    for uy in range(g.h8):
+        for ux in range(g.w8):
+            b = int(bl[uy, ux]); n8 = 1 << (b - 3)
+            if (ux | uy) & (n8 - 1) or b > 4:
+                continue
+            for p in range(3):
+                ss = 1 if p else 0
+                n = 1 << (b - ss)
+                eob = int(blocks["eob"][uy * g.w8 + ux][p])
+                if eob == 0:
+                    continue
+                x, y = (ux * 8) >> ss, (uy * 8) >> ss
+                lsb, lu = 6 - ss, 3 - ss
+                uxx, uyy = (x >> lu) & 7, (y >> lu) & 7
+                m = (uxx & 1) | ((uyy & 1) << 1) | ((uxx & 2) << 1) | ((uyy & 2) << 2) | ((uxx & 4) << 2) | ((uyy & 4) << 3)
+                off = ((((y >> lsb) * g.sb_cols + (x >> lsb)) << (2 * lsb)) + (m << (2 * lu)))
+                flat = coef[p].reshape(-1)
+                lv = flat[off:off + n * n].astype(np.int32).reshape(n, n)
+                if np.abs(lv).max() >= 15:
+                    continue
+                scan, nzo = T[n]
+                a = np.zeros((n + 2, n + 2), np.int32); a[:n, :n] = np.abs(lv)
+                words = flat[off:off + n * n].copy().view(np.uint16)
+                for i in range(eob):
+                    pos = int(scan[i]); r, c = pos // n, pos % n
+                    m3 = sum(min(int(v), 3) for v in (a[r, c + 1], a[r + 1, c], a[r + 1, c + 1], a[r, c + 2], a[r + 2, c]))
+                    bctx = 0 if pos == 0 else min((m3 + 1) >> 1, 4) + int(nzo[pos])
+                    m15 = int(a[r, c + 1] + a[r + 1, c] + a[r + 1, c + 1])
+                    brctx = min((m15 + 1) >> 1, 6) + (0 if pos == 0 else (7 if (r < 2 and c < 2) else 14))
+                    words[i] = ((1 if lv[r, c] < 0 else 0) << 15) | (int(a[r, c]) << 11) | (brctx << 6) | bctx
+                flat[off:off + n * n] = words.view(np.int16)
+                for yy in range(n8):
+                    for xx in range(n8):
+                        blocks["eob"][(uy + yy) * g.w8 + ux + xx][p] = eob | 0x8000
+    return blocks, coef
+
+
+@pytest.mark.parametrize("w,h,bd,q", [(200, 136, 10, 60), (328, 248, 8, 150)])
+def test_device_digested_coefficients_pack_to_identical_bytes(w, h, bd, q):
+    """The host entropy coder must emit exactly the same bytes from the device-digested symbol form as from
+    raster levels (the GPU side of the same statement is tests/test_gpu_inter_parity.py)."""
+    rng = np.random.default_rng(q)
+    g = O.geom(w, h, 1, 0)
+    frames = synth.synth_clip(w, h, bd, 2, seed=9, scene_len=100)
+    pm = O.partition_fixed(g, 4)
+    r0 = O.encode_intra_frame(g, frames[0], bd, q, pm)
+    r1 = O.encode_inter_frame(g, frames[1], bd, q, pm, random_mvs(g, pm, rng), r0.rec)
+    seq = abi.SeqParams(w, h, bd, 0, 0, 30, 1, 0)
+    fp = abi.FrameParams()
+    fp.frame_type, fp.base_q_idx = 1, q
+    fp.tile_cols_log2, fp.tile_rows_log2 = g.tile_cols_log2, g.tile_rows_log2
+    fp.cdef_damping = 3
+    raster = packer.pack_frame(seq, fp, packer.make_syms(g, r1.blocks, r1.coef))
+    b2, c2 = digest_like_device(g, r1.blocks, r1.coef)
+    assert (b2["eob"] & 0x8000).any()
+    digested = packer.pack_frame(seq, fp, packer.make_syms(g, b2, c2))
+    assert raster == digested
