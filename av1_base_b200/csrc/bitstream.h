@@ -44,9 +44,11 @@ class RangeEncoder {
       // spec 8.2.6 CDF adaptation, expressed on the inverted CDF
       const int cnt = icdf[n];
       const int rate = 3 + (cnt > 15) + (cnt > 31) + (n > 3 ? 2 : 1);   // + min(floor(log2(n)), 2)
+      // branch-free: the symbol value is data dependent, a branch per entry mispredicts about once a symbol
       for (int i = 0; i < n - 1; i++) {
-        if (i < s) icdf[i] += (uint16_t)((32768 - icdf[i]) >> rate);
-        else icdf[i] -= (uint16_t)(icdf[i] >> rate);
+        const int x = icdf[i];
+        const int up = x + ((32768 - x) >> rate), down = x - (x >> rate);
+        icdf[i] = (uint16_t)(i < s ? up : down);
       }
       icdf[n] = (uint16_t)(cnt + (cnt < 32));
     }
