@@ -81,6 +81,9 @@ def lib():
                               "(there is no CPU fallback)" % LIB_PATH)
         L = C.CDLL(LIB_PATH)
         L.av1b_last_error.restype = C.c_char_p
+        L.av1b_host_alloc.restype = C.c_void_p
+        L.av1b_host_alloc.argtypes = [C.c_int, C.c_size_t]
+        L.av1b_host_free.argtypes = [C.c_void_p]
         _lib = L
     return _lib
 

@@ -285,7 +285,22 @@ int lease_device(int dev, bool block) {
 
 // A group buffer holds kGroup consecutive frames (each Y U V contiguous); the parts cut out of it share it
 // and it goes back to the pool when the last of them has been encoded.
-struct GroupBuf { std::vector<uint16_t> v; };
+// Frames of one read group.  Page-locked when the library can provide it (the encoder's copy engine then
+// reads the frames where pread() put them); plain memory otherwise.
+struct GroupBuf {
+  uint16_t* p = nullptr;
+  bool pinned = false;
+  GroupBuf(int device, size_t samples) {
+    p = static_cast<uint16_t*>(av1b_host_alloc(device, samples * 2));
+    pinned = p != nullptr;
+    if (!p) p = static_cast<uint16_t*>(malloc(samples * 2));
+    if (!p) throw std::bad_alloc();
+  }
+  ~GroupBuf() { if (pinned) av1b_host_free(p); else free(p); }
+  GroupBuf(const GroupBuf&) = delete;
+  GroupBuf& operator=(const GroupBuf&) = delete;
+  uint16_t* data() { return p; }
+};
 struct Part {
   int64_t chunk = 0, first_frame = 0;
   bool first_part = false;
@@ -459,7 +474,7 @@ int main(int argc, char** argv) {
         if (sh.failed || !enc) continue;   // drain
         std::vector<av1b_frame_src> fs((size_t)part.n);
         for (int k = 0; k < part.n; k++) {
-          uint16_t* b = part.buf->v.data() + (part.first_slot + (size_t)k) * frame_samples;
+          uint16_t* b = part.buf->data() + (part.first_slot + (size_t)k) * frame_samples;
           fs[k].planes[0] = b; fs[k].planes[1] = b + (size_t)in.w * in.h; fs[k].planes[2] = b + (size_t)in.w * in.h * 5 / 4;
           fs[k].stride[0] = in.w; fs[k].stride[1] = fs[k].stride[2] = in.w / 2;
         }
@@ -486,7 +501,7 @@ int main(int argc, char** argv) {
       std::lock_guard<std::mutex> l(sh.m);
       if (!sh.free_bufs.empty()) { g = sh.free_bufs.back(); sh.free_bufs.pop_back(); }
     }
-    if (!g) { g = new GroupBuf(); g->v.resize((size_t)kPart * frame_samples); }
+    if (!g) g = new GroupBuf(dev[0], (size_t)kPart * frame_samples);
     Shared* shp = &sh;
     return std::shared_ptr<GroupBuf>(g, [shp](GroupBuf* p) { std::lock_guard<std::mutex> l(shp->m); shp->free_bufs.push_back(p); });
   };
@@ -521,7 +536,7 @@ int main(int argc, char** argv) {
     int got = 0;
     if (in.pipe || in.n_frames < 0) {
       while (got < kPart) {
-        uint16_t* slot = buf->v.data() + (size_t)got * frame_samples;
+        uint16_t* slot = buf->data() + (size_t)got * frame_samples;
         if (!y4m_read_frame(in, raw, slot, shift)) { eof = true; break; }
         make_thumb(slot, thumbs.data() + (size_t)got * tw * th);
         got++;
@@ -536,7 +551,7 @@ int main(int argc, char** argv) {
         for (;;) {
           const int k = next.fetch_add(1);
           if (k >= got) break;
-          uint16_t* slot = buf->v.data() + (size_t)k * frame_samples;
+          uint16_t* slot = buf->data() + (size_t)k * frame_samples;
           const off_t off = (off_t)in.header_len + (off_t)(frame + k) * (off_t)(6 + in.frame_bytes) + 6;
           uint8_t* dst = in.bits > 8 ? reinterpret_cast<uint8_t*>(slot) : (tmp.resize(in.frame_bytes), tmp.data());
           size_t done = 0;

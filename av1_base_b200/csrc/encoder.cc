@@ -160,7 +160,7 @@ struct av1b_encoder {
   // statistics of the last chunk / resident run
   double t_h2d_ms = 0, t_kernel_ms = 0, t_intra_ms = 0, t_inter_ms = 0, t_me_ms = 0, t_d2h_ms = 0, t_pack_ms = 0,
          t_deblock_ms = 0, t_cdef_ms = 0;
-  int64_t kernel_launches = 0, intra_launches = 0, inter_launches = 0, frames_done = 0, bytes_out = 0, key_frames = 0;
+  int64_t kernel_launches = 0, intra_launches = 0, inter_launches = 0, frames_done = 0, bytes_out = 0, key_frames = 0, staged_direct = 0;
 };
 
 static void free_all(av1b_encoder* e) {
@@ -185,10 +185,34 @@ static void free_all(av1b_encoder* e) {
   delete e->pool;
 }
 
-// upload n frames (host pointers) into a slot: rows are gathered into the pinned staging buffer by the
-// host pool, then copied on the input copy stream (overlaps the kernels of the previous batch)
+// true when the whole plane lies in page-locked memory the device can read directly (av1b_host_alloc,
+// cudaHostAlloc / cudaHostRegister of the caller)
+static bool is_pinned(const void* p) {
+  cudaPointerAttributes a;
+  if (cudaPointerGetAttributes(&a, p) != cudaSuccess) { cudaGetLastError(); return false; }
+  return a.type == cudaMemoryTypeHost;
+}
+
+// upload n frames (host pointers) into a slot on the input copy stream (overlaps the kernels of the
+// previous batch).  Page-locked sources are read by the copy engine where they lie; pageable ones are
+// first gathered into the slot's pinned staging buffer by the host pool.
 static int stage(av1b_encoder* e, Slot& s, const av1b_frame_src* frames, int n) {
   const Av1bGeom& g = e->g;
+  bool direct = true;
+  for (int b = 0; b < n && direct; b++)
+    for (int p = 0; p < 3 && direct; p++) direct = is_pinned(frames[b].planes[p]);
+  if (direct) {
+    CK(cudaEventRecord(s.ev_h2d, e->s_in));
+    for (int b = 0; b < n; b++)
+      for (int p = 0; p < 3; p++) {
+        const int w = p ? g.width >> 1 : g.width, h = p ? g.height >> 1 : g.height;
+        CK(cudaMemcpy2DAsync(s.d_src[p] + (size_t)b * e->plane_elems[p], (size_t)g.stride[p] * 2, frames[b].planes[p],
+                             (size_t)frames[b].stride[p] * 2, (size_t)w * 2, h, cudaMemcpyHostToDevice, e->s_in));
+      }
+    CK(cudaEventRecord(s.ev_src, e->s_in));
+    e->staged_direct += n;
+    return AV1B_OK;
+  }
   const int kSplit = 4;   // row bands per plane
   e->pool->parallel_for(n * 3 * kSplit, [&](int task) {
     const int b = task / (3 * kSplit), p = (task / kSplit) % 3, band = task % kSplit;
@@ -396,7 +420,7 @@ static void reset_stats(av1b_encoder* e) {
   e->kept.clear();
   e->t_h2d_ms = e->t_kernel_ms = e->t_intra_ms = e->t_inter_ms = e->t_me_ms = e->t_d2h_ms = e->t_pack_ms = 0;
   e->t_deblock_ms = e->t_cdef_ms = 0;
-  e->kernel_launches = e->intra_launches = e->inter_launches = e->frames_done = e->bytes_out = e->key_frames = 0;
+  e->kernel_launches = e->intra_launches = e->inter_launches = e->frames_done = e->bytes_out = e->key_frames = e->staged_direct = 0;
 }
 
 extern "C" {
@@ -655,13 +679,26 @@ int av1b_get_geom(av1b_encoder* e, Av1bGeom* g) {
   return AV1B_OK;
 }
 
+void* av1b_host_alloc(int device, size_t bytes) {
+  void* p = nullptr;
+  if (bytes == 0) return nullptr;
+  if (cudaSetDevice(device) != cudaSuccess) { set_error("cudaSetDevice(%d) failed", device); cudaGetLastError(); return nullptr; }
+  const cudaError_t err = cudaHostAlloc(&p, bytes, cudaHostAllocPortable);
+  if (err != cudaSuccess) { set_error("cudaHostAlloc(%zu): %s", bytes, cudaGetErrorString(err)); cudaGetLastError(); return nullptr; }
+  return p;
+}
+
+void av1b_host_free(void* p) {
+  if (p) cudaFreeHost(p);
+}
+
 int av1b_get_stats(av1b_encoder* e, double* stats, int n) {
   if (!e || !stats) return AV1B_ERR_INVALID;
-  const double v[16] = {e->t_h2d_ms, e->t_kernel_ms, e->t_d2h_ms, e->t_pack_ms, (double)e->kernel_launches,
+  const double v[17] = {e->t_h2d_ms, e->t_kernel_ms, e->t_d2h_ms, e->t_pack_ms, (double)e->kernel_launches,
                         (double)e->base_q_idx, e->t_intra_ms, (double)e->intra_launches, (double)e->frames_done,
                         (double)e->bytes_out, e->t_deblock_ms, e->t_cdef_ms, e->t_inter_ms, e->t_me_ms,
-                        (double)e->inter_launches, (double)e->key_frames};
-  for (int i = 0; i < n && i < 16; i++) stats[i] = v[i];
+                        (double)e->inter_launches, (double)e->key_frames, (double)e->staged_direct};
+  for (int i = 0; i < n && i < 17; i++) stats[i] = v[i];
   return AV1B_OK;
 }
 

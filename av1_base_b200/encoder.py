@@ -62,17 +62,23 @@ class Encoder:
         except Exception:
             pass
 
-    def encode_chunk(self, frames, progress=None):
+    def encode_chunk_strided(self, frames, progress=None):
+        """Like encode_chunk, but row-strided uint16 views are handed over as they are (plane pointer + stride)."""
+        return self.encode_chunk(frames, progress, _strided=True)
+
+    def encode_chunk(self, frames, progress=None, _strided=False):
         """frames: list of [Y,U,V] uint16 arrays. Returns the list of temporal units (bytes)."""
         n = len(frames)
         srcs = (abi.FrameSrc * n)()
         keep = []
         for i, fr in enumerate(frames):
             for p in range(3):
-                a = np.ascontiguousarray(fr[p], dtype=np.uint16)
+                a = fr[p]
+                if not (_strided and a.dtype == np.uint16 and a.strides[1] == 2 and a.strides[0] % 2 == 0):
+                    a = np.ascontiguousarray(a, dtype=np.uint16)
                 keep.append(a)
                 srcs[i].planes[p] = a.ctypes.data
-                srcs[i].stride[p] = a.shape[1]
+                srcs[i].stride[p] = a.strides[0] // 2
         out = []
 
         def on_packet(user, data, size, idx, is_key):
@@ -106,12 +112,12 @@ class Encoder:
         return blocks, coef
 
     def stats(self):
-        s = (C.c_double * 16)()
-        _check(abi.lib().av1b_get_stats(self._h, s, 16))
+        s = (C.c_double * 17)()
+        _check(abi.lib().av1b_get_stats(self._h, s, 17))
         return dict(h2d_ms=s[0], kernel_ms=s[1], d2h_ms=s[2], pack_ms=s[3], kernel_launches=int(s[4]),
                     base_q_idx=int(s[5]), intra_ms=s[6], intra_launches=int(s[7]), frames_done=int(s[8]),
                     bytes_out=int(s[9]), deblock_ms=s[10], cdef_ms=s[11], inter_ms=s[12], me_ms=s[13],
-                    inter_launches=int(s[14]), key_frames=int(s[15]))
+                    inter_launches=int(s[14]), key_frames=int(s[15]), staged_direct=int(s[16]))
 
     def frame_params(self):
         fp = abi.FrameParams()
@@ -167,6 +173,53 @@ class Encoder:
         cb = abi.PACKET_CB(on_packet)
         _check(abi.lib().av1b_encode_resident(self._h, n_steps, cb, None))
         return out
+
+
+class PinnedFrames:
+    """Source frames held in page-locked host memory (av1b_host_alloc): the encoder's copy engine reads them
+    where they lie instead of going through its pageable-source staging copy.  Behaves like a list of
+    [Y, U, V] uint16 arrays; the memory is released by close() / garbage collection."""
+
+    def __init__(self, frames, device_id=0):
+        self._ptr = None
+        total = sum(int(np.asarray(pl).size) for fr in frames for pl in fr) * 2
+        ptr = abi.lib().av1b_host_alloc(device_id, total)
+        if not ptr:
+            raise EncodeError(-1, "av1b_host_alloc(%d)" % total)
+        self._ptr = ptr
+        buf = (C.c_uint8 * total).from_address(ptr)
+        flat = np.frombuffer(buf, dtype=np.uint16)
+        self.frames, off = [], 0
+        for fr in frames:
+            planes = []
+            for pl in fr:
+                pl = np.asarray(pl, dtype=np.uint16)
+                v = flat[off:off + pl.size].reshape(pl.shape)
+                v[...] = pl
+                planes.append(v)
+                off += pl.size
+            self.frames.append(planes)
+
+    def __len__(self):
+        return len(self.frames)
+
+    def __getitem__(self, i):
+        return self.frames[i]
+
+    def __iter__(self):
+        return iter(self.frames)
+
+    def close(self):
+        if self._ptr:
+            self.frames = []
+            abi.lib().av1b_host_free(self._ptr)
+            self._ptr = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
 
 
 def device_count():

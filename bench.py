@@ -5,9 +5,9 @@ A "step" is one pass of the hot path over one batch of F synthetic frames (one c
 SURVEY.md 8e: chunks share no state, so ranks never communicate on the data path; weak scaling).
   value : frames/s with the source frames already resident in HBM (av1b_encode_resident): device
           kernels + symbol download + host entropy coding, pipelined; whole job over all ranks.
-  e2e   : frames/s through av1b_encode_chunk with HOST buffers (pageable -> pinned staging -> H2D ->
-          kernels -> D2H -> entropy coding -> packets), the call a reference-side binding makes.
-  roofline : the dominant kernel (intra_encode_kernel), algorithmic bytes / CUDA-event duration
+  e2e   : frames/s through av1b_encode_chunk with HOST buffers in page-locked memory (H2D -> kernels ->
+          D2H -> entropy coding -> packets), the call a reference-side binding makes.
+  roofline : the dominant kernel by device time, algorithmic bytes / CUDA-event duration
              against the measured HBM copy bandwidth in MEASURED_PEAKS.json.
   cpu_baseline : the CPU oracle port of the same path on the host cores (bounded sample).
 --impl reference times the CPU path (oracle port; the reference's av1an + SVT-AV1 cannot run here,
@@ -38,32 +38,83 @@ def peaks():
 
 
 class ClockSampler:
-    """Samples SM clocks / throttle reasons with nvidia-smi during the timed region."""
+    """Samples SM clocks / throttle reasons DURING the timed region: NVML in a thread every few milliseconds
+    (the timed region of a short run is shorter than one nvidia-smi start-up), nvidia-smi -lms as a fallback."""
     Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
          "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+    BITS = {0x8: "hw_slowdown", 0x40: "hw_thermal_slowdown", 0x20: "sw_thermal_slowdown", 0x4: "sw_power_cap"}
 
-    def __init__(self, gpu_index):
+    def __init__(self, gpu_index, uuid=None):
         self.idx = gpu_index
+        self.uuid = uuid
         self.proc = None
         self.lines = []
+        self.samples = []      # (sm_mhz, reasons bitmask)
+        self.max_mhz = None
+        self.nvml = None
+        self.stop_flag = threading.Event()
 
     def start(self):
         try:
+            import pynvml
+            pynvml.nvmlInit()
+            h = None
+            if self.uuid:
+                try:      # CUDA_VISIBLE_DEVICES may renumber the devices: address the GPU by UUID
+                    h = pynvml.nvmlDeviceGetHandleByUUID("GPU-" + str(self.uuid))
+                except Exception:
+                    h = None
+            if h is None:
+                h = pynvml.nvmlDeviceGetHandleByIndex(self.idx)
+            self.max_mhz = float(pynvml.nvmlDeviceGetMaxClockInfo(h, pynvml.NVML_CLOCK_SM))
+            pynvml.nvmlDeviceGetClockInfo(h, pynvml.NVML_CLOCK_SM)
+            self.nvml = (pynvml, h)
+            self.th = threading.Thread(target=self._poll, daemon=True)
+            self.th.start()
+            return
+        except Exception:
+            self.nvml = None
+        try:
             self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.idx), "--query-gpu=" + self.Q,
-                                          "--format=csv,noheader,nounits", "-lms", "200"],
+                                          "--format=csv,noheader,nounits", "-lms", "100"],
                                          stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             self.th = threading.Thread(target=self._read, daemon=True)
             self.th.start()
         except Exception:
             self.proc = None
 
+    def _poll(self):
+        nv, h = self.nvml
+        while not self.stop_flag.is_set():
+            try:
+                mhz = float(nv.nvmlDeviceGetClockInfo(h, nv.NVML_CLOCK_SM))
+                try:
+                    mask = int(nv.nvmlDeviceGetCurrentClocksEventReasons(h))
+                except Exception:
+                    mask = int(nv.nvmlDeviceGetCurrentClocksThrottleReasons(h))
+                self.samples.append((mhz, mask))
+            except Exception:
+                pass
+            self.stop_flag.wait(0.004)
+
     def _read(self):
         for ln in self.proc.stdout:
             self.lines.append(ln.strip())
 
     def stop(self):
+        if self.nvml:
+            self.stop_flag.set()
+            self.th.join(timeout=1)
+            sm = [s[0] for s in self.samples]
+            reasons = set()
+            for _, mask in self.samples:
+                for bit, nm in self.BITS.items():
+                    if mask & bit:
+                        reasons.add(nm)
+            return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": self.max_mhz,
+                    "reasons": sorted(reasons), "samples": len(sm), "source": "nvml"}
         if not self.proc:
-            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"], "samples": 0}
         self.proc.terminate()
         try:
             self.proc.wait(timeout=2)
@@ -83,7 +134,7 @@ class ClockSampler:
                 if f[5 + k].lower().startswith("active"):
                     reasons.add(nm)
         return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(mx) if mx else None,
-                "reasons": sorted(reasons), "samples": len(sm)}
+                "reasons": sorted(reasons), "samples": len(sm), "source": "nvidia-smi"}
 
 
 def make_frames(w, h, bd, n, hdr):
@@ -177,7 +228,7 @@ def run_reference(args, rank, world):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=6)
+    ap.add_argument("--steps", type=int, default=24)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default="4k10", choices=sorted(WORKLOADS))
@@ -230,9 +281,13 @@ def main():
     enc.stage_frames(0, frames)
     enc.stage_frames(1, frames[::-1])
     enc.encode_resident(max(args.warmup, 3))
-    sampler = ClockSampler(local_rank)
-    barrier()
+    try:
+        dev_uuid = torch.cuda.get_device_properties(local_rank).uuid
+    except Exception:
+        dev_uuid = None
+    sampler = ClockSampler(local_rank, dev_uuid)
     sampler.start()
+    barrier()
     t0 = time.perf_counter()
     enc.encode_resident(args.steps)
     torch.cuda.synchronize()
@@ -244,7 +299,11 @@ def main():
     value = world * args.steps * F / tmax
 
     # ---------------- e2e: host buffers through av1b_encode_chunk ----------------
-    pal = frames + frames[::-1]
+    # the host copies of the sources live in page-locked memory (av1b_host_alloc), as a capture / decode front
+    # end would hand them over; the timed region holds their H2D copies, the kernels, the D2H of the
+    # symbol streams, host entropy coding and packet delivery
+    pinned = encoder.PinnedFrames(frames, device_id=local_rank)
+    pal = list(pinned) + list(pinned)[::-1]
     chunk = [pal[i % len(pal)] for i in range(args.steps * F)]
     enc.encode_chunk(chunk[:2 * F])                      # warm-up
     barrier()
@@ -294,6 +353,7 @@ def main():
                              "kernel times from CUDA events on the encoder stream"},
         "e2e": {"value": e2e, "unit": "frames/s", "h2d_bytes_per_step": F * frame_bytes, "d2h_bytes_per_step": d2h_per_step,
                 "bitrate_bytes_per_frame": sum(map(len, tus)) / len(tus),
+                "host_buffers": "page-locked (av1b_host_alloc), %d of %d frames read in place by the copy engine" % (st_e["staged_direct"], len(chunk)),
                 "breakdown_ms_per_step": {k: st_e[k] / args.steps for k in ("h2d_ms", "kernel_ms", "d2h_ms", "pack_ms")}},
         "gpu_launches": st["kernel_launches"],
         "breakdown_ms_per_step": {k: st[k] / args.steps for k in ("kernel_ms", "me_ms", "intra_ms", "inter_ms", "deblock_ms",

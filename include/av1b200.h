@@ -105,9 +105,16 @@ int av1b_get_frame_is_key(av1b_encoder* enc, uint32_t frame_in_chunk);
 int av1b_get_cdef_idx(av1b_encoder* enc, uint32_t frame_in_chunk, uint8_t* idx);
 /* pure function (no device): deblock levels and CDEF presets from bit depth / quantiser / frame type */
 int av1b_select_frame_params(int bit_depth, int base_q_idx, int frame_type, int loop_filters, struct Av1bFrameParams* fp);
-/* stats[0..15] = h2d_ms, kernel_ms, d2h_ms, pack_ms, kernel_launches, base_q_idx, intra_kernel_ms,
+/* Page-locked host memory for source frames.  Planes that lie in page-locked memory (from here, or the
+ * caller's own cudaHostAlloc / cudaHostRegister) are read by the copy engine where they are; pageable
+ * planes go through one extra host copy into the encoder's own staging buffer.  The allocation is made in
+ * the context of `device` (one the caller encodes on) and is usable from every device.  NULL on failure. */
+void* av1b_host_alloc(int device, size_t bytes);
+void av1b_host_free(void* p);
+/* stats[0..16] = h2d_ms, kernel_ms, d2h_ms, pack_ms, kernel_launches, base_q_idx, intra_kernel_ms,
  * intra_kernel_launches, frames_done, bytes_out, deblock_ms, cdef_ms, inter_kernel_ms, me_ms (pyramid + search),
- * inter_kernel_launches, key_frames of the last chunk / resident run (CUDA-event times) */
+ * inter_kernel_launches, key_frames, frames uploaded straight from page-locked caller memory, of the last
+ * chunk / resident run (CUDA-event times) */
 int av1b_get_stats(av1b_encoder* enc, double* stats, int n);
 
 /* ---- kernel suite (BASELINE.json config 2 "kernel bit-exact suite") -----------------------------

@@ -48,3 +48,29 @@ def test_empty_and_tiny_chunks():
         encoder.Encoder(20, 16, 10)          # not a multiple of 8
     with pytest.raises(encoder.EncodeError):
         encoder.Encoder(64, 64, 12)          # unsupported bit depth
+
+
+def test_page_locked_sources_are_read_in_place_and_give_the_same_stream():
+    """av1b_host_alloc: page-locked source planes skip the encoder's staging copy (stats: staged_direct) and the
+    stream is byte-identical to the one from pageable sources; a batch mixing both kinds takes the staged path."""
+    w, h, bd, n = 328, 248, 10, 7
+    frames = synth.synth_clip(w, h, bd, n, seed=6, scene_len=100)
+    enc = encoder.Encoder(w, h, bd, crf=32, frames_in_flight=3)
+    ref = enc.encode_chunk(frames)
+    assert enc.stats()["staged_direct"] == 0
+    pinned = encoder.PinnedFrames(frames)
+    got = enc.encode_chunk(list(pinned))
+    assert enc.stats()["staged_direct"] == n
+    assert got == ref
+    mixed = [pinned[i] if i % 2 else frames[i] for i in range(n)]
+    got = enc.encode_chunk(mixed)
+    assert enc.stats()["staged_direct"] == 0
+    assert got == ref
+    # strided page-locked planes (a wider allocation): rows are gathered by the copy engine
+    wide = encoder.PinnedFrames([[np.pad(p, ((0, 0), (0, 24))) for p in fr] for fr in frames])
+    views = [[p[:, :p.shape[1] - 24] for p in fr] for fr in wide]
+    got = enc.encode_chunk_strided(views)
+    assert enc.stats()["staged_direct"] == n
+    assert got == ref
+    pinned.close(); wide.close()
+    enc.close()
