@@ -6,6 +6,7 @@
 #include <thread>
 #include <atomic>
 #include "av1_tables.h"
+#include "tokens.h"
 
 namespace av1b {
 
@@ -220,43 +221,6 @@ static void write_frame_header(const Av1bSeqParams& seq, const Av1bFrameParams& 
 // Tile entropy coding (spec 5.11, coefficients 5.11.39)
 // ------------------------------------------------------------------------------------------------
 namespace {
-
-struct TileCdfs {
-  uint16_t partition[20][11];
-  uint16_t skip[3][3];
-  uint16_t kf_y_mode[5][5][14];
-  uint16_t uv_mode[2][13][15];
-  uint16_t angle_delta[8][8];
-  uint16_t intra_ext_tx[3][4][13][17];
-  uint16_t txb_skip[5][13][3];
-  uint16_t eob_extra[5][2][9][3];
-  uint16_t dc_sign[2][3][3];
-  uint16_t eob_pt_16[2][2][6];
-  uint16_t eob_pt_32[2][2][7];
-  uint16_t eob_pt_64[2][2][8];
-  uint16_t eob_pt_128[2][2][9];
-  uint16_t eob_pt_256[2][2][10];
-  uint16_t eob_pt_512[2][2][11];
-  uint16_t eob_pt_1024[2][2][12];
-  uint16_t coeff_base_eob[5][2][4][4];
-  uint16_t coeff_base[5][2][42][5];
-  uint16_t coeff_br[5][2][21][5];
-  uint16_t cfl_sign[9];
-  uint16_t cfl_alpha[6][17];
-  uint16_t switchable_restore[4];
-  uint16_t wiener_restore[3];
-  uint16_t sgrproj_restore[3];
-  // inter frames
-  uint16_t intra_inter[4][3];
-  uint16_t single_ref[3][6][3];
-  uint16_t newmv[6][3], zeromv[2][3], refmv[6][3], drl[3][3];
-  uint16_t inter_ext_tx[4][4][17];
-  uint16_t y_mode[4][14];
-  uint16_t mv_joints[5];
-  struct MvComp {
-    uint16_t classes[12], class0_fp[2][5], fp[5], sign[3], class0_hp[3], hp[3], class0[3], bits[10][3];
-  } mvc[2];
-};
 
 void init_cdfs(TileCdfs& c, int base_q_idx) {
   const int q = base_q_idx <= 20 ? 0 : base_q_idx <= 60 ? 1 : base_q_idx <= 120 ? 2 : 3;
@@ -1068,6 +1032,40 @@ void pack_tile(const Av1bSeqParams& seq, const Av1bFrameParams& fp, const Av1bGe
                int tile, std::vector<uint8_t>& out) {
   TileWriter tw(seq, fp, g, syms);
   tw.run(tile / g.tile_cols, tile % g.tile_cols, out);
+}
+
+// Tile payload from a device-produced token list (tokens.h): the host keeps only the state that is serial by
+// nature -- the range coder and the adapting CDFs.
+void pack_tile_tokens(const Av1bFrameParams& fp, const uint32_t* tok, size_t n, std::vector<uint8_t>& out) {
+  TileCdfs cdf;
+  init_cdfs(cdf, fp.base_q_idx);
+  RangeEncoder ec(!fp.disable_cdf_update);
+  uint16_t* base = reinterpret_cast<uint16_t*>(&cdf);
+  for (size_t i = 0; i < n; i++) {
+    const uint32_t t = tok[i], off = t & 0xFFFFu;
+    if (off < TOK_PART_EDGE) {
+      ec.symbol((int)(t >> 21), base + off, (int)((t >> 16) & 31));
+    } else if (off == TOK_RAW) {
+      ec.literal(t >> 21, (int)((t >> 16) & 31));
+    } else if (off == TOK_GOLOMB) {
+      const uint32_t x = t >> 16;
+      const int len = 32 - __builtin_clz(x);
+      for (int k = 0; k < len - 1; k++) ec.boolean(0);
+      for (int k = len - 1; k >= 0; k--) ec.boolean((x >> k) & 1);
+    } else {
+      // forced split at the picture edge: binary symbol whose probability is gathered from the adaptive
+      // partition CDF (spec 8.3.2); the derived CDF's adaptation is discarded
+      const uint16_t* pc = cdf.partition[(t >> 16) & 31];
+      const bool has_cols = (t >> 21) & 1, is8 = (t >> 22) & 1;
+      auto prob = [&](int k) -> int { return (k > 0 ? pc[k - 1] : 32768) - pc[k]; };
+      int psum;
+      if (has_cols) { psum = prob(2) + prob(3); if (!is8) psum += prob(4) + prob(6) + prob(7) + prob(9); }
+      else { psum = prob(1) + prob(3); if (!is8) psum += prob(4) + prob(5) + prob(6) + prob(8); }
+      uint16_t tmp[3] = {(uint16_t)psum, 0, 0};
+      ec.symbol(1, tmp, 2);
+    }
+  }
+  ec.finish(out);
 }
 
 void assemble_frame(const FramePack& fpk, std::vector<uint8_t>& out) {

@@ -128,6 +128,13 @@ void pack_frame_header(const Av1bSeqParams& seq, const Av1bFrameParams& fp, cons
 void pack_tile(const Av1bSeqParams& seq, const Av1bFrameParams& fp, const Av1bGeom& g, const Av1bFrameSyms& syms,
                int tile, std::vector<uint8_t>& out);
 void assemble_frame(const FramePack& fpk, std::vector<uint8_t>& out);   // appends one OBU_FRAME
+// Tile payload of an inter frame from its token list (tokens.h): range coding + CDF adaptation only.
+void pack_tile_tokens(const Av1bFrameParams& fp, const uint32_t* tok, size_t n, std::vector<uint8_t>& out);
+// CPU statement of the device tokenizer (token_kernel.cu) for an inter frame: digests the raster levels like
+// the inter kernel does, derives the mode classes and walks the blocks in coding order; one token list per
+// tile.  Test infrastructure for the token path (the product tokenizes on the device).
+void tokenize_frame_host(const Av1bFrameParams& fp, const Av1bSeqParams& seq, const Av1bGeom& g, const Av1bFrameSyms& syms,
+                         std::vector<std::vector<uint32_t>>& tiles);
 
 // One OBU_FRAME (frame header + all tiles). n_threads > 1 entropy-codes tiles in parallel.
 // Returns 0 on success.

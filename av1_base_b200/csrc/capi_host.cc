@@ -112,4 +112,31 @@ int av1b_pack_frame(const Av1bSeqParams* seq, const Av1bFrameParams* fp, const A
   return AV1B_OK;
 }
 
+// Same frame through the token path: tokens derived by the CPU statement of the device tokenizer, then
+// range-coded tile by tile.  Inter frames only.  Must give the bytes of av1b_pack_frame.
+int av1b_pack_frame_tokens(const Av1bSeqParams* seq, const Av1bFrameParams* fp, const Av1bFrameSyms* syms,
+                           int with_td, uint8_t* out, size_t cap, size_t* len, uint64_t* n_tokens) {
+  if (!seq || !fp || !syms || !out || !len) { av1b::set_error("null argument"); return AV1B_ERR_INVALID; }
+  if (fp->frame_type != AV1B_INTER_FRAME) { av1b::set_error("token path codes inter frames only"); return AV1B_ERR_INVALID; }
+  Av1bGeom g;
+  if (av1b_geom_init(&g, seq->width, seq->height, fp->tile_cols_log2, fp->tile_rows_log2)) {
+    av1b::set_error("unsupported frame size %dx%d", seq->width, seq->height);
+    return AV1B_ERR_INVALID;
+  }
+  std::vector<std::vector<uint32_t>> toks;
+  av1b::tokenize_frame_host(*fp, *seq, g, *syms, toks);
+  av1b::FramePack fpk;
+  av1b::pack_frame_header(*seq, *fp, g, fpk);
+  uint64_t nt = 0;
+  for (size_t t = 0; t < toks.size(); t++) { av1b::pack_tile_tokens(*fp, toks[t].data(), toks[t].size(), fpk.tiles[t]); nt += toks[t].size(); }
+  std::vector<uint8_t> v;
+  if (with_td) av1b::write_temporal_delimiter(v);
+  av1b::assemble_frame(fpk, v);
+  if (v.size() > cap) { av1b::set_error("output buffer too small"); return AV1B_ERR_NOMEM; }
+  memcpy(out, v.data(), v.size());
+  *len = v.size();
+  if (n_tokens) *n_tokens = nt;
+  return AV1B_OK;
+}
+
 }  // extern "C"

@@ -42,3 +42,16 @@ def pack_frame(seq, fp, syms, n_threads=1, with_td=True, cap=None):
     if rc:
         raise RuntimeError("av1b_pack_frame: %d %s" % (rc, abi.last_error()))
     return out[:n.value].tobytes()
+
+
+def pack_frame_tokens(seq, fp, syms, with_td=True, cap=None):
+    """Inter frame through the token path (CPU statement of the device tokenizer). Returns (bytes, n_tokens)."""
+    cap = cap or (16 << 20)
+    out = np.empty(cap, np.uint8)
+    n = C.c_size_t(0)
+    nt = C.c_uint64(0)
+    rc = abi.lib().av1b_pack_frame_tokens(C.byref(seq), C.byref(fp), C.byref(syms), int(with_td),
+                                          out.ctypes.data_as(C.c_void_p), C.c_size_t(cap), C.byref(n), C.byref(nt))
+    if rc:
+        raise RuntimeError("av1b_pack_frame_tokens: %d %s" % (rc, abi.last_error()))
+    return out[:n.value].tobytes(), nt.value

@@ -166,6 +166,13 @@ int av1b_pack_frame(const struct Av1bSeqParams* seq, const struct Av1bFrameParam
                     const struct Av1bFrameSyms* syms, int n_threads, int with_temporal_delimiter,
                     uint8_t* out, size_t cap, size_t* len);
 
+/* The same inter frame through the token path ("device-produced symbol streams"): the CPU
+ * statement of the device tokenizer derives one token per coded symbol, the tokens are range-coded tile by
+ * tile.  Gives the bytes of av1b_pack_frame; n_tokens (may be NULL) = tokens of the frame. */
+int av1b_pack_frame_tokens(const struct Av1bSeqParams* seq, const struct Av1bFrameParams* fp,
+                           const struct Av1bFrameSyms* syms, int with_temporal_delimiter,
+                           uint8_t* out, size_t cap, size_t* len, uint64_t* n_tokens);
+
 #ifdef __cplusplus
 }
 #endif
