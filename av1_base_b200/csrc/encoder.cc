@@ -109,6 +109,18 @@ struct Slot {
   int16_t* d_coef[3] = {nullptr, nullptr, nullptr};   // device side of the symbol streams (downloaded on the copy stream
   Av1bBlockInfo* d_blocks = nullptr;                  //  while the next batch is being encoded)
   uint8_t* d_cdef_idx = nullptr;
+  // token path (inter frames): packed coefficient symbols, tokenizer scratch, token list + superblock offsets
+  uint16_t* d_digest[3] = {nullptr, nullptr, nullptr};
+  uint8_t* d_mode_cls = nullptr;
+  uint32_t* d_blk_count = nullptr;
+  uint32_t* d_sb_off = nullptr;
+  uint32_t* h_sb_off = nullptr;
+  uint32_t* d_tokens = nullptr;
+  uint32_t* h_tokens = nullptr;
+  size_t tok_cap = 0;                                 // capacity of d_tokens / h_tokens (tokens)
+  TokLaunch tl;                                       // the batch's tokenizer launch (re-run after growing the buffers)
+  bool has_tokens = false;
+  cudaEvent_t ev_tok0 = nullptr, ev_tok1 = nullptr;
   cudaEvent_t ev_src = nullptr;                       // sources of this slot are resident
   uint16_t* h_src[3] = {nullptr, nullptr, nullptr};
   uint16_t* h_rec[3] = {nullptr, nullptr, nullptr};
@@ -152,6 +164,12 @@ struct av1b_encoder {
   uint16_t* d_pyr[3] = {nullptr, nullptr, nullptr};   // luma pyramid levels 0..2; [0] = last frame of the previous batch
   int16_t* d_mv2 = nullptr;
   int16_t* d_mvs = nullptr;
+  bool token_path = true;             // inter frames: device tokenizer + host range coder over tokens
+  int legacy_pack_levels = 0;         // token_path off: 0 raster levels, 1 in-place packed symbols
+  uint32_t* d_sb_of_order = nullptr;  // inter-frame tile layout: coding order -> superblock
+  uint16_t* d_tile_of_sb = nullptr;
+  std::vector<uint32_t> tile_first_k; // [tiles + 1] first coding-order index of each inter-frame tile
+  cudaStream_t s_tok = nullptr;       // token list download (issued once the batch's total is known)
   Slot slot[2];
   ThreadPool* pool = nullptr;
   int host_threads = 1;
@@ -159,7 +177,8 @@ struct av1b_encoder {
   std::vector<KeptFrame> kept;
   // statistics of the last chunk / resident run
   double t_h2d_ms = 0, t_kernel_ms = 0, t_intra_ms = 0, t_inter_ms = 0, t_me_ms = 0, t_d2h_ms = 0, t_pack_ms = 0,
-         t_deblock_ms = 0, t_cdef_ms = 0;
+         t_deblock_ms = 0, t_cdef_ms = 0, t_tok_ms = 0;
+  int64_t n_tokens = 0;
   int64_t kernel_launches = 0, intra_launches = 0, inter_launches = 0, frames_done = 0, bytes_out = 0, key_frames = 0, staged_direct = 0;
 };
 
@@ -171,7 +190,10 @@ static void free_all(av1b_encoder* e) {
     }
     cudaFreeHost(s.h_blocks); cudaFreeHost(s.h_cdef_idx);
     cudaFree(s.d_blocks); cudaFree(s.d_cdef_idx);
-    for (cudaEvent_t ev : {s.ev_h2d, s.ev_k0, s.ev_me, s.ev_k1, s.ev_d2h, s.ev_src}) if (ev) cudaEventDestroy(ev);
+    for (int p = 0; p < 3; p++) cudaFree(s.d_digest[p]);
+    cudaFree(s.d_mode_cls); cudaFree(s.d_blk_count); cudaFree(s.d_sb_off); cudaFree(s.d_tokens);
+    cudaFreeHost(s.h_sb_off); cudaFreeHost(s.h_tokens);
+    for (cudaEvent_t ev : {s.ev_h2d, s.ev_k0, s.ev_me, s.ev_k1, s.ev_d2h, s.ev_src, s.ev_tok0, s.ev_tok1}) if (ev) cudaEventDestroy(ev);
     for (cudaEvent_t ev : s.ev_frame) if (ev) cudaEventDestroy(ev);
   }
   for (int p = 0; p < 3; p++) {
@@ -179,6 +201,8 @@ static void free_all(av1b_encoder* e) {
   }
   cudaFree(e->d_map_key); cudaFree(e->d_map_inter);
   cudaFree(e->d_mv2); cudaFree(e->d_mvs);
+  cudaFree(e->d_sb_of_order); cudaFree(e->d_tile_of_sb);
+  if (e->s_tok) cudaStreamDestroy(e->s_tok);
   if (e->stream) cudaStreamDestroy(e->stream);
   if (e->s_in) cudaStreamDestroy(e->s_in);
   if (e->s_out) cudaStreamDestroy(e->s_out);
@@ -301,7 +325,8 @@ static int launch(av1b_encoder* e, Slot& s, int n, int64_t first_index) {
       L.g = g; L.bit_depth = bd; L.base_q_idx = e->base_q_idx; L.quant_rnd = 48; L.dc_q = dcq; L.ac_q = acq;
       for (int p = 0; p < 3; p++) { L.src[p] = src[p]; L.ref[p] = prev[p]; L.rec[p] = e->loop_filters ? rec[p] : fin[p]; L.coef[p] = coef[p]; }
       L.blocks = blocks; L.part_map = e->d_map_inter; L.mvs = e->d_mvs + (size_t)b * e->map_elems * 2;
-      L.pack_levels = (e->keep || e->cfg.reserved[5]) ? 0 : 1;   // debug keeps raster levels for the oracle comparison
+      L.pack_levels = e->token_path ? 2 : e->legacy_pack_levels;
+      for (int p = 0; p < 3; p++) L.digest[p] = e->token_path ? s.d_digest[p] + (size_t)b * e->plane_elems[p] : nullptr;
       L.tb_zero_thr = e->cfg.reserved[4];   // experiment knob: drop transform blocks with sum|level| <= thr
       CK(launch_inter_encode(L, e->stream));
       CK(launch_merge_skip(g, blocks, e->stream));
@@ -338,13 +363,38 @@ static int launch(av1b_encoder* e, Slot& s, int n, int64_t first_index) {
   }
   for (int p = 0; p < 3; p++)
     CK(cudaMemcpyAsync(e->d_fin[p], e->d_fin[p] + e->plane_elems[p] * n, e->plane_elems[p] * 2, cudaMemcpyDeviceToDevice, e->stream));
+  // ---- inter frames of the batch: tokens for the host range coder ----
+  s.has_tokens = e->token_path && any_inter;
+  CK(cudaEventRecord(s.ev_tok0, e->stream));
+  if (s.has_tokens) {
+    TokLaunch& T = s.tl;
+    T.g = e->g_inter; T.n_frames = n; T.inter_mask = 0;
+    for (int b = 0; b < n; b++) if (!s.is_key[b]) T.inter_mask |= (uint64_t)1 << b;
+    T.cdef_bits = e->loop_filters ? e->fp_inter.cdef_bits : 0;
+    T.blocks = s.d_blocks; T.cdef_idx = s.d_cdef_idx;
+    for (int p = 0; p < 3; p++) { T.digest[p] = s.d_digest[p]; T.coef[p] = s.d_coef[p]; T.plane_elems[p] = e->plane_elems[p]; }
+    T.map_elems = e->map_elems;
+    T.mode_cls = s.d_mode_cls; T.blk_count = s.d_blk_count; T.sb_off = s.d_sb_off;
+    T.sb_of_order = e->d_sb_of_order; T.tile_of_sb = e->d_tile_of_sb;
+    T.tokens = s.d_tokens; T.cap = (uint32_t)s.tok_cap;
+    CK(launch_tok_count(T, e->stream));
+    CK(launch_tok_emit(T, e->stream));
+    e->kernel_launches += 4;
+  }
+  CK(cudaEventRecord(s.ev_tok1, e->stream));
   CK(cudaEventRecord(s.ev_k1, e->stream));
-  // symbol streams go home on the output copy stream while the compute stream starts the next batch
+  // symbol streams go home on the output copy stream while the compute stream starts the next batch:
+  // token offsets for the inter frames (the token list itself follows once its size is known), levels and
+  // block info only for the frames the block-walking tile writer codes (key frames; everything in debug mode)
   CK(cudaStreamWaitEvent(e->s_out, s.ev_k1, 0));
-  for (int p = 0; p < 3; p++)
-    CK(cudaMemcpyAsync(s.h_coef[p], s.d_coef[p], e->plane_elems[p] * n * 2, cudaMemcpyDeviceToHost, e->s_out));
-  CK(cudaMemcpyAsync(s.h_cdef_idx, s.d_cdef_idx, nsb * n, cudaMemcpyDeviceToHost, e->s_out));
-  CK(cudaMemcpyAsync(s.h_blocks, s.d_blocks, e->map_elems * n * sizeof(Av1bBlockInfo), cudaMemcpyDeviceToHost, e->s_out));
+  if (s.has_tokens) CK(cudaMemcpyAsync(s.h_sb_off, s.d_sb_off, (nsb * n + 1) * sizeof(uint32_t), cudaMemcpyDeviceToHost, e->s_out));
+  for (int b = 0; b < n; b++) {
+    if (!(e->keep || s.is_key[b] || !e->token_path)) continue;
+    for (int p = 0; p < 3; p++)
+      CK(cudaMemcpyAsync(s.h_coef[p] + (size_t)b * e->plane_elems[p], s.d_coef[p] + (size_t)b * e->plane_elems[p], e->plane_elems[p] * 2, cudaMemcpyDeviceToHost, e->s_out));
+    CK(cudaMemcpyAsync(s.h_cdef_idx + (size_t)b * nsb, s.d_cdef_idx + (size_t)b * nsb, nsb, cudaMemcpyDeviceToHost, e->s_out));
+    CK(cudaMemcpyAsync(s.h_blocks + (size_t)b * e->map_elems, s.d_blocks + (size_t)b * e->map_elems, e->map_elems * sizeof(Av1bBlockInfo), cudaMemcpyDeviceToHost, e->s_out));
+  }
   CK(cudaEventRecord(s.ev_d2h, e->s_out));
   return AV1B_OK;
 }
@@ -369,6 +419,28 @@ static int finish(av1b_encoder* e, Slot& s, bool staged, av1b_packet_cb out_cb, 
       cudaEventElapsedTime(&ms, ev[2], ev[3]); e->t_cdef_ms += ms;
     }
   }
+  cudaEventElapsedTime(&ms, s.ev_tok0, s.ev_tok1); e->t_tok_ms += ms;
+  const size_t nsb = (size_t)g.sb_rows * g.sb_cols;
+  if (s.has_tokens) {
+    // the batch's token total is known now: make room if needed (then the tokens are written again), fetch them
+    size_t total = s.h_sb_off[nsb * n];
+    if (total > s.tok_cap) {
+      const size_t cap = total + total / 4;
+      cudaFree(s.d_tokens); cudaFreeHost(s.h_tokens); s.d_tokens = nullptr; s.h_tokens = nullptr; s.tok_cap = 0;
+      if (cudaMalloc(&s.d_tokens, cap * 4) != cudaSuccess || cudaMallocHost(&s.h_tokens, cap * 4) != cudaSuccess) {
+        set_error("token buffers (%zu tokens): out of memory", cap); return AV1B_ERR_NOMEM;
+      }
+      s.tok_cap = cap;
+      s.tl.tokens = s.d_tokens; s.tl.cap = (uint32_t)cap;
+      CK(launch_tok_emit(s.tl, e->stream));
+      CK(cudaStreamSynchronize(e->stream));
+    }
+    const auto tc0 = std::chrono::steady_clock::now();
+    CK(cudaMemcpyAsync(s.h_tokens, s.d_tokens, total * 4, cudaMemcpyDeviceToHost, e->s_tok));
+    CK(cudaStreamSynchronize(e->s_tok));
+    e->t_d2h_ms += std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - tc0).count();
+    e->n_tokens += (int64_t)total;
+  }
   const auto tp0 = std::chrono::steady_clock::now();
   std::vector<Av1bFrameSyms> sy(n);
   std::vector<FramePack> packs(n);
@@ -384,7 +456,15 @@ static int finish(av1b_encoder* e, Slot& s, bool staged, av1b_packet_cb out_cb, 
   }
   e->pool->parallel_for((int)tasks.size(), [&](int t) {
     const int b = tasks[t].first, tile = tasks[t].second;
-    pack_tile(e->seq, s.is_key[b] ? e->fp_key : e->fp_inter, s.is_key[b] ? e->g : e->g_inter, sy[b], tile, packs[b].tiles[tile]);
+    if (!s.is_key[b] && s.has_tokens) {
+      const uint32_t* off = s.h_sb_off + (size_t)b * nsb;
+      const uint32_t t0 = off[e->tile_first_k[tile]];
+      // the entry after a frame's last superblock is the next frame's first (or the batch total)
+      const uint32_t t1 = off[e->tile_first_k[tile + 1]];
+      pack_tile_tokens(e->fp_inter, s.h_tokens + t0, t1 - t0, packs[b].tiles[tile]);
+    } else {
+      pack_tile(e->seq, s.is_key[b] ? e->fp_key : e->fp_inter, s.is_key[b] ? e->g : e->g_inter, sy[b], tile, packs[b].tiles[tile]);
+    }
   });
   std::vector<uint8_t> tu;
   for (int b = 0; b < n; b++) {
@@ -419,7 +499,7 @@ static int finish(av1b_encoder* e, Slot& s, bool staged, av1b_packet_cb out_cb, 
 static void reset_stats(av1b_encoder* e) {
   e->kept.clear();
   e->t_h2d_ms = e->t_kernel_ms = e->t_intra_ms = e->t_inter_ms = e->t_me_ms = e->t_d2h_ms = e->t_pack_ms = 0;
-  e->t_deblock_ms = e->t_cdef_ms = 0;
+  e->t_deblock_ms = e->t_cdef_ms = e->t_tok_ms = 0; e->n_tokens = 0;
   e->kernel_launches = e->intra_launches = e->inter_launches = e->frames_done = e->bytes_out = e->key_frames = e->staged_direct = 0;
 }
 
@@ -475,6 +555,8 @@ int av1b_encoder_create(const av1b_config* cfg, av1b_encoder** out) {
   e->blk_log2 = cfg->reserved[1] ? cfg->reserved[1] : 4;
   if (e->blk_log2 < 3 || e->blk_log2 > 6) { set_error("block log2 must be 3..6"); delete e; return AV1B_ERR_INVALID; }
   e->keep = cfg->reserved[0] != 0;
+  e->token_path = cfg->reserved[5] == 0;
+  e->legacy_pack_levels = (cfg->reserved[5] == 2 && !e->keep) ? 1 : 0;
   e->intra_only = cfg->reserved[3] != 0;      // reserved[3] = 1: every frame is a key frame
   e->keyint = cfg->keyint > 0 ? cfg->keyint : 240;
   av1b_select_frame_params(cfg->bit_depth, e->base_q_idx_key, AV1B_KEY_FRAME, e->loop_filters ? 1 : 0, &e->fp_key);
@@ -482,6 +564,7 @@ int av1b_encoder_create(const av1b_config* cfg, av1b_encoder** out) {
   e->fp_key.tile_cols_log2 = e->g.tile_cols_log2; e->fp_key.tile_rows_log2 = e->g.tile_rows_log2;
   e->fp_inter.tile_cols_log2 = e->g_inter.tile_cols_log2; e->fp_inter.tile_rows_log2 = e->g_inter.tile_rows_log2;
   e->batch = cfg->frames_in_flight > 0 ? cfg->frames_in_flight : 8;
+  if (e->batch > 64) { set_error("frames_in_flight must be <= 64"); delete e; return AV1B_ERR_INVALID; }
   e->host_threads = cfg->host_threads > 0 ? cfg->host_threads : (int)std::max(1u, std::thread::hardware_concurrency());
   if (cudaSetDevice(cfg->device_id) != cudaSuccess) { set_error("cudaSetDevice failed"); delete e; return AV1B_ERR_CUDA; }
   cudaError_t err = cudaSuccess;
@@ -489,12 +572,13 @@ int av1b_encoder_create(const av1b_config* cfg, av1b_encoder** out) {
   A(cudaStreamCreateWithFlags(&e->stream, cudaStreamNonBlocking));
   A(cudaStreamCreateWithFlags(&e->s_in, cudaStreamNonBlocking));
   A(cudaStreamCreateWithFlags(&e->s_out, cudaStreamNonBlocking));
+  A(cudaStreamCreateWithFlags(&e->s_tok, cudaStreamNonBlocking));
   e->map_elems = (size_t)e->g.w8 * e->g.h8;
   const size_t nsb = (size_t)e->g.sb_rows * e->g.sb_cols;
   for (int p = 0; p < 3; p++) e->plane_elems[p] = (size_t)e->g.stride[p] * e->g.rows[p];
   const int F = e->batch;
   for (auto& s : e->slot) {
-    for (cudaEvent_t* ev : {&s.ev_h2d, &s.ev_k0, &s.ev_me, &s.ev_k1, &s.ev_d2h, &s.ev_src}) A(cudaEventCreate(ev));
+    for (cudaEvent_t* ev : {&s.ev_h2d, &s.ev_k0, &s.ev_me, &s.ev_k1, &s.ev_d2h, &s.ev_src, &s.ev_tok0, &s.ev_tok1}) A(cudaEventCreate(ev));
     s.ev_frame.assign((size_t)F * 4, nullptr);
     for (auto& ev : s.ev_frame) A(cudaEventCreate(&ev));
     for (int p = 0; p < 3; p++) {
@@ -509,6 +593,40 @@ int av1b_encoder_create(const av1b_config* cfg, av1b_encoder** out) {
     A(cudaMalloc(&s.d_blocks, e->map_elems * F * sizeof(Av1bBlockInfo)));
     A(cudaMalloc(&s.d_cdef_idx, nsb * F));
     if (err == cudaSuccess) { A(cudaMemset(s.d_blocks, 0, e->map_elems * F * sizeof(Av1bBlockInfo))); A(cudaMemset(s.d_cdef_idx, 0, nsb * F)); }
+    if (e->token_path && !e->intra_only) {
+      for (int p = 0; p < 3; p++) A(cudaMalloc(&s.d_digest[p], e->plane_elems[p] * F * 2));
+      A(cudaMalloc(&s.d_mode_cls, e->map_elems * F));
+      A(cudaMalloc(&s.d_blk_count, e->map_elems * F * sizeof(uint32_t)));
+      A(cudaMalloc(&s.d_sb_off, (nsb * F + 1) * sizeof(uint32_t)));
+      A(cudaMallocHost(&s.h_sb_off, (nsb * F + 1) * sizeof(uint32_t)));
+      // room for one token per four luma samples (several times what CRF 30 produces); grows on demand
+      s.tok_cap = (size_t)cfg->width * cfg->height / 4 * F;
+      A(cudaMalloc(&s.d_tokens, s.tok_cap * 4));
+      A(cudaMallocHost(&s.h_tokens, s.tok_cap * 4));
+    }
+  }
+  if (e->token_path && !e->intra_only) {
+    // coding order of the superblocks of an inter frame: tile by tile, raster order inside a tile
+    const Av1bGeom& gi = e->g_inter;
+    std::vector<uint32_t> order; std::vector<uint16_t> tile_of(nsb, 0);
+    e->tile_first_k.clear();
+    for (int tr = 0; tr < gi.tile_rows; tr++)
+      for (int tc = 0; tc < gi.tile_cols; tc++) {
+        e->tile_first_k.push_back((uint32_t)order.size());
+        for (int r = gi.tile_row_start_sb[tr]; r < gi.tile_row_start_sb[tr + 1]; r++)
+          for (int c = gi.tile_col_start_sb[tc]; c < gi.tile_col_start_sb[tc + 1]; c++) {
+            order.push_back((uint32_t)(r * gi.sb_cols + c));
+            tile_of[(size_t)r * gi.sb_cols + c] = (uint16_t)(tr * gi.tile_cols + tc);
+          }
+      }
+    e->tile_first_k.push_back((uint32_t)order.size());
+    A(cudaMalloc(&e->d_sb_of_order, nsb * sizeof(uint32_t)));
+    A(cudaMalloc(&e->d_tile_of_sb, nsb * sizeof(uint16_t)));
+    if (err == cudaSuccess) {
+      A(cudaMemcpy(e->d_sb_of_order, order.data(), nsb * sizeof(uint32_t), cudaMemcpyHostToDevice));
+      A(cudaMemcpy(e->d_tile_of_sb, tile_of.data(), nsb * sizeof(uint16_t), cudaMemcpyHostToDevice));
+    }
+    if (av1t_ext_tx_ind[4][AV1B_DCT_DCT] != 3 || av1t_ext_tx_ind[5][AV1B_DCT_DCT] != 7) { set_error("transform-type symbol tables changed"); free_all(e); delete e; return AV1B_ERR_INTERNAL; }
   }
   for (int p = 0; p < 3; p++) {
     const size_t n = e->plane_elems[p] * F;
@@ -694,11 +812,11 @@ void av1b_host_free(void* p) {
 
 int av1b_get_stats(av1b_encoder* e, double* stats, int n) {
   if (!e || !stats) return AV1B_ERR_INVALID;
-  const double v[17] = {e->t_h2d_ms, e->t_kernel_ms, e->t_d2h_ms, e->t_pack_ms, (double)e->kernel_launches,
+  const double v[19] = {e->t_h2d_ms, e->t_kernel_ms, e->t_d2h_ms, e->t_pack_ms, (double)e->kernel_launches,
                         (double)e->base_q_idx, e->t_intra_ms, (double)e->intra_launches, (double)e->frames_done,
                         (double)e->bytes_out, e->t_deblock_ms, e->t_cdef_ms, e->t_inter_ms, e->t_me_ms,
-                        (double)e->inter_launches, (double)e->key_frames, (double)e->staged_direct};
-  for (int i = 0; i < n && i < 17; i++) stats[i] = v[i];
+                        (double)e->inter_launches, (double)e->key_frames, (double)e->staged_direct, e->t_tok_ms, (double)e->n_tokens};
+  for (int i = 0; i < n && i < 19; i++) stats[i] = v[i];
   return AV1B_OK;
 }
 

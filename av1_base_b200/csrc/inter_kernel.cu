@@ -176,12 +176,15 @@ __device__ __forceinline__ int code_tb(const InterLaunch& P, int p, int x, int y
   }
   // ---------------- pre-digested symbol stream for the host entropy coder ----------------
   // (levels up to 14 only: larger ones need Golomb escapes and stay in the raster form)
+  // pack_levels == 2 (token path): every coded transform block, into the separate digest plane (levels saturate
+  // at 15 there; the raster levels stay in place for the Golomb remainders)
   bool packed = false;
-  if (P.pack_levels && eob > 0 && max_lv < 15u) {
-    packed = true;
+  const bool to_side = P.pack_levels == 2;
+  if (P.pack_levels && eob > 0 && (to_side || max_lv < 15u)) {
+    packed = !to_side;
     __syncwarp(gmask);
     if (active) {
-      uint16_t* wdst = reinterpret_cast<uint16_t*>(cbase);
+      uint16_t* wdst = to_side ? P.digest[p] + (cbase - P.coef[p]) : reinterpret_cast<uint16_t*>(cbase);
 #pragma unroll
       for (int l = 0; l < N; l++) {
         const int pos = t * N + l, si = TxTab<N>::iscan(pos);

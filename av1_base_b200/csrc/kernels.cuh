@@ -103,10 +103,36 @@ struct InterLaunch {
   uint32_t dc_magic, ac_magic; // floor(2^32 / dc_q), floor(2^32 / ac_q): set by launch_inter_encode
   int32_t pack_levels;        // 1: transform blocks whose levels are all < 15 are stored as scan-ordered packed
                               //    symbols (sign | level | br ctx | base ctx) and flagged with bit 15 of eob
+                              // 2: every coded transform block also gets its packed symbols in `digest` (token path)
+  uint16_t* digest[3];        // pack_levels == 2: same layout as coef
 };
 cudaError_t launch_inter_encode(const InterLaunch& p, cudaStream_t s);
 // Bottom-up merge of skipped inter siblings with equal vectors into 32x32 / 64x64 blocks (side info only).
 cudaError_t launch_merge_skip(const Av1bGeom& g, Av1bBlockInfo* blocks, cudaStream_t s);
+
+// Device tokenizer for inter frames (token_kernel.cu, tokens.h): one token per coded symbol, per tile in coding
+// order.  All frames of a batch in one set of launches; key frames produce no tokens.
+struct TokLaunch {
+  Av1bGeom g;                    // inter-frame tile layout
+  int32_t n_frames;
+  uint64_t inter_mask;           // bit b: frame b of the batch is an inter frame
+  int32_t cdef_bits;             // 0 when CDEF is off
+  const Av1bBlockInfo* blocks;   // [n_frames][map_elems]
+  const uint16_t* digest[3];     // [n_frames][plane_elems[p]]
+  const int16_t* coef[3];
+  const uint8_t* cdef_idx;       // [n_frames][nsb]
+  size_t map_elems, plane_elems[3];
+  uint8_t* mode_cls;             // scratch [n_frames][map_elems]
+  uint32_t* blk_count;           // scratch [n_frames][map_elems]: tokens of the block whose origin the unit is
+  uint32_t* sb_off;              // [n_frames * nsb + 1]: exclusive token offsets of the superblocks in coding order (+ total)
+  const uint32_t* sb_of_order;   // [nsb]: coding order (tile by tile, raster inside a tile) -> superblock raster index
+  const uint16_t* tile_of_sb;    // [nsb]
+  uint32_t* tokens;
+  uint32_t cap;                  // capacity of `tokens`
+};
+// mode classes + token counts + offsets (exclusive scan); then launch_tok_emit writes the tokens
+cudaError_t launch_tok_count(const TokLaunch& p, cudaStream_t s);
+cudaError_t launch_tok_emit(const TokLaunch& p, cudaStream_t s);
 
 cudaError_t launch_deblock(const DeblockLaunch& p, int n_frames, cudaStream_t s);
 cudaError_t launch_cdef(const CdefLaunch& p, int n_frames, cudaStream_t s);

@@ -67,21 +67,30 @@ def test_chunk_parity(w, h, bd, crf, tcl, trl, lf, nfr, fif, keyint):
     enc.close()
 
 
-@pytest.mark.parametrize("w,h,bd,crf", [(200, 136, 10, 20), (328, 248, 8, 40), (640, 360, 10, 30)])
-def test_device_digested_symbols_give_identical_streams(w, h, bd, crf):
-    """Production mode hands the host scan-ordered packed coefficient symbols instead of raster levels; the
-    bitstream must not change by a single byte, and it must still decode to the reconstruction."""
-    frames = synth.synth_clip(w, h, bd, 5, seed=3, scene_len=100)
-    a = encoder.Encoder(w, h, bd, crf=crf, frames_in_flight=2, raster_levels=True)
-    b = encoder.Encoder(w, h, bd, crf=crf, frames_in_flight=2)
-    ta, tb = a.encode_chunk(frames), b.encode_chunk(frames)
+@pytest.mark.parametrize("w,h,bd,crf,tcl,trl", [(200, 136, 10, 20, -1, -1), (328, 248, 8, 40, 1, 1), (640, 360, 10, 30, -1, -1),
+                                                (328, 248, 10, 2, 0, 1), (1920, 1080, 10, 35, -1, -1)])
+def test_token_path_gives_identical_streams(w, h, bd, crf, tcl, trl):
+    """Production mode tokenizes inter frames on the device (one token per coded symbol, tokens.h) and the host only
+    range-codes the token lists.  The bitstream must equal, byte for byte, what the host block walker writes from
+    raster levels and from in-place packed symbols, and it must decode to the reconstruction.  CRF 2 exercises
+    the Golomb escapes, 1080p the picture-edge 8x8 blocks and several tiles."""
+    nfr = 5 if w < 1000 else 3
+    frames = synth.synth_clip(w, h, bd, nfr, seed=3, scene_len=100)
+    kw = dict(crf=crf, frames_in_flight=2, tile_cols_log2=tcl, tile_rows_log2=trl)
+    a = encoder.Encoder(w, h, bd, pack_path=1, **kw)
+    b = encoder.Encoder(w, h, bd, **kw)
+    d = encoder.Encoder(w, h, bd, pack_path=2, **kw)
+    ta, tb, td = a.encode_chunk(frames), b.encode_chunk(frames), d.encode_chunk(frames)
+    assert b.stats()["tokens"] > 0 and a.stats()["tokens"] == 0
+    assert [len(x) for x in ta] == [len(x) for x in tb]
     assert ta == tb
-    c = encoder.Encoder(w, h, bd, crf=crf, frames_in_flight=2, keep_debug=True)
+    assert td == tb
+    c = encoder.Encoder(w, h, bd, keep_debug=True, **kw)
     tc = c.encode_chunk(frames)
     assert tc == tb
     dec = D.dav1d_decode(tb)
     for i in range(len(frames)):
         for p in range(3):
             assert np.array_equal(dec[i][p], c.recon(i)[p])
-    for e in (a, b, c):
+    for e in (a, b, c, d):
         e.close()
