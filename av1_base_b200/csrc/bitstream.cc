@@ -1036,13 +1036,14 @@ void pack_tile(const Av1bSeqParams& seq, const Av1bFrameParams& fp, const Av1bGe
 
 // Tile payload from a device-produced token list (tokens.h): the host keeps only the state that is serial by
 // nature -- the range coder and the adapting CDFs.
-void pack_tile_tokens(const Av1bFrameParams& fp, const uint32_t* tok, size_t n, std::vector<uint8_t>& out) {
+namespace {
+struct TokenCoder {
   TileCdfs cdf;
-  init_cdfs(cdf, fp.base_q_idx);
-  RangeEncoder ec(!fp.disable_cdf_update);
-  uint16_t* base = reinterpret_cast<uint16_t*>(&cdf);
-  for (size_t i = 0; i < n; i++) {
-    const uint32_t t = tok[i], off = t & 0xFFFFu;
+  RangeEncoder ec;
+  uint16_t* base;
+  TokenCoder(const Av1bFrameParams& fp) : ec(!fp.disable_cdf_update), base(reinterpret_cast<uint16_t*>(&cdf)) { init_cdfs(cdf, fp.base_q_idx); }
+  inline void step(uint32_t t) {
+    const uint32_t off = t & 0xFFFFu;
     if (off < TOK_PART_EDGE) {
       ec.symbol((int)(t >> 21), base + off, (int)((t >> 16) & 31));
     } else if (off == TOK_RAW) {
@@ -1065,7 +1066,13 @@ void pack_tile_tokens(const Av1bFrameParams& fp, const uint32_t* tok, size_t n, 
       ec.symbol(1, tmp, 2);
     }
   }
-  ec.finish(out);
+};
+}  // namespace
+
+void pack_tile_tokens(const Av1bFrameParams& fp, const uint32_t* tok, size_t n, std::vector<uint8_t>& out) {
+  TokenCoder c(fp);
+  for (size_t i = 0; i < n; i++) c.step(tok[i]);
+  c.ec.finish(out);
 }
 
 void assemble_frame(const FramePack& fpk, std::vector<uint8_t>& out) {

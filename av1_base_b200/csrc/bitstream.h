@@ -6,6 +6,7 @@
 #include <stdint.h>
 #include <stddef.h>
 #include <stdlib.h>
+#include <emmintrin.h>
 #include <vector>
 #include "av1b_types.h"
 
@@ -37,21 +38,42 @@ class RangeEncoder {
   ~RangeEncoder() { free(pre_); }
   RangeEncoder(const RangeEncoder&) = delete;
   RangeEncoder& operator=(const RangeEncoder&) = delete;
-  // icdf: inverted CDF (32768 - cdf), n symbols, icdf[n-1] == 0, icdf[n] = adaptation counter
-  inline void symbol(int s, uint16_t* icdf, int n) {
+  // icdf: inverted CDF (32768 - cdf), n symbols, icdf[n-1] == 0, icdf[n] = adaptation counter.
+  // The adaptation (spec 8.2.6, expressed on the inverted CDF) is written without data-dependent branches:
+  // the symbol value and the alphabet size change from call to call, a loop over n - 1 entries mispredicts
+  // its exit about once a symbol.  Alphabets of 2 and 4 (most of the stream) are unrolled, larger ones
+  // update 8 / 16 entries with SSE2 and keep the entries from n - 1 on unchanged.
+  __attribute__((always_inline)) inline void symbol(int s, uint16_t* icdf, int n) {
     encode(s, icdf, n);
-    if (adapt_) {
-      // spec 8.2.6 CDF adaptation, expressed on the inverted CDF
-      const int cnt = icdf[n];
-      const int rate = 3 + (cnt > 15) + (cnt > 31) + (n > 3 ? 2 : 1);   // + min(floor(log2(n)), 2)
-      // branch-free: the symbol value is data dependent, a branch per entry mispredicts about once a symbol
-      for (int i = 0; i < n - 1; i++) {
-        const int x = icdf[i];
-        const int up = x + ((32768 - x) >> rate), down = x - (x >> rate);
-        icdf[i] = (uint16_t)(i < s ? up : down);
+    if (!adapt_) return;
+    const int cnt = icdf[n];
+    const int rate = 3 + (cnt > 15) + (cnt > 31) + (n > 3 ? 2 : 1);   // + min(floor(log2(n)), 2)
+    if (n == 2) {
+      const int x = icdf[0];
+      icdf[0] = (uint16_t)(s ? x + ((32768 - x) >> rate) : x - (x >> rate));
+    } else if (n == 4) {
+#define AV1B_ADAPT1(i) { const int x = icdf[i]; icdf[i] = (uint16_t)((i) < s ? x + ((32768 - x) >> rate) : x - (x >> rate)); }
+      AV1B_ADAPT1(0) AV1B_ADAPT1(1) AV1B_ADAPT1(2)
+    } else if (n == 3) {
+      AV1B_ADAPT1(0) AV1B_ADAPT1(1)
+#undef AV1B_ADAPT1
+    } else {
+      // lanes i < s move towards 32768, lanes s <= i < n - 1 towards 0, lanes >= n - 1 stay
+      const __m128i sh = _mm_cvtsi32_si128(rate), top = _mm_set1_epi16((short)0x8000);
+      const __m128i idx = _mm_setr_epi16(0, 1, 2, 3, 4, 5, 6, 7);
+      const __m128i vs = _mm_set1_epi16((short)s), vn = _mm_set1_epi16((short)(n - 1));
+      for (int k = 0; k < n - 1; k += 8) {
+        const __m128i i8 = _mm_add_epi16(idx, _mm_set1_epi16((short)k));
+        const __m128i x = _mm_loadu_si128(reinterpret_cast<const __m128i*>(icdf + k));
+        const __m128i up = _mm_add_epi16(x, _mm_srl_epi16(_mm_sub_epi16(top, x), sh));
+        const __m128i dn = _mm_sub_epi16(x, _mm_srl_epi16(x, sh));
+        const __m128i m_up = _mm_cmplt_epi16(i8, vs), m_live = _mm_cmplt_epi16(i8, vn);
+        __m128i y = _mm_or_si128(_mm_and_si128(m_up, up), _mm_andnot_si128(m_up, dn));
+        y = _mm_or_si128(_mm_and_si128(m_live, y), _mm_andnot_si128(m_live, x));
+        _mm_storeu_si128(reinterpret_cast<__m128i*>(icdf + k), y);
       }
-      icdf[n] = (uint16_t)(cnt + (cnt < 32));
     }
+    icdf[n] = (uint16_t)(cnt + (cnt < 32));
   }
   // binary symbol with an adaptive CDF: icdf[0] = 32768 - P(0), icdf[1] = 0, icdf[2] = counter
   inline void bit(int b, uint16_t* icdf) {
@@ -74,19 +96,18 @@ class RangeEncoder {
     pre_ = static_cast<uint16_t*>(realloc(pre_, cap * sizeof(uint16_t)));
     cap_ = cap;
   }
-  inline void encode(int s, const uint16_t* icdf, int n) {
+  __attribute__((always_inline)) inline void encode(int s, const uint16_t* icdf, int n) {
     // The decoder partitions [0, rng) from the top: symbol k owns [cur_k, cur_{k-1}) with
     // cur_k = ((rng >> 8) * (icdf[k] >> 6) >> 1) + 4 * (n - 1 - k), cur_{-1} = rng.
     uint32_t r = rng_, l = low_;
     const int N = n - 1;
     const uint32_t v = ((r >> 8) * (uint32_t)(icdf[s] >> 6) >> 1) + 4 * (N - s);
-    if (s > 0) {
-      const uint32_t u = ((r >> 8) * (uint32_t)(icdf[s - 1] >> 6) >> 1) + 4 * (N - (s - 1));
-      l += r - u;
-      r = u - v;
-    } else {
-      r -= v;
-    }
+    // symbol 0 owns the top of the range (u = r); a select instead of a branch on the symbol value
+    const int nz = s > 0;
+    const uint32_t uc = ((r >> 8) * (uint32_t)(icdf[s - nz] >> 6) >> 1) + 4 * (N - s + 1);
+    const uint32_t u = nz ? uc : r;
+    l += r - u;
+    r = u - v;
     const int d = __builtin_clz(r) - 16;   // r < 2^16: make bit 15 the top bit
     int c = cnt_;
     int sft = c + d;

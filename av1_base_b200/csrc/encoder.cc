@@ -237,6 +237,7 @@ static int stage(av1b_encoder* e, Slot& s, const av1b_frame_src* frames, int n) 
     e->staged_direct += n;
     return AV1B_OK;
   }
+  CK(cudaEventSynchronize(s.ev_src));   // the previous upload out of this slot's staging buffer has finished
   const int kSplit = 4;   // row bands per plane
   e->pool->parallel_for(n * 3 * kSplit, [&](int task) {
     const int b = task / (3 * kSplit), p = (task / kSplit) % 3, band = task % kSplit;
@@ -673,23 +674,36 @@ void av1b_encoder_destroy(av1b_encoder* e) {
   delete e;
 }
 
+// Batches of one call: the sources of batch k+1 are uploaded while the kernels of batch k run (their slot's
+// device buffers were last read by batch k-1), and the host entropy-codes batch k-1 meanwhile.
+static int run_batches(av1b_encoder* e, const av1b_frame_src* frames, uint32_t n_frames, int64_t first_index,
+                       int64_t total_frames, av1b_packet_cb out_cb, av1b_progress_cb prog_cb, void* user) {
+  const auto t0 = std::chrono::steady_clock::now();
+  const uint32_t B = (uint32_t)e->batch;
+  int rc, i = 0;
+  if ((rc = stage(e, e->slot[0], frames, (int)std::min<uint32_t>(B, n_frames))) != AV1B_OK) return rc;
+  for (uint32_t f0 = 0; f0 < n_frames; f0 += B, i++) {
+    const int nb = (int)std::min<uint32_t>(B, n_frames - f0);
+    if ((rc = launch(e, e->slot[i & 1], nb, first_index + f0)) != AV1B_OK) return rc;
+    if (f0 + B < n_frames) {
+      Slot& nx = e->slot[(i + 1) & 1];
+      if (i > 0) CK(cudaStreamWaitEvent(e->s_in, nx.ev_k1, 0));   // batch i-1 has read that slot's sources
+      if ((rc = stage(e, nx, frames + f0 + B, (int)std::min<uint32_t>(B, n_frames - f0 - B))) != AV1B_OK) return rc;
+    }
+    if (i > 0 && (rc = finish(e, e->slot[(i - 1) & 1], true, out_cb, prog_cb, user, total_frames, t0)) != AV1B_OK) return rc;
+  }
+  if (i > 0 && (rc = finish(e, e->slot[(i - 1) & 1], true, out_cb, prog_cb, user, total_frames, t0)) != AV1B_OK) return rc;
+  return AV1B_OK;
+}
+
 int av1b_encode_chunk(av1b_encoder* e, const av1b_frame_src* frames, uint32_t n_frames, av1b_packet_cb out_cb,
                       av1b_progress_cb prog_cb, void* user) {
   if (!e || !frames || !out_cb) { set_error("null argument"); return AV1B_ERR_INVALID; }
+  if (n_frames == 0) return AV1B_OK;
   CK(cudaSetDevice(e->cfg.device_id));
   reset_stats(e);
   e->chunk_pos = 0;               // a chunk is a closed GOP: it starts with a key frame
-  const auto t0 = std::chrono::steady_clock::now();
-  int rc, i = 0;
-  for (uint32_t f0 = 0; f0 < n_frames; f0 += e->batch, i++) {
-    const int nb = (int)std::min<uint32_t>(e->batch, n_frames - f0);
-    Slot& s = e->slot[i & 1];
-    if ((rc = stage(e, s, frames + f0, nb)) != AV1B_OK) return rc;
-    if ((rc = launch(e, s, nb, f0)) != AV1B_OK) return rc;
-    if (i > 0 && (rc = finish(e, e->slot[(i - 1) & 1], true, out_cb, prog_cb, user, n_frames, t0)) != AV1B_OK) return rc;
-  }
-  if (i > 0 && (rc = finish(e, e->slot[(i - 1) & 1], true, out_cb, prog_cb, user, n_frames, t0)) != AV1B_OK) return rc;
-  return AV1B_OK;
+  return run_batches(e, frames, n_frames, 0, n_frames, out_cb, prog_cb, user);
 }
 
 // Streaming variant: a chunk handed over in parts (bounded host memory for long chunks).  The part
@@ -700,17 +714,7 @@ int av1b_encode_part(av1b_encoder* e, const av1b_frame_src* frames, uint32_t n_f
   if (!e || !frames || !out_cb || n_frames == 0) { set_error("null argument"); return AV1B_ERR_INVALID; }
   CK(cudaSetDevice(e->cfg.device_id));
   if (first_part) { reset_stats(e); e->chunk_pos = 0; }
-  const auto t0 = std::chrono::steady_clock::now();
-  int rc, i = 0;
-  for (uint32_t f0 = 0; f0 < n_frames; f0 += e->batch, i++) {
-    const int nb = (int)std::min<uint32_t>(e->batch, n_frames - f0);
-    Slot& s = e->slot[i & 1];
-    if ((rc = stage(e, s, frames + f0, nb)) != AV1B_OK) return rc;
-    if ((rc = launch(e, s, nb, first_frame_index + f0)) != AV1B_OK) return rc;
-    if (i > 0 && (rc = finish(e, e->slot[(i - 1) & 1], true, out_cb, prog_cb, user, 0, t0)) != AV1B_OK) return rc;
-  }
-  if (i > 0 && (rc = finish(e, e->slot[(i - 1) & 1], true, out_cb, prog_cb, user, 0, t0)) != AV1B_OK) return rc;
-  return AV1B_OK;
+  return run_batches(e, frames, n_frames, first_frame_index, 0, out_cb, prog_cb, user);
 }
 
 // ---- device-resident flow (bench: "inputs already resident in HBM") -----------------------------

@@ -37,3 +37,11 @@ for ft, (blocks, coef) in enumerate(res):
     nz = sum(int(np.count_nonzero(c)) for c in coef)
     print("%s frame: %d bytes, %d nonzero levels, pack %.2f ms (1 thread) = %.1f ns/byte" %
           ("key" if ft == 0 else "inter", len(out), nz, best * 1e3, best * 1e9 / len(out)))
+    if ft == 1:
+        best = 1e9
+        for rep in range(5):
+            t0 = time.perf_counter()
+            out2, ntok = packer.pack_frame_tokens(seq, fp, sy)
+            best = min(best, time.perf_counter() - t0)
+        assert out2 == out
+        print("inter frame, token path (CPU tokenizer + range coder): %d tokens, %.2f ms" % (ntok, best * 1e3))
