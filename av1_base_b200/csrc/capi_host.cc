@@ -73,7 +73,7 @@ int av1b_select_frame_params(int bit_depth, int base_q_idx, int frame_type, int 
       {std::min(15, y1 * 3 / 2 + 1), y2, std::min(15, u1 * 3 / 2), u2},
       {std::min(15, y1 * 2 + 1), std::min(3, y2 + 1), std::min(15, u1 * 2), u2},
       {y1, std::min(3, y2 + 1), u1, std::min(3, u2 + 1)},
-      {0, std::max(1, y2), 0, u2},
+      {std::min(15, y1 * 3 / 2 + 1), std::min(3, y2 + 1), std::min(15, u1 * 3 / 2), std::min(3, u2 + 1)},
   };
   for (int i = 0; i < 8; i++) {
     fp->cdef_y_strength[i] = P[i][0] * 4 + P[i][1];

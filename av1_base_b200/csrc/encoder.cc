@@ -120,6 +120,7 @@ struct Slot {
   size_t tok_cap = 0;                                 // capacity of d_tokens / h_tokens (tokens)
   TokLaunch tl;                                       // the batch's tokenizer launch (re-run after growing the buffers)
   bool has_tokens = false;
+  size_t tok_fetched = 0;                             // tokens already downloaded with the offsets
   cudaEvent_t ev_tok0 = nullptr, ev_tok1 = nullptr;
   cudaEvent_t ev_src = nullptr;                       // sources of this slot are resident
   uint16_t* h_src[3] = {nullptr, nullptr, nullptr};
@@ -170,7 +171,8 @@ struct av1b_encoder {
   uint16_t* d_tile_of_sb = nullptr;
   std::vector<uint32_t> tile_first_k; // [tiles + 1] first coding-order index of each inter-frame tile
   cudaStream_t s_tok = nullptr;       // token list download (issued once the batch's total is known)
-  Slot slot[2];
+  Slot slot[3];                       // batch k+1 uploads / batch k on the GPU / batches k-1, k-2 with the host
+  size_t tok_guess = 0;               // tokens of the last batch: that much is downloaded before the total is known
   ThreadPool* pool = nullptr;
   int host_threads = 1;
   int64_t chunk_pos = 0;              // frames since the last key frame
@@ -178,7 +180,7 @@ struct av1b_encoder {
   // statistics of the last chunk / resident run
   double t_h2d_ms = 0, t_kernel_ms = 0, t_intra_ms = 0, t_inter_ms = 0, t_me_ms = 0, t_d2h_ms = 0, t_pack_ms = 0,
          t_deblock_ms = 0, t_cdef_ms = 0, t_tok_ms = 0;
-  int64_t n_tokens = 0;
+  int64_t n_tokens = 0, d2h_bytes = 0;
   int64_t kernel_launches = 0, intra_launches = 0, inter_launches = 0, frames_done = 0, bytes_out = 0, key_frames = 0, staged_direct = 0;
 };
 
@@ -260,7 +262,7 @@ static int stage(av1b_encoder* e, Slot& s, const av1b_frame_src* frames, int n) 
 }
 
 // device work + symbol download for the n frames resident in the slot; asynchronous
-static int launch(av1b_encoder* e, Slot& s, int n, int64_t first_index) {
+static int launch(av1b_encoder* e, Slot& s, const Slot& in, int n, int64_t first_index) {
   const Av1bGeom& g = e->g;
   const int bd = e->cfg.bit_depth;
   const size_t nsb = (size_t)g.sb_rows * g.sb_cols;
@@ -272,13 +274,13 @@ static int launch(av1b_encoder* e, Slot& s, int n, int64_t first_index) {
     s.is_key[b] = key;
     any_inter |= !key;
   }
-  CK(cudaStreamWaitEvent(e->stream, s.ev_src, 0));
+  CK(cudaStreamWaitEvent(e->stream, in.ev_src, 0));
   CK(cudaEventRecord(s.ev_k0, e->stream));
   const int acq0 = bd == 8 ? av1t_ac_q_8[e->base_q_idx] : av1t_ac_q_10[e->base_q_idx];
   // ---- open-loop motion estimation for the whole batch (source pictures only) ----
   if (!e->intra_only) {
     const size_t e0 = e->plane_elems[0];
-    CK(cudaMemcpyAsync(e->d_pyr[0] + e0, s.d_src[0], e0 * n * 2, cudaMemcpyDeviceToDevice, e->stream));
+    CK(cudaMemcpyAsync(e->d_pyr[0] + e0, in.d_src[0], e0 * n * 2, cudaMemcpyDeviceToDevice, e->stream));
     CK(launch_pyramid(e->d_pyr[0] + e0, e->d_pyr[1] + e0 / 4, e->d_pyr[2] + e0 / 16, g.stride[0], g.rows[0], e0, n, e->stream));
     e->kernel_launches += 1;
     if (any_inter) {
@@ -308,7 +310,7 @@ static int launch(av1b_encoder* e, Slot& s, int n, int64_t first_index) {
       const size_t off = (size_t)b * e->plane_elems[p];
       rec[p] = e->d_rec[p] + off; deb[p] = e->d_deb[p] ? e->d_deb[p] + off : nullptr;
       prev[p] = e->d_fin[p] + off; fin[p] = e->d_fin[p] + off + e->plane_elems[p];
-      src[p] = s.d_src[p] + off; coef[p] = s.d_coef[p] + off;
+      src[p] = in.d_src[p] + off; coef[p] = s.d_coef[p] + off;
     }
     Av1bBlockInfo* blocks = s.d_blocks + (size_t)b * e->map_elems;
     if (key) {
@@ -388,13 +390,24 @@ static int launch(av1b_encoder* e, Slot& s, int n, int64_t first_index) {
   // token offsets for the inter frames (the token list itself follows once its size is known), levels and
   // block info only for the frames the block-walking tile writer codes (key frames; everything in debug mode)
   CK(cudaStreamWaitEvent(e->s_out, s.ev_k1, 0));
-  if (s.has_tokens) CK(cudaMemcpyAsync(s.h_sb_off, s.d_sb_off, (nsb * n + 1) * sizeof(uint32_t), cudaMemcpyDeviceToHost, e->s_out));
+  s.tok_fetched = 0;
+  if (s.has_tokens) {
+    CK(cudaMemcpyAsync(s.h_sb_off, s.d_sb_off, (nsb * n + 1) * sizeof(uint32_t), cudaMemcpyDeviceToHost, e->s_out));
+    e->d2h_bytes += (int64_t)((nsb * n + 1) * sizeof(uint32_t));
+    // the token total is only known once the offsets are home: fetch as many tokens as the last batch had (+25 %)
+    // right away, finish() fetches what is missing
+    s.tok_fetched = std::min(s.tok_cap, e->tok_guess + e->tok_guess / 4 + 65536);
+    if (e->tok_guess == 0) s.tok_fetched = 0;
+    if (s.tok_fetched) CK(cudaMemcpyAsync(s.h_tokens, s.d_tokens, s.tok_fetched * 4, cudaMemcpyDeviceToHost, e->s_out));
+    e->d2h_bytes += (int64_t)s.tok_fetched * 4;
+  }
   for (int b = 0; b < n; b++) {
     if (!(e->keep || s.is_key[b] || !e->token_path)) continue;
     for (int p = 0; p < 3; p++)
       CK(cudaMemcpyAsync(s.h_coef[p] + (size_t)b * e->plane_elems[p], s.d_coef[p] + (size_t)b * e->plane_elems[p], e->plane_elems[p] * 2, cudaMemcpyDeviceToHost, e->s_out));
     CK(cudaMemcpyAsync(s.h_cdef_idx + (size_t)b * nsb, s.d_cdef_idx + (size_t)b * nsb, nsb, cudaMemcpyDeviceToHost, e->s_out));
     CK(cudaMemcpyAsync(s.h_blocks + (size_t)b * e->map_elems, s.d_blocks + (size_t)b * e->map_elems, e->map_elems * sizeof(Av1bBlockInfo), cudaMemcpyDeviceToHost, e->s_out));
+    e->d2h_bytes += (int64_t)((e->plane_elems[0] + e->plane_elems[1] + e->plane_elems[2]) * 2 + nsb + e->map_elems * sizeof(Av1bBlockInfo));
   }
   CK(cudaEventRecord(s.ev_d2h, e->s_out));
   return AV1B_OK;
@@ -435,11 +448,16 @@ static int finish(av1b_encoder* e, Slot& s, bool staged, av1b_packet_cb out_cb, 
       s.tl.tokens = s.d_tokens; s.tl.cap = (uint32_t)cap;
       CK(launch_tok_emit(s.tl, e->stream));
       CK(cudaStreamSynchronize(e->stream));
+      s.tok_fetched = 0;
     }
-    const auto tc0 = std::chrono::steady_clock::now();
-    CK(cudaMemcpyAsync(s.h_tokens, s.d_tokens, total * 4, cudaMemcpyDeviceToHost, e->s_tok));
-    CK(cudaStreamSynchronize(e->s_tok));
-    e->t_d2h_ms += std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - tc0).count();
+    if (total > s.tok_fetched) {
+      const auto tc0 = std::chrono::steady_clock::now();
+      CK(cudaMemcpyAsync(s.h_tokens + s.tok_fetched, s.d_tokens + s.tok_fetched, (total - s.tok_fetched) * 4, cudaMemcpyDeviceToHost, e->s_tok));
+      CK(cudaStreamSynchronize(e->s_tok));
+      e->d2h_bytes += (int64_t)(total - s.tok_fetched) * 4;
+      e->t_d2h_ms += std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - tc0).count();
+    }
+    e->tok_guess = total;
     e->n_tokens += (int64_t)total;
   }
   const auto tp0 = std::chrono::steady_clock::now();
@@ -500,7 +518,7 @@ static int finish(av1b_encoder* e, Slot& s, bool staged, av1b_packet_cb out_cb, 
 static void reset_stats(av1b_encoder* e) {
   e->kept.clear();
   e->t_h2d_ms = e->t_kernel_ms = e->t_intra_ms = e->t_inter_ms = e->t_me_ms = e->t_d2h_ms = e->t_pack_ms = 0;
-  e->t_deblock_ms = e->t_cdef_ms = e->t_tok_ms = 0; e->n_tokens = 0;
+  e->t_deblock_ms = e->t_cdef_ms = e->t_tok_ms = 0; e->n_tokens = 0; e->d2h_bytes = 0;
   e->kernel_launches = e->intra_launches = e->inter_launches = e->frames_done = e->bytes_out = e->key_frames = e->staged_direct = 0;
 }
 
@@ -684,15 +702,18 @@ static int run_batches(av1b_encoder* e, const av1b_frame_src* frames, uint32_t n
   if ((rc = stage(e, e->slot[0], frames, (int)std::min<uint32_t>(B, n_frames))) != AV1B_OK) return rc;
   for (uint32_t f0 = 0; f0 < n_frames; f0 += B, i++) {
     const int nb = (int)std::min<uint32_t>(B, n_frames - f0);
-    if ((rc = launch(e, e->slot[i & 1], nb, first_index + f0)) != AV1B_OK) return rc;
+    Slot& cur = e->slot[i % 3];
+    if ((rc = launch(e, cur, cur, nb, first_index + f0)) != AV1B_OK) return rc;
     if (f0 + B < n_frames) {
-      Slot& nx = e->slot[(i + 1) & 1];
-      if (i > 0) CK(cudaStreamWaitEvent(e->s_in, nx.ev_k1, 0));   // batch i-1 has read that slot's sources
+      Slot& nx = e->slot[(i + 1) % 3];
+      if (i > 1) CK(cudaStreamWaitEvent(e->s_in, nx.ev_k1, 0));   // batch i-2 has read that slot's sources
       if ((rc = stage(e, nx, frames + f0 + B, (int)std::min<uint32_t>(B, n_frames - f0 - B))) != AV1B_OK) return rc;
     }
-    if (i > 0 && (rc = finish(e, e->slot[(i - 1) & 1], true, out_cb, prog_cb, user, total_frames, t0)) != AV1B_OK) return rc;
+    // the slot of batch i+1 is that of batch i-2: its packets must be out before the next launch
+    if (i > 1 && (rc = finish(e, e->slot[(i - 2) % 3], true, out_cb, prog_cb, user, total_frames, t0)) != AV1B_OK) return rc;
   }
-  if (i > 0 && (rc = finish(e, e->slot[(i - 1) & 1], true, out_cb, prog_cb, user, total_frames, t0)) != AV1B_OK) return rc;
+  for (int k = std::max(0, i - 2); k < i; k++)
+    if ((rc = finish(e, e->slot[k % 3], true, out_cb, prog_cb, user, total_frames, t0)) != AV1B_OK) return rc;
   return AV1B_OK;
 }
 
@@ -738,14 +759,16 @@ int av1b_encode_resident(av1b_encoder* e, uint32_t n_steps, av1b_packet_cb out_c
   int rc;
   int64_t idx = 0;
   const int n0 = e->slot[0].n_frames, n1 = e->slot[1].n_frames;
+  // sources alternate between the two staged slots; results go through all three slots like in run_batches
   for (uint32_t i = 0; i < n_steps; i++) {
-    Slot& s = e->slot[i & 1];
     const int nb = (i & 1) ? n1 : n0;
-    if ((rc = launch(e, s, nb, idx)) != AV1B_OK) return rc;
+    if ((rc = launch(e, e->slot[i % 3], e->slot[i & 1], nb, idx)) != AV1B_OK) return rc;
     idx += nb;
-    if (i > 0 && (rc = finish(e, e->slot[(i - 1) & 1], false, out_cb, nullptr, user, 0, t0)) != AV1B_OK) return rc;
+    if (i > 1 && (rc = finish(e, e->slot[(i - 2) % 3], false, out_cb, nullptr, user, 0, t0)) != AV1B_OK) return rc;
   }
-  if ((rc = finish(e, e->slot[(n_steps - 1) & 1], false, out_cb, nullptr, user, 0, t0)) != AV1B_OK) return rc;
+  for (uint32_t k = n_steps > 2 ? n_steps - 2 : 0; k < n_steps; k++)
+    if ((rc = finish(e, e->slot[k % 3], false, out_cb, nullptr, user, 0, t0)) != AV1B_OK) return rc;
+  e->slot[0].n_frames = n0; e->slot[1].n_frames = n1;
   return AV1B_OK;
 }
 
@@ -816,11 +839,11 @@ void av1b_host_free(void* p) {
 
 int av1b_get_stats(av1b_encoder* e, double* stats, int n) {
   if (!e || !stats) return AV1B_ERR_INVALID;
-  const double v[19] = {e->t_h2d_ms, e->t_kernel_ms, e->t_d2h_ms, e->t_pack_ms, (double)e->kernel_launches,
+  const double v[20] = {e->t_h2d_ms, e->t_kernel_ms, e->t_d2h_ms, e->t_pack_ms, (double)e->kernel_launches,
                         (double)e->base_q_idx, e->t_intra_ms, (double)e->intra_launches, (double)e->frames_done,
                         (double)e->bytes_out, e->t_deblock_ms, e->t_cdef_ms, e->t_inter_ms, e->t_me_ms,
-                        (double)e->inter_launches, (double)e->key_frames, (double)e->staged_direct, e->t_tok_ms, (double)e->n_tokens};
-  for (int i = 0; i < n && i < 19; i++) stats[i] = v[i];
+                        (double)e->inter_launches, (double)e->key_frames, (double)e->staged_direct, e->t_tok_ms, (double)e->n_tokens, (double)e->d2h_bytes};
+  for (int i = 0; i < n && i < 20; i++) stats[i] = v[i];
   return AV1B_OK;
 }
 

@@ -313,7 +313,7 @@ def main():
     st_e = enc.stats()
     dte = sharding.max_over_ranks(dte, dist, "cuda")
     e2e = world * len(chunk) / dte
-    d2h_per_step = F * (frame_bytes + g.w8 * g.h8 * 20 + g.sb_rows * g.sb_cols)
+    d2h_per_step = st_e["d2h_bytes"] // args.steps   # counted by the encoder: token lists + offsets, key-frame levels / block info
 
     if rank != 0:
         return
@@ -328,9 +328,11 @@ def main():
         "deblock_kernel": (st["deblock_ms"] / max(1, nf), 2 * S),
         "cdef_kernel": (st["cdef_ms"] / max(1, nf), 3 * S),
         "pyramid+hme (per batch)": (st["me_ms"] / max(1, args.steps), int((1.3125 + 0.625 + 2.0) * (w * h * 2)) * F),
+        # tokenizer: reads the block info (20 B per 8x8 unit) twice (count + emit), writes 4 B per token
+        "tokenizer (per batch)": (st["tok_ms"] / max(1, args.steps), 2 * 20 * g.w8 * g.h8 * F + 4 * st["tokens"] // max(1, args.steps)),
     }
     share = {"inter_encode_kernel": st["inter_ms"], "intra_encode_kernel": st["intra_ms"], "deblock_kernel": st["deblock_ms"],
-             "cdef_kernel": st["cdef_ms"], "pyramid+hme (per batch)": st["me_ms"]}
+             "cdef_kernel": st["cdef_ms"], "pyramid+hme (per batch)": st["me_ms"], "tokenizer (per batch)": st["tok_ms"]}
     dom = max(share, key=lambda k: share[k])
     dom_ms, dom_bytes = kern[dom]
     achieved = dom_bytes / (dom_ms * 1e-3) / 1e9 if dom_ms > 0 else 0.0
@@ -357,7 +359,8 @@ def main():
                 "breakdown_ms_per_step": {k: st_e[k] / args.steps for k in ("h2d_ms", "kernel_ms", "d2h_ms", "pack_ms")}},
         "gpu_launches": st["kernel_launches"],
         "breakdown_ms_per_step": {k: st[k] / args.steps for k in ("kernel_ms", "me_ms", "intra_ms", "inter_ms", "deblock_ms",
-                                                                   "cdef_ms", "d2h_ms", "pack_ms")},
+                                                                   "cdef_ms", "tok_ms", "d2h_ms", "pack_ms")},
+        "tokens_per_frame": st["tokens"] / max(1, st["inter_launches"]),
         "roofline": {"kernel": dom, "bound": "hbm", "achieved": achieved, "peak": pk["hbm_gbs"],
                      "unit": "GB/s", "frac": achieved / pk["hbm_gbs"], "traffic": traffic, "peak_source": pk_src,
                      "ms_per_launch": dom_ms, "algorithmic_bytes_per_launch": dom_bytes,

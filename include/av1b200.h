@@ -112,10 +112,10 @@ int av1b_select_frame_params(int bit_depth, int base_q_idx, int frame_type, int 
  * the context of `device` (one the caller encodes on) and is usable from every device.  NULL on failure. */
 void* av1b_host_alloc(int device, size_t bytes);
 void av1b_host_free(void* p);
-/* stats[0..18] = h2d_ms, kernel_ms, d2h_ms, pack_ms, kernel_launches, base_q_idx, intra_kernel_ms,
+/* stats[0..19] = h2d_ms, kernel_ms, d2h_ms, pack_ms, kernel_launches, base_q_idx, intra_kernel_ms,
  * intra_kernel_launches, frames_done, bytes_out, deblock_ms, cdef_ms, inter_kernel_ms, me_ms (pyramid + search),
  * inter_kernel_launches, key_frames, frames uploaded straight from page-locked caller memory, tokenizer_ms,
- * tokens produced, of the last chunk / resident run (CUDA-event times) */
+ * tokens produced, bytes copied device -> host, of the last chunk / resident run (CUDA-event times) */
 int av1b_get_stats(av1b_encoder* enc, double* stats, int n);
 
 /* ---- kernel suite (BASELINE.json config 2 "kernel bit-exact suite") -----------------------------
