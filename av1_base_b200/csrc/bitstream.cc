@@ -314,6 +314,32 @@ const int8_t* nz_offset_for(int ns_log2) {
   }
 }
 
+// Sub-exponential codes of the loop-restoration coefficients (spec 4.10.10 / 5.11.58), as literals of the range coder.
+inline void lr_put_uniform(RangeEncoder& ec, int v, int n) {
+  const int w = 32 - __builtin_clz((unsigned)n), m = (1 << w) - n;
+  if (v < m) { ec.literal(v, w - 1); }
+  else { ec.literal(m + ((v - m) >> 1), w - 1); ec.literal((v - m) & 1, 1); }
+}
+inline void lr_put_subexp(RangeEncoder& ec, int x, int num_syms, int k) {
+  int i = 0, mk = 0;
+  for (;;) {
+    const int b2 = i ? k + i - 1 : k, a = 1 << b2;
+    if (num_syms <= mk + 3 * a) { lr_put_uniform(ec, x - mk, num_syms - mk); return; }
+    const int more = x >= mk + a;
+    ec.literal(more, 1);
+    if (more) { i++; mk += a; }
+    else { ec.literal(x - mk, b2); return; }
+  }
+}
+inline int lr_recenter(int r, int v) { return v > 2 * r ? v : (v >= r ? (v - r) << 1 : ((r - v) << 1) - 1); }
+inline void lr_put_signed_subexp_with_ref(RangeEncoder& ec, int v, int low, int high, int k, int r) {
+  const int mx = high - low, vv = v - low, rr = r - low;
+  const int x = (rr << 1) <= mx ? lr_recenter(rr, vv) : lr_recenter(mx - 1 - rr, mx - 1 - vv);
+  lr_put_subexp(ec, x, mx, k);
+}
+const int kLrTapMin[3] = {-5, -23, -17}, kLrTapMax[3] = {10, 8, 46}, kLrTapK[3] = {1, 2, 3};
+const int kLrXqdMin[2] = {-96, -32}, kLrXqdMax[2] = {31, 95};
+
 struct TileWriter {
   const Av1bSeqParams& seq;
   const Av1bFrameParams& fp;
@@ -1041,11 +1067,32 @@ struct TokenCoder {
   TileCdfs cdf;
   RangeEncoder ec;
   uint16_t* base;
-  TokenCoder(const Av1bFrameParams& fp) : ec(!fp.disable_cdf_update), base(reinterpret_cast<uint16_t*>(&cdf)) { init_cdfs(cdf, fp.base_q_idx); }
+  int ref_wiener[3][2][3], ref_sgr[3][2];   // running references of the restoration coefficients (reset per tile)
+  TokenCoder(const Av1bFrameParams& fp) : ec(!fp.disable_cdf_update), base(reinterpret_cast<uint16_t*>(&cdf)) {
+    init_cdfs(cdf, fp.base_q_idx);
+    for (int p = 0; p < 3; p++) {
+      for (int k = 0; k < 2; k++) { ref_wiener[p][k][0] = 3; ref_wiener[p][k][1] = -7; ref_wiener[p][k][2] = 15; }
+      ref_sgr[p][0] = -32; ref_sgr[p][1] = 31;
+    }
+  }
   inline void step(uint32_t t) {
     const uint32_t off = t & 0xFFFFu;
-    if (off < TOK_PART_EDGE) {
+    if (off < TOK_FIRST_SPECIAL) {
       ec.symbol((int)(t >> 21), base + off, (int)((t >> 16) & 31));
+    } else if (off == TOK_LR) {
+      const int kind = (t >> 16) & 1, p = (t >> 17) & 3, pass = (t >> 19) & 1, j = (t >> 20) & 15, v = (int)(t >> 24) - 128;
+      if (kind == 0) {
+        lr_put_signed_subexp_with_ref(ec, v, kLrTapMin[j], kLrTapMax[j] + 1, kLrTapK[j], ref_wiener[p][pass][j]);
+        ref_wiener[p][pass][j] = v;
+      } else if (av1t_sgr_params[j][pass]) {      // j = parameter set, pass = weight index
+        lr_put_signed_subexp_with_ref(ec, v, kLrXqdMin[pass], kLrXqdMax[pass] + 1, 4, ref_sgr[p][pass]);
+        ref_sgr[p][pass] = v;
+      } else {
+        // radius 0: not coded, the decoder infers 0 (first weight) or clip(128 - ref[0]) (second)
+        int w = 0;
+        if (pass == 1) w = std::min(std::max(128 - ref_sgr[p][0], kLrXqdMin[1]), kLrXqdMax[1]);
+        ref_sgr[p][pass] = w;
+      }
     } else if (off == TOK_RAW) {
       ec.literal(t >> 21, (int)((t >> 16) & 31));
     } else if (off == TOK_GOLOMB) {

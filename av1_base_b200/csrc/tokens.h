@@ -6,7 +6,7 @@
 // which CDF (the context), in which order.  The functions below derive that -- partition, skip, reference,
 // motion vector prediction stack (spec 7.10.2) and mode, motion vector residual, transform-block contexts,
 // end-of-block, coefficient and sign symbols -- and emit one 32-bit token per coded symbol:
-//     bits  0..15  offset of the CDF inside TileCdfs (in uint16 units) | TOK_RAW | TOK_GOLOMB | TOK_PART_EDGE
+//     bits  0..15  offset of the CDF inside TileCdfs (in uint16 units) | TOK_RAW | TOK_GOLOMB | TOK_PART_EDGE | TOK_LR
 //     bits 16..20  number of symbols of that CDF              (TOK_RAW: number of literal bits, <= 11)
 //     bits 21..31  symbol value                               (TOK_RAW: the literal, MSB first)
 // The host then only walks the token list of a tile through the range coder (pack_tile_tokens, bitstream.cc).
@@ -60,13 +60,19 @@ struct TileCdfs {
 };
 static_assert(sizeof(TileCdfs) / 2 < 0xFFF0, "CDF offsets must fit 16 bits");
 
-enum : uint32_t { TOK_RAW = 0xFFFFu, TOK_GOLOMB = 0xFFFEu, TOK_PART_EDGE = 0xFFFDu };
+enum : uint32_t { TOK_RAW = 0xFFFFu, TOK_GOLOMB = 0xFFFEu, TOK_PART_EDGE = 0xFFFDu, TOK_LR = 0xFFFCu, TOK_FIRST_SPECIAL = TOK_LR };
+// TOK_LR: one loop-restoration coefficient, coded by the host against its running reference (spec 5.11.58):
+//   bit 16 kind (0 Wiener tap, 1 self-guided weight), bits 17..18 plane, bit 19 pass (Wiener: 0 vertical, 1 horizontal;
+//   self-guided: weight index), bits 20..23 tap index j (Wiener) / parameter set (self-guided), bits 24..31 value + 128
 
 #define AV1B_CDF_OFF(member) ((uint32_t)(offsetof(TileCdfs, member) / 2))
 
 static inline AV1B_HD uint32_t tok_sym(uint32_t off, int nsym, int s) { return off | ((uint32_t)nsym << 16) | ((uint32_t)s << 21); }
 static inline AV1B_HD uint32_t tok_raw(int nbits, uint32_t v) { return TOK_RAW | ((uint32_t)nbits << 16) | (v << 21); }
 static inline AV1B_HD uint32_t tok_golomb(uint32_t x) { return TOK_GOLOMB | (x << 16); }
+static inline AV1B_HD uint32_t tok_lr(int kind, int plane, int pass, int j_or_set, int value) {
+  return TOK_LR | ((uint32_t)kind << 16) | ((uint32_t)plane << 17) | ((uint32_t)pass << 19) | ((uint32_t)j_or_set << 20) | ((uint32_t)(value + 128) << 24);
+}
 
 // What the token functions read of one inter frame and one tile.
 struct TokFrame {
@@ -78,6 +84,8 @@ struct TokFrame {
   int32_t w8, h8, mi_cols, mi_rows, sb_cols;
   int32_t cdef_bits;             // 0 when CDEF is off
   const int16_t* scan[3];        // default scan of 4x4 / 8x8 / 16x16 (scan index -> raster position)
+  const Av1bLrUnit* lr_units;    // luma restoration units [lr_rows][lr_cols] of 64x64 (frame type SWITCHABLE), or nullptr
+  int32_t lr_rows, lr_cols;
   int32_t tx_sym_16, tx_sym_8;   // inter_ext_tx symbol of DCT_DCT in the 16x16 set (12 symbols) and the 8x8 / 4x4 set (16 symbols)
 };
 struct TokTile { int32_t mi_row_start, mi_row_end, mi_col_start, mi_col_end; };
@@ -296,6 +304,23 @@ static inline AV1B_HD int tok_mode_class(const TokFrame& F, const TokTile& T, in
   MvStack S;
   mv_stack(F, T, r, c, bl, false, S);
   return choose_mode(S, b.mv[0], b.mv[1]).kind == 3 ? 3 : 2;
+}
+
+// Tokens that precede the blocks of the superblock at (sr, sc): the parameters of the luma restoration unit that
+// starts in it (64x64 units: at most one per superblock).  Mirrors TileWriter::write_lr (bitstream.cc).
+static inline AV1B_HD void tok_sb_lr(const TokFrame& F, int sr, int sc, TokSink& K) {
+  if (!F.lr_units) return;
+  const int ur = sr >> 4, uc = sc >> 4;
+  if (ur >= F.lr_rows || uc >= F.lr_cols) return;
+  const Av1bLrUnit& u = F.lr_units[ur * F.lr_cols + uc];
+  K.put(tok_sym(AV1B_CDF_OFF(switchable_restore), 3, u.type));
+  if (u.type == AV1B_RESTORE_WIENER) {
+    for (int pass = 0; pass < 2; pass++)
+      for (int j = 0; j < 3; j++) K.put(tok_lr(0, 0, pass, j, pass ? u.wiener_h[j] : u.wiener_v[j]));
+  } else if (u.type == AV1B_RESTORE_SGRPROJ) {
+    K.put(tok_raw(4, (uint32_t)u.sgr_set));
+    for (int i = 0; i < 2; i++) K.put(tok_lr(1, 0, i, u.sgr_set, u.sgr_xqd[i]));
+  }
 }
 
 // All tokens of the block whose origin is (r, c) (4x4 units), in coding order: partition symbols of the

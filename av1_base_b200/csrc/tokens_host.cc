@@ -60,6 +60,8 @@ void tokenize_frame_host(const Av1bFrameParams& fp, const Av1bSeqParams& seq, co
   F.w8 = g.w8; F.h8 = g.h8; F.mi_cols = g.mi_cols; F.mi_rows = g.mi_rows; F.sb_cols = g.sb_cols;
   F.cdef_bits = seq.enable_cdef ? fp.cdef_bits : 0;
   for (int i = 0; i < 3; i++) F.scan[i] = scans[i];
+  F.lr_units = (seq.enable_restoration && fp.lr_type[0] != AV1B_RESTORE_NONE) ? sy.lr_units[0] : nullptr;
+  F.lr_rows = sy.lr_unit_rows[0]; F.lr_cols = sy.lr_unit_cols[0];
   F.tx_sym_16 = av1t_ext_tx_ind[4][AV1B_DCT_DCT]; F.tx_sym_8 = av1t_ext_tx_ind[5][AV1B_DCT_DCT];
   const int n_tiles = g.tile_cols * g.tile_rows;
   std::vector<TokTile> T(n_tiles);
@@ -91,6 +93,11 @@ void tokenize_frame_host(const Av1bFrameParams& fp, const Av1bSeqParams& seq, co
     for (int sr = T[t].mi_row_start; sr < T[t].mi_row_end; sr += 16)
       for (int sc = T[t].mi_col_start; sc < T[t].mi_col_end; sc += 16) {
         bool cdef_pending = true;
+        {
+          TokSink K{buf.data(), 0, (uint32_t)buf.size()};
+          tok_sb_lr(F, sr, sc, K);
+          tiles[t].insert(tiles[t].end(), buf.begin(), buf.begin() + K.n);
+        }
         for (int m = 0; m < 64; m++) {
           // Z order over the 8x8 units of the superblock
           const int ux = (m & 1) | ((m >> 1) & 2) | ((m >> 2) & 4), uy = ((m >> 1) & 1) | ((m >> 2) & 2) | ((m >> 3) & 4);

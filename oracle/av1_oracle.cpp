@@ -1159,3 +1159,55 @@ extern "C" void orc_lr_frame(const Av1bGeom* g, int bd, const Av1bFrameParams* f
       }
   }
 }
+
+// ------------------------------------------------------------------------------------------------
+// Encoder-side loop-restoration decision (ours; SURVEY.md 8a row E8 "search"), luma only: every restoration
+// unit picks among NONE, WIENER with the taps cand->wiener_v / wiener_h and SGRPROJ with cand->sgr_set /
+// sgr_xqd the one with the smallest squared error against the source over the unit's samples (a sample at
+// row y belongs to unit row min(rows - 1, (y + 8) / 64), as in the filter itself); a restoring candidate must
+// beat NONE by more than `bias` (the rate of its parameters in squared-error units).  Ties keep the earlier
+// candidate in the order NONE, WIENER, SGRPROJ.  Frame-level type of the luma plane: SWITCHABLE.
+// sse_out (may be NULL): [3][unit_rows * unit_cols] squared errors of NONE / WIENER / SGRPROJ.
+// ------------------------------------------------------------------------------------------------
+extern "C" void orc_lr_search(const Av1bGeom* g, int bd, const Av1bFrameParams* fp, const Av1bLrUnit* cand,
+                              const uint16_t* cdef_y, const uint16_t* cdef_u, const uint16_t* cdef_v,
+                              const uint16_t* deb_y, const uint16_t* deb_u, const uint16_t* deb_v,
+                              const uint16_t* src_y, int64_t bias, Av1bLrUnit* units_y, uint64_t* sse_out) {
+  int us, urows, ucols;
+  orc_lr_unit_grid(g, fp, 0, &us, &urows, &ucols);
+  const size_t n = (size_t)urows * ucols;
+  std::vector<uint64_t> sse(3 * n, 0);
+  std::vector<uint16_t> out[3];
+  for (int p = 0; p < 3; p++) out[p].resize((size_t)g->stride[p] * g->rows[p]);
+  Av1bFrameParams f1 = *fp;
+  f1.lr_type[0] = AV1B_RESTORE_SWITCHABLE; f1.lr_type[1] = f1.lr_type[2] = AV1B_RESTORE_NONE;
+  std::vector<Av1bLrUnit> all(n);
+  for (int k = 0; k < 3; k++) {
+    const uint16_t* res = cdef_y;
+    if (k > 0) {
+      for (size_t i = 0; i < n; i++) { all[i] = *cand; all[i].type = (int8_t)(k == 1 ? AV1B_RESTORE_WIENER : AV1B_RESTORE_SGRPROJ); }
+      orc_lr_frame(g, bd, &f1, cdef_y, cdef_u, cdef_v, deb_y, deb_u, deb_v, out[0].data(), out[1].data(), out[2].data(),
+                   all.data(), nullptr, nullptr);
+      res = out[0].data();
+    }
+    for (int y = 0; y < g->height; y++) {
+      const int ur = std::min(urows - 1, (y + 8) / us);
+      for (int x = 0; x < g->width; x++) {
+        const int uc = std::min(ucols - 1, x / us);
+        const int64_t d = (int64_t)res[(size_t)y * g->stride[0] + x] - (int64_t)src_y[(size_t)y * g->stride[0] + x];
+        sse[k * n + (size_t)ur * ucols + uc] += (uint64_t)(d * d);
+      }
+    }
+  }
+  for (size_t i = 0; i < n; i++) {
+    int best = 0;
+    uint64_t bv = sse[i];
+    for (int k = 1; k < 3; k++) {
+      const uint64_t v = sse[k * n + i] + (uint64_t)bias;
+      if (v < bv) { bv = v; best = k; }
+    }
+    units_y[i] = *cand;
+    units_y[i].type = (int8_t)(best == 0 ? AV1B_RESTORE_NONE : best == 1 ? AV1B_RESTORE_WIENER : AV1B_RESTORE_SGRPROJ);
+  }
+  if (sse_out) memcpy(sse_out, sse.data(), 3 * n * sizeof(uint64_t));
+}

@@ -147,3 +147,20 @@ def encode_inter_frame(g, frame, bit_depth, base_q_idx, part_map, mvs, ref_plane
                                       ptr(r.coef[0]), ptr(r.coef[1]), ptr(r.coef[2]))
     assert rc == 0
     return r
+
+
+def lr_candidate(wiener_v=(3, -7, 15), wiener_h=(3, -7, 15), sgr_set=4, sgr_xqd=(-32, 31)):
+    c = np.zeros(1, abi.LR_UNIT_DTYPE)
+    c["wiener_v"], c["wiener_h"], c["sgr_set"], c["sgr_xqd"] = wiener_v, wiener_h, sgr_set, sgr_xqd
+    return c
+
+
+def lr_search(g, bit_depth, fp, cand, cdef, deblocked, src_luma_padded, bias):
+    """Per-unit choice among NONE / WIENER(cand) / SGRPROJ(cand) for the luma plane. Returns (units [rows, cols], sse [3, n])."""
+    us, ur, uc = lr_unit_grid(g, fp, 0)
+    units = np.zeros((ur, uc), abi.LR_UNIT_DTYPE)
+    sse = np.zeros((3, ur * uc), np.uint64)
+    lib().orc_lr_search(C.byref(g), bit_depth, C.byref(fp), ptr(cand), ptr(cdef[0]), ptr(cdef[1]), ptr(cdef[2]),
+                        ptr(deblocked[0]), ptr(deblocked[1]), ptr(deblocked[2]), ptr(src_luma_padded), C.c_int64(int(bias)),
+                        ptr(units), ptr(sse))
+    return units, sse

@@ -85,3 +85,31 @@ def test_token_path_stream_decodes():
     for i, r in enumerate((r0, r1)):
         for p in range(3):
             assert np.array_equal(dec[i][p], O.crop(g, r.rec)[p])
+
+
+@pytest.mark.parametrize("w,h,tcl,trl", [(328, 248, 1, 1), (200, 136, 0, 0), (640, 360, 1, 0)])
+def test_token_path_with_restoration_units(w, h, tcl, trl):
+    """Luma restoration units (frame type SWITCHABLE, 64x64 units) go through the token path as one symbol plus
+    coefficient tokens the host codes against its running references: same bytes as the tile writer."""
+    bd, q = 10, 110
+    g, r0, r1, cdef_idx, _ = inter_frame(w, h, bd, q, tcl, trl, 11, "hme")
+    rng = np.random.default_rng(w)
+    seq = abi.SeqParams(w, h, bd, 1, 1, 30, 1, 0)
+    fp = abi.FrameParams()
+    abi.lib().av1b_select_frame_params(bd, q, 1, 1, C.byref(fp))
+    fp.tile_cols_log2, fp.tile_rows_log2 = g.tile_cols_log2, g.tile_rows_log2
+    fp.lr_type[0], fp.lr_type[1], fp.lr_type[2] = 3, 0, 0
+    us, ur, uc = O.lr_unit_grid(g, fp, 0)
+    assert us == 64
+    units = np.zeros((ur, uc), abi.LR_UNIT_DTYPE)
+    units["type"] = rng.integers(0, 3, (ur, uc))
+    units["sgr_set"] = rng.integers(0, 16, (ur, uc))
+    for j, (lo, hi) in enumerate([(-5, 10), (-23, 8), (-17, 46)]):
+        units["wiener_v"][..., j] = rng.integers(lo, hi + 1, (ur, uc))
+        units["wiener_h"][..., j] = rng.integers(lo, hi + 1, (ur, uc))
+    units["sgr_xqd"][..., 0] = rng.integers(-96, 32, (ur, uc))
+    units["sgr_xqd"][..., 1] = rng.integers(-32, 96, (ur, uc))
+    sy = packer.make_syms(g, r1.blocks, r1.coef, cdef_idx=cdef_idx, lr_units=[units, None, None])
+    ref = packer.pack_frame(seq, fp, sy, with_td=False)
+    got, _ = packer.pack_frame_tokens(seq, fp, sy, with_td=False)
+    assert got == ref

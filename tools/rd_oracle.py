@@ -29,7 +29,8 @@ def encode(args):
     acq = table("av1t_ac_q_%d" % bd)[qidx]
     g = O.geom(w, h, 0, 0)
     pm = O.partition_fixed(g, 4)
-    seq = abi.SeqParams(w, h, bd, 1, 0, 30, 1, 0)
+    seq = abi.SeqParams(w, h, bd, 1, 1 if opts.get("lr") else 0, 30, 1, 0)
+    nlr = np.zeros(3, np.int64)
     fps = []
     for ft in (0, 1):
         fp = abi.FrameParams()
@@ -38,7 +39,7 @@ def encode(args):
         fps.append(fp)
     prev_fin = prev_pyr = None
     nbytes, psnr, nskip = 0, [], 0
-    tus = []
+    tus, fins = [], []
     for i, fr in enumerate(frames):
         src = O.pad_planes(g, fr)
         pyr = O.pyramid(g, src[0])
@@ -53,17 +54,28 @@ def encode(args):
         O.deblock_frame(g, bd, r.blocks, r.rec, list(fp.lf_level), fp.lf_sharpness)
         idx = O.cdef_search(g, bd, r.blocks, fp, r.rec, src)
         fin = O.cdef_frame(g, bd, r.blocks, fp, idx, r.rec)
-        sy = packer.make_syms(g, r.blocks, r.coef, cdef_idx=idx)
+        lr_units = None
+        if opts.get("lr"):
+            fp.lr_type[0], fp.lr_type[1], fp.lr_type[2] = 3, 0, 0
+            q_acq = table("av1t_ac_q_%d" % bd)[fp.base_q_idx]
+            cand = O.lr_candidate(sgr_set=opts.get("sgr_set", 4), wiener_v=opts["wv"], wiener_h=opts["wv"], sgr_xqd=opts["xqd"])
+            units, sse = O.lr_search(g, bd, fp, cand, fin, r.rec, src[0], (q_acq * q_acq * 5) >> 8)
+            fin = O.lr_frame(g, bd, fp, fin, r.rec, [units, None, None])
+            lr_units = [units, None, None]
+            nlr += np.bincount(units["type"].ravel().astype(np.int64), minlength=3)
+        sy = packer.make_syms(g, r.blocks, r.coef, cdef_idx=idx, lr_units=lr_units)
         tu = b"\x12\x00" + (packer.pack_sequence_header(seq) if i == 0 else b"") + packer.pack_frame(seq, fp, sy, with_td=False)
         tus.append(tu)
         nbytes += len(tu)
         psnr.append(D.psnr(O.crop(g, fin)[0], fr[0], bd))
         prev_fin, prev_pyr = fin, pyr
+        fins.append(fin)
     if opts.get("verify"):
         dec = D.dav1d_decode(tus)
-        assert np.array_equal(dec[-1][0], O.crop(g, prev_fin)[0]), "decode != recon"
+        for i in (0, 1, len(dec) - 1):
+            assert np.array_equal(dec[i][0], O.crop(g, fins[i])[0]), "decode != recon (frame %d)" % i
     return dict(crf=crf, kbps=nbytes * 8 * 30.0 / nfr / 1000, psnr_y=float(np.mean(psnr)),
-                skip_frac=nskip / max(1, (nfr - 1) * g.h8 * g.w8))
+                skip_frac=nskip / max(1, (nfr - 1) * g.h8 * g.w8), lr_types=[int(v) for v in nlr])
 
 
 def main():
@@ -77,9 +89,13 @@ def main():
     ap.add_argument("--rnd", type=int, default=48)
     ap.add_argument("--thr", type=int, default=0)
     ap.add_argument("--verify", action="store_true")
+    ap.add_argument("--lr", action="store_true", help="loop restoration decision on (preset <= 5)")
+    ap.add_argument("--sgr-set", type=int, default=4)
+    ap.add_argument("--wv", default="3,-7,15")
+    ap.add_argument("--xqd", default="-32,31")
     a = ap.parse_args()
     w, h = map(int, a.size.split("x"))
-    opts = dict(rnd=a.rnd, thr=a.thr, verify=a.verify)
+    opts = dict(rnd=a.rnd, thr=a.thr, verify=a.verify, lr=a.lr, sgr_set=a.sgr_set, wv=tuple(map(int, a.wv.split(','))), xqd=tuple(map(int, a.xqd.split(','))))
     jobs = [(w, h, a.bd, a.frames, a.seed, a.noise, crf, opts) for crf in map(int, a.crfs.split(","))]
     with ProcessPoolExecutor(min(8, len(jobs))) as ex:
         res = list(ex.map(encode, jobs))
