@@ -99,6 +99,7 @@ struct KeptFrame {
   std::vector<int16_t> coef[3];
   std::vector<Av1bBlockInfo> blocks;
   std::vector<uint8_t> cdef_idx;
+  std::vector<Av1bLrUnit> lr_units;
   int is_key = 1;
 };
 
@@ -109,6 +110,8 @@ struct Slot {
   int16_t* d_coef[3] = {nullptr, nullptr, nullptr};   // device side of the symbol streams (downloaded on the copy stream
   Av1bBlockInfo* d_blocks = nullptr;                  //  while the next batch is being encoded)
   uint8_t* d_cdef_idx = nullptr;
+  Av1bLrUnit* d_lr_units = nullptr;                   // luma restoration units [batch][lr_n] (loop restoration on)
+  Av1bLrUnit* h_lr_units = nullptr;
   // token path (inter frames): packed coefficient symbols, tokenizer scratch, token list + superblock offsets
   uint16_t* d_digest[3] = {nullptr, nullptr, nullptr};
   uint8_t* d_mode_cls = nullptr;
@@ -129,7 +132,7 @@ struct Slot {
   Av1bBlockInfo* h_blocks = nullptr;
   uint8_t* h_cdef_idx = nullptr;
   cudaEvent_t ev_h2d = nullptr, ev_k0 = nullptr, ev_me = nullptr, ev_k1 = nullptr, ev_d2h = nullptr;
-  std::vector<cudaEvent_t> ev_frame;     // 4 per frame: before encode, after encode, after deblock, after CDEF
+  std::vector<cudaEvent_t> ev_frame;     // 5 per frame: before encode, after encode, after deblock, after CDEF, after loop restoration
   std::vector<uint8_t> is_key;
   int n_frames = 0;
   int64_t first_index = 0;
@@ -165,6 +168,11 @@ struct av1b_encoder {
   uint16_t* d_pyr[3] = {nullptr, nullptr, nullptr};   // luma pyramid levels 0..2; [0] = last frame of the previous batch
   int16_t* d_mv2 = nullptr;
   int16_t* d_mvs = nullptr;
+  bool lr_on = false;                 // loop restoration with per-unit decision (preset <= 5)
+  int lr_rows = 0, lr_cols = 0;
+  size_t lr_n = 0;
+  Av1bLrUnit lr_cand;                 // the Wiener taps / self-guided parameters the units choose from
+  unsigned long long* d_lr_sse = nullptr;
   bool token_path = true;             // inter frames: device tokenizer + host range coder over tokens
   int legacy_pack_levels = 0;         // token_path off: 0 raster levels, 1 in-place packed symbols
   uint32_t* d_sb_of_order = nullptr;  // inter-frame tile layout: coding order -> superblock
@@ -179,7 +187,7 @@ struct av1b_encoder {
   std::vector<KeptFrame> kept;
   // statistics of the last chunk / resident run
   double t_h2d_ms = 0, t_kernel_ms = 0, t_intra_ms = 0, t_inter_ms = 0, t_me_ms = 0, t_d2h_ms = 0, t_pack_ms = 0,
-         t_deblock_ms = 0, t_cdef_ms = 0, t_tok_ms = 0;
+         t_deblock_ms = 0, t_cdef_ms = 0, t_tok_ms = 0, t_lr_ms = 0;
   int64_t n_tokens = 0, d2h_bytes = 0;
   int64_t kernel_launches = 0, intra_launches = 0, inter_launches = 0, frames_done = 0, bytes_out = 0, key_frames = 0, staged_direct = 0;
 };
@@ -192,6 +200,7 @@ static void free_all(av1b_encoder* e) {
     }
     cudaFreeHost(s.h_blocks); cudaFreeHost(s.h_cdef_idx);
     cudaFree(s.d_blocks); cudaFree(s.d_cdef_idx);
+    cudaFree(s.d_lr_units); cudaFreeHost(s.h_lr_units);
     for (int p = 0; p < 3; p++) cudaFree(s.d_digest[p]);
     cudaFree(s.d_mode_cls); cudaFree(s.d_blk_count); cudaFree(s.d_sb_off); cudaFree(s.d_tokens);
     cudaFreeHost(s.h_sb_off); cudaFreeHost(s.h_tokens);
@@ -203,7 +212,7 @@ static void free_all(av1b_encoder* e) {
   }
   cudaFree(e->d_map_key); cudaFree(e->d_map_inter);
   cudaFree(e->d_mv2); cudaFree(e->d_mvs);
-  cudaFree(e->d_sb_of_order); cudaFree(e->d_tile_of_sb);
+  cudaFree(e->d_sb_of_order); cudaFree(e->d_tile_of_sb); cudaFree(e->d_lr_sse);
   if (e->s_tok) cudaStreamDestroy(e->s_tok);
   if (e->stream) cudaStreamDestroy(e->stream);
   if (e->s_in) cudaStreamDestroy(e->s_in);
@@ -303,7 +312,7 @@ static int launch(av1b_encoder* e, Slot& s, const Slot& in, int n, int64_t first
   const int acq = bd == 8 ? av1t_ac_q_8[e->base_q_idx] : av1t_ac_q_10[e->base_q_idx];
   for (int b = 0; b < n; b++) {
     const bool key = s.is_key[b];
-    cudaEvent_t* ev = &s.ev_frame[(size_t)b * 4];
+    cudaEvent_t* ev = &s.ev_frame[(size_t)b * 5];
     CK(cudaEventRecord(ev[0], e->stream));
     uint16_t* rec[3]; uint16_t* deb[3]; uint16_t* fin[3]; const uint16_t* prev[3]; const uint16_t* src[3]; int16_t* coef[3];
     for (int p = 0; p < 3; p++) {
@@ -348,14 +357,33 @@ static int launch(av1b_encoder* e, Slot& s, const Slot& in, int n, int64_t first
       CdefLaunch Cd;
       Cd.g = g; Cd.bit_depth = bd; Cd.cdef_damping = fp.cdef_damping; Cd.cdef_bits = fp.cdef_bits;
       for (int i = 0; i < 8; i++) { Cd.y_strength[i] = fp.cdef_y_strength[i]; Cd.uv_strength[i] = fp.cdef_uv_strength[i]; }
-      for (int p = 0; p < 3; p++) { Cd.in[p] = deb[p]; Cd.src[p] = src[p]; Cd.out[p] = fin[p]; Cd.plane_elems[p] = e->plane_elems[p]; }
+      // with loop restoration the CDEF output goes to the (now free) pre-filter buffer and restoration writes the picture
+      for (int p = 0; p < 3; p++) { Cd.in[p] = deb[p]; Cd.src[p] = src[p]; Cd.out[p] = e->lr_on ? rec[p] : fin[p]; Cd.plane_elems[p] = e->plane_elems[p]; }
       Cd.blocks = blocks; Cd.map_elems = e->map_elems; Cd.cdef_idx = s.d_cdef_idx + (size_t)b * nsb; Cd.forced_idx = nullptr;
       CK(launch_cdef(Cd, 1, e->stream));
       e->kernel_launches += 2;
+      CK(cudaEventRecord(ev[3], e->stream));
+      if (e->lr_on) {
+        LrLaunch R;
+        R.g = g; R.bit_depth = bd;
+        for (int p = 0; p < 3; p++) {
+          R.lr_type[p] = p ? AV1B_RESTORE_NONE : AV1B_RESTORE_SWITCHABLE;
+          R.unit_size[p] = 64 >> (p > 0); R.unit_rows[p] = e->lr_rows; R.unit_cols[p] = e->lr_cols;
+          R.cdef[p] = rec[p]; R.deb[p] = deb[p]; R.out[p] = fin[p]; R.plane_elems[p] = e->plane_elems[p]; R.units[p] = nullptr;
+        }
+        Av1bLrUnit* units = s.d_lr_units + (size_t)b * e->lr_n;
+        R.src_y = src[0]; R.cand = e->lr_cand; R.sse = e->d_lr_sse;
+        const long long aq = key ? (bd == 8 ? av1t_ac_q_8[e->base_q_idx_key] : av1t_ac_q_10[e->base_q_idx_key]) : acq;
+        CK(launch_lr_search(R, 1, (aq * aq * 5) >> 8, units, e->stream));   // rate of a unit's parameters in squared-error units
+        R.units[0] = units;
+        CK(launch_lr(R, 1, e->stream));
+        e->kernel_launches += 3;
+      }
     } else {
       CK(cudaEventRecord(ev[2], e->stream));
+      CK(cudaEventRecord(ev[3], e->stream));
     }
-    CK(cudaEventRecord(ev[3], e->stream));
+    CK(cudaEventRecord(ev[4], e->stream));
   }
   e->chunk_pos += n;
   // the last reconstructed picture becomes reference slot 0 of the next batch
@@ -380,6 +408,7 @@ static int launch(av1b_encoder* e, Slot& s, const Slot& in, int n, int64_t first
     T.mode_cls = s.d_mode_cls; T.blk_count = s.d_blk_count; T.sb_off = s.d_sb_off;
     T.sb_of_order = e->d_sb_of_order; T.tile_of_sb = e->d_tile_of_sb;
     T.tokens = s.d_tokens; T.cap = (uint32_t)s.tok_cap;
+    T.lr_units = e->lr_on ? s.d_lr_units : nullptr; T.lr_rows = e->lr_rows; T.lr_cols = e->lr_cols;
     CK(launch_tok_count(T, e->stream));
     CK(launch_tok_emit(T, e->stream));
     e->kernel_launches += 4;
@@ -390,6 +419,10 @@ static int launch(av1b_encoder* e, Slot& s, const Slot& in, int n, int64_t first
   // token offsets for the inter frames (the token list itself follows once its size is known), levels and
   // block info only for the frames the block-walking tile writer codes (key frames; everything in debug mode)
   CK(cudaStreamWaitEvent(e->s_out, s.ev_k1, 0));
+  if (e->lr_on) {
+    CK(cudaMemcpyAsync(s.h_lr_units, s.d_lr_units, e->lr_n * n * sizeof(Av1bLrUnit), cudaMemcpyDeviceToHost, e->s_out));
+    e->d2h_bytes += (int64_t)(e->lr_n * n * sizeof(Av1bLrUnit));
+  }
   s.tok_fetched = 0;
   if (s.has_tokens) {
     CK(cudaMemcpyAsync(s.h_sb_off, s.d_sb_off, (nsb * n + 1) * sizeof(uint32_t), cudaMemcpyDeviceToHost, e->s_out));
@@ -425,12 +458,13 @@ static int finish(av1b_encoder* e, Slot& s, bool staged, av1b_packet_cb out_cb, 
   cudaEventElapsedTime(&ms, s.ev_k1, s.ev_d2h); e->t_d2h_ms += ms;
   const int n = s.n_frames;
   for (int b = 0; b < n; b++) {
-    cudaEvent_t* ev = &s.ev_frame[(size_t)b * 4];
+    cudaEvent_t* ev = &s.ev_frame[(size_t)b * 5];
     cudaEventElapsedTime(&ms, ev[0], ev[1]);
     if (s.is_key[b]) e->t_intra_ms += ms; else e->t_inter_ms += ms;
     if (e->loop_filters) {
       cudaEventElapsedTime(&ms, ev[1], ev[2]); e->t_deblock_ms += ms;
       cudaEventElapsedTime(&ms, ev[2], ev[3]); e->t_cdef_ms += ms;
+      cudaEventElapsedTime(&ms, ev[3], ev[4]); e->t_lr_ms += ms;
     }
   }
   cudaEventElapsedTime(&ms, s.ev_tok0, s.ev_tok1); e->t_tok_ms += ms;
@@ -470,6 +504,7 @@ static int finish(av1b_encoder* e, Slot& s, bool staged, av1b_packet_cb out_cb, 
     sy[b].blocks = s.h_blocks + (size_t)b * e->map_elems;
     for (int p = 0; p < 3; p++) { sy[b].coef[p] = s.h_coef[p] + (size_t)b * e->plane_elems[p]; sy[b].coef_stride[p] = g.stride[p]; }
     sy[b].cdef_idx = s.h_cdef_idx + (size_t)b * g.sb_rows * g.sb_cols;
+    if (e->lr_on) { sy[b].lr_units[0] = s.h_lr_units + (size_t)b * e->lr_n; sy[b].lr_unit_rows[0] = e->lr_rows; sy[b].lr_unit_cols[0] = e->lr_cols; }
     pack_frame_header(e->seq, s.is_key[b] ? e->fp_key : e->fp_inter, gb, packs[b]);
     for (int t = 0; t < gb.tile_cols * gb.tile_rows; t++) tasks.emplace_back(b, t);
   }
@@ -500,6 +535,7 @@ static int finish(av1b_encoder* e, Slot& s, bool staged, av1b_packet_cb out_cb, 
       }
       k.blocks.assign(sy[b].blocks, sy[b].blocks + e->map_elems);
       k.cdef_idx.assign(sy[b].cdef_idx, sy[b].cdef_idx + (size_t)g.sb_rows * g.sb_cols);
+      if (e->lr_on) k.lr_units.assign(sy[b].lr_units[0], sy[b].lr_units[0] + e->lr_n);
       k.is_key = s.is_key[b];
     }
     e->bytes_out += (int64_t)tu.size();
@@ -518,7 +554,7 @@ static int finish(av1b_encoder* e, Slot& s, bool staged, av1b_packet_cb out_cb, 
 static void reset_stats(av1b_encoder* e) {
   e->kept.clear();
   e->t_h2d_ms = e->t_kernel_ms = e->t_intra_ms = e->t_inter_ms = e->t_me_ms = e->t_d2h_ms = e->t_pack_ms = 0;
-  e->t_deblock_ms = e->t_cdef_ms = e->t_tok_ms = 0; e->n_tokens = 0; e->d2h_bytes = 0;
+  e->t_deblock_ms = e->t_cdef_ms = e->t_tok_ms = 0; e->t_lr_ms = 0; e->n_tokens = 0; e->d2h_bytes = 0;
   e->kernel_launches = e->intra_launches = e->inter_launches = e->frames_done = e->bytes_out = e->key_frames = e->staged_direct = 0;
 }
 
@@ -566,7 +602,9 @@ int av1b_encoder_create(const av1b_config* cfg, av1b_encoder** out) {
   }
   e->seq.width = cfg->width; e->seq.height = cfg->height; e->seq.bit_depth = cfg->bit_depth;
   e->loop_filters = cfg->reserved[2] == 0;     // reserved[2] = 1 switches the in-loop filters off (tests)
-  e->seq.enable_cdef = e->loop_filters ? 1 : 0; e->seq.enable_restoration = 0;
+  // --preset <= 5 (the daemon passes 3, av1an.rs:14) adds loop restoration with a per-unit decision; reserved[6] = 1 keeps it off
+  e->lr_on = e->loop_filters && cfg->preset <= 5 && cfg->reserved[6] == 0;
+  e->seq.enable_cdef = e->loop_filters ? 1 : 0; e->seq.enable_restoration = e->lr_on ? 1 : 0;
   e->seq.fps_num = cfg->fps_num; e->seq.fps_den = cfg->fps_den; e->seq.color_hdr = cfg->hdr;
   e->base_q_idx = av1t_quantizer_to_qindex[cfg->crf];
   if (e->base_q_idx < 1) e->base_q_idx = 1;   // lossless (qindex 0) is not supported
@@ -580,6 +618,14 @@ int av1b_encoder_create(const av1b_config* cfg, av1b_encoder** out) {
   e->keyint = cfg->keyint > 0 ? cfg->keyint : 240;
   av1b_select_frame_params(cfg->bit_depth, e->base_q_idx_key, AV1B_KEY_FRAME, e->loop_filters ? 1 : 0, &e->fp_key);
   av1b_select_frame_params(cfg->bit_depth, e->base_q_idx, AV1B_INTER_FRAME, e->loop_filters ? 1 : 0, &e->fp_inter);
+  if (e->lr_on) {
+    for (Av1bFrameParams* f : {&e->fp_key, &e->fp_inter}) { f->lr_type[0] = AV1B_RESTORE_SWITCHABLE; f->lr_type[1] = f->lr_type[2] = AV1B_RESTORE_NONE; f->lr_unit_shift = 0; f->lr_uv_shift = 0; }
+    e->lr_rows = std::max((cfg->height + 32) / 64, 1); e->lr_cols = std::max((cfg->width + 32) / 64, 1);
+    e->lr_n = (size_t)e->lr_rows * e->lr_cols;
+    memset(&e->lr_cand, 0, sizeof(e->lr_cand));
+    // a mild symmetric smoother and the radius-1 self-guided filter with a small weight: what the decision picks from
+    e->lr_cand.wiener_v[2] = 8; e->lr_cand.wiener_h[2] = 8; e->lr_cand.sgr_set = 12; e->lr_cand.sgr_xqd[0] = 0; e->lr_cand.sgr_xqd[1] = 95;
+  }
   e->fp_key.tile_cols_log2 = e->g.tile_cols_log2; e->fp_key.tile_rows_log2 = e->g.tile_rows_log2;
   e->fp_inter.tile_cols_log2 = e->g_inter.tile_cols_log2; e->fp_inter.tile_rows_log2 = e->g_inter.tile_rows_log2;
   e->batch = cfg->frames_in_flight > 0 ? cfg->frames_in_flight : 8;
@@ -598,7 +644,7 @@ int av1b_encoder_create(const av1b_config* cfg, av1b_encoder** out) {
   const int F = e->batch;
   for (auto& s : e->slot) {
     for (cudaEvent_t* ev : {&s.ev_h2d, &s.ev_k0, &s.ev_me, &s.ev_k1, &s.ev_d2h, &s.ev_src, &s.ev_tok0, &s.ev_tok1}) A(cudaEventCreate(ev));
-    s.ev_frame.assign((size_t)F * 4, nullptr);
+    s.ev_frame.assign((size_t)F * 5, nullptr);
     for (auto& ev : s.ev_frame) A(cudaEventCreate(&ev));
     for (int p = 0; p < 3; p++) {
       const size_t n = e->plane_elems[p] * F;
@@ -612,6 +658,7 @@ int av1b_encoder_create(const av1b_config* cfg, av1b_encoder** out) {
     A(cudaMalloc(&s.d_blocks, e->map_elems * F * sizeof(Av1bBlockInfo)));
     A(cudaMalloc(&s.d_cdef_idx, nsb * F));
     if (err == cudaSuccess) { A(cudaMemset(s.d_blocks, 0, e->map_elems * F * sizeof(Av1bBlockInfo))); A(cudaMemset(s.d_cdef_idx, 0, nsb * F)); }
+    if (e->lr_on) { A(cudaMalloc(&s.d_lr_units, e->lr_n * F * sizeof(Av1bLrUnit))); A(cudaMallocHost(&s.h_lr_units, e->lr_n * F * sizeof(Av1bLrUnit))); }
     if (e->token_path && !e->intra_only) {
       for (int p = 0; p < 3; p++) A(cudaMalloc(&s.d_digest[p], e->plane_elems[p] * F * 2));
       A(cudaMalloc(&s.d_mode_cls, e->map_elems * F));
@@ -658,6 +705,7 @@ int av1b_encoder_create(const av1b_config* cfg, av1b_encoder** out) {
     }
   }
   A(cudaMalloc(&e->d_map_key, e->map_elems)); A(cudaMalloc(&e->d_map_inter, e->map_elems));
+  if (e->lr_on) A(cudaMalloc(&e->d_lr_sse, 3 * e->lr_n * sizeof(unsigned long long)));
   if (!e->intra_only) {
     for (int l = 0; l < 3; l++) {
       const size_t el = e->plane_elems[0] >> (2 * l);
@@ -818,6 +866,14 @@ int av1b_get_cdef_idx(av1b_encoder* e, uint32_t frame, uint8_t* idx) {
   return AV1B_OK;
 }
 
+int av1b_get_lr_units(av1b_encoder* e, uint32_t frame, Av1bLrUnit* units, int32_t* rows, int32_t* cols) {
+  if (!e || !e->lr_on || !e->keep || frame >= e->kept.size()) { set_error("restoration units not kept (preset <= 5 and config.reserved[0] = 1) or bad index"); return AV1B_ERR_INVALID; }
+  if (rows) *rows = e->lr_rows;
+  if (cols) *cols = e->lr_cols;
+  if (units) memcpy(units, e->kept[frame].lr_units.data(), e->lr_n * sizeof(Av1bLrUnit));
+  return AV1B_OK;
+}
+
 int av1b_get_geom(av1b_encoder* e, Av1bGeom* g) {
   if (!e || !g) return AV1B_ERR_INVALID;
   *g = e->g;
@@ -839,11 +895,11 @@ void av1b_host_free(void* p) {
 
 int av1b_get_stats(av1b_encoder* e, double* stats, int n) {
   if (!e || !stats) return AV1B_ERR_INVALID;
-  const double v[20] = {e->t_h2d_ms, e->t_kernel_ms, e->t_d2h_ms, e->t_pack_ms, (double)e->kernel_launches,
+  const double v[21] = {e->t_h2d_ms, e->t_kernel_ms, e->t_d2h_ms, e->t_pack_ms, (double)e->kernel_launches,
                         (double)e->base_q_idx, e->t_intra_ms, (double)e->intra_launches, (double)e->frames_done,
                         (double)e->bytes_out, e->t_deblock_ms, e->t_cdef_ms, e->t_inter_ms, e->t_me_ms,
-                        (double)e->inter_launches, (double)e->key_frames, (double)e->staged_direct, e->t_tok_ms, (double)e->n_tokens, (double)e->d2h_bytes};
-  for (int i = 0; i < n && i < 20; i++) stats[i] = v[i];
+                        (double)e->inter_launches, (double)e->key_frames, (double)e->staged_direct, e->t_tok_ms, (double)e->n_tokens, (double)e->d2h_bytes, e->t_lr_ms};
+  for (int i = 0; i < n && i < 21; i++) stats[i] = v[i];
   return AV1B_OK;
 }
 

@@ -224,6 +224,44 @@ int av1b_k_lr(int device, int width, int height, int bit_depth, int n_frames, co
   return download_planes(n_frames, out, bo, t.s);
 }
 
+int av1b_k_lr_search(int device, int width, int height, int bit_depth, const Av1bLrUnit* cand,
+                     const uint16_t* const cdef[3], const uint16_t* const deb[3], const uint16_t* src_y, int64_t bias,
+                     Av1bLrUnit* units_out, uint64_t* sse_out, int reps, double* ms_per_launch) {
+  if (!cand || !cdef || !deb || !src_y || !units_out) { set_error("bad argument"); return AV1B_ERR_INVALID; }
+  LrLaunch L;
+  if (av1b_geom_init(&L.g, width, height, 0, 0)) { set_error("unsupported size"); return AV1B_ERR_INVALID; }
+  int rc = select_device(device);
+  if (rc) return rc;
+  Timer t; CKS(t.init());
+  FrameBufs bc, bd, bs;
+  const uint16_t* const srcs[3] = {src_y, cdef[1], cdef[2]};
+  if ((rc = upload_planes(L.g, 1, cdef, bc, t.s))) return rc;
+  if ((rc = upload_planes(L.g, 1, deb, bd, t.s))) return rc;
+  if ((rc = upload_planes(L.g, 1, srcs, bs, t.s))) return rc;
+  L.bit_depth = bit_depth;
+  for (int p = 0; p < 3; p++) {
+    const int ss = p > 0, us = 64 >> ss;
+    const int ph = (height + ss) >> ss, pw = (width + ss) >> ss;
+    L.lr_type[p] = p ? AV1B_RESTORE_NONE : AV1B_RESTORE_SWITCHABLE;
+    L.unit_size[p] = us;
+    L.unit_rows[p] = std::max((ph + (us >> 1)) / us, 1);
+    L.unit_cols[p] = std::max((pw + (us >> 1)) / us, 1);
+    L.units[p] = nullptr;
+    L.cdef[p] = bc.d[p].as<uint16_t>(); L.deb[p] = bd.d[p].as<uint16_t>(); L.out[p] = nullptr;
+    L.plane_elems[p] = bc.elems[p];
+  }
+  const size_t n = (size_t)L.unit_rows[0] * L.unit_cols[0];
+  DevBuf dsse, du;
+  CKS(dsse.alloc(3 * n * sizeof(unsigned long long)));
+  CKS(du.alloc(n * sizeof(Av1bLrUnit)));
+  L.src_y = bs.d[0].as<uint16_t>(); L.cand = *cand; L.sse = dsse.as<unsigned long long>();
+  if ((rc = timed(t, reps, ms_per_launch, [&]() { return launch_lr_search(L, 1, bias, du.as<Av1bLrUnit>(), t.s); }))) return rc;
+  CKS(cudaMemcpyAsync(units_out, du.p, n * sizeof(Av1bLrUnit), cudaMemcpyDeviceToHost, t.s));
+  if (sse_out) CKS(cudaMemcpyAsync(sse_out, dsse.p, 3 * n * sizeof(uint64_t), cudaMemcpyDeviceToHost, t.s));
+  CKS(cudaStreamSynchronize(t.s));
+  return AV1B_OK;
+}
+
 int av1b_k_pyramid(int device, int width, int height, int n_frames, const uint16_t* l0, uint16_t* l1, uint16_t* l2,
                    int reps, double* ms_per_launch) {
   if (!l0 || !l1 || !l2 || n_frames <= 0) { set_error("bad argument"); return AV1B_ERR_INVALID; }

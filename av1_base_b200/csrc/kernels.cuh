@@ -63,6 +63,10 @@ struct LrLaunch {
   uint16_t* out[3];
   size_t plane_elems[3];
   const Av1bLrUnit* units[3]; // [n_frames][unit_rows*unit_cols] per plane, or nullptr
+  // decision (launch_lr_search), luma only:
+  const uint16_t* src_y;      // source luma
+  Av1bLrUnit cand;            // the Wiener taps and the self-guided set / weights every unit may choose
+  unsigned long long* sse;    // scratch [n_frames][3][unit_rows*unit_cols]: squared errors of none / Wiener / self-guided
 };
 
 // Batched normative inverse transform + reconstruction, all 19 AV1 sizes (txfm_kernel.cu).
@@ -129,6 +133,8 @@ struct TokLaunch {
   const uint16_t* tile_of_sb;    // [nsb]
   uint32_t* tokens;
   uint32_t cap;                  // capacity of `tokens`
+  const Av1bLrUnit* lr_units;    // [n_frames][lr_rows*lr_cols] luma restoration units, or nullptr
+  int32_t lr_rows, lr_cols;
 };
 // mode classes + token counts + offsets (exclusive scan); then launch_tok_emit writes the tokens
 cudaError_t launch_tok_count(const TokLaunch& p, cudaStream_t s);
@@ -137,6 +143,9 @@ cudaError_t launch_tok_emit(const TokLaunch& p, cudaStream_t s);
 cudaError_t launch_deblock(const DeblockLaunch& p, int n_frames, cudaStream_t s);
 cudaError_t launch_cdef(const CdefLaunch& p, int n_frames, cudaStream_t s);
 cudaError_t launch_lr(const LrLaunch& p, int n_frames, cudaStream_t s);
+// Per-unit choice among NONE / WIENER(cand) / SGRPROJ(cand) for the luma plane against the source: a candidate must
+// beat NONE by more than `bias`.  units_out: [n_frames][unit_rows*unit_cols].
+cudaError_t launch_lr_search(const LrLaunch& p, int n_frames, long long bias, Av1bLrUnit* units_out, cudaStream_t s);
 cudaError_t launch_partition_fixed(const Av1bGeom& g, int blk_log2, uint8_t* map, int n_frames, cudaStream_t s);
 cudaError_t launch_intra_encode(const IntraLaunch& p, int n_frames, cudaStream_t s);
 // Fast key-frame path for 16x16 blocks (8x8 at the picture edge): open-loop mode kernel + closed-loop

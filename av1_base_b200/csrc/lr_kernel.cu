@@ -54,13 +54,18 @@ __device__ __forceinline__ void sgr_ab(const Smem& sm, int i, int j, int r, int 
   *b_out = (int)((b2 + (1u << 11)) >> 12);
 }
 
+// kSearch: no output; the luma plane is filtered with the Wiener and the self-guided parameters of P.cand and the
+// squared errors against the source (and that of the unfiltered CDEF output) are added to P.sse[3][units].
+template <bool kSearch>
 __global__ void __launch_bounds__(kThreads) lr_kernel(const LrLaunch P) {
   __shared__ Smem sm;
   const Av1bGeom& g = P.g;
   const int tid = threadIdx.x;
   const int tx = blockIdx.x, stripe = blockIdx.y, frame = blockIdx.z;
   const int bd = P.bit_depth, maxv = (1 << bd) - 1;
-  for (int p = 0; p < 3; p++) {
+  unsigned acc[3] = {0, 0, 0};   // search: squared errors of this thread (none, Wiener, self-guided)
+  int s_urow = 0, s_ucol = 0;
+  for (int p = 0; p < (kSearch ? 1 : 3); p++) {
     const int ss = p > 0;
     const int TW = 64 >> ss;
     const int pw = (g.width + ss) >> ss, ph = (g.height + ss) >> ss;
@@ -76,14 +81,21 @@ __global__ void __launch_bounds__(kThreads) lr_kernel(const LrLaunch P) {
     if (h <= 0 || x0 >= stride) continue;
     int type = AV1B_RESTORE_NONE;
     Av1bLrUnit unit;
-    if (P.lr_type[p] != AV1B_RESTORE_NONE && P.units[p]) {
+    const uint16_t* srcp = nullptr;
+    if (kSearch) {
+      if (x0 >= pw) continue;
+      unit = P.cand;
+      srcp = P.src_y + (size_t)frame * P.plane_elems[0];
+      s_urow = min(P.unit_rows[0] - 1, (ys + 8) / P.unit_size[0]);
+      s_ucol = min(P.unit_cols[0] - 1, x0 / P.unit_size[0]);
+    } else if (P.lr_type[p] != AV1B_RESTORE_NONE && P.units[p]) {
       const int us = P.unit_size[p];
       const int urow = min(P.unit_rows[p] - 1, (((ys << ss) + 8) >> ss) / us);
       const int ucol = min(P.unit_cols[p] - 1, x0 / us);
       unit = P.units[p][(size_t)frame * P.unit_rows[p] * P.unit_cols[p] + urow * P.unit_cols[p] + ucol];
       type = x0 < pw ? unit.type : AV1B_RESTORE_NONE;
     }
-    if (type == AV1B_RESTORE_NONE) {
+    if (!kSearch && type == AV1B_RESTORE_NONE) {
       for (int o = tid; o < h * (TW / 8); o += kThreads) {
         const int r = o / (TW / 8), v = o % (TW / 8);
         const size_t off = (size_t)(ys + r) * stride + x0 + v * 8;
@@ -103,6 +115,8 @@ __global__ void __launch_bounds__(kThreads) lr_kernel(const LrLaunch P) {
       sm.win[r * kWinStride + c] = srcp[(size_t)y * stride + x];
     }
     __syncthreads();
+    for (int pass = 0; pass < (kSearch ? 2 : 1); pass++) {
+    if (kSearch) { type = pass ? AV1B_RESTORE_SGRPROJ : AV1B_RESTORE_WIENER; if (pass) __syncthreads(); }
     if (type == AV1B_RESTORE_WIENER) {
       int hf[7], vf[7];
       hf[3] = vf[3] = 128;
@@ -132,7 +146,11 @@ __global__ void __launch_bounds__(kThreads) lr_kernel(const LrLaunch P) {
         } else {
           v = sm.win[(r + kH) * kWinStride + c + kH];
         }
-        out[(size_t)(ys + r) * stride + x0 + c] = (uint16_t)v;
+        if (kSearch) {
+          if (x0 + c < pw) { const int d = v - (int)srcp[(size_t)(ys + r) * stride + x0 + c]; acc[1] += (unsigned)(d * d); }
+        } else {
+          out[(size_t)(ys + r) * stride + x0 + c] = (uint16_t)v;
+        }
       }
     } else {
       const int set = unit.sgr_set;
@@ -210,11 +228,54 @@ __global__ void __launch_bounds__(kThreads) lr_kernel(const LrLaunch P) {
             }
             v = clampi((w1 * uu + w0 * f0 + w2 * f1 + (1 << 10)) >> 11, 0, maxv);
           }
-          out[(size_t)(ys + i) * stride + x0 + j] = (uint16_t)v;
+          if (kSearch) {
+            if (x0 + j < pw) { const int d = v - (int)srcp[(size_t)(ys + i) * stride + x0 + j]; acc[2] += (unsigned)(d * d); }
+          } else {
+            out[(size_t)(ys + i) * stride + x0 + j] = (uint16_t)v;
+          }
+        }
+      }
+    }
+    }   // pass
+    if (kSearch) {
+      for (int o = tid; o < h * TW; o += kThreads) {
+        const int r = o / TW, c = o % TW;
+        if (x0 + c < pw) {
+          const int d = (int)sm.win[(r + kH) * kWinStride + c + kH] - (int)srcp[(size_t)(ys + r) * stride + x0 + c];
+          acc[0] += (unsigned)(d * d);
         }
       }
     }
   }
+  if (kSearch) {
+    const size_t n_units = (size_t)P.unit_rows[0] * P.unit_cols[0];
+    unsigned long long* sse = P.sse + (size_t)frame * 3 * n_units + (size_t)s_urow * P.unit_cols[0] + s_ucol;
+#pragma unroll
+    for (int k = 0; k < 3; k++) {
+      unsigned a = acc[k];
+      for (int o = 16; o; o >>= 1) a += __shfl_xor_sync(0xffffffffu, a, o);
+      if ((tid & 31) == 0 && a) atomicAdd(sse + k * n_units, (unsigned long long)a);
+    }
+  }
+}
+
+// one thread per restoration unit: NONE unless a candidate beats it by more than the bias; ties keep the earlier
+// of NONE, WIENER, SGRPROJ (orc_lr_search)
+__global__ void lr_decide_kernel(const unsigned long long* sse, int n_units, int n_frames, unsigned long long bias, Av1bLrUnit cand,
+                                 Av1bLrUnit* units) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n_units * n_frames) return;
+  const int f = i / n_units, u = i % n_units;
+  const unsigned long long* s = sse + (size_t)f * 3 * n_units + u;
+  int best = 0;
+  unsigned long long bv = s[0];
+  for (int k = 1; k < 3; k++) {
+    const unsigned long long v = s[(size_t)k * n_units] + bias;
+    if (v < bv) { bv = v; best = k; }
+  }
+  Av1bLrUnit o = cand;
+  o.type = (int8_t)(best == 0 ? AV1B_RESTORE_NONE : best == 1 ? AV1B_RESTORE_WIENER : AV1B_RESTORE_SGRPROJ);
+  units[i] = o;
 }
 
 }  // namespace
@@ -222,7 +283,18 @@ __global__ void __launch_bounds__(kThreads) lr_kernel(const LrLaunch P) {
 cudaError_t launch_lr(const LrLaunch& p, int n_frames, cudaStream_t s) {
   const int stripes = (p.g.height + 8 + 63) / 64;
   dim3 grid(p.g.sb_cols, stripes, n_frames);
-  lr_kernel<<<grid, kThreads, 0, s>>>(p);
+  lr_kernel<false><<<grid, kThreads, 0, s>>>(p);
+  return cudaGetLastError();
+}
+
+cudaError_t launch_lr_search(const LrLaunch& p, int n_frames, long long bias, Av1bLrUnit* units_out, cudaStream_t s) {
+  const int stripes = (p.g.height + 8 + 63) / 64;
+  const int n_units = p.unit_rows[0] * p.unit_cols[0];
+  cudaError_t e = cudaMemsetAsync(p.sse, 0, (size_t)n_frames * 3 * n_units * sizeof(unsigned long long), s);
+  if (e != cudaSuccess) return e;
+  dim3 grid(p.g.sb_cols, stripes, n_frames);
+  lr_kernel<true><<<grid, kThreads, 0, s>>>(p);
+  lr_decide_kernel<<<(n_units * n_frames + 127) / 128, 128, 0, s>>>(p.sse, n_units, n_frames, (unsigned long long)bias, p.cand, units_out);
   return cudaGetLastError();
 }
 

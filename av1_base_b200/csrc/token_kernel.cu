@@ -28,6 +28,8 @@ __device__ __forceinline__ TokFrame frame_view(const TokLaunch& P, int f) {
   F.w8 = P.g.w8; F.h8 = P.g.h8; F.mi_cols = P.g.mi_cols; F.mi_rows = P.g.mi_rows; F.sb_cols = P.g.sb_cols;
   F.cdef_bits = P.cdef_bits;
   F.scan[0] = tbl::scan_default_4; F.scan[1] = tbl::scan_default_8; F.scan[2] = tbl::scan_default_16;
+  F.lr_units = P.lr_units ? P.lr_units + (size_t)f * P.lr_rows * P.lr_cols : nullptr;
+  F.lr_rows = P.lr_rows; F.lr_cols = P.lr_cols;
   F.tx_sym_16 = 3; F.tx_sym_8 = 7;   // av1t_ext_tx_ind[4][DCT_DCT], av1t_ext_tx_ind[5][DCT_DCT] (checked on the host at launch)
   return F;
 }
@@ -99,6 +101,17 @@ __global__ void __launch_bounds__(128) tok_walk_kernel(const __grid_constant__ T
   uint32_t* bc = P.blk_count + (size_t)f * P.map_elems;
   uint32_t base = kEmit ? P.sb_off[(size_t)f * nsb + k] : 0;
   uint32_t sb_total = 0;
+  {
+    // restoration unit parameters precede the superblock's blocks
+    uint32_t n_pre = 0;
+    if (lane == 0) {
+      TokSink K{kEmit ? P.tokens + base : nullptr, 0, (kEmit && base < P.cap) ? P.cap - base : 0};
+      tok_sb_lr(F, sby * 16, sbx * 16, K);
+      n_pre = K.n;
+    }
+    n_pre = __shfl_sync(0xffffffffu, n_pre, 0);
+    base += n_pre; sb_total += n_pre;
+  }
   for (int j0 = 0; j0 < nblk; j0 += 32) {
     const int j = j0 + lane;
     const bool act = j < nblk;

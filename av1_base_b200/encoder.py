@@ -115,13 +115,21 @@ class Encoder:
         return blocks, coef
 
     def stats(self):
-        s = (C.c_double * 20)()
-        _check(abi.lib().av1b_get_stats(self._h, s, 20))
+        s = (C.c_double * 21)()
+        _check(abi.lib().av1b_get_stats(self._h, s, 21))
         return dict(h2d_ms=s[0], kernel_ms=s[1], d2h_ms=s[2], pack_ms=s[3], kernel_launches=int(s[4]),
                     base_q_idx=int(s[5]), intra_ms=s[6], intra_launches=int(s[7]), frames_done=int(s[8]),
                     bytes_out=int(s[9]), deblock_ms=s[10], cdef_ms=s[11], inter_ms=s[12], me_ms=s[13],
                     inter_launches=int(s[14]), key_frames=int(s[15]), staged_direct=int(s[16]), tok_ms=s[17],
-                    tokens=int(s[18]), d2h_bytes=int(s[19]))
+                    tokens=int(s[18]), d2h_bytes=int(s[19]), lr_ms=s[20])
+
+    def lr_units(self, frame):
+        """Luma restoration units [rows, cols] of a kept frame (preset <= 5, keep_debug=True)."""
+        r, c = C.c_int32(0), C.c_int32(0)
+        _check(abi.lib().av1b_get_lr_units(self._h, frame, None, C.byref(r), C.byref(c)))
+        u = np.zeros((r.value, c.value), abi.LR_UNIT_DTYPE)
+        _check(abi.lib().av1b_get_lr_units(self._h, frame, u.ctypes.data_as(C.c_void_p), None, None))
+        return u
 
     def frame_params(self):
         fp = abi.FrameParams()

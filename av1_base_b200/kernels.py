@@ -86,6 +86,23 @@ def loop_restoration(width, height, bit_depth, fp, cdef_planes, deb_planes, unit
     return [[out[p][i] for p in range(3)] for i in range(n)], ms.value
 
 
+def lr_search(width, height, bit_depth, cand, cdef_planes, deb_planes, src_luma, bias, device=0, reps=1):
+    """Per-unit luma restoration decision (NONE / Wiener(cand) / self-guided(cand)) for ONE frame of padded planes.
+    Returns (units [rows, cols], sse [3, rows*cols], ms)."""
+    c = [np.ascontiguousarray(p, np.uint16) for p in cdef_planes]
+    d = [np.ascontiguousarray(p, np.uint16) for p in deb_planes]
+    sy = np.ascontiguousarray(src_luma, np.uint16)
+    ur, uc = max((height + 32) // 64, 1), max((width + 32) // 64, 1)
+    units = np.zeros((ur, uc), abi.LR_UNIT_DTYPE)
+    sse = np.zeros((3, ur * uc), np.uint64)
+    cand = np.ascontiguousarray(cand)
+    ms = C.c_double(0)
+    _ck(abi.lib().av1b_k_lr_search(device, width, height, bit_depth, cand.ctypes.data_as(C.c_void_p), _p3(c), _p3(d),
+                                   sy.ctypes.data_as(C.c_void_p), C.c_int64(int(bias)), units.ctypes.data_as(C.c_void_p),
+                                   sse.ctypes.data_as(C.c_void_p), reps, C.byref(ms)))
+    return units, sse, ms.value
+
+
 def pyramid(width, height, l0_frames, device=0, reps=1):
     """l0_frames: [n, rows, stride] uint16 padded luma. Returns (l1, l2, ms)."""
     l0 = np.ascontiguousarray(l0_frames, np.uint16)

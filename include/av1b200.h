@@ -36,7 +36,7 @@ typedef struct av1b_config {
   int32_t bit_depth;              /* 8 or 10 (input samples are uint16 either way)                 */
   int32_t fps_num, fps_den;
   int32_t crf;                    /* 0..63, SVT-AV1 --crf                                          */
-  int32_t preset;                 /* SVT-AV1 --preset (speed/quality trade-off)                    */
+  int32_t preset;                 /* SVT-AV1 --preset: <= 5 adds loop restoration (per-unit decision) */
   int32_t keyint;                 /* --keyint                                                      */
   int32_t lookahead;              /* --lookahead (accepted; unused by the all-intra path)          */
   int32_t film_grain;             /* --film-grain (accepted; synthesis not implemented: row f-4)   */
@@ -50,7 +50,8 @@ typedef struct av1b_config {
                                      [2]: 1 = in-loop filters off; [3]: 1 = every frame is a key frame;
                                      [4]: inter transform-block drop threshold (0 = off);
                                      [5]: inter-frame entropy coding path: 0 = device tokenizer + host range coder over tokens (default),
-                                          1 = host block walker over raster levels, 2 = host block walker over in-place packed symbols */
+                                          1 = host block walker over raster levels, 2 = host block walker over in-place packed symbols;
+                                     [6]: 1 = loop restoration off whatever the preset */
 } av1b_config;
 
 typedef struct av1b_encoder av1b_encoder;
@@ -102,6 +103,9 @@ int av1b_get_inter_frame_params(av1b_encoder* enc, struct Av1bFrameParams* fp);
 int av1b_get_me_lambda(av1b_encoder* enc);
 /* 1 / 0: whether kept frame `frame_in_chunk` was coded as a key frame (needs config.reserved[0] = 1) */
 int av1b_get_frame_is_key(av1b_encoder* enc, uint32_t frame_in_chunk);
+/* luma restoration units of a kept frame (preset <= 5: loop restoration on): units[rows*cols] (may be NULL to query the grid) */
+struct Av1bLrUnit;
+int av1b_get_lr_units(av1b_encoder* enc, uint32_t frame_in_chunk, struct Av1bLrUnit* units, int32_t* rows, int32_t* cols);
 /* chosen CDEF preset per 64x64 superblock of a kept frame: idx[sb_rows*sb_cols] */
 int av1b_get_cdef_idx(av1b_encoder* enc, uint32_t frame_in_chunk, uint8_t* idx);
 /* pure function (no device): deblock levels and CDEF presets from bit depth / quantiser / frame type */
@@ -112,10 +116,10 @@ int av1b_select_frame_params(int bit_depth, int base_q_idx, int frame_type, int 
  * the context of `device` (one the caller encodes on) and is usable from every device.  NULL on failure. */
 void* av1b_host_alloc(int device, size_t bytes);
 void av1b_host_free(void* p);
-/* stats[0..19] = h2d_ms, kernel_ms, d2h_ms, pack_ms, kernel_launches, base_q_idx, intra_kernel_ms,
+/* stats[0..20] = h2d_ms, kernel_ms, d2h_ms, pack_ms, kernel_launches, base_q_idx, intra_kernel_ms,
  * intra_kernel_launches, frames_done, bytes_out, deblock_ms, cdef_ms, inter_kernel_ms, me_ms (pyramid + search),
  * inter_kernel_launches, key_frames, frames uploaded straight from page-locked caller memory, tokenizer_ms,
- * tokens produced, bytes copied device -> host, of the last chunk / resident run (CUDA-event times) */
+ * tokens produced, bytes copied device -> host, loop_restoration_ms, of the last chunk / resident run (CUDA-event times) */
 int av1b_get_stats(av1b_encoder* enc, double* stats, int n);
 
 /* ---- kernel suite (BASELINE.json config 2 "kernel bit-exact suite") -----------------------------
@@ -142,6 +146,14 @@ int av1b_k_cdef(int device, int width, int height, int bit_depth, int n_frames, 
 int av1b_k_lr(int device, int width, int height, int bit_depth, int n_frames, const struct Av1bFrameParams* fp,
               const uint16_t* const cdef[3], const uint16_t* const deb[3], const struct Av1bLrUnit* const units[3],
               uint16_t* const out[3], int reps, double* ms_per_launch);
+
+/* Encoder-side loop-restoration decision (E8 "search"), luma plane, 64x64 units, frame type SWITCHABLE: every unit
+ * picks NONE, WIENER with cand's taps or SGRPROJ with cand's set / weights, whichever has the smallest squared error
+ * against the source; a restoring candidate must beat NONE by more than `bias`.  units_out: [rows*cols];
+ * sse_out (may be NULL): [3][rows*cols] (none, Wiener, self-guided). */
+int av1b_k_lr_search(int device, int width, int height, int bit_depth, const struct Av1bLrUnit* cand,
+                     const uint16_t* const cdef[3], const uint16_t* const deb[3], const uint16_t* src_y, int64_t bias,
+                     struct Av1bLrUnit* units_out, uint64_t* sse_out, int reps, double* ms_per_launch);
 
 /* Source pyramid: l0 = n_frames padded luma planes; l1 / l2 = the 1/2 and 1/4 planes
  * (strides stride0/2, stride0/4). */

@@ -10,25 +10,42 @@ from oracle import pyoracle as O, decoders as D
 pytestmark = pytest.mark.gpu
 
 CASES = [
-    # w, h, bd, crf, tcl, trl, loop_filters, n_frames, frames_in_flight, keyint
-    (64, 64, 8, 30, 0, 0, False, 4, 2, 240),
-    (200, 136, 10, 30, 0, 0, True, 5, 2, 240),
-    (328, 248, 8, 45, 1, 1, True, 6, 4, 4),
-    (640, 360, 10, 25, 2, 1, True, 5, 3, 240),
+    # w, h, bd, crf, tcl, trl, loop_filters, n_frames, frames_in_flight, keyint, preset (<= 5: loop restoration on)
+    (64, 64, 8, 30, 0, 0, False, 4, 2, 240, 6),
+    (200, 136, 10, 30, 0, 0, True, 5, 2, 240, 6),
+    (328, 248, 8, 45, 1, 1, True, 6, 4, 4, 6),
+    (640, 360, 10, 25, 2, 1, True, 5, 3, 240, 6),
+    (200, 136, 10, 40, 0, 0, True, 5, 2, 3, 4),
+    (328, 248, 8, 30, 1, 1, True, 7, 3, 240, 3),
+    (640, 360, 10, 35, -1, -1, True, 4, 4, 240, 5),
 ]
 
 
-def oracle_filters(g, bd, fp, res, frame):
+def oracle_filters(g, bd, fp, res, frame, lr, acq):
     O.deblock_frame(g, bd, res.blocks, res.rec, list(fp.lf_level), fp.lf_sharpness)
-    idx = O.cdef_search(g, bd, res.blocks, fp, res.rec, O.pad_planes(g, frame))
-    return O.cdef_frame(g, bd, res.blocks, fp, idx, res.rec), idx
+    src = O.pad_planes(g, frame)
+    idx = O.cdef_search(g, bd, res.blocks, fp, res.rec, src)
+    fin, units = O.cdef_frame(g, bd, res.blocks, fp, idx, res.rec), None
+    if lr:
+        cand = O.lr_candidate((0, 0, 8), (0, 0, 8), 12, (0, 95))
+        units, _ = O.lr_search(g, bd, fp, cand, fin, res.rec, src[0], (acq * acq * 5) >> 8)
+        fin = O.lr_frame(g, bd, fp, fin, res.rec, [units, None, None])
+    return fin, idx, units
 
 
-@pytest.mark.parametrize("w,h,bd,crf,tcl,trl,lf,nfr,fif,keyint", CASES)
-def test_chunk_parity(w, h, bd, crf, tcl, trl, lf, nfr, fif, keyint):
+def ac_q(bd, qidx):
+    import re, os
+    txt = open(os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "av1_base_b200", "csrc", "av1_tables.h")).read()
+    m = re.search(r"av1t_ac_q_%d\[\d+\] = \{(.*?)\};" % bd, txt, re.S)
+    return [int(v) for v in re.findall(r"-?\d+", m.group(1))][qidx]
+
+
+@pytest.mark.parametrize("w,h,bd,crf,tcl,trl,lf,nfr,fif,keyint,preset", CASES)
+def test_chunk_parity(w, h, bd, crf, tcl, trl, lf, nfr, fif, keyint, preset):
     frames = synth.synth_clip(w, h, bd, nfr, seed=w + bd, scene_len=100)
     enc = encoder.Encoder(w, h, bd, crf=crf, keep_debug=True, tile_cols_log2=tcl, tile_rows_log2=trl,
-                          frames_in_flight=fif, loop_filters=lf, keyint=keyint)
+                          frames_in_flight=fif, loop_filters=lf, keyint=keyint, preset=preset)
+    lr = lf and preset <= 5
     tus = enc.encode_chunk(frames)
     assert len(tus) == nfr
     g = enc.geom
@@ -54,7 +71,11 @@ def test_chunk_parity(w, h, bd, crf, tcl, trl, lf, nfr, fif, keyint):
             assert np.array_equal(blocks[f], ref.blocks[f]), (f, i)
         fin = ref.rec
         if lf:
-            fin, idx = oracle_filters(g, bd, fp_key if key else fp_inter, ref, fr)
+            fpf = fp_key if key else fp_inter
+            fin, idx, units = oracle_filters(g, bd, fpf, ref, fr, lr, ac_q(bd, fpf.base_q_idx))
+            if lr:
+                assert (fpf.lr_type[0], fpf.lr_type[1], fpf.lr_type[2]) == (3, 0, 0)
+                assert enc.lr_units(i).tobytes() == units.tobytes(), ("restoration units", i)
         rec = enc.recon(i)
         orc = O.crop(g, fin)
         for p in range(3):

@@ -187,6 +187,24 @@ def test_loop_restoration_vs_oracle(w, h, bd, q, lrt, ushift, uvshift):
             assert np.array_equal(O.crop(g, got[i])[p], O.crop(g, ref)[p]), (i, p)
 
 
+@pytest.mark.parametrize("w,h,bd,q", FRAME_CASES)
+def test_lr_search_vs_oracle(w, h, bd, q):
+    """Encoder-side restoration decision: squared errors of NONE / Wiener / self-guided per unit and the choice."""
+    g, frames, res, rng = encoded_frames(w, h, bd, q, 1, w * 3 + q)
+    fp = cdef_params(rng, 1)
+    fp.lr_type[0], fp.lr_type[1], fp.lr_type[2] = 3, 0, 0
+    r = res[0]
+    O.deblock_frame(g, bd, r.blocks, r.rec, [20, 20, 10, 10], 0)
+    cdf = O.cdef_frame(g, bd, r.blocks, fp, rng.integers(0, 2, g.sb_rows * g.sb_cols).astype(np.uint8), r.rec)
+    src = O.pad_planes(g, frames[0])
+    for cand, bias in ((O.lr_candidate((0, 0, 8), (0, 0, 8), 12, (0, 95)), 3000), (O.lr_candidate(), 0),
+                       (O.lr_candidate((2, -5, 20), (-3, 4, -10), 3, (-40, 70)), 100)):
+        ref_units, ref_sse = O.lr_search(g, bd, fp, cand, cdf, r.rec, src[0], bias)
+        units, sse, _ = kernels.lr_search(w, h, bd, cand, cdf, r.rec, src[0], bias)
+        assert np.array_equal(sse, ref_sse)
+        assert units.tobytes() == ref_units.tobytes()
+
+
 ME_CASES = [(64, 64, 8), (200, 136, 10), (328, 248, 8), (640, 360, 10)]
 
 
