@@ -1116,6 +1116,9 @@ struct TokenCoder {
 };
 }  // namespace
 
+void tile_cdfs_default(int base_q_idx, void* dst) { init_cdfs(*static_cast<TileCdfs*>(dst), base_q_idx); }
+size_t tile_cdfs_size() { return sizeof(TileCdfs); }
+
 void pack_tile_tokens(const Av1bFrameParams& fp, const uint32_t* tok, size_t n, std::vector<uint8_t>& out) {
   TokenCoder c(fp);
   for (size_t i = 0; i < n; i++) c.step(tok[i]);

@@ -151,6 +151,9 @@ void pack_tile(const Av1bSeqParams& seq, const Av1bFrameParams& fp, const Av1bGe
 void assemble_frame(const FramePack& fpk, std::vector<uint8_t>& out);   // appends one OBU_FRAME
 // Tile payload of an inter frame from its token list (tokens.h): range coding + CDF adaptation only.
 void pack_tile_tokens(const Av1bFrameParams& fp, const uint32_t* tok, size_t n, std::vector<uint8_t>& out);
+// default CDF set of a tile (TileCdfs image, tile_cdfs_size() bytes) for the device range coder (rc_kernel.cu)
+void tile_cdfs_default(int base_q_idx, void* dst);
+size_t tile_cdfs_size();
 // CPU statement of the device tokenizer (token_kernel.cu) for an inter frame: digests the raster levels like
 // the inter kernel does, derives the mode classes and walks the blocks in coding order; one token list per
 // tile.  Test infrastructure for the token path (the product tokenizes on the device).

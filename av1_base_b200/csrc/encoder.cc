@@ -123,6 +123,17 @@ struct Slot {
   size_t tok_cap = 0;                                 // capacity of d_tokens / h_tokens (tokens)
   TokLaunch tl;                                       // the batch's tokenizer launch (re-run after growing the buffers)
   bool has_tokens = false;
+  // device range coder: per-tile regions, byte counts / offsets, contiguous payloads
+  uint8_t* d_rc_region = nullptr;
+  uint32_t* d_rc_len = nullptr;
+  uint32_t* h_rc_len = nullptr;
+  uint8_t* d_rc_bytes = nullptr;
+  uint8_t* h_rc_bytes = nullptr;
+  size_t rc_cap = 0;                                  // capacity of d_rc_bytes / h_rc_bytes
+  size_t rc_fetched = 0;
+  RcLaunch rl;
+  cudaStream_t s_rc = nullptr;                        // the slot's range coder: overlaps the next batches' kernels
+  cudaEvent_t ev_rc0 = nullptr, ev_rc1 = nullptr;
   size_t tok_fetched = 0;                             // tokens already downloaded with the offsets
   cudaEvent_t ev_tok0 = nullptr, ev_tok1 = nullptr;
   cudaEvent_t ev_src = nullptr;                       // sources of this slot are resident
@@ -178,6 +189,12 @@ struct av1b_encoder {
   uint32_t* d_sb_of_order = nullptr;  // inter-frame tile layout: coding order -> superblock
   uint16_t* d_tile_of_sb = nullptr;
   std::vector<uint32_t> tile_first_k; // [tiles + 1] first coding-order index of each inter-frame tile
+  bool rc_on = true;                  // range coding of the token lists on the device (else on the host pool)
+  void* d_cdf_init = nullptr;         // default CDF set of the inter frames' quantiser class
+  uint32_t* d_tile_first_k = nullptr;
+  uint32_t* d_rc_overflow = nullptr;
+  size_t rc_guess = 0;
+  double t_rc_ms = 0;
   cudaStream_t s_tok = nullptr;       // token list download (issued once the batch's total is known)
   Slot slot[3];                       // batch k+1 uploads / batch k on the GPU / batches k-1, k-2 with the host
   size_t tok_guess = 0;               // tokens of the last batch: that much is downloaded before the total is known
@@ -202,9 +219,11 @@ static void free_all(av1b_encoder* e) {
     cudaFree(s.d_blocks); cudaFree(s.d_cdef_idx);
     cudaFree(s.d_lr_units); cudaFreeHost(s.h_lr_units);
     for (int p = 0; p < 3; p++) cudaFree(s.d_digest[p]);
+    if (s.s_rc) cudaStreamDestroy(s.s_rc);
+    cudaFree(s.d_rc_region); cudaFree(s.d_rc_len); cudaFree(s.d_rc_bytes); cudaFreeHost(s.h_rc_len); cudaFreeHost(s.h_rc_bytes);
     cudaFree(s.d_mode_cls); cudaFree(s.d_blk_count); cudaFree(s.d_sb_off); cudaFree(s.d_tokens);
     cudaFreeHost(s.h_sb_off); cudaFreeHost(s.h_tokens);
-    for (cudaEvent_t ev : {s.ev_h2d, s.ev_k0, s.ev_me, s.ev_k1, s.ev_d2h, s.ev_src, s.ev_tok0, s.ev_tok1}) if (ev) cudaEventDestroy(ev);
+    for (cudaEvent_t ev : {s.ev_h2d, s.ev_k0, s.ev_me, s.ev_k1, s.ev_d2h, s.ev_src, s.ev_tok0, s.ev_tok1, s.ev_rc0, s.ev_rc1}) if (ev) cudaEventDestroy(ev);
     for (cudaEvent_t ev : s.ev_frame) if (ev) cudaEventDestroy(ev);
   }
   for (int p = 0; p < 3; p++) {
@@ -213,6 +232,7 @@ static void free_all(av1b_encoder* e) {
   cudaFree(e->d_map_key); cudaFree(e->d_map_inter);
   cudaFree(e->d_mv2); cudaFree(e->d_mvs);
   cudaFree(e->d_sb_of_order); cudaFree(e->d_tile_of_sb); cudaFree(e->d_lr_sse);
+  cudaFree(e->d_cdf_init); cudaFree(e->d_tile_first_k); cudaFree(e->d_rc_overflow);
   if (e->s_tok) cudaStreamDestroy(e->s_tok);
   if (e->stream) cudaStreamDestroy(e->stream);
   if (e->s_in) cudaStreamDestroy(e->s_in);
@@ -415,6 +435,19 @@ static int launch(av1b_encoder* e, Slot& s, const Slot& in, int n, int64_t first
   }
   CK(cudaEventRecord(s.ev_tok1, e->stream));
   CK(cudaEventRecord(s.ev_k1, e->stream));
+  const bool rc = s.has_tokens && e->rc_on;
+  if (rc) {
+    // the range coder of this batch runs beside the kernels of the next one
+    RcLaunch& R = s.rl;
+    R.n_frames = n; R.n_tiles = e->g_inter.tile_cols * e->g_inter.tile_rows; R.nsb = (int)nsb; R.inter_mask = s.tl.inter_mask;
+    R.tokens = s.d_tokens; R.tok_cap = (uint32_t)s.tok_cap; R.sb_off = s.d_sb_off; R.tile_first_k = e->d_tile_first_k; R.cdf_init = e->d_cdf_init;
+    R.region = s.d_rc_region; R.tile_len = s.d_rc_len; R.bytes = s.d_rc_bytes; R.cap_bytes = (uint32_t)s.rc_cap; R.overflow = e->d_rc_overflow;
+    CK(cudaStreamWaitEvent(s.s_rc, s.ev_k1, 0));
+    CK(cudaEventRecord(s.ev_rc0, s.s_rc));
+    CK(launch_rc(R, s.s_rc));
+    CK(cudaEventRecord(s.ev_rc1, s.s_rc));
+    e->kernel_launches += 3;
+  }
   // symbol streams go home on the output copy stream while the compute stream starts the next batch:
   // token offsets for the inter frames (the token list itself follows once its size is known), levels and
   // block info only for the frames the block-walking tile writer codes (key frames; everything in debug mode)
@@ -430,7 +463,7 @@ static int launch(av1b_encoder* e, Slot& s, const Slot& in, int n, int64_t first
     // the token total is only known once the offsets are home: fetch as many tokens as the last batch had (+25 %)
     // right away, finish() fetches what is missing
     s.tok_fetched = std::min(s.tok_cap, e->tok_guess + e->tok_guess / 4 + 65536);
-    if (e->tok_guess == 0) s.tok_fetched = 0;
+    if (e->tok_guess == 0 || rc) s.tok_fetched = 0;   // with the device range coder the tokens stay on the device
     if (s.tok_fetched) CK(cudaMemcpyAsync(s.h_tokens, s.d_tokens, s.tok_fetched * 4, cudaMemcpyDeviceToHost, e->s_out));
     e->d2h_bytes += (int64_t)s.tok_fetched * 4;
   }
@@ -441,6 +474,16 @@ static int launch(av1b_encoder* e, Slot& s, const Slot& in, int n, int64_t first
     CK(cudaMemcpyAsync(s.h_cdef_idx + (size_t)b * nsb, s.d_cdef_idx + (size_t)b * nsb, nsb, cudaMemcpyDeviceToHost, e->s_out));
     CK(cudaMemcpyAsync(s.h_blocks + (size_t)b * e->map_elems, s.d_blocks + (size_t)b * e->map_elems, e->map_elems * sizeof(Av1bBlockInfo), cudaMemcpyDeviceToHost, e->s_out));
     e->d2h_bytes += (int64_t)((e->plane_elems[0] + e->plane_elems[1] + e->plane_elems[2]) * 2 + nsb + e->map_elems * sizeof(Av1bBlockInfo));
+  }
+  s.rc_fetched = 0;
+  if (rc) {
+    const size_t nt = (size_t)s.rl.n_tiles * n + 1;
+    CK(cudaStreamWaitEvent(e->s_out, s.ev_rc1, 0));
+    CK(cudaMemcpyAsync(s.h_rc_len, s.d_rc_len, nt * sizeof(uint32_t), cudaMemcpyDeviceToHost, e->s_out));
+    e->d2h_bytes += (int64_t)(nt * sizeof(uint32_t));
+    s.rc_fetched = e->rc_guess ? std::min(s.rc_cap, e->rc_guess + e->rc_guess / 4 + 65536) : 0;
+    if (s.rc_fetched) CK(cudaMemcpyAsync(s.h_rc_bytes, s.d_rc_bytes, s.rc_fetched, cudaMemcpyDeviceToHost, e->s_out));
+    e->d2h_bytes += (int64_t)s.rc_fetched;
   }
   CK(cudaEventRecord(s.ev_d2h, e->s_out));
   return AV1B_OK;
@@ -469,9 +512,11 @@ static int finish(av1b_encoder* e, Slot& s, bool staged, av1b_packet_cb out_cb, 
   }
   cudaEventElapsedTime(&ms, s.ev_tok0, s.ev_tok1); e->t_tok_ms += ms;
   const size_t nsb = (size_t)g.sb_rows * g.sb_cols;
+  const bool rc = s.has_tokens && e->rc_on;
   if (s.has_tokens) {
     // the batch's token total is known now: make room if needed (then the tokens are written again), fetch them
     size_t total = s.h_sb_off[nsb * n];
+    bool redo = false;
     if (total > s.tok_cap) {
       const size_t cap = total + total / 4;
       cudaFree(s.d_tokens); cudaFreeHost(s.h_tokens); s.d_tokens = nullptr; s.h_tokens = nullptr; s.tok_cap = 0;
@@ -480,11 +525,45 @@ static int finish(av1b_encoder* e, Slot& s, bool staged, av1b_packet_cb out_cb, 
       }
       s.tok_cap = cap;
       s.tl.tokens = s.d_tokens; s.tl.cap = (uint32_t)cap;
+      if (e->rc_on) {
+        cudaFree(s.d_rc_region); s.d_rc_region = nullptr;
+        if (cudaMalloc(&s.d_rc_region, 2 * cap + 64 * (size_t)s.rl.n_tiles * e->batch) != cudaSuccess) { set_error("range coder scratch: out of memory"); return AV1B_ERR_NOMEM; }
+        s.rl.tokens = s.d_tokens; s.rl.tok_cap = (uint32_t)cap; s.rl.region = s.d_rc_region;
+      }
       CK(launch_tok_emit(s.tl, e->stream));
       CK(cudaStreamSynchronize(e->stream));
       s.tok_fetched = 0;
+      redo = true;
     }
-    if (total > s.tok_fetched) {
+    if (rc) {
+      const size_t nt = (size_t)s.rl.n_tiles * n;
+      for (int attempt = 0; attempt < 3; attempt++) {
+        if (redo) {
+          CK(launch_rc(s.rl, e->stream));
+          CK(cudaMemcpyAsync(s.h_rc_len, s.d_rc_len, (nt + 1) * sizeof(uint32_t), cudaMemcpyDeviceToHost, e->stream));
+          CK(cudaStreamSynchronize(e->stream));
+          s.rc_fetched = 0;
+        }
+        const size_t bytes = s.h_rc_len[nt];
+        if (bytes <= s.rc_cap) break;
+        // payloads larger than the byte buffers: grow them and code again
+        const size_t cap = bytes + bytes / 4;
+        cudaFree(s.d_rc_bytes); cudaFreeHost(s.h_rc_bytes); s.d_rc_bytes = nullptr; s.h_rc_bytes = nullptr; s.rc_cap = 0;
+        if (cudaMalloc(&s.d_rc_bytes, cap) != cudaSuccess || cudaMallocHost(&s.h_rc_bytes, cap) != cudaSuccess) { set_error("payload buffers: out of memory"); return AV1B_ERR_NOMEM; }
+        s.rc_cap = cap; s.rl.bytes = s.d_rc_bytes; s.rl.cap_bytes = (uint32_t)cap;
+        redo = true;
+      }
+      const size_t bytes = s.h_rc_len[nt];
+      if (bytes > s.rc_fetched) {
+        const auto tc0 = std::chrono::steady_clock::now();
+        CK(cudaMemcpyAsync(s.h_rc_bytes + s.rc_fetched, s.d_rc_bytes + s.rc_fetched, bytes - s.rc_fetched, cudaMemcpyDeviceToHost, e->s_tok));
+        CK(cudaStreamSynchronize(e->s_tok));
+        e->d2h_bytes += (int64_t)(bytes - s.rc_fetched);
+        e->t_d2h_ms += std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - tc0).count();
+      }
+      e->rc_guess = bytes;
+      cudaEventElapsedTime(&ms, s.ev_rc0, s.ev_rc1); e->t_rc_ms += ms;
+    } else if (total > s.tok_fetched) {
       const auto tc0 = std::chrono::steady_clock::now();
       CK(cudaMemcpyAsync(s.h_tokens + s.tok_fetched, s.d_tokens + s.tok_fetched, (total - s.tok_fetched) * 4, cudaMemcpyDeviceToHost, e->s_tok));
       CK(cudaStreamSynchronize(e->s_tok));
@@ -510,7 +589,10 @@ static int finish(av1b_encoder* e, Slot& s, bool staged, av1b_packet_cb out_cb, 
   }
   e->pool->parallel_for((int)tasks.size(), [&](int t) {
     const int b = tasks[t].first, tile = tasks[t].second;
-    if (!s.is_key[b] && s.has_tokens) {
+    if (!s.is_key[b] && rc) {
+      const uint32_t* o = s.h_rc_len + (size_t)b * s.rl.n_tiles + tile;
+      packs[b].tiles[tile].assign(s.h_rc_bytes + o[0], s.h_rc_bytes + o[1]);
+    } else if (!s.is_key[b] && s.has_tokens) {
       const uint32_t* off = s.h_sb_off + (size_t)b * nsb;
       const uint32_t t0 = off[e->tile_first_k[tile]];
       // the entry after a frame's last superblock is the next frame's first (or the batch total)
@@ -554,7 +636,7 @@ static int finish(av1b_encoder* e, Slot& s, bool staged, av1b_packet_cb out_cb, 
 static void reset_stats(av1b_encoder* e) {
   e->kept.clear();
   e->t_h2d_ms = e->t_kernel_ms = e->t_intra_ms = e->t_inter_ms = e->t_me_ms = e->t_d2h_ms = e->t_pack_ms = 0;
-  e->t_deblock_ms = e->t_cdef_ms = e->t_tok_ms = 0; e->t_lr_ms = 0; e->n_tokens = 0; e->d2h_bytes = 0;
+  e->t_deblock_ms = e->t_cdef_ms = e->t_tok_ms = 0; e->t_lr_ms = 0; e->t_rc_ms = 0; e->n_tokens = 0; e->d2h_bytes = 0;
   e->kernel_launches = e->intra_launches = e->inter_launches = e->frames_done = e->bytes_out = e->key_frames = e->staged_direct = 0;
 }
 
@@ -595,9 +677,17 @@ int av1b_encoder_create(const av1b_config* cfg, av1b_encoder** out) {
   if (trl < 0) trl = av1b_tile_log2(2, probe.sb_rows);
   av1b_geom_init(&e->g, cfg->width, cfg->height, tcl, trl);
   {
-    // tiles of inter frames only serve host-side parallelism: about 12x12 superblocks each unless given explicitly
-    const int itc = cfg->tile_cols_log2 >= 0 ? cfg->tile_cols_log2 : av1b_tile_log2(12, probe.sb_cols);
-    const int itr = cfg->tile_rows_log2 >= 0 ? cfg->tile_rows_log2 : av1b_tile_log2(12, probe.sb_rows);
+    // tiles of inter frames are the unit of entropy-coder parallelism.  The host coder wants few large ones (longer
+    // CDF adaptation): about 12x12 superblocks.  The device coder walks a tile with one warp, a serial chain of about
+    // 100 ns per symbol, so its latency is that of the largest tile: about 6x6 superblocks (reserved[7] overrides).
+    // Where the range coder runs (reserved[5] = 0: automatic): a tile costs one host thread about 15 ns per symbol
+    // and one warp about 0.5 us beside the other kernels, so with a dozen host threads for this GPU the host is the
+    // faster place; with fewer (8 GPUs on a 32-core box: 4 each) the host would throttle the GPU and the device codes.
+    const int ht = cfg->host_threads > 0 ? cfg->host_threads : (int)std::max(1u, std::thread::hardware_concurrency());
+    e->rc_on = cfg->reserved[5] == 4 || (cfg->reserved[5] == 0 && ht < 12);
+    const int tsb = cfg->reserved[7] > 0 ? cfg->reserved[7] : (e->rc_on ? 6 : 12);
+    const int itc = cfg->tile_cols_log2 >= 0 ? cfg->tile_cols_log2 : av1b_tile_log2(tsb, probe.sb_cols);
+    const int itr = cfg->tile_rows_log2 >= 0 ? cfg->tile_rows_log2 : av1b_tile_log2(tsb, probe.sb_rows);
     av1b_geom_init(&e->g_inter, cfg->width, cfg->height, itc, itr);
   }
   e->seq.width = cfg->width; e->seq.height = cfg->height; e->seq.bit_depth = cfg->bit_depth;
@@ -612,7 +702,7 @@ int av1b_encoder_create(const av1b_config* cfg, av1b_encoder** out) {
   e->blk_log2 = cfg->reserved[1] ? cfg->reserved[1] : 4;
   if (e->blk_log2 < 3 || e->blk_log2 > 6) { set_error("block log2 must be 3..6"); delete e; return AV1B_ERR_INVALID; }
   e->keep = cfg->reserved[0] != 0;
-  e->token_path = cfg->reserved[5] == 0;
+  e->token_path = cfg->reserved[5] == 0 || cfg->reserved[5] == 3 || cfg->reserved[5] == 4;
   e->legacy_pack_levels = (cfg->reserved[5] == 2 && !e->keep) ? 1 : 0;
   e->intra_only = cfg->reserved[3] != 0;      // reserved[3] = 1: every frame is a key frame
   e->keyint = cfg->keyint > 0 ? cfg->keyint : 240;
@@ -638,12 +728,17 @@ int av1b_encoder_create(const av1b_config* cfg, av1b_encoder** out) {
   A(cudaStreamCreateWithFlags(&e->s_in, cudaStreamNonBlocking));
   A(cudaStreamCreateWithFlags(&e->s_out, cudaStreamNonBlocking));
   A(cudaStreamCreateWithFlags(&e->s_tok, cudaStreamNonBlocking));
+  {
+    int lo = 0, hi = 0;
+    cudaDeviceGetStreamPriorityRange(&lo, &hi);
+    for (auto& s : e->slot) A(cudaStreamCreateWithPriority(&s.s_rc, cudaStreamNonBlocking, hi));   // its few warps should start promptly
+  }
   e->map_elems = (size_t)e->g.w8 * e->g.h8;
   const size_t nsb = (size_t)e->g.sb_rows * e->g.sb_cols;
   for (int p = 0; p < 3; p++) e->plane_elems[p] = (size_t)e->g.stride[p] * e->g.rows[p];
   const int F = e->batch;
   for (auto& s : e->slot) {
-    for (cudaEvent_t* ev : {&s.ev_h2d, &s.ev_k0, &s.ev_me, &s.ev_k1, &s.ev_d2h, &s.ev_src, &s.ev_tok0, &s.ev_tok1}) A(cudaEventCreate(ev));
+    for (cudaEvent_t* ev : {&s.ev_h2d, &s.ev_k0, &s.ev_me, &s.ev_k1, &s.ev_d2h, &s.ev_src, &s.ev_tok0, &s.ev_tok1, &s.ev_rc0, &s.ev_rc1}) A(cudaEventCreate(ev));
     s.ev_frame.assign((size_t)F * 5, nullptr);
     for (auto& ev : s.ev_frame) A(cudaEventCreate(&ev));
     for (int p = 0; p < 3; p++) {
@@ -669,6 +764,15 @@ int av1b_encoder_create(const av1b_config* cfg, av1b_encoder** out) {
       s.tok_cap = (size_t)cfg->width * cfg->height / 4 * F;
       A(cudaMalloc(&s.d_tokens, s.tok_cap * 4));
       A(cudaMallocHost(&s.h_tokens, s.tok_cap * 4));
+      if (e->rc_on) {
+        const size_t nt = (size_t)e->g_inter.tile_cols * e->g_inter.tile_rows * F;
+        A(cudaMalloc(&s.d_rc_region, 2 * s.tok_cap + 64 * nt));
+        A(cudaMalloc(&s.d_rc_len, (nt + 1) * sizeof(uint32_t)));
+        A(cudaMallocHost(&s.h_rc_len, (nt + 1) * sizeof(uint32_t)));
+        s.rc_cap = s.tok_cap / 2;   // bytes; grows on demand
+        A(cudaMalloc(&s.d_rc_bytes, s.rc_cap));
+        A(cudaMallocHost(&s.h_rc_bytes, s.rc_cap));
+      }
     }
   }
   if (e->token_path && !e->intra_only) {
@@ -691,6 +795,18 @@ int av1b_encoder_create(const av1b_config* cfg, av1b_encoder** out) {
     if (err == cudaSuccess) {
       A(cudaMemcpy(e->d_sb_of_order, order.data(), nsb * sizeof(uint32_t), cudaMemcpyHostToDevice));
       A(cudaMemcpy(e->d_tile_of_sb, tile_of.data(), nsb * sizeof(uint16_t), cudaMemcpyHostToDevice));
+    }
+    if (e->rc_on) {
+      std::vector<uint8_t> img(tile_cdfs_size());
+      tile_cdfs_default(e->base_q_idx, img.data());
+      A(cudaMalloc(&e->d_cdf_init, img.size()));
+      A(cudaMalloc(&e->d_tile_first_k, e->tile_first_k.size() * sizeof(uint32_t)));
+      A(cudaMalloc(&e->d_rc_overflow, sizeof(uint32_t)));
+      if (err == cudaSuccess) {
+        A(cudaMemcpy(e->d_cdf_init, img.data(), img.size(), cudaMemcpyHostToDevice));
+        A(cudaMemcpy(e->d_tile_first_k, e->tile_first_k.data(), e->tile_first_k.size() * sizeof(uint32_t), cudaMemcpyHostToDevice));
+        A(cudaMemset(e->d_rc_overflow, 0, sizeof(uint32_t)));
+      }
     }
     if (av1t_ext_tx_ind[4][AV1B_DCT_DCT] != 3 || av1t_ext_tx_ind[5][AV1B_DCT_DCT] != 7) { set_error("transform-type symbol tables changed"); free_all(e); delete e; return AV1B_ERR_INTERNAL; }
   }
@@ -895,11 +1011,11 @@ void av1b_host_free(void* p) {
 
 int av1b_get_stats(av1b_encoder* e, double* stats, int n) {
   if (!e || !stats) return AV1B_ERR_INVALID;
-  const double v[21] = {e->t_h2d_ms, e->t_kernel_ms, e->t_d2h_ms, e->t_pack_ms, (double)e->kernel_launches,
+  const double v[22] = {e->t_h2d_ms, e->t_kernel_ms, e->t_d2h_ms, e->t_pack_ms, (double)e->kernel_launches,
                         (double)e->base_q_idx, e->t_intra_ms, (double)e->intra_launches, (double)e->frames_done,
                         (double)e->bytes_out, e->t_deblock_ms, e->t_cdef_ms, e->t_inter_ms, e->t_me_ms,
-                        (double)e->inter_launches, (double)e->key_frames, (double)e->staged_direct, e->t_tok_ms, (double)e->n_tokens, (double)e->d2h_bytes, e->t_lr_ms};
-  for (int i = 0; i < n && i < 21; i++) stats[i] = v[i];
+                        (double)e->inter_launches, (double)e->key_frames, (double)e->staged_direct, e->t_tok_ms, (double)e->n_tokens, (double)e->d2h_bytes, e->t_lr_ms, e->t_rc_ms};
+  for (int i = 0; i < n && i < 22; i++) stats[i] = v[i];
   return AV1B_OK;
 }
 

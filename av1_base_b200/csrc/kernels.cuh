@@ -136,6 +136,24 @@ struct TokLaunch {
   const Av1bLrUnit* lr_units;    // [n_frames][lr_rows*lr_cols] luma restoration units, or nullptr
   int32_t lr_rows, lr_cols;
 };
+// Range coding of the token lists on the device (rc_kernel.cu): one warp per (frame, tile) of the batch's inter frames.
+struct RcLaunch {
+  int32_t n_frames, n_tiles, nsb;
+  uint64_t inter_mask;
+  const uint32_t* tokens;
+  uint32_t tok_cap;              // capacity of `tokens`: tiles that end beyond it are left for the retry
+  const uint32_t* sb_off;        // [n_frames * nsb + 1] token offsets (TokLaunch)
+  const uint32_t* tile_first_k;  // [n_tiles + 1] first coding-order superblock of each tile
+  const void* cdf_init;          // TileCdfs image of the frame's quantiser class (default CDFs)
+  uint8_t* region;               // scratch: tile (f, t) writes at 2 * (its first token) + 64 * (f * n_tiles + t)
+  uint32_t* tile_len;            // [n_frames * n_tiles + 1]: byte counts, then (after the scan) offsets + total
+  uint8_t* bytes;                // the batch's tile payloads, contiguous in (frame, tile) order
+  uint32_t cap_bytes;
+  uint32_t* overflow;            // set to 1 when a tile's region was too small
+};
+cudaError_t launch_rc(const RcLaunch& p, cudaStream_t s);
+// in-place exclusive scan of v[0..n) on the device, v[n] = total
+cudaError_t launch_scan_u32(uint32_t* v, int n, cudaStream_t s);
 // mode classes + token counts + offsets (exclusive scan); then launch_tok_emit writes the tokens
 cudaError_t launch_tok_count(const TokLaunch& p, cudaStream_t s);
 cudaError_t launch_tok_emit(const TokLaunch& p, cudaStream_t s);

@@ -175,6 +175,11 @@ __global__ void __launch_bounds__(1024) tok_scan_kernel(uint32_t* v, int n) {
 
 }  // namespace
 
+cudaError_t launch_scan_u32(uint32_t* v, int n, cudaStream_t s) {
+  tok_scan_kernel<<<1, 1024, 0, s>>>(v, n);
+  return cudaGetLastError();
+}
+
 cudaError_t launch_tok_count(const TokLaunch& p, cudaStream_t s) {
   const int units = p.g.w8 * p.g.h8, nsb = p.g.sb_rows * p.g.sb_cols;
   tok_mode_kernel<<<dim3((units + 127) / 128, p.n_frames), 128, 0, s>>>(p);

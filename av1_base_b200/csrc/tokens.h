@@ -57,7 +57,9 @@ struct TileCdfs {
   struct MvComp {
     uint16_t classes[12], class0_fp[2][5], fp[5], sign[3], class0_hp[3], hp[3], class0[3], bits[10][3];
   } mvc[2];
+  uint16_t pad_[1];   // size multiple of 4 bytes (copied as 32-bit words on the device)
 };
+static_assert(sizeof(TileCdfs) % 4 == 0, "TileCdfs is copied as 32-bit words");
 static_assert(sizeof(TileCdfs) / 2 < 0xFFF0, "CDF offsets must fit 16 bits");
 
 enum : uint32_t { TOK_RAW = 0xFFFFu, TOK_GOLOMB = 0xFFFEu, TOK_PART_EDGE = 0xFFFDu, TOK_LR = 0xFFFCu, TOK_FIRST_SPECIAL = TOK_LR };

@@ -28,7 +28,7 @@ class Encoder:
     def __init__(self, width, height, bit_depth=10, crf=30, preset=6, keyint=240, fps=(30, 1), device_id=0,
                  tile_cols_log2=-1, tile_rows_log2=-1, hdr=False, host_threads=0, frames_in_flight=0,
                  keep_debug=False, blk_log2=0, loop_filters=True, intra_only=False, tb_zero_thr=0, raster_levels=False,
-                 pack_path=0):
+                 pack_path=0, lr_off=False, tile_sb=0):
         L = abi.lib()
         cfg = abi.Config()
         L.av1b_config_default(C.byref(cfg))
@@ -45,9 +45,11 @@ class Encoder:
         cfg.reserved[2] = 0 if loop_filters else 1
         cfg.reserved[3] = 1 if intra_only else 0
         cfg.reserved[4] = tb_zero_thr
-        # inter-frame entropy coding path: 0 device tokenizer (default), 1 host block walker over raster levels,
-        # 2 host block walker over in-place packed symbols
+        # inter-frame entropy coding path: 0 device tokenizer, range coder where it is faster (default), 3 device tokenizer +
+        # host range coder, 4 device tokenizer + device range coder, 1 host block walker over raster levels, 2 host block walker over in-place packed symbols
         cfg.reserved[5] = 1 if raster_levels else pack_path
+        cfg.reserved[6] = int(lr_off)
+        cfg.reserved[7] = tile_sb          # inter-frame tile size in superblocks (0 = default)
         self.cfg = cfg
         self._h = C.c_void_p()
         _check(L.av1b_encoder_create(C.byref(cfg), C.byref(self._h)))
@@ -115,13 +117,13 @@ class Encoder:
         return blocks, coef
 
     def stats(self):
-        s = (C.c_double * 21)()
-        _check(abi.lib().av1b_get_stats(self._h, s, 21))
+        s = (C.c_double * 22)()
+        _check(abi.lib().av1b_get_stats(self._h, s, 22))
         return dict(h2d_ms=s[0], kernel_ms=s[1], d2h_ms=s[2], pack_ms=s[3], kernel_launches=int(s[4]),
                     base_q_idx=int(s[5]), intra_ms=s[6], intra_launches=int(s[7]), frames_done=int(s[8]),
                     bytes_out=int(s[9]), deblock_ms=s[10], cdef_ms=s[11], inter_ms=s[12], me_ms=s[13],
                     inter_launches=int(s[14]), key_frames=int(s[15]), staged_direct=int(s[16]), tok_ms=s[17],
-                    tokens=int(s[18]), d2h_bytes=int(s[19]), lr_ms=s[20])
+                    tokens=int(s[18]), d2h_bytes=int(s[19]), lr_ms=s[20], rc_ms=s[21])
 
     def lr_units(self, frame):
         """Luma restoration units [rows, cols] of a kept frame (preset <= 5, keep_debug=True)."""

@@ -236,6 +236,8 @@ def main():
     ap.add_argument("--crf", type=int, default=30)
     ap.add_argument("--keyint", type=int, default=240)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--tile-sb", type=int, default=0, help="inter-frame tile size in superblocks (0 = encoder default)")
+    ap.add_argument("--pack-path", type=int, default=0, help="0 auto, 3 device tokenizer + host range coder, 4 device tokenizer + device range coder")
     ap.add_argument("--preset", type=int, default=6, help="<= 5 adds loop restoration (the BASELINE configs name preset 6)")
     args = ap.parse_args()
 
@@ -270,7 +272,7 @@ def main():
         frames = frames[rank % len(frames):] + frames[:rank % len(frames)]
     from av1_base_b200 import sharding
     # ranks share the node's host cores: each rank entropy-codes with its share of them
-    enc = encoder.Encoder(w, h, bd, crf=args.crf, device_id=local_rank, hdr=hdr, frames_in_flight=F, keyint=args.keyint, preset=args.preset,
+    enc = encoder.Encoder(w, h, bd, crf=args.crf, device_id=local_rank, hdr=hdr, frames_in_flight=F, keyint=args.keyint, preset=args.preset, tile_sb=args.tile_sb, pack_path=args.pack_path,
                           host_threads=sharding.host_threads_per_rank(world))
     g = enc.geom
     frame_bytes = sum(g.stride[p] * (h if p == 0 else h // 2) * 2 for p in range(3))
@@ -350,7 +352,7 @@ def main():
         "scaling": "weak", "vs_baseline": None, "dtype": "u16/i32", "data": "synthetic",
         "config": {"workload": desc, "frames_per_step": F, "crf": args.crf, "preset": args.preset, "base_q_idx": st["base_q_idx"],
                    "keyint": args.keyint, "key_frames": st["key_frames"], "inter_frames": st["inter_launches"],
-                   "tiles_key_frames": "%dx%d" % (g.tile_cols, g.tile_rows), "host_threads": sharding.host_threads_per_rank(world),
+                   "tiles_key_frames": "%dx%d" % (g.tile_cols, g.tile_rows), "tile_sb_inter": args.tile_sb, "pack_path": args.pack_path, "host_threads": sharding.host_threads_per_rank(world),
                    "l2": "inputs larger than L2 (%.0f MB working set per step)" % (5 * F * frame_bytes / 1e6),
                    "timing": "wall clock between synchronize+barrier pairs (host entropy coding is part of the step); "
                              "kernel times from CUDA events on the encoder stream"},
@@ -360,7 +362,7 @@ def main():
                 "breakdown_ms_per_step": {k: st_e[k] / args.steps for k in ("h2d_ms", "kernel_ms", "d2h_ms", "pack_ms")}},
         "gpu_launches": st["kernel_launches"],
         "breakdown_ms_per_step": {k: st[k] / args.steps for k in ("kernel_ms", "me_ms", "intra_ms", "inter_ms", "deblock_ms",
-                                                                   "cdef_ms", "lr_ms", "tok_ms", "d2h_ms", "pack_ms")},
+                                                                   "cdef_ms", "lr_ms", "tok_ms", "rc_ms", "d2h_ms", "pack_ms")},
         "tokens_per_frame": st["tokens"] / max(1, st["inter_launches"]),
         "roofline": {"kernel": dom, "bound": "hbm", "achieved": achieved, "peak": pk["hbm_gbs"],
                      "unit": "GB/s", "frac": achieved / pk["hbm_gbs"], "traffic": traffic, "peak_source": pk_src,

@@ -49,9 +49,12 @@ typedef struct av1b_config {
   int32_t reserved[8];            /* [0]: keep recon+symbols per frame (tests); [1]: fixed block log2 (3..6), 0 = default;
                                      [2]: 1 = in-loop filters off; [3]: 1 = every frame is a key frame;
                                      [4]: inter transform-block drop threshold (0 = off);
-                                     [5]: inter-frame entropy coding path: 0 = device tokenizer + host range coder over tokens (default),
+                                     [5]: inter-frame entropy coding path: 0 = device tokenizer, range coder on the device when this encoder has fewer
+                                          than 12 host threads, else on the host (default); 3 = device tokenizer + host range coder; 4 = device
+                                          tokenizer + device range coder;
                                           1 = host block walker over raster levels, 2 = host block walker over in-place packed symbols;
-                                     [6]: 1 = loop restoration off whatever the preset */
+                                     [6]: 1 = loop restoration off whatever the preset;
+                                     [7]: target inter-frame tile size in superblocks (0 = default: 6 with the device range coder, else 12) */
 } av1b_config;
 
 typedef struct av1b_encoder av1b_encoder;
@@ -116,10 +119,10 @@ int av1b_select_frame_params(int bit_depth, int base_q_idx, int frame_type, int 
  * the context of `device` (one the caller encodes on) and is usable from every device.  NULL on failure. */
 void* av1b_host_alloc(int device, size_t bytes);
 void av1b_host_free(void* p);
-/* stats[0..20] = h2d_ms, kernel_ms, d2h_ms, pack_ms, kernel_launches, base_q_idx, intra_kernel_ms,
+/* stats[0..21] = h2d_ms, kernel_ms, d2h_ms, pack_ms, kernel_launches, base_q_idx, intra_kernel_ms,
  * intra_kernel_launches, frames_done, bytes_out, deblock_ms, cdef_ms, inter_kernel_ms, me_ms (pyramid + search),
  * inter_kernel_launches, key_frames, frames uploaded straight from page-locked caller memory, tokenizer_ms,
- * tokens produced, bytes copied device -> host, loop_restoration_ms, of the last chunk / resident run (CUDA-event times) */
+ * tokens produced, bytes copied device -> host, loop_restoration_ms, range_coder_ms (overlaps the next batch), of the last chunk / resident run (CUDA-event times) */
 int av1b_get_stats(av1b_encoder* enc, double* stats, int n);
 
 /* ---- kernel suite (BASELINE.json config 2 "kernel bit-exact suite") -----------------------------

@@ -19,6 +19,8 @@ CASES = [
     (328, 248, 8, 30, 1, 1, True, 7, 3, 240, 3),
     (640, 360, 10, 35, -1, -1, True, 4, 4, 240, 5),
 ]
+# every case also through the device range coder (pack_path 4); 0 = automatic placement
+CASES = [c + (pp,) for c in CASES for pp in (0, 4)]
 
 
 def oracle_filters(g, bd, fp, res, frame, lr, acq):
@@ -40,11 +42,11 @@ def ac_q(bd, qidx):
     return [int(v) for v in re.findall(r"-?\d+", m.group(1))][qidx]
 
 
-@pytest.mark.parametrize("w,h,bd,crf,tcl,trl,lf,nfr,fif,keyint,preset", CASES)
-def test_chunk_parity(w, h, bd, crf, tcl, trl, lf, nfr, fif, keyint, preset):
+@pytest.mark.parametrize("w,h,bd,crf,tcl,trl,lf,nfr,fif,keyint,preset,pack_path", CASES)
+def test_chunk_parity(w, h, bd, crf, tcl, trl, lf, nfr, fif, keyint, preset, pack_path):
     frames = synth.synth_clip(w, h, bd, nfr, seed=w + bd, scene_len=100)
     enc = encoder.Encoder(w, h, bd, crf=crf, keep_debug=True, tile_cols_log2=tcl, tile_rows_log2=trl,
-                          frames_in_flight=fif, loop_filters=lf, keyint=keyint, preset=preset)
+                          frames_in_flight=fif, loop_filters=lf, keyint=keyint, preset=preset, pack_path=pack_path)
     lr = lf and preset <= 5
     tus = enc.encode_chunk(frames)
     assert len(tus) == nfr
@@ -91,27 +93,31 @@ def test_chunk_parity(w, h, bd, crf, tcl, trl, lf, nfr, fif, keyint, preset):
 @pytest.mark.parametrize("w,h,bd,crf,tcl,trl", [(200, 136, 10, 20, -1, -1), (328, 248, 8, 40, 1, 1), (640, 360, 10, 30, -1, -1),
                                                 (328, 248, 10, 2, 0, 1), (1920, 1080, 10, 35, -1, -1)])
 def test_token_path_gives_identical_streams(w, h, bd, crf, tcl, trl):
-    """Production mode tokenizes inter frames on the device (one token per coded symbol, tokens.h) and the host only
-    range-codes the token lists.  The bitstream must equal, byte for byte, what the host block walker writes from
+    """Production mode tokenizes inter frames on the device (one token per coded symbol, tokens.h) and range-codes
+    the token lists there too (one warp per tile, rc_kernel.cu); the host range coder over the same tokens is the
+    CPU statement.  The bitstream must equal, byte for byte, what the host block walker writes from
     raster levels and from in-place packed symbols, and it must decode to the reconstruction.  CRF 2 exercises
     the Golomb escapes, 1080p the picture-edge 8x8 blocks and several tiles."""
     nfr = 5 if w < 1000 else 3
     frames = synth.synth_clip(w, h, bd, nfr, seed=3, scene_len=100)
-    kw = dict(crf=crf, frames_in_flight=2, tile_cols_log2=tcl, tile_rows_log2=trl)
+    kw = dict(crf=crf, frames_in_flight=2, tile_cols_log2=tcl, tile_rows_log2=trl, tile_sb=6)
     a = encoder.Encoder(w, h, bd, pack_path=1, **kw)
-    b = encoder.Encoder(w, h, bd, **kw)
+    b = encoder.Encoder(w, h, bd, pack_path=4, **kw)    # device tokenizer + device range coder
     d = encoder.Encoder(w, h, bd, pack_path=2, **kw)
-    ta, tb, td = a.encode_chunk(frames), b.encode_chunk(frames), d.encode_chunk(frames)
+    h3 = encoder.Encoder(w, h, bd, pack_path=3, **kw)   # device tokenizer, range coder on the host
+    ta, tb, td, th = a.encode_chunk(frames), b.encode_chunk(frames), d.encode_chunk(frames), h3.encode_chunk(frames)
     assert b.stats()["tokens"] > 0 and a.stats()["tokens"] == 0
+    assert th == tb                                      # device range coder == host range coder
     assert [len(x) for x in ta] == [len(x) for x in tb]
     assert ta == tb
     assert td == tb
-    c = encoder.Encoder(w, h, bd, keep_debug=True, **kw)
+    c = encoder.Encoder(w, h, bd, keep_debug=True, pack_path=4, **kw)
     tc = c.encode_chunk(frames)
     assert tc == tb
+    assert b.stats()["rc_ms"] > 0 and h3.stats()["rc_ms"] == 0
     dec = D.dav1d_decode(tb)
     for i in range(len(frames)):
         for p in range(3):
             assert np.array_equal(dec[i][p], c.recon(i)[p])
-    for e in (a, b, c, d):
+    for e in (a, b, c, d, h3):
         e.close()
