@@ -685,7 +685,8 @@ int av1b_encoder_create(const av1b_config* cfg, av1b_encoder** out) {
     // faster place; with fewer (8 GPUs on a 32-core box: 4 each) the host would throttle the GPU and the device codes.
     const int ht = cfg->host_threads > 0 ? cfg->host_threads : (int)std::max(1u, std::thread::hardware_concurrency());
     e->rc_on = cfg->reserved[5] == 4 || (cfg->reserved[5] == 0 && ht < 12);
-    const int tsb = cfg->reserved[7] > 0 ? cfg->reserved[7] : (e->rc_on ? 6 : 12);
+    // (4x4 up to 1080p, where a batch is short and the frame has few tiles)
+    const int tsb = cfg->reserved[7] > 0 ? cfg->reserved[7] : (e->rc_on ? (probe.sb_cols * probe.sb_rows <= 600 ? 4 : 6) : 12);
     const int itc = cfg->tile_cols_log2 >= 0 ? cfg->tile_cols_log2 : av1b_tile_log2(tsb, probe.sb_cols);
     const int itr = cfg->tile_rows_log2 >= 0 ? cfg->tile_rows_log2 : av1b_tile_log2(tsb, probe.sb_rows);
     av1b_geom_init(&e->g_inter, cfg->width, cfg->height, itc, itr);
