@@ -987,8 +987,8 @@ extern "C" void orc_cdef_search(const Av1bGeom* g, int bd, const Av1bBlockInfo* 
         uint64_t e = 0;
         for (int p = 0; p < 3; p++) {
           const int n = p ? 4 : 8;
-          for (int i = 0; i < n; i += 2)      // even rows only (the decision subsamples rows)
-            for (int j = 0; j < n; j++) {
+          for (int i = 0; i < n; i += 2)      // the decision looks at a checkerboard of the even rows (a quarter of the samples)
+            for (int j = (i >> 1) & 1; j < n; j += 2) {
               const size_t o = (size_t)(r8 * n + i) * g->stride[p] + c8 * n + j;
               const int d = (int)out[p][o] - (int)src[p][o];
               e += (uint64_t)(d * d);
