@@ -480,7 +480,8 @@ static int launch(av1b_encoder* e, Slot& s, const Slot& in, int n, int64_t first
     const size_t nt = (size_t)s.rl.n_tiles * n + 1;
     CK(cudaStreamWaitEvent(e->s_out, s.ev_rc1, 0));
     CK(cudaMemcpyAsync(s.h_rc_len, s.d_rc_len, nt * sizeof(uint32_t), cudaMemcpyDeviceToHost, e->s_out));
-    e->d2h_bytes += (int64_t)(nt * sizeof(uint32_t));
+    CK(cudaMemcpyAsync(s.h_rc_len + (size_t)s.rl.n_tiles * e->batch + 1, e->d_rc_overflow, sizeof(uint32_t), cudaMemcpyDeviceToHost, e->s_out));
+    e->d2h_bytes += (int64_t)((nt + 1) * sizeof(uint32_t));
     s.rc_fetched = e->rc_guess ? std::min(s.rc_cap, e->rc_guess + e->rc_guess / 4 + 65536) : 0;
     if (s.rc_fetched) CK(cudaMemcpyAsync(s.h_rc_bytes, s.d_rc_bytes, s.rc_fetched, cudaMemcpyDeviceToHost, e->s_out));
     e->d2h_bytes += (int64_t)s.rc_fetched;
@@ -562,6 +563,7 @@ static int finish(av1b_encoder* e, Slot& s, bool staged, av1b_packet_cb out_cb, 
         e->t_d2h_ms += std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - tc0).count();
       }
       e->rc_guess = bytes;
+      if (s.h_rc_len[(size_t)s.rl.n_tiles * e->batch + 1]) { set_error("range coder: a tile outgrew its region (2 bytes per token + 64)"); return AV1B_ERR_INTERNAL; }
       cudaEventElapsedTime(&ms, s.ev_rc0, s.ev_rc1); e->t_rc_ms += ms;
     } else if (total > s.tok_fetched) {
       const auto tc0 = std::chrono::steady_clock::now();
@@ -769,7 +771,7 @@ int av1b_encoder_create(const av1b_config* cfg, av1b_encoder** out) {
         const size_t nt = (size_t)e->g_inter.tile_cols * e->g_inter.tile_rows * F;
         A(cudaMalloc(&s.d_rc_region, 2 * s.tok_cap + 64 * nt));
         A(cudaMalloc(&s.d_rc_len, (nt + 1) * sizeof(uint32_t)));
-        A(cudaMallocHost(&s.h_rc_len, (nt + 1) * sizeof(uint32_t)));
+        A(cudaMallocHost(&s.h_rc_len, (nt + 2) * sizeof(uint32_t)));   // + the overflow flag
         s.rc_cap = s.tok_cap / 2;   // bytes; grows on demand
         A(cudaMalloc(&s.d_rc_bytes, s.rc_cap));
         A(cudaMallocHost(&s.h_rc_bytes, s.rc_cap));

@@ -47,8 +47,15 @@ def encode(args):
             r, fp = O.encode_intra_frame(g, fr, bd, qkey, pm), fps[0]
         else:
             mv = O.hme(g, pyr, prev_pyr, acq >> 1)
-            r, fp = O.encode_inter_frame(g, fr, bd, qidx, pm, mv, prev_fin, quant_rnd=opts.get("rnd", 48),
-                                         tb_zero_thr=opts.get("thr", 0)), fps[1]
+            qf = qidx
+            if opts.get("qmod"):   # experiment: periodic quantiser modulation inside the P chain
+                per, lo, hi = opts["qmod"]
+                qf = max(1, min(255, qidx + (lo if i % per == 0 else hi)))
+            fp = abi.FrameParams()
+            abi.lib().av1b_select_frame_params(bd, qf, 1, 1, C.byref(fp))
+            fp.tile_cols_log2, fp.tile_rows_log2 = g.tile_cols_log2, g.tile_rows_log2
+            r = O.encode_inter_frame(g, fr, bd, qf, pm, mv, prev_fin, quant_rnd=opts.get("rnd", 48),
+                                     tb_zero_thr=opts.get("thr", 0))
             O.merge_skip_blocks(g, r.blocks)
             nskip += int(np.count_nonzero(r.blocks["skip"]))
         O.deblock_frame(g, bd, r.blocks, r.rec, list(fp.lf_level), fp.lf_sharpness)
@@ -91,11 +98,12 @@ def main():
     ap.add_argument("--verify", action="store_true")
     ap.add_argument("--lr", action="store_true", help="loop restoration decision on (preset <= 5)")
     ap.add_argument("--sgr-set", type=int, default=4)
+    ap.add_argument("--qmod", default="", help="period,delta_low,delta_high: quantiser index offsets inside the P chain (experiment)")
     ap.add_argument("--wv", default="3,-7,15")
     ap.add_argument("--xqd", default="-32,31")
     a = ap.parse_args()
     w, h = map(int, a.size.split("x"))
-    opts = dict(rnd=a.rnd, thr=a.thr, verify=a.verify, lr=a.lr, sgr_set=a.sgr_set, wv=tuple(map(int, a.wv.split(','))), xqd=tuple(map(int, a.xqd.split(','))))
+    opts = dict(rnd=a.rnd, thr=a.thr, verify=a.verify, lr=a.lr, sgr_set=a.sgr_set, wv=tuple(map(int, a.wv.split(','))), xqd=tuple(map(int, a.xqd.split(','))), qmod=tuple(map(int, a.qmod.split(','))) if a.qmod else None)
     jobs = [(w, h, a.bd, a.frames, a.seed, a.noise, crf, opts) for crf in map(int, a.crfs.split(","))]
     with ProcessPoolExecutor(min(8, len(jobs))) as ex:
         res = list(ex.map(encode, jobs))
