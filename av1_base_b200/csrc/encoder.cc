@@ -196,7 +196,8 @@ struct av1b_encoder {
   size_t rc_guess = 0;
   double t_rc_ms = 0;
   cudaStream_t s_tok = nullptr;       // token list download (issued once the batch's total is known)
-  Slot slot[3];                       // batch k+1 uploads / batch k on the GPU / batches k-1, k-2 with the host
+  Slot slot[4];                       // batch k+1 uploads / batch k on the GPU / the batches before with the host or the range coder
+  int n_slots = 3;                    // 4 with the device range coder: its latency (the largest tile) may span two more batches
   size_t tok_guess = 0;               // tokens of the last batch: that much is downloaded before the total is known
   ThreadPool* pool = nullptr;
   int host_threads = 1;
@@ -687,6 +688,7 @@ int av1b_encoder_create(const av1b_config* cfg, av1b_encoder** out) {
     // faster place; with fewer (8 GPUs on a 32-core box: 4 each) the host would throttle the GPU and the device codes.
     const int ht = cfg->host_threads > 0 ? cfg->host_threads : (int)std::max(1u, std::thread::hardware_concurrency());
     e->rc_on = cfg->reserved[5] == 4 || (cfg->reserved[5] == 0 && ht < 12);
+    e->n_slots = (e->rc_on && e->token_path && cfg->reserved[3] == 0) ? 4 : 3;
     // (4x4 up to 1080p, where a batch is short and the frame has few tiles)
     const int tsb = cfg->reserved[7] > 0 ? cfg->reserved[7] : (e->rc_on ? (probe.sb_cols * probe.sb_rows <= 600 ? 4 : 6) : 12);
     const int itc = cfg->tile_cols_log2 >= 0 ? cfg->tile_cols_log2 : av1b_tile_log2(tsb, probe.sb_cols);
@@ -734,13 +736,14 @@ int av1b_encoder_create(const av1b_config* cfg, av1b_encoder** out) {
   {
     int lo = 0, hi = 0;
     cudaDeviceGetStreamPriorityRange(&lo, &hi);
-    for (auto& s : e->slot) A(cudaStreamCreateWithPriority(&s.s_rc, cudaStreamNonBlocking, hi));   // its few warps should start promptly
+    for (int si = 0; si < e->n_slots; si++) A(cudaStreamCreateWithPriority(&e->slot[si].s_rc, cudaStreamNonBlocking, hi));   // its few warps should start promptly
   }
   e->map_elems = (size_t)e->g.w8 * e->g.h8;
   const size_t nsb = (size_t)e->g.sb_rows * e->g.sb_cols;
   for (int p = 0; p < 3; p++) e->plane_elems[p] = (size_t)e->g.stride[p] * e->g.rows[p];
   const int F = e->batch;
-  for (auto& s : e->slot) {
+  for (int si = 0; si < e->n_slots; si++) {
+    Slot& s = e->slot[si];
     for (cudaEvent_t* ev : {&s.ev_h2d, &s.ev_k0, &s.ev_me, &s.ev_k1, &s.ev_d2h, &s.ev_src, &s.ev_tok0, &s.ev_tok1, &s.ev_rc0, &s.ev_rc1}) A(cudaEventCreate(ev));
     s.ev_frame.assign((size_t)F * 5, nullptr);
     for (auto& ev : s.ev_frame) A(cudaEventCreate(&ev));
@@ -867,20 +870,21 @@ static int run_batches(av1b_encoder* e, const av1b_frame_src* frames, uint32_t n
   const uint32_t B = (uint32_t)e->batch;
   int rc, i = 0;
   if ((rc = stage(e, e->slot[0], frames, (int)std::min<uint32_t>(B, n_frames))) != AV1B_OK) return rc;
+  const int S = e->n_slots, L = S - 1;
   for (uint32_t f0 = 0; f0 < n_frames; f0 += B, i++) {
     const int nb = (int)std::min<uint32_t>(B, n_frames - f0);
-    Slot& cur = e->slot[i % 3];
+    Slot& cur = e->slot[i % S];
     if ((rc = launch(e, cur, cur, nb, first_index + f0)) != AV1B_OK) return rc;
     if (f0 + B < n_frames) {
-      Slot& nx = e->slot[(i + 1) % 3];
-      if (i > 1) CK(cudaStreamWaitEvent(e->s_in, nx.ev_k1, 0));   // batch i-2 has read that slot's sources
+      Slot& nx = e->slot[(i + 1) % S];
+      if (i >= L) CK(cudaStreamWaitEvent(e->s_in, nx.ev_k1, 0));   // batch i+1-S has read that slot's sources
       if ((rc = stage(e, nx, frames + f0 + B, (int)std::min<uint32_t>(B, n_frames - f0 - B))) != AV1B_OK) return rc;
     }
-    // the slot of batch i+1 is that of batch i-2: its packets must be out before the next launch
-    if (i > 1 && (rc = finish(e, e->slot[(i - 2) % 3], true, out_cb, prog_cb, user, total_frames, t0)) != AV1B_OK) return rc;
+    // the slot of batch i+1 is that of batch i+1-S: its packets must be out before the next launch
+    if (i >= L && (rc = finish(e, e->slot[(i - L) % S], true, out_cb, prog_cb, user, total_frames, t0)) != AV1B_OK) return rc;
   }
-  for (int k = std::max(0, i - 2); k < i; k++)
-    if ((rc = finish(e, e->slot[k % 3], true, out_cb, prog_cb, user, total_frames, t0)) != AV1B_OK) return rc;
+  for (int k = std::max(0, i - L); k < i; k++)
+    if ((rc = finish(e, e->slot[k % S], true, out_cb, prog_cb, user, total_frames, t0)) != AV1B_OK) return rc;
   return AV1B_OK;
 }
 
@@ -926,15 +930,16 @@ int av1b_encode_resident(av1b_encoder* e, uint32_t n_steps, av1b_packet_cb out_c
   int rc;
   int64_t idx = 0;
   const int n0 = e->slot[0].n_frames, n1 = e->slot[1].n_frames;
-  // sources alternate between the two staged slots; results go through all three slots like in run_batches
+  // sources alternate between the two staged slots; results go through all slots like in run_batches
+  const int S = e->n_slots, L = S - 1;
   for (uint32_t i = 0; i < n_steps; i++) {
     const int nb = (i & 1) ? n1 : n0;
-    if ((rc = launch(e, e->slot[i % 3], e->slot[i & 1], nb, idx)) != AV1B_OK) return rc;
+    if ((rc = launch(e, e->slot[i % S], e->slot[i & 1], nb, idx)) != AV1B_OK) return rc;
     idx += nb;
-    if (i > 1 && (rc = finish(e, e->slot[(i - 2) % 3], false, out_cb, nullptr, user, 0, t0)) != AV1B_OK) return rc;
+    if ((int)i >= L && (rc = finish(e, e->slot[(i - L) % S], false, out_cb, nullptr, user, 0, t0)) != AV1B_OK) return rc;
   }
-  for (uint32_t k = n_steps > 2 ? n_steps - 2 : 0; k < n_steps; k++)
-    if ((rc = finish(e, e->slot[k % 3], false, out_cb, nullptr, user, 0, t0)) != AV1B_OK) return rc;
+  for (uint32_t k = n_steps > (uint32_t)L ? n_steps - L : 0; k < n_steps; k++)
+    if ((rc = finish(e, e->slot[k % S], false, out_cb, nullptr, user, 0, t0)) != AV1B_OK) return rc;
   e->slot[0].n_frames = n0; e->slot[1].n_frames = n1;
   return AV1B_OK;
 }
