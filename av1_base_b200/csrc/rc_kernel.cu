@@ -112,8 +112,9 @@ __device__ void rc_signed_subexp_with_ref(Rc& c, int v, int low, int high, int k
 }
 
 __global__ void __launch_bounds__(32) rc_code_kernel(const __grid_constant__ RcLaunch P) {
-  __shared__ TileCdfs cdf;
-  static_assert(sizeof(TileCdfs) % 4 == 0, "copied as 32-bit words");
+  // only the CDFs inter frames code (the head of TileCdfs) live in shared memory
+  constexpr int kWords = (int)(offsetof(TileCdfs, kf_y_mode) / 4);
+  __shared__ uint32_t cdf_words[kWords];
   const int tile = blockIdx.x, f = blockIdx.y, lane = threadIdx.x;
   const int nsb = P.nsb, n_tiles = P.n_tiles;
   uint32_t* len_out = P.tile_len + (size_t)f * n_tiles + tile;
@@ -123,12 +124,11 @@ __global__ void __launch_bounds__(32) rc_code_kernel(const __grid_constant__ RcL
   if (t1 > P.tok_cap) { if (lane == 0) *len_out = 0; return; }   // token buffer overflowed: the host grows it and codes again
   {
     const uint32_t* src = reinterpret_cast<const uint32_t*>(P.cdf_init);
-    uint32_t* dst = reinterpret_cast<uint32_t*>(&cdf);
-    for (int i = lane; i < (int)(sizeof(TileCdfs) / 4); i += 32) dst[i] = src[i];
+    for (int i = lane; i < kWords; i += 32) cdf_words[i] = src[i];
   }
   int ref_wiener[2][3] = {{3, -7, 15}, {3, -7, 15}}, ref_sgr[2] = {-32, 31};   // luma plane only
   __syncwarp();
-  uint16_t* base = reinterpret_cast<uint16_t*>(&cdf);
+  uint16_t* base = reinterpret_cast<uint16_t*>(cdf_words);
   Rc c;
   c.low = 0; c.rng = 0x8000; c.cnt = -9; c.n = 0;
   // a symbol emits at most two bytes (15 bits): the region of a tile holds 2 bytes per token + 64 for the
@@ -168,7 +168,7 @@ __global__ void __launch_bounds__(32) rc_code_kernel(const __grid_constant__ RcL
         }
       } else {
         // forced split at the picture edge: probability gathered from the adaptive partition CDF, no adaptation
-        const uint16_t* pc = cdf.partition[(t >> 16) & 31];
+        const uint16_t* pc = base + AV1B_CDF_OFF(partition) + ((t >> 16) & 31) * 11;
         const bool has_cols = (t >> 21) & 1, is8 = (t >> 22) & 1;
         auto prob = [&](int q) -> int { return (q > 0 ? (int)pc[q - 1] : 32768) - (int)pc[q]; };
         int psum;

@@ -23,12 +23,9 @@ namespace av1b {
 
 // Adaptive CDF set of one tile (inverted CDFs, each vector followed by its terminator and counter).
 struct TileCdfs {
+  // ---- what inter frames code: the device range coder (rc_kernel.cu) keeps only this part in shared memory ----
   uint16_t partition[20][11];
   uint16_t skip[3][3];
-  uint16_t kf_y_mode[5][5][14];
-  uint16_t uv_mode[2][13][15];
-  uint16_t angle_delta[8][8];
-  uint16_t intra_ext_tx[3][4][13][17];
   uint16_t txb_skip[5][13][3];
   uint16_t eob_extra[5][2][9][3];
   uint16_t dc_sign[2][3][3];
@@ -42,24 +39,30 @@ struct TileCdfs {
   uint16_t coeff_base_eob[5][2][4][4];
   uint16_t coeff_base[5][2][42][5];
   uint16_t coeff_br[5][2][21][5];
-  uint16_t cfl_sign[9];
-  uint16_t cfl_alpha[6][17];
   uint16_t switchable_restore[4];
   uint16_t wiener_restore[3];
   uint16_t sgrproj_restore[3];
-  // inter frames
   uint16_t intra_inter[4][3];
   uint16_t single_ref[3][6][3];
   uint16_t newmv[6][3], zeromv[2][3], refmv[6][3], drl[3][3];
   uint16_t inter_ext_tx[4][4][17];
-  uint16_t y_mode[4][14];
   uint16_t mv_joints[5];
   struct MvComp {
     uint16_t classes[12], class0_fp[2][5], fp[5], sign[3], class0_hp[3], hp[3], class0[3], bits[10][3];
   } mvc[2];
-  uint16_t pad_[1];   // size multiple of 4 bytes (copied as 32-bit words on the device)
+  uint16_t inter_end_[16];   // the SSE2 adaptation of the host coder may touch up to 16 entries from a CDF's start
+  // ---- intra blocks only (key frames; intra blocks inside inter frames are not produced) ----
+  uint16_t kf_y_mode[5][5][14];
+  uint16_t uv_mode[2][13][15];
+  uint16_t angle_delta[8][8];
+  uint16_t intra_ext_tx[3][4][13][17];
+  uint16_t cfl_sign[9];
+  uint16_t cfl_alpha[6][17];
+  uint16_t y_mode[4][14];
+  uint16_t pad_[17];   // size multiple of 4 bytes; room behind the last CDF for the 16-entry vector update
 };
 static_assert(sizeof(TileCdfs) % 4 == 0, "TileCdfs is copied as 32-bit words");
+static_assert(offsetof(TileCdfs, kf_y_mode) % 4 == 0, "the inter part is copied as 32-bit words");
 static_assert(sizeof(TileCdfs) / 2 < 0xFFF0, "CDF offsets must fit 16 bits");
 
 enum : uint32_t { TOK_RAW = 0xFFFFu, TOK_GOLOMB = 0xFFFEu, TOK_PART_EDGE = 0xFFFDu, TOK_LR = 0xFFFCu, TOK_FIRST_SPECIAL = TOK_LR };
