@@ -129,8 +129,8 @@ __global__ void __launch_bounds__(256) hme_l2_kernel(const HmeLaunch P) {
 struct RefineSmem {
   uint16_t cur1[8][8 * 8];
   uint16_t ref1[8][12 * 13];
-  uint16_t cur0[8][16 * 16];
-  uint16_t ref0[8][20 * 21];
+  alignas(4) uint16_t cur0[8][16 * 16];
+  alignas(4) uint16_t ref0[8][20 * 22];   // row pitch 22: rows start word aligned (sad25_rows16)
 };
 
 // 25 candidates (+-2), lanes = candidates; returns the chosen (dy, dx) in all lanes
@@ -143,18 +143,71 @@ __device__ __forceinline__ int subpel_parabola(int sm, int s0, int sp, int lambd
   return clampi(q, -2, 2);
 }
 
+// The 25 SADs of a 16x16 block with the lanes laid over the BLOCK instead of the candidates: lane (r, h) owns
+// row r, columns 8h .. 8h+7 of the current block in registers, reads the five window rows r .. r+4 as aligned
+// 32-bit words (12 samples each) and accumulates its 8-sample share of all 25 candidates; a reduce-scatter adds the
+// shares.  39 shared-memory loads per lane instead of 512 (the candidate-per-lane form was bound by them).
+// Window row pitch: 22 samples (rows start word aligned).  Lane k < 25 returns the SAD of candidate k.
+constexpr int kRS0 = 22;
+__device__ __forceinline__ int sad25_rows16(const uint16_t* cur, const uint16_t* ref, int lane) {
+  const int r = lane >> 1, h = lane & 1;
+  unsigned c[8];
+  {
+    const uint32_t* cw = reinterpret_cast<const uint32_t*>(cur + r * 16 + 8 * h);
+#pragma unroll
+    for (int k = 0; k < 4; k++) { const uint32_t w = cw[k]; c[2 * k] = w & 0xFFFFu; c[2 * k + 1] = w >> 16; }
+  }
+  unsigned acc[25];
+#pragma unroll
+  for (int k = 0; k < 25; k++) acc[k] = 0;
+#pragma unroll
+  for (int wr = 0; wr < 5; wr++) {
+    const uint32_t* rw = reinterpret_cast<const uint32_t*>(ref + (r + wr) * kRS0 + 8 * h);
+    unsigned s[12];
+#pragma unroll
+    for (int k = 0; k < 6; k++) { const uint32_t w = rw[k]; s[2 * k] = w & 0xFFFFu; s[2 * k + 1] = w >> 16; }
+#pragma unroll
+    for (int dx = 0; dx < 5; dx++)
+#pragma unroll
+      for (int j = 0; j < 8; j++) acc[wr * 5 + dx] = __usad(c[j], s[dx + j], acc[wr * 5 + dx]);
+  }
+  // reduce-scatter over the lanes: at step o the lanes with bit o set keep the upper half of the (padded to 32)
+  // candidate list and hand the lower half to their partner, and vice versa; after five steps lane k holds the
+  // total of candidate k (31 exchanges instead of 125 for a full butterfly of every candidate)
+  unsigned v[32];
+#pragma unroll
+  for (int k = 0; k < 32; k++) v[k] = k < 25 ? acc[k] : 0u;
+#pragma unroll
+  for (int o = 16; o; o >>= 1) {
+    const bool hi = (lane & o) != 0;
+#pragma unroll
+    for (int i = 0; i < o; i++) {
+      const unsigned a = v[i], b = v[i + o];
+      const unsigned keep = hi ? b : a, send = hi ? a : b;
+      v[i] = keep + __shfl_xor_sync(0xffffffffu, send, o);
+    }
+  }
+  return (int)v[0];
+}
+
 template <int N, int RS, bool kSubpel>
 __device__ __forceinline__ void refine25(const uint16_t* cur, const uint16_t* ref, int lane, int lam, int lam_sub,
                                          int* bdy, int* bdx, int* qy, int* qx) {
   unsigned key = 0xFFFFFFFFu;
   int my_sad = 0;
+  int pre_sad = 0;
+  if (N == 16) pre_sad = sad25_rows16(cur, ref, lane);   // all lanes take part
   if (lane < 25) {
     const int dy = lane / 5 - 2, dx = lane % 5 - 2;
-    const uint16_t* rp = ref + (2 + dy) * RS + 2 + dx;
     unsigned usad = 0;
-    for (int i = 0; i < N; i++)
+    if (N == 16) {
+      usad = (unsigned)pre_sad;
+    } else {
+      const uint16_t* rp = ref + (2 + dy) * RS + 2 + dx;
+      for (int i = 0; i < N; i++)
 #pragma unroll
-      for (int j = 0; j < N; j++) usad = __usad((unsigned)cur[i * N + j], (unsigned)rp[i * RS + j], usad);
+        for (int j = 0; j < N; j++) usad = __usad((unsigned)cur[i * N + j], (unsigned)rp[i * RS + j], usad);
+    }
     const int sad = (int)usad;
     const int order = lane == 12 ? 0 : (lane < 12 ? lane + 1 : lane);
     key = ((unsigned)(sad + lam * (abs(dy) + abs(dx))) << 5) | (unsigned)order;
@@ -207,11 +260,11 @@ __global__ void __launch_bounds__(256) hme_refine_kernel(const HmeLaunch P) {
     sm.cur0[warp][o] = cur0[(size_t)clampi(by * 16 + (o >> 4), 0, P.height - 1) * P.stride0 + clampi(bx * 16 + (o & 15), 0, P.width - 1)];
   for (int o = lane; o < 400; o += 32) {
     const int r = o / 20, c = o % 20;
-    sm.ref0[warp][r * 21 + c] =
+    sm.ref0[warp][r * kRS0 + c] =
         ref0[(size_t)clampi(by * 16 + qy0 - 2 + r, 0, P.height - 1) * P.stride0 + clampi(bx * 16 + qx0 - 2 + c, 0, P.width - 1)];
   }
   __syncwarp();
-  refine25<16, 21, true>(sm.cur0[warp], sm.ref0[warp], lane, P.lambda, P.lambda, &dy, &dx, &qy, &qx);
+  refine25<16, kRS0, true>(sm.cur0[warp], sm.ref0[warp], lane, P.lambda, P.lambda, &dy, &dx, &qy, &qx);
   if (lane < 4) {
     const int uy = by * 2 + (lane >> 1), ux = bx * 2 + (lane & 1);
     const int w8 = P.width >> 3, h8 = P.height >> 3;
