@@ -5,7 +5,8 @@
 //                    Streaming, HBM-bound: algorithmic bytes 1.3125 * Y.
 //   hme_l2_kernel  : full search +-12 on the 1/4 picture for every 8x8 block (= 32x32 luma).  One CTA
 //                    stages a 32x32 patch of the current picture and its (32+24)^2 search window of
-//                    the reference in shared memory; one warp per block, lanes = candidates,
+//                    the reference in shared memory; one warp per block, lane = candidate column, the 25
+//                    candidate rows of a lane accumulate in registers from a sliding window row,
 //                    warp-shuffle arg-min on (cost, visiting order).
 //   hme_refine_kernel : per 16x16 luma block, +-2 on L1 around twice the L2 vector, then +-2 on L0
 //                    around twice the L1 vector; one warp per block, windows staged in shared memory.
@@ -99,20 +100,36 @@ __global__ void __launch_bounds__(256) hme_l2_kernel(const HmeLaunch P) {
         c[i * 8 + 2 * j] = w & 0xFFFF; c[i * 8 + 2 * j + 1] = w >> 16;
       }
     unsigned best = 0xFFFFFFFFu;   // (cost << 10) | visiting order
-    for (int k = lane; k < kCand; k += 32) {
-      const int dy = k / kSide - kR2, dx = k % kSide - kR2;
-      const uint16_t* rp = sm.ref + (by * 8 + kR2 + dy) * kW2S + bx * 8 + kR2 + dx;
-      // |a - b| + acc is one instruction (VABSDIFF.U32 with accumulate)
-      unsigned sad = 0;
+    // lane = candidate column (dx + 12), all 25 candidate rows in registers: a window row is loaded once (8 samples)
+    // and feeds the up to eight candidate rows that overlap it -- 256 shared loads per lane and block instead of 1280
+    if (lane < kSide) {
+      unsigned acc[kSide];
 #pragma unroll
-      for (int i = 0; i < 8; i++)
+      for (int k = 0; k < kSide; k++) acc[k] = 0;
+      const uint16_t* rp0 = sm.ref + (by * 8) * kW2S + bx * 8 + lane;
 #pragma unroll
-        for (int j = 0; j < 8; j++) sad = __usad(c[i * 8 + j], (unsigned)rp[i * kW2S + j], sad);
-      // visiting order: centre first, then raster
-      const int order = k == kCentre ? 0 : (k < kCentre ? k + 1 : k);
-      const int cost = (int)sad + lam2 * (abs(dx) + abs(dy));
-      const unsigned key = ((unsigned)cost << 10) | (unsigned)order;
-      best = min(best, key);
+      for (int wr = 0; wr < 8 + 2 * kR2; wr++) {
+        unsigned s[8];
+#pragma unroll
+        for (int j = 0; j < 8; j++) s[j] = rp0[wr * kW2S + j];
+#pragma unroll
+        for (int i = 0; i < 8; i++) {
+          const int dyi = wr - i;
+          if (dyi >= 0 && dyi < kSide) {
+#pragma unroll
+            for (int j = 0; j < 8; j++) acc[dyi] = __usad(c[i * 8 + j], s[j], acc[dyi]);
+          }
+        }
+      }
+      const int dx = lane - kR2;
+#pragma unroll
+      for (int dyi = 0; dyi < kSide; dyi++) {
+        const int k = dyi * kSide + lane, dy = dyi - kR2;
+        // visiting order: centre first, then raster
+        const int order = k == kCentre ? 0 : (k < kCentre ? k + 1 : k);
+        const int cost = (int)acc[dyi] + lam2 * (abs(dx) + abs(dy));
+        best = min(best, ((unsigned)cost << 10) | (unsigned)order);
+      }
     }
     for (int o = 16; o; o >>= 1) best = min(best, __shfl_xor_sync(0xffffffffu, best, o));
     if (lane == 0) {
