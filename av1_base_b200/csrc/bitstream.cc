@@ -408,30 +408,7 @@ struct TileWriter {
       ref_sgr[p][0] = -32; ref_sgr[p][1] = 31;
     }
   }
-  void put_uniform(int v, int n) {
-    const int w = 32 - __builtin_clz((unsigned)n), m = (1 << w) - n;
-    if (v < m) { ec.literal(v, w - 1); }
-    else { ec.literal(m + ((v - m) >> 1), w - 1); ec.literal((v - m) & 1, 1); }
-  }
-  void put_subexp(int x, int num_syms, int k) {
-    int i = 0, mk = 0;
-    for (;;) {
-      const int b2 = i ? k + i - 1 : k, a = 1 << b2;
-      if (num_syms <= mk + 3 * a) { put_uniform(x - mk, num_syms - mk); return; }
-      const int more = x >= mk + a;
-      ec.literal(more, 1);
-      if (more) { i++; mk += a; }
-      else { ec.literal(x - mk, b2); return; }
-    }
-  }
-  static int recenter(int r, int v) { return v > 2 * r ? v : (v >= r ? (v - r) << 1 : ((r - v) << 1) - 1); }
-  void put_signed_subexp_with_ref(int v, int low, int high, int k, int r) {
-    const int mx = high - low, vv = v - low, rr = r - low;
-    const int x = (rr << 1) <= mx ? recenter(rr, vv) : recenter(mx - 1 - rr, mx - 1 - vv);
-    put_subexp(x, mx, k);
-  }
   void write_lr(int r, int c) {
-    static const int tap_min[3] = {-5, -23, -17}, tap_max[3] = {10, 8, 46}, tap_k[3] = {1, 2, 3};
     for (int p = 0; p < 3; p++) {
       if (fp.lr_type[p] == AV1B_RESTORE_NONE) continue;
       const int ss = p > 0;
@@ -452,22 +429,21 @@ struct TileWriter {
             for (int pass = 0; pass < 2; pass++) {
               const int8_t* co = pass ? u.wiener_h : u.wiener_v;
               for (int j = p ? 1 : 0; j < 3; j++) {
-                put_signed_subexp_with_ref(co[j], tap_min[j], tap_max[j] + 1, tap_k[j], ref_wiener[p][pass][j]);
+                lr_put_signed_subexp_with_ref(ec, co[j], kLrTapMin[j], kLrTapMax[j] + 1, kLrTapK[j], ref_wiener[p][pass][j]);
                 ref_wiener[p][pass][j] = co[j];
               }
             }
           } else if (u.type == AV1B_RESTORE_SGRPROJ) {
-            static const int xqd_min[2] = {-96, -32}, xqd_max[2] = {31, 95};
             ec.literal(u.sgr_set, 4);
             for (int i = 0; i < 2; i++) {
               const int radius = av1t_sgr_params[u.sgr_set][i];
               if (radius) {
-                put_signed_subexp_with_ref(u.sgr_xqd[i], xqd_min[i], xqd_max[i] + 1, 4, ref_sgr[p][i]);
+                lr_put_signed_subexp_with_ref(ec, u.sgr_xqd[i], kLrXqdMin[i], kLrXqdMax[i] + 1, 4, ref_sgr[p][i]);
                 ref_sgr[p][i] = u.sgr_xqd[i];
               } else {
                 // not coded: decoder infers 0 (i == 0) or clip(128 - ref[0]) (i == 1)
                 int v = 0;
-                if (i == 1) v = std::min(std::max(128 - ref_sgr[p][0], xqd_min[1]), xqd_max[1]);
+                if (i == 1) v = std::min(std::max(128 - ref_sgr[p][0], kLrXqdMin[1]), kLrXqdMax[1]);
                 ref_sgr[p][i] = v;
               }
             }
