@@ -482,7 +482,7 @@ struct TileWriter {
           psum = prob(1) + prob(3);
           if (bl != 3) psum += prob(4) + prob(5) + prob(6) + prob(8);   // HORZ_A HORZ_B VERT_A HORZ_4
         }
-        uint16_t tmp[3] = {(uint16_t)psum, 0, 0};   // icdf[0] = 32768 - P(not split) = psum
+        uint16_t tmp[16] = {(uint16_t)psum, 0, 0};   // icdf[0] = 32768 - P(not split) = psum (16 entries: the vector update)
         ec.symbol(1, tmp, 2);                        // derived CDF: its adaptation is discarded
       }
     }
@@ -1051,7 +1051,7 @@ struct TokenCoder {
       ref_sgr[p][0] = -32; ref_sgr[p][1] = 31;
     }
   }
-  inline void step(uint32_t t) {
+  __attribute__((always_inline)) inline void step(uint32_t t) {
     const uint32_t off = t & 0xFFFFu;
     if (off < TOK_FIRST_SPECIAL) {
       ec.symbol((int)(t >> 21), base + off, (int)((t >> 16) & 31));
@@ -1085,7 +1085,7 @@ struct TokenCoder {
       int psum;
       if (has_cols) { psum = prob(2) + prob(3); if (!is8) psum += prob(4) + prob(6) + prob(7) + prob(9); }
       else { psum = prob(1) + prob(3); if (!is8) psum += prob(4) + prob(5) + prob(6) + prob(8); }
-      uint16_t tmp[3] = {(uint16_t)psum, 0, 0};
+      uint16_t tmp[16] = {(uint16_t)psum, 0, 0};   // 16 entries: the vector update of symbol()
       ec.symbol(1, tmp, 2);
     }
   }

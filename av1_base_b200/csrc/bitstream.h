@@ -41,29 +41,20 @@ class RangeEncoder {
   // icdf: inverted CDF (32768 - cdf), n symbols, icdf[n-1] == 0, icdf[n] = adaptation counter.
   // The adaptation (spec 8.2.6, expressed on the inverted CDF) is written without data-dependent branches:
   // the symbol value and the alphabet size change from call to call, a loop over n - 1 entries mispredicts
-  // its exit about once a symbol.  Alphabets of 2 and 4 (most of the stream) are unrolled, larger ones
-  // update 8 / 16 entries with SSE2 and keep the entries from n - 1 on unchanged.
+  // its exit about once a symbol, and so does a switch on the alphabet size: every alphabet takes the same SSE2 path.
   __attribute__((always_inline)) inline void symbol(int s, uint16_t* icdf, int n) {
     encode(s, icdf, n);
     if (!adapt_) return;
     const int cnt = icdf[n];
     const int rate = 3 + (cnt > 15) + (cnt > 31) + (n > 3 ? 2 : 1);   // + min(floor(log2(n)), 2)
-    if (n == 2) {
-      const int x = icdf[0];
-      icdf[0] = (uint16_t)(s ? x + ((32768 - x) >> rate) : x - (x >> rate));
-    } else if (n == 4) {
-#define AV1B_ADAPT1(i) { const int x = icdf[i]; icdf[i] = (uint16_t)((i) < s ? x + ((32768 - x) >> rate) : x - (x >> rate)); }
-      AV1B_ADAPT1(0) AV1B_ADAPT1(1) AV1B_ADAPT1(2)
-    } else if (n == 3) {
-      AV1B_ADAPT1(0) AV1B_ADAPT1(1)
-#undef AV1B_ADAPT1
-    } else {
-      // lanes i < s move towards 32768, lanes s <= i < n - 1 towards 0, lanes >= n - 1 stay
+    {
+      // one SSE2 step updates entries 0..7 (all of an alphabet of up to 9 symbols), a second one entries 8..15:
+      // lanes i < s move towards 32768, lanes s <= i < n - 1 towards 0, lanes >= n - 1 keep their value (they belong
+      // to the counter / the next CDF: every CDF handed to symbol() has 16 readable and writable entries behind its start)
       const __m128i sh = _mm_cvtsi32_si128(rate), top = _mm_set1_epi16((short)0x8000);
-      const __m128i idx = _mm_setr_epi16(0, 1, 2, 3, 4, 5, 6, 7);
       const __m128i vs = _mm_set1_epi16((short)s), vn = _mm_set1_epi16((short)(n - 1));
+      __m128i i8 = _mm_setr_epi16(0, 1, 2, 3, 4, 5, 6, 7);
       for (int k = 0; k < n - 1; k += 8) {
-        const __m128i i8 = _mm_add_epi16(idx, _mm_set1_epi16((short)k));
         const __m128i x = _mm_loadu_si128(reinterpret_cast<const __m128i*>(icdf + k));
         const __m128i up = _mm_add_epi16(x, _mm_srl_epi16(_mm_sub_epi16(top, x), sh));
         const __m128i dn = _mm_sub_epi16(x, _mm_srl_epi16(x, sh));
@@ -71,6 +62,7 @@ class RangeEncoder {
         __m128i y = _mm_or_si128(_mm_and_si128(m_up, up), _mm_andnot_si128(m_up, dn));
         y = _mm_or_si128(_mm_and_si128(m_live, y), _mm_andnot_si128(m_live, x));
         _mm_storeu_si128(reinterpret_cast<__m128i*>(icdf + k), y);
+        i8 = _mm_add_epi16(i8, _mm_set1_epi16(8));
       }
     }
     icdf[n] = (uint16_t)(cnt + (cnt < 32));
