@@ -256,7 +256,7 @@ __device__ __forceinline__ void group_buffers(Smem& sm, int group, int32_t** buf
   *lv8 = base + kBuf + kPred;
 }
 
-__global__ void __launch_bounds__(kThreads) inter_encode_kernel(const InterLaunch P) {
+__global__ void __launch_bounds__(kThreads, 3) inter_encode_kernel(const InterLaunch P) {
   __shared__ Smem sm;
   const Av1bGeom& g = P.g;
   const int tid = threadIdx.x, lane = tid & 31;
