@@ -184,7 +184,7 @@ class Encoder:
                 out.append(C.string_at(data, size))
             return 0
 
-        cb = abi.PACKET_CB(on_packet)
+        cb = abi.PACKET_CB(on_packet) if collect else None   # no per-packet trip through the interpreter when nobody listens
         _check(abi.lib().av1b_encode_resident(self._h, n_steps, cb, None))
         return out
 
