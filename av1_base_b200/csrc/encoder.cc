@@ -7,6 +7,7 @@
 #include <cuda_runtime.h>
 #include <stdio.h>
 #include <string.h>
+#include <algorithm>
 #include <atomic>
 #include <chrono>
 #include <condition_variable>
@@ -589,6 +590,15 @@ static int finish(av1b_encoder* e, Slot& s, bool staged, av1b_packet_cb out_cb, 
     if (e->lr_on) { sy[b].lr_units[0] = s.h_lr_units + (size_t)b * e->lr_n; sy[b].lr_unit_rows[0] = e->lr_rows; sy[b].lr_unit_cols[0] = e->lr_cols; }
     pack_frame_header(e->seq, s.is_key[b] ? e->fp_key : e->fp_inter, gb, packs[b]);
     for (int t = 0; t < gb.tile_cols * gb.tile_rows; t++) tasks.emplace_back(b, t);
+  }
+  if (s.has_tokens && !rc) {
+    // longest tiles first: the pool's tail is then a short tile, not a long one
+    auto cost = [&](const std::pair<int, int>& x) -> uint32_t {
+      if (s.is_key[x.first]) return 0xFFFFFFFFu;
+      const uint32_t* off = s.h_sb_off + (size_t)x.first * nsb;
+      return off[e->tile_first_k[x.second + 1]] - off[e->tile_first_k[x.second]];
+    };
+    std::stable_sort(tasks.begin(), tasks.end(), [&](const std::pair<int, int>& a, const std::pair<int, int>& b) { return cost(a) > cost(b); });
   }
   e->pool->parallel_for((int)tasks.size(), [&](int t) {
     const int b = tasks[t].first, tile = tasks[t].second;
