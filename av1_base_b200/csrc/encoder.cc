@@ -694,8 +694,8 @@ int av1b_encoder_create(const av1b_config* cfg, av1b_encoder** out) {
     // CDF adaptation): about 12x12 superblocks.  The device coder walks a tile with one warp, a serial chain of about
     // 100 ns per symbol, so its latency is that of the largest tile: about 6x6 superblocks (reserved[7] overrides).
     // Where the range coder runs (reserved[5] = 0: automatic): a tile costs one host thread about 15 ns per symbol
-    // and one warp about 0.5 us beside the other kernels, so with a dozen host threads for this GPU the host is the
-    // faster place; with fewer (8 GPUs on a 32-core box: 4 each) the host would throttle the GPU and the device codes.
+    // and one warp up to 0.5 us beside the other kernels (latency, hidden behind the next batches), so with a dozen
+    // host threads for this GPU the host is the faster place; with fewer (8 GPUs on a 32-core box: 4 each) the host would throttle the GPU and the device codes.
     const int ht = cfg->host_threads > 0 ? cfg->host_threads : (int)std::max(1u, std::thread::hardware_concurrency());
     e->rc_on = cfg->reserved[5] == 4 || (cfg->reserved[5] == 0 && ht < 12);
     e->n_slots = (e->rc_on && e->token_path && cfg->reserved[3] == 0) ? 4 : 3;

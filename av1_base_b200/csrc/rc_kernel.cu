@@ -1,10 +1,11 @@
 // Range coding of the token lists on the device: one warp per (frame, tile).
 //
 // The arithmetic coder of a tile is a serial chain (range / low and the adapting CDFs), but tiles are
-// independent: a batch of 8 4K inter frames has 256 of them, and with the token lists already on the device
-// the chain costs a warp about 100 ns a symbol while the 148 SMs are busy with the next batch's kernels.  That
-// frees the host (32 cores for 8 GPUs on these boxes: with the coder on the host the box stops scaling at two
-// GPUs) for headers and concatenation only.
+// independent: a batch of 8 4K inter frames has 840 of them (about 6x6 superblocks each), and with the token lists
+// already on the device the chain costs a warp about 80 instructions (0.25 to 0.5 us) a symbol while the 148 SMs
+// are busy with the next batches' kernels; the latency of the kernel is that of the tile with the most tokens
+// (12 ms at 4K, hidden behind two to three batches).  That frees the host (32 cores for 8 GPUs on these boxes: with
+// the coder on the host the box stops scaling at two GPUs) for headers and concatenation only.
 //   rc_code_kernel    warp per tile: CDFs of the tile in shared memory (lane i adapts entry i), range coder state
 //                     in registers (warp-uniform), bytes with in-place carry propagation into a per-tile region
 //   tok_scan (reused) exclusive scan of the tile byte counts
