@@ -1,7 +1,7 @@
-// C-ABI encoder object: owns the device buffers and stream of ONE GPU and drives, per batch of
-// frames, source upload -> device encode kernels -> symbol-stream download -> host entropy coding.
-// Two buffer slots are ping-ponged so that the host entropy-codes batch k-1 while the GPU encodes
-// batch k ("double-buffered D2H").
+// C-ABI encoder object: owns the device buffers and streams of ONE GPU and drives, per batch of frames,
+// source upload -> device encode kernels -> tokenizer -> range coding (host pool over downloaded token lists, or
+// on the device) -> packets.  Three or four buffer slots rotate: batch k+1 uploads while batch k is on the GPU
+// and the batches before it are with the host / the device range coder.
 // Boundary replaced: /root/reference/crates/daemon/src/encode/av1an.rs:126-139 (run_av1an).
 // There is no CPU fallback: without a CUDA device av1b_encoder_create fails with AV1B_ERR_NO_DEVICE.
 #include <cuda_runtime.h>
@@ -104,8 +104,8 @@ struct KeptFrame {
   int is_key = 1;
 };
 
-// Host-visible side of one batch: pinned staging of the sources and pinned mirrors of the symbol
-// streams.  Two slots are ping-ponged: the host entropy-codes slot k-1 while the GPU works on slot k.
+// One batch in flight: device sources and symbol streams, pinned staging of the sources and pinned mirrors of
+// what the host reads (token lists or coded tile payloads; levels and block info for key frames).
 struct Slot {
   uint16_t* d_src[3] = {nullptr, nullptr, nullptr};
   int16_t* d_coef[3] = {nullptr, nullptr, nullptr};   // device side of the symbol streams (downloaded on the copy stream
