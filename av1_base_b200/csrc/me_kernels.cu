@@ -144,9 +144,9 @@ __global__ void __launch_bounds__(256) hme_l2_kernel(const HmeLaunch P) {
 
 // ---------------------------------------------------------------------------------------------
 struct RefineSmem {
-  uint16_t cur1[8][8 * 8];
+  alignas(16) uint16_t cur1[8][8 * 8];
   uint16_t ref1[8][12 * 13];
-  alignas(4) uint16_t cur0[8][16 * 16];
+  alignas(16) uint16_t cur0[8][16 * 16];
   alignas(4) uint16_t ref0[8][20 * 22];   // row pitch 22: rows start word aligned (sad25_rows16)
 };
 
@@ -262,23 +262,49 @@ __global__ void __launch_bounds__(256) hme_refine_kernel(const HmeLaunch P) {
   const int16_t* m2 = P.mv2 + ((size_t)frame * n2x * n2y + (size_t)(by >> 1) * n2x + (bx >> 1)) * 2;
   const int py = 2 * m2[0], px = 2 * m2[1];
   // ---- L1: 8x8 block at (8bx, 8by), +-2 around (px, py) ----
-  for (int o = lane; o < 64; o += 32)
-    sm.cur1[warp][o] = cur1[(size_t)clampi(by * 8 + (o >> 3), 0, h1 - 1) * s1 + clampi(bx * 8 + (o & 7), 0, w1 - 1)];
-  for (int o = lane; o < 144; o += 32) {
-    const int r = o / 12, c = o % 12;
-    sm.ref1[warp][r * 13 + c] = ref1[(size_t)clampi(by * 8 + py - 2 + r, 0, h1 - 1) * s1 + clampi(bx * 8 + px - 2 + c, 0, w1 - 1)];
+  // windows that lie inside the picture (almost all) are staged without clamping, the block itself as 16-byte rows
+  const bool in1 = by * 8 + 8 <= h1 && bx * 8 + 8 <= w1 && by * 8 + py - 2 >= 0 && by * 8 + py + 10 <= h1 &&
+                   bx * 8 + px - 2 >= 0 && bx * 8 + px + 10 <= w1;
+  if (in1) {
+    if (lane < 8)
+      *reinterpret_cast<uint4*>(&sm.cur1[warp][lane * 8]) = *reinterpret_cast<const uint4*>(cur1 + (size_t)(by * 8 + lane) * s1 + bx * 8);
+    const uint16_t* rbase = ref1 + (size_t)(by * 8 + py - 2) * s1 + bx * 8 + px - 2;
+    for (int o = lane; o < 144; o += 32) {
+      const int r = o / 12, c = o % 12;
+      sm.ref1[warp][r * 13 + c] = rbase[(size_t)r * s1 + c];
+    }
+  } else {
+    for (int o = lane; o < 64; o += 32)
+      sm.cur1[warp][o] = cur1[(size_t)clampi(by * 8 + (o >> 3), 0, h1 - 1) * s1 + clampi(bx * 8 + (o & 7), 0, w1 - 1)];
+    for (int o = lane; o < 144; o += 32) {
+      const int r = o / 12, c = o % 12;
+      sm.ref1[warp][r * 13 + c] = ref1[(size_t)clampi(by * 8 + py - 2 + r, 0, h1 - 1) * s1 + clampi(bx * 8 + px - 2 + c, 0, w1 - 1)];
+    }
   }
   __syncwarp();
   int dy, dx, qy = 0, qx = 0;
   refine25<8, 13, false>(sm.cur1[warp], sm.ref1[warp], lane, P.lambda >> 2, 0, &dy, &dx, &qy, &qx);
   const int qy0 = 2 * (py + dy), qx0 = 2 * (px + dx);
   // ---- L0: 16x16 block at (16bx, 16by), +-2 around (qx, qy) ----
-  for (int o = lane; o < 256; o += 32)
-    sm.cur0[warp][o] = cur0[(size_t)clampi(by * 16 + (o >> 4), 0, P.height - 1) * P.stride0 + clampi(bx * 16 + (o & 15), 0, P.width - 1)];
-  for (int o = lane; o < 400; o += 32) {
-    const int r = o / 20, c = o % 20;
-    sm.ref0[warp][r * kRS0 + c] =
-        ref0[(size_t)clampi(by * 16 + qy0 - 2 + r, 0, P.height - 1) * P.stride0 + clampi(bx * 16 + qx0 - 2 + c, 0, P.width - 1)];
+  const bool in0 = by * 16 + 16 <= P.height && bx * 16 + 16 <= P.width && by * 16 + qy0 - 2 >= 0 && by * 16 + qy0 + 18 <= P.height &&
+                   bx * 16 + qx0 - 2 >= 0 && bx * 16 + qx0 + 18 <= P.width;
+  if (in0) {
+    // lane (r, h): 8 samples of row r as one 16-byte load
+    *reinterpret_cast<uint4*>(&sm.cur0[warp][(lane >> 1) * 16 + 8 * (lane & 1)]) =
+        *reinterpret_cast<const uint4*>(cur0 + (size_t)(by * 16 + (lane >> 1)) * P.stride0 + bx * 16 + 8 * (lane & 1));
+    const uint16_t* rbase = ref0 + (size_t)(by * 16 + qy0 - 2) * P.stride0 + bx * 16 + qx0 - 2;
+    for (int o = lane; o < 400; o += 32) {
+      const int r = o / 20, c = o % 20;
+      sm.ref0[warp][r * kRS0 + c] = rbase[(size_t)r * P.stride0 + c];
+    }
+  } else {
+    for (int o = lane; o < 256; o += 32)
+      sm.cur0[warp][o] = cur0[(size_t)clampi(by * 16 + (o >> 4), 0, P.height - 1) * P.stride0 + clampi(bx * 16 + (o & 15), 0, P.width - 1)];
+    for (int o = lane; o < 400; o += 32) {
+      const int r = o / 20, c = o % 20;
+      sm.ref0[warp][r * kRS0 + c] =
+          ref0[(size_t)clampi(by * 16 + qy0 - 2 + r, 0, P.height - 1) * P.stride0 + clampi(bx * 16 + qx0 - 2 + c, 0, P.width - 1)];
+    }
   }
   __syncwarp();
   refine25<16, kRS0, true>(sm.cur0[warp], sm.ref0[warp], lane, P.lambda, P.lambda, &dy, &dx, &qy, &qx);
