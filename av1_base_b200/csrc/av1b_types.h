@@ -48,6 +48,8 @@ typedef struct Av1bFrameParams {
   int32_t lr_type[3];           // AV1B_RESTORE_* per plane
   int32_t lr_unit_shift;        // 0..2 : luma unit size 64 << shift
   int32_t lr_uv_shift;          // 0/1
+  int32_t non_reference;        // 1: inter frame that updates no reference slot (refresh_frame_flags = 0): the frames after it
+                                //    keep predicting from the last frame that did (one-level hierarchy, tools/rd_oracle.py --hier)
 } Av1bFrameParams;
 
 // Frame geometry derived from (width, height): all in luma 4x4 "mode info" units unless noted.

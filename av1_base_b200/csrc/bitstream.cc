@@ -132,7 +132,7 @@ static void write_frame_header(const Av1bSeqParams& seq, const Av1bFrameParams& 
   w.bit(0);                    // frame_size_override_flag
   // order_hint: 0 bits (enable_order_hint = 0)
   if (inter) w.put(7, 3);      // primary_ref_frame = PRIMARY_REF_NONE: every frame starts from the default CDFs
-  if (!key) w.put(inter ? 0xFF : 0x01, 8);   // refresh_frame_flags (intra_only frames must not use 0xFF)
+  if (!key) w.put(inter ? (fp.non_reference ? 0x00 : 0xFF) : 0x01, 8);   // refresh_frame_flags (intra_only frames must not use 0xFF)
   if (inter) {
     // single reference design: all seven reference names point at slot 0 = the previous frame
     for (int i = 0; i < 7; i++) w.put(0, 3);   // ref_frame_idx[i]

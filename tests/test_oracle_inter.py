@@ -183,3 +183,35 @@ def test_device_digested_coefficients_pack_to_identical_bytes(w, h, bd, q):
     assert (b2["eob"] & 0x8000).any()
     digested = packer.pack_frame(seq, fp, packer.make_syms(g, b2, c2))
     assert raster == digested
+
+
+def test_non_reference_frames_decode_bit_exact():
+    """One-level hierarchy (Av1bFrameParams.non_reference): every second inter frame updates no reference slot and the
+    frames after it keep predicting from the last frame that did.  dav1d and libaom must follow the same references."""
+    w, h, bd, q = 128, 96, 10, 100
+    g = O.geom(w, h, 0, 0)
+    frames = synth.synth_clip(w, h, bd, 6, seed=21, scene_len=100)
+    seq = abi.SeqParams(w, h, bd, 0, 0, 30, 1, 0)
+    pm = O.partition_fixed(g, 4)
+    tus, recs, anchor, anchor_src = [], [], None, None
+    for fi, fr in enumerate(frames):
+        fp = abi.FrameParams()
+        fp.base_q_idx = q + (0 if fi % 2 == 0 else 40)
+        fp.cdef_damping = 3
+        fp.frame_type = 0 if fi == 0 else 1
+        fp.non_reference = 1 if (fi > 0 and fi % 2 == 1) else 0
+        if fi == 0:
+            r = O.encode_intra_frame(g, fr, bd, fp.base_q_idx, pm)
+        else:
+            mvs = O.hme(g, O.pyramid(g, O.pad_planes(g, fr)[0]), O.pyramid(g, O.pad_planes(g, anchor_src)[0]), 20)
+            r = O.encode_inter_frame(g, fr, bd, fp.base_q_idx, pm, mvs, anchor)
+        sy = packer.make_syms(g, r.blocks, r.coef)
+        tus.append(b"\x12\x00" + (packer.pack_sequence_header(seq) if fi == 0 else b"") + packer.pack_frame(seq, fp, sy, with_td=False))
+        recs.append(O.crop(g, r.rec))
+        if not fp.non_reference:
+            anchor, anchor_src = r.rec, fr
+    for dec in (D.dav1d_decode(tus), D.aom_decode(tus)):
+        assert len(dec) == len(frames)
+        for i in range(len(frames)):
+            for p in range(3):
+                assert np.array_equal(dec[i][p], recs[i][p]), (i, p)

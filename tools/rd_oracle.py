@@ -3,7 +3,7 @@
 tune encoder-side decisions (quantiser rounding, transform-block drop threshold, ...) without a GPU.
 The device path must then match the oracle bit for bit, so the curve measured here is the product's curve.
 Compares with stored libaom points of the same clip (profiles/r01g_bdrate_*.json, profiles/r01l_*.json).
-Usage: tools/rd_oracle.py [--noise 1.0] [--frames 30] [--crfs 20,28,36,44,52] [--rnd R] [--thr T]"""
+Usage: tools/rd_oracle.py [--noise 1.0] [--frames 30] [--crfs 20,28,36,44,52] [--rnd R] [--thr T] [--lr] [--qmod P,L,H] [--hier P,A,O]"""
 import argparse, json, os, re, sys
 import ctypes as C
 from concurrent.futures import ProcessPoolExecutor
@@ -40,20 +40,29 @@ def encode(args):
     prev_fin = prev_pyr = None
     nbytes, psnr, nskip = 0, [], 0
     tus, fins = [], []
+    hier = opts.get("hier")
+    anchor_fin = anchor_pyr = None
     for i, fr in enumerate(frames):
         src = O.pad_planes(g, fr)
         pyr = O.pyramid(g, src[0])
+        if hier and i > 0:
+            per, da, dn = hier
+            is_anchor = i % per == 0
+            prev_fin, prev_pyr = anchor_fin, anchor_pyr
         if i == 0:
             r, fp = O.encode_intra_frame(g, fr, bd, qkey, pm), fps[0]
         else:
             mv = O.hme(g, pyr, prev_pyr, acq >> 1)
             qf = qidx
+            if hier:
+                qf = max(1, min(255, qidx + (hier[1] if i % hier[0] == 0 else hier[2])))
             if opts.get("qmod"):   # experiment: periodic quantiser modulation inside the P chain
                 per, lo, hi = opts["qmod"]
                 qf = max(1, min(255, qidx + (lo if i % per == 0 else hi)))
             fp = abi.FrameParams()
             abi.lib().av1b_select_frame_params(bd, qf, 1, 1, C.byref(fp))
             fp.tile_cols_log2, fp.tile_rows_log2 = g.tile_cols_log2, g.tile_rows_log2
+            fp.non_reference = 1 if (hier and i % hier[0] != 0) else 0
             r = O.encode_inter_frame(g, fr, bd, qf, pm, mv, prev_fin, quant_rnd=opts.get("rnd", 48),
                                      tb_zero_thr=opts.get("thr", 0))
             O.merge_skip_blocks(g, r.blocks)
@@ -76,6 +85,8 @@ def encode(args):
         nbytes += len(tu)
         psnr.append(D.psnr(O.crop(g, fin)[0], fr[0], bd))
         prev_fin, prev_pyr = fin, pyr
+        if i == 0 or (hier and i % hier[0] == 0):
+            anchor_fin, anchor_pyr = fin, pyr
         fins.append(fin)
     if opts.get("verify"):
         dec = D.dav1d_decode(tus)
@@ -99,11 +110,13 @@ def main():
     ap.add_argument("--lr", action="store_true", help="loop restoration decision on (preset <= 5)")
     ap.add_argument("--sgr-set", type=int, default=4)
     ap.add_argument("--qmod", default="", help="period,delta_low,delta_high: quantiser index offsets inside the P chain (experiment)")
+    ap.add_argument("--hier", default="", help="period,delta_anchor,delta_other: one-level hierarchy -- every period-th frame is an anchor (the only frames "
+                                               "that update the reference), the others predict from the last anchor and are not referenced (experiment)")
     ap.add_argument("--wv", default="3,-7,15")
     ap.add_argument("--xqd", default="-32,31")
     a = ap.parse_args()
     w, h = map(int, a.size.split("x"))
-    opts = dict(rnd=a.rnd, thr=a.thr, verify=a.verify, lr=a.lr, sgr_set=a.sgr_set, wv=tuple(map(int, a.wv.split(','))), xqd=tuple(map(int, a.xqd.split(','))), qmod=tuple(map(int, a.qmod.split(','))) if a.qmod else None)
+    opts = dict(rnd=a.rnd, thr=a.thr, verify=a.verify, lr=a.lr, sgr_set=a.sgr_set, wv=tuple(map(int, a.wv.split(','))), xqd=tuple(map(int, a.xqd.split(','))), qmod=tuple(map(int, a.qmod.split(','))) if a.qmod else None, hier=tuple(map(int, a.hier.split(','))) if a.hier else None)
     jobs = [(w, h, a.bd, a.frames, a.seed, a.noise, crf, opts) for crf in map(int, a.crfs.split(","))]
     with ProcessPoolExecutor(min(8, len(jobs))) as ex:
         res = list(ex.map(encode, jobs))
