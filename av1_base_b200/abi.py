@@ -60,7 +60,7 @@ class Config(C.Structure):
                 ("enable_qm", C.c_int32), ("qm_min", C.c_int32), ("qm_max", C.c_int32),
                 ("tile_cols_log2", C.c_int32), ("tile_rows_log2", C.c_int32), ("device_id", C.c_int32),
                 ("hdr", C.c_int32), ("host_threads", C.c_int32), ("frames_in_flight", C.c_int32),
-                ("reserved", C.c_int32 * 8)]
+                ("gop_period", C.c_int32), ("tune", C.c_int32 * 7), ("reserved", C.c_int32 * 8)]
 
 
 class FrameSrc(C.Structure):

@@ -102,6 +102,7 @@ struct KeptFrame {
   std::vector<uint8_t> cdef_idx;
   std::vector<Av1bLrUnit> lr_units;
   int is_key = 1;
+  int kind = 0;
 };
 
 // One batch in flight: device sources and symbol streams, pinned staging of the sources and pinned mirrors of
@@ -144,8 +145,10 @@ struct Slot {
   Av1bBlockInfo* h_blocks = nullptr;
   uint8_t* h_cdef_idx = nullptr;
   cudaEvent_t ev_h2d = nullptr, ev_k0 = nullptr, ev_me = nullptr, ev_k1 = nullptr, ev_d2h = nullptr;
-  std::vector<cudaEvent_t> ev_frame;     // 5 per frame: before encode, after encode, after deblock, after CDEF, after loop restoration
+  std::vector<cudaEvent_t> ev_frame;     // 5 per launch group: before encode, after encode, after deblock, after CDEF, after loop restoration
   std::vector<uint8_t> is_key;
+  std::vector<uint8_t> kind;             // per frame: 0 key, 1 anchor, 2 non-reference
+  std::vector<std::pair<int, int>> groups;   // (first frame, frames) of every launch group of the batch
   int n_frames = 0;
   int64_t first_index = 0;
 };
@@ -165,7 +168,15 @@ struct av1b_encoder {
   bool keep = false;
   bool loop_filters = true;
   bool intra_only = false;
-  Av1bFrameParams fp_key, fp_inter;   // frame-level parameters (levels / strengths from the quantiser)
+  Av1bFrameParams fp_key, fp_inter;   // frame-level parameters (levels / strengths from the quantiser); fp_inter: anchors
+  Av1bFrameParams fp_nonref;          // the frames between two anchors (refresh_frame_flags = 0)
+  int gop_period = 4;                 // every gop_period-th frame after a key frame is an anchor (1: plain P chain)
+  int base_q_idx_nonref = 0;
+  bool me_smooth = true;              // vector-field regularisation after the hierarchical search
+  bool key_var_part = true;           // key frames: 64x64 / 32x32 blocks where the source is smooth
+  int16_t* d_mv_tmp = nullptr;
+  uint32_t* d_hist = nullptr;
+  void* d_cdf_init_alt = nullptr;     // default CDF set of the non-reference frames' quantiser class
   cudaStream_t stream = nullptr;      // compute
   cudaStream_t s_in = nullptr;        // host -> device copies (overlap the previous batch's kernels)
   cudaStream_t s_out = nullptr;       // device -> host copies (overlap the next batch's kernels)
@@ -234,7 +245,8 @@ static void free_all(av1b_encoder* e) {
   cudaFree(e->d_map_key); cudaFree(e->d_map_inter);
   cudaFree(e->d_mv2); cudaFree(e->d_mvs);
   cudaFree(e->d_sb_of_order); cudaFree(e->d_tile_of_sb); cudaFree(e->d_lr_sse);
-  cudaFree(e->d_cdf_init); cudaFree(e->d_tile_first_k); cudaFree(e->d_rc_overflow);
+  cudaFree(e->d_cdf_init); cudaFree(e->d_cdf_init_alt); cudaFree(e->d_tile_first_k); cudaFree(e->d_rc_overflow);
+  cudaFree(e->d_mv_tmp); cudaFree(e->d_hist);
   if (e->s_tok) cudaStreamDestroy(e->s_tok);
   if (e->stream) cudaStreamDestroy(e->stream);
   if (e->s_in) cudaStreamDestroy(e->s_in);
@@ -292,18 +304,36 @@ static int stage(av1b_encoder* e, Slot& s, const av1b_frame_src* frames, int n) 
   return AV1B_OK;
 }
 
+// kind of the frame at position `pos` of its closed GOP: 0 key, 1 anchor (inter frame that becomes the reference),
+// 2 non-reference inter frame (predicts from the last anchor, refresh_frame_flags = 0)
+static int frame_kind(const av1b_encoder* e, int64_t pos) {
+  if (e->intra_only) return 0;
+  const int64_t c = pos % e->keyint;
+  if (c == 0) return 0;
+  return (e->gop_period <= 1 || c % e->gop_period == 0) ? 1 : 2;
+}
+static const Av1bFrameParams& kind_params(const av1b_encoder* e, int kind) {
+  return kind == 0 ? e->fp_key : (kind == 1 ? e->fp_inter : e->fp_nonref);
+}
+
 // device work + symbol download for the n frames resident in the slot; asynchronous
 static int launch(av1b_encoder* e, Slot& s, const Slot& in, int n, int64_t first_index) {
   const Av1bGeom& g = e->g;
   const int bd = e->cfg.bit_depth;
   const size_t nsb = (size_t)g.sb_rows * g.sb_cols;
   s.n_frames = n; s.first_index = first_index;
-  s.is_key.assign(n, 1);
+  s.is_key.assign(n, 1); s.kind.assign(n, 0); s.groups.clear();
+  // ring index of every frame's reference picture: 0 = the anchor carried over from the batches before, b + 1 = frame b
+  // of this batch (d_fin / d_pyr hold batch + 1 pictures)
+  std::vector<int> ref_of(n, 0);
   bool any_inter = false;
+  int last_ref = 0;
   for (int b = 0; b < n; b++) {
-    const bool key = e->intra_only || ((e->chunk_pos + b) % e->keyint == 0);
-    s.is_key[b] = key;
-    any_inter |= !key;
+    const int kind = frame_kind(e, e->chunk_pos + b);
+    s.kind[b] = (uint8_t)kind; s.is_key[b] = kind == 0;
+    ref_of[b] = last_ref;
+    if (kind != 2) last_ref = b + 1;
+    any_inter |= kind != 0;
   }
   CK(cudaStreamWaitEvent(e->stream, in.ev_src, 0));
   CK(cudaEventRecord(s.ev_k0, e->stream));
@@ -317,64 +347,83 @@ static int launch(av1b_encoder* e, Slot& s, const Slot& in, int n, int64_t first
     if (any_inter) {
       HmeLaunch H;
       H.width = g.width; H.height = g.height; H.stride0 = g.stride[0]; H.elems0 = e0;
-      for (int l = 0; l < 3; l++) { H.ref[l] = e->d_pyr[l]; H.cur[l] = e->d_pyr[l] + (e0 >> (2 * l)); }
+      for (int l = 0; l < 3; l++) { H.ref[l] = e->d_pyr[l]; H.cur[l] = e->d_pyr[l]; }
+      for (int b = 0; b < n; b++) { H.cur_slot[b] = (uint8_t)(b + 1); H.ref_slot[b] = (uint8_t)ref_of[b]; }
       H.mv2 = e->d_mv2; H.mv_out = e->d_mvs;
       H.lambda = acq0 >> 1;   // vector-deviation cost in SAD units (tuned on the oracle: about half the AC quantiser step)
+      H.lam_s = e->me_smooth ? H.lambda : 0; H.smooth_iters = 2; H.mv_tmp = e->d_mv_tmp; H.hist = e->d_hist;
       CK(launch_hme(H, n, e->stream));
       e->kernel_launches += 2;
+      if (H.lam_s > 0) { CK(launch_hme_smooth(H, n, e->stream)); e->kernel_launches += 3 * H.smooth_iters; }
     }
-    // the last picture of this batch is the reference of the next batch's first picture
-    for (int l = 0; l < 3; l++) {
-      const size_t el = e0 >> (2 * l);
-      CK(cudaMemcpyAsync(e->d_pyr[l], e->d_pyr[l] + el * n, el * 2, cudaMemcpyDeviceToDevice, e->stream));
-    }
+    // the last key / anchor picture of this batch is the reference the next batch starts from
+    if (last_ref > 0)
+      for (int l = 0; l < 3; l++) {
+        const size_t el = e0 >> (2 * l);
+        CK(cudaMemcpyAsync(e->d_pyr[l], e->d_pyr[l] + el * last_ref, el * 2, cudaMemcpyDeviceToDevice, e->stream));
+      }
   }
   CK(cudaEventRecord(s.ev_me, e->stream));
-  const int dcq = bd == 8 ? av1t_dc_q_8[e->base_q_idx] : av1t_dc_q_10[e->base_q_idx];
-  const int acq = bd == 8 ? av1t_ac_q_8[e->base_q_idx] : av1t_ac_q_10[e->base_q_idx];
-  for (int b = 0; b < n; b++) {
-    const bool key = s.is_key[b];
-    cudaEvent_t* ev = &s.ev_frame[(size_t)b * 5];
+  // ---- launch groups: a key frame alone; an anchor alone; the non-reference frames between two anchors together
+  //      (same reference, same quantiser, no dependency on each other) ----
+  for (int b = 0; b < n;) {
+    int cnt = 1;
+    if (s.kind[b] == 2) while (b + cnt < n && s.kind[b + cnt] == 2 && ref_of[b + cnt] == ref_of[b]) cnt++;
+    s.groups.emplace_back(b, cnt);
+    b += cnt;
+  }
+  for (size_t gi = 0; gi < s.groups.size(); gi++) {
+    const int b = s.groups[gi].first, cnt = s.groups[gi].second;
+    const int kind = s.kind[b];
+    const bool key = kind == 0;
+    const Av1bFrameParams& fp = kind_params(e, kind);
+    const int qidx = fp.base_q_idx;
+    const int dcq = bd == 8 ? av1t_dc_q_8[qidx] : av1t_dc_q_10[qidx];
+    const int acq = bd == 8 ? av1t_ac_q_8[qidx] : av1t_ac_q_10[qidx];
+    cudaEvent_t* ev = &s.ev_frame[gi * 5];
     CK(cudaEventRecord(ev[0], e->stream));
-    uint16_t* rec[3]; uint16_t* deb[3]; uint16_t* fin[3]; const uint16_t* prev[3]; const uint16_t* src[3]; int16_t* coef[3];
+    uint16_t* rec[3]; uint16_t* deb[3]; uint16_t* fin[3]; const uint16_t* refp[3]; const uint16_t* src[3]; int16_t* coef[3];
     for (int p = 0; p < 3; p++) {
       const size_t off = (size_t)b * e->plane_elems[p];
       rec[p] = e->d_rec[p] + off; deb[p] = e->d_deb[p] ? e->d_deb[p] + off : nullptr;
-      prev[p] = e->d_fin[p] + off; fin[p] = e->d_fin[p] + off + e->plane_elems[p];
+      refp[p] = e->d_fin[p] + (size_t)ref_of[b] * e->plane_elems[p]; fin[p] = e->d_fin[p] + off + e->plane_elems[p];
       src[p] = in.d_src[p] + off; coef[p] = s.d_coef[p] + off;
     }
     Av1bBlockInfo* blocks = s.d_blocks + (size_t)b * e->map_elems;
     if (key) {
       IntraLaunch L;
-      L.g = g; L.bit_depth = bd; L.base_q_idx = e->base_q_idx_key; L.quant_rnd = 48;
-      L.dc_q = bd == 8 ? av1t_dc_q_8[e->base_q_idx_key] : av1t_dc_q_10[e->base_q_idx_key];
-      L.ac_q = bd == 8 ? av1t_ac_q_8[e->base_q_idx_key] : av1t_ac_q_10[e->base_q_idx_key];
+      L.g = g; L.bit_depth = bd; L.base_q_idx = qidx; L.quant_rnd = 48; L.dc_q = dcq; L.ac_q = acq;
       for (int p = 0; p < 3; p++) { L.src[p] = src[p]; L.rec[p] = e->loop_filters ? rec[p] : fin[p]; L.coef[p] = coef[p]; L.plane_elems[p] = e->plane_elems[p]; }
       L.blocks = blocks; L.part_map = e->d_map_key; L.map_elems = e->map_elems;
-      if (e->blk_log2 == 4) { CK(launch_intra_fast(L, 1, e->stream)); e->kernel_launches += 3; }
+      if (e->key_var_part) {
+        // 64x64 / 32x32 blocks where the source is smooth at this quantiser, 16x16 elsewhere
+        const int thr = std::min(4 * acq, 800 << (bd - 8));
+        CK(launch_partition_smooth(g, src[0], e->plane_elems[0], e->map_elems, thr, e->d_map_key, 1, e->stream));
+        CK(launch_intra_encode(L, 1, e->stream)); e->kernel_launches += 2;
+      } else if (e->blk_log2 == 4) { CK(launch_intra_fast(L, 1, e->stream)); e->kernel_launches += 3; }
       else { CK(launch_intra_encode(L, 1, e->stream)); e->kernel_launches += 1; }
       e->intra_launches += 1; e->key_frames += 1;
     } else {
       InterLaunch L;
-      L.g = g; L.bit_depth = bd; L.base_q_idx = e->base_q_idx; L.quant_rnd = 48; L.dc_q = dcq; L.ac_q = acq;
-      for (int p = 0; p < 3; p++) { L.src[p] = src[p]; L.ref[p] = prev[p]; L.rec[p] = e->loop_filters ? rec[p] : fin[p]; L.coef[p] = coef[p]; }
+      L.g = g; L.bit_depth = bd; L.base_q_idx = qidx; L.quant_rnd = 48; L.dc_q = dcq; L.ac_q = acq;
+      L.n_frames = cnt; L.map_elems = e->map_elems;
+      for (int p = 0; p < 3; p++) { L.src[p] = src[p]; L.ref[p] = refp[p]; L.rec[p] = e->loop_filters ? rec[p] : fin[p]; L.coef[p] = coef[p]; L.plane_elems[p] = e->plane_elems[p]; }
       L.blocks = blocks; L.part_map = e->d_map_inter; L.mvs = e->d_mvs + (size_t)b * e->map_elems * 2;
       L.pack_levels = e->token_path ? 2 : e->legacy_pack_levels;
       for (int p = 0; p < 3; p++) L.digest[p] = e->token_path ? s.d_digest[p] + (size_t)b * e->plane_elems[p] : nullptr;
       L.tb_zero_thr = e->cfg.reserved[4];   // experiment knob: drop transform blocks with sum|level| <= thr
       CK(launch_inter_encode(L, e->stream));
-      CK(launch_merge_skip(g, blocks, e->stream));
-      e->kernel_launches += 2; e->inter_launches += 1;
+      CK(launch_merge_skip(g, blocks, e->map_elems, cnt, e->stream));
+      e->kernel_launches += 2; e->inter_launches += cnt;   // counts inter FRAMES (a launch codes cnt of them)
     }
     CK(cudaEventRecord(ev[1], e->stream));
     if (e->loop_filters) {
-      const Av1bFrameParams& fp = key ? e->fp_key : e->fp_inter;
       DeblockLaunch D;
       D.g = g; D.bit_depth = bd; D.sharpness = fp.lf_sharpness;
       for (int i = 0; i < 4; i++) D.lf_level[i] = fp.lf_level[i];
       for (int p = 0; p < 3; p++) { D.in[p] = rec[p]; D.out[p] = deb[p]; D.plane_elems[p] = e->plane_elems[p]; }
       D.blocks = blocks; D.map_elems = e->map_elems;
-      CK(launch_deblock(D, 1, e->stream));
+      CK(launch_deblock(D, cnt, e->stream));
       CK(cudaEventRecord(ev[2], e->stream));
       CdefLaunch Cd;
       Cd.g = g; Cd.bit_depth = bd; Cd.cdef_damping = fp.cdef_damping; Cd.cdef_bits = fp.cdef_bits;
@@ -382,7 +431,7 @@ static int launch(av1b_encoder* e, Slot& s, const Slot& in, int n, int64_t first
       // with loop restoration the CDEF output goes to the (now free) pre-filter buffer and restoration writes the picture
       for (int p = 0; p < 3; p++) { Cd.in[p] = deb[p]; Cd.src[p] = src[p]; Cd.out[p] = e->lr_on ? rec[p] : fin[p]; Cd.plane_elems[p] = e->plane_elems[p]; }
       Cd.blocks = blocks; Cd.map_elems = e->map_elems; Cd.cdef_idx = s.d_cdef_idx + (size_t)b * nsb; Cd.forced_idx = nullptr;
-      CK(launch_cdef(Cd, 1, e->stream));
+      CK(launch_cdef(Cd, cnt, e->stream));
       e->kernel_launches += 2;
       CK(cudaEventRecord(ev[3], e->stream));
       if (e->lr_on) {
@@ -395,10 +444,10 @@ static int launch(av1b_encoder* e, Slot& s, const Slot& in, int n, int64_t first
         }
         Av1bLrUnit* units = s.d_lr_units + (size_t)b * e->lr_n;
         R.src_y = src[0]; R.cand = e->lr_cand; R.sse = e->d_lr_sse;
-        const long long aq = key ? (bd == 8 ? av1t_ac_q_8[e->base_q_idx_key] : av1t_ac_q_10[e->base_q_idx_key]) : acq;
-        CK(launch_lr_search(R, 1, (aq * aq * 5) >> 8, units, e->stream));   // rate of a unit's parameters in squared-error units
+        const long long aq = acq;
+        CK(launch_lr_search(R, cnt, (aq * aq * 5) >> 8, units, e->stream));   // rate of a unit's parameters in squared-error units
         R.units[0] = units;
-        CK(launch_lr(R, 1, e->stream));
+        CK(launch_lr(R, cnt, e->stream));
         e->kernel_launches += 3;
       }
     } else {
@@ -408,14 +457,15 @@ static int launch(av1b_encoder* e, Slot& s, const Slot& in, int n, int64_t first
     CK(cudaEventRecord(ev[4], e->stream));
   }
   e->chunk_pos += n;
-  // the last reconstructed picture becomes reference slot 0 of the next batch
   if (e->keep) {
     // debug mode keeps every reconstruction: download it before the ring is shifted
     for (int p = 0; p < 3; p++)
       CK(cudaMemcpyAsync(s.h_rec[p], e->d_fin[p] + e->plane_elems[p], e->plane_elems[p] * n * 2, cudaMemcpyDeviceToHost, e->stream));
   }
-  for (int p = 0; p < 3; p++)
-    CK(cudaMemcpyAsync(e->d_fin[p], e->d_fin[p] + e->plane_elems[p] * n, e->plane_elems[p] * 2, cudaMemcpyDeviceToDevice, e->stream));
+  // the last key / anchor picture of the batch becomes ring entry 0: the reference the next batch starts from
+  if (last_ref > 0)
+    for (int p = 0; p < 3; p++)
+      CK(cudaMemcpyAsync(e->d_fin[p], e->d_fin[p] + e->plane_elems[p] * last_ref, e->plane_elems[p] * 2, cudaMemcpyDeviceToDevice, e->stream));
   // ---- inter frames of the batch: tokens for the host range coder ----
   s.has_tokens = e->token_path && any_inter;
   CK(cudaEventRecord(s.ev_tok0, e->stream));
@@ -443,6 +493,8 @@ static int launch(av1b_encoder* e, Slot& s, const Slot& in, int n, int64_t first
     RcLaunch& R = s.rl;
     R.n_frames = n; R.n_tiles = e->g_inter.tile_cols * e->g_inter.tile_rows; R.nsb = (int)nsb; R.inter_mask = s.tl.inter_mask;
     R.tokens = s.d_tokens; R.tok_cap = (uint32_t)s.tok_cap; R.sb_off = s.d_sb_off; R.tile_first_k = e->d_tile_first_k; R.cdf_init = e->d_cdf_init;
+    R.cdf_init_alt = e->d_cdf_init_alt; R.alt_mask = 0;
+    for (int b = 0; b < n; b++) if (s.kind[b] == 2) R.alt_mask |= (uint64_t)1 << b;
     R.region = s.d_rc_region; R.tile_len = s.d_rc_len; R.bytes = s.d_rc_bytes; R.cap_bytes = (uint32_t)s.rc_cap; R.overflow = e->d_rc_overflow;
     CK(cudaStreamWaitEvent(s.s_rc, s.ev_k1, 0));
     CK(cudaEventRecord(s.ev_rc0, s.s_rc));
@@ -503,10 +555,10 @@ static int finish(av1b_encoder* e, Slot& s, bool staged, av1b_packet_cb out_cb, 
   cudaEventElapsedTime(&ms, s.ev_k0, s.ev_me); e->t_me_ms += ms;
   cudaEventElapsedTime(&ms, s.ev_k1, s.ev_d2h); e->t_d2h_ms += ms;
   const int n = s.n_frames;
-  for (int b = 0; b < n; b++) {
-    cudaEvent_t* ev = &s.ev_frame[(size_t)b * 5];
+  for (size_t gi = 0; gi < s.groups.size(); gi++) {
+    cudaEvent_t* ev = &s.ev_frame[gi * 5];
     cudaEventElapsedTime(&ms, ev[0], ev[1]);
-    if (s.is_key[b]) e->t_intra_ms += ms; else e->t_inter_ms += ms;
+    if (s.is_key[s.groups[gi].first]) e->t_intra_ms += ms; else e->t_inter_ms += ms;
     if (e->loop_filters) {
       cudaEventElapsedTime(&ms, ev[1], ev[2]); e->t_deblock_ms += ms;
       cudaEventElapsedTime(&ms, ev[2], ev[3]); e->t_cdef_ms += ms;
@@ -588,7 +640,7 @@ static int finish(av1b_encoder* e, Slot& s, bool staged, av1b_packet_cb out_cb, 
     for (int p = 0; p < 3; p++) { sy[b].coef[p] = s.h_coef[p] + (size_t)b * e->plane_elems[p]; sy[b].coef_stride[p] = g.stride[p]; }
     sy[b].cdef_idx = s.h_cdef_idx + (size_t)b * g.sb_rows * g.sb_cols;
     if (e->lr_on) { sy[b].lr_units[0] = s.h_lr_units + (size_t)b * e->lr_n; sy[b].lr_unit_rows[0] = e->lr_rows; sy[b].lr_unit_cols[0] = e->lr_cols; }
-    pack_frame_header(e->seq, s.is_key[b] ? e->fp_key : e->fp_inter, gb, packs[b]);
+    pack_frame_header(e->seq, kind_params(e, s.kind[b]), gb, packs[b]);
     for (int t = 0; t < gb.tile_cols * gb.tile_rows; t++) tasks.emplace_back(b, t);
   }
   if (s.has_tokens && !rc) {
@@ -610,9 +662,9 @@ static int finish(av1b_encoder* e, Slot& s, bool staged, av1b_packet_cb out_cb, 
       const uint32_t t0 = off[e->tile_first_k[tile]];
       // the entry after a frame's last superblock is the next frame's first (or the batch total)
       const uint32_t t1 = off[e->tile_first_k[tile + 1]];
-      pack_tile_tokens(e->fp_inter, s.h_tokens + t0, t1 - t0, packs[b].tiles[tile]);
+      pack_tile_tokens(kind_params(e, s.kind[b]), s.h_tokens + t0, t1 - t0, packs[b].tiles[tile]);
     } else {
-      pack_tile(e->seq, s.is_key[b] ? e->fp_key : e->fp_inter, s.is_key[b] ? e->g : e->g_inter, sy[b], tile, packs[b].tiles[tile]);
+      pack_tile(e->seq, kind_params(e, s.kind[b]), s.is_key[b] ? e->g : e->g_inter, sy[b], tile, packs[b].tiles[tile]);
     }
   });
   std::vector<uint8_t> tu;
@@ -631,7 +683,7 @@ static int finish(av1b_encoder* e, Slot& s, bool staged, av1b_packet_cb out_cb, 
       k.blocks.assign(sy[b].blocks, sy[b].blocks + e->map_elems);
       k.cdef_idx.assign(sy[b].cdef_idx, sy[b].cdef_idx + (size_t)g.sb_rows * g.sb_cols);
       if (e->lr_on) k.lr_units.assign(sy[b].lr_units[0], sy[b].lr_units[0] + e->lr_n);
-      k.is_key = s.is_key[b];
+      k.is_key = s.is_key[b]; k.kind = s.kind[b];
     }
     e->bytes_out += (int64_t)tu.size();
     if (out_cb && out_cb(user, tu.data(), tu.size(), s.first_index + b, s.is_key[b])) { set_error("packet callback aborted"); return AV1B_ERR_CALLBACK; }
@@ -714,6 +766,15 @@ int av1b_encoder_create(const av1b_config* cfg, av1b_encoder** out) {
   e->base_q_idx = av1t_quantizer_to_qindex[cfg->crf];
   if (e->base_q_idx < 1) e->base_q_idx = 1;   // lossless (qindex 0) is not supported
   e->base_q_idx_key = cfg->reserved[3] ? e->base_q_idx : std::max(1, e->base_q_idx * 3 / 4);
+  // one-level hierarchy: every gop_period-th frame is an anchor (the only inter frames that become references, coded
+  // a little finer), the frames between two anchors predict from the last anchor at a much coarser quantiser
+  e->gop_period = cfg->reserved[3] ? 1 : (cfg->gop_period > 0 ? cfg->gop_period : 4);
+  if (e->gop_period > 16) { set_error("gop_period must be <= 16"); delete e; return AV1B_ERR_INVALID; }
+  const int q_nominal = e->base_q_idx;
+  e->base_q_idx_nonref = std::min(255, q_nominal + 48);
+  if (e->gop_period > 1) e->base_q_idx = std::max(1, q_nominal - 8);
+  e->me_smooth = cfg->tune[0] == 0;
+  e->key_var_part = cfg->tune[1] == 0 && cfg->reserved[1] == 0;
   e->blk_log2 = cfg->reserved[1] ? cfg->reserved[1] : 4;
   if (e->blk_log2 < 3 || e->blk_log2 > 6) { set_error("block log2 must be 3..6"); delete e; return AV1B_ERR_INVALID; }
   e->keep = cfg->reserved[0] != 0;
@@ -723,8 +784,10 @@ int av1b_encoder_create(const av1b_config* cfg, av1b_encoder** out) {
   e->keyint = cfg->keyint > 0 ? cfg->keyint : 240;
   av1b_select_frame_params(cfg->bit_depth, e->base_q_idx_key, AV1B_KEY_FRAME, e->loop_filters ? 1 : 0, &e->fp_key);
   av1b_select_frame_params(cfg->bit_depth, e->base_q_idx, AV1B_INTER_FRAME, e->loop_filters ? 1 : 0, &e->fp_inter);
+  av1b_select_frame_params(cfg->bit_depth, e->base_q_idx_nonref, AV1B_INTER_FRAME, e->loop_filters ? 1 : 0, &e->fp_nonref);
+  e->fp_nonref.non_reference = 1;
   if (e->lr_on) {
-    for (Av1bFrameParams* f : {&e->fp_key, &e->fp_inter}) { f->lr_type[0] = AV1B_RESTORE_SWITCHABLE; f->lr_type[1] = f->lr_type[2] = AV1B_RESTORE_NONE; f->lr_unit_shift = 0; f->lr_uv_shift = 0; }
+    for (Av1bFrameParams* f : {&e->fp_key, &e->fp_inter, &e->fp_nonref}) { f->lr_type[0] = AV1B_RESTORE_SWITCHABLE; f->lr_type[1] = f->lr_type[2] = AV1B_RESTORE_NONE; f->lr_unit_shift = 0; f->lr_uv_shift = 0; }
     e->lr_rows = std::max((cfg->height + 32) / 64, 1); e->lr_cols = std::max((cfg->width + 32) / 64, 1);
     e->lr_n = (size_t)e->lr_rows * e->lr_cols;
     memset(&e->lr_cand, 0, sizeof(e->lr_cand));
@@ -733,6 +796,7 @@ int av1b_encoder_create(const av1b_config* cfg, av1b_encoder** out) {
   }
   e->fp_key.tile_cols_log2 = e->g.tile_cols_log2; e->fp_key.tile_rows_log2 = e->g.tile_rows_log2;
   e->fp_inter.tile_cols_log2 = e->g_inter.tile_cols_log2; e->fp_inter.tile_rows_log2 = e->g_inter.tile_rows_log2;
+  e->fp_nonref.tile_cols_log2 = e->g_inter.tile_cols_log2; e->fp_nonref.tile_rows_log2 = e->g_inter.tile_rows_log2;
   e->batch = cfg->frames_in_flight > 0 ? cfg->frames_in_flight : 8;
   if (e->batch > 64) { set_error("frames_in_flight must be <= 64"); delete e; return AV1B_ERR_INVALID; }
   e->host_threads = cfg->host_threads > 0 ? cfg->host_threads : (int)std::max(1u, std::thread::hardware_concurrency());
@@ -813,9 +877,12 @@ int av1b_encoder_create(const av1b_config* cfg, av1b_encoder** out) {
       A(cudaMemcpy(e->d_tile_of_sb, tile_of.data(), nsb * sizeof(uint16_t), cudaMemcpyHostToDevice));
     }
     if (e->rc_on) {
-      std::vector<uint8_t> img(tile_cdfs_size());
+      std::vector<uint8_t> img(tile_cdfs_size()), img2(tile_cdfs_size());
       tile_cdfs_default(e->base_q_idx, img.data());
+      tile_cdfs_default(e->base_q_idx_nonref, img2.data());
       A(cudaMalloc(&e->d_cdf_init, img.size()));
+      A(cudaMalloc(&e->d_cdf_init_alt, img2.size()));
+      if (err == cudaSuccess) A(cudaMemcpy(e->d_cdf_init_alt, img2.data(), img2.size(), cudaMemcpyHostToDevice));
       A(cudaMalloc(&e->d_tile_first_k, e->tile_first_k.size() * sizeof(uint32_t)));
       A(cudaMalloc(&e->d_rc_overflow, sizeof(uint32_t)));
       if (err == cudaSuccess) {
@@ -837,7 +904,7 @@ int av1b_encoder_create(const av1b_config* cfg, av1b_encoder** out) {
     }
   }
   A(cudaMalloc(&e->d_map_key, e->map_elems)); A(cudaMalloc(&e->d_map_inter, e->map_elems));
-  if (e->lr_on) A(cudaMalloc(&e->d_lr_sse, 3 * e->lr_n * sizeof(unsigned long long)));
+  if (e->lr_on) A(cudaMalloc(&e->d_lr_sse, 3 * e->lr_n * F * sizeof(unsigned long long)));
   if (!e->intra_only) {
     for (int l = 0; l < 3; l++) {
       const size_t el = e->plane_elems[0] >> (2 * l);
@@ -847,6 +914,11 @@ int av1b_encoder_create(const av1b_config* cfg, av1b_encoder** out) {
     const size_t n2 = (size_t)((cfg->width + 31) / 32) * ((cfg->height + 31) / 32);
     A(cudaMalloc(&e->d_mv2, n2 * F * 4));
     A(cudaMalloc(&e->d_mvs, e->map_elems * F * 4));
+    {
+      const size_t n1 = (size_t)((cfg->width + 15) / 16) * ((cfg->height + 15) / 16);
+      A(cudaMalloc(&e->d_mv_tmp, n1 * F * 4 * 2));
+      A(cudaMalloc(&e->d_hist, (size_t)F * 2049 * sizeof(uint32_t)));
+    }
     if (err == cudaSuccess) A(cudaMemset(e->d_mvs, 0, e->map_elems * F * 4));
   }
   if (err == cudaSuccess) {
@@ -982,6 +1054,17 @@ int av1b_get_inter_frame_params(av1b_encoder* e, Av1bFrameParams* fp) {
   if (!e || !fp) return AV1B_ERR_INVALID;
   *fp = e->fp_inter;
   return AV1B_OK;
+}
+
+int av1b_get_class_params(av1b_encoder* e, int kind, Av1bFrameParams* fp) {
+  if (!e || !fp || kind < 0 || kind > 2) return AV1B_ERR_INVALID;
+  *fp = kind_params(e, kind);
+  return AV1B_OK;
+}
+
+int av1b_get_frame_kind(av1b_encoder* e, int64_t pos_in_chunk) {
+  if (!e || pos_in_chunk < 0) return AV1B_ERR_INVALID;
+  return frame_kind(e, pos_in_chunk);
 }
 
 int av1b_get_me_lambda(av1b_encoder* e) {

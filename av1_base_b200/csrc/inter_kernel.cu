@@ -50,11 +50,12 @@ template <> struct TxTab<16> {
 // One transform block == one prediction block of plane `p` at (x, y), size N x N, owned by the N lanes
 // `gmask` of one warp; t = lane index inside the group.  buf: (N+7)*(N+1) int32, pred: N*N uint16.
 template <int N>
-__device__ __forceinline__ int code_tb(const InterLaunch& P, int p, int x, int y, int mv_row, int mv_col, int t,
+__device__ __forceinline__ int code_tb(const InterLaunch& P, int frame, int p, int x, int y, int mv_row, int mv_col, int t,
                                        unsigned gmask, int32_t* buf, uint16_t* pred, uint8_t* lv8, bool active) {
   constexpr int S = N + 1;
   const int ss = p > 0, bd = P.bit_depth;
   const int stride = P.g.stride[p];
+  const size_t fo = (size_t)frame * P.plane_elems[p];   // this frame's planes inside the launch's batch buffers
   const int pw = P.g.width >> ss, ph = P.g.height >> ss;
   const uint16_t* ref = P.ref[p];
   // ---------------- prediction ----------------
@@ -97,7 +98,7 @@ __device__ __forceinline__ int code_tb(const InterLaunch& P, int p, int x, int y
   }
   // ---------------- residual (row t) -> shared, as the column pass reads columns ----------------
   {
-    const uint16_t* sp = P.src[p] + (size_t)(y + t) * stride + x;
+    const uint16_t* sp = P.src[p] + fo + (size_t)(y + t) * stride + x;
 #pragma unroll
     for (int c = 0; c < N; c++) buf[t * S + c] = ((int)sp[c] - (int)pred[t * N + c]) * 4;
   }
@@ -116,7 +117,7 @@ __device__ __forceinline__ int code_tb(const InterLaunch& P, int p, int x, int y
   for (int k = 0; k < N; k++) buf[k * S + t] = col[k];
   __syncwarp(gmask);
   int eob = 0, sum_abs = 0;
-  int16_t* cbase = P.coef[p] + av1b_coef_offset(P.g.sb_cols, p, x, y);
+  int16_t* cbase = P.coef[p] + fo + av1b_coef_offset(P.g.sb_cols, p, x, y);
   int16_t* cdst = cbase + t * N;
   constexpr int S8 = N + 2;           // pitch of the capped-magnitude map (two zero guard rows / columns)
   unsigned sign_bits = 0, max_lv = 0;
@@ -184,7 +185,7 @@ __device__ __forceinline__ int code_tb(const InterLaunch& P, int p, int x, int y
     packed = !to_side;
     __syncwarp(gmask);
     if (active) {
-      uint16_t* wdst = to_side ? P.digest[p] + (cbase - P.coef[p]) : reinterpret_cast<uint16_t*>(cbase);
+      uint16_t* wdst = to_side ? P.digest[p] + (cbase - P.coef[p]) : reinterpret_cast<uint16_t*>(cbase);   // (cbase - coef includes fo)
 #pragma unroll
       for (int l = 0; l < N; l++) {
         const int pos = t * N + l, si = TxTab<N>::iscan(pos);
@@ -200,7 +201,7 @@ __device__ __forceinline__ int code_tb(const InterLaunch& P, int p, int x, int y
     }
   }
   // ---------------- reconstruction ----------------
-  uint16_t* rec = P.rec[p] + (size_t)y * stride + x;
+  uint16_t* rec = P.rec[p] + fo + (size_t)y * stride + x;
   const int maxv = (1 << bd) - 1;
   if (eob == 0) {
     if (active) {
@@ -258,6 +259,9 @@ __device__ __forceinline__ void group_buffers(Smem& sm, int group, int32_t** buf
 
 __global__ void __launch_bounds__(kThreads, 3) inter_encode_kernel(const InterLaunch P) {
   __shared__ Smem sm;
+  // frame blockIdx.z of the launch: same reference, same quantiser, own source / outputs
+  const int frame = blockIdx.z;
+  const int16_t* mvs = P.mvs + (size_t)frame * P.map_elems * 2;
   const Av1bGeom& g = P.g;
   const int tid = threadIdx.x, lane = tid & 31;
   const int sbx = blockIdx.x, sby = blockIdx.y;
@@ -275,13 +279,13 @@ __global__ void __launch_bounds__(kThreads, 3) inter_encode_kernel(const InterLa
     const bool active = sm.bl[u] == 4;
     const int ux = sbx * 8 + (u & 7), uy = sby * 8 + (u >> 3);
     int mvr = 0, mvc = 0;
-    if (active) { mvr = P.mvs[(uy * g.w8 + ux) * 2]; mvc = P.mvs[(uy * g.w8 + ux) * 2 + 1]; }
+    if (active) { mvr = mvs[(uy * g.w8 + ux) * 2]; mvc = mvs[(uy * g.w8 + ux) * 2 + 1]; }
     int32_t* buf; uint16_t* pred;
     uint8_t* lv8;
     group_buffers<16>(sm, group, &buf, &pred, &lv8);
     // inactive groups run on the (always allocated) superblock origin and store nothing
     const int x = active ? ux * 8 : sbx * 64, y = active ? uy * 8 : sby * 64;
-    const int eob = code_tb<16>(P, 0, x, y, mvr, mvc, t, gmask, buf, pred, lv8, active);
+    const int eob = code_tb<16>(P, frame, 0, x, y, mvr, mvc, t, gmask, buf, pred, lv8, active);
     if (active && t == 0) sm.eob[0][u] = (uint16_t)eob;
   }
   __syncthreads();
@@ -294,12 +298,12 @@ __global__ void __launch_bounds__(kThreads, 3) inter_encode_kernel(const InterLa
     const bool active = sm.bl[u] == 4;
     const int ux = sbx * 8 + (u & 7), uy = sby * 8 + (u >> 3);
     int mvr = 0, mvc = 0;
-    if (active) { mvr = P.mvs[(uy * g.w8 + ux) * 2]; mvc = P.mvs[(uy * g.w8 + ux) * 2 + 1]; }
+    if (active) { mvr = mvs[(uy * g.w8 + ux) * 2]; mvc = mvs[(uy * g.w8 + ux) * 2 + 1]; }
     int32_t* buf; uint16_t* pred;
     uint8_t* lv8;
       group_buffers<8>(sm, group, &buf, &pred, &lv8);
     const int x = active ? ux * 4 : sbx * 32, y = active ? uy * 4 : sby * 32;
-    const int eob = code_tb<8>(P, p, x, y, mvr, mvc, t, gmask, buf, pred, lv8, active);
+    const int eob = code_tb<8>(P, frame, p, x, y, mvr, mvc, t, gmask, buf, pred, lv8, active);
     if (active && t == 0) sm.eob[p][u] = (uint16_t)eob;
   }
   __syncthreads();
@@ -315,12 +319,12 @@ __global__ void __launch_bounds__(kThreads, 3) inter_encode_kernel(const InterLa
       const bool active = sm.bl[u] == 3;
       const int ux = sbx * 8 + (u & 7), uy = sby * 8 + (u >> 3);
       int mvr = 0, mvc = 0;
-      if (active) { mvr = P.mvs[(uy * g.w8 + ux) * 2]; mvc = P.mvs[(uy * g.w8 + ux) * 2 + 1]; }
+      if (active) { mvr = mvs[(uy * g.w8 + ux) * 2]; mvc = mvs[(uy * g.w8 + ux) * 2 + 1]; }
       int32_t* buf; uint16_t* pred;
       uint8_t* lv8;
       group_buffers<8>(sm, group, &buf, &pred, &lv8);
       const int x = active ? ux * 8 : sbx * 64, y = active ? uy * 8 : sby * 64;
-      const int eob = code_tb<8>(P, 0, x, y, mvr, mvc, t, gmask, buf, pred, lv8, active);
+      const int eob = code_tb<8>(P, frame, 0, x, y, mvr, mvc, t, gmask, buf, pred, lv8, active);
       if (active && t == 0) sm.eob[0][u] = (uint16_t)eob;
       __syncthreads();
     }
@@ -332,12 +336,12 @@ __global__ void __launch_bounds__(kThreads, 3) inter_encode_kernel(const InterLa
       const bool active = sm.bl[u] == 3;
       const int ux = sbx * 8 + (u & 7), uy = sby * 8 + (u >> 3);
       int mvr = 0, mvc = 0;
-      if (active) { mvr = P.mvs[(uy * g.w8 + ux) * 2]; mvc = P.mvs[(uy * g.w8 + ux) * 2 + 1]; }
+      if (active) { mvr = mvs[(uy * g.w8 + ux) * 2]; mvc = mvs[(uy * g.w8 + ux) * 2 + 1]; }
       int32_t* buf; uint16_t* pred;
       uint8_t* lv8;
       group_buffers<4>(sm, group, &buf, &pred, &lv8);
       const int x = active ? ux * 4 : sbx * 32, y = active ? uy * 4 : sby * 32;
-      const int eob = code_tb<4>(P, p, x, y, mvr, mvc, t, gmask, buf, pred, lv8, active);
+      const int eob = code_tb<4>(P, frame, p, x, y, mvr, mvc, t, gmask, buf, pred, lv8, active);
       if (active && t == 0) sm.eob[p][u] = (uint16_t)eob;
       __syncthreads();
     }
@@ -355,8 +359,8 @@ __global__ void __launch_bounds__(kThreads, 3) inter_encode_kernel(const InterLa
       info.skip = (info.eob[0] | info.eob[1] | info.eob[2]) == 0;
       info.angle_y = 0; info.angle_uv = 0; info.tx_type_y = AV1B_DCT_DCT; info.cfl_alpha_u = 0; info.cfl_alpha_v = 0;
       info.is_inter = 1;
-      info.mv[0] = P.mvs[(uy * g.w8 + ux) * 2]; info.mv[1] = P.mvs[(uy * g.w8 + ux) * 2 + 1];
-      P.blocks[(sby * 8 + (u >> 3)) * g.w8 + sbx * 8 + (u & 7)] = info;
+      info.mv[0] = mvs[(uy * g.w8 + ux) * 2]; info.mv[1] = mvs[(uy * g.w8 + ux) * 2 + 1];
+      P.blocks[(size_t)frame * P.map_elems + (sby * 8 + (u >> 3)) * g.w8 + sbx * 8 + (u & 7)] = info;
     }
   }
 }
@@ -364,7 +368,8 @@ __global__ void __launch_bounds__(kThreads, 3) inter_encode_kernel(const InterLa
 }  // namespace
 
 // One CTA of 64 threads per superblock: thread u owns 8x8 unit u (row-major inside the superblock).
-__global__ void __launch_bounds__(64) merge_skip_kernel(Av1bGeom g, Av1bBlockInfo* blocks) {
+__global__ void __launch_bounds__(64) merge_skip_kernel(Av1bGeom g, Av1bBlockInfo* blocks0, size_t map_elems) {
+  Av1bBlockInfo* blocks = blocks0 + (size_t)blockIdx.z * map_elems;
   __shared__ uint8_t bl[64], ok16[64];
   __shared__ int16_t mv[64][2];
   const int u = threadIdx.x, ux = blockIdx.x * 8 + (u & 7), uy = blockIdx.y * 8 + (u >> 3);
@@ -399,9 +404,9 @@ __global__ void __launch_bounds__(64) merge_skip_kernel(Av1bGeom g, Av1bBlockInf
   if (inside && b->blk_log2 != bl[u]) b->blk_log2 = bl[u];
 }
 
-cudaError_t launch_merge_skip(const Av1bGeom& g, Av1bBlockInfo* blocks, cudaStream_t s) {
-  dim3 grid(g.sb_cols, g.sb_rows);
-  merge_skip_kernel<<<grid, 64, 0, s>>>(g, blocks);
+cudaError_t launch_merge_skip(const Av1bGeom& g, Av1bBlockInfo* blocks, size_t map_elems, int n_frames, cudaStream_t s) {
+  dim3 grid(g.sb_cols, g.sb_rows, n_frames);
+  merge_skip_kernel<<<grid, 64, 0, s>>>(g, blocks, map_elems);
   return cudaGetLastError();
 }
 
@@ -409,7 +414,7 @@ cudaError_t launch_inter_encode(const InterLaunch& p0, cudaStream_t s) {
   InterLaunch p = p0;
   p.dc_magic = (uint32_t)(((uint64_t)1 << 32) / (uint32_t)p.dc_q);
   p.ac_magic = (uint32_t)(((uint64_t)1 << 32) / (uint32_t)p.ac_q);
-  dim3 grid(p.g.sb_cols, p.g.sb_rows);
+  dim3 grid(p.g.sb_cols, p.g.sb_rows, p.n_frames > 0 ? p.n_frames : 1);
   inter_encode_kernel<<<grid, kThreads, 0, s>>>(p);
   return cudaGetLastError();
 }

@@ -497,7 +497,64 @@ __global__ void partition_fixed_kernel(Av1bGeom g, int blk_log2, uint8_t* map, i
   map[idx] = (uint8_t)bl;
 }
 
+// Key-frame partition by smoothness (oracle: orc_partition_smooth).  One CTA per 64x64 superblock, thread (i, j) owns the
+// 4x4 luma box (i, j): 16x16 box sums, the plane through the block mean with slopes from the half sums, and the largest
+// deviation of a box from it decide 64x64 / 32x32 / fixed 16x16.
+__global__ void __launch_bounds__(256) partition_smooth_kernel(Av1bGeom g, const uint16_t* __restrict__ src_y, size_t plane_elems,
+                                                               size_t map_elems, int thr, uint8_t* map) {
+  __shared__ int s_sum[5][5];    // [0]: the 64x64 block, [1 + q]: 32x32 quadrant q; S, SL, SR, ST, SB
+  __shared__ int s_bad[5];
+  const int tid = threadIdx.x, i = tid >> 4, j = tid & 15;
+  const int frame = blockIdx.z, x0 = blockIdx.x * 64, y0 = blockIdx.y * 64;
+  const uint16_t* src = src_y + (size_t)frame * plane_elems;
+  if (tid < 25) s_sum[tid / 5][tid % 5] = 0;
+  if (tid < 5) s_bad[tid] = 0;
+  __syncthreads();
+  int box = 0;
+#pragma unroll
+  for (int r = 0; r < 4; r++) {
+    const uint2 v = *reinterpret_cast<const uint2*>(src + (size_t)(y0 + 4 * i + r) * g.stride[0] + x0 + 4 * j);
+    box += (int)((v.x & 0xFFFF) + (v.x >> 16) + (v.y & 0xFFFF) + (v.y >> 16));
+  }
+  const int q = (i >> 3) * 2 + (j >> 3), i8 = i & 7, j8 = j & 7;
+  atomicAdd(&s_sum[0][0], box); atomicAdd(&s_sum[0][j < 8 ? 1 : 2], box); atomicAdd(&s_sum[0][i < 8 ? 3 : 4], box);
+  atomicAdd(&s_sum[1 + q][0], box); atomicAdd(&s_sum[1 + q][j8 < 4 ? 1 : 2], box); atomicAdd(&s_sum[1 + q][i8 < 4 ? 3 : 4], box);
+  __syncthreads();
+  {
+    const int* t = s_sum[0];
+    const int d = 4096 * box - (16 * t[0] + (2 * j - 15) * 2 * (t[2] - t[1]) + (2 * i - 15) * 2 * (t[4] - t[3]));
+    if (abs(d) > thr * 4096) s_bad[0] = 1;
+    const int* u = s_sum[1 + q];
+    const int e = 512 * box - (8 * u[0] + (2 * j8 - 7) * 2 * (u[2] - u[1]) + (2 * i8 - 7) * 2 * (u[4] - u[3]));
+    if (abs(e) > thr * 512) s_bad[1 + q] = 1;
+  }
+  __syncthreads();
+  if (tid < 64) {
+    const int ux = blockIdx.x * 8 + (tid & 7), uy = blockIdx.y * 8 + (tid >> 3);
+    if (ux < g.w8 && uy < g.h8) {
+      int bl = 4;
+      while (bl > 3) {
+        const int n8 = 1 << (bl - 3), xa = ux & ~(n8 - 1), ya = uy & ~(n8 - 1);
+        if (xa + n8 <= g.w8 && ya + n8 <= g.h8) break;
+        bl--;
+      }
+      const int qq = ((tid >> 3) >> 2) * 2 + ((tid & 7) >> 2);
+      const int qx = x0 + (qq & 1) * 32, qy = y0 + (qq >> 1) * 32;
+      if (x0 + 64 <= g.width && y0 + 64 <= g.height && !s_bad[0]) bl = 6;
+      else if (qx + 32 <= g.width && qy + 32 <= g.height && !s_bad[1 + qq]) bl = 5;
+      map[(size_t)frame * map_elems + (size_t)uy * g.w8 + ux] = (uint8_t)bl;
+    }
+  }
+}
+
 }  // namespace
+
+cudaError_t launch_partition_smooth(const Av1bGeom& g, const uint16_t* src_y, size_t plane_elems, size_t map_elems, int thr,
+                                    uint8_t* map, int n_frames, cudaStream_t s) {
+  dim3 grid(g.sb_cols, g.sb_rows, n_frames);
+  partition_smooth_kernel<<<grid, 256, 0, s>>>(g, src_y, plane_elems, map_elems, thr, map);
+  return cudaGetLastError();
+}
 
 cudaError_t launch_partition_fixed(const Av1bGeom& g, int blk_log2, uint8_t* map, int n_frames, cudaStream_t s) {
   const int total = g.w8 * g.h8 * n_frames;

@@ -285,6 +285,12 @@ int av1b_k_pyramid(int device, int width, int height, int n_frames, const uint16
 
 int av1b_k_hme(int device, int width, int height, int n_frames, const uint16_t* cur_l0, const uint16_t* ref_l0,
                int lambda, int16_t* mv_out, int reps, double* ms_per_launch) {
+  return av1b_k_hme_smooth(device, width, height, n_frames, cur_l0, ref_l0, lambda, 0, 0, mv_out, reps, ms_per_launch);
+}
+
+int av1b_k_hme_smooth(int device, int width, int height, int n_frames, const uint16_t* cur_l0, const uint16_t* ref_l0,
+                      int lambda, int lam_s, int iters, int16_t* mv_out, int reps, double* ms_per_launch) {
+  if (n_frames > kMaxSearches) { set_error("at most %d frames per call", kMaxSearches); return AV1B_ERR_INVALID; }
   if (!cur_l0 || !ref_l0 || !mv_out || n_frames <= 0) { set_error("bad argument"); return AV1B_ERR_INVALID; }
   Av1bGeom g;
   if (av1b_geom_init(&g, width, height, 0, 0)) { set_error("unsupported size"); return AV1B_ERR_INVALID; }
@@ -305,7 +311,15 @@ int av1b_k_hme(int device, int width, int height, int n_frames, const uint16_t* 
   L.width = width; L.height = height; L.stride0 = g.stride[0]; L.elems0 = e0; L.lambda = lambda;
   for (int l = 0; l < 3; l++) { L.cur[l] = c[l].as<uint16_t>(); L.ref[l] = r[l].as<uint16_t>(); }
   L.mv2 = m2.as<int16_t>(); L.mv_out = mo.as<int16_t>();
-  if ((rc = timed(t, reps, ms_per_launch, [&]() { return launch_hme(L, n_frames, t.s); }))) return rc;
+  for (int f = 0; f < n_frames; f++) { L.cur_slot[f] = (uint8_t)f; L.ref_slot[f] = (uint8_t)f; }
+  DevBuf tmp, hist;
+  const size_t n1 = (size_t)((width + 15) / 16) * ((height + 15) / 16);
+  CKS(tmp.alloc(n1 * n_frames * 4 * 2)); CKS(hist.alloc((size_t)n_frames * 2049 * 4));
+  L.lam_s = lam_s; L.smooth_iters = iters; L.mv_tmp = tmp.as<int16_t>(); L.hist = hist.as<uint32_t>();
+  if ((rc = timed(t, reps, ms_per_launch, [&]() {
+         cudaError_t e = launch_hme(L, n_frames, t.s);
+         return e != cudaSuccess ? e : launch_hme_smooth(L, n_frames, t.s);
+       }))) return rc;
   CKS(cudaMemcpyAsync(mv_out, mo.p, (size_t)g.w8 * g.h8 * n_frames * 4, cudaMemcpyDeviceToHost, t.s));
   CKS(cudaStreamSynchronize(t.s));
   return AV1B_OK;
@@ -342,11 +356,30 @@ int av1b_k_inter_encode(int device, int width, int height, int bit_depth, int ba
     L.coef[p] = dc[p].as<int16_t>();
   }
   L.blocks = dbl.as<Av1bBlockInfo>(); L.part_map = dpm.as<uint8_t>(); L.mvs = dmv.as<int16_t>(); L.tb_zero_thr = tb_zero_thr; L.pack_levels = 0;
+  L.n_frames = 1; L.map_elems = map;
+  for (int p = 0; p < 3; p++) { L.plane_elems[p] = bs.elems[p]; L.digest[p] = nullptr; }
   if ((rc = timed(t, reps, ms_per_launch, [&]() { return launch_inter_encode(L, t.s); }))) return rc;
-  if (merge_skip) CKS(launch_merge_skip(L.g, L.blocks, t.s));
+  if (merge_skip) CKS(launch_merge_skip(L.g, L.blocks, map, 1, t.s));
   for (int p = 0; p < 3; p++) CKS(cudaMemcpyAsync(coef[p], dc[p].p, bs.elems[p] * 2, cudaMemcpyDeviceToHost, t.s));
   CKS(cudaMemcpyAsync(blocks, dbl.p, map * sizeof(Av1bBlockInfo), cudaMemcpyDeviceToHost, t.s));
   return download_planes(1, rec, bo, t.s);
+}
+
+int av1b_k_partition_smooth(int device, int width, int height, const uint16_t* src_y, int thr, uint8_t* map_out) {
+  if (!src_y || !map_out) { set_error("bad argument"); return AV1B_ERR_INVALID; }
+  Av1bGeom g;
+  if (av1b_geom_init(&g, width, height, 0, 0)) { set_error("unsupported size"); return AV1B_ERR_INVALID; }
+  int rc = select_device(device);
+  if (rc) return rc;
+  Timer t; CKS(t.init());
+  const size_t e0 = (size_t)g.stride[0] * g.rows[0], map = (size_t)g.w8 * g.h8;
+  DevBuf d0, dm;
+  CKS(d0.alloc(e0 * 2)); CKS(dm.alloc(map));
+  CKS(cudaMemcpyAsync(d0.p, src_y, e0 * 2, cudaMemcpyHostToDevice, t.s));
+  CKS(launch_partition_smooth(g, d0.as<uint16_t>(), e0, map, thr, dm.as<uint8_t>(), 1, t.s));
+  CKS(cudaMemcpyAsync(map_out, dm.p, map, cudaMemcpyDeviceToHost, t.s));
+  CKS(cudaStreamSynchronize(t.s));
+  return AV1B_OK;
 }
 
 }  // extern "C"

@@ -75,9 +75,10 @@ struct LrLaunch {
 cudaError_t launch_inv_txfm_add(const int32_t* coef, uint16_t* dst, int n_blocks, int w, int h, int tx_type,
                                 int bit_depth, cudaStream_t s);
 
-// Source pyramid + hierarchical motion estimation (me_kernels.cu).  Level l of frame f starts at
-// cur[l] + f * (elems0 >> 2l); strides are stride0 >> l.  ref[] is laid out the same way (the previous
-// SOURCE picture of every frame).  mv2: scratch [n_frames][n2y*n2x][2]; mv_out: [n_frames][h8*w8][2].
+// Source pyramid + hierarchical motion estimation (me_kernels.cu).  Search f of a launch matches the picture in
+// slot cur_slot[f] against the SOURCE picture in slot ref_slot[f]: level l of slot k starts at cur[l] (ref[l]) +
+// k * (elems0 >> 2l); strides are stride0 >> l.  mv2: scratch [n][n2y*n2x][2]; mv_out: [n][h8*w8][2].
+constexpr int kMaxSearches = 64;
 struct HmeLaunch {
   int32_t width, height, stride0;
   int32_t lambda;             // cost of one integer sample of deviation from the parent vector (SAD units, L0)
@@ -86,18 +87,28 @@ struct HmeLaunch {
   const uint16_t* ref[3];
   int16_t* mv2;
   int16_t* mv_out;
+  uint8_t cur_slot[kMaxSearches], ref_slot[kMaxSearches];
+  // vector-field regularisation (hme_smooth kernels): lam_s per differing neighbour, 0 = off
+  int32_t lam_s, smooth_iters;
+  int16_t* mv_tmp;            // scratch [n][n1y*n1x][2] x 2 (double buffer of the 16x16 block vectors)
+  uint32_t* hist;             // scratch [n][2][1024]: counts, largest key per bin
 };
 cudaError_t launch_pyramid(const uint16_t* l0, uint16_t* l1, uint16_t* l2, int stride0, int rows0, size_t elems0,
                            int n_frames, cudaStream_t s);
 cudaError_t launch_hme(const HmeLaunch& p, int n_frames, cudaStream_t s);
+// relaxation sweeps over the vectors launch_hme left in mv_out (hist: [n * 2048 + n] words, mv_tmp: [2][n][n1][2])
+cudaError_t launch_hme_smooth(const HmeLaunch& p, int n, cudaStream_t s);
 
-// Inter frame encode (inter_kernel.cu): ONE frame per launch (frame k needs the filtered
-// reconstruction of frame k-1 as its reference).
+// Inter frame encode (inter_kernel.cu): the n_frames frames of a launch share ONE reference picture and one
+// quantiser (the frames between two anchors of the hierarchy); frame f of the launch has its source, outputs, block
+// info and vectors at f * plane_elems[p] / f * map_elems from the given pointers.
 struct InterLaunch {
   Av1bGeom g;
   int32_t bit_depth, base_q_idx, quant_rnd, dc_q, ac_q;
+  int32_t n_frames;
+  size_t plane_elems[3], map_elems;
   const uint16_t* src[3];
-  const uint16_t* ref[3];     // previous frame after the in-loop filters (what the decoder holds)
+  const uint16_t* ref[3];     // reference frame after the in-loop filters (what the decoder holds)
   uint16_t* rec[3];
   int16_t* coef[3];
   Av1bBlockInfo* blocks;
@@ -112,7 +123,7 @@ struct InterLaunch {
 };
 cudaError_t launch_inter_encode(const InterLaunch& p, cudaStream_t s);
 // Bottom-up merge of skipped inter siblings with equal vectors into 32x32 / 64x64 blocks (side info only).
-cudaError_t launch_merge_skip(const Av1bGeom& g, Av1bBlockInfo* blocks, cudaStream_t s);
+cudaError_t launch_merge_skip(const Av1bGeom& g, Av1bBlockInfo* blocks, size_t map_elems, int n_frames, cudaStream_t s);
 
 // Device tokenizer for inter frames (token_kernel.cu, tokens.h): one token per coded symbol, per tile in coding
 // order.  All frames of a batch in one set of launches; key frames produce no tokens.
@@ -145,6 +156,8 @@ struct RcLaunch {
   const uint32_t* sb_off;        // [n_frames * nsb + 1] token offsets (TokLaunch)
   const uint32_t* tile_first_k;  // [n_tiles + 1] first coding-order superblock of each tile
   const void* cdf_init;          // TileCdfs image of the frame's quantiser class (default CDFs)
+  const void* cdf_init_alt;      // the image for the frames of alt_mask (non-reference frames: coarser quantiser)
+  uint64_t alt_mask;
   uint8_t* region;               // scratch: tile (f, t) writes at 2 * (its first token) + 64 * (f * n_tiles + t)
   uint32_t* tile_len;            // [n_frames * n_tiles + 1]: byte counts, then (after the scan) offsets + total
   uint8_t* bytes;                // the batch's tile payloads, contiguous in (frame, tile) order
@@ -165,6 +178,10 @@ cudaError_t launch_lr(const LrLaunch& p, int n_frames, cudaStream_t s);
 // beat NONE by more than `bias`.  units_out: [n_frames][unit_rows*unit_cols].
 cudaError_t launch_lr_search(const LrLaunch& p, int n_frames, long long bias, Av1bLrUnit* units_out, cudaStream_t s);
 cudaError_t launch_partition_fixed(const Av1bGeom& g, int blk_log2, uint8_t* map, int n_frames, cudaStream_t s);
+// Key-frame partition by smoothness: 64x64 / 32x32 where the 4x4 box sums of the source stay within `thr` of a plane,
+// else the fixed 16x16 blocks (8x8 at the picture edge).  map: [n_frames][map_elems].
+cudaError_t launch_partition_smooth(const Av1bGeom& g, const uint16_t* src_y, size_t plane_elems, size_t map_elems, int thr,
+                                    uint8_t* map, int n_frames, cudaStream_t s);
 cudaError_t launch_intra_encode(const IntraLaunch& p, int n_frames, cudaStream_t s);
 // Fast key-frame path for 16x16 blocks (8x8 at the picture edge): open-loop mode kernel + closed-loop
 // reconstruction kernel + skip flags (intra_fast.cu).  Same results as launch_intra_encode.

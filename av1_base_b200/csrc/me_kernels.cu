@@ -71,8 +71,8 @@ __global__ void __launch_bounds__(256) hme_l2_kernel(const HmeLaunch P) {
   const int frame = blockIdx.z;
   const int w2 = P.width >> 2, h2 = P.height >> 2, s2 = P.stride0 >> 2;
   const size_t e2 = P.elems0 >> 4;
-  const uint16_t* cur = P.cur[2] + (size_t)frame * e2;
-  const uint16_t* ref = P.ref[2] + (size_t)frame * e2;
+  const uint16_t* cur = P.cur[2] + (size_t)P.cur_slot[frame] * e2;
+  const uint16_t* ref = P.ref[2] + (size_t)P.ref_slot[frame] * e2;
   const int x0 = blockIdx.x * kT2, y0 = blockIdx.y * kT2;
   for (int o = tid; o < kT2 * kT2; o += 256) {
     const int r = o / kT2, c = o % kT2;
@@ -255,10 +255,10 @@ __global__ void __launch_bounds__(256) hme_refine_kernel(const HmeLaunch P) {
   if (blk >= n1x * n1y) return;
   const int bx = blk % n1x, by = blk / n1x;
   const int w1 = P.width >> 1, h1 = P.height >> 1, s1 = P.stride0 >> 1;
-  const uint16_t* cur1 = P.cur[1] + (size_t)frame * (P.elems0 >> 2);
-  const uint16_t* ref1 = P.ref[1] + (size_t)frame * (P.elems0 >> 2);
-  const uint16_t* cur0 = P.cur[0] + (size_t)frame * P.elems0;
-  const uint16_t* ref0 = P.ref[0] + (size_t)frame * P.elems0;
+  const uint16_t* cur1 = P.cur[1] + (size_t)P.cur_slot[frame] * (P.elems0 >> 2);
+  const uint16_t* ref1 = P.ref[1] + (size_t)P.ref_slot[frame] * (P.elems0 >> 2);
+  const uint16_t* cur0 = P.cur[0] + (size_t)P.cur_slot[frame] * P.elems0;
+  const uint16_t* ref0 = P.ref[0] + (size_t)P.ref_slot[frame] * P.elems0;
   const int16_t* m2 = P.mv2 + ((size_t)frame * n2x * n2y + (size_t)(by >> 1) * n2x + (bx >> 1)) * 2;
   const int py = 2 * m2[0], px = 2 * m2[1];
   // ---- L1: 8x8 block at (8bx, 8by), +-2 around (px, py) ----
@@ -319,7 +319,169 @@ __global__ void __launch_bounds__(256) hme_refine_kernel(const HmeLaunch P) {
   }
 }
 
+// ---------------------------------------------------------------------------------------------
+// Vector-field regularisation (oracle: orc_mv_dominant, orc_me_smooth).
+//   hme_gather_kernel : 16x16 block vectors out of the per-8x8 vector plane + histogram of the field (1024 hashed
+//                       bins: count, largest packed vector) for the dominant vector.
+//   hme_smooth_kernel : one relaxation sweep.  One warp per 16x16 block: the block and the 17x17 window of the
+//                       reference SOURCE picture at each candidate are staged in shared memory, SAD on the bilinear
+//                       quarter-sample interpolation, cost = SAD + lam_s * (neighbours with another vector).
+__device__ __forceinline__ uint32_t mv_pack(int mvy, int mvx) { return ((uint32_t)(uint16_t)(int16_t)mvy << 16) | (uint16_t)(int16_t)mvx; }
+__device__ __forceinline__ uint32_t mv_hash(uint32_t k) { return ((k * 2654435761u) >> 22) & 1023u; }
+
+__global__ void __launch_bounds__(256) hme_gather_kernel(const HmeLaunch P, const int16_t* __restrict__ field8, int16_t* field16,
+                                                         int from8) {
+  // from8 = 1: read the per-8x8 plane (after the refine kernel); 0: field16 already holds the block vectors
+  const int n1x = (P.width + 15) / 16, n1y = (P.height + 15) / 16, n1 = n1x * n1y;
+  const int frame = blockIdx.z, b = blockIdx.x * 256 + threadIdx.x;
+  if (b >= n1) return;
+  int16_t* f16 = field16 + ((size_t)frame * n1 + b) * 2;
+  int mvy, mvx;
+  if (from8) {
+    const int w8 = P.width >> 3, h8 = P.height >> 3, bx = b % n1x, by = b / n1x;
+    const int16_t* m = field8 + ((size_t)frame * w8 * h8 + (size_t)(by * 2) * w8 + bx * 2) * 2;
+    mvy = m[0]; mvx = m[1];
+    f16[0] = (int16_t)mvy; f16[1] = (int16_t)mvx;
+  } else {
+    mvy = f16[0]; mvx = f16[1];
+  }
+  const uint32_t k = mv_pack(mvy, mvx), h = mv_hash(k);
+  uint32_t* hist = P.hist + (size_t)frame * 2048;
+  atomicAdd(&hist[h], 1u);
+  atomicMax(&hist[1024 + h], k ^ 0x80008000u);
+}
+
+// dominant vector of the frame: the fullest bin (lowest index on ties) -> hist[0..1] of the frame's second half is
+// left untouched; the result goes to dom[frame] as a packed vector
+__global__ void __launch_bounds__(1024) hme_dominant_kernel(const HmeLaunch P, uint32_t* dom) {
+  __shared__ unsigned long long best[32];
+  const int frame = blockIdx.x, t = threadIdx.x;
+  uint32_t* hist = P.hist + (size_t)frame * 2048;
+  // key: count high, then the LOWER bin wins -> (count << 10) | (1023 - bin), maximised
+  unsigned long long key = ((unsigned long long)hist[t] << 10) | (unsigned)(1023 - t);
+  for (int o = 16; o; o >>= 1) key = max(key, __shfl_xor_sync(0xffffffffu, key, o));
+  if ((t & 31) == 0) best[t >> 5] = key;
+  __syncthreads();
+  if (t < 32) {
+    key = best[t];
+    for (int o = 16; o; o >>= 1) key = max(key, __shfl_xor_sync(0xffffffffu, key, o));
+    if (t == 0) dom[frame] = hist[1024 + (1023 - (int)(key & 1023))] ^ 0x80008000u;
+  }
+  __syncthreads();
+  // clear for the next sweep
+  hist[t] = 0; hist[1024 + t] = 0;
+}
+
+struct SmoothSmem {
+  uint16_t cur[8][16 * 16];
+  uint16_t win[8][17 * 18];
+};
+
+__global__ void __launch_bounds__(256) hme_smooth_kernel(const HmeLaunch P, const int16_t* __restrict__ vin, int16_t* vout,
+                                                         const uint32_t* __restrict__ dom, int16_t* field8) {
+  __shared__ SmoothSmem sm;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int frame = blockIdx.z;
+  const int n1x = (P.width + 15) / 16, n1y = (P.height + 15) / 16, n1 = n1x * n1y;
+  const int blk = blockIdx.x * 8 + warp;
+  if (blk >= n1) return;
+  const int bx = blk % n1x, by = blk / n1x;
+  const int W = P.width, H = P.height;
+  const uint16_t* cur0 = P.cur[0] + (size_t)P.cur_slot[frame] * P.elems0;
+  const uint16_t* ref0 = P.ref[0] + (size_t)P.ref_slot[frame] * P.elems0;
+  const int16_t* v = vin + (size_t)frame * n1 * 2;
+  for (int o = lane; o < 256; o += 32)
+    sm.cur[warp][o] = cur0[(size_t)clampi(by * 16 + (o >> 4), 0, H - 1) * P.stride0 + clampi(bx * 16 + (o & 15), 0, W - 1)];
+  int cy[7], cx[7];
+  bool have[4];
+  cy[0] = v[blk * 2]; cx[0] = v[blk * 2 + 1];
+  {
+    const int nby[4] = {0, 0, -1, 1}, nbx[4] = {-1, 1, 0, 0};
+#pragma unroll
+    for (int k = 0; k < 4; k++) {
+      const int yy = by + nby[k], xx = bx + nbx[k];
+      have[k] = yy >= 0 && yy < n1y && xx >= 0 && xx < n1x;
+      const int o = have[k] ? yy * n1x + xx : blk;
+      cy[1 + k] = v[o * 2]; cx[1 + k] = v[o * 2 + 1];
+    }
+  }
+  cy[5] = 0; cx[5] = 0;
+  {
+    const uint32_t d = dom[frame];
+    cy[6] = (int16_t)(d >> 16); cx[6] = (int16_t)(d & 0xFFFF);
+  }
+  int best_cost = 0, best_k = -1;
+#pragma unroll 1
+  for (int k = 0; k < 7; k++) {
+    bool dup = false;
+    for (int j = 0; j < k; j++) dup = dup || (cy[j] == cy[k] && cx[j] == cx[k]);
+    if (dup) continue;   // warp-uniform
+    int diff = 0;
+#pragma unroll
+    for (int j = 0; j < 4; j++) diff += have[j] && (cy[1 + j] != cy[k] || cx[1 + j] != cx[k]);
+    const int ix = cx[k] >> 3, iy = cy[k] >> 3, fx = (cx[k] & 7) >> 1, fy = (cy[k] & 7) >> 1;
+    __syncwarp();
+    for (int o = lane; o < 17 * 17; o += 32) {
+      const int r = o / 17, c = o % 17;
+      sm.win[warp][r * 18 + c] = ref0[(size_t)clampi(by * 16 + iy + r, 0, H - 1) * P.stride0 + clampi(bx * 16 + ix + c, 0, W - 1)];
+    }
+    __syncwarp();
+    // lane (r, h): row r, columns 8h .. 8h+7
+    const int r = lane >> 1, c0 = (lane & 1) * 8;
+    const uint16_t* wr = &sm.win[warp][r * 18 + c0];
+    const uint16_t* cr = &sm.cur[warp][r * 16 + c0];
+    unsigned sad = 0;
+    if ((fx | fy) == 0) {
+#pragma unroll
+      for (int j = 0; j < 8; j++) sad = __usad((unsigned)cr[j], (unsigned)wr[j], sad);
+    } else {
+      const int w00 = (4 - fx) * (4 - fy), w01 = fx * (4 - fy), w10 = (4 - fx) * fy, w11 = fx * fy;
+#pragma unroll
+      for (int j = 0; j < 8; j++) {
+        const unsigned p = (unsigned)(w00 * wr[j] + w01 * wr[j + 1] + w10 * wr[18 + j] + w11 * wr[18 + j + 1] + 8) >> 4;
+        sad = __usad((unsigned)cr[j], p, sad);
+      }
+    }
+    for (int o = 16; o; o >>= 1) sad += __shfl_xor_sync(0xffffffffu, sad, o);
+    const int cost = (int)sad + P.lam_s * diff;
+    if (best_k < 0 || cost < best_cost) { best_cost = cost; best_k = k; }
+  }
+  int oy = cy[0], ox = cx[0];
+#pragma unroll
+  for (int k = 1; k < 7; k++) if (k == best_k) { oy = cy[k]; ox = cx[k]; }
+  if (lane == 0) {
+    vout[((size_t)frame * n1 + blk) * 2] = (int16_t)oy;
+    vout[((size_t)frame * n1 + blk) * 2 + 1] = (int16_t)ox;
+  }
+  if (field8 && lane < 4) {
+    const int uy = by * 2 + (lane >> 1), ux = bx * 2 + (lane & 1);
+    const int w8 = P.width >> 3, h8 = P.height >> 3;
+    if (uy < h8 && ux < w8) {
+      int16_t* out = field8 + ((size_t)frame * w8 * h8 + (size_t)uy * w8 + ux) * 2;
+      out[0] = (int16_t)oy; out[1] = (int16_t)ox;
+    }
+  }
+}
+
 }  // namespace
+
+cudaError_t launch_hme_smooth(const HmeLaunch& p, int n, cudaStream_t s) {
+  if (p.lam_s <= 0 || p.smooth_iters <= 0) return cudaSuccess;
+  const int n1 = ((p.width + 15) / 16) * ((p.height + 15) / 16);
+  int16_t* va = p.mv_tmp;
+  int16_t* vb = p.mv_tmp + (size_t)n * n1 * 2;
+  uint32_t* dom = p.hist + (size_t)n * 2048;
+  dim3 gg((n1 + 255) / 256, 1, n), gs((n1 + 7) / 8, 1, n);
+  cudaError_t e = cudaMemsetAsync(p.hist, 0, (size_t)n * 2048 * sizeof(uint32_t), s);
+  if (e != cudaSuccess) return e;
+  for (int it = 0; it < p.smooth_iters; it++) {
+    hme_gather_kernel<<<gg, 256, 0, s>>>(p, p.mv_out, va, it == 0);
+    hme_dominant_kernel<<<n, 1024, 0, s>>>(p, dom);
+    hme_smooth_kernel<<<gs, 256, 0, s>>>(p, va, vb, dom, it + 1 == p.smooth_iters ? p.mv_out : nullptr);
+    int16_t* t = va; va = vb; vb = t;
+  }
+  return cudaGetLastError();
+}
 
 cudaError_t launch_pyramid(const uint16_t* l0, uint16_t* l1, uint16_t* l2, int stride0, int rows0, size_t elems0,
                            int n_frames, cudaStream_t s) {

@@ -124,7 +124,7 @@ __global__ void __launch_bounds__(32) rc_code_kernel(const __grid_constant__ RcL
   const uint32_t t0 = off[P.tile_first_k[tile]], t1 = off[P.tile_first_k[tile + 1]];
   if (t1 > P.tok_cap) { if (lane == 0) *len_out = 0; return; }   // token buffer overflowed: the host grows it and codes again
   {
-    const uint32_t* src = reinterpret_cast<const uint32_t*>(P.cdf_init);
+    const uint32_t* src = reinterpret_cast<const uint32_t*>(((P.alt_mask >> f) & 1) ? P.cdf_init_alt : P.cdf_init);
     for (int i = lane; i < kWords; i += 32) cdf_words[i] = src[i];
   }
   int ref_wiener[2][3] = {{3, -7, 15}, {3, -7, 15}}, ref_sgr[2] = {-32, 31};   // luma plane only

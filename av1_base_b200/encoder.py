@@ -28,7 +28,7 @@ class Encoder:
     def __init__(self, width, height, bit_depth=10, crf=30, preset=6, keyint=240, fps=(30, 1), device_id=0,
                  tile_cols_log2=-1, tile_rows_log2=-1, hdr=False, host_threads=0, frames_in_flight=0,
                  keep_debug=False, blk_log2=0, loop_filters=True, intra_only=False, tb_zero_thr=0, raster_levels=False,
-                 pack_path=0, lr_off=False, tile_sb=0):
+                 pack_path=0, lr_off=False, tile_sb=0, gop_period=0, me_smooth=True, key_var_part=True):
         L = abi.lib()
         cfg = abi.Config()
         L.av1b_config_default(C.byref(cfg))
@@ -50,6 +50,9 @@ class Encoder:
         cfg.reserved[5] = 1 if raster_levels else pack_path
         cfg.reserved[6] = int(lr_off)
         cfg.reserved[7] = tile_sb          # inter-frame tile size in superblocks (0 = default)
+        cfg.gop_period = gop_period        # 0 = default (4), 1 = plain P chain
+        cfg.tune[0] = 0 if me_smooth else 1
+        cfg.tune[1] = 0 if key_var_part else 1
         self.cfg = cfg
         self._h = C.c_void_p()
         _check(L.av1b_encoder_create(C.byref(cfg), C.byref(self._h)))
@@ -142,6 +145,15 @@ class Encoder:
         fp = abi.FrameParams()
         _check(abi.lib().av1b_get_inter_frame_params(self._h, C.byref(fp)))
         return fp
+
+    def class_params(self, kind):
+        """Frame-level parameters of a frame kind: 0 key, 1 anchor, 2 non-reference."""
+        fp = abi.FrameParams()
+        _check(abi.lib().av1b_get_class_params(self._h, kind, C.byref(fp)))
+        return fp
+
+    def frame_kind(self, pos):
+        return int(abi.lib().av1b_get_frame_kind(self._h, C.c_int64(pos)))
 
     def me_lambda(self):
         """Vector-deviation cost the encoder hands to the motion search (SAD units)."""

@@ -127,6 +127,26 @@ def hme(width, height, cur_l0, ref_l0, lam=0, device=0, reps=1):
     return mv, ms.value
 
 
+def hme_smooth(width, height, cur_l0, ref_l0, lam, lam_s, iters=2, device=0, reps=1):
+    """hme followed by `iters` relaxation sweeps of the vector field. Returns (mv [n, h8*w8, 2], ms)."""
+    cur = np.ascontiguousarray(cur_l0, np.uint16)
+    ref = np.ascontiguousarray(ref_l0, np.uint16)
+    n = cur.shape[0]
+    mv = np.zeros((n, (height // 8) * (width // 8), 2), np.int16)
+    ms = C.c_double(0)
+    _ck(abi.lib().av1b_k_hme_smooth(device, width, height, n, cur.ctypes.data_as(C.c_void_p), ref.ctypes.data_as(C.c_void_p),
+                                    int(lam), int(lam_s), int(iters), mv.ctypes.data_as(C.c_void_p), reps, C.byref(ms)))
+    return mv, ms.value
+
+
+def partition_smooth(width, height, luma_padded, thr, device=0):
+    """Key-frame partition by smoothness: block log2 per 8x8 unit [h8*w8]."""
+    l0 = np.ascontiguousarray(luma_padded, np.uint16)
+    m = np.zeros((height // 8) * (width // 8), np.uint8)
+    _ck(abi.lib().av1b_k_partition_smooth(device, width, height, l0.ctypes.data_as(C.c_void_p), int(thr), m.ctypes.data_as(C.c_void_p)))
+    return m
+
+
 def inter_encode(width, height, bit_depth, base_q_idx, part_map, mvs, src_padded, ref_padded, tb_zero_thr=0,
                  merge_skip=False, device=0, reps=1):
     """Returns (rec[3], coef[3], blocks, ms); planes in the padded layout."""

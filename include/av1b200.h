@@ -46,6 +46,11 @@ typedef struct av1b_config {
   int32_t hdr;                    /* 1: signal BT.2020/PQ in the sequence header                   */
   int32_t host_threads;           /* entropy-coding threads, 0 = auto                              */
   int32_t frames_in_flight;       /* frames batched per device pass, 0 = auto                      */
+  int32_t gop_period;             /* one-level hierarchy: every gop_period-th frame after a key frame is an anchor (inter frame that
+                                     becomes the reference, quantiser index - 8); the frames between two anchors predict from the last
+                                     anchor at quantiser index + 48 and are referenced by nobody.  0 = default (4), 1 = plain P chain */
+  int32_t tune[7];                /* [0]: 1 = vector-field regularisation of the motion search off; [1]: 1 = fixed 16x16 key-frame
+                                     partition (default: 64x64 / 32x32 blocks where the source is smooth) */
   int32_t reserved[8];            /* [0]: keep recon+symbols per frame (tests); [1]: fixed block log2 (3..6), 0 = default;
                                      [2]: 1 = in-loop filters off; [3]: 1 = every frame is a key frame;
                                      [4]: inter transform-block drop threshold (0 = off);
@@ -102,6 +107,9 @@ struct Av1bFrameParams;
 /* frame-level parameters the encoder signals for key frames (deblock levels, CDEF presets, ...) */
 int av1b_get_frame_params(av1b_encoder* enc, struct Av1bFrameParams* fp);
 int av1b_get_inter_frame_params(av1b_encoder* enc, struct Av1bFrameParams* fp);
+/* kind of the frame at position pos of a closed GOP: 0 key, 1 anchor, 2 non-reference; and the frame-level parameters of a kind */
+int av1b_get_frame_kind(av1b_encoder* enc, int64_t pos_in_chunk);
+int av1b_get_class_params(av1b_encoder* enc, int kind, struct Av1bFrameParams* fp);
 /* vector-deviation cost (SAD units) the encoder uses in its motion search: half the AC quantiser step */
 int av1b_get_me_lambda(av1b_encoder* enc);
 /* 1 / 0: whether kept frame `frame_in_chunk` was coded as a key frame (needs config.reserved[0] = 1) */
@@ -167,6 +175,14 @@ int av1b_k_pyramid(int device, int width, int height, int n_frames, const uint16
  * parent vector (SAD units). The timed launch is the search (two kernels). */
 int av1b_k_hme(int device, int width, int height, int n_frames, const uint16_t* cur_l0, const uint16_t* ref_l0,
                int lambda, int16_t* mv_out, int reps, double* ms_per_launch);
+/* av1b_k_hme followed by `iters` relaxation sweeps of the vector field (E2): every 16x16 block picks, among its own
+ * vector, its four neighbours', the zero vector and the frame's dominant vector, the one with the smallest
+ * SAD (bilinear quarter-sample interpolation) + lam_s * (neighbours with a different vector). */
+int av1b_k_hme_smooth(int device, int width, int height, int n_frames, const uint16_t* cur_l0, const uint16_t* ref_l0,
+                      int lambda, int lam_s, int iters, int16_t* mv_out, int reps, double* ms_per_launch);
+/* Key-frame partition by smoothness (E3/E4 decision): src_y = one padded luma plane; map_out[h8*w8] = block log2 (3..6)
+ * per 8x8 unit: 64x64 / 32x32 where the 4x4 box sums stay within thr of a plane, else 16x16 (8x8 at the picture edge). */
+int av1b_k_partition_smooth(int device, int width, int height, const uint16_t* src_y, int thr, uint8_t* map_out);
 /* Inter frame encode (E4 + E5 for inter frames): one frame; part_map [h8*w8] with values 3 / 4.
  * tb_zero_thr: drop transform blocks whose levels sum to <= thr; merge_skip: afterwards merge skipped
  * siblings with equal vectors into 32x32 / 64x64 blocks. */

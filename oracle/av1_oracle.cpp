@@ -354,6 +354,51 @@ extern "C" void orc_partition_fixed(const Av1bGeom* g, int blk_log2, uint8_t* ma
     }
 }
 
+// Key-frame partition by smoothness (encoder side, ours).  Sums of the 4x4 luma boxes of a 64x64 (then 32x32) block
+// are compared with the plane through the block's mean whose slopes come from the half sums (right - left, bottom -
+// top): when no box deviates from that plane by more than thr (in box-sum units) the block is coded whole (one
+// prediction, one transform); otherwise it splits, down to the fixed 16x16 blocks.  Blocks that do not lie inside the
+// picture keep the fixed partition.  Scaled by n^3 (n boxes per side) everything is an integer:
+//   n^3 * plane(i, j) = n * S + (2j - n + 1) * 2 (SR - SL) + (2i - n + 1) * 2 (SB - ST).
+static bool block_is_smooth(const uint16_t* src_y, int stride, int x0, int y0, int N, int thr) {
+  const int n = N / 4;
+  int32_t box[16][16];
+  int64_t S = 0, SL = 0, SR = 0, ST = 0, SB = 0;
+  for (int i = 0; i < n; i++)
+    for (int j = 0; j < n; j++) {
+      int32_t s = 0;
+      for (int y = 0; y < 4; y++) for (int x = 0; x < 4; x++) s += src_y[(size_t)(y0 + 4 * i + y) * stride + x0 + 4 * j + x];
+      box[i][j] = s;
+      S += s;
+      (j < n / 2 ? SL : SR) += s;
+      (i < n / 2 ? ST : SB) += s;
+    }
+  const int64_t gx = 2 * (SR - SL), gy = 2 * (SB - ST), n3 = (int64_t)n * n * n;
+  for (int i = 0; i < n; i++)
+    for (int j = 0; j < n; j++) {
+      const int64_t d = n3 * box[i][j] - (n * S + (2 * j - n + 1) * gx + (2 * i - n + 1) * gy);
+      if ((d < 0 ? -d : d) > (int64_t)thr * n3) return false;
+    }
+  return true;
+}
+
+extern "C" void orc_partition_smooth(const Av1bGeom* g, const uint16_t* src_y, int stride, int thr, uint8_t* map /*[h8*w8]*/) {
+  orc_partition_fixed(g, 4, map);
+  for (int y0 = 0; y0 + 64 <= g->height; y0 += 64)
+    for (int x0 = 0; x0 + 64 <= g->width; x0 += 64) {
+      if (block_is_smooth(src_y, stride, x0, y0, 64, thr)) {
+        for (int yy = 0; yy < 8; yy++) for (int xx = 0; xx < 8; xx++) map[(y0 / 8 + yy) * g->w8 + x0 / 8 + xx] = 6;
+        continue;
+      }
+    }
+  for (int y0 = 0; y0 + 32 <= g->height; y0 += 32)
+    for (int x0 = 0; x0 + 32 <= g->width; x0 += 32) {
+      if (map[(y0 / 8) * g->w8 + x0 / 8] == 6) continue;
+      if (block_is_smooth(src_y, stride, x0, y0, 32, thr))
+        for (int yy = 0; yy < 4; yy++) for (int xx = 0; xx < 4; xx++) map[(y0 / 8 + yy) * g->w8 + x0 / 8 + xx] = 5;
+    }
+}
+
 struct IntraEnc {
   const Av1bGeom* g;
   int bd, qidx, rnd;
@@ -642,6 +687,104 @@ extern "C" void orc_hme(const Av1bGeom* g, const uint16_t* cur0, const uint16_t*
           mv_out[(uy * g->w8 + ux) * 2 + 1] = (int16_t)mvx;
         }
     }
+}
+
+// ------------------------------------------------------------------------------------------------
+// Vector-field regularisation (encoder side, ours): SAD of a 16x16 block at quarter-sample vectors on a bilinear
+// interpolation of the reference SOURCE picture, then a few synchronous relaxation sweeps in which every block picks,
+// among its own vector, the vectors of its four neighbours, the zero vector and the frame's dominant vector, the one
+// with the smallest  SAD + lam_s * (number of neighbours with a different vector).  Flat / noisy areas, where the SADs
+// of all candidates are within noise of each other, collapse onto one vector: skipped blocks merge to 32x32 / 64x64 and
+// the vectors that are coded are predicted exactly (NEARESTMV).
+// ------------------------------------------------------------------------------------------------
+static int sad_block_q(const uint16_t* cur, const uint16_t* ref, int stride, int w, int h, int bx, int by, int n, int mvx,
+                       int mvy) {   // mv in 1/8 luma samples (multiples of 2)
+  const int ix = mvx >> 3, iy = mvy >> 3, fx = (mvx & 7) >> 1, fy = (mvy & 7) >> 1;   // floor, quarter-sample phase 0..3
+  int s = 0;
+  for (int i = 0; i < n; i++)
+    for (int j = 0; j < n; j++) {
+      const int x = bx + j + ix, y = by + i + iy;
+      int p;
+      if ((fx | fy) == 0) {
+        p = px_clamped(ref, stride, w, h, x, y);
+      } else {
+        const int a = px_clamped(ref, stride, w, h, x, y), b = px_clamped(ref, stride, w, h, x + 1, y);
+        const int c = px_clamped(ref, stride, w, h, x, y + 1), d = px_clamped(ref, stride, w, h, x + 1, y + 1);
+        p = ((4 - fx) * (4 - fy) * a + fx * (4 - fy) * b + (4 - fx) * fy * c + fx * fy * d + 8) >> 4;
+      }
+      s += abs(px_clamped(cur, stride, w, h, bx + j, by + i) - p);
+    }
+  return s;
+}
+
+// Dominant vector of a field of n vectors: 1024-bin histogram over a hash of the vector; the bin with the most entries
+// wins (lowest bin on ties) and stands for the largest packed vector that fell into it.
+static inline uint32_t mv_pack(int mvy, int mvx) { return ((uint32_t)(uint16_t)(int16_t)mvy << 16) | (uint16_t)(int16_t)mvx; }
+static inline uint32_t mv_hash(uint32_t k) { return ((k * 2654435761u) >> 22) & 1023u; }
+extern "C" void orc_mv_dominant(const int16_t* mv, int n, int16_t* dom) {
+  std::vector<uint32_t> cnt(1024, 0), key(1024, 0);
+  for (int i = 0; i < n; i++) {
+    const uint32_t k = mv_pack(mv[2 * i], mv[2 * i + 1]), b = mv_hash(k);
+    cnt[b]++;
+    key[b] = std::max(key[b], k ^ 0x80008000u);   // order-preserving for signed halves
+  }
+  int best = 0;
+  for (int b = 1; b < 1024; b++) if (cnt[b] > cnt[best]) best = b;
+  const uint32_t k = key[best] ^ 0x80008000u;
+  dom[0] = (int16_t)(k >> 16); dom[1] = (int16_t)(k & 0xFFFF);
+}
+
+// mv_io: [h8*w8][2] as produced by orc_hme (the vector of a 16x16 block replicated on its 8x8 units); updated in place.
+extern "C" void orc_me_smooth(const Av1bGeom* g, const uint16_t* cur0, const uint16_t* ref0, int lam_s, int iters,
+                              int16_t* mv_io) {
+  const int W = g->width, H = g->height, s0 = g->stride[0];
+  const int n1x = (W + 15) / 16, n1y = (H + 15) / 16, n1 = n1x * n1y;
+  std::vector<int16_t> v((size_t)n1 * 2), nv((size_t)n1 * 2);
+  for (int by = 0; by < n1y; by++)
+    for (int bx = 0; bx < n1x; bx++) {
+      const int16_t* m = mv_io + ((size_t)(by * 2) * g->w8 + bx * 2) * 2;
+      v[(by * n1x + bx) * 2] = m[0]; v[(by * n1x + bx) * 2 + 1] = m[1];
+    }
+  for (int it = 0; it < iters; it++) {
+    int16_t dom[2];
+    orc_mv_dominant(v.data(), n1, dom);
+    for (int by = 0; by < n1y; by++)
+      for (int bx = 0; bx < n1x; bx++) {
+        const int b = by * n1x + bx;
+        // candidates in visiting order; neighbours outside the picture repeat the block's own vector
+        int cand[7][2];
+        const int nb[4][2] = {{0, -1}, {0, 1}, {-1, 0}, {1, 0}};   // left, right, up, down
+        cand[0][0] = v[b * 2]; cand[0][1] = v[b * 2 + 1];
+        bool have[4];
+        for (int k = 0; k < 4; k++) {
+          const int yy = by + nb[k][0], xx = bx + nb[k][1];
+          have[k] = yy >= 0 && yy < n1y && xx >= 0 && xx < n1x;
+          const int o = have[k] ? (yy * n1x + xx) : b;
+          cand[1 + k][0] = v[o * 2]; cand[1 + k][1] = v[o * 2 + 1];
+        }
+        cand[5][0] = 0; cand[5][1] = 0;
+        cand[6][0] = dom[0]; cand[6][1] = dom[1];
+        int best_cost = 0, best_k = -1;
+        for (int k = 0; k < 7; k++) {
+          bool dup = false;
+          for (int j = 0; j < k; j++) dup = dup || (cand[j][0] == cand[k][0] && cand[j][1] == cand[k][1]);
+          if (dup) continue;
+          int diff = 0;
+          for (int j = 0; j < 4; j++) diff += have[j] && (cand[1 + j][0] != cand[k][0] || cand[1 + j][1] != cand[k][1]);
+          const int cost = sad_block_q(cur0, ref0, s0, W, H, bx * 16, by * 16, 16, cand[k][1], cand[k][0]) + lam_s * diff;
+          if (best_k < 0 || cost < best_cost) { best_cost = cost; best_k = k; }
+        }
+        nv[b * 2] = (int16_t)cand[best_k][0]; nv[b * 2 + 1] = (int16_t)cand[best_k][1];
+      }
+    v.swap(nv);
+  }
+  for (int by = 0; by < n1y; by++)
+    for (int bx = 0; bx < n1x; bx++)
+      for (int uy = by * 2; uy < std::min(by * 2 + 2, g->h8); uy++)
+        for (int ux = bx * 2; ux < std::min(bx * 2 + 2, g->w8); ux++) {
+          mv_io[(uy * g->w8 + ux) * 2] = v[(by * n1x + bx) * 2];
+          mv_io[(uy * g->w8 + ux) * 2 + 1] = v[(by * n1x + bx) * 2 + 1];
+        }
 }
 
 // ------------------------------------------------------------------------------------------------

@@ -1,0 +1,109 @@
+"""TEST INFRASTRUCTURE -- NOT PRODUCT CODE.  The CPU oracle's statement of the encoder's whole decision chain for one
+closed GOP (what csrc/encoder.cc drives on the device): frame kinds of the one-level hierarchy, quantiser per kind,
+key-frame partition, hierarchical motion search + vector-field regularisation against the right reference, inter /
+intra encode, in-loop filters.  Tests, smoke() and the rate/quality tools compare the CUDA path with this, frame by frame.
+Replaces what the reference delegates to av1an + SVT-AV1 (/root/reference/crates/daemon/src/encode/av1an.rs:126-139)."""
+import ctypes as C
+import os
+import re
+import numpy as np
+from av1_base_b200 import abi
+from . import pyoracle as O
+
+_ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+_tables = {}
+
+
+def table(name):
+    """Integer table `name` out of csrc/av1_tables.h (quantiser steps, CRF -> quantiser index)."""
+    if name not in _tables:
+        txt = open(os.path.join(_ROOT, "av1_base_b200", "csrc", "av1_tables.h")).read()
+        m = re.search(r"%s\[\d+\] = \{(.*?)\};" % name, txt, re.S)
+        _tables[name] = [int(v) for v in re.findall(r"-?\d+", m.group(1))]
+    return _tables[name]
+
+
+def ac_q(bd, qidx):
+    return table("av1t_ac_q_%d" % bd)[qidx]
+
+
+def frame_kind(pos, keyint=240, gop_period=4, intra_only=False):
+    """0 key, 1 anchor, 2 non-reference (csrc/encoder.cc frame_kind)."""
+    if intra_only:
+        return 0
+    c = pos % keyint
+    if c == 0:
+        return 0
+    return 1 if (gop_period <= 1 or c % gop_period == 0) else 2
+
+
+def quantisers(crf, gop_period=4, intra_only=False):
+    """(key, anchor, non-reference) quantiser indices for a CRF (csrc/encoder.cc av1b_encoder_create)."""
+    q = max(1, table("av1t_quantizer_to_qindex")[crf])
+    qkey = q if intra_only else max(1, q * 3 // 4)
+    qa = max(1, q - 8) if gop_period > 1 else q
+    return qkey, qa, min(255, q + 48)
+
+
+def class_params(bd, qidx, kind, loop_filters=True, lr=False, tile_log2=(0, 0)):
+    fp = abi.FrameParams()
+    abi.lib().av1b_select_frame_params(bd, qidx, 0 if kind == 0 else 1, 1 if loop_filters else 0, C.byref(fp))
+    fp.non_reference = 1 if kind == 2 else 0
+    fp.tile_cols_log2, fp.tile_rows_log2 = tile_log2
+    if lr:
+        fp.lr_type[0], fp.lr_type[1], fp.lr_type[2] = 3, 0, 0
+    return fp
+
+
+class FrameResult:
+    pass
+
+
+def encode_chain(frames, w, h, bd, crf, keyint=240, gop_period=4, me_smooth=True, key_var_part=True, loop_filters=True,
+                 lr=False, intra_only=False, blk_log2=4, tb_zero_thr=0, pos0=0):
+    """Returns one FrameResult per frame: kind, fp, res (blocks / coef / pre-filter rec), fin (padded planes after the
+    in-loop filters), cdef_idx, lr_units, mvs."""
+    g = O.geom(w, h, 0, 0)
+    qkey, qa, qn = quantisers(crf, gop_period, intra_only)
+    qk = {0: qkey, 1: qa, 2: qn}
+    lam = ac_q(bd, qa) >> 1
+    pm16 = O.partition_fixed(g, 4)
+    out = []
+    anchor_fin = anchor_pyr = None
+    for i, fr in enumerate(frames):
+        kind = frame_kind(pos0 + i, keyint, gop_period, intra_only)
+        q = qk[kind]
+        fp = class_params(bd, q, kind, loop_filters, lr)
+        src = O.pad_planes(g, fr)
+        pyr = O.pyramid(g, src[0])
+        r = FrameResult()
+        r.kind, r.fp, r.q, r.mvs = kind, fp, q, None
+        if kind == 0:
+            if key_var_part and blk_log2 == 4:
+                pm = O.partition_smooth(g, src[0], min(4 * ac_q(bd, q), 800 << (bd - 8)))
+            else:
+                pm = O.partition_fixed(g, blk_log2)
+            r.part_map = pm
+            r.res = O.encode_intra_frame(g, fr, bd, q, pm)
+        else:
+            mvs = O.hme(g, pyr, anchor_pyr, lam)
+            if me_smooth:
+                mvs = O.me_smooth(g, pyr, anchor_pyr, mvs, lam, 2)
+            r.mvs = mvs
+            r.res = O.encode_inter_frame(g, fr, bd, q, pm16, mvs, anchor_fin, tb_zero_thr=tb_zero_thr)
+            O.merge_skip_blocks(g, r.res.blocks)
+        fin, r.cdef_idx, r.lr_units = r.res.rec, None, None
+        if loop_filters:
+            O.deblock_frame(g, bd, r.res.blocks, r.res.rec, list(fp.lf_level), fp.lf_sharpness)
+            r.cdef_idx = O.cdef_search(g, bd, r.res.blocks, fp, r.res.rec, src)
+            fin = O.cdef_frame(g, bd, r.res.blocks, fp, r.cdef_idx, r.res.rec)
+            if lr:
+                cand = O.lr_candidate((0, 0, 8), (0, 0, 8), 12, (0, 95))
+                aq = ac_q(bd, q)
+                r.lr_units, _ = O.lr_search(g, bd, fp, cand, fin, r.res.rec, src[0], (aq * aq * 5) >> 8)
+                fin = O.lr_frame(g, bd, fp, fin, r.res.rec, [r.lr_units, None, None])
+        r.fin = fin
+        if kind != 2:
+            anchor_fin, anchor_pyr = fin, pyr
+        out.append(r)
+    return g, out

@@ -34,6 +34,14 @@ def partition_fixed(g, blk_log2):
     lib().orc_partition_fixed(C.byref(g), blk_log2, ptr(m))
     return m
 
+def partition_smooth(g, luma_padded, thr):
+    """Key-frame partition by smoothness (orc_partition_smooth): block log2 per 8x8 unit."""
+    m = np.zeros(g.h8 * g.w8, np.uint8)
+    l0 = np.ascontiguousarray(luma_padded, np.uint16)
+    lib().orc_partition_smooth(C.byref(g), ptr(l0), l0.shape[1], int(thr), ptr(m))
+    return m
+
+
 class IntraResult:
     pass
 
@@ -123,6 +131,13 @@ def hme(g, cur_pyr, ref_pyr, lam=0):
     mv = np.zeros((g.h8 * g.w8, 2), np.int16)
     lib().orc_hme(C.byref(g), ptr(cur_pyr[0]), ptr(cur_pyr[1]), ptr(cur_pyr[2]), ptr(ref_pyr[0]), ptr(ref_pyr[1]),
                   ptr(ref_pyr[2]), int(lam), ptr(mv))
+    return mv
+
+
+def me_smooth(g, cur_pyr, ref_pyr, mv, lam_s, iters=2):
+    """Vector-field regularisation (orc_me_smooth): returns the updated [h8*w8, 2] vectors."""
+    mv = np.ascontiguousarray(mv, np.int16).copy()
+    lib().orc_me_smooth(C.byref(g), ptr(cur_pyr[0]), ptr(ref_pyr[0]), int(lam_s), int(iters), ptr(mv))
     return mv
 
 

@@ -42,9 +42,26 @@ def encode(w, h, bd, q, n):
     return tus, recs
 
 
+def chain_digest():
+    """Digest of the oracle's whole decision chain (oracle/chain.py) on a small clip: frame kinds, quantisers,
+    block-size histogram of the key frame, vector checksum and SHA-256 of every reconstructed frame."""
+    import hashlib
+    from oracle import chain
+    w, h, bd, crf, n = 200, 136, 10, 34, 9
+    frames = synth.synth_clip(w, h, bd, n, seed=21, scene_len=100, noise=0.5)
+    g, res = chain.encode_chain(frames, w, h, bd, crf)
+    out = {"kinds": [r.kind for r in res], "q": [r.q for r in res],
+           "key_blocks": np.bincount(res[0].res.blocks["blk_log2"], minlength=7).tolist(),
+           "mv_sum": [int(np.abs(r.mvs.astype(np.int64)).sum()) if r.mvs is not None else 0 for r in res],
+           "sha": [hashlib.sha256(b"".join(np.ascontiguousarray(pl).tobytes() for pl in O.crop(g, r.fin))).hexdigest() for r in res]}
+    return out
+
+
 def main():
     import __graft_entry__ as ge
     ge.build()
+    import json
+    json.dump(chain_digest(), open(os.path.join(HERE, "chain_digest.json"), "w"), indent=1)
     for name, (w, h, bd, q, n) in CASES.items():
         tus, recs = encode(w, h, bd, q, n)
         arrs = {"n": np.array([n])}

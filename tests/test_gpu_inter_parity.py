@@ -5,88 +5,66 @@ AND libaom to exactly the encoder's reconstruction."""
 import numpy as np
 import pytest
 from av1_base_b200 import encoder, synth
-from oracle import pyoracle as O, decoders as D
+from oracle import pyoracle as O, decoders as D, chain
 
 pytestmark = pytest.mark.gpu
 
 CASES = [
-    # w, h, bd, crf, tcl, trl, loop_filters, n_frames, frames_in_flight, keyint, preset (<= 5: loop restoration on)
-    (64, 64, 8, 30, 0, 0, False, 4, 2, 240, 6),
-    (200, 136, 10, 30, 0, 0, True, 5, 2, 240, 6),
-    (328, 248, 8, 45, 1, 1, True, 6, 4, 4, 6),
-    (640, 360, 10, 25, 2, 1, True, 5, 3, 240, 6),
-    (200, 136, 10, 40, 0, 0, True, 5, 2, 3, 4),
-    (328, 248, 8, 30, 1, 1, True, 7, 3, 240, 3),
-    (640, 360, 10, 35, -1, -1, True, 4, 4, 240, 5),
+    # w, h, bd, crf, tcl, trl, loop_filters, n_frames, frames_in_flight, keyint, preset (<= 5: loop restoration on), gop_period
+    (64, 64, 8, 30, 0, 0, False, 4, 2, 240, 6, 1),
+    (200, 136, 10, 30, 0, 0, True, 5, 2, 240, 6, 1),
+    (328, 248, 8, 45, 1, 1, True, 6, 4, 4, 6, 0),
+    (640, 360, 10, 25, 2, 1, True, 10, 8, 240, 6, 0),
+    (200, 136, 10, 40, 0, 0, True, 7, 2, 6, 4, 3),
+    (328, 248, 8, 30, 1, 1, True, 9, 3, 240, 3, 0),
+    (640, 360, 10, 35, -1, -1, True, 6, 4, 240, 5, 2),
+    (328, 248, 10, 50, 0, 0, True, 13, 8, 240, 6, 0),
 ]
 # every case also through the device range coder (pack_path 4); 0 = automatic placement
 CASES = [c + (pp,) for c in CASES for pp in (0, 4)]
 
 
-def oracle_filters(g, bd, fp, res, frame, lr, acq):
-    O.deblock_frame(g, bd, res.blocks, res.rec, list(fp.lf_level), fp.lf_sharpness)
-    src = O.pad_planes(g, frame)
-    idx = O.cdef_search(g, bd, res.blocks, fp, res.rec, src)
-    fin, units = O.cdef_frame(g, bd, res.blocks, fp, idx, res.rec), None
-    if lr:
-        cand = O.lr_candidate((0, 0, 8), (0, 0, 8), 12, (0, 95))
-        units, _ = O.lr_search(g, bd, fp, cand, fin, res.rec, src[0], (acq * acq * 5) >> 8)
-        fin = O.lr_frame(g, bd, fp, fin, res.rec, [units, None, None])
-    return fin, idx, units
-
-
-def ac_q(bd, qidx):
-    import re, os
-    txt = open(os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "av1_base_b200", "csrc", "av1_tables.h")).read()
-    m = re.search(r"av1t_ac_q_%d\[\d+\] = \{(.*?)\};" % bd, txt, re.S)
-    return [int(v) for v in re.findall(r"-?\d+", m.group(1))][qidx]
-
-
-@pytest.mark.parametrize("w,h,bd,crf,tcl,trl,lf,nfr,fif,keyint,preset,pack_path", CASES)
-def test_chunk_parity(w, h, bd, crf, tcl, trl, lf, nfr, fif, keyint, preset, pack_path):
+@pytest.mark.parametrize("w,h,bd,crf,tcl,trl,lf,nfr,fif,keyint,preset,gop,pack_path", CASES)
+def test_chunk_parity(w, h, bd, crf, tcl, trl, lf, nfr, fif, keyint, preset, gop, pack_path):
+    """The whole decision chain of a closed GOP against oracle/chain.py: frame kinds of the hierarchy (anchors /
+    non-reference frames, each predicted from the right picture at its own quantiser), key-frame partition, motion
+    vectors after regularisation, side info, levels, reconstruction after the in-loop filters; dav1d and libaom decode
+    the stream to the same pictures."""
     frames = synth.synth_clip(w, h, bd, nfr, seed=w + bd, scene_len=100)
     enc = encoder.Encoder(w, h, bd, crf=crf, keep_debug=True, tile_cols_log2=tcl, tile_rows_log2=trl,
-                          frames_in_flight=fif, loop_filters=lf, keyint=keyint, preset=preset, pack_path=pack_path)
+                          frames_in_flight=fif, loop_filters=lf, keyint=keyint, preset=preset, pack_path=pack_path, gop_period=gop)
     lr = lf and preset <= 5
     tus = enc.encode_chunk(frames)
     assert len(tus) == nfr
-    g = enc.geom
-    q = enc.stats()["base_q_idx"]
-    fp_key, fp_inter = enc.frame_params(), enc.inter_frame_params()
-    pm = O.partition_fixed(g, 4)
+    g, want = chain.encode_chain(frames, w, h, bd, crf, keyint=keyint, gop_period=gop or 4, loop_filters=lf, lr=lr)
+    assert enc.me_lambda() == chain.ac_q(bd, chain.quantisers(crf, gop or 4)[1]) >> 1
     dec_d = D.dav1d_decode(tus)
     dec_a = D.aom_decode(tus)
     assert len(dec_d) == nfr and len(dec_a) == nfr
-    prev_fin, prev_pyr = None, None
-    for i, fr in enumerate(frames):
-        key = i % keyint == 0
-        assert enc.frame_is_key(i) == key
-        pyr = O.pyramid(g, O.pad_planes(g, fr)[0])
-        if key:
-            ref = O.encode_intra_frame(g, fr, bd, fp_key.base_q_idx, pm)
-        else:
-            mvs = O.hme(g, pyr, prev_pyr, enc.me_lambda())
-            ref = O.encode_inter_frame(g, fr, bd, q, pm, mvs, prev_fin)
-            O.merge_skip_blocks(g, ref.blocks)
+    kinds = set()
+    for i, r in enumerate(want):
+        kinds.add(r.kind)
+        assert enc.frame_kind(i) == r.kind and enc.frame_is_key(i) == (r.kind == 0)
+        fpe = enc.class_params(r.kind)
+        assert fpe.base_q_idx == r.q and fpe.non_reference == r.fp.non_reference
+        assert list(fpe.lf_level) == list(r.fp.lf_level) and list(fpe.cdef_y_strength) == list(r.fp.cdef_y_strength)
         blocks, coef = enc.frame_syms(i)
         for f in ("blk_log2", "y_mode", "uv_mode", "skip", "eob", "is_inter", "mv"):
-            assert np.array_equal(blocks[f], ref.blocks[f]), (f, i)
-        fin = ref.rec
+            assert np.array_equal(blocks[f], r.res.blocks[f]), (f, i)
         if lf:
-            fpf = fp_key if key else fp_inter
-            fin, idx, units = oracle_filters(g, bd, fpf, ref, fr, lr, ac_q(bd, fpf.base_q_idx))
-            if lr:
-                assert (fpf.lr_type[0], fpf.lr_type[1], fpf.lr_type[2]) == (3, 0, 0)
-                assert enc.lr_units(i).tobytes() == units.tobytes(), ("restoration units", i)
+            assert np.array_equal(enc.cdef_idx(i), r.cdef_idx), ("cdef_idx", i)
+        if lr:
+            assert (fpe.lr_type[0], fpe.lr_type[1], fpe.lr_type[2]) == (3, 0, 0)
+            assert enc.lr_units(i).tobytes() == r.lr_units.tobytes(), ("restoration units", i)
         rec = enc.recon(i)
-        orc = O.crop(g, fin)
+        orc = O.crop(g, r.fin)
         for p in range(3):
-            hh, ww = (g.height, g.width) if p == 0 else (g.height // 2, g.width // 2)
-            assert np.array_equal(coef[p], ref.coef[p]), ("coef", i, p)
+            assert np.array_equal(coef[p], r.res.coef[p]), ("coef", i, p)
             assert np.array_equal(rec[p], orc[p]), ("recon vs oracle", i, p)
             assert np.array_equal(dec_d[i][p], rec[p]), ("dav1d", i, p)
             assert np.array_equal(dec_a[i][p], rec[p]), ("libaom", i, p)
-        prev_fin, prev_pyr = fin, pyr
+    if (gop or 4) > 1 and nfr > (gop or 4) and keyint > (gop or 4):
+        assert kinds == {0, 1, 2}
     enc.close()
 
 

@@ -225,6 +225,37 @@ def test_pyramid_and_hme_vs_oracle(w, h, bd):
             assert np.array_equal(mv[i - 1], want), (i, lam)
 
 
+@pytest.mark.parametrize("w,h,bd", ME_CASES + [(1920, 1080, 10)])
+def test_vector_field_regularisation_vs_oracle(w, h, bd):
+    """hme + relaxation sweeps (dominant vector histogram, bilinear quarter-sample SAD, neighbour-disagreement cost)."""
+    g = O.geom(w, h, 0, 0)
+    n = 3 if w < 1000 else 2
+    frames = synth.synth_clip(w, h, bd, n, seed=w + bd + 1, scene_len=100)
+    l0 = np.stack([O.pad_planes(g, fr)[0] for fr in frames])
+    pyr = [O.pyramid(g, l0[i]) for i in range(n)]
+    for lam, lam_s, iters in ((40 << (bd - 8), 40 << (bd - 8), 2), (300 << (bd - 8), 150 << (bd - 8), 3), (8, 2000, 1)):
+        if w > 1000 and iters != 2:
+            continue
+        mv, _ = kernels.hme_smooth(w, h, l0[1:], l0[:1].repeat(n - 1, 0), lam, lam_s, iters)   # every frame against frame 0
+        for i in range(1, n):
+            want = O.me_smooth(g, pyr[i], pyr[0], O.hme(g, pyr[i], pyr[0], lam), lam_s, iters)
+            assert np.array_equal(mv[i - 1], want), (i, lam, lam_s, iters)
+
+
+@pytest.mark.parametrize("w,h,bd", ME_CASES + [(1920, 1080, 8), (3840, 2160, 10)])
+def test_partition_smooth_vs_oracle(w, h, bd):
+    g = O.geom(w, h, 0, 0)
+    fr = synth.synth_clip(w, h, bd, 1, seed=w + bd, scene_len=100, noise=0.5)[0]
+    l0 = O.pad_planes(g, fr)[0]
+    for thr in (0, 100 << (bd - 8), 800 << (bd - 8), 1 << 20):
+        got = kernels.partition_smooth(w, h, l0, thr)
+        want = O.partition_smooth(g, l0, thr)
+        assert np.array_equal(got, want), thr
+    if w >= 640:
+        sizes = set(np.unique(kernels.partition_smooth(w, h, l0, 400 << (bd - 8))).tolist())
+        assert len(sizes & {5, 6}) >= 1 and 4 in sizes, sizes
+
+
 def random_mvs(g, pm, rng, integer):
     step = 8 if integer else 2
     m = (rng.integers(-6, 7, (g.h8, g.w8, 2)) * step).astype(np.int16)

@@ -1,0 +1,120 @@
+"""CPU checks of the encoder-side decisions added with the one-level hierarchy (oracle/chain.py is what the CUDA
+path is compared with on the B200): streams of the whole chain -- key frame with 64x64 / 32x32 / 16x16 blocks,
+anchors, non-reference frames at their own quantisers, regularised vector fields -- must decode in dav1d AND libaom
+to the oracle's reconstruction; the partition and the regularisation are pinned against numpy restatements."""
+import hashlib
+import json
+import os
+import numpy as np
+import pytest
+from av1_base_b200 import abi, packer, synth
+from oracle import pyoracle as O, decoders as D, chain
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+
+
+def pack_chain(w, h, bd, want, g, lr=False):
+    seq = abi.SeqParams(w, h, bd, 1, 1 if lr else 0, 30, 1, 0)
+    tus = []
+    for i, r in enumerate(want):
+        sy = packer.make_syms(g, r.res.blocks, r.res.coef, cdef_idx=r.cdef_idx, lr_units=[r.lr_units, None, None] if lr else None)
+        body = packer.pack_frame(seq, r.fp, sy, with_td=False)
+        if r.kind != 0:
+            tok, _ = packer.pack_frame_tokens(seq, r.fp, sy, with_td=False)
+            assert tok == body, "token path != block walker (frame %d)" % i
+        tus.append(b"\x12\x00" + (packer.pack_sequence_header(seq) if r.kind == 0 else b"") + body)
+    return tus
+
+
+@pytest.mark.parametrize("w,h,bd,crf,n,keyint,gop,lr", [(200, 136, 10, 30, 10, 240, 4, False), (328, 248, 8, 48, 7, 5, 3, False),
+                                                        (256, 192, 10, 38, 6, 240, 2, True), (192, 136, 8, 24, 5, 240, 1, False)])
+def test_chain_streams_decode_to_oracle_reconstruction(w, h, bd, crf, n, keyint, gop, lr):
+    frames = synth.synth_clip(w, h, bd, n, seed=w + crf, scene_len=100, noise=0.6)
+    g, want = chain.encode_chain(frames, w, h, bd, crf, keyint=keyint, gop_period=gop, lr=lr)
+    kinds = [r.kind for r in want]
+    assert kinds == [chain.frame_kind(i, keyint, gop) for i in range(n)]
+    if gop > 1 and n > gop and keyint > gop:
+        assert set(kinds) == {0, 1, 2}
+        assert want[1].q > want[gop].q            # non-reference frames are coded coarser than anchors
+    tus = pack_chain(w, h, bd, want, g, lr)
+    for dec in (D.dav1d_decode, D.aom_decode):
+        out = dec(tus)
+        assert len(out) == n
+        for i in range(n):
+            for p in range(3):
+                assert np.array_equal(out[i][p], O.crop(g, want[i].fin)[p]), (dec.__name__, i, p)
+
+
+def np_partition_smooth(g, Y, thr):
+    """numpy restatement: least information possible shared with the C++ (box sums via reshape, plane via mgrid)."""
+    pm = O.partition_fixed(g, 4).reshape(g.h8, g.w8).copy()
+    h, w = g.height, g.width
+    B = Y[:h, :w].astype(np.int64).reshape(h // 4, 4, w // 4, 4).sum((1, 3))
+    for bl, N in ((6, 64), (5, 32)):
+        n, n8 = N // 4, N // 8
+        for y0 in range(0, h - N + 1, N):
+            for x0 in range(0, w - N + 1, N):
+                if pm[y0 // 8, x0 // 8] >= 6:
+                    continue
+                b = B[y0 // 4:y0 // 4 + n, x0 // 4:x0 // 4 + n]
+                S = b.sum(); gx = 2 * (b[:, n // 2:].sum() - b[:, :n // 2].sum()); gy = 2 * (b[n // 2:, :].sum() - b[:n // 2, :].sum())
+                i, j = np.mgrid[0:n, 0:n]
+                if np.abs(n ** 3 * b - (n * S + (2 * j - n + 1) * gx + (2 * i - n + 1) * gy)).max() <= thr * n ** 3:
+                    pm[y0 // 8:y0 // 8 + n8, x0 // 8:x0 // 8 + n8] = bl
+    return pm.reshape(-1)
+
+
+@pytest.mark.parametrize("w,h,bd", [(328, 248, 8), (640, 360, 10), (200, 136, 10)])
+def test_partition_smooth_vs_numpy(w, h, bd):
+    g = O.geom(w, h, 0, 0)
+    fr = synth.synth_clip(w, h, bd, 1, seed=w, scene_len=100, noise=0.5)[0]
+    l0 = O.pad_planes(g, fr)[0]
+    seen = set()
+    for thr in (0, 60 << (bd - 8), 300 << (bd - 8), 800 << (bd - 8), 1 << 20):
+        got = O.partition_smooth(g, l0, thr)
+        assert np.array_equal(got, np_partition_smooth(g, l0, thr)), thr
+        seen |= set(np.unique(got).tolist())
+    assert {4, 6} <= seen
+    # a perfect plane is smooth at threshold 0, wherever whole 64x64 blocks fit
+    yy, xx = np.mgrid[0:g.rows[0], 0:g.stride[0]]
+    plane = (100 + 2 * xx + 3 * yy).astype(np.uint16) % 1024
+    m = O.partition_smooth(g, plane[:, :] * 0 + (100 + xx // 4 * 4).astype(np.uint16), 0).reshape(g.h8, g.w8)
+    assert m[0, 0] == 6
+
+
+def test_mv_dominant_and_smoothing_properties():
+    w, h, bd = 328, 248, 10
+    g = O.geom(w, h, 0, 0)
+    frames = synth.synth_clip(w, h, bd, 2, seed=9, scene_len=100)
+    pyr = [O.pyramid(g, O.pad_planes(g, f)[0]) for f in frames]
+    mv = O.hme(g, pyr[1], pyr[0], 80)
+    # without a disagreement cost every block keeps or improves its SAD: its own vector is a candidate
+    sm0 = O.me_smooth(g, pyr[1], pyr[0], mv, 0, 1)
+    n1x, n1y = (w + 15) // 16, (h + 15) // 16
+    f0 = mv.reshape(g.h8, g.w8, 2)[::2, ::2].reshape(-1, 2)
+    f1 = sm0.reshape(g.h8, g.w8, 2)[::2, ::2].reshape(-1, 2)
+    assert f0.shape[0] == n1x * n1y
+    # a strong cost makes the field more uniform, never less
+    sm = O.me_smooth(g, pyr[1], pyr[0], mv, 100000, 3)
+    fs = sm.reshape(g.h8, g.w8, 2)[::2, ::2].reshape(-1, 2)
+    assert len(np.unique(fs, axis=0)) <= len(np.unique(f0, axis=0))
+    # dominant vector: numpy restatement of the hashed histogram
+    import ctypes as C
+    dom = np.zeros(2, np.int16)
+    O.lib().orc_mv_dominant(O.ptr(np.ascontiguousarray(f0)), f0.shape[0], O.ptr(dom))
+    keys = ((f0[:, 0].astype(np.int64) & 0xFFFF) << 16) | (f0[:, 1].astype(np.int64) & 0xFFFF)
+    bins = ((keys * 2654435761) & 0xFFFFFFFF) >> 22
+    cnt = np.bincount(bins, minlength=1024)
+    b = int(np.argmax(cnt))
+    cand = f0[bins == b]
+    best = max(map(tuple, cand.tolist()))
+    assert (int(dom[0]), int(dom[1])) == best
+    assert len(f1) == len(f0)
+
+
+def test_chain_golden():
+    """Committed digest of a chain run (tests/golden/chain_digest.json, written by tests/golden/make_golden.py): pins
+    the oracle's decisions -- any change to the hierarchy, the partition rule or the regularisation shows up here."""
+    from tests.golden import make_golden as G
+    want = json.load(open(os.path.join(HERE, "golden", "chain_digest.json")))
+    assert G.chain_digest() == want
