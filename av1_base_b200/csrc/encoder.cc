@@ -34,6 +34,9 @@ using namespace av1b;
 
 namespace {
 
+// pyramid ring: kHist pictures before the batch, the carried anchor, then the batch
+constexpr int kHist = 2, kSlotCarried = kHist, kSlotFrame0 = kHist + 1;
+
 // Minimal persistent pool: parallel_for blocks the caller (who also works) until all tasks ran.
 class ThreadPool {
  public:
@@ -144,7 +147,7 @@ struct Slot {
   int16_t* h_coef[3] = {nullptr, nullptr, nullptr};
   Av1bBlockInfo* h_blocks = nullptr;
   uint8_t* h_cdef_idx = nullptr;
-  cudaEvent_t ev_h2d = nullptr, ev_k0 = nullptr, ev_me = nullptr, ev_k1 = nullptr, ev_d2h = nullptr;
+  cudaEvent_t ev_h2d = nullptr, ev_k0 = nullptr, ev_me = nullptr, ev_k1 = nullptr, ev_d2h = nullptr, ev_tf0 = nullptr, ev_tf1 = nullptr;
   std::vector<cudaEvent_t> ev_frame;     // 5 per launch group: before encode, after encode, after deblock, after CDEF, after loop restoration
   std::vector<uint8_t> is_key;
   std::vector<uint8_t> kind;             // per frame: 0 key, 1 anchor, 2 non-reference
@@ -174,6 +177,15 @@ struct av1b_encoder {
   int base_q_idx_nonref = 0;
   bool me_smooth = true;              // vector-field regularisation after the hierarchical search
   bool key_var_part = true;           // key frames: 64x64 / 32x32 blocks where the source is smooth
+  bool mctf_on = true;                // key / anchor source pictures are temporally filtered before they are coded
+  int mctf_radius = 2, mctf_key_fwd = 4;
+  int hist_count = 0;                 // source pictures of the previous batch that are kept (same GOP): at most kHist
+  uint16_t* d_hist_src[3] = {nullptr, nullptr, nullptr};   // [kHist] source pictures before the batch (temporal filter)
+  uint16_t* d_flt[3] = {nullptr, nullptr, nullptr};        // [batch] filtered key / anchor sources
+  int16_t* d_mvs_tf = nullptr;        // vectors of the temporal filter's searches [kMaxSearches][map_elems][2]
+  int16_t* d_mv2_tf = nullptr;
+  int64_t mctf_frames = 0;
+  double t_mctf_ms = 0;
   int16_t* d_mv_tmp = nullptr;
   uint32_t* d_hist = nullptr;
   void* d_cdf_init_alt = nullptr;     // default CDF set of the non-reference frames' quantiser class
@@ -236,7 +248,7 @@ static void free_all(av1b_encoder* e) {
     cudaFree(s.d_rc_region); cudaFree(s.d_rc_len); cudaFree(s.d_rc_bytes); cudaFreeHost(s.h_rc_len); cudaFreeHost(s.h_rc_bytes);
     cudaFree(s.d_mode_cls); cudaFree(s.d_blk_count); cudaFree(s.d_sb_off); cudaFree(s.d_tokens);
     cudaFreeHost(s.h_sb_off); cudaFreeHost(s.h_tokens);
-    for (cudaEvent_t ev : {s.ev_h2d, s.ev_k0, s.ev_me, s.ev_k1, s.ev_d2h, s.ev_src, s.ev_tok0, s.ev_tok1, s.ev_rc0, s.ev_rc1}) if (ev) cudaEventDestroy(ev);
+    for (cudaEvent_t ev : {s.ev_h2d, s.ev_k0, s.ev_me, s.ev_k1, s.ev_d2h, s.ev_src, s.ev_tok0, s.ev_tok1, s.ev_rc0, s.ev_rc1, s.ev_tf0, s.ev_tf1}) if (ev) cudaEventDestroy(ev);
     for (cudaEvent_t ev : s.ev_frame) if (ev) cudaEventDestroy(ev);
   }
   for (int p = 0; p < 3; p++) {
@@ -246,7 +258,8 @@ static void free_all(av1b_encoder* e) {
   cudaFree(e->d_mv2); cudaFree(e->d_mvs);
   cudaFree(e->d_sb_of_order); cudaFree(e->d_tile_of_sb); cudaFree(e->d_lr_sse);
   cudaFree(e->d_cdf_init); cudaFree(e->d_cdf_init_alt); cudaFree(e->d_tile_first_k); cudaFree(e->d_rc_overflow);
-  cudaFree(e->d_mv_tmp); cudaFree(e->d_hist);
+  cudaFree(e->d_mv_tmp); cudaFree(e->d_hist); cudaFree(e->d_mvs_tf); cudaFree(e->d_mv2_tf);
+  for (int p = 0; p < 3; p++) { cudaFree(e->d_hist_src[p]); cudaFree(e->d_flt[p]); }
   if (e->s_tok) cudaStreamDestroy(e->s_tok);
   if (e->stream) cudaStreamDestroy(e->stream);
   if (e->s_in) cudaStreamDestroy(e->s_in);
@@ -339,29 +352,95 @@ static int launch(av1b_encoder* e, Slot& s, const Slot& in, int n, int64_t first
   CK(cudaEventRecord(s.ev_k0, e->stream));
   const int acq0 = bd == 8 ? av1t_ac_q_8[e->base_q_idx] : av1t_ac_q_10[e->base_q_idx];
   // ---- open-loop motion estimation for the whole batch (source pictures only) ----
+  std::vector<uint8_t> filtered(n, 0);
   if (!e->intra_only) {
     const size_t e0 = e->plane_elems[0];
-    CK(cudaMemcpyAsync(e->d_pyr[0] + e0, in.d_src[0], e0 * n * 2, cudaMemcpyDeviceToDevice, e->stream));
-    CK(launch_pyramid(e->d_pyr[0] + e0, e->d_pyr[1] + e0 / 4, e->d_pyr[2] + e0 / 16, g.stride[0], g.rows[0], e0, n, e->stream));
+    if (e->chunk_pos == 0) e->hist_count = 0;   // a new closed GOP: nothing before it may be looked at
+    auto lvl = [&](int l, int slot) { return e->d_pyr[l] + (e0 >> (2 * l)) * (size_t)slot; };
+    CK(cudaMemcpyAsync(lvl(0, kSlotFrame0), in.d_src[0], e0 * n * 2, cudaMemcpyDeviceToDevice, e->stream));
+    CK(launch_pyramid(lvl(0, kSlotFrame0), lvl(1, kSlotFrame0), lvl(2, kSlotFrame0), g.stride[0], g.rows[0], e0, n, e->stream));
     e->kernel_launches += 1;
+    HmeLaunch H;
+    H.width = g.width; H.height = g.height; H.stride0 = g.stride[0]; H.elems0 = e0;
+    for (int l = 0; l < 3; l++) { H.ref[l] = e->d_pyr[l]; H.cur[l] = e->d_pyr[l]; }
+    H.lambda = acq0 >> 1;   // vector-deviation cost in SAD units (tuned on the oracle: about half the AC quantiser step)
+    H.lam_s = e->me_smooth ? H.lambda : 0; H.smooth_iters = 2; H.mv_tmp = e->d_mv_tmp; H.hist = e->d_hist;
     if (any_inter) {
-      HmeLaunch H;
-      H.width = g.width; H.height = g.height; H.stride0 = g.stride[0]; H.elems0 = e0;
-      for (int l = 0; l < 3; l++) { H.ref[l] = e->d_pyr[l]; H.cur[l] = e->d_pyr[l]; }
-      for (int b = 0; b < n; b++) { H.cur_slot[b] = (uint8_t)(b + 1); H.ref_slot[b] = (uint8_t)ref_of[b]; }
+      for (int b = 0; b < n; b++) { H.cur_slot[b] = (uint8_t)(kSlotFrame0 + b); H.ref_slot[b] = (uint8_t)(ref_of[b] == 0 ? kSlotCarried : kSlotFrame0 + ref_of[b] - 1); }
       H.mv2 = e->d_mv2; H.mv_out = e->d_mvs;
-      H.lambda = acq0 >> 1;   // vector-deviation cost in SAD units (tuned on the oracle: about half the AC quantiser step)
-      H.lam_s = e->me_smooth ? H.lambda : 0; H.smooth_iters = 2; H.mv_tmp = e->d_mv_tmp; H.hist = e->d_hist;
       CK(launch_hme(H, n, e->stream));
       e->kernel_launches += 2;
       if (H.lam_s > 0) { CK(launch_hme_smooth(H, n, e->stream)); e->kernel_launches += 3 * H.smooth_iters; }
     }
+    // ---- temporal filter of the key / anchor sources: searches of the picture against its neighbours in time, then
+    //      one filter launch per picture ----
+    if (e->mctf_on) {
+      CK(cudaEventRecord(s.ev_tf0, e->stream));
+      struct Job { int b, first, count; int nb[kMaxNb]; };
+      std::vector<Job> jobs;
+      int n_pairs = 0;
+      for (int b = 0; b < n; b++) {
+        if (s.kind[b] == 2) continue;
+        const int64_t pos = e->chunk_pos + b, in_gop = pos % e->keyint;
+        int lo = s.kind[b] == 0 ? 0 : -e->mctf_radius, hi = s.kind[b] == 0 ? e->mctf_key_fwd : e->mctf_radius;
+        if (e->cfg.lookahead >= 0) hi = std::min(hi, e->cfg.lookahead);
+        Job j; j.b = b; j.first = n_pairs; j.count = 0;
+        for (int d = lo; d <= hi && j.count < kMaxNb; d++) {
+          if (d == 0) continue;
+          const int r = b + d;
+          if (r >= n || r < -e->hist_count) continue;
+          if (in_gop + d < 0 || in_gop + d >= e->keyint) continue;   // stay inside the closed GOP
+          if (n_pairs >= kMaxSearches) break;
+          H.cur_slot[n_pairs] = (uint8_t)(kSlotFrame0 + b);
+          H.ref_slot[n_pairs] = (uint8_t)(r >= 0 ? kSlotFrame0 + r : kHist + r);
+          j.nb[j.count++] = r; n_pairs++;
+        }
+        if (j.count) jobs.push_back(j);
+      }
+      if (n_pairs) {
+        H.mv2 = e->d_mv2_tf; H.mv_out = e->d_mvs_tf;
+        CK(launch_hme(H, n_pairs, e->stream));
+        e->kernel_launches += 2;
+        if (H.lam_s > 0) { CK(launch_hme_smooth(H, n_pairs, e->stream)); e->kernel_launches += 3 * H.smooth_iters; }
+      }
+      for (const Job& j : jobs) {
+        const Av1bFrameParams& fpk = kind_params(e, s.kind[j.b]);
+        const long long aq = bd == 8 ? av1t_ac_q_8[fpk.base_q_idx] : av1t_ac_q_10[fpk.base_q_idx];
+        MctfLaunch M;
+        M.g = g; M.bit_depth = bd; M.n_nb = j.count;
+        // strength follows the quantiser (what it would quantise away anyway may as well be averaged away) and --film-grain
+        M.thr_b = (int)std::max<long long>(1, (aq * aq * (10 + e->cfg.film_grain)) / 2560);
+        M.thr_p = 3 * M.thr_b;
+        for (int p = 0; p < 3; p++) { M.cur[p] = in.d_src[p] + (size_t)j.b * e->plane_elems[p]; M.out[p] = e->d_flt[p] + (size_t)j.b * e->plane_elems[p]; }
+        for (int k = 0; k < kMaxNb; k++) {
+          const int r = k < j.count ? j.nb[k] : 0;
+          for (int p = 0; p < 3; p++)
+            M.nb[k][p] = k >= j.count ? nullptr : (r >= 0 ? in.d_src[p] + (size_t)r * e->plane_elems[p] : e->d_hist_src[p] + (size_t)(kHist + r) * e->plane_elems[p]);
+          M.mvs[k] = k < j.count ? e->d_mvs_tf + (size_t)(j.first + k) * e->map_elems * 2 : nullptr;
+        }
+        CK(launch_mctf(M, e->stream));
+        e->kernel_launches += 1; e->mctf_frames += 1;
+        filtered[j.b] = 1;
+      }
+      CK(cudaEventRecord(s.ev_tf1, e->stream));
+    }
     // the last key / anchor picture of this batch is the reference the next batch starts from
     if (last_ref > 0)
-      for (int l = 0; l < 3; l++) {
-        const size_t el = e0 >> (2 * l);
-        CK(cudaMemcpyAsync(e->d_pyr[l], e->d_pyr[l] + el * last_ref, el * 2, cudaMemcpyDeviceToDevice, e->stream));
+      for (int l = 0; l < 3; l++)
+        CK(cudaMemcpyAsync(lvl(l, kSlotCarried), lvl(l, kSlotFrame0 + last_ref - 1), (e0 >> (2 * l)) * 2, cudaMemcpyDeviceToDevice, e->stream));
+    // the last kHist source pictures stay for the next batch's temporal filter (ascending: an old entry moves down first)
+    if (e->mctf_on) {
+      for (int k = 0; k < kHist; k++) {
+        const int rel = n - kHist + k;
+        for (int l = 0; l < 3; l++)
+          CK(cudaMemcpyAsync(lvl(l, k), lvl(l, rel >= 0 ? kSlotFrame0 + rel : kHist + rel), (e0 >> (2 * l)) * 2, cudaMemcpyDeviceToDevice, e->stream));
+        for (int p = 0; p < 3; p++)
+          CK(cudaMemcpyAsync(e->d_hist_src[p] + (size_t)k * e->plane_elems[p],
+                             rel >= 0 ? in.d_src[p] + (size_t)rel * e->plane_elems[p] : e->d_hist_src[p] + (size_t)(kHist + rel) * e->plane_elems[p],
+                             e->plane_elems[p] * 2, cudaMemcpyDeviceToDevice, e->stream));
       }
+      e->hist_count = std::min(kHist, e->hist_count + n);
+    }
   }
   CK(cudaEventRecord(s.ev_me, e->stream));
   // ---- launch groups: a key frame alone; an anchor alone; the non-reference frames between two anchors together
@@ -387,7 +466,7 @@ static int launch(av1b_encoder* e, Slot& s, const Slot& in, int n, int64_t first
       const size_t off = (size_t)b * e->plane_elems[p];
       rec[p] = e->d_rec[p] + off; deb[p] = e->d_deb[p] ? e->d_deb[p] + off : nullptr;
       refp[p] = e->d_fin[p] + (size_t)ref_of[b] * e->plane_elems[p]; fin[p] = e->d_fin[p] + off + e->plane_elems[p];
-      src[p] = in.d_src[p] + off; coef[p] = s.d_coef[p] + off;
+      src[p] = (filtered[b] ? e->d_flt[p] : in.d_src[p]) + off; coef[p] = s.d_coef[p] + off;
     }
     Av1bBlockInfo* blocks = s.d_blocks + (size_t)b * e->map_elems;
     if (key) {
@@ -553,6 +632,7 @@ static int finish(av1b_encoder* e, Slot& s, bool staged, av1b_packet_cb out_cb, 
   if (staged) { cudaEventElapsedTime(&ms, s.ev_h2d, s.ev_src); e->t_h2d_ms += ms; }
   cudaEventElapsedTime(&ms, s.ev_k0, s.ev_k1); e->t_kernel_ms += ms;
   cudaEventElapsedTime(&ms, s.ev_k0, s.ev_me); e->t_me_ms += ms;
+  if (e->mctf_on && !e->intra_only) { cudaEventElapsedTime(&ms, s.ev_tf0, s.ev_tf1); e->t_mctf_ms += ms; }
   cudaEventElapsedTime(&ms, s.ev_k1, s.ev_d2h); e->t_d2h_ms += ms;
   const int n = s.n_frames;
   for (size_t gi = 0; gi < s.groups.size(); gi++) {
@@ -701,7 +781,7 @@ static int finish(av1b_encoder* e, Slot& s, bool staged, av1b_packet_cb out_cb, 
 static void reset_stats(av1b_encoder* e) {
   e->kept.clear();
   e->t_h2d_ms = e->t_kernel_ms = e->t_intra_ms = e->t_inter_ms = e->t_me_ms = e->t_d2h_ms = e->t_pack_ms = 0;
-  e->t_deblock_ms = e->t_cdef_ms = e->t_tok_ms = 0; e->t_lr_ms = 0; e->t_rc_ms = 0; e->n_tokens = 0; e->d2h_bytes = 0;
+  e->t_deblock_ms = e->t_cdef_ms = e->t_tok_ms = 0; e->t_lr_ms = 0; e->t_rc_ms = 0; e->n_tokens = 0; e->d2h_bytes = 0; e->t_mctf_ms = 0; e->mctf_frames = 0;
   e->kernel_launches = e->intra_launches = e->inter_launches = e->frames_done = e->bytes_out = e->key_frames = e->staged_direct = 0;
 }
 
@@ -716,7 +796,7 @@ int av1b_device_count(void) {
 void av1b_config_default(av1b_config* c) {
   memset(c, 0, sizeof(*c));
   c->bit_depth = 10; c->fps_num = 30; c->fps_den = 1;
-  c->crf = 30; c->preset = 6; c->keyint = 240; c->lookahead = 0;
+  c->crf = 30; c->preset = 6; c->keyint = 240; c->lookahead = -1;
   c->tile_cols_log2 = -1; c->tile_rows_log2 = -1;
 }
 
@@ -773,6 +853,7 @@ int av1b_encoder_create(const av1b_config* cfg, av1b_encoder** out) {
   const int q_nominal = e->base_q_idx;
   e->base_q_idx_nonref = std::min(255, q_nominal + 48);
   if (e->gop_period > 1) e->base_q_idx = std::max(1, q_nominal - 8);
+  e->mctf_on = cfg->tune[2] == 0 && cfg->reserved[3] == 0;
   e->me_smooth = cfg->tune[0] == 0;
   e->key_var_part = cfg->tune[1] == 0 && cfg->reserved[1] == 0;
   e->blk_log2 = cfg->reserved[1] ? cfg->reserved[1] : 4;
@@ -818,7 +899,7 @@ int av1b_encoder_create(const av1b_config* cfg, av1b_encoder** out) {
   const int F = e->batch;
   for (int si = 0; si < e->n_slots; si++) {
     Slot& s = e->slot[si];
-    for (cudaEvent_t* ev : {&s.ev_h2d, &s.ev_k0, &s.ev_me, &s.ev_k1, &s.ev_d2h, &s.ev_src, &s.ev_tok0, &s.ev_tok1, &s.ev_rc0, &s.ev_rc1}) A(cudaEventCreate(ev));
+    for (cudaEvent_t* ev : {&s.ev_h2d, &s.ev_k0, &s.ev_me, &s.ev_k1, &s.ev_d2h, &s.ev_src, &s.ev_tok0, &s.ev_tok1, &s.ev_rc0, &s.ev_rc1, &s.ev_tf0, &s.ev_tf1}) A(cudaEventCreate(ev));
     s.ev_frame.assign((size_t)F * 5, nullptr);
     for (auto& ev : s.ev_frame) A(cudaEventCreate(&ev));
     for (int p = 0; p < 3; p++) {
@@ -908,16 +989,25 @@ int av1b_encoder_create(const av1b_config* cfg, av1b_encoder** out) {
   if (!e->intra_only) {
     for (int l = 0; l < 3; l++) {
       const size_t el = e->plane_elems[0] >> (2 * l);
-      A(cudaMalloc(&e->d_pyr[l], el * (F + 1) * 2));
-      if (err == cudaSuccess) A(cudaMemset(e->d_pyr[l], 0, el * (F + 1) * 2));
+      A(cudaMalloc(&e->d_pyr[l], el * (F + kSlotFrame0) * 2));
+      if (err == cudaSuccess) A(cudaMemset(e->d_pyr[l], 0, el * (F + kSlotFrame0) * 2));
+    }
+    if (e->mctf_on) {
+      for (int p = 0; p < 3; p++) {
+        A(cudaMalloc(&e->d_hist_src[p], e->plane_elems[p] * kHist * 2));
+        A(cudaMalloc(&e->d_flt[p], e->plane_elems[p] * F * 2));
+        if (err == cudaSuccess) { A(cudaMemset(e->d_hist_src[p], 0, e->plane_elems[p] * kHist * 2)); A(cudaMemset(e->d_flt[p], 0, e->plane_elems[p] * F * 2)); }
+      }
+      A(cudaMalloc(&e->d_mvs_tf, e->map_elems * kMaxSearches * 4));
+      A(cudaMalloc(&e->d_mv2_tf, (size_t)((cfg->width + 31) / 32) * ((cfg->height + 31) / 32) * kMaxSearches * 4));
     }
     const size_t n2 = (size_t)((cfg->width + 31) / 32) * ((cfg->height + 31) / 32);
     A(cudaMalloc(&e->d_mv2, n2 * F * 4));
     A(cudaMalloc(&e->d_mvs, e->map_elems * F * 4));
     {
       const size_t n1 = (size_t)((cfg->width + 15) / 16) * ((cfg->height + 15) / 16);
-      A(cudaMalloc(&e->d_mv_tmp, n1 * F * 4 * 2));
-      A(cudaMalloc(&e->d_hist, (size_t)F * 2049 * sizeof(uint32_t)));
+      A(cudaMalloc(&e->d_mv_tmp, n1 * kMaxSearches * 4 * 2));
+      A(cudaMalloc(&e->d_hist, (size_t)kMaxSearches * 2049 * sizeof(uint32_t)));
     }
     if (err == cudaSuccess) A(cudaMemset(e->d_mvs, 0, e->map_elems * F * 4));
   }
@@ -1112,11 +1202,11 @@ void av1b_host_free(void* p) {
 
 int av1b_get_stats(av1b_encoder* e, double* stats, int n) {
   if (!e || !stats) return AV1B_ERR_INVALID;
-  const double v[22] = {e->t_h2d_ms, e->t_kernel_ms, e->t_d2h_ms, e->t_pack_ms, (double)e->kernel_launches,
+  const double v[24] = {e->t_h2d_ms, e->t_kernel_ms, e->t_d2h_ms, e->t_pack_ms, (double)e->kernel_launches,
                         (double)e->base_q_idx, e->t_intra_ms, (double)e->intra_launches, (double)e->frames_done,
                         (double)e->bytes_out, e->t_deblock_ms, e->t_cdef_ms, e->t_inter_ms, e->t_me_ms,
-                        (double)e->inter_launches, (double)e->key_frames, (double)e->staged_direct, e->t_tok_ms, (double)e->n_tokens, (double)e->d2h_bytes, e->t_lr_ms, e->t_rc_ms};
-  for (int i = 0; i < n && i < 22; i++) stats[i] = v[i];
+                        (double)e->inter_launches, (double)e->key_frames, (double)e->staged_direct, e->t_tok_ms, (double)e->n_tokens, (double)e->d2h_bytes, e->t_lr_ms, e->t_rc_ms, e->t_mctf_ms, (double)e->mctf_frames};
+  for (int i = 0; i < n && i < 24; i++) stats[i] = v[i];
   return AV1B_OK;
 }
 

@@ -552,6 +552,9 @@ __global__ void __launch_bounds__(256) partition_smooth_kernel(Av1bGeom g, const
 cudaError_t launch_partition_smooth(const Av1bGeom& g, const uint16_t* src_y, size_t plane_elems, size_t map_elems, int thr,
                                     uint8_t* map, int n_frames, cudaStream_t s) {
   dim3 grid(g.sb_cols, g.sb_rows, n_frames);
+  // a box sum deviates from the plane by less than 2^15 whatever the picture: larger thresholds mean "always smooth"
+  // (and thr * 4096 stays inside 32 bits)
+  thr = thr > (1 << 17) ? (1 << 17) : thr;
   partition_smooth_kernel<<<grid, 256, 0, s>>>(g, src_y, plane_elems, map_elems, thr, map);
   return cudaGetLastError();
 }

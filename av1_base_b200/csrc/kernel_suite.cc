@@ -365,6 +365,35 @@ int av1b_k_inter_encode(int device, int width, int height, int bit_depth, int ba
   return download_planes(1, rec, bo, t.s);
 }
 
+int av1b_k_mctf(int device, int width, int height, int bit_depth, const uint16_t* const cur[3], int n_nb,
+                const uint16_t* const* nb_planes, const int16_t* const* mvs, int thr_b, int thr_p, uint16_t* const out[3],
+                int reps, double* ms_per_launch) {
+  if (!cur || !out || n_nb < 0 || n_nb > kMaxNb || (n_nb && (!nb_planes || !mvs)) || thr_b < 1 || thr_p < 1) { set_error("bad argument"); return AV1B_ERR_INVALID; }
+  MctfLaunch L;
+  if (av1b_geom_init(&L.g, width, height, 0, 0)) { set_error("unsupported size"); return AV1B_ERR_INVALID; }
+  int rc = select_device(device);
+  if (rc) return rc;
+  Timer t; CKS(t.init());
+  FrameBufs bc, bo, bn[kMaxNb];
+  DevBuf dmv[kMaxNb];
+  if ((rc = upload_planes(L.g, 1, cur, bc, t.s))) return rc;
+  if ((rc = upload_planes(L.g, 1, nullptr, bo, t.s))) return rc;
+  const size_t map = (size_t)L.g.w8 * L.g.h8;
+  for (int k = 0; k < n_nb; k++) {
+    if ((rc = upload_planes(L.g, 1, nb_planes + 3 * k, bn[k], t.s))) return rc;
+    CKS(dmv[k].alloc(map * 4));
+    CKS(cudaMemcpyAsync(dmv[k].p, mvs[k], map * 4, cudaMemcpyHostToDevice, t.s));
+  }
+  L.bit_depth = bit_depth; L.n_nb = n_nb; L.thr_b = thr_b; L.thr_p = thr_p;
+  for (int p = 0; p < 3; p++) { L.cur[p] = bc.d[p].as<uint16_t>(); L.out[p] = bo.d[p].as<uint16_t>(); }
+  for (int k = 0; k < kMaxNb; k++) {
+    for (int p = 0; p < 3; p++) L.nb[k][p] = k < n_nb ? bn[k].d[p].as<uint16_t>() : nullptr;
+    L.mvs[k] = k < n_nb ? dmv[k].as<int16_t>() : nullptr;
+  }
+  if ((rc = timed(t, reps, ms_per_launch, [&]() { return launch_mctf(L, t.s); }))) return rc;
+  return download_planes(1, out, bo, t.s);
+}
+
 int av1b_k_partition_smooth(int device, int width, int height, const uint16_t* src_y, int thr, uint8_t* map_out) {
   if (!src_y || !map_out) { set_error("bad argument"); return AV1B_ERR_INVALID; }
   Av1bGeom g;

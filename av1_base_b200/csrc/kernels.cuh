@@ -99,6 +99,20 @@ cudaError_t launch_hme(const HmeLaunch& p, int n_frames, cudaStream_t s);
 // relaxation sweeps over the vectors launch_hme left in mv_out (hist: [n * 2048 + n] words, mv_tmp: [2][n][n1][2])
 cudaError_t launch_hme_smooth(const HmeLaunch& p, int n, cudaStream_t s);
 
+// Motion-compensated temporal filter of one key / anchor source picture (mctf_kernel.cu): weighted mean of the picture and
+// up to kMaxNb neighbours in time, each compensated with mvs[k] (the picture searched against neighbour k).
+constexpr int kMaxNb = 6;
+struct MctfLaunch {
+  Av1bGeom g;
+  int32_t bit_depth, n_nb;
+  int32_t thr_b, thr_p;       // block weight falls to zero at this luma mean squared error / sample weight at this squared difference
+  const uint16_t* cur[3];
+  uint16_t* out[3];
+  const uint16_t* nb[kMaxNb][3];
+  const int16_t* mvs[kMaxNb]; // [h8*w8][2] each
+};
+cudaError_t launch_mctf(const MctfLaunch& p, cudaStream_t s);
+
 // Inter frame encode (inter_kernel.cu): the n_frames frames of a launch share ONE reference picture and one
 // quantiser (the frames between two anchors of the hierarchy); frame f of the launch has its source, outputs, block
 // info and vectors at f * plane_elems[p] / f * map_elems from the given pointers.

@@ -1,0 +1,156 @@
+// Motion-compensated temporal filter of key / anchor SOURCE pictures for sm_100a (oracle: orc_mctf).
+//
+// One warp per 16x16 luma block of the picture that is filtered.  For every neighbour in time the warp stages the
+// (16+7)^2 luma window (and the two (8+7)^2 chroma windows) the block's vector points at, runs the normative separable
+// 8-tap interpolation (spec 7.11.3.4: the same arithmetic the inter prediction uses), derives the block weight from the
+// luma mean squared error and the sample weights from the sample differences, and accumulates weighted sums in
+// registers; the picture and every neighbour are read once, the filtered picture is written once:
+//   algorithmic bytes = (2 + n_nb) * S  per filtered picture.
+//
+// Replaces arithmetic the reference delegates to av1an + SVT-AV1 (/root/reference/crates/daemon/src/encode/av1an.rs:14
+// `--film-grain 20` = denoise + synthesis, `--lookahead 40`).
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include "av1_tables_dev.cuh"
+#include "kernels.cuh"
+
+namespace av1b {
+namespace {
+
+__device__ __forceinline__ int clampi(int v, int lo, int hi) { return v < lo ? lo : (v > hi ? hi : v); }
+
+constexpr int kWarps = 8;
+struct MctfSmem {
+  uint16_t win[kWarps][23 * 24];     // staged reference window (luma 23x23, chroma 15x15)
+  int32_t mid[kWarps][23 * 16];      // after the horizontal pass
+  uint16_t pred[kWarps][16 * 16];
+};
+
+// Normative prediction of an N x N block at (x, y) of a plane from `ref` with the vector (mv_row, mv_col) in 1/8 luma
+// samples (oracle: orc_inter_predict): all lanes of the warp take part, result in pred[N*N].
+template <int N>
+__device__ __forceinline__ void mc_block(const uint16_t* __restrict__ ref, int stride, int pw, int ph, int x, int y, int mv_row,
+                                         int mv_col, int ss, int bd, int lane, uint16_t* win, int32_t* mid, uint16_t* pred) {
+  const int x16 = (x << 4) + ((2 * mv_col) >> ss), y16 = (y << 4) + ((2 * mv_row) >> ss);
+  const int ix = x16 >> 4, iy = y16 >> 4, fx = x16 & 15, fy = y16 & 15;
+  constexpr int WN = N + 7, WS = N + 8;
+  for (int o = lane; o < WN * WN; o += 32) {
+    const int r = o / WN, c = o - r * WN;
+    win[r * WS + c] = ref[(size_t)clampi(iy + r - 3, 0, ph - 1) * stride + clampi(ix + c - 3, 0, pw - 1)];
+  }
+  __syncwarp();
+  for (int o = lane; o < WN * N; o += 32) {
+    const int r = o / N, c = o - r * N;
+    int s = 0;
+#pragma unroll
+    for (int t = 0; t < 8; t++) s += tbl::sub_pel_filters_8[fx][t] * (int)win[r * WS + c + t];
+    mid[r * N + c] = (s + 4) >> 3;
+  }
+  __syncwarp();
+  const int maxv = (1 << bd) - 1;
+  for (int o = lane; o < N * N; o += 32) {
+    const int r = o / N, c = o - r * N;
+    int s = 0;
+#pragma unroll
+    for (int t = 0; t < 8; t++) s += tbl::sub_pel_filters_8[fy][t] * mid[(r + t) * N + c];
+    pred[o] = (uint16_t)clampi((s + 1024) >> 11, 0, maxv);
+  }
+  __syncwarp();
+}
+
+__global__ void __launch_bounds__(kWarps * 32) mctf_kernel(const MctfLaunch P) {
+  __shared__ MctfSmem sm;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const Av1bGeom& g = P.g;
+  const int W = g.width, H = g.height;
+  const int n1x = (W + 15) / 16, n1y = (H + 15) / 16;
+  const int blk = blockIdx.x * kWarps + warp;
+  if (blk >= n1x * n1y) return;
+  const int bx = blk % n1x, by = blk / n1x;
+  const int bw = min(16, W - bx * 16), bh = min(16, H - by * 16);
+  uint16_t* win = sm.win[warp];
+  int32_t* mid = sm.mid[warp];
+  uint16_t* pred = sm.pred[warp];
+  // lane (r, h): luma row r, columns 8h .. 8h+7; chroma: samples 2 lane, 2 lane + 1 of the 8x8 block
+  const int lr = lane >> 1, lc = (lane & 1) * 8;
+  uint32_t numy[8], deny[8], numc[2][2], denc[2][2];
+  int cury[8], curc[2][2];
+  {
+    const uint16_t* cp = P.cur[0] + (size_t)(by * 16 + lr) * g.stride[0] + bx * 16 + lc;
+#pragma unroll
+    for (int j = 0; j < 8; j++) {
+      const bool in = lr < bh && lc + j < bw;
+      cury[j] = in ? cp[j] : 0;
+      numy[j] = 256u * (uint32_t)cury[j]; deny[j] = 256u;
+    }
+#pragma unroll
+    for (int p = 0; p < 2; p++)
+#pragma unroll
+      for (int j = 0; j < 2; j++) {
+        const int o = 2 * lane + j, r = o >> 3, c = o & 7;
+        const bool in = r < (bh >> 1) && c < (bw >> 1);
+        curc[p][j] = in ? P.cur[1 + p][(size_t)(by * 8 + r) * g.stride[1] + bx * 8 + c] : 0;
+        numc[p][j] = 256u * (uint32_t)curc[p][j]; denc[p][j] = 256u;
+      }
+  }
+  for (int k = 0; k < P.n_nb; k++) {
+    const int16_t* mv = P.mvs[k] + ((size_t)(by * 2) * g.w8 + bx * 2) * 2;
+    const int mvr = mv[0], mvc = mv[1];
+    mc_block<16>(P.nb[k][0], g.stride[0], W, H, bx * 16, by * 16, mvr, mvc, 0, P.bit_depth, lane, win, mid, pred);
+    int py[8];
+    unsigned sse = 0;
+#pragma unroll
+    for (int j = 0; j < 8; j++) {
+      py[j] = pred[lr * 16 + lc + j];
+      const int d = (lr < bh && lc + j < bw) ? py[j] - cury[j] : 0;
+      sse += (unsigned)(d * d);
+    }
+    for (int o = 16; o; o >>= 1) sse += __shfl_xor_sync(0xffffffffu, sse, o);
+    const int mse = (int)(sse / (unsigned)(bw * bh));
+    const int wb = clampi(16 - (int)(((long long)16 * mse) / P.thr_b), 0, 16);
+    if (wb == 0) continue;   // warp-uniform
+#pragma unroll
+    for (int j = 0; j < 8; j++) {
+      const int d = py[j] - cury[j];
+      const int w = wb * clampi(16 - (16 * d * d) / P.thr_p, 0, 16);
+      numy[j] += (uint32_t)w * (uint32_t)py[j]; deny[j] += (uint32_t)w;
+    }
+#pragma unroll
+    for (int p = 0; p < 2; p++) {
+      __syncwarp();
+      mc_block<8>(P.nb[k][1 + p], g.stride[1], W >> 1, H >> 1, bx * 8, by * 8, mvr, mvc, 1, P.bit_depth, lane, win, mid, pred);
+#pragma unroll
+      for (int j = 0; j < 2; j++) {
+        const int pv = pred[2 * lane + j];
+        const int d = pv - curc[p][j];
+        const int w = wb * clampi(16 - (16 * d * d) / P.thr_p, 0, 16);
+        numc[p][j] += (uint32_t)w * (uint32_t)pv; denc[p][j] += (uint32_t)w;
+      }
+    }
+    __syncwarp();
+  }
+  {
+    uint16_t* op = P.out[0] + (size_t)(by * 16 + lr) * g.stride[0] + bx * 16 + lc;
+#pragma unroll
+    for (int j = 0; j < 8; j++)
+      if (lr < bh && lc + j < bw) op[j] = (uint16_t)((numy[j] + deny[j] / 2) / deny[j]);
+#pragma unroll
+    for (int p = 0; p < 2; p++)
+#pragma unroll
+      for (int j = 0; j < 2; j++) {
+        const int o = 2 * lane + j, r = o >> 3, c = o & 7;
+        if (r < (bh >> 1) && c < (bw >> 1))
+          P.out[1 + p][(size_t)(by * 8 + r) * g.stride[1] + bx * 8 + c] = (uint16_t)((numc[p][j] + denc[p][j] / 2) / denc[p][j]);
+      }
+  }
+}
+
+}  // namespace
+
+cudaError_t launch_mctf(const MctfLaunch& p, cudaStream_t s) {
+  const int n1 = ((p.g.width + 15) / 16) * ((p.g.height + 15) / 16);
+  mctf_kernel<<<(n1 + kWarps - 1) / kWarps, kWarps * 32, 0, s>>>(p);
+  return cudaGetLastError();
+}
+
+}  // namespace av1b

@@ -28,7 +28,8 @@ class Encoder:
     def __init__(self, width, height, bit_depth=10, crf=30, preset=6, keyint=240, fps=(30, 1), device_id=0,
                  tile_cols_log2=-1, tile_rows_log2=-1, hdr=False, host_threads=0, frames_in_flight=0,
                  keep_debug=False, blk_log2=0, loop_filters=True, intra_only=False, tb_zero_thr=0, raster_levels=False,
-                 pack_path=0, lr_off=False, tile_sb=0, gop_period=0, me_smooth=True, key_var_part=True):
+                 pack_path=0, lr_off=False, tile_sb=0, gop_period=0, me_smooth=True, key_var_part=True, mctf=True,
+                 lookahead=-1, film_grain=0):
         L = abi.lib()
         cfg = abi.Config()
         L.av1b_config_default(C.byref(cfg))
@@ -53,6 +54,9 @@ class Encoder:
         cfg.gop_period = gop_period        # 0 = default (4), 1 = plain P chain
         cfg.tune[0] = 0 if me_smooth else 1
         cfg.tune[1] = 0 if key_var_part else 1
+        cfg.tune[2] = 0 if mctf else 1     # temporal filter of key / anchor sources
+        cfg.lookahead = lookahead          # -1 = default; frames the temporal filter may look ahead
+        cfg.film_grain = film_grain
         self.cfg = cfg
         self._h = C.c_void_p()
         _check(L.av1b_encoder_create(C.byref(cfg), C.byref(self._h)))
@@ -120,13 +124,13 @@ class Encoder:
         return blocks, coef
 
     def stats(self):
-        s = (C.c_double * 22)()
-        _check(abi.lib().av1b_get_stats(self._h, s, 22))
+        s = (C.c_double * 24)()
+        _check(abi.lib().av1b_get_stats(self._h, s, 24))
         return dict(h2d_ms=s[0], kernel_ms=s[1], d2h_ms=s[2], pack_ms=s[3], kernel_launches=int(s[4]),
                     base_q_idx=int(s[5]), intra_ms=s[6], intra_launches=int(s[7]), frames_done=int(s[8]),
                     bytes_out=int(s[9]), deblock_ms=s[10], cdef_ms=s[11], inter_ms=s[12], me_ms=s[13],
                     inter_launches=int(s[14]), key_frames=int(s[15]), staged_direct=int(s[16]), tok_ms=s[17],
-                    tokens=int(s[18]), d2h_bytes=int(s[19]), lr_ms=s[20], rc_ms=s[21])
+                    tokens=int(s[18]), d2h_bytes=int(s[19]), lr_ms=s[20], rc_ms=s[21], mctf_ms=s[22], mctf_frames=int(s[23]))
 
     def lr_units(self, frame):
         """Luma restoration units [rows, cols] of a kept frame (preset <= 5, keep_debug=True)."""

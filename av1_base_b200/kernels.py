@@ -139,6 +139,21 @@ def hme_smooth(width, height, cur_l0, ref_l0, lam, lam_s, iters=2, device=0, rep
     return mv, ms.value
 
 
+def mctf(width, height, bit_depth, cur_padded, nb_padded, nb_mvs, thr_b, thr_p, device=0, reps=1):
+    """Temporal filter of one picture: cur_padded = 3 padded planes, nb_padded = list of 3 padded planes per neighbour,
+    nb_mvs = list of [h8*w8, 2] vectors. Returns (out[3], ms)."""
+    cur = [np.ascontiguousarray(p, np.uint16) for p in cur_padded]
+    nbs = [[np.ascontiguousarray(p, np.uint16) for p in nb] for nb in nb_padded]
+    mvs = [np.ascontiguousarray(m, np.int16) for m in nb_mvs]
+    n = len(nbs)
+    pp = (C.c_void_p * max(1, 3 * n))(*[p.ctypes.data for nb in nbs for p in nb])
+    mp = (C.c_void_p * max(1, n))(*[m.ctypes.data for m in mvs])
+    out = [np.zeros_like(p) for p in cur]
+    ms = C.c_double(0)
+    _ck(abi.lib().av1b_k_mctf(device, width, height, bit_depth, _p3(cur), n, pp, mp, int(thr_b), int(thr_p), _p3(out), reps, C.byref(ms)))
+    return out, ms.value
+
+
 def partition_smooth(width, height, luma_padded, thr, device=0):
     """Key-frame partition by smoothness: block log2 per 8x8 unit [h8*w8]."""
     l0 = np.ascontiguousarray(luma_padded, np.uint16)

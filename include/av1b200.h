@@ -38,8 +38,10 @@ typedef struct av1b_config {
   int32_t crf;                    /* 0..63, SVT-AV1 --crf                                          */
   int32_t preset;                 /* SVT-AV1 --preset: <= 5 adds loop restoration (per-unit decision) */
   int32_t keyint;                 /* --keyint                                                      */
-  int32_t lookahead;              /* --lookahead (accepted; unused by the all-intra path)          */
-  int32_t film_grain;             /* --film-grain (accepted; synthesis not implemented: row f-4)   */
+  int32_t lookahead;              /* --lookahead: source pictures the temporal filter of key / anchor pictures may look ahead
+                                     (it uses up to 4); -1 = default, 0 = none                                        */
+  int32_t film_grain;             /* --film-grain 0..50: strength of the temporal (denoising) filter on top of what the
+                                     quantiser asks for                                                               */
   int32_t enable_qm, qm_min, qm_max; /* accepted; flat quantisation matrices only                  */
   int32_t tile_cols_log2, tile_rows_log2; /* -1 = auto (fill the GPU)                              */
   int32_t device_id;
@@ -50,7 +52,8 @@ typedef struct av1b_config {
                                      becomes the reference, quantiser index - 8); the frames between two anchors predict from the last
                                      anchor at quantiser index + 48 and are referenced by nobody.  0 = default (4), 1 = plain P chain */
   int32_t tune[7];                /* [0]: 1 = vector-field regularisation of the motion search off; [1]: 1 = fixed 16x16 key-frame
-                                     partition (default: 64x64 / 32x32 blocks where the source is smooth) */
+                                     partition (default: 64x64 / 32x32 blocks where the source is smooth); [2]: 1 = temporal filter of
+                                     key / anchor source pictures off */
   int32_t reserved[8];            /* [0]: keep recon+symbols per frame (tests); [1]: fixed block log2 (3..6), 0 = default;
                                      [2]: 1 = in-loop filters off; [3]: 1 = every frame is a key frame;
                                      [4]: inter transform-block drop threshold (0 = off);
@@ -127,10 +130,10 @@ int av1b_select_frame_params(int bit_depth, int base_q_idx, int frame_type, int 
  * the context of `device` (one the caller encodes on) and is usable from every device.  NULL on failure. */
 void* av1b_host_alloc(int device, size_t bytes);
 void av1b_host_free(void* p);
-/* stats[0..21] = h2d_ms, kernel_ms, d2h_ms, pack_ms, kernel_launches, base_q_idx, intra_kernel_ms,
+/* stats[0..23] = h2d_ms, kernel_ms, d2h_ms, pack_ms, kernel_launches, base_q_idx, intra_kernel_ms,
  * intra_kernel_launches, frames_done, bytes_out, deblock_ms, cdef_ms, inter_kernel_ms, me_ms (pyramid + search),
  * inter_kernel_launches, key_frames, frames uploaded straight from page-locked caller memory, tokenizer_ms,
- * tokens produced, bytes copied device -> host, loop_restoration_ms, range_coder_ms (overlaps the next batch), of the last chunk / resident run (CUDA-event times) */
+ * tokens produced, bytes copied device -> host, loop_restoration_ms, range_coder_ms (overlaps the next batch), temporal_filter_ms (its searches + filter), pictures filtered, of the last chunk / resident run (CUDA-event times) */
 int av1b_get_stats(av1b_encoder* enc, double* stats, int n);
 
 /* ---- kernel suite (BASELINE.json config 2 "kernel bit-exact suite") -----------------------------
@@ -180,6 +183,14 @@ int av1b_k_hme(int device, int width, int height, int n_frames, const uint16_t* 
  * SAD (bilinear quarter-sample interpolation) + lam_s * (neighbours with a different vector). */
 int av1b_k_hme_smooth(int device, int width, int height, int n_frames, const uint16_t* cur_l0, const uint16_t* ref_l0,
                       int lambda, int lam_s, int iters, int16_t* mv_out, int reps, double* ms_per_launch);
+/* Motion-compensated temporal filter of one source picture (encoder side; `--film-grain` denoising and `--lookahead`,
+ * av1an.rs:14): weighted mean of the picture and n_nb <= 6 neighbours in time, neighbour k compensated onto the picture
+ * with the normative interpolation and the vectors mvs[k] ([h8*w8][2], from av1b_k_hme of the picture against it).
+ * nb_planes: [n_nb * 3] padded planes.  thr_b / thr_p: the block weight falls to zero at this luma mean squared
+ * error, the sample weight at this squared difference. */
+int av1b_k_mctf(int device, int width, int height, int bit_depth, const uint16_t* const cur[3], int n_nb,
+                const uint16_t* const* nb_planes, const int16_t* const* mvs, int thr_b, int thr_p, uint16_t* const out[3],
+                int reps, double* ms_per_launch);
 /* Key-frame partition by smoothness (E3/E4 decision): src_y = one padded luma plane; map_out[h8*w8] = block log2 (3..6)
  * per 8x8 unit: 64x64 / 32x32 where the 4x4 box sums stay within thr of a plane, else 16x16 (8x8 at the picture edge). */
 int av1b_k_partition_smooth(int device, int width, int height, const uint16_t* src_y, int thr, uint8_t* map_out);

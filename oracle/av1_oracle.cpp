@@ -788,6 +788,64 @@ extern "C" void orc_me_smooth(const Av1bGeom* g, const uint16_t* cur0, const uin
 }
 
 // ------------------------------------------------------------------------------------------------
+// Motion-compensated temporal filter of a key / anchor SOURCE picture (encoder side, ours): the picture is replaced
+// by a weighted mean of itself (weight 256) and of its neighbours in time, each motion-compensated onto it with the
+// normative interpolation (16x16 luma blocks, vectors mvs[k] from the motion search of the picture against neighbour
+// k).  Per neighbour and block:  mse = SSE_luma / samples;  wb = clamp(16 - 16 mse / thr_b, 0, 16);  per sample of
+// every plane  w = wb * clamp(16 - 16 d^2 / thr_p, 0, 16)  with d = prediction - picture.  Noise that is independent
+// from frame to frame averages out, anything the vectors do not explain keeps the picture's own samples.
+// ------------------------------------------------------------------------------------------------
+extern "C" void orc_mctf(const Av1bGeom* g, int bd, const uint16_t* cur_y, const uint16_t* cur_u, const uint16_t* cur_v,
+                         int n_nb, const uint16_t* const* nb_planes /*[n_nb*3]*/, const int16_t* const* mvs /*[n_nb]*/,
+                         int thr_b, int thr_p, uint16_t* out_y, uint16_t* out_u, uint16_t* out_v) {
+  const uint16_t* cur[3] = {cur_y, cur_u, cur_v};
+  uint16_t* out[3] = {out_y, out_u, out_v};
+  const int W = g->width, H = g->height;
+  std::vector<uint32_t> num[3], den[3];
+  for (int p = 0; p < 3; p++) {
+    const size_t n = (size_t)g->stride[p] * g->rows[p];
+    num[p].assign(n, 0); den[p].assign(n, 256);
+    for (size_t i = 0; i < n; i++) num[p][i] = 256u * cur[p][i];
+  }
+  uint16_t pred[3][16 * 16];
+  for (int k = 0; k < n_nb; k++)
+    for (int by = 0; by * 16 < H; by++)
+      for (int bx = 0; bx * 16 < W; bx++) {
+        const int16_t* mv = mvs[k] + ((size_t)(by * 2) * g->w8 + bx * 2) * 2;
+        for (int p = 0; p < 3; p++) {
+          const int ss = p > 0, n = 16 >> ss;
+          orc_inter_predict(nb_planes[k * 3 + p], g->stride[p], W >> ss, H >> ss, (bx * 16) >> ss, (by * 16) >> ss, n, n, mv[0],
+                            mv[1], ss, bd, pred[p], n);
+        }
+        const int bw = std::min(16, W - bx * 16), bh = std::min(16, H - by * 16);
+        int64_t sse = 0;
+        for (int i = 0; i < bh; i++)
+          for (int j = 0; j < bw; j++) {
+            const int d = (int)pred[0][i * 16 + j] - (int)cur[0][(size_t)(by * 16 + i) * g->stride[0] + bx * 16 + j];
+            sse += d * d;
+          }
+        const int mse = (int)(sse / (bw * bh));
+        const int wb = clampi(16 - (int)(((int64_t)16 * mse) / thr_b), 0, 16);
+        if (wb == 0) continue;
+        for (int p = 0; p < 3; p++) {
+          const int ss = p > 0, n = 16 >> ss;
+          for (int i = 0; i < (bh >> ss); i++)
+            for (int j = 0; j < (bw >> ss); j++) {
+              const size_t o = (size_t)(((by * 16) >> ss) + i) * g->stride[p] + ((bx * 16) >> ss) + j;
+              const int d = (int)pred[p][i * n + j] - (int)cur[p][o];
+              const int w = wb * clampi(16 - (16 * d * d) / thr_p, 0, 16);
+              num[p][o] += (uint32_t)w * pred[p][i * n + j];
+              den[p][o] += (uint32_t)w;
+            }
+        }
+      }
+  for (int p = 0; p < 3; p++) {
+    const size_t n = (size_t)g->stride[p] * g->rows[p];
+    for (size_t i = 0; i < n; i++) out[p][i] = (uint16_t)((num[p][i] + den[p][i] / 2) / den[p][i]);
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
 // Inter frame encode: every block is predicted from the previous reconstructed frame with the given
 // vector (one per 8x8 unit; all units of a block carry the same vector), DCT_DCT residual coding with
 // the same quantiser as the intra path.  Blocks are independent of each other.

@@ -60,24 +60,53 @@ class FrameResult:
 
 
 def encode_chain(frames, w, h, bd, crf, keyint=240, gop_period=4, me_smooth=True, key_var_part=True, loop_filters=True,
-                 lr=False, intra_only=False, blk_log2=4, tb_zero_thr=0, pos0=0):
+                 lr=False, intra_only=False, blk_log2=4, tb_zero_thr=0, pos0=0, geom=None, mctf=True, batch=8, lookahead=-1,
+                 film_grain=0, mctf_radius=2, mctf_key_fwd=4):
     """Returns one FrameResult per frame: kind, fp, res (blocks / coef / pre-filter rec), fin (padded planes after the
     in-loop filters), cdef_idx, lr_units, mvs."""
-    g = O.geom(w, h, 0, 0)
+    g = geom if geom is not None else O.geom(w, h, 0, 0)   # key-frame tiling: no intra prediction across tile edges
     qkey, qa, qn = quantisers(crf, gop_period, intra_only)
     qk = {0: qkey, 1: qa, 2: qn}
     lam = ac_q(bd, qa) >> 1
     pm16 = O.partition_fixed(g, 4)
     out = []
     anchor_fin = anchor_pyr = None
+    padded = [O.pad_planes(g, fr) for fr in frames]
+    pyrs = [O.pyramid(g, pl[0]) for pl in padded]
+    n = len(frames)
     for i, fr in enumerate(frames):
         kind = frame_kind(pos0 + i, keyint, gop_period, intra_only)
         q = qk[kind]
         fp = class_params(bd, q, kind, loop_filters, lr)
-        src = O.pad_planes(g, fr)
-        pyr = O.pyramid(g, src[0])
+        src = padded[i]
+        pyr = pyrs[i]          # the motion search always sees the unfiltered source pictures
+        nb = []
+        if mctf and kind != 2 and not intra_only:
+            # temporal filter of key / anchor sources (csrc/encoder.cc launch()): neighbours inside the closed GOP; ahead of
+            # the picture only what the same batch holds (and --lookahead allows), behind it up to mctf_radius pictures
+            lo, hi = (0, mctf_key_fwd) if kind == 0 else (-mctf_radius, mctf_radius)
+            if lookahead >= 0:
+                hi = min(hi, lookahead)
+            in_gop = (pos0 + i) % keyint
+            for d in range(lo, hi + 1):
+                j = i + d
+                if d == 0 or j < 0 or j >= n or (d > 0 and j // batch != i // batch):
+                    continue
+                if in_gop + d < 0 or in_gop + d >= keyint:
+                    continue
+                nb.append(j)
+            nb = nb[:6]
+        if nb:
+            mvs_tf = []
+            for j in nb:
+                mv = O.hme(g, pyrs[i], pyrs[j], lam)
+                mvs_tf.append(O.me_smooth(g, pyrs[i], pyrs[j], mv, lam, 2) if me_smooth else mv)
+            aq = ac_q(bd, q)
+            thr_b = max(1, (aq * aq * (10 + film_grain)) // 2560)
+            src = O.mctf(g, bd, padded[i], [padded[j] for j in nb], mvs_tf, thr_b, 3 * thr_b)
+            fr = O.crop(g, src)
         r = FrameResult()
-        r.kind, r.fp, r.q, r.mvs = kind, fp, q, None
+        r.kind, r.fp, r.q, r.mvs, r.src, r.filtered_from = kind, fp, q, None, src, nb
         if kind == 0:
             if key_var_part and blk_log2 == 4:
                 pm = O.partition_smooth(g, src[0], min(4 * ac_q(bd, q), 800 << (bd - 8)))

@@ -141,6 +141,21 @@ def me_smooth(g, cur_pyr, ref_pyr, mv, lam_s, iters=2):
     return mv
 
 
+def mctf(g, bit_depth, cur_planes, nb_planes, nb_mvs, thr_b, thr_p):
+    """Motion-compensated temporal filter (orc_mctf): cur_planes = 3 padded planes, nb_planes = list of 3 padded planes per
+    neighbour, nb_mvs = list of [h8*w8, 2] vectors (cur against that neighbour). Returns 3 padded planes."""
+    cur = [np.ascontiguousarray(p, np.uint16) for p in cur_planes]
+    nbs = [[np.ascontiguousarray(p, np.uint16) for p in nb] for nb in nb_planes]
+    mvs = [np.ascontiguousarray(m, np.int16) for m in nb_mvs]
+    n = len(nbs)
+    pp = (C.c_void_p * max(1, 3 * n))(*[p.ctypes.data for nb in nbs for p in nb])
+    mp = (C.c_void_p * max(1, n))(*[m.ctypes.data for m in mvs])
+    out = [np.zeros_like(p) for p in cur]
+    lib().orc_mctf(C.byref(g), bit_depth, ptr(cur[0]), ptr(cur[1]), ptr(cur[2]), n, pp, mp, int(thr_b), int(thr_p),
+                   ptr(out[0]), ptr(out[1]), ptr(out[2]))
+    return out
+
+
 def merge_skip_blocks(g, blocks):
     """In place: merges skipped inter siblings with equal vectors into 32x32 / 64x64 blocks."""
     lib().orc_merge_skip_blocks(C.byref(g), ptr(blocks))

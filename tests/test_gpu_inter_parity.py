@@ -19,6 +19,7 @@ CASES = [
     (328, 248, 8, 30, 1, 1, True, 9, 3, 240, 3, 0),
     (640, 360, 10, 35, -1, -1, True, 6, 4, 240, 5, 2),
     (328, 248, 10, 50, 0, 0, True, 13, 8, 240, 6, 0),
+    (640, 360, 8, 38, -1, -1, True, 18, 8, 240, 6, 0),
 ]
 # every case also through the device range coder (pack_path 4); 0 = automatic placement
 CASES = [c + (pp,) for c in CASES for pp in (0, 4)]
@@ -36,7 +37,7 @@ def test_chunk_parity(w, h, bd, crf, tcl, trl, lf, nfr, fif, keyint, preset, gop
     lr = lf and preset <= 5
     tus = enc.encode_chunk(frames)
     assert len(tus) == nfr
-    g, want = chain.encode_chain(frames, w, h, bd, crf, keyint=keyint, gop_period=gop or 4, loop_filters=lf, lr=lr)
+    g, want = chain.encode_chain(frames, w, h, bd, crf, keyint=keyint, gop_period=gop or 4, loop_filters=lf, lr=lr, geom=enc.geom, batch=fif)
     assert enc.me_lambda() == chain.ac_q(bd, chain.quantisers(crf, gop or 4)[1]) >> 1
     dec_d = D.dav1d_decode(tus)
     dec_a = D.aom_decode(tus)
@@ -65,6 +66,7 @@ def test_chunk_parity(w, h, bd, crf, tcl, trl, lf, nfr, fif, keyint, preset, gop
             assert np.array_equal(dec_a[i][p], rec[p]), ("libaom", i, p)
     if (gop or 4) > 1 and nfr > (gop or 4) and keyint > (gop or 4):
         assert kinds == {0, 1, 2}
+    assert enc.stats()["mctf_frames"] == sum(1 for r in want if r.filtered_from)
     enc.close()
 
 

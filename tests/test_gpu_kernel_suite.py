@@ -256,6 +256,28 @@ def test_partition_smooth_vs_oracle(w, h, bd):
         assert len(sizes & {5, 6}) >= 1 and 4 in sizes, sizes
 
 
+@pytest.mark.parametrize("w,h,bd", ME_CASES + [(1920, 1080, 10)])
+def test_temporal_filter_vs_oracle(w, h, bd):
+    """mctf_kernel: normative interpolation of every neighbour + block / sample weights + weighted mean, all planes."""
+    g = O.geom(w, h, 0, 0)
+    n = 4 if w < 1000 else 3
+    frames = synth.synth_clip(w, h, bd, n, seed=w + bd + 2, scene_len=100)
+    padded = [O.pad_planes(g, fr) for fr in frames]
+    pyr = [O.pyramid(g, p[0]) for p in padded]
+    lam = 60 << (bd - 8)
+    mvs = [O.me_smooth(g, pyr[1], pyr[j], O.hme(g, pyr[1], pyr[j], lam), lam, 2) for j in range(n) if j != 1]
+    nbs = [padded[j] for j in range(n) if j != 1]
+    for thr_b in (3 << (2 * (bd - 8)), 40 << (2 * (bd - 8)), 4000 << (2 * (bd - 8))):
+        got, _ = kernels.mctf(w, h, bd, padded[1], nbs, mvs, thr_b, 3 * thr_b)
+        want = O.mctf(g, bd, padded[1], nbs, mvs, thr_b, 3 * thr_b)
+        for p in range(3):
+            assert np.array_equal(got[p], want[p]), (thr_b, p)
+    assert not np.array_equal(want[0], padded[1][0])          # the strong filter changes the picture
+    got, _ = kernels.mctf(w, h, bd, padded[1], [], [], 10, 30)   # no neighbours: identity
+    for p in range(3):
+        assert np.array_equal(got[p], padded[1][p])
+
+
 def random_mvs(g, pm, rng, integer):
     step = 8 if integer else 2
     m = (rng.integers(-6, 7, (g.h8, g.w8, 2)) * step).astype(np.int16)

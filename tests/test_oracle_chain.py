@@ -112,6 +112,49 @@ def test_mv_dominant_and_smoothing_properties():
     assert len(f1) == len(f0)
 
 
+def test_temporal_filter_properties():
+    """orc_mctf against a numpy restatement built on pyoracle.inter_predict (the normative predictor pinned elsewhere),
+    and what it is for: independent noise averages out."""
+    w, h, bd = 200, 136, 10
+    g = O.geom(w, h, 0, 0)
+    clean = synth.synth_clip(w, h, bd, 3, seed=5, scene_len=100, noise=0.0)
+    noisy = synth.synth_clip(w, h, bd, 3, seed=5, scene_len=100, noise=1.0)
+    padded = [O.pad_planes(g, f) for f in noisy]
+    pyr = [O.pyramid(g, p[0]) for p in padded]
+    mvs = [O.hme(g, pyr[1], pyr[j], 100) for j in (0, 2)]
+    thr_b, thr_p = 900, 2700
+    got = O.mctf(g, bd, padded[1], [padded[0], padded[2]], mvs, thr_b, thr_p)
+    # numpy restatement
+    num = [p.astype(np.int64) * 256 for p in padded[1]]
+    den = [np.full(p.shape, 256, np.int64) for p in padded[1]]
+    for nb, mv in zip((padded[0], padded[2]), mvs):
+        m = mv.reshape(g.h8, g.w8, 2)
+        for by in range((h + 15) // 16):
+            for bx in range((w + 15) // 16):
+                v = m[by * 2, bx * 2]
+                bw, bh = min(16, w - bx * 16), min(16, h - by * 16)
+                preds = [O.inter_predict(nb[p], (bx * 16) >> (p > 0), (by * 16) >> (p > 0), 16 >> (p > 0), 16 >> (p > 0), v, int(p > 0), bd,
+                                         ref_w=w >> (p > 0), ref_h=h >> (p > 0)).astype(np.int64) for p in range(3)]
+                cy = padded[1][0][by * 16:by * 16 + bh, bx * 16:bx * 16 + bw].astype(np.int64)
+                mse = int(((preds[0][:bh, :bw] - cy) ** 2).sum()) // (bw * bh)
+                wb = min(16, max(0, 16 - (16 * mse) // thr_b))
+                if wb == 0:
+                    continue
+                for p in range(3):
+                    ss = int(p > 0)
+                    y0, x0, hh, ww = (by * 16) >> ss, (bx * 16) >> ss, bh >> ss, bw >> ss
+                    pr = preds[p][:hh, :ww]
+                    d = pr - padded[1][p][y0:y0 + hh, x0:x0 + ww].astype(np.int64)
+                    wgt = wb * np.clip(16 - (16 * d * d) // thr_p, 0, 16)
+                    num[p][y0:y0 + hh, x0:x0 + ww] += wgt * pr
+                    den[p][y0:y0 + hh, x0:x0 + ww] += wgt
+    for p in range(3):
+        assert np.array_equal(got[p], ((num[p] + den[p] // 2) // den[p]).astype(np.uint16)), p
+    cy = clean[1][0].astype(np.float64)
+    e_in = ((noisy[1][0] - cy) ** 2).mean(); e_out = ((O.crop(g, got)[0] - cy) ** 2).mean()
+    assert e_out < 0.7 * e_in, (e_in, e_out)
+
+
 def test_chain_golden():
     """Committed digest of a chain run (tests/golden/chain_digest.json, written by tests/golden/make_golden.py): pins
     the oracle's decisions -- any change to the hierarchy, the partition rule or the regularisation shows up here."""

@@ -78,6 +78,21 @@ def encode(args):
         for i in range(nfr):
             if i == 0 or (hier and i % hier[0] == 0) or not hier:
                 enc_src[i] = mctf(O, g, frames, pyrs, i, int(rad), strength, bd, acq >> 1)
+    if opts.get("mctf2"):
+        rad, kb, kp = opts["mctf2"]
+        thr_b = max(1, int(kb * acq * acq / 256)); thr_p = max(1, int(kp * thr_b))
+        padded = [O.pad_planes(g, fr) for fr in frames]
+        for i in range(nfr):
+            if i == 0 or (hier and i % hier[0] == 0) or not hier:
+                lo, hi = (0, int(opts.get("keyfwd", 6))) if i == 0 else (-int(rad), int(rad))
+                nb = [j for j in range(i + lo, i + hi + 1) if 0 <= j < nfr and j != i]
+                mvs = []
+                for j in nb:
+                    mv = O.hme(g, pyrs[i], pyrs[j], acq >> 1)
+                    if opts.get("smooth"):
+                        mv = O.me_smooth(g, pyrs[i], pyrs[j], mv, int((acq >> 1) * opts["smooth"][0]), int(opts["smooth"][1]))
+                    mvs.append(mv)
+                enc_src[i] = O.crop(g, O.mctf(g, bd, padded[i], [padded[j] for j in nb], mvs, thr_b, thr_p))
     nbytes, psnr = 0, []
     per_frame = []
     anchor_fin = anchor_pyr = prev_fin = prev_pyr = None
@@ -89,7 +104,11 @@ def encode(args):
         fp = abi.FrameParams()
         if i == 0:
             abi.lib().av1b_select_frame_params(bd, qkey, 0, 1, C.byref(fp))
-            r = O.encode_intra_frame(g, fr, bd, qkey, pm)
+            pmk = pm
+            if opts.get("varpart"):
+                acqk = table("av1t_ac_q_%d" % bd)[qkey]
+                pmk = O.partition_smooth(g, src[0], min(4 * acqk, 800 << (bd - 8)))
+            r = O.encode_intra_frame(g, fr, bd, qkey, pmk)
         else:
             mv = O.hme(g, pyr, prev_pyr, acq >> 1)
             if opts.get("smooth"):
@@ -129,13 +148,17 @@ def main():
     ap.add_argument("--hier", default="")
     ap.add_argument("--mctf", default="", help="radius,strength")
     ap.add_argument("--dkey", type=int, default=None)
+    ap.add_argument("--mctf2", default="", help="radius,kb,kp: oracle temporal filter, thr_b = kb acq^2 / 256, thr_p = kp thr_b")
+    ap.add_argument("--keyfwd", type=int, default=6)
+    ap.add_argument("--varpart", action="store_true")
     ap.add_argument("--me-filtered", action="store_true")
     ap.add_argument("--smooth", default="", help="k,iters: vector-field regularisation with lam_s = k * lambda")
     a = ap.parse_args()
     w, h = map(int, a.size.split("x"))
     opts = dict(hier=tuple(map(int, a.hier.split(','))) if a.hier else None,
                 mctf=tuple(map(float, a.mctf.split(','))) if a.mctf else None, me_filtered=a.me_filtered,
-                smooth=tuple(map(float, a.smooth.split(','))) if a.smooth else None)
+                smooth=tuple(map(float, a.smooth.split(','))) if a.smooth else None,
+                mctf2=tuple(map(float, a.mctf2.split(','))) if a.mctf2 else None, keyfwd=a.keyfwd, varpart=a.varpart)
     if a.dkey is not None:
         opts["dkey"] = a.dkey
     jobs = [(w, h, a.bd, a.frames, a.seed, a.noise, crf, opts) for crf in map(int, a.crfs.split(","))]
