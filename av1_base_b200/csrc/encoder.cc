@@ -142,6 +142,7 @@ struct Slot {
   size_t tok_fetched = 0;                             // tokens already downloaded with the offsets
   cudaEvent_t ev_tok0 = nullptr, ev_tok1 = nullptr;
   cudaEvent_t ev_src = nullptr;                       // sources of this slot are resident
+  bool h2d_pending = false;                           // ev_h2d .. ev_src of the last upload have not been read yet
   uint16_t* h_src[3] = {nullptr, nullptr, nullptr};
   uint16_t* h_rec[3] = {nullptr, nullptr, nullptr};
   int16_t* h_coef[3] = {nullptr, nullptr, nullptr};
@@ -186,6 +187,8 @@ struct av1b_encoder {
   int16_t* d_mv2_tf = nullptr;
   int64_t mctf_frames = 0;
   double t_mctf_ms = 0;
+  uint16_t* d_clip[3] = {nullptr, nullptr, nullptr};       // resident clip (av1b_stage_clip): n_clip source pictures in HBM
+  uint32_t n_clip = 0;
   int16_t* d_mv_tmp = nullptr;
   uint32_t* d_hist = nullptr;
   void* d_cdf_init_alt = nullptr;     // default CDF set of the non-reference frames' quantiser class
@@ -259,7 +262,7 @@ static void free_all(av1b_encoder* e) {
   cudaFree(e->d_sb_of_order); cudaFree(e->d_tile_of_sb); cudaFree(e->d_lr_sse);
   cudaFree(e->d_cdf_init); cudaFree(e->d_cdf_init_alt); cudaFree(e->d_tile_first_k); cudaFree(e->d_rc_overflow);
   cudaFree(e->d_mv_tmp); cudaFree(e->d_hist); cudaFree(e->d_mvs_tf); cudaFree(e->d_mv2_tf);
-  for (int p = 0; p < 3; p++) { cudaFree(e->d_hist_src[p]); cudaFree(e->d_flt[p]); }
+  for (int p = 0; p < 3; p++) { cudaFree(e->d_hist_src[p]); cudaFree(e->d_flt[p]); cudaFree(e->d_clip[p]); }
   if (e->s_tok) cudaStreamDestroy(e->s_tok);
   if (e->stream) cudaStreamDestroy(e->stream);
   if (e->s_in) cudaStreamDestroy(e->s_in);
@@ -275,11 +278,22 @@ static bool is_pinned(const void* p) {
   return a.type == cudaMemoryTypeHost;
 }
 
+// upload time of the slot's last staging, once its events have completed (the slot may have been staged again for a later
+// batch before the batch that used it is finished: then the reading waits for the next call)
+static void collect_h2d(av1b_encoder* e, Slot& s) {
+  if (!s.h2d_pending) return;
+  float ms = 0;
+  if (cudaEventElapsedTime(&ms, s.ev_h2d, s.ev_src) == cudaSuccess) { e->t_h2d_ms += ms; s.h2d_pending = false; }
+  else cudaGetLastError();
+}
+
 // upload n frames (host pointers) into a slot on the input copy stream (overlaps the kernels of the
 // previous batch).  Page-locked sources are read by the copy engine where they lie; pageable ones are
 // first gathered into the slot's pinned staging buffer by the host pool.
 static int stage(av1b_encoder* e, Slot& s, const av1b_frame_src* frames, int n) {
   const Av1bGeom& g = e->g;
+  collect_h2d(e, s);
+  s.h2d_pending = true;
   bool direct = true;
   for (int b = 0; b < n && direct; b++)
     for (int p = 0; p < 3 && direct; p++) direct = is_pinned(frames[b].planes[p]);
@@ -399,9 +413,9 @@ static int launch(av1b_encoder* e, Slot& s, const Slot& in, int n, int64_t first
       }
       if (n_pairs) {
         H.mv2 = e->d_mv2_tf; H.mv_out = e->d_mvs_tf;
+        // (no regularisation sweeps here: they pay for vectors that are coded, the filter gains 0.5 % from them)
         CK(launch_hme(H, n_pairs, e->stream));
         e->kernel_launches += 2;
-        if (H.lam_s > 0) { CK(launch_hme_smooth(H, n_pairs, e->stream)); e->kernel_launches += 3 * H.smooth_iters; }
       }
       for (const Job& j : jobs) {
         const Av1bFrameParams& fpk = kind_params(e, s.kind[j.b]);
@@ -628,8 +642,8 @@ static int finish(av1b_encoder* e, Slot& s, bool staged, av1b_packet_cb out_cb, 
                   int64_t total_frames, std::chrono::steady_clock::time_point t_start) {
   const Av1bGeom& g = e->g;
   CK(cudaEventSynchronize(s.ev_d2h));
-  float ms;
-  if (staged) { cudaEventElapsedTime(&ms, s.ev_h2d, s.ev_src); e->t_h2d_ms += ms; }
+  float ms = 0;
+  if (staged) collect_h2d(e, s);
   cudaEventElapsedTime(&ms, s.ev_k0, s.ev_k1); e->t_kernel_ms += ms;
   cudaEventElapsedTime(&ms, s.ev_k0, s.ev_me); e->t_me_ms += ms;
   if (e->mctf_on && !e->intra_only) { cudaEventElapsedTime(&ms, s.ev_tf0, s.ev_tf1); e->t_mctf_ms += ms; }
@@ -1036,12 +1050,25 @@ void av1b_encoder_destroy(av1b_encoder* e) {
 
 // Batches of one call: the sources of batch k+1 are uploaded while the kernels of batch k run (their slot's
 // device buffers were last read by batch k-1), and the host entropy-codes batch k-1 meanwhile.
-static int run_batches(av1b_encoder* e, const av1b_frame_src* frames, uint32_t n_frames, int64_t first_index,
+// frames != nullptr: host sources; else order[] indexes the resident clip (device-to-device gather on the input stream).
+static int stage_any(av1b_encoder* e, Slot& s, const av1b_frame_src* frames, const uint32_t* order, uint32_t f0, int n) {
+  if (frames) return stage(e, s, frames + f0, n);
+  CK(cudaEventRecord(s.ev_h2d, e->s_in));
+  for (int b = 0; b < n; b++)
+    for (int p = 0; p < 3; p++)
+      CK(cudaMemcpyAsync(s.d_src[p] + (size_t)b * e->plane_elems[p], e->d_clip[p] + (size_t)order[f0 + b] * e->plane_elems[p],
+                         e->plane_elems[p] * 2, cudaMemcpyDeviceToDevice, e->s_in));
+  CK(cudaEventRecord(s.ev_src, e->s_in));
+  return AV1B_OK;
+}
+
+static int run_batches(av1b_encoder* e, const av1b_frame_src* frames, const uint32_t* order, uint32_t n_frames, int64_t first_index,
                        int64_t total_frames, av1b_packet_cb out_cb, av1b_progress_cb prog_cb, void* user) {
   const auto t0 = std::chrono::steady_clock::now();
   const uint32_t B = (uint32_t)e->batch;
+  const bool staged = frames != nullptr;
   int rc, i = 0;
-  if ((rc = stage(e, e->slot[0], frames, (int)std::min<uint32_t>(B, n_frames))) != AV1B_OK) return rc;
+  if ((rc = stage_any(e, e->slot[0], frames, order, 0, (int)std::min<uint32_t>(B, n_frames))) != AV1B_OK) return rc;
   const int S = e->n_slots, L = S - 1;
   for (uint32_t f0 = 0; f0 < n_frames; f0 += B, i++) {
     const int nb = (int)std::min<uint32_t>(B, n_frames - f0);
@@ -1050,13 +1077,14 @@ static int run_batches(av1b_encoder* e, const av1b_frame_src* frames, uint32_t n
     if (f0 + B < n_frames) {
       Slot& nx = e->slot[(i + 1) % S];
       if (i >= L) CK(cudaStreamWaitEvent(e->s_in, nx.ev_k1, 0));   // batch i+1-S has read that slot's sources
-      if ((rc = stage(e, nx, frames + f0 + B, (int)std::min<uint32_t>(B, n_frames - f0 - B))) != AV1B_OK) return rc;
+      if ((rc = stage_any(e, nx, frames, order, f0 + B, (int)std::min<uint32_t>(B, n_frames - f0 - B))) != AV1B_OK) return rc;
     }
     // the slot of batch i+1 is that of batch i+1-S: its packets must be out before the next launch
-    if (i >= L && (rc = finish(e, e->slot[(i - L) % S], true, out_cb, prog_cb, user, total_frames, t0)) != AV1B_OK) return rc;
+    if (i >= L && (rc = finish(e, e->slot[(i - L) % S], staged, out_cb, prog_cb, user, total_frames, t0)) != AV1B_OK) return rc;
   }
   for (int k = std::max(0, i - L); k < i; k++)
-    if ((rc = finish(e, e->slot[k % S], true, out_cb, prog_cb, user, total_frames, t0)) != AV1B_OK) return rc;
+    if ((rc = finish(e, e->slot[k % S], staged, out_cb, prog_cb, user, total_frames, t0)) != AV1B_OK) return rc;
+  for (Slot& sl : e->slot) collect_h2d(e, sl);
   return AV1B_OK;
 }
 
@@ -1067,7 +1095,7 @@ int av1b_encode_chunk(av1b_encoder* e, const av1b_frame_src* frames, uint32_t n_
   CK(cudaSetDevice(e->cfg.device_id));
   reset_stats(e);
   e->chunk_pos = 0;               // a chunk is a closed GOP: it starts with a key frame
-  return run_batches(e, frames, n_frames, 0, n_frames, out_cb, prog_cb, user);
+  return run_batches(e, frames, nullptr, n_frames, 0, n_frames, out_cb, prog_cb, user);
 }
 
 // Streaming variant: a chunk handed over in parts (bounded host memory for long chunks).  The part
@@ -1078,7 +1106,7 @@ int av1b_encode_part(av1b_encoder* e, const av1b_frame_src* frames, uint32_t n_f
   if (!e || !frames || !out_cb || n_frames == 0) { set_error("null argument"); return AV1B_ERR_INVALID; }
   CK(cudaSetDevice(e->cfg.device_id));
   if (first_part) { reset_stats(e); e->chunk_pos = 0; }
-  return run_batches(e, frames, n_frames, first_frame_index, 0, out_cb, prog_cb, user);
+  return run_batches(e, frames, nullptr, n_frames, first_frame_index, 0, out_cb, prog_cb, user);
 }
 
 // ---- device-resident flow (bench: "inputs already resident in HBM") -----------------------------
@@ -1114,6 +1142,39 @@ int av1b_encode_resident(av1b_encoder* e, uint32_t n_steps, av1b_packet_cb out_c
     if ((rc = finish(e, e->slot[k % S], false, out_cb, nullptr, user, 0, t0)) != AV1B_OK) return rc;
   e->slot[0].n_frames = n0; e->slot[1].n_frames = n1;
   return AV1B_OK;
+}
+
+// ---- resident clip: n source pictures uploaded once, then closed chunks are coded out of them by index ----
+int av1b_stage_clip(av1b_encoder* e, const av1b_frame_src* frames, uint32_t n) {
+  if (!e || !frames || n == 0) { set_error("bad argument"); return AV1B_ERR_INVALID; }
+  CK(cudaSetDevice(e->cfg.device_id));
+  CK(cudaDeviceSynchronize());
+  if (n != e->n_clip) {
+    for (int p = 0; p < 3; p++) { cudaFree(e->d_clip[p]); e->d_clip[p] = nullptr; }
+    e->n_clip = 0;
+    for (int p = 0; p < 3; p++)
+      if (cudaMalloc(&e->d_clip[p], e->plane_elems[p] * n * 2) != cudaSuccess) { cudaGetLastError(); set_error("resident clip: out of device memory"); return AV1B_ERR_NOMEM; }
+    e->n_clip = n;
+  }
+  for (int p = 0; p < 3; p++) CK(cudaMemset(e->d_clip[p], 0, e->plane_elems[p] * n * 2));
+  const Av1bGeom& g = e->g;
+  for (uint32_t b = 0; b < n; b++)
+    for (int p = 0; p < 3; p++) {
+      const int w = p ? g.width >> 1 : g.width, h = p ? g.height >> 1 : g.height;
+      CK(cudaMemcpy2D(e->d_clip[p] + (size_t)b * e->plane_elems[p], (size_t)g.stride[p] * 2, frames[b].planes[p],
+                      (size_t)frames[b].stride[p] * 2, (size_t)w * 2, h, cudaMemcpyHostToDevice));
+    }
+  return AV1B_OK;
+}
+
+int av1b_encode_clip(av1b_encoder* e, const uint32_t* order, uint32_t n_frames, int accumulate_stats, av1b_packet_cb out_cb, void* user) {
+  if (!e || !order || n_frames == 0) { set_error("bad argument"); return AV1B_ERR_INVALID; }
+  if (!e->n_clip) { set_error("stage a clip first (av1b_stage_clip)"); return AV1B_ERR_INVALID; }
+  for (uint32_t i = 0; i < n_frames; i++) if (order[i] >= e->n_clip) { set_error("clip index out of range"); return AV1B_ERR_INVALID; }
+  CK(cudaSetDevice(e->cfg.device_id));
+  if (!accumulate_stats) reset_stats(e);
+  e->chunk_pos = 0;               // a closed chunk: it starts with a key frame
+  return run_batches(e, nullptr, order, n_frames, 0, n_frames, out_cb, nullptr, user);
 }
 
 int av1b_get_recon(av1b_encoder* e, uint32_t frame, uint16_t* const dst[3], const int32_t stride[3]) {

@@ -192,6 +192,24 @@ class Encoder:
         srcs, keep = self._srcs(frames)
         _check(abi.lib().av1b_stage_frames(self._h, slot, srcs, len(frames)))
 
+    def stage_clip(self, frames):
+        """Upload a clip into HBM once (resident clip); encode_clip then codes closed chunks made of its pictures."""
+        srcs, keep = self._srcs(frames)
+        _check(abi.lib().av1b_stage_clip(self._h, srcs, len(frames)))
+
+    def encode_clip(self, order, accumulate=False, collect=False):
+        """One closed chunk: frame i = resident clip picture order[i]."""
+        out = []
+
+        def on_packet(user, data, size, idx, is_key):
+            out.append(C.string_at(data, size))
+            return 0
+
+        cb = abi.PACKET_CB(on_packet) if collect else None
+        o = np.ascontiguousarray(order, np.uint32)
+        _check(abi.lib().av1b_encode_clip(self._h, o.ctypes.data_as(C.c_void_p), len(o), int(accumulate), cb, None))
+        return out
+
     def encode_resident(self, n_steps, collect=False):
         out = []
 

@@ -10,14 +10,15 @@ def _smooth_noise(rng, h, w, sigma):
     return n * sigma
 
 
-def synth_clip(width, height, bit_depth, n_frames, seed=1, scene_len=80, hdr=False, noise=1.0):
-    """Returns a list of [Y, U, V] uint16 arrays."""
+def synth_clip(width, height, bit_depth, n_frames, seed=1, scene_len=80, hdr=False, noise=1.0, start=0):
+    """Returns a list of [Y, U, V] uint16 arrays: frames start .. start + n_frames - 1 of the clip (every frame is a pure
+    function of (seed, frame number), so slices of a clip can be made independently)."""
     scale = 1 << (bit_depth - 8)
     lo, hi = 16 * scale, 235 * scale
     frames = []
     yy, xx = np.mgrid[0:height, 0:width].astype(np.float32)
     scene = None
-    for f in range(n_frames):
+    for f in range(start, start + n_frames):
         sc = f // scene_len
         if scene is None or scene["id"] != sc:
             rng = np.random.default_rng(seed * 1000 + sc)

@@ -1,17 +1,20 @@
 #!/usr/bin/env python3
 """bench.py -- AV1 encode fps of the B200 backend (BASELINE.json metric), one rank per GPU.
 
-A "step" is one pass of the hot path over one batch of F synthetic frames (one chunk stream per GPU,
-SURVEY.md 8e: chunks share no state, so ranks never communicate on the data path; weak scaling).
-  value : frames/s with the source frames already resident in HBM (av1b_encode_resident): device
-          kernels + symbol download + host entropy coding, pipelined; whole job over all ranks.
+A "step" is one closed chunk of the workload's clip (C4: 150 frames of 3840x2160 10-bit, one scene of the scene_len-150
+generator = what the chunker cuts; 1 key frame + 149 inter frames) through the hot path, one chunk stream per GPU
+(chunks share no state, so ranks never communicate on the data path; weak scaling).
+  value : frames/s with the clip resident in HBM (av1b_stage_clip + av1b_encode_clip): device kernels + symbol
+          download + host entropy coding, pipelined; whole job over all ranks.
   e2e   : frames/s through av1b_encode_chunk with HOST buffers in page-locked memory (H2D -> kernels ->
           D2H -> entropy coding -> packets), the call a reference-side binding makes.
   roofline : the dominant kernel by device time, algorithmic bytes / CUDA-event duration
              against the measured HBM copy bandwidth in MEASURED_PEAKS.json.
-  cpu_baseline : the CPU oracle port of the same path on the host cores (bounded sample).
---impl reference times the CPU path (oracle port; the reference's av1an + SVT-AV1 cannot run here,
-BASELINE.md section 2) with all host threads on the same workload.
+  cpu_baseline : libaom 3.13.1 cpu-used=6 (the stand-in SURVEY.md 8d names for the reference's av1an + SVT-AV1, which
+             cannot run in this image) on the same clip, av1an style: nproc/2 chunk workers; bounded sample.
+  bd_rate : Bjontegaard rate difference of this encoder against libaom cpu-used=6 on the 960x544 clip of tools/bdrate.py.
+--impl reference times that libaom stand-in alone (no product library is loaded), streaming the same chunk through
+nproc/2 encoder instances at steady state.
 """
 import argparse, json, os, statistics, subprocess, sys, threading, time
 import numpy as np
@@ -20,10 +23,10 @@ ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
 WORKLOADS = {
-    # name: (width, height, bit_depth, description)
-    "4k10": (3840, 2160, 10, "C4: 3840x2160 10-bit HDR 4:2:0 synthetic, CRF 30, one chunk stream per GPU"),
-    "1080p10": (1920, 1080, 10, "C3: 1920x1080 10-bit 4:2:0 synthetic, CRF 30"),
-    "1080p8": (1920, 1080, 8, "C1: 1920x1080 8-bit 4:2:0 synthetic, CRF 30"),
+    # name: (width, height, bit_depth, description, scene_len of the generator, frames of one chunk = one step)
+    "4k10": (3840, 2160, 10, "C4: 3840x2160 10-bit HDR 4:2:0 synthetic, CRF 30, one chunk stream per GPU", 150, 150),
+    "1080p10": (1920, 1080, 10, "C3: 1920x1080 10-bit 4:2:0 synthetic, CRF 30", 240, 240),
+    "1080p8": (1920, 1080, 8, "C1: 1920x1080 8-bit 4:2:0 synthetic, CRF 30", 80, 80),
 }
 
 
@@ -137,108 +140,175 @@ class ClockSampler:
                 "reasons": sorted(reasons), "samples": len(sm), "source": "nvidia-smi"}
 
 
-def make_frames(w, h, bd, n, hdr):
+def _gen(args):
+    w, h, bd, seed, scene_len, hdr, start = args
     from av1_base_b200 import synth
-    # two scenes so that the batch is not one static picture; deterministic
-    return synth.synth_clip(w, h, bd, n, seed=4, scene_len=max(1, n // 2), hdr=hdr)
+    return synth.synth_clip(w, h, bd, 1, seed=seed, scene_len=scene_len, hdr=hdr, start=start)[0]
 
 
-def abi_tables_acq(bd, qidx):
-    """AC quantiser step of a qindex (read from the generated table header: no device needed)."""
-    import re
-    txt = open(os.path.join(ROOT, "av1_base_b200", "csrc", "av1_tables.h")).read()
-    m = re.search(r"av1t_ac_q_%d\[\d+\] = \{(.*?)\};" % bd, txt, re.S)
-    return [int(v) for v in re.findall(r"-?\d+", m.group(1))][qidx]
+def make_clip(w, h, bd, n, hdr, scene_len):
+    """The first n frames of the workload's clip (SURVEY.md 8d generator, seed 4), generated by the host cores in parallel."""
+    from concurrent.futures import ProcessPoolExecutor
+    jobs = [(w, h, bd, 4, scene_len, hdr, i) for i in range(n)]
+    with ProcessPoolExecutor(min(len(jobs), max(1, (os.cpu_count() or 2) // 2), 16)) as ex:
+        return list(ex.map(_gen, jobs))
 
 
-def oracle_chunk(frames, w, h, bd, qidx):
-    """CPU port of the same path (oracle/av1_oracle.cpp) for one chunk: key frame, then inter frames
-    (hierarchical ME on the source pyramid, motion-compensated residual coding), deblock + CDEF
-    decision + CDEF after every frame.  Scalar code, one thread per chunk."""
-    from av1_base_b200 import abi
-    from oracle import pyoracle as O
-    import ctypes as C
-    g = O.geom(w, h, 0, 0)
-    pm = O.partition_fixed(g, 4)
-    lam = (abi_tables_acq(bd, qidx)) >> 1
-    fps = []
-    for ft in (0, 1):
-        fp = abi.FrameParams()
-        abi.lib().av1b_select_frame_params(bd, qidx if ft else max(1, qidx * 3 // 4), ft, 1, C.byref(fp))
-        fps.append(fp)
-    prev_fin = prev_pyr = None
-    for i, fr in enumerate(frames):
-        pyr = O.pyramid(g, O.pad_planes(g, fr)[0])
-        if i == 0:
-            r, fp = O.encode_intra_frame(g, fr, bd, max(1, qidx * 3 // 4), pm), fps[0]
-        else:
-            r, fp = O.encode_inter_frame(g, fr, bd, qidx, pm, O.hme(g, pyr, prev_pyr, lam), prev_fin), fps[1]
-            O.merge_skip_blocks(g, r.blocks)
-        O.deblock_frame(g, bd, r.blocks, r.rec, list(fp.lf_level), fp.lf_sharpness)
-        src = O.pad_planes(g, fr)
-        prev_fin = O.cdef_frame(g, bd, r.blocks, fp, O.cdef_search(g, bd, r.blocks, fp, r.rec, src), r.rec)
-        prev_pyr = pyr
-    return len(frames)
+def chunk_order(n_distinct, n_frames):
+    """A closed chunk of n_frames made of n_distinct pictures: forwards, then backwards without repeating the end points
+    (continuous motion, no frame equals its predecessor)."""
+    period = list(range(n_distinct)) + list(range(n_distinct - 2, 0, -1))
+    return [period[i % len(period)] for i in range(n_frames)]
 
 
-def oracle_fps(frames, w, h, bd, qidx, threads, chunk_len):
-    """threads independent chunks of chunk_len frames each (av1an-style chunk parallelism; ctypes drops the GIL)."""
+def workload_config(args):
+    w, h, bd, desc, scene_len, chunk = WORKLOADS[args.workload]
+    return {"workload": desc, "clip": "synth_clip seed 4, scene_len %d" % scene_len, "frames_per_step": chunk,
+            "chunk": "one closed chunk per step: 1 key frame + %d inter frames" % (chunk - 1),
+            "distinct_frames": args.distinct, "crf": args.crf, "preset": args.preset, "keyint": args.keyint}
+
+
+LIBAOM_LAG = 19
+
+
+def libaom_stream_fps(frames, order, w, h, bd, cq, workers, threads, fpw, warm_steps, steps):
+    """av1an-style CPU stand-in: `workers` libaom encoder instances (cpu-used 6, constant quality, `threads` threads each)
+    each code the same closed chunk; every step hands fpw more frames to every worker.  Before the clock starts each
+    worker is fed until its first packet appears (lag_in_frames + 1 frames: the key frame and the look-ahead are behind it)
+    and warm_steps more steps: the timed steps run at steady state, one frame coded per frame handed in.
+    Returns (fps, seconds, seconds per step list)."""
     from concurrent.futures import ThreadPoolExecutor
-    chunks = [[frames[(c + i) % len(frames)] for i in range(chunk_len)] for c in range(threads)]
-    t0 = time.perf_counter()
-    with ThreadPoolExecutor(threads) as ex:
-        n = sum(ex.map(lambda ch: oracle_chunk(ch, w, h, bd, qidx), chunks))
-    return n / (time.perf_counter() - t0)
+    from oracle import decoders as D
+    tiles = (1, 1) if w > 2000 else (1, 0)
+    encs = [D.AomStream(w, h, bd, cq_level=cq, cpu_used=6, threads=threads, lag=LIBAOM_LAG, tile_cols_log2=tiles[0],
+                        tile_rows_log2=tiles[1]) for _ in range(workers)]
+    pos = [0] * workers
+
+    def feed(k, n, until_packet=False):
+        e = encs[k]
+        for _ in range(n):
+            got = e.push(frames[order[pos[k] % len(order)]])
+            pos[k] += 1
+            if until_packet and got > 0:
+                break
+        return n
+
+    with ThreadPoolExecutor(workers) as ex:
+        list(ex.map(lambda k: feed(k, LIBAOM_LAG + 8, True), range(workers)))
+        for _ in range(warm_steps):
+            list(ex.map(lambda k: feed(k, fpw), range(workers)))
+        per = []
+        t0 = time.perf_counter()
+        for _ in range(steps):
+            ts = time.perf_counter()
+            list(ex.map(lambda k: feed(k, fpw), range(workers)))
+            per.append(time.perf_counter() - ts)
+        dt = time.perf_counter() - t0
+    for e in encs:
+        e.close()
+    return steps * workers * fpw / dt, dt, per
+
+
+def libaom_plan(w):
+    cores = os.cpu_count() or 2
+    workers = max(1, cores // 2)
+    threads = max(1, cores // workers)
+    fpw = 2 if w > 2000 else 6        # frames per worker and step: a bounded sample (a step of the 4K clip takes seconds)
+    return cores, workers, threads, fpw
 
 
 def run_reference(args, rank, world):
-    """CPU arm: rank 0 only."""
+    """CPU arm: rank 0 only.  Loads libaom and numpy only: no product library, no device."""
     if rank != 0:
         return
-    w, h, bd, desc = WORKLOADS[args.workload]
-    cores = os.cpu_count() or 1
-    from av1_base_b200 import abi  # noqa: F401  (tables only; no device use)
-    qidx = 120   # CRF 30 -> quantizer_to_qindex[30]
-    workers = max(1, min(cores, 32))
-    chunk_len = 2 if w > 2000 else 3   # bounded sample: key + inter frame(s) per worker and step
-    per_step = workers * chunk_len
-    frames = make_frames(w, h, bd, 4, args.workload == "4k10")
-    for _ in range(min(args.warmup, 1)):
-        oracle_fps(frames, w, h, bd, qidx, workers, 1)
-    t0 = time.perf_counter()
-    for _ in range(args.steps):
-        oracle_fps(frames, w, h, bd, qidx, workers, chunk_len)
-    dt = time.perf_counter() - t0
-    fps = args.steps * per_step / dt
+    w, h, bd, desc, scene_len, chunk = WORKLOADS[args.workload]
+    cores, workers, threads, fpw = libaom_plan(w)
+    nd = args.distinct
+    frames = make_clip(w, h, bd, nd, args.workload == "4k10", scene_len)
+    order = chunk_order(nd, chunk)
+    fps, dt, per = libaom_stream_fps(frames, order, w, h, bd, args.crf, workers, threads, fpw, args.warmup, args.steps)
     line = {
         "impl": "reference", "metric": "AV1 encode fps", "value": fps, "unit": "frames/s", "n_gpus": args.gpus,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1000 * dt / args.steps,
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u16/i32", "data": "synthetic",
-        "config": {"workload": desc, "frames_per_step": per_step, "crf": 30, "chunk_len": chunk_len},
-        "cpu_baseline": {"value": fps, "unit": "frames/s", "cores": workers, "kind": "port",
-                         "sample": "%d steps x %d chunks of %d frames (key + inter) of the workload, one chunk per host thread, "
-                                   "scalar oracle/av1_oracle.cpp (av1an+SVT-AV1 itself cannot run in this image: BASELINE.md "
-                                   "section 2)" % (args.steps, workers, chunk_len)},
+        "config": workload_config(args),
+        "cpu_baseline": {"value": fps, "unit": "frames/s", "cores": cores, "kind": "stand-in-libaom",
+                         "encoder": "libaom 3.13.1 cpu-used=6, end-usage=q, cq-level=%d, lag_in_frames=%d, row-mt, %d threads per worker" % (args.crf, LIBAOM_LAG, threads),
+                         "workers": workers,
+                         "sample": "%d workers (av1an --workers style, nproc/2) each stream the step's closed chunk through their own encoder: "
+                                   "%d frames per worker and step at steady state (the key frame and the look-ahead fill are before the clock), "
+                                   "%d timed frames in all; av1an + SVT-AV1 itself cannot run in this image (BASELINE.md section 2)"
+                                   % (workers, fpw, args.steps * workers * fpw)},
         "e2e": {"value": fps, "unit": "frames/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "svt_av1_fps": None,
     }
     print(json.dumps(line), flush=True)
 
 
+def port_fps(frames, w, h, bd, crf, threads):
+    """Second CPU figure: the scalar oracle restatement of THIS encoder's path (oracle/chain.py), one 2-frame chunk per thread."""
+    from concurrent.futures import ThreadPoolExecutor
+    from oracle import chain
+    t0 = time.perf_counter()
+    with ThreadPoolExecutor(threads) as ex:
+        list(ex.map(lambda k: chain.encode_chain(frames[k % (len(frames) - 1):][:2], w, h, bd, crf), range(threads)))
+    return 2 * threads / (time.perf_counter() - t0)
+
+
+def bd_rate_check(device_id):
+    """Rate/quality of this encoder against libaom cpu-used=6 on the 960x544 10-bit clip of tools/bdrate.py (same run, same
+    clip): five points each, PSNR-Y on the dav1d-decoded streams, Bjontegaard cubic fit; every B200 stream must also
+    decode to the encoder's reconstruction."""
+    sys.path.insert(0, os.path.join(ROOT, "tools"))
+    from bdrate import bd_rate
+    from av1_base_b200 import encoder, synth
+    from oracle import decoders as D
+    w, h, bd, n = 960, 544, 10, 30
+    frames = synth.synth_clip(w, h, bd, n, seed=4, scene_len=1000, noise=1.0)
+
+    def point(tus):
+        dec = D.dav1d_decode(tus)
+        return sum(map(len, tus)) * 8 * 30.0 / n / 1000, float(np.mean([D.psnr(d[0], f[0], bd) for d, f in zip(dec, frames)])), dec
+
+    ours, match = [], True
+    for crf in (12, 20, 28, 36, 44, 52):
+        enc = encoder.Encoder(w, h, bd, crf=crf, device_id=device_id, keep_debug=True)
+        kbps, ps, dec = point(enc.encode_chunk(frames))
+        for i in (0, 1, 4, n - 1):
+            match = match and all(np.array_equal(dec[i][p], enc.recon(i)[p]) for p in range(3))
+        enc.close()
+        ours.append((kbps, ps))
+    out = {"clip": "960x544 10-bit, 30 frames, synth seed 4 noise 1.0", "ours": [{"kbps": k, "psnr_y": p} for k, p in ours],
+           "decode_matches_recon": bool(match)}
+    cores = os.cpu_count() or 1
+    for name, lag in (("libaom_cpu6", LIBAOM_LAG), ("libaom_cpu6_lag0", 0)):
+        pts = []
+        for cq in (24, 32, 40, 48, 56):
+            k, p, _ = point(D.aom_encode(frames, bd, cq_level=cq, cpu_used=6, threads=cores, lag=lag))
+            pts.append((k, p))
+        out[name] = [{"kbps": k, "psnr_y": p} for k, p in pts]
+        out["vs_%s_psnr_y_pct" % name] = bd_rate([x[0] for x in pts], [x[1] for x in pts], [x[0] for x in ours], [x[1] for x in ours])
+    return out
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=24)
+    ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default="4k10", choices=sorted(WORKLOADS))
-    ap.add_argument("--frames-per-step", type=int, default=8)
+    ap.add_argument("--frames-in-flight", type=int, default=8, help="frames per device batch")
+    ap.add_argument("--distinct", type=int, default=30, help="distinct pictures generated for the chunk (it walks them back and forth)")
     ap.add_argument("--crf", type=int, default=30)
     ap.add_argument("--keyint", type=int, default=240)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-bd-rate", action="store_true")
     ap.add_argument("--tile-sb", type=int, default=0, help="inter-frame tile size in superblocks (0 = encoder default)")
     ap.add_argument("--pack-path", type=int, default=0, help="0 auto, 3 device tokenizer + host range coder, 4 device tokenizer + device range coder")
     ap.add_argument("--preset", type=int, default=6, help="<= 5 adds loop restoration (the BASELINE configs name preset 6)")
+    ap.add_argument("--gop-period", type=int, default=0)
+    ap.add_argument("--no-mctf", action="store_true")
     args = ap.parse_args()
 
     rank = int(os.environ.get("RANK", "0"))
@@ -264,26 +334,25 @@ def main():
             dist.barrier()
         torch.cuda.synchronize()
 
-    w, h, bd, desc = WORKLOADS[args.workload]
-    F = args.frames_per_step
+    w, h, bd, desc, scene_len, chunk = WORKLOADS[args.workload]
+    F = args.frames_in_flight
     hdr = args.workload == "4k10"
-    frames = make_frames(w, h, bd, F, hdr)               # F consecutive frames of one scene
-    if rank:
-        frames = frames[rank % len(frames):] + frames[:rank % len(frames)]
+    frames = make_clip(w, h, bd, args.distinct, hdr, scene_len)
+    order = chunk_order(args.distinct, chunk)
+    if rank:     # other ranks code other chunks: the same pictures, started elsewhere
+        order = [(o + 3 * rank) % args.distinct for o in order]
     from av1_base_b200 import sharding
     # ranks share the node's host cores: each rank entropy-codes with its share of them
     enc = encoder.Encoder(w, h, bd, crf=args.crf, device_id=local_rank, hdr=hdr, frames_in_flight=F, keyint=args.keyint, preset=args.preset, tile_sb=args.tile_sb, pack_path=args.pack_path,
-                          host_threads=sharding.host_threads_per_rank(world))
+                          host_threads=sharding.host_threads_per_rank(world), gop_period=args.gop_period, mctf=not args.no_mctf)
     g = enc.geom
     frame_bytes = sum(g.stride[p] * (h if p == 0 else h // 2) * 2 for p in range(3))
     S = int(1.5 * w * h * 2)                             # bytes of one 4:2:0 frame at 2 B/sample
 
-    # ---------------- value: inputs resident in HBM ----------------
-    # slot 0 = frames 0..F-1, slot 1 = the same frames in reverse order: the resident sequence is a
-    # palindrome (0..F-1, F-1..0, 0..F-1, ...), i.e. continuous motion without artificial scene cuts
-    enc.stage_frames(0, frames)
-    enc.stage_frames(1, frames[::-1])
-    enc.encode_resident(max(args.warmup, 3))
+    # ---------------- value: the clip resident in HBM ----------------
+    enc.stage_clip(frames)
+    for _ in range(max(args.warmup, 3)):
+        enc.encode_clip(order)
     try:
         dev_uuid = torch.cuda.get_device_properties(local_rank).uuid
     except Exception:
@@ -292,50 +361,59 @@ def main():
     sampler.start()
     barrier()
     t0 = time.perf_counter()
-    enc.encode_resident(args.steps)
+    for k in range(args.steps):
+        enc.encode_clip(order, accumulate=k > 0)
     torch.cuda.synchronize()
     dt = time.perf_counter() - t0
     st = enc.stats()
     barrier()
     clocks = sampler.stop()
     tmax = sharding.max_over_ranks(dt, dist, "cuda")
-    value = world * args.steps * F / tmax
+    value = world * args.steps * chunk / tmax
 
     # ---------------- e2e: host buffers through av1b_encode_chunk ----------------
     # the host copies of the sources live in page-locked memory (av1b_host_alloc), as a capture / decode front
     # end would hand them over; the timed region holds their H2D copies, the kernels, the D2H of the
     # symbol streams, host entropy coding and packet delivery
     pinned = encoder.PinnedFrames(frames, device_id=local_rank)
-    pal = list(pinned) + list(pinned)[::-1]
-    chunk = [pal[i % len(pal)] for i in range(args.steps * F)]
-    enc.encode_chunk(chunk[:2 * F])                      # warm-up
+    host_chunk = [pinned[o] for o in order]
+    enc.encode_chunk(host_chunk[:4 * F])                 # warm-up
+    e2e_steps = max(1, min(args.steps, 8))
     barrier()
     t0 = time.perf_counter()
-    tus = enc.encode_chunk(chunk)
+    h2d_ms = kern_ms = d2h_ms = pack_ms = 0.0
+    d2h_bytes = staged_direct = 0
+    for _ in range(e2e_steps):
+        tus = enc.encode_chunk(host_chunk)
+        se = enc.stats()
+        h2d_ms += se["h2d_ms"]; kern_ms += se["kernel_ms"]; d2h_ms += se["d2h_ms"]; pack_ms += se["pack_ms"]
+        d2h_bytes += se["d2h_bytes"]; staged_direct += se["staged_direct"]
     dte = time.perf_counter() - t0
-    st_e = enc.stats()
     dte = sharding.max_over_ranks(dte, dist, "cuda")
-    e2e = world * len(chunk) / dte
-    d2h_per_step = st_e["d2h_bytes"] // args.steps   # counted by the encoder: token lists + offsets, key-frame levels / block info
+    e2e = world * e2e_steps * chunk / dte
 
     if rank != 0:
         return
     pk, pk_src = peaks()
     n_inter, n_key = max(1, st["inter_launches"]), max(1, st["key_frames"])
     nf = st["frames_done"]
-    # per-kernel CUDA-event time per launch (one launch = one frame, except ME = one batch) and
-    # algorithmic bytes per launch
+    n_batches = args.steps * ((chunk + F - 1) // F)
+    n_tf = max(1, st["mctf_frames"])
+    # per-kernel CUDA-event time per unit (frame; ME and tokenizer per batch) and algorithmic bytes per unit
     kern = {
         "inter_encode_kernel": (st["inter_ms"] / n_inter, 4 * S),
         "intra_encode_kernel": (st["intra_ms"] / n_key, 3 * S),
         "deblock_kernel": (st["deblock_ms"] / max(1, nf), 2 * S),
         "cdef_kernel": (st["cdef_ms"] / max(1, nf), 3 * S),
-        "pyramid+hme (per batch)": (st["me_ms"] / max(1, args.steps), int((1.3125 + 0.625 + 2.0) * (w * h * 2)) * F),
+        "pyramid+hme+regularisation (per batch)": ((st["me_ms"] - st["mctf_ms"]) / n_batches, int((1.3125 + 0.625 + 2.0 + 2 * 2.0) * (w * h * 2)) * F),
+        # temporal filter of one key / anchor picture: 4 searches (2.625 Y each) + the filter itself ((2 + 4) S)
+        "temporal filter: hme + mctf_kernel (per filtered picture)": (st["mctf_ms"] / n_tf, int(4 * 2.625 * (w * h * 2)) + 6 * S),
         # tokenizer: reads the block info (20 B per 8x8 unit) twice (count + emit), writes 4 B per token
-        "tokenizer (per batch)": (st["tok_ms"] / max(1, args.steps), 2 * 20 * g.w8 * g.h8 * F + 4 * st["tokens"] // max(1, args.steps)),
+        "tokenizer (per batch)": (st["tok_ms"] / n_batches, 2 * 20 * g.w8 * g.h8 * F + 4 * st["tokens"] // n_batches),
     }
     share = {"inter_encode_kernel": st["inter_ms"], "intra_encode_kernel": st["intra_ms"], "deblock_kernel": st["deblock_ms"],
-             "cdef_kernel": st["cdef_ms"], "pyramid+hme (per batch)": st["me_ms"], "tokenizer (per batch)": st["tok_ms"]}
+             "cdef_kernel": st["cdef_ms"], "pyramid+hme+regularisation (per batch)": st["me_ms"] - st["mctf_ms"],
+             "temporal filter: hme + mctf_kernel (per filtered picture)": st["mctf_ms"], "tokenizer (per batch)": st["tok_ms"]}
     dom = max(share, key=lambda k: share[k])
     dom_ms, dom_bytes = kern[dom]
     achieved = dom_bytes / (dom_ms * 1e-3) / 1e9 if dom_ms > 0 else 0.0
@@ -346,22 +424,24 @@ def main():
             traffic = json.load(open(tp)).get(args.workload, {}).get(dom)
         except Exception:
             traffic = None
+    cfg = workload_config(args)
     line = {
         "metric": "AV1 encode fps", "value": value, "unit": "frames/s", "n_gpus": world, "steps": args.steps,
         "warmup": max(args.warmup, 3), "ms_per_step": 1000 * tmax / args.steps, "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": "u16/i32", "data": "synthetic",
-        "config": {"workload": desc, "frames_per_step": F, "crf": args.crf, "preset": args.preset, "base_q_idx": st["base_q_idx"],
-                   "keyint": args.keyint, "key_frames": st["key_frames"], "inter_frames": st["inter_launches"],
-                   "tiles_key_frames": "%dx%d" % (g.tile_cols, g.tile_rows), "tile_sb_inter": args.tile_sb, "pack_path": args.pack_path, "host_threads": sharding.host_threads_per_rank(world),
-                   "l2": "inputs larger than L2 (%.0f MB working set per step)" % (5 * F * frame_bytes / 1e6),
-                   "timing": "wall clock between synchronize+barrier pairs (host entropy coding is part of the step); "
-                             "kernel times from CUDA events on the encoder stream"},
-        "e2e": {"value": e2e, "unit": "frames/s", "h2d_bytes_per_step": F * frame_bytes, "d2h_bytes_per_step": d2h_per_step,
-                "bitrate_bytes_per_frame": sum(map(len, tus)) / len(tus),
-                "host_buffers": "page-locked (av1b_host_alloc), %d of %d frames read in place by the copy engine" % (st_e["staged_direct"], len(chunk)),
-                "breakdown_ms_per_step": {k: st_e[k] / args.steps for k in ("h2d_ms", "kernel_ms", "d2h_ms", "pack_ms")}},
+        "config": cfg,
+        "encoder": {"base_q_idx_anchor": st["base_q_idx"], "frames_in_flight": F, "key_frames": st["key_frames"], "inter_frames": st["inter_launches"],
+                    "temporally_filtered_frames": st["mctf_frames"], "tiles_key_frames": "%dx%d" % (g.tile_cols, g.tile_rows),
+                    "tile_sb_inter": args.tile_sb, "pack_path": args.pack_path, "host_threads": sharding.host_threads_per_rank(world),
+                    "l2": "inputs larger than L2 (%.0f MB of distinct source pictures, %.0f MB working set per batch)" % (args.distinct * frame_bytes / 1e6, 5 * F * frame_bytes / 1e6),
+                    "timing": "wall clock between synchronize+barrier pairs (host entropy coding is part of the step); "
+                              "kernel times from CUDA events on the encoder stream"},
+        "e2e": {"value": e2e, "unit": "frames/s", "h2d_bytes_per_step": chunk * frame_bytes, "d2h_bytes_per_step": d2h_bytes // e2e_steps,
+                "steps": e2e_steps, "bitrate_bytes_per_frame": sum(map(len, tus)) / len(tus),
+                "host_buffers": "page-locked (av1b_host_alloc), %d of %d frames read in place by the copy engine" % (staged_direct, e2e_steps * chunk),
+                "breakdown_ms_per_step": {"h2d_ms": h2d_ms / e2e_steps, "kernel_ms": kern_ms / e2e_steps, "d2h_ms": d2h_ms / e2e_steps, "pack_ms": pack_ms / e2e_steps}},
         "gpu_launches": st["kernel_launches"],
-        "breakdown_ms_per_step": {k: st[k] / args.steps for k in ("kernel_ms", "me_ms", "intra_ms", "inter_ms", "deblock_ms",
+        "breakdown_ms_per_step": {k: st[k] / args.steps for k in ("kernel_ms", "me_ms", "mctf_ms", "intra_ms", "inter_ms", "deblock_ms",
                                                                    "cdef_ms", "lr_ms", "tok_ms", "rc_ms", "d2h_ms", "pack_ms")},
         "tokens_per_frame": st["tokens"] / max(1, st["inter_launches"]),
         "roofline": {"kernel": dom, "bound": "hbm", "achieved": achieved, "peak": pk["hbm_gbs"],
@@ -373,14 +453,20 @@ def main():
         "clocks": clocks,
         "svt_av1_fps": None,
     }
-    if not args.no_cpu_baseline and world == 1:
-        cores = os.cpu_count() or 1
-        workers = max(1, min(cores, 32))
-        chunk_len = 2 if w > 2000 else 3
-        fps = oracle_fps(frames, w, h, bd, st["base_q_idx"], workers, chunk_len)
-        line["cpu_baseline"] = {"value": fps, "unit": "frames/s", "cores": workers, "kind": "port",
-                                "sample": "%d chunks of %d frames (key + inter) of the workload, one chunk per host thread, scalar "
-                                          "oracle/av1_oracle.cpp" % (workers, chunk_len)}
+    pinned.close()
+    if world == 1:
+        enc.close()
+        if not args.no_cpu_baseline:
+            cores, workers, threads, fpw = libaom_plan(w)
+            steps = 4 if w > 2000 else 6
+            fps, dtl, _ = libaom_stream_fps(frames, order, w, h, bd, args.crf, workers, threads, fpw, 1, steps)
+            line["cpu_baseline"] = {"value": fps, "unit": "frames/s", "cores": cores, "kind": "stand-in-libaom", "workers": workers,
+                                    "encoder": "libaom 3.13.1 cpu-used=6, end-usage=q, cq-level=%d, lag_in_frames=%d, row-mt, %d threads per worker" % (args.crf, LIBAOM_LAG, threads),
+                                    "sample": "%d workers x %d frames x %d steps of the same chunk at steady state (%.1f s)" % (workers, fpw, steps, dtl),
+                                    "port": {"value": port_fps(frames, w, h, bd, args.crf, min(cores, 8)), "unit": "frames/s", "cores": min(cores, 8),
+                                             "kind": "port", "sample": "oracle/chain.py (scalar restatement of this encoder), one 2-frame chunk per thread"}}
+        if not args.no_bd_rate:
+            line["bd_rate"] = bd_rate_check(local_rank)
     print(json.dumps(line), flush=True)
     if dist is not None:
         dist.destroy_process_group()

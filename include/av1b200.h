@@ -102,6 +102,12 @@ int av1b_get_recon(av1b_encoder* enc, uint32_t frame_in_chunk, uint16_t* const d
 int av1b_stage_frames(av1b_encoder* enc, int slot, const av1b_frame_src* frames, uint32_t n_frames);
 int av1b_encode_resident(av1b_encoder* enc, uint32_t n_steps, av1b_packet_cb out_cb, void* user);
 
+/* ---- resident clip: upload n source pictures into HBM once (av1b_stage_clip), then code closed chunks made of them:
+ * chunk frame i is clip picture order[i] (device-to-device gather into the pipeline's batch buffers, same pipelining as
+ * av1b_encode_chunk).  accumulate_stats != 0 keeps adding to the statistics of the previous call.  out_cb may be NULL. ---- */
+int av1b_stage_clip(av1b_encoder* enc, const av1b_frame_src* frames, uint32_t n_frames);
+int av1b_encode_clip(av1b_encoder* enc, const uint32_t* order, uint32_t n_frames, int accumulate_stats, av1b_packet_cb out_cb, void* user);
+
 /* ---- diagnostics (need config.reserved[0] = 1: keep per-frame reconstruction and symbols) ---- */
 struct Av1bBlockInfo; struct Av1bGeom;
 int av1b_get_frame_syms(av1b_encoder* enc, uint32_t frame_in_chunk, struct Av1bBlockInfo* blocks, int16_t* const coef[3]);

@@ -99,8 +99,7 @@ def encode_chain(frames, w, h, bd, crf, keyint=240, gop_period=4, me_smooth=True
         if nb:
             mvs_tf = []
             for j in nb:
-                mv = O.hme(g, pyrs[i], pyrs[j], lam)
-                mvs_tf.append(O.me_smooth(g, pyrs[i], pyrs[j], mv, lam, 2) if me_smooth else mv)
+                mvs_tf.append(O.hme(g, pyrs[i], pyrs[j], lam))   # no regularisation for the filter's searches
             aq = ac_q(bd, q)
             thr_b = max(1, (aq * aq * (10 + film_grain)) // 2560)
             src = O.mctf(g, bd, padded[i], [padded[j] for j in nb], mvs_tf, thr_b, 3 * thr_b)

@@ -220,6 +220,83 @@ def aom_encode(frames, bit_depth, cq_level=30, cpu_used=6, threads=1, lag=0, til
         A.aom_codec_destroy(ctx)
     return tus
 
+class AomStream:
+    """libaom encoder driven frame by frame (CPU baseline of bench.py: frames are pushed while a clock runs; packets
+    come out lag_in_frames later).  Constant-quality mode, as aom_encode."""
+
+    def __init__(self, w, h, bit_depth, cq_level=30, cpu_used=6, threads=1, lag=19, tile_cols_log2=0, tile_rows_log2=0):
+        A = aom()
+        self.A, self.hbd = A, bit_depth > 8
+        iface = ctypes.c_void_p(A.aom_codec_av1_cx())
+        cfg = ctypes.create_string_buffer(4096)
+        rc = A.aom_codec_enc_config_default(iface, cfg, 0)
+        assert rc == 0, rc
+        c32 = ctypes.cast(cfg, ctypes.POINTER(ctypes.c_uint32))
+        c32[1] = threads
+        c32[3] = w; c32[4] = h
+        c32[8] = bit_depth; c32[9] = bit_depth
+        c32[10] = 1; c32[11] = 30
+        c32[14] = lag
+        c32[24] = 3               # rc_end_usage = AOM_Q
+        self.ctx = ctypes.create_string_buffer(256)
+        rc = A.aom_codec_enc_init_ver(self.ctx, iface, cfg, 0x40000 if self.hbd else 0, 25)
+        if rc:
+            raise RuntimeError("aom enc init %d" % rc)
+        for k, v in (("cpu-used", cpu_used), ("cq-level", cq_level), ("row-mt", 1), ("tile-columns", tile_cols_log2),
+                     ("tile-rows", tile_rows_log2)):
+            rc = A.aom_codec_set_option(self.ctx, k.encode(), str(v).encode())
+            if rc:
+                raise RuntimeError("set_option %s rc=%d" % (k, rc))
+        self.img = A.aom_img_alloc(None, 0x102 | (0x800 if self.hbd else 0), w, h, 32)
+        raw = (ctypes.c_uint8 * 160).from_address(self.img)
+        self.planes = np.frombuffer(raw, dtype=np.uint64, count=3, offset=64)
+        self.strides = np.frombuffer(raw, dtype=np.int32, count=3, offset=88)
+        self.pts, self.packets, self.bytes_out = 0, 0, 0
+
+    def _pull(self):
+        it = ctypes.c_void_p(0)
+        while True:
+            pkt = self.A.aom_codec_get_cx_data(self.ctx, ctypes.byref(it))
+            if not pkt:
+                break
+            if ctypes.c_int.from_address(pkt).value == 0:
+                self.packets += 1
+                self.bytes_out += ctypes.c_size_t.from_address(pkt + 16).value
+
+    def push(self, fr):
+        """Hands one frame ([Y,U,V] uint16) to the encoder; returns the number of packets produced so far."""
+        for p in range(3):
+            ph, pw = fr[p].shape
+            st = int(self.strides[p])
+            dst = (ctypes.c_uint8 * (st * ph)).from_address(int(self.planes[p]))
+            d = np.frombuffer(dst, dtype=np.uint8).reshape(ph, st)
+            if self.hbd:
+                d.view(np.uint16)[:, :pw] = fr[p]
+            else:
+                d[:, :pw] = fr[p].astype(np.uint8)
+        rc = self.A.aom_codec_encode(self.ctx, ctypes.c_void_p(self.img), ctypes.c_int64(self.pts), ctypes.c_ulong(1), ctypes.c_long(0))
+        if rc:
+            raise RuntimeError("aom_codec_encode rc=%d" % rc)
+        self.pts += 1
+        self._pull()
+        return self.packets
+
+    def flush(self):
+        while True:
+            n0 = self.packets
+            self.A.aom_codec_encode(self.ctx, None, ctypes.c_int64(0), ctypes.c_ulong(1), ctypes.c_long(0))
+            self._pull()
+            if self.packets == n0:
+                break
+        return self.packets
+
+    def close(self):
+        if self.img:
+            self.A.aom_img_free(ctypes.c_void_p(self.img))
+            self.A.aom_codec_destroy(self.ctx)
+            self.img = None
+
+
 def psnr(a, b, bit_depth):
     a = a.astype(np.float64); b = b.astype(np.float64)
     mse = np.mean((a - b) ** 2)

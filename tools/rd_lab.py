@@ -89,7 +89,7 @@ def encode(args):
                 mvs = []
                 for j in nb:
                     mv = O.hme(g, pyrs[i], pyrs[j], acq >> 1)
-                    if opts.get("smooth"):
+                    if opts.get("smooth") and not opts.get("tf_nosmooth"):
                         mv = O.me_smooth(g, pyrs[i], pyrs[j], mv, int((acq >> 1) * opts["smooth"][0]), int(opts["smooth"][1]))
                     mvs.append(mv)
                 enc_src[i] = O.crop(g, O.mctf(g, bd, padded[i], [padded[j] for j in nb], mvs, thr_b, thr_p))
@@ -151,6 +151,7 @@ def main():
     ap.add_argument("--mctf2", default="", help="radius,kb,kp: oracle temporal filter, thr_b = kb acq^2 / 256, thr_p = kp thr_b")
     ap.add_argument("--keyfwd", type=int, default=6)
     ap.add_argument("--varpart", action="store_true")
+    ap.add_argument("--tf-nosmooth", action="store_true")
     ap.add_argument("--me-filtered", action="store_true")
     ap.add_argument("--smooth", default="", help="k,iters: vector-field regularisation with lam_s = k * lambda")
     a = ap.parse_args()
@@ -158,7 +159,7 @@ def main():
     opts = dict(hier=tuple(map(int, a.hier.split(','))) if a.hier else None,
                 mctf=tuple(map(float, a.mctf.split(','))) if a.mctf else None, me_filtered=a.me_filtered,
                 smooth=tuple(map(float, a.smooth.split(','))) if a.smooth else None,
-                mctf2=tuple(map(float, a.mctf2.split(','))) if a.mctf2 else None, keyfwd=a.keyfwd, varpart=a.varpart)
+                mctf2=tuple(map(float, a.mctf2.split(','))) if a.mctf2 else None, keyfwd=a.keyfwd, varpart=a.varpart, tf_nosmooth=a.tf_nosmooth)
     if a.dkey is not None:
         opts["dkey"] = a.dkey
     jobs = [(w, h, a.bd, a.frames, a.seed, a.noise, crf, opts) for crf in map(int, a.crfs.split(","))]
