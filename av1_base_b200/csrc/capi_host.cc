@@ -82,6 +82,22 @@ int av1b_select_frame_params(int bit_depth, int base_q_idx, int frame_type, int 
   return AV1B_OK;
 }
 
+// Noise level out of the histogram noise_hist_kernel fills (oracle: orc_noise_estimate): centre of the bin that holds the
+// lower quartile of the 16x16 blocks outside bin 0; 0 when all blocks are noiseless.
+int av1b_noise_from_hist(const uint32_t* hist) {
+  if (!hist) return 0;
+  uint64_t n = 0;
+  for (int b = 1; b < 4096; b++) n += hist[b];
+  if (n == 0) return 0;
+  const uint64_t want = (n + 3) / 4;
+  uint64_t acc = 0;
+  for (int b = 1; b < 4096; b++) {
+    acc += hist[b];
+    if (acc >= want) return (b << 4) + 8;
+  }
+  return (4095 << 4) + 8;
+}
+
 const char* av1b_last_error(void) { return av1b::g_last_error.c_str(); }
 
 int av1b_pack_sequence_header(const Av1bSeqParams* seq, uint8_t* out, size_t cap, size_t* len) {

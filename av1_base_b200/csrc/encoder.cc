@@ -178,6 +178,14 @@ struct av1b_encoder {
   int base_q_idx_nonref = 0;
   bool me_smooth = true;              // vector-field regularisation after the hierarchical search
   bool key_var_part = true;           // key frames: 64x64 / 32x32 blocks where the source is smooth
+  int q_nominal = 0;                  // quantiser index of the CRF
+  bool gop_auto = true;               // structure chosen per chunk from the source's noise level (config.gop_period == 0)
+  bool mctf_cfg = true;               // temporal filter allowed by the configuration
+  int noise_b = 0;                    // noise estimate of the chunk's first picture (av1b_noise_from_hist)
+  uint32_t* d_noise_hist = nullptr;
+  uint32_t* h_noise_hist = nullptr;
+  cudaEvent_t ev_noise = nullptr;
+  int cdf_q[2] = {-1, -1};            // quantisers the device CDF images were made for
   bool mctf_on = true;                // key / anchor source pictures are temporally filtered before they are coded
   int mctf_radius = 2, mctf_key_fwd = 4;
   int hist_count = 0;                 // source pictures of the previous batch that are kept (same GOP): at most kHist
@@ -262,6 +270,7 @@ static void free_all(av1b_encoder* e) {
   cudaFree(e->d_sb_of_order); cudaFree(e->d_tile_of_sb); cudaFree(e->d_lr_sse);
   cudaFree(e->d_cdf_init); cudaFree(e->d_cdf_init_alt); cudaFree(e->d_tile_first_k); cudaFree(e->d_rc_overflow);
   cudaFree(e->d_mv_tmp); cudaFree(e->d_hist); cudaFree(e->d_mvs_tf); cudaFree(e->d_mv2_tf);
+  cudaFree(e->d_noise_hist); cudaFreeHost(e->h_noise_hist); if (e->ev_noise) cudaEventDestroy(e->ev_noise);
   for (int p = 0; p < 3; p++) { cudaFree(e->d_hist_src[p]); cudaFree(e->d_flt[p]); cudaFree(e->d_clip[p]); }
   if (e->s_tok) cudaStreamDestroy(e->s_tok);
   if (e->stream) cudaStreamDestroy(e->stream);
@@ -814,6 +823,8 @@ void av1b_config_default(av1b_config* c) {
   c->tile_cols_log2 = -1; c->tile_rows_log2 = -1;
 }
 
+static void set_structure(av1b_encoder* e, int gop_period);
+
 int av1b_encoder_create(const av1b_config* cfg, av1b_encoder** out) {
   if (!cfg || !out) { set_error("null argument"); return AV1B_ERR_INVALID; }
   *out = nullptr;
@@ -861,13 +872,12 @@ int av1b_encoder_create(const av1b_config* cfg, av1b_encoder** out) {
   if (e->base_q_idx < 1) e->base_q_idx = 1;   // lossless (qindex 0) is not supported
   e->base_q_idx_key = cfg->reserved[3] ? e->base_q_idx : std::max(1, e->base_q_idx * 3 / 4);
   // one-level hierarchy: every gop_period-th frame is an anchor (the only inter frames that become references, coded
-  // a little finer), the frames between two anchors predict from the last anchor at a much coarser quantiser
-  e->gop_period = cfg->reserved[3] ? 1 : (cfg->gop_period > 0 ? cfg->gop_period : 4);
-  if (e->gop_period > 16) { set_error("gop_period must be <= 16"); delete e; return AV1B_ERR_INVALID; }
-  const int q_nominal = e->base_q_idx;
-  e->base_q_idx_nonref = std::min(255, q_nominal + 48);
-  if (e->gop_period > 1) e->base_q_idx = std::max(1, q_nominal - 8);
-  e->mctf_on = cfg->tune[2] == 0 && cfg->reserved[3] == 0;
+  // a little finer), the frames between two anchors predict from the last anchor at a much coarser quantiser;
+  // config.gop_period == 0: chosen per chunk from the noise level of the source (begin_chunk)
+  if (cfg->gop_period > 16) { set_error("gop_period must be <= 16"); delete e; return AV1B_ERR_INVALID; }
+  e->q_nominal = e->base_q_idx;
+  e->gop_auto = cfg->gop_period == 0 && cfg->reserved[3] == 0;
+  e->mctf_cfg = cfg->tune[2] == 0 && cfg->reserved[3] == 0;
   e->me_smooth = cfg->tune[0] == 0;
   e->key_var_part = cfg->tune[1] == 0 && cfg->reserved[1] == 0;
   e->blk_log2 = cfg->reserved[1] ? cfg->reserved[1] : 4;
@@ -878,11 +888,8 @@ int av1b_encoder_create(const av1b_config* cfg, av1b_encoder** out) {
   e->intra_only = cfg->reserved[3] != 0;      // reserved[3] = 1: every frame is a key frame
   e->keyint = cfg->keyint > 0 ? cfg->keyint : 240;
   av1b_select_frame_params(cfg->bit_depth, e->base_q_idx_key, AV1B_KEY_FRAME, e->loop_filters ? 1 : 0, &e->fp_key);
-  av1b_select_frame_params(cfg->bit_depth, e->base_q_idx, AV1B_INTER_FRAME, e->loop_filters ? 1 : 0, &e->fp_inter);
-  av1b_select_frame_params(cfg->bit_depth, e->base_q_idx_nonref, AV1B_INTER_FRAME, e->loop_filters ? 1 : 0, &e->fp_nonref);
-  e->fp_nonref.non_reference = 1;
   if (e->lr_on) {
-    for (Av1bFrameParams* f : {&e->fp_key, &e->fp_inter, &e->fp_nonref}) { f->lr_type[0] = AV1B_RESTORE_SWITCHABLE; f->lr_type[1] = f->lr_type[2] = AV1B_RESTORE_NONE; f->lr_unit_shift = 0; f->lr_uv_shift = 0; }
+    for (Av1bFrameParams* f : {&e->fp_key}) { f->lr_type[0] = AV1B_RESTORE_SWITCHABLE; f->lr_type[1] = f->lr_type[2] = AV1B_RESTORE_NONE; f->lr_unit_shift = 0; f->lr_uv_shift = 0; }
     e->lr_rows = std::max((cfg->height + 32) / 64, 1); e->lr_cols = std::max((cfg->width + 32) / 64, 1);
     e->lr_n = (size_t)e->lr_rows * e->lr_cols;
     memset(&e->lr_cand, 0, sizeof(e->lr_cand));
@@ -890,8 +897,7 @@ int av1b_encoder_create(const av1b_config* cfg, av1b_encoder** out) {
     e->lr_cand.wiener_v[2] = 8; e->lr_cand.wiener_h[2] = 8; e->lr_cand.sgr_set = 12; e->lr_cand.sgr_xqd[0] = 0; e->lr_cand.sgr_xqd[1] = 95;
   }
   e->fp_key.tile_cols_log2 = e->g.tile_cols_log2; e->fp_key.tile_rows_log2 = e->g.tile_rows_log2;
-  e->fp_inter.tile_cols_log2 = e->g_inter.tile_cols_log2; e->fp_inter.tile_rows_log2 = e->g_inter.tile_rows_log2;
-  e->fp_nonref.tile_cols_log2 = e->g_inter.tile_cols_log2; e->fp_nonref.tile_rows_log2 = e->g_inter.tile_rows_log2;
+  set_structure(e, e->intra_only ? 1 : (cfg->gop_period > 0 ? cfg->gop_period : 4));
   e->batch = cfg->frames_in_flight > 0 ? cfg->frames_in_flight : 8;
   if (e->batch > 64) { set_error("frames_in_flight must be <= 64"); delete e; return AV1B_ERR_INVALID; }
   e->host_threads = cfg->host_threads > 0 ? cfg->host_threads : (int)std::max(1u, std::thread::hardware_concurrency());
@@ -999,6 +1005,8 @@ int av1b_encoder_create(const av1b_config* cfg, av1b_encoder** out) {
     }
   }
   A(cudaMalloc(&e->d_map_key, e->map_elems)); A(cudaMalloc(&e->d_map_inter, e->map_elems));
+  A(cudaMalloc(&e->d_noise_hist, 4096 * sizeof(uint32_t))); A(cudaMallocHost(&e->h_noise_hist, 4096 * sizeof(uint32_t)));
+  A(cudaEventCreate(&e->ev_noise));
   if (e->lr_on) A(cudaMalloc(&e->d_lr_sse, 3 * e->lr_n * F * sizeof(unsigned long long)));
   if (!e->intra_only) {
     for (int l = 0; l < 3; l++) {
@@ -1006,7 +1014,7 @@ int av1b_encoder_create(const av1b_config* cfg, av1b_encoder** out) {
       A(cudaMalloc(&e->d_pyr[l], el * (F + kSlotFrame0) * 2));
       if (err == cudaSuccess) A(cudaMemset(e->d_pyr[l], 0, el * (F + kSlotFrame0) * 2));
     }
-    if (e->mctf_on) {
+    if (e->mctf_cfg) {
       for (int p = 0; p < 3; p++) {
         A(cudaMalloc(&e->d_hist_src[p], e->plane_elems[p] * kHist * 2));
         A(cudaMalloc(&e->d_flt[p], e->plane_elems[p] * F * 2));
@@ -1062,6 +1070,51 @@ static int stage_any(av1b_encoder* e, Slot& s, const av1b_frame_src* frames, con
   return AV1B_OK;
 }
 
+// Frame-level parameters of the three frame kinds for the structure in force
+static void set_structure(av1b_encoder* e, int gop_period) {
+  const av1b_config& c = e->cfg;
+  e->gop_period = gop_period;
+  e->base_q_idx = gop_period > 1 ? std::max(1, e->q_nominal - 8) : e->q_nominal;
+  e->base_q_idx_nonref = std::min(255, e->q_nominal + 48);
+  e->mctf_on = e->mctf_cfg && gop_period > 1;
+  av1b_select_frame_params(c.bit_depth, e->base_q_idx, AV1B_INTER_FRAME, e->loop_filters ? 1 : 0, &e->fp_inter);
+  av1b_select_frame_params(c.bit_depth, e->base_q_idx_nonref, AV1B_INTER_FRAME, e->loop_filters ? 1 : 0, &e->fp_nonref);
+  e->fp_nonref.non_reference = 1;
+  for (Av1bFrameParams* f : {&e->fp_inter, &e->fp_nonref}) {
+    if (e->lr_on) { f->lr_type[0] = AV1B_RESTORE_SWITCHABLE; f->lr_type[1] = f->lr_type[2] = AV1B_RESTORE_NONE; f->lr_unit_shift = 0; f->lr_uv_shift = 0; }
+    f->tile_cols_log2 = e->g_inter.tile_cols_log2; f->tile_rows_log2 = e->g_inter.tile_rows_log2;
+  }
+}
+
+// A closed chunk starts (the pipeline is empty): with config.gop_period == 0 the structure follows the noise level of the
+// chunk's first picture -- where the quantiser is fine enough to code the noise (ac step < noise sum / 7.5) a flat
+// P chain is the cheaper structure, otherwise the one-level hierarchy with temporally filtered anchors.
+static int begin_chunk(av1b_encoder* e, Slot& first) {
+  if (e->intra_only) return AV1B_OK;
+  int gop = e->cfg.gop_period > 0 ? e->cfg.gop_period : 4;
+  if (e->gop_auto) {
+    CK(cudaStreamWaitEvent(e->s_in, first.ev_src, 0));
+    CK(launch_noise_hist(e->g, first.d_src[0], e->d_noise_hist, e->s_in));
+    CK(cudaMemcpyAsync(e->h_noise_hist, e->d_noise_hist, 4096 * sizeof(uint32_t), cudaMemcpyDeviceToHost, e->s_in));
+    CK(cudaEventRecord(e->ev_noise, e->s_in));
+    CK(cudaEventSynchronize(e->ev_noise));
+    e->kernel_launches += 1;
+    e->noise_b = av1b_noise_from_hist(e->h_noise_hist);
+    const int acq = e->cfg.bit_depth == 8 ? av1t_ac_q_8[e->q_nominal] : av1t_ac_q_10[e->q_nominal];
+    if (2 * e->noise_b > 15 * acq) gop = 1;
+  }
+  if (gop != e->gop_period) set_structure(e, gop);
+  if (e->rc_on && e->token_path && (e->cdf_q[0] != e->base_q_idx || e->cdf_q[1] != e->base_q_idx_nonref)) {
+    std::vector<uint8_t> img(tile_cdfs_size());
+    tile_cdfs_default(e->base_q_idx, img.data());
+    CK(cudaMemcpy(e->d_cdf_init, img.data(), img.size(), cudaMemcpyHostToDevice));
+    tile_cdfs_default(e->base_q_idx_nonref, img.data());
+    CK(cudaMemcpy(e->d_cdf_init_alt, img.data(), img.size(), cudaMemcpyHostToDevice));
+    e->cdf_q[0] = e->base_q_idx; e->cdf_q[1] = e->base_q_idx_nonref;
+  }
+  return AV1B_OK;
+}
+
 static int run_batches(av1b_encoder* e, const av1b_frame_src* frames, const uint32_t* order, uint32_t n_frames, int64_t first_index,
                        int64_t total_frames, av1b_packet_cb out_cb, av1b_progress_cb prog_cb, void* user) {
   const auto t0 = std::chrono::steady_clock::now();
@@ -1069,6 +1122,7 @@ static int run_batches(av1b_encoder* e, const av1b_frame_src* frames, const uint
   const bool staged = frames != nullptr;
   int rc, i = 0;
   if ((rc = stage_any(e, e->slot[0], frames, order, 0, (int)std::min<uint32_t>(B, n_frames))) != AV1B_OK) return rc;
+  if (e->chunk_pos == 0 && (rc = begin_chunk(e, e->slot[0])) != AV1B_OK) return rc;
   const int S = e->n_slots, L = S - 1;
   for (uint32_t f0 = 0; f0 < n_frames; f0 += B, i++) {
     const int nb = (int)std::min<uint32_t>(B, n_frames - f0);
@@ -1210,6 +1264,13 @@ int av1b_get_inter_frame_params(av1b_encoder* e, Av1bFrameParams* fp) {
 int av1b_get_class_params(av1b_encoder* e, int kind, Av1bFrameParams* fp) {
   if (!e || !fp || kind < 0 || kind > 2) return AV1B_ERR_INVALID;
   *fp = kind_params(e, kind);
+  return AV1B_OK;
+}
+
+int av1b_get_chunk_info(av1b_encoder* e, int32_t info[8]) {
+  if (!e || !info) return AV1B_ERR_INVALID;
+  const int32_t v[8] = {e->gop_period, e->base_q_idx_key, e->base_q_idx, e->base_q_idx_nonref, e->mctf_on ? 1 : 0, e->noise_b, e->q_nominal, e->gop_auto ? 1 : 0};
+  for (int i = 0; i < 8; i++) info[i] = v[i];
   return AV1B_OK;
 }
 

@@ -394,6 +394,25 @@ int av1b_k_mctf(int device, int width, int height, int bit_depth, const uint16_t
   return download_planes(1, out, bo, t.s);
 }
 
+int av1b_k_noise_estimate(int device, int width, int height, const uint16_t* src_y, int32_t* noise_out) {
+  if (!src_y || !noise_out) { set_error("bad argument"); return AV1B_ERR_INVALID; }
+  Av1bGeom g;
+  if (av1b_geom_init(&g, width, height, 0, 0)) { set_error("unsupported size"); return AV1B_ERR_INVALID; }
+  int rc = select_device(device);
+  if (rc) return rc;
+  Timer t; CKS(t.init());
+  const size_t e0 = (size_t)g.stride[0] * g.rows[0];
+  DevBuf d0, dh;
+  CKS(d0.alloc(e0 * 2)); CKS(dh.alloc(4096 * sizeof(uint32_t)));
+  CKS(cudaMemcpyAsync(d0.p, src_y, e0 * 2, cudaMemcpyHostToDevice, t.s));
+  CKS(launch_noise_hist(g, d0.as<uint16_t>(), dh.as<uint32_t>(), t.s));
+  std::vector<uint32_t> hist(4096);
+  CKS(cudaMemcpyAsync(hist.data(), dh.p, 4096 * sizeof(uint32_t), cudaMemcpyDeviceToHost, t.s));
+  CKS(cudaStreamSynchronize(t.s));
+  *noise_out = av1b_noise_from_hist(hist.data());
+  return AV1B_OK;
+}
+
 int av1b_k_partition_smooth(int device, int width, int height, const uint16_t* src_y, int thr, uint8_t* map_out) {
   if (!src_y || !map_out) { set_error("bad argument"); return AV1B_ERR_INVALID; }
   Av1bGeom g;

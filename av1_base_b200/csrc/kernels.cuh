@@ -112,6 +112,9 @@ struct MctfLaunch {
   const int16_t* mvs[kMaxNb]; // [h8*w8][2] each
 };
 cudaError_t launch_mctf(const MctfLaunch& p, cudaStream_t s);
+// Noise level of one source luma plane: hist[4096] (device) = histogram of the 16x16 blocks' sums of |I * N| >> 4
+// (N = the 3x3 noise mask); the host takes the lower quartile outside bin 0 (capi_host.cc av1b_noise_from_hist).
+cudaError_t launch_noise_hist(const Av1bGeom& g, const uint16_t* src_y, uint32_t* hist, cudaStream_t s);
 
 // Inter frame encode (inter_kernel.cu): the n_frames frames of a launch share ONE reference picture and one
 // quantiser (the frames between two anchors of the hierarchy); frame f of the launch has its source, outputs, block

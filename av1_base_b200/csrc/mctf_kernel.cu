@@ -145,7 +145,38 @@ __global__ void __launch_bounds__(kWarps * 32) mctf_kernel(const MctfLaunch P) {
   }
 }
 
+// Noise level of a source picture (oracle: orc_noise_estimate): one CTA per 64x64 superblock = 16 blocks of 16x16, 16
+// lanes per block (lane j = row j of the block); |I * N| over the 14x14 inner samples, block sums into a 4096-bin histogram.
+__global__ void __launch_bounds__(256) noise_hist_kernel(Av1bGeom g, const uint16_t* __restrict__ src_y, uint32_t* hist) {
+  const int tid = threadIdx.x, blk = tid >> 4, j = tid & 15;
+  const int bx = blockIdx.x * 4 + (blk & 3), by = blockIdx.y * 4 + (blk >> 2);
+  const bool inside = bx * 16 + 16 <= g.width && by * 16 + 16 <= g.height;
+  int sum = 0;
+  if (inside && j >= 1 && j <= 14) {
+    const uint16_t* p = src_y + (size_t)(by * 16 + j) * g.stride[0] + bx * 16;
+    const int st = g.stride[0];
+    int a0 = p[-st], a1 = p[-st + 1], b0 = p[0], b1 = p[1], c0 = p[st], c1 = p[st + 1];
+#pragma unroll
+    for (int x = 1; x < 15; x++) {
+      const int a2 = p[-st + x + 1], b2 = p[x + 1], c2 = p[st + x + 1];
+      sum += abs(a0 - 2 * a1 + a2 - 2 * b0 + 4 * b1 - 2 * b2 + c0 - 2 * c1 + c2);
+      a0 = a1; a1 = a2; b0 = b1; b1 = b2; c0 = c1; c1 = c2;
+    }
+  }
+#pragma unroll
+  for (int o = 8; o; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
+  if (inside && j == 0) atomicAdd(&hist[min(sum >> 4, 4095)], 1u);
+}
+
 }  // namespace
+
+cudaError_t launch_noise_hist(const Av1bGeom& g, const uint16_t* src_y, uint32_t* hist, cudaStream_t s) {
+  cudaError_t e = cudaMemsetAsync(hist, 0, 4096 * sizeof(uint32_t), s);
+  if (e != cudaSuccess) return e;
+  dim3 grid(g.sb_cols, g.sb_rows);
+  noise_hist_kernel<<<grid, 256, 0, s>>>(g, src_y, hist);
+  return cudaGetLastError();
+}
 
 cudaError_t launch_mctf(const MctfLaunch& p, cudaStream_t s) {
   const int n1 = ((p.g.width + 15) / 16) * ((p.g.height + 15) / 16);

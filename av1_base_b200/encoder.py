@@ -156,6 +156,12 @@ class Encoder:
         _check(abi.lib().av1b_get_class_params(self._h, kind, C.byref(fp)))
         return fp
 
+    def chunk_info(self):
+        """Structure of the chunk coded last (av1b_get_chunk_info)."""
+        v = (C.c_int32 * 8)()
+        _check(abi.lib().av1b_get_chunk_info(self._h, v))
+        return dict(gop_period=v[0], q_key=v[1], q_anchor=v[2], q_nonref=v[3], mctf=bool(v[4]), noise_b=v[5], q_nominal=v[6], auto=bool(v[7]))
+
     def frame_kind(self, pos):
         return int(abi.lib().av1b_get_frame_kind(self._h, C.c_int64(pos)))
 

@@ -154,6 +154,13 @@ def mctf(width, height, bit_depth, cur_padded, nb_padded, nb_mvs, thr_b, thr_p, 
     return out, ms.value
 
 
+def noise_estimate(width, height, luma_padded, device=0):
+    l0 = np.ascontiguousarray(luma_padded, np.uint16)
+    out = C.c_int32(0)
+    _ck(abi.lib().av1b_k_noise_estimate(device, width, height, l0.ctypes.data_as(C.c_void_p), C.byref(out)))
+    return out.value
+
+
 def partition_smooth(width, height, luma_padded, thr, device=0):
     """Key-frame partition by smoothness: block log2 per 8x8 unit [h8*w8]."""
     l0 = np.ascontiguousarray(luma_padded, np.uint16)

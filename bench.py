@@ -271,7 +271,7 @@ def bd_rate_check(device_id):
         return sum(map(len, tus)) * 8 * 30.0 / n / 1000, float(np.mean([D.psnr(d[0], f[0], bd) for d, f in zip(dec, frames)])), dec
 
     ours, match = [], True
-    for crf in (12, 20, 28, 36, 44, 52):
+    for crf in (6, 10, 14, 20, 28, 36, 44, 52):
         enc = encoder.Encoder(w, h, bd, crf=crf, device_id=device_id, keep_debug=True)
         kbps, ps, dec = point(enc.encode_chunk(frames))
         for i in (0, 1, 4, n - 1):
@@ -458,7 +458,7 @@ def main():
         enc.close()
         if not args.no_cpu_baseline:
             cores, workers, threads, fpw = libaom_plan(w)
-            steps = 4 if w > 2000 else 6
+            steps = 12 if w > 2000 else 8
             fps, dtl, _ = libaom_stream_fps(frames, order, w, h, bd, args.crf, workers, threads, fpw, 1, steps)
             line["cpu_baseline"] = {"value": fps, "unit": "frames/s", "cores": cores, "kind": "stand-in-libaom", "workers": workers,
                                     "encoder": "libaom 3.13.1 cpu-used=6, end-usage=q, cq-level=%d, lag_in_frames=%d, row-mt, %d threads per worker" % (args.crf, LIBAOM_LAG, threads),

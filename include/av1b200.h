@@ -50,7 +50,9 @@ typedef struct av1b_config {
   int32_t frames_in_flight;       /* frames batched per device pass, 0 = auto                      */
   int32_t gop_period;             /* one-level hierarchy: every gop_period-th frame after a key frame is an anchor (inter frame that
                                      becomes the reference, quantiser index - 8); the frames between two anchors predict from the last
-                                     anchor at quantiser index + 48 and are referenced by nobody.  0 = default (4), 1 = plain P chain */
+                                     anchor at quantiser index + 48 and are referenced by nobody.  1 = plain P chain.
+                                     0 = chosen per chunk: 4, or the P chain where the quantiser is fine enough to code the source's noise
+                                     (noise estimate of the chunk's first picture against the quantiser step) */
   int32_t tune[7];                /* [0]: 1 = vector-field regularisation of the motion search off; [1]: 1 = fixed 16x16 key-frame
                                      partition (default: 64x64 / 32x32 blocks where the source is smooth); [2]: 1 = temporal filter of
                                      key / anchor source pictures off */
@@ -116,6 +118,11 @@ struct Av1bFrameParams;
 /* frame-level parameters the encoder signals for key frames (deblock levels, CDEF presets, ...) */
 int av1b_get_frame_params(av1b_encoder* enc, struct Av1bFrameParams* fp);
 int av1b_get_inter_frame_params(av1b_encoder* enc, struct Av1bFrameParams* fp);
+/* structure of the chunk coded last: info[0..7] = gop_period in force, quantiser index of key / anchor / non-reference frames,
+ * temporal filter on, noise estimate of the chunk's first picture, quantiser index of the CRF, structure chosen automatically */
+int av1b_get_chunk_info(av1b_encoder* enc, int32_t info[8]);
+/* noise level from the 4096-bin histogram of 16x16-block noise sums (lower quartile outside bin 0); pure function */
+int av1b_noise_from_hist(const uint32_t* hist4096);
 /* kind of the frame at position pos of a closed GOP: 0 key, 1 anchor, 2 non-reference; and the frame-level parameters of a kind */
 int av1b_get_frame_kind(av1b_encoder* enc, int64_t pos_in_chunk);
 int av1b_get_class_params(av1b_encoder* enc, int kind, struct Av1bFrameParams* fp);
@@ -197,6 +204,9 @@ int av1b_k_hme_smooth(int device, int width, int height, int n_frames, const uin
 int av1b_k_mctf(int device, int width, int height, int bit_depth, const uint16_t* const cur[3], int n_nb,
                 const uint16_t* const* nb_planes, const int16_t* const* mvs, int thr_b, int thr_p, uint16_t* const out[3],
                 int reps, double* ms_per_launch);
+/* Noise level of one padded luma plane (structure decision, temporal filter): lower-quartile 16x16-block sum of the
+ * noise-mask response |I * [1 -2 1; -2 4 -2; 1 -2 1]| over the 14x14 inner samples; sigma ~= 0.0010658 * result. */
+int av1b_k_noise_estimate(int device, int width, int height, const uint16_t* src_y, int32_t* noise_out);
 /* Key-frame partition by smoothness (E3/E4 decision): src_y = one padded luma plane; map_out[h8*w8] = block log2 (3..6)
  * per 8x8 unit: 64x64 / 32x32 where the 4x4 box sums stay within thr of a plane, else 16x16 (8x8 at the picture edge). */
 int av1b_k_partition_smooth(int device, int width, int height, const uint16_t* src_y, int thr, uint8_t* map_out);

@@ -788,6 +788,41 @@ extern "C" void orc_me_smooth(const Av1bGeom* g, const uint16_t* cur0, const uin
 }
 
 // ------------------------------------------------------------------------------------------------
+// Noise level of a source picture (encoder side, ours; Immerkaer's fast estimate made robust by a percentile): for
+// every 16x16 luma block that lies inside the picture, B = sum over its 14x14 inner samples of |I * N| with the
+// noise-sensitive mask N = [1 -2 1; -2 4 -2; 1 -2 1] (it cancels constant, linear and many quadratic structures).  The
+// blocks go into a histogram of 4096 bins of width 16; the result is the centre of the bin that holds the lower
+// quartile of the blocks outside bin 0 (saturated areas and letterbox bars carry no noise at all and say nothing about
+// the rest of the picture); 0 when every block is in bin 0.  sigma ~= sqrt(pi / 2) * B / (6 * 196).
+// ------------------------------------------------------------------------------------------------
+extern "C" int orc_noise_estimate(const Av1bGeom* g, const uint16_t* src_y, int stride) {
+  std::vector<uint32_t> hist(4096, 0);
+  uint32_t n = 0;
+  for (int by = 0; by * 16 + 16 <= g->height; by++)
+    for (int bx = 0; bx * 16 + 16 <= g->width; bx++) {
+      int64_t B = 0;
+      for (int i = 1; i < 15; i++)
+        for (int j = 1; j < 15; j++) {
+          const uint16_t* p = src_y + (size_t)(by * 16 + i) * stride + bx * 16 + j;
+          const int v = (int)p[-stride - 1] - 2 * (int)p[-stride] + (int)p[-stride + 1] - 2 * (int)p[-1] + 4 * (int)p[0] - 2 * (int)p[1] +
+                        (int)p[stride - 1] - 2 * (int)p[stride] + (int)p[stride + 1];
+          B += abs(v);
+        }
+      hist[std::min<int64_t>(B >> 4, 4095)]++;
+      n++;
+    }
+  n -= hist[0];
+  if (n == 0) return 0;
+  const uint32_t want = (n + 3) / 4;
+  uint32_t acc = 0;
+  for (int b = 1; b < 4096; b++) {
+    acc += hist[b];
+    if (acc >= want) return (b << 4) + 8;
+  }
+  return (4095 << 4) + 8;
+}
+
+// ------------------------------------------------------------------------------------------------
 // Motion-compensated temporal filter of a key / anchor SOURCE picture (encoder side, ours): the picture is replaced
 // by a weighted mean of itself (weight 256) and of its neighbours in time, each motion-compensated onto it with the
 // normative interpolation (16x16 luma blocks, vectors mvs[k] from the motion search of the picture against neighbour

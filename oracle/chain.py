@@ -59,12 +59,24 @@ class FrameResult:
     pass
 
 
+def choose_structure(g, bd, crf, first_luma_padded):
+    """config.gop_period == 0 (csrc/encoder.cc begin_chunk): the P chain where the quantiser is fine enough to code the
+    noise of the chunk's first picture, else the one-level hierarchy of period 4.  Returns (gop_period, noise estimate)."""
+    q = max(1, table("av1t_quantizer_to_qindex")[crf])
+    nb = O.noise_estimate(g, first_luma_padded)
+    return (1 if 2 * nb > 15 * ac_q(bd, q) else 4), nb
+
+
 def encode_chain(frames, w, h, bd, crf, keyint=240, gop_period=4, me_smooth=True, key_var_part=True, loop_filters=True,
                  lr=False, intra_only=False, blk_log2=4, tb_zero_thr=0, pos0=0, geom=None, mctf=True, batch=8, lookahead=-1,
                  film_grain=0, mctf_radius=2, mctf_key_fwd=4):
     """Returns one FrameResult per frame: kind, fp, res (blocks / coef / pre-filter rec), fin (padded planes after the
     in-loop filters), cdef_idx, lr_units, mvs."""
     g = geom if geom is not None else O.geom(w, h, 0, 0)   # key-frame tiling: no intra prediction across tile edges
+    if gop_period == 0:
+        gop_period, _ = choose_structure(g, bd, crf, O.pad_planes(g, frames[0])[0])
+    if gop_period <= 1:
+        mctf = False
     qkey, qa, qn = quantisers(crf, gop_period, intra_only)
     qk = {0: qkey, 1: qa, 2: qn}
     lam = ac_q(bd, qa) >> 1

@@ -141,6 +141,12 @@ def me_smooth(g, cur_pyr, ref_pyr, mv, lam_s, iters=2):
     return mv
 
 
+def noise_estimate(g, luma_padded):
+    """Lower-quartile block sum of |I * N| (orc_noise_estimate); sigma ~= 0.0010658 * result."""
+    l0 = np.ascontiguousarray(luma_padded, np.uint16)
+    return int(lib().orc_noise_estimate(C.byref(g), ptr(l0), l0.shape[1]))
+
+
 def mctf(g, bit_depth, cur_planes, nb_planes, nb_mvs, thr_b, thr_p):
     """Motion-compensated temporal filter (orc_mctf): cur_planes = 3 padded planes, nb_planes = list of 3 padded planes per
     neighbour, nb_mvs = list of [h8*w8, 2] vectors (cur against that neighbour). Returns 3 padded planes."""

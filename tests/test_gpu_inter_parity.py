@@ -20,6 +20,8 @@ CASES = [
     (640, 360, 10, 35, -1, -1, True, 6, 4, 240, 5, 2),
     (328, 248, 10, 50, 0, 0, True, 13, 8, 240, 6, 0),
     (640, 360, 8, 38, -1, -1, True, 18, 8, 240, 6, 0),
+    (328, 248, 10, 14, 0, 0, True, 6, 4, 240, 6, 0),      # fine quantiser on a noisy source: the automatic structure is the P chain
+    (328, 248, 10, 14, 0, 0, True, 6, 4, 240, 6, 4),
 ]
 # every case also through the device range coder (pack_path 4); 0 = automatic placement
 CASES = [c + (pp,) for c in CASES for pp in (0, 4)]
@@ -37,8 +39,13 @@ def test_chunk_parity(w, h, bd, crf, tcl, trl, lf, nfr, fif, keyint, preset, gop
     lr = lf and preset <= 5
     tus = enc.encode_chunk(frames)
     assert len(tus) == nfr
-    g, want = chain.encode_chain(frames, w, h, bd, crf, keyint=keyint, gop_period=gop or 4, loop_filters=lf, lr=lr, geom=enc.geom, batch=fif)
-    assert enc.me_lambda() == chain.ac_q(bd, chain.quantisers(crf, gop or 4)[1]) >> 1
+    g, want = chain.encode_chain(frames, w, h, bd, crf, keyint=keyint, gop_period=gop, loop_filters=lf, lr=lr, geom=enc.geom, batch=fif)
+    info = enc.chunk_info()
+    if gop == 0:   # structure chosen from the noise level of the first picture
+        gop, nb = chain.choose_structure(g, bd, crf, O.pad_planes(g, frames[0])[0])
+        assert info["noise_b"] == nb and info["auto"]
+    assert info["gop_period"] == gop
+    assert enc.me_lambda() == chain.ac_q(bd, chain.quantisers(crf, gop)[1]) >> 1
     dec_d = D.dav1d_decode(tus)
     dec_a = D.aom_decode(tus)
     assert len(dec_d) == nfr and len(dec_a) == nfr
@@ -64,7 +71,7 @@ def test_chunk_parity(w, h, bd, crf, tcl, trl, lf, nfr, fif, keyint, preset, gop
             assert np.array_equal(rec[p], orc[p]), ("recon vs oracle", i, p)
             assert np.array_equal(dec_d[i][p], rec[p]), ("dav1d", i, p)
             assert np.array_equal(dec_a[i][p], rec[p]), ("libaom", i, p)
-    if (gop or 4) > 1 and nfr > (gop or 4) and keyint > (gop or 4):
+    if gop > 1 and nfr > gop and keyint > gop:
         assert kinds == {0, 1, 2}
     assert enc.stats()["mctf_frames"] == sum(1 for r in want if r.filtered_from)
     enc.close()

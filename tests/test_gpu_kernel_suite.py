@@ -243,6 +243,19 @@ def test_vector_field_regularisation_vs_oracle(w, h, bd):
 
 
 @pytest.mark.parametrize("w,h,bd", ME_CASES + [(1920, 1080, 8), (3840, 2160, 10)])
+def test_noise_estimate_vs_oracle(w, h, bd):
+    g = O.geom(w, h, 0, 0)
+    vals = []
+    for noise in (0.0, 0.3, 1.0):
+        fr = synth.synth_clip(w, h, bd, 1, seed=w + bd, scene_len=100, noise=noise, hdr=(w > 3000))[0]
+        l0 = O.pad_planes(g, fr)[0]
+        got = kernels.noise_estimate(w, h, l0)
+        assert got == O.noise_estimate(g, l0), noise
+        vals.append(got)
+    assert vals[0] < vals[1] < vals[2]
+
+
+@pytest.mark.parametrize("w,h,bd", ME_CASES + [(1920, 1080, 8), (3840, 2160, 10)])
 def test_partition_smooth_vs_oracle(w, h, bd):
     g = O.geom(w, h, 0, 0)
     fr = synth.synth_clip(w, h, bd, 1, seed=w + bd, scene_len=100, noise=0.5)[0]

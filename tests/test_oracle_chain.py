@@ -112,6 +112,38 @@ def test_mv_dominant_and_smoothing_properties():
     assert len(f1) == len(f0)
 
 
+def test_noise_estimate_and_structure_choice():
+    """orc_noise_estimate against a numpy restatement; the estimate follows the noise, ignores noiseless (saturated /
+    letterbox) blocks, and the structure choice turns to the P chain only where the quantiser is fine against it."""
+    w, h, bd = 328, 248, 10
+    g = O.geom(w, h, 0, 0)
+    est = []
+    for noise in (0.0, 0.25, 1.0, 2.0):
+        fr = synth.synth_clip(w, h, bd, 1, seed=2, scene_len=100, noise=noise)[0]
+        l0 = O.pad_planes(g, fr)[0]
+        I = l0[:h, :w].astype(np.int64)
+        L = np.abs(I[:-2, :-2] - 2 * I[:-2, 1:-1] + I[:-2, 2:] - 2 * I[1:-1, :-2] + 4 * I[1:-1, 1:-1] - 2 * I[1:-1, 2:] + I[2:, :-2] - 2 * I[2:, 1:-1] + I[2:, 2:])
+        Lp = np.zeros((h, w), np.int64); Lp[1:-1, 1:-1] = L
+        B = np.array([[Lp[by * 16 + 1:by * 16 + 15, bx * 16 + 1:bx * 16 + 15].sum() for bx in range(w // 16)] for by in range(h // 16)]).ravel()
+        bins = np.minimum(B >> 4, 4095)
+        bins = np.sort(bins[bins > 0])
+        want = 0 if len(bins) == 0 else int(bins[(len(bins) + 3) // 4 - 1]) * 16 + 8
+        got = O.noise_estimate(g, l0)
+        assert got == want, noise
+        est.append(got)
+    assert est[0] < est[1] < est[2] < est[3]
+    # a letterboxed picture (noiseless bars) keeps the estimate of its active area
+    fr = synth.synth_clip(w, h, bd, 1, seed=2, scene_len=100, noise=1.0)[0]
+    l0 = O.pad_planes(g, fr)[0]
+    full = O.noise_estimate(g, l0)
+    l0[:64, :] = 64; l0[h - 64:h, :] = 64
+    assert abs(O.noise_estimate(g, l0) - full) <= 0.15 * full
+    noisy = O.pad_planes(g, synth.synth_clip(w, h, bd, 1, seed=2, scene_len=100, noise=1.0)[0])[0]
+    clean = O.pad_planes(g, synth.synth_clip(w, h, bd, 1, seed=2, scene_len=100, noise=0.1)[0])[0]
+    assert chain.choose_structure(g, bd, 14, noisy)[0] == 1 and chain.choose_structure(g, bd, 44, noisy)[0] == 4
+    assert chain.choose_structure(g, bd, 14, clean)[0] == 4
+
+
 def test_temporal_filter_properties():
     """orc_mctf against a numpy restatement built on pyoracle.inter_predict (the normative predictor pinned elsewhere),
     and what it is for: independent noise averages out."""
