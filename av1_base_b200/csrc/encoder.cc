@@ -142,6 +142,7 @@ struct Slot {
   size_t tok_fetched = 0;                             // tokens already downloaded with the offsets
   cudaEvent_t ev_tok0 = nullptr, ev_tok1 = nullptr;
   cudaEvent_t ev_src = nullptr;                       // sources of this slot are resident
+  bool staged = false;                                // sources came from the host (statistics)
   bool h2d_pending = false;                           // ev_h2d .. ev_src of the last upload have not been read yet
   uint16_t* h_src[3] = {nullptr, nullptr, nullptr};
   uint16_t* h_rec[3] = {nullptr, nullptr, nullptr};
@@ -178,6 +179,9 @@ struct av1b_encoder {
   int base_q_idx_nonref = 0;
   bool me_smooth = true;              // vector-field regularisation after the hierarchical search
   bool key_var_part = true;           // key frames: 64x64 / 32x32 blocks where the source is smooth
+  int pipe_next = 0, pipe_done = 0;   // batches launched / finished since the encoder was created (slot = index mod n_slots)
+  av1b_packet_cb last_cb = nullptr;   // of the last av1b_encode_stream call (packets still in flight belong to it)
+  void* last_user = nullptr;
   int q_nominal = 0;                  // quantiser index of the CRF
   bool gop_auto = true;               // structure chosen per chunk from the source's noise level (config.gop_period == 0)
   bool mctf_cfg = true;               // temporal filter allowed by the configuration
@@ -1115,30 +1119,57 @@ static int begin_chunk(av1b_encoder* e, Slot& first) {
   return AV1B_OK;
 }
 
+// finish the batches in flight, oldest first, until at most `keep` remain
+static int drain_to(av1b_encoder* e, int keep, av1b_packet_cb out_cb, av1b_progress_cb prog_cb, void* user, int64_t total_frames,
+                    std::chrono::steady_clock::time_point t0) {
+  const int S = e->n_slots;
+  while (e->pipe_next - e->pipe_done > keep) {
+    Slot& sl = e->slot[e->pipe_done % S];
+    int rc = finish(e, sl, sl.staged, out_cb, prog_cb, user, total_frames, t0);
+    if (rc != AV1B_OK) return rc;
+    e->pipe_done++;
+  }
+  return AV1B_OK;
+}
+
+// drain = false (av1b_encode_stream): the call returns with up to n_slots - 1 batches still on the device; their packets
+// come out during the next call or av1b_encode_flush, so consecutive parts of a chunk keep the pipeline full.
 static int run_batches(av1b_encoder* e, const av1b_frame_src* frames, const uint32_t* order, uint32_t n_frames, int64_t first_index,
-                       int64_t total_frames, av1b_packet_cb out_cb, av1b_progress_cb prog_cb, void* user) {
+                       int64_t total_frames, av1b_packet_cb out_cb, av1b_progress_cb prog_cb, void* user, bool drain = true) {
   const auto t0 = std::chrono::steady_clock::now();
   const uint32_t B = (uint32_t)e->batch;
   const bool staged = frames != nullptr;
-  int rc, i = 0;
-  if ((rc = stage_any(e, e->slot[0], frames, order, 0, (int)std::min<uint32_t>(B, n_frames))) != AV1B_OK) return rc;
-  if (e->chunk_pos == 0 && (rc = begin_chunk(e, e->slot[0])) != AV1B_OK) return rc;
   const int S = e->n_slots, L = S - 1;
-  for (uint32_t f0 = 0; f0 < n_frames; f0 += B, i++) {
+  int rc;
+  {
+    Slot& s0 = e->slot[e->pipe_next % S];
+    if (e->pipe_next >= S) CK(cudaStreamWaitEvent(e->s_in, s0.ev_k1, 0));   // the batch that used this slot has read its sources
+    if ((rc = stage_any(e, s0, frames, order, 0, (int)std::min<uint32_t>(B, n_frames))) != AV1B_OK) return rc;
+    if (e->chunk_pos == 0 && (rc = begin_chunk(e, s0)) != AV1B_OK) return rc;
+  }
+  Slot* last_staged = nullptr;
+  for (uint32_t f0 = 0; f0 < n_frames; f0 += B) {
     const int nb = (int)std::min<uint32_t>(B, n_frames - f0);
+    const int i = e->pipe_next;
     Slot& cur = e->slot[i % S];
+    cur.staged = staged;
     if ((rc = launch(e, cur, cur, nb, first_index + f0)) != AV1B_OK) return rc;
+    e->pipe_next++;
+    last_staged = &cur;
     if (f0 + B < n_frames) {
       Slot& nx = e->slot[(i + 1) % S];
-      if (i >= L) CK(cudaStreamWaitEvent(e->s_in, nx.ev_k1, 0));   // batch i+1-S has read that slot's sources
+      if (i + 1 >= S) CK(cudaStreamWaitEvent(e->s_in, nx.ev_k1, 0));   // batch i+1-S has read that slot's sources
       if ((rc = stage_any(e, nx, frames, order, f0 + B, (int)std::min<uint32_t>(B, n_frames - f0 - B))) != AV1B_OK) return rc;
     }
-    // the slot of batch i+1 is that of batch i+1-S: its packets must be out before the next launch
-    if (i >= L && (rc = finish(e, e->slot[(i - L) % S], staged, out_cb, prog_cb, user, total_frames, t0)) != AV1B_OK) return rc;
+    // at most L batches stay in flight: the slot the next batch is staged into belongs to a finished one
+    if ((rc = drain_to(e, L, out_cb, prog_cb, user, total_frames, t0)) != AV1B_OK) return rc;
   }
-  for (int k = std::max(0, i - L); k < i; k++)
-    if ((rc = finish(e, e->slot[k % S], staged, out_cb, prog_cb, user, total_frames, t0)) != AV1B_OK) return rc;
-  for (Slot& sl : e->slot) collect_h2d(e, sl);
+  if (drain) {
+    if ((rc = drain_to(e, 0, out_cb, prog_cb, user, total_frames, t0)) != AV1B_OK) return rc;
+    for (Slot& sl : e->slot) collect_h2d(e, sl);
+  } else if (staged && last_staged) {
+    CK(cudaEventSynchronize(last_staged->ev_src));   // the caller's buffers have been read
+  }
   return AV1B_OK;
 }
 
@@ -1148,6 +1179,7 @@ int av1b_encode_chunk(av1b_encoder* e, const av1b_frame_src* frames, uint32_t n_
   if (n_frames == 0) return AV1B_OK;
   CK(cudaSetDevice(e->cfg.device_id));
   reset_stats(e);
+  { int rc0 = drain_to(e, 0, e->last_cb, nullptr, e->last_user, 0, std::chrono::steady_clock::now()); if (rc0 != AV1B_OK) return rc0; }
   e->chunk_pos = 0;               // a chunk is a closed GOP: it starts with a key frame
   return run_batches(e, frames, nullptr, n_frames, 0, n_frames, out_cb, prog_cb, user);
 }
@@ -1159,8 +1191,33 @@ int av1b_encode_part(av1b_encoder* e, const av1b_frame_src* frames, uint32_t n_f
                      int64_t first_frame_index, av1b_packet_cb out_cb, av1b_progress_cb prog_cb, void* user) {
   if (!e || !frames || !out_cb || n_frames == 0) { set_error("null argument"); return AV1B_ERR_INVALID; }
   CK(cudaSetDevice(e->cfg.device_id));
+  { int rc0 = drain_to(e, 0, e->last_cb, nullptr, e->last_user, 0, std::chrono::steady_clock::now()); if (rc0 != AV1B_OK) return rc0; }
   if (first_part) { reset_stats(e); e->chunk_pos = 0; }
   return run_batches(e, frames, nullptr, n_frames, first_frame_index, 0, out_cb, prog_cb, user);
+}
+
+// Streaming without a drain between the parts of a chunk: the call returns once the frames have been uploaded; their
+// packets may be delivered by a later av1b_encode_stream / av1b_encode_flush call (always in order).  A part with
+// first_part != 0 first flushes what is in flight (to the callback of the call that submitted it).
+int av1b_encode_stream(av1b_encoder* e, const av1b_frame_src* frames, uint32_t n_frames, int first_part,
+                       int64_t first_frame_index, av1b_packet_cb out_cb, av1b_progress_cb prog_cb, void* user) {
+  if (!e || !frames || !out_cb || n_frames == 0) { set_error("null argument"); return AV1B_ERR_INVALID; }
+  CK(cudaSetDevice(e->cfg.device_id));
+  if (first_part) {
+    int rc = drain_to(e, 0, e->last_cb, nullptr, e->last_user, 0, std::chrono::steady_clock::now());
+    if (rc != AV1B_OK) return rc;
+    reset_stats(e); e->chunk_pos = 0;
+  }
+  e->last_cb = out_cb; e->last_user = user;
+  return run_batches(e, frames, nullptr, n_frames, first_frame_index, 0, out_cb, prog_cb, user, false);
+}
+
+int av1b_encode_flush(av1b_encoder* e, av1b_packet_cb out_cb, av1b_progress_cb prog_cb, void* user) {
+  if (!e) { set_error("null argument"); return AV1B_ERR_INVALID; }
+  CK(cudaSetDevice(e->cfg.device_id));
+  int rc = drain_to(e, 0, out_cb ? out_cb : e->last_cb, prog_cb, out_cb ? user : e->last_user, 0, std::chrono::steady_clock::now());
+  for (Slot& sl : e->slot) collect_h2d(e, sl);
+  return rc;
 }
 
 // ---- device-resident flow (bench: "inputs already resident in HBM") -----------------------------
@@ -1226,6 +1283,7 @@ int av1b_encode_clip(av1b_encoder* e, const uint32_t* order, uint32_t n_frames, 
   if (!e->n_clip) { set_error("stage a clip first (av1b_stage_clip)"); return AV1B_ERR_INVALID; }
   for (uint32_t i = 0; i < n_frames; i++) if (order[i] >= e->n_clip) { set_error("clip index out of range"); return AV1B_ERR_INVALID; }
   CK(cudaSetDevice(e->cfg.device_id));
+  { int rc0 = drain_to(e, 0, e->last_cb, nullptr, e->last_user, 0, std::chrono::steady_clock::now()); if (rc0 != AV1B_OK) return rc0; }
   if (!accumulate_stats) reset_stats(e);
   e->chunk_pos = 0;               // a closed chunk: it starts with a key frame
   return run_batches(e, nullptr, order, n_frames, 0, n_frames, out_cb, nullptr, user);

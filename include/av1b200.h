@@ -94,6 +94,14 @@ int av1b_encode_chunk(av1b_encoder* enc, const av1b_frame_src* frames, uint32_t 
  * with first_part != 0 starts a new closed GOP.  frame_index passed to out_cb = first_frame_index + k. */
 int av1b_encode_part(av1b_encoder* enc, const av1b_frame_src* frames, uint32_t n_frames, int first_part,
                      int64_t first_frame_index, av1b_packet_cb out_cb, av1b_progress_cb prog_cb, void* user);
+/* Like av1b_encode_part, but without draining the pipeline between the parts of a chunk: the call returns as soon as its
+ * frames have been uploaded (the caller may reuse the buffers); packets are delivered in order by this or a later
+ * av1b_encode_stream / av1b_encode_flush call, to the callback of the call that delivers them (a part with first_part != 0
+ * first delivers everything still in flight to the callback of the call that submitted it). */
+int av1b_encode_stream(av1b_encoder* enc, const av1b_frame_src* frames, uint32_t n_frames, int first_part,
+                       int64_t first_frame_index, av1b_packet_cb out_cb, av1b_progress_cb prog_cb, void* user);
+/* Delivers every packet still in flight (out_cb NULL: to the callback of the last av1b_encode_stream call). */
+int av1b_encode_flush(av1b_encoder* enc, av1b_packet_cb out_cb, av1b_progress_cb prog_cb, void* user);
 /* Reconstruction of the most recently encoded frame `frame_in_chunk` of the last chunk (post loop
  * filter), for the recon-vs-decode check. dst planes: uint16, strides in samples. */
 int av1b_get_recon(av1b_encoder* enc, uint32_t frame_in_chunk, uint16_t* const dst[3], const int32_t stride[3]);
