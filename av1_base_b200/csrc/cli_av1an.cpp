@@ -1,8 +1,9 @@
 // `av1an`-compatible command line front end of the B200 AV1 encode backend: the PATH executable the
 // reference daemon execs (/root/reference/crates/daemon/src/encode/av1an.rs:79-107 build_av1an_command,
 // :126-139 run_av1an; `av1an --version` in startup.rs:98-116).  Same argv, same exit-code contract
-// (0 = success, non-zero = EncodeError::Av1anFailed(code)), complete file at -o or no file at all,
-// everything temporary under --temp.
+// (0 = success, non-zero = EncodeError::Av1anFailed(code)), complete file at -o or no file at all (a failed
+// decode pipe or a failed audio copy is a failed job: the daemon replaces the source file with what it finds at -o),
+// everything temporary under --temp: finished chunks wait there as packet files until the container is written.
 //
 //   av1an -i IN -o OUT --encoder svt-av1 --pix-format yuv420p10le --video-params "--crf 30 --preset 6 ..."
 //         --audio-params "-c:a copy" --workers N --temp DIR
@@ -22,6 +23,7 @@
 #include <string.h>
 #include <sys/file.h>
 #include <sys/stat.h>
+#include <sys/wait.h>
 #include <unistd.h>
 #include <algorithm>
 #include <atomic>
@@ -192,22 +194,60 @@ void ebml_float(std::vector<uint8_t>& o, uint32_t id, double v) {
   for (int i = 7; i >= 0; i--) o.push_back((uint8_t)(u >> (8 * i)));
 }
 
-// Minimal Matroska (video only): EBML header, Segment { Info, Tracks { V_AV1 }, Cluster* { SimpleBlock* } }
-bool write_mkv(const std::string& path, const std::vector<Packet>& pk, int w, int h, int fps_num, int fps_den, bool hbd) {
+// Packets of a finished chunk wait in <temp>/chunk_NNNNNN.pkt as [u32 size][u8 key][bytes]; the container is written
+// by streaming them back in chunk order, so the memory a job needs does not grow with the length of the film.
+struct PacketReader {
+  std::vector<std::string> files;
+  size_t next_file = 0;
+  FILE* f = nullptr;
+  bool next(Packet& p) {
+    for (;;) {
+      if (!f) {
+        if (next_file >= files.size()) return false;
+        f = fopen(files[next_file++].c_str(), "rb");
+        if (!f) continue;     // a chunk without packets has no file
+      }
+      uint8_t h[5];
+      if (fread(h, 1, 5, f) != 5) { fclose(f); f = nullptr; continue; }
+      const uint32_t n = (uint32_t)h[0] | ((uint32_t)h[1] << 8) | ((uint32_t)h[2] << 16) | ((uint32_t)h[3] << 24);
+      p.key = h[4] != 0;
+      p.data.resize(n);
+      if (fread(p.data.data(), 1, n, f) != n) { fclose(f); f = nullptr; return false; }
+      return true;
+    }
+  }
+  ~PacketReader() { if (f) fclose(f); }
+};
+
+bool put(FILE* f, const std::vector<uint8_t>& v) { return v.empty() || fwrite(v.data(), 1, v.size(), f) == v.size(); }
+
+// Minimal Matroska (video only): EBML header, Segment { Info, Tracks { V_AV1 }, Cluster* { SimpleBlock* } }.
+// Clusters are written as they fill (one per key frame / 30 s); the Segment size and the Duration are patched at the end.
+bool write_mkv(const std::string& path, PacketReader& rd, int64_t* n_out, int w, int h, int fps_num, int fps_den, bool hbd) {
+  FILE* f = fopen(path.c_str(), "wb");
+  if (!f) return false;
+  Packet pk;
+  bool have = rd.next(pk);
   std::vector<uint8_t> out, hdr;
   ebml_uint(hdr, 0x4286, 1); ebml_uint(hdr, 0x42F7, 1); ebml_uint(hdr, 0x42F2, 4); ebml_uint(hdr, 0x42F3, 8);
   ebml_str(hdr, 0x4282, "matroska"); ebml_uint(hdr, 0x4287, 4); ebml_uint(hdr, 0x4285, 2);
   ebml_master(out, 0x1A45DFA3, hdr);
-  std::vector<uint8_t> seg, info, tracks, te, video;
+  ebml_id(out, 0x18538067);
+  const long seg_size_pos = (long)out.size();
+  ebml_size(out, 0);                                             // patched below
+  const long seg_start = (long)out.size();
+  std::vector<uint8_t> info, tracks, te, video;
   const double frame_ms = 1000.0 * fps_den / fps_num;
   ebml_uint(info, 0x2AD7B1, 1000000);                           // TimestampScale: 1 ms
-  ebml_float(info, 0x4489, frame_ms * pk.size());               // Duration
+  const long dur_in_info = (long)info.size() + 2 + 1;           // id (2) + size byte, then 8 bytes of float
+  ebml_float(info, 0x4489, 0.0);                                // Duration: patched below
   ebml_str(info, 0x4D80, "av1b200"); ebml_str(info, 0x5741, "av1b200");
-  ebml_master(seg, 0x1549A966, info);
+  const long info_body_pos = (long)out.size() + 4 + 8;          // id (4) + 8-byte size
+  ebml_master(out, 0x1549A966, info);
   // CodecPrivate = AV1CodecConfigurationRecord: marker/version, profile/level, flags, then the sequence header OBU
   std::vector<uint8_t> av1c;
   const uint8_t* sh = nullptr; size_t shn = 0;
-  if (!pk.empty()) find_obu(pk[0].data.data(), pk[0].data.size(), 1, &sh, &shn);
+  if (have) find_obu(pk.data.data(), pk.data.size(), 1, &sh, &shn);
   av1c.push_back(0x81);
   av1c.push_back((uint8_t)((0 << 5) | 31));                       // seq_profile 0, seq_level_idx_0 31
   av1c.push_back((uint8_t)((0 << 7) | ((hbd ? 1 : 0) << 6) | (0 << 5) | (0 << 4) | (1 << 3) | (1 << 2) | 0));
@@ -220,66 +260,92 @@ bool write_mkv(const std::string& path, const std::vector<Packet>& pk, int w, in
   ebml_uint(te, 0x23E383, (uint64_t)(frame_ms * 1e6));          // DefaultDuration (ns)
   ebml_master(te, 0xE0, video);
   ebml_master(tracks, 0xAE, te);
-  ebml_master(seg, 0x1654AE6B, tracks);
+  ebml_master(out, 0x1654AE6B, tracks);
+  bool ok = put(f, out);
+  uint64_t seg_bytes = out.size() - (size_t)seg_start;
   // clusters: a new one at every key frame and at least every 30000 ms of timestamps (int16 block offsets)
-  std::vector<uint8_t> cl;
+  std::vector<uint8_t> cl, clm;
   double cl_t0 = 0;
-  auto flush = [&]() { if (!cl.empty()) { ebml_master(seg, 0x1F43B675, cl); cl.clear(); } };
-  for (size_t k = 0; k < pk.size(); k++) {
+  auto flush = [&]() {
+    if (cl.empty()) return;
+    clm.clear();
+    ebml_master(clm, 0x1F43B675, cl);
+    ok = ok && put(f, clm);
+    seg_bytes += clm.size();
+    cl.clear();
+  };
+  int64_t k = 0;
+  for (; have && ok; have = rd.next(pk), k++) {
     const double ts = frame_ms * k;
-    if (cl.empty() || pk[k].key || ts - cl_t0 > 30000) { flush(); cl_t0 = ts; ebml_uint(cl, 0xE7, (uint64_t)(ts + 0.5)); }
-    size_t n = pk[k].data.size();
-    const uint8_t* p = skip_td(pk[k].data.data(), n);
-    std::vector<uint8_t> blk;
-    blk.push_back(0x81);
+    if (cl.empty() || pk.key || ts - cl_t0 > 30000) { flush(); cl_t0 = ts; ebml_uint(cl, 0xE7, (uint64_t)(ts + 0.5)); }
+    size_t n = pk.data.size();
+    const uint8_t* p = skip_td(pk.data.data(), n);
     const int rel = (int)(ts - cl_t0 + 0.5);
-    blk.push_back((uint8_t)(rel >> 8)); blk.push_back((uint8_t)rel);
-    blk.push_back(pk[k].key ? 0x80 : 0x00);
-    blk.insert(blk.end(), p, p + n);
-    ebml_bytes(cl, 0xA3, blk.data(), blk.size());
+    ebml_id(cl, 0xA3);
+    ebml_size(cl, 4 + n);
+    cl.push_back(0x81);
+    cl.push_back((uint8_t)(rel >> 8)); cl.push_back((uint8_t)rel);
+    cl.push_back(pk.key ? 0x80 : 0x00);
+    cl.insert(cl.end(), p, p + n);
   }
   flush();
-  ebml_master(out, 0x18538067, seg);
-  FILE* f = fopen(path.c_str(), "wb");
-  if (!f) return false;
-  const bool ok = fwrite(out.data(), 1, out.size(), f) == out.size();
+  *n_out = k;
+  // patch the Segment size and the Duration
+  std::vector<uint8_t> sz, du;
+  ebml_size(sz, seg_bytes);
+  ebml_float(du, 0x4489, frame_ms * k);
+  ok = ok && fseek(f, seg_size_pos, SEEK_SET) == 0 && put(f, sz);
+  ok = ok && fseek(f, info_body_pos + dur_in_info, SEEK_SET) == 0 && fwrite(du.data() + 3, 1, 8, f) == 8;
   return fclose(f) == 0 && ok;
 }
 
-bool write_ivf(const std::string& path, const std::vector<Packet>& pk, int w, int h, int fps_num, int fps_den) {
+bool write_ivf(const std::string& path, PacketReader& rd, int64_t* n_out, int w, int h, int fps_num, int fps_den) {
+  FILE* f = fopen(path.c_str(), "wb");
+  if (!f) return false;
   std::vector<uint8_t> o;
   o.insert(o.end(), {'D', 'K', 'I', 'F'});
   put_le(o, 0, 2); put_le(o, 32, 2);
   o.insert(o.end(), {'A', 'V', '0', '1'});
   put_le(o, (uint64_t)w, 2); put_le(o, (uint64_t)h, 2); put_le(o, (uint64_t)fps_num, 4); put_le(o, (uint64_t)fps_den, 4);
-  put_le(o, pk.size(), 4); put_le(o, 0, 4);
-  for (size_t k = 0; k < pk.size(); k++) {
-    put_le(o, pk[k].data.size(), 4); put_le(o, k, 8);
-    o.insert(o.end(), pk[k].data.begin(), pk[k].data.end());
+  put_le(o, 0, 4); put_le(o, 0, 4);                              // frame count: patched below
+  bool ok = put(f, o);
+  Packet pk;
+  int64_t k = 0;
+  for (; ok && rd.next(pk); k++) {
+    o.clear();
+    put_le(o, pk.data.size(), 4); put_le(o, (uint64_t)k, 8);
+    ok = put(f, o) && put(f, pk.data);
   }
-  FILE* f = fopen(path.c_str(), "wb");
-  if (!f) return false;
-  const bool ok = fwrite(o.data(), 1, o.size(), f) == o.size();
+  *n_out = k;
+  o.clear(); put_le(o, (uint64_t)k, 4);
+  ok = ok && fseek(f, 24, SEEK_SET) == 0 && put(f, o);
   return fclose(f) == 0 && ok;
 }
 
-bool write_obu(const std::string& path, const std::vector<Packet>& pk) {
+bool write_obu(const std::string& path, PacketReader& rd, int64_t* n_out) {
   FILE* f = fopen(path.c_str(), "wb");
   if (!f) return false;
   bool ok = true;
-  for (auto& p : pk) ok = ok && fwrite(p.data.data(), 1, p.data.size(), f) == p.data.size();
+  Packet pk;
+  int64_t k = 0;
+  for (; ok && rd.next(pk); k++) ok = put(f, pk.data);
+  *n_out = k;
   return fclose(f) == 0 && ok;
 }
 
 // ---------------------------------------------------------------------------------------------
 // GPU leases: concurrent jobs of the daemon (max_concurrent_jobs > 1) must not share a device
 // ---------------------------------------------------------------------------------------------
-int lease_device(int dev, bool block) {
+// Never blocks: a job takes the devices that are free now and, when there is none, polls until ANY one is released
+// (blocking on a particular device while holding others deadlocks two jobs that each hold what the other waits for).
+int lease_device(int dev) {
   char path[128];
   snprintf(path, sizeof(path), "/tmp/av1b200-gpu%d.lock", dev);
-  const int fd = open(path, O_CREAT | O_RDWR, 0666);
+  int fd = open(path, O_CREAT | O_RDWR, 0666);
+  if (fd < 0) fd = open(path, O_RDONLY);      // another user's lock file: flock needs no write permission
   if (fd < 0) return -1;
-  if (flock(fd, LOCK_EX | (block ? 0 : LOCK_NB)) != 0) { close(fd); return -1; }
+  fchmod(fd, 0666);                           // whatever the umask was: the next job may run as another user
+  if (flock(fd, LOCK_EX | LOCK_NB) != 0) { close(fd); return -1; }
   return fd;
 }
 
@@ -311,7 +377,12 @@ struct Part {
 
 struct Shared {
   std::mutex m;
-  std::vector<std::vector<Packet>> chunk_out;   // [chunk] packets in order
+  std::string pkt_dir;                          // finished chunks wait here as packet files
+  std::atomic<int64_t> n_chunks{0};
+  std::atomic<int64_t> packets{0}, bytes_out{0};
+  double fps_num = 30, fps_den = 1;
+  // PSNR / SSIM of the frames coded so far: per worker (its encoder's running means of the current chunk + closed chunks)
+  std::vector<double> q_psnr_sum, q_ssim_sum, q_frames;
   std::atomic<int64_t> frames_done{0};
   std::atomic<int> failed{0};
   std::string error;
@@ -322,15 +393,24 @@ struct Shared {
   std::vector<GroupBuf*> free_bufs;   // recycled group buffers (allocation + first touch of ~0.4 GB is slow)
 };
 
-struct PacketCtx { Shared* sh; int64_t chunk; };
+std::string chunk_file(const Shared& sh, int64_t chunk) {
+  char name[64];
+  snprintf(name, sizeof(name), "/chunk_%06lld.pkt", (long long)chunk);
+  return sh.pkt_dir + name;
+}
+
+// one per worker: the chunk it is coding and that chunk's packet file
+struct PacketCtx { Shared* sh; int64_t chunk = -1; FILE* f = nullptr; bool io_error = false; };
 
 int on_packet(void* user, const uint8_t* data, size_t size, int64_t, int is_key) {
   PacketCtx* c = static_cast<PacketCtx*>(user);
-  Packet p;
-  p.data.assign(data, data + size);
-  p.key = is_key != 0;
-  std::lock_guard<std::mutex> l(c->sh->m);
-  c->sh->chunk_out[(size_t)c->chunk].push_back(std::move(p));
+  if (!c->f) {
+    c->f = fopen(chunk_file(*c->sh, c->chunk).c_str(), "wb");
+    if (!c->f) { c->io_error = true; return 1; }
+  }
+  const uint8_t h[5] = {(uint8_t)size, (uint8_t)(size >> 8), (uint8_t)(size >> 16), (uint8_t)(size >> 24), (uint8_t)(is_key != 0)};
+  if (fwrite(h, 1, 5, c->f) != 5 || fwrite(data, 1, size, c->f) != size) { c->io_error = true; return 1; }
+  c->sh->packets++; c->sh->bytes_out += (int64_t)size;
   return 0;
 }
 
@@ -338,9 +418,20 @@ void report_progress(Shared& sh, bool final_line) {
   const int64_t done = sh.frames_done.load();
   const double el = std::chrono::duration<double>(std::chrono::steady_clock::now() - sh.t0).count();
   const double fps = el > 0 ? done / el : 0;
-  char line[256];
-  snprintf(line, sizeof(line), "{\"frames_encoded\": %lld, \"total_frames\": %lld, \"fps\": %.2f, \"done\": %s}",
-           (long long)done, (long long)sh.total_frames, fps, final_line ? "true" : "false");
+  // the fields of JobMetrics the reference leaves at zero (metrics.rs:12-30, job_executor.rs:117-137)
+  const int64_t pk = sh.packets.load();
+  const double kbps = pk > 0 ? (double)sh.bytes_out.load() * 8.0 / 1000.0 * (sh.fps_num / sh.fps_den) / (double)pk : 0.0;
+  const double eta = (fps > 0 && sh.total_frames > done) ? (double)(sh.total_frames - done) / fps : 0.0;
+  double ps = 0, ss = 0, qf = 0;
+  {
+    std::lock_guard<std::mutex> l(sh.m);
+    for (size_t k = 0; k < sh.q_frames.size(); k++) { ps += sh.q_psnr_sum[k]; ss += sh.q_ssim_sum[k]; qf += sh.q_frames[k]; }
+  }
+  char line[512];
+  snprintf(line, sizeof(line), "{\"frames_encoded\": %lld, \"total_frames\": %lld, \"fps\": %.2f, \"bitrate_kbps\": %.1f, "
+           "\"est_remaining_secs\": %.1f, \"psnr\": %.3f, \"ssim\": %.5f, \"progress\": %.4f, \"done\": %s}",
+           (long long)done, (long long)sh.total_frames, fps, kbps, eta, qf > 0 ? ps / qf : 0.0, qf > 0 ? ss / qf : 0.0,
+           sh.total_frames > 0 ? (double)done / (double)sh.total_frames : 0.0, final_line ? "true" : "false");
   if (!sh.quiet) { printf("%s\n", line); fflush(stdout); }
   if (!sh.progress_path.empty()) {
     const std::string tmp = sh.progress_path + ".tmp";
@@ -408,7 +499,7 @@ int main(int argc, char** argv) {
       die(3, "%s is not YUV4MPEG2 and no ffmpeg is on PATH to decode it", o.input.c_str());
     std::string q;
     for (char c : o.input) { if (c == '\'') q += "'\\''"; else q += c; }
-    const std::string cmd = "ffmpeg -v error -i '" + q + "' -map 0:v:0 -pix_fmt " + o.pix_format + " -strict -1 -f yuv4mpegpipe -";
+    const std::string cmd = "ffmpeg -v error -i '" + q + "' -map 0:v:0 -pix_fmt " + std::string(out_bits == 8 ? "yuv420p" : "yuv420p10le") + " -strict -1 -f yuv4mpegpipe -";
     in.f = popen(cmd.c_str(), "r");
     in.pipe = true;
     if (!in.f || !y4m_parse_header(in)) die(3, "ffmpeg could not decode %s", o.input.c_str());
@@ -426,23 +517,28 @@ int main(int argc, char** argv) {
   sh.total_frames = in.n_frames;
   sh.t0 = std::chrono::steady_clock::now();
   sh.quiet = o.quiet;
-  if (!o.temp.empty()) { mkdir(o.temp.c_str(), 0777); sh.progress_path = o.temp + "/progress.json"; }
+  sh.fps_num = in.fps_num; sh.fps_den = in.fps_den;
+  if (!o.temp.empty()) { mkdir(o.temp.c_str(), 0777); sh.progress_path = o.temp + "/progress.json"; sh.pkt_dir = o.temp; }
+  else { sh.pkt_dir = o.output + ".av1b200.tmp"; mkdir(sh.pkt_dir.c_str(), 0777); }
 
   // ---- devices ----
   std::vector<int> dev, lease;
-  for (int pass = 0; pass < 2 && (int)dev.size() < n_workers; pass++)
+  for (int waited_ms = 0; dev.empty(); waited_ms += 200) {
     for (int d = 0; d < ndev && (int)dev.size() < n_workers; d++) {
-      if (std::find(dev.begin(), dev.end(), d) != dev.end()) continue;
-      const int fd = lease_device(d, pass == 1);
+      const int fd = lease_device(d);
       if (fd >= 0) { dev.push_back(d); lease.push_back(fd); }
     }
-  if (dev.empty()) die(4, "no GPU lease available");
+    if (!dev.empty()) break;
+    if (waited_ms == 0 && !o.quiet) fprintf(stderr, "av1an (av1b200): all %d GPUs are leased by other jobs, waiting for one\n", ndev);
+    usleep(200 * 1000);
+  }
   if (share) while ((int)dev.size() < n_workers) dev.push_back(dev[dev.size() % lease.size()]);
 
   // ---- workers: one encoder handle (= one GPU) each, fed with chunk parts through a bounded queue ----
   const int kPart = 16;   // frames per hand-over: two device batches; buffers are recycled through sh.free_bufs
   struct Queue { std::mutex m; std::condition_variable cv; std::deque<Part> q; bool closed = false; };
   const int W = (int)dev.size();
+  sh.q_psnr_sum.assign(W, 0); sh.q_ssim_sum.assign(W, 0); sh.q_frames.assign(W, 0);
   std::vector<Queue> queues(W);
   std::vector<std::thread> threads;
   for (int wk = 0; wk < W; wk++) {
@@ -454,8 +550,11 @@ int main(int argc, char** argv) {
       cfg.crf = o.crf; cfg.preset = o.preset; cfg.keyint = o.keyint; cfg.lookahead = o.lookahead;
       cfg.film_grain = o.film_grain; cfg.enable_qm = o.enable_qm; cfg.qm_min = o.qm_min; cfg.qm_max = o.qm_max;
       cfg.device_id = dev[wk];
+      cfg.tune[3] = 1;                 // PSNR / SSIM for the progress events
       cfg.host_threads = std::max(1u, std::thread::hardware_concurrency() / (unsigned)W);
       av1b_encoder* enc = nullptr;
+      PacketCtx ctx;
+      ctx.sh = &sh;
       int rc = av1b_encoder_create(&cfg, &enc);
       if (rc != AV1B_OK) {
         std::lock_guard<std::mutex> l(sh.m);
@@ -472,14 +571,29 @@ int main(int argc, char** argv) {
         }
         queues[wk].cv.notify_all();
         if (sh.failed || !enc) continue;   // drain
+        if (part.n == 0) {
+          // end of a chunk: everything still in flight belongs to it; then its packet file is complete
+          rc = av1b_encode_flush(enc, on_packet, nullptr, &ctx);
+          if (ctx.f) { if (fclose(ctx.f) != 0) ctx.io_error = true; ctx.f = nullptr; }
+          double ps = 0, ss = 0; int64_t qf = 0;
+          if (av1b_get_quality(enc, &ps, &ss, &qf) == AV1B_OK) {
+            std::lock_guard<std::mutex> l(sh.m);
+            sh.q_psnr_sum[wk] += ps * qf; sh.q_ssim_sum[wk] += ss * qf; sh.q_frames[wk] += (double)qf;
+          }
+          if (rc != AV1B_OK || ctx.io_error) {
+            std::lock_guard<std::mutex> l(sh.m);
+            if (!sh.failed) { sh.failed = ctx.io_error ? 6 : -rc; sh.error = ctx.io_error ? "cannot write the chunk's packet file (disk full?)" : av1b_last_error(); }
+          }
+          continue;
+        }
+        ctx.chunk = part.chunk;
         std::vector<av1b_frame_src> fs((size_t)part.n);
         for (int k = 0; k < part.n; k++) {
           uint16_t* b = part.buf->data() + (part.first_slot + (size_t)k) * frame_samples;
           fs[k].planes[0] = b; fs[k].planes[1] = b + (size_t)in.w * in.h; fs[k].planes[2] = b + (size_t)in.w * in.h * 5 / 4;
           fs[k].stride[0] = in.w; fs[k].stride[1] = fs[k].stride[2] = in.w / 2;
         }
-        PacketCtx ctx{&sh, part.chunk};
-        rc = av1b_encode_part(enc, fs.data(), (uint32_t)part.n, part.first_part ? 1 : 0, part.first_frame, on_packet, nullptr, &ctx);
+        rc = av1b_encode_stream(enc, fs.data(), (uint32_t)part.n, part.first_part ? 1 : 0, part.first_frame, on_packet, nullptr, &ctx);
         part.buf.reset();   // the last part of a group returns the buffer to the pool (custom deleter)
         if (rc != AV1B_OK) {
           std::lock_guard<std::mutex> l(sh.m);
@@ -506,10 +620,7 @@ int main(int argc, char** argv) {
     return std::shared_ptr<GroupBuf>(g, [shp](GroupBuf* p) { std::lock_guard<std::mutex> l(shp->m); shp->free_bufs.push_back(p); });
   };
   auto submit = [&](Part&& part) {
-    {
-      std::lock_guard<std::mutex> l(sh.m);
-      if ((int64_t)sh.chunk_out.size() <= part.chunk) sh.chunk_out.resize((size_t)part.chunk + 1);
-    }
+    if (part.chunk + 1 > sh.n_chunks) sh.n_chunks = part.chunk + 1;
     Queue& q = queues[(size_t)(part.chunk % W)];
     {
       std::unique_lock<std::mutex> l(q.m);
@@ -553,6 +664,8 @@ int main(int argc, char** argv) {
           if (k >= got) break;
           uint16_t* slot = buf->data() + (size_t)k * frame_samples;
           const off_t off = (off_t)in.header_len + (off_t)(frame + k) * (off_t)(6 + in.frame_bytes) + 6;
+          char mark[6];
+          if (pread(fd, mark, 6, off - 6) != 6 || memcmp(mark, "FRAME\n", 6) != 0) { bad = 2; break; }   // frame headers with parameters: not seekable this way
           uint8_t* dst = in.bits > 8 ? reinterpret_cast<uint8_t*>(slot) : (tmp.resize(in.frame_bytes), tmp.data());
           size_t done = 0;
           while (done < in.frame_bytes) {
@@ -568,6 +681,7 @@ int main(int argc, char** argv) {
       for (int t = 1; t < io_threads; t++) io.emplace_back(work);
       work();
       for (auto& t : io) t.join();
+      if (bad == 2) die(3, "Y4M frame headers carry parameters (or the file is corrupt): pipe it through ffmpeg or rewrite it with plain FRAME markers");
       if (bad) die(3, "truncated Y4M file");
       if (frame + got >= in.n_frames) eof = true;
     }
@@ -597,6 +711,7 @@ int main(int argc, char** argv) {
       if (frame > 0 && (cut || in_chunk >= o.keyint)) {
         emit(run_start, k);
         run_start = k;
+        { Part end; end.chunk = chunk; end.n = 0; submit(std::move(end)); }   // end of chunk: flush
         chunk++; in_chunk = 0;
       }
       frame++; in_chunk++;
@@ -605,39 +720,59 @@ int main(int argc, char** argv) {
     const auto now = std::chrono::steady_clock::now();
     if (std::chrono::duration<double>(now - last_report).count() > 1.0) { report_progress(sh, false); last_report = now; }
   }
+  if (frame > 0) { Part end; end.chunk = chunk; end.n = 0; submit(std::move(end)); }
   for (auto& q : queues) { { std::lock_guard<std::mutex> l(q.m); q.closed = true; } q.cv.notify_all(); }
   for (auto& t : threads) t.join();
-  if (in.pipe) pclose(in.f); else fclose(in.f);
+  auto cleanup_packets = [&]() {
+    for (int64_t c = 0; c < sh.n_chunks; c++) unlink(chunk_file(sh, c).c_str());
+    if (o.temp.empty()) rmdir(sh.pkt_dir.c_str());
+  };
+  if (in.pipe) {
+    // a decoder that died looks like end of stream to the reader: its exit status is what tells a truncated job from a whole one
+    const int st = pclose(in.f);
+    if (!(st != -1 && WIFEXITED(st) && WEXITSTATUS(st) == 0)) {
+      cleanup_packets(); unlink(o.output.c_str());
+      die(3, "the ffmpeg decode pipe failed (status %d): the input was not read completely", st);
+    }
+  } else fclose(in.f);
   for (int lfd : lease) close(lfd);
   for (GroupBuf* gb : sh.free_bufs) delete gb;
   sh.free_bufs.clear();
   if (sh.total_frames < 0) sh.total_frames = frame;
 
   if (sh.failed) {
+    cleanup_packets();
     unlink(o.output.c_str());
     die(sh.failed, "encode failed: %s", sh.error.c_str());
   }
-  if (frame == 0) die(3, "input has no frames");
+  if (frame == 0) { cleanup_packets(); die(3, "input has no frames"); }
 
-  // ---- concatenate the chunk streams in order and write the container ----
-  std::vector<Packet> all;
-  for (auto& c : sh.chunk_out) for (auto& p : c) all.push_back(std::move(p));
-  if ((int64_t)all.size() != frame) { unlink(o.output.c_str()); die(5, "internal error: %zu packets for %lld frames", all.size(), (long long)frame); }
+  // ---- concatenate the chunk streams in order and write the container (streamed from the packet files) ----
+  PacketReader rd;
+  for (int64_t c = 0; c < sh.n_chunks; c++) rd.files.push_back(chunk_file(sh, c));
   const std::string tmp_out = o.output + ".part";
   bool ok;
+  int64_t written = 0;
   const size_t dot = o.output.rfind('.');
   const std::string ext = dot == std::string::npos ? "" : o.output.substr(dot);
-  if (ext == ".ivf") ok = write_ivf(tmp_out, all, in.w, in.h, in.fps_num, in.fps_den);
-  else if (ext == ".obu") ok = write_obu(tmp_out, all);
-  else ok = write_mkv(tmp_out, all, in.w, in.h, in.fps_num, in.fps_den, out_bits > 8);
+  if (ext == ".ivf") ok = write_ivf(tmp_out, rd, &written, in.w, in.h, in.fps_num, in.fps_den);
+  else if (ext == ".obu") ok = write_obu(tmp_out, rd, &written);
+  else ok = write_mkv(tmp_out, rd, &written, in.w, in.h, in.fps_num, in.fps_den, out_bits > 8);
+  cleanup_packets();
+  if (ok && written != frame) { unlink(tmp_out.c_str()); unlink(o.output.c_str()); die(5, "internal error: %lld packets for %lld frames", (long long)written, (long long)frame); }
   if (ok && in.pipe && ext != ".ivf" && ext != ".obu" && o.audio_params.find("copy") != std::string::npos) {
-    // the source went through ffmpeg, so ffmpeg is available: copy its audio streams next to our video
+    // the source went through ffmpeg, so ffmpeg is available: copy its audio streams next to our video.  The daemon asked
+    // for the audio (av1an.rs:97) and replaces the source with our output: a failed copy is a failed job, not a silent loss
     std::string qi, qo;
     for (char c : o.input) { if (c == '\'') qi += "'\\''"; else qi += c; }
     for (char c : tmp_out) { if (c == '\'') qo += "'\\''"; else qo += c; }
     const std::string mux = "ffmpeg -v error -y -i '" + qo + "' -i '" + qi + "' -map 0:v:0 -map 1:a? -c copy -f matroska '" + qo + ".mux'";
-    if (system(mux.c_str()) == 0) rename((tmp_out + ".mux").c_str(), tmp_out.c_str());
-    else unlink((tmp_out + ".mux").c_str());   // keep the video-only file
+    const int st = system(mux.c_str());
+    if (st != -1 && WIFEXITED(st) && WEXITSTATUS(st) == 0 && rename((tmp_out + ".mux").c_str(), tmp_out.c_str()) == 0) {
+    } else {
+      unlink((tmp_out + ".mux").c_str()); unlink(tmp_out.c_str()); unlink(o.output.c_str());
+      die(7, "copying the audio streams failed (ffmpeg status %d): no output written", st);
+    }
   }
   if (!ok || rename(tmp_out.c_str(), o.output.c_str()) != 0) { unlink(tmp_out.c_str()); die(6, "cannot write %s", o.output.c_str()); }
   report_progress(sh, true);

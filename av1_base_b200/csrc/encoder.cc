@@ -5,6 +5,7 @@
 // Boundary replaced: /root/reference/crates/daemon/src/encode/av1an.rs:126-139 (run_av1an).
 // There is no CPU fallback: without a CUDA device av1b_encoder_create fails with AV1B_ERR_NO_DEVICE.
 #include <cuda_runtime.h>
+#include <math.h>
 #include <stdio.h>
 #include <string.h>
 #include <algorithm>
@@ -115,6 +116,8 @@ struct Slot {
   int16_t* d_coef[3] = {nullptr, nullptr, nullptr};   // device side of the symbol streams (downloaded on the copy stream
   Av1bBlockInfo* d_blocks = nullptr;                  //  while the next batch is being encoded)
   uint8_t* d_cdef_idx = nullptr;
+  QualityAcc* d_quality = nullptr;                    // per frame: squared error / SSIM of the reconstruction (config.tune[3])
+  QualityAcc* h_quality = nullptr;
   Av1bLrUnit* d_lr_units = nullptr;                   // luma restoration units [batch][lr_n] (loop restoration on)
   Av1bLrUnit* h_lr_units = nullptr;
   // token path (inter frames): packed coefficient symbols, tokenizer scratch, token list + superblock offsets
@@ -179,6 +182,8 @@ struct av1b_encoder {
   int base_q_idx_nonref = 0;
   bool me_smooth = true;              // vector-field regularisation after the hierarchical search
   bool key_var_part = true;           // key frames: 64x64 / 32x32 blocks where the source is smooth
+  bool quality_on = false;            // config.tune[3]: PSNR / SSIM of every frame (progress events)
+  double q_sse = 0, q_ssim = 0, q_blocks = 0, q_frames = 0, q_psnr_sum = 0;
   int pipe_next = 0, pipe_done = 0;   // batches launched / finished since the encoder was created (slot = index mod n_slots)
   av1b_packet_cb last_cb = nullptr;   // of the last av1b_encode_stream call (packets still in flight belong to it)
   void* last_user = nullptr;
@@ -258,6 +263,7 @@ static void free_all(av1b_encoder* e) {
     cudaFreeHost(s.h_blocks); cudaFreeHost(s.h_cdef_idx);
     cudaFree(s.d_blocks); cudaFree(s.d_cdef_idx);
     cudaFree(s.d_lr_units); cudaFreeHost(s.h_lr_units);
+    cudaFree(s.d_quality); cudaFreeHost(s.h_quality);
     for (int p = 0; p < 3; p++) cudaFree(s.d_digest[p]);
     if (s.s_rc) cudaStreamDestroy(s.s_rc);
     cudaFree(s.d_rc_region); cudaFree(s.d_rc_len); cudaFree(s.d_rc_bytes); cudaFreeHost(s.h_rc_len); cudaFreeHost(s.h_rc_bytes);
@@ -563,6 +569,10 @@ static int launch(av1b_encoder* e, Slot& s, const Slot& in, int n, int64_t first
     CK(cudaEventRecord(ev[4], e->stream));
   }
   e->chunk_pos += n;
+  if (e->quality_on) {
+    CK(launch_quality(g, bd, e->d_fin[0] + e->plane_elems[0], in.d_src[0], e->plane_elems[0], s.d_quality, n, e->stream));
+    e->kernel_launches += 1;
+  }
   if (e->keep) {
     // debug mode keeps every reconstruction: download it before the ring is shifted
     for (int p = 0; p < 3; p++)
@@ -615,6 +625,10 @@ static int launch(av1b_encoder* e, Slot& s, const Slot& in, int n, int64_t first
   if (e->lr_on) {
     CK(cudaMemcpyAsync(s.h_lr_units, s.d_lr_units, e->lr_n * n * sizeof(Av1bLrUnit), cudaMemcpyDeviceToHost, e->s_out));
     e->d2h_bytes += (int64_t)(e->lr_n * n * sizeof(Av1bLrUnit));
+  }
+  if (e->quality_on) {
+    CK(cudaMemcpyAsync(s.h_quality, s.d_quality, sizeof(QualityAcc) * n, cudaMemcpyDeviceToHost, e->s_out));
+    e->d2h_bytes += (int64_t)(sizeof(QualityAcc) * n);
   }
   s.tok_fetched = 0;
   if (s.has_tokens) {
@@ -796,6 +810,15 @@ static int finish(av1b_encoder* e, Slot& s, bool staged, av1b_packet_cb out_cb, 
     if (out_cb && out_cb(user, tu.data(), tu.size(), s.first_index + b, s.is_key[b])) { set_error("packet callback aborted"); return AV1B_ERR_CALLBACK; }
   }
   e->frames_done += n;
+  if (e->quality_on)
+    for (int b = 0; b < n; b++) {
+      const QualityAcc& qa = s.h_quality[b];
+      const double px = (double)qa.blocks * 64, peak = (double)((1 << e->cfg.bit_depth) - 1);
+      if (px > 0) {
+        e->q_psnr_sum += qa.sse ? 10.0 * log10(peak * peak * px / (double)qa.sse) : 100.0;
+        e->q_ssim += qa.ssim_sum / qa.blocks; e->q_frames += 1;
+      }
+    }
   const auto tp1 = std::chrono::steady_clock::now();
   e->t_pack_ms += std::chrono::duration<double, std::milli>(tp1 - tp0).count();
   if (prog_cb) {
@@ -808,6 +831,7 @@ static int finish(av1b_encoder* e, Slot& s, bool staged, av1b_packet_cb out_cb, 
 static void reset_stats(av1b_encoder* e) {
   e->kept.clear();
   e->t_h2d_ms = e->t_kernel_ms = e->t_intra_ms = e->t_inter_ms = e->t_me_ms = e->t_d2h_ms = e->t_pack_ms = 0;
+  e->q_psnr_sum = e->q_ssim = e->q_frames = 0;
   e->t_deblock_ms = e->t_cdef_ms = e->t_tok_ms = 0; e->t_lr_ms = 0; e->t_rc_ms = 0; e->n_tokens = 0; e->d2h_bytes = 0; e->t_mctf_ms = 0; e->mctf_frames = 0;
   e->kernel_launches = e->intra_launches = e->inter_launches = e->frames_done = e->bytes_out = e->key_frames = e->staged_direct = 0;
 }
@@ -882,6 +906,7 @@ int av1b_encoder_create(const av1b_config* cfg, av1b_encoder** out) {
   e->q_nominal = e->base_q_idx;
   e->gop_auto = cfg->gop_period == 0 && cfg->reserved[3] == 0;
   e->mctf_cfg = cfg->tune[2] == 0 && cfg->reserved[3] == 0;
+  e->quality_on = cfg->tune[3] != 0;
   e->me_smooth = cfg->tune[0] == 0;
   e->key_var_part = cfg->tune[1] == 0 && cfg->reserved[1] == 0;
   e->blk_log2 = cfg->reserved[1] ? cfg->reserved[1] : 4;
@@ -937,6 +962,7 @@ int av1b_encoder_create(const av1b_config* cfg, av1b_encoder** out) {
     A(cudaMallocHost(&s.h_cdef_idx, nsb * F));
     A(cudaMalloc(&s.d_blocks, e->map_elems * F * sizeof(Av1bBlockInfo)));
     A(cudaMalloc(&s.d_cdef_idx, nsb * F));
+    if (cfg->tune[3]) { A(cudaMalloc(&s.d_quality, sizeof(QualityAcc) * F)); A(cudaMallocHost(&s.h_quality, sizeof(QualityAcc) * F)); }
     if (err == cudaSuccess) { A(cudaMemset(s.d_blocks, 0, e->map_elems * F * sizeof(Av1bBlockInfo))); A(cudaMemset(s.d_cdef_idx, 0, nsb * F)); }
     if (e->lr_on) { A(cudaMalloc(&s.d_lr_units, e->lr_n * F * sizeof(Av1bLrUnit))); A(cudaMallocHost(&s.h_lr_units, e->lr_n * F * sizeof(Av1bLrUnit))); }
     if (e->token_path && !e->intra_only) {
@@ -1322,6 +1348,15 @@ int av1b_get_inter_frame_params(av1b_encoder* e, Av1bFrameParams* fp) {
 int av1b_get_class_params(av1b_encoder* e, int kind, Av1bFrameParams* fp) {
   if (!e || !fp || kind < 0 || kind > 2) return AV1B_ERR_INVALID;
   *fp = kind_params(e, kind);
+  return AV1B_OK;
+}
+
+int av1b_get_quality(av1b_encoder* e, double* psnr_y, double* ssim_y, int64_t* frames) {
+  if (!e) return AV1B_ERR_INVALID;
+  if (!e->quality_on) { set_error("quality statistics are off (config.tune[3] = 1 switches them on)"); return AV1B_ERR_INVALID; }
+  if (psnr_y) *psnr_y = e->q_frames > 0 ? e->q_psnr_sum / e->q_frames : 0.0;
+  if (ssim_y) *ssim_y = e->q_frames > 0 ? e->q_ssim / e->q_frames : 0.0;
+  if (frames) *frames = (int64_t)e->q_frames;
   return AV1B_OK;
 }
 

@@ -188,6 +188,11 @@ cudaError_t launch_scan_u32(uint32_t* v, int n, cudaStream_t s);
 cudaError_t launch_tok_count(const TokLaunch& p, cudaStream_t s);
 cudaError_t launch_tok_emit(const TokLaunch& p, cudaStream_t s);
 
+// Luma squared error and SSIM (8x8 windows) of n_frames reconstructions against their sources (quality_kernel.cu): reporting only.
+struct QualityAcc { unsigned long long sse; float ssim_sum; uint32_t blocks; };
+cudaError_t launch_quality(const Av1bGeom& g, int bit_depth, const uint16_t* rec_y, const uint16_t* src_y, size_t plane_elems,
+                           QualityAcc* out, int n_frames, cudaStream_t s);
+
 cudaError_t launch_deblock(const DeblockLaunch& p, int n_frames, cudaStream_t s);
 cudaError_t launch_cdef(const CdefLaunch& p, int n_frames, cudaStream_t s);
 cudaError_t launch_lr(const LrLaunch& p, int n_frames, cudaStream_t s);

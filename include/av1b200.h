@@ -55,7 +55,7 @@ typedef struct av1b_config {
                                      (noise estimate of the chunk's first picture against the quantiser step) */
   int32_t tune[7];                /* [0]: 1 = vector-field regularisation of the motion search off; [1]: 1 = fixed 16x16 key-frame
                                      partition (default: 64x64 / 32x32 blocks where the source is smooth); [2]: 1 = temporal filter of
-                                     key / anchor source pictures off */
+                                     key / anchor source pictures off; [3]: 1 = PSNR / SSIM of every frame on the device (av1b_get_quality) */
   int32_t reserved[8];            /* [0]: keep recon+symbols per frame (tests); [1]: fixed block log2 (3..6), 0 = default;
                                      [2]: 1 = in-loop filters off; [3]: 1 = every frame is a key frame;
                                      [4]: inter transform-block drop threshold (0 = off);
@@ -126,6 +126,9 @@ struct Av1bFrameParams;
 /* frame-level parameters the encoder signals for key frames (deblock levels, CDEF presets, ...) */
 int av1b_get_frame_params(av1b_encoder* enc, struct Av1bFrameParams* fp);
 int av1b_get_inter_frame_params(av1b_encoder* enc, struct Av1bFrameParams* fp);
+/* config.tune[3] = 1: mean luma PSNR (dB) and SSIM (non-overlapping 8x8 windows) of the frames coded since the last chunk
+ * start, reconstruction against the source as handed in (JobMetrics.psnr / .ssim, metrics.rs:12-30) */
+int av1b_get_quality(av1b_encoder* enc, double* psnr_y, double* ssim_y, int64_t* frames);
 /* structure of the chunk coded last: info[0..7] = gop_period in force, quantiser index of key / anchor / non-reference frames,
  * temporal filter on, noise estimate of the chunk's first picture, quantiser index of the CRF, structure chosen automatically */
 int av1b_get_chunk_info(av1b_encoder* enc, int32_t info[8]);

@@ -146,3 +146,78 @@ def test_cli_splits_chunks_at_scene_cuts(tmp_path):
     assert r.returncode == 0, r.stderr
     assert open(out2, "rb").read() == b"".join(enc.encode_chunk(frames))
     enc.close()
+
+
+@pytest.mark.gpu
+def test_cli_progress_fields(tmp_path):
+    """f-1: progress.json carries the JobMetrics fields the reference leaves at zero (metrics.rs:12-30, job_executor.rs:117-137)."""
+    import json
+    from av1_base_b200 import synth
+    w, h, bd, n = 200, 136, 10, 10
+    frames = synth.synth_clip(w, h, bd, n, seed=5, scene_len=100)
+    y4m = str(tmp_path / "in.y4m")
+    write_y4m(y4m, frames, bd)
+    out, tmp = str(tmp_path / "o.mkv"), str(tmp_path / "t")
+    r = subprocess.run([CLI, "-i", y4m, "-o", out, "--video-params", "--crf 30 --keyint 5", "--temp", tmp], capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+    pr = json.load(open(os.path.join(tmp, "progress.json")))
+    assert pr["done"] is True and pr["frames_encoded"] == n and pr["total_frames"] == n and pr["progress"] == 1.0
+    size_kbps = os.path.getsize(out) * 8 / 1000 * 30 / n
+    assert 0.8 * size_kbps < pr["bitrate_kbps"] <= size_kbps           # payload of the packets; the file adds the container
+    assert 30 < pr["psnr"] < 70 and 0.8 < pr["ssim"] <= 1.0 and pr["est_remaining_secs"] == 0
+    # the chunks' packet files are gone, only progress.json stays under --temp
+    assert sorted(os.listdir(tmp)) == ["progress.json"]
+    # the same numbers from a decode of the stream
+    from oracle import decoders as D
+    _, _, blocks = mkv_blocks(open(out, "rb").read())
+    dec = D.dav1d_decode([b"\x12\x00" + b for b in blocks])
+    ps = [10 * np.log10(1023.0 ** 2 / np.mean((dec[i][0].astype(np.float64) - frames[i][0]) ** 2)) for i in range(n)]
+    assert abs(np.mean(ps) - pr["psnr"]) < 0.01
+
+
+def _fake_ffmpeg(dirpath, body):
+    p = os.path.join(dirpath, "ffmpeg")
+    open(p, "w").write("#!/bin/bash\n[ \"$1\" = \"-version\" ] && exit 0\n" + body)
+    os.chmod(p, 0o755)
+    return dict(os.environ, PATH=dirpath + ":" + os.environ["PATH"])
+
+
+@pytest.mark.gpu
+def test_cli_failed_decoder_or_audio_copy_is_a_failed_job(tmp_path):
+    """A decode pipe that dies mid-stream or an audio copy that fails must not leave a file at -o
+    (the daemon replaces the source with whatever it finds there: replacer.rs / size_gate.rs)."""
+    from av1_base_b200 import synth
+    w, h, bd, n = 200, 136, 8, 4
+    frames = synth.synth_clip(w, h, bd, n, seed=3, scene_len=100)
+    y4m = str(tmp_path / "src.y4m")
+    write_y4m(y4m, frames, bd)
+    src = str(tmp_path / "in.mp4")                      # not Y4M: goes through "ffmpeg"
+    open(src, "wb").write(b"not a real mp4")
+    out = str(tmp_path / "o.mkv")
+    bindir = str(tmp_path / "bin"); os.mkdir(bindir)
+    # 1. decoder delivers whole frames, then dies with a non-zero status
+    env = _fake_ffmpeg(bindir, 'cat "%s"; exit 1\n' % y4m)
+    r = subprocess.run([CLI, "-i", src, "-o", out, "--quiet"], capture_output=True, text=True, env=env)
+    assert r.returncode != 0 and not os.path.exists(out) and not os.path.exists(out + ".part"), r.stderr
+    # 2. decoder fine, audio mux (the call that has two -i) fails
+    env = _fake_ffmpeg(bindir, 'n=0; for a in "$@"; do [ "$a" = "-i" ] && n=$((n+1)); done\n'
+                               'if [ $n -ge 2 ]; then exit 1; fi\ncat "%s"\n' % y4m)
+    r = subprocess.run([CLI, "-i", src, "-o", out, "--quiet", "--audio-params", "-c:a copy"], capture_output=True, text=True, env=env)
+    assert r.returncode != 0 and not os.path.exists(out) and not os.path.exists(out + ".part"), r.stderr
+    # 3. both fine (the mux "copies" the video-only file): success
+    env = _fake_ffmpeg(bindir, 'n=0; for a in "$@"; do [ "$a" = "-i" ] && n=$((n+1)); last="$a"; done\n'
+                               'if [ $n -ge 2 ]; then cp "$5" "$last"; exit 0; fi\ncat "%s"\n' % y4m)
+    r = subprocess.run([CLI, "-i", src, "-o", out, "--quiet", "--audio-params", "-c:a copy"], capture_output=True, text=True, env=env)
+    assert r.returncode == 0 and os.path.getsize(out) > 0, r.stderr
+
+
+@pytest.mark.gpu
+def test_cli_rejects_y4m_with_frame_parameters(tmp_path):
+    bad = str(tmp_path / "p.y4m")
+    with open(bad, "wb") as f:
+        f.write(b"YUV4MPEG2 W64 H64 F30:1 C420jpeg\n")
+        for _ in range(2):
+            f.write(b"FRAME Ip\n" + b"\x80" * (64 * 64 * 3 // 2))
+    out = str(tmp_path / "o.obu")
+    r = subprocess.run([CLI, "-i", bad, "-o", out, "--quiet"], capture_output=True, text=True)
+    assert r.returncode != 0 and not os.path.exists(out)
