@@ -180,7 +180,7 @@ struct av1b_encoder {
   Av1bFrameParams fp_nonref;          // the frames between two anchors (refresh_frame_flags = 0)
   int gop_period = 4;                 // every gop_period-th frame after a key frame is an anchor (1: plain P chain)
   int base_q_idx_nonref = 0;
-  bool me_smooth = true;              // vector-field regularisation after the hierarchical search
+  bool me_smooth = true;              // superblock-level rate-distortion regularisation of the vector field after the search
   bool key_var_part = true;           // key frames: 64x64 / 32x32 blocks where the source is smooth
   bool quality_on = false;            // config.tune[3]: PSNR / SSIM of every frame (progress events)
   double q_sse = 0, q_ssim = 0, q_blocks = 0, q_frames = 0, q_psnr_sum = 0;
@@ -397,13 +397,13 @@ static int launch(av1b_encoder* e, Slot& s, const Slot& in, int n, int64_t first
     H.width = g.width; H.height = g.height; H.stride0 = g.stride[0]; H.elems0 = e0;
     for (int l = 0; l < 3; l++) { H.ref[l] = e->d_pyr[l]; H.cur[l] = e->d_pyr[l]; }
     H.lambda = acq0 >> 1;   // vector-deviation cost in SAD units (tuned on the oracle: about half the AC quantiser step)
-    H.lam_s = e->me_smooth ? H.lambda : 0; H.smooth_iters = 2; H.mv_tmp = e->d_mv_tmp; H.hist = e->d_hist;
+    H.lam_s = e->me_smooth ? H.lambda : 0; H.lam_r = H.lambda >> 2; H.sbrd_passes = 2; H.mv_tmp = e->d_mv_tmp; H.hist = e->d_hist;
     if (any_inter) {
       for (int b = 0; b < n; b++) { H.cur_slot[b] = (uint8_t)(kSlotFrame0 + b); H.ref_slot[b] = (uint8_t)(ref_of[b] == 0 ? kSlotCarried : kSlotFrame0 + ref_of[b] - 1); }
       H.mv2 = e->d_mv2; H.mv_out = e->d_mvs;
       CK(launch_hme(H, n, e->stream));
       e->kernel_launches += 2;
-      if (H.lam_s > 0) { CK(launch_hme_smooth(H, n, e->stream)); e->kernel_launches += 3 * H.smooth_iters; }
+      if (H.lam_s > 0) { CK(launch_hme_sbrd(H, n, e->stream)); e->kernel_launches += 2 + 2 * H.sbrd_passes; }
     }
     // ---- temporal filter of the key / anchor sources: searches of the picture against its neighbours in time, then
     //      one filter launch per picture ----
@@ -1058,7 +1058,7 @@ int av1b_encoder_create(const av1b_config* cfg, av1b_encoder** out) {
     A(cudaMalloc(&e->d_mvs, e->map_elems * F * 4));
     {
       const size_t n1 = (size_t)((cfg->width + 15) / 16) * ((cfg->height + 15) / 16);
-      A(cudaMalloc(&e->d_mv_tmp, n1 * kMaxSearches * 4 * 2));
+      A(cudaMalloc(&e->d_mv_tmp, n1 * kMaxSearches * 4));
       A(cudaMalloc(&e->d_hist, (size_t)kMaxSearches * 2049 * sizeof(uint32_t)));
     }
     if (err == cudaSuccess) A(cudaMemset(e->d_mvs, 0, e->map_elems * F * 4));

@@ -285,11 +285,11 @@ int av1b_k_pyramid(int device, int width, int height, int n_frames, const uint16
 
 int av1b_k_hme(int device, int width, int height, int n_frames, const uint16_t* cur_l0, const uint16_t* ref_l0,
                int lambda, int16_t* mv_out, int reps, double* ms_per_launch) {
-  return av1b_k_hme_smooth(device, width, height, n_frames, cur_l0, ref_l0, lambda, 0, 0, mv_out, reps, ms_per_launch);
+  return av1b_k_hme_sbrd(device, width, height, n_frames, cur_l0, ref_l0, lambda, 0, 0, 0, mv_out, reps, ms_per_launch);
 }
 
-int av1b_k_hme_smooth(int device, int width, int height, int n_frames, const uint16_t* cur_l0, const uint16_t* ref_l0,
-                      int lambda, int lam_s, int iters, int16_t* mv_out, int reps, double* ms_per_launch) {
+int av1b_k_hme_sbrd(int device, int width, int height, int n_frames, const uint16_t* cur_l0, const uint16_t* ref_l0,
+                    int lambda, int lam_s, int lam_r, int passes, int16_t* mv_out, int reps, double* ms_per_launch) {
   if (n_frames > kMaxSearches) { set_error("at most %d frames per call", kMaxSearches); return AV1B_ERR_INVALID; }
   if (!cur_l0 || !ref_l0 || !mv_out || n_frames <= 0) { set_error("bad argument"); return AV1B_ERR_INVALID; }
   Av1bGeom g;
@@ -314,11 +314,11 @@ int av1b_k_hme_smooth(int device, int width, int height, int n_frames, const uin
   for (int f = 0; f < n_frames; f++) { L.cur_slot[f] = (uint8_t)f; L.ref_slot[f] = (uint8_t)f; }
   DevBuf tmp, hist;
   const size_t n1 = (size_t)((width + 15) / 16) * ((height + 15) / 16);
-  CKS(tmp.alloc(n1 * n_frames * 4 * 2)); CKS(hist.alloc((size_t)n_frames * 2049 * 4));
-  L.lam_s = lam_s; L.smooth_iters = iters; L.mv_tmp = tmp.as<int16_t>(); L.hist = hist.as<uint32_t>();
+  CKS(tmp.alloc(n1 * n_frames * 4)); CKS(hist.alloc((size_t)n_frames * 2049 * 4));
+  L.lam_s = lam_s; L.lam_r = lam_r; L.sbrd_passes = passes; L.mv_tmp = tmp.as<int16_t>(); L.hist = hist.as<uint32_t>();
   if ((rc = timed(t, reps, ms_per_launch, [&]() {
          cudaError_t e = launch_hme(L, n_frames, t.s);
-         return e != cudaSuccess ? e : launch_hme_smooth(L, n_frames, t.s);
+         return e != cudaSuccess ? e : launch_hme_sbrd(L, n_frames, t.s);
        }))) return rc;
   CKS(cudaMemcpyAsync(mv_out, mo.p, (size_t)g.w8 * g.h8 * n_frames * 4, cudaMemcpyDeviceToHost, t.s));
   CKS(cudaStreamSynchronize(t.s));

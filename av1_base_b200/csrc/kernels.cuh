@@ -88,16 +88,16 @@ struct HmeLaunch {
   int16_t* mv2;
   int16_t* mv_out;
   uint8_t cur_slot[kMaxSearches], ref_slot[kMaxSearches];
-  // vector-field regularisation (hme_smooth kernels): lam_s per differing neighbour, 0 = off
-  int32_t lam_s, smooth_iters;
-  int16_t* mv_tmp;            // scratch [n][n1y*n1x][2] x 2 (double buffer of the 16x16 block vectors)
+  // vector-field regularisation (hme_sbrd kernels): lam_s per differing neighbour (0 = off), lam_r per bit of vector rate
+  int32_t lam_s, lam_r, sbrd_passes;
+  int16_t* mv_tmp;            // scratch [n][n1y*n1x][2]: the 16x16 block vectors
   uint32_t* hist;             // scratch [n][2][1024]: counts, largest key per bin
 };
 cudaError_t launch_pyramid(const uint16_t* l0, uint16_t* l1, uint16_t* l2, int stride0, int rows0, size_t elems0,
                            int n_frames, cudaStream_t s);
 cudaError_t launch_hme(const HmeLaunch& p, int n_frames, cudaStream_t s);
-// relaxation sweeps over the vectors launch_hme left in mv_out (hist: [n * 2048 + n] words, mv_tmp: [2][n][n1][2])
-cudaError_t launch_hme_smooth(const HmeLaunch& p, int n, cudaStream_t s);
+// superblock-level rate-distortion sweeps over the vectors launch_hme left in mv_out (hist: [n * 2048 + n] words, mv_tmp: [n][n1][2])
+cudaError_t launch_hme_sbrd(const HmeLaunch& p, int n, cudaStream_t s);
 
 // Motion-compensated temporal filter of one key / anchor source picture (mctf_kernel.cu): weighted mean of the picture and
 // up to kMaxNb neighbours in time, each compensated with mvs[k] (the picture searched against neighbour k).

@@ -320,12 +320,10 @@ __global__ void __launch_bounds__(256) hme_refine_kernel(const HmeLaunch P) {
 }
 
 // ---------------------------------------------------------------------------------------------
-// Vector-field regularisation (oracle: orc_mv_dominant, orc_me_smooth).
+// Vector-field regularisation (oracle: orc_mv_dominant, orc_me_sbrd).
 //   hme_gather_kernel : 16x16 block vectors out of the per-8x8 vector plane + histogram of the field (1024 hashed
 //                       bins: count, largest packed vector) for the dominant vector.
-//   hme_smooth_kernel : one relaxation sweep.  One warp per 16x16 block: the block and the 17x17 window of the
-//                       reference SOURCE picture at each candidate are staged in shared memory, SAD on the bilinear
-//                       quarter-sample interpolation, cost = SAD + lam_s * (neighbours with another vector).
+//   hme_sbrd_kernel   : one half sweep of the superblock-level rate-distortion regularisation (below).
 __device__ __forceinline__ uint32_t mv_pack(int mvy, int mvx) { return ((uint32_t)(uint16_t)(int16_t)mvy << 16) | (uint16_t)(int16_t)mvx; }
 __device__ __forceinline__ uint32_t mv_hash(uint32_t k) { return ((k * 2654435761u) >> 22) & 1023u; }
 
@@ -372,114 +370,215 @@ __global__ void __launch_bounds__(1024) hme_dominant_kernel(const HmeLaunch P, u
   hist[t] = 0; hist[1024 + t] = 0;
 }
 
-struct SmoothSmem {
-  uint16_t cur[8][16 * 16];
-  uint16_t win[8][17 * 18];
+// Superblock-level rate-distortion regularisation (oracle: orc_me_sbrd).  One CTA of 16 warps per 64x64 superblock of
+// the checkerboard colour of this half sweep; warp w owns the 16x16 block (w >> 2, w & 3).  For every candidate vector the
+// CTA stages the 65x65 window of the reference SOURCE picture the superblock points at (aligned 32-bit words, 68-sample
+// row pitch, the odd start handled when the words are read), lane (i, h) of a warp computes the bilinear quarter-sample
+// SAD of 8 samples of row i of its block and the warp adds them up: T[candidate][block].  Warp 0 then takes the
+// decisions with one lane per candidate: relaxation of the blocks in raster order, the 64x64 merge test, the 32x32 tests.
+// Superblocks of one colour share no edge, so the field is updated in place.
+constexpr int kSbCand = 22;
+constexpr int kWinPitch = 68;   // samples (34 words)
+struct SbrdSmem {
+  uint32_t win[65 * kWinPitch / 2];
+  int T[kSbCand][16];
+  uint32_t cand[kSbCand];
+  uint32_t loc[6][6];        // vectors of the superblock's blocks and the blocks around it ([r + 1][c + 1]); 0xFFFFFFFF outside
+  uint8_t have[6][6];        // that block lies inside the picture
+  int li[16];                // candidate index of the vector a block holds
+  int ncand;
 };
 
-__global__ void __launch_bounds__(256) hme_smooth_kernel(const HmeLaunch P, const int16_t* __restrict__ vin, int16_t* vout,
-                                                         const uint32_t* __restrict__ dom, int16_t* field8) {
-  __shared__ SmoothSmem sm;
+__device__ __forceinline__ uint32_t hw(const uint32_t* w, int i) { return (i & 1) ? (w[i >> 1] >> 16) : (w[i >> 1] & 0xFFFFu); }
+
+__global__ void __launch_bounds__(512) hme_sbrd_kernel(const HmeLaunch P, uint32_t* field16, const uint32_t* __restrict__ dom,
+                                                       int colour, int16_t* field8) {
+  __shared__ SbrdSmem sm;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int frame = blockIdx.z;
-  const int n1x = (P.width + 15) / 16, n1y = (P.height + 15) / 16, n1 = n1x * n1y;
-  const int blk = blockIdx.x * 8 + warp;
-  if (blk >= n1) return;
-  const int bx = blk % n1x, by = blk / n1x;
   const int W = P.width, H = P.height;
+  const int n1x = (W + 15) / 16, n1y = (H + 15) / 16, n1 = n1x * n1y;
+  const int nsx = (n1x + 3) / 4;
+  const int sby = blockIdx.y, sbx = 2 * blockIdx.x + ((sby + colour) & 1);
+  if (sbx >= nsx) return;
+  const int y0 = sby * 4, x0 = sbx * 4, nr = min(4, n1y - y0), nc = min(4, n1x - x0);
+  uint32_t* F = field16 + (size_t)frame * n1;
   const uint16_t* cur0 = P.cur[0] + (size_t)P.cur_slot[frame] * P.elems0;
   const uint16_t* ref0 = P.ref[0] + (size_t)P.ref_slot[frame] * P.elems0;
-  const int16_t* v = vin + (size_t)frame * n1 * 2;
-  for (int o = lane; o < 256; o += 32)
-    sm.cur[warp][o] = cur0[(size_t)clampi(by * 16 + (o >> 4), 0, H - 1) * P.stride0 + clampi(bx * 16 + (o & 15), 0, W - 1)];
-  int cy[7], cx[7];
-  bool have[4];
-  cy[0] = v[blk * 2]; cx[0] = v[blk * 2 + 1];
-  {
-    const int nby[4] = {0, 0, -1, 1}, nbx[4] = {-1, 1, 0, 0};
-#pragma unroll
-    for (int k = 0; k < 4; k++) {
-      const int yy = by + nby[k], xx = bx + nbx[k];
-      have[k] = yy >= 0 && yy < n1y && xx >= 0 && xx < n1x;
-      const int o = have[k] ? yy * n1x + xx : blk;
-      cy[1 + k] = v[o * 2]; cx[1 + k] = v[o * 2 + 1];
-    }
+  // ---- the field around the superblock, the candidate list ----
+  if (tid < 36) {
+    const int r = tid / 6 - 1, c = tid % 6 - 1;
+    const int by = y0 + r, bx = x0 + c;
+    const bool in = by >= 0 && by < n1y && bx >= 0 && bx < n1x && r <= nr && c <= nc;
+    sm.loc[r + 1][c + 1] = in ? F[by * n1x + bx] : 0xFFFFFFFFu;
+    sm.have[r + 1][c + 1] = in ? 1 : 0;
   }
-  cy[5] = 0; cx[5] = 0;
-  {
-    const uint32_t d = dom[frame];
-    cy[6] = (int16_t)(d >> 16); cx[6] = (int16_t)(d & 0xFFFF);
-  }
-  int best_cost = 0, best_k = -1;
-#pragma unroll 1
-  for (int k = 0; k < 7; k++) {
-    bool dup = false;
-    for (int j = 0; j < k; j++) dup = dup || (cy[j] == cy[k] && cx[j] == cx[k]);
-    if (dup) continue;   // warp-uniform
-    int diff = 0;
-#pragma unroll
-    for (int j = 0; j < 4; j++) diff += have[j] && (cy[1 + j] != cy[k] || cx[1 + j] != cx[k]);
-    const int ix = cx[k] >> 3, iy = cy[k] >> 3, fx = (cx[k] & 7) >> 1, fy = (cy[k] & 7) >> 1;
-    __syncwarp();
-    for (int o = lane; o < 17 * 17; o += 32) {
-      const int r = o / 17, c = o % 17;
-      sm.win[warp][r * 18 + c] = ref0[(size_t)clampi(by * 16 + iy + r, 0, H - 1) * P.stride0 + clampi(bx * 16 + ix + c, 0, W - 1)];
+  __syncthreads();
+  if (warp == 0) {
+    // entry i of the ordered list: zero, dominant, left, above, right, below, own vectors in raster order
+    uint32_t k = 0; bool valid = false;
+    if (lane == 0) { k = 0; valid = true; }
+    else if (lane == 1) { const uint32_t d = dom[frame]; k = (d >> 16) | (d << 16); valid = true; }   // mv_pack -> (col << 16) | row
+    else if (lane == 2) { valid = x0 > 0; k = sm.loc[1][0]; }
+    else if (lane == 3) { valid = y0 > 0; k = sm.loc[0][1]; }
+    else if (lane == 4) { valid = x0 + nc < n1x; k = sm.loc[1][nc + 1]; }
+    else if (lane == 5) { valid = y0 + nr < n1y; k = sm.loc[nr + 1][1]; }
+    else if (lane < 22) { const int b = lane - 6, r = b >> 2, c = b & 3; valid = r < nr && c < nc; k = sm.loc[r + 1][c + 1]; }
+    bool first = valid;
+    for (int j = 0; j < 21; j++) {
+      const uint32_t kj = __shfl_sync(0xffffffffu, k, j);
+      const bool vj = __shfl_sync(0xffffffffu, (int)valid, j) != 0;
+      if (j < lane && vj && kj == k) first = false;
     }
-    __syncwarp();
-    // lane (r, h): row r, columns 8h .. 8h+7
-    const int r = lane >> 1, c0 = (lane & 1) * 8;
-    const uint16_t* wr = &sm.win[warp][r * 18 + c0];
-    const uint16_t* cr = &sm.cur[warp][r * 16 + c0];
-    unsigned sad = 0;
-    if ((fx | fy) == 0) {
-#pragma unroll
-      for (int j = 0; j < 8; j++) sad = __usad((unsigned)cr[j], (unsigned)wr[j], sad);
+    const unsigned m = __ballot_sync(0xffffffffu, first);
+    if (first) sm.cand[__popc(m & ((1u << lane) - 1))] = k;
+    if (lane == 0) sm.ncand = __popc(m);
+  }
+  // ---- this lane's 8 samples of its block row (clamped at the picture edge) ----
+  const int br = warp >> 2, bc = warp & 3, li = lane >> 1, lh = lane & 1;
+  const bool blk_on = br < nr && bc < nc;
+  unsigned c8[8];
+  {
+    const int y = (y0 + br) * 16 + li, x = (x0 + bc) * 16 + 8 * lh;
+    if (blk_on && y < H && x + 8 <= W) {
+      const uint4 v = *reinterpret_cast<const uint4*>(cur0 + (size_t)y * P.stride0 + x);
+      c8[0] = v.x & 0xFFFFu; c8[1] = v.x >> 16; c8[2] = v.y & 0xFFFFu; c8[3] = v.y >> 16;
+      c8[4] = v.z & 0xFFFFu; c8[5] = v.z >> 16; c8[6] = v.w & 0xFFFFu; c8[7] = v.w >> 16;
     } else {
-      const int w00 = (4 - fx) * (4 - fy), w01 = fx * (4 - fy), w10 = (4 - fx) * fy, w11 = fx * fy;
 #pragma unroll
-      for (int j = 0; j < 8; j++) {
-        const unsigned p = (unsigned)(w00 * wr[j] + w01 * wr[j + 1] + w10 * wr[18 + j] + w11 * wr[18 + j + 1] + 8) >> 4;
-        sad = __usad((unsigned)cr[j], p, sad);
+      for (int j = 0; j < 8; j++) c8[j] = blk_on ? cur0[(size_t)clampi(y, 0, H - 1) * P.stride0 + clampi(x + j, 0, W - 1)] : 0;
+    }
+  }
+  __syncthreads();
+  const int ncand = sm.ncand;
+  for (int k = 0; k < ncand; k++) {
+    const uint32_t cv = sm.cand[k];
+    const int mvy = (int16_t)(cv & 0xFFFFu), mvx = (int16_t)(cv >> 16);
+    const int ix = mvx >> 3, iy = mvy >> 3, fx = (mvx & 7) >> 1, fy = (mvy & 7) >> 1;
+    const int wy = y0 * 16 + iy, wx = x0 * 16 + ix;        // window origin in the picture
+    const int wxa = wx & ~1, xo = wx & 1;                  // first staged column (even), offset of the window in the row
+    __syncthreads();                                       // the window of the candidate before has been read
+    if (wy >= 0 && wy + 65 <= H && wxa >= 0 && wx + 65 <= W && wxa + kWinPitch <= P.stride0) {
+      const uint32_t* base = reinterpret_cast<const uint32_t*>(ref0 + (size_t)wy * P.stride0 + wxa);
+      for (int o = tid; o < 65 * (kWinPitch / 2); o += 512) {
+        const int r = o / (kWinPitch / 2), c = o - r * (kWinPitch / 2);
+        sm.win[o] = base[(size_t)r * (P.stride0 >> 1) + c];
+      }
+    } else {
+      for (int o = tid; o < 65 * (kWinPitch / 2); o += 512) {
+        const int r = o / (kWinPitch / 2), c = o - r * (kWinPitch / 2);
+        const uint16_t* row = ref0 + (size_t)clampi(wy + r, 0, H - 1) * P.stride0;
+        sm.win[o] = (uint32_t)row[clampi(wxa + 2 * c, 0, W - 1)] | ((uint32_t)row[clampi(wxa + 2 * c + 1, 0, W - 1)] << 16);
       }
     }
-    for (int o = 16; o; o >>= 1) sad += __shfl_xor_sync(0xffffffffu, sad, o);
-    const int cost = (int)sad + P.lam_s * diff;
-    if (best_k < 0 || cost < best_cost) { best_cost = cost; best_k = k; }
-  }
-  int oy = cy[0], ox = cx[0];
+    __syncthreads();
+    if (blk_on) {
+      const int w00 = (4 - fx) * (4 - fy), w01 = fx * (4 - fy), w10 = (4 - fx) * fy, w11 = fx * fy;
+      const uint32_t* r0 = &sm.win[(br * 16 + li) * (kWinPitch / 2) + bc * 8 + 4 * lh];
+      uint32_t a[5], b[5];
 #pragma unroll
-  for (int k = 1; k < 7; k++) if (k == best_k) { oy = cy[k]; ox = cx[k]; }
-  if (lane == 0) {
-    vout[((size_t)frame * n1 + blk) * 2] = (int16_t)oy;
-    vout[((size_t)frame * n1 + blk) * 2 + 1] = (int16_t)ox;
+      for (int j = 0; j < 5; j++) { a[j] = r0[j]; b[j] = r0[kWinPitch / 2 + j]; }
+      unsigned sad = 0;
+      if (xo == 0) {
+#pragma unroll
+        for (int j = 0; j < 8; j++) {
+          const unsigned p = (unsigned)(w00 * (int)hw(a, j) + w01 * (int)hw(a, j + 1) + w10 * (int)hw(b, j) + w11 * (int)hw(b, j + 1) + 8) >> 4;
+          sad = __usad(c8[j], p, sad);
+        }
+      } else {
+#pragma unroll
+        for (int j = 0; j < 8; j++) {
+          const unsigned p = (unsigned)(w00 * (int)hw(a, j + 1) + w01 * (int)hw(a, j + 2) + w10 * (int)hw(b, j + 1) + w11 * (int)hw(b, j + 2) + 8) >> 4;
+          sad = __usad(c8[j], p, sad);
+        }
+      }
+      sad = __reduce_add_sync(0xffffffffu, sad);
+      if (lane == 0) sm.T[k][warp] = (int)sad;
+    }
   }
-  if (field8 && lane < 4) {
-    const int uy = by * 2 + (lane >> 1), ux = bx * 2 + (lane & 1);
-    const int w8 = P.width >> 3, h8 = P.height >> 3;
-    if (uy < h8 && ux < w8) {
-      int16_t* out = field8 + ((size_t)frame * w8 * h8 + (size_t)uy * w8 + ux) * 2;
-      out[0] = (int16_t)oy; out[1] = (int16_t)ox;
+  __syncthreads();
+  if (warp != 0) return;
+  // ---- decisions: lane = candidate ----
+  const uint32_t myc = lane < ncand ? sm.cand[lane] : 0;
+  const unsigned kInf = 0xFFFFFFFFu;
+  for (int b = 0; b < 16; b++) {
+    const int r = b >> 2, c = b & 3;
+    if (r >= nr || c >= nc) continue;
+    unsigned key = kInf;
+    if (lane < ncand) {
+      const int diff = (sm.have[r + 1][c] && sm.loc[r + 1][c] != myc) + (sm.have[r + 1][c + 2] && sm.loc[r + 1][c + 2] != myc) +
+                       (sm.have[r][c + 1] && sm.loc[r][c + 1] != myc) + (sm.have[r + 2][c + 1] && sm.loc[r + 2][c + 1] != myc);
+      key = ((unsigned)(sm.T[lane][b] + P.lam_s * diff) << 5) | (unsigned)lane;
+    }
+    key = __reduce_min_sync(0xffffffffu, key);
+    const int bk = key & 31;
+    __syncwarp();
+    if (lane == 0) { sm.loc[r + 1][c + 1] = sm.cand[bk]; sm.li[b] = bk; }
+    __syncwarp();
+  }
+  auto test = [&](int r0, int c0, int r1, int c1) -> bool {
+    // the field as it stands: lane = block
+    int jc = 0;
+    {
+      const int r = lane >> 2, c = lane & 3;
+      if (lane < 16 && r >= r0 && r < r1 && c >= c0 && c < c1) {
+        const uint32_t k = sm.loc[r + 1][c + 1];
+        const bool same = (sm.have[r + 1][c] && sm.loc[r + 1][c] == k) || (sm.have[r][c + 1] && sm.loc[r][c + 1] == k);
+        jc = sm.T[sm.li[lane]][lane] + P.lam_r * (same ? 1 : 12);
+      }
+    }
+    jc = (int)__reduce_add_sync(0xffffffffu, (unsigned)jc);
+    unsigned key = kInf;
+    if (lane < ncand) {
+      const bool nb = myc == 0 || (sm.have[r0 + 1][c0] && sm.loc[r0 + 1][c0] == myc) || (sm.have[r0][c0 + 1] && sm.loc[r0][c0 + 1] == myc);
+      int j = P.lam_r * (nb ? 1 : 12);
+      for (int r = r0; r < r1; r++) for (int c = c0; c < c1; c++) j += sm.T[lane][r * 4 + c];
+      key = ((unsigned)j << 5) | (unsigned)lane;
+    }
+    key = __reduce_min_sync(0xffffffffu, key);
+    const bool take = (int)(key >> 5) < jc;
+    __syncwarp();
+    if (take) {
+      const int r = lane >> 2, c = lane & 3;
+      if (lane < 16 && r >= r0 && r < r1 && c >= c0 && c < c1) { sm.loc[r + 1][c + 1] = sm.cand[key & 31]; sm.li[lane] = key & 31; }
+    }
+    __syncwarp();
+    return take;
+  };
+  if (!test(0, 0, nr, nc))
+    for (int qr = 0; qr < nr; qr += 2)
+      for (int qc = 0; qc < nc; qc += 2) test(qr, qc, min(qr + 2, nr), min(qc + 2, nc));
+  if (lane < 16) {
+    const int r = lane >> 2, c = lane & 3;
+    if (r < nr && c < nc) {
+      const uint32_t k = sm.loc[r + 1][c + 1];
+      F[(y0 + r) * n1x + x0 + c] = k;
+      if (field8) {
+        const int w8 = W >> 3, h8 = H >> 3;
+        for (int u = 0; u < 4; u++) {
+          const int uy = (y0 + r) * 2 + (u >> 1), ux = (x0 + c) * 2 + (u & 1);
+          if (uy < h8 && ux < w8) reinterpret_cast<uint32_t*>(field8)[(size_t)frame * w8 * h8 + (size_t)uy * w8 + ux] = k;
+        }
+      }
     }
   }
 }
 
 }  // namespace
 
-cudaError_t launch_hme_smooth(const HmeLaunch& p, int n, cudaStream_t s) {
-  if (p.lam_s <= 0 || p.smooth_iters <= 0) return cudaSuccess;
-  const int n1 = ((p.width + 15) / 16) * ((p.height + 15) / 16);
-  int16_t* va = p.mv_tmp;
-  int16_t* vb = p.mv_tmp + (size_t)n * n1 * 2;
+cudaError_t launch_hme_sbrd(const HmeLaunch& p, int n, cudaStream_t s) {
+  if (p.lam_s <= 0 || p.sbrd_passes <= 0) return cudaSuccess;
+  const int n1x = (p.width + 15) / 16, n1y = (p.height + 15) / 16, n1 = n1x * n1y;
+  const int nsx = (n1x + 3) / 4, nsy = (n1y + 3) / 4;
+  uint32_t* field = reinterpret_cast<uint32_t*>(p.mv_tmp);
   uint32_t* dom = p.hist + (size_t)n * 2048;
-  dim3 gg((n1 + 255) / 256, 1, n), gs((n1 + 7) / 8, 1, n);
   cudaError_t e = cudaMemsetAsync(p.hist, 0, (size_t)n * 2048 * sizeof(uint32_t), s);
   if (e != cudaSuccess) return e;
-  for (int it = 0; it < p.smooth_iters; it++) {
-    hme_gather_kernel<<<gg, 256, 0, s>>>(p, p.mv_out, va, it == 0);
-    hme_dominant_kernel<<<n, 1024, 0, s>>>(p, dom);
-    hme_smooth_kernel<<<gs, 256, 0, s>>>(p, va, vb, dom, it + 1 == p.smooth_iters ? p.mv_out : nullptr);
-    int16_t* t = va; va = vb; vb = t;
-  }
+  hme_gather_kernel<<<dim3((n1 + 255) / 256, 1, n), 256, 0, s>>>(p, p.mv_out, p.mv_tmp, 1);
+  hme_dominant_kernel<<<n, 1024, 0, s>>>(p, dom);
+  const dim3 grid((nsx + 1) / 2, nsy, n);
+  for (int half = 0; half < 2 * p.sbrd_passes; half++)
+    hme_sbrd_kernel<<<grid, 512, 0, s>>>(p, field, dom, half & 1, half + 1 == 2 * p.sbrd_passes || half + 2 == 2 * p.sbrd_passes ? p.mv_out : nullptr);
   return cudaGetLastError();
 }
 

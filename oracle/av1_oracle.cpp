@@ -691,11 +691,8 @@ extern "C" void orc_hme(const Av1bGeom* g, const uint16_t* cur0, const uint16_t*
 
 // ------------------------------------------------------------------------------------------------
 // Vector-field regularisation (encoder side, ours): SAD of a 16x16 block at quarter-sample vectors on a bilinear
-// interpolation of the reference SOURCE picture, then a few synchronous relaxation sweeps in which every block picks,
-// among its own vector, the vectors of its four neighbours, the zero vector and the frame's dominant vector, the one
-// with the smallest  SAD + lam_s * (number of neighbours with a different vector).  Flat / noisy areas, where the SADs
-// of all candidates are within noise of each other, collapse onto one vector: skipped blocks merge to 32x32 / 64x64 and
-// the vectors that are coded are predicted exactly (NEARESTMV).
+// interpolation of the reference SOURCE picture (sad_block_q), the frame's dominant vector (orc_mv_dominant) and the
+// superblock-level rate-distortion sweeps (orc_me_sbrd).
 // ------------------------------------------------------------------------------------------------
 static int sad_block_q(const uint16_t* cur, const uint16_t* ref, int stride, int w, int h, int bx, int by, int n, int mvx,
                        int mvy) {   // mv in 1/8 luma samples (multiples of 2)
@@ -734,50 +731,105 @@ extern "C" void orc_mv_dominant(const int16_t* mv, int n, int16_t* dom) {
   dom[0] = (int16_t)(k >> 16); dom[1] = (int16_t)(k & 0xFFFF);
 }
 
+// Superblock-level rate-distortion regularisation of the vector field (orc_me_sbrd).
 // mv_io: [h8*w8][2] as produced by orc_hme (the vector of a 16x16 block replicated on its 8x8 units); updated in place.
-extern "C" void orc_me_smooth(const Av1bGeom* g, const uint16_t* cur0, const uint16_t* ref0, int lam_s, int iters,
-                              int16_t* mv_io) {
+//
+// The field of 16x16-block vectors is swept `passes` times; a sweep visits the 64x64 superblocks of one checkerboard
+// colour, then those of the other (superblocks of one colour share no edge, so within a half sweep they are independent
+// of each other and may run in any order or in parallel; every half sweep sees the result of the one before).
+// For a superblock (up to 4x4 blocks):
+//   candidates, in this order and without repeats: zero, the frame's dominant vector (of the field the first sweep
+//     starts from), the vector of the block left of / above / right of / below the superblock's first block row / column
+//     (where the picture has one), the superblock's own vectors in raster order;
+//   T[c][b] = SAD of block b at candidate c (sad_block_q);
+//   relaxation, blocks in raster order: b takes the candidate with the smallest T[c][b] + lam_s * (number of its four
+//     neighbours inside the picture that hold another vector), first candidate on ties;
+//   merge at 64x64: the cost of the field as it stands, sum over the blocks of T[own][b] + lam_r * bits(b) with
+//     bits = 1 when the block left of or above b holds the same vector, else 12, against the best single candidate for
+//     the whole superblock, sum of T[c][b] + lam_r * (1 when c is zero or held by the block left of / above the
+//     superblock's first block, else 12): the single candidate is taken when it is strictly cheaper;
+//   else the same test for each of the four 32x32 quadrants in raster order.
+// Flat / noisy areas, where the SADs of all candidates are within noise of each other, collapse onto one vector per
+// superblock (and, through the neighbour candidates, per region): skipped blocks merge to 32x32 / 64x64, and the vectors
+// that are coded are predicted exactly (NEARESTMV).
+extern "C" void orc_me_sbrd(const Av1bGeom* g, const uint16_t* cur0, const uint16_t* ref0, int lam_s, int lam_r, int passes,
+                            int16_t* mv_io) {
   const int W = g->width, H = g->height, s0 = g->stride[0];
   const int n1x = (W + 15) / 16, n1y = (H + 15) / 16, n1 = n1x * n1y;
-  std::vector<int16_t> v((size_t)n1 * 2), nv((size_t)n1 * 2);
+  std::vector<int16_t> v((size_t)n1 * 2);
   for (int by = 0; by < n1y; by++)
     for (int bx = 0; bx < n1x; bx++) {
       const int16_t* m = mv_io + ((size_t)(by * 2) * g->w8 + bx * 2) * 2;
       v[(by * n1x + bx) * 2] = m[0]; v[(by * n1x + bx) * 2 + 1] = m[1];
     }
-  for (int it = 0; it < iters; it++) {
-    int16_t dom[2];
-    orc_mv_dominant(v.data(), n1, dom);
-    for (int by = 0; by < n1y; by++)
-      for (int bx = 0; bx < n1x; bx++) {
-        const int b = by * n1x + bx;
-        // candidates in visiting order; neighbours outside the picture repeat the block's own vector
-        int cand[7][2];
-        const int nb[4][2] = {{0, -1}, {0, 1}, {-1, 0}, {1, 0}};   // left, right, up, down
-        cand[0][0] = v[b * 2]; cand[0][1] = v[b * 2 + 1];
-        bool have[4];
-        for (int k = 0; k < 4; k++) {
-          const int yy = by + nb[k][0], xx = bx + nb[k][1];
-          have[k] = yy >= 0 && yy < n1y && xx >= 0 && xx < n1x;
-          const int o = have[k] ? (yy * n1x + xx) : b;
-          cand[1 + k][0] = v[o * 2]; cand[1 + k][1] = v[o * 2 + 1];
-        }
-        cand[5][0] = 0; cand[5][1] = 0;
-        cand[6][0] = dom[0]; cand[6][1] = dom[1];
-        int best_cost = 0, best_k = -1;
-        for (int k = 0; k < 7; k++) {
-          bool dup = false;
-          for (int j = 0; j < k; j++) dup = dup || (cand[j][0] == cand[k][0] && cand[j][1] == cand[k][1]);
-          if (dup) continue;
-          int diff = 0;
-          for (int j = 0; j < 4; j++) diff += have[j] && (cand[1 + j][0] != cand[k][0] || cand[1 + j][1] != cand[k][1]);
-          const int cost = sad_block_q(cur0, ref0, s0, W, H, bx * 16, by * 16, 16, cand[k][1], cand[k][0]) + lam_s * diff;
-          if (best_k < 0 || cost < best_cost) { best_cost = cost; best_k = k; }
-        }
-        nv[b * 2] = (int16_t)cand[best_k][0]; nv[b * 2 + 1] = (int16_t)cand[best_k][1];
+  int16_t dom[2];
+  orc_mv_dominant(v.data(), n1, dom);
+  auto pk = [&](int by, int bx) { return mv_pack(v[(by * n1x + bx) * 2], v[(by * n1x + bx) * 2 + 1]); };
+  const int nsx = (n1x + 3) / 4, nsy = (n1y + 3) / 4;
+  for (int half = 0; half < 2 * passes; half++)
+    for (int sby = 0; sby < nsy; sby++)
+      for (int sbx = 0; sbx < nsx; sbx++) {
+        if (((sbx + sby) & 1) != (half & 1)) continue;
+        const int y0 = sby * 4, x0 = sbx * 4, nr = std::min(4, n1y - y0), nc = std::min(4, n1x - x0);
+        uint32_t cand[22]; int ncand = 0;
+        auto add = [&](uint32_t k) { for (int i = 0; i < ncand; i++) if (cand[i] == k) return; cand[ncand++] = k; };
+        add(mv_pack(0, 0)); add(mv_pack(dom[0], dom[1]));
+        if (x0 > 0) add(pk(y0, x0 - 1));
+        if (y0 > 0) add(pk(y0 - 1, x0));
+        if (x0 + nc < n1x) add(pk(y0, x0 + nc));
+        if (y0 + nr < n1y) add(pk(y0 + nr, x0));
+        for (int r = 0; r < nr; r++) for (int c = 0; c < nc; c++) add(pk(y0 + r, x0 + c));
+        int T[22][16];
+        for (int k = 0; k < ncand; k++)
+          for (int r = 0; r < nr; r++)
+            for (int c = 0; c < nc; c++)
+              T[k][r * 4 + c] = sad_block_q(cur0, ref0, s0, W, H, (x0 + c) * 16, (y0 + r) * 16, 16, (int16_t)(cand[k] & 0xFFFF), (int16_t)(cand[k] >> 16));
+        auto set = [&](int by, int bx, uint32_t k) { v[(by * n1x + bx) * 2] = (int16_t)(k >> 16); v[(by * n1x + bx) * 2 + 1] = (int16_t)(k & 0xFFFF); };
+        auto idx_of = [&](uint32_t k) { for (int i = 0; i < ncand; i++) if (cand[i] == k) return i; return 0; };
+        // relaxation
+        for (int r = 0; r < nr; r++)
+          for (int c = 0; c < nc; c++) {
+            const int by = y0 + r, bx = x0 + c;
+            int best = 0, bk = -1;
+            for (int k = 0; k < ncand; k++) {
+              int diff = 0;
+              if (bx > 0) diff += pk(by, bx - 1) != cand[k];
+              if (bx + 1 < n1x) diff += pk(by, bx + 1) != cand[k];
+              if (by > 0) diff += pk(by - 1, bx) != cand[k];
+              if (by + 1 < n1y) diff += pk(by + 1, bx) != cand[k];
+              const int cost = T[k][r * 4 + c] + lam_s * diff;
+              if (bk < 0 || cost < best) { best = cost; bk = k; }
+            }
+            set(by, bx, cand[bk]);
+          }
+        // merge tests
+        auto test = [&](int r0, int c0, int r1, int c1) {
+          int jc = 0;
+          for (int r = r0; r < r1; r++)
+            for (int c = c0; c < c1; c++) {
+              const int by = y0 + r, bx = x0 + c;
+              const uint32_t k = pk(by, bx);
+              const bool same = (bx > 0 && pk(by, bx - 1) == k) || (by > 0 && pk(by - 1, bx) == k);
+              jc += T[idx_of(k)][r * 4 + c] + lam_r * (same ? 1 : 12);
+            }
+          int best = 0, bk = -1;
+          const int by = y0 + r0, bx = x0 + c0;
+          for (int k = 0; k < ncand; k++) {
+            const bool nb = cand[k] == mv_pack(0, 0) || (bx > 0 && pk(by, bx - 1) == cand[k]) || (by > 0 && pk(by - 1, bx) == cand[k]);
+            int j = lam_r * (nb ? 1 : 12);
+            for (int r = r0; r < r1; r++) for (int c = c0; c < c1; c++) j += T[k][r * 4 + c];
+            if (bk < 0 || j < best) { best = j; bk = k; }
+          }
+          if (best < jc) {
+            for (int r = r0; r < r1; r++) for (int c = c0; c < c1; c++) set(y0 + r, x0 + c, cand[bk]);
+            return true;
+          }
+          return false;
+        };
+        if (!test(0, 0, nr, nc))
+          for (int qr = 0; qr < nr; qr += 2)
+            for (int qc = 0; qc < nc; qc += 2) test(qr, qc, std::min(qr + 2, nr), std::min(qc + 2, nc));
       }
-    v.swap(nv);
-  }
   for (int by = 0; by < n1y; by++)
     for (int bx = 0; bx < n1x; bx++)
       for (int uy = by * 2; uy < std::min(by * 2 + 2, g->h8); uy++)

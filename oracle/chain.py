@@ -128,7 +128,7 @@ def encode_chain(frames, w, h, bd, crf, keyint=240, gop_period=4, me_smooth=True
         else:
             mvs = O.hme(g, pyr, anchor_pyr, lam)
             if me_smooth:
-                mvs = O.me_smooth(g, pyr, anchor_pyr, mvs, lam, 2)
+                mvs = O.me_sbrd(g, pyr, anchor_pyr, mvs, lam, lam >> 2, 2)
             r.mvs = mvs
             r.res = O.encode_inter_frame(g, fr, bd, q, pm16, mvs, anchor_fin, tb_zero_thr=tb_zero_thr)
             O.merge_skip_blocks(g, r.res.blocks)

@@ -134,10 +134,10 @@ def hme(g, cur_pyr, ref_pyr, lam=0):
     return mv
 
 
-def me_smooth(g, cur_pyr, ref_pyr, mv, lam_s, iters=2):
-    """Vector-field regularisation (orc_me_smooth): returns the updated [h8*w8, 2] vectors."""
+def me_sbrd(g, cur_pyr, ref_pyr, mv, lam_s, lam_r, passes=2):
+    """Superblock-level rate-distortion regularisation of the vector field (orc_me_sbrd): returns the updated [h8*w8, 2] vectors."""
     mv = np.ascontiguousarray(mv, np.int16).copy()
-    lib().orc_me_smooth(C.byref(g), ptr(cur_pyr[0]), ptr(ref_pyr[0]), int(lam_s), int(iters), ptr(mv))
+    lib().orc_me_sbrd(C.byref(g), ptr(cur_pyr[0]), ptr(ref_pyr[0]), int(lam_s), int(lam_r), int(passes), ptr(mv))
     return mv
 
 

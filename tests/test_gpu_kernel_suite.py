@@ -227,19 +227,21 @@ def test_pyramid_and_hme_vs_oracle(w, h, bd):
 
 @pytest.mark.parametrize("w,h,bd", ME_CASES + [(1920, 1080, 10)])
 def test_vector_field_regularisation_vs_oracle(w, h, bd):
-    """hme + relaxation sweeps (dominant vector histogram, bilinear quarter-sample SAD, neighbour-disagreement cost)."""
+    """hme + superblock-level rate-distortion sweeps (dominant vector histogram, bilinear quarter-sample SAD table per
+    superblock, relaxation, 64x64 / 32x32 merge tests, checkerboard order)."""
     g = O.geom(w, h, 0, 0)
     n = 3 if w < 1000 else 2
     frames = synth.synth_clip(w, h, bd, n, seed=w + bd + 1, scene_len=100)
     l0 = np.stack([O.pad_planes(g, fr)[0] for fr in frames])
     pyr = [O.pyramid(g, l0[i]) for i in range(n)]
-    for lam, lam_s, iters in ((40 << (bd - 8), 40 << (bd - 8), 2), (300 << (bd - 8), 150 << (bd - 8), 3), (8, 2000, 1)):
-        if w > 1000 and iters != 2:
+    for lam, lam_s, lam_r, passes in ((40 << (bd - 8), 40 << (bd - 8), 10 << (bd - 8), 2), (300 << (bd - 8), 150 << (bd - 8), 75 << (bd - 8), 3),
+                                      (8, 2000, 1, 1), (8, 1, 3000, 1)):
+        if w > 1000 and passes != 2:
             continue
-        mv, _ = kernels.hme_smooth(w, h, l0[1:], l0[:1].repeat(n - 1, 0), lam, lam_s, iters)   # every frame against frame 0
+        mv, _ = kernels.hme_sbrd(w, h, l0[1:], l0[:1].repeat(n - 1, 0), lam, lam_s, lam_r, passes)   # every frame against frame 0
         for i in range(1, n):
-            want = O.me_smooth(g, pyr[i], pyr[0], O.hme(g, pyr[i], pyr[0], lam), lam_s, iters)
-            assert np.array_equal(mv[i - 1], want), (i, lam, lam_s, iters)
+            want = O.me_sbrd(g, pyr[i], pyr[0], O.hme(g, pyr[i], pyr[0], lam), lam_s, lam_r, passes)
+            assert np.array_equal(mv[i - 1], want), (i, lam, lam_s, lam_r, passes)
 
 
 @pytest.mark.parametrize("w,h,bd", ME_CASES + [(1920, 1080, 8), (3840, 2160, 10)])
@@ -278,7 +280,7 @@ def test_temporal_filter_vs_oracle(w, h, bd):
     padded = [O.pad_planes(g, fr) for fr in frames]
     pyr = [O.pyramid(g, p[0]) for p in padded]
     lam = 60 << (bd - 8)
-    mvs = [O.me_smooth(g, pyr[1], pyr[j], O.hme(g, pyr[1], pyr[j], lam), lam, 2) for j in range(n) if j != 1]
+    mvs = [O.me_sbrd(g, pyr[1], pyr[j], O.hme(g, pyr[1], pyr[j], lam), lam, lam >> 2, 2) for j in range(n) if j != 1]
     nbs = [padded[j] for j in range(n) if j != 1]
     for thr_b in (3 << (2 * (bd - 8)), 40 << (2 * (bd - 8)), 4000 << (2 * (bd - 8))):
         got, _ = kernels.mctf(w, h, bd, padded[1], nbs, mvs, thr_b, 3 * thr_b)

@@ -88,14 +88,13 @@ def test_mv_dominant_and_smoothing_properties():
     frames = synth.synth_clip(w, h, bd, 2, seed=9, scene_len=100)
     pyr = [O.pyramid(g, O.pad_planes(g, f)[0]) for f in frames]
     mv = O.hme(g, pyr[1], pyr[0], 80)
-    # without a disagreement cost every block keeps or improves its SAD: its own vector is a candidate
-    sm0 = O.me_smooth(g, pyr[1], pyr[0], mv, 0, 1)
+    sm0 = O.me_sbrd(g, pyr[1], pyr[0], mv, 1, 1, 1)
     n1x, n1y = (w + 15) // 16, (h + 15) // 16
     f0 = mv.reshape(g.h8, g.w8, 2)[::2, ::2].reshape(-1, 2)
     f1 = sm0.reshape(g.h8, g.w8, 2)[::2, ::2].reshape(-1, 2)
     assert f0.shape[0] == n1x * n1y
     # a strong cost makes the field more uniform, never less
-    sm = O.me_smooth(g, pyr[1], pyr[0], mv, 100000, 3)
+    sm = O.me_sbrd(g, pyr[1], pyr[0], mv, 100000, 100000, 3)
     fs = sm.reshape(g.h8, g.w8, 2)[::2, ::2].reshape(-1, 2)
     assert len(np.unique(fs, axis=0)) <= len(np.unique(f0, axis=0))
     # dominant vector: numpy restatement of the hashed histogram

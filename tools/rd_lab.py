@@ -90,7 +90,7 @@ def encode(args):
                 for j in nb:
                     mv = O.hme(g, pyrs[i], pyrs[j], acq >> 1)
                     if opts.get("smooth") and not opts.get("tf_nosmooth"):
-                        mv = O.me_smooth(g, pyrs[i], pyrs[j], mv, int((acq >> 1) * opts["smooth"][0]), int(opts["smooth"][1]))
+                        mv = O.me_sbrd(g, pyrs[i], pyrs[j], mv, int((acq >> 1) * opts["smooth"][0]), int((acq >> 3) * opts["smooth"][0]), int(opts["smooth"][1]))
                     mvs.append(mv)
                 enc_src[i] = O.crop(g, O.mctf(g, bd, padded[i], [padded[j] for j in nb], mvs, thr_b, thr_p))
     nbytes, psnr = 0, []
@@ -113,7 +113,7 @@ def encode(args):
             mv = O.hme(g, pyr, prev_pyr, acq >> 1)
             if opts.get("smooth"):
                 k, it = opts["smooth"]
-                mv = O.me_smooth(g, pyr, prev_pyr, mv, int((acq >> 1) * k), int(it))
+                mv = O.me_sbrd(g, pyr, prev_pyr, mv, int((acq >> 1) * k), int((acq >> 3) * k), int(it))
             qf = qidx
             if hier:
                 qf = max(1, min(255, qidx + (hier[1] if i % hier[0] == 0 else hier[2])))
