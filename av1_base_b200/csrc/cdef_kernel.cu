@@ -229,10 +229,11 @@ __device__ __forceinline__ void find_dir_quad(const uint16_t* img, int stride, i
   else { c0 = dir_cost<6>(px); c1 = dir_cost<7>(px); }
   int cost[8];
   const int base = (threadIdx.x & 31) & ~3;
+  const unsigned qmask = 0xFu << base;   // the quad only: quads of skipped blocks do not come here
 #pragma unroll
   for (int q = 0; q < 4; q++) {
-    cost[2 * q] = __shfl_sync(0xffffffffu, c0, base + q);
-    cost[2 * q + 1] = __shfl_sync(0xffffffffu, c1, base + q);
+    cost[2 * q] = __shfl_sync(qmask, c0, base + q);
+    cost[2 * q + 1] = __shfl_sync(qmask, c1, base + q);
   }
   int best = 0, dir = 0;
 #pragma unroll
@@ -251,7 +252,40 @@ __global__ void __launch_bounds__(kThreads, 3) cdef_kernel(const CdefLaunch P) {
   const int sbx = blockIdx.x, sby = blockIdx.y, frame = blockIdx.z;
   const int bd = P.bit_depth, cs = bd - 8;
   const Av1bBlockInfo* blocks = P.blocks + (size_t)frame * P.map_elems;
-  // ---- stage: deblocked windows (unavailable samples marked), source tiles, skip flags ----
+  const size_t sb_index = (size_t)frame * g.sb_rows * g.sb_cols + sby * g.sb_cols + sbx;
+  // ---- skip flags first: a superblock without a coded block is copied (CDEF leaves skipped blocks alone) ----
+  bool live_blk = false;
+  if (tid < 64) {
+    const int by = tid >> 3, bx = tid & 7;
+    const int uy = sby * 8 + by, ux = sbx * 8 + bx;
+    const bool sk = (uy < g.h8 && ux < g.w8) ? (blocks[uy * g.w8 + ux].skip != 0) : true;
+    sm.skip[by][bx] = sk;
+    live_blk = !sk;
+  }
+  if (!__syncthreads_or(live_blk)) {
+    for (int p = 0; p < 3; p++) {
+      const int ss = p > 0, T = 64 >> ss;
+      const int stride = g.stride[p];
+      const int pw = (g.mi_cols * 4) >> ss, ph = (g.mi_rows * 4) >> ss;
+      const int x0 = sbx * T, y0 = sby * T;
+      const uint16_t* in = P.in[p] + (size_t)frame * P.plane_elems[p];
+      uint16_t* out = P.out[p] + (size_t)frame * P.plane_elems[p];
+      for (int o = tid; o < T * (T / 8); o += kThreads) {
+        const int r = o / (T / 8), v = o % (T / 8);
+        const int y = y0 + r, x = x0 + v * 8;
+        // samples outside the picture read as "unavailable", like in the staged window of the filter path
+        uint4 d = make_uint4(0xFFFFFFFFu, 0xFFFFFFFFu, 0xFFFFFFFFu, 0xFFFFFFFFu);
+        if (y < ph && x < pw) {
+          d = *reinterpret_cast<const uint4*>(in + (size_t)y * stride + x);
+          if (x + 8 > pw) { d.z = 0xFFFFFFFFu; d.w = 0xFFFFFFFFu; }
+        }
+        *reinterpret_cast<uint4*>(out + (size_t)y * stride + x) = d;
+      }
+    }
+    if (tid == 0 && P.cdef_idx) P.cdef_idx[sb_index] = P.forced_idx ? P.forced_idx[sb_index] : 0;
+    return;
+  }
+  // ---- stage: deblocked windows (unavailable samples marked), source tiles ----
   for (int p = 0; p < 3; p++) {
     const int ss = p > 0, T = 64 >> ss;
     const int stride = g.stride[p];
@@ -281,11 +315,6 @@ __global__ void __launch_bounds__(kThreads, 3) cdef_kernel(const CdefLaunch P) {
       *reinterpret_cast<uint4*>(st + r * T + v * 8) =
           *reinterpret_cast<const uint4*>(src + (size_t)(y0 + r) * stride + x0 + v * 8);
     }
-  }
-  if (tid < 64) {
-    const int by = tid >> 3, bx = tid & 7;
-    const int uy = sby * 8 + by, ux = sbx * 8 + bx;
-    sm.skip[by][bx] = (uy < g.h8 && ux < g.w8) ? (blocks[uy * g.w8 + ux].skip != 0) : 1;
   }
   if (tid < 16) {
     const int d = tid >> 1, k = tid & 1;
@@ -322,8 +351,7 @@ __global__ void __launch_bounds__(kThreads, 3) cdef_kernel(const CdefLaunch P) {
     const int b = tid >> 2, by = b >> 3, bx = b & 7;
     int dir = 0, var = 0;
     // all four lanes of a quad take the same branch (the skip flag is per block)
-    find_dir_quad(sm.y + (kHalo + by * 8) * kLStride + 8 + bx * 8, kLStride, bd, tid & 3, &dir, &var);
-    if (sm.skip[by][bx]) { dir = 0; var = 0; }
+    if (!sm.skip[by][bx]) find_dir_quad(sm.y + (kHalo + by * 8) * kLStride + 8 + bx * 8, kLStride, bd, tid & 3, &dir, &var);
     if ((tid & 3) == 0) { sm.dir[by][bx] = (uint8_t)dir; sm.var[by][bx] = var; }
   }
   __syncthreads();
@@ -360,7 +388,6 @@ __global__ void __launch_bounds__(kThreads, 3) cdef_kernel(const CdefLaunch P) {
   };
 
   int best = 0;
-  const size_t sb_index = (size_t)frame * g.sb_rows * g.sb_cols + sby * g.sb_cols + sbx;
   if (P.forced_idx) {
     best = P.forced_idx[sb_index];
   } else if (n_cand > 1) {

@@ -102,6 +102,26 @@ __device__ __forceinline__ int code_tb(const InterLaunch& P, int frame, int p, i
 #pragma unroll
     for (int c = 0; c < N; c++) buf[t * S + c] = ((int)sp[c] - (int)pred[t * N + c]) * 4;
   }
+  // ---------------- early skip (oracle: orc_encode_inter_frame): residual sums to less than dc_q * N / 16 ----------
+  {
+    int sad4 = 0;
+#pragma unroll
+    for (int c = 0; c < N; c++) sad4 += abs(buf[t * S + c]);
+#pragma unroll
+    for (int o = N / 2; o; o >>= 1) sad4 += __shfl_xor_sync(gmask, sad4, o);
+    if (sad4 < 4 * ((P.dc_q * N) >> 4)) {
+      if (active) {
+        int16_t* cz = P.coef[p] + fo + av1b_coef_offset(P.g.sb_cols, p, x, y) + t * N;
+#pragma unroll
+        for (int l = 0; l < N; l += 4) *reinterpret_cast<uint2*>(cz + l) = make_uint2(0u, 0u);
+        uint16_t* rec = P.rec[p] + fo + (size_t)y * stride + x;
+#pragma unroll
+        for (int i = 0; i < N; i++) rec[(size_t)i * stride + t] = pred[i * N + t];
+      }
+      __syncwarp(gmask);
+      return 0;
+    }
+  }
   __syncwarp(gmask);
   // ---------------- forward DCT: column pass (thread t = column t), then row pass (thread t = row t) -----
   int32_t col[N];

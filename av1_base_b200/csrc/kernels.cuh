@@ -149,6 +149,7 @@ struct TokLaunch {
   int32_t n_frames;
   uint64_t inter_mask;           // bit b: frame b of the batch is an inter frame
   int32_t cdef_bits;             // 0 when CDEF is off
+  uint64_t nocdef_mask;          // bit b: frame b signals no CDEF (cdef_bits = 0 in its header: the non-reference frames)
   const Av1bBlockInfo* blocks;   // [n_frames][map_elems]
   const uint16_t* digest[3];     // [n_frames][plane_elems[p]]
   const int16_t* coef[3];

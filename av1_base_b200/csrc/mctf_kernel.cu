@@ -20,40 +20,93 @@ namespace {
 __device__ __forceinline__ int clampi(int v, int lo, int hi) { return v < lo ? lo : (v > hi ? hi : v); }
 
 constexpr int kWarps = 8;
+constexpr int kWinPitch = 26;        // samples per staged row (13 words): 23 + an odd start
 struct MctfSmem {
-  uint16_t win[kWarps][23 * 24];     // staged reference window (luma 23x23, chroma 15x15)
-  int32_t mid[kWarps][23 * 16];      // after the horizontal pass
+  uint32_t win[kWarps][23 * kWinPitch / 2];   // staged reference window (luma 23x23, chroma 15x15), rows as aligned words
+  int32_t mid[kWarps][23 * 17];               // after the horizontal pass (pitch N + 1)
   uint16_t pred[kWarps][16 * 16];
 };
 
 // Normative prediction of an N x N block at (x, y) of a plane from `ref` with the vector (mv_row, mv_col) in 1/8 luma
 // samples (oracle: orc_inter_predict): all lanes of the warp take part, result in pred[N*N].
+//   whole-sample vectors copy the block (both filter passes are the identity then);
+//   windows inside the picture are staged as aligned 32-bit words without clamping (an odd start is an offset at read time);
+//   a lane filters four neighbouring outputs from eleven inputs held in registers.
 template <int N>
 __device__ __forceinline__ void mc_block(const uint16_t* __restrict__ ref, int stride, int pw, int ph, int x, int y, int mv_row,
-                                         int mv_col, int ss, int bd, int lane, uint16_t* win, int32_t* mid, uint16_t* pred) {
+                                         int mv_col, int ss, int bd, int lane, uint32_t* winw, int32_t* mid, uint16_t* pred) {
   const int x16 = (x << 4) + ((2 * mv_col) >> ss), y16 = (y << 4) + ((2 * mv_row) >> ss);
   const int ix = x16 >> 4, iy = y16 >> 4, fx = x16 & 15, fy = y16 & 15;
-  constexpr int WN = N + 7, WS = N + 8;
-  for (int o = lane; o < WN * WN; o += 32) {
-    const int r = o / WN, c = o - r * WN;
-    win[r * WS + c] = ref[(size_t)clampi(iy + r - 3, 0, ph - 1) * stride + clampi(ix + c - 3, 0, pw - 1)];
+  constexpr int WN = N + 7, MP = N + 1;
+  if ((fx | fy) == 0) {
+    if (ix >= 0 && iy >= 0 && ix + N <= pw && iy + N <= ph) {
+      for (int o = lane; o < N * N; o += 32) pred[o] = ref[(size_t)(iy + o / N) * stride + ix + o % N];
+    } else {
+      for (int o = lane; o < N * N; o += 32) pred[o] = ref[(size_t)clampi(iy + o / N, 0, ph - 1) * stride + clampi(ix + o % N, 0, pw - 1)];
+    }
+    __syncwarp();
+    return;
+  }
+  uint16_t* win = reinterpret_cast<uint16_t*>(winw);
+  const int wx = ix - 3, wy = iy - 3;
+  int xo = 0;
+  if (wx >= 1 && wy >= 0 && wx + WN + 1 <= pw && wy + WN <= ph) {
+    xo = wx & 1;
+    constexpr int WW = (WN + 2) / 2;   // words per row that cover WN samples from an even or odd start
+    const uint32_t* base = reinterpret_cast<const uint32_t*>(ref + (size_t)wy * stride + (wx - xo));
+    for (int o = lane; o < WN * WW; o += 32) {
+      const int r = o / WW, c = o - r * WW;
+      winw[r * (kWinPitch / 2) + c] = base[(size_t)r * (stride >> 1) + c];
+    }
+  } else {
+    for (int o = lane; o < WN * WN; o += 32) {
+      const int r = o / WN, c = o - r * WN;
+      win[r * kWinPitch + c] = ref[(size_t)clampi(wy + r, 0, ph - 1) * stride + clampi(wx + c, 0, pw - 1)];
+    }
   }
   __syncwarp();
-  for (int o = lane; o < WN * N; o += 32) {
-    const int r = o / N, c = o - r * N;
-    int s = 0;
+  // horizontal pass: task = (row, group of four outputs)
+  {
+    int kx[8];
 #pragma unroll
-    for (int t = 0; t < 8; t++) s += tbl::sub_pel_filters_8[fx][t] * (int)win[r * WS + c + t];
-    mid[r * N + c] = (s + 4) >> 3;
+    for (int t = 0; t < 8; t++) kx[t] = tbl::sub_pel_filters_8[fx][t];
+    constexpr int G = N / 4;
+    for (int o = lane; o < WN * G; o += 32) {
+      const int r = o / G, c0 = (o - r * G) * 4;
+      const uint16_t* wp = win + r * kWinPitch + xo + c0;
+      int v[11];
+#pragma unroll
+      for (int j = 0; j < 11; j++) v[j] = wp[j];
+#pragma unroll
+      for (int j = 0; j < 4; j++) {
+        int sacc = 0;
+#pragma unroll
+        for (int t = 0; t < 8; t++) sacc += kx[t] * v[j + t];
+        mid[r * MP + c0 + j] = (sacc + 4) >> 3;
+      }
+    }
   }
   __syncwarp();
-  const int maxv = (1 << bd) - 1;
-  for (int o = lane; o < N * N; o += 32) {
-    const int r = o / N, c = o - r * N;
-    int s = 0;
+  // vertical pass: task = (column, group of four output rows)
+  {
+    int ky[8];
 #pragma unroll
-    for (int t = 0; t < 8; t++) s += tbl::sub_pel_filters_8[fy][t] * mid[(r + t) * N + c];
-    pred[o] = (uint16_t)clampi((s + 1024) >> 11, 0, maxv);
+    for (int t = 0; t < 8; t++) ky[t] = tbl::sub_pel_filters_8[fy][t];
+    const int maxv = (1 << bd) - 1;
+    constexpr int G = N / 4;
+    for (int o = lane; o < N * G; o += 32) {
+      const int c = o % N, r0 = (o / N) * 4;
+      int v[11];
+#pragma unroll
+      for (int j = 0; j < 11; j++) v[j] = mid[(r0 + j) * MP + c];
+#pragma unroll
+      for (int j = 0; j < 4; j++) {
+        int sacc = 0;
+#pragma unroll
+        for (int t = 0; t < 8; t++) sacc += ky[t] * v[j + t];
+        pred[(r0 + j) * N + c] = (uint16_t)clampi((sacc + 1024) >> 11, 0, maxv);
+      }
+    }
   }
   __syncwarp();
 }
@@ -68,7 +121,7 @@ __global__ void __launch_bounds__(kWarps * 32) mctf_kernel(const MctfLaunch P) {
   if (blk >= n1x * n1y) return;
   const int bx = blk % n1x, by = blk / n1x;
   const int bw = min(16, W - bx * 16), bh = min(16, H - by * 16);
-  uint16_t* win = sm.win[warp];
+  uint32_t* win = sm.win[warp];
   int32_t* mid = sm.mid[warp];
   uint16_t* pred = sm.pred[warp];
   // lane (r, h): luma row r, columns 8h .. 8h+7; chroma: samples 2 lane, 2 lane + 1 of the 8x8 block

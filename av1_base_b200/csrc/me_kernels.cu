@@ -145,9 +145,9 @@ __global__ void __launch_bounds__(256) hme_l2_kernel(const HmeLaunch P) {
 // ---------------------------------------------------------------------------------------------
 struct RefineSmem {
   alignas(16) uint16_t cur1[8][8 * 8];
-  uint16_t ref1[8][12 * 13];
+  alignas(4) uint16_t ref1[8][12 * 14];   // row pitch 14 (7 words): 12 samples + an odd start
   alignas(16) uint16_t cur0[8][16 * 16];
-  alignas(4) uint16_t ref0[8][20 * 22];   // row pitch 22: rows start word aligned (sad25_rows16)
+  alignas(4) uint16_t ref0[8][20 * 24];   // row pitch 24 (12 words): 20 samples + an odd start (sad25_rows16 reads words)
 };
 
 // 25 candidates (+-2), lanes = candidates; returns the chosen (dy, dx) in all lanes
@@ -165,8 +165,8 @@ __device__ __forceinline__ int subpel_parabola(int sm, int s0, int sp, int lambd
 // 32-bit words (12 samples each) and accumulates its 8-sample share of all 25 candidates; a reduce-scatter adds the
 // shares.  39 shared-memory loads per lane instead of 512 (the candidate-per-lane form was bound by them).
 // Window row pitch: 22 samples (rows start word aligned).  Lane k < 25 returns the SAD of candidate k.
-constexpr int kRS0 = 22;
-__device__ __forceinline__ int sad25_rows16(const uint16_t* cur, const uint16_t* ref, int lane) {
+constexpr int kRS0 = 24;
+__device__ __forceinline__ int sad25_rows16(const uint16_t* cur, const uint16_t* ref, int lane, int xo) {
   const int r = lane >> 1, h = lane & 1;
   unsigned c[8];
   {
@@ -180,9 +180,17 @@ __device__ __forceinline__ int sad25_rows16(const uint16_t* cur, const uint16_t*
 #pragma unroll
   for (int wr = 0; wr < 5; wr++) {
     const uint32_t* rw = reinterpret_cast<const uint32_t*>(ref + (r + wr) * kRS0 + 8 * h);
+    uint32_t w[7];
+#pragma unroll
+    for (int k = 0; k < 6; k++) w[k] = rw[k];
+    if (xo) {   // warp-uniform: the window starts one sample into its first word
+      w[6] = rw[6];
+#pragma unroll
+      for (int k = 0; k < 6; k++) w[k] = __funnelshift_r(w[k], w[k + 1], 16);
+    }
     unsigned s[12];
 #pragma unroll
-    for (int k = 0; k < 6; k++) { const uint32_t w = rw[k]; s[2 * k] = w & 0xFFFFu; s[2 * k + 1] = w >> 16; }
+    for (int k = 0; k < 6; k++) { s[2 * k] = w[k] & 0xFFFFu; s[2 * k + 1] = w[k] >> 16; }
 #pragma unroll
     for (int dx = 0; dx < 5; dx++)
 #pragma unroll
@@ -208,19 +216,19 @@ __device__ __forceinline__ int sad25_rows16(const uint16_t* cur, const uint16_t*
 }
 
 template <int N, int RS, bool kSubpel>
-__device__ __forceinline__ void refine25(const uint16_t* cur, const uint16_t* ref, int lane, int lam, int lam_sub,
+__device__ __forceinline__ void refine25(const uint16_t* cur, const uint16_t* ref, int xo, int lane, int lam, int lam_sub,
                                          int* bdy, int* bdx, int* qy, int* qx) {
   unsigned key = 0xFFFFFFFFu;
   int my_sad = 0;
   int pre_sad = 0;
-  if (N == 16) pre_sad = sad25_rows16(cur, ref, lane);   // all lanes take part
+  if (N == 16) pre_sad = sad25_rows16(cur, ref, lane, xo);   // all lanes take part
   if (lane < 25) {
     const int dy = lane / 5 - 2, dx = lane % 5 - 2;
     unsigned usad = 0;
     if (N == 16) {
       usad = (unsigned)pre_sad;
     } else {
-      const uint16_t* rp = ref + (2 + dy) * RS + 2 + dx;
+      const uint16_t* rp = ref + (2 + dy) * RS + 2 + dx + xo;
       for (int i = 0; i < N; i++)
 #pragma unroll
         for (int j = 0; j < N; j++) usad = __usad((unsigned)cur[i * N + j], (unsigned)rp[i * RS + j], usad);
@@ -264,38 +272,50 @@ __global__ void __launch_bounds__(256) hme_refine_kernel(const HmeLaunch P) {
   // ---- L1: 8x8 block at (8bx, 8by), +-2 around (px, py) ----
   // windows that lie inside the picture (almost all) are staged without clamping, the block itself as 16-byte rows
   const bool in1 = by * 8 + 8 <= h1 && bx * 8 + 8 <= w1 && by * 8 + py - 2 >= 0 && by * 8 + py + 10 <= h1 &&
-                   bx * 8 + px - 2 >= 0 && bx * 8 + px + 10 <= w1;
+                   bx * 8 + px - 2 >= 0 && bx * 8 + px + 10 <= w1 && bx * 8 + px + 12 <= s1;
+  int xo1 = 0;
   if (in1) {
     if (lane < 8)
       *reinterpret_cast<uint4*>(&sm.cur1[warp][lane * 8]) = *reinterpret_cast<const uint4*>(cur1 + (size_t)(by * 8 + lane) * s1 + bx * 8);
-    const uint16_t* rbase = ref1 + (size_t)(by * 8 + py - 2) * s1 + bx * 8 + px - 2;
-    for (int o = lane; o < 144; o += 32) {
-      const int r = o / 12, c = o % 12;
-      sm.ref1[warp][r * 13 + c] = rbase[(size_t)r * s1 + c];
+    // 12 rows of 12 samples as aligned words (7 per row cover an odd start): lane = (row of four, word)
+    const int wx = bx * 8 + px - 2;
+    xo1 = wx & 1;
+    const int wr = lane >> 3, wc = lane & 7;
+    if (wc < 7) {
+      const uint32_t* src = reinterpret_cast<const uint32_t*>(ref1 + (size_t)(by * 8 + py - 2 + wr) * s1 + (wx - xo1)) + wc;
+      uint32_t* dst = reinterpret_cast<uint32_t*>(sm.ref1[warp]) + wr * 7 + wc;
+#pragma unroll
+      for (int i = 0; i < 3; i++) dst[i * 28] = src[(size_t)i * 2 * s1];   // rows wr, wr + 4, wr + 8 (s1 samples = s1 / 2 words)
     }
   } else {
     for (int o = lane; o < 64; o += 32)
       sm.cur1[warp][o] = cur1[(size_t)clampi(by * 8 + (o >> 3), 0, h1 - 1) * s1 + clampi(bx * 8 + (o & 7), 0, w1 - 1)];
     for (int o = lane; o < 144; o += 32) {
       const int r = o / 12, c = o % 12;
-      sm.ref1[warp][r * 13 + c] = ref1[(size_t)clampi(by * 8 + py - 2 + r, 0, h1 - 1) * s1 + clampi(bx * 8 + px - 2 + c, 0, w1 - 1)];
+      sm.ref1[warp][r * 14 + c] = ref1[(size_t)clampi(by * 8 + py - 2 + r, 0, h1 - 1) * s1 + clampi(bx * 8 + px - 2 + c, 0, w1 - 1)];
     }
   }
   __syncwarp();
   int dy, dx, qy = 0, qx = 0;
-  refine25<8, 13, false>(sm.cur1[warp], sm.ref1[warp], lane, P.lambda >> 2, 0, &dy, &dx, &qy, &qx);
+  refine25<8, 14, false>(sm.cur1[warp], sm.ref1[warp], xo1, lane, P.lambda >> 2, 0, &dy, &dx, &qy, &qx);
   const int qy0 = 2 * (py + dy), qx0 = 2 * (px + dx);
   // ---- L0: 16x16 block at (16bx, 16by), +-2 around (qx, qy) ----
   const bool in0 = by * 16 + 16 <= P.height && bx * 16 + 16 <= P.width && by * 16 + qy0 - 2 >= 0 && by * 16 + qy0 + 18 <= P.height &&
-                   bx * 16 + qx0 - 2 >= 0 && bx * 16 + qx0 + 18 <= P.width;
+                   bx * 16 + qx0 - 2 >= 0 && bx * 16 + qx0 + 18 <= P.width && bx * 16 + qx0 + 20 <= P.stride0;
+  int xo0 = 0;
   if (in0) {
     // lane (r, h): 8 samples of row r as one 16-byte load
     *reinterpret_cast<uint4*>(&sm.cur0[warp][(lane >> 1) * 16 + 8 * (lane & 1)]) =
         *reinterpret_cast<const uint4*>(cur0 + (size_t)(by * 16 + (lane >> 1)) * P.stride0 + bx * 16 + 8 * (lane & 1));
-    const uint16_t* rbase = ref0 + (size_t)(by * 16 + qy0 - 2) * P.stride0 + bx * 16 + qx0 - 2;
-    for (int o = lane; o < 400; o += 32) {
-      const int r = o / 20, c = o % 20;
-      sm.ref0[warp][r * kRS0 + c] = rbase[(size_t)r * P.stride0 + c];
+    // 20 rows of 20 samples as aligned words (11 per row cover an odd start): lane = (row of two, word)
+    const int wx = bx * 16 + qx0 - 2;
+    xo0 = wx & 1;
+    const int wr = lane >> 4, wc = lane & 15;
+    if (wc < 11) {
+      const uint32_t* src = reinterpret_cast<const uint32_t*>(ref0 + (size_t)(by * 16 + qy0 - 2 + wr) * P.stride0 + (wx - xo0)) + wc;
+      uint32_t* dst = reinterpret_cast<uint32_t*>(sm.ref0[warp]) + wr * (kRS0 / 2) + wc;
+#pragma unroll
+      for (int i = 0; i < 10; i++) dst[i * kRS0] = src[(size_t)i * P.stride0];   // rows wr, wr + 2, ...: two rows = stride0 words
     }
   } else {
     for (int o = lane; o < 256; o += 32)
@@ -307,7 +327,7 @@ __global__ void __launch_bounds__(256) hme_refine_kernel(const HmeLaunch P) {
     }
   }
   __syncwarp();
-  refine25<16, kRS0, true>(sm.cur0[warp], sm.ref0[warp], lane, P.lambda, P.lambda, &dy, &dx, &qy, &qx);
+  refine25<16, kRS0, true>(sm.cur0[warp], sm.ref0[warp], xo0, lane, P.lambda, P.lambda, &dy, &dx, &qy, &qx);
   if (lane < 4) {
     const int uy = by * 2 + (lane >> 1), ux = bx * 2 + (lane & 1);
     const int w8 = P.width >> 3, h8 = P.height >> 3;
@@ -459,10 +479,18 @@ __global__ void __launch_bounds__(512) hme_sbrd_kernel(const HmeLaunch P, uint32
     const int wxa = wx & ~1, xo = wx & 1;                  // first staged column (even), offset of the window in the row
     __syncthreads();                                       // the window of the candidate before has been read
     if (wy >= 0 && wy + 65 <= H && wxa >= 0 && wx + 65 <= W && wxa + kWinPitch <= P.stride0) {
-      const uint32_t* base = reinterpret_cast<const uint32_t*>(ref0 + (size_t)wy * P.stride0 + wxa);
-      for (int o = tid; o < 65 * (kWinPitch / 2); o += 512) {
-        const int r = o / (kWinPitch / 2), c = o - r * (kWinPitch / 2);
-        sm.win[o] = base[(size_t)r * (P.stride0 >> 1) + c];
+      // warp w stages rows w, w + 16, w + 32, w + 48 (and warp 0 row 64): lane = word, lanes 0 and 1 also words 32 and 33
+      const uint32_t* src = reinterpret_cast<const uint32_t*>(ref0 + (size_t)(wy + warp) * P.stride0 + wxa) + lane;
+      uint32_t* dst = sm.win + warp * (kWinPitch / 2) + lane;
+      const size_t step = (size_t)8 * P.stride0;   // 16 rows in words
+#pragma unroll
+      for (int i = 0; i < 4; i++) {
+        dst[i * 16 * (kWinPitch / 2)] = src[i * step];
+        if (lane < 2) dst[i * 16 * (kWinPitch / 2) + 32] = src[i * step + 32];
+      }
+      if (warp == 0) {
+        dst[64 * (kWinPitch / 2)] = src[4 * step];
+        if (lane < 2) dst[64 * (kWinPitch / 2) + 32] = src[4 * step + 32];
       }
     } else {
       for (int o = tid; o < 65 * (kWinPitch / 2); o += 512) {
@@ -479,7 +507,15 @@ __global__ void __launch_bounds__(512) hme_sbrd_kernel(const HmeLaunch P, uint32
 #pragma unroll
       for (int j = 0; j < 5; j++) { a[j] = r0[j]; b[j] = r0[kWinPitch / 2 + j]; }
       unsigned sad = 0;
-      if (xo == 0) {
+      if ((fx | fy) == 0) {   // whole-sample vector: the interpolation is the identity
+        if (xo == 0) {
+#pragma unroll
+          for (int j = 0; j < 8; j++) sad = __usad(c8[j], hw(a, j), sad);
+        } else {
+#pragma unroll
+          for (int j = 0; j < 8; j++) sad = __usad(c8[j], hw(a, j + 1), sad);
+        }
+      } else if (xo == 0) {
 #pragma unroll
         for (int j = 0; j < 8; j++) {
           const unsigned p = (unsigned)(w00 * (int)hw(a, j) + w01 * (int)hw(a, j + 1) + w10 * (int)hw(b, j) + w11 * (int)hw(b, j + 1) + 8) >> 4;

@@ -26,7 +26,7 @@ __device__ __forceinline__ TokFrame frame_view(const TokLaunch& P, int f) {
   for (int p = 0; p < 3; p++) { F.digest[p] = P.digest[p] + (size_t)f * P.plane_elems[p]; F.coef[p] = P.coef[p] + (size_t)f * P.plane_elems[p]; }
   F.cdef_idx = P.cdef_idx + (size_t)f * nsb;
   F.w8 = P.g.w8; F.h8 = P.g.h8; F.mi_cols = P.g.mi_cols; F.mi_rows = P.g.mi_rows; F.sb_cols = P.g.sb_cols;
-  F.cdef_bits = P.cdef_bits;
+  F.cdef_bits = ((P.nocdef_mask >> f) & 1) ? 0 : P.cdef_bits;
   F.scan[0] = tbl::scan_default_4; F.scan[1] = tbl::scan_default_8; F.scan[2] = tbl::scan_default_16;
   F.lr_units = P.lr_units ? P.lr_units + (size_t)f * P.lr_rows * P.lr_cols : nullptr;
   F.lr_rows = P.lr_rows; F.lr_cols = P.lr_cols;

@@ -975,8 +975,18 @@ extern "C" int orc_encode_inter_frame(const Av1bGeom* g, int bit_depth, int base
         for (int i = 0; i < n; i++) for (int j = 0; j < n; j++)
           resid[i * n + j] = (int16_t)((int)src[p][(size_t)(y + i) * sstride[p] + x + j] - (int)pred[i * n + j]);
         const int cn = std::min(n, 32);
-        orc_fwd_txfm2d(resid.data(), n, cf.data(), cn, n, n, AV1B_DCT_DCT);
-        orc_quant_dequant(cf.data(), cn, lv.data(), cn, dq.data(), cn, n, n, base_q_idx, bit_depth, quant_rnd);
+        // early skip (encoder decision, ours): a transform block whose residual sums (in magnitude) to less than
+        // dc_q * n / 16 is not coded -- a coefficient is about 0.6 * SAD at most (all of the residual in one basis
+        // function), so such a block quantises to zero anyway except in contrived cases, and the transform is saved
+        int sad = 0;
+        for (int i = 0; i < n * n; i++) sad += abs(resid[i]);
+        const int dcq = bit_depth == 8 ? av1t_dc_q_8[base_q_idx] : av1t_dc_q_10[base_q_idx];
+        if (sad < ((dcq * n) >> 4)) {
+          for (int i = 0; i < cn * cn; i++) { lv[i] = 0; dq[i] = 0; }
+        } else {
+          orc_fwd_txfm2d(resid.data(), n, cf.data(), cn, n, n, AV1B_DCT_DCT);
+          orc_quant_dequant(cf.data(), cn, lv.data(), cn, dq.data(), cn, n, n, base_q_idx, bit_depth, quant_rnd);
+        }
         {
           const int thr = n >= 16 ? tb_zero_thr : (n == 8 ? tb_zero_thr >> 1 : 0);
           int sum = 0;

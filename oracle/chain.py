@@ -49,6 +49,11 @@ def class_params(bd, qidx, kind, loop_filters=True, lr=False, tile_log2=(0, 0)):
     fp = abi.FrameParams()
     abi.lib().av1b_select_frame_params(bd, qidx, 0 if kind == 0 else 1, 1 if loop_filters else 0, C.byref(fp))
     fp.non_reference = 1 if kind == 2 else 0
+    if kind == 2:   # no CDEF in the frames nobody predicts from (csrc/encoder.cc set_structure)
+        fp.cdef_bits = 0
+        for i in range(8):
+            fp.cdef_y_strength[i] = 0
+            fp.cdef_uv_strength[i] = 0
     fp.tile_cols_log2, fp.tile_rows_log2 = tile_log2
     if lr:
         fp.lr_type[0], fp.lr_type[1], fp.lr_type[2] = 3, 0, 0
@@ -135,8 +140,12 @@ def encode_chain(frames, w, h, bd, crf, keyint=240, gop_period=4, me_smooth=True
         fin, r.cdef_idx, r.lr_units = r.res.rec, None, None
         if loop_filters:
             O.deblock_frame(g, bd, r.res.blocks, r.res.rec, list(fp.lf_level), fp.lf_sharpness)
-            r.cdef_idx = O.cdef_search(g, bd, r.res.blocks, fp, r.res.rec, src)
-            fin = O.cdef_frame(g, bd, r.res.blocks, fp, r.cdef_idx, r.res.rec)
+            if fp.cdef_bits > 0 or fp.cdef_y_strength[0] > 0 or fp.cdef_uv_strength[0] > 0:
+                r.cdef_idx = O.cdef_search(g, bd, r.res.blocks, fp, r.res.rec, src)
+                fin = O.cdef_frame(g, bd, r.res.blocks, fp, r.cdef_idx, r.res.rec)
+            else:
+                r.cdef_idx = np.zeros(g.sb_rows * g.sb_cols, np.uint8)
+                fin = r.res.rec
             if lr:
                 cand = O.lr_candidate((0, 0, 8), (0, 0, 8), 12, (0, 95))
                 aq = ac_q(bd, q)
