@@ -396,6 +396,7 @@ static int launch(av1b_encoder* e, Slot& s, const Slot& in, int n, int64_t first
     HmeLaunch H;
     H.width = g.width; H.height = g.height; H.stride0 = g.stride[0]; H.elems0 = e0;
     for (int l = 0; l < 3; l++) { H.ref[l] = e->d_pyr[l]; H.cur[l] = e->d_pyr[l]; }
+    H.shift2 = bd - 8;
     H.lambda = acq0 >> 1;   // vector-deviation cost in SAD units (tuned on the oracle: about half the AC quantiser step)
     H.lam_s = e->me_smooth ? H.lambda : 0; H.lam_r = H.lambda >> 2; H.sbrd_passes = 2; H.mv_tmp = e->d_mv_tmp; H.hist = e->d_hist;
     if (any_inter) {

@@ -61,10 +61,28 @@ __device__ __forceinline__ int code_tb(const InterLaunch& P, int frame, int p, i
   // ---------------- prediction ----------------
   const int x16 = (x << 4) + ((2 * mv_col) >> ss), y16 = (y << 4) + ((2 * mv_row) >> ss);
   const int ix = x16 >> 4, iy = y16 >> 4, fx = x16 & 15, fy = y16 & 15;
+  // rows that lie inside the picture with their whole window are read as aligned 32-bit words without clamping (an odd
+  // start is a funnel shift); N = 4 keeps the sample loads
+  const bool interior = N >= 8 && ix >= 4 && iy >= 3 && ix + N + 5 <= pw && iy + N + 4 <= ph;
   if (fx == 0 && fy == 0) {
-    const uint16_t* rr = ref + (size_t)clampi(iy + t, 0, ph - 1) * stride;
+    if (interior) {
+      const int xo = ix & 1;
+      const uint32_t* rw = reinterpret_cast<const uint32_t*>(ref + (size_t)(iy + t) * stride + (ix - xo));
+      uint32_t w[N / 2 + 1];
 #pragma unroll
-    for (int c = 0; c < N; c++) pred[t * N + c] = rr[clampi(ix + c, 0, pw - 1)];
+      for (int k = 0; k < N / 2 + 1; k++) w[k] = rw[k];
+      if (xo) {
+#pragma unroll
+        for (int k = 0; k < N / 2; k++) w[k] = __funnelshift_r(w[k], w[k + 1], 16);
+      }
+      uint32_t* pw32 = reinterpret_cast<uint32_t*>(pred + t * N);
+#pragma unroll
+      for (int k = 0; k < N / 2; k++) pw32[k] = w[k];
+    } else {
+      const uint16_t* rr = ref + (size_t)clampi(iy + t, 0, ph - 1) * stride;
+#pragma unroll
+      for (int c = 0; c < N; c++) pred[t * N + c] = rr[clampi(ix + c, 0, pw - 1)];
+    }
   } else {
     int kx[8], ky[8];
 #pragma unroll
@@ -73,10 +91,25 @@ __device__ __forceinline__ int code_tb(const InterLaunch& P, int frame, int p, i
       ky[k] = N <= 4 ? tbl::sub_pel_filters_4[fy][k] : tbl::sub_pel_filters_8[fy][k];
     }
     for (int r = t; r < N + 7; r += N) {
-      const uint16_t* rr = ref + (size_t)clampi(iy + r - 3, 0, ph - 1) * stride;
       int win[N + 7];
+      if (interior) {
+        const int wx = ix - 3, xo = wx & 1;
+        const uint32_t* rw = reinterpret_cast<const uint32_t*>(ref + (size_t)(iy + r - 3) * stride + (wx - xo));
+        constexpr int WW = (N + 7 + 2) / 2;   // words that cover N + 7 samples from an even or odd start
+        uint32_t w[WW];
 #pragma unroll
-      for (int c = 0; c < N + 7; c++) win[c] = rr[clampi(ix + c - 3, 0, pw - 1)];
+        for (int k = 0; k < WW; k++) w[k] = rw[k];
+        if (xo) {
+#pragma unroll
+          for (int k = 0; k < WW - 1; k++) w[k] = __funnelshift_r(w[k], w[k + 1], 16);
+        }
+#pragma unroll
+        for (int c = 0; c < N + 7; c++) win[c] = (c & 1) ? (int)(w[c >> 1] >> 16) : (int)(w[c >> 1] & 0xFFFFu);
+      } else {
+        const uint16_t* rr = ref + (size_t)clampi(iy + r - 3, 0, ph - 1) * stride;
+#pragma unroll
+        for (int c = 0; c < N + 7; c++) win[c] = rr[clampi(ix + c - 3, 0, pw - 1)];
+      }
 #pragma unroll
       for (int c = 0; c < N; c++) {
         int s = 0;

@@ -283,15 +283,15 @@ int av1b_k_pyramid(int device, int width, int height, int n_frames, const uint16
   return AV1B_OK;
 }
 
-int av1b_k_hme(int device, int width, int height, int n_frames, const uint16_t* cur_l0, const uint16_t* ref_l0,
+int av1b_k_hme(int device, int width, int height, int bit_depth, int n_frames, const uint16_t* cur_l0, const uint16_t* ref_l0,
                int lambda, int16_t* mv_out, int reps, double* ms_per_launch) {
-  return av1b_k_hme_sbrd(device, width, height, n_frames, cur_l0, ref_l0, lambda, 0, 0, 0, mv_out, reps, ms_per_launch);
+  return av1b_k_hme_sbrd(device, width, height, bit_depth, n_frames, cur_l0, ref_l0, lambda, 0, 0, 0, mv_out, reps, ms_per_launch);
 }
 
-int av1b_k_hme_sbrd(int device, int width, int height, int n_frames, const uint16_t* cur_l0, const uint16_t* ref_l0,
+int av1b_k_hme_sbrd(int device, int width, int height, int bit_depth, int n_frames, const uint16_t* cur_l0, const uint16_t* ref_l0,
                     int lambda, int lam_s, int lam_r, int passes, int16_t* mv_out, int reps, double* ms_per_launch) {
   if (n_frames > kMaxSearches) { set_error("at most %d frames per call", kMaxSearches); return AV1B_ERR_INVALID; }
-  if (!cur_l0 || !ref_l0 || !mv_out || n_frames <= 0) { set_error("bad argument"); return AV1B_ERR_INVALID; }
+  if (!cur_l0 || !ref_l0 || !mv_out || n_frames <= 0 || (bit_depth != 8 && bit_depth != 10)) { set_error("bad argument"); return AV1B_ERR_INVALID; }
   Av1bGeom g;
   if (av1b_geom_init(&g, width, height, 0, 0)) { set_error("unsupported size"); return AV1B_ERR_INVALID; }
   int rc = select_device(device);
@@ -308,7 +308,7 @@ int av1b_k_hme_sbrd(int device, int width, int height, int n_frames, const uint1
   CKS(launch_pyramid(c[0].as<uint16_t>(), c[1].as<uint16_t>(), c[2].as<uint16_t>(), g.stride[0], g.rows[0], e0, n_frames, t.s));
   CKS(launch_pyramid(r[0].as<uint16_t>(), r[1].as<uint16_t>(), r[2].as<uint16_t>(), g.stride[0], g.rows[0], e0, n_frames, t.s));
   HmeLaunch L;
-  L.width = width; L.height = height; L.stride0 = g.stride[0]; L.elems0 = e0; L.lambda = lambda;
+  L.width = width; L.height = height; L.stride0 = g.stride[0]; L.elems0 = e0; L.lambda = lambda; L.shift2 = bit_depth - 8;
   for (int l = 0; l < 3; l++) { L.cur[l] = c[l].as<uint16_t>(); L.ref[l] = r[l].as<uint16_t>(); }
   L.mv2 = m2.as<int16_t>(); L.mv_out = mo.as<int16_t>();
   for (int f = 0; f < n_frames; f++) { L.cur_slot[f] = (uint8_t)f; L.ref_slot[f] = (uint8_t)f; }

@@ -82,6 +82,7 @@ constexpr int kMaxSearches = 64;
 struct HmeLaunch {
   int32_t width, height, stride0;
   int32_t lambda;             // cost of one integer sample of deviation from the parent vector (SAD units, L0)
+  int32_t shift2;             // bit depth - 8: the quarter-resolution search compares min(sample >> shift2, 255)
   size_t elems0;
   const uint16_t* cur[3];
   const uint16_t* ref[3];

@@ -3,11 +3,11 @@
 //   pyramid_kernel : L0 luma -> L1 (1/2) and L2 (1/4) in one pass; one thread per L2 sample reads a
 //                    4x4 patch (four 8-byte loads), writes 2x2 L1 samples and one L2 sample.
 //                    Streaming, HBM-bound: algorithmic bytes 1.3125 * Y.
-//   hme_l2_kernel  : full search +-12 on the 1/4 picture for every 8x8 block (= 32x32 luma).  One CTA
-//                    stages a 32x32 patch of the current picture and its (32+24)^2 search window of
-//                    the reference in shared memory; one warp per block, lane = candidate column, the 25
-//                    candidate rows of a lane accumulate in registers from a sliding window row,
-//                    warp-shuffle arg-min on (cost, visiting order).
+//   hme_l2_kernel  : full search +-12 on the 1/4 picture for every 8x8 block (= 32x32 luma), on 8-bit samples.  One
+//                    CTA stages a 32x32 patch of the current picture and its (32+24)^2 search window of the
+//                    reference in shared memory as bytes; one warp per block, lane = candidate column, the 25
+//                    candidate rows of a lane accumulate in registers from a sliding window row (VABSDIFF4.U8.ACC),
+//                    warp arg-min on (cost, visiting order).
 //   hme_refine_kernel : per 16x16 luma block, +-2 on L1 around twice the L2 vector, then +-2 on L0
 //                    around twice the L1 vector; one warp per block, windows staged in shared memory.
 //
@@ -58,11 +58,13 @@ __global__ void __launch_bounds__(256) pyramid_kernel(const uint16_t* __restrict
 constexpr int kR2 = 12;
 constexpr int kT2 = 32;                     // L2 samples per CTA side (4x4 blocks of 8x8)
 constexpr int kW2 = kT2 + 2 * kR2;          // 56
-constexpr int kW2S = kW2 + 1;
+constexpr int kW2P = 64;                    // staged window row pitch in bytes (16 words)
 
+// The quarter-resolution search works on 8-bit samples, min(v >> shift2, 255) (shift2 = bit depth - 8): four samples
+// per 32-bit word and one VABSDIFF4.U8.ACC per four absolute differences.
 struct L2Smem {
-  uint16_t cur[kT2 * kT2];
-  uint16_t ref[kW2 * kW2S];
+  uint32_t cur[kT2 * kT2 / 4];
+  uint32_t ref[kW2 * kW2P / 4];
 };
 
 __global__ void __launch_bounds__(256) hme_l2_kernel(const HmeLaunch P) {
@@ -74,51 +76,54 @@ __global__ void __launch_bounds__(256) hme_l2_kernel(const HmeLaunch P) {
   const uint16_t* cur = P.cur[2] + (size_t)P.cur_slot[frame] * e2;
   const uint16_t* ref = P.ref[2] + (size_t)P.ref_slot[frame] * e2;
   const int x0 = blockIdx.x * kT2, y0 = blockIdx.y * kT2;
-  for (int o = tid; o < kT2 * kT2; o += 256) {
-    const int r = o / kT2, c = o % kT2;
-    sm.cur[o] = cur[(size_t)clampi(y0 + r, 0, h2 - 1) * s2 + clampi(x0 + c, 0, w2 - 1)];
+  const int sh = P.shift2;
+  // one thread packs four neighbouring samples into a word
+  for (int o = tid; o < kT2 * kT2 / 4; o += 256) {
+    const int r = o / (kT2 / 4), c = (o % (kT2 / 4)) * 4;
+    const uint16_t* row = cur + (size_t)clampi(y0 + r, 0, h2 - 1) * s2;
+    uint32_t w = 0;
+#pragma unroll
+    for (int j = 0; j < 4; j++) w |= min((uint32_t)row[clampi(x0 + c + j, 0, w2 - 1)] >> sh, 255u) << (8 * j);
+    sm.cur[o] = w;
   }
-  for (int o = tid; o < kW2 * kW2; o += 256) {
-    const int r = o / kW2, c = o % kW2;
-    sm.ref[r * kW2S + c] = ref[(size_t)clampi(y0 - kR2 + r, 0, h2 - 1) * s2 + clampi(x0 - kR2 + c, 0, w2 - 1)];
+  for (int o = tid; o < kW2 * (kW2 / 4); o += 256) {
+    const int r = o / (kW2 / 4), c = (o % (kW2 / 4)) * 4;
+    const uint16_t* row = ref + (size_t)clampi(y0 - kR2 + r, 0, h2 - 1) * s2;
+    uint32_t w = 0;
+#pragma unroll
+    for (int j = 0; j < 4; j++) w |= min((uint32_t)row[clampi(x0 - kR2 + c + j, 0, w2 - 1)] >> sh, 255u) << (8 * j);
+    sm.ref[r * (kW2P / 4) + (c >> 2)] = w;
   }
   __syncthreads();
   const int n2x = (P.width + 31) / 32, n2y = (P.height + 31) / 32;
   constexpr int kSide = 2 * kR2 + 1, kCand = kSide * kSide, kCentre = kR2 * kSide + kR2;
-  const int lam2 = max(1, P.lambda >> 4);
+  const int lam2 = max(1, (P.lambda >> sh) >> 4);
   for (int b = warp; b < 16; b += 8) {
     const int bx = b & 3, by = b >> 2;
     const int gbx = blockIdx.x * 4 + bx, gby = blockIdx.y * 4 + by;
     if (gbx >= n2x || gby >= n2y) continue;
-    // current block in registers: 64 samples
-    uint32_t c[64];
+    // current block in registers: 8 rows of two words
+    uint32_t c[8][2];
 #pragma unroll
-    for (int i = 0; i < 8; i++)
-#pragma unroll
-      for (int j = 0; j < 4; j++) {
-        const uint32_t w = *reinterpret_cast<const uint32_t*>(&sm.cur[(by * 8 + i) * kT2 + bx * 8 + 2 * j]);
-        c[i * 8 + 2 * j] = w & 0xFFFF; c[i * 8 + 2 * j + 1] = w >> 16;
-      }
+    for (int i = 0; i < 8; i++) { c[i][0] = sm.cur[(by * 8 + i) * (kT2 / 4) + bx * 2]; c[i][1] = sm.cur[(by * 8 + i) * (kT2 / 4) + bx * 2 + 1]; }
     unsigned best = 0xFFFFFFFFu;   // (cost << 10) | visiting order
-    // lane = candidate column (dx + 12), all 25 candidate rows in registers: a window row is loaded once (8 samples)
-    // and feeds the up to eight candidate rows that overlap it -- 256 shared loads per lane and block instead of 1280
+    // lane = candidate column (dx + 12), all 25 candidate rows in registers: a window row is read once (three aligned
+    // words, shifted to the lane's byte offset) and feeds the up to eight candidate rows that overlap it
     if (lane < kSide) {
       unsigned acc[kSide];
 #pragma unroll
       for (int k = 0; k < kSide; k++) acc[k] = 0;
-      const uint16_t* rp0 = sm.ref + (by * 8) * kW2S + bx * 8 + lane;
+      const int boff = bx * 8 + lane;                 // first byte of the lane's 8-sample row inside the window row
+      const uint32_t* rp0 = sm.ref + (by * 8) * (kW2P / 4) + (boff >> 2);
+      const int fs = (boff & 3) * 8;
 #pragma unroll
       for (int wr = 0; wr < 8 + 2 * kR2; wr++) {
-        unsigned s[8];
-#pragma unroll
-        for (int j = 0; j < 8; j++) s[j] = rp0[wr * kW2S + j];
+        const uint32_t w0 = rp0[wr * (kW2P / 4)], w1 = rp0[wr * (kW2P / 4) + 1], w2w = rp0[wr * (kW2P / 4) + 2];
+        const uint32_t s0 = __funnelshift_r(w0, w1, fs), s1 = __funnelshift_r(w1, w2w, fs);
 #pragma unroll
         for (int i = 0; i < 8; i++) {
           const int dyi = wr - i;
-          if (dyi >= 0 && dyi < kSide) {
-#pragma unroll
-            for (int j = 0; j < 8; j++) acc[dyi] = __usad(c[i * 8 + j], s[j], acc[dyi]);
-          }
+          if (dyi >= 0 && dyi < kSide) acc[dyi] = __vsadu4(c[i][1], s1) + (__vsadu4(c[i][0], s0) + acc[dyi]);
         }
       }
       const int dx = lane - kR2;
@@ -131,7 +136,7 @@ __global__ void __launch_bounds__(256) hme_l2_kernel(const HmeLaunch P) {
         best = min(best, ((unsigned)cost << 10) | (unsigned)order);
       }
     }
-    for (int o = 16; o; o >>= 1) best = min(best, __shfl_xor_sync(0xffffffffu, best, o));
+    best = __reduce_min_sync(0xffffffffu, best);
     if (lane == 0) {
       const int order = best & 1023;
       const int k = order == 0 ? kCentre : (order <= kCentre ? order - 1 : order);

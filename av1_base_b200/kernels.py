@@ -115,26 +115,27 @@ def pyramid(width, height, l0_frames, device=0, reps=1):
     return l1, l2, ms.value
 
 
-def hme(width, height, cur_l0, ref_l0, lam=0, device=0, reps=1):
-    """cur_l0 / ref_l0: [n, rows, stride] padded luma. Returns (mv [n, h8*w8, 2], ms)."""
+def hme(width, height, cur_l0, ref_l0, lam=0, device=0, reps=1, bd=8):
+    """cur_l0 / ref_l0: [n, rows, stride] padded luma; bd: bit depth (the quarter-resolution level compares
+    min(v >> (bd - 8), 255)). Returns (mv [n, h8*w8, 2], ms)."""
     cur = np.ascontiguousarray(cur_l0, np.uint16)
     ref = np.ascontiguousarray(ref_l0, np.uint16)
     n = cur.shape[0]
     mv = np.zeros((n, (height // 8) * (width // 8), 2), np.int16)
     ms = C.c_double(0)
-    _ck(abi.lib().av1b_k_hme(device, width, height, n, cur.ctypes.data_as(C.c_void_p), ref.ctypes.data_as(C.c_void_p),
+    _ck(abi.lib().av1b_k_hme(device, width, height, bd, n, cur.ctypes.data_as(C.c_void_p), ref.ctypes.data_as(C.c_void_p),
                              int(lam), mv.ctypes.data_as(C.c_void_p), reps, C.byref(ms)))
     return mv, ms.value
 
 
-def hme_sbrd(width, height, cur_l0, ref_l0, lam, lam_s, lam_r, passes=2, device=0, reps=1):
+def hme_sbrd(width, height, cur_l0, ref_l0, lam, lam_s, lam_r, passes=2, device=0, reps=1, bd=8):
     """hme followed by `passes` sweeps of the superblock-level regularisation of the vector field. Returns (mv [n, h8*w8, 2], ms)."""
     cur = np.ascontiguousarray(cur_l0, np.uint16)
     ref = np.ascontiguousarray(ref_l0, np.uint16)
     n = cur.shape[0]
     mv = np.zeros((n, (height // 8) * (width // 8), 2), np.int16)
     ms = C.c_double(0)
-    _ck(abi.lib().av1b_k_hme_sbrd(device, width, height, n, cur.ctypes.data_as(C.c_void_p), ref.ctypes.data_as(C.c_void_p),
+    _ck(abi.lib().av1b_k_hme_sbrd(device, width, height, bd, n, cur.ctypes.data_as(C.c_void_p), ref.ctypes.data_as(C.c_void_p),
                                   int(lam), int(lam_s), int(lam_r), int(passes), mv.ctypes.data_as(C.c_void_p), reps, C.byref(ms)))
     return mv, ms.value
 

@@ -199,15 +199,16 @@ int av1b_k_pyramid(int device, int width, int height, int n_frames, const uint16
                    int reps, double* ms_per_launch);
 /* Hierarchical motion estimation (E2): cur / ref = n_frames padded luma planes each; mv_out =
  * [n_frames][h8*w8][2] (row, col) in 1/8 luma samples. lambda = cost of one sample of deviation from the
- * parent vector (SAD units). The timed launch is the search (two kernels). */
-int av1b_k_hme(int device, int width, int height, int n_frames, const uint16_t* cur_l0, const uint16_t* ref_l0,
+ * parent vector (SAD units). The quarter-resolution level compares 8-bit samples, min(v >> (bit_depth - 8), 255).
+ * The timed launch is the search (two kernels). */
+int av1b_k_hme(int device, int width, int height, int bit_depth, int n_frames, const uint16_t* cur_l0, const uint16_t* ref_l0,
                int lambda, int16_t* mv_out, int reps, double* ms_per_launch);
 /* av1b_k_hme followed by `passes` checkerboard sweeps of the superblock-level rate-distortion regularisation of the
  * vector field (E2): per 64x64 superblock the SADs (bilinear quarter-sample interpolation) of its 16x16 blocks at every
  * candidate vector (zero, the frame's dominant vector, the neighbouring superblocks', its own), a relaxation of the blocks
  * with lam_s per neighbour that holds another vector, then one vector for the whole superblock / a 32x32 quadrant where
  * that is cheaper at lam_r per bit of vector rate. */
-int av1b_k_hme_sbrd(int device, int width, int height, int n_frames, const uint16_t* cur_l0, const uint16_t* ref_l0,
+int av1b_k_hme_sbrd(int device, int width, int height, int bit_depth, int n_frames, const uint16_t* cur_l0, const uint16_t* ref_l0,
                     int lambda, int lam_s, int lam_r, int passes, int16_t* mv_out, int reps, double* ms_per_launch);
 /* Motion-compensated temporal filter of one source picture (encoder side; `--film-grain` denoising and `--lookahead`,
  * av1an.rs:14): weighted mean of the picture and n_nb <= 6 neighbours in time, neighbour k compensated onto the picture

@@ -19,8 +19,8 @@
 #include <vector>
 #include "../av1_base_b200/csrc/av1b_types.h"
 #include "../av1_base_b200/csrc/av1_inv_txfm1d.h"   // normative butterfly graphs (pinned vs libaom av1_idct*)
-#include "av1_tables.h"
-#include "av1_fwd_matrices.h"
+#include "../av1_base_b200/csrc/av1_tables.h"         // normative constant tables (extracted from the libaom binary): one copy
+#include "../av1_base_b200/csrc/av1_fwd_matrices.h"   // generated from the normative inverse transforms
 
 using namespace av1tx;
 
@@ -631,13 +631,19 @@ static inline int subpel_parabola(int sm, int s0, int sp, int lambda) {
 // cur/ref: three luma levels each (L0 stride = g->stride[0]; L1, L2 have strides stride[0]/2, stride[0]/4).
 // mv_out: [h8*w8][2] (row, col) in 1/8 luma samples, the vector of a 16x16 block replicated on its 8x8 units.
 // lambda: cost of one integer sample of deviation from the projected parent vector at L0, in SAD units
-// (L1 uses lambda/4, L2 max(1, lambda/16) per quarter-resolution sample from the zero vector); a
+// (L1 uses lambda/4, L2 max(1, (lambda >> shift2)/16) per quarter-resolution sample from the zero vector); a
 // quarter-sample offset is kept on an axis only if the parabola predicts a SAD gain above lambda.
-extern "C" void orc_hme(const Av1bGeom* g, const uint16_t* cur0, const uint16_t* cur1, const uint16_t* cur2,
-                        const uint16_t* ref0, const uint16_t* ref1, const uint16_t* ref2, int lambda, int16_t* mv_out) {
-  const int lam1 = lambda >> 2, lam2 = std::max(1, lambda >> 4);
+// shift2 (bit depth - 8): the quarter-resolution search compares 8-bit samples, min(v >> shift2, 255), with lambda
+// scaled alike.
+extern "C" void orc_hme(const Av1bGeom* g, const uint16_t* cur0, const uint16_t* cur1, const uint16_t* cur2_in,
+                        const uint16_t* ref0, const uint16_t* ref1, const uint16_t* ref2_in, int lambda, int shift2, int16_t* mv_out) {
+  const int lam1 = lambda >> 2, lam2 = std::max(1, (lambda >> shift2) >> 4);
   const int W = g->width, H = g->height, s0 = g->stride[0], s1 = s0 / 2, s2 = s0 / 4;
   const int w1 = W / 2, h1 = H / 2, w2 = W / 4, h2 = H / 4;
+  std::vector<uint16_t> c2((size_t)s2 * h2), r2((size_t)s2 * h2);
+  for (size_t i = 0; i < c2.size(); i++) { c2[i] = (uint16_t)std::min(cur2_in[i] >> shift2, 255); r2[i] = (uint16_t)std::min(ref2_in[i] >> shift2, 255); }
+  const uint16_t* cur2 = c2.data();
+  const uint16_t* ref2 = r2.data();
   const int n2x = (W + 31) / 32, n2y = (H + 31) / 32, n1x = (W + 15) / 16, n1y = (H + 15) / 16;
   std::vector<int> mv2((size_t)n2x * n2y * 2), mv1((size_t)n1x * n1y * 2);
   for (int by = 0; by < n2y; by++)

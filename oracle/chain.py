@@ -116,7 +116,7 @@ def encode_chain(frames, w, h, bd, crf, keyint=240, gop_period=4, me_smooth=True
         if nb:
             mvs_tf = []
             for j in nb:
-                mvs_tf.append(O.hme(g, pyrs[i], pyrs[j], lam))   # no regularisation for the filter's searches
+                mvs_tf.append(O.hme(g, pyrs[i], pyrs[j], lam, bd))   # no regularisation for the filter's searches
             aq = ac_q(bd, q)
             thr_b = max(1, (aq * aq * (10 + film_grain)) // 2560)
             src = O.mctf(g, bd, padded[i], [padded[j] for j in nb], mvs_tf, thr_b, 3 * thr_b)
@@ -131,7 +131,7 @@ def encode_chain(frames, w, h, bd, crf, keyint=240, gop_period=4, me_smooth=True
             r.part_map = pm
             r.res = O.encode_intra_frame(g, fr, bd, q, pm)
         else:
-            mvs = O.hme(g, pyr, anchor_pyr, lam)
+            mvs = O.hme(g, pyr, anchor_pyr, lam, bd)
             if me_smooth:
                 mvs = O.me_sbrd(g, pyr, anchor_pyr, mvs, lam, lam >> 2, 2)
             r.mvs = mvs

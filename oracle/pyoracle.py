@@ -126,11 +126,12 @@ def pyramid(g, luma_padded):
     return [l0, l1, l2]
 
 
-def hme(g, cur_pyr, ref_pyr, lam=0):
-    """Motion vectors [h8*w8, 2] (row, col) in 1/8 luma samples. lam: vector-deviation cost (SAD units)."""
+def hme(g, cur_pyr, ref_pyr, lam=0, bd=8):
+    """Motion vectors [h8*w8, 2] (row, col) in 1/8 luma samples. lam: vector-deviation cost (SAD units); bd: bit depth of
+    the samples (the quarter-resolution search compares min(v >> (bd - 8), 255))."""
     mv = np.zeros((g.h8 * g.w8, 2), np.int16)
     lib().orc_hme(C.byref(g), ptr(cur_pyr[0]), ptr(cur_pyr[1]), ptr(cur_pyr[2]), ptr(ref_pyr[0]), ptr(ref_pyr[1]),
-                  ptr(ref_pyr[2]), int(lam), ptr(mv))
+                  ptr(ref_pyr[2]), int(lam), int(bd) - 8, ptr(mv))
     return mv
 
 

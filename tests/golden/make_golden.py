@@ -30,7 +30,7 @@ def encode(w, h, bd, q, n):
         if i == 0:
             r = O.encode_intra_frame(g, fr, bd, q, pm)
         else:
-            r = O.encode_inter_frame(g, fr, bd, q, pm, O.hme(g, pyr, prev_pyr, 40 << (bd - 8)), prev)
+            r = O.encode_inter_frame(g, fr, bd, q, pm, O.hme(g, pyr, prev_pyr, 40 << (bd - 8), bd), prev)
             O.merge_skip_blocks(g, r.blocks)
         O.deblock_frame(g, bd, r.blocks, r.rec, list(fp.lf_level), fp.lf_sharpness)
         idx = O.cdef_search(g, bd, r.blocks, fp, r.rec, O.pad_planes(g, fr))

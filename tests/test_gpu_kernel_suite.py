@@ -219,9 +219,9 @@ def test_pyramid_and_hme_vs_oracle(w, h, bd):
         assert np.array_equal(l1[i][:h // 2, :w // 2], pyr[i][1][:h // 2, :w // 2])
         assert np.array_equal(l2[i][:h // 4, :w // 4], pyr[i][2][:h // 4, :w // 4])
     for lam in (0, 40 << (bd - 8), 300 << (bd - 8)):
-        mv, _ = kernels.hme(w, h, l0[1:], l0[:-1], lam=lam)
+        mv, _ = kernels.hme(w, h, l0[1:], l0[:-1], lam=lam, bd=bd)
         for i in range(1, len(frames)):
-            want = O.hme(g, pyr[i], pyr[i - 1], lam)
+            want = O.hme(g, pyr[i], pyr[i - 1], lam, bd)
             assert np.array_equal(mv[i - 1], want), (i, lam)
 
 
@@ -238,9 +238,9 @@ def test_vector_field_regularisation_vs_oracle(w, h, bd):
                                       (8, 2000, 1, 1), (8, 1, 3000, 1)):
         if w > 1000 and passes != 2:
             continue
-        mv, _ = kernels.hme_sbrd(w, h, l0[1:], l0[:1].repeat(n - 1, 0), lam, lam_s, lam_r, passes)   # every frame against frame 0
+        mv, _ = kernels.hme_sbrd(w, h, l0[1:], l0[:1].repeat(n - 1, 0), lam, lam_s, lam_r, passes, bd=bd)   # every frame against frame 0
         for i in range(1, n):
-            want = O.me_sbrd(g, pyr[i], pyr[0], O.hme(g, pyr[i], pyr[0], lam), lam_s, lam_r, passes)
+            want = O.me_sbrd(g, pyr[i], pyr[0], O.hme(g, pyr[i], pyr[0], lam, bd), lam_s, lam_r, passes)
             assert np.array_equal(mv[i - 1], want), (i, lam, lam_s, lam_r, passes)
 
 
@@ -280,7 +280,7 @@ def test_temporal_filter_vs_oracle(w, h, bd):
     padded = [O.pad_planes(g, fr) for fr in frames]
     pyr = [O.pyramid(g, p[0]) for p in padded]
     lam = 60 << (bd - 8)
-    mvs = [O.me_sbrd(g, pyr[1], pyr[j], O.hme(g, pyr[1], pyr[j], lam), lam, lam >> 2, 2) for j in range(n) if j != 1]
+    mvs = [O.me_sbrd(g, pyr[1], pyr[j], O.hme(g, pyr[1], pyr[j], lam, bd), lam, lam >> 2, 2) for j in range(n) if j != 1]
     nbs = [padded[j] for j in range(n) if j != 1]
     for thr_b in (3 << (2 * (bd - 8)), 40 << (2 * (bd - 8)), 4000 << (2 * (bd - 8))):
         got, _ = kernels.mctf(w, h, bd, padded[1], nbs, mvs, thr_b, 3 * thr_b)

@@ -87,7 +87,7 @@ def test_mv_dominant_and_smoothing_properties():
     g = O.geom(w, h, 0, 0)
     frames = synth.synth_clip(w, h, bd, 2, seed=9, scene_len=100)
     pyr = [O.pyramid(g, O.pad_planes(g, f)[0]) for f in frames]
-    mv = O.hme(g, pyr[1], pyr[0], 80)
+    mv = O.hme(g, pyr[1], pyr[0], 80, bd)
     sm0 = O.me_sbrd(g, pyr[1], pyr[0], mv, 1, 1, 1)
     n1x, n1y = (w + 15) // 16, (h + 15) // 16
     f0 = mv.reshape(g.h8, g.w8, 2)[::2, ::2].reshape(-1, 2)
@@ -152,7 +152,7 @@ def test_temporal_filter_properties():
     noisy = synth.synth_clip(w, h, bd, 3, seed=5, scene_len=100, noise=1.0)
     padded = [O.pad_planes(g, f) for f in noisy]
     pyr = [O.pyramid(g, p[0]) for p in padded]
-    mvs = [O.hme(g, pyr[1], pyr[j], 100) for j in (0, 2)]
+    mvs = [O.hme(g, pyr[1], pyr[j], 100, bd) for j in (0, 2)]
     thr_b, thr_p = 900, 2700
     got = O.mctf(g, bd, padded[1], [padded[0], padded[2]], mvs, thr_b, thr_p)
     # numpy restatement

@@ -50,7 +50,7 @@ def encode_clip(w, h, bd, q, nfr, mode, blk, tcl, trl, lf, seed):
             elif mode == "rand":
                 mvs = random_mvs(g, pm, rng)
             else:
-                mvs = O.hme(g, O.pyramid(g, O.pad_planes(g, fr)[0]), O.pyramid(g, O.pad_planes(g, prev_src)[0]))
+                mvs = O.hme(g, O.pyramid(g, O.pad_planes(g, fr)[0]), O.pyramid(g, O.pad_planes(g, prev_src)[0]), 0, bd)
             r = O.encode_inter_frame(g, fr, bd, q, pm, mvs, prev)
         if lf:
             O.deblock_frame(g, bd, r.blocks, r.rec, list(fp.lf_level), 0)
@@ -104,7 +104,7 @@ def test_hme_finds_global_translation():
     ref = base[32:32 + h, 32:32 + w].astype(np.uint16)
     cur = base[32 + 5:32 + 5 + h, 32 - 9:32 - 9 + w].astype(np.uint16)     # cur(x,y) = ref(x-9, y+5)
     mv = O.hme(g, O.pyramid(g, O.pad_planes(g, [cur, cur[::2, ::2], cur[::2, ::2]])[0]),
-               O.pyramid(g, O.pad_planes(g, [ref, ref[::2, ::2], ref[::2, ::2]])[0])).reshape(g.h8, g.w8, 2)
+               O.pyramid(g, O.pad_planes(g, [ref, ref[::2, ::2], ref[::2, ::2]])[0]), 0, 10).reshape(g.h8, g.w8, 2)
     inner = mv[4:-4, 4:-4]
     assert np.all(inner[..., 0] == 5 * 8) and np.all(inner[..., 1] == -9 * 8)
 
@@ -203,7 +203,7 @@ def test_non_reference_frames_decode_bit_exact():
         if fi == 0:
             r = O.encode_intra_frame(g, fr, bd, fp.base_q_idx, pm)
         else:
-            mvs = O.hme(g, O.pyramid(g, O.pad_planes(g, fr)[0]), O.pyramid(g, O.pad_planes(g, anchor_src)[0]), 20)
+            mvs = O.hme(g, O.pyramid(g, O.pad_planes(g, fr)[0]), O.pyramid(g, O.pad_planes(g, anchor_src)[0]), 20, bd)
             r = O.encode_inter_frame(g, fr, bd, fp.base_q_idx, pm, mvs, anchor)
         sy = packer.make_syms(g, r.blocks, r.coef)
         tus.append(b"\x12\x00" + (packer.pack_sequence_header(seq) if fi == 0 else b"") + packer.pack_frame(seq, fp, sy, with_td=False))

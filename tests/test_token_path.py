@@ -31,7 +31,7 @@ def inter_frame(w, h, bd, q, tcl, trl, seed, mode):
     if mode == "rand":
         mvs = random_mvs(g, pm, rng)
     else:
-        mvs = O.hme(g, O.pyramid(g, O.pad_planes(g, frames[1])[0]), O.pyramid(g, O.pad_planes(g, frames[0])[0]), 40)
+        mvs = O.hme(g, O.pyramid(g, O.pad_planes(g, frames[1])[0]), O.pyramid(g, O.pad_planes(g, frames[0])[0]), 40, bd)
     r1 = O.encode_inter_frame(g, frames[1], bd, q, pm, mvs, r0.rec)
     O.merge_skip_blocks(g, r1.blocks)
     cdef_idx = rng.integers(0, 8, g.sb_rows * g.sb_cols).astype(np.uint8)

@@ -18,7 +18,7 @@ else:
     frames = synth.synth_clip(w, h, bd, 2, seed=4, scene_len=100)
     pm = O.partition_fixed(g, 4)
     r0 = O.encode_intra_frame(g, frames[0], bd, q, pm)
-    mv = O.hme(g, O.pyramid(g, O.pad_planes(g, frames[1])[0]), O.pyramid(g, O.pad_planes(g, frames[0])[0]), 280)
+    mv = O.hme(g, O.pyramid(g, O.pad_planes(g, frames[1])[0]), O.pyramid(g, O.pad_planes(g, frames[0])[0]), 280, bd)
     r1 = O.encode_inter_frame(g, frames[1], bd, q, pm, mv, r0.rec)
     O.merge_skip_blocks(g, r1.blocks)
     res = [(r.blocks, r.coef) for r in (r0, r1)]

@@ -12,7 +12,7 @@ libaom >= 3.5 keeps coefficient blocks transposed with respect to the specificat
 and nz-map-offset tables are transposed back here: everything emitted is in SPECIFICATION layout
 (pos = row * tx_width + col).
 
-Usage: python tools/extract_tables.py   (writes av1_base_b200/csrc/av1_tables.h and oracle/av1_tables.h)
+Usage: python tools/extract_tables.py   (writes av1_base_b200/csrc/av1_tables.h; the oracle includes the same file)
 """
 import ctypes, os, sys
 import numpy as np
@@ -219,7 +219,7 @@ def main():
                 "av1_sub_pel_filters_4", "av1_sub_pel_filters_4smooth"]:
         emit_array(f, "int16_t AV1T_ATTR", "av1t_" + sym[4:], rd(sym, np.int16).reshape(16, 8), per_line=8)
     txt = f.getvalue()
-    for out in ["av1_base_b200/csrc/av1_tables.h", "oracle/av1_tables.h"]:
+    for out in ["av1_base_b200/csrc/av1_tables.h"]:
         p = os.path.join(ROOT, out)
         os.makedirs(os.path.dirname(p), exist_ok=True)
         with open(p, "w") as g:

@@ -94,10 +94,10 @@ if want("pyramid") or want("hme"):
         _, _, ms = kernels.pyramid(w, h, l0, reps=a.reps)
         report("pyramid_kernel", ms, int(1.3125 * Y) * n)
     if want("hme"):
-        _, ms = kernels.hme(w, h, l0[1:], l0[:-1], lam=280, reps=a.reps)
+        _, ms = kernels.hme(w, h, l0[1:], l0[:-1], lam=280, reps=a.reps, bd=bd)
         report("hme_l2_kernel + hme_refine_kernel", ms, int(2.625 * Y) * (n - 1))
 if want("inter"):
-    mv, _ = kernels.hme(w, h, np.stack([srcs[1][0]]), np.stack([srcs[0][0]]), lam=280)
+    mv, _ = kernels.hme(w, h, np.stack([srcs[1][0]]), np.stack([srcs[0][0]]), lam=280, bd=bd)
     pm = np.full(g.h8 * g.w8, 4, np.uint8)
     pmm = pm.reshape(g.h8, g.w8)
     if g.h8 & 1:

@@ -37,7 +37,7 @@ def mctf(O, g, frames, pyrs, i, radius, strength, bd, lam):
     for j in range(max(0, i - radius), min(len(frames), i + radius + 1)):
         if j == i:
             continue
-        mv = O.hme(g, pyrs[i], pyrs[j], lam)
+        mv = O.hme(g, pyrs[i], pyrs[j], lam, bd)
         for p in range(3):
             ss = 1 if p else 0
             pred = mc_bilinear(np.asarray(frames[j][p]), mv, g, ss)
@@ -88,7 +88,7 @@ def encode(args):
                 nb = [j for j in range(i + lo, i + hi + 1) if 0 <= j < nfr and j != i]
                 mvs = []
                 for j in nb:
-                    mv = O.hme(g, pyrs[i], pyrs[j], acq >> 1)
+                    mv = O.hme(g, pyrs[i], pyrs[j], acq >> 1, bd)
                     if opts.get("smooth") and not opts.get("tf_nosmooth"):
                         mv = O.me_sbrd(g, pyrs[i], pyrs[j], mv, int((acq >> 1) * opts["smooth"][0]), int((acq >> 3) * opts["smooth"][0]), int(opts["smooth"][1]))
                     mvs.append(mv)
@@ -110,7 +110,7 @@ def encode(args):
                 pmk = O.partition_smooth(g, src[0], min(4 * acqk, 800 << (bd - 8)))
             r = O.encode_intra_frame(g, fr, bd, qkey, pmk)
         else:
-            mv = O.hme(g, pyr, prev_pyr, acq >> 1)
+            mv = O.hme(g, pyr, prev_pyr, acq >> 1, bd)
             if opts.get("smooth"):
                 k, it = opts["smooth"]
                 mv = O.me_sbrd(g, pyr, prev_pyr, mv, int((acq >> 1) * k), int((acq >> 3) * k), int(it))

@@ -52,7 +52,7 @@ def encode(args):
         if i == 0:
             r, fp = O.encode_intra_frame(g, fr, bd, qkey, pm), fps[0]
         else:
-            mv = O.hme(g, pyr, prev_pyr, acq >> 1)
+            mv = O.hme(g, pyr, prev_pyr, acq >> 1, bd)
             qf = qidx
             if hier:
                 qf = max(1, min(255, qidx + (hier[1] if i % hier[0] == 0 else hier[2])))
