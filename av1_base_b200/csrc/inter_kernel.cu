@@ -29,19 +29,59 @@ __device__ __forceinline__ int clampi(int v, int lo, int hi) { return v < lo ? l
 
 template <int N> struct TxTab;
 template <> struct TxTab<4> {
-  static __device__ __forceinline__ int f(int k, int i) { return tbl::fwd_dct4[k][i]; }
+  // forward DCT matrix (av1_fwd_matrices.h) as a function-local constexpr table: after unrolling every entry is an
+  // immediate operand instead of a constant-bank load
+  static __device__ __forceinline__ int f(int k, int i) {
+    constexpr int16_t t[4][4] = {{2896, 2896, 2896, 2896},
+                                  {3784, 1567, -1567, -3784},
+                                  {2896, -2896, -2896, 2896},
+                                  {1567, -3784, 3784, -1567}};
+    return t[k][i];
+  }
   static __device__ __forceinline__ int iscan(int p) { return tbl::iscan_default_4[p]; }
   static __device__ __forceinline__ int nz_off(int p) { return tbl::nz_map_ctx_offset_4[p]; }
   static constexpr int kLog2 = 2, kRowShift = 0;
 };
 template <> struct TxTab<8> {
-  static __device__ __forceinline__ int f(int k, int i) { return tbl::fwd_dct8[k][i]; }
+  // forward DCT matrix (av1_fwd_matrices.h) as a function-local constexpr table: after unrolling every entry is an
+  // immediate operand instead of a constant-bank load
+  static __device__ __forceinline__ int f(int k, int i) {
+    constexpr int16_t t[8][8] = {{2896, 2896, 2896, 2896, 2896, 2896, 2896, 2896},
+                                  {4017, 3406, 2276, 799, -799, -2276, -3406, -4017},
+                                  {3784, 1567, -1567, -3784, -3784, -1567, 1567, 3784},
+                                  {3406, -799, -4017, -2276, 2276, 4017, 799, -3406},
+                                  {2896, -2896, -2896, 2896, 2896, -2896, -2896, 2896},
+                                  {2276, -4017, 799, 3406, -3406, -799, 4017, -2276},
+                                  {1567, -3784, 3784, -1567, -1567, 3784, -3784, 1567},
+                                  {799, -2276, 3406, -4017, 4017, -3406, 2276, -799}};
+    return t[k][i];
+  }
   static __device__ __forceinline__ int iscan(int p) { return tbl::iscan_default_8[p]; }
   static __device__ __forceinline__ int nz_off(int p) { return tbl::nz_map_ctx_offset_8[p]; }
   static constexpr int kLog2 = 3, kRowShift = 1;
 };
 template <> struct TxTab<16> {
-  static __device__ __forceinline__ int f(int k, int i) { return tbl::fwd_dct16[k][i]; }
+  // forward DCT matrix (av1_fwd_matrices.h) as a function-local constexpr table: after unrolling every entry is an
+  // immediate operand instead of a constant-bank load
+  static __device__ __forceinline__ int f(int k, int i) {
+    constexpr int16_t t[16][16] = {{2896, 2896, 2896, 2896, 2896, 2896, 2896, 2896, 2896, 2896, 2896, 2896, 2896, 2896, 2896, 2896},
+                                  {4076, 3920, 3612, 3166, 2598, 1931, 1189, 401, -401, -1189, -1931, -2598, -3166, -3612, -3920, -4076},
+                                  {4017, 3406, 2276, 799, -799, -2276, -3406, -4017, -4017, -3406, -2276, -799, 799, 2276, 3406, 4017},
+                                  {3920, 2598, 401, -1931, -3612, -4076, -3166, -1189, 1189, 3166, 4076, 3612, 1931, -401, -2598, -3920},
+                                  {3784, 1567, -1567, -3784, -3784, -1567, 1567, 3784, 3784, 1567, -1567, -3784, -3784, -1567, 1567, 3784},
+                                  {3612, 401, -3166, -3920, -1189, 2598, 4076, 1931, -1931, -4076, -2598, 1189, 3920, 3166, -401, -3612},
+                                  {3406, -799, -4017, -2276, 2276, 4017, 799, -3406, -3406, 799, 4017, 2276, -2276, -4017, -799, 3406},
+                                  {3166, -1931, -3920, 401, 4076, 1189, -3612, -2598, 2598, 3612, -1189, -4076, -401, 3920, 1931, -3166},
+                                  {2896, -2896, -2896, 2896, 2896, -2896, -2896, 2896, 2896, -2896, -2896, 2896, 2896, -2896, -2896, 2896},
+                                  {2598, -3612, -1189, 4076, -401, -3920, 1931, 3166, -3166, -1931, 3920, 401, -4076, 1189, 3612, -2598},
+                                  {2276, -4017, 799, 3406, -3406, -799, 4017, -2276, -2276, 4017, -799, -3406, 3406, 799, -4017, 2276},
+                                  {1931, -4076, 2598, 1189, -3920, 3166, 401, -3612, 3612, -401, -3166, 3920, -1189, -2598, 4076, -1931},
+                                  {1567, -3784, 3784, -1567, -1567, 3784, -3784, 1567, 1567, -3784, 3784, -1567, -1567, 3784, -3784, 1567},
+                                  {1189, -3166, 4076, -3612, 1931, 401, -2598, 3920, -3920, 2598, -401, -1931, 3612, -4076, 3166, -1189},
+                                  {799, -2276, 3406, -4017, 4017, -3406, 2276, -799, -799, 2276, -3406, 4017, -4017, 3406, -2276, 799},
+                                  {401, -1189, 1931, -2598, 3166, -3612, 3920, -4076, 4076, -3920, 3612, -3166, 2598, -1931, 1189, -401}};
+    return t[k][i];
+  }
   static __device__ __forceinline__ int iscan(int p) { return tbl::iscan_default_16[p]; }
   static __device__ __forceinline__ int nz_off(int p) { return tbl::nz_map_ctx_offset_16[p]; }
   static constexpr int kLog2 = 4, kRowShift = 2;
@@ -157,13 +197,23 @@ __device__ __forceinline__ int code_tb(const InterLaunch& P, int frame, int p, i
   }
   __syncwarp(gmask);
   // ---------------- forward DCT: column pass (thread t = column t), then row pass (thread t = row t) -----
+  // F[k][N-1-i] = F[k][i] for even k and -F[k][i] for odd k (checked when the tables were generated): the sums below
+  // are the full matrix products term for term, with half the multiplications
   int32_t col[N];
+  {
+    int32_t se[N / 2], so[N / 2];
 #pragma unroll
-  for (int k = 0; k < N; k++) {
-    int32_t acc = 0;
+    for (int i = 0; i < N / 2; i++) {
+      const int32_t a = buf[i * S + t], b = buf[(N - 1 - i) * S + t];
+      se[i] = a + b; so[i] = a - b;
+    }
 #pragma unroll
-    for (int i = 0; i < N; i++) acc += TxTab<N>::f(k, i) * buf[i * S + t];
-    col[k] = (acc + 2048) >> 12;
+    for (int k = 0; k < N; k++) {
+      int32_t acc = 0;
+#pragma unroll
+      for (int i = 0; i < N / 2; i++) acc += TxTab<N>::f(k, i) * ((k & 1) ? so[i] : se[i]);
+      col[k] = (acc + 2048) >> 12;
+    }
   }
   __syncwarp(gmask);
 #pragma unroll
@@ -175,18 +225,21 @@ __device__ __forceinline__ int code_tb(const InterLaunch& P, int frame, int p, i
   constexpr int S8 = N + 2;           // pitch of the capped-magnitude map (two zero guard rows / columns)
   unsigned sign_bits = 0, max_lv = 0;
   {
-    int32_t row[N];
+    int32_t rse[N / 2], rso[N / 2];
 #pragma unroll
-    for (int j = 0; j < N; j++) row[j] = buf[t * S + j];
+    for (int j = 0; j < N / 2; j++) {
+      const int32_t a = buf[t * S + j], b = buf[t * S + N - 1 - j];
+      rse[j] = a + b; rso[j] = a - b;
+    }
     constexpr int sh = 24 + 2 * TxTab<N>::kLog2 - TxTab<N>::kRowShift - 4;
     const int lim = (1 << (7 + bd)) - 1;
     const uint32_t rnd_dc = (uint32_t)((P.dc_q * P.quant_rnd) >> 7), rnd_ac = (uint32_t)((P.ac_q * P.quant_rnd) >> 7);
     // the dequantised row goes back to this thread's own row of buf (it has been consumed into row[])
-#pragma unroll 2
+#pragma unroll
     for (int l = 0; l < N; l++) {
       int64_t acc = 0;
 #pragma unroll
-      for (int j = 0; j < N; j++) acc += (int64_t)TxTab<N>::f(l, j) * row[j];
+      for (int j = 0; j < N / 2; j++) acc += (int64_t)TxTab<N>::f(l, j) * ((l & 1) ? rso[j] : rse[j]);
       const int32_t c = (int32_t)((acc * 4096 + ((int64_t)1 << (sh - 1))) >> sh);
       const bool dc = (t | l) == 0;
       const uint32_t dqv = dc ? (uint32_t)P.dc_q : (uint32_t)P.ac_q;

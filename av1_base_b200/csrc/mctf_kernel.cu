@@ -111,7 +111,7 @@ __device__ __forceinline__ void mc_block(const uint16_t* __restrict__ ref, int s
   __syncwarp();
 }
 
-__global__ void __launch_bounds__(kWarps * 32) mctf_kernel(const MctfLaunch P) {
+__global__ void __launch_bounds__(kWarps * 32, 3) mctf_kernel(const MctfLaunch P) {
   __shared__ MctfSmem sm;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const Av1bGeom& g = P.g;

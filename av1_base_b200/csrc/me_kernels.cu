@@ -395,8 +395,9 @@ __global__ void __launch_bounds__(1024) hme_dominant_kernel(const HmeLaunch P, u
   hist[t] = 0; hist[1024 + t] = 0;
 }
 
-// Superblock-level rate-distortion regularisation (oracle: orc_me_sbrd).  One CTA of 16 warps per 64x64 superblock of
-// the checkerboard colour of this half sweep; warp w owns the 16x16 block (w >> 2, w & 3).  For every candidate vector the
+// Superblock-level rate-distortion regularisation (oracle: orc_me_sbrd).  One CTA of 8 warps per 64x64 superblock of
+// the checkerboard colour of this half sweep (8 warps: the decisions are taken by one warp, so small CTAs keep more
+// superblocks in flight per SM); warp w owns the 16x16 blocks w and w + 8 (block b = (b >> 2, b & 3)).  For every candidate vector the
 // CTA stages the 65x65 window of the reference SOURCE picture the superblock points at (aligned 32-bit words, 68-sample
 // row pitch, the odd start handled when the words are read), lane (i, h) of a warp computes the bilinear quarter-sample
 // SAD of 8 samples of row i of its block and the warp adds them up: T[candidate][block].  Warp 0 then takes the
@@ -416,7 +417,7 @@ struct SbrdSmem {
 
 __device__ __forceinline__ uint32_t hw(const uint32_t* w, int i) { return (i & 1) ? (w[i >> 1] >> 16) : (w[i >> 1] & 0xFFFFu); }
 
-__global__ void __launch_bounds__(512) hme_sbrd_kernel(const HmeLaunch P, uint32_t* field16, const uint32_t* __restrict__ dom,
+__global__ void __launch_bounds__(256) hme_sbrd_kernel(const HmeLaunch P, uint32_t* field16, const uint32_t* __restrict__ dom,
                                                        int colour, int16_t* field8) {
   __shared__ SbrdSmem sm;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -459,23 +460,40 @@ __global__ void __launch_bounds__(512) hme_sbrd_kernel(const HmeLaunch P, uint32
     if (first) sm.cand[__popc(m & ((1u << lane) - 1))] = k;
     if (lane == 0) sm.ncand = __popc(m);
   }
-  // ---- this lane's 8 samples of its block row (clamped at the picture edge) ----
-  const int br = warp >> 2, bc = warp & 3, li = lane >> 1, lh = lane & 1;
-  const bool blk_on = br < nr && bc < nc;
-  unsigned c8[8];
-  {
+  // ---- this lane's 8 samples of a row of each of the warp's two blocks (warp w: blocks w and w + 8; clamped at the picture edge) ----
+  const int li = lane >> 1, lh = lane & 1;
+  unsigned c8[2][8];
+  bool blk_on[2];
+#pragma unroll
+  for (int hb = 0; hb < 2; hb++) {
+    const int blk = warp + 8 * hb, br = blk >> 2, bc = blk & 3;
+    blk_on[hb] = br < nr && bc < nc;
     const int y = (y0 + br) * 16 + li, x = (x0 + bc) * 16 + 8 * lh;
-    if (blk_on && y < H && x + 8 <= W) {
+    if (blk_on[hb] && y < H && x + 8 <= W) {
       const uint4 v = *reinterpret_cast<const uint4*>(cur0 + (size_t)y * P.stride0 + x);
-      c8[0] = v.x & 0xFFFFu; c8[1] = v.x >> 16; c8[2] = v.y & 0xFFFFu; c8[3] = v.y >> 16;
-      c8[4] = v.z & 0xFFFFu; c8[5] = v.z >> 16; c8[6] = v.w & 0xFFFFu; c8[7] = v.w >> 16;
+      c8[hb][0] = v.x & 0xFFFFu; c8[hb][1] = v.x >> 16; c8[hb][2] = v.y & 0xFFFFu; c8[hb][3] = v.y >> 16;
+      c8[hb][4] = v.z & 0xFFFFu; c8[hb][5] = v.z >> 16; c8[hb][6] = v.w & 0xFFFFu; c8[hb][7] = v.w >> 16;
     } else {
 #pragma unroll
-      for (int j = 0; j < 8; j++) c8[j] = blk_on ? cur0[(size_t)clampi(y, 0, H - 1) * P.stride0 + clampi(x + j, 0, W - 1)] : 0;
+      for (int j = 0; j < 8; j++) c8[hb][j] = blk_on[hb] ? cur0[(size_t)clampi(y, 0, H - 1) * P.stride0 + clampi(x + j, 0, W - 1)] : 0;
     }
   }
   __syncthreads();
   const int ncand = sm.ncand;
+  if (ncand == 1) {
+    // every block of the superblock and everything around it holds the zero vector: nothing can change
+    if (field8 && tid < 16) {
+      const int r = tid >> 2, c = tid & 3;
+      if (r < nr && c < nc) {
+        const int w8 = W >> 3, h8 = H >> 3;
+        for (int u = 0; u < 4; u++) {
+          const int uy = (y0 + r) * 2 + (u >> 1), ux = (x0 + c) * 2 + (u & 1);
+          if (uy < h8 && ux < w8) reinterpret_cast<uint32_t*>(field8)[(size_t)frame * w8 * h8 + (size_t)uy * w8 + ux] = 0u;
+        }
+      }
+    }
+    return;
+  }
   for (int k = 0; k < ncand; k++) {
     const uint32_t cv = sm.cand[k];
     const int mvy = (int16_t)(cv & 0xFFFFu), mvx = (int16_t)(cv >> 16);
@@ -484,29 +502,32 @@ __global__ void __launch_bounds__(512) hme_sbrd_kernel(const HmeLaunch P, uint32
     const int wxa = wx & ~1, xo = wx & 1;                  // first staged column (even), offset of the window in the row
     __syncthreads();                                       // the window of the candidate before has been read
     if (wy >= 0 && wy + 65 <= H && wxa >= 0 && wx + 65 <= W && wxa + kWinPitch <= P.stride0) {
-      // warp w stages rows w, w + 16, w + 32, w + 48 (and warp 0 row 64): lane = word, lanes 0 and 1 also words 32 and 33
+      // warp w stages rows w, w + 8, ..., w + 56 (and warp 0 row 64): lane = word, lanes 0 and 1 also words 32 and 33
       const uint32_t* src = reinterpret_cast<const uint32_t*>(ref0 + (size_t)(wy + warp) * P.stride0 + wxa) + lane;
       uint32_t* dst = sm.win + warp * (kWinPitch / 2) + lane;
-      const size_t step = (size_t)8 * P.stride0;   // 16 rows in words
+      const size_t step = (size_t)4 * P.stride0;   // 8 rows in words
 #pragma unroll
-      for (int i = 0; i < 4; i++) {
-        dst[i * 16 * (kWinPitch / 2)] = src[i * step];
-        if (lane < 2) dst[i * 16 * (kWinPitch / 2) + 32] = src[i * step + 32];
+      for (int i = 0; i < 8; i++) {
+        dst[i * 8 * (kWinPitch / 2)] = src[i * step];
+        if (lane < 2) dst[i * 8 * (kWinPitch / 2) + 32] = src[i * step + 32];
       }
       if (warp == 0) {
-        dst[64 * (kWinPitch / 2)] = src[4 * step];
-        if (lane < 2) dst[64 * (kWinPitch / 2) + 32] = src[4 * step + 32];
+        dst[64 * (kWinPitch / 2)] = src[8 * step];
+        if (lane < 2) dst[64 * (kWinPitch / 2) + 32] = src[8 * step + 32];
       }
     } else {
-      for (int o = tid; o < 65 * (kWinPitch / 2); o += 512) {
+      for (int o = tid; o < 65 * (kWinPitch / 2); o += 256) {
         const int r = o / (kWinPitch / 2), c = o - r * (kWinPitch / 2);
         const uint16_t* row = ref0 + (size_t)clampi(wy + r, 0, H - 1) * P.stride0;
         sm.win[o] = (uint32_t)row[clampi(wxa + 2 * c, 0, W - 1)] | ((uint32_t)row[clampi(wxa + 2 * c + 1, 0, W - 1)] << 16);
       }
     }
     __syncthreads();
-    if (blk_on) {
-      const int w00 = (4 - fx) * (4 - fy), w01 = fx * (4 - fy), w10 = (4 - fx) * fy, w11 = fx * fy;
+    const int w00 = (4 - fx) * (4 - fy), w01 = fx * (4 - fy), w10 = (4 - fx) * fy, w11 = fx * fy;
+#pragma unroll
+    for (int hb = 0; hb < 2; hb++) {
+      if (!blk_on[hb]) continue;   // warp-uniform
+      const int blk = warp + 8 * hb, br = blk >> 2, bc = blk & 3;
       const uint32_t* r0 = &sm.win[(br * 16 + li) * (kWinPitch / 2) + bc * 8 + 4 * lh];
       uint32_t a[5], b[5];
 #pragma unroll
@@ -515,26 +536,26 @@ __global__ void __launch_bounds__(512) hme_sbrd_kernel(const HmeLaunch P, uint32
       if ((fx | fy) == 0) {   // whole-sample vector: the interpolation is the identity
         if (xo == 0) {
 #pragma unroll
-          for (int j = 0; j < 8; j++) sad = __usad(c8[j], hw(a, j), sad);
+          for (int j = 0; j < 8; j++) sad = __usad(c8[hb][j], hw(a, j), sad);
         } else {
 #pragma unroll
-          for (int j = 0; j < 8; j++) sad = __usad(c8[j], hw(a, j + 1), sad);
+          for (int j = 0; j < 8; j++) sad = __usad(c8[hb][j], hw(a, j + 1), sad);
         }
       } else if (xo == 0) {
 #pragma unroll
         for (int j = 0; j < 8; j++) {
           const unsigned p = (unsigned)(w00 * (int)hw(a, j) + w01 * (int)hw(a, j + 1) + w10 * (int)hw(b, j) + w11 * (int)hw(b, j + 1) + 8) >> 4;
-          sad = __usad(c8[j], p, sad);
+          sad = __usad(c8[hb][j], p, sad);
         }
       } else {
 #pragma unroll
         for (int j = 0; j < 8; j++) {
           const unsigned p = (unsigned)(w00 * (int)hw(a, j + 1) + w01 * (int)hw(a, j + 2) + w10 * (int)hw(b, j + 1) + w11 * (int)hw(b, j + 2) + 8) >> 4;
-          sad = __usad(c8[j], p, sad);
+          sad = __usad(c8[hb][j], p, sad);
         }
       }
       sad = __reduce_add_sync(0xffffffffu, sad);
-      if (lane == 0) sm.T[k][warp] = (int)sad;
+      if (lane == 0) sm.T[k][blk] = (int)sad;
     }
   }
   __syncthreads();
@@ -619,7 +640,7 @@ cudaError_t launch_hme_sbrd(const HmeLaunch& p, int n, cudaStream_t s) {
   hme_dominant_kernel<<<n, 1024, 0, s>>>(p, dom);
   const dim3 grid((nsx + 1) / 2, nsy, n);
   for (int half = 0; half < 2 * p.sbrd_passes; half++)
-    hme_sbrd_kernel<<<grid, 512, 0, s>>>(p, field, dom, half & 1, half + 1 == 2 * p.sbrd_passes || half + 2 == 2 * p.sbrd_passes ? p.mv_out : nullptr);
+    hme_sbrd_kernel<<<grid, 256, 0, s>>>(p, field, dom, half & 1, half + 1 == 2 * p.sbrd_passes || half + 2 == 2 * p.sbrd_passes ? p.mv_out : nullptr);
   return cudaGetLastError();
 }
 

@@ -51,7 +51,7 @@ class Encoder:
         cfg.reserved[5] = 1 if raster_levels else pack_path
         cfg.reserved[6] = int(lr_off)
         cfg.reserved[7] = tile_sb          # inter-frame tile size in superblocks (0 = default)
-        cfg.gop_period = gop_period        # 0 = default (4), 1 = plain P chain
+        cfg.gop_period = gop_period        # 0 = default (6, or a P chain where the quantiser codes the noise), 1 = plain P chain
         cfg.tune[0] = 0 if me_smooth else 1
         cfg.tune[1] = 0 if key_var_part else 1
         cfg.tune[2] = 0 if mctf else 1     # temporal filter of key / anchor sources

@@ -12,6 +12,7 @@ from . import pyoracle as O
 
 _ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 _tables = {}
+DEFAULT_GOP_PERIOD = 6   # csrc/encoder.cc kDefaultGopPeriod
 
 
 def table(name):
@@ -27,7 +28,7 @@ def ac_q(bd, qidx):
     return table("av1t_ac_q_%d" % bd)[qidx]
 
 
-def frame_kind(pos, keyint=240, gop_period=4, intra_only=False):
+def frame_kind(pos, keyint=240, gop_period=DEFAULT_GOP_PERIOD, intra_only=False):
     """0 key, 1 anchor, 2 non-reference (csrc/encoder.cc frame_kind)."""
     if intra_only:
         return 0
@@ -37,7 +38,7 @@ def frame_kind(pos, keyint=240, gop_period=4, intra_only=False):
     return 1 if (gop_period <= 1 or c % gop_period == 0) else 2
 
 
-def quantisers(crf, gop_period=4, intra_only=False):
+def quantisers(crf, gop_period=DEFAULT_GOP_PERIOD, intra_only=False):
     """(key, anchor, non-reference) quantiser indices for a CRF (csrc/encoder.cc av1b_encoder_create)."""
     q = max(1, table("av1t_quantizer_to_qindex")[crf])
     qkey = q if intra_only else max(1, q * 3 // 4)
@@ -66,13 +67,13 @@ class FrameResult:
 
 def choose_structure(g, bd, crf, first_luma_padded):
     """config.gop_period == 0 (csrc/encoder.cc begin_chunk): the P chain where the quantiser is fine enough to code the
-    noise of the chunk's first picture, else the one-level hierarchy of period 4.  Returns (gop_period, noise estimate)."""
+    noise of the chunk's first picture, else the one-level hierarchy of the default period.  Returns (gop_period, noise estimate)."""
     q = max(1, table("av1t_quantizer_to_qindex")[crf])
     nb = O.noise_estimate(g, first_luma_padded)
-    return (1 if 2 * nb > 15 * ac_q(bd, q) else 4), nb
+    return (1 if 2 * nb > 15 * ac_q(bd, q) else DEFAULT_GOP_PERIOD), nb
 
 
-def encode_chain(frames, w, h, bd, crf, keyint=240, gop_period=4, me_smooth=True, key_var_part=True, loop_filters=True,
+def encode_chain(frames, w, h, bd, crf, keyint=240, gop_period=DEFAULT_GOP_PERIOD, me_smooth=True, key_var_part=True, loop_filters=True,
                  lr=False, intra_only=False, blk_log2=4, tb_zero_thr=0, pos0=0, geom=None, mctf=True, batch=8, lookahead=-1,
                  film_grain=0, mctf_radius=2, mctf_key_fwd=4):
     """Returns one FrameResult per frame: kind, fp, res (blocks / coef / pre-filter rec), fin (padded planes after the

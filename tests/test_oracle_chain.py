@@ -139,8 +139,8 @@ def test_noise_estimate_and_structure_choice():
     assert abs(O.noise_estimate(g, l0) - full) <= 0.15 * full
     noisy = O.pad_planes(g, synth.synth_clip(w, h, bd, 1, seed=2, scene_len=100, noise=1.0)[0])[0]
     clean = O.pad_planes(g, synth.synth_clip(w, h, bd, 1, seed=2, scene_len=100, noise=0.1)[0])[0]
-    assert chain.choose_structure(g, bd, 14, noisy)[0] == 1 and chain.choose_structure(g, bd, 44, noisy)[0] == 4
-    assert chain.choose_structure(g, bd, 14, clean)[0] == 4
+    assert chain.choose_structure(g, bd, 14, noisy)[0] == 1 and chain.choose_structure(g, bd, 44, noisy)[0] == chain.DEFAULT_GOP_PERIOD
+    assert chain.choose_structure(g, bd, 14, clean)[0] == chain.DEFAULT_GOP_PERIOD
 
 
 def test_temporal_filter_properties():
