@@ -260,7 +260,7 @@ def bd_rate_check(device_id):
     clip): five points each, PSNR-Y on the dav1d-decoded streams, Bjontegaard cubic fit; every B200 stream must also
     decode to the encoder's reconstruction."""
     sys.path.insert(0, os.path.join(ROOT, "tools"))
-    from bdrate import bd_rate
+    from bdrate import bd_rate, bd_rate_pchip
     from av1_base_b200 import encoder, synth
     from oracle import decoders as D
     w, h, bd, n = 960, 544, 10, 30
@@ -288,6 +288,7 @@ def bd_rate_check(device_id):
             pts.append((k, p))
         out[name] = [{"kbps": k, "psnr_y": p} for k, p in pts]
         out["vs_%s_psnr_y_pct" % name] = bd_rate([x[0] for x in pts], [x[1] for x in pts], [x[0] for x in ours], [x[1] for x in ours])
+        out["vs_%s_psnr_y_pchip_pct" % name] = bd_rate_pchip([x[0] for x in pts], [x[1] for x in pts], [x[0] for x in ours], [x[1] for x in ours])
     return out
 
 

@@ -50,7 +50,7 @@ typedef struct av1b_config {
   int32_t frames_in_flight;       /* frames batched per device pass, 0 = auto                      */
   int32_t gop_period;             /* one-level hierarchy: every gop_period-th frame after a key frame is an anchor (inter frame that
                                      becomes the reference, quantiser index - 8); the frames between two anchors predict from the last
-                                     anchor at quantiser index + 48 and are referenced by nobody.  1 = plain P chain.
+                                     anchor at quantiser index + 64 and are referenced by nobody.  1 = plain P chain.
                                      0 = chosen per chunk: 6, or the P chain where the quantiser is fine enough to code the source's noise
                                      (noise estimate of the chunk's first picture against the quantiser step) */
   int32_t tune[7];                /* [0]: 1 = vector-field regularisation of the motion search off; [1]: 1 = fixed 16x16 key-frame

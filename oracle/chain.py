@@ -43,7 +43,7 @@ def quantisers(crf, gop_period=DEFAULT_GOP_PERIOD, intra_only=False):
     q = max(1, table("av1t_quantizer_to_qindex")[crf])
     qkey = q if intra_only else max(1, q * 3 // 4)
     qa = max(1, q - 8) if gop_period > 1 else q
-    return qkey, qa, min(255, q + 48)
+    return qkey, qa, min(255, q + 64)
 
 
 def class_params(bd, qidx, kind, loop_filters=True, lr=False, tile_log2=(0, 0)):

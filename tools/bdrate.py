@@ -46,6 +46,21 @@ def bd_rate(r1, q1, r2, q2):
     return float((np.exp(a2 - a1) - 1) * 100)
 
 
+def bd_rate_pchip(r1, q1, r2, q2):
+    """Bjontegaard delta rate (%) of curve 2 against curve 1 with piecewise cubic Hermite interpolation of log-rate over
+    quality (the AOM common-test-conditions form: no overshoot between the measured points, unlike one cubic through all)."""
+    from scipy.interpolate import PchipInterpolator
+    o1, o2 = np.argsort(q1), np.argsort(q2)
+    q1, l1 = np.asarray(q1, float)[o1], np.log(np.asarray(r1, float)[o1])
+    q2, l2 = np.asarray(q2, float)[o2], np.log(np.asarray(r2, float)[o2])
+    lo, hi = max(q1[0], q2[0]), min(q1[-1], q2[-1])
+    if hi <= lo:
+        return None
+    a1 = PchipInterpolator(q1, l1).integrate(lo, hi) / (hi - lo)
+    a2 = PchipInterpolator(q2, l2).integrate(lo, hi) / (hi - lo)
+    return float((np.exp(a2 - a1) - 1) * 100)
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--size", default="960x544")

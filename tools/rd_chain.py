@@ -49,13 +49,14 @@ def main():
         res = list(ex.map(encode, jobs))
     for r in res:
         print(json.dumps(r))
-    from bdrate import bd_rate
+    from bdrate import bd_rate, bd_rate_pchip
     if a.ref and os.path.exists(a.ref) and a.noise == 1.0 and a.frames == 30 and (w, h) == (960, 544):
         d = json.load(open(a.ref))["bd_rate"]
         for name in ("libaom_cpu6", "libaom_cpu6_lag0"):
             pts = d[name]
             v = bd_rate([x["kbps"] for x in pts], [x["psnr_y"] for x in pts], [x["kbps"] for x in res], [x["psnr_y"] for x in res])
-            print("BD-rate (PSNR-Y) vs %s: %s" % (name, "%.1f %%" % v if v is not None else "no overlap"))
+            vp = bd_rate_pchip([x["kbps"] for x in pts], [x["psnr_y"] for x in pts], [x["kbps"] for x in res], [x["psnr_y"] for x in res])
+            print("BD-rate (PSNR-Y) vs %s: cubic %s, pchip %s" % (name, "%.1f %%" % v if v is not None else "no overlap", "%.1f %%" % vp if vp is not None else "no overlap"))
 
 
 if __name__ == "__main__":
