@@ -14,7 +14,7 @@ LIB_PATH = os.environ.get("AV1B200_LIB", os.path.join(_HERE, "libav1b200.so"))
 class SeqParams(C.Structure):
     _fields_ = [("width", C.c_int32), ("height", C.c_int32), ("bit_depth", C.c_int32),
                 ("enable_cdef", C.c_int32), ("enable_restoration", C.c_int32),
-                ("fps_num", C.c_int32), ("fps_den", C.c_int32), ("color_hdr", C.c_int32)]
+                ("fps_num", C.c_int32), ("fps_den", C.c_int32), ("color_hdr", C.c_int32), ("film_grain_present", C.c_int32)]
 
 
 class FrameParams(C.Structure):
@@ -24,7 +24,7 @@ class FrameParams(C.Structure):
                 ("cdef_damping", C.c_int32), ("cdef_bits", C.c_int32),
                 ("cdef_y_strength", C.c_int32 * 8), ("cdef_uv_strength", C.c_int32 * 8),
                 ("lr_type", C.c_int32 * 3), ("lr_unit_shift", C.c_int32), ("lr_uv_shift", C.c_int32),
-                ("non_reference", C.c_int32)]
+                ("non_reference", C.c_int32), ("grain_scaling", C.c_int32), ("grain_seed", C.c_int32)]
 
 
 class Geom(C.Structure):

@@ -32,6 +32,7 @@ typedef struct Av1bSeqParams {
   int32_t enable_restoration;
   int32_t fps_num, fps_den;
   int32_t color_hdr;            // 1: signal BT.2020 / PQ
+  int32_t film_grain_present;   // 1: frame headers carry film grain parameters (--film-grain > 0)
 } Av1bSeqParams;
 
 typedef struct Av1bFrameParams {
@@ -50,6 +51,9 @@ typedef struct Av1bFrameParams {
   int32_t lr_uv_shift;          // 0/1
   int32_t non_reference;        // 1: inter frame that updates no reference slot (refresh_frame_flags = 0): the frames after it
                                 //    keep predicting from the last frame that did (one-level hierarchy, tools/rd_oracle.py --hier)
+  int32_t grain_scaling;        // film grain synthesis (spec 5.9.30, only with seq.film_grain_present): 0 = apply_grain 0, else the
+                                //    flat luma scaling value 1..255 (noise sigma = scaling / 64 in 8-bit units; chroma scaled from luma)
+  int32_t grain_seed;           // 16 bits, varied from frame to frame
 } Av1bFrameParams;
 
 // Frame geometry derived from (width, height): all in luma 4x4 "mode info" units unless noted.

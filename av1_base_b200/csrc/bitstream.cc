@@ -111,7 +111,7 @@ void write_sequence_header(const Av1bSeqParams& seq, std::vector<uint8_t>& out) 
   w.bit(0);                   // color_range (studio)
   w.put(0, 2);                // chroma_sample_position
   w.bit(0);                   // separate_uv_delta_q
-  w.bit(0);                   // film_grain_params_present
+  w.bit(seq.film_grain_present ? 1 : 0);   // film_grain_params_present
   w.trailing_bits();
   append_obu(out, 1, w.bytes());
 }
@@ -214,7 +214,28 @@ static void write_frame_header(const Av1bSeqParams& seq, const Av1bFrameParams& 
   // skip_mode_params: skip mode needs order hints (not coded); allow_warped_motion: enable_warped_motion = 0
   w.bit(0);   // reduced_tx_set
   if (inter) for (int i = 0; i < 7; i++) w.bit(0);   // global_motion_params(): is_global = 0 for LAST..ALTREF
-  // film grain: not present
+  // film_grain_params() (spec 5.9.30; every frame is shown): white grain (no auto-regression) with one flat luma scaling
+  // value, chroma scaled from luma -- what the temporal filter and the skipped blocks took out of the source comes back
+  // as synthetic grain in the decoder (--film-grain, av1an.rs:14)
+  if (seq.film_grain_present) {
+    const int s = std::min(255, std::max(0, fp.grain_scaling));
+    w.bit(s > 0);              // apply_grain
+    if (s > 0) {
+      w.put(fp.grain_seed & 0xFFFF, 16);
+      if (inter) w.bit(1);     // update_grain: the parameters follow (no load from a reference)
+      w.put(2, 4);             // num_y_points
+      w.put(0, 8); w.put(s, 8); w.put(255, 8); w.put(s, 8);   // (point_y_value, point_y_scaling) x 2
+      w.bit(1);                // chroma_scaling_from_luma  (num_cb_points = num_cr_points = 0)
+      w.put(3, 2);             // grain_scaling_minus_8: noise = scaling * grain >> 11
+      w.put(0, 2);             // ar_coeff_lag = 0: numPosLuma = 0, numPosChroma = 1
+      w.put(128, 8);           // ar_coeffs_cb_plus_128[0]: no luma contribution
+      w.put(128, 8);           // ar_coeffs_cr_plus_128[0]
+      w.put(0, 2);             // ar_coeff_shift_minus_6
+      w.put(0, 2);             // grain_scale_shift
+      w.bit(1);                // overlap_flag
+      w.bit(0);                // clip_to_restricted_range
+    }
+  }
 }
 
 // ------------------------------------------------------------------------------------------------

@@ -373,6 +373,9 @@ struct Part {
   int n = 0;
   std::shared_ptr<GroupBuf> buf;
   size_t first_slot = 0;           // index of the part's first frame inside buf
+  // seekable input: a whole chunk as a frame range, the worker reads its frames itself (job_n > 0, no buffer attached)
+  int64_t job_first = 0;
+  int job_n = 0;
 };
 
 struct Shared {
@@ -536,6 +539,45 @@ int main(int argc, char** argv) {
 
   // ---- workers: one encoder handle (= one GPU) each, fed with chunk parts through a bounded queue ----
   const int kPart = 16;   // frames per hand-over: two device batches; buffers are recycled through sh.free_bufs
+  // AV1B_CLI_TIMING=1: where the wall clock of the job goes (stderr, at the end)
+  const bool timing = getenv("AV1B_CLI_TIMING") != nullptr;
+  const auto t_job0 = std::chrono::steady_clock::now();
+  auto since = [](std::chrono::steady_clock::time_point t0) { return std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count(); };
+  std::atomic<int64_t> us_create{0}, us_encode{0}, us_flush{0}, us_wread{0};
+  double s_alloc = 0, s_read = 0, s_submit = 0;
+  // seekable Y4M files: frames [first, first + n) into dst (uint16 planes, one frame after the other) with parallel
+  // pread(2), one frame per task; returns 0, 1 (truncated) or 2 (a frame header that is not the plain marker)
+  const int in_fd = in.pipe ? -1 : fileno(in.f);
+  const int kJobPart = 8;            // frames per hand-over of a self-feeding worker: one device batch
+  const int hw_threads = (int)std::max(1u, std::thread::hardware_concurrency());
+  const int worker_io_threads = std::max(1, std::min(8, hw_threads / (2 * std::max(1, (int)dev.size()))));
+  auto read_frames = [&](int64_t first, int n, uint16_t* dst, int n_threads) -> int {
+    std::atomic<int> next{0}, bad{0};
+    auto work = [&]() {
+      std::vector<uint8_t> tmp;
+      for (;;) {
+        const int k = next.fetch_add(1);
+        if (k >= n || bad) break;
+        uint16_t* slot = dst + (size_t)k * frame_samples;
+        const off_t off = (off_t)in.header_len + (off_t)(first + k) * (off_t)(6 + in.frame_bytes) + 6;
+        char mark[6];
+        if (pread(in_fd, mark, 6, off - 6) != 6 || memcmp(mark, "FRAME\n", 6) != 0) { bad = 2; break; }
+        uint8_t* d8 = in.bits > 8 ? reinterpret_cast<uint8_t*>(slot) : (tmp.resize(in.frame_bytes), tmp.data());
+        size_t done = 0;
+        while (done < in.frame_bytes) {
+          const ssize_t r = pread(in_fd, d8 + done, in.frame_bytes - done, off + (off_t)done);
+          if (r <= 0) { bad = 1; break; }
+          done += (size_t)r;
+        }
+        if (in.bits <= 8) for (size_t i = 0; i < in.frame_bytes; i++) slot[i] = (uint16_t)(tmp[i] << shift);
+      }
+    };
+    std::vector<std::thread> io;
+    for (int t = 1; t < n_threads; t++) io.emplace_back(work);
+    work();
+    for (auto& t : io) t.join();
+    return bad.load();
+  };
   struct Queue { std::mutex m; std::condition_variable cv; std::deque<Part> q; bool closed = false; };
   const int W = (int)dev.size();
   sh.q_psnr_sum.assign(W, 0); sh.q_ssim_sum.assign(W, 0); sh.q_frames.assign(W, 0);
@@ -553,9 +595,12 @@ int main(int argc, char** argv) {
       cfg.tune[3] = 1;                 // PSNR / SSIM for the progress events
       cfg.host_threads = std::max(1u, std::thread::hardware_concurrency() / (unsigned)W);
       av1b_encoder* enc = nullptr;
+      std::unique_ptr<GroupBuf> own_buf;   // seekable input: the part buffer this worker reads into
       PacketCtx ctx;
       ctx.sh = &sh;
+      const auto tc0 = std::chrono::steady_clock::now();
       int rc = av1b_encoder_create(&cfg, &enc);
+      us_create += (int64_t)(since(tc0) * 1e6);
       if (rc != AV1B_OK) {
         std::lock_guard<std::mutex> l(sh.m);
         if (!sh.failed) { sh.failed = -rc; sh.error = av1b_last_error(); }
@@ -571,9 +616,11 @@ int main(int argc, char** argv) {
         }
         queues[wk].cv.notify_all();
         if (sh.failed || !enc) continue;   // drain
-        if (part.n == 0) {
+        auto end_chunk = [&]() {
           // end of a chunk: everything still in flight belongs to it; then its packet file is complete
+          const auto tf0 = std::chrono::steady_clock::now();
           rc = av1b_encode_flush(enc, on_packet, nullptr, &ctx);
+          us_flush += (int64_t)(since(tf0) * 1e6);
           if (ctx.f) { if (fclose(ctx.f) != 0) ctx.io_error = true; ctx.f = nullptr; }
           double ps = 0, ss = 0; int64_t qf = 0;
           if (av1b_get_quality(enc, &ps, &ss, &qf) == AV1B_OK) {
@@ -584,8 +631,43 @@ int main(int argc, char** argv) {
             std::lock_guard<std::mutex> l(sh.m);
             if (!sh.failed) { sh.failed = ctx.io_error ? 6 : -rc; sh.error = ctx.io_error ? "cannot write the chunk's packet file (disk full?)" : av1b_last_error(); }
           }
+        };
+        if (part.job_n > 0) {
+          // a whole chunk of a seekable file: this worker reads its frames itself, a part at a time into its own page-locked
+          // buffer (av1b_encode_stream returns once the part has been uploaded, so the next read overlaps the kernels);
+          // the workers read side by side, nobody waits for a common reader
+          ctx.chunk = part.chunk;
+          if (!own_buf) own_buf.reset(new GroupBuf(dev[wk], (size_t)kJobPart * frame_samples));
+          for (int f0 = 0; f0 < part.job_n && !sh.failed; f0 += kJobPart) {
+            const int n = std::min(kJobPart, part.job_n - f0);
+            const auto tr0 = std::chrono::steady_clock::now();
+            const int bad = read_frames(part.job_first + f0, n, own_buf->data(), worker_io_threads);
+            us_wread += (int64_t)(since(tr0) * 1e6);
+            if (bad) {
+              std::lock_guard<std::mutex> l(sh.m);
+              if (!sh.failed) { sh.failed = 3; sh.error = bad == 2 ? "Y4M frame headers carry parameters (or the file is corrupt): pipe it through ffmpeg or rewrite it with plain FRAME markers" : "truncated Y4M file"; }
+              break;
+            }
+            std::vector<av1b_frame_src> fs((size_t)n);
+            for (int k = 0; k < n; k++) {
+              uint16_t* b = own_buf->data() + (size_t)k * frame_samples;
+              fs[k].planes[0] = b; fs[k].planes[1] = b + (size_t)in.w * in.h; fs[k].planes[2] = b + (size_t)in.w * in.h * 5 / 4;
+              fs[k].stride[0] = in.w; fs[k].stride[1] = fs[k].stride[2] = in.w / 2;
+            }
+            const auto te0 = std::chrono::steady_clock::now();
+            rc = av1b_encode_stream(enc, fs.data(), (uint32_t)n, f0 == 0 ? 1 : 0, part.job_first + f0, on_packet, nullptr, &ctx);
+            us_encode += (int64_t)(since(te0) * 1e6);
+            if (rc != AV1B_OK) {
+              std::lock_guard<std::mutex> l(sh.m);
+              if (!sh.failed) { sh.failed = -rc; sh.error = av1b_last_error(); }
+              break;
+            }
+            sh.frames_done += n;
+          }
+          if (!sh.failed) end_chunk();
           continue;
         }
+        if (part.n == 0) { end_chunk(); continue; }
         ctx.chunk = part.chunk;
         std::vector<av1b_frame_src> fs((size_t)part.n);
         for (int k = 0; k < part.n; k++) {
@@ -593,7 +675,9 @@ int main(int argc, char** argv) {
           fs[k].planes[0] = b; fs[k].planes[1] = b + (size_t)in.w * in.h; fs[k].planes[2] = b + (size_t)in.w * in.h * 5 / 4;
           fs[k].stride[0] = in.w; fs[k].stride[1] = fs[k].stride[2] = in.w / 2;
         }
+        const auto te0 = std::chrono::steady_clock::now();
         rc = av1b_encode_stream(enc, fs.data(), (uint32_t)part.n, part.first_part ? 1 : 0, part.first_frame, on_packet, nullptr, &ctx);
+        us_encode += (int64_t)(since(te0) * 1e6);
         part.buf.reset();   // the last part of a group returns the buffer to the pool (custom deleter)
         if (rc != AV1B_OK) {
           std::lock_guard<std::mutex> l(sh.m);
@@ -607,8 +691,9 @@ int main(int argc, char** argv) {
   }
 
   // ---- reader: av1an-style chunking = a new closed GOP at every detected scene cut and at the latest after
-  //      --keyint frames; chunk c -> worker c mod W.  Frames are read in groups of kPart; a regular Y4M file
-  //      is read with parallel pread(2) (one frame per task), a pipe sequentially. ----
+  //      --keyint frames; chunk c -> worker c mod W.  A pipe is read sequentially in groups of kPart frames that travel to
+  //      the workers as parts; of a regular Y4M file the reader only samples the thumbnail rows, the workers read the
+  //      frames of their chunks themselves with parallel pread(2) (one frame per task). ----
   auto take_buffer = [&]() -> std::shared_ptr<GroupBuf> {
     GroupBuf* g = nullptr;
     {
@@ -622,12 +707,14 @@ int main(int argc, char** argv) {
   auto submit = [&](Part&& part) {
     if (part.chunk + 1 > sh.n_chunks) sh.n_chunks = part.chunk + 1;
     Queue& q = queues[(size_t)(part.chunk % W)];
+    const auto ts0 = std::chrono::steady_clock::now();
     {
       std::unique_lock<std::mutex> l(q.m);
       q.cv.wait(l, [&] { return q.q.size() < 3; });
       q.q.push_back(std::move(part));
     }
     q.cv.notify_all();
+    s_submit += since(ts0);
   };
   const int tw = (in.w - 4 + 7) / 8, th = (in.h - 4 + 7) / 8;      // thumbnail: every 8th sample from (4, 4)
   auto make_thumb = [&](const uint16_t* luma, uint16_t* t) {
@@ -642,49 +729,89 @@ int main(int argc, char** argv) {
   double score_avg = -1;
   bool eof = false;
   auto last_report = std::chrono::steady_clock::now();
-  while (!eof && !sh.failed) {
-    std::shared_ptr<GroupBuf> buf = take_buffer();
-    int got = 0;
-    if (in.pipe || in.n_frames < 0) {
-      while (got < kPart) {
-        uint16_t* slot = buf->data() + (size_t)got * frame_samples;
-        if (!y4m_read_frame(in, raw, slot, shift)) { eof = true; break; }
-        make_thumb(slot, thumbs.data() + (size_t)got * tw * th);
-        got++;
-      }
-    } else {
-      got = (int)std::min<int64_t>(kPart, in.n_frames - frame);
-      if (got <= 0) { eof = true; break; }
-      std::atomic<int> next{0};
-      std::atomic<int> bad{0};
+  // scene-cut score: mean absolute luma difference on the 1/8 x 1/8 thumbnails, in 8-bit units;
+  // a cut = a jump well above both an absolute floor and the recent level of change
+  auto is_cut = [&](const uint16_t* tc) -> bool {
+    bool cut = false;
+    if (!thumb_prev.empty() && !o.no_scene_detection) {
+      uint64_t sad = 0;
+      for (int i = 0; i < tw * th; i++) sad += (uint64_t)std::abs((int)tc[i] - (int)thumb_prev[i]);
+      const double score = (double)sad / (tw * th) / (1 << (out_bits - 8));
+      if (in_chunk >= o.min_scene_len && score > 10.0 && (score_avg < 0 || score > 3.0 * score_avg + 2.0)) cut = true;
+      score_avg = score_avg < 0 ? score : 0.8 * score_avg + 0.2 * score;
+      if (cut) score_avg = -1;
+    }
+    thumb_prev.assign(tc, tc + (size_t)tw * th);
+    return cut;
+  };
+  const bool seekable = !in.pipe && in.n_frames >= 0;
+  if (seekable) {
+    // A regular Y4M file: the reader only looks at the thumbnails (the sampled rows: a twelfth of the file), decides the
+    // cuts and hands whole chunks to the workers as frame ranges; every worker reads its own frames (see above).
+    const int kScan = 64;
+    const size_t bps = in.bits > 8 ? 2 : 1;
+    std::vector<uint16_t> sthumbs((size_t)kScan * tw * th);
+    int64_t chunk_first = 0;
+    auto submit_job = [&](int64_t first, int64_t n) {
+      if (n <= 0) return;
+      Part job; job.chunk = chunk; job.job_first = first; job.job_n = (int)n;
+      submit(std::move(job));
+    };
+    while (frame < in.n_frames && !sh.failed) {
+      const auto tr0 = std::chrono::steady_clock::now();
+      const int got = (int)std::min<int64_t>(kScan, in.n_frames - frame);
+      std::atomic<int> next{0}, bad{0};
       auto work = [&]() {
-        std::vector<uint8_t> tmp;
+        std::vector<uint8_t> row((size_t)in.w * bps);
         for (;;) {
           const int k = next.fetch_add(1);
-          if (k >= got) break;
-          uint16_t* slot = buf->data() + (size_t)k * frame_samples;
+          if (k >= got || bad) break;
           const off_t off = (off_t)in.header_len + (off_t)(frame + k) * (off_t)(6 + in.frame_bytes) + 6;
           char mark[6];
-          if (pread(fd, mark, 6, off - 6) != 6 || memcmp(mark, "FRAME\n", 6) != 0) { bad = 2; break; }   // frame headers with parameters: not seekable this way
-          uint8_t* dst = in.bits > 8 ? reinterpret_cast<uint8_t*>(slot) : (tmp.resize(in.frame_bytes), tmp.data());
-          size_t done = 0;
-          while (done < in.frame_bytes) {
-            const ssize_t r = pread(fd, dst + done, in.frame_bytes - done, off + (off_t)done);
-            if (r <= 0) { bad = 1; break; }
-            done += (size_t)r;
+          if (pread(fd, mark, 6, off - 6) != 6 || memcmp(mark, "FRAME\n", 6) != 0) { bad = 2; break; }
+          uint16_t* t = sthumbs.data() + (size_t)k * tw * th;
+          int q = 0;
+          for (int y = 4; y < in.h && !bad; y += 8) {
+            if (pread(fd, row.data(), row.size(), off + (off_t)y * (off_t)row.size()) != (ssize_t)row.size()) { bad = 1; break; }
+            if (bps == 2) { const uint16_t* r16 = reinterpret_cast<const uint16_t*>(row.data()); for (int x = 4; x < in.w; x += 8) t[q++] = r16[x]; }
+            else for (int x = 4; x < in.w; x += 8) t[q++] = (uint16_t)(row[x] << shift);
           }
-          if (in.bits <= 8) for (size_t i = 0; i < in.frame_bytes; i++) slot[i] = (uint16_t)(tmp[i] << shift);
-          make_thumb(slot, thumbs.data() + (size_t)k * tw * th);
         }
       };
       std::vector<std::thread> io;
       for (int t = 1; t < io_threads; t++) io.emplace_back(work);
       work();
       for (auto& t : io) t.join();
+      s_read += since(tr0);
       if (bad == 2) die(3, "Y4M frame headers carry parameters (or the file is corrupt): pipe it through ffmpeg or rewrite it with plain FRAME markers");
       if (bad) die(3, "truncated Y4M file");
-      if (frame + got >= in.n_frames) eof = true;
+      for (int k = 0; k < got; k++) {
+        const bool cut = is_cut(sthumbs.data() + (size_t)k * tw * th);
+        if (frame > 0 && (cut || in_chunk >= o.keyint)) {
+          submit_job(chunk_first, frame - chunk_first);
+          chunk_first = frame; chunk++; in_chunk = 0;
+        }
+        frame++; in_chunk++;
+      }
+      const auto now = std::chrono::steady_clock::now();
+      if (std::chrono::duration<double>(now - last_report).count() > 1.0) { report_progress(sh, false); last_report = now; }
     }
+    submit_job(chunk_first, frame - chunk_first);
+    eof = true;
+  }
+  while (!eof && !sh.failed) {
+    const auto ta0 = std::chrono::steady_clock::now();
+    std::shared_ptr<GroupBuf> buf = take_buffer();
+    s_alloc += since(ta0);
+    const auto tr0 = std::chrono::steady_clock::now();
+    int got = 0;
+    while (got < kPart) {   // a pipe (or a file of unknown length): frames arrive in order
+      uint16_t* slot = buf->data() + (size_t)got * frame_samples;
+      if (!y4m_read_frame(in, raw, slot, shift)) { eof = true; break; }
+      make_thumb(slot, thumbs.data() + (size_t)got * tw * th);
+      got++;
+    }
+    s_read += since(tr0);
     // cut decisions in display order; a part never crosses a chunk boundary
     int run_start = 0;
     auto emit = [&](int from, int to) {
@@ -695,19 +822,7 @@ int main(int argc, char** argv) {
       submit(std::move(part));
     };
     for (int k = 0; k < got; k++) {
-      const uint16_t* tc = thumbs.data() + (size_t)k * tw * th;
-      bool cut = false;
-      if (!thumb_prev.empty() && !o.no_scene_detection) {
-        uint64_t sad = 0;
-        for (int i = 0; i < tw * th; i++) sad += (uint64_t)std::abs((int)tc[i] - (int)thumb_prev[i]);
-        // scene-cut score: mean absolute luma difference on the 1/8 x 1/8 thumbnails, in 8-bit units;
-        // a cut = a jump well above both an absolute floor and the recent level of change
-        const double score = (double)sad / (tw * th) / (1 << (out_bits - 8));
-        if (in_chunk >= o.min_scene_len && score > 10.0 && (score_avg < 0 || score > 3.0 * score_avg + 2.0)) cut = true;
-        score_avg = score_avg < 0 ? score : 0.8 * score_avg + 0.2 * score;
-        if (cut) score_avg = -1;
-      }
-      thumb_prev.assign(tc, tc + (size_t)tw * th);
+      const bool cut = is_cut(thumbs.data() + (size_t)k * tw * th);
       if (frame > 0 && (cut || in_chunk >= o.keyint)) {
         emit(run_start, k);
         run_start = k;
@@ -720,9 +835,24 @@ int main(int argc, char** argv) {
     const auto now = std::chrono::steady_clock::now();
     if (std::chrono::duration<double>(now - last_report).count() > 1.0) { report_progress(sh, false); last_report = now; }
   }
-  if (frame > 0) { Part end; end.chunk = chunk; end.n = 0; submit(std::move(end)); }
+  if (frame > 0 && !seekable) { Part end; end.chunk = chunk; end.n = 0; submit(std::move(end)); }
   for (auto& q : queues) { { std::lock_guard<std::mutex> l(q.m); q.closed = true; } q.cv.notify_all(); }
-  for (auto& t : threads) t.join();
+  // the workers of a seekable job still have whole chunks ahead of them: keep the progress events coming
+  {
+    std::atomic<bool> joined{false};
+    std::thread reporter([&]() {
+      auto last = std::chrono::steady_clock::now();
+      while (!joined) {
+        usleep(100 * 1000);
+        const auto now = std::chrono::steady_clock::now();
+        if (!joined && std::chrono::duration<double>(now - last).count() > 1.0) { report_progress(sh, false); last = now; }
+      }
+    });
+    for (auto& t : threads) t.join();
+    joined = true;
+    reporter.join();
+  }
+  const double s_encode_phase = since(t_job0);
   auto cleanup_packets = [&]() {
     for (int64_t c = 0; c < sh.n_chunks; c++) unlink(chunk_file(sh, c).c_str());
     if (o.temp.empty()) rmdir(sh.pkt_dir.c_str());
@@ -776,5 +906,9 @@ int main(int argc, char** argv) {
   }
   if (!ok || rename(tmp_out.c_str(), o.output.c_str()) != 0) { unlink(tmp_out.c_str()); die(6, "cannot write %s", o.output.c_str()); }
   report_progress(sh, true);
+  if (timing)
+    fprintf(stderr, "av1an timing: total %.2f s = read+encode phase %.2f s + container %.2f s; reader: buffers %.2f s, read %.2f s, waiting for workers %.2f s; "
+                    "workers (summed over %d): encoder create %.2f s, own reads %.2f s, encode calls %.2f s, flushes %.2f s\n",
+            since(t_job0), s_encode_phase, since(t_job0) - s_encode_phase, s_alloc, s_read, s_submit, W, us_create / 1e6, us_wread / 1e6, us_encode / 1e6, us_flush / 1e6);
   return 0;
 }

@@ -194,6 +194,7 @@ struct av1b_encoder {
   bool gop_auto = true;               // structure chosen per chunk from the source's noise level (config.gop_period == 0)
   bool mctf_cfg = true;               // temporal filter allowed by the configuration
   int noise_b = 0;                    // noise estimate of the chunk's first picture (av1b_noise_from_hist)
+  int grain_scaling = 0;              // film grain synthesis strength of the chunk (--film-grain > 0 and a filtered structure)
   uint32_t* d_noise_hist = nullptr;
   uint32_t* h_noise_hist = nullptr;
   cudaEvent_t ev_noise = nullptr;
@@ -332,6 +333,12 @@ static int stage(av1b_encoder* e, Slot& s, const av1b_frame_src* frames, int n) 
     return AV1B_OK;
   }
   CK(cudaEventSynchronize(s.ev_src));   // the previous upload out of this slot's staging buffer has finished
+  for (int p = 0; p < 3; p++)
+    if (!s.h_src[p]) {
+      const size_t bytes = e->plane_elems[p] * (size_t)e->batch * 2;
+      CK(cudaMallocHost(&s.h_src[p], bytes));
+      memset(s.h_src[p], 0, bytes);
+    }
   const int kSplit = 4;   // row bands per plane
   e->pool->parallel_for(n * 3 * kSplit, [&](int task) {
     const int b = task / (3 * kSplit), p = (task / kSplit) % 3, band = task % kSplit;
@@ -652,8 +659,10 @@ static int launch(av1b_encoder* e, Slot& s, const Slot& in, int n, int64_t first
   }
   for (int b = 0; b < n; b++) {
     if (!(e->keep || s.is_key[b] || !e->token_path)) continue;
-    for (int p = 0; p < 3; p++)
+    for (int p = 0; p < 3; p++) {
+      if (!s.h_coef[p]) CK(cudaMallocHost(&s.h_coef[p], e->plane_elems[p] * (size_t)e->batch * 2));
       CK(cudaMemcpyAsync(s.h_coef[p] + (size_t)b * e->plane_elems[p], s.d_coef[p] + (size_t)b * e->plane_elems[p], e->plane_elems[p] * 2, cudaMemcpyDeviceToHost, e->s_out));
+    }
     CK(cudaMemcpyAsync(s.h_cdef_idx + (size_t)b * nsb, s.d_cdef_idx + (size_t)b * nsb, nsb, cudaMemcpyDeviceToHost, e->s_out));
     CK(cudaMemcpyAsync(s.h_blocks + (size_t)b * e->map_elems, s.d_blocks + (size_t)b * e->map_elems, e->map_elems * sizeof(Av1bBlockInfo), cudaMemcpyDeviceToHost, e->s_out));
     e->d2h_bytes += (int64_t)((e->plane_elems[0] + e->plane_elems[1] + e->plane_elems[2]) * 2 + nsb + e->map_elems * sizeof(Av1bBlockInfo));
@@ -767,10 +776,16 @@ static int finish(av1b_encoder* e, Slot& s, bool staged, av1b_packet_cb out_cb, 
     const Av1bGeom& gb = s.is_key[b] ? e->g : e->g_inter;
     memset(&sy[b], 0, sizeof(Av1bFrameSyms));
     sy[b].blocks = s.h_blocks + (size_t)b * e->map_elems;
-    for (int p = 0; p < 3; p++) { sy[b].coef[p] = s.h_coef[p] + (size_t)b * e->plane_elems[p]; sy[b].coef_stride[p] = g.stride[p]; }
+    for (int p = 0; p < 3; p++) { sy[b].coef[p] = s.h_coef[p] ? s.h_coef[p] + (size_t)b * e->plane_elems[p] : nullptr; sy[b].coef_stride[p] = g.stride[p]; }
     sy[b].cdef_idx = s.h_cdef_idx + (size_t)b * g.sb_rows * g.sb_cols;
     if (e->lr_on) { sy[b].lr_units[0] = s.h_lr_units + (size_t)b * e->lr_n; sy[b].lr_unit_rows[0] = e->lr_rows; sy[b].lr_unit_cols[0] = e->lr_cols; }
-    pack_frame_header(e->seq, kind_params(e, s.kind[b]), gb, packs[b]);
+    Av1bFrameParams fph = kind_params(e, s.kind[b]);
+    if (e->grain_scaling > 0) {
+      const uint32_t fi = (uint32_t)(s.first_index + b);
+      fph.grain_scaling = e->grain_scaling;
+      fph.grain_seed = (int32_t)(((fi + 1) * 2654435761u) >> 16);   // another seed for every frame
+    }
+    pack_frame_header(e->seq, fph, gb, packs[b]);
     for (int t = 0; t < gb.tile_cols * gb.tile_rows; t++) tasks.emplace_back(b, t);
   }
   if (s.has_tokens && !rc) {
@@ -887,11 +902,12 @@ int av1b_encoder_create(const av1b_config* cfg, av1b_encoder** out) {
     // tiles of inter frames are the unit of entropy-coder parallelism.  The host coder wants few large ones (longer
     // CDF adaptation): about 12x12 superblocks.  The device coder walks a tile with one warp, a serial chain of about
     // 100 ns per symbol, so its latency is that of the largest tile: about 6x6 superblocks (reserved[7] overrides).
-    // Where the range coder runs (reserved[5] = 0: automatic): a tile costs one host thread about 15 ns per symbol
-    // and one warp up to 0.5 us beside the other kernels (latency, hidden behind the next batches), so with a dozen
-    // host threads for this GPU the host is the faster place; with fewer (8 GPUs on a 32-core box: 4 each) the host would throttle the GPU and the device codes.
+    // Where the range coder runs (reserved[5] = 0: automatic): a 150-frame 4K chunk at CRF 30 is about 230 thread-ms of host
+    // range coding against 75 ms of kernels, so four host threads for this GPU keep up with it (8 GPUs on a 32-core box:
+    // 14156 fps with the host coder, 13041 fps with the device coder whose single-warp chains then bound the step,
+    // profiles/r02j_scale_n8_*.json); with fewer threads the host would throttle the GPU and the device codes.
     const int ht = cfg->host_threads > 0 ? cfg->host_threads : (int)std::max(1u, std::thread::hardware_concurrency());
-    e->rc_on = cfg->reserved[5] == 4 || (cfg->reserved[5] == 0 && ht < 12);
+    e->rc_on = cfg->reserved[5] == 4 || (cfg->reserved[5] == 0 && ht < 4);
     e->n_slots = (e->rc_on && e->token_path && cfg->reserved[3] == 0) ? 4 : 3;
     // (4x4 up to 1080p, where a batch is short and the frame has few tiles)
     const int tsb = cfg->reserved[7] > 0 ? cfg->reserved[7] : (e->rc_on ? (probe.sb_cols * probe.sb_rows <= 600 ? 4 : 6) : 12);
@@ -905,6 +921,7 @@ int av1b_encoder_create(const av1b_config* cfg, av1b_encoder** out) {
   e->lr_on = e->loop_filters && cfg->preset <= 5 && cfg->reserved[6] == 0;
   e->seq.enable_cdef = e->loop_filters ? 1 : 0; e->seq.enable_restoration = e->lr_on ? 1 : 0;
   e->seq.fps_num = cfg->fps_num; e->seq.fps_den = cfg->fps_den; e->seq.color_hdr = cfg->hdr;
+  e->seq.film_grain_present = cfg->film_grain > 0 ? 1 : 0;
   e->base_q_idx = av1t_quantizer_to_qindex[cfg->crf];
   if (e->base_q_idx < 1) e->base_q_idx = 1;   // lossless (qindex 0) is not supported
   e->base_q_idx_key = cfg->reserved[3] ? e->base_q_idx : std::max(1, e->base_q_idx * 3 / 4);
@@ -963,9 +980,11 @@ int av1b_encoder_create(const av1b_config* cfg, av1b_encoder** out) {
     for (int p = 0; p < 3; p++) {
       const size_t n = e->plane_elems[p] * F;
       A(cudaMalloc(&s.d_src[p], n * 2)); A(cudaMalloc(&s.d_coef[p], n * 2));
-      A(cudaMallocHost(&s.h_src[p], n * 2)); A(cudaMallocHost(&s.h_coef[p], n * 2));
+      // the page-locked staging copy of the sources (pageable callers) and the page-locked mirror of the levels (key frames,
+      // debug mode) are allocated when they are first needed: 400 MB per slot at 4K that a job with page-locked sources and
+      // one key frame per chunk hardly touches, and pinning memory is what makes encoder start-up slow
       if (e->keep) A(cudaMallocHost(&s.h_rec[p], n * 2));
-      if (err == cudaSuccess) { A(cudaMemset(s.d_src[p], 0, n * 2)); A(cudaMemset(s.d_coef[p], 0, n * 2)); memset(s.h_src[p], 0, n * 2); }
+      if (err == cudaSuccess) { A(cudaMemset(s.d_src[p], 0, n * 2)); A(cudaMemset(s.d_coef[p], 0, n * 2)); }
     }
     A(cudaMallocHost(&s.h_blocks, e->map_elems * F * sizeof(Av1bBlockInfo)));
     A(cudaMallocHost(&s.h_cdef_idx, nsb * F));
@@ -1135,7 +1154,7 @@ static void set_structure(av1b_encoder* e, int gop_period) {
 static int begin_chunk(av1b_encoder* e, Slot& first) {
   if (e->intra_only) return AV1B_OK;
   int gop = e->cfg.gop_period > 0 ? e->cfg.gop_period : kDefaultGopPeriod;
-  if (e->gop_auto) {
+  if (e->gop_auto || e->cfg.film_grain > 0) {
     CK(cudaStreamWaitEvent(e->s_in, first.ev_src, 0));
     CK(launch_noise_hist(e->g, first.d_src[0], e->d_noise_hist, e->s_in));
     CK(cudaMemcpyAsync(e->h_noise_hist, e->d_noise_hist, 4096 * sizeof(uint32_t), cudaMemcpyDeviceToHost, e->s_in));
@@ -1144,8 +1163,14 @@ static int begin_chunk(av1b_encoder* e, Slot& first) {
     e->kernel_launches += 1;
     e->noise_b = av1b_noise_from_hist(e->h_noise_hist);
     const int acq = e->cfg.bit_depth == 8 ? av1t_ac_q_8[e->q_nominal] : av1t_ac_q_10[e->q_nominal];
-    if (2 * e->noise_b > 15 * acq) gop = 1;
+    if (e->gop_auto && 2 * e->noise_b > 15 * acq) gop = 1;
   }
+  // film grain synthesis: where the structure takes the noise out (temporally filtered anchors, skipped blocks elsewhere) the
+  // decoder puts grain of three quarters of the measured strength back; sigma = 0.0010658 * noise_b samples at the source's
+  // bit depth, a scaling value of 64 stands for sigma 1 in 8-bit units.  The P chain codes the noise itself: no grain there.
+  e->grain_scaling = 0;
+  if (e->cfg.film_grain > 0 && gop > 1)
+    e->grain_scaling = (int)std::min<long long>(255, ((long long)e->noise_b * 51 + (500 << (e->cfg.bit_depth - 8))) / (1000 << (e->cfg.bit_depth - 8)));
   if (gop != e->gop_period) set_structure(e, gop);
   if (e->rc_on && e->token_path && (e->cdf_q[0] != e->base_q_idx || e->cdf_q[1] != e->base_q_idx_nonref)) {
     std::vector<uint8_t> img(tile_cdfs_size());

@@ -400,12 +400,14 @@ def main():
     nf = st["frames_done"]
     n_batches = args.steps * ((chunk + F - 1) // F)
     n_tf = max(1, st["mctf_frames"])
+    # CDEF runs on the key and anchor frames only (the non-reference frames signal none)
+    n_cdef = max(1, args.steps * sum(1 for pos in range(chunk) if enc.frame_kind(pos) != 2))
     # per-kernel CUDA-event time per unit (frame; ME and tokenizer per batch) and algorithmic bytes per unit
     kern = {
         "inter_encode_kernel": (st["inter_ms"] / n_inter, 4 * S),
         "intra_encode_kernel": (st["intra_ms"] / n_key, 3 * S),
         "deblock_kernel": (st["deblock_ms"] / max(1, nf), 2 * S),
-        "cdef_kernel": (st["cdef_ms"] / max(1, nf), 3 * S),
+        "cdef_kernel": (st["cdef_ms"] / n_cdef, 3 * S),
         "pyramid+hme+regularisation (per batch)": ((st["me_ms"] - st["mctf_ms"]) / n_batches, int((1.3125 + 0.625 + 2.0 + 2 * 2.0) * (w * h * 2)) * F),
         # temporal filter of one key / anchor picture: 4 searches (2.625 Y each) + the filter itself ((2 + 4) S)
         "temporal filter: hme + mctf_kernel (per filtered picture)": (st["mctf_ms"] / n_tf, int(4 * 2.625 * (w * h * 2)) + 6 * S),
@@ -432,7 +434,7 @@ def main():
         "scaling": "weak", "vs_baseline": None, "dtype": "u16/i32", "data": "synthetic",
         "config": cfg,
         "encoder": {"base_q_idx_anchor": st["base_q_idx"], "frames_in_flight": F, "key_frames": st["key_frames"], "inter_frames": st["inter_launches"],
-                    "temporally_filtered_frames": st["mctf_frames"], "tiles_key_frames": "%dx%d" % (g.tile_cols, g.tile_rows),
+                    "temporally_filtered_frames": st["mctf_frames"], "cdef_frames": n_cdef, "gop_period": enc.chunk_info()["gop_period"], "tiles_key_frames": "%dx%d" % (g.tile_cols, g.tile_rows),
                     "tile_sb_inter": args.tile_sb, "pack_path": args.pack_path, "host_threads": sharding.host_threads_per_rank(world),
                     "l2": "inputs larger than L2 (%.0f MB of distinct source pictures, %.0f MB working set per batch)" % (args.distinct * frame_bytes / 1e6, 5 * F * frame_bytes / 1e6),
                     "timing": "wall clock between synchronize+barrier pairs (host entropy coding is part of the step); "

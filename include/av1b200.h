@@ -41,7 +41,10 @@ typedef struct av1b_config {
   int32_t lookahead;              /* --lookahead: source pictures the temporal filter of key / anchor pictures may look ahead
                                      (it uses up to 4); -1 = default, 0 = none                                        */
   int32_t film_grain;             /* --film-grain 0..50: strength of the temporal (denoising) filter on top of what the
-                                     quantiser asks for                                                               */
+                                     quantiser asks for; > 0 also signals film grain parameters (spec 5.9.30: flat luma scaling
+                                     from the noise level measured on the chunk's first picture, chroma from luma, white grain)
+                                     in the chunks that are coded with the filtered structure, so that decoders put back
+                                     what the filter and the skipped blocks took out                                  */
   int32_t enable_qm, qm_min, qm_max; /* accepted; flat quantisation matrices only                  */
   int32_t tile_cols_log2, tile_rows_log2; /* -1 = auto (fill the GPU)                              */
   int32_t device_id;

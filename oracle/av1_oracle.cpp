@@ -97,6 +97,12 @@ extern "C" void orc_inv_txfm2d_add(const int32_t* dq, int cstride, uint16_t* dst
   }
 }
 
+// n blocks in a row: block b reads dq + b * min(w,32) * min(h,32) and updates dst + b * w * h (the 4096-block suite).
+extern "C" void orc_inv_txfm2d_add_batch(int n, const int32_t* dq, uint16_t* dst, int w, int h, int tx_type, int bd) {
+  const int cw = std::min(w, 32), ch = std::min(h, 32);
+  for (int b = 0; b < n; b++) orc_inv_txfm2d_add(dq + (size_t)b * cw * ch, cw, dst + (size_t)b * w * h, w, w, h, tx_type, bd);
+}
+
 static inline int fwd_coef(int t, int n, int k, int i) {
   if (t == T_IDT) {
     if (k != i) return 0;
@@ -617,6 +623,10 @@ static int sad_block(const uint16_t* cur, const uint16_t* ref, int stride, int w
     for (int j = 0; j < n; j++)
       s += abs(px_clamped(cur, stride, w, h, bx + j, by + i) - px_clamped(ref, stride, w, h, bx + j + dx, by + i + dy));
   return s;
+}
+// the block SAD of the motion search, exported so that tests can pin it against libaom's aom_highbd_sad*_c
+extern "C" int orc_sad_block(const uint16_t* cur, const uint16_t* ref, int stride, int w, int h, int bx, int by, int n, int dx, int dy) {
+  return sad_block(cur, ref, stride, w, h, bx, by, n, dx, dy);
 }
 enum { kR2 = 12 };
 // offset of the minimum in quarter samples (-2..2) from the costs at -1, 0, +1 (0 when the three points are not convex)

@@ -55,7 +55,7 @@ def _img_to_planes(img_ptr):
             a = a.view(np.uint16)[:, :w]
         else:
             a = a[:, :w].astype(np.uint16)
-        out.append(np.ascontiguousarray(a))
+        out.append(np.array(a, dtype=np.uint16, order="C", copy=True))   # the decoder reuses / frees its buffers
     return out
 
 def aom_decode(temporal_units):
@@ -83,12 +83,13 @@ def aom_decode(temporal_units):
         A.aom_codec_destroy(ctx)
     return frames
 
-def dav1d_decode(temporal_units):
+def dav1d_decode(temporal_units, apply_grain=False):
+    """apply_grain: let dav1d add the film grain a stream signals (the reconstruction checks decode without it)."""
     D = dav1d()
     settings = ctypes.create_string_buffer(512)
     D.dav1d_default_settings(settings)
     s32 = ctypes.cast(settings, ctypes.POINTER(ctypes.c_int32))
-    s32[0] = 1; s32[1] = 1; s32[2] = 0      # n_threads, max_frame_delay, apply_grain
+    s32[0] = 1; s32[1] = 1; s32[2] = 1 if apply_grain else 0      # n_threads, max_frame_delay, apply_grain
     c = ctypes.c_void_p(0)
     rc = D.dav1d_open(ctypes.byref(c), settings)
     if rc:

@@ -26,7 +26,7 @@ def test_inv_txfm_add_vs_libaom_and_oracle(w, h, bd):
     rng = np.random.default_rng(w * 131 + h * 7 + bd)
     cw, ch = min(w, 32), min(h, 32)
     lim = 1 << (bd + 7)
-    n = 96
+    n = 4096    # 4096 blocks per size and type
     for tx in legal_types(w, h):
         co = rng.integers(-lim, lim, (n, ch, cw))
         co[n // 3:2 * n // 3] = rng.integers(-300, 300, (n // 3, ch, cw)) * (rng.random((n // 3, ch, cw)) < 0.15)
@@ -35,10 +35,10 @@ def test_inv_txfm_add_vs_libaom_and_oracle(w, h, bd):
         co = np.ascontiguousarray(co, np.int32)
         pred = rng.integers(0, 1 << bd, (n, h, w)).astype(np.uint16)
         got, _ = kernels.inv_txfm_add(co, pred, w, h, tx, bd)
-        for b in range(0, n, 5):
-            mine = pred[b].copy()
-            O.lib().orc_inv_txfm2d_add(O.ptr(co[b]), cw, O.ptr(mine), w, w, h, tx, bd)
-            assert np.array_equal(got[b], mine), ("oracle", w, h, tx, b)
+        mine = pred.copy()                       # every block against the oracle
+        O.lib().orc_inv_txfm2d_add_batch(n, O.ptr(co), O.ptr(mine), w, h, tx, bd)
+        assert np.array_equal(got, mine), ("oracle", w, h, tx, np.nonzero((got != mine).any(axis=(1, 2)))[0][:4])
+        for b in range(0, n, 37):                # and a sample of them against libaom's C function
             theirs = pred[b].copy()
             buf = np.zeros(64 * 64, np.int32)
             ci = np.ascontiguousarray(co[b].T, np.int32)

@@ -107,3 +107,37 @@ def test_full_key_frame_decodes_bit_exact(w, h, bd, q, tcl, trl, lf, cdef_bits, 
         for fi in range(len(frames)):
             for p in range(3):
                 assert np.array_equal(out[fi][p], recs[fi][p]), (name, fi, p)
+
+
+def test_film_grain_parameters_decode_and_add_grain():
+    """Row f-4 (--film-grain): a stream whose sequence header announces film grain and whose frame headers carry our
+    parameter set (spec 5.9.30: two luma scaling points, chroma from luma, no auto-regression) must decode in dav1d and
+    libaom, and the decoders must add grain of about the signalled strength on top of the encoder's reconstruction."""
+    from av1_base_b200 import abi, packer, synth
+    from oracle import chain, decoders as D
+    w, h, bd, n = 200, 136, 10, 3
+    frames = synth.synth_clip(w, h, bd, n, seed=11, scene_len=100, noise=0.0)
+    g, res = chain.encode_chain(frames, w, h, bd, 36, gop_period=2)
+    for scaling in (0, 96):
+        seq = abi.SeqParams(w, h, bd, 1, 0, 30, 1, 0, 1)
+        tus = []
+        for i, r in enumerate(res):
+            fp = r.fp
+            fp.tile_cols_log2, fp.tile_rows_log2 = g.tile_cols_log2, g.tile_rows_log2
+            fp.grain_scaling, fp.grain_seed = scaling, 1234 + 77 * i
+            sy = packer.make_syms(g, r.res.blocks, r.res.coef, cdef_idx=r.cdef_idx)
+            tus.append(b"\x12\x00" + (packer.pack_sequence_header(seq) if i == 0 else b"") + packer.pack_frame(seq, fp, sy, with_td=False))
+        for name, dec in (("dav1d", D.dav1d_decode(tus)), ("dav1d+grain", D.dav1d_decode(tus, apply_grain=True)), ("libaom", D.aom_decode(tus))):
+            assert len(dec) == n, name
+            for i, r in enumerate(res):
+                for p in range(3):
+                    rec = O.crop(g, r.fin)[p].astype(np.int64)
+                    d = dec[i][p].astype(np.int64) - rec
+                    if scaling == 0 or name == "dav1d":
+                        # apply_grain = 0, or a decoder asked for the pictures without grain: the plain reconstruction -- the
+                        # parameters were parsed exactly, or the tile data behind them would not decode
+                        assert not d.any(), (name, i, p)
+                    else:             # sigma = scaling / 64 in 8-bit units, x4 at 10 bits (clipping at the range ends aside)
+                        sigma = d.std()
+                        assert 0.5 * (scaling / 64.0) * 4 < sigma < 1.6 * (scaling / 64.0) * 4, (name, i, p, sigma)
+                        assert abs(d.mean()) < 1.0, (name, i, p, d.mean())

@@ -102,3 +102,24 @@ def test_intra_predictors_vs_libaom(n, bd):
                 O.lib().orc_intra_predict(O.ptr(b), n, n, n, C.c_void_p(above.ctypes.data),
                                           C.c_void_p(left.ctypes.data), mode, delta, 1, 1, bd)
                 assert np.array_equal(a, b), (mode, delta, n)
+
+
+@pytest.mark.parametrize("n", [8, 16])
+@pytest.mark.parametrize("bd", [8, 10])
+def test_motion_search_sad_vs_libaom(n, bd):
+    """the block SAD the motion search is built on against libaom's aom_highbd_sad{8x8,16x16}_c on the same
+    samples (high-bit-depth buffers are passed as CONVERT_TO_BYTEPTR pointers: the address shifted right by one)."""
+    f = aomsym.func("aom_highbd_sad%dx%d_c" % (n, n), C.c_uint, [C.c_void_p, C.c_int, C.c_void_p, C.c_int])
+    rng = np.random.default_rng(n + bd)
+    w, h, stride = 96, 80, 128
+    cur = np.zeros((h, stride), np.uint16); ref = np.zeros((h, stride), np.uint16)
+    cur[:, :w] = rng.integers(0, 1 << bd, (h, w)); ref[:, :w] = rng.integers(0, 1 << bd, (h, w))
+    for _ in range(200):
+        bx, by = int(rng.integers(8, w - n - 8)), int(rng.integers(8, h - n - 8))
+        dx, dy = int(rng.integers(-8, 9)), int(rng.integers(-8, 9))
+        mine = O.lib().orc_sad_block(O.ptr(cur), O.ptr(ref), stride, w, h, bx, by, n, dx, dy)
+        a = cur.ctypes.data + 2 * (by * stride + bx)
+        b = ref.ctypes.data + 2 * ((by + dy) * stride + bx + dx)
+        assert a % 2 == 0 and b % 2 == 0
+        theirs = f(C.c_void_p(a >> 1), stride, C.c_void_p(b >> 1), stride)
+        assert mine == theirs, (bx, by, dx, dy)

@@ -65,7 +65,7 @@ def main():
         t0 = time.perf_counter()
         r = subprocess.run(cmd, capture_output=True, text=True)
         dt = time.perf_counter() - t0
-        rec = dict(workers=wk, returncode=r.returncode, seconds=round(dt, 2), fps=round(frames / dt, 1), stderr=r.stderr[-300:])
+        rec = dict(workers=wk, returncode=r.returncode, seconds=round(dt, 2), fps=round(frames / dt, 1), stderr=r.stderr[-700:])
         if r.returncode == 0:
             data = open(out, "rb").read()
             codec, _, blocks = mkv_blocks(data)
