@@ -595,7 +595,7 @@ int main(int argc, char** argv) {
       cfg.tune[3] = 1;                 // PSNR / SSIM for the progress events
       cfg.host_threads = std::max(1u, std::thread::hardware_concurrency() / (unsigned)W);
       av1b_encoder* enc = nullptr;
-      std::unique_ptr<GroupBuf> own_buf;   // seekable input: the part buffer this worker reads into
+      std::unique_ptr<GroupBuf> own_buf[2];   // seekable input: the part buffers this worker reads into
       PacketCtx ctx;
       ctx.sh = &sh;
       const auto tc0 = std::chrono::steady_clock::now();
@@ -637,26 +637,37 @@ int main(int argc, char** argv) {
           // buffer (av1b_encode_stream returns once the part has been uploaded, so the next read overlaps the kernels);
           // the workers read side by side, nobody waits for a common reader
           ctx.chunk = part.chunk;
-          if (!own_buf) own_buf.reset(new GroupBuf(dev[wk], (size_t)kJobPart * frame_samples));
-          for (int f0 = 0; f0 < part.job_n && !sh.failed; f0 += kJobPart) {
+          for (auto& ob : own_buf) if (!ob) ob.reset(new GroupBuf(dev[wk], (size_t)kJobPart * frame_samples));
+          // two part buffers: the next part is read (by a helper thread) while the current one is uploaded and coded
+          auto read_part = [&](int f0, int which) -> int {
             const int n = std::min(kJobPart, part.job_n - f0);
             const auto tr0 = std::chrono::steady_clock::now();
-            const int bad = read_frames(part.job_first + f0, n, own_buf->data(), worker_io_threads);
+            const int bad = read_frames(part.job_first + f0, n, own_buf[which]->data(), worker_io_threads);
             us_wread += (int64_t)(since(tr0) * 1e6);
+            return bad;
+          };
+          int bad = read_part(0, 0);
+          for (int f0 = 0, which = 0; f0 < part.job_n && !sh.failed; f0 += kJobPart, which ^= 1) {
+            const int n = std::min(kJobPart, part.job_n - f0);
             if (bad) {
               std::lock_guard<std::mutex> l(sh.m);
               if (!sh.failed) { sh.failed = 3; sh.error = bad == 2 ? "Y4M frame headers carry parameters (or the file is corrupt): pipe it through ffmpeg or rewrite it with plain FRAME markers" : "truncated Y4M file"; }
               break;
             }
+            int next_bad = 0;
+            std::thread ahead;
+            if (f0 + kJobPart < part.job_n) ahead = std::thread([&, f0, which]() { next_bad = read_part(f0 + kJobPart, which ^ 1); });
             std::vector<av1b_frame_src> fs((size_t)n);
             for (int k = 0; k < n; k++) {
-              uint16_t* b = own_buf->data() + (size_t)k * frame_samples;
+              uint16_t* b = own_buf[which]->data() + (size_t)k * frame_samples;
               fs[k].planes[0] = b; fs[k].planes[1] = b + (size_t)in.w * in.h; fs[k].planes[2] = b + (size_t)in.w * in.h * 5 / 4;
               fs[k].stride[0] = in.w; fs[k].stride[1] = fs[k].stride[2] = in.w / 2;
             }
             const auto te0 = std::chrono::steady_clock::now();
             rc = av1b_encode_stream(enc, fs.data(), (uint32_t)n, f0 == 0 ? 1 : 0, part.job_first + f0, on_packet, nullptr, &ctx);
             us_encode += (int64_t)(since(te0) * 1e6);
+            if (ahead.joinable()) ahead.join();
+            bad = next_bad;
             if (rc != AV1B_OK) {
               std::lock_guard<std::mutex> l(sh.m);
               if (!sh.failed) { sh.failed = -rc; sh.error = av1b_last_error(); }

@@ -148,6 +148,10 @@ struct Slot {
   size_t tok_fetched = 0;                             // tokens already downloaded with the offsets
   cudaEvent_t ev_tok0 = nullptr, ev_tok1 = nullptr;
   cudaEvent_t ev_src = nullptr;                       // sources of this slot are resident
+  uint32_t* d_score = nullptr;                        // scene-change score of every picture against the one before it
+  uint32_t* h_score = nullptr;
+  cudaEvent_t ev_score = nullptr;
+  bool has_score = false;                             // the scores of the pictures now in d_src have been asked for
   bool staged = false;                                // sources came from the host (statistics)
   bool h2d_pending = false;                           // ev_h2d .. ev_src of the last upload have not been read yet
   uint16_t* h_src[3] = {nullptr, nullptr, nullptr};
@@ -194,6 +198,9 @@ struct av1b_encoder {
   bool gop_auto = true;               // structure chosen per chunk from the source's noise level (config.gop_period == 0)
   bool mctf_cfg = true;               // temporal filter allowed by the configuration
   int noise_b = 0;                    // noise estimate of the chunk's first picture (av1b_noise_from_hist)
+  bool scene_on = true;               // key frame at a scene change inside a chunk (config.tune[4] = 1: off)
+  int64_t scene_cuts = 0;             // key frames the scene scores put inside chunks (statistics)
+  long long sc_level = -1;            // running level of change (scene scores), -1: none yet
   int grain_scaling = 0;              // film grain synthesis strength of the chunk (--film-grain > 0 and a filtered structure)
   uint32_t* d_noise_hist = nullptr;
   uint32_t* h_noise_hist = nullptr;
@@ -268,6 +275,7 @@ static void free_all(av1b_encoder* e) {
     cudaFree(s.d_blocks); cudaFree(s.d_cdef_idx);
     cudaFree(s.d_lr_units); cudaFreeHost(s.h_lr_units);
     cudaFree(s.d_quality); cudaFreeHost(s.h_quality);
+    cudaFree(s.d_score); cudaFreeHost(s.h_score); if (s.ev_score) cudaEventDestroy(s.ev_score);
     for (int p = 0; p < 3; p++) cudaFree(s.d_digest[p]);
     if (s.s_rc) cudaStreamDestroy(s.s_rc);
     cudaFree(s.d_rc_region); cudaFree(s.d_rc_len); cudaFree(s.d_rc_bytes); cudaFreeHost(s.h_rc_len); cudaFreeHost(s.h_rc_bytes);
@@ -317,6 +325,7 @@ static int stage(av1b_encoder* e, Slot& s, const av1b_frame_src* frames, int n) 
   const Av1bGeom& g = e->g;
   collect_h2d(e, s);
   s.h2d_pending = true;
+  s.has_score = false;
   bool direct = true;
   for (int b = 0; b < n && direct; b++)
     for (int p = 0; p < 3 && direct; p++) direct = is_pinned(frames[b].planes[p]);
@@ -384,8 +393,27 @@ static int launch(av1b_encoder* e, Slot& s, const Slot& in, int n, int64_t first
   std::vector<int> ref_of(n, 0);
   bool any_inter = false;
   int last_ref = 0;
+  // position of every frame in its closed GOP: it restarts at a scene change the scores of this batch show (the scores were
+  // computed on the upload stream when the pictures arrived, normally a batch ago: no stall); integer rule, see orc_scene_score
+  std::vector<int64_t> gop_pos(n);
+  {
+    const bool use = in.has_score && e->scene_on && !e->intra_only;
+    if (use) CK(cudaEventSynchronize(in.ev_score));
+    if (e->chunk_pos == 0) e->sc_level = -1;
+    const long long unit = (long long)((g.width - 4 + 7) / 8) * ((g.height - 4 + 7) / 8) << (bd - 8);
+    int64_t pos = e->chunk_pos;
+    for (int b = 0; b < n; b++) {
+      if (use && !(b == 0 && e->chunk_pos == 0)) {
+        const long long sc = in.h_score[b];
+        const bool cut = pos >= 12 && sc > 10 * unit && (e->sc_level < 0 || sc > 3 * e->sc_level + 2 * unit);
+        e->sc_level = e->sc_level < 0 ? sc : (4 * e->sc_level + sc) / 5;
+        if (cut) { e->sc_level = -1; pos = 0; e->scene_cuts++; }
+      }
+      gop_pos[b] = pos++;
+    }
+  }
   for (int b = 0; b < n; b++) {
-    const int kind = frame_kind(e, e->chunk_pos + b);
+    const int kind = frame_kind(e, gop_pos[b]);
     s.kind[b] = (uint8_t)kind; s.is_key[b] = kind == 0;
     ref_of[b] = last_ref;
     if (kind != 2) last_ref = b + 1;
@@ -425,7 +453,7 @@ static int launch(av1b_encoder* e, Slot& s, const Slot& in, int n, int64_t first
       int n_pairs = 0;
       for (int b = 0; b < n; b++) {
         if (s.kind[b] == 2) continue;
-        const int64_t pos = e->chunk_pos + b, in_gop = pos % e->keyint;
+        const int64_t in_gop = gop_pos[b] % e->keyint;
         int lo = s.kind[b] == 0 ? 0 : -e->mctf_radius, hi = s.kind[b] == 0 ? e->mctf_key_fwd : e->mctf_radius;
         if (e->cfg.lookahead >= 0) hi = std::min(hi, e->cfg.lookahead);
         Job j; j.b = b; j.first = n_pairs; j.count = 0;
@@ -434,6 +462,7 @@ static int launch(av1b_encoder* e, Slot& s, const Slot& in, int n, int64_t first
           const int r = b + d;
           if (r >= n || r < -e->hist_count) continue;
           if (in_gop + d < 0 || in_gop + d >= e->keyint) continue;   // stay inside the closed GOP
+          if (d > 0 && gop_pos[r] != gop_pos[b] + d) continue;       // (a scene change between the two)
           if (n_pairs >= kMaxSearches) break;
           H.cur_slot[n_pairs] = (uint8_t)(kSlotFrame0 + b);
           H.ref_slot[n_pairs] = (uint8_t)(r >= 0 ? kSlotFrame0 + r : kHist + r);
@@ -582,7 +611,7 @@ static int launch(av1b_encoder* e, Slot& s, const Slot& in, int n, int64_t first
     }
     CK(cudaEventRecord(ev[4], e->stream));
   }
-  e->chunk_pos += n;
+  e->chunk_pos = gop_pos[n - 1] + 1;
   if (e->quality_on) {
     CK(launch_quality(g, bd, e->d_fin[0] + e->plane_elems[0], in.d_src[0], e->plane_elems[0], s.d_quality, n, e->stream));
     e->kernel_launches += 1;
@@ -858,6 +887,7 @@ static void reset_stats(av1b_encoder* e) {
   e->q_psnr_sum = e->q_ssim = e->q_frames = 0;
   e->t_deblock_ms = e->t_cdef_ms = e->t_tok_ms = 0; e->t_lr_ms = 0; e->t_rc_ms = 0; e->n_tokens = 0; e->d2h_bytes = 0; e->t_mctf_ms = 0; e->mctf_frames = 0;
   e->kernel_launches = e->intra_launches = e->inter_launches = e->frames_done = e->bytes_out = e->key_frames = e->staged_direct = 0;
+  e->scene_cuts = 0;
 }
 
 extern "C" {
@@ -934,6 +964,7 @@ int av1b_encoder_create(const av1b_config* cfg, av1b_encoder** out) {
   e->mctf_cfg = cfg->tune[2] == 0 && cfg->reserved[3] == 0;
   e->quality_on = cfg->tune[3] != 0;
   e->me_smooth = cfg->tune[0] == 0;
+  e->scene_on = cfg->tune[4] == 0;
   e->key_var_part = cfg->tune[1] == 0 && cfg->reserved[1] == 0;
   e->blk_log2 = cfg->reserved[1] ? cfg->reserved[1] : 4;
   if (e->blk_log2 < 3 || e->blk_log2 > 6) { set_error("block log2 must be 3..6"); delete e; return AV1B_ERR_INVALID; }
@@ -986,6 +1017,7 @@ int av1b_encoder_create(const av1b_config* cfg, av1b_encoder** out) {
       if (e->keep) A(cudaMallocHost(&s.h_rec[p], n * 2));
       if (err == cudaSuccess) { A(cudaMemset(s.d_src[p], 0, n * 2)); A(cudaMemset(s.d_coef[p], 0, n * 2)); }
     }
+    A(cudaMalloc(&s.d_score, F * sizeof(uint32_t))); A(cudaMallocHost(&s.h_score, F * sizeof(uint32_t))); A(cudaEventCreate(&s.ev_score));
     A(cudaMallocHost(&s.h_blocks, e->map_elems * F * sizeof(Av1bBlockInfo)));
     A(cudaMallocHost(&s.h_cdef_idx, nsb * F));
     A(cudaMalloc(&s.d_blocks, e->map_elems * F * sizeof(Av1bBlockInfo)));
@@ -1117,14 +1149,29 @@ void av1b_encoder_destroy(av1b_encoder* e) {
 // Batches of one call: the sources of batch k+1 are uploaded while the kernels of batch k run (their slot's
 // device buffers were last read by batch k-1), and the host entropy-codes batch k-1 meanwhile.
 // frames != nullptr: host sources; else order[] indexes the resident clip (device-to-device gather on the input stream).
-static int stage_any(av1b_encoder* e, Slot& s, const av1b_frame_src* frames, const uint32_t* order, uint32_t f0, int n) {
-  if (frames) return stage(e, s, frames + f0, n);
-  CK(cudaEventRecord(s.ev_h2d, e->s_in));
-  for (int b = 0; b < n; b++)
-    for (int p = 0; p < 3; p++)
-      CK(cudaMemcpyAsync(s.d_src[p] + (size_t)b * e->plane_elems[p], e->d_clip[p] + (size_t)order[f0 + b] * e->plane_elems[p],
-                         e->plane_elems[p] * 2, cudaMemcpyDeviceToDevice, e->s_in));
-  CK(cudaEventRecord(s.ev_src, e->s_in));
+// prev: the slot that holds the batch before this one in the same chunk (nullptr at a chunk start): its last picture is what
+// the first picture's scene score is taken against.  The scores follow the upload on the input stream.
+static int stage_any(av1b_encoder* e, Slot& s, const Slot* prev, const av1b_frame_src* frames, const uint32_t* order, uint32_t f0, int n) {
+  if (frames) {
+    const int rc = stage(e, s, frames + f0, n);
+    if (rc != AV1B_OK) return rc;
+  } else {
+    s.has_score = false;
+    CK(cudaEventRecord(s.ev_h2d, e->s_in));
+    for (int b = 0; b < n; b++)
+      for (int p = 0; p < 3; p++)
+        CK(cudaMemcpyAsync(s.d_src[p] + (size_t)b * e->plane_elems[p], e->d_clip[p] + (size_t)order[f0 + b] * e->plane_elems[p],
+                           e->plane_elems[p] * 2, cudaMemcpyDeviceToDevice, e->s_in));
+    CK(cudaEventRecord(s.ev_src, e->s_in));
+  }
+  if (e->scene_on && !e->intra_only) {
+    const uint16_t* last = (prev && prev->n_frames > 0) ? prev->d_src[0] + (size_t)(prev->n_frames - 1) * e->plane_elems[0] : nullptr;
+    CK(launch_scene_score(e->g, s.d_src[0], e->plane_elems[0], last, n, s.d_score, e->s_in));
+    CK(cudaMemcpyAsync(s.h_score, s.d_score, (size_t)n * sizeof(uint32_t), cudaMemcpyDeviceToHost, e->s_in));
+    CK(cudaEventRecord(s.ev_score, e->s_in));
+    e->kernel_launches += 1;
+    s.has_score = true;
+  }
   return AV1B_OK;
 }
 
@@ -1208,7 +1255,8 @@ static int run_batches(av1b_encoder* e, const av1b_frame_src* frames, const uint
   {
     Slot& s0 = e->slot[e->pipe_next % S];
     if (e->pipe_next >= S) CK(cudaStreamWaitEvent(e->s_in, s0.ev_k1, 0));   // the batch that used this slot has read its sources
-    if ((rc = stage_any(e, s0, frames, order, 0, (int)std::min<uint32_t>(B, n_frames))) != AV1B_OK) return rc;
+    const Slot* before = (e->chunk_pos > 0 && e->pipe_next > 0) ? &e->slot[(e->pipe_next - 1) % S] : nullptr;
+    if ((rc = stage_any(e, s0, before, frames, order, 0, (int)std::min<uint32_t>(B, n_frames))) != AV1B_OK) return rc;
     if (e->chunk_pos == 0 && (rc = begin_chunk(e, s0)) != AV1B_OK) return rc;
   }
   Slot* last_staged = nullptr;
@@ -1223,7 +1271,7 @@ static int run_batches(av1b_encoder* e, const av1b_frame_src* frames, const uint
     if (f0 + B < n_frames) {
       Slot& nx = e->slot[(i + 1) % S];
       if (i + 1 >= S) CK(cudaStreamWaitEvent(e->s_in, nx.ev_k1, 0));   // batch i+1-S has read that slot's sources
-      if ((rc = stage_any(e, nx, frames, order, f0 + B, (int)std::min<uint32_t>(B, n_frames - f0 - B))) != AV1B_OK) return rc;
+      if ((rc = stage_any(e, nx, &cur, frames, order, f0 + B, (int)std::min<uint32_t>(B, n_frames - f0 - B))) != AV1B_OK) return rc;
     }
     // at most L batches stay in flight: the slot the next batch is staged into belongs to a finished one
     if ((rc = drain_to(e, L, out_cb, prog_cb, user, total_frames, t0)) != AV1B_OK) return rc;
@@ -1407,6 +1455,8 @@ int av1b_get_chunk_info(av1b_encoder* e, int32_t info[8]) {
 
 int av1b_get_frame_kind(av1b_encoder* e, int64_t pos_in_chunk) {
   if (!e || pos_in_chunk < 0) return AV1B_ERR_INVALID;
+  // debug mode knows what the frame was coded as (a scene change inside the chunk restarts the structure)
+  if (e->keep && (size_t)pos_in_chunk < e->kept.size()) return e->kept[(size_t)pos_in_chunk].kind;
   return frame_kind(e, pos_in_chunk);
 }
 

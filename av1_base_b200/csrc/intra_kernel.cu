@@ -278,6 +278,9 @@ __device__ void code_plane(Smem& sm, const IntraLaunch& P, int plane, int slot, 
       coef[k * cn + l] = (int16_t)(c < 0 ? -(int32_t)lv : (int32_t)lv);
       if (lv) atomicMax(&sm.eob[plane], (int)iscan[k * cn + l] + 1);
     }
+    // a 64x64 block owns 4096 elements of the level plane and codes 32x32 of them: the rest reads as zero, whatever the
+    // batch slot held before (the symbol streams of a frame are compared as a whole in debug mode)
+    for (int o = cn * cn + tid; o < npx; o += kThreads) coef[o] = 0;
   }
   __syncthreads();
   const int eob = sm.eob[plane];

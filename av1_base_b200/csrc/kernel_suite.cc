@@ -102,6 +102,28 @@ int av1b_k_inv_txfm_add(int device, const int32_t* coef, uint16_t* dst, int n_bl
   return AV1B_OK;
 }
 
+int av1b_k_fwd_txfm(int device, const int16_t* resid, int32_t* coef, int n_blocks, int w, int h, int tx_type, int reps,
+                    double* ms_per_launch) {
+  auto size_ok = [](int n) { return n == 4 || n == 8 || n == 16 || n == 32 || n == 64; };
+  if (!resid || !coef || n_blocks <= 0 || tx_type < 0 || tx_type > 15 || !size_ok(w) || !size_ok(h) || w > 4 * h || h > 4 * w) {
+    set_error("bad argument"); return AV1B_ERR_INVALID;
+  }
+  const int m = std::max(w, h);
+  if ((m == 64 && tx_type != 0) || (m == 32 && tx_type != 0 && tx_type != 9)) { set_error("transform type not legal at this size"); return AV1B_ERR_INVALID; }
+  int rc = select_device(device);
+  if (rc) return rc;
+  Timer t; CKS(t.init());
+  DevBuf dr, dc;
+  const size_t rb = (size_t)n_blocks * w * h * 2, cb = (size_t)n_blocks * std::min(w, 32) * std::min(h, 32) * 4;
+  CKS(dr.alloc(rb)); CKS(dc.alloc(cb));
+  CKS(cudaMemcpyAsync(dr.p, resid, rb, cudaMemcpyHostToDevice, t.s));
+  rc = timed(t, reps, ms_per_launch, [&]() { return launch_fwd_txfm(dr.as<int16_t>(), dc.as<int32_t>(), n_blocks, w, h, tx_type, t.s); });
+  if (rc) return rc;
+  CKS(cudaMemcpyAsync(coef, dc.p, cb, cudaMemcpyDeviceToHost, t.s));
+  CKS(cudaStreamSynchronize(t.s));
+  return AV1B_OK;
+}
+
 struct FrameBufs {
   DevBuf d[3];
   size_t elems[3];

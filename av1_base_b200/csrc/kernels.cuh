@@ -74,6 +74,9 @@ struct LrLaunch {
 // prediction/reconstruction at dst + b*w*h (row-major).
 cudaError_t launch_inv_txfm_add(const int32_t* coef, uint16_t* dst, int n_blocks, int w, int h, int tx_type,
                                 int bit_depth, cudaStream_t s);
+// Batched encoder-side forward transform, every size and type (txfm_kernel.cu): block b reads resid + b*w*h (row-major) and
+// writes coef + b * min(w,32) * min(h,32) (row-major, spec layout).
+cudaError_t launch_fwd_txfm(const int16_t* resid, int32_t* coef, int n_blocks, int w, int h, int tx_type, cudaStream_t s);
 
 // Source pyramid + hierarchical motion estimation (me_kernels.cu).  Search f of a launch matches the picture in
 // slot cur_slot[f] against the SOURCE picture in slot ref_slot[f]: level l of slot k starts at cur[l] (ref[l]) +
@@ -116,6 +119,10 @@ cudaError_t launch_mctf(const MctfLaunch& p, cudaStream_t s);
 // Noise level of one source luma plane: hist[4096] (device) = histogram of the 16x16 blocks' sums of |I * N| >> 4
 // (N = the 3x3 noise mask); the host takes the lower quartile outside bin 0 (capi_host.cc av1b_noise_from_hist).
 cudaError_t launch_noise_hist(const Av1bGeom& g, const uint16_t* src_y, uint32_t* hist, cudaStream_t s);
+// Scene-change scores of the n_frames luma planes at src_y (elems0 apart) against the picture before each (prev for the first;
+// nullptr: no score): sum of absolute differences on the 1/8 x 1/8 sample grid from (4, 4).
+cudaError_t launch_scene_score(const Av1bGeom& g, const uint16_t* src_y, size_t elems0, const uint16_t* prev, int n_frames,
+                               uint32_t* score, cudaStream_t s);
 
 // Inter frame encode (inter_kernel.cu): the n_frames frames of a launch share ONE reference picture and one
 // quantiser (the frames between two anchors of the hierarchy); frame f of the launch has its source, outputs, block

@@ -221,7 +221,36 @@ __global__ void __launch_bounds__(256) noise_hist_kernel(Av1bGeom g, const uint1
   if (inside && j == 0) atomicAdd(&hist[min(sum >> 4, 4095)], 1u);
 }
 
+// Scene-change score of every picture of a batch against the picture before it (oracle: orc_scene_score): sum of absolute
+// luma differences on the 1/8 x 1/8 grid that starts at sample (4, 4) -- the thumbnails the drop-in executable cuts its chunks
+// by, computed where the pictures already are.  Picture 0 is compared with `prev` (the last picture of the batch before; no
+// score when there is none).
+__global__ void __launch_bounds__(256) scene_score_kernel(Av1bGeom g, const uint16_t* __restrict__ src_y, size_t elems0,
+                                                          const uint16_t* __restrict__ prev, uint32_t* score) {
+  const int b = blockIdx.y;
+  const int tw = (g.width - 4 + 7) / 8, th = (g.height - 4 + 7) / 8;
+  const int i = blockIdx.x * 256 + threadIdx.x;
+  const uint16_t* cur = src_y + (size_t)b * elems0;
+  const uint16_t* old = b ? cur - elems0 : prev;
+  unsigned d = 0;
+  if (i < tw * th && old) {
+    const size_t o = (size_t)(4 + 8 * (i / tw)) * g.stride[0] + 4 + 8 * (i % tw);
+    d = (unsigned)abs((int)cur[o] - (int)old[o]);
+  }
+  d = __reduce_add_sync(0xffffffffu, d);
+  if ((threadIdx.x & 31) == 0 && d) atomicAdd(&score[b], d);
+}
+
 }  // namespace
+
+cudaError_t launch_scene_score(const Av1bGeom& g, const uint16_t* src_y, size_t elems0, const uint16_t* prev, int n_frames,
+                               uint32_t* score, cudaStream_t s) {
+  cudaError_t e = cudaMemsetAsync(score, 0, (size_t)n_frames * sizeof(uint32_t), s);
+  if (e != cudaSuccess) return e;
+  const int tw = (g.width - 4 + 7) / 8, th = (g.height - 4 + 7) / 8;
+  scene_score_kernel<<<dim3((tw * th + 255) / 256, n_frames), 256, 0, s>>>(g, src_y, elems0, prev, score);
+  return cudaGetLastError();
+}
 
 cudaError_t launch_noise_hist(const Av1bGeom& g, const uint16_t* src_y, uint32_t* hist, cudaStream_t s) {
   cudaError_t e = cudaMemsetAsync(hist, 0, 4096 * sizeof(uint32_t), s);

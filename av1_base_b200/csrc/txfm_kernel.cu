@@ -10,6 +10,7 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 #include "av1_inv_txfm1d.h"
+#include "av1_tables_dev.cuh"
 #include "kernels.cuh"
 
 namespace av1b {
@@ -89,6 +90,60 @@ inv_txfm_add_kernel(const int32_t* __restrict__ coef, uint16_t* __restrict__ dst
   }
 }
 
+// ---------------------------------------------------------------------------------------------
+// Encoder-side forward transform of every size and type (oracle: orc_fwd_txfm2d): DCT / ADST / flipADST / identity,
+// 4x4 .. 64x64 with the 2:1 and 4:1 rectangles, in the exact integer matrix form the encode kernels use --
+//   x' = residual << 2 (flipped for flipADST), t = (Fv x' + 2^11) >> 12 down the columns,
+//   coefficient = (Fh t * mul + rnd) >> (24 + log2(w h) - Transform_Row_Shift - 4) along the rows (64-bit),
+// mul = 4096, or 5793 for 2:1 rectangles; only min(w,32) x min(h,32) coefficients exist (AV1 zeroes the rest).
+// One CTA per block: the residual and the intermediate live in shared memory, a thread per output.
+__device__ __forceinline__ int fwd_coef(int t, int n, int k, int i) {
+  if (t == T_IDT) return k != i ? 0 : (n == 4 ? 5793 : n == 8 ? 8192 : n == 16 ? 11585 : 16384);
+  if (t == T_DCT) {
+    switch (n) {
+      case 4: return tbl::fwd_dct4[k][i];
+      case 8: return tbl::fwd_dct8[k][i];
+      case 16: return tbl::fwd_dct16[k][i];
+      case 32: return tbl::fwd_dct32[k][i];
+      default: return tbl::fwd_dct64[k][i];
+    }
+  }
+  return n == 4 ? tbl::fwd_adst4[k][i] : (n == 8 ? tbl::fwd_adst8[k][i] : tbl::fwd_adst16[k][i]);
+}
+
+__global__ void __launch_bounds__(256) fwd_txfm_kernel(const int16_t* __restrict__ resid, int32_t* __restrict__ coef, int w, int h,
+                                                       int tx_type) {
+  __shared__ int16_t r[64 * 64];
+  __shared__ int32_t t[32 * 64];
+  const int tid = threadIdx.x;
+  const int cw = min(w, 32), ch = min(h, 32);
+  const int vt = k_vtype[tx_type], ht = k_htype[tx_type];
+  const int lw = 31 - __clz(w), lh = 31 - __clz(h);
+  const bool rect = abs(lw - lh) == 1;
+  const int s = lw + lh;
+  const int row_shift = s == 4 ? 0 : s == 5 ? 0 : s == 6 ? 1 : s == 7 ? 1 : s == 8 ? 2 : s == 9 ? 1 : s == 10 ? 2 : s == 11 ? 1 : 2;
+  const int sh = 24 + lw + lh - row_shift - 4;
+  const long long mul = rect ? 5793 : 4096;
+  const int16_t* src = resid + (size_t)blockIdx.x * w * h;
+  for (int o = tid; o < w * h; o += 256) r[o] = src[o];
+  __syncthreads();
+  for (int o = tid; o < ch * w; o += 256) {
+    const int k = o / w, j = o - k * w;
+    const int jj = ht == T_FLIP ? w - 1 - j : j;
+    int32_t acc = 0;
+    for (int i = 0; i < h; i++) acc += fwd_coef(vt, h, k, i) * ((int32_t)r[(vt == T_FLIP ? h - 1 - i : i) * w + jj] * 4);
+    t[o] = (acc + 2048) >> 12;
+  }
+  __syncthreads();
+  int32_t* dst = coef + (size_t)blockIdx.x * cw * ch;
+  for (int o = tid; o < ch * cw; o += 256) {
+    const int k = o / cw, l = o - k * cw;
+    long long acc = 0;
+    for (int j = 0; j < w; j++) acc += (long long)fwd_coef(ht, w, l, j) * t[k * w + j];
+    dst[o] = (int32_t)((acc * mul + (1ll << (sh - 1))) >> sh);
+  }
+}
+
 template <int W, int H>
 cudaError_t launch_one(const int32_t* coef, uint16_t* dst, int n, int tx_type, int bd, cudaStream_t s) {
   constexpr int T = (W > H ? W : H) < 32 ? 32 : (W > H ? W : H);
@@ -97,6 +152,11 @@ cudaError_t launch_one(const int32_t* coef, uint16_t* dst, int n, int tx_type, i
 }
 
 }  // namespace
+
+cudaError_t launch_fwd_txfm(const int16_t* resid, int32_t* coef, int n_blocks, int w, int h, int tx_type, cudaStream_t s) {
+  fwd_txfm_kernel<<<n_blocks, 256, 0, s>>>(resid, coef, w, h, tx_type);
+  return cudaGetLastError();
+}
 
 cudaError_t launch_inv_txfm_add(const int32_t* coef, uint16_t* dst, int n_blocks, int w, int h, int tx_type,
                                 int bit_depth, cudaStream_t s) {

@@ -29,7 +29,7 @@ class Encoder:
                  tile_cols_log2=-1, tile_rows_log2=-1, hdr=False, host_threads=0, frames_in_flight=0,
                  keep_debug=False, blk_log2=0, loop_filters=True, intra_only=False, tb_zero_thr=0, raster_levels=False,
                  pack_path=0, lr_off=False, tile_sb=0, gop_period=0, me_smooth=True, key_var_part=True, mctf=True,
-                 lookahead=-1, film_grain=0):
+                 lookahead=-1, film_grain=0, scene_cut=True):
         L = abi.lib()
         cfg = abi.Config()
         L.av1b_config_default(C.byref(cfg))
@@ -55,6 +55,7 @@ class Encoder:
         cfg.tune[0] = 0 if me_smooth else 1
         cfg.tune[1] = 0 if key_var_part else 1
         cfg.tune[2] = 0 if mctf else 1     # temporal filter of key / anchor sources
+        cfg.tune[4] = 0 if scene_cut else 1   # key frame at a scene change inside a chunk (scores from the GPU)
         cfg.lookahead = lookahead          # -1 = default; frames the temporal filter may look ahead
         cfg.film_grain = film_grain
         self.cfg = cfg

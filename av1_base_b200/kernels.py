@@ -115,6 +115,16 @@ def pyramid(width, height, l0_frames, device=0, reps=1):
     return l1, l2, ms.value
 
 
+def fwd_txfm(resid, w, h, tx_type, device=0, reps=1):
+    """resid: [n, h, w] int16. Returns (coef [n, min(h,32), min(w,32)] int32, ms)."""
+    r = np.ascontiguousarray(resid, np.int16)
+    n = r.shape[0]
+    co = np.zeros((n, min(h, 32), min(w, 32)), np.int32)
+    ms = C.c_double(0)
+    _ck(abi.lib().av1b_k_fwd_txfm(device, r.ctypes.data_as(C.c_void_p), co.ctypes.data_as(C.c_void_p), n, w, h, tx_type, reps, C.byref(ms)))
+    return co, ms.value
+
+
 def hme(width, height, cur_l0, ref_l0, lam=0, device=0, reps=1, bd=8):
     """cur_l0 / ref_l0: [n, rows, stride] padded luma; bd: bit depth (the quarter-resolution level compares
     min(v >> (bd - 8), 255)). Returns (mv [n, h8*w8, 2], ms)."""

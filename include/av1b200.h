@@ -58,7 +58,9 @@ typedef struct av1b_config {
                                      (noise estimate of the chunk's first picture against the quantiser step) */
   int32_t tune[7];                /* [0]: 1 = vector-field regularisation of the motion search off; [1]: 1 = fixed 16x16 key-frame
                                      partition (default: 64x64 / 32x32 blocks where the source is smooth); [2]: 1 = temporal filter of
-                                     key / anchor source pictures off; [3]: 1 = PSNR / SSIM of every frame on the device (av1b_get_quality) */
+                                     key / anchor source pictures off; [3]: 1 = PSNR / SSIM of every frame on the device (av1b_get_quality);
+                                     [4]: 1 = no key frame at scene changes inside a chunk (default: scene scores are computed on the GPU as the
+                                     pictures arrive and a change restarts the structure) */
   int32_t reserved[8];            /* [0]: keep recon+symbols per frame (tests); [1]: fixed block log2 (3..6), 0 = default;
                                      [2]: 1 = in-loop filters off; [3]: 1 = every frame is a key frame;
                                      [4]: inter transform-block drop threshold (0 = off);
@@ -175,6 +177,11 @@ struct Av1bLrUnit;
  * reconstruction out */
 int av1b_k_inv_txfm_add(int device, const int32_t* coef, uint16_t* dst, int n_blocks, int w, int h, int tx_type,
                         int bit_depth, int reps, double* ms_per_launch);
+/* Encoder-side forward transform (E4), every size (4x4 .. 64x64, 2:1 and 4:1 rectangles) and every legal type
+ * (DCT / ADST / flipADST / identity): block b reads resid + b*w*h (row-major int16 residual) and writes
+ * coef + b * min(w,32) * min(h,32) (row-major, spec layout; what dequantisation + av1b_k_inv_txfm_add invert). */
+int av1b_k_fwd_txfm(int device, const int16_t* resid, int32_t* coef, int n_blocks, int w, int h, int tx_type, int reps,
+                    double* ms_per_launch);
 int av1b_k_deblock(int device, int width, int height, int bit_depth, int n_frames, const struct Av1bBlockInfo* blocks,
                    const uint16_t* const in[3], uint16_t* const out[3], const int32_t lf_level[4], int sharpness,
                    int reps, double* ms_per_launch);

@@ -147,6 +147,12 @@ extern "C" void orc_fwd_txfm2d(const int16_t* resid, int rstride, int32_t* coef,
     }
 }
 
+// n blocks in a row (the forward-transform suite): block b reads resid + b*w*h, writes coef + b * min(w,32) * min(h,32)
+extern "C" void orc_fwd_txfm2d_batch(int n, const int16_t* resid, int32_t* coef, int w, int h, int tx_type) {
+  const int cw = std::min(w, 32), ch = std::min(h, 32);
+  for (int b = 0; b < n; b++) orc_fwd_txfm2d(resid + (size_t)b * w * h, w, coef + (size_t)b * cw * ch, cw, w, h, tx_type);
+}
+
 // ------------------------------------------------------------------------------------------------
 // quantiser
 // ------------------------------------------------------------------------------------------------
@@ -853,6 +859,19 @@ extern "C" void orc_me_sbrd(const Av1bGeom* g, const uint16_t* cur0, const uint1
           mv_io[(uy * g->w8 + ux) * 2] = v[(by * n1x + bx) * 2];
           mv_io[(uy * g->w8 + ux) * 2 + 1] = v[(by * n1x + bx) * 2 + 1];
         }
+}
+
+// ------------------------------------------------------------------------------------------------
+// Scene-change score between two source pictures (encoder side, ours): sum of absolute luma differences on the 1/8 x 1/8
+// sample grid that starts at (4, 4).  The decision rule on top of it is integer only (chain.py scene_cuts / encoder.cc):
+// a cut = a score above 10 per sample (8-bit units) AND above three times the running level of change plus 2 per sample,
+// at least 12 frames after the last key frame; the running level is (4 * level + score) / 5, restarted at a cut.
+// ------------------------------------------------------------------------------------------------
+extern "C" uint32_t orc_scene_score(const Av1bGeom* g, const uint16_t* cur_y, const uint16_t* prev_y, int stride) {
+  uint32_t s = 0;
+  for (int y = 4; y < g->height; y += 8)
+    for (int x = 4; x < g->width; x += 8) s += (uint32_t)abs((int)cur_y[(size_t)y * stride + x] - (int)prev_y[(size_t)y * stride + x]);
+  return s;
 }
 
 // ------------------------------------------------------------------------------------------------

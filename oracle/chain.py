@@ -73,9 +73,28 @@ def choose_structure(g, bd, crf, first_luma_padded):
     return (1 if 2 * nb > 15 * ac_q(bd, q) else DEFAULT_GOP_PERIOD), nb
 
 
+def scene_positions(g, bd, padded, pos0=0, scene_cut=True):
+    """Position of every frame in its closed GOP (csrc/encoder.cc launch()): it restarts at a scene change -- a score
+    (O.scene_score against the picture before) above 10 per sample in 8-bit units and above three times the running level
+    of change plus 2 per sample, at least 12 frames after the last key frame; level = (4 * level + score) // 5, restarted
+    at a cut.  Integer arithmetic throughout."""
+    unit = (((g.width - 4 + 7) // 8) * ((g.height - 4 + 7) // 8)) << (bd - 8)
+    pos, level, out = pos0, -1, []
+    for i, pl in enumerate(padded):
+        if scene_cut and not (i == 0 and pos0 == 0) and i > 0:
+            sc = O.scene_score(g, pl[0], padded[i - 1][0])
+            cut = pos >= 12 and sc > 10 * unit and (level < 0 or sc > 3 * level + 2 * unit)
+            level = sc if level < 0 else (4 * level + sc) // 5
+            if cut:
+                level, pos = -1, 0
+        out.append(pos)
+        pos += 1
+    return out
+
+
 def encode_chain(frames, w, h, bd, crf, keyint=240, gop_period=DEFAULT_GOP_PERIOD, me_smooth=True, key_var_part=True, loop_filters=True,
                  lr=False, intra_only=False, blk_log2=4, tb_zero_thr=0, pos0=0, geom=None, mctf=True, batch=8, lookahead=-1,
-                 film_grain=0, mctf_radius=2, mctf_key_fwd=4):
+                 film_grain=0, mctf_radius=2, mctf_key_fwd=4, scene_cut=True):
     """Returns one FrameResult per frame: kind, fp, res (blocks / coef / pre-filter rec), fin (padded planes after the
     in-loop filters), cdef_idx, lr_units, mvs."""
     g = geom if geom is not None else O.geom(w, h, 0, 0)   # key-frame tiling: no intra prediction across tile edges
@@ -92,8 +111,9 @@ def encode_chain(frames, w, h, bd, crf, keyint=240, gop_period=DEFAULT_GOP_PERIO
     padded = [O.pad_planes(g, fr) for fr in frames]
     pyrs = [O.pyramid(g, pl[0]) for pl in padded]
     n = len(frames)
+    gop_pos = scene_positions(g, bd, padded, pos0, scene_cut and not intra_only)
     for i, fr in enumerate(frames):
-        kind = frame_kind(pos0 + i, keyint, gop_period, intra_only)
+        kind = frame_kind(gop_pos[i], keyint, gop_period, intra_only)
         q = qk[kind]
         fp = class_params(bd, q, kind, loop_filters, lr)
         src = padded[i]
@@ -105,12 +125,14 @@ def encode_chain(frames, w, h, bd, crf, keyint=240, gop_period=DEFAULT_GOP_PERIO
             lo, hi = (0, mctf_key_fwd) if kind == 0 else (-mctf_radius, mctf_radius)
             if lookahead >= 0:
                 hi = min(hi, lookahead)
-            in_gop = (pos0 + i) % keyint
+            in_gop = gop_pos[i] % keyint
             for d in range(lo, hi + 1):
                 j = i + d
                 if d == 0 or j < 0 or j >= n or (d > 0 and j // batch != i // batch):
                     continue
                 if in_gop + d < 0 or in_gop + d >= keyint:
+                    continue
+                if d > 0 and gop_pos[j] != gop_pos[i] + d:   # a scene change between the two
                     continue
                 nb.append(j)
             nb = nb[:6]

@@ -142,6 +142,13 @@ def me_sbrd(g, cur_pyr, ref_pyr, mv, lam_s, lam_r, passes=2):
     return mv
 
 
+def scene_score(g, cur_luma_padded, prev_luma_padded):
+    """Sum of absolute luma differences on the 1/8 x 1/8 grid from (4, 4) (orc_scene_score)."""
+    a = np.ascontiguousarray(cur_luma_padded, np.uint16); b = np.ascontiguousarray(prev_luma_padded, np.uint16)
+    lib().orc_scene_score.restype = C.c_uint32
+    return int(lib().orc_scene_score(C.byref(g), ptr(a), ptr(b), a.shape[1]))
+
+
 def noise_estimate(g, luma_padded):
     """Lower-quartile block sum of |I * N| (orc_noise_estimate); sigma ~= 0.0010658 * result."""
     l0 = np.ascontiguousarray(luma_padded, np.uint16)

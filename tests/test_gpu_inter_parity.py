@@ -34,6 +34,25 @@ def test_chunk_parity(w, h, bd, crf, tcl, trl, lf, nfr, fif, keyint, preset, gop
     vectors after regularisation, side info, levels, reconstruction after the in-loop filters; dav1d and libaom decode
     the stream to the same pictures."""
     frames = synth.synth_clip(w, h, bd, nfr, seed=w + bd, scene_len=100)
+    _check_chunk(frames, w, h, bd, crf, tcl, trl, lf, nfr, fif, keyint, preset, gop, pack_path)
+
+
+def test_scene_change_inside_a_chunk_becomes_a_key_frame():
+    """Row f-3: scene scores computed on the GPU as the pictures arrive (scene_score_kernel on the upload stream) restart the
+    structure inside a chunk -- key frame at the cut, no motion search or temporal filter across it; frame kinds, vectors,
+    levels and reconstruction equal the oracle chain's, which takes the same integer decision from orc_scene_score."""
+    w, h, bd, nfr = 328, 248, 10, 30
+    frames = synth.synth_clip(w, h, bd, nfr, seed=77, scene_len=13)      # cuts at 13 and 26: both at least 12 frames after a key frame
+    kinds = _check_chunk(frames, w, h, bd, 36, 0, 0, True, nfr, 8, 240, 6, 0, 0)
+    assert [i for i, k in enumerate(kinds) if k == 0] == [0, 13, 26]
+    # the same clip with the detection off: one key frame
+    enc = encoder.Encoder(w, h, bd, crf=36, keep_debug=True, frames_in_flight=8, scene_cut=False)
+    enc.encode_chunk(frames)
+    assert [i for i in range(nfr) if enc.frame_kind(i) == 0] == [0]
+    enc.close()
+
+
+def _check_chunk(frames, w, h, bd, crf, tcl, trl, lf, nfr, fif, keyint, preset, gop, pack_path):
     enc = encoder.Encoder(w, h, bd, crf=crf, keep_debug=True, tile_cols_log2=tcl, tile_rows_log2=trl,
                           frames_in_flight=fif, loop_filters=lf, keyint=keyint, preset=preset, pack_path=pack_path, gop_period=gop)
     lr = lf and preset <= 5
@@ -75,6 +94,7 @@ def test_chunk_parity(w, h, bd, crf, tcl, trl, lf, nfr, fif, keyint, preset, gop
         assert kinds == {0, 1, 2}
     assert enc.stats()["mctf_frames"] == sum(1 for r in want if r.filtered_from)
     enc.close()
+    return [r.kind for r in want]
 
 
 @pytest.mark.parametrize("w,h,bd,crf,tcl,trl", [(200, 136, 10, 20, -1, -1), (328, 248, 8, 40, 1, 1), (640, 360, 10, 30, -1, -1),
