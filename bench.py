@@ -1,8 +1,8 @@
 #!/usr/bin/env python3
 """bench.py -- AV1 encode fps of the B200 backend (BASELINE.json metric), one rank per GPU.
 
-A "step" is one closed chunk of the workload's clip (C4: 150 frames of 3840x2160 10-bit, one scene of the scene_len-150
-generator = what the chunker cuts; 1 key frame + 149 inter frames) through the hot path, one chunk stream per GPU
+A "step" is two closed chunks of the workload's clip (C4: 2 x 150 frames of 3840x2160 10-bit, a chunk = one scene of the
+scene_len-150 generator = what the chunker cuts; 1 key frame + 149 inter frames each) through the hot path, one chunk stream per GPU
 (chunks share no state, so ranks never communicate on the data path; weak scaling).
   value : frames/s with the clip resident in HBM (av1b_stage_clip + av1b_encode_clip): device kernels + symbol
           download + host entropy coding, pipelined; whole job over all ranks.
@@ -23,11 +23,15 @@ ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
 WORKLOADS = {
-    # name: (width, height, bit_depth, description, scene_len of the generator, frames of one chunk = one step)
+    # name: (width, height, bit_depth, description, scene_len of the generator, frames of one chunk); a step is
+    # CHUNKS_PER_STEP closed chunks, so that the driver's 20 steps give a timed region of more than 2 s
     "4k10": (3840, 2160, 10, "C4: 3840x2160 10-bit HDR 4:2:0 synthetic, CRF 30, one chunk stream per GPU", 150, 150),
     "1080p10": (1920, 1080, 10, "C3: 1920x1080 10-bit 4:2:0 synthetic, CRF 30", 240, 240),
     "1080p8": (1920, 1080, 8, "C1: 1920x1080 8-bit 4:2:0 synthetic, CRF 30", 80, 80),
 }
+
+
+CHUNKS_PER_STEP = 2
 
 
 def peaks():
@@ -163,8 +167,8 @@ def chunk_order(n_distinct, n_frames):
 
 def workload_config(args):
     w, h, bd, desc, scene_len, chunk = WORKLOADS[args.workload]
-    return {"workload": desc, "clip": "synth_clip seed 4, scene_len %d" % scene_len, "frames_per_step": chunk,
-            "chunk": "one closed chunk per step: 1 key frame + %d inter frames" % (chunk - 1),
+    return {"workload": desc, "clip": "synth_clip seed 4, scene_len %d" % scene_len, "frames_per_step": CHUNKS_PER_STEP * chunk,
+            "chunk": "%d closed chunks (scenes) per step, each 1 key frame + %d inter frames" % (CHUNKS_PER_STEP, chunk - 1),
             "distinct_frames": args.distinct, "crf": args.crf, "preset": args.preset, "keyint": args.keyint}
 
 
@@ -363,14 +367,15 @@ def main():
     barrier()
     t0 = time.perf_counter()
     for k in range(args.steps):
-        enc.encode_clip(order, accumulate=k > 0)
+        for c in range(CHUNKS_PER_STEP):
+            enc.encode_clip(order, accumulate=(k > 0 or c > 0))
     torch.cuda.synchronize()
     dt = time.perf_counter() - t0
     st = enc.stats()
     barrier()
     clocks = sampler.stop()
     tmax = sharding.max_over_ranks(dt, dist, "cuda")
-    value = world * args.steps * chunk / tmax
+    value = world * args.steps * CHUNKS_PER_STEP * chunk / tmax
 
     # ---------------- e2e: host buffers through av1b_encode_chunk ----------------
     # the host copies of the sources live in page-locked memory (av1b_host_alloc), as a capture / decode front
@@ -384,24 +389,24 @@ def main():
     t0 = time.perf_counter()
     h2d_ms = kern_ms = d2h_ms = pack_ms = 0.0
     d2h_bytes = staged_direct = 0
-    for _ in range(e2e_steps):
+    for _ in range(e2e_steps * CHUNKS_PER_STEP):
         tus = enc.encode_chunk(host_chunk)
         se = enc.stats()
         h2d_ms += se["h2d_ms"]; kern_ms += se["kernel_ms"]; d2h_ms += se["d2h_ms"]; pack_ms += se["pack_ms"]
         d2h_bytes += se["d2h_bytes"]; staged_direct += se["staged_direct"]
     dte = time.perf_counter() - t0
     dte = sharding.max_over_ranks(dte, dist, "cuda")
-    e2e = world * e2e_steps * chunk / dte
+    e2e = world * e2e_steps * CHUNKS_PER_STEP * chunk / dte
 
     if rank != 0:
         return
     pk, pk_src = peaks()
     n_inter, n_key = max(1, st["inter_launches"]), max(1, st["key_frames"])
     nf = st["frames_done"]
-    n_batches = args.steps * ((chunk + F - 1) // F)
+    n_batches = args.steps * CHUNKS_PER_STEP * ((chunk + F - 1) // F)
     n_tf = max(1, st["mctf_frames"])
     # CDEF runs on the key and anchor frames only (the non-reference frames signal none)
-    n_cdef = max(1, args.steps * sum(1 for pos in range(chunk) if enc.frame_kind(pos) != 2))
+    n_cdef = max(1, args.steps * CHUNKS_PER_STEP * sum(1 for pos in range(chunk) if enc.frame_kind(pos) != 2))
     # per-kernel CUDA-event time per unit (frame; ME and tokenizer per batch) and algorithmic bytes per unit
     kern = {
         "inter_encode_kernel": (st["inter_ms"] / n_inter, 4 * S),
@@ -439,9 +444,9 @@ def main():
                     "l2": "inputs larger than L2 (%.0f MB of distinct source pictures, %.0f MB working set per batch)" % (args.distinct * frame_bytes / 1e6, 5 * F * frame_bytes / 1e6),
                     "timing": "wall clock between synchronize+barrier pairs (host entropy coding is part of the step); "
                               "kernel times from CUDA events on the encoder stream"},
-        "e2e": {"value": e2e, "unit": "frames/s", "h2d_bytes_per_step": chunk * frame_bytes, "d2h_bytes_per_step": d2h_bytes // e2e_steps,
+        "e2e": {"value": e2e, "unit": "frames/s", "h2d_bytes_per_step": CHUNKS_PER_STEP * chunk * frame_bytes, "d2h_bytes_per_step": d2h_bytes // e2e_steps,
                 "steps": e2e_steps, "bitrate_bytes_per_frame": sum(map(len, tus)) / len(tus),
-                "host_buffers": "page-locked (av1b_host_alloc), %d of %d frames read in place by the copy engine" % (staged_direct, e2e_steps * chunk),
+                "host_buffers": "page-locked (av1b_host_alloc), %d of %d frames read in place by the copy engine" % (staged_direct, e2e_steps * CHUNKS_PER_STEP * chunk),
                 "breakdown_ms_per_step": {"h2d_ms": h2d_ms / e2e_steps, "kernel_ms": kern_ms / e2e_steps, "d2h_ms": d2h_ms / e2e_steps, "pack_ms": pack_ms / e2e_steps}},
         "gpu_launches": st["kernel_launches"],
         "breakdown_ms_per_step": {k: st[k] / args.steps for k in ("kernel_ms", "me_ms", "mctf_ms", "intra_ms", "inter_ms", "deblock_ms",

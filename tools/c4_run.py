@@ -44,13 +44,21 @@ def main():
     t0 = time.perf_counter()
     with ProcessPoolExecutor(min(16, os.cpu_count() or 1)) as ex:
         scenes = list(ex.map(scene_pictures, [(w, h, a.bd, s, a.scene_len, a.distinct, w > 3000) for s in range(n_scenes)]))
+    hdr = ("YUV4MPEG2 W%d H%d F60:1 Ip A1:1 C%s\n" % (w, h, "420p10" if a.bd > 8 else "420jpeg")).encode()
     with open(y4m, "wb") as f:
-        f.write(("YUV4MPEG2 W%d H%d F60:1 Ip A1:1 C%s\n" % (w, h, "420p10" if a.bd > 8 else "420jpeg")).encode())
-        for i in range(frames):
-            s, k = divmod(i, a.scene_len)
-            k %= 2 * a.distinct - 2
-            f.write(b"FRAME\n")
-            f.write(scenes[s][k if k < a.distinct else 2 * a.distinct - 2 - k])
+        f.write(hdr)
+        f.truncate(len(hdr) + frames * (6 + fbytes))
+    fd = os.open(y4m, os.O_WRONLY)
+
+    def put(i):
+        s_, k = divmod(i, a.scene_len)
+        k %= 2 * a.distinct - 2
+        os.pwrite(fd, b"FRAME\n" + scenes[s_][k if k < a.distinct else 2 * a.distinct - 2 - k], len(hdr) + i * (6 + fbytes))
+
+    from concurrent.futures import ThreadPoolExecutor
+    with ThreadPoolExecutor(8) as tp:      # tmpfs takes parallel writers
+        list(tp.map(put, range(frames)))
+    os.close(fd)
     del scenes
     t_gen = time.perf_counter() - t0
     sys.path.insert(0, os.path.join(ROOT, "tests"))
