@@ -406,7 +406,7 @@ __global__ void __launch_bounds__(1024) hme_dominant_kernel(const HmeLaunch P, u
 constexpr int kSbCand = 22;
 constexpr int kWinPitch = 68;   // samples (34 words)
 struct SbrdSmem {
-  uint32_t win[65 * kWinPitch / 2];
+  uint32_t win[2][65 * kWinPitch / 2];   // two candidate windows per round
   int T[kSbCand][16];
   uint32_t cand[kSbCand];
   uint32_t loc[6][6];        // vectors of the superblock's blocks and the blocks around it ([r + 1][c + 1]); 0xFFFFFFFF outside
@@ -494,17 +494,17 @@ __global__ void __launch_bounds__(256) hme_sbrd_kernel(const HmeLaunch P, uint32
     }
     return;
   }
-  for (int k = 0; k < ncand; k++) {
+  // two candidates per round: both windows are loaded back to back (their global-load latencies overlap), one barrier
+  // pair serves two SAD passes
+  auto stage_window = [&](int k, uint32_t* win) {
     const uint32_t cv = sm.cand[k];
     const int mvy = (int16_t)(cv & 0xFFFFu), mvx = (int16_t)(cv >> 16);
-    const int ix = mvx >> 3, iy = mvy >> 3, fx = (mvx & 7) >> 1, fy = (mvy & 7) >> 1;
-    const int wy = y0 * 16 + iy, wx = x0 * 16 + ix;        // window origin in the picture
-    const int wxa = wx & ~1, xo = wx & 1;                  // first staged column (even), offset of the window in the row
-    __syncthreads();                                       // the window of the candidate before has been read
+    const int wy = y0 * 16 + (mvy >> 3), wx = x0 * 16 + (mvx >> 3);   // window origin in the picture
+    const int wxa = wx & ~1;                                           // first staged column (even)
     if (wy >= 0 && wy + 65 <= H && wxa >= 0 && wx + 65 <= W && wxa + kWinPitch <= P.stride0) {
       // warp w stages rows w, w + 8, ..., w + 56 (and warp 0 row 64): lane = word, lanes 0 and 1 also words 32 and 33
       const uint32_t* src = reinterpret_cast<const uint32_t*>(ref0 + (size_t)(wy + warp) * P.stride0 + wxa) + lane;
-      uint32_t* dst = sm.win + warp * (kWinPitch / 2) + lane;
+      uint32_t* dst = win + warp * (kWinPitch / 2) + lane;
       const size_t step = (size_t)4 * P.stride0;   // 8 rows in words
 #pragma unroll
       for (int i = 0; i < 8; i++) {
@@ -519,16 +519,21 @@ __global__ void __launch_bounds__(256) hme_sbrd_kernel(const HmeLaunch P, uint32
       for (int o = tid; o < 65 * (kWinPitch / 2); o += 256) {
         const int r = o / (kWinPitch / 2), c = o - r * (kWinPitch / 2);
         const uint16_t* row = ref0 + (size_t)clampi(wy + r, 0, H - 1) * P.stride0;
-        sm.win[o] = (uint32_t)row[clampi(wxa + 2 * c, 0, W - 1)] | ((uint32_t)row[clampi(wxa + 2 * c + 1, 0, W - 1)] << 16);
+        win[o] = (uint32_t)row[clampi(wxa + 2 * c, 0, W - 1)] | ((uint32_t)row[clampi(wxa + 2 * c + 1, 0, W - 1)] << 16);
       }
     }
-    __syncthreads();
+  };
+  auto sad_pass = [&](int k, const uint32_t* win) {
+    const uint32_t cv = sm.cand[k];
+    const int mvy = (int16_t)(cv & 0xFFFFu), mvx = (int16_t)(cv >> 16);
+    const int fx = (mvx & 7) >> 1, fy = (mvy & 7) >> 1;
+    const int xo = (x0 * 16 + (mvx >> 3)) & 1;              // offset of the window in its staged rows
     const int w00 = (4 - fx) * (4 - fy), w01 = fx * (4 - fy), w10 = (4 - fx) * fy, w11 = fx * fy;
 #pragma unroll
     for (int hb = 0; hb < 2; hb++) {
       if (!blk_on[hb]) continue;   // warp-uniform
       const int blk = warp + 8 * hb, br = blk >> 2, bc = blk & 3;
-      const uint32_t* r0 = &sm.win[(br * 16 + li) * (kWinPitch / 2) + bc * 8 + 4 * lh];
+      const uint32_t* r0 = &win[(br * 16 + li) * (kWinPitch / 2) + bc * 8 + 4 * lh];
       uint32_t a[5], b[5];
 #pragma unroll
       for (int j = 0; j < 5; j++) { a[j] = r0[j]; b[j] = r0[kWinPitch / 2 + j]; }
@@ -557,6 +562,14 @@ __global__ void __launch_bounds__(256) hme_sbrd_kernel(const HmeLaunch P, uint32
       sad = __reduce_add_sync(0xffffffffu, sad);
       if (lane == 0) sm.T[k][blk] = (int)sad;
     }
+  };
+  for (int k = 0; k < ncand; k += 2) {
+    __syncthreads();                                       // the windows of the round before have been read
+    stage_window(k, sm.win[0]);
+    if (k + 1 < ncand) stage_window(k + 1, sm.win[1]);
+    __syncthreads();
+    sad_pass(k, sm.win[0]);
+    if (k + 1 < ncand) sad_pass(k + 1, sm.win[1]);
   }
   __syncthreads();
   if (warp != 0) return;
