@@ -490,7 +490,7 @@ int main(int argc, char** argv) {
   // AV1B_SHARE_GPU=1 (tests): let several workers share one device so that chunk scheduling and
   // concatenation can be exercised on a single-GPU box
   const bool share = getenv("AV1B_SHARE_GPU") && atoi(getenv("AV1B_SHARE_GPU")) != 0;
-  const int n_workers = share ? o.workers : std::min(o.workers, ndev);
+  int n_workers = share ? o.workers : std::min(o.workers, ndev);
 
   // ---- input ----
   Y4m in;
@@ -512,6 +512,14 @@ int main(int argc, char** argv) {
       in.n_frames = (st.st_size - in.header_len) / (int64_t)(6 + in.frame_bytes);
   }
   if ((in.w & 7) || (in.h & 7)) die(3, "frame size %dx%d is not a multiple of 8", in.w, in.h);
+  // A worker costs a CUDA context and an encoder (about 3 s on an 8-GPU box, one after the other in the driver) and codes
+  // 4K at some 800 frames/s from a Y4M file: below about 1200 frames per worker more GPUs make a job slower, not faster
+  // (profiles/r02p_c4_cli_4k10_2400frames.json), and leave fewer for the other jobs of the queue.  AV1B_MIN_FRAMES_PER_WORKER overrides.
+  if (!share && in.n_frames > 0) {
+    const char* ev = getenv("AV1B_MIN_FRAMES_PER_WORKER");
+    const int64_t per = ev ? std::max<int64_t>(1, atoll(ev)) : 1200;
+    n_workers = (int)std::max<int64_t>(1, std::min<int64_t>(n_workers, in.n_frames / per));
+  }
   if (in.bits > out_bits) die(3, "input is %d-bit but --pix-format asks for %d-bit", in.bits, out_bits);
   const int shift = out_bits - in.bits;
   const size_t frame_samples = (size_t)in.w * in.h * 3 / 2;

@@ -221,3 +221,48 @@ def test_cli_rejects_y4m_with_frame_parameters(tmp_path):
     out = str(tmp_path / "o.obu")
     r = subprocess.run([CLI, "-i", bad, "-o", out, "--quiet"], capture_output=True, text=True)
     assert r.returncode != 0 and not os.path.exists(out)
+
+
+@pytest.mark.gpu
+def test_cli_film_grain_and_lookahead_reach_the_encoder(tmp_path):
+    """Row f-4 through the drop-in executable: `--film-grain 20` (av1an.rs:14) makes the stream carry film grain parameters
+    (a decoder that applies grain gives other pictures than one that does not; without the flag both agree) and
+    `--lookahead 0` changes the stream (the temporal filter of the key picture may no longer look ahead)."""
+    from av1_base_b200 import synth
+    from oracle import decoders as D
+    w, h, bd, n = 328, 248, 10, 8
+    frames = synth.synth_clip(w, h, bd, n, seed=5, scene_len=100, noise=1.0)
+    y4m = str(tmp_path / "in.y4m")
+    write_y4m(y4m, frames, bd)
+    outs = {}
+    for name, vp in (("plain", "--crf 40 --preset 6 --keyint 240"), ("grain", "--crf 40 --preset 6 --keyint 240 --film-grain 20"),
+                     ("nolook", "--crf 40 --preset 6 --keyint 240 --lookahead 0")):
+        out = str(tmp_path / (name + ".obu"))
+        r = subprocess.run([CLI, "-i", y4m, "-o", out, "--encoder", "svt-av1", "--pix-format", "yuv420p10le", "--video-params", vp,
+                            "--workers", "1", "--temp", str(tmp_path / ("tmp_" + name)), "--quiet"], capture_output=True, text=True)
+        assert r.returncode == 0, r.stderr
+        outs[name] = open(out, "rb").read()
+    def tus_of(stream):   # walk the OBUs (header, optional extension byte, leb128 size): a temporal delimiter starts a unit
+        starts, i = [], 0
+        while i < len(stream):
+            hdr = stream[i]
+            if (hdr >> 3) & 15 == 2:
+                starts.append(i)
+            j = i + 1 + ((hdr >> 2) & 1)
+            size, shift = 0, 0
+            while True:
+                b = stream[j]; j += 1
+                size |= (b & 0x7F) << shift; shift += 7
+                if not b & 0x80:
+                    break
+            i = j + size
+        return [stream[a:b] for a, b in zip(starts, starts[1:] + [len(stream)])]
+    for name in ("plain", "grain"):
+        tus = tus_of(outs[name])
+        assert len(tus) == n
+        a = D.dav1d_decode(tus)
+        b = D.dav1d_decode(tus, apply_grain=True)
+        assert len(a) == n and len(b) == n
+        same = all(np.array_equal(a[i][0], b[i][0]) for i in range(n))
+        assert same == (name == "plain"), name
+    assert outs["nolook"] != outs["plain"]

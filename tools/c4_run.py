@@ -71,7 +71,8 @@ def main():
                "yuv420p10le" if a.bd > 8 else "yuv420p", "--video-params", "--crf %d --preset 6 --keyint 240 --lookahead 40" % a.crf,
                "--audio-params", "-c:a copy", "--workers", str(wk), "--temp", os.path.join(tmp, "chunks_w%d" % wk), "--quiet"]
         t0 = time.perf_counter()
-        r = subprocess.run(cmd, capture_output=True, text=True)
+        # (the executable would by itself use fewer workers for so short a clip: the scaling run asks for all of them)
+        r = subprocess.run(cmd, capture_output=True, text=True, env=dict(os.environ, AV1B_MIN_FRAMES_PER_WORKER="1"))
         dt = time.perf_counter() - t0
         rec = dict(workers=wk, returncode=r.returncode, seconds=round(dt, 2), fps=round(frames / dt, 1), stderr=r.stderr[-700:])
         if r.returncode == 0:
