@@ -24,7 +24,8 @@ class FrameParams(C.Structure):
                 ("cdef_damping", C.c_int32), ("cdef_bits", C.c_int32),
                 ("cdef_y_strength", C.c_int32 * 8), ("cdef_uv_strength", C.c_int32 * 8),
                 ("lr_type", C.c_int32 * 3), ("lr_unit_shift", C.c_int32), ("lr_uv_shift", C.c_int32),
-                ("non_reference", C.c_int32), ("grain_scaling", C.c_int32), ("grain_seed", C.c_int32)]
+                ("non_reference", C.c_int32), ("grain_scaling", C.c_int32), ("grain_seed", C.c_int32),
+                ("using_qmatrix", C.c_int32), ("qm_level", C.c_int32 * 2)]
 
 
 class Geom(C.Structure):

@@ -54,6 +54,8 @@ typedef struct Av1bFrameParams {
   int32_t grain_scaling;        // film grain synthesis (spec 5.9.30, only with seq.film_grain_present): 0 = apply_grain 0, else the
                                 //    flat luma scaling value 1..255 (noise sigma = scaling / 64 in 8-bit units; chroma scaled from luma)
   int32_t grain_seed;           // 16 bits, varied from frame to frame
+  int32_t using_qmatrix;        // 1: quantisation matrices (--enable-qm; spec 5.9.12 / 7.12.3) at the levels below
+  int32_t qm_level[2];          // luma, chroma (qm_y; qm_u = qm_v): 0 (steepest) .. 15 (flat), from the quantiser index
 } Av1bFrameParams;
 
 // Frame geometry derived from (width, height): all in luma 4x4 "mode info" units unless noted.

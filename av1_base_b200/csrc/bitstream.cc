@@ -172,7 +172,11 @@ static void write_frame_header(const Av1bSeqParams& seq, const Av1bFrameParams& 
   w.bit(0);   // DeltaQYDc: delta_coded
   w.bit(0);   // DeltaQUDc
   w.bit(0);   // DeltaQUAc
-  w.bit(0);   // using_qmatrix
+  w.bit(fp.using_qmatrix ? 1 : 0);   // using_qmatrix
+  if (fp.using_qmatrix) {
+    w.put(fp.qm_level[0], 4);   // qm_y
+    w.put(fp.qm_level[1], 4);   // qm_u; qm_v = qm_u (separate_uv_delta_q = 0)
+  }
   w.bit(0);   // segmentation_enabled
   if (fp.base_q_idx > 0) w.bit(0);   // delta_q_present
   // loop_filter_params()   (base_q_idx > 0 => not CodedLossless)

@@ -52,7 +52,7 @@ namespace {
 struct Options {
   std::string input, output, temp, encoder = "svt-av1", pix_format = "yuv420p10le", video_params, audio_params;
   int workers = 1;
-  int crf = 30, preset = 6, keyint = 240, lookahead = -1, film_grain = 0, enable_qm = 0, qm_min = 0, qm_max = 15;
+  int crf = 30, preset = 6, keyint = 240, lookahead = -1, film_grain = 0, enable_qm = 0, qm_min = 8, qm_max = 15;   // SVT-AV1 defaults
   bool quiet = false;
   bool no_scene_detection = false;   // --sc-method none / --no-scene-detection: split at --keyint only
   int min_scene_len = 12;            // --min-scene-len

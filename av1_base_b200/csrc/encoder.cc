@@ -18,6 +18,7 @@
 #include <vector>
 #include "../../include/av1b200.h"
 #include "av1_tables.h"
+#include "av1_qm_tables.h"
 #include "bitstream.h"
 #include "capi_internal.h"
 #include "kernels.cuh"
@@ -203,6 +204,7 @@ struct av1b_encoder {
   long long sc_level = -1;            // running level of change (scene scores), -1: none yet
   int grain_scaling = 0;              // film grain synthesis strength of the chunk (--film-grain > 0 and a filtered structure)
   uint32_t* d_noise_hist = nullptr;
+  uint8_t* d_qm = nullptr;            // --enable-qm: av1t_qm_sq on the device ([15 levels][luma, chroma][1360])
   uint32_t* h_noise_hist = nullptr;
   cudaEvent_t ev_noise = nullptr;
   int cdf_q[2] = {-1, -1};            // quantisers the device CDF images were made for
@@ -292,6 +294,7 @@ static void free_all(av1b_encoder* e) {
   cudaFree(e->d_sb_of_order); cudaFree(e->d_tile_of_sb); cudaFree(e->d_lr_sse);
   cudaFree(e->d_cdf_init); cudaFree(e->d_cdf_init_alt); cudaFree(e->d_tile_first_k); cudaFree(e->d_rc_overflow);
   cudaFree(e->d_mv_tmp); cudaFree(e->d_hist); cudaFree(e->d_mvs_tf); cudaFree(e->d_mv2_tf);
+  cudaFree(e->d_qm);
   cudaFree(e->d_noise_hist); cudaFreeHost(e->h_noise_hist); if (e->ev_noise) cudaEventDestroy(e->ev_noise);
   for (int p = 0; p < 3; p++) { cudaFree(e->d_hist_src[p]); cudaFree(e->d_flt[p]); cudaFree(e->d_clip[p]); }
   if (e->s_tok) cudaStreamDestroy(e->s_tok);
@@ -376,6 +379,19 @@ static int frame_kind(const av1b_encoder* e, int64_t pos) {
   const int64_t c = pos % e->keyint;
   if (c == 0) return 0;
   return (e->gop_period <= 1 || c % e->gop_period == 0) ? 1 : 2;
+}
+// --enable-qm 1 --qm-min A --qm-max B (av1an.rs:14 passes 1 / 1 / 15): quantisation matrices at the level SVT-AV1 / libaom map the
+// frame's quantiser index to (aom_get_qmlevel: min + qindex * (max + 1 - min) / 256), luma and chroma alike; 15 = flat
+static void set_qm_levels(const av1b_encoder* e, Av1bFrameParams* fp) {
+  const av1b_config& c = e->cfg;
+  fp->using_qmatrix = c.enable_qm ? 1 : 0;
+  const int lvl = c.enable_qm ? std::min(15, std::max(0, c.qm_min + (fp->base_q_idx * (c.qm_max + 1 - c.qm_min)) / 256)) : 15;
+  fp->qm_level[0] = fp->qm_level[1] = lvl;
+}
+// the device matrices of plane class pc (0 luma, 1 chroma) for a frame, nullptr = flat
+static const uint8_t* qm_ptr(const av1b_encoder* e, const Av1bFrameParams& fp, int pc) {
+  if (!fp.using_qmatrix || !e->d_qm || fp.qm_level[pc] >= 15) return nullptr;
+  return e->d_qm + ((size_t)fp.qm_level[pc] * 2 + pc) * AV1T_QM_SQ_SIZE;
 }
 static const Av1bFrameParams& kind_params(const av1b_encoder* e, int kind) {
   return kind == 0 ? e->fp_key : (kind == 1 ? e->fp_inter : e->fp_nonref);
@@ -547,6 +563,7 @@ static int launch(av1b_encoder* e, Slot& s, const Slot& in, int n, int64_t first
       L.g = g; L.bit_depth = bd; L.base_q_idx = qidx; L.quant_rnd = 48; L.dc_q = dcq; L.ac_q = acq;
       for (int p = 0; p < 3; p++) { L.src[p] = src[p]; L.rec[p] = e->loop_filters ? rec[p] : fin[p]; L.coef[p] = coef[p]; L.plane_elems[p] = e->plane_elems[p]; }
       L.blocks = blocks; L.part_map = e->d_map_key; L.map_elems = e->map_elems;
+      L.qm[0] = qm_ptr(e, fp, 0); L.qm[1] = qm_ptr(e, fp, 1);
       if (e->key_var_part) {
         // 64x64 / 32x32 blocks where the source is smooth at this quantiser, 16x16 elsewhere
         const int thr = std::min(4 * acq, 800 << (bd - 8));
@@ -564,6 +581,7 @@ static int launch(av1b_encoder* e, Slot& s, const Slot& in, int n, int64_t first
       L.pack_levels = e->token_path ? 2 : e->legacy_pack_levels;
       for (int p = 0; p < 3; p++) L.digest[p] = e->token_path ? s.d_digest[p] + (size_t)b * e->plane_elems[p] : nullptr;
       L.tb_zero_thr = e->cfg.reserved[4];   // experiment knob: drop transform blocks with sum|level| <= thr
+      L.qm[0] = qm_ptr(e, fp, 0); L.qm[1] = qm_ptr(e, fp, 1);
       CK(launch_inter_encode(L, e->stream));
       CK(launch_merge_skip(g, blocks, e->map_elems, cnt, e->stream));
       e->kernel_launches += 2; e->inter_launches += cnt;   // counts inter FRAMES (a launch codes cnt of them)
@@ -903,6 +921,7 @@ void av1b_config_default(av1b_config* c) {
   c->bit_depth = 10; c->fps_num = 30; c->fps_den = 1;
   c->crf = 30; c->preset = 6; c->keyint = 240; c->lookahead = -1;
   c->tile_cols_log2 = -1; c->tile_rows_log2 = -1;
+  c->qm_min = 8; c->qm_max = 15;   // SVT-AV1's defaults; only read with enable_qm
 }
 
 static void set_structure(av1b_encoder* e, int gop_period);
@@ -912,6 +931,9 @@ int av1b_encoder_create(const av1b_config* cfg, av1b_encoder** out) {
   *out = nullptr;
   if (cfg->bit_depth != 8 && cfg->bit_depth != 10) { set_error("bit_depth must be 8 or 10"); return AV1B_ERR_INVALID; }
   if (cfg->crf < 0 || cfg->crf > 63) { set_error("crf out of range 0..63"); return AV1B_ERR_INVALID; }
+  if (cfg->enable_qm && (cfg->qm_min < 0 || cfg->qm_max > 15 || cfg->qm_min > cfg->qm_max)) {
+    set_error("qm_min / qm_max must satisfy 0 <= qm_min <= qm_max <= 15"); return AV1B_ERR_INVALID;
+  }
   Av1bGeom probe;
   if (av1b_geom_init(&probe, cfg->width, cfg->height, 0, 0)) {
     set_error("unsupported frame size %dx%d (multiples of 8, 16..8192 x 16..4352)", cfg->width, cfg->height);
@@ -974,6 +996,7 @@ int av1b_encoder_create(const av1b_config* cfg, av1b_encoder** out) {
   e->intra_only = cfg->reserved[3] != 0;      // reserved[3] = 1: every frame is a key frame
   e->keyint = cfg->keyint > 0 ? cfg->keyint : 240;
   av1b_select_frame_params(cfg->bit_depth, e->base_q_idx_key, AV1B_KEY_FRAME, e->loop_filters ? 1 : 0, &e->fp_key);
+  set_qm_levels(e, &e->fp_key);
   if (e->lr_on) {
     for (Av1bFrameParams* f : {&e->fp_key}) { f->lr_type[0] = AV1B_RESTORE_SWITCHABLE; f->lr_type[1] = f->lr_type[2] = AV1B_RESTORE_NONE; f->lr_unit_shift = 0; f->lr_uv_shift = 0; }
     e->lr_rows = std::max((cfg->height + 32) / 64, 1); e->lr_cols = std::max((cfg->width + 32) / 64, 1);
@@ -1097,6 +1120,10 @@ int av1b_encoder_create(const av1b_config* cfg, av1b_encoder** out) {
   A(cudaMalloc(&e->d_map_key, e->map_elems)); A(cudaMalloc(&e->d_map_inter, e->map_elems));
   A(cudaMalloc(&e->d_noise_hist, 4096 * sizeof(uint32_t))); A(cudaMallocHost(&e->h_noise_hist, 4096 * sizeof(uint32_t)));
   A(cudaEventCreate(&e->ev_noise));
+  if (cfg->enable_qm) {
+    A(cudaMalloc(&e->d_qm, sizeof(av1t_qm_sq)));
+    A(cudaMemcpy(e->d_qm, av1t_qm_sq, sizeof(av1t_qm_sq), cudaMemcpyHostToDevice));
+  }
   if (e->lr_on) A(cudaMalloc(&e->d_lr_sse, 3 * e->lr_n * F * sizeof(unsigned long long)));
   if (!e->intra_only) {
     for (int l = 0; l < 3; l++) {
@@ -1185,6 +1212,7 @@ static void set_structure(av1b_encoder* e, int gop_period) {
   av1b_select_frame_params(c.bit_depth, e->base_q_idx, AV1B_INTER_FRAME, e->loop_filters ? 1 : 0, &e->fp_inter);
   av1b_select_frame_params(c.bit_depth, e->base_q_idx_nonref, AV1B_INTER_FRAME, e->loop_filters ? 1 : 0, &e->fp_nonref);
   e->fp_nonref.non_reference = 1;
+  set_qm_levels(e, &e->fp_inter); set_qm_levels(e, &e->fp_nonref);
   // no CDEF in the frames nobody predicts from: at their quantiser almost every block is skipped (CDEF leaves those
   // alone), the index per superblock costs more than the filter gains (-2 % bytes, -0.02 dB) and the kernel is saved
   e->fp_nonref.cdef_bits = 0;

@@ -89,7 +89,9 @@ template <> struct TxTab<16> {
 
 // One transform block == one prediction block of plane `p` at (x, y), size N x N, owned by the N lanes
 // `gmask` of one warp; t = lane index inside the group.  buf: (N+7)*(N+1) int32, pred: N*N uint16.
-template <int N>
+// QM: quantisation matrices in force (P.qm: the step of every position is weighted, spec 7.12.3); the <false> instance is
+// the code as it was without them.
+template <int N, bool QM>
 __device__ __forceinline__ int code_tb(const InterLaunch& P, int frame, int p, int x, int y, int mv_row, int mv_col, int t,
                                        unsigned gmask, int32_t* buf, uint16_t* pred, uint8_t* lv8, bool active) {
   constexpr int S = N + 1;
@@ -234,6 +236,8 @@ __device__ __forceinline__ int code_tb(const InterLaunch& P, int frame, int p, i
     constexpr int sh = 24 + 2 * TxTab<N>::kLog2 - TxTab<N>::kRowShift - 4;
     const int lim = (1 << (7 + bd)) - 1;
     const uint32_t rnd_dc = (uint32_t)((P.dc_q * P.quant_rnd) >> 7), rnd_ac = (uint32_t)((P.ac_q * P.quant_rnd) >> 7);
+    // row t of the N x N matrix of this plane (av1_qm_tables.h: 4x4 at 0, 8x8 at 16, 16x16 at 80)
+    const uint8_t* qmw = (QM && P.qm[ss]) ? P.qm[ss] + (N == 4 ? 0 : N == 8 ? 16 : 80) + t * N : nullptr;
     // the dequantised row goes back to this thread's own row of buf (it has been consumed into row[])
 #pragma unroll
     for (int l = 0; l < N; l++) {
@@ -242,13 +246,21 @@ __device__ __forceinline__ int code_tb(const InterLaunch& P, int frame, int p, i
       for (int j = 0; j < N / 2; j++) acc += (int64_t)TxTab<N>::f(l, j) * ((l & 1) ? rso[j] : rse[j]);
       const int32_t c = (int32_t)((acc * 4096 + ((int64_t)1 << (sh - 1))) >> sh);
       const bool dc = (t | l) == 0;
-      const uint32_t dqv = dc ? (uint32_t)P.dc_q : (uint32_t)P.ac_q;
-      const uint32_t a = (uint32_t)(c < 0 ? -c : c) + (dc ? rnd_dc : rnd_ac);
-      // exact floor(a / dqv) by multiplication with floor(2^32 / dqv) and at most two corrections
-      uint32_t lv = __umulhi(a, dc ? P.dc_magic : P.ac_magic);
-      uint32_t rem = a - lv * dqv;
-      if (rem >= dqv) { lv++; rem -= dqv; }
-      if (rem >= dqv) lv++;
+      uint32_t dqv = dc ? (uint32_t)P.dc_q : (uint32_t)P.ac_q;
+      uint32_t lv;
+      if (QM) {
+        // the position's step: Round2(q * weight, 5); no quantisation matrix for a plane = weight 32 everywhere
+        if (qmw) dqv = (dqv * (uint32_t)qmw[l] + 16u) >> 5;
+        const uint32_t a = (uint32_t)(c < 0 ? -c : c) + ((dqv * (uint32_t)P.quant_rnd) >> 7);
+        lv = a / dqv;
+      } else {
+        const uint32_t a = (uint32_t)(c < 0 ? -c : c) + (dc ? rnd_dc : rnd_ac);
+        // exact floor(a / dqv) by multiplication with floor(2^32 / dqv) and at most two corrections
+        lv = __umulhi(a, dc ? P.dc_magic : P.ac_magic);
+        uint32_t rem = a - lv * dqv;
+        if (rem >= dqv) { lv++; rem -= dqv; }
+        if (rem >= dqv) lv++;
+      }
       if (lv > 32767u) lv = 32767u;
       int32_t d = (int32_t)((lv * dqv) & 0xFFFFFFu);
       if (d > lim) d = lim;
@@ -363,6 +375,7 @@ __device__ __forceinline__ void group_buffers(Smem& sm, int group, int32_t** buf
   *lv8 = base + kBuf + kPred;
 }
 
+template <bool QM>
 __global__ void __launch_bounds__(kThreads, 3) inter_encode_kernel(const InterLaunch P) {
   __shared__ Smem sm;
   // frame blockIdx.z of the launch: same reference, same quantiser, own source / outputs
@@ -391,7 +404,7 @@ __global__ void __launch_bounds__(kThreads, 3) inter_encode_kernel(const InterLa
     group_buffers<16>(sm, group, &buf, &pred, &lv8);
     // inactive groups run on the (always allocated) superblock origin and store nothing
     const int x = active ? ux * 8 : sbx * 64, y = active ? uy * 8 : sby * 64;
-    const int eob = code_tb<16>(P, frame, 0, x, y, mvr, mvc, t, gmask, buf, pred, lv8, active);
+    const int eob = code_tb<16, QM>(P, frame, 0, x, y, mvr, mvc, t, gmask, buf, pred, lv8, active);
     if (active && t == 0) sm.eob[0][u] = (uint16_t)eob;
   }
   __syncthreads();
@@ -409,7 +422,7 @@ __global__ void __launch_bounds__(kThreads, 3) inter_encode_kernel(const InterLa
     uint8_t* lv8;
       group_buffers<8>(sm, group, &buf, &pred, &lv8);
     const int x = active ? ux * 4 : sbx * 32, y = active ? uy * 4 : sby * 32;
-    const int eob = code_tb<8>(P, frame, p, x, y, mvr, mvc, t, gmask, buf, pred, lv8, active);
+    const int eob = code_tb<8, QM>(P, frame, p, x, y, mvr, mvc, t, gmask, buf, pred, lv8, active);
     if (active && t == 0) sm.eob[p][u] = (uint16_t)eob;
   }
   __syncthreads();
@@ -430,7 +443,7 @@ __global__ void __launch_bounds__(kThreads, 3) inter_encode_kernel(const InterLa
       uint8_t* lv8;
       group_buffers<8>(sm, group, &buf, &pred, &lv8);
       const int x = active ? ux * 8 : sbx * 64, y = active ? uy * 8 : sby * 64;
-      const int eob = code_tb<8>(P, frame, 0, x, y, mvr, mvc, t, gmask, buf, pred, lv8, active);
+      const int eob = code_tb<8, QM>(P, frame, 0, x, y, mvr, mvc, t, gmask, buf, pred, lv8, active);
       if (active && t == 0) sm.eob[0][u] = (uint16_t)eob;
       __syncthreads();
     }
@@ -447,7 +460,7 @@ __global__ void __launch_bounds__(kThreads, 3) inter_encode_kernel(const InterLa
       uint8_t* lv8;
       group_buffers<4>(sm, group, &buf, &pred, &lv8);
       const int x = active ? ux * 4 : sbx * 32, y = active ? uy * 4 : sby * 32;
-      const int eob = code_tb<4>(P, frame, p, x, y, mvr, mvc, t, gmask, buf, pred, lv8, active);
+      const int eob = code_tb<4, QM>(P, frame, p, x, y, mvr, mvc, t, gmask, buf, pred, lv8, active);
       if (active && t == 0) sm.eob[p][u] = (uint16_t)eob;
       __syncthreads();
     }
@@ -521,7 +534,8 @@ cudaError_t launch_inter_encode(const InterLaunch& p0, cudaStream_t s) {
   p.dc_magic = (uint32_t)(((uint64_t)1 << 32) / (uint32_t)p.dc_q);
   p.ac_magic = (uint32_t)(((uint64_t)1 << 32) / (uint32_t)p.ac_q);
   dim3 grid(p.g.sb_cols, p.g.sb_rows, p.n_frames > 0 ? p.n_frames : 1);
-  inter_encode_kernel<<<grid, kThreads, 0, s>>>(p);
+  if (p.qm[0] || p.qm[1]) inter_encode_kernel<true><<<grid, kThreads, 0, s>>>(p);
+  else inter_encode_kernel<false><<<grid, kThreads, 0, s>>>(p);
   return cudaGetLastError();
 }
 

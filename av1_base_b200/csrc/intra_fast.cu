@@ -378,13 +378,16 @@ __device__ __forceinline__ int intra_tb(const IntraLaunch& P, int frame, int p, 
     for (int j = 0; j < N; j++) row[j] = G.buf[t * S + j];
     constexpr int sh = 24 + 2 * LN - FwdTab<N>::kRowShift - 4;
     const int lim = (1 << (7 + bd)) - 1;
+    // row t of the N x N matrix of this plane's level (av1_qm_tables.h: 4x4 at 0, 8x8 at 16, 16x16 at 80) or flat
+    const uint8_t* qmw = P.qm[ss] ? P.qm[ss] + (N == 4 ? 0 : N == 8 ? 16 : 80) + t * N : nullptr;
 #pragma unroll 2
     for (int l = 0; l < N; l++) {
       int64_t acc = 0;
 #pragma unroll
       for (int j = 0; j < N; j++) acc += (int64_t)Fh[l * N + j] * row[j];
       const int32_t c = (int32_t)((acc * 4096 + ((int64_t)1 << (sh - 1))) >> sh);
-      const uint32_t dqv = (t | l) ? (uint32_t)P.ac_q : (uint32_t)P.dc_q;
+      uint32_t dqv = (t | l) ? (uint32_t)P.ac_q : (uint32_t)P.dc_q;
+      if (qmw) dqv = (dqv * (uint32_t)qmw[l] + 16u) >> 5;   // quantisation matrix: Round2(q * weight, 5), spec 7.12.3
       const uint32_t a = (uint32_t)(c < 0 ? -c : c);
       uint32_t lv = (a + ((dqv * (uint32_t)P.quant_rnd) >> 7)) / dqv;
       if (lv > 32767u) lv = 32767u;

@@ -261,13 +261,16 @@ __device__ void code_plane(Smem& sm, const IntraLaunch& P, int plane, int slot, 
     const int lim = (1 << (7 + P.bit_depth)) - 1;
     const int16_t* iscan = cn == 4 ? tbl::iscan_default_4 : cn == 8 ? tbl::iscan_default_8
                            : cn == 16 ? tbl::iscan_default_16 : tbl::iscan_default_32;
+    // the cn x cn matrix of this plane's level (av1_qm_tables.h: 4x4 at 0, 8x8 at 16, 16x16 at 80, 32x32 at 336) or flat
+    const uint8_t* qmw = P.qm[plane > 0] ? P.qm[plane > 0] + (cn == 4 ? 0 : cn == 8 ? 16 : cn == 16 ? 80 : 336) : nullptr;
     for (int o = tid; o < cn * cn; o += kThreads) {
       // lanes run over k (rows) so that F[l][j] is warp-uniform
       const int k = o & (cn - 1), l = o >> lcn;
       int64_t acc = 0;
       for (int j = 0; j < n; j++) acc += (int64_t)F[l * n + j] * sm.bufT[k * (n + 1) + j];
       const int32_t c = (int32_t)((acc * 4096 + ((int64_t)1 << (sh - 1))) >> sh);
-      const int dqv = (k | l) ? P.ac_q : P.dc_q;
+      int dqv = (k | l) ? P.ac_q : P.dc_q;
+      if (qmw) dqv = (dqv * (int)qmw[k * cn + l] + 16) >> 5;   // quantisation matrix: Round2(q * weight, 5), spec 7.12.3
       const uint32_t a = (uint32_t)(c < 0 ? -c : c) << s;
       uint32_t lv = (a + (uint32_t)((dqv * P.quant_rnd) >> 7)) / (uint32_t)dqv;
       if (lv > 32767u) lv = 32767u;

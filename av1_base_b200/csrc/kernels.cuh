@@ -21,6 +21,9 @@ struct IntraLaunch {
   Av1bBlockInfo* blocks;      // [n_frames][h8*w8]
   const uint8_t* part_map;    // [n_frames][h8*w8]   (per-frame partition quadtree)
   size_t map_elems;
+  // quantisation matrices (spec 7.12.3): luma / chroma weights of the frame's level (av1_qm_tables.h: the four square
+  // sizes, 1360 bytes, device memory) or nullptr = flat
+  const uint8_t* qm[2] = {nullptr, nullptr};
 };
 
 // Deblocking filter (deblock_kernel.cu): in -> out, one CTA per superblock.
@@ -145,6 +148,7 @@ struct InterLaunch {
                               //    symbols (sign | level | br ctx | base ctx) and flagged with bit 15 of eob
                               // 2: every coded transform block also gets its packed symbols in `digest` (token path)
   uint16_t* digest[3];        // pack_levels == 2: same layout as coef
+  const uint8_t* qm[2] = {nullptr, nullptr};   // quantisation matrices as in IntraLaunch (a launch with one runs the <true> kernel)
 };
 cudaError_t launch_inter_encode(const InterLaunch& p, cudaStream_t s);
 // Bottom-up merge of skipped inter siblings with equal vectors into 32x32 / 64x64 blocks (side info only).

@@ -29,7 +29,7 @@ class Encoder:
                  tile_cols_log2=-1, tile_rows_log2=-1, hdr=False, host_threads=0, frames_in_flight=0,
                  keep_debug=False, blk_log2=0, loop_filters=True, intra_only=False, tb_zero_thr=0, raster_levels=False,
                  pack_path=0, lr_off=False, tile_sb=0, gop_period=0, me_smooth=True, key_var_part=True, mctf=True,
-                 lookahead=-1, film_grain=0, scene_cut=True):
+                 lookahead=-1, film_grain=0, scene_cut=True, qm=None):
         L = abi.lib()
         cfg = abi.Config()
         L.av1b_config_default(C.byref(cfg))
@@ -58,6 +58,8 @@ class Encoder:
         cfg.tune[4] = 0 if scene_cut else 1   # key frame at a scene change inside a chunk (scores from the GPU)
         cfg.lookahead = lookahead          # -1 = default; frames the temporal filter may look ahead
         cfg.film_grain = film_grain
+        if qm is not None:                 # (qm_min, qm_max): --enable-qm 1 --qm-min .. --qm-max ..
+            cfg.enable_qm, cfg.qm_min, cfg.qm_max = 1, qm[0], qm[1]
         self.cfg = cfg
         self._h = C.c_void_p()
         _check(L.av1b_encoder_create(C.byref(cfg), C.byref(self._h)))

@@ -45,7 +45,9 @@ typedef struct av1b_config {
                                      from the noise level measured on the chunk's first picture, chroma from luma, white grain)
                                      in the chunks that are coded with the filtered structure, so that decoders put back
                                      what the filter and the skipped blocks took out                                  */
-  int32_t enable_qm, qm_min, qm_max; /* accepted; flat quantisation matrices only                  */
+  int32_t enable_qm, qm_min, qm_max; /* --enable-qm 1 --qm-min A --qm-max B (0 <= A <= B <= 15): quantisation matrices (spec 7.12.3) at the
+                                     level the frame's quantiser index maps to, A + qindex * (B + 1 - A) / 256 as in SVT-AV1 / libaom
+                                     (0 steepest .. 15 flat), luma and chroma alike; defaults 0 / 8 / 15                */
   int32_t tile_cols_log2, tile_rows_log2; /* -1 = auto (fill the GPU)                              */
   int32_t device_id;
   int32_t hdr;                    /* 1: signal BT.2020/PQ in the sequence header                   */

@@ -21,6 +21,7 @@
 #include "../av1_base_b200/csrc/av1_inv_txfm1d.h"   // normative butterfly graphs (pinned vs libaom av1_idct*)
 #include "../av1_base_b200/csrc/av1_tables.h"         // normative constant tables (extracted from the libaom binary): one copy
 #include "../av1_base_b200/csrc/av1_fwd_matrices.h"   // generated from the normative inverse transforms
+#include "../av1_base_b200/csrc/av1_qm_tables.h"      // Quantizer_Matrix of the square sizes (same origin; the decoders pin it)
 
 using namespace av1tx;
 
@@ -160,16 +161,31 @@ static inline int dc_q(int qidx, int bd) { return bd == 8 ? av1t_dc_q_8[qidx] : 
 static inline int ac_q(int qidx, int bd) { return bd == 8 ? av1t_ac_q_8[qidx] : bd == 10 ? av1t_ac_q_10[qidx] : av1t_ac_q_12[qidx]; }
 static inline int tx_scale_shift(int w, int h) { const int p = w * h; return (p > 256) + (p > 1024); }
 
+// Quantisation matrices (spec 7.12.3, using_qmatrix = 1): the step of coefficient (i, j) becomes
+//   q2 = Round2(q * Quantizer_Matrix[level][plane > 0][offset(size) + i * tw + j], 5)
+// for levels 0..14 (15 = flat).  The frame's levels are oracle state set by orc_set_qm (tests / chain.py) so that the
+// frame functions keep their signatures; product: Av1bFrameParams.qm_level -> IntraLaunch / InterLaunch.qm.
+static int g_qm_level[2] = {15, 15};
+extern "C" void orc_set_qm(int level_y, int level_uv) { g_qm_level[0] = level_y; g_qm_level[1] = level_uv; }
+// the level SVT-AV1 / libaom derive from the quantiser index (aom_get_qmlevel): first + qindex * (last + 1 - first) / 256
+extern "C" int orc_qm_level(int qidx, int first, int last) { return first + (qidx * (last + 1 - first)) / 256; }
+static inline int qm_step(int q, int plane, int cw, int i, int j) {
+  const int lvl = g_qm_level[plane > 0];
+  if (lvl >= 15) return q;
+  return (q * av1t_qm_sq[lvl][plane > 0][av1t_qm_sq_offset(cw) + i * cw + j] + 16) >> 5;
+}
+
 // Encoder quantiser (ours): level = min((|c| << s) + ((dqv * rnd) >> 7)) / dqv, 32767)
 // Dequantiser (normative, spec 7.12.3): dq = ((level * dqv) & 0xFFFFFF) >> s, clipped to bd+8 bits.
-// Returns eob-independent stats; levels/dq in SPEC layout.
+// dqv = the step of the position (dc / ac quantiser, weighted by the quantisation matrix when one is in force).
+// Returns eob-independent stats; levels/dq in SPEC layout.  Square 2-D transforms only when a matrix is in force.
 extern "C" void orc_quant_dequant(const int32_t* coef, int cstride, int16_t* lev, int lstride, int32_t* dq,
-                                  int dstride, int w, int h, int qidx, int bd, int rnd) {
+                                  int dstride, int w, int h, int qidx, int bd, int rnd, int plane) {
   const int cw = std::min(w, 32), ch = std::min(h, 32), s = tx_scale_shift(w, h);
   const int lim = (1 << (7 + bd)) - 1;
   for (int i = 0; i < ch; i++)
     for (int j = 0; j < cw; j++) {
-      const int dqv = (i | j) ? ac_q(qidx, bd) : dc_q(qidx, bd);
+      const int dqv = qm_step((i | j) ? ac_q(qidx, bd) : dc_q(qidx, bd), plane, cw, i, j);
       const int32_t c = coef[i * cstride + j];
       const int64_t a = (int64_t)(c < 0 ? -(int64_t)c : c) << s;
       int64_t l = (a + ((dqv * rnd) >> 7)) / dqv;
@@ -183,12 +199,12 @@ extern "C" void orc_quant_dequant(const int32_t* coef, int cstride, int16_t* lev
     }
 }
 
-extern "C" void orc_dequant(const int16_t* lev, int lstride, int32_t* dq, int dstride, int w, int h, int qidx, int bd) {
+extern "C" void orc_dequant(const int16_t* lev, int lstride, int32_t* dq, int dstride, int w, int h, int qidx, int bd, int plane) {
   const int cw = std::min(w, 32), ch = std::min(h, 32), s = tx_scale_shift(w, h);
   const int lim = (1 << (7 + bd)) - 1;
   for (int i = 0; i < ch; i++)
     for (int j = 0; j < cw; j++) {
-      const int dqv = (i | j) ? ac_q(qidx, bd) : dc_q(qidx, bd);
+      const int dqv = qm_step((i | j) ? ac_q(qidx, bd) : dc_q(qidx, bd), plane, cw, i, j);
       const int l = lev[i * lstride + j];
       const int64_t a = l < 0 ? -l : l;
       int64_t d = ((a * dqv) & 0xFFFFFF) >> s;
@@ -503,7 +519,7 @@ struct IntraEnc {
           resid[i * n + j] = (int16_t)((int)src[p][(size_t)(y + i) * sstride[p] + x + j] - (int)pred[i * n + j]);
         const int cn = std::min(n, 32);
         orc_fwd_txfm2d(resid, n, cf, cn, n, n, tx_type);
-        orc_quant_dequant(cf, cn, lv, cn, dq, cn, n, n, qidx, bd, rnd);
+        orc_quant_dequant(cf, cn, lv, cn, dq, cn, n, n, qidx, bd, rnd, p);
         // eob = 1 + last non-zero position in scan order
         const int16_t* scan = cn == 4 ? av1t_scan_default_4x4 : cn == 8 ? av1t_scan_default_8x8
                               : cn == 16 ? av1t_scan_default_16x16 : av1t_scan_default_32x32;
@@ -1020,7 +1036,7 @@ extern "C" int orc_encode_inter_frame(const Av1bGeom* g, int bit_depth, int base
           for (int i = 0; i < cn * cn; i++) { lv[i] = 0; dq[i] = 0; }
         } else {
           orc_fwd_txfm2d(resid.data(), n, cf.data(), cn, n, n, AV1B_DCT_DCT);
-          orc_quant_dequant(cf.data(), cn, lv.data(), cn, dq.data(), cn, n, n, base_q_idx, bit_depth, quant_rnd);
+          orc_quant_dequant(cf.data(), cn, lv.data(), cn, dq.data(), cn, n, n, base_q_idx, bit_depth, quant_rnd, p);
         }
         {
           const int thr = n >= 16 ? tb_zero_thr : (n == 8 ? tb_zero_thr >> 1 : 0);

@@ -94,9 +94,10 @@ def scene_positions(g, bd, padded, pos0=0, scene_cut=True):
 
 def encode_chain(frames, w, h, bd, crf, keyint=240, gop_period=DEFAULT_GOP_PERIOD, me_smooth=True, key_var_part=True, loop_filters=True,
                  lr=False, intra_only=False, blk_log2=4, tb_zero_thr=0, pos0=0, geom=None, mctf=True, batch=8, lookahead=-1,
-                 film_grain=0, mctf_radius=2, mctf_key_fwd=4, scene_cut=True):
+                 film_grain=0, mctf_radius=2, mctf_key_fwd=4, scene_cut=True, qm=None):
     """Returns one FrameResult per frame: kind, fp, res (blocks / coef / pre-filter rec), fin (padded planes after the
-    in-loop filters), cdef_idx, lr_units, mvs."""
+    in-loop filters), cdef_idx, lr_units, mvs.  qm = (qm_min, qm_max): quantisation matrices at the level the frame's quantiser
+    index maps to (csrc/encoder.cc set_qm_levels), luma and chroma alike."""
     g = geom if geom is not None else O.geom(w, h, 0, 0)   # key-frame tiling: no intra prediction across tile edges
     if gop_period == 0:
         gop_period, _ = choose_structure(g, bd, crf, O.pad_planes(g, frames[0])[0])
@@ -116,6 +117,10 @@ def encode_chain(frames, w, h, bd, crf, keyint=240, gop_period=DEFAULT_GOP_PERIO
         kind = frame_kind(gop_pos[i], keyint, gop_period, intra_only)
         q = qk[kind]
         fp = class_params(bd, q, kind, loop_filters, lr)
+        if qm is not None:
+            fp.using_qmatrix = 1
+            fp.qm_level[0] = fp.qm_level[1] = O.qm_level(q, qm[0], qm[1])
+        O.set_qm(fp.qm_level[0], fp.qm_level[1]) if qm is not None else O.set_qm()
         src = padded[i]
         pyr = pyrs[i]          # the motion search always sees the unfiltered source pictures
         nb = []
@@ -175,6 +180,7 @@ def encode_chain(frames, w, h, bd, crf, keyint=240, gop_period=DEFAULT_GOP_PERIO
                 r.lr_units, _ = O.lr_search(g, bd, fp, cand, fin, r.res.rec, src[0], (aq * aq * 5) >> 8)
                 fin = O.lr_frame(g, bd, fp, fin, r.res.rec, [r.lr_units, None, None])
         r.fin = fin
+        O.set_qm()
         if kind != 2:
             anchor_fin, anchor_pyr = fin, pyr
         out.append(r)

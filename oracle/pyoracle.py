@@ -42,6 +42,15 @@ def partition_smooth(g, luma_padded, thr):
     return m
 
 
+def set_qm(level_y=15, level_uv=15):
+    """Quantisation matrix levels of the frames coded from here on (orc_set_qm): 0 steepest .. 14, 15 = flat (off)."""
+    lib().orc_set_qm(int(level_y), int(level_uv))
+
+def qm_level(qidx, first, last):
+    """aom_get_qmlevel: the level a quantiser index maps to between --qm-min and --qm-max."""
+    return int(lib().orc_qm_level(int(qidx), int(first), int(last)))
+
+
 class IntraResult:
     pass
 

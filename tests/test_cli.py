@@ -227,7 +227,8 @@ def test_cli_rejects_y4m_with_frame_parameters(tmp_path):
 def test_cli_film_grain_and_lookahead_reach_the_encoder(tmp_path):
     """Row f-4 through the drop-in executable: `--film-grain 20` (av1an.rs:14) makes the stream carry film grain parameters
     (a decoder that applies grain gives other pictures than one that does not; without the flag both agree) and
-    `--lookahead 0` changes the stream (the temporal filter of the key picture may no longer look ahead)."""
+    `--lookahead 0` changes the stream (the temporal filter of the key picture may no longer look ahead); `--enable-qm 1
+    --qm-min 1 --qm-max 15` codes with quantisation matrices."""
     from av1_base_b200 import synth
     from oracle import decoders as D
     w, h, bd, n = 328, 248, 10, 8
@@ -236,7 +237,8 @@ def test_cli_film_grain_and_lookahead_reach_the_encoder(tmp_path):
     write_y4m(y4m, frames, bd)
     outs = {}
     for name, vp in (("plain", "--crf 40 --preset 6 --keyint 240"), ("grain", "--crf 40 --preset 6 --keyint 240 --film-grain 20"),
-                     ("nolook", "--crf 40 --preset 6 --keyint 240 --lookahead 0")):
+                     ("nolook", "--crf 40 --preset 6 --keyint 240 --lookahead 0"),
+                     ("qm", "--crf 40 --preset 6 --keyint 240 --enable-qm 1 --qm-min 1 --qm-max 15")):
         out = str(tmp_path / (name + ".obu"))
         r = subprocess.run([CLI, "-i", y4m, "-o", out, "--encoder", "svt-av1", "--pix-format", "yuv420p10le", "--video-params", vp,
                             "--workers", "1", "--temp", str(tmp_path / ("tmp_" + name)), "--quiet"], capture_output=True, text=True)
@@ -266,3 +268,8 @@ def test_cli_film_grain_and_lookahead_reach_the_encoder(tmp_path):
         same = all(np.array_equal(a[i][0], b[i][0]) for i in range(n))
         assert same == (name == "plain"), name
     assert outs["nolook"] != outs["plain"]
+    # --enable-qm 1 --qm-min 1 --qm-max 15 (av1an.rs:14): quantisation matrices are signalled and used; both decoders agree on the pictures
+    assert outs["qm"] != outs["plain"]
+    tus = tus_of(outs["qm"])
+    a, b = D.dav1d_decode(tus), D.aom_decode(tus)
+    assert len(a) == n and len(b) == n and all(np.array_equal(a[i][p], b[i][p]) for i in range(n) for p in range(3))

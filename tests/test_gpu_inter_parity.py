@@ -37,6 +37,23 @@ def test_chunk_parity(w, h, bd, crf, tcl, trl, lf, nfr, fif, keyint, preset, gop
     _check_chunk(frames, w, h, bd, crf, tcl, trl, lf, nfr, fif, keyint, preset, gop, pack_path)
 
 
+@pytest.mark.parametrize("w,h,bd,crf,gop,qm,kvp,pack_path", [
+    (200, 136, 10, 30, 3, (1, 15), True, 0),      # the daemon's flags (av1an.rs:14); 8x8 / 4x4 blocks at the picture edge
+    (328, 248, 8, 44, 2, (0, 0), False, 4),       # steepest level; fixed 16x16 key-frame blocks (intra_fast.cu)
+    (640, 360, 10, 12, 1, (1, 15), True, 0),      # fine quantiser, P chain
+    (328, 248, 10, 36, 0, (5, 9), True, 4),
+    (200, 136, 8, 55, 2, (15, 15), True, 0),      # level 15 = flat: signalled, nothing weighted
+])
+def test_chunk_parity_with_quantisation_matrices(w, h, bd, crf, gop, qm, kvp, pack_path):
+    """Row f-4, --enable-qm 1 --qm-min A --qm-max B: the level follows each frame kind's quantiser index, every encode kernel
+    (intra_encode_kernel, intra_recon_kernel, inter_encode_kernel<true>) weights the step of every position with the level's
+    matrix (spec 7.12.3) exactly as the oracle chain does; dav1d and libaom decode to the reconstruction."""
+    nfr = 7
+    frames = synth.synth_clip(w, h, bd, nfr, seed=w + crf, scene_len=100, noise=0.3)
+    kinds = _check_chunk(frames, w, h, bd, crf, -1, -1, True, nfr, 4, 240, 6, gop, pack_path, qm=qm, key_var_part=kvp)
+    assert kinds[0] == 0 and 1 in kinds
+
+
 def test_scene_change_inside_a_chunk_becomes_a_key_frame():
     """Row f-3: scene scores computed on the GPU as the pictures arrive (scene_score_kernel on the upload stream) restart the
     structure inside a chunk -- key frame at the cut, no motion search or temporal filter across it; frame kinds, vectors,
@@ -52,13 +69,15 @@ def test_scene_change_inside_a_chunk_becomes_a_key_frame():
     enc.close()
 
 
-def _check_chunk(frames, w, h, bd, crf, tcl, trl, lf, nfr, fif, keyint, preset, gop, pack_path):
+def _check_chunk(frames, w, h, bd, crf, tcl, trl, lf, nfr, fif, keyint, preset, gop, pack_path, qm=None, key_var_part=True):
     enc = encoder.Encoder(w, h, bd, crf=crf, keep_debug=True, tile_cols_log2=tcl, tile_rows_log2=trl,
-                          frames_in_flight=fif, loop_filters=lf, keyint=keyint, preset=preset, pack_path=pack_path, gop_period=gop)
+                          frames_in_flight=fif, loop_filters=lf, keyint=keyint, preset=preset, pack_path=pack_path, gop_period=gop,
+                          qm=qm, key_var_part=key_var_part)
     lr = lf and preset <= 5
     tus = enc.encode_chunk(frames)
     assert len(tus) == nfr
-    g, want = chain.encode_chain(frames, w, h, bd, crf, keyint=keyint, gop_period=gop, loop_filters=lf, lr=lr, geom=enc.geom, batch=fif)
+    g, want = chain.encode_chain(frames, w, h, bd, crf, keyint=keyint, gop_period=gop, loop_filters=lf, lr=lr, geom=enc.geom, batch=fif,
+                                 qm=qm, key_var_part=key_var_part)
     info = enc.chunk_info()
     if gop == 0:   # structure chosen from the noise level of the first picture
         gop, nb = chain.choose_structure(g, bd, crf, O.pad_planes(g, frames[0])[0])
@@ -75,6 +94,7 @@ def _check_chunk(frames, w, h, bd, crf, tcl, trl, lf, nfr, fif, keyint, preset, 
         fpe = enc.class_params(r.kind)
         assert fpe.base_q_idx == r.q and fpe.non_reference == r.fp.non_reference
         assert list(fpe.lf_level) == list(r.fp.lf_level) and list(fpe.cdef_y_strength) == list(r.fp.cdef_y_strength)
+        assert fpe.using_qmatrix == r.fp.using_qmatrix and list(fpe.qm_level) == list(r.fp.qm_level)
         blocks, coef = enc.frame_syms(i)
         for f in ("blk_log2", "y_mode", "uv_mode", "skip", "eob", "is_inter", "mv"):
             assert np.array_equal(blocks[f], r.res.blocks[f]), (f, i)

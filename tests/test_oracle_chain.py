@@ -45,6 +45,42 @@ def test_chain_streams_decode_to_oracle_reconstruction(w, h, bd, crf, n, keyint,
                 assert np.array_equal(out[i][p], O.crop(g, want[i].fin)[p]), (dec.__name__, i, p)
 
 
+@pytest.mark.parametrize("w,h,bd,crf,n,gop,qm", [(200, 136, 10, 30, 7, 3, (1, 15)), (328, 248, 8, 44, 5, 2, (0, 0)),
+                                                 (256, 192, 10, 12, 4, 1, (1, 15)), (192, 136, 8, 55, 4, 2, (15, 15)),
+                                                 (320, 192, 10, 36, 3, 1, (5, 9))])
+def test_quantisation_matrices_decode(w, h, bd, crf, n, gop, qm):
+    """Row f-4, --enable-qm 1 --qm-min A --qm-max B (av1an.rs:14): frame headers signal using_qmatrix with the level the
+    frame's quantiser index maps to, the quantiser / dequantiser weight every position's step with Quantizer_Matrix (spec
+    7.12.3; csrc/av1_qm_tables.h, read out of the libaom binary).  dav1d (its own copy of the constants) and libaom must
+    decode the chain's streams to the oracle's reconstruction: that pins the tables, the header syntax and the arithmetic.
+    Smooth clips make the key frames use 64x64 / 32x32 transforms (the 32x32 matrix) besides 16x16 / 8x8 / 4x4."""
+    frames = synth.synth_clip(w, h, bd, n, seed=w + crf, scene_len=100, noise=0.3)
+    g, want = chain.encode_chain(frames, w, h, bd, crf, gop_period=gop, qm=qm)
+    g0, flat = chain.encode_chain(frames, w, h, bd, crf, gop_period=gop)
+    lv = [O.qm_level(r.q, qm[0], qm[1]) for r in want]
+    for r, l in zip(want, lv):
+        assert r.fp.using_qmatrix == 1 and list(r.fp.qm_level) == [l, l] and qm[0] <= l <= qm[1]
+    if qm[0] < 15:
+        assert {5, 6} & set(np.unique(want[0].res.blocks["blk_log2"]).tolist())      # large transforms are in the test
+        # the matrices change what is coded (steps of the high frequencies grow), level 15 is the flat quantiser
+        assert any(not np.array_equal(a.res.coef[0], b.res.coef[0]) for a, b in zip(want, flat))
+    else:
+        assert all(np.array_equal(a.res.coef[p], b.res.coef[p]) for a, b in zip(want, flat) for p in range(3))
+    tus = pack_chain(w, h, bd, want, g)
+    for dec in (D.dav1d_decode, D.aom_decode):
+        out = dec(tus)
+        assert len(out) == n
+        for i in range(n):
+            for p in range(3):
+                assert np.array_equal(out[i][p], O.crop(g, want[i].fin)[p]), (dec.__name__, i, p)
+
+
+def test_qm_level_mapping():
+    """aom_get_qmlevel (SVT-AV1 and libaom map the quantiser index to a level the same way)."""
+    assert O.qm_level(0, 1, 15) == 1 and O.qm_level(255, 1, 15) == 15 and O.qm_level(128, 0, 15) == 8
+    assert [O.qm_level(q, 8, 15) for q in (0, 31, 32, 255)] == [8, 8, 9, 15]
+
+
 def np_partition_smooth(g, Y, thr):
     """numpy restatement: least information possible shared with the C++ (box sums via reshape, plane via mgrid)."""
     pm = O.partition_fixed(g, 4).reshape(g.h8, g.w8).copy()
