@@ -14,7 +14,8 @@ LIB_PATH = os.environ.get("AV1B200_LIB", os.path.join(_HERE, "libav1b200.so"))
 class SeqParams(C.Structure):
     _fields_ = [("width", C.c_int32), ("height", C.c_int32), ("bit_depth", C.c_int32),
                 ("enable_cdef", C.c_int32), ("enable_restoration", C.c_int32),
-                ("fps_num", C.c_int32), ("fps_den", C.c_int32), ("color_hdr", C.c_int32), ("film_grain_present", C.c_int32)]
+                ("fps_num", C.c_int32), ("fps_den", C.c_int32), ("color_hdr", C.c_int32), ("film_grain_present", C.c_int32),
+                ("render_width", C.c_int32), ("render_height", C.c_int32)]
 
 
 class FrameParams(C.Structure):

@@ -33,6 +33,8 @@ typedef struct Av1bSeqParams {
   int32_t fps_num, fps_den;
   int32_t color_hdr;            // 1: signal BT.2020 / PQ
   int32_t film_grain_present;   // 1: frame headers carry film grain parameters (--film-grain > 0)
+  int32_t render_width, render_height;   // source size when it is not a multiple of 8 (the coded frame is the source padded by edge
+                                //    replication; every frame header then carries render_size, spec 5.9.6); 0 = the coded size
 } Av1bSeqParams;
 
 typedef struct Av1bFrameParams {

@@ -119,6 +119,16 @@ void write_sequence_header(const Av1bSeqParams& seq, std::vector<uint8_t>& out) 
 // ------------------------------------------------------------------------------------------------
 // Frame header (spec 5.9)
 // ------------------------------------------------------------------------------------------------
+// render_size() (spec 5.9.6): the size to present, when the source was padded to the coded size
+static void write_render_size(const Av1bSeqParams& seq, BitWriter& w) {
+  const bool diff = seq.render_width > 0 && seq.render_height > 0 && (seq.render_width != seq.width || seq.render_height != seq.height);
+  w.bit(diff ? 1 : 0);         // render_and_frame_size_different
+  if (diff) {
+    w.put(seq.render_width - 1, 16);
+    w.put(seq.render_height - 1, 16);
+  }
+}
+
 static void write_frame_header(const Av1bSeqParams& seq, const Av1bFrameParams& fp, const Av1bGeom& g,
                                BitWriter& w) {
   const bool key = fp.frame_type == AV1B_KEY_FRAME;
@@ -137,14 +147,14 @@ static void write_frame_header(const Av1bSeqParams& seq, const Av1bFrameParams& 
     // single reference design: all seven reference names point at slot 0 = the previous frame
     for (int i = 0; i < 7; i++) w.put(0, 3);   // ref_frame_idx[i]
     // frame_size(): from the sequence header; superres off
-    w.bit(0);                  // render_and_frame_size_different
+    write_render_size(seq, w);
     w.bit(0);                  // allow_high_precision_mv
     w.bit(0);                  // is_filter_switchable
     w.put(0, 2);               // interpolation_filter = EIGHTTAP (regular)
     w.bit(0);                  // is_motion_mode_switchable
     // use_ref_frame_mvs = 0 (enable_ref_frame_mvs = 0, not coded)
   } else {
-    w.bit(0);                  // render_and_frame_size_different
+    write_render_size(seq, w);
   }
   if (!fp.disable_cdf_update) w.bit(1);   // disable_frame_end_update_cdf
   // tile_info()

@@ -223,7 +223,8 @@ bool put(FILE* f, const std::vector<uint8_t>& v) { return v.empty() || fwrite(v.
 
 // Minimal Matroska (video only): EBML header, Segment { Info, Tracks { V_AV1 }, Cluster* { SimpleBlock* } }.
 // Clusters are written as they fill (one per key frame / 30 s); the Segment size and the Duration are patched at the end.
-bool write_mkv(const std::string& path, PacketReader& rd, int64_t* n_out, int w, int h, int fps_num, int fps_den, bool hbd) {
+// w x h: the coded frame; show_w x show_h: the source size (smaller when the encoder padded it to multiples of 8)
+bool write_mkv(const std::string& path, PacketReader& rd, int64_t* n_out, int w, int h, int show_w, int show_h, int fps_num, int fps_den, bool hbd) {
   FILE* f = fopen(path.c_str(), "wb");
   if (!f) return false;
   Packet pk;
@@ -254,6 +255,12 @@ bool write_mkv(const std::string& path, PacketReader& rd, int64_t* n_out, int w,
   av1c.push_back(0);
   if (sh) av1c.insert(av1c.end(), sh, sh + shn);
   ebml_uint(video, 0xB0, (uint64_t)w); ebml_uint(video, 0xBA, (uint64_t)h);
+  if (show_w != w || show_h != h) {
+    // PixelCropBottom / PixelCropRight: the padding; DisplayWidth / DisplayHeight: what is left
+    if (show_h != h) ebml_uint(video, 0x54AA, (uint64_t)(h - show_h));
+    if (show_w != w) ebml_uint(video, 0x54DD, (uint64_t)(w - show_w));
+    ebml_uint(video, 0x54B0, (uint64_t)show_w); ebml_uint(video, 0x54BA, (uint64_t)show_h);
+  }
   ebml_uint(te, 0xD7, 1); ebml_uint(te, 0x73C5, 1); ebml_uint(te, 0x83, 1); ebml_uint(te, 0x9C, 0);
   ebml_str(te, 0x86, "V_AV1");
   ebml_bytes(te, 0x63A2, av1c.data(), av1c.size());
@@ -511,7 +518,12 @@ int main(int argc, char** argv) {
     if (fstat(fileno(in.f), &st) == 0 && S_ISREG(st.st_mode))
       in.n_frames = (st.st_size - in.header_len) / (int64_t)(6 + in.frame_bytes);
   }
-  if ((in.w & 7) || (in.h & 7)) die(3, "frame size %dx%d is not a multiple of 8", in.w, in.h);
+  if (in.w < 16 || in.h < 16 || in.w > 8192 || in.h > 4352) die(3, "unsupported frame size %dx%d (16..8192 x 16..4352)", in.w, in.h);
+  // sizes that are not multiples of 8 (1920x804 and the like): the library codes the picture padded by edge replication and
+  // signals the source size as render_size; the Matroska track carries the padding as PixelCrop
+  const int coded_w = (in.w + 7) & ~7, coded_h = (in.h + 7) & ~7;
+  const int cw2 = (in.w + 1) / 2, ch2 = (in.h + 1) / 2;     // chroma plane of the source (4:2:0)
+  const size_t luma_samples = (size_t)in.w * in.h, chroma_samples = (size_t)cw2 * ch2;
   // A worker costs a CUDA context and an encoder (about 3 s on an 8-GPU box, one after the other in the driver) and codes
   // 4K at some 800 frames/s from a Y4M file: below about 1200 frames per worker more GPUs make a job slower, not faster
   // (profiles/r02p_c4_cli_4k10_2400frames.json), and leave fewer for the other jobs of the queue.  AV1B_MIN_FRAMES_PER_WORKER overrides.
@@ -522,7 +534,7 @@ int main(int argc, char** argv) {
   }
   if (in.bits > out_bits) die(3, "input is %d-bit but --pix-format asks for %d-bit", in.bits, out_bits);
   const int shift = out_bits - in.bits;
-  const size_t frame_samples = (size_t)in.w * in.h * 3 / 2;
+  const size_t frame_samples = luma_samples + 2 * chroma_samples;
 
   Shared sh;
   sh.total_frames = in.n_frames;
@@ -668,8 +680,8 @@ int main(int argc, char** argv) {
             std::vector<av1b_frame_src> fs((size_t)n);
             for (int k = 0; k < n; k++) {
               uint16_t* b = own_buf[which]->data() + (size_t)k * frame_samples;
-              fs[k].planes[0] = b; fs[k].planes[1] = b + (size_t)in.w * in.h; fs[k].planes[2] = b + (size_t)in.w * in.h * 5 / 4;
-              fs[k].stride[0] = in.w; fs[k].stride[1] = fs[k].stride[2] = in.w / 2;
+              fs[k].planes[0] = b; fs[k].planes[1] = b + luma_samples; fs[k].planes[2] = b + luma_samples + chroma_samples;
+              fs[k].stride[0] = in.w; fs[k].stride[1] = fs[k].stride[2] = cw2;
             }
             const auto te0 = std::chrono::steady_clock::now();
             rc = av1b_encode_stream(enc, fs.data(), (uint32_t)n, f0 == 0 ? 1 : 0, part.job_first + f0, on_packet, nullptr, &ctx);
@@ -691,8 +703,8 @@ int main(int argc, char** argv) {
         std::vector<av1b_frame_src> fs((size_t)part.n);
         for (int k = 0; k < part.n; k++) {
           uint16_t* b = part.buf->data() + (part.first_slot + (size_t)k) * frame_samples;
-          fs[k].planes[0] = b; fs[k].planes[1] = b + (size_t)in.w * in.h; fs[k].planes[2] = b + (size_t)in.w * in.h * 5 / 4;
-          fs[k].stride[0] = in.w; fs[k].stride[1] = fs[k].stride[2] = in.w / 2;
+          fs[k].planes[0] = b; fs[k].planes[1] = b + luma_samples; fs[k].planes[2] = b + luma_samples + chroma_samples;
+          fs[k].stride[0] = in.w; fs[k].stride[1] = fs[k].stride[2] = cw2;
         }
         const auto te0 = std::chrono::steady_clock::now();
         rc = av1b_encode_stream(enc, fs.data(), (uint32_t)part.n, part.first_part ? 1 : 0, part.first_frame, on_packet, nullptr, &ctx);
@@ -904,9 +916,9 @@ int main(int argc, char** argv) {
   int64_t written = 0;
   const size_t dot = o.output.rfind('.');
   const std::string ext = dot == std::string::npos ? "" : o.output.substr(dot);
-  if (ext == ".ivf") ok = write_ivf(tmp_out, rd, &written, in.w, in.h, in.fps_num, in.fps_den);
+  if (ext == ".ivf") ok = write_ivf(tmp_out, rd, &written, coded_w, coded_h, in.fps_num, in.fps_den);
   else if (ext == ".obu") ok = write_obu(tmp_out, rd, &written);
-  else ok = write_mkv(tmp_out, rd, &written, in.w, in.h, in.fps_num, in.fps_den, out_bits > 8);
+  else ok = write_mkv(tmp_out, rd, &written, coded_w, coded_h, in.w, in.h, in.fps_num, in.fps_den, out_bits > 8);
   cleanup_packets();
   if (ok && written != frame) { unlink(tmp_out.c_str()); unlink(o.output.c_str()); die(5, "internal error: %lld packets for %lld frames", (long long)written, (long long)frame); }
   if (ok && in.pipe && ext != ".ivf" && ext != ".obu" && o.audio_params.find("copy") != std::string::npos) {

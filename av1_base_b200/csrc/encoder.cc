@@ -204,6 +204,8 @@ struct av1b_encoder {
   long long sc_level = -1;            // running level of change (scene scores), -1: none yet
   int grain_scaling = 0;              // film grain synthesis strength of the chunk (--film-grain > 0 and a filtered structure)
   uint32_t* d_noise_hist = nullptr;
+  int src_w = 0, src_h = 0;           // size of the pictures handed in (config.width / height); g.width / g.height = the coded size
+  bool padded_src = false;            // the source is not a multiple of 8: stage() pads it by edge replication
   uint8_t* d_qm = nullptr;            // --enable-qm: av1t_qm_sq on the device ([15 levels][luma, chroma][1360])
   uint32_t* h_noise_hist = nullptr;
   cudaEvent_t ev_noise = nullptr;
@@ -329,7 +331,7 @@ static int stage(av1b_encoder* e, Slot& s, const av1b_frame_src* frames, int n) 
   collect_h2d(e, s);
   s.h2d_pending = true;
   s.has_score = false;
-  bool direct = true;
+  bool direct = !e->padded_src;        // a padded source is completed in the staging buffer
   for (int b = 0; b < n && direct; b++)
     for (int p = 0; p < 3 && direct; p++) direct = is_pinned(frames[b].planes[p]);
   if (direct) {
@@ -354,12 +356,20 @@ static int stage(av1b_encoder* e, Slot& s, const av1b_frame_src* frames, int n) 
   const int kSplit = 4;   // row bands per plane
   e->pool->parallel_for(n * 3 * kSplit, [&](int task) {
     const int b = task / (3 * kSplit), p = (task / kSplit) % 3, band = task % kSplit;
-    const int w = p ? g.width >> 1 : g.width, h = p ? g.height >> 1 : g.height;
+    // w x h: the plane as handed in; cw x ch: the coded plane (equal unless the source is padded)
+    const int w = p ? (e->src_w + 1) >> 1 : e->src_w, h = p ? (e->src_h + 1) >> 1 : e->src_h;
+    const int cw = p ? g.width >> 1 : g.width, ch = p ? g.height >> 1 : g.height;
     const int y0 = h * band / kSplit, y1 = h * (band + 1) / kSplit;
     uint16_t* hs = s.h_src[p] + (size_t)b * e->plane_elems[p];
     const uint16_t* sp = frames[b].planes[p];
     const int sst = frames[b].stride[p];
-    for (int y = y0; y < y1; y++) memcpy(hs + (size_t)y * g.stride[p], sp + (size_t)y * sst, (size_t)w * 2);
+    for (int y = y0; y < y1; y++) {
+      uint16_t* row = hs + (size_t)y * g.stride[p];
+      memcpy(row, sp + (size_t)y * sst, (size_t)w * 2);
+      for (int x = w; x < cw; x++) row[x] = row[w - 1];
+    }
+    if (band == kSplit - 1)
+      for (int y = h; y < ch; y++) memcpy(hs + (size_t)y * g.stride[p], hs + (size_t)(h - 1) * g.stride[p], (size_t)cw * 2);
   });
   CK(cudaEventRecord(s.ev_h2d, e->s_in));
   for (int p = 0; p < 3; p++) {
@@ -934,9 +944,12 @@ int av1b_encoder_create(const av1b_config* cfg, av1b_encoder** out) {
   if (cfg->enable_qm && (cfg->qm_min < 0 || cfg->qm_max > 15 || cfg->qm_min > cfg->qm_max)) {
     set_error("qm_min / qm_max must satisfy 0 <= qm_min <= qm_max <= 15"); return AV1B_ERR_INVALID;
   }
+  // the coded frame: the source padded to multiples of 8 by edge replication (stage()); the frame headers then carry the
+  // source size as render_size (1920x804 and the like: scope crops of 1080p / 2160p material)
+  const int coded_w = (cfg->width + 7) & ~7, coded_h = (cfg->height + 7) & ~7;
   Av1bGeom probe;
-  if (av1b_geom_init(&probe, cfg->width, cfg->height, 0, 0)) {
-    set_error("unsupported frame size %dx%d (multiples of 8, 16..8192 x 16..4352)", cfg->width, cfg->height);
+  if (cfg->width < 16 || cfg->height < 16 || av1b_geom_init(&probe, coded_w, coded_h, 0, 0)) {
+    set_error("unsupported frame size %dx%d (16..8192 x 16..4352)", cfg->width, cfg->height);
     return AV1B_ERR_INVALID;
   }
   int ndev = av1b_device_count();
@@ -944,12 +957,14 @@ int av1b_encoder_create(const av1b_config* cfg, av1b_encoder** out) {
   if (cfg->device_id < 0 || cfg->device_id >= ndev) { set_error("device_id %d out of range", cfg->device_id); return AV1B_ERR_INVALID; }
   av1b_encoder* e = new av1b_encoder();
   e->cfg = *cfg;
+  e->src_w = cfg->width; e->src_h = cfg->height;
+  e->padded_src = coded_w != cfg->width || coded_h != cfg->height;
   // key-frame tiles: auto = 2x2 superblocks per tile (every tile is one serial chain of the closed-loop intra
   // kernel, so many small tiles = many parallel chains; key frames are rare, the extra tile overhead is cheap)
   int tcl = cfg->tile_cols_log2, trl = cfg->tile_rows_log2;
   if (tcl < 0) tcl = av1b_tile_log2(2, probe.sb_cols);
   if (trl < 0) trl = av1b_tile_log2(2, probe.sb_rows);
-  av1b_geom_init(&e->g, cfg->width, cfg->height, tcl, trl);
+  av1b_geom_init(&e->g, coded_w, coded_h, tcl, trl);
   {
     // tiles of inter frames are the unit of entropy-coder parallelism.  The host coder wants few large ones (longer
     // CDF adaptation): about 12x12 superblocks.  The device coder walks a tile with one warp, a serial chain of about
@@ -965,9 +980,10 @@ int av1b_encoder_create(const av1b_config* cfg, av1b_encoder** out) {
     const int tsb = cfg->reserved[7] > 0 ? cfg->reserved[7] : (e->rc_on ? (probe.sb_cols * probe.sb_rows <= 600 ? 4 : 6) : 12);
     const int itc = cfg->tile_cols_log2 >= 0 ? cfg->tile_cols_log2 : av1b_tile_log2(tsb, probe.sb_cols);
     const int itr = cfg->tile_rows_log2 >= 0 ? cfg->tile_rows_log2 : av1b_tile_log2(tsb, probe.sb_rows);
-    av1b_geom_init(&e->g_inter, cfg->width, cfg->height, itc, itr);
+    av1b_geom_init(&e->g_inter, coded_w, coded_h, itc, itr);
   }
-  e->seq.width = cfg->width; e->seq.height = cfg->height; e->seq.bit_depth = cfg->bit_depth;
+  e->seq.width = coded_w; e->seq.height = coded_h; e->seq.bit_depth = cfg->bit_depth;
+  e->seq.render_width = e->padded_src ? cfg->width : 0; e->seq.render_height = e->padded_src ? cfg->height : 0;
   e->loop_filters = cfg->reserved[2] == 0;     // reserved[2] = 1 switches the in-loop filters off (tests)
   // --preset <= 5 (the daemon passes 3, av1an.rs:14) adds loop restoration with a per-unit decision; reserved[6] = 1 keeps it off
   e->lr_on = e->loop_filters && cfg->preset <= 5 && cfg->reserved[6] == 0;
@@ -999,7 +1015,7 @@ int av1b_encoder_create(const av1b_config* cfg, av1b_encoder** out) {
   set_qm_levels(e, &e->fp_key);
   if (e->lr_on) {
     for (Av1bFrameParams* f : {&e->fp_key}) { f->lr_type[0] = AV1B_RESTORE_SWITCHABLE; f->lr_type[1] = f->lr_type[2] = AV1B_RESTORE_NONE; f->lr_unit_shift = 0; f->lr_uv_shift = 0; }
-    e->lr_rows = std::max((cfg->height + 32) / 64, 1); e->lr_cols = std::max((cfg->width + 32) / 64, 1);
+    e->lr_rows = std::max((coded_h + 32) / 64, 1); e->lr_cols = std::max((coded_w + 32) / 64, 1);
     e->lr_n = (size_t)e->lr_rows * e->lr_cols;
     memset(&e->lr_cand, 0, sizeof(e->lr_cand));
     // a mild symmetric smoother and the radius-1 self-guided filter with a small weight: what the decision picks from
@@ -1055,7 +1071,7 @@ int av1b_encoder_create(const av1b_config* cfg, av1b_encoder** out) {
       A(cudaMalloc(&s.d_sb_off, (nsb * F + 1) * sizeof(uint32_t)));
       A(cudaMallocHost(&s.h_sb_off, (nsb * F + 1) * sizeof(uint32_t)));
       // room for one token per four luma samples (several times what CRF 30 produces); grows on demand
-      s.tok_cap = (size_t)cfg->width * cfg->height / 4 * F;
+      s.tok_cap = (size_t)coded_w * coded_h / 4 * F;
       A(cudaMalloc(&s.d_tokens, s.tok_cap * 4));
       A(cudaMallocHost(&s.h_tokens, s.tok_cap * 4));
       if (e->rc_on) {
@@ -1138,13 +1154,13 @@ int av1b_encoder_create(const av1b_config* cfg, av1b_encoder** out) {
         if (err == cudaSuccess) { A(cudaMemset(e->d_hist_src[p], 0, e->plane_elems[p] * kHist * 2)); A(cudaMemset(e->d_flt[p], 0, e->plane_elems[p] * F * 2)); }
       }
       A(cudaMalloc(&e->d_mvs_tf, e->map_elems * kMaxSearches * 4));
-      A(cudaMalloc(&e->d_mv2_tf, (size_t)((cfg->width + 31) / 32) * ((cfg->height + 31) / 32) * kMaxSearches * 4));
+      A(cudaMalloc(&e->d_mv2_tf, (size_t)((coded_w + 31) / 32) * ((coded_h + 31) / 32) * kMaxSearches * 4));
     }
-    const size_t n2 = (size_t)((cfg->width + 31) / 32) * ((cfg->height + 31) / 32);
+    const size_t n2 = (size_t)((coded_w + 31) / 32) * ((coded_h + 31) / 32);
     A(cudaMalloc(&e->d_mv2, n2 * F * 4));
     A(cudaMalloc(&e->d_mvs, e->map_elems * F * 4));
     {
-      const size_t n1 = (size_t)((cfg->width + 15) / 16) * ((cfg->height + 15) / 16);
+      const size_t n1 = (size_t)((coded_w + 15) / 16) * ((coded_h + 15) / 16);
       A(cudaMalloc(&e->d_mv_tmp, n1 * kMaxSearches * 4));
       A(cudaMalloc(&e->d_hist, (size_t)kMaxSearches * 2049 * sizeof(uint32_t)));
     }
@@ -1398,6 +1414,7 @@ int av1b_encode_resident(av1b_encoder* e, uint32_t n_steps, av1b_packet_cb out_c
 // ---- resident clip: n source pictures uploaded once, then closed chunks are coded out of them by index ----
 int av1b_stage_clip(av1b_encoder* e, const av1b_frame_src* frames, uint32_t n) {
   if (!e || !frames || n == 0) { set_error("bad argument"); return AV1B_ERR_INVALID; }
+  if (e->padded_src) { set_error("the resident clip takes sizes that are multiples of 8"); return AV1B_ERR_INVALID; }
   CK(cudaSetDevice(e->cfg.device_id));
   CK(cudaDeviceSynchronize());
   if (n != e->n_clip) {

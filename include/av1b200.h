@@ -32,7 +32,9 @@ extern "C" {
 
 /* Mirrors the knobs the daemon passes through `--video-params` (av1an.rs:14 SVT_PARAMS) plus geometry. */
 typedef struct av1b_config {
-  int32_t width, height;          /* luma samples; multiples of 8                                  */
+  int32_t width, height;          /* luma samples of the source, 16..8192 x 16..4352.  Sizes that are not multiples of 8 are coded
+                                     padded (edge replication) to the next multiple; the frame headers then carry the source size
+                                     as render_size and decoders output the padded frame (av1b_get_recon / av1b_get_geom too)   */
   int32_t bit_depth;              /* 8 or 10 (input samples are uint16 either way)                 */
   int32_t fps_num, fps_den;
   int32_t crf;                    /* 0..63, SVT-AV1 --crf                                          */

@@ -305,3 +305,41 @@ def psnr(a, b, bit_depth):
         return 100.0
     peak = (1 << bit_depth) - 1
     return 10 * np.log10(peak * peak / mse)
+
+
+def obus(tu):
+    """(type, payload) of every OBU of a temporal unit (low-overhead format with size fields)."""
+    out, i = [], 0
+    while i < len(tu):
+        hdr = tu[i]
+        j = i + 1 + ((hdr >> 2) & 1)
+        size, shift = 0, 0
+        while True:
+            b = tu[j]; j += 1
+            size |= (b & 0x7F) << shift; shift += 7
+            if not b & 0x80:
+                break
+        out.append(((hdr >> 3) & 15, bytes(tu[j:j + size])))
+        i = j + size
+    return out
+
+
+def render_size_in_tu(tu):
+    """render_size() of the frame header in a temporal unit as THIS encoder writes headers (spec 5.9.2 with no order hints,
+    no frame ids, no superres, frame_size_override_flag = 0): (render_width, render_height), or None when the header says
+    render_and_frame_size_different = 0.  Test-side bit reader; the decoders check everything behind these bits."""
+    for typ, pl in obus(tu):
+        if typ not in (3, 6):
+            continue
+        bits = "".join("{:08b}".format(b) for b in pl[:16])
+        assert bits[0] == "0"                        # show_existing_frame
+        frame_type, show = int(bits[1:3], 2), bits[3]
+        if frame_type == 0 and show == "1":
+            pos = 6                                  # disable_cdf_update, frame_size_override_flag
+        else:
+            assert frame_type == 1                   # error_resilient_mode, disable_cdf_update, frame_size_override_flag,
+            pos = 7 + 3 + 8 + 21                     # primary_ref_frame, refresh_frame_flags, ref_frame_idx[7]
+        if bits[pos] == "0":
+            return None
+        return int(bits[pos + 1:pos + 17], 2) + 1, int(bits[pos + 17:pos + 33], 2) + 1
+    raise ValueError("no frame header in the temporal unit")

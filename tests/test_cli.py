@@ -65,6 +65,61 @@ def mkv_blocks(data):
     return info.get("codec"), info.get("private"), out
 
 
+def mkv_video_fields(data):
+    """Unsigned elements of the Video master of our Matroska file: {element id: value}."""
+    out = {}
+
+    def walk(b, lo, hi, inside):
+        i = lo
+        while i < hi:
+            first = b[i]
+            n = 1
+            while not (first & (0x80 >> (n - 1))):
+                n += 1
+            eid = int.from_bytes(b[i:i + n], "big")
+            size, j = read_ebml_size(b, i + n)
+            if eid in (0x18538067, 0x1654AE6B, 0xAE, 0xE0):
+                walk(b, j, j + size, eid == 0xE0)
+            elif inside:
+                out[eid] = int.from_bytes(b[j:j + size], "big")
+            i = j + size
+    walk(data, 0, len(data), False)
+    return out
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("w,h,bd", [(202, 132, 10), (197, 131, 8)])
+def test_cli_codes_sizes_that_are_not_multiples_of_8(tmp_path, w, h, bd):
+    """Scope crops (1920x804, 3840x1606, ...) are ordinary daemon jobs: the picture is coded padded to multiples of 8 by edge
+    replication, the frame headers carry the source size as render_size and the Matroska track the padding as PixelCrop."""
+    from oracle import decoders as D
+    from tests.test_oracle_chain import unaligned_clip
+    n = 6
+    src, padded, cw, ch = unaligned_clip(w, h, bd, n, seed=w)
+    y4m = str(tmp_path / "in.y4m")
+    write_y4m(y4m, src, bd)
+    out = str(tmp_path / "out.mkv")
+    r = subprocess.run([CLI, "-i", y4m, "-o", out, "--encoder", "svt-av1", "--pix-format", "yuv420p10le" if bd > 8 else "yuv420p",
+                        "--video-params", "--crf 30 --preset 6 --keyint 240", "--workers", "1", "--temp", str(tmp_path / "tmp"), "--quiet"],
+                       capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+    data = open(out, "rb").read()
+    v = mkv_video_fields(data)
+    assert (v[0xB0], v[0xBA]) == (cw, ch) and (v[0x54B0], v[0x54BA]) == (w, h)
+    assert v.get(0x54DD, 0) == cw - w and v.get(0x54AA, 0) == ch - h
+    codec, priv, blocks = mkv_blocks(data)
+    tus = [b"\x12\x00" + b for b in blocks]
+    assert codec == "V_AV1" and len(tus) == n
+    assert [D.render_size_in_tu(t) for t in tus] == [(w, h)] * n
+    for dec in (D.dav1d_decode(tus), D.aom_decode(tus)):
+        assert len(dec) == n
+        for i in range(n):
+            assert dec[i][0].shape == (ch, cw) and dec[i][1].shape == (ch // 2, cw // 2)
+            assert D.psnr(dec[i][0][:h, :w], src[i][0], bd) > 30
+            # the padding is the edge, coded like any other part of the picture
+            assert D.psnr(dec[i][0], padded[i][0], bd) > 30
+
+
 @pytest.mark.gpu
 @pytest.mark.parametrize("bd", [8, 10])
 def test_cli_encodes_chunks_and_containers(tmp_path, bd):

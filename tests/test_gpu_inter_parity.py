@@ -54,6 +54,29 @@ def test_chunk_parity_with_quantisation_matrices(w, h, bd, crf, gop, qm, kvp, pa
     assert kinds[0] == 0 and 1 in kinds
 
 
+@pytest.mark.parametrize("w,h,bd", [(202, 132, 10), (197, 131, 8)])
+def test_sources_that_are_not_multiples_of_8(w, h, bd):
+    """The library pads such a source to the coded size (edge replication, in the staging buffer), codes the padded frame like
+    any other (CUDA == oracle chain on the padded pictures == both decoders) and signals the source size as render_size."""
+    from tests.test_oracle_chain import unaligned_clip
+    n, crf = 6, 34
+    src, padded, cw, ch = unaligned_clip(w, h, bd, n, seed=w)
+    enc = encoder.Encoder(w, h, bd, crf=crf, keep_debug=True, frames_in_flight=4, gop_period=2)
+    assert (enc.geom.width, enc.geom.height) == (cw, ch)
+    tus = enc.encode_chunk(src)
+    assert len(tus) == n and [D.render_size_in_tu(t) for t in tus] == [(w, h)] * n
+    g, want = chain.encode_chain(padded, cw, ch, bd, crf, gop_period=2, geom=enc.geom, batch=4)
+    dec_d, dec_a = D.dav1d_decode(tus), D.aom_decode(tus)
+    for i, r in enumerate(want):
+        rec, orc = enc.recon(i), O.crop(g, r.fin)
+        blocks, coef = enc.frame_syms(i)
+        assert np.array_equal(blocks["mv"], r.res.blocks["mv"]) and np.array_equal(blocks["eob"], r.res.blocks["eob"]), i
+        for p in range(3):
+            assert np.array_equal(rec[p], orc[p]), ("recon vs oracle", i, p)
+            assert np.array_equal(dec_d[i][p], rec[p]) and np.array_equal(dec_a[i][p], rec[p]), ("decoders", i, p)
+    enc.close()
+
+
 def test_scene_change_inside_a_chunk_becomes_a_key_frame():
     """Row f-3: scene scores computed on the GPU as the pictures arrive (scene_score_kernel on the upload stream) restart the
     structure inside a chunk -- key frame at the cut, no motion search or temporal filter across it; frame kinds, vectors,

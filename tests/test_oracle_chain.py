@@ -13,8 +13,8 @@ from oracle import pyoracle as O, decoders as D, chain
 HERE = os.path.dirname(os.path.abspath(__file__))
 
 
-def pack_chain(w, h, bd, want, g, lr=False):
-    seq = abi.SeqParams(w, h, bd, 1, 1 if lr else 0, 30, 1, 0)
+def pack_chain(w, h, bd, want, g, lr=False, render=(0, 0)):
+    seq = abi.SeqParams(w, h, bd, 1, 1 if lr else 0, 30, 1, 0, 0, render[0], render[1])
     tus = []
     for i, r in enumerate(want):
         sy = packer.make_syms(g, r.res.blocks, r.res.coef, cdef_idx=r.cdef_idx, lr_units=[r.lr_units, None, None] if lr else None)
@@ -73,6 +73,42 @@ def test_quantisation_matrices_decode(w, h, bd, crf, n, gop, qm):
         for i in range(n):
             for p in range(3):
                 assert np.array_equal(out[i][p], O.crop(g, want[i].fin)[p]), (dec.__name__, i, p)
+
+
+def unaligned_clip(w, h, bd, n, seed):
+    """n pictures of w x h (any size; 4:2:0 chroma rounded up) and the same pictures padded to multiples of 8 by edge
+    replication: what csrc/encoder.cc stage() makes of a source that is not a multiple of 8."""
+    cw, ch = (w + 7) & ~7, (h + 7) & ~7
+    big = synth.synth_clip(cw, ch, bd, n, seed=seed, scene_len=100, noise=0.4)
+    src = [[np.ascontiguousarray(f[0][:h, :w]), np.ascontiguousarray(f[1][:(h + 1) // 2, :(w + 1) // 2]),
+            np.ascontiguousarray(f[2][:(h + 1) // 2, :(w + 1) // 2])] for f in big]
+    padded = [[np.pad(f[0], ((0, ch - h), (0, cw - w)), mode="edge"),
+               np.pad(f[1], ((0, ch // 2 - (h + 1) // 2), (0, cw // 2 - (w + 1) // 2)), mode="edge"),
+               np.pad(f[2], ((0, ch // 2 - (h + 1) // 2), (0, cw // 2 - (w + 1) // 2)), mode="edge")] for f in src]
+    return src, padded, cw, ch
+
+
+@pytest.mark.parametrize("w,h,bd", [(202, 132, 10), (197, 131, 8)])
+def test_render_size_for_sources_that_are_not_multiples_of_8(w, h, bd):
+    """1920x804-like sources: the coded frame is the source padded to multiples of 8, every frame header carries the source size
+    as render_size (spec 5.9.6).  Both decoders parse the headers (the tile data behind them decodes to the reconstruction of
+    the padded frame) and the bits at the header positions hold the source size."""
+    n = 4
+    src, padded, cw, ch = unaligned_clip(w, h, bd, n, seed=w)
+    assert (cw, ch) != (w, h)
+    g, want = chain.encode_chain(padded, cw, ch, bd, 34, gop_period=2)
+    tus = pack_chain(cw, ch, bd, want, g, render=(w, h))
+    assert [D.render_size_in_tu(t) for t in tus] == [(w, h)] * n
+    assert [D.render_size_in_tu(t) for t in pack_chain(cw, ch, bd, want, g)] == [None] * n
+    for dec in (D.dav1d_decode, D.aom_decode):
+        out = dec(tus)
+        assert len(out) == n
+        for i in range(n):
+            assert out[i][0].shape == (ch, cw)
+            for p in range(3):
+                assert np.array_equal(out[i][p], O.crop(g, want[i].fin)[p]), (dec.__name__, i, p)
+            # inside the source area the coded picture is the source's reconstruction; the rest is padding
+            assert D.psnr(out[i][0][:h, :w], src[i][0], bd) > 30
 
 
 def test_qm_level_mapping():
