@@ -54,6 +54,7 @@ struct Options {
   int workers = 1;
   int crf = 30, preset = 6, keyint = 240, lookahead = -1, film_grain = 0, enable_qm = 0, qm_min = 8, qm_max = 15;   // SVT-AV1 defaults
   bool quiet = false;
+  std::string mux_packets, mux_format;   // --mux-packets DIR --mux-format CWxCH,SWxSH,NUM:DEN,BITS (see main)
   bool no_scene_detection = false;   // --sc-method none / --no-scene-detection: split at --keyint only
   int min_scene_len = 12;            // --min-scene-len
 };
@@ -477,10 +478,43 @@ int main(int argc, char** argv) {
     else if (a == "--workers" || a == "-w") o.workers = atoi(val("--workers").c_str());
     else if (a == "--temp") o.temp = val("--temp");
     else if (a == "--quiet" || a == "-q") o.quiet = true;
+    else if (a == "--mux-packets") o.mux_packets = val("--mux-packets");
+    else if (a == "--mux-format") o.mux_format = val("--mux-format");
     else if (a == "--no-scene-detection") o.no_scene_detection = true;
     else if (a == "--min-scene-len") o.min_scene_len = atoi(val("--min-scene-len").c_str());
     else if (a == "--sc-method" || a == "--split-method") { if (val(a.c_str()) == "none") o.no_scene_detection = true; }
     else die(2, "unknown argument %s", a.c_str());
+  }
+  if (!o.mux_packets.empty()) {
+    // Container writers alone (no GPU, no input): the packet files DIR/chunk_NNNNNN.pkt (what the workers leave under --temp:
+    // 4-byte little-endian size, key flag, temporal unit) are concatenated in order into -o by its extension.  The CPU tests
+    // mux oracle-coded streams with it and hand the Matroska file to FFmpeg's demuxer (tests/test_mux.py); also a way to
+    // finish a job whose packet files survived.
+    if (o.output.empty()) die(2, "-o is required");
+    int cw = 0, ch = 0, sw = 0, shh = 0, fn = 30, fd = 1, bits = 10;
+    if (sscanf(o.mux_format.c_str(), "%dx%d,%dx%d,%d:%d,%d", &cw, &ch, &sw, &shh, &fn, &fd, &bits) != 7 || cw < 16 || ch < 16 || sw < 1 || sw > cw ||
+        shh < 1 || shh > ch || fn < 1 || fd < 1)
+      die(2, "--mux-format wants CWxCH,SWxSH,NUM:DEN,BITS (coded size, source size, frame rate, bit depth)");
+    Shared msh;
+    msh.pkt_dir = o.mux_packets;
+    PacketReader rd;
+    for (int64_t c = 0;; c++) {
+      const std::string f = chunk_file(msh, c);
+      if (access(f.c_str(), R_OK) != 0) break;
+      rd.files.push_back(f);
+    }
+    if (rd.files.empty()) die(3, "no packet files (chunk_000000.pkt ...) under %s", o.mux_packets.c_str());
+    const std::string tmp_out = o.output + ".part";
+    int64_t written = 0;
+    const size_t dot = o.output.rfind('.');
+    const std::string ext = dot == std::string::npos ? "" : o.output.substr(dot);
+    bool ok;
+    if (ext == ".ivf") ok = write_ivf(tmp_out, rd, &written, cw, ch, fn, fd);
+    else if (ext == ".obu") ok = write_obu(tmp_out, rd, &written);
+    else ok = write_mkv(tmp_out, rd, &written, cw, ch, sw, shh, fn, fd, bits > 8);
+    if (!ok || written == 0 || rename(tmp_out.c_str(), o.output.c_str()) != 0) { unlink(tmp_out.c_str()); die(6, "cannot write %s", o.output.c_str()); }
+    if (!o.quiet) printf("{\"muxed_packets\": %lld}\n", (long long)written);
+    return 0;
   }
   if (o.input.empty() || o.output.empty()) die(2, "-i and -o are required");
   if (o.encoder != "svt-av1") die(2, "unsupported --encoder %s (the daemon passes svt-av1)", o.encoder.c_str());

@@ -160,6 +160,12 @@ def test_cli_encodes_chunks_and_containers(tmp_path, bd):
     codec, priv, blocks = mkv_blocks(outs[".mkv"])
     assert codec == "V_AV1" and priv[0] == 0x81 and len(blocks) == n
     assert [b"\x12\x00" + b for b in blocks] == want          # blocks = temporal units without the delimiter
+    # FFmpeg's Matroska / IVF demuxers (libavformat inside the OpenCV wheel) read the same packets out of the files
+    from tests.test_mux import demux
+    props, pk = demux(str(tmp_path / "out.mkv"))
+    assert (props["w"], props["h"], props["n"], props["fourcc"]) == (w, h, n, b"AV01") and abs(props["fps"] - 30) < 0.01
+    assert [b"\x12\x00" + b for b in pk] == want
+    assert demux(str(tmp_path / "out.ivf"))[1] == want
     dec = D.dav1d_decode(want)
     assert len(dec) == n
     for i in range(n):
