@@ -465,9 +465,22 @@ int main(int argc, char** argv) {
       av1b_version(buf, sizeof(buf));
       printf("av1an-compatible front end: %s\n", buf);
       return 0;
+    } else if (a == "--gpu-plan") {
+      // What replaces the daemon's core-count heuristics (concurrency.rs:67-84: 8 workers from 32 cores, 1 job from 24): the
+      // unit of parallelism is a GPU.  A job may ask for every GPU (--workers = gpus: the executable leases the free ones and
+      // takes at most one per 1200 frames of input), and as many jobs as there are GPUs may run side by side (a queue of short
+      // files is start-up bound and runs best as one GPU per job, profiles/r02p_c5_queue_16files_8jobs.json); every job's
+      // entropy coder gets cores / workers host threads, and below 4 per GPU the range coder moves onto the device.
+      const int gpus = av1b_device_count();
+      const int cores = (int)std::max(1u, std::thread::hardware_concurrency());
+      if (gpus <= 0) die(4, "no CUDA device visible: this backend has no CPU fallback");
+      printf("{\"gpus\": %d, \"host_cores\": %d, \"av1an_workers\": %d, \"max_concurrent_jobs\": %d, \"host_threads_per_gpu\": %d, "
+             "\"min_frames_per_worker\": 1200}\n", gpus, cores, gpus, gpus, std::max(1, cores / gpus));
+      return 0;
     } else if (a == "--help" || a == "-h") {
       printf("usage: av1an -i IN -o OUT [--encoder svt-av1] [--pix-format yuv420p10le] [--video-params \"--crf N --preset N --keyint N ...\"]\n"
-             "             [--audio-params S] [--workers N(GPUs)] [--temp DIR] [--quiet]\n");
+             "             [--audio-params S] [--workers N(GPUs)] [--temp DIR] [--quiet]\n"
+             "       av1an --gpu-plan    (JSON: GPUs, workers per job and concurrent jobs for the daemon's ConcurrencyPlan)\n");
       return 0;
     } else if (a == "-i") o.input = val("-i");
     else if (a == "-o") o.output = val("-o");

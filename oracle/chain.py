@@ -94,7 +94,7 @@ def scene_positions(g, bd, padded, pos0=0, scene_cut=True):
 
 def encode_chain(frames, w, h, bd, crf, keyint=240, gop_period=DEFAULT_GOP_PERIOD, me_smooth=True, key_var_part=True, loop_filters=True,
                  lr=False, intra_only=False, blk_log2=4, tb_zero_thr=0, pos0=0, geom=None, mctf=True, batch=8, lookahead=-1,
-                 film_grain=0, mctf_radius=2, mctf_key_fwd=4, scene_cut=True, qm=None):
+                 film_grain=0, mctf_radius=2, mctf_key_fwd=4, scene_cut=True, qm=None, rnd=(48, 48, 48)):
     """Returns one FrameResult per frame: kind, fp, res (blocks / coef / pre-filter rec), fin (padded planes after the
     in-loop filters), cdef_idx, lr_units, mvs.  qm = (qm_min, qm_max): quantisation matrices at the level the frame's quantiser
     index maps to (csrc/encoder.cc set_qm_levels), luma and chroma alike."""
@@ -157,13 +157,13 @@ def encode_chain(frames, w, h, bd, crf, keyint=240, gop_period=DEFAULT_GOP_PERIO
             else:
                 pm = O.partition_fixed(g, blk_log2)
             r.part_map = pm
-            r.res = O.encode_intra_frame(g, fr, bd, q, pm)
+            r.res = O.encode_intra_frame(g, fr, bd, q, pm, quant_rnd=rnd[0])
         else:
             mvs = O.hme(g, pyr, anchor_pyr, lam, bd)
             if me_smooth:
                 mvs = O.me_sbrd(g, pyr, anchor_pyr, mvs, lam, lam >> 2, 2)
             r.mvs = mvs
-            r.res = O.encode_inter_frame(g, fr, bd, q, pm16, mvs, anchor_fin, tb_zero_thr=tb_zero_thr)
+            r.res = O.encode_inter_frame(g, fr, bd, q, pm16, mvs, anchor_fin, quant_rnd=rnd[kind], tb_zero_thr=tb_zero_thr)
             O.merge_skip_blocks(g, r.res.blocks)
         fin, r.cdef_idx, r.lr_units = r.res.rec, None, None
         if loop_filters:

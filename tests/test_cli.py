@@ -28,6 +28,28 @@ def test_bad_arguments_exit_nonzero(tmp_path):
     assert subprocess.run([CLI, "-i", "a", "-o", "b", "--frobnicate"], capture_output=True).returncode == 2
 
 
+def test_gpu_plan_without_a_gpu_is_an_error():
+    """`av1an --gpu-plan` (what replaces concurrency.rs:67-84) answers only where there is a GPU; exit 4 keeps the
+    daemon on its core-count plan."""
+    from av1_base_b200 import abi
+    if abi.lib().av1b_device_count() > 0:
+        pytest.skip("a GPU is visible")
+    r = subprocess.run([CLI, "--gpu-plan"], capture_output=True, text=True)
+    assert r.returncode == 4 and "no CUDA device" in r.stderr and r.stdout == ""
+
+
+@pytest.mark.gpu
+def test_gpu_plan():
+    import json
+    from av1_base_b200 import abi
+    r = subprocess.run([CLI, "--gpu-plan"], capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+    plan = json.loads(r.stdout)
+    n = abi.lib().av1b_device_count()
+    assert plan["gpus"] == n and plan["av1an_workers"] == n and plan["max_concurrent_jobs"] == n
+    assert plan["host_cores"] >= 1 and plan["host_threads_per_gpu"] == max(1, plan["host_cores"] // n)
+
+
 def read_ebml_size(b, i):
     first = b[i]
     n = 1
