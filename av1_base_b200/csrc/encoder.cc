@@ -462,7 +462,7 @@ static int launch(av1b_encoder* e, Slot& s, const Slot& in, int n, int64_t first
     for (int l = 0; l < 3; l++) { H.ref[l] = e->d_pyr[l]; H.cur[l] = e->d_pyr[l]; }
     H.shift2 = bd - 8;
     H.lambda = acq0 >> 1;   // vector-deviation cost in SAD units (tuned on the oracle: about half the AC quantiser step)
-    H.lam_s = e->me_smooth ? H.lambda : 0; H.lam_r = H.lambda >> 2; H.sbrd_passes = 2; H.mv_tmp = e->d_mv_tmp; H.hist = e->d_hist;
+    H.lam_s = e->me_smooth ? H.lambda : 0; H.lam_r = H.lambda >> 2; H.sbrd_passes = e->cfg.preset <= 3 ? 3 : 2; H.mv_tmp = e->d_mv_tmp; H.hist = e->d_hist;
     if (any_inter) {
       for (int b = 0; b < n; b++) { H.cur_slot[b] = (uint8_t)(kSlotFrame0 + b); H.ref_slot[b] = (uint8_t)(ref_of[b] == 0 ? kSlotCarried : kSlotFrame0 + ref_of[b] - 1); }
       H.mv2 = e->d_mv2; H.mv_out = e->d_mvs;

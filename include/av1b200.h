@@ -38,7 +38,8 @@ typedef struct av1b_config {
   int32_t bit_depth;              /* 8 or 10 (input samples are uint16 either way)                 */
   int32_t fps_num, fps_den;
   int32_t crf;                    /* 0..63, SVT-AV1 --crf                                          */
-  int32_t preset;                 /* SVT-AV1 --preset: <= 5 adds loop restoration (per-unit decision) */
+  int32_t preset;                 /* SVT-AV1 --preset: <= 5 adds loop restoration (per-unit decision), <= 3 a third sweep of the
+                                     superblock-level regularisation of the vector field (-4 % bytes at equal PSNR) */
   int32_t keyint;                 /* --keyint                                                      */
   int32_t lookahead;              /* --lookahead: source pictures the temporal filter of key / anchor pictures may look ahead
                                      (it uses up to 4); -1 = default, 0 = none                                        */

@@ -94,10 +94,12 @@ def scene_positions(g, bd, padded, pos0=0, scene_cut=True):
 
 def encode_chain(frames, w, h, bd, crf, keyint=240, gop_period=DEFAULT_GOP_PERIOD, me_smooth=True, key_var_part=True, loop_filters=True,
                  lr=False, intra_only=False, blk_log2=4, tb_zero_thr=0, pos0=0, geom=None, mctf=True, batch=8, lookahead=-1,
-                 film_grain=0, mctf_radius=2, mctf_key_fwd=4, scene_cut=True, qm=None, rnd=(48, 48, 48)):
+                 film_grain=0, mctf_radius=2, mctf_key_fwd=4, scene_cut=True, qm=None, rnd=(48, 48, 48), sbrd_passes=2):
     """Returns one FrameResult per frame: kind, fp, res (blocks / coef / pre-filter rec), fin (padded planes after the
     in-loop filters), cdef_idx, lr_units, mvs.  qm = (qm_min, qm_max): quantisation matrices at the level the frame's quantiser
-    index maps to (csrc/encoder.cc set_qm_levels), luma and chroma alike."""
+    index maps to (csrc/encoder.cc set_qm_levels), luma and chroma alike.  sbrd_passes: sweeps of the superblock-level regularisation
+    (csrc/encoder.cc: 3 for --preset <= 3, else 2).  rnd: quantiser rounding offsets (/128) of key / anchor / non-reference frames
+    (experiments; the product uses 48 throughout)."""
     g = geom if geom is not None else O.geom(w, h, 0, 0)   # key-frame tiling: no intra prediction across tile edges
     if gop_period == 0:
         gop_period, _ = choose_structure(g, bd, crf, O.pad_planes(g, frames[0])[0])
@@ -161,7 +163,7 @@ def encode_chain(frames, w, h, bd, crf, keyint=240, gop_period=DEFAULT_GOP_PERIO
         else:
             mvs = O.hme(g, pyr, anchor_pyr, lam, bd)
             if me_smooth:
-                mvs = O.me_sbrd(g, pyr, anchor_pyr, mvs, lam, lam >> 2, 2)
+                mvs = O.me_sbrd(g, pyr, anchor_pyr, mvs, lam, lam >> 2, sbrd_passes)
             r.mvs = mvs
             r.res = O.encode_inter_frame(g, fr, bd, q, pm16, mvs, anchor_fin, quant_rnd=rnd[kind], tb_zero_thr=tb_zero_thr)
             O.merge_skip_blocks(g, r.res.blocks)

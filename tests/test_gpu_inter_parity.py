@@ -100,7 +100,7 @@ def _check_chunk(frames, w, h, bd, crf, tcl, trl, lf, nfr, fif, keyint, preset, 
     tus = enc.encode_chunk(frames)
     assert len(tus) == nfr
     g, want = chain.encode_chain(frames, w, h, bd, crf, keyint=keyint, gop_period=gop, loop_filters=lf, lr=lr, geom=enc.geom, batch=fif,
-                                 qm=qm, key_var_part=key_var_part)
+                                 qm=qm, key_var_part=key_var_part, sbrd_passes=3 if preset <= 3 else 2)
     info = enc.chunk_info()
     if gop == 0:   # structure chosen from the noise level of the first picture
         gop, nb = chain.choose_structure(g, bd, crf, O.pad_planes(g, frames[0])[0])
