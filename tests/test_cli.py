@@ -307,6 +307,37 @@ def test_cli_rejects_y4m_with_frame_parameters(tmp_path):
 
 
 @pytest.mark.gpu
+def test_cli_with_the_daemons_exact_command_line(tmp_path):
+    """argv exactly as build_av1an_command makes it (av1an.rs:79-107) with SVT_PARAMS as they stand (av1an.rs:14) and the
+    daemon's `.mkv` output (jobs.rs:187): exit 0, a Matroska file FFmpeg's demuxer reads, every frame decodes, the quality is what
+    CRF 8 stands for, the progress file ends with done = true and the JobMetrics fields."""
+    import json
+    from av1_base_b200 import synth
+    from oracle import decoders as D
+    from tests.test_mux import demux
+    w, h, bd, n = 328, 248, 10, 12
+    frames = synth.synth_clip(w, h, bd, n, seed=9, scene_len=100, noise=0.5)
+    y4m = str(tmp_path / "in.y4m")
+    write_y4m(y4m, frames, bd)
+    out, tmp = str(tmp_path / "out.mkv"), str(tmp_path / "chunks")
+    svt_params = "--crf 8 --preset 3 --film-grain 20 --enable-qm 1 --qm-min 1 --qm-max 15 --keyint 240 --lookahead 40"
+    r = subprocess.run([CLI, "-i", y4m, "-o", out, "--encoder", "svt-av1", "--pix-format", "yuv420p10le", "--video-params", svt_params,
+                        "--audio-params", "-c:a copy", "--workers", "8", "--temp", tmp], capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+    props, pk = demux(out)
+    assert (props["w"], props["h"], props["n"]) == (w, h, n) and len(pk) == n
+    tus = [b"\x12\x00" + p for p in pk]
+    dec = D.dav1d_decode(tus)
+    assert len(dec) == n
+    for i in range(n):
+        assert D.psnr(dec[i][0], frames[i][0], bd) > 42, i
+    prog = json.load(open(os.path.join(tmp, "progress.json")))
+    assert prog["done"] is True and prog["frames_encoded"] == n and prog["total_frames"] == n
+    assert prog["bitrate_kbps"] > 0 and prog["psnr"] > 42 and 0.9 < prog["ssim"] <= 1.0
+    assert not os.path.exists(out + ".part")
+
+
+@pytest.mark.gpu
 def test_cli_film_grain_and_lookahead_reach_the_encoder(tmp_path):
     """Row f-4 through the drop-in executable: `--film-grain 20` (av1an.rs:14) makes the stream carry film grain parameters
     (a decoder that applies grain gives other pictures than one that does not; without the flag both agree) and

@@ -77,6 +77,17 @@ def test_sources_that_are_not_multiples_of_8(w, h, bd):
     enc.close()
 
 
+@pytest.mark.parametrize("noise,pack_path", [(1.0, 0), (0.05, 4)])
+def test_daemon_settings_parity(noise, pack_path):
+    """The daemon's fixed settings (av1an.rs:14: --crf 8 --preset 3 --film-grain 20 --enable-qm 1 --qm-min 1 --qm-max 15 --keyint 240
+    --lookahead 40) all at once through the library: structure from the noise level (the P chain on the noisy clip, the
+    hierarchy on the clean one), loop restoration, three regularisation sweeps, film-grain-strength temporal filter,
+    quantisation matrices -- CUDA == oracle chain == dav1d (== libaom where no grain is signalled)."""
+    w, h, bd, nfr = 328, 248, 10, 8
+    frames = synth.synth_clip(w, h, bd, nfr, seed=21, scene_len=100, noise=noise)
+    _check_chunk(frames, w, h, bd, 8, -1, -1, True, nfr, 8, 240, 3, 0, pack_path, qm=(1, 15), film_grain=20, lookahead=40)
+
+
 def test_scene_change_inside_a_chunk_becomes_a_key_frame():
     """Row f-3: scene scores computed on the GPU as the pictures arrive (scene_score_kernel on the upload stream) restart the
     structure inside a chunk -- key frame at the cut, no motion search or temporal filter across it; frame kinds, vectors,
@@ -92,15 +103,17 @@ def test_scene_change_inside_a_chunk_becomes_a_key_frame():
     enc.close()
 
 
-def _check_chunk(frames, w, h, bd, crf, tcl, trl, lf, nfr, fif, keyint, preset, gop, pack_path, qm=None, key_var_part=True):
+def _check_chunk(frames, w, h, bd, crf, tcl, trl, lf, nfr, fif, keyint, preset, gop, pack_path, qm=None, key_var_part=True,
+                 film_grain=0, lookahead=-1):
     enc = encoder.Encoder(w, h, bd, crf=crf, keep_debug=True, tile_cols_log2=tcl, tile_rows_log2=trl,
                           frames_in_flight=fif, loop_filters=lf, keyint=keyint, preset=preset, pack_path=pack_path, gop_period=gop,
-                          qm=qm, key_var_part=key_var_part)
+                          qm=qm, key_var_part=key_var_part, film_grain=film_grain, lookahead=lookahead)
     lr = lf and preset <= 5
     tus = enc.encode_chunk(frames)
     assert len(tus) == nfr
     g, want = chain.encode_chain(frames, w, h, bd, crf, keyint=keyint, gop_period=gop, loop_filters=lf, lr=lr, geom=enc.geom, batch=fif,
-                                 qm=qm, key_var_part=key_var_part, sbrd_passes=3 if preset <= 3 else 2)
+                                 qm=qm, key_var_part=key_var_part, sbrd_passes=3 if preset <= 3 else 2, film_grain=film_grain,
+                                 lookahead=lookahead)
     info = enc.chunk_info()
     if gop == 0:   # structure chosen from the noise level of the first picture
         gop, nb = chain.choose_structure(g, bd, crf, O.pad_planes(g, frames[0])[0])
@@ -132,7 +145,8 @@ def _check_chunk(frames, w, h, bd, crf, tcl, trl, lf, nfr, fif, keyint, preset, 
             assert np.array_equal(coef[p], r.res.coef[p]), ("coef", i, p)
             assert np.array_equal(rec[p], orc[p]), ("recon vs oracle", i, p)
             assert np.array_equal(dec_d[i][p], rec[p]), ("dav1d", i, p)
-            assert np.array_equal(dec_a[i][p], rec[p]), ("libaom", i, p)
+            if not film_grain:   # libaom always applies the grain a stream signals (dav1d above was asked not to)
+                assert np.array_equal(dec_a[i][p], rec[p]), ("libaom", i, p)
     if gop > 1 and nfr > gop and keyint > gop:
         assert kinds == {0, 1, 2}
     assert enc.stats()["mctf_frames"] == sum(1 for r in want if r.filtered_from)

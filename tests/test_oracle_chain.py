@@ -111,6 +111,26 @@ def test_render_size_for_sources_that_are_not_multiples_of_8(w, h, bd):
             assert D.psnr(out[i][0][:h, :w], src[i][0], bd) > 30
 
 
+@pytest.mark.parametrize("noise", [1.0, 0.05])
+def test_daemon_settings_chain_decodes(noise):
+    """The daemon's fixed settings (av1an.rs:14: --crf 8 --preset 3 --film-grain 20 --enable-qm 1 --qm-min 1 --qm-max 15 --keyint 240
+    --lookahead 40) all at once: structure from the noise level, loop restoration (preset <= 5), three regularisation sweeps
+    (preset <= 3), film-grain-strength temporal filter, quantisation matrices.  Both decoders reproduce the reconstruction."""
+    w, h, bd, n = 328, 248, 10, 8
+    frames = synth.synth_clip(w, h, bd, n, seed=21, scene_len=100, noise=noise)
+    g, want = chain.encode_chain(frames, w, h, bd, 8, keyint=240, gop_period=0, lr=True, film_grain=20, lookahead=40, qm=(1, 15), sbrd_passes=3)
+    gop, _ = chain.choose_structure(g, bd, 8, O.pad_planes(g, frames[0])[0])
+    assert gop == (1 if noise >= 1.0 else chain.DEFAULT_GOP_PERIOD)      # a fine quantiser on a noisy source: the P chain
+    tus = pack_chain(w, h, bd, want, g, lr=True)
+    for dec in (D.dav1d_decode, D.aom_decode):
+        out = dec(tus)
+        assert len(out) == n
+        for i in range(n):
+            for p in range(3):
+                assert np.array_equal(out[i][p], O.crop(g, want[i].fin)[p]), (dec.__name__, i, p)
+            assert D.psnr(out[i][0], frames[i][0], bd) > (44 if noise < 1 else 40)
+
+
 def test_qm_level_mapping():
     """aom_get_qmlevel (SVT-AV1 and libaom map the quantiser index to a level the same way)."""
     assert O.qm_level(0, 1, 15) == 1 and O.qm_level(255, 1, 15) == 15 and O.qm_level(128, 0, 15) == 8
