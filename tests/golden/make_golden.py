@@ -13,10 +13,20 @@ import ctypes as C
 from av1_base_b200 import abi, packer, synth
 from oracle import pyoracle as O
 
-CASES = {"key_inter_96x64_8bit": (96, 64, 8, 110, 3), "key_inter_72x88_10bit": (72, 88, 10, 140, 3)}
+# name -> (w, h, bit depth, quantiser index, frames[, quantisation matrix level (--enable-qm, spec 7.12.3)])
+CASES = {"key_inter_96x64_8bit": (96, 64, 8, 110, 3), "key_inter_72x88_10bit": (72, 88, 10, 140, 3),
+         "key_inter_qm4_96x64_10bit": (96, 64, 10, 90, 3, 4)}
 
 
-def encode(w, h, bd, q, n):
+def encode(w, h, bd, q, n, qm=None):
+    try:
+        O.set_qm(*((qm, qm) if qm is not None else (15, 15)))
+        return _encode(w, h, bd, q, n, qm)
+    finally:
+        O.set_qm()
+
+
+def _encode(w, h, bd, q, n, qm):
     g = O.geom(w, h, 0, 0)
     frames = synth.synth_clip(w, h, bd, n, seed=w + h, scene_len=100)
     seq = abi.SeqParams(w, h, bd, 1, 0, 30, 1, 0)
@@ -26,6 +36,8 @@ def encode(w, h, bd, q, n):
     for i, fr in enumerate(frames):
         fp = abi.FrameParams()
         abi.lib().av1b_select_frame_params(bd, q, 0 if i == 0 else 1, 1, C.byref(fp))
+        if qm is not None:
+            fp.using_qmatrix, fp.qm_level[0], fp.qm_level[1] = 1, qm, qm
         pyr = O.pyramid(g, O.pad_planes(g, fr)[0])
         if i == 0:
             r = O.encode_intra_frame(g, fr, bd, q, pm)
@@ -62,8 +74,9 @@ def main():
     ge.build()
     import json
     json.dump(chain_digest(), open(os.path.join(HERE, "chain_digest.json"), "w"), indent=1)
-    for name, (w, h, bd, q, n) in CASES.items():
-        tus, recs = encode(w, h, bd, q, n)
+    for name, case in CASES.items():
+        n = case[4]
+        tus, recs = encode(*case)
         arrs = {"n": np.array([n])}
         for i in range(n):
             arrs["tu%d" % i] = np.frombuffer(tus[i], np.uint8)
