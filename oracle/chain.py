@@ -119,6 +119,7 @@ def encode_chain(frames, w, h, bd, crf, keyint=240, gop_period=DEFAULT_GOP_PERIO
         kind = frame_kind(gop_pos[i], keyint, gop_period, intra_only)
         q = qk[kind]
         fp = class_params(bd, q, kind, loop_filters, lr)
+        fp.qm_level[0] = fp.qm_level[1] = 15      # flat (csrc/encoder.cc set_qm_levels without --enable-qm)
         if qm is not None:
             fp.using_qmatrix = 1
             fp.qm_level[0] = fp.qm_level[1] = O.qm_level(q, qm[0], qm[1])

@@ -45,7 +45,9 @@ def test_empty_and_tiny_chunks():
                 assert np.array_equal(dec[i][p], enc.recon(i)[p]), (w, h, i, p)
         enc.close()
     with pytest.raises(encoder.EncodeError):
-        encoder.Encoder(20, 16, 10)          # not a multiple of 8
+        encoder.Encoder(12, 16, 10)          # below 16 x 16 (sizes that are not multiples of 8 are padded: test_gpu_inter_parity.py)
+    with pytest.raises(encoder.EncodeError):
+        encoder.Encoder(8200, 64, 10)        # wider than 8192
     with pytest.raises(encoder.EncodeError):
         encoder.Encoder(64, 64, 12)          # unsupported bit depth
 
