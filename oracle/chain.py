@@ -115,76 +115,79 @@ def encode_chain(frames, w, h, bd, crf, keyint=240, gop_period=DEFAULT_GOP_PERIO
     pyrs = [O.pyramid(g, pl[0]) for pl in padded]
     n = len(frames)
     gop_pos = scene_positions(g, bd, padded, pos0, scene_cut and not intra_only)
-    for i, fr in enumerate(frames):
-        kind = frame_kind(gop_pos[i], keyint, gop_period, intra_only)
-        q = qk[kind]
-        fp = class_params(bd, q, kind, loop_filters, lr)
-        fp.qm_level[0] = fp.qm_level[1] = 15      # flat (csrc/encoder.cc set_qm_levels without --enable-qm)
-        if qm is not None:
-            fp.using_qmatrix = 1
-            fp.qm_level[0] = fp.qm_level[1] = O.qm_level(q, qm[0], qm[1])
-        O.set_qm(fp.qm_level[0], fp.qm_level[1]) if qm is not None else O.set_qm()
-        src = padded[i]
-        pyr = pyrs[i]          # the motion search always sees the unfiltered source pictures
-        nb = []
-        if mctf and kind != 2 and not intra_only:
-            # temporal filter of key / anchor sources (csrc/encoder.cc launch()): neighbours inside the closed GOP; ahead of
-            # the picture only what the same batch holds (and --lookahead allows), behind it up to mctf_radius pictures
-            lo, hi = (0, mctf_key_fwd) if kind == 0 else (-mctf_radius, mctf_radius)
-            if lookahead >= 0:
-                hi = min(hi, lookahead)
-            in_gop = gop_pos[i] % keyint
-            for d in range(lo, hi + 1):
-                j = i + d
-                if d == 0 or j < 0 or j >= n or (d > 0 and j // batch != i // batch):
-                    continue
-                if in_gop + d < 0 or in_gop + d >= keyint:
-                    continue
-                if d > 0 and gop_pos[j] != gop_pos[i] + d:   # a scene change between the two
-                    continue
-                nb.append(j)
-            nb = nb[:6]
-        if nb:
-            mvs_tf = []
-            for j in nb:
-                mvs_tf.append(O.hme(g, pyrs[i], pyrs[j], lam, bd))   # no regularisation for the filter's searches
-            aq = ac_q(bd, q)
-            thr_b = max(1, (aq * aq * (10 + film_grain)) // 2560)
-            src = O.mctf(g, bd, padded[i], [padded[j] for j in nb], mvs_tf, thr_b, 3 * thr_b)
-            fr = O.crop(g, src)
-        r = FrameResult()
-        r.kind, r.fp, r.q, r.mvs, r.src, r.filtered_from = kind, fp, q, None, src, nb
-        if kind == 0:
-            if key_var_part and blk_log2 == 4:
-                pm = O.partition_smooth(g, src[0], min(4 * ac_q(bd, q), 800 << (bd - 8)))
-            else:
-                pm = O.partition_fixed(g, blk_log2)
-            r.part_map = pm
-            r.res = O.encode_intra_frame(g, fr, bd, q, pm, quant_rnd=rnd[0])
-        else:
-            mvs = O.hme(g, pyr, anchor_pyr, lam, bd)
-            if me_smooth:
-                mvs = O.me_sbrd(g, pyr, anchor_pyr, mvs, lam, lam >> 2, sbrd_passes)
-            r.mvs = mvs
-            r.res = O.encode_inter_frame(g, fr, bd, q, pm16, mvs, anchor_fin, quant_rnd=rnd[kind], tb_zero_thr=tb_zero_thr)
-            O.merge_skip_blocks(g, r.res.blocks)
-        fin, r.cdef_idx, r.lr_units = r.res.rec, None, None
-        if loop_filters:
-            O.deblock_frame(g, bd, r.res.blocks, r.res.rec, list(fp.lf_level), fp.lf_sharpness)
-            if fp.cdef_bits > 0 or fp.cdef_y_strength[0] > 0 or fp.cdef_uv_strength[0] > 0:
-                r.cdef_idx = O.cdef_search(g, bd, r.res.blocks, fp, r.res.rec, src)
-                fin = O.cdef_frame(g, bd, r.res.blocks, fp, r.cdef_idx, r.res.rec)
-            else:
-                r.cdef_idx = np.zeros(g.sb_rows * g.sb_cols, np.uint8)
-                fin = r.res.rec
-            if lr:
-                cand = O.lr_candidate((0, 0, 8), (0, 0, 8), 12, (0, 95))
+    try:        # the quantisation matrix levels are oracle state (O.set_qm): never leave them set behind a failure
+        for i, fr in enumerate(frames):
+            kind = frame_kind(gop_pos[i], keyint, gop_period, intra_only)
+            q = qk[kind]
+            fp = class_params(bd, q, kind, loop_filters, lr)
+            fp.qm_level[0] = fp.qm_level[1] = 15      # flat (csrc/encoder.cc set_qm_levels without --enable-qm)
+            if qm is not None:
+                fp.using_qmatrix = 1
+                fp.qm_level[0] = fp.qm_level[1] = O.qm_level(q, qm[0], qm[1])
+            O.set_qm(fp.qm_level[0], fp.qm_level[1]) if qm is not None else O.set_qm()
+            src = padded[i]
+            pyr = pyrs[i]          # the motion search always sees the unfiltered source pictures
+            nb = []
+            if mctf and kind != 2 and not intra_only:
+                # temporal filter of key / anchor sources (csrc/encoder.cc launch()): neighbours inside the closed GOP; ahead of
+                # the picture only what the same batch holds (and --lookahead allows), behind it up to mctf_radius pictures
+                lo, hi = (0, mctf_key_fwd) if kind == 0 else (-mctf_radius, mctf_radius)
+                if lookahead >= 0:
+                    hi = min(hi, lookahead)
+                in_gop = gop_pos[i] % keyint
+                for d in range(lo, hi + 1):
+                    j = i + d
+                    if d == 0 or j < 0 or j >= n or (d > 0 and j // batch != i // batch):
+                        continue
+                    if in_gop + d < 0 or in_gop + d >= keyint:
+                        continue
+                    if d > 0 and gop_pos[j] != gop_pos[i] + d:   # a scene change between the two
+                        continue
+                    nb.append(j)
+                nb = nb[:6]
+            if nb:
+                mvs_tf = []
+                for j in nb:
+                    mvs_tf.append(O.hme(g, pyrs[i], pyrs[j], lam, bd))   # no regularisation for the filter's searches
                 aq = ac_q(bd, q)
-                r.lr_units, _ = O.lr_search(g, bd, fp, cand, fin, r.res.rec, src[0], (aq * aq * 5) >> 8)
-                fin = O.lr_frame(g, bd, fp, fin, r.res.rec, [r.lr_units, None, None])
-        r.fin = fin
+                thr_b = max(1, (aq * aq * (10 + film_grain)) // 2560)
+                src = O.mctf(g, bd, padded[i], [padded[j] for j in nb], mvs_tf, thr_b, 3 * thr_b)
+                fr = O.crop(g, src)
+            r = FrameResult()
+            r.kind, r.fp, r.q, r.mvs, r.src, r.filtered_from = kind, fp, q, None, src, nb
+            if kind == 0:
+                if key_var_part and blk_log2 == 4:
+                    pm = O.partition_smooth(g, src[0], min(4 * ac_q(bd, q), 800 << (bd - 8)))
+                else:
+                    pm = O.partition_fixed(g, blk_log2)
+                r.part_map = pm
+                r.res = O.encode_intra_frame(g, fr, bd, q, pm, quant_rnd=rnd[0])
+            else:
+                mvs = O.hme(g, pyr, anchor_pyr, lam, bd)
+                if me_smooth:
+                    mvs = O.me_sbrd(g, pyr, anchor_pyr, mvs, lam, lam >> 2, sbrd_passes)
+                r.mvs = mvs
+                r.res = O.encode_inter_frame(g, fr, bd, q, pm16, mvs, anchor_fin, quant_rnd=rnd[kind], tb_zero_thr=tb_zero_thr)
+                O.merge_skip_blocks(g, r.res.blocks)
+            fin, r.cdef_idx, r.lr_units = r.res.rec, None, None
+            if loop_filters:
+                O.deblock_frame(g, bd, r.res.blocks, r.res.rec, list(fp.lf_level), fp.lf_sharpness)
+                if fp.cdef_bits > 0 or fp.cdef_y_strength[0] > 0 or fp.cdef_uv_strength[0] > 0:
+                    r.cdef_idx = O.cdef_search(g, bd, r.res.blocks, fp, r.res.rec, src)
+                    fin = O.cdef_frame(g, bd, r.res.blocks, fp, r.cdef_idx, r.res.rec)
+                else:
+                    r.cdef_idx = np.zeros(g.sb_rows * g.sb_cols, np.uint8)
+                    fin = r.res.rec
+                if lr:
+                    cand = O.lr_candidate((0, 0, 8), (0, 0, 8), 12, (0, 95))
+                    aq = ac_q(bd, q)
+                    r.lr_units, _ = O.lr_search(g, bd, fp, cand, fin, r.res.rec, src[0], (aq * aq * 5) >> 8)
+                    fin = O.lr_frame(g, bd, fp, fin, r.res.rec, [r.lr_units, None, None])
+            r.fin = fin
+            O.set_qm()
+            if kind != 2:
+                anchor_fin, anchor_pyr = fin, pyr
+            out.append(r)
+    finally:
         O.set_qm()
-        if kind != 2:
-            anchor_fin, anchor_pyr = fin, pyr
-        out.append(r)
     return g, out
