@@ -28,6 +28,21 @@ def test_bad_arguments_exit_nonzero(tmp_path):
     assert subprocess.run([CLI, "-i", "a", "-o", "b", "--frobnicate"], capture_output=True).returncode == 2
 
 
+def test_argv_contract_holds_no_forbidden_hardware_substring():
+    """The daemon's startup policy rejects argv that contains any of FORBIDDEN_HW_FLAGS (startup.rs:13-15: nvenc, qsv, vaapi,
+    cuda, amf, vce, qsvenc).  Nothing the daemon would put on our command line -- the executable's name, the flags of
+    build_av1an_command (av1an.rs:79-107) and the flags our --help lists -- contains one."""
+    forbidden = ("nvenc", "qsv", "vaapi", "cuda", "amf", "vce", "qsvenc")
+    help_text = subprocess.run([CLI, "--help"], capture_output=True, text=True).stdout
+    flags = [w.strip("[]()") for w in help_text.split() if w.lstrip("[").startswith("-")]
+    argv = [os.path.basename(CLI), "-i", "-o", "--encoder", "svt-av1", "--pix-format", "yuv420p10le", "--video-params",
+            "--crf 8 --preset 3 --film-grain 20 --enable-qm 1 --qm-min 1 --qm-max 15 --keyint 240 --lookahead 40",
+            "--audio-params", "-c:a copy", "--workers", "--temp"] + flags
+    assert len(flags) >= 8
+    for a in argv:
+        assert not any(f in a.lower() for f in forbidden), a
+
+
 def test_gpu_plan_without_a_gpu_is_an_error():
     """`av1an --gpu-plan` (what replaces concurrency.rs:67-84) answers only where there is a GPU; exit 4 keeps the
     daemon on its core-count plan."""
