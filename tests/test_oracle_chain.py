@@ -131,6 +131,16 @@ def test_daemon_settings_chain_decodes(noise):
             assert D.psnr(out[i][0], frames[i][0], bd) > (44 if noise < 1 else 40)
 
 
+def test_random_configurations_decode():
+    """A seeded sample of tools/fuzz_chain.py (3600 random configurations were run in round 2 without a mismatch): sizes that are and
+    are not multiples of 8, bit depths, quantisers, structures, loop restoration, quantisation matrices -- both decoders reproduce
+    the chain's reconstruction."""
+    import subprocess, sys
+    root = os.path.dirname(HERE)
+    r = subprocess.run([sys.executable, os.path.join(root, "tools", "fuzz_chain.py"), "424242", "16"], capture_output=True, text=True, cwd=root)
+    assert r.returncode == 0 and "FINISHED 16 bad 0" in r.stdout, r.stdout[-2000:] + r.stderr[-2000:]
+
+
 def test_qm_level_mapping():
     """aom_get_qmlevel (SVT-AV1 and libaom map the quantiser index to a level the same way)."""
     assert O.qm_level(0, 1, 15) == 1 and O.qm_level(255, 1, 15) == 15 and O.qm_level(128, 0, 15) == 8
