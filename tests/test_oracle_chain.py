@@ -132,7 +132,7 @@ def test_daemon_settings_chain_decodes(noise):
 
 
 def test_random_configurations_decode():
-    """A seeded sample of tools/fuzz_chain.py (3600 random configurations were run in round 2 without a mismatch): sizes that are and
+    """A seeded sample of tools/fuzz_chain.py (6000 random configurations were run in round 2 without a mismatch): sizes that are and
     are not multiples of 8, bit depths, quantisers, structures, loop restoration, quantisation matrices -- both decoders reproduce
     the chain's reconstruction."""
     import subprocess, sys

@@ -3,9 +3,10 @@
 compared with) through the host bitstream writer and BOTH decoders: picture sizes 16..334 (multiples of 8 and not: padded +
 render_size), 8 / 10 bits, CRF 1..63, P chain / hierarchies / automatic structure, key frames every 3 / 5 / 240 frames and at scene
 cuts, loop restoration, quantisation matrix ranges, two or three regularisation sweeps, film-grain-strength temporal filter, fixed or
-smoothness-driven key-frame partition, 1..7 frames.  dav1d and libaom must reproduce the chain's reconstruction of every frame.
+smoothness-driven key-frame partition, up to 4 x 4 tiles, 1..7 frames.  dav1d and libaom must reproduce the chain's reconstruction of every frame.
 CPU only.  Usage: tools/fuzz_chain.py SEED ITERATIONS   (run several seeds side by side; about 8 configurations per second and core)
-Record: seeds 1000-4000 x 150 and 5000-10000 x 500 = 3600 configurations, no mismatch (round 2)."""
+Record: seeds 1000-4000 x 150, 5000-10000 x 500 (single tile) and 11000-16000 x 400 (random tilings) = 6000 configurations, no
+mismatch (round 2)."""
 import sys, os, random, json, traceback
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import numpy as np
@@ -23,7 +24,7 @@ for it in range(n_iter):
     qm = None if rng.random() < 0.4 else tuple(sorted((rng.randint(0, 15), rng.randint(0, 15))))
     noise = rng.choice([0.0, 0.3, 1.0, 2.0]); keyint = rng.choice([240, 3, 5])
     passes = rng.choice([2, 3]); fg = rng.choice([0, 20]); kvp = rng.random() < 0.7
-    cfg = dict(w=w, h=h, bd=bd, crf=crf, n=n, gop=gop, lr=lr, qm=qm, noise=noise, keyint=keyint, passes=passes, fg=fg, kvp=kvp)
+    cfg = dict(seed=seed0, it=it, w=w, h=h, bd=bd, crf=crf, n=n, gop=gop, lr=lr, qm=qm, noise=noise, keyint=keyint, passes=passes, fg=fg, kvp=kvp)
     try:
         src, padded, cw, ch = unaligned_clip(w, h, bd, n, seed=it + seed0)
         if noise != 0.4:
@@ -31,7 +32,11 @@ for it in range(n_iter):
             padded = [[np.pad(f[0][:h, :w], ((0, ch - h), (0, cw - w)), mode="edge"),
                        np.pad(f[1][:(h + 1) // 2, :(w + 1) // 2], ((0, ch // 2 - (h + 1) // 2), (0, cw // 2 - (w + 1) // 2)), mode="edge"),
                        np.pad(f[2][:(h + 1) // 2, :(w + 1) // 2], ((0, ch // 2 - (h + 1) // 2), (0, cw // 2 - (w + 1) // 2)), mode="edge")] for f in big]
-        g, want = chain.encode_chain(padded, cw, ch, bd, crf, keyint=keyint, gop_period=gop, lr=lr, qm=qm, sbrd_passes=passes, film_grain=fg, key_var_part=kvp)
+        tiles = (rng.choice([0, 0, 1, 2]), rng.choice([0, 0, 1, 2]))      # uniform tiling of every frame (clamped to what the size allows)
+        g0 = O.geom(cw, ch, tiles[0], tiles[1])
+        g, want = chain.encode_chain(padded, cw, ch, bd, crf, keyint=keyint, gop_period=gop, lr=lr, qm=qm, sbrd_passes=passes, film_grain=fg, key_var_part=kvp, geom=g0)
+        for r in want:
+            r.fp.tile_cols_log2, r.fp.tile_rows_log2 = g.tile_cols_log2, g.tile_rows_log2
         tus = pack_chain(cw, ch, bd, want, g, lr=lr, render=(w, h) if (cw, ch) != (w, h) else (0, 0))
         for dec in (D.dav1d_decode, D.aom_decode):
             out = dec(tus)
