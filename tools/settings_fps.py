@@ -13,7 +13,7 @@ sys.path.insert(0, ROOT)
 def _gen(job):
     from av1_base_b200 import synth
     w, h, bd, i = job
-    return synth.synth_clip(w, h, bd, 1, seed=4, scene_len=150, hdr=True, start=i)[0]
+    return synth.synth_clip(w, h, bd, 1, seed=4, scene_len=150, hdr=(bd == 10 and w >= 3840), start=i)[0]
 
 
 def chunk_order(n_distinct, n_frames):
@@ -28,12 +28,13 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--chunk-len", type=int, default=150)
     ap.add_argument("--size", default="3840x2160")
+    ap.add_argument("--bd", type=int, default=10)
     ap.add_argument("--out", default="")
     ap.add_argument("--only", type=int, default=-1, help="run only this row of the settings table")
     ap.add_argument("--pack-paths", default="0", help="comma list: 0 automatic placement of the range coder, 3 host, 4 device")
     a = ap.parse_args()
     w, h = map(int, a.size.split("x"))
-    bd = 10
+    bd = a.bd
     t0 = time.perf_counter()
     with ProcessPoolExecutor(min(a.distinct, max(1, (os.cpu_count() or 2) // 2), 16)) as ex:
         frames = list(ex.map(_gen, [(w, h, bd, i) for i in range(a.distinct)]))
@@ -50,7 +51,7 @@ def main():
     configs = [(name + (" [range coder: %s]" % {0: "automatic", 3: "host", 4: "device"}[pp] if a.pack_paths != "0" else ""), dict(kw, pack_path=pp))
                for name, kw in configs for pp in map(int, a.pack_paths.split(","))]
     for name, kw in configs:
-        enc = encoder.Encoder(w, h, bd, hdr=True, frames_in_flight=8, keyint=240, **kw)
+        enc = encoder.Encoder(w, h, bd, hdr=(bd == 10 and w >= 3840), frames_in_flight=8, keyint=240, **kw)
         enc.stage_clip(frames)
         for _ in range(a.warmup):                    # warm-up chunks (clocks, lazily loaded kernels, staging buffers)
             enc.encode_clip(order)
@@ -68,7 +69,7 @@ def main():
                      "bytes_per_frame": round(st["bytes_out"] / max(1, st["frames_done"]), 1), "gop_period": info["gop_period"],
                      "q_key_anchor_nonref": [info["q_key"], info["q_anchor"], info["q_nonref"]], "temporal_filter": info["mctf"], "ms_of_each_chunk": per})
         enc.close()
-    out = {"what": "resident 150-frame chunks, one B200, %dx%d 10-bit, %d distinct pictures" % (w, h, a.distinct),
+    out = {"what": "resident 150-frame chunks, one B200, %dx%d %d-bit, %d distinct pictures" % (w, h, bd, a.distinct),
            "timed_chunks": a.chunks, "warmup_chunks": a.warmup, "synth_s": round(t_synth, 1), "host_cores": os.cpu_count(), "rows": rows}
     txt = json.dumps(out, indent=1)
     print(txt)
