@@ -222,8 +222,31 @@ struct PacketReader {
 
 bool put(FILE* f, const std::vector<uint8_t>& v) { return v.empty() || fwrite(v.data(), 1, v.size(), f) == v.size(); }
 
-// Minimal Matroska (video only): EBML header, Segment { Info, Tracks { V_AV1 }, Cluster* { SimpleBlock* } }.
-// Clusters are written as they fill (one per key frame / 30 s); the Segment size and the Duration are patched at the end.
+void ebml_uint_fixed8(std::vector<uint8_t>& o, uint32_t id, uint64_t v) {   // patchable: always 8 payload bytes
+  ebml_id(o, id);
+  o.push_back(0x88);
+  for (int i = 7; i >= 0; i--) o.push_back((uint8_t)(v >> (8 * i)));
+}
+// SeekHead with the positions (relative to the Segment's data) of Info, Tracks and Cues; fixed size whatever the values
+std::vector<uint8_t> mkv_seekhead(uint64_t info_pos, uint64_t tracks_pos, uint64_t cues_pos) {
+  std::vector<uint8_t> sh;
+  const uint32_t ids[3] = {0x1549A966, 0x1654AE6B, 0x1C53BB6B};
+  const uint64_t pos[3] = {info_pos, tracks_pos, cues_pos};
+  for (int k = 0; k < 3; k++) {
+    std::vector<uint8_t> seek;
+    const uint8_t idb[4] = {(uint8_t)(ids[k] >> 24), (uint8_t)(ids[k] >> 16), (uint8_t)(ids[k] >> 8), (uint8_t)ids[k]};
+    ebml_bytes(seek, 0x53AB, idb, 4);
+    ebml_uint_fixed8(seek, 0x53AC, pos[k]);
+    ebml_master(sh, 0x4DBB, seek);
+  }
+  std::vector<uint8_t> out;
+  ebml_master(out, 0x114D9B74, sh);
+  return out;
+}
+
+// Minimal Matroska (video only): EBML header, Segment { SeekHead, Info, Tracks { V_AV1 }, Cluster* { SimpleBlock* }, Cues }.
+// Clusters are written as they fill (one per key frame / 30 s); the Segment size, the Duration and the SeekHead are patched at
+// the end, when the Cues (one point per cluster that starts with a key frame: what players seek by) have been written.
 // w x h: the coded frame; show_w x show_h: the source size (smaller when the encoder padded it to multiples of 8)
 bool write_mkv(const std::string& path, PacketReader& rd, int64_t* n_out, int w, int h, int show_w, int show_h, int fps_num, int fps_den, bool hbd) {
   FILE* f = fopen(path.c_str(), "wb");
@@ -238,6 +261,8 @@ bool write_mkv(const std::string& path, PacketReader& rd, int64_t* n_out, int w,
   const long seg_size_pos = (long)out.size();
   ebml_size(out, 0);                                             // patched below
   const long seg_start = (long)out.size();
+  const long seekhead_pos = (long)out.size();
+  { const std::vector<uint8_t> ph = mkv_seekhead(0, 0, 0); out.insert(out.end(), ph.begin(), ph.end()); }   // patched below
   std::vector<uint8_t> info, tracks, te, video;
   const double frame_ms = 1000.0 * fps_den / fps_num;
   ebml_uint(info, 0x2AD7B1, 1000000);                           // TimestampScale: 1 ms
@@ -245,6 +270,7 @@ bool write_mkv(const std::string& path, PacketReader& rd, int64_t* n_out, int w,
   ebml_float(info, 0x4489, 0.0);                                // Duration: patched below
   ebml_str(info, 0x4D80, "av1b200"); ebml_str(info, 0x5741, "av1b200");
   const long info_body_pos = (long)out.size() + 4 + 8;          // id (4) + 8-byte size
+  const uint64_t info_seg_pos = (uint64_t)(out.size() - (size_t)seg_start);
   ebml_master(out, 0x1549A966, info);
   // CodecPrivate = AV1CodecConfigurationRecord: marker/version, profile/level, flags, then the sequence header OBU
   std::vector<uint8_t> av1c;
@@ -268,14 +294,24 @@ bool write_mkv(const std::string& path, PacketReader& rd, int64_t* n_out, int w,
   ebml_uint(te, 0x23E383, (uint64_t)(frame_ms * 1e6));          // DefaultDuration (ns)
   ebml_master(te, 0xE0, video);
   ebml_master(tracks, 0xAE, te);
+  const uint64_t tracks_seg_pos = (uint64_t)(out.size() - (size_t)seg_start);
   ebml_master(out, 0x1654AE6B, tracks);
   bool ok = put(f, out);
   uint64_t seg_bytes = out.size() - (size_t)seg_start;
   // clusters: a new one at every key frame and at least every 30000 ms of timestamps (int16 block offsets)
-  std::vector<uint8_t> cl, clm;
+  std::vector<uint8_t> cl, clm, cues;
   double cl_t0 = 0;
+  bool cl_key = false;
   auto flush = [&]() {
     if (cl.empty()) return;
+    if (cl_key) {
+      // CuePoint { CueTime, CueTrackPositions { CueTrack 1, CueClusterPosition } }
+      std::vector<uint8_t> cp, ctp;
+      ebml_uint(cp, 0xB3, (uint64_t)(cl_t0 + 0.5));
+      ebml_uint(ctp, 0xF7, 1); ebml_uint(ctp, 0xF1, seg_bytes);
+      ebml_master(cp, 0xB7, ctp);
+      ebml_master(cues, 0xBB, cp);
+    }
     clm.clear();
     ebml_master(clm, 0x1F43B675, cl);
     ok = ok && put(f, clm);
@@ -285,7 +321,7 @@ bool write_mkv(const std::string& path, PacketReader& rd, int64_t* n_out, int w,
   int64_t k = 0;
   for (; have && ok; have = rd.next(pk), k++) {
     const double ts = frame_ms * k;
-    if (cl.empty() || pk.key || ts - cl_t0 > 30000) { flush(); cl_t0 = ts; ebml_uint(cl, 0xE7, (uint64_t)(ts + 0.5)); }
+    if (cl.empty() || pk.key || ts - cl_t0 > 30000) { flush(); cl_t0 = ts; cl_key = pk.key || k == 0; ebml_uint(cl, 0xE7, (uint64_t)(ts + 0.5)); }
     size_t n = pk.data.size();
     const uint8_t* p = skip_td(pk.data.data(), n);
     const int rel = (int)(ts - cl_t0 + 0.5);
@@ -298,7 +334,18 @@ bool write_mkv(const std::string& path, PacketReader& rd, int64_t* n_out, int w,
   }
   flush();
   *n_out = k;
-  // patch the Segment size and the Duration
+  const uint64_t cues_seg_pos = seg_bytes;
+  if (!cues.empty()) {
+    clm.clear();
+    ebml_master(clm, 0x1C53BB6B, cues);
+    ok = ok && put(f, clm);
+    seg_bytes += clm.size();
+  }
+  // patch the Segment size, the Duration and the SeekHead
+  {
+    const std::vector<uint8_t> shd = mkv_seekhead(info_seg_pos, tracks_seg_pos, cues_seg_pos);
+    if (!cues.empty()) ok = ok && fseek(f, seekhead_pos, SEEK_SET) == 0 && put(f, shd);
+  }
   std::vector<uint8_t> sz, du;
   ebml_size(sz, seg_bytes);
   ebml_float(du, 0x4489, frame_ms * k);

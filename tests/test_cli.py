@@ -261,7 +261,7 @@ def test_cli_progress_fields(tmp_path):
     pr = json.load(open(os.path.join(tmp, "progress.json")))
     assert pr["done"] is True and pr["frames_encoded"] == n and pr["total_frames"] == n and pr["progress"] == 1.0
     size_kbps = os.path.getsize(out) * 8 / 1000 * 30 / n
-    assert 0.8 * size_kbps < pr["bitrate_kbps"] <= size_kbps           # payload of the packets; the file adds the container
+    assert 0.7 * size_kbps < pr["bitrate_kbps"] <= size_kbps           # payload of the packets; the file adds the container (SeekHead, Cues, block headers)
     assert 30 < pr["psnr"] < 70 and 0.8 < pr["ssim"] <= 1.0 and pr["est_remaining_secs"] == 0
     # the chunks' packet files are gone, only progress.json stays under --temp
     assert sorted(os.listdir(tmp)) == ["progress.json"]

@@ -76,6 +76,61 @@ def test_ffmpeg_demuxes_our_matroska_and_ivf(tmp_path, w, h, bd, fps):
     assert open(out, "rb").read() == b"".join(tus)
 
 
+def _elems(b, lo, hi):
+    """(id, payload start, payload size, element start) of the EBML elements in b[lo:hi]."""
+    i = lo
+    while i < hi:
+        n = 1
+        while not (b[i] & (0x80 >> (n - 1))):
+            n += 1
+        eid = int.from_bytes(b[i:i + n], "big")
+        first, m = b[i + n], 1
+        while not (first & (0x80 >> (m - 1))):
+            m += 1
+        size = int.from_bytes(bytes([first & (0xFF >> m)]) + b[i + n + 1:i + n + m], "big")
+        yield eid, i + n + m, size, i
+        i += n + m + size
+
+
+def test_matroska_index_and_seeking(tmp_path):
+    """What players seek by: the SeekHead points at Info, Tracks and Cues, every CuePoint at a Cluster that starts with a key
+    frame and carries that cluster's timestamp; FFmpeg seeks to the key frames and returns their packets."""
+    w, h, bd, n, keyint = 200, 136, 8, 12, 3
+    frames = synth.synth_clip(w, h, bd, n, seed=3, scene_len=100, noise=0.3)
+    g, want = chain.encode_chain(frames, w, h, bd, 32, keyint=keyint, gop_period=2)
+    tus = pack_chain(w, h, bd, want, g)
+    d, out = str(tmp_path / "pk"), str(tmp_path / "out.mkv")
+    write_packet_files(d, tus, [r.kind == 0 for r in want], keyint)
+    mux(d, out, w, h, w, h, (30, 1), bd)
+    data = open(out, "rb").read()
+    seg = [e for e in _elems(data, 0, len(data)) if e[0] == 0x18538067][0]
+    assert seg[1] + seg[2] == len(data)                                   # the patched Segment size
+    kids = list(_elems(data, seg[1], seg[1] + seg[2]))
+    assert [k[0] for k in kids] == [0x114D9B74, 0x1549A966, 0x1654AE6B] + [0x1F43B675] * (n // keyint) + [0x1C53BB6B]
+    targets = {}
+    for s in _elems(data, kids[0][1], kids[0][1] + kids[0][2]):           # SeekHead -> Seek { SeekID, SeekPosition }
+        f = {e[0]: int.from_bytes(data[e[1]:e[1] + e[2]], "big") for e in _elems(data, s[1], s[1] + s[2])}
+        targets[f[0x53AB]] = seg[1] + f[0x53AC]
+    assert targets == {k[0]: k[3] for k in kids if k[0] in (0x1549A966, 0x1654AE6B, 0x1C53BB6B)}
+    clusters = [k for k in kids if k[0] == 0x1F43B675]
+    cues = []
+    for cp in _elems(data, kids[-1][1], kids[-1][1] + kids[-1][2]):       # Cues -> CuePoint { CueTime, CueTrackPositions { .. } }
+        f = {}
+        for e in _elems(data, cp[1], cp[1] + cp[2]):
+            if e[0] == 0xB3:
+                f["t"] = int.from_bytes(data[e[1]:e[1] + e[2]], "big")
+            elif e[0] == 0xB7:
+                f.update({q[0]: int.from_bytes(data[q[1]:q[1] + q[2]], "big") for q in _elems(data, e[1], e[1] + e[2])})
+        cues.append((f["t"], f[0xF7], seg[1] + f[0xF1]))
+    assert cues == [(round(1000 * c * keyint / 30), 1, clusters[c][3]) for c in range(n // keyint)]
+    cap = cv2.VideoCapture(out, cv2.CAP_FFMPEG, [cv2.CAP_PROP_FORMAT, -1])
+    for k in (6, 3, 9, 0):
+        assert cap.set(cv2.CAP_PROP_POS_FRAMES, k)
+        ok, p = cap.read()
+        assert ok and p.tobytes() == tus[k][2:], k
+    cap.release()
+
+
 def test_ffmpeg_demuxes_a_cropped_track(tmp_path):
     """Sources that are not multiples of 8: PixelCrop / DisplayWidth / DisplayHeight in the track do not disturb the demuxer; the
     track's pixel size is the coded size and the packets come back unchanged."""
