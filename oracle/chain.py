@@ -109,7 +109,7 @@ def scene_positions(g, bd, padded, pos0=0, scene_cut=True):
 
 def encode_chain(frames, w, h, bd, crf, keyint=240, gop_period=DEFAULT_GOP_PERIOD, me_smooth=True, key_var_part=True, loop_filters=True,
                  lr=False, intra_only=False, blk_log2=4, tb_zero_thr=0, pos0=0, geom=None, mctf=True, batch=8, lookahead=-1,
-                 film_grain=0, mctf_radius=2, mctf_key_fwd=4, scene_cut=True, qm=None, rnd=(48, 48, 48), sbrd_passes=2, inter_merge=False):
+                 film_grain=0, mctf_radius=2, mctf_key_fwd=4, scene_cut=True, qm=None, rnd=(48, 48, 48), sbrd_passes=2, inter_merge=False, anchor_boost=None):
     """Returns one FrameResult per frame: kind, fp, res (blocks / coef / pre-filter rec), fin (padded planes after the
     in-loop filters), cdef_idx, lr_units, mvs.  qm = (qm_min, qm_max): quantisation matrices at the level the frame's quantiser
     index maps to (csrc/encoder.cc set_qm_levels), luma and chroma alike.  sbrd_passes: sweeps of the superblock-level regularisation
@@ -130,10 +130,15 @@ def encode_chain(frames, w, h, bd, crf, keyint=240, gop_period=DEFAULT_GOP_PERIO
     pyrs = [O.pyramid(g, pl[0]) for pl in padded]
     n = len(frames)
     gop_pos = scene_positions(g, bd, padded, pos0, scene_cut and not intra_only)
+    n_anchor = 0
     try:        # the quantisation matrix levels are oracle state (O.set_qm): never leave them set behind a failure
         for i, fr in enumerate(frames):
             kind = frame_kind(gop_pos[i], keyint, gop_period, intra_only)
             q = qk[kind]
+            if anchor_boost and kind == 1:      # EXPERIMENT (not in the product): every anchor_boost[0]-th anchor anchor_boost[1] quantiser steps finer
+                n_anchor += 1
+                if n_anchor % anchor_boost[0] == 0:
+                    q = max(1, q - anchor_boost[1])
             fp = class_params(bd, q, kind, loop_filters, lr)
             fp.qm_level[0] = fp.qm_level[1] = 15      # flat (csrc/encoder.cc set_qm_levels without --enable-qm)
             if qm is not None:
