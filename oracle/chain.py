@@ -65,18 +65,19 @@ class FrameResult:
     pass
 
 
-def merged_partition(g, pm16, mvs):
+def merged_partition(g, pm16, mvs, tol=0):
     """EXPERIMENT (roadmap measurement, tools/rd_chain.py --kw '{"inter_merge": true}'; not in the product): inter blocks of 32x32 /
     64x64 wherever the four (sixteen) 16x16 blocks of an aligned square that lies inside the picture carry one vector -- coded
     with one prediction and one 32x32 / 64x64 transform instead of four (sixteen) 16x16 ones."""
     pm = np.array(pm16, np.uint8).reshape(g.h8, g.w8).copy()
-    mv = np.asarray(mvs).reshape(g.h8, g.w8, 2)
+    mv = mvs.reshape(g.h8, g.w8, 2)
     for bl, n8 in ((5, 4), (6, 8)):
         for y0 in range(0, g.h8 - n8 + 1, n8):
             for x0 in range(0, g.w8 - n8 + 1, n8):
                 blk = mv[y0:y0 + n8, x0:x0 + n8].reshape(-1, 2)
-                if (pm[y0:y0 + n8, x0:x0 + n8] >= 4).all() and (blk == blk[0]).all():
+                if (pm[y0:y0 + n8, x0:x0 + n8] >= 4).all() and (np.abs(blk.astype(np.int32) - blk[0]) <= tol).all():
                     pm[y0:y0 + n8, x0:x0 + n8] = bl
+                    mv[y0:y0 + n8, x0:x0 + n8] = blk[0]     # tol > 0: the block takes the vector of its first unit (mvs is updated in place)
     return pm.reshape(-1)
 
 
@@ -109,7 +110,7 @@ def scene_positions(g, bd, padded, pos0=0, scene_cut=True):
 
 def encode_chain(frames, w, h, bd, crf, keyint=240, gop_period=DEFAULT_GOP_PERIOD, me_smooth=True, key_var_part=True, loop_filters=True,
                  lr=False, intra_only=False, blk_log2=4, tb_zero_thr=0, pos0=0, geom=None, mctf=True, batch=8, lookahead=-1,
-                 film_grain=0, mctf_radius=2, mctf_key_fwd=4, scene_cut=True, qm=None, rnd=(48, 48, 48), sbrd_passes=2, inter_merge=False, anchor_boost=None):
+                 film_grain=0, mctf_radius=2, mctf_key_fwd=4, scene_cut=True, qm=None, rnd=(48, 48, 48), sbrd_passes=2, inter_merge=False, anchor_boost=None, lam_r_shift=2):
     """Returns one FrameResult per frame: kind, fp, res (blocks / coef / pre-filter rec), fin (padded planes after the
     in-loop filters), cdef_idx, lr_units, mvs.  qm = (qm_min, qm_max): quantisation matrices at the level the frame's quantiser
     index maps to (csrc/encoder.cc set_qm_levels), luma and chroma alike.  sbrd_passes: sweeps of the superblock-level regularisation
@@ -185,9 +186,9 @@ def encode_chain(frames, w, h, bd, crf, keyint=240, gop_period=DEFAULT_GOP_PERIO
             else:
                 mvs = O.hme(g, pyr, anchor_pyr, lam, bd)
                 if me_smooth:
-                    mvs = O.me_sbrd(g, pyr, anchor_pyr, mvs, lam, lam >> 2, sbrd_passes)
+                    mvs = O.me_sbrd(g, pyr, anchor_pyr, mvs, lam, lam >> lam_r_shift, sbrd_passes)   # lam_r_shift != 2: experiment
                 r.mvs = mvs
-                pm_inter = merged_partition(g, pm16, mvs) if inter_merge else pm16
+                pm_inter = merged_partition(g, pm16, mvs, int(inter_merge) - 1) if inter_merge else pm16   # inter_merge = 1 + tolerance (1/8 samples)
                 r.res = O.encode_inter_frame(g, fr, bd, q, pm_inter, mvs, anchor_fin, quant_rnd=rnd[kind], tb_zero_thr=tb_zero_thr)
                 O.merge_skip_blocks(g, r.res.blocks)
             fin, r.cdef_idx, r.lr_units = r.res.rec, None, None
