@@ -4,9 +4,9 @@ compared with) through the host bitstream writer and BOTH decoders: picture size
 render_size), 8 / 10 bits, CRF 1..63, P chain / hierarchies / automatic structure, key frames every 3 / 5 / 240 frames and at scene
 cuts, loop restoration, quantisation matrix ranges, two or three regularisation sweeps, film-grain-strength temporal filter, fixed or
 smoothness-driven key-frame partition, up to 4 x 4 tiles, 1..7 frames.  dav1d and libaom must reproduce the chain's reconstruction of every frame.
-CPU only.  Usage: tools/fuzz_chain.py SEED ITERATIONS   (run several seeds side by side; about 8 configurations per second and core)
-Record: seeds 1000-4000 x 150, 5000-10000 x 500 (single tile) and 11000-16000 x 400 (random tilings) = 6000 configurations, no
-mismatch (round 2)."""
+CPU only.  Usage: tools/fuzz_chain.py SEED ITERATIONS [big]   (run several seeds side by side; about 8 configurations per second and core)
+Record: seeds 1000-4000 x 150, 5000-10000 x 500 (single tile) and 11000-16000 x 400 (random tilings) = 6000 configurations, plus seeds 21000-27000 x 250 `big` = 1750 larger
+ones, no mismatch (round 2)."""
 import sys, os, random, json, traceback
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import numpy as np
@@ -14,12 +14,15 @@ from av1_base_b200 import abi, packer, synth
 from oracle import pyoracle as O, decoders as D, chain
 from tests.test_oracle_chain import pack_chain, unaligned_clip
 seed0 = int(sys.argv[1]); n_iter = int(sys.argv[2])
+BIG = len(sys.argv) > 3 and sys.argv[3] == "big"      # larger pictures (up to 648 x 366), up to 12 frames: about 1 configuration per second and core
 rng = random.Random(seed0)
 bad = 0
 for it in range(n_iter):
     w = rng.choice([16, 24, 40, 64, 72, 104, 136, 200, 264, 328]) + rng.choice([0, 0, 0, 2, 3, 5])
     h = rng.choice([16, 24, 40, 64, 88, 136, 184, 248]) + rng.choice([0, 0, 0, 1, 4, 6])
-    bd = rng.choice([8, 10]); crf = rng.randint(1, 63); n = rng.randint(1, 7)
+    if BIG:
+        w = rng.choice([328, 400, 512, 640]) + rng.choice([0, 0, 4, 7, 8]); h = rng.choice([184, 248, 288, 360]) + rng.choice([0, 0, 2, 6])
+    bd = rng.choice([8, 10]); crf = rng.randint(1, 63); n = rng.randint(1, 12 if BIG else 7)
     gop = rng.choice([0, 1, 2, 3, 6]); lr = rng.random() < 0.4
     qm = None if rng.random() < 0.4 else tuple(sorted((rng.randint(0, 15), rng.randint(0, 15))))
     noise = rng.choice([0.0, 0.3, 1.0, 2.0]); keyint = rng.choice([240, 3, 5])
