@@ -4,7 +4,8 @@
 a one-level pyramid, no TPL model, three reference frames, DCT only, no OBMC / warped / global motion, no masked / weighted /
 inter-intra compound -- on the clip of the bench line's `bd_rate` (960x544 10-bit, 30 frames, synth seed 4, noise 1.0).  Separates
 "which tools are missing" (tools/aom_ablation.py) from "how good are the decisions with the tools that are there".
-Usage: tools/aom_matched.py [OUT.json]      Record: profiles/r02z_vs_libaom_matched_tools_960x544.json"""
+Usage: tools/aom_matched.py [OUT.json]      Record: profiles/r02z_vs_libaom_matched_tools_960x544.json (+4.8 % on these 30 frames -- a
+quarter of which is the key frame, where the restriction hurts libaom most -- and +60 % over a whole 150-frame chunk, `over_150_frames`)"""
 import sys, os, json
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT); sys.path.insert(0, os.path.join(ROOT, 'tools'))
